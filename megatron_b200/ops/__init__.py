@@ -1,0 +1,483 @@
+"""Operator library: hand-written sm_100a kernels with PyTorch references.
+
+Every public function dispatches on the device of its input:
+
+* CUDA tensor → the in-tree extension ``megatron_b200/ops/_C*.so`` (built by
+  ``megatron_b200.ops.build``; sources in ``ops/csrc``).  A CUDA tensor with no
+  extension available raises — there is no silent eager fallback on a GPU box
+  (set ``MEGATRON_B200_ALLOW_FALLBACK=1`` to override for debugging).
+* CPU tensor → ``ops.reference`` (plain PyTorch).
+
+Replaces what the reference reaches through TransformerEngine / Apex /
+``torch.compile``.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+import torch
+
+from . import reference as ref
+
+_EXT = None
+_EXT_ERR = None
+
+
+def _load_ext():
+    global _EXT, _EXT_ERR
+    if _EXT is not None or _EXT_ERR is not None:
+        return _EXT
+    try:
+        from . import _C  # type: ignore
+
+        _EXT = _C
+    except Exception as e:  # pragma: no cover - depends on build
+        _EXT_ERR = e
+    return _EXT
+
+
+def ext():
+    """The native extension module (raises if it is not built/loadable)."""
+    e = _load_ext()
+    if e is None:
+        raise RuntimeError(
+            f"megatron_b200 native extension is not available ({_EXT_ERR!r}); run `python -m megatron_b200.ops.build`"
+        )
+    return e
+
+
+def has_ext() -> bool:
+    return _load_ext() is not None
+
+
+def _use_cuda(t: torch.Tensor) -> bool:
+    if not t.is_cuda:
+        return False
+    if _load_ext() is None:
+        if os.environ.get("MEGATRON_B200_ALLOW_FALLBACK") == "1":
+            return False
+        raise RuntimeError(
+            f"CUDA tensor passed to megatron_b200.ops but the native extension failed to load: {_EXT_ERR!r}"
+        )
+    return True
+
+
+# launch counter: bench.py reports how many of *our* kernels ran in the timed region
+_LAUNCHES = 0
+
+
+def _count(n=1):
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+def reset_launch_count():
+    global _LAUNCHES
+    _LAUNCHES = 0
+
+
+# =============================================================================
+# GEMM
+# =============================================================================
+
+_GEMM_BACKEND = os.environ.get("MEGATRON_B200_GEMM", "auto")  # auto|tcgen05|cublas
+
+
+def set_gemm_backend(name: str):
+    global _GEMM_BACKEND
+    assert name in ("auto", "tcgen05", "cublas")
+    _GEMM_BACKEND = name
+
+
+def _tc_ok(*ts) -> bool:
+    if _GEMM_BACKEND == "cublas":
+        return False
+    for t in ts:
+        if t.dtype != torch.bfloat16:
+            return False
+    return True
+
+
+def gemm_nt(x: torch.Tensor, w: torch.Tensor, out_dtype=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``x[..., K] @ w[N, K]ᵀ`` → ``[..., N]`` (forward of every linear)."""
+    if _use_cuda(x) and _tc_ok(x, w) and x.shape[-1] % 64 == 0 and w.shape[0] % 16 == 0:
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        od = out_dtype or x.dtype
+        y = out if out is not None else torch.empty((x2.shape[0], w.shape[0]), dtype=od, device=x.device)
+        ext().gemm_bf16(x2, w.contiguous(), y.view(x2.shape[0], w.shape[0]), 0, False)  # layout 0: A[M,K] B[N,K]
+        _count()
+        return y.view(*x.shape[:-1], w.shape[0])
+    return ref.gemm_nt(x, w, out_dtype)
+
+
+def gemm_nn(gy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """``gy[..., N] @ w[N, K]`` → ``[..., K]`` (dgrad)."""
+    if _use_cuda(gy) and _tc_ok(gy, w) and gy.shape[-1] % 64 == 0 and w.shape[1] % 16 == 0:
+        g2 = gy.reshape(-1, gy.shape[-1])
+        if not g2.is_contiguous():
+            g2 = g2.contiguous()
+        y = torch.empty((g2.shape[0], w.shape[1]), dtype=gy.dtype, device=gy.device)
+        ext().gemm_bf16(g2, w.contiguous(), y, 1, False)  # layout 1: A[M,K] B[K,N]
+        _count()
+        return y.view(*gy.shape[:-1], w.shape[1])
+    return ref.gemm_nn(gy, w)
+
+
+def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False, out_dtype=None) -> torch.Tensor:
+    """``a[M, N]ᵀ @ b[M, K]`` → ``[N, K]`` (wgrad); ``accumulate`` adds into fp32/bf16 ``out``."""
+    if _use_cuda(a) and _tc_ok(a, b) and a.shape[0] % 64 == 0 and b.shape[1] % 16 == 0 and a.shape[1] % 16 == 0:
+        if out is None:
+            out = torch.empty((a.shape[1], b.shape[1]), dtype=out_dtype or a.dtype, device=a.device)
+            accumulate = False
+        ext().gemm_bf16(a.contiguous(), b.contiguous(), out, 2, accumulate)  # layout 2: A[K,M] B[K,N]
+        _count()
+        return out
+    return ref.gemm_tn(a, b, out, accumulate, out_dtype)
+
+
+# =============================================================================
+# Norms
+# =============================================================================
+
+
+class _RMSNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, eps, zero_centered):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1])
+        if _use_cuda(x):
+            x2 = x2.contiguous()
+            y, rstd = ext().rmsnorm_fwd(x2, w, eps, zero_centered)
+            _count()
+        else:
+            y, rstd = ref.rms_norm_fwd(x2, w, eps, zero_centered)
+        ctx.save_for_backward(x2, w, rstd)
+        ctx.zero_centered, ctx.shape = zero_centered, shape
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, w, rstd = ctx.saved_tensors
+        g2 = gy.reshape(x2.shape)
+        if _use_cuda(g2):
+            gx, gw = ext().rmsnorm_bwd(g2.contiguous(), x2, w, rstd, ctx.zero_centered)
+            _count(2)
+        else:
+            gx, gw = ref.rms_norm_bwd(g2, x2, w, rstd, ctx.zero_centered)
+        return gx.view(ctx.shape), gw, None, None
+
+
+def rms_norm(x, weight, eps: float = 1e-5, zero_centered_gamma: bool = False):
+    return _RMSNormFn.apply(x, weight, eps, zero_centered_gamma)
+
+
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps, zero_centered):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1])
+        if _use_cuda(x):
+            x2 = x2.contiguous()
+            y, mu, rstd = ext().layernorm_fwd(x2, w, b, eps, zero_centered)
+            _count()
+        else:
+            y, mu, rstd = ref.layer_norm_fwd(x2, w, b, eps, zero_centered)
+        ctx.save_for_backward(x2, w, mu, rstd)
+        ctx.zero_centered, ctx.shape, ctx.has_bias = zero_centered, shape, b is not None
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, w, mu, rstd = ctx.saved_tensors
+        g2 = gy.reshape(x2.shape)
+        if _use_cuda(g2):
+            gx, gw, gb = ext().layernorm_bwd(g2.contiguous(), x2, w, mu, rstd, ctx.zero_centered)
+            _count(2)
+            if not ctx.has_bias:
+                gb = None
+        else:
+            gx, gw, gb = ref.layer_norm_bwd(g2, x2, w, mu, rstd, ctx.zero_centered, ctx.has_bias)
+        return gx.view(ctx.shape), gw, gb, None, None
+
+
+def layer_norm(x, weight, bias, eps: float = 1e-5, zero_centered_gamma: bool = False):
+    return _LayerNormFn.apply(x, weight, bias, eps, zero_centered_gamma)
+
+
+# =============================================================================
+# Gated activations
+# =============================================================================
+
+
+class _SwiGLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, bias, probs):
+        ctx.save_for_backward(y, bias, probs)
+        if _use_cuda(y):
+            y2 = y.reshape(-1, y.shape[-1]).contiguous()
+            out = ext().swiglu_fwd(y2, bias, probs.reshape(-1) if probs is not None else None)
+            _count()
+            return out.view(*y.shape[:-1], y.shape[-1] // 2)
+        return ref.swiglu_fwd(y, bias, probs)
+
+    @staticmethod
+    def backward(ctx, g):
+        y, bias, probs = ctx.saved_tensors
+        if _use_cuda(g):
+            y2 = y.reshape(-1, y.shape[-1]).contiguous()
+            g2 = g.reshape(-1, g.shape[-1]).contiguous()
+            dy, dprobs = ext().swiglu_bwd(g2, y2, bias, probs.reshape(-1) if probs is not None else None)
+            _count()
+            dy = dy.view(y.shape)
+            if dprobs is not None:
+                dprobs = dprobs.view(probs.shape)
+        else:
+            dy, dprobs = ref.swiglu_bwd(g, y, bias, probs)
+        gb = dy.reshape(-1, dy.shape[-1]).sum(0).to(bias.dtype) if bias is not None else None
+        return dy, gb, dprobs
+
+
+def swiglu(y, bias=None, probs=None):
+    """``silu(a) * b`` with ``a, b = (y + bias).chunk(2, -1)``; optional per-token ``probs`` weight (MoE)."""
+    return _SwiGLUFn.apply(y, bias, probs)
+
+
+def bias_swiglu(y, bias):
+    return _SwiGLUFn.apply(y, bias, None)
+
+
+def geglu(y, bias=None):
+    yb = y if bias is None else y + bias
+    a, b = yb.chunk(2, dim=-1)
+    return torch.nn.functional.gelu(a, approximate="tanh") * b
+
+
+def bias_gelu(y, bias=None):
+    yb = y if bias is None else y + bias
+    return torch.nn.functional.gelu(yb, approximate="tanh")
+
+
+# =============================================================================
+# RoPE
+# =============================================================================
+
+
+class _RoPEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t, freqs, interleaved, mscale):
+        ctx.save_for_backward(freqs)
+        ctx.interleaved, ctx.mscale = interleaved, mscale
+        if _use_cuda(t) and not interleaved and t.dim() == 4:
+            out = ext().rope_fwd(t.contiguous(), freqs.reshape(freqs.shape[0], -1).float().contiguous(), float(mscale), False)
+            _count()
+            return out
+        return ref.rope_fwd(t, freqs, interleaved, mscale, conj=False)
+
+    @staticmethod
+    def backward(ctx, g):
+        (freqs,) = ctx.saved_tensors
+        if _use_cuda(g) and not ctx.interleaved and g.dim() == 4:
+            out = ext().rope_fwd(g.contiguous(), freqs.reshape(freqs.shape[0], -1).float().contiguous(), float(ctx.mscale), True)
+            _count()
+            return out, None, None, None
+        return ref.rope_fwd(g, freqs, ctx.interleaved, ctx.mscale, conj=True), None, None, None
+
+
+def apply_rope(t, freqs, interleaved: bool = False, mscale: float = 1.0):
+    """Rotary embedding on ``t[s, b, h, d]`` with angles ``freqs[s, 1, 1, d_rot]``."""
+    return _RoPEFn.apply(t, freqs, interleaved, mscale)
+
+
+# =============================================================================
+# bias + dropout + residual add
+# =============================================================================
+
+
+def bias_dropout_add(x, bias, residual, prob: float, training: bool):
+    if bias is not None:
+        x = x + bias
+    if prob > 0.0 and training:
+        x = torch.nn.functional.dropout(x, p=prob, training=True)
+    return residual + x
+
+
+# =============================================================================
+# Attention
+# =============================================================================
+
+
+class _FlashAttnFn(torch.autograd.Function):
+    """sm_100a flash attention (``csrc/flash_attn_sm100.cu``); q/k/v layout [s, b, h, d]."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, causal, scale):
+        o, lse = ext().flash_attn_fwd(q, k, v, causal, scale)
+        _count()
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.causal, ctx.scale = causal, scale
+        return o
+
+    @staticmethod
+    def backward(ctx, go):
+        q, k, v, o, lse = ctx.saved_tensors
+        dq, dk, dv = ext().flash_attn_bwd(go.contiguous(), q, k, v, o, lse, ctx.causal, ctx.scale)
+        _count(3)
+        return dq, dk, dv, None, None
+
+
+def flash_attention(q, k, v, causal: bool = True, scale: Optional[float] = None, window=None):
+    """Fused attention; GQA when ``k.shape[2] < q.shape[2]``.  Returns ``[sq, b, hq, d]``."""
+    import math
+
+    scale = scale if scale is not None else 1.0 / math.sqrt(q.shape[-1])
+    if _use_cuda(q) and window is None and hasattr(ext(), "flash_attn_fwd") and q.dtype == torch.bfloat16 and q.shape[-1] in (64, 128):
+        return _FlashAttnFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), causal, scale)
+    if q.is_cuda:
+        # library path (cuDNN/flash SDPA) for shapes the native kernel does not cover
+        qb, kb, vb = (t.permute(1, 2, 0, 3) for t in (q, k, v))
+        if window is None:
+            o = torch.nn.functional.scaled_dot_product_attention(
+                qb, kb, vb, is_causal=causal and q.shape[0] == k.shape[0], scale=scale, enable_gqa=kb.shape[1] != qb.shape[1]
+            )
+            return o.permute(2, 0, 1, 3).contiguous()
+    return ref.attention_fwd(q, k, v, causal, scale, window)
+
+
+# =============================================================================
+# Cross entropy (vocab-parallel, fused)
+# =============================================================================
+
+
+class _VocabParallelCEFn(torch.autograd.Function):
+    """Fused vocab-parallel CE: one pass for (max, sum-exp, target logit) per row,
+    ONE all-reduce-able stats tensor, and an in-place backward that overwrites the
+    logits buffer with ``softmax - onehot`` (reference: 3 ARs, ``cross_entropy.py:130-152``)."""
+
+    @staticmethod
+    def forward(ctx, logits, target, group, label_smoothing, vocab_start, reduce_fn):
+        shape = logits.shape
+        V = shape[-1]
+        l2 = logits.reshape(-1, V)
+        t1 = target.reshape(-1)
+        if _use_cuda(l2):
+            l2 = l2.contiguous()
+            stats = ext().ce_stats(l2, t1, int(vocab_start))  # [3, rows] fp32: max, sumexp(rel. to max), picked
+            _count()
+        else:
+            lf = l2.float()
+            m = lf.max(dim=-1).values
+            se = torch.exp(lf - m.unsqueeze(-1)).sum(-1)
+            local = t1 - vocab_start
+            inr = (local >= 0) & (local < V)
+            picked = torch.where(inr, lf.gather(-1, local.clamp(0, V - 1).unsqueeze(-1)).squeeze(-1), torch.zeros_like(m))
+            stats = torch.stack([m, se, picked])
+        if reduce_fn is not None:
+            gmax = reduce_fn(stats[0].clone(), "max")
+            se = stats[1] * torch.exp(stats[0] - gmax)
+            both = reduce_fn(torch.stack([se, stats[2]]), "sum")
+            se, picked = both[0], both[1]
+        else:
+            gmax, se, picked = stats[0], stats[1], stats[2]
+        lse = gmax + torch.log(se)
+        loss = lse - picked
+        ctx.label_smoothing = label_smoothing
+        if label_smoothing > 0:
+            # needs mean log-prob over the full vocab
+            sum_logits = l2.float().sum(-1)
+            nvocab = torch.tensor(float(V), device=l2.device)
+            if reduce_fn is not None:
+                sum_logits = reduce_fn(sum_logits, "sum")
+                nvocab = reduce_fn(nvocab.reshape(1), "sum")[0]
+            mean_logprob = sum_logits / nvocab - lse
+            smooth = label_smoothing * nvocab / (nvocab - 1)
+            loss = (1 - smooth) * loss - smooth * mean_logprob
+            ctx.smooth, ctx.nvocab = smooth, nvocab
+        ctx.save_for_backward(l2, t1, lse)
+        ctx.vocab_start, ctx.shape = vocab_start, shape
+        return loss.view(shape[:-1])
+
+    @staticmethod
+    def backward(ctx, gloss):
+        l2, t1, lse = ctx.saved_tensors
+        g = gloss.reshape(-1).float().contiguous()
+        V = l2.shape[-1]
+        if _use_cuda(l2) and ctx.label_smoothing == 0:
+            grad = ext().ce_bwd(l2, t1, lse, g, int(ctx.vocab_start))  # in place on l2's storage
+            _count()
+        else:
+            p = torch.exp(l2.float() - lse.unsqueeze(-1))
+            local = t1 - ctx.vocab_start
+            inr = (local >= 0) & (local < V)
+            onehot = torch.zeros_like(p)
+            onehot.scatter_(1, local.clamp(0, V - 1).unsqueeze(-1), inr.float().unsqueeze(-1))
+            if ctx.label_smoothing > 0:
+                s = ctx.smooth
+                grad = p - (1 - s) * onehot - s / ctx.nvocab
+            else:
+                grad = p - onehot
+            grad = (grad * g.unsqueeze(-1)).to(l2.dtype)
+        return grad.view(ctx.shape), None, None, None, None, None
+
+
+def vocab_parallel_cross_entropy(logits, target, group=None, label_smoothing: float = 0.0, vocab_start: int = 0):
+    """Per-token CE for logits sharded along the vocab axis over ``group``."""
+    import torch.distributed as dist
+
+    reduce_fn = None
+    if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
+        def reduce_fn(t, op):
+            dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM, group=group)
+            return t
+
+    return _VocabParallelCEFn.apply(logits, target, group, label_smoothing, vocab_start, reduce_fn)
+
+
+# =============================================================================
+# multi-tensor optimizer kernels
+# =============================================================================
+
+
+def multi_tensor_l2norm(tensors: List[torch.Tensor]) -> torch.Tensor:
+    """sqrt(sum_i ||t_i||²) as a 0-d fp32 tensor on the tensors' device."""
+    if tensors and _use_cuda(tensors[0]):
+        out = ext().multi_l2norm([t.detach() for t in tensors])
+        _count()
+        return out
+    return ref.l2norm(tensors)
+
+
+def multi_tensor_scale(tensors: List[torch.Tensor], scale) -> None:
+    if not tensors:
+        return
+    if _use_cuda(tensors[0]) and isinstance(scale, torch.Tensor):
+        ext().multi_scale([t.detach() for t in tensors], scale.float().reshape(1))
+        _count()
+        return
+    for t in tensors:
+        t.mul_(scale)
+
+
+def fused_adam(params32, grads, exp_avgs, exp_avg_sqs, lowp_params, *, lr, beta1, beta2, eps, weight_decay, step, adamw=True, grad_scale=None):
+    """One launch updates fp32 master, moments and the bf16 model copy for a list of tensors.
+
+    ``grad_scale`` (0-d/1-elem fp32 tensor or None) multiplies the gradient first — it
+    carries 1/loss_scale * clip_coef so no separate unscale/clip pass over memory is needed.
+    """
+    if params32 and _use_cuda(params32[0]):
+        gs = grad_scale if grad_scale is not None else torch.ones(1, dtype=torch.float32, device=params32[0].device)
+        ext().multi_adam(
+            params32, grads, exp_avgs, exp_avg_sqs, [p if p is not None else params32[i] for i, p in enumerate(lowp_params)],
+            float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step), bool(adamw), gs.float().reshape(1),
+        )
+        _count()
+        return
+    gsv = float(grad_scale) if grad_scale is not None else 1.0
+    for p, g, m, v, lp in zip(params32, grads, exp_avgs, exp_avg_sqs, lowp_params):
+        ref.adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, adamw, gsv, lp)
