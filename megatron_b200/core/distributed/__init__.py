@@ -1,0 +1,5 @@
+from .distributed_data_parallel import DistributedDataParallel
+from .distributed_data_parallel_config import DistributedDataParallelConfig
+from .finalize_model_grads import finalize_model_grads
+
+__all__ = ["DistributedDataParallel", "DistributedDataParallelConfig", "finalize_model_grads"]

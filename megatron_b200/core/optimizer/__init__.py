@@ -1,0 +1,106 @@
+"""Optimizer factory (reference ``optimizer/__init__.py:993`` ``get_megatron_optimizer``)."""
+from __future__ import annotations
+
+import logging
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from .. import parallel_state as ps
+from ..utils import get_model_config, get_pg_size
+from .distrib_optimizer import DistributedOptimizer
+from .grad_scaler import ConstantGradScaler, DynamicGradScaler
+from .optimizer import ChainedOptimizer, Float16OptimizerWithFloat16Params, FP32Optimizer, MegatronOptimizer
+from .optimizer_config import OptimizerConfig
+
+logger = logging.getLogger(__name__)
+
+
+def _get_param_groups(model_chunks: List, no_weight_decay_cond: Optional[Callable], scale_lr_cond: Optional[Callable], lr_mult: float,
+                      lr: float, min_lr: float, decoupled_lr: Optional[float], decoupled_min_lr: Optional[float], default_wd: float = 0.01) -> List[Dict]:
+    """Bucket params by (wd_mult, lr_mult, is_expert_parallel, is_decoupled_lr).
+    Default rule: biases and 1-D tensors (norm gains) get no weight decay."""
+    use_decoupled = decoupled_lr is not None
+    buckets: Dict[Tuple, List] = {}
+    for chunk in model_chunks:
+        for name, p in chunk.named_parameters():
+            if not p.requires_grad:
+                continue
+            is_expert = not getattr(p, "allreduce", True)
+            if no_weight_decay_cond is not None:
+                no_wd = no_weight_decay_cond(name, p)
+            else:
+                no_wd = name.endswith(".bias") or p.dim() == 1
+            scale_lr = scale_lr_cond(name, p) if scale_lr_cond is not None else False
+            wd_mult = 0.0 if no_wd else 1.0
+            lm = lr_mult if scale_lr else 1.0
+            dec = use_decoupled and getattr(p, "is_embedding_or_output_parameter", False)
+            buckets.setdefault((wd_mult, lm, is_expert, dec), []).append(p)
+    groups = []
+    for (wd_mult, lm, is_expert, dec), params in buckets.items():
+        g = dict(params=params, wd_mult=wd_mult, lr_mult=lm, is_expert_parallel=is_expert, is_decoupled_lr=dec,
+                 max_lr=(decoupled_lr if dec else lr), min_lr=(decoupled_min_lr if dec and decoupled_min_lr is not None else min_lr),
+                 lr=(decoupled_lr if dec else lr) * lm if lr is not None else None, weight_decay=default_wd * wd_mult)
+        groups.append(g)
+    return groups
+
+
+def _make_scaler(config: OptimizerConfig):
+    if config.loss_scale:
+        return ConstantGradScaler(config.loss_scale)
+    if config.fp16:
+        return DynamicGradScaler(config.initial_loss_scale, config.min_loss_scale, 2.0, 0.5, config.loss_scale_window, config.hysteresis)
+    return None
+
+
+def _get_megatron_optimizer_based_on_param_groups(config: OptimizerConfig, model_chunks, param_groups, per_model_buffers=None,
+                                                  model_parallel_group=None, data_parallel_group=None, data_parallel_group_gloo=None,
+                                                  data_parallel_group_idx=0, distributed_optimizer_instance_id=0) -> MegatronOptimizer:
+    for g in param_groups:
+        g.setdefault("betas", (config.adam_beta1, config.adam_beta2))
+        g.setdefault("eps", config.adam_eps)
+    lowp = config.fp16 or config.bf16
+    scaler = _make_scaler(config)
+    if config.use_distributed_optimizer:
+        opt = DistributedOptimizer(param_groups, config, scaler, None, model_chunks, per_model_buffers or {}, data_parallel_group,
+                                   data_parallel_group_gloo, data_parallel_group_idx, distributed_optimizer_instance_id)
+    elif lowp:
+        opt = Float16OptimizerWithFloat16Params(param_groups, config, scaler)
+        opt.model_chunks = model_chunks
+    else:
+        opt = FP32Optimizer(param_groups, config)
+        opt.model_chunks = model_chunks
+    if model_parallel_group is not None and not config.use_distributed_optimizer:
+        opt.grad_stats_parallel_group = model_parallel_group
+    return opt
+
+
+def get_megatron_optimizer(config: OptimizerConfig, model_chunks: List, no_weight_decay_cond: Optional[Callable] = None,
+                           scale_lr_cond: Optional[Callable] = None, lr_mult: float = 1.0, config_overrides=None,
+                           use_gloo_process_groups: bool = True, pg_collection=None, dump_param_to_param_group_map=None) -> MegatronOptimizer:
+    """Dense and expert-parallel parameters get separate optimizers (their data-parallel
+    groups differ) chained into one."""
+    groups = _get_param_groups(model_chunks, no_weight_decay_cond, scale_lr_cond, lr_mult, config.lr, config.min_lr,
+                               config.decoupled_lr, config.decoupled_min_lr, config.weight_decay)
+    dense = [g for g in groups if not g["is_expert_parallel"]]
+    expert = [g for g in groups if g["is_expert_parallel"]]
+    init = ps.is_initialized()
+    opts = []
+    dense_buffers = {i: getattr(c, "buffers", []) for i, c in enumerate(model_chunks)}
+    expert_buffers = {i: getattr(c, "expert_parallel_buffers", []) for i, c in enumerate(model_chunks)}
+    if dense or not expert:
+        dpg = (pg_collection.dp_cp if pg_collection is not None else (ps.get_data_parallel_group(with_context_parallel=True, partial_data_parallel=True) if init else None))
+        opts.append(_get_megatron_optimizer_based_on_param_groups(
+            config, model_chunks, dense, dense_buffers,
+            model_parallel_group=(ps.get_model_parallel_group(check_initialized=False) if init else None),
+            data_parallel_group=dpg, data_parallel_group_idx=(ps.get_model_parallel_rank() if init and False else 0),
+        ))
+    if expert:
+        opts.append(_get_megatron_optimizer_based_on_param_groups(
+            config, model_chunks, expert, expert_buffers,
+            model_parallel_group=(ps.get_group("tp_ep_pp", check_initialized=False) if init else None),
+            data_parallel_group=(ps.get_expert_data_parallel_group() if init else None), data_parallel_group_idx=1,
+        ))
+    for o in opts:
+        o.tp_group = ps.get_tensor_model_parallel_group(check_initialized=False) if init else None
+    return ChainedOptimizer(opts)

@@ -1,0 +1,49 @@
+"""Optimizer configuration (reference ``optimizer/optimizer_config.py``)."""
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import torch
+
+
+@dataclass
+class OptimizerConfig:
+    optimizer: str = "adam"
+    lr: Optional[float] = None
+    min_lr: Optional[float] = None
+    decoupled_lr: Optional[float] = None
+    decoupled_min_lr: Optional[float] = None
+    weight_decay: float = 0.01
+    fp16: bool = False
+    bf16: bool = False
+    params_dtype: torch.dtype = torch.float32
+    use_precision_aware_optimizer: bool = False
+    main_grads_dtype: torch.dtype = torch.float32
+    main_params_dtype: torch.dtype = torch.float32
+    exp_avg_dtype: torch.dtype = torch.float32
+    exp_avg_sq_dtype: torch.dtype = torch.float32
+    loss_scale: Optional[float] = None
+    initial_loss_scale: float = 2**32
+    min_loss_scale: float = 1.0
+    loss_scale_window: float = 1000
+    hysteresis: int = 2
+    adam_beta1: float = 0.9
+    adam_beta2: float = 0.999
+    adam_eps: float = 1e-08
+    decoupled_weight_decay: bool = True
+    sgd_momentum: float = 0.9
+    use_distributed_optimizer: bool = False
+    overlap_param_gather: bool = False
+    overlap_param_gather_with_optimizer_step: bool = False
+    optimizer_cpu_offload: bool = False
+    optimizer_offload_fraction: float = 0.0
+    clip_grad: float = 1.0
+    log_num_zeros_in_grad: bool = False
+    barrier_with_L1_time: bool = False
+    timers: Optional[Callable] = None
+    config_logger_dir: str = ""
+
+    def __post_init__(self):
+        if self.fp16 and self.bf16:
+            raise ValueError("fp16 and bf16 are mutually exclusive")
+        if self.optimizer not in ("adam", "sgd", "lion", "muon"):
+            raise ValueError(f"unknown optimizer {self.optimizer}")

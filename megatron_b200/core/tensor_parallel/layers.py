@@ -216,7 +216,7 @@ class _TPLinearFn(torch.autograd.Function):
             if wgrad_needed:
                 gw = fused.wgrad(gy, x, weight, ctx.grad_accum_fusion)
             if handle is not None:
-                gx = handle.wait() or gx
+                handle.wait()
         if ctx.use_bias:
             gb = gy.reshape(-1, gy.shape[-1]).sum(dim=0)
         return gx, gw, gb, None, None, None, None, None, None

@@ -252,10 +252,10 @@ class CheckpointWithoutOutput:
         _restore_rng(now)
         outs = outs if isinstance(outs, tuple) else (outs,)
         for kept, fresh in zip(self.outputs, outs):
-            st = kept.untyped_storage()
-            st.resize_(fresh.untyped_storage().size())
-            with torch.no_grad():
-                kept.copy_(fresh) if kept.shape == fresh.shape else st.copy_(fresh.untyped_storage())
+            # refill the freed storage through `.data` (separate version counter) so autograd's
+            # saved-tensor version check still sees the tensor as unmodified
+            kept.untyped_storage().resize_(kept.numel() * kept.element_size())
+            kept.data.copy_(fresh.detach().reshape(kept.shape))
         self._recomputed = (detached, outs)
 
     def discard_output_and_register_recompute(self, hook_tensor: torch.Tensor):

@@ -257,7 +257,7 @@ class TransformerConfig(ModelParallelConfig):
                     self.recompute_modules = ["core_attn"]
         if self.recompute_modules is None:
             self.recompute_modules = []
-        allowed = {"core_attn", "moe_act", "layernorm", "mla_up_proj", "mlp", "moe", "shared_experts", "mhc"}
+        allowed = {"core_attn", "moe_act", "mlp_act", "layernorm", "mla_up_proj", "mlp", "moe", "shared_experts", "mhc"}
         bad = set(self.recompute_modules) - allowed
         if bad:
             raise ValueError(f"unknown recompute modules {sorted(bad)}; allowed {sorted(allowed)}")

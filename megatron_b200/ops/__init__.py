@@ -105,7 +105,7 @@ def _tc_ok(*ts) -> bool:
 
 def gemm_nt(x: torch.Tensor, w: torch.Tensor, out_dtype=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``x[..., K] @ w[N, K]ᵀ`` → ``[..., N]`` (forward of every linear)."""
-    if _use_cuda(x) and _tc_ok(x, w) and x.shape[-1] % 64 == 0 and w.shape[0] % 16 == 0:
+    if _use_cuda(x) and _tc_ok(x, w) and x.shape[-1] % 8 == 0 and w.shape[0] % 8 == 0:
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
@@ -119,7 +119,7 @@ def gemm_nt(x: torch.Tensor, w: torch.Tensor, out_dtype=None, out: Optional[torc
 
 def gemm_nn(gy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """``gy[..., N] @ w[N, K]`` → ``[..., K]`` (dgrad)."""
-    if _use_cuda(gy) and _tc_ok(gy, w) and gy.shape[-1] % 64 == 0 and w.shape[1] % 16 == 0:
+    if _use_cuda(gy) and _tc_ok(gy, w) and gy.shape[-1] % 8 == 0 and w.shape[1] % 8 == 0:
         g2 = gy.reshape(-1, gy.shape[-1])
         if not g2.is_contiguous():
             g2 = g2.contiguous()
@@ -132,7 +132,7 @@ def gemm_nn(gy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
 
 def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False, out_dtype=None) -> torch.Tensor:
     """``a[M, N]ᵀ @ b[M, K]`` → ``[N, K]`` (wgrad); ``accumulate`` adds into fp32/bf16 ``out``."""
-    if _use_cuda(a) and _tc_ok(a, b) and a.shape[0] % 64 == 0 and b.shape[1] % 16 == 0 and a.shape[1] % 16 == 0:
+    if _use_cuda(a) and _tc_ok(a, b) and b.shape[1] % 8 == 0 and a.shape[1] % 8 == 0:
         if out is None:
             out = torch.empty((a.shape[1], b.shape[1]), dtype=out_dtype or a.dtype, device=a.device)
             accumulate = False

@@ -1,0 +1,289 @@
+// PyTorch bindings for the megatron_b200 sm_100a kernels.
+// Kernels live in plain .cu translation units with C launchers (common.cuh); this file only
+// validates tensors, allocates outputs and forwards raw pointers + the current stream.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <unordered_map>
+#include <vector>
+
+#include "launchers.h"
+
+namespace {
+
+using at::Tensor;
+using c10::optional;
+
+int dtype_code(const Tensor& t) {
+  switch (t.scalar_type()) {
+    case at::kFloat: return mb200::kF32;
+    case at::kBFloat16: return mb200::kBF16;
+    case at::kHalf: return mb200::kF16;
+    default: TORCH_CHECK(false, "megatron_b200: unsupported dtype ", t.scalar_type());
+  }
+}
+int vec_elems(const Tensor& t) { return t.scalar_type() == at::kFloat ? 4 : 8; }
+cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream(); }
+void check_cuda_contig(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
+}
+void check_aligned16(const Tensor& t, const char* name) {
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(t.data_ptr()) & 15) == 0, name, " must be 16-byte aligned");
+}
+int persistent_blocks() {
+  static int n = 0;
+  if (n == 0) n = at::cuda::getCurrentDeviceProperties()->multiProcessorCount * 4;
+  return n;
+}
+
+// ---- norms -------------------------------------------------------------------------------------
+std::vector<Tensor> rmsnorm_fwd(const Tensor& x, const Tensor& w, double eps, bool zero_centered) {
+  check_cuda_contig(x, "x"); check_cuda_contig(w, "weight");
+  TORCH_CHECK(x.dim() == 2 && x.size(1) == w.numel() && x.scalar_type() == w.scalar_type());
+  TORCH_CHECK(x.size(1) % vec_elems(x) == 0, "hidden size must be a multiple of ", vec_elems(x));
+  check_aligned16(x, "x");
+  c10::cuda::CUDAGuard g(x.device());
+  auto y = at::empty_like(x);
+  auto rstd = at::empty({x.size(0)}, x.options().dtype(at::kFloat));
+  mb200_rmsnorm_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), rstd.data_ptr<float>(), (int)x.size(0), (int)x.size(1), (float)eps, zero_centered,
+                    dtype_code(x), cur_stream());
+  return {y, rstd};
+}
+
+std::vector<Tensor> rmsnorm_bwd(const Tensor& gy, const Tensor& x, const Tensor& w, const Tensor& rstd, bool zero_centered) {
+  check_cuda_contig(gy, "gy"); check_cuda_contig(x, "x");
+  TORCH_CHECK(gy.sizes() == x.sizes() && gy.scalar_type() == x.scalar_type());
+  c10::cuda::CUDAGuard g(x.device());
+  const int rows = (int)x.size(0), H = (int)x.size(1);
+  const int nblocks = std::min(rows, persistent_blocks());
+  auto gx = at::empty_like(x);
+  auto gw = at::empty_like(w);
+  auto partial = at::empty({nblocks, 2, H}, x.options().dtype(at::kFloat));
+  mb200_rmsnorm_bwd(gy.data_ptr(), x.data_ptr(), w.data_ptr(), rstd.data_ptr<float>(), gx.data_ptr(), partial.data_ptr<float>(), gw.data_ptr(), rows, H,
+                    zero_centered, dtype_code(x), nblocks, cur_stream());
+  return {gx, gw};
+}
+
+std::vector<Tensor> layernorm_fwd(const Tensor& x, const Tensor& w, const optional<Tensor>& b, double eps, bool zero_centered) {
+  check_cuda_contig(x, "x"); check_cuda_contig(w, "weight");
+  TORCH_CHECK(x.dim() == 2 && x.size(1) == w.numel() && x.scalar_type() == w.scalar_type());
+  TORCH_CHECK(x.size(1) % vec_elems(x) == 0);
+  c10::cuda::CUDAGuard g(x.device());
+  auto y = at::empty_like(x);
+  auto mu = at::empty({x.size(0)}, x.options().dtype(at::kFloat));
+  auto rstd = at::empty({x.size(0)}, x.options().dtype(at::kFloat));
+  mb200_layernorm_fwd(x.data_ptr(), w.data_ptr(), b.has_value() ? b->data_ptr() : nullptr, y.data_ptr(), mu.data_ptr<float>(), rstd.data_ptr<float>(),
+                      (int)x.size(0), (int)x.size(1), (float)eps, zero_centered, dtype_code(x), cur_stream());
+  return {y, mu, rstd};
+}
+
+std::vector<Tensor> layernorm_bwd(const Tensor& gy, const Tensor& x, const Tensor& w, const Tensor& mu, const Tensor& rstd, bool zero_centered) {
+  check_cuda_contig(gy, "gy"); check_cuda_contig(x, "x");
+  c10::cuda::CUDAGuard g(x.device());
+  const int rows = (int)x.size(0), H = (int)x.size(1);
+  const int nblocks = std::min(rows, persistent_blocks());
+  auto gx = at::empty_like(x);
+  auto gw = at::empty_like(w);
+  auto gb = at::empty_like(w);
+  auto partial = at::empty({nblocks, 2, H}, x.options().dtype(at::kFloat));
+  mb200_layernorm_bwd(gy.data_ptr(), x.data_ptr(), w.data_ptr(), mu.data_ptr<float>(), rstd.data_ptr<float>(), gx.data_ptr(), partial.data_ptr<float>(),
+                      gw.data_ptr(), gb.data_ptr(), rows, H, zero_centered, dtype_code(x), nblocks, cur_stream());
+  return {gx, gw, gb};
+}
+
+// ---- activations ---------------------------------------------------------------------------------
+Tensor swiglu_fwd(const Tensor& y, const optional<Tensor>& bias, const optional<Tensor>& probs) {
+  check_cuda_contig(y, "y");
+  TORCH_CHECK(y.dim() == 2 && y.size(1) % 2 == 0);
+  const int F = (int)(y.size(1) / 2);
+  TORCH_CHECK(F % vec_elems(y) == 0, "ffn size must be a multiple of ", vec_elems(y));
+  c10::cuda::CUDAGuard g(y.device());
+  auto out = at::empty({y.size(0), F}, y.options());
+  Tensor pf;
+  if (probs.has_value()) pf = probs->to(at::kFloat).contiguous();
+  mb200_swiglu_fwd(y.data_ptr(), bias.has_value() ? bias->data_ptr() : nullptr, probs.has_value() ? pf.data_ptr<float>() : nullptr, out.data_ptr(),
+                   (long)y.size(0), F, dtype_code(y), cur_stream());
+  return out;
+}
+
+std::vector<optional<Tensor>> swiglu_bwd(const Tensor& gout, const Tensor& y, const optional<Tensor>& bias, const optional<Tensor>& probs) {
+  check_cuda_contig(gout, "g"); check_cuda_contig(y, "y");
+  const int F = (int)(y.size(1) / 2);
+  c10::cuda::CUDAGuard g(y.device());
+  auto dy = at::empty_like(y);
+  Tensor pf, dprobs;
+  if (probs.has_value()) {
+    pf = probs->to(at::kFloat).contiguous();
+    dprobs = at::empty({y.size(0)}, y.options().dtype(at::kFloat));
+  }
+  mb200_swiglu_bwd(gout.data_ptr(), y.data_ptr(), bias.has_value() ? bias->data_ptr() : nullptr, probs.has_value() ? pf.data_ptr<float>() : nullptr,
+                   dy.data_ptr(), probs.has_value() ? dprobs.data_ptr<float>() : nullptr, (long)y.size(0), F, dtype_code(y), cur_stream());
+  optional<Tensor> dp;
+  if (probs.has_value()) dp = dprobs.to(probs->scalar_type());
+  return {dy, dp};
+}
+
+Tensor rope_fwd(const Tensor& t, const Tensor& freqs, double mscale, bool conj) {
+  check_cuda_contig(t, "t"); check_cuda_contig(freqs, "freqs");
+  TORCH_CHECK(t.dim() == 4 && freqs.dim() == 2 && freqs.scalar_type() == at::kFloat);
+  const int S = (int)t.size(0), B = (int)t.size(1), Hh = (int)t.size(2), D = (int)t.size(3), Drot = (int)freqs.size(1);
+  TORCH_CHECK(freqs.size(0) >= S, "rope: freqs has fewer positions than the sequence");
+  const int vn = vec_elems(t);
+  TORCH_CHECK(Drot <= D && (Drot / 2) % vn == 0 && (D - Drot) % vn == 0, "rope: head dim / rotary dim not vectorisable");
+  c10::cuda::CUDAGuard g(t.device());
+  auto out = at::empty_like(t);
+  mb200_rope(t.data_ptr(), freqs.data_ptr<float>(), out.data_ptr(), S, B, Hh, D, Drot, (float)mscale, conj, dtype_code(t), cur_stream());
+  return out;
+}
+
+// ---- cross entropy -------------------------------------------------------------------------------
+Tensor ce_stats(const Tensor& logits, const Tensor& target, int64_t vocab_start) {
+  check_cuda_contig(logits, "logits"); check_cuda_contig(target, "target");
+  TORCH_CHECK(logits.dim() == 2 && target.scalar_type() == at::kLong && target.numel() == logits.size(0));
+  TORCH_CHECK((logits.size(1) * logits.element_size()) % 16 == 0, "vocab shard row must be 16-byte aligned");
+  c10::cuda::CUDAGuard g(logits.device());
+  auto stats = at::empty({3, logits.size(0)}, logits.options().dtype(at::kFloat));
+  mb200_ce_stats(logits.data_ptr(), target.data_ptr<long>(), stats.data_ptr<float>(), (int)logits.size(0), (int)logits.size(1), vocab_start,
+                 dtype_code(logits), cur_stream());
+  return stats;
+}
+
+Tensor ce_bwd(Tensor logits, const Tensor& target, const Tensor& lse, const Tensor& gloss, int64_t vocab_start) {
+  check_cuda_contig(logits, "logits");
+  TORCH_CHECK(lse.scalar_type() == at::kFloat && gloss.scalar_type() == at::kFloat && lse.is_contiguous() && gloss.is_contiguous());
+  c10::cuda::CUDAGuard g(logits.device());
+  mb200_ce_bwd(logits.data_ptr(), target.data_ptr<long>(), lse.data_ptr<float>(), gloss.data_ptr<float>(), (int)logits.size(0), (int)logits.size(1),
+               vocab_start, dtype_code(logits), cur_stream());
+  return logits;
+}
+
+// ---- multi-tensor ----------------------------------------------------------------------------------
+// Device-side metadata (pointer tables, sizes, chunk prefix) is cached per distinct tensor list:
+// optimizer buffers are persistent, so after the first step a launch costs no H2D traffic.
+constexpr long kChunk = 8192;
+
+struct MetaCache {
+  std::unordered_map<uint64_t, std::pair<std::vector<int64_t>, Tensor>> map;
+  Tensor get(const std::vector<int64_t>& host, const at::Device& dev) {
+    uint64_t h = 1469598103934665603ull;
+    for (auto v : host) { h ^= (uint64_t)v; h *= 1099511628211ull; }
+    auto it = map.find(h);
+    if (it != map.end() && it->second.first == host) return it->second.second;
+    auto cpu = at::empty({(long)host.size()}, at::TensorOptions().dtype(at::kLong).pinned_memory(true));
+    std::memcpy(cpu.data_ptr(), host.data(), host.size() * sizeof(int64_t));
+    auto devt = cpu.to(dev, /*non_blocking=*/false);
+    if (map.size() > 4096) map.clear();
+    map[h] = {host, devt};
+    return devt;
+  }
+};
+MetaCache& meta_cache() { static MetaCache c; return c; }
+
+// layout (int64 words): [n_lists * n pointers][n sizes][n+1 prefix][n_dt * n dtype codes packed 2/word as int32]
+struct Packed { Tensor t; int n; };
+
+Packed pack_meta(const std::vector<std::vector<Tensor>>& lists, const std::vector<int>& dtype_lists) {
+  const int n = (int)lists[0].size();
+  std::vector<int64_t> host;
+  host.reserve(lists.size() * n + 2 * n + 1 + (dtype_lists.size() * n + 1) / 2 + 2);
+  for (auto& l : lists) {
+    TORCH_CHECK((int)l.size() == n, "multi-tensor lists differ in length");
+    for (auto& t : l) host.push_back((int64_t)t.data_ptr());
+  }
+  for (auto& t : lists[0]) host.push_back(t.numel());
+  int64_t acc = 0;
+  host.push_back(0);
+  for (auto& t : lists[0]) { acc += (t.numel() + kChunk - 1) / kChunk; host.push_back(acc); }
+  std::vector<int32_t> dts;
+  for (int li : dtype_lists) for (auto& t : lists[li]) dts.push_back(dtype_code(t));
+  if (dts.size() % 2) dts.push_back(0);
+  for (size_t i = 0; i < dts.size(); i += 2) host.push_back((int64_t)(uint32_t)dts[i] | ((int64_t)(uint32_t)dts[i + 1] << 32));
+  return {meta_cache().get(host, lists[0][0].device()), n};
+}
+
+Tensor multi_l2norm(const std::vector<Tensor>& tensors) {
+  TORCH_CHECK(!tensors.empty());
+  for (auto& t : tensors) check_cuda_contig(t, "tensor");
+  c10::cuda::CUDAGuard g(tensors[0].device());
+  auto pk = pack_meta({tensors}, {0});
+  const int n = pk.n;
+  const int64_t* base = pk.t.data_ptr<int64_t>();
+  const int nblocks = persistent_blocks();
+  auto partial = at::empty({nblocks}, tensors[0].options().dtype(at::kFloat));
+  auto out = at::empty({}, tensors[0].options().dtype(at::kFloat));
+  mb200_multi_l2norm((const void* const*)base, (const long*)(base + n), (const int*)(base + 3 * n + 1), n, partial.data_ptr<float>(),
+                     out.data_ptr<float>(), nblocks, cur_stream());
+  return out;
+}
+
+void multi_scale(const std::vector<Tensor>& tensors, const Tensor& scale) {
+  if (tensors.empty()) return;
+  c10::cuda::CUDAGuard g(tensors[0].device());
+  auto pk = pack_meta({tensors}, {0});
+  const int n = pk.n;
+  const int64_t* base = pk.t.data_ptr<int64_t>();
+  mb200_multi_scale((void* const*)base, (const long*)(base + n), (const int*)(base + 3 * n + 1), n, scale.data_ptr<float>(), persistent_blocks(),
+                    cur_stream());
+}
+
+void multi_adam(const std::vector<Tensor>& p32, const std::vector<Tensor>& grads, const std::vector<Tensor>& m, const std::vector<Tensor>& v,
+                const std::vector<Tensor>& lowp, double lr, double b1, double b2, double eps, double wd, int64_t step, bool adamw,
+                const Tensor& grad_scale) {
+  if (p32.empty()) return;
+  for (size_t i = 0; i < p32.size(); ++i) {
+    TORCH_CHECK(p32[i].scalar_type() == at::kFloat && m[i].scalar_type() == at::kFloat && v[i].scalar_type() == at::kFloat,
+                "master weights and Adam moments must be fp32");
+    TORCH_CHECK(p32[i].is_contiguous() && grads[i].is_contiguous() && m[i].is_contiguous() && v[i].is_contiguous() && lowp[i].is_contiguous());
+    TORCH_CHECK(p32[i].numel() == grads[i].numel() && p32[i].numel() == lowp[i].numel());
+  }
+  c10::cuda::CUDAGuard g(p32[0].device());
+  // pointer lists: 0 p32, 1 grads, 2 m, 3 v, 4 lowp; sizes; prefix; dtype lists: grads(1), lowp(4)
+  auto pk = pack_meta({p32, grads, m, v, lowp}, {1, 4});
+  const int n = pk.n;
+  const int64_t* base = pk.t.data_ptr<int64_t>();
+  const int64_t* sizes = base + 5 * n;
+  const int* dts = (const int*)(base + 5 * n + n + (n + 1));
+  const double bc1 = 1.0 - std::pow(b1, (double)step), bc2 = 1.0 - std::pow(b2, (double)step);
+  mb200_multi_adam((float* const*)base, (const void* const*)(base + n), (float* const*)(base + 2 * n), (float* const*)(base + 3 * n),
+                   (void* const*)(base + 4 * n), (const long*)sizes, dts, dts + n, n, (float)lr, (float)b1, (float)b2, (float)eps, (float)wd,
+                   (float)bc1, (float)bc2, adamw, grad_scale.data_ptr<float>(), persistent_blocks(), cur_stream());
+}
+
+// ---- GEMM -------------------------------------------------------------------------------------------
+void gemm_bf16(const Tensor& a, const Tensor& b, Tensor c, int64_t layout, bool accumulate) {
+  check_cuda_contig(a, "a"); check_cuda_contig(b, "b"); check_cuda_contig(c, "c");
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16, "gemm_bf16 expects bf16 operands");
+  TORCH_CHECK(c.scalar_type() == at::kBFloat16 || c.scalar_type() == at::kFloat, "gemm_bf16 output must be bf16 or fp32");
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && c.dim() == 2);
+  int64_t M, N, K;
+  if (layout == 0) { M = a.size(0); K = a.size(1); N = b.size(0); TORCH_CHECK(b.size(1) == K); }
+  else if (layout == 1) { M = a.size(0); K = a.size(1); N = b.size(1); TORCH_CHECK(b.size(0) == K); }
+  else { K = a.size(0); M = a.size(1); N = b.size(1); TORCH_CHECK(b.size(0) == K); }
+  TORCH_CHECK(c.size(0) == M && c.size(1) == N, "gemm_bf16: output shape mismatch");
+  check_aligned16(a, "a"); check_aligned16(b, "b"); check_aligned16(c, "c");
+  TORCH_CHECK((a.size(1) % 8) == 0 && (b.size(1) % 8) == 0, "gemm_bf16: row pitch must be a multiple of 16 bytes");
+  c10::cuda::CUDAGuard g(a.device());
+  const int rc = mb200_gemm_bf16(a.data_ptr(), b.data_ptr(), c.data_ptr(), (int)M, (int)N, (int)K, (int)layout, accumulate ? 1 : 0, dtype_code(c),
+                                 cur_stream());
+  TORCH_CHECK(rc == 0, "mb200_gemm_bf16 failed with code ", rc);
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("rmsnorm_fwd", &rmsnorm_fwd);
+  m.def("rmsnorm_bwd", &rmsnorm_bwd);
+  m.def("layernorm_fwd", &layernorm_fwd);
+  m.def("layernorm_bwd", &layernorm_bwd);
+  m.def("swiglu_fwd", &swiglu_fwd);
+  m.def("swiglu_bwd", &swiglu_bwd);
+  m.def("rope_fwd", &rope_fwd);
+  m.def("ce_stats", &ce_stats);
+  m.def("ce_bwd", &ce_bwd);
+  m.def("multi_l2norm", &multi_l2norm);
+  m.def("multi_scale", &multi_scale);
+  m.def("multi_adam", &multi_adam);
+  m.def("gemm_bf16", &gemm_bf16);
+}

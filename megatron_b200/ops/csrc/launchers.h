@@ -1,0 +1,30 @@
+// C launcher declarations shared by the kernel translation units and bindings.cpp (host-only safe).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mb200 {
+enum DType : int { kF32 = 0, kBF16 = 1, kF16 = 2 };
+}
+
+// ---- C launchers (implemented in the .cu files, called from bindings.cpp) ---------------
+extern "C" {
+void mb200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, int H, float eps, int zero_centered, int dtype, cudaStream_t s);
+void mb200_rmsnorm_bwd(const void* gy, const void* x, const void* w, const float* rstd, void* gx, float* gw_partial, void* gw, int rows, int H,
+                       int zero_centered, int dtype, int nblocks, cudaStream_t s);
+void mb200_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mu, float* rstd, int rows, int H, float eps, int zero_centered,
+                         int dtype, cudaStream_t s);
+void mb200_layernorm_bwd(const void* gy, const void* x, const void* w, const float* mu, const float* rstd, void* gx, float* partial, void* gw, void* gb,
+                         int rows, int H, int zero_centered, int dtype, int nblocks, cudaStream_t s);
+void mb200_swiglu_fwd(const void* y, const void* bias, const float* probs, void* out, long rows, int F, int dtype, cudaStream_t s);
+void mb200_swiglu_bwd(const void* g, const void* y, const void* bias, const float* probs, void* dy, float* dprobs, long rows, int F, int dtype, cudaStream_t s);
+void mb200_rope(const void* t, const float* freqs, void* out, int S, int B, int Hh, int D, int Drot, float mscale, int conj, int dtype, cudaStream_t s);
+void mb200_ce_stats(const void* logits, const long* target, float* stats, int rows, int V, long vocab_start, int dtype, cudaStream_t s);
+void mb200_ce_bwd(void* logits, const long* target, const float* lse, const float* gloss, int rows, int V, long vocab_start, int dtype, cudaStream_t s);
+void mb200_multi_l2norm(const void* const* ptrs, const long* sizes, const int* dtypes, int n, float* partial, float* out, int nblocks, cudaStream_t s);
+void mb200_multi_scale(void* const* ptrs, const long* sizes, const int* dtypes, int n, const float* scale, int nblocks, cudaStream_t s);
+void mb200_multi_adam(float* const* p32, const void* const* grads, float* const* m, float* const* v, void* const* lowp, const long* sizes,
+                      const int* gdtypes, const int* ldtypes, int n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, int adamw,
+                      const float* grad_scale, int nblocks, cudaStream_t s);
+int mb200_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int layout, int accumulate, int c_dtype, cudaStream_t s);
+}
