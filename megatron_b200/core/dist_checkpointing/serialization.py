@@ -1,0 +1,172 @@
+"""``save`` / ``load`` entry points (reference ``dist_checkpointing/serialization.py:69,341``)."""
+from __future__ import annotations
+
+import logging
+import os
+from pathlib import Path
+from typing import Any, Callable, Dict, Optional, Set, Tuple, Union
+
+import torch
+import torch.distributed as dist
+
+from . import core as _core
+from .core import CheckpointingConfig, CheckpointingException, maybe_load_config, save_config
+from .dict_utils import dict_list_map_inplace, extract_matching_values, merge, nested_values
+from .mapping import (
+    LocalNonpersistentObject,
+    ShardedBase,
+    ShardedObject,
+    ShardedStateDict,
+    ShardedTensor,
+    ShardedTensorFactory,
+    StateDict,
+    apply_factories,
+    apply_factory_merges,
+)
+from .strategies import torch_dist
+from .strategies.async_utils import AsyncRequest
+from .validation import StrictHandling, validate_integrity_and_strict_load, validate_sharding_integrity
+
+logger = logging.getLogger(__name__)
+COMMON_STATE_FNAME = "common.pt"
+
+
+def _rank():
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def _barrier(group=None):
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier(group=group)
+
+
+def _split(sharded_state_dict):
+    """→ (sharded part incl. factories, common part, nonpersistent part)."""
+    sharded, rest = extract_matching_values(sharded_state_dict, lambda v: isinstance(v, ShardedBase))
+    nonpers, common = extract_matching_values(rest, lambda v: isinstance(v, LocalNonpersistentObject))
+    return sharded, common, nonpers
+
+
+def save(sharded_state_dict: ShardedStateDict, checkpoint_dir: str, sharded_strategy=None, common_strategy=None, validate_access_integrity: bool = True,
+         async_sharded_save: bool = False, preprocess_common_before_consistancy_check: Optional[Callable] = None, content_metadata: Optional[dict] = None,
+         async_strategy: str = "thread", verify_integrity: bool = False, process_group=None) -> Optional[AsyncRequest]:
+    """Write a sharded state dict.  ShardedTensors/Objects go to DCP ``.distcp`` files (each main
+    replica writes its shard), everything else goes to ``common.pt`` (rank 0)."""
+    checkpoint_dir = Path(checkpoint_dir)
+    if _rank() == 0:
+        checkpoint_dir.mkdir(parents=True, exist_ok=True)
+        if any(checkpoint_dir.iterdir()):
+            raise CheckpointingException(f"checkpoint destination directory ({checkpoint_dir}) is not empty")
+    _barrier(process_group)
+    if not checkpoint_dir.exists():
+        raise CheckpointingException(f"checkpoint destination directory does not exist: {checkpoint_dir}")
+    sharded, common, _ = _split(sharded_state_dict)
+    apply_factories(sharded)
+    if sharded_strategy is not None and hasattr(sharded_strategy, "apply_saving_parallelization"):
+        sharded_strategy.apply_saving_parallelization(sharded)
+    if validate_access_integrity:
+        validate_sharding_integrity(sharded, process_group)
+    tensors = [s for s in nested_values(sharded) if isinstance(s, ShardedTensor)]
+    objects = [s for s in nested_values(sharded) if isinstance(s, ShardedObject)]
+
+    def write_common_and_config():
+        if _rank() == 0:
+            torch.save(common, checkpoint_dir / COMMON_STATE_FNAME)
+            if content_metadata is not None:
+                torch.save(content_metadata, checkpoint_dir / "content_metadata.pt")
+            save_config(CheckpointingConfig("torch_dist", 1), str(checkpoint_dir))
+
+    if not async_sharded_save:
+        torch_dist.save_sharded(tensors, objects, str(checkpoint_dir), process_group)
+        write_common_and_config()
+        _barrier(process_group)
+        return None
+    # async: stage device tensors to host now, write in the background, finalize later
+    for st in tensors:
+        if st.data is not None and st.data.is_cuda:
+            st.data = st.data.detach().to("cpu", non_blocking=True)
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    req = AsyncRequest(torch_dist.save_sharded, (tensors, objects, str(checkpoint_dir), process_group), [write_common_and_config])
+    return req
+
+
+def load_common_state_dict(checkpoint_dir: str) -> StateDict:
+    p = Path(checkpoint_dir) / COMMON_STATE_FNAME
+    if not p.exists():
+        return {}
+    return torch.load(p, map_location="cpu", weights_only=False)
+
+
+def load_content_metadata(checkpoint_dir: str) -> Optional[dict]:
+    p = Path(checkpoint_dir) / "content_metadata.pt"
+    return torch.load(p, weights_only=False) if p.exists() else None
+
+
+def load(sharded_state_dict: ShardedStateDict, checkpoint_dir: str, sharded_strategy=None, common_strategy=None, validate_access_integrity: bool = True,
+         strict: Union[str, StrictHandling] = StrictHandling.ASSUME_OK_UNEXPECTED, verify_integrity: bool = False, process_group=None):
+    """Fill the requested shards from a checkpoint; returns a plain state dict with the same nesting
+    (ShardedTensor → tensor, ShardedObject → object, factories merged back)."""
+    cfg = maybe_load_config(str(checkpoint_dir))
+    if cfg is None:
+        raise CheckpointingException(f"{checkpoint_dir} is not a distributed checkpoint")
+    if cfg.sharded_backend not in ("torch_dist",):
+        raise CheckpointingException(f"unsupported sharded backend {cfg.sharded_backend}")
+    strict = StrictHandling(strict) if not isinstance(strict, StrictHandling) else strict
+    common = load_common_state_dict(checkpoint_dir)
+    sharded, _, nonpers = _split(sharded_state_dict)
+    template, _ = extract_matching_values(sharded, lambda v: isinstance(v, ShardedTensorFactory), return_lists_as_dicts=True)
+    apply_factories(sharded)
+    tensors = [s for s in nested_values(sharded) if isinstance(s, ShardedTensor)]
+    objects = [s for s in nested_values(sharded) if isinstance(s, ShardedObject)]
+    missing = unexpected = set()
+    if StrictHandling.requires_explicit_ckpt_mismatch_check(strict):
+        md = torch_dist.FileSystemReader(str(checkpoint_dir)).read_metadata()
+        missing, unexpected = validate_integrity_and_strict_load(sharded, strict, set(md.state_dict_metadata.keys()))
+        if missing and strict in (StrictHandling.LOG_UNEXPECTED, StrictHandling.LOG_ALL, StrictHandling.IGNORE_ALL, StrictHandling.RETURN_ALL, StrictHandling.RETURN_UNEXPECTED):
+            tensors = [t for t in tensors if t.key not in missing]
+            objects = [o for o in objects if o.unique_key not in missing]
+            logger.warning("keys missing from the checkpoint are left untouched: %s", sorted(missing)[:20])
+    loaded_objs = torch_dist.load_sharded(tensors, objects, str(checkpoint_dir), process_group)
+
+    def unwrap(v):
+        if isinstance(v, ShardedTensor):
+            return v.data
+        if isinstance(v, ShardedObject):
+            return loaded_objs.get(v.unique_key, v.data)
+        return v
+
+    dict_list_map_inplace(unwrap, sharded)
+    if template:
+        # factories were expanded in place into lists/dicts of tensors: merge them back
+        sharded = apply_factory_merges(sharded, _factory_template(sharded_state_dict))
+    out = common
+    merge(out, sharded)
+    np_unwrapped = nonpers
+    dict_list_map_inplace(lambda o: o.unwrap() if isinstance(o, LocalNonpersistentObject) else o, np_unwrapped)
+    if np_unwrapped:
+        merge(out, np_unwrapped)
+    if StrictHandling.requires_returning_mismatch_keys(strict):
+        return out, missing, unexpected
+    return out
+
+
+def _factory_template(original):
+    """Nested structure with the original ShardedTensorFactory leaves (others dropped)."""
+    t, _ = extract_matching_values(original, lambda v: isinstance(v, ShardedTensorFactory))
+    return t
+
+
+def load_tensors_metadata(checkpoint_dir: str, sharded_strategy=None):
+    return torch_dist.load_tensors_metadata(str(checkpoint_dir))
+
+
+def load_plain_tensors(checkpoint_dir: str) -> StateDict:
+    """Load every tensor of a checkpoint fully (no sharding) — debugging / conversion."""
+    md = load_tensors_metadata(checkpoint_dir)
+    sd = dict(md)
+    return load(sd, checkpoint_dir, validate_access_integrity=False)
+
+
+def remove_sharded_tensors(checkpoint_dir: str, key_prefix: str):
+    raise NotImplementedError("in-place checkpoint surgery is not supported; rewrite the checkpoint instead")

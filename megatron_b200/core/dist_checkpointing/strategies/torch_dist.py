@@ -1,0 +1,168 @@
+"""``torch_dist`` save/load strategy on top of ``torch.distributed.checkpoint`` (DCP).
+
+On-disk layout matches the reference's default format (``strategies/torch.py:588,852``):
+``<dir>/.metadata`` (DCP global metadata), ``__{rank}_{n}.distcp`` data files, ``common.pt`` and
+``metadata.json``.  Instead of converting to PyTorch ``ShardedTensor`` objects first (reference
+``mcore_to_pyt_state_dict``) the planners below emit DCP ``WriteItem``/``ReadItem``s directly
+from the ``(global_shape, global_offset, local_shape)`` triplet of each mcore ShardedTensor.
+"""
+from __future__ import annotations
+
+import io
+import os
+import pickle
+from collections import defaultdict
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch.distributed.checkpoint import FileSystemReader, FileSystemWriter
+from torch.distributed.checkpoint.default_planner import DefaultLoadPlanner, DefaultSavePlanner
+from torch.distributed.checkpoint.metadata import BytesStorageMetadata, ChunkStorageMetadata, Metadata, MetadataIndex, TensorProperties, TensorStorageMetadata
+from torch.distributed.checkpoint.planner import LoadPlan, ReadItem, SavePlan, TensorWriteData, WriteItem, WriteItemType
+from torch.distributed.checkpoint.planner_helpers import create_read_items_for_chunk_list
+from torch.distributed.checkpoint.state_dict_loader import load as dcp_load
+from torch.distributed.checkpoint.state_dict_saver import save as dcp_save
+
+from ..mapping import ShardedObject, ShardedTensor, is_main_replica
+
+
+def _full_shape(st: ShardedTensor) -> Tuple[int, ...]:
+    return (1,) * st.prepend_axis_num + tuple(st.local_shape)
+
+
+def _view(st: ShardedTensor) -> torch.Tensor:
+    return st.data.detach().reshape(_full_shape(st))
+
+
+class MCoreSavePlanner(DefaultSavePlanner):
+    """Every main-replica ShardedTensor becomes one SHARD write item; ShardedObjects become BYTE_IO."""
+
+    def __init__(self, sharded_tensors: List[ShardedTensor], sharded_objects: List[ShardedObject], **kw):
+        super().__init__()
+        self._sts = [s for s in sharded_tensors if is_main_replica(s.replica_id)]
+        self._sos = [s for s in sharded_objects if is_main_replica(s.replica_id)]
+        self._by_index: Dict[MetadataIndex, Any] = {}
+
+    def set_up_planner(self, state_dict=None, storage_meta=None, is_coordinator=False, **kw):
+        self.is_coordinator = is_coordinator
+        self.state_dict = {}
+
+    def create_local_plan(self) -> SavePlan:
+        items = []
+        for st in self._sts:
+            idx = MetadataIndex(st.key, torch.Size(st.global_offset))
+            self._by_index[idx] = st
+            items.append(WriteItem(
+                index=idx, type=WriteItemType.SHARD,
+                tensor_data=TensorWriteData(
+                    chunk=ChunkStorageMetadata(offsets=torch.Size(st.global_offset), sizes=torch.Size(_full_shape(st))),
+                    properties=TensorProperties(dtype=st.dtype), size=torch.Size(st.global_shape)),
+            ))
+        for so in self._sos:
+            idx = MetadataIndex(so.unique_key)
+            self._by_index[idx] = so
+            items.append(WriteItem(index=idx, type=WriteItemType.BYTE_IO))
+        self.plan = SavePlan(items, planner_data={})
+        return self.plan
+
+    def resolve_data(self, write_item: WriteItem):
+        obj = self._by_index[write_item.index]
+        if isinstance(obj, ShardedObject):
+            buf = io.BytesIO()
+            torch.save(obj.data, buf)
+            buf.seek(0)
+            return buf
+        return _view(obj).contiguous()
+
+
+class MCoreLoadPlanner(DefaultLoadPlanner):
+    def __init__(self, sharded_tensors: List[ShardedTensor], sharded_objects: List[ShardedObject]):
+        super().__init__()
+        self._sts, self._sos = sharded_tensors, sharded_objects
+        self._dst: Dict[Tuple[str, Tuple[int, ...]], ShardedTensor] = {}
+        self._objs: Dict[str, ShardedObject] = {}
+        self.loaded_objects: Dict[str, Any] = {}
+
+    def set_up_planner(self, state_dict, metadata: Metadata = None, is_coordinator: bool = False):
+        self.metadata, self.is_coordinator, self.state_dict = metadata, is_coordinator, {}
+
+    def create_local_plan(self) -> LoadPlan:
+        reqs: List[ReadItem] = []
+        md = self.metadata.state_dict_metadata
+        for st in self._sts:
+            if st.key not in md:
+                raise KeyError(f"{st.key} not found in the checkpoint")
+            smd = md[st.key]
+            stored = tuple(smd.size)
+            want = tuple(st.global_shape)
+            if stored != want and not st.allow_shape_mismatch:
+                raise ValueError(f"global shape mismatch for {st.key}: checkpoint {stored} vs requested {want}")
+            chunk = ChunkStorageMetadata(offsets=torch.Size(st.global_offset), sizes=torch.Size(_full_shape(st)))
+            items = create_read_items_for_chunk_list(st.key, smd, [chunk])
+            for it in items:
+                # several requested shards may share an fqn: make the destination resolvable
+                self._dst[(st.key, tuple(it.dest_index.offset))] = st
+            reqs += items
+        for so in self._sos:
+            if so.unique_key not in md:
+                raise KeyError(f"{so.unique_key} not found in the checkpoint")
+            self._objs[so.unique_key] = so
+            reqs.append(ReadItem(type=LoadItemTypeBYTE, dest_index=MetadataIndex(so.unique_key), dest_offsets=torch.Size([0]),
+                                 storage_index=MetadataIndex(so.unique_key), storage_offsets=torch.Size([0]), lengths=torch.Size([0])))
+        return LoadPlan(reqs)
+
+    def create_global_plan(self, global_plan):
+        return global_plan
+
+    def finish_plan(self, new_plan):
+        return new_plan
+
+    def load_bytes(self, read_item: ReadItem, value: io.BytesIO) -> None:
+        self.loaded_objects[read_item.dest_index.fqn] = torch.load(value, weights_only=False)
+
+    def resolve_tensor(self, read_item: ReadItem) -> torch.Tensor:
+        st = self._dst[(read_item.dest_index.fqn, tuple(read_item.dest_index.offset))]
+        t = _view(st)
+        for d, (off, ln) in enumerate(zip(read_item.dest_offsets, read_item.lengths)):
+            t = t.narrow(d, off, ln)
+        return t
+
+    def commit_tensor(self, read_item: ReadItem, tensor: torch.Tensor) -> None:
+        pass
+
+
+from torch.distributed.checkpoint.planner import LoadItemType as _LIT  # noqa: E402
+
+LoadItemTypeBYTE = _LIT.BYTE_IO
+
+
+def _no_dist(process_group) -> bool:
+    return not (dist.is_available() and dist.is_initialized())
+
+
+def save_sharded(sharded_tensors: List[ShardedTensor], sharded_objects: List[ShardedObject], checkpoint_dir: str, process_group=None, thread_count: int = 2):
+    planner = MCoreSavePlanner(sharded_tensors, sharded_objects)
+    writer = FileSystemWriter(checkpoint_dir, thread_count=thread_count, sync_files=False)
+    dcp_save({}, storage_writer=writer, planner=planner, process_group=process_group, no_dist=_no_dist(process_group))
+
+
+def load_sharded(sharded_tensors: List[ShardedTensor], sharded_objects: List[ShardedObject], checkpoint_dir: str, process_group=None) -> Dict[str, Any]:
+    """Fills ``st.data`` of every requested ShardedTensor in place; returns {unique_key: object}."""
+    for st in sharded_tensors:
+        if st.data is None:
+            st.init_data(device="cpu")
+    planner = MCoreLoadPlanner(sharded_tensors, sharded_objects)
+    dcp_load({}, storage_reader=FileSystemReader(checkpoint_dir), planner=planner, process_group=process_group, no_dist=_no_dist(process_group))
+    return planner.loaded_objects
+
+
+def load_tensors_metadata(checkpoint_dir: str) -> Dict[str, ShardedTensor]:
+    """Global shapes/dtypes of everything in a checkpoint, without data."""
+    md = FileSystemReader(checkpoint_dir).read_metadata()
+    out = {}
+    for k, v in md.state_dict_metadata.items():
+        if isinstance(v, TensorStorageMetadata):
+            shape = tuple(v.size)
+            out[k] = ShardedTensor(k, None, v.properties.dtype, shape, shape, (0,) * len(shape), (1,) * len(shape))
+    return out
