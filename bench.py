@@ -21,6 +21,7 @@ import threading
 import time
 
 REPO = os.path.dirname(os.path.abspath(__file__))
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 
 
 def parse():
@@ -302,7 +303,9 @@ def run_reference(args):
             torch.cuda.synchronize()
             used = name
             break
-        except torch.cuda.OutOfMemoryError:
+        except torch.cuda.OutOfMemoryError as e:
+            if rank == 0:
+                print(f"[reference] OOM with recompute={name}: {str(e)[:300]}", file=sys.stderr, flush=True)
             state.clear()
             import gc
 

@@ -388,7 +388,7 @@ class _RowLinearFn(torch.autograd.Function):
 
         ctx.save_for_backward(x, weight)
         ctx.sequence_parallel, ctx.tp_group, ctx.grad_accum_fusion = sequence_parallel, tp_group, grad_accum_fusion
-        if get_pg_size(tp_group) == 1:
+        if tp_group is None or get_pg_size(tp_group) == 1:
             return fused.gemm_nt(x, weight)
         if sequence_parallel:
             return fused.gemm_reduce_scatter(x, weight, tp_group)
@@ -400,7 +400,7 @@ class _RowLinearFn(torch.autograd.Function):
 
         x, weight = ctx.saved_tensors
         gy = gy.contiguous()
-        if ctx.sequence_parallel and get_pg_size(ctx.tp_group) > 1:
+        if ctx.sequence_parallel and ctx.tp_group is not None and get_pg_size(ctx.tp_group) > 1:
             # all-gather(dY) feeds both dgrad and wgrad
             gx, gw = fused.row_linear_backward_sp(gy, x, weight, ctx.tp_group, weight.requires_grad, ctx.grad_accum_fusion)
         else:

@@ -223,7 +223,18 @@ class _AllToAll(torch.autograd.Function):
             outs = list(out.split(output_split_sizes if output_split_sizes is not None else out.shape[0] // ws, dim=0))
             ins = [t.contiguous() for t in ins]
             outs_c = [torch.empty_like(t) for t in outs]
-            dist.all_to_all(outs_c, ins, group=group)
+            ranks = dist.get_process_group_ranks(group)
+            me = dist.get_rank(group)
+            outs_c[me].copy_(ins[me])
+            reqs = []
+            for peer in range(ws):
+                if peer != me:
+                    reqs.append(dist.irecv(outs_c[peer], ranks[peer], group=group))
+            for peer in range(ws):
+                if peer != me:
+                    reqs.append(dist.isend(ins[peer], ranks[peer], group=group))
+            for r in reqs:
+                r.wait()
             for o, oc in zip(outs, outs_c):
                 o.copy_(oc)
         return out

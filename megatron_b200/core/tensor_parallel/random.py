@@ -283,6 +283,12 @@ class _CheckpointWithoutOutputFn(torch.autograd.Function):
         pairs = [(o, g) for o, g in zip(outs, grads) if torch.is_tensor(o) and o.requires_grad and g is not None]
         if pairs:
             torch.autograd.backward([p[0] for p in pairs], [p[1] for p in pairs])
-        owner.ctx_inputs = None
-        owner._recomputed = None
-        return (None, None) + tuple(x.grad if isinstance(x, torch.Tensor) else None for x in detached)
+        grads_in = tuple(x.grad if isinstance(x, torch.Tensor) else None for x in detached)
+        # Break the cycle owner → outputs → tensor → grad_fn(ctx) → owner: it runs through a C++
+        # autograd node, so Python's GC cannot collect it and the recomputed activations would
+        # otherwise stay alive forever (measured: 352 MiB / layer / micro-batch on Llama-3 8B).
+        for o in owner.outputs or ():
+            o.untyped_storage().resize_(0)
+        owner.ctx_inputs = owner._recomputed = owner.outputs = owner.run_function = None
+        ctx.owner = None
+        return (None, None) + grads_in

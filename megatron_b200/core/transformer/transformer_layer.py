@@ -199,10 +199,9 @@ class TransformerLayer(GraphableMegatronModule, BaseTransformerLayer):
             for k, v in sd.items():
                 for old, new in pm.items():
                     if k.startswith(old):
-                        k2 = k.replace(old, new, 1)
+                        # only the *checkpoint* key is remapped; the dict key stays the module path
                         if hasattr(v, "key"):
                             v.key = v.key.replace(old, new, 1)
-                        k = k2
                         break
                 out[k] = v
             sd = out

@@ -343,9 +343,14 @@ def flash_attention(q, k, v, causal: bool = True, scale: Optional[float] = None,
         # library path (cuDNN/flash SDPA) for shapes the native kernel does not cover
         qb, kb, vb = (t.permute(1, 2, 0, 3) for t in (q, k, v))
         if window is None:
-            o = torch.nn.functional.scaled_dot_product_attention(
-                qb, kb, vb, is_causal=causal and q.shape[0] == k.shape[0], scale=scale, enable_gqa=kb.shape[1] != qb.shape[1]
-            )
+            from torch.nn.attention import SDPBackend, sdpa_kernel
+
+            # cuDNN's Blackwell kernel first (measured 1.1-1.2 PF on B200 vs 0.3 PF for the sm_80 flash
+            # kernel); never the O(s^2)-memory math path.
+            with sdpa_kernel([SDPBackend.CUDNN_ATTENTION, SDPBackend.FLASH_ATTENTION], set_priority=True):
+                o = torch.nn.functional.scaled_dot_product_attention(
+                    qb, kb, vb, is_causal=causal and q.shape[0] == k.shape[0], scale=scale, enable_gqa=kb.shape[1] != qb.shape[1]
+                )
             return o.permute(2, 0, 1, 3).contiguous()
     return ref.attention_fwd(q, k, v, causal, scale, window)
 

@@ -1,0 +1,297 @@
+"""Multi-process (gloo) equivalence tests: pipeline schedules, expert parallel, data parallel +
+distributed optimizer, checkpoint save → reshard → load."""
+import os
+import tempfile
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dist_utils import run_distributed
+
+SEQ, VOCAB = 32, 128
+
+
+def _cfg(**kw):
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    base = dict(num_layers=4, hidden_size=64, num_attention_heads=4, num_query_groups=2, ffn_hidden_size=128, use_cpu_initialization=True,
+                normalization="RMSNorm", gated_linear_unit=True, activation_func=F.silu, add_bias_linear=False, hidden_dropout=0.0, attention_dropout=0.0)
+    base.update(kw)
+    return TransformerConfig(**base)
+
+
+def _model(cfg, pre=True, post=True, vp_stage=None, tie=False):
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_decoder_block_spec, get_gpt_layer_local_spec
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+
+    spec = get_gpt_decoder_block_spec(cfg, vp_stage=vp_stage) if cfg.num_moe_experts else get_gpt_layer_local_spec(normalization="RMSNorm")
+    return GPTModel(cfg, spec, vocab_size=VOCAB, max_sequence_length=SEQ, pre_process=pre, post_process=post, position_embedding_type="rope",
+                    share_embeddings_and_output_weights=tie, vp_stage=vp_stage)
+
+
+def _batches(n, b=2, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    return [dict(tokens=torch.randint(0, VOCAB, (b, SEQ), generator=g), labels=torch.randint(0, VOCAB, (b, SEQ), generator=g)) for _ in range(n)]
+
+
+def _fstep(it, model):
+    b = next(it)
+    pos = torch.arange(SEQ)[None].expand(b["tokens"].shape[0], -1)
+    out = model(b["tokens"], pos, None, labels=b["labels"])
+
+    def loss_fn(o):
+        l = o.float().mean()
+        return l, {"lm loss": l.detach()}
+
+    return out, loss_fn
+
+
+def _reference(num_mb, seed=11, **cfgkw):
+    torch.manual_seed(seed)
+    m = _model(_cfg(**cfgkw))
+    state = {n: p.detach().clone() for n, p in m.named_parameters()}
+    losses = []
+    for b in _batches(num_mb):
+        out, lf = _fstep(iter([b]), m)
+        l, _ = lf(out)
+        (l / num_mb).backward()
+        losses.append(l.item())
+    grads = {n: p.grad.clone() for n, p in m.named_parameters()}
+    return state, losses, grads
+
+
+# ------------------------------------------------------------------------------- pipeline
+def _pp_worker(rank, world, vp, num_mb, ref_state):
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.pipeline_parallel.schedules import get_forward_backward_func
+    from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
+    from megatron_b200.core.transformer.transformer_layer import get_transformer_layer_offset
+
+    ps.initialize_model_parallel(pipeline_model_parallel_size=world, virtual_pipeline_model_parallel_size=vp)
+    model_parallel_cuda_manual_seed(1)
+    cfg = _cfg(pipeline_model_parallel_size=world, virtual_pipeline_model_parallel_size=vp, pipeline_dtype=torch.float32)
+    chunks = []
+    for v in range(vp or 1):
+        if vp:
+            ps.set_virtual_pipeline_model_parallel_rank(v)
+        pre = ps.is_pipeline_first_stage(ignore_virtual=False, vp_stage=v if vp else None)
+        post = ps.is_pipeline_last_stage(ignore_virtual=False, vp_stage=v if vp else None)
+        m = _model(cfg, pre, post, vp_stage=v if vp else None)
+        off = get_transformer_layer_offset(cfg, v if vp else None)
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                if n.startswith("decoder.layers."):
+                    parts = n.split(".")
+                    parts[2] = str(int(parts[2]) + off)
+                    p.copy_(ref_state[".".join(parts)])
+                else:
+                    p.copy_(ref_state[n])
+        m.config = cfg
+        chunks.append((m, off))
+    if vp:
+        ps.set_virtual_pipeline_model_parallel_rank(0)
+    data = _batches(num_mb)
+    fb = get_forward_backward_func()
+    models = [c[0] for c in chunks]
+    its = [iter(data) for _ in models]
+    losses = fb(forward_step_func=_fstep, data_iterator=its if vp else its[0], model=models if vp else models[0], num_microbatches=num_mb,
+                seq_length=SEQ, micro_batch_size=2, forward_only=False)
+    grads = {}
+    for m, off in chunks:
+        for n, p in m.named_parameters():
+            if n.startswith("decoder.layers."):
+                parts = n.split(".")
+                parts[2] = str(int(parts[2]) + off)
+                n = ".".join(parts)
+            grads[n] = p.grad.clone() if p.grad is not None else None
+    return [float(d["lm loss"]) for d in losses], grads
+
+
+@pytest.mark.parametrize("world,vp,num_mb", [(2, None, 4), (4, None, 6), (2, 2, 4), (2, 2, 6), (4, None, 2)])
+def test_pipeline_schedules_match_single_process(world, vp, num_mb):
+    state, ref_losses, ref_grads = _reference(num_mb)
+    res = run_distributed(_pp_worker, world, vp, num_mb, state)
+    last = res[world - 1]
+    assert len(last[0]) == num_mb
+    for a, b in zip(sorted(last[0]), sorted(ref_losses)):
+        assert abs(a - b) < 1e-4
+    seen = set()
+    for r in range(world):
+        for n, g in res[r][1].items():
+            assert g is not None, f"rank {r} param {n} got no grad"
+            assert torch.allclose(g, ref_grads[n], atol=2e-5, rtol=1e-4), (r, n, (g - ref_grads[n]).abs().max())
+            seen.add(n)
+    assert seen == set(ref_grads)
+
+
+def test_interleaved_plan_is_well_formed():
+    from megatron_b200.core.pipeline_parallel.schedules import build_interleaved_plan, get_schedule_table
+
+    assert get_schedule_table(5, 2, 3) == [(0, 0), (1, 0), (2, 0), (0, 1), (1, 1), (2, 1), (3, 0), (4, 0), (3, 1), (4, 1)]
+    for pp, vp, m in [(2, 2, 4), (4, 2, 8), (4, 3, 8), (2, 2, 2)]:
+        for rank in range(pp):
+            plan = build_interleaved_plan(m, vp, pp, rank, pp)
+            f = [(mb, ch) for op, _, mb, ch in plan if op == "F"]
+            b = [(mb, ch) for op, _, mb, ch in plan if op == "B"]
+            assert sorted(f) == sorted(b) == sorted((i, c) for i in range(m) for c in range(vp))
+            done = set()
+            for op, _, mb, ch in plan:  # a backward never precedes its forward
+                if op == "F":
+                    done.add((mb, ch))
+                else:
+                    assert (mb, ch) in done
+
+
+# ------------------------------------------------------------------------------- expert parallel
+def _ep_worker(rank, world, dispatcher, grouped, ref_state):
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
+
+    ps.initialize_model_parallel(expert_model_parallel_size=world)
+    model_parallel_cuda_manual_seed(1)
+    cfg = _cfg(num_layers=2, num_moe_experts=4, moe_router_topk=2, moe_token_dispatcher_type=dispatcher, moe_grouped_gemm=grouped,
+               expert_model_parallel_size=world, moe_aux_loss_coeff=0.0)
+    m = _model(cfg)
+    L = 4 // world
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if ".experts.weight" in n:  # grouped: [L, ...] slice of the [E, ...] reference
+                p.copy_(ref_state[n][rank * L : (rank + 1) * L])
+            elif ".local_experts." in n:
+                parts = n.split(".")
+                i = parts.index("local_experts")
+                parts[i + 1] = str(int(parts[i + 1]) + rank * L)
+                p.copy_(ref_state[".".join(parts)])
+            else:
+                p.copy_(ref_state[n])
+    # every EP rank is also a DP rank: feed different data, compare against the matching reference run
+    b = _batches(world, seed=5)[rank]
+    out, lf = _fstep(iter([b]), m)
+    l, _ = lf(out)
+    l.backward()
+    return l.item(), {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+
+
+@pytest.mark.parametrize("dispatcher,grouped", [("alltoall", True), ("allgather", False), ("alltoall", False), ("flex", True)])
+def test_expert_parallel_matches_single_process(dispatcher, grouped):
+    world = 2
+    torch.manual_seed(21)
+    cfg = _cfg(num_layers=2, num_moe_experts=4, moe_router_topk=2, moe_token_dispatcher_type="alltoall", moe_grouped_gemm=grouped, moe_aux_loss_coeff=0.0)
+    ref = _model(cfg)
+    state = {n: p.detach().clone() for n, p in ref.named_parameters()}
+    ref_losses, ref_grads = [], None
+    for b in _batches(world, seed=5):
+        out, lf = _fstep(iter([b]), ref)
+        l, _ = lf(out)
+        l.backward()
+        ref_losses.append(l.item())
+    ref_grads = {n: p.grad.clone() for n, p in ref.named_parameters()}
+    res = run_distributed(_ep_worker, world, dispatcher, grouped, state)
+    for r in range(world):
+        assert abs(res[r][0] - ref_losses[r]) < 1e-4, (res[r][0], ref_losses[r])
+    # expert grads: each rank owns distinct experts and has seen the tokens of BOTH ranks → equals the summed reference grad
+    L = 4 // world
+    for n, g_ref in ref_grads.items():
+        if ".experts.weight" in n:
+            got = torch.cat([res[r][1][n] for r in range(world)], 0)
+            assert torch.allclose(got, g_ref, atol=2e-5, rtol=1e-4), n
+        elif ".local_experts." in n:
+            parts = n.split(".")
+            i = parts.index("local_experts")
+            e = int(parts[i + 1])
+            parts[i + 1] = str(e % L)
+            got = res[e // L][1][".".join(parts)]
+            assert torch.allclose(got, g_ref, atol=2e-5, rtol=1e-4), n
+        else:
+            got = sum(res[r][1][n] for r in range(world))
+            assert torch.allclose(got, g_ref, atol=2e-5, rtol=1e-4), n
+
+
+# ------------------------------------------------------------------------------- DP + distributed optimizer
+def _dp_worker(rank, world, dist_opt, overlap, steps):
+    from megatron_b200.training.engine import TrainEngine
+
+    eng = TrainEngine("tiny_llama", micro_batch_size=1, global_batch_size=4, bf16=False, use_distributed_optimizer=dist_opt,
+                      overlap_grad_reduce=overlap, overlap_param_gather=False, seed=99, ddp_bucket_size=20000,
+                      model_overrides=dict(num_layers=2, hidden_size=64, ffn_hidden_size=128, num_attention_heads=4, num_query_groups=2, kv_channels=16,
+                                           vocab_size=256, seq_length=32))
+    g = torch.Generator().manual_seed(123)
+    full = torch.randint(0, 256, (4, 33), generator=g)
+    per = 4 // world
+    mine = full[rank * per : (rank + 1) * per]
+    losses = [float(eng.train_step(mine)) for _ in range(steps)]
+    params = torch.cat([p.detach().reshape(-1) for p in eng.model_chunks[0].parameters()])
+    return losses, params
+
+
+@pytest.mark.parametrize("dist_opt,overlap", [(True, True), (True, False), (False, False)])
+def test_data_parallel_and_distributed_optimizer_match_single_process(dist_opt, overlap):
+    ref = run_distributed(_dp_worker, 1, dist_opt, False, 3)[0]
+    res = run_distributed(_dp_worker, 2, dist_opt, overlap, 3)
+    assert torch.allclose(res[0][1], res[1][1], atol=1e-7), "DP replicas diverged"
+    assert torch.allclose(res[0][1], ref[1], atol=1e-5, rtol=1e-4), (res[0][1] - ref[1]).abs().max()
+    mean_losses = [(a + b) / 2 for a, b in zip(res[0][0], res[1][0])]
+    for a, b in zip(mean_losses, ref[0]):
+        assert abs(a - b) < 1e-4
+
+
+# ------------------------------------------------------------------------------- checkpoint resharding
+def _ckpt_save_worker(rank, world, tp, pp, path, ref_state):
+    from megatron_b200.core import dist_checkpointing as dc
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
+    from megatron_b200.core.transformer.transformer_layer import get_transformer_layer_offset
+    from test_tp_cpu import _shard_from_full
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=tp, pipeline_model_parallel_size=pp)
+    model_parallel_cuda_manual_seed(1)
+    cfg = _cfg(tensor_model_parallel_size=tp, pipeline_model_parallel_size=pp, pipeline_dtype=torch.float32)
+    m = _model(cfg, ps.is_pipeline_first_stage(), ps.is_pipeline_last_stage())
+    off = get_transformer_layer_offset(cfg)
+    tpr = ps.get_tensor_model_parallel_rank()
+    if ref_state is not None:
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                key = n
+                if n.startswith("decoder.layers."):
+                    parts = n.split(".")
+                    parts[2] = str(int(parts[2]) + off)
+                    key = ".".join(parts)
+                p.copy_(_shard_from_full(key, ref_state[key], p, tpr, tp, True))
+        dc.save(m.sharded_state_dict(), path)
+        return None
+    sd = dc.load(m.sharded_state_dict(), path)
+    m.load_state_dict(sd)
+    out = {}
+    for n, p in m.named_parameters():
+        key = n
+        if n.startswith("decoder.layers."):
+            parts = n.split(".")
+            parts[2] = str(int(parts[2]) + off)
+            key = ".".join(parts)
+        out[key] = (p.detach().clone(), getattr(p, "tensor_model_parallel", False), getattr(p, "partition_dim", -1), tpr)
+    return out
+
+
+def test_checkpoint_save_tp2_pp2_load_tp1_pp4_and_tp4():
+    from test_tp_cpu import _shard_from_full
+
+    torch.manual_seed(5)
+    ref = _model(_cfg())
+    state = {n: p.detach().clone() for n, p in ref.named_parameters()}
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "ckpt")
+        run_distributed(_ckpt_save_worker, 4, 2, 2, path, state)
+        assert os.path.exists(os.path.join(path, ".metadata")) and os.path.exists(os.path.join(path, "metadata.json"))
+        for tp, pp in [(1, 4), (4, 1), (2, 1)]:
+            res = run_distributed(_ckpt_save_worker, tp * pp, tp, pp, path, None)
+            seen = set()
+            for r, out in enumerate(res):
+                for key, (val, is_tp, dim, tpr) in out.items():
+                    class P:  # minimal stand-in carrying the TP attributes for the slicer
+                        tensor_model_parallel, partition_dim = is_tp, dim
+                    exp = _shard_from_full(key, state[key], P, tpr, tp, True)
+                    assert torch.equal(val, exp), (tp, pp, r, key)
+                    seen.add(key)
+            assert seen == set(state)

@@ -1,0 +1,31 @@
+"""Which library attention backends work for the Llama-3 shape on this box (time + peak memory)."""
+import time, torch, math
+s,b,hq,hk,d = 8192,1,32,8,128
+q = torch.randn(s,b,hq,d, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+k = torch.randn(s,b,hk,d, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+v = torch.randn(s,b,hk,d, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+def bench(name, fn):
+    try:
+        torch.cuda.reset_peak_memory_stats(); base = torch.cuda.memory_allocated()
+        for _ in range(2):
+            o = fn(); o.backward(torch.ones_like(o))
+        torch.cuda.synchronize(); e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True); e2=torch.cuda.Event(enable_timing=True)
+        e0.record(); o = fn(); e1.record(); o.backward(torch.ones_like(o)); e2.record(); torch.cuda.synchronize()
+        fl = 4*s*s*hq*d/2
+        print(f"{name}: fwd {e0.elapsed_time(e1):.2f} ms ({fl/e0.elapsed_time(e1)/1e9:.0f} TF)  bwd {e1.elapsed_time(e2):.2f} ms ({2.5*fl/e1.elapsed_time(e2)/1e9:.0f} TF) peak +{(torch.cuda.max_memory_allocated()-base)/2**30:.2f} GiB", flush=True)
+    except Exception as e:
+        print(f"{name}: FAILED {type(e).__name__}: {str(e)[:200]}", flush=True)
+from torch.nn.attention import sdpa_kernel, SDPBackend
+def sdpa(backend):
+    def f():
+        with sdpa_kernel(backend):
+            o = torch.nn.functional.scaled_dot_product_attention(q.permute(1,2,0,3), k.permute(1,2,0,3), v.permute(1,2,0,3), is_causal=True, enable_gqa=True)
+        return o.permute(2,0,1,3)
+    return f
+for n,be in [("sdpa-flash",SDPBackend.FLASH_ATTENTION),("sdpa-cudnn",SDPBackend.CUDNN_ATTENTION),("sdpa-efficient",SDPBackend.EFFICIENT_ATTENTION)]:
+    bench(n, sdpa(be))
+try:
+    from flash_attn import flash_attn_func
+    bench("flash_attn2", lambda: flash_attn_func(q.transpose(0,1), k.transpose(0,1), v.transpose(0,1), causal=True).transpose(0,1))
+except Exception as e:
+    print("flash_attn import failed", e)
