@@ -114,20 +114,28 @@ def gemm_nt(x: torch.Tensor, w: torch.Tensor, out_dtype=None, out: Optional[torc
         ext().gemm_bf16(x2, w.contiguous(), y.view(x2.shape[0], w.shape[0]), 0, False)  # layout 0: A[M,K] B[N,K]
         _count()
         return y.view(*x.shape[:-1], w.shape[0])
-    return ref.gemm_nt(x, w, out_dtype)
+    r = ref.gemm_nt(x, w, out_dtype)
+    if out is not None:
+        out.view(r.shape).copy_(r)
+        return out.view(r.shape)
+    return r
 
 
-def gemm_nn(gy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
-    """``gy[..., N] @ w[N, K]`` → ``[..., K]`` (dgrad)."""
+def gemm_nn(gy: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``gy[..., N] @ w[N, K]`` → ``[..., K]`` (dgrad); ``out`` may be a symmetric-memory tensor."""
     if _use_cuda(gy) and _tc_ok(gy, w) and gy.shape[-1] % 8 == 0 and w.shape[1] % 8 == 0:
         g2 = gy.reshape(-1, gy.shape[-1])
         if not g2.is_contiguous():
             g2 = g2.contiguous()
-        y = torch.empty((g2.shape[0], w.shape[1]), dtype=gy.dtype, device=gy.device)
+        y = out.view(g2.shape[0], w.shape[1]) if out is not None else torch.empty((g2.shape[0], w.shape[1]), dtype=gy.dtype, device=gy.device)
         ext().gemm_bf16(g2, w.contiguous(), y, 1, False)  # layout 1: A[M,K] B[K,N]
         _count()
         return y.view(*gy.shape[:-1], w.shape[1])
-    return ref.gemm_nn(gy, w)
+    r = ref.gemm_nn(gy, w)
+    if out is not None:
+        out.view(r.shape).copy_(r)
+        return out.view(r.shape)
+    return r
 
 
 def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False, out_dtype=None) -> torch.Tensor:

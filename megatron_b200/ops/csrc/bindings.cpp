@@ -270,6 +270,40 @@ void gemm_bf16(const Tensor& a, const Tensor& b, Tensor c, int64_t layout, bool 
   TORCH_CHECK(rc == 0, "mb200_gemm_bf16 failed with code ", rc);
 }
 
+// ---- NVLink collectives over symmetric memory ------------------------------------------------------
+// `ptrs` / `flags`: per-rank peer-mapped addresses (python ints); `mc`: multicast address or 0.
+#ifdef MB200_HAVE_NVLINK_COLLECTIVES
+void nvl_barrier(const std::vector<int64_t>& ptrs, const std::vector<int64_t>& flags, int64_t rank, int64_t epoch, int64_t slot) {
+  mb200_nvl_barrier(ptrs.data(), flags.data(), (int)rank, (int)ptrs.size(), (uint32_t)epoch, (int)slot, cur_stream());
+}
+void nvl_allgather(const std::vector<int64_t>& ptrs, const std::vector<int64_t>& flags, int64_t mc, const Tensor& src, int64_t dst_off_bytes, int64_t rank,
+                   int64_t epoch, const Tensor& ctrl, int64_t slot, int64_t nblocks) {
+  check_cuda_contig(src, "src");
+  check_aligned16(src, "src");
+  const size_t bytes = (size_t)src.numel() * src.element_size();
+  TORCH_CHECK(bytes % 16 == 0 && dst_off_bytes % 16 == 0, "all-gather shard must be a multiple of 16 bytes");
+  c10::cuda::CUDAGuard g(src.device());
+  mb200_nvl_allgather(ptrs.data(), flags.data(), mc, src.data_ptr(), (size_t)dst_off_bytes, bytes, (int)rank, (int)ptrs.size(), (uint32_t)epoch,
+                      ctrl.data_ptr(), (int)slot, (int)nblocks, cur_stream());
+}
+void nvl_reducescatter(const std::vector<int64_t>& ptrs, const std::vector<int64_t>& flags, int64_t mc, int64_t src_off_bytes, Tensor out, double scale,
+                       int64_t rank, int64_t epoch, const Tensor& ctrl, int64_t slot, bool trailing, int64_t nblocks) {
+  check_cuda_contig(out, "out");
+  check_aligned16(out, "out");
+  TORCH_CHECK(out.scalar_type() == at::kBFloat16 || out.scalar_type() == at::kFloat, "reduce-scatter supports bf16/fp32");
+  TORCH_CHECK(((size_t)out.numel() * out.element_size()) % 16 == 0 && src_off_bytes % 16 == 0);
+  c10::cuda::CUDAGuard g(out.device());
+  mb200_nvl_reducescatter(ptrs.data(), flags.data(), mc, (size_t)src_off_bytes, out.data_ptr(), (size_t)out.numel(), (float)scale, dtype_code(out), (int)rank,
+                          (int)ptrs.size(), (uint32_t)epoch, ctrl.data_ptr(), (int)slot, trailing ? 1 : 0, (int)nblocks, cur_stream());
+}
+void nvl_allreduce(const std::vector<int64_t>& ptrs, const std::vector<int64_t>& flags, int64_t mc, int64_t off_bytes, int64_t elems, int64_t dtype, double scale,
+                   int64_t rank, int64_t epoch, const Tensor& ctrl, int64_t slot, int64_t nblocks) {
+  c10::cuda::CUDAGuard g(ctrl.device());
+  mb200_nvl_allreduce(ptrs.data(), flags.data(), mc, (size_t)off_bytes, (size_t)elems, (float)scale, (int)dtype, (int)rank, (int)ptrs.size(), (uint32_t)epoch,
+                      ctrl.data_ptr(), (int)slot, (int)nblocks, cur_stream());
+}
+#endif
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -286,4 +320,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("multi_scale", &multi_scale);
   m.def("multi_adam", &multi_adam);
   m.def("gemm_bf16", &gemm_bf16);
+#ifdef MB200_HAVE_NVLINK_COLLECTIVES
+  m.def("nvl_barrier", &nvl_barrier);
+  m.def("nvl_allgather", &nvl_allgather);
+  m.def("nvl_reducescatter", &nvl_reducescatter);
+  m.def("nvl_allreduce", &nvl_allreduce);
+#endif
 }

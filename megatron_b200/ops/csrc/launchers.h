@@ -26,5 +26,12 @@ void mb200_multi_scale(void* const* ptrs, const long* sizes, const int* dtypes, 
 void mb200_multi_adam(float* const* p32, const void* const* grads, float* const* m, float* const* v, void* const* lowp, const long* sizes,
                       const int* gdtypes, const int* ldtypes, int n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, int adamw,
                       const float* grad_scale, int nblocks, cudaStream_t s);
+void mb200_nvl_barrier(const int64_t* ptrs, const int64_t* flags, int rank, int world, uint32_t epoch, int slot, cudaStream_t s);
+void mb200_nvl_allgather(const int64_t* ptrs, const int64_t* flags, int64_t mc, const void* src, size_t dst_off, size_t shard_bytes, int rank, int world,
+                         uint32_t epoch, void* ctrl, int slot, int nblocks, cudaStream_t s);
+void mb200_nvl_reducescatter(const int64_t* ptrs, const int64_t* flags, int64_t mc, size_t src_off, void* out, size_t shard_elems, float scale, int dtype,
+                             int rank, int world, uint32_t epoch, void* ctrl, int slot, int trailing, int nblocks, cudaStream_t s);
+void mb200_nvl_allreduce(const int64_t* ptrs, const int64_t* flags, int64_t mc, size_t off, size_t elems, float scale, int dtype, int rank, int world,
+                         uint32_t epoch, void* ctrl, int slot, int nblocks, cudaStream_t s);
 int mb200_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int layout, int accumulate, int c_dtype, cudaStream_t s);
 }

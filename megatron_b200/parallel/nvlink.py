@@ -1,0 +1,287 @@
+"""Symmetric-memory runtime + NVLink collectives for one process group (``NVLinkBackend``).
+
+Substrate: a per-group *symmetric heap* — one VMM allocation per rank, peer-mapped into every
+rank of the group, with an NVLS multicast alias when the fabric supports it.  Allocation and
+handle exchange go through ``torch.distributed._symmetric_memory`` (plumbing, like
+``torch.distributed`` itself); everything that moves data is our own sm_100a kernel
+(``ops/csrc/nvlink_collectives.cu``, ``ops/csrc/fused_tp_gemm.cu``).
+
+Layout of the heap: ``[ flags | workspace A | workspace B | user allocations … ]``.
+Workspaces are double-buffered so a collective needs ONE cross-GPU barrier: by the time a
+buffer is reused (two ops later) every peer has passed the barrier of the op in between and
+therefore finished reading it.
+
+Replaces: NCCL AG/RS/AR on the TP path, TE userbuffers, the NCCL-window allocator
+(N3) and the reference's Triton NVLS collectives (§2.4).
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .. import ops
+
+MAX_RANKS = 16
+NUM_SLOTS = 8
+_FLAG_BYTES = NUM_SLOTS * MAX_RANKS * 4
+
+
+def _align(n: int, a: int = 1024) -> int:
+    return (n + a - 1) // a * a
+
+
+class _Handle:
+    """Completion handle for collectives issued on the backend's side stream."""
+
+    def __init__(self, event: Optional[torch.cuda.Event]):
+        self.event = event
+
+    def wait(self):
+        if self.event is not None:
+            torch.cuda.current_stream().wait_event(self.event)
+            self.event = None
+
+
+class NVLinkBackend:
+    SLOT_MAIN, SLOT_SIDE, SLOT_DDP = 0, 1, 2
+
+    def __init__(self, group, workspace_bytes: Optional[int] = None, heap_bytes: int = 0, use_multicast: Optional[bool] = None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        assert ops.has_ext() and hasattr(ops.ext(), "nvl_allgather"), "native NVLink kernels are not built"
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        assert self.world <= MAX_RANKS
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        if workspace_bytes is None:
+            workspace_bytes = int(os.environ.get("MEGATRON_B200_NVL_WORKSPACE_MB", "320")) << 20
+        self.ws_bytes = _align(workspace_bytes, 1 << 16)
+        self.heap_bytes = _align(_FLAG_BYTES, 1 << 16) + 2 * self.ws_bytes + _align(heap_bytes, 1 << 16)
+        self._symm = symm_mem
+        self.buf = symm_mem.empty(self.heap_bytes, dtype=torch.uint8, device=self.device)
+        self.buf.zero_()
+        torch.cuda.synchronize()
+        try:
+            self.hdl = symm_mem.rendezvous(self.buf, group=group)
+        except TypeError:
+            self.hdl = symm_mem.rendezvous(self.buf, group.group_name)
+        self.ptrs: List[int] = [int(p) for p in self.hdl.buffer_ptrs]
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        if use_multicast is None:
+            use_multicast = os.environ.get("MEGATRON_B200_NVLS", "1") != "0"
+        self.mc = mc if use_multicast else 0
+        self.flags = list(self.ptrs)  # flag arrays live at offset 0 of every heap
+        self.ws_off = [_align(_FLAG_BYTES, 1 << 16), _align(_FLAG_BYTES, 1 << 16) + self.ws_bytes]
+        self.user_off = self.ws_off[1] + self.ws_bytes
+        self._user_cursor = self.user_off
+        self.ctrl = torch.zeros(NUM_SLOTS * 4, dtype=torch.int32, device=self.device)
+        self.epoch = [0] * NUM_SLOTS
+        self._ws_turn = [0] * NUM_SLOTS
+        self.side_stream = torch.cuda.Stream()
+        self.nblocks = int(os.environ.get("MEGATRON_B200_NVL_BLOCKS", "32"))
+        dist.barrier(group=group)
+        self.barrier()
+
+    # ---- plumbing -----------------------------------------------------------------------------------
+    def _next_epoch(self, slot: int, n: int = 1) -> int:
+        e = self.epoch[slot] + 1
+        self.epoch[slot] += n
+        return e
+
+    def _view(self, off: int, numel: int, dtype: torch.dtype) -> torch.Tensor:
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        return self.buf[off : off + nbytes].view(dtype)
+
+    def _workspace(self, slot: int, nbytes: int) -> int:
+        """Alternate between the two workspaces; main and side slots use disjoint halves."""
+        assert nbytes <= self.ws_bytes // 2, f"NVLink workspace too small: need {nbytes} bytes, have {self.ws_bytes // 2} (MEGATRON_B200_NVL_WORKSPACE_MB)"
+        turn = self._ws_turn[slot]
+        self._ws_turn[slot] ^= 1
+        half = 0 if slot == self.SLOT_MAIN else self.ws_bytes // 2
+        return self.ws_off[turn] + half
+
+    def alloc_symmetric(self, numel: int, dtype: torch.dtype) -> torch.Tensor:
+        """Bump-allocate from the user region (all ranks must call in the same order)."""
+        nbytes = _align(numel * torch.empty((), dtype=dtype).element_size(), 1 << 16)
+        if self._user_cursor + nbytes > self.heap_bytes:
+            # grow: separate symmetric allocation with its own peer mapping
+            extra = _ExtraRegion(self, nbytes)
+            self._extras = getattr(self, "_extras", []) + [extra]
+            return extra.tensor(numel, dtype)
+        off = self._user_cursor
+        self._user_cursor += nbytes
+        t = self._view(off, numel, dtype)
+        t.zero_()
+        return t
+
+    def _region_of(self, t: torch.Tensor) -> Optional[Tuple[List[int], int, int]]:
+        """(peer base pointers, multicast base, byte offset) if ``t`` lives in symmetric memory."""
+        p = t.data_ptr()
+        if self.ptrs[self.rank] <= p < self.ptrs[self.rank] + self.heap_bytes:
+            return self.ptrs, self.mc, p - self.ptrs[self.rank]
+        for ex in getattr(self, "_extras", []):
+            if ex.ptrs[self.rank] <= p < ex.ptrs[self.rank] + ex.nbytes:
+                return ex.ptrs, ex.mc, p - ex.ptrs[self.rank]
+        return None
+
+    def barrier(self, slot: int = 0):
+        ops.ext().nvl_barrier(self.ptrs, self.flags, self.rank, self._next_epoch(slot), slot)
+
+    # ---- raw collectives -------------------------------------------------------------------------------
+    def _ag_into(self, x: torch.Tensor, ptrs, mc, dst_off: int, slot: int):
+        ops.ext().nvl_allgather(ptrs, self.flags, mc, x, dst_off, self.rank, self._next_epoch(slot), self.ctrl, slot, self.nblocks)
+        ops._count()
+
+    def all_gather(self, x: torch.Tensor, slot: int = 0) -> torch.Tensor:
+        """[n, …] → [world*n, …] (view into the symmetric workspace; valid until two collectives later)."""
+        x = x.contiguous()
+        nbytes = x.numel() * x.element_size()
+        off = self._workspace(slot, nbytes * self.world)
+        self._ag_into(x, self.ptrs, self.mc, off, slot)
+        return self._view(off, x.numel() * self.world, x.dtype).view(x.shape[0] * self.world, *x.shape[1:])
+
+    def symmetric_like(self, shape, dtype, slot: int = 0) -> torch.Tensor:
+        """Workspace tensor a producer kernel (GEMM epilogue) can write so that peers can read it."""
+        numel = 1
+        for s in shape:
+            numel *= s
+        off = self._workspace(slot, numel * torch.empty((), dtype=dtype).element_size())
+        return self._view(off, numel, dtype).view(*shape)
+
+    def reduce_scatter(self, x: torch.Tensor, slot: int = 0, scale: float = 1.0, out: Optional[torch.Tensor] = None, trailing: bool = False) -> torch.Tensor:
+        """[world*n, …] → [n, …], summed over ranks with fp32 accumulation in the switch."""
+        reg = self._region_of(x)
+        if reg is None:
+            ws = self.symmetric_like(x.shape, x.dtype, slot)
+            ws.copy_(x)
+            x, reg = ws, self._region_of(ws)
+        ptrs, mc, off = reg
+        n0 = x.shape[0] // self.world
+        if out is None:
+            out = torch.empty((n0, *x.shape[1:]), dtype=x.dtype, device=x.device)
+        e = self._next_epoch(slot, 2)
+        ops.ext().nvl_reducescatter(ptrs, self.flags, mc, off, out, float(scale), self.rank, e, self.ctrl, slot, trailing, self.nblocks)
+        ops._count()
+        return out
+
+    def all_reduce(self, x: torch.Tensor, slot: int = 0, scale: float = 1.0) -> torch.Tensor:
+        reg = self._region_of(x)
+        copy_back = None
+        if reg is None:
+            ws = self.symmetric_like(x.shape, x.dtype, slot)
+            ws.copy_(x)
+            copy_back, x, reg = x, ws, self._region_of(ws)
+        ptrs, mc, off = reg
+        code = {torch.float32: 0, torch.bfloat16: 1}[x.dtype]
+        e = self._next_epoch(slot, 2)
+        ops.ext().nvl_allreduce(ptrs, self.flags, mc, off, x.numel(), code, float(scale), self.rank, e, self.ctrl, slot, self.nblocks)
+        ops._count()
+        if copy_back is not None:
+            copy_back.copy_(x)
+            return copy_back
+        return x
+
+    def all_reduce_async(self, t: torch.Tensor) -> _Handle:
+        s = self.side_stream
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.all_reduce(t, slot=self.SLOT_SIDE)
+            ev = torch.cuda.Event()
+            ev.record(s)
+        t.record_stream(s)
+        return _Handle(ev)
+
+    # ---- DDP / distributed-optimizer buffers (must be allocated with alloc_symmetric) --------------------
+    def reduce_scatter_scaled_(self, grad_data: torch.Tensor, scale: float, async_op: bool = False):
+        """In place: my shard of ``grad_data`` ← scale * Σ_ranks shard (scale + reduce + cast fused)."""
+        n = grad_data.numel() // self.world
+        mine = grad_data[self.rank * n : (self.rank + 1) * n]
+        if self._region_of(grad_data) is None:
+            dist.reduce_scatter_tensor(mine, grad_data.mul_(scale), group=self.group)
+            return None
+        self.reduce_scatter(grad_data.view(self.world, n), slot=self.SLOT_DDP, scale=scale, out=mine.view(1, n), trailing=True)
+        return None
+
+    def all_reduce_scaled_(self, grad_data: torch.Tensor, scale: float, async_op: bool = False):
+        if self._region_of(grad_data) is None:
+            dist.all_reduce(grad_data.mul_(scale), group=self.group)
+            return None
+        self.all_reduce(grad_data, slot=self.SLOT_DDP, scale=scale)
+        return None
+
+    def all_gather_inplace_(self, param_data: torch.Tensor, async_op: bool = False):
+        """Publish my shard of ``param_data`` to the same offset on every rank (multicast store)."""
+        n = param_data.numel() // self.world
+        mine = param_data[self.rank * n : (self.rank + 1) * n]
+        reg = self._region_of(param_data)
+        if reg is None:
+            dist.all_gather_into_tensor(param_data, mine.clone(), group=self.group)
+            return None
+        ptrs, mc, off = reg
+        self._ag_into(mine, ptrs, mc, off, self.SLOT_DDP)
+        return None
+
+    # ---- pair ops used by the TP layers ---------------------------------------------------------------------
+    def all_gather_gemm(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+        from . import fused
+
+        if fused.get_mode() == "fused" and hasattr(ops.ext(), "ag_gemm_bf16"):
+            return self._fused_ag_gemm(x, w)
+        full = self.all_gather(x)
+        return ops.gemm_nt(full, w)
+
+    def gemm_reduce_scatter(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+        y = self.symmetric_like((*x.shape[:-1], w.shape[0]), x.dtype)
+        ops.gemm_nt(x, w, out=y.view(-1, w.shape[0]))
+        return self.reduce_scatter(y)
+
+    def sp_linear_backward(self, gy, x, weight, wgrad_needed: bool, accumulate: bool, wgrad_fn):
+        """dgrad GEMM → RS on the main stream; AG(x) on the side stream feeding the wgrad GEMM."""
+        cur = torch.cuda.current_stream()
+        full_x = ev = None
+        if wgrad_needed:
+            s = self.side_stream
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                full_x = self.all_gather(x, slot=self.SLOT_SIDE)
+                ev = torch.cuda.Event()
+                ev.record(s)
+        gx_full = self.symmetric_like((*gy.shape[:-1], weight.shape[1]), gy.dtype)
+        ops.gemm_nn(gy, weight, out=gx_full)
+        gx = self.reduce_scatter(gx_full)
+        gw = None
+        if wgrad_needed:
+            cur.wait_event(ev)
+            gw = wgrad_fn(gy, full_x, weight, accumulate)
+        return gx, gw
+
+    def row_linear_backward_sp(self, gy, x, weight, wgrad_needed: bool, accumulate: bool, wgrad_fn):
+        full_gy = self.all_gather(gy)
+        gx = ops.gemm_nn(full_gy, weight)
+        gw = wgrad_fn(full_gy, x, weight, accumulate) if wgrad_needed else None
+        return gx, gw
+
+
+class _ExtraRegion:
+    """A separately rendezvoused symmetric allocation (DDP buffers larger than the heap)."""
+
+    def __init__(self, be: NVLinkBackend, nbytes: int):
+        self.nbytes = nbytes
+        self.buf = be._symm.empty(nbytes, dtype=torch.uint8, device=be.device)
+        self.buf.zero_()
+        torch.cuda.synchronize()
+        try:
+            self.hdl = be._symm.rendezvous(self.buf, group=be.group)
+        except TypeError:
+            self.hdl = be._symm.rendezvous(self.buf, be.group.group_name)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        self.mc = mc if be.mc else 0
+
+    def tensor(self, numel, dtype):
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        return self.buf[:nbytes].view(dtype)

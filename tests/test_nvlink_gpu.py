@@ -1,0 +1,92 @@
+"""NVLink collectives and TP pair ops vs NCCL on >= 2 GPUs (spawned ranks, one per GPU)."""
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def _worker(rank, world, port, q):
+    import traceback
+
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+        import torch.distributed as dist
+
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from megatron_b200.parallel import collectives
+
+        g = dist.group.WORLD
+        be = collectives.enable_for_group(g)
+        out = {"mc": be.mc != 0}
+        torch.manual_seed(rank)
+        for it in range(3):  # repeated use exercises workspace double-buffering + epochs
+            x = torch.randn(1024, 4096, device="cuda").bfloat16()
+            ref = torch.empty(world * 1024, 4096, device="cuda", dtype=torch.bfloat16)
+            dist.all_gather_into_tensor(ref, x)
+            got = be.all_gather(x)
+            assert torch.equal(got, ref), f"all_gather mismatch iter {it}"
+            y = torch.randn(world * 512, 2048, device="cuda").bfloat16()
+            ref = torch.empty(512, 2048, device="cuda", dtype=torch.bfloat16)
+            dist.reduce_scatter_tensor(ref, y.clone())
+            got = be.reduce_scatter(y)
+            assert torch.allclose(got.float(), ref.float(), atol=0.06, rtol=0.02), f"reduce_scatter mismatch {(got.float()-ref.float()).abs().max()}"
+            z = torch.randn(777 * 8, device="cuda")
+            ref = z.clone()
+            dist.all_reduce(ref)
+            got = be.all_reduce(z.clone())
+            assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4), "all_reduce fp32 mismatch"
+        # pair ops
+        from megatron_b200.parallel import fused
+
+        w = (0.02 * torch.randn(768, 4096, device="cuda")).bfloat16()
+        x = torch.randn(256, 1, 4096, device="cuda").bfloat16()
+        full = torch.empty(world * 256, 1, 4096, device="cuda", dtype=torch.bfloat16)
+        dist.all_gather_into_tensor(full, x)
+        ref = (full.float() @ w.float().t())
+        got = fused.all_gather_gemm(x, w, g)
+        assert torch.allclose(got.float(), ref, atol=0.05, rtol=0.05), "all_gather_gemm mismatch"
+        w2 = (0.02 * torch.randn(4096, 512, device="cuda")).bfloat16()
+        xs = torch.randn(world * 256, 1, 512, device="cuda").bfloat16()
+        part = xs.float() @ w2.float().t()
+        ref = torch.empty(256, 1, 4096, device="cuda")
+        dist.reduce_scatter_tensor(ref, part.contiguous())
+        got = fused.gemm_reduce_scatter(xs, w2, g)
+        assert torch.allclose(got.float(), ref, atol=0.08, rtol=0.05), f"gemm_reduce_scatter mismatch {(got.float()-ref).abs().max()}"
+        torch.cuda.synchronize()
+        dist.barrier()
+        q.put((rank, "ok", out))
+        dist.destroy_process_group()
+    except Exception:
+        q.put((rank, "err", traceback.format_exc()))
+
+
+def test_nvlink_collectives_match_nccl():
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = min(n, 8)
+    import socket
+
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=20)
+        if p.is_alive():
+            p.kill()
+    for rank, status, payload in res:
+        assert status == "ok", f"rank {rank}:\n{payload}"
+    print("multicast (NVLS) active:", res[0][2]["mc"])
