@@ -289,8 +289,16 @@ def run_reference(args):
             state["loss"] = float(l) if sync_loss else l
         return step
 
+    full = dict(recompute_granularity="full", recompute_method="uniform", recompute_num_layers=1)
     attempts = [("selective(core_attn)", dict(recompute_granularity="selective", recompute_modules=["core_attn"])),
-                ("full(uniform,1)", dict(recompute_granularity="full", recompute_method="uniform", recompute_num_layers=1))]
+                ("full(uniform,1)", full),
+                ("full(uniform,1)+bf16-softmax", dict(full, attention_softmax_in_fp32=False))]
+    if world == 1:
+        # measured on the 180 GB part: selective recompute OOMs at TP=1 (fp32 [32,8192,8192] scores on top of
+        # 120 GiB of parameter/optimizer state) and a failed attempt fragments the heap — start from full recompute
+        attempts = attempts[1:]
+    if os.environ.get("REF_RECOMPUTE"):
+        attempts = [a for a in attempts if a[0].startswith(os.environ["REF_RECOMPUTE"])] or attempts
     used = None
     for name, rc in attempts:
         try:

@@ -1,0 +1,173 @@
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from typing import Any, Dict, List, Optional, Union
+
+
+class MegatronTokenizerBase(ABC):
+    @abstractmethod
+    def tokenize(self, text: str) -> List[int]:
+        ...
+
+    def detokenize(self, ids: List[int]) -> str:
+        raise NotImplementedError
+
+    @property
+    @abstractmethod
+    def vocab_size(self) -> int:
+        ...
+
+    @property
+    def eod(self) -> int:
+        raise NotImplementedError
+
+    @property
+    def pad(self) -> int:
+        return -1
+
+    @property
+    def bos(self) -> Optional[int]:
+        return None
+
+    @property
+    def eos(self) -> Optional[int]:
+        return self.eod
+
+    def offsets(self, ids: List[int], text: str) -> List[int]:
+        out, pos = [], 0
+        for i in ids:
+            out.append(pos)
+            pos += len(self.detokenize([i]))
+        return out
+
+
+class NullTokenizer(MegatronTokenizerBase):
+    """Whitespace-separated integers; the last id is EOD (``--tokenizer-type NullTokenizer``)."""
+
+    def __init__(self, vocab_size: int):
+        self._vocab_size_without_eod = int(vocab_size)
+        self._eod_id = self._vocab_size_without_eod
+
+    def tokenize(self, text: str) -> List[int]:
+        return [int(x) for x in text.split()]
+
+    def detokenize(self, ids: List[int]) -> str:
+        return " ".join(str(int(i)) for i in ids)
+
+    @property
+    def vocab_size(self) -> int:
+        return self._vocab_size_without_eod + 1
+
+    @property
+    def eod(self) -> int:
+        return self._eod_id
+
+    @property
+    def unique_identifiers(self):
+        return {"class": "NullTokenizer", "vocab_size": self.vocab_size}
+
+
+class ByteLevelTokenizer(MegatronTokenizerBase):
+    def tokenize(self, text: str) -> List[int]:
+        return list(text.encode("utf-8"))
+
+    def detokenize(self, ids: List[int]) -> str:
+        return bytes(int(i) for i in ids if i < 256).decode("utf-8", errors="replace")
+
+    @property
+    def vocab_size(self) -> int:
+        return 257
+
+    @property
+    def eod(self) -> int:
+        return 256
+
+
+class SentencePieceTokenizer(MegatronTokenizerBase):
+    def __init__(self, model_file: str):
+        import sentencepiece
+
+        self.sp = sentencepiece.SentencePieceProcessor(model_file=model_file)
+
+    def tokenize(self, text: str) -> List[int]:
+        return self.sp.encode(text)
+
+    def detokenize(self, ids: List[int]) -> str:
+        return self.sp.decode(list(map(int, ids)))
+
+    @property
+    def vocab_size(self) -> int:
+        return self.sp.get_piece_size()
+
+    @property
+    def eod(self) -> int:
+        return self.sp.eos_id()
+
+    @property
+    def bos(self):
+        return self.sp.bos_id()
+
+    @property
+    def pad(self):
+        return self.sp.pad_id()
+
+
+class HuggingFaceTokenizer(MegatronTokenizerBase):
+    def __init__(self, path: str, **kw):
+        import transformers
+
+        self.tk = transformers.AutoTokenizer.from_pretrained(path, **kw)
+
+    def tokenize(self, text: str) -> List[int]:
+        return self.tk.encode(text, add_special_tokens=False)
+
+    def detokenize(self, ids: List[int]) -> str:
+        return self.tk.decode(list(map(int, ids)))
+
+    @property
+    def vocab_size(self) -> int:
+        return len(self.tk)
+
+    @property
+    def eod(self) -> int:
+        return self.tk.eos_token_id
+
+    @property
+    def bos(self):
+        return self.tk.bos_token_id
+
+    @property
+    def pad(self):
+        return self.tk.pad_token_id if self.tk.pad_token_id is not None else -1
+
+
+class MegatronTokenizer:
+    """Factory mirroring ``MegatronTokenizer.from_pretrained(metadata_path={"library": ...}, ...)``."""
+
+    @staticmethod
+    def from_pretrained(tokenizer_path: Optional[str] = None, metadata_path: Optional[Union[str, Dict[str, Any]]] = None, **kwargs):
+        lib = None
+        if isinstance(metadata_path, dict):
+            lib = metadata_path.get("library")
+        if lib in ("null", "null-text"):
+            return NullTokenizer(kwargs.get("vocab_size", 256))
+        if lib == "byte-level":
+            return ByteLevelTokenizer()
+        if lib == "sentencepiece":
+            return SentencePieceTokenizer(tokenizer_path)
+        if lib in ("huggingface", None) and tokenizer_path:
+            return HuggingFaceTokenizer(tokenizer_path, **{k: v for k, v in kwargs.items() if k != "vocab_size"})
+        raise ValueError(f"cannot build a tokenizer from library={lib!r}, path={tokenizer_path!r}")
+
+
+def build_tokenizer(tokenizer_type: str, vocab_size: Optional[int] = None, tokenizer_model: Optional[str] = None, **kw):
+    t = tokenizer_type.lower()
+    if t == "nulltokenizer":
+        return NullTokenizer(vocab_size)
+    if t in ("bytelevel", "byteleveltokenizer"):
+        return ByteLevelTokenizer()
+    if t in ("sentencepiecetokenizer", "llama2tokenizer", "gptsentencepiecetokenizer"):
+        return SentencePieceTokenizer(tokenizer_model)
+    if t in ("huggingfacetokenizer", "hf"):
+        return HuggingFaceTokenizer(tokenizer_model, **kw)
+    raise ValueError(f"unknown tokenizer type {tokenizer_type}")
