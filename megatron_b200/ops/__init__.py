@@ -82,72 +82,9 @@ def reset_launch_count():
 
 
 # =============================================================================
-# GEMM
+# GEMM (see ops/gemm.py: tcgen05 variants + cuBLAS, autotuned per problem)
 # =============================================================================
-
-_GEMM_BACKEND = os.environ.get("MEGATRON_B200_GEMM", "auto")  # auto|tcgen05|cublas
-
-
-def set_gemm_backend(name: str):
-    global _GEMM_BACKEND
-    assert name in ("auto", "tcgen05", "cublas")
-    _GEMM_BACKEND = name
-
-
-def _tc_ok(*ts) -> bool:
-    if _GEMM_BACKEND == "cublas":
-        return False
-    for t in ts:
-        if t.dtype != torch.bfloat16:
-            return False
-    return True
-
-
-def gemm_nt(x: torch.Tensor, w: torch.Tensor, out_dtype=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``x[..., K] @ w[N, K]ᵀ`` → ``[..., N]`` (forward of every linear)."""
-    if _use_cuda(x) and _tc_ok(x, w) and x.shape[-1] % 8 == 0 and w.shape[0] % 8 == 0:
-        x2 = x.reshape(-1, x.shape[-1])
-        if not x2.is_contiguous():
-            x2 = x2.contiguous()
-        od = out_dtype or x.dtype
-        y = out if out is not None else torch.empty((x2.shape[0], w.shape[0]), dtype=od, device=x.device)
-        ext().gemm_bf16(x2, w.contiguous(), y.view(x2.shape[0], w.shape[0]), 0, False)  # layout 0: A[M,K] B[N,K]
-        _count()
-        return y.view(*x.shape[:-1], w.shape[0])
-    r = ref.gemm_nt(x, w, out_dtype)
-    if out is not None:
-        out.view(r.shape).copy_(r)
-        return out.view(r.shape)
-    return r
-
-
-def gemm_nn(gy: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``gy[..., N] @ w[N, K]`` → ``[..., K]`` (dgrad); ``out`` may be a symmetric-memory tensor."""
-    if _use_cuda(gy) and _tc_ok(gy, w) and gy.shape[-1] % 8 == 0 and w.shape[1] % 8 == 0:
-        g2 = gy.reshape(-1, gy.shape[-1])
-        if not g2.is_contiguous():
-            g2 = g2.contiguous()
-        y = out.view(g2.shape[0], w.shape[1]) if out is not None else torch.empty((g2.shape[0], w.shape[1]), dtype=gy.dtype, device=gy.device)
-        ext().gemm_bf16(g2, w.contiguous(), y, 1, False)  # layout 1: A[M,K] B[K,N]
-        _count()
-        return y.view(*gy.shape[:-1], w.shape[1])
-    r = ref.gemm_nn(gy, w)
-    if out is not None:
-        out.view(r.shape).copy_(r)
-        return out.view(r.shape)
-    return r
-
-
-def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False, out_dtype=None) -> torch.Tensor:
-    """``a[M, N]ᵀ @ b[M, K]`` → ``[N, K]`` (wgrad); ``accumulate`` adds into fp32/bf16 ``out``."""
-    if _use_cuda(a) and _tc_ok(a, b) and b.shape[1] % 8 == 0 and a.shape[1] % 8 == 0:
-        if out is None:
-            out = torch.empty((a.shape[1], b.shape[1]), dtype=out_dtype or a.dtype, device=a.device)
-            accumulate = False
-        ext().gemm_bf16(a.contiguous(), b.contiguous(), out, 2, accumulate)  # layout 2: A[K,M] B[K,N]
-        _count()
-        return out
-    return ref.gemm_tn(a, b, out, accumulate, out_dtype)
+from .gemm import gemm_nn, gemm_nt, gemm_tn, get_gemm_backend, set_gemm_backend  # noqa: E402
 
 
 # =============================================================================

@@ -252,7 +252,7 @@ void multi_adam(const std::vector<Tensor>& p32, const std::vector<Tensor>& grads
 }
 
 // ---- GEMM -------------------------------------------------------------------------------------------
-void gemm_bf16(const Tensor& a, const Tensor& b, Tensor c, int64_t layout, bool accumulate) {
+void gemm_bf16(const Tensor& a, const Tensor& b, Tensor c, int64_t layout, bool accumulate, int64_t variant) {
   check_cuda_contig(a, "a"); check_cuda_contig(b, "b"); check_cuda_contig(c, "c");
   TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16, "gemm_bf16 expects bf16 operands");
   TORCH_CHECK(c.scalar_type() == at::kBFloat16 || c.scalar_type() == at::kFloat, "gemm_bf16 output must be bf16 or fp32");
@@ -265,8 +265,8 @@ void gemm_bf16(const Tensor& a, const Tensor& b, Tensor c, int64_t layout, bool 
   check_aligned16(a, "a"); check_aligned16(b, "b"); check_aligned16(c, "c");
   TORCH_CHECK((a.size(1) % 8) == 0 && (b.size(1) % 8) == 0, "gemm_bf16: row pitch must be a multiple of 16 bytes");
   c10::cuda::CUDAGuard g(a.device());
-  const int rc = mb200_gemm_bf16(a.data_ptr(), b.data_ptr(), c.data_ptr(), (int)M, (int)N, (int)K, (int)layout, accumulate ? 1 : 0, dtype_code(c),
-                                 cur_stream());
+  const int rc = mb200_gemm_bf16_v(a.data_ptr(), b.data_ptr(), c.data_ptr(), (int)M, (int)N, (int)K, (int)layout, accumulate ? 1 : 0, dtype_code(c),
+                                   (int)variant, cur_stream());
   TORCH_CHECK(rc == 0, "mb200_gemm_bf16 failed with code ", rc);
 }
 
@@ -319,7 +319,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("multi_l2norm", &multi_l2norm);
   m.def("multi_scale", &multi_scale);
   m.def("multi_adam", &multi_adam);
-  m.def("gemm_bf16", &gemm_bf16);
+  m.def("gemm_bf16", &gemm_bf16, pybind11::arg("a"), pybind11::arg("b"), pybind11::arg("c"), pybind11::arg("layout"), pybind11::arg("accumulate"),
+        pybind11::arg("variant") = 0);
 #ifdef MB200_HAVE_NVLINK_COLLECTIVES
   m.def("nvl_barrier", &nvl_barrier);
   m.def("nvl_allgather", &nvl_allgather);

@@ -33,5 +33,6 @@ void mb200_nvl_reducescatter(const int64_t* ptrs, const int64_t* flags, int64_t 
                              int rank, int world, uint32_t epoch, void* ctrl, int slot, int trailing, int nblocks, cudaStream_t s);
 void mb200_nvl_allreduce(const int64_t* ptrs, const int64_t* flags, int64_t mc, size_t off, size_t elems, float scale, int dtype, int rank, int world,
                          uint32_t epoch, void* ctrl, int slot, int nblocks, cudaStream_t s);
+int mb200_gemm_bf16_v(const void* A, const void* B, void* C, int M, int N, int K, int layout, int accumulate, int c_dtype, int variant, cudaStream_t s);
 int mb200_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int layout, int accumulate, int c_dtype, cudaStream_t s);
 }

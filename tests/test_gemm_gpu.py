@@ -1,4 +1,4 @@
-"""tcgen05/TMA GEMM (ops/csrc/gemm_sm100.cu) vs torch fp32 reference, all three layouts."""
+"""tcgen05/TMA GEMMs (ops/csrc/gemm_sm100.cu) vs torch fp32 reference: 3 layouts x 4 tile/cluster variants."""
 import pytest
 import torch
 
@@ -12,13 +12,14 @@ SHAPES = [
     (8192, 4096, 512),   # proj @ tp=8
     (384, 16032, 1024),  # LM-head shard, N not a multiple of 256
 ]
+VARIANTS = [1, 2, 3, 4]  # 1cta-128x256, 1cta-128x128, 2cta-256x256, 2cta-256x128
 
 
-def _ops():
+def _ops(variant):
     from megatron_b200 import ops
 
     assert ops.has_ext(), f"native extension missing: {ops._EXT_ERR!r}"
-    ops.set_gemm_backend("tcgen05")
+    ops.set_gemm_backend(f"tcgen05:{variant}")
     return ops
 
 
@@ -28,30 +29,31 @@ def _check(out, ref, K):
     assert err <= 2e-2 * scale + 1e-2, f"max abs err {err} (ref scale {scale}, K={K})"
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("M,N,K", SHAPES)
-def test_gemm_nt(M, N, K):
-    ops = _ops()
+def test_gemm_nt(M, N, K, variant):
+    ops = _ops(variant)
     torch.manual_seed(0)
     a = torch.randn(M, K, device="cuda").bfloat16()
     b = torch.randn(N, K, device="cuda").bfloat16()
-    out = ops.gemm_nt(a, b)
-    _check(out, a.float() @ b.float().t(), K)
+    _check(ops.gemm_nt(a, b), a.float() @ b.float().t(), K)
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("M,N,K", SHAPES)
-def test_gemm_nn(M, N, K):
-    ops = _ops()
+def test_gemm_nn(M, N, K, variant):
+    ops = _ops(variant)
     torch.manual_seed(0)
     a = torch.randn(M, K, device="cuda").bfloat16()
     b = torch.randn(K, N, device="cuda").bfloat16()
-    out = ops.gemm_nn(a, b)
-    _check(out, a.float() @ b.float(), K)
+    _check(ops.gemm_nn(a, b), a.float() @ b.float(), K)
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("M,N,K", SHAPES)
 @pytest.mark.parametrize("acc", [False, True])
-def test_gemm_tn_wgrad(M, N, K, acc):
-    ops = _ops()
+def test_gemm_tn_wgrad(M, N, K, acc, variant):
+    ops = _ops(variant)
     torch.manual_seed(0)
     a = torch.randn(K, M, device="cuda").bfloat16()  # dY  [tokens, out]
     b = torch.randn(K, N, device="cuda").bfloat16()  # X   [tokens, in]
@@ -65,9 +67,11 @@ def test_gemm_tn_wgrad(M, N, K, acc):
     _check(out, ref, K)
 
 
-def test_gemm_matches_cublas_bitwise_class():
-    """Same inputs through cuBLAS: both are fp32-accumulated bf16 GEMMs, errors must be comparable."""
-    ops = _ops()
+def test_autotuner_picks_a_candidate_and_is_correct():
+    from megatron_b200 import ops
+    from megatron_b200.ops import gemm as g
+
+    ops.set_gemm_backend("auto")
     torch.manual_seed(0)
     a = torch.randn(2048, 4096, device="cuda").bfloat16()
     b = torch.randn(3584, 4096, device="cuda").bfloat16()
@@ -75,3 +79,5 @@ def test_gemm_matches_cublas_bitwise_class():
     ours = ops.gemm_nt(a, b).float()
     lib = (a @ b.t()).float()
     assert (ours - ref).abs().max() <= 2 * (lib - ref).abs().max() + 1e-3
+    assert g.tuning_report(), "autotuner did not run"
+    print(g.tuning_report()[-1])
