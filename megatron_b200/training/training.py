@@ -1,0 +1,366 @@
+"""``pretrain()`` — argument-driven training loop (reference ``megatron/training/training.py:1500-4554``).
+
+init distributed + model-parallel groups → build model chunks (per virtual stage) → DDP → optimizer +
+LR scheduler → (load checkpoint) → data iterators → ``train()``: step / log / eval / checkpoint / exit.
+"""
+from __future__ import annotations
+
+import gc
+import math
+import os
+import signal
+import sys
+import time
+from typing import Callable, Dict, Iterator, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from ..core import parallel_state as ps
+from ..core.distributed import DistributedDataParallel, DistributedDataParallelConfig, finalize_model_grads
+from ..core.enums import ModelType
+from ..core.num_microbatches_calculator import (
+    destroy_num_microbatches_calculator,
+    get_current_global_batch_size,
+    get_num_microbatches,
+    init_num_microbatches_calculator,
+    update_num_microbatches,
+)
+from ..core.optimizer import OptimizerConfig, get_megatron_optimizer
+from ..core.optimizer_param_scheduler import OptimizerParamScheduler
+from ..core.pipeline_parallel.schedules import get_forward_backward_func
+from ..core.rerun_state_machine import RerunDataIterator, get_rerun_state_machine, initialize_rerun_state_machine
+from ..core.tensor_parallel.random import model_parallel_cuda_manual_seed
+from ..core.timers import Timers
+from ..core.utils import StragglerDetector
+from . import checkpointing
+from .arguments import core_transformer_config_from_args, parse_and_validate_args
+from .engine import initialize_distributed
+from .flops import num_floating_point_operations
+
+_GLOBALS: Dict[str, object] = {}
+
+
+def get_args():
+    return _GLOBALS["args"]
+
+
+def get_timers() -> Timers:
+    return _GLOBALS["timers"]
+
+
+def print_rank_0(*a):
+    if not dist.is_initialized() or dist.get_rank() == 0:
+        print(*a, flush=True)
+
+
+def print_rank_last(*a):
+    if not dist.is_initialized() or dist.get_rank() == dist.get_world_size() - 1:
+        print(*a, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def initialize_megatron(argv=None, extra_args_provider=None, args_defaults: Optional[dict] = None):
+    args = parse_and_validate_args(argv, extra_args_provider=extra_args_provider)
+    for k, v in (args_defaults or {}).items():
+        if getattr(args, k, None) is None:
+            setattr(args, k, v)
+    _GLOBALS["args"] = args
+    initialize_distributed("gloo" if (args.distributed_backend == "gloo" or not torch.cuda.is_available()) else "nccl")
+    if not ps.is_initialized():
+        ps.initialize_model_parallel(
+            tensor_model_parallel_size=args.tensor_model_parallel_size, pipeline_model_parallel_size=args.pipeline_model_parallel_size,
+            virtual_pipeline_model_parallel_size=args.virtual_pipeline_model_parallel_size, context_parallel_size=args.context_parallel_size,
+            expert_model_parallel_size=args.expert_model_parallel_size, expert_tensor_parallel_size=args.expert_tensor_parallel_size,
+            distributed_timeout_minutes=args.distributed_timeout_minutes, create_gloo_process_groups=False,
+        )
+    model_parallel_cuda_manual_seed(args.seed)
+    _GLOBALS["timers"] = Timers(args.timing_log_level, args.timing_log_option)
+    initialize_rerun_state_machine(mode=args.rerun_mode, error_injection_rate=args.error_injection_rate)
+    destroy_num_microbatches_calculator()
+    init_num_microbatches_calculator(dist.get_rank(), args.rampup_batch_size, args.global_batch_size, args.micro_batch_size, args.data_parallel_size)
+    if args.tp_comm != "auto":
+        from ..parallel import fused
+
+        fused.set_mode(args.tp_comm)
+    if torch.cuda.is_available() and args.tensor_model_parallel_size > 1 and args.tp_comm != "nccl" and dist.get_backend() == "nccl":
+        from ..parallel import collectives
+
+        collectives.enable_for_group(ps.get_tensor_model_parallel_group())
+    return args
+
+
+def get_model(model_provider_func: Callable, wrap_with_ddp: bool = True) -> List[torch.nn.Module]:
+    """One model chunk per virtual pipeline stage, moved to the device and wrapped in DDP (reference :2358)."""
+    args = get_args()
+    vp = args.virtual_pipeline_model_parallel_size
+    chunks = []
+    for v in range(vp or 1):
+        if vp:
+            ps.set_virtual_pipeline_model_parallel_rank(v)
+        pre = ps.is_pipeline_first_stage(ignore_virtual=False, vp_stage=v if vp else None)
+        post = ps.is_pipeline_last_stage(ignore_virtual=False, vp_stage=v if vp else None)
+        m = model_provider_func(pre_process=pre, post_process=post, vp_stage=v if vp else None)
+        m.model_type = ModelType.encoder_or_decoder
+        chunks.append(m)
+    if vp:
+        ps.set_virtual_pipeline_model_parallel_rank(0)
+    n_params = sum(p.numel() for c in chunks for p in c.parameters())
+    if ps.get_data_parallel_rank() == 0:
+        print(f" > number of parameters on (tensor, pipeline) model parallel rank ({ps.get_tensor_model_parallel_rank()}, "
+              f"{ps.get_pipeline_model_parallel_rank()}): {n_params}", flush=True)
+    dev = torch.device("cuda", torch.cuda.current_device()) if (torch.cuda.is_available() and dist.get_backend() != "gloo") else torch.device("cpu")
+    chunks = [c.to(dev) for c in chunks]
+    if not wrap_with_ddp:
+        return chunks
+    config = chunks[0].config
+    ddp_config = DistributedDataParallelConfig(
+        grad_reduce_in_fp32=args.accumulate_allreduce_grads_in_fp32, overlap_grad_reduce=args.overlap_grad_reduce,
+        overlap_param_gather=args.overlap_param_gather, use_distributed_optimizer=args.use_distributed_optimizer,
+        check_for_nan_in_grad=args.check_for_nan_in_loss_and_grad, bucket_size=args.ddp_bucket_size,
+    )
+    model = [DistributedDataParallel(config, ddp_config, c, disable_bucketing=(i > 0)) for i, c in enumerate(chunks)]
+    for c in chunks:
+        c.config = config
+    if ps.get_data_parallel_world_size() > 1:
+        for m in model:
+            m.broadcast_params()
+    return model
+
+
+def get_optimizer_param_scheduler(optimizer):
+    args = get_args()
+    gbs = args.global_batch_size
+    if args.train_iters:
+        decay = (args.lr_decay_iters or args.train_iters) * gbs
+        wd_steps = args.train_iters * gbs
+        warm = args.lr_warmup_fraction * decay if args.lr_warmup_fraction is not None else args.lr_warmup_iters * gbs
+        wsd = args.lr_wsd_decay_iters * gbs if args.lr_wsd_decay_iters else None
+    else:
+        decay = args.lr_decay_samples or args.train_samples
+        wd_steps = args.train_samples
+        warm = args.lr_warmup_fraction * decay if args.lr_warmup_fraction is not None else args.lr_warmup_samples
+        wsd = None
+    return OptimizerParamScheduler(
+        optimizer, init_lr=args.lr_warmup_init, max_lr=args.lr, min_lr=args.min_lr, lr_warmup_steps=int(warm), lr_decay_steps=max(int(decay), int(warm) + 1),
+        lr_decay_style=args.lr_decay_style, start_wd=args.start_weight_decay if args.start_weight_decay is not None else args.weight_decay,
+        end_wd=args.end_weight_decay if args.end_weight_decay is not None else args.weight_decay, wd_incr_steps=max(int(wd_steps), 1),
+        wd_incr_style=args.weight_decay_incr_style, use_checkpoint_opt_param_scheduler=False, wsd_decay_steps=wsd, lr_wsd_decay_style=args.lr_wsd_decay_style,
+    )
+
+
+def setup_model_and_optimizer(model_provider_func: Callable):
+    args = get_args()
+    model = get_model(model_provider_func)
+    opt_cfg = OptimizerConfig(
+        optimizer=args.optimizer, lr=args.lr, min_lr=args.min_lr, weight_decay=args.weight_decay, fp16=args.fp16, bf16=args.bf16, params_dtype=args.params_dtype,
+        clip_grad=args.clip_grad, use_distributed_optimizer=args.use_distributed_optimizer, adam_beta1=args.adam_beta1, adam_beta2=args.adam_beta2,
+        adam_eps=args.adam_eps, loss_scale=args.loss_scale, initial_loss_scale=args.initial_loss_scale, min_loss_scale=args.min_loss_scale,
+        loss_scale_window=args.loss_scale_window, hysteresis=args.hysteresis, overlap_param_gather=args.overlap_param_gather, timers=get_timers(),
+    )
+    optimizer = get_megatron_optimizer(opt_cfg, model)
+    scheduler = get_optimizer_param_scheduler(optimizer)
+    args.iteration, args.num_floating_point_operations_so_far = 0, 0.0
+    if args.load:
+        it, fl = checkpointing.load_checkpoint(model, optimizer, scheduler, args.load, load_optim=not (args.no_load_optim or args.finetune),
+                                               load_rng=not (args.no_load_rng or args.finetune))
+        args.iteration = 0 if args.finetune else it
+        args.num_floating_point_operations_so_far = fl
+        print_rank_0(f" > loaded checkpoint from {args.load} at iteration {it}")
+    return model, optimizer, scheduler
+
+
+# ---------------------------------------------------------------------------------------------------------
+def train_step(forward_step_func, data_iterator, model, optimizer, opt_param_scheduler, config):
+    """One optimizer step, wrapped by the rerun state machine (fault attribution, reference :3010-3260)."""
+    args, timers = get_args(), get_timers()
+    rerun = get_rerun_state_machine()
+    while rerun.should_run_forward_backward(data_iterator):
+        for m in model:
+            m.zero_grad_buffer()
+        optimizer.zero_grad()
+        fb = get_forward_backward_func()
+        losses_reduced = fb(forward_step_func=forward_step_func, data_iterator=data_iterator, model=model if len(model) > 1 else model[0],
+                            num_microbatches=get_num_microbatches(), seq_length=args.seq_length, micro_batch_size=args.micro_batch_size, forward_only=False)
+    should_checkpoint, should_exit, exit_code = rerun.should_checkpoint_and_exit()
+    if should_exit:
+        return {}, True, should_checkpoint, should_exit, exit_code, None, None
+    timers("optimizer", log_level=1).start(barrier=args.timing_log_level > 1)
+    update_successful, grad_norm, num_zeros = optimizer.step()
+    timers("optimizer").stop()
+    if update_successful:
+        opt_param_scheduler.step(increment=get_num_microbatches() * args.micro_batch_size * args.data_parallel_size)
+        skipped = 0
+    else:
+        skipped = 1
+    loss_reduced = {}
+    if ps.is_pipeline_last_stage(ignore_virtual=True) and losses_reduced:
+        for key in losses_reduced[0]:
+            vals = torch.stack([d[key].float().reshape(()) for d in losses_reduced])
+            v = vals.mean()
+            if ps.get_data_parallel_world_size(with_context_parallel=True) > 1:
+                dist.all_reduce(v, group=ps.get_data_parallel_group(with_context_parallel=True))
+                v = v / ps.get_data_parallel_world_size(with_context_parallel=True)
+            loss_reduced[key] = v
+    return loss_reduced, skipped, should_checkpoint, should_exit, exit_code, grad_norm, num_zeros
+
+
+def training_log(loss_dict, total_loss_dict, learning_rate, iteration, loss_scale, grad_norm, elapsed_per_iter, model_flops_per_iter):
+    args = get_args()
+    for k, v in loss_dict.items():
+        total_loss_dict[k] = total_loss_dict.get(k, 0.0) + float(v)
+    if iteration % args.log_interval != 0:
+        return
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    tput = model_flops_per_iter / (elapsed_per_iter * 1e12 * world)
+    tok_s = get_current_global_batch_size() * args.seq_length / elapsed_per_iter
+    s = f" iteration {iteration:8d}/{args.train_iters:8d} | consumed samples: {args.consumed_train_samples:12d} |"
+    s += f" elapsed time per iteration (ms): {elapsed_per_iter * 1000.0:.1f} | throughput per GPU (TFLOP/s/GPU): {tput:.1f} | tokens/s: {tok_s:.0f} |"
+    s += f" learning rate: {learning_rate:.6E} | global batch size: {get_current_global_batch_size():5d} |"
+    for k in list(total_loss_dict):
+        s += f" {k}: {total_loss_dict[k] / args.log_interval:.6E} |"
+        total_loss_dict[k] = 0.0
+    s += f" loss scale: {float(loss_scale):.1f} |"
+    if grad_norm is not None:
+        s += f" grad norm: {float(grad_norm):.3f} |"
+    if torch.cuda.is_available():
+        s += f" mem-max-allocated-GiB: {torch.cuda.max_memory_allocated() / 2**30:.2f} |"
+    print_rank_last(s)
+    tb = _GLOBALS.get("tensorboard")
+    if tb is not None:
+        tb.add_scalar("iteration-time", elapsed_per_iter, iteration)
+        tb.add_scalar("throughput", tput, iteration)
+    get_timers().log(normalizer=args.log_interval)
+
+
+def evaluate(forward_step_func, data_iterator, model, eval_iters: int) -> Dict[str, float]:
+    args = get_args()
+    for m in model:
+        m.eval()
+    total: Dict[str, float] = {}
+    fb = get_forward_backward_func()
+    with torch.no_grad():
+        for _ in range(eval_iters):
+            out = fb(forward_step_func=forward_step_func, data_iterator=data_iterator, model=model if len(model) > 1 else model[0],
+                     num_microbatches=get_num_microbatches(), seq_length=args.seq_length, micro_batch_size=args.micro_batch_size, forward_only=True)
+            if ps.is_pipeline_last_stage(ignore_virtual=True):
+                for d in out:
+                    for k, v in d.items():
+                        total[k] = total.get(k, 0.0) + float(v) / (eval_iters * len(out))
+    for m in model:
+        m.train()
+    return total
+
+
+def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_iterator, valid_data_iterator, config):
+    args, timers = get_args(), get_timers()
+    for m in model:
+        m.train()
+    iteration = args.iteration
+    args.consumed_train_samples = getattr(args, "consumed_train_samples", iteration * args.global_batch_size)
+    config.finalize_model_grads_func = finalize_model_grads
+    config.grad_scale_func = optimizer.scale_loss if args.fp16 else None
+    config.timers = timers if args.timing_log_level > 0 else None
+    config.no_sync_func = model[0].no_sync if len(model) == 1 else [m.no_sync for m in model]
+    if args.overlap_grad_reduce and args.pipeline_model_parallel_size > 1:
+        config.grad_sync_func = model[0].start_grad_sync if len(model) == 1 else [m.start_grad_sync for m in model]
+    total_loss_dict: Dict[str, float] = {}
+    exit_flag = {"sig": False}
+    signal.signal(signal.SIGTERM, lambda *_: exit_flag.__setitem__("sig", True))
+    flops_per_iter = num_floating_point_operations(
+        num_layers=args.num_layers, hidden_size=args.hidden_size, ffn_hidden_size=args.ffn_hidden_size, num_attention_heads=args.num_attention_heads,
+        num_query_groups=args.num_query_groups, kv_channels=args.kv_channels or args.hidden_size // args.num_attention_heads,
+        vocab_size=getattr(args, "padded_vocab_size", args.vocab_size), seq_length=args.seq_length, batch_size=args.global_batch_size, swiglu=args.swiglu,
+        num_moe_experts=args.num_experts, moe_router_topk=args.moe_router_topk,
+    )
+    straggler = StragglerDetector()
+    straggler.configure(dist.get_world_size() if dist.is_initialized() else 1, dist.get_rank() if dist.is_initialized() else 0, enabled=args.log_straggler)
+    if args.manual_gc:
+        gc.disable()
+        gc.collect()
+    t_start = time.time()
+    t_log = time.time()
+    while iteration < args.train_iters:
+        if args.profile and iteration == args.profile_step_start and torch.cuda.is_available():
+            torch.cuda.cudart().cudaProfilerStart()
+        update_num_microbatches(args.consumed_train_samples, consistency_check=True)
+        with straggler():
+            loss_dict, skipped, should_ckpt, should_exit, exit_code, grad_norm, _ = train_step(forward_step_func, train_data_iterator, model, optimizer, opt_param_scheduler, config)
+        if should_ckpt and args.save:
+            checkpointing.save_checkpoint(iteration, model, optimizer, opt_param_scheduler, args.save, vars_for_ckpt(args), args.num_floating_point_operations_so_far,
+                                          rerun_state=get_rerun_state_machine().state_dict(None, False))
+        if should_exit:
+            sys.exit(exit_code)
+        iteration += 1
+        args.consumed_train_samples += get_current_global_batch_size()
+        args.num_floating_point_operations_so_far += flops_per_iter
+        if iteration % args.log_interval == 0:
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            el = (time.time() - t_log) / args.log_interval
+            t_log = time.time()
+            lr = max((g["lr"] for g in optimizer.param_groups), default=0.0)
+            training_log(loss_dict, total_loss_dict, lr, iteration, optimizer.get_loss_scale(), grad_norm, el, flops_per_iter)
+            if args.log_straggler:
+                straggler.report(flops_per_iter * args.log_interval, args.log_interval)
+        else:
+            for k, v in loss_dict.items():
+                total_loss_dict[k] = total_loss_dict.get(k, 0.0) + float(v)
+        if args.profile and iteration == args.profile_step_end and torch.cuda.is_available():
+            torch.cuda.cudart().cudaProfilerStop()
+        if args.eval_interval and args.eval_iters and iteration % args.eval_interval == 0 and valid_data_iterator is not None:
+            res = evaluate(forward_step_func, valid_data_iterator, model, args.eval_iters)
+            print_rank_last(f" validation loss at iteration {iteration} | " + " | ".join(f"{k}: {v:.6E}" for k, v in res.items()))
+        if args.manual_gc and args.manual_gc_interval and iteration % args.manual_gc_interval == 0:
+            gc.collect()
+        checkpointing.maybe_finalize_async_save(blocking=False)
+        saved = False
+        if args.save and args.save_interval and iteration % args.save_interval == 0:
+            checkpointing.save_checkpoint(iteration, model, optimizer if not args.no_save_optim else None, opt_param_scheduler, args.save, vars_for_ckpt(args),
+                                          args.num_floating_point_operations_so_far, async_save=args.async_save, keep_last=args.keep_last_checkpoints)
+            saved = True
+        stop = exit_flag["sig"] or (args.exit_interval and iteration % args.exit_interval == 0) or \
+            (args.exit_duration_in_mins and (time.time() - t_start) / 60.0 > args.exit_duration_in_mins)
+        if dist.is_initialized() and (exit_flag["sig"] or args.exit_duration_in_mins):
+            t = torch.tensor([1 if stop else 0], device="cuda" if dist.get_backend() == "nccl" else "cpu")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            stop = bool(t.item())
+        if stop:
+            if args.save and not saved:
+                checkpointing.save_checkpoint(iteration, model, optimizer, opt_param_scheduler, args.save, vars_for_ckpt(args), args.num_floating_point_operations_so_far)
+            print_rank_0(f"exiting program at iteration {iteration}")
+            break
+    checkpointing.maybe_finalize_async_save(blocking=True)
+    args.iteration = iteration
+    return iteration
+
+
+def vars_for_ckpt(args) -> dict:
+    return {k: v for k, v in vars(args).items() if isinstance(v, (int, float, str, bool, type(None), list, tuple))}
+
+
+def pretrain(train_valid_test_dataset_provider: Callable, model_provider: Callable, forward_step_func: Callable, argv=None,
+             extra_args_provider=None, args_defaults: Optional[dict] = None):
+    """Main entry (reference ``pretrain`` :1500).  ``dataset_provider(num_samples[3]) -> (train, valid, test)``
+    datasets; ``model_provider(pre_process, post_process, vp_stage) -> module``;
+    ``forward_step_func(data_iterator, model) -> (output, loss_func)``."""
+    args = initialize_megatron(argv, extra_args_provider, args_defaults)
+    model, optimizer, scheduler = setup_model_and_optimizer(model_provider)
+    config = model[0].module.config if hasattr(model[0], "module") else model[0].config
+    n_train = args.train_iters * args.global_batch_size
+    n_eval = (args.train_iters // max(args.eval_interval, 1) + 1) * args.eval_iters * args.global_batch_size
+    train_ds, valid_ds, test_ds = train_valid_test_dataset_provider([n_train, n_eval, args.eval_iters * args.global_batch_size])
+    from .data import build_pretraining_data_loader
+
+    consumed = args.iteration * args.global_batch_size
+    train_it = RerunDataIterator(iter(build_pretraining_data_loader(train_ds, consumed, args))) if train_ds is not None else None
+    valid_it = iter(build_pretraining_data_loader(valid_ds, 0, args)) if valid_ds is not None else None
+    print_rank_0("training ...")
+    if args.train_iters > 0:
+        train(forward_step_func, model, optimizer, scheduler, train_it, valid_it, config)
+    if args.eval_iters and valid_it is not None:
+        res = evaluate(forward_step_func, valid_it, model, args.eval_iters)
+        print_rank_last(" final validation | " + " | ".join(f"{k}: {v:.6E}" for k, v in res.items()))
+    if args.save and args.iteration and (not args.save_interval or args.iteration % args.save_interval != 0):
+        checkpointing.save_checkpoint(args.iteration, model, optimizer, scheduler, args.save, vars_for_ckpt(args), args.num_floating_point_operations_so_far)
+    return model, optimizer
