@@ -66,9 +66,15 @@ def extract_matching_values(x, predicate: Callable, return_lists_as_dicts: bool 
             if isinstance(v, (dict, list)) and v:
                 a, b = extract_matching_values(v, predicate, return_lists_as_dicts)
                 if a:
-                    m[i] = a if return_lists_as_dicts else m.append(a)
+                    if return_lists_as_dicts:
+                        m[i] = a
+                    else:
+                        m.append(a)
                 if b or not a:
-                    n[i] = b if return_lists_as_dicts else n.append(b)
+                    if return_lists_as_dicts:
+                        n[i] = b
+                    else:
+                        n.append(b)
             else:
                 tgt = m if predicate(v) else n
                 if return_lists_as_dicts:

@@ -9,7 +9,7 @@
 //               limiter; halving the B traffic per SM removes it.
 //
 //   warp 0 : TMA producer (one elected lane)          warp 2 : TMEM allocator
-//   warp 1 : MMA issuer   (one elected lane)          warps 4-7 : epilogue (tcgen05.ld → cvt → st.global)
+//   warp 1 : MMA issuer   (one elected lane)          warps 4-11 : epilogue (tcgen05.ld → cvt → 256-bit st.global)
 //
 // Layouts (row-major bf16 tensors):
 //   0 NT : C[M,N] = A[M,K]  · B[N,K]^T     forward          (A, B K-major)
@@ -28,7 +28,8 @@ namespace mb200 {
 using namespace ptx;
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;  // warps 0-3: producer / issuer / allocator / spare; warps 4-11: epilogue
+constexpr int EPI_WARPS = 8;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB per CTA
 constexpr int SMEM_BUDGET = 200 * 1024;
 
@@ -89,17 +90,31 @@ template <uint32_t NCOLS> __device__ __forceinline__ void tmem_dealloc_2sm(uint3
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
 }
 
-// ---- shared epilogue: 128 rows (this CTA's TMEM lanes) x BN columns ------------------------------------
-template <bool C_F32, int BN>
-__device__ __forceinline__ void epilogue_tile(void* __restrict__ Cptr, const GemmParams& p, uint32_t t_base, int row, int col_base, int lane, uint64_t* done_bar,
-                                              bool done_remote) {
+// ---- 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256) -----------------------------------------------
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+
+// ---- shared epilogue: this warp's 32 TMEM lanes (rows) x columns [c_begin*32, c_end*32) -----------------------
+// 8 epilogue warps: warp%4 selects the TMEM lane quarter (hardware restriction), warp/4 the column half, so two
+// warps drain each quarter concurrently.  Every thread owns one output row and writes whole 32-byte sectors.
+template <bool C_F32>
+__device__ __forceinline__ void epilogue_tile(void* __restrict__ Cptr, const GemmParams& p, uint32_t t_base, int row, int col_base, int c_begin, int c_end, int lane,
+                                              uint64_t* done_bar, bool done_remote) {
   const bool row_ok = row < p.M;
+  const bool vec32 = (p.ldc % (C_F32 ? 8 : 16)) == 0;  // 32-byte aligned rows → 256-bit stores
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     uint32_t r[32];
     tmem_ld_32x32b_x32(t_base + c * 32, r);
     tmem_ld_wait();
-    if (c == BN / 32 - 1) {
+    if (c == c_end - 1) {
       // all of this warp's TMEM reads are done → hand the accumulator back before the global stores
       tc_fence_before();
       __syncwarp();
@@ -111,22 +126,47 @@ __device__ __forceinline__ void epilogue_tile(void* __restrict__ Cptr, const Gem
     if (!row_ok || col0 >= p.N) continue;
     if (C_F32) {
       float* crow = reinterpret_cast<float*>(Cptr) + (size_t)row * p.ldc + col0;
-      if (col0 + 32 <= p.N) {
+      if (col0 + 32 <= p.N && vec32) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        for (int j = 0; j < 32; j += 8) {
+          uint32_t v[8];
           if (p.accumulate) {
-            const float4 o = *reinterpret_cast<const float4*>(crow + j);
-            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            ld_global_v8(crow + j, v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(r[j + q]));
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = r[j + q];
           }
-          *reinterpret_cast<float4*>(crow + j) = v;
+          st_global_v8(crow + j, v);
         }
       } else {
         for (int j = 0; j < 32 && col0 + j < p.N; ++j) crow[j] = __uint_as_float(r[j]) + (p.accumulate ? crow[j] : 0.f);
       }
     } else {
       __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(Cptr) + (size_t)row * p.ldc + col0;
-      if (col0 + 32 <= p.N) {
+      if (col0 + 32 <= p.N && vec32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 16) {
+          float f[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(r[j + q]);
+          if (p.accumulate) {
+            uint32_t o[8];
+            ld_global_v8(crow + j, o);
+            const __nv_bfloat16* ob = reinterpret_cast<const __nv_bfloat16*>(o);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) f[q] += __bfloat162float(ob[q]);
+          }
+          uint32_t v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+            v[q] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          st_global_v8(crow + j, v);
+        }
+      } else if (col0 + 32 <= p.N) {
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           float f[8];
@@ -192,7 +232,7 @@ gemm_1cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -258,7 +298,8 @@ gemm_1cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    const int ew = warp - 4;
+    const int ew = (warp - 4) & 3, half = (warp - 4) >> 2;
+    constexpr int CH = BN / 32 / 2;  // 32-column chunks per column half
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -266,7 +307,8 @@ gemm_1cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tile_coords(tile, tiles_m, tiles_n, p.group_m, m_blk, n_blk);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<C_F32, BN>(Cptr, p, tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16), m_blk * BM + ew * 32 + lane, n_blk * BN, lane, &tmem_empty[acc], false);
+      epilogue_tile<C_F32>(Cptr, p, tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16), m_blk * BM + ew * 32 + lane, n_blk * BN, half * CH, (half + 1) * CH, lane,
+                           &tmem_empty[acc], false);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -317,7 +359,7 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);   // multicast tcgen05.commit
-      mbar_init(&tmem_empty[i], 8);  // 4 epilogue warps of each CTA (leader's copy is the one waited on)
+      mbar_init(&tmem_empty[i], 2 * EPI_WARPS);  // epilogue warps of BOTH CTAs (the leader's copy is the one waited on)
     }
     fence_mbar_init();
   }
@@ -388,7 +430,8 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp >= 4) {
     // ================= epilogue: every CTA drains its own 128 TMEM lanes =====================================
-    const int ew = warp - 4;
+    const int ew = (warp - 4) & 3, half = (warp - 4) >> 2;
+    constexpr int CH = BN / 32 / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -396,8 +439,8 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tile_coords(tile, tiles_m, tiles_n, p.group_m, m_blk, n_blk);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<C_F32, BN>(Cptr, p, tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16), m_blk * PM + (int)cta_rank * BM + ew * 32 + lane, n_blk * BN, lane,
-                               &tmem_empty[acc], !leader);
+      epilogue_tile<C_F32>(Cptr, p, tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16), m_blk * PM + (int)cta_rank * BM + ew * 32 + lane, n_blk * BN, half * CH,
+                           (half + 1) * CH, lane, &tmem_empty[acc], !leader);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }

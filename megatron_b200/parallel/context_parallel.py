@@ -1,0 +1,204 @@
+"""Context parallelism for attention (reference: delegated to TransformerEngine).
+
+Every CP rank holds two zig-zag chunks of the sequence (chunks ``r`` and ``2cp-1-r`` of ``2cp``), so the
+causal work is balanced.  Two communication types:
+
+* ``all_gather`` — all-gather K/V over the CP group, restore natural order, attend each local query chunk to
+  its causal prefix.  Backward = reduce-scatter of dK/dV through the differentiable gather.
+* ``p2p``        — ring attention: K/V blocks circulate with ``isend/irecv`` (next block prefetched while the
+  current one is used); partial results are merged with the online-softmax (log-sum-exp) rule.  The block
+  kernel returns (out, lse) and is differentiable in both, so autograd produces the ring backward.
+* ``a2a``        — DeepSpeed-Ulysses: all-to-all swaps sequence sharding for head sharding around a plain
+  full-sequence attention.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ..core import parallel_state as ps
+from ..core.tensor_parallel.mappings import _AllToAll, _gather_along_first_dim, _reduce_scatter_along_first_dim
+
+
+class _GatherSeq(torch.autograd.Function):
+    """all-gather along dim 0 over ``group``; backward reduce-scatters."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        return _gather_along_first_dim(x.contiguous(), group)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _reduce_scatter_along_first_dim(g.contiguous(), ctx.group), None
+
+
+def _zigzag_to_natural(full: torch.Tensor, cp: int) -> torch.Tensor:
+    """[cp * 2 * c, ...] in rank order (r → chunks r, 2cp-1-r) → natural chunk order."""
+    c = full.shape[0] // (2 * cp)
+    chunks = full.view(cp, 2, c, *full.shape[1:])
+    order = [None] * (2 * cp)
+    for r in range(cp):
+        order[r] = chunks[r, 0]
+        order[2 * cp - 1 - r] = chunks[r, 1]
+    return torch.cat(order, dim=0)
+
+
+def attention_with_lse(q, k, v, scale: float, causal: bool, q_offset: int = 0, k_offset: int = 0):
+    """Blockwise attention returning (out [sq,b,h,d] fp32, lse [b,h,sq] fp32); differentiable in both.
+
+    ``q_offset``/``k_offset`` are the global positions of the first query/key (for the causal mask).
+    GQA: k/v heads are repeated.  O(sq·sk) memory for the block — this is the portable ring building
+    block (CPU tests + any GPU); the fused kernel replaces it on B200."""
+    sq, b, hq, d = q.shape
+    sk, hk = k.shape[0], k.shape[2]
+    rep = hq // hk
+    qf = q.permute(1, 2, 0, 3).float()
+    kf = k.permute(1, 2, 0, 3).float()
+    vf = v.permute(1, 2, 0, 3).float()
+    if rep > 1:
+        kf, vf = kf.repeat_interleave(rep, dim=1), vf.repeat_interleave(rep, dim=1)
+    s = torch.matmul(qf, kf.transpose(-1, -2)) * scale
+    if causal:
+        qi = torch.arange(sq, device=q.device)[:, None] + q_offset
+        ki = torch.arange(sk, device=q.device)[None, :] + k_offset
+        s = s.masked_fill(ki > qi, float("-inf"))
+    lse = torch.logsumexp(s, dim=-1)
+    lse_safe = torch.where(torch.isinf(lse), torch.zeros_like(lse), lse)
+    p = torch.exp(s - lse_safe.unsqueeze(-1))
+    out = torch.matmul(p, vf).permute(2, 0, 1, 3)
+    return out, lse
+
+
+def merge_partials(outs: List[torch.Tensor], lses: List[torch.Tensor]) -> torch.Tensor:
+    """Online-softmax merge: out = Σ_i exp(lse_i − lse) · out_i with lse = logsumexp_i lse_i."""
+    L = torch.stack(lses)  # [n, b, h, sq]
+    tot = torch.logsumexp(L, dim=0)
+    w = torch.exp(L - tot.unsqueeze(0))  # [n, b, h, sq]
+    w = torch.nan_to_num(w, nan=0.0)
+    acc = 0
+    for o, wi in zip(outs, w):
+        acc = acc + o * wi.permute(2, 0, 1).unsqueeze(-1)
+    return acc
+
+
+class _RingShift(torch.autograd.Function):
+    """Send a tensor to the next CP rank and receive from the previous one (backward: the reverse)."""
+
+    @staticmethod
+    def forward(ctx, x, group, reverse):
+        ctx.group, ctx.reverse = group, reverse
+        return _RingShift._shift(x, group, reverse)
+
+    @staticmethod
+    def _shift(x, group, reverse):
+        ranks = dist.get_process_group_ranks(group)
+        me = dist.get_rank(group)
+        n = len(ranks)
+        dst = ranks[(me - 1) % n] if reverse else ranks[(me + 1) % n]
+        src = ranks[(me + 1) % n] if reverse else ranks[(me - 1) % n]
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        if me % 2 == 0:
+            reqs = [dist.isend(x, dst, group=group), dist.irecv(out, src, group=group)]
+        else:
+            reqs = [dist.irecv(out, src, group=group), dist.isend(x, dst, group=group)]
+        for r in reqs:
+            r.wait()
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return _RingShift._shift(g, ctx.group, not ctx.reverse), None, None
+
+
+class RingAttention(torch.nn.Module):
+    """Drop-in core attention for ``context_parallel_size > 1`` (``DotProductAttention`` delegates here)."""
+
+    def __init__(self, config, cp_comm_type: str = "p2p", pg_collection=None):
+        super().__init__()
+        self.config = config
+        self.kind = cp_comm_type if isinstance(cp_comm_type, str) else "p2p"
+        self.group = pg_collection.cp if (pg_collection is not None and getattr(pg_collection, "cp", None) is not None) else ps.get_context_parallel_group()
+        self.cp = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+
+    def _chunk_offsets(self, s_local: int) -> Tuple[int, List[int]]:
+        c = s_local // 2
+        return c, [self.rank * c, (2 * self.cp - 1 - self.rank) * c]
+
+    def forward(self, q, k, v, causal: bool, scale: float):
+        if self.kind in ("all_gather",):
+            return self._all_gather(q, k, v, causal, scale)
+        if self.kind in ("a2a",):
+            return self._ulysses(q, k, v, causal, scale)
+        return self._ring(q, k, v, causal, scale)
+
+    # ---- all-gather KV ------------------------------------------------------------------------------------
+    def _all_gather(self, q, k, v, causal, scale):
+        c, offs = self._chunk_offsets(q.shape[0])
+        kf = _zigzag_to_natural(_GatherSeq.apply(k, self.group), self.cp)
+        vf = _zigzag_to_natural(_GatherSeq.apply(v, self.group), self.cp)
+        outs = []
+        for i, off in enumerate(offs):
+            qc = q[i * c : (i + 1) * c]
+            end = off + c if causal else kf.shape[0]
+            o, _ = attention_with_lse(qc, kf[:end], vf[:end], scale, causal, q_offset=off, k_offset=0)
+            outs.append(o)
+        return torch.cat(outs, dim=0).to(q.dtype)
+
+    # ---- ring (p2p) -------------------------------------------------------------------------------------------
+    def _ring(self, q, k, v, causal, scale):
+        c, my_offs = self._chunk_offsets(q.shape[0])
+        kv = torch.cat([k, v], dim=-1)
+        outs = [[], []]
+        lses = [[], []]
+        cur = kv
+        for step in range(self.cp):
+            src_rank = (self.rank - step) % self.cp
+            nxt = _RingShift.apply(cur, self.group, False) if step < self.cp - 1 else None
+            kk, vv = cur[..., : k.shape[-1]], cur[..., k.shape[-1] :]
+            src_offs = [src_rank * c, (2 * self.cp - 1 - src_rank) * c]
+            for qi, qoff in enumerate(my_offs):
+                qc = q[qi * c : (qi + 1) * c]
+                for ki, koff in enumerate(src_offs):
+                    if causal and koff > qoff + c - 1:
+                        continue  # block entirely in the future
+                    o, l = attention_with_lse(qc, kk[ki * c : (ki + 1) * c], vv[ki * c : (ki + 1) * c], scale, causal, q_offset=qoff, k_offset=koff)
+                    outs[qi].append(o), lses[qi].append(l)
+            cur = nxt
+        merged = [merge_partials(outs[i], lses[i]) for i in range(2)]
+        return torch.cat(merged, dim=0).to(q.dtype)
+
+    # ---- Ulysses (a2a) --------------------------------------------------------------------------------------------
+    def _ulysses(self, q, k, v, causal, scale):
+        """[s/cp, b, h, d] → all-to-all → [s, b, h/cp, d] → attention → all-to-all back."""
+        from .. import ops
+
+        cp = self.cp
+
+        def seq_to_head(t):
+            s, b, h, d = t.shape
+            assert h % cp == 0, "Ulysses needs heads divisible by the context-parallel size"
+            x = t.view(s, b, cp, h // cp, d).permute(2, 0, 1, 3, 4).contiguous().view(cp * s, b, h // cp, d)
+            y = _AllToAll.apply(self.group, x, None, None)
+            return _zigzag_to_natural(y, cp)
+
+        def head_to_seq(t, s_local):
+            # inverse of the above: natural → zig-zag rank order, then a2a
+            c = s_local // 2
+            chunks = t.view(2 * cp, c, *t.shape[1:])
+            order = []
+            for r in range(cp):
+                order += [chunks[r], chunks[2 * cp - 1 - r]]
+            x = torch.cat(order, dim=0).contiguous()
+            y = _AllToAll.apply(self.group, x, None, None)
+            s, b, hh, d = s_local, y.shape[1], y.shape[2], y.shape[3]
+            return y.view(cp, s, b, hh, d).permute(1, 2, 0, 3, 4).reshape(s, b, cp * hh, d)
+
+        qf, kf, vf = seq_to_head(q), seq_to_head(k), seq_to_head(v)
+        o = ops.flash_attention(qf, kf, vf, causal=causal, scale=scale)
+        return head_to_seq(o, q.shape[0])

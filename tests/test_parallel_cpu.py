@@ -295,3 +295,43 @@ def test_checkpoint_save_tp2_pp2_load_tp1_pp4_and_tp4():
                     assert torch.equal(val, exp), (tp, pp, r, key)
                     seen.add(key)
             assert seen == set(state)
+
+
+# ------------------------------------------------------------------------------- context parallel
+def _cp_worker(rank, world, kind, state):
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
+    from megatron_b200.core.utils import get_batch_on_this_cp_rank
+
+    ps.initialize_model_parallel(context_parallel_size=world)
+    model_parallel_cuda_manual_seed(1)
+    cfg = _cfg(num_layers=2, context_parallel_size=world, cp_comm_type=kind)
+    m = _model(cfg)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            p.copy_(state[n])
+    b = _batches(1, seed=9)[0]
+    pos = torch.arange(SEQ)[None].expand(2, -1)
+    local = get_batch_on_this_cp_rank({"tokens": b["tokens"], "labels": b["labels"], "position_ids": pos})
+    out = m(local["tokens"], local["position_ids"], None, labels=local["labels"])
+    loss_sum = out.float().sum()
+    (loss_sum / (2 * SEQ)).backward()
+    return float(loss_sum), {n: p.grad.clone() for n, p in m.named_parameters()}
+
+
+@pytest.mark.parametrize("kind", ["all_gather", "p2p", "a2a"])
+def test_context_parallel_matches_single_process(kind):
+    world = 2
+    torch.manual_seed(33)
+    ref = _model(_cfg(num_layers=2))
+    state = {n: p.detach().clone() for n, p in ref.named_parameters()}
+    b = _batches(1, seed=9)[0]
+    pos = torch.arange(SEQ)[None].expand(2, -1)
+    out = ref(b["tokens"], pos, None, labels=b["labels"])
+    out.float().mean().backward()
+    res = run_distributed(_cp_worker, world, kind, state)
+    total = sum(r[0] for r in res) / (2 * SEQ)
+    assert abs(total - float(out.float().mean())) < 1e-4
+    for n, p in ref.named_parameters():
+        got = sum(r[1][n] for r in res)
+        assert torch.allclose(got, p.grad, atol=3e-5, rtol=1e-4), (n, (got - p.grad).abs().max())
