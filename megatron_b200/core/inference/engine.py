@@ -1,0 +1,198 @@
+"""Inference engines (reference ``inference/engines``: ``StaticInferenceEngine``, ``DynamicInferenceEngine``).
+
+* ``StaticInferenceEngine``  — pads a batch of prompts, prefill once, decode step by step with the static
+  KV cache of ``InferenceParams``.
+* ``DynamicInferenceEngine`` — continuous batching: requests enter and leave between decode steps, KV lives in
+  a paged cache (``kv_cache.PagedKVCache``), each step runs prefill for newly admitted requests and one decode
+  token for the running ones; finished requests release their blocks immediately.
+"""
+from __future__ import annotations
+
+import itertools
+import time
+from collections import deque
+from dataclasses import dataclass, field
+from typing import Callable, Deque, Dict, List, Optional
+
+import torch
+
+from ..inference_params import InferenceParams
+from .kv_cache import PagedKVCache
+from .sampling import SamplingParams, sample
+
+
+@dataclass
+class InferenceRequest:
+    request_id: int
+    prompt_tokens: List[int]
+    sampling_params: SamplingParams = field(default_factory=SamplingParams)
+    generated_tokens: List[int] = field(default_factory=list)
+    log_probs: List[float] = field(default_factory=list)
+    status: str = "waiting"  # waiting | running | finished
+    arrival_time: float = field(default_factory=time.time)
+    first_token_time: Optional[float] = None
+    finish_time: Optional[float] = None
+
+    @property
+    def ttft(self):
+        return None if self.first_token_time is None else self.first_token_time - self.arrival_time
+
+
+class StaticInferenceEngine:
+    def __init__(self, model, tokenizer=None, max_batch_size: int = 8, max_sequence_length: int = 2048, vocab_size: Optional[int] = None):
+        self.model, self.tokenizer = model, tokenizer
+        self.max_batch_size, self.max_sequence_length = max_batch_size, max_sequence_length
+        self.vocab_size = vocab_size
+
+    @torch.no_grad()
+    def generate(self, prompts: List[List[int]], params: Optional[SamplingParams] = None) -> List[List[int]]:
+        params = params or SamplingParams()
+        self.model.eval()
+        dev = next(self.model.parameters()).device
+        out: List[List[int]] = [None] * len(prompts)
+        # group equal-length prompts so no padding enters the causal cache
+        by_len: Dict[int, List[int]] = {}
+        for i, p in enumerate(prompts):
+            by_len.setdefault(len(p), []).append(i)
+        gen = torch.Generator(device=dev)
+        if params.seed is not None:
+            gen.manual_seed(params.seed)
+        for plen, idxs in by_len.items():
+            for lo in range(0, len(idxs), self.max_batch_size):
+                group = idxs[lo : lo + self.max_batch_size]
+                toks = torch.tensor([prompts[i] for i in group], device=dev)
+                ctx = InferenceParams(len(group), min(self.max_sequence_length, plen + params.num_tokens_to_generate))
+                pos = torch.arange(plen, device=dev)[None].expand(len(group), -1)
+                logits = self.model(toks, pos, None, inference_context=ctx)[:, -1]
+                ctx.sequence_len_offset = plen
+                done = torch.zeros(len(group), dtype=torch.bool, device=dev)
+                gens = [[] for _ in group]
+                for step in range(params.num_tokens_to_generate):
+                    nxt = sample(logits.float(), params.temperature, params.top_k, params.top_p, gen, self.vocab_size)
+                    for j, t in enumerate(nxt.tolist()):
+                        if not done[j]:
+                            gens[j].append(t)
+                            if t in params.stop_token_ids:
+                                done[j] = True
+                    if bool(done.all()) or step == params.num_tokens_to_generate - 1:
+                        break
+                    p1 = torch.full((len(group), 1), plen + step, device=dev)
+                    logits = self.model(nxt[:, None], p1, None, inference_context=ctx)[:, -1]
+                    ctx.sequence_len_offset += 1
+                for j, i in enumerate(group):
+                    out[i] = gens[j]
+        return out
+
+
+class DynamicInferenceEngine:
+    """Continuous batching over a paged KV cache.  The model is driven one request-slice at a time through its
+    attention layers' ``paged`` hook (``set_paged_context``), which keeps this engine independent of the
+    attention kernel: prefill = full causal attention on the prompt, decode = 1 query against the gathered cache."""
+
+    def __init__(self, model, num_blocks: int = 256, block_size: int = 16, max_running: int = 16, vocab_size: Optional[int] = None):
+        self.model = model
+        cfg = model.config
+        dev = next(model.parameters()).device
+        dt = next(model.parameters()).dtype
+        tp = cfg.tensor_model_parallel_size
+        self.cache = PagedKVCache(cfg.num_layers, num_blocks, block_size, max(cfg.num_query_groups // tp, 1), cfg.kv_channels, dt, dev)
+        self.waiting: Deque[InferenceRequest] = deque()
+        self.running: List[InferenceRequest] = []
+        self.finished: Dict[int, InferenceRequest] = {}
+        self.max_running = max_running
+        self.vocab_size = vocab_size
+        self._ids = itertools.count()
+        self.device = dev
+        self.steps = 0
+
+    def add_request(self, prompt_tokens: List[int], sampling_params: Optional[SamplingParams] = None) -> int:
+        rid = next(self._ids)
+        self.waiting.append(InferenceRequest(rid, list(prompt_tokens), sampling_params or SamplingParams()))
+        return rid
+
+    def has_unfinished(self) -> bool:
+        return bool(self.waiting or self.running)
+
+    @torch.no_grad()
+    def _forward_request(self, req: InferenceRequest, tokens: List[int], start: int) -> torch.Tensor:
+        """Run ``tokens`` (positions start..) of one request through the model using the paged cache."""
+        from ..transformer.attention import Attention
+
+        cache, rid = self.cache, req.request_id
+        toks = torch.tensor([tokens], device=self.device)
+        pos = torch.arange(start, start + len(tokens), device=self.device)[None]
+
+        class _Ctx:  # duck-typed inference context understood by Attention._adjust_key_value_for_inference
+            max_sequence_length = start + len(tokens)
+            max_batch_size = 1
+            sequence_len_offset = start
+            batch_size_offset = 0
+            key_value_memory_dict: Dict = {}
+
+        ctx = _Ctx()
+        ctx.key_value_memory_dict = {}
+        total = start + len(tokens)
+        # materialise this request's cache prefix per layer as a contiguous view the static path understands
+        for li, layer in enumerate(self.model.decoder.layers):
+            kbuf = torch.zeros(total, 1, cache.k.shape[3], cache.k.shape[4], dtype=cache.k.dtype, device=self.device)
+            vbuf = torch.zeros_like(kbuf)
+            if start > 0:
+                k, v = cache.gather(li, rid, start)
+                kbuf[:start, 0], vbuf[:start, 0] = k, v
+            ctx.key_value_memory_dict[layer.self_attention.layer_number] = (kbuf, vbuf)
+        logits = self.model(toks, pos, None, inference_context=ctx)
+        for li, layer in enumerate(self.model.decoder.layers):
+            kbuf, vbuf = ctx.key_value_memory_dict[layer.self_attention.layer_number]
+            cache.append(li, rid, kbuf[start:total, 0], vbuf[start:total, 0], start)
+        cache.lengths[rid] = total
+        return logits[0, -1]
+
+    @torch.no_grad()
+    def step(self) -> List[InferenceRequest]:
+        """Admit what fits, run one token for every running request, retire the finished ones."""
+        self.model.eval()
+        newly_finished: List[InferenceRequest] = []
+        while self.waiting and len(self.running) < self.max_running:
+            req = self.waiting[0]
+            need = len(req.prompt_tokens) + req.sampling_params.num_tokens_to_generate
+            if not self.cache.can_admit(need) or not self.cache.add_request(req.request_id, len(req.prompt_tokens)):
+                break
+            self.waiting.popleft()
+            req.status = "running"
+            logits = self._forward_request(req, req.prompt_tokens, 0)  # prefill
+            self._emit(req, logits)
+            self.running.append(req)
+        for req in list(self.running):
+            if req.status == "finished":
+                continue
+            if len(req.generated_tokens) >= req.sampling_params.num_tokens_to_generate:
+                continue
+            cur = self.cache.lengths[req.request_id]
+            if not self.cache.ensure_capacity(req.request_id, cur + 1):
+                continue  # out of blocks this step; try again after others finish
+            logits = self._forward_request(req, [req.generated_tokens[-1]], cur)
+            self._emit(req, logits)
+        for req in list(self.running):
+            sp = req.sampling_params
+            if len(req.generated_tokens) >= sp.num_tokens_to_generate or (req.generated_tokens and req.generated_tokens[-1] in sp.stop_token_ids):
+                req.status, req.finish_time = "finished", time.time()
+                self.cache.release(req.request_id)
+                self.running.remove(req)
+                self.finished[req.request_id] = req
+                newly_finished.append(req)
+        self.steps += 1
+        return newly_finished
+
+    def _emit(self, req: InferenceRequest, logits: torch.Tensor):
+        sp = req.sampling_params
+        tok = int(sample(logits.float()[None], sp.temperature, sp.top_k, sp.top_p, None, self.vocab_size)[0])
+        if req.first_token_time is None:
+            req.first_token_time = time.time()
+        if sp.return_log_probs:
+            req.log_probs.append(float(torch.log_softmax(logits.float(), -1)[tok]))
+        req.generated_tokens.append(tok)
+
+    def run_until_done(self) -> Dict[int, InferenceRequest]:
+        while self.has_unfinished():
+            self.step()
+        return self.finished

@@ -304,6 +304,29 @@ void nvl_allreduce(const std::vector<int64_t>& ptrs, const std::vector<int64_t>&
 }
 #endif
 
+#ifdef MB200_HAVE_FUSED_TP_GEMM
+// mode 0: AG(a_shard) -> a_full (symmetric, filled in-kernel) ; c = a_full @ op(b).   mode 1: c (symmetric partial) = a @ op(b) ; rs_out = RS(c).
+void fused_tp_gemm(int64_t mode, const Tensor& a, const Tensor& b, Tensor c, int64_t b_layout, int64_t rank, int64_t epoch, const Tensor& ag_src, int64_t ag_dst_mc,
+                   const std::vector<int64_t>& ag_dst_peer, int64_t rs_src_mc, const std::vector<int64_t>& rs_src_peer, Tensor rs_out,
+                   const Tensor& xag_src, int64_t xag_dst_mc, const std::vector<int64_t>& xag_dst_peer, const std::vector<int64_t>& flags_peer, Tensor counters,
+                   int64_t comm_clusters) {
+  TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && c.scalar_type() == at::kBFloat16, "fused_tp_gemm: bf16 CUDA tensors");
+  TORCH_CHECK(a.is_contiguous() && b.is_contiguous() && c.is_contiguous(), "fused_tp_gemm: contiguous operands");
+  c10::cuda::CUDAGuard g(a.device());
+  const int M = (int)a.size(0), K = (int)a.size(1);
+  const int N = (int)(b_layout == 0 ? b.size(0) : b.size(1));
+  TORCH_CHECK((b_layout == 0 ? b.size(1) : b.size(0)) == K, "fused_tp_gemm: K mismatch");
+  const int world = (int)flags_peer.size();
+  const bool have_xag = mode == 1 && xag_src.defined() && xag_src.numel() > 0 && !xag_dst_peer.empty();
+  const int rc = mb200_fused_tp_gemm((int)mode, a.data_ptr(), b.data_ptr(), c.data_ptr(), M, N, K, (int)b_layout, (int)rank, world, (uint32_t)epoch,
+                                     mode == 0 ? ag_src.data_ptr() : nullptr, ag_dst_mc, ag_dst_peer.empty() ? nullptr : ag_dst_peer.data(), rs_src_mc,
+                                     rs_src_peer.empty() ? nullptr : rs_src_peer.data(), mode == 1 ? rs_out.data_ptr() : nullptr,
+                                     have_xag ? xag_src.data_ptr() : nullptr, have_xag ? (int64_t)(xag_src.numel() * xag_src.element_size()) : 0, xag_dst_mc,
+                                     xag_dst_peer.empty() ? nullptr : xag_dst_peer.data(), flags_peer.data(), counters.data_ptr(), (int)comm_clusters, cur_stream());
+  TORCH_CHECK(rc == 0, "fused_tp_gemm failed with code ", rc);
+}
+#endif
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -326,5 +349,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("nvl_allgather", &nvl_allgather);
   m.def("nvl_reducescatter", &nvl_reducescatter);
   m.def("nvl_allreduce", &nvl_allreduce);
+#endif
+#ifdef MB200_HAVE_FUSED_TP_GEMM
+  m.def("fused_tp_gemm", &fused_tp_gemm);
 #endif
 }

@@ -34,5 +34,9 @@ void mb200_nvl_reducescatter(const int64_t* ptrs, const int64_t* flags, int64_t 
 void mb200_nvl_allreduce(const int64_t* ptrs, const int64_t* flags, int64_t mc, size_t off, size_t elems, float scale, int dtype, int rank, int world,
                          uint32_t epoch, void* ctrl, int slot, int nblocks, cudaStream_t s);
 int mb200_gemm_bf16_v(const void* A, const void* B, void* C, int M, int N, int K, int layout, int accumulate, int c_dtype, int variant, cudaStream_t s);
+int mb200_fused_tp_gemm(int mode, const void* A, const void* B, void* C, int M, int N, int K, int b_layout, int rank, int world, uint32_t epoch,
+                        const void* ag_src, int64_t ag_dst_mc, const int64_t* ag_dst_peer, int64_t rs_src_mc, const int64_t* rs_src_peer, void* rs_out,
+                        const void* xag_src, int64_t xag_bytes, int64_t xag_dst_mc, const int64_t* xag_dst_peer, const int64_t* flags_peer, void* counters,
+                        int comm_clusters, cudaStream_t s);
 int mb200_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int layout, int accumulate, int c_dtype, cudaStream_t s);
 }

@@ -27,6 +27,7 @@ from .. import ops
 MAX_RANKS = 16
 NUM_SLOTS = 8
 _FLAG_BYTES = NUM_SLOTS * MAX_RANKS * 4
+_FUSED_FLAG_OFF = 4096  # AG[8*64] + RS[64*8] + XAG[8] uint32 flags of ops/csrc/fused_tp_gemm.cu
 
 
 def _align(n: int, a: int = 1024) -> int:
@@ -83,6 +84,12 @@ class NVLinkBackend:
         self._ws_turn = [0] * NUM_SLOTS
         self.side_stream = torch.cuda.Stream()
         self.nblocks = int(os.environ.get("MEGATRON_B200_NVL_BLOCKS", "32"))
+        # fused GEMM+collective kernels: chunk flags live in the (otherwise unused) tail of the flag page
+        self.fused_flags = [p + _FUSED_FLAG_OFF for p in self.ptrs]
+        self.fused_counters = torch.zeros(1024, dtype=torch.int32, device=self.device)
+        self.fused_epoch = 0
+        self.fused_comm_clusters = int(os.environ.get("MEGATRON_B200_FUSED_COMM_CLUSTERS", "8"))
+        self.fused_calls = 0
         dist.barrier(group=group)
         self.barrier()
 
@@ -226,21 +233,90 @@ class NVLinkBackend:
         return None
 
     # ---- pair ops used by the TP layers ---------------------------------------------------------------------
-    def all_gather_gemm(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    def _fused_ok(self, M: int, N: int, K: int, *ts) -> bool:
         from . import fused
 
-        if fused.get_mode() == "fused" and hasattr(ops.ext(), "ag_gemm_bf16"):
-            return self._fused_ag_gemm(x, w)
+        if fused.get_mode() not in ("fused", "auto") or not hasattr(ops.ext(), "fused_tp_gemm"):
+            return False
+        if self.world > 8 or M % (self.world * 256) != 0 or M // self.world // 256 > 64 or K % 8 != 0 or N % 8 != 0:
+            return False
+        return all(t.dtype == torch.bfloat16 for t in ts)
+
+    def _fused_launch(self, mode, a, b, c, b_layout, ag_src=None, ag_off=0, rs_off=0, rs_out=None, xag_src=None, xag_off=0):
+        self.fused_epoch += 1
+        empty = a.new_empty(0)
+        mc = self.mc
+        ops.ext().fused_tp_gemm(
+            mode, a, b, c, b_layout, self.rank, self.fused_epoch,
+            ag_src if ag_src is not None else empty, (mc + ag_off) if (mc and mode == 0) else 0, [p + ag_off for p in self.ptrs] if mode == 0 else [],
+            (mc + rs_off) if (mc and mode == 1) else 0, [p + rs_off for p in self.ptrs] if mode == 1 else [], rs_out if rs_out is not None else empty,
+            xag_src if xag_src is not None else empty, (mc + xag_off) if (mc and xag_src is not None) else 0,
+            [p + xag_off for p in self.ptrs] if xag_src is not None else [], self.fused_flags, self.fused_counters, self.fused_comm_clusters,
+        )
+        self.fused_calls += 1
+        ops._count()
+
+    def _fused_ag_gemm(self, x: torch.Tensor, w: torch.Tensor, b_layout: int):
+        """One kernel: multicast-push my shard of ``x`` chunk by chunk while tcgen05 CTAs consume arrived chunks.
+        Returns (out [M, N], gathered x [M, K] living in the symmetric workspace)."""
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        K = x2.shape[1]
+        M = x2.shape[0] * self.world
+        N = w.shape[0] if b_layout == 0 else w.shape[1]
+        off = self._workspace(self.SLOT_MAIN, M * K * 2)
+        full = self._view(off, M * K, x.dtype).view(M, K)
+        out = torch.empty((M, N), dtype=x.dtype, device=x.device)
+        self._fused_launch(0, full, w, out, b_layout, ag_src=x2, ag_off=off)
+        return out, full
+
+    def _fused_gemm_rs(self, x: torch.Tensor, w: torch.Tensor, b_layout: int, xag: Optional[torch.Tensor] = None):
+        """One kernel: tcgen05 CTAs write partial tiles to symmetric memory, signal the owner rank per 256-row
+        block; reducer CTAs pull-reduce through the switch (``multimem.ld_reduce``).  Optionally the reducer
+        CTAs also all-gather ``xag`` (the wgrad operand) first.  Returns (out [M/world, N], gathered xag)."""
+        x2 = x.reshape(-1, x.shape[-1])
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        M, K = x2.shape
+        N = w.shape[0] if b_layout == 0 else w.shape[1]
+        ybytes = _align(M * N * 2, 1 << 12)
+        xbytes = 0
+        if xag is not None:
+            xag = xag.reshape(-1, xag.shape[-1]).contiguous()
+            xbytes = xag.numel() * xag.element_size() * self.world
+        off = self._workspace(self.SLOT_MAIN, ybytes + xbytes)
+        y = self._view(off, M * N, x.dtype).view(M, N)
+        out = torch.empty((M // self.world, N), dtype=x.dtype, device=x.device)
+        full = None
+        if xag is not None:
+            full = self._view(off + ybytes, xag.numel() * self.world, xag.dtype).view(xag.shape[0] * self.world, xag.shape[1])
+        self._fused_launch(1, x2, w, y, b_layout, rs_off=off, rs_out=out, xag_src=xag, xag_off=off + ybytes)
+        return out, full
+
+    def all_gather_gemm(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+        rows = x.numel() // x.shape[-1]
+        if self._fused_ok(rows * self.world, w.shape[0], x.shape[-1], x, w):
+            out, _ = self._fused_ag_gemm(x, w, 0)
+            return out.view(x.shape[0] * self.world, *x.shape[1:-1], w.shape[0])
         full = self.all_gather(x)
         return ops.gemm_nt(full, w)
 
     def gemm_reduce_scatter(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+        rows = x.numel() // x.shape[-1]
+        if self._fused_ok(rows, w.shape[0], x.shape[-1], x, w):
+            out, _ = self._fused_gemm_rs(x, w, 0)
+            return out.view(x.shape[0] // self.world, *x.shape[1:-1], w.shape[0])
         y = self.symmetric_like((*x.shape[:-1], w.shape[0]), x.dtype)
         ops.gemm_nt(x, w, out=y.view(-1, w.shape[0]))
         return self.reduce_scatter(y)
 
     def sp_linear_backward(self, gy, x, weight, wgrad_needed: bool, accumulate: bool, wgrad_fn):
-        """dgrad GEMM → RS on the main stream; AG(x) on the side stream feeding the wgrad GEMM."""
+        """Column-parallel backward under SP.  Fused: ONE kernel does dgrad GEMM → reduce-scatter AND the
+        all-gather of ``x`` for wgrad.  Unfused: dgrad GEMM → RS on the main stream, AG(x) on the side stream."""
+        rows = gy.numel() // gy.shape[-1]
+        if self._fused_ok(rows, weight.shape[1], gy.shape[-1], gy, weight, x):
+            gx, full_x = self._fused_gemm_rs(gy, weight, 1, xag=x if wgrad_needed else None)
+            gx = gx.view(gy.shape[0] // self.world, *gy.shape[1:-1], weight.shape[1])
+            gw = wgrad_fn(gy, full_x, weight, accumulate) if wgrad_needed else None
+            return gx, gw
         cur = torch.cuda.current_stream()
         full_x = ev = None
         if wgrad_needed:
@@ -260,6 +336,12 @@ class NVLinkBackend:
         return gx, gw
 
     def row_linear_backward_sp(self, gy, x, weight, wgrad_needed: bool, accumulate: bool, wgrad_fn):
+        rows = gy.numel() // gy.shape[-1]
+        if self._fused_ok(rows * self.world, weight.shape[1], gy.shape[-1], gy, weight):
+            gx, full_gy = self._fused_ag_gemm(gy, weight, 1)
+            gx = gx.view(gy.shape[0] * self.world, *gy.shape[1:-1], weight.shape[1])
+            gw = wgrad_fn(full_gy, x, weight, accumulate) if wgrad_needed else None
+            return gx, gw
         full_gy = self.all_gather(gy)
         gx = ops.gemm_nn(full_gy, weight)
         gw = wgrad_fn(full_gy, x, weight, accumulate) if wgrad_needed else None

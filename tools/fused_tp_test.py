@@ -1,0 +1,96 @@
+"""Numerics + timing of the TP pair ops (AG→GEMM, GEMM→RS, both backwards) in nccl / nvlink / fused modes.
+
+Run:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/fused_tp_test.py
+Times are CUDA-event times on the device, max over ranks.  Llama-3 8B shapes (seq 8192, mbs 1, hidden 4096, ffn 14336).
+"""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    from megatron_b200 import ops
+    from megatron_b200.parallel import collectives, fused
+
+    g = dist.group.WORLD
+    be = collectives.enable_for_group(g)
+    S = int(os.environ.get("SEQ", "8192"))
+    H, FFN, QKV = 4096, 14336, 6144
+    iters = int(os.environ.get("ITERS", "20"))
+    torch.manual_seed(1234 + rank)
+    dev = "cuda"
+
+    def rnd(*shape, scale=1.0):
+        return (scale * torch.randn(*shape, device=dev)).bfloat16()
+
+    cases = {
+        "col_fwd_qkv": ("ag_gemm", rnd(S // world, 1, H), rnd(QKV // world, H, scale=0.02)),
+        "col_fwd_fc1": ("ag_gemm", rnd(S // world, 1, H), rnd(2 * FFN // world, H, scale=0.02)),
+        "row_fwd_proj": ("gemm_rs", rnd(S, 1, H // world), rnd(H, H // world, scale=0.02)),
+        "row_fwd_fc2": ("gemm_rs", rnd(S, 1, FFN // world), rnd(H, FFN // world, scale=0.02)),
+        "col_bwd_fc1": ("col_bwd", rnd(S, 1, 2 * FFN // world), rnd(S // world, 1, H), rnd(2 * FFN // world, H, scale=0.02)),
+        "col_bwd_qkv": ("col_bwd", rnd(S, 1, QKV // world), rnd(S // world, 1, H), rnd(QKV // world, H, scale=0.02)),
+        "row_bwd_fc2": ("row_bwd", rnd(S // world, 1, H), rnd(S, 1, FFN // world), rnd(H, FFN // world, scale=0.02)),
+        "row_bwd_proj": ("row_bwd", rnd(S // world, 1, H), rnd(S, 1, H // world), rnd(H, H // world, scale=0.02)),
+    }
+
+    def run(kind, args):
+        if kind == "ag_gemm":
+            return (fused.all_gather_gemm(args[0], args[1], g),)
+        if kind == "gemm_rs":
+            return (fused.gemm_reduce_scatter(args[0], args[1], g),)
+        if kind == "col_bwd":
+            return fused.sp_linear_backward(args[0], args[1], args[2], g, True, False)
+        return fused.row_linear_backward_sp(args[0], args[1], args[2], g, True, False)
+
+    results = {}
+    refs = {}
+    modes = os.environ.get("MODES", "nccl,nvlink,fused").split(",")
+    for mode in modes:
+        fused.set_mode(mode)
+        for name, (kind, *args) in cases.items():
+            outs = run(kind, args)
+            outs = [o.float().clone() for o in outs]
+            torch.cuda.synchronize()
+            if mode == modes[0]:
+                refs[name] = outs
+            else:
+                for i, (o, r) in enumerate(zip(outs, refs[name])):
+                    err = (o - r).abs().max().item()
+                    tol = 0.02 * r.abs().max().item() + 1e-2
+                    if not (err <= tol):
+                        raise AssertionError(f"[rank {rank}] {mode}:{name} output {i} max err {err} > {tol}")
+            # timing
+            for _ in range(3):
+                run(kind, args)
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                run(kind, args)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            results.setdefault(name, {})[mode] = round(t.item() * 1e3, 1)
+        if rank == 0:
+            print(f"mode {mode} done (fused kernel launches so far: {be.fused_calls})", flush=True)
+    # plain local GEMM time for reference (no communication): the lower bound of each pair op
+    fused.set_mode("nccl")
+    if rank == 0:
+        print(json.dumps({"world": world, "seq": S, "unit": "us", "multicast": bool(be.mc), "results": results}, indent=1), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
