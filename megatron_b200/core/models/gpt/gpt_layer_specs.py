@@ -99,3 +99,11 @@ def get_gpt_decoder_block_spec(config: TransformerConfig, use_transformer_engine
     from ...transformer.torch_norm import FusedNorm
 
     return TransformerBlockSubmodules(layer_specs=specs[off : off + n], layer_norm=FusedNorm)
+
+
+def get_gpt_mtp_block_spec(config: TransformerConfig, spec, use_transformer_engine: bool = False, vp_stage: Optional[int] = None):
+    """MTP block spec built from a decoder-layer spec (reference ``gpt_layer_specs.py:get_gpt_mtp_block_spec``)."""
+    from ...transformer.multi_token_prediction import get_mtp_block_spec
+
+    layer_spec = spec.layer_specs[-1] if isinstance(spec, TransformerBlockSubmodules) else spec
+    return get_mtp_block_spec(config, layer_spec, use_transformer_engine, vp_stage)

@@ -1,0 +1,45 @@
+"""Specs for the hybrid Mamba stack (reference ``models/mamba/mamba_layer_specs.py``)."""
+from ...ssm.mamba_block import MambaStack, MambaStackSubmodules
+from ...ssm.mamba_layer import MambaLayer, MambaLayerSubmodules
+from ...ssm.mamba_mixer import MambaMixer, MambaMixerSubmodules
+from ...transformer.attention import SelfAttention, SelfAttentionSubmodules
+from ...transformer.enums import AttnMaskType
+from ...transformer.identity_op import IdentityOp
+from ...transformer.mlp import MLP, MLPSubmodules
+from ...transformer.spec_utils import ModuleSpec
+from ...transformer.transformer_layer import TransformerLayer, TransformerLayerSubmodules, get_bias_dropout_add
+from ..backends import B200SpecProvider
+
+_b = B200SpecProvider()
+
+mamba_stack_spec = ModuleSpec(
+    module=MambaStack,
+    submodules=MambaStackSubmodules(
+        mamba_layer=ModuleSpec(
+            module=MambaLayer,
+            submodules=MambaLayerSubmodules(
+                norm=_b.layer_norm(),
+                mixer=ModuleSpec(module=MambaMixer, submodules=MambaMixerSubmodules(in_proj=_b.column_parallel_linear(), out_proj=_b.row_parallel_linear())),
+                mamba_bda=get_bias_dropout_add,
+            ),
+        ),
+        attention_layer=ModuleSpec(
+            module=TransformerLayer,
+            submodules=TransformerLayerSubmodules(
+                input_layernorm=_b.layer_norm(),
+                self_attention=ModuleSpec(module=SelfAttention, params={"attn_mask_type": AttnMaskType.causal},
+                                          submodules=SelfAttentionSubmodules(linear_qkv=_b.column_parallel_linear(), core_attention=_b.core_attention(),
+                                                                             linear_proj=_b.row_parallel_linear())),
+                self_attn_bda=get_bias_dropout_add,
+            ),
+        ),
+        mlp_layer=ModuleSpec(
+            module=TransformerLayer,
+            submodules=TransformerLayerSubmodules(
+                pre_mlp_layernorm=_b.layer_norm(),
+                mlp=ModuleSpec(module=MLP, submodules=MLPSubmodules(linear_fc1=_b.column_parallel_linear(), linear_fc2=_b.row_parallel_linear())),
+                mlp_bda=get_bias_dropout_add,
+            ),
+        ),
+    ),
+)

@@ -1,0 +1,39 @@
+"""Hybrid layer pattern: ``M`` = Mamba, ``*`` = attention, ``-`` = MLP, ``E`` = MoE (reference ``ssm/mamba_hybrid_layer_allocation.py``)."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+
+class Symbols:
+    MAMBA, ATTENTION, MLP, MOE = "M", "*", "-", "E"
+    VALID = {MAMBA, ATTENTION, MLP, MOE}
+
+
+def _allocate_auto(total: int, attn_ratio: float, mlp_ratio: float) -> List[str]:
+    n_attn, n_mlp = round(total * attn_ratio), round(total * mlp_ratio)
+    n_mamba = total - n_attn - n_mlp
+    assert n_mamba >= 0
+    layout = [Symbols.MAMBA] * total
+    # spread attention layers evenly, then MLP layers evenly over the remaining slots
+    if n_attn:
+        step = total / n_attn
+        for i in range(n_attn):
+            layout[min(total - 1, int(step * i + step / 2))] = Symbols.ATTENTION
+    free = [i for i, s in enumerate(layout) if s == Symbols.MAMBA]
+    if n_mlp:
+        step = len(free) / n_mlp
+        for i in range(n_mlp):
+            layout[free[min(len(free) - 1, int(step * i + step / 2))]] = Symbols.MLP
+    return layout
+
+
+def allocate_layers(total_layers: int, target_attention_ratio: float = 0.0, target_mlp_ratio: float = 0.0, override_pattern: Optional[str] = None) -> List[str]:
+    if override_pattern:
+        layout = list(override_pattern)
+        bad = set(layout) - Symbols.VALID
+        if bad:
+            raise ValueError(f"invalid symbols {bad} in hybrid pattern; valid: {sorted(Symbols.VALID)}")
+        if len(layout) != total_layers:
+            raise ValueError(f"hybrid pattern has {len(layout)} layers, model has {total_layers}")
+        return layout
+    return _allocate_auto(total_layers, target_attention_ratio, target_mlp_ratio)

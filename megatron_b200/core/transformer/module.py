@@ -63,6 +63,9 @@ class GraphableMegatronModule(MegatronModule):
             return self.cudagraph_manager(self, args, kwargs)
         return super().__call__(*args, **kwargs)
 
+    def _eager_forward(self, *args, **kwargs):
+        return torch.nn.Module.__call__(self, *args, **kwargs)
+
 
 def _convert(val, fn):
     if isinstance(val, (tuple, list)):
