@@ -272,9 +272,42 @@ class _FlashAttnFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, go):
         q, k, v, o, lse = ctx.saved_tensors
-        dq, dk, dv = ext().flash_attn_bwd(go.contiguous(), q, k, v, o, lse, ctx.causal, ctx.scale)
-        _count(3)
+        # backward = cuDNN library kernel fed with OUR forward's (out, log-sum-exp); a native tcgen05 backward is the next step
+        lse_lib = lse.unsqueeze(-1) if _cudnn_lse_ndim() == 4 else lse
+        dq, dk, dv = ext().attn_bwd_cudnn(go.contiguous(), q, k, v, o, lse_lib, ctx.causal, ctx.scale)
         return dq, dk, dv, None, None
+
+
+_CUDNN_LSE_NDIM = None
+
+
+def _cudnn_lse_ndim() -> int:
+    """Rank of the log-sum-exp tensor this torch build's cuDNN SDPA produces ([b,h,s] or [b,h,s,1])."""
+    global _CUDNN_LSE_NDIM
+    if _CUDNN_LSE_NDIM is None:
+        t = torch.zeros(1, 1, 128, 64, device="cuda", dtype=torch.bfloat16)
+        _CUDNN_LSE_NDIM = torch.ops.aten._scaled_dot_product_cudnn_attention(t, t, t, None, True, 0.0, True)[1].dim()
+    return _CUDNN_LSE_NDIM
+
+
+_ATTN_IMPL = os.environ.get("MEGATRON_B200_ATTN", "auto")  # auto | native | library
+
+
+def set_attention_impl(impl: str) -> None:
+    global _ATTN_IMPL
+    assert impl in ("auto", "native", "library")
+    _ATTN_IMPL = impl
+
+
+def _native_attention_ok(q, k, v, causal, window) -> bool:
+    if _ATTN_IMPL == "library" or window is not None or not hasattr(ext(), "flash_attn_fwd"):
+        return False
+    if q.dtype != torch.bfloat16 or q.shape[-1] not in (64, 128) or k.shape[-1] != q.shape[-1] or v.shape[-1] != q.shape[-1]:
+        return False
+    if causal and k.shape[0] < q.shape[0]:
+        return False
+    strides_ok = all(t.stride(-1) == 1 and all(s % 8 == 0 for s in t.stride()[:-1]) and t.data_ptr() % 16 == 0 for t in (q, k, v))
+    return strides_ok
 
 
 def flash_attention(q, k, v, causal: bool = True, scale: Optional[float] = None, window=None):
@@ -282,8 +315,8 @@ def flash_attention(q, k, v, causal: bool = True, scale: Optional[float] = None,
     import math
 
     scale = scale if scale is not None else 1.0 / math.sqrt(q.shape[-1])
-    if _use_cuda(q) and window is None and hasattr(ext(), "flash_attn_fwd") and q.dtype == torch.bfloat16 and q.shape[-1] in (64, 128):
-        return _FlashAttnFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), causal, scale)
+    if _use_cuda(q) and _native_attention_ok(q, k, v, causal, window):
+        return _FlashAttnFn.apply(q, k, v, causal, scale)
     if q.is_cuda:
         # library path (cuDNN/flash SDPA) for shapes the native kernel does not cover
         qb, kb, vb = (t.permute(1, 2, 0, 3) for t in (q, k, v))

@@ -304,6 +304,35 @@ void nvl_allreduce(const std::vector<int64_t>& ptrs, const std::vector<int64_t>&
 }
 #endif
 
+#ifdef MB200_HAVE_FLASH_ATTN_SM100
+// q [sq, b, hq, d], k/v [sk, b, hk, d] (any s/b/h strides, d contiguous) -> (out [sq, b, hq, d], lse [b, hq, sq] fp32)
+std::vector<Tensor> flash_attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, bool causal, double scale) {
+  TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kBFloat16 && k.scalar_type() == at::kBFloat16 && v.scalar_type() == at::kBFloat16, "flash_attn_fwd: bf16 CUDA tensors");
+  TORCH_CHECK(q.dim() == 4 && k.dim() == 4 && v.dim() == 4 && q.stride(3) == 1 && k.stride(3) == 1 && v.stride(3) == 1, "flash_attn_fwd: [s, b, h, d] with contiguous d");
+  TORCH_CHECK(((uintptr_t)q.data_ptr() | (uintptr_t)k.data_ptr() | (uintptr_t)v.data_ptr()) % 16 == 0, "flash_attn_fwd: 16-byte aligned tensors");
+  c10::cuda::CUDAGuard g(q.device());
+  const int sq = (int)q.size(0), b = (int)q.size(1), hq = (int)q.size(2), d = (int)q.size(3), sk = (int)k.size(0), hk = (int)k.size(2);
+  TORCH_CHECK(!causal || sk >= sq, "flash_attn_fwd: causal needs sk >= sq");
+  auto out = at::empty({sq, b, hq, d}, q.options());
+  auto lse = at::empty({b, hq, sq}, q.options().dtype(at::kFloat));
+  const int rc = mb200_flash_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), sq, sk, b, hq, hk, d, q.stride(0), q.stride(1),
+                                      q.stride(2), k.stride(0), k.stride(1), k.stride(2), v.stride(0), v.stride(1), v.stride(2), (float)scale, causal ? 1 : 0,
+                                      cur_stream());
+  TORCH_CHECK(rc == 0, "flash_attn_fwd failed with code ", rc);
+  return {out, lse};
+}
+#endif
+
+// Attention backward through the cuDNN library (consumes OUR forward's out + log-sum-exp); [s, b, h, d] tensors in and out.
+std::vector<Tensor> attn_bwd_cudnn(const Tensor& go, const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& o, const Tensor& lse, bool causal, double scale) {
+  c10::cuda::CUDAGuard g(q.device());
+  auto P = [](const Tensor& t) { return t.permute({1, 2, 0, 3}); };
+  auto seed = at::zeros({}, q.options().dtype(at::kLong));
+  auto r = at::_scaled_dot_product_cudnn_attention_backward(P(go), P(q), P(k), P(v), P(o), lse, seed, seed, Tensor(), Tensor(), Tensor(), q.size(0), k.size(0), 0.0,
+                                                            causal, scale);
+  return {std::get<0>(r).permute({2, 0, 1, 3}), std::get<1>(r).permute({2, 0, 1, 3}), std::get<2>(r).permute({2, 0, 1, 3})};
+}
+
 #ifdef MB200_HAVE_FUSED_TP_GEMM
 // mode 0: AG(a_shard) -> a_full (symmetric, filled in-kernel) ; c = a_full @ op(b).   mode 1: c (symmetric partial) = a @ op(b) ; rs_out = RS(c).
 void fused_tp_gemm(int64_t mode, const Tensor& a, const Tensor& b, Tensor c, int64_t b_layout, int64_t rank, int64_t epoch, const Tensor& ag_src, int64_t ag_dst_mc,
@@ -349,6 +378,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("nvl_allgather", &nvl_allgather);
   m.def("nvl_reducescatter", &nvl_reducescatter);
   m.def("nvl_allreduce", &nvl_allreduce);
+#endif
+  m.def("attn_bwd_cudnn", &attn_bwd_cudnn);
+#ifdef MB200_HAVE_FLASH_ATTN_SM100
+  m.def("flash_attn_fwd", &flash_attn_fwd);
 #endif
 #ifdef MB200_HAVE_FUSED_TP_GEMM
   m.def("fused_tp_gemm", &fused_tp_gemm);

@@ -1,0 +1,338 @@
+// Flash attention forward for sm_100a: tcgen05 MMAs with S and O accumulators in tensor memory, TMA-fed K/V ring,
+// two 128-row query tiles per CTA whose softmax warpgroups ping-pong against ONE MMA-issuing thread.
+//
+//   warps 0-3  : softmax warpgroup of query tile 0 (thread = one query row = one TMEM lane)
+//   warps 4-7  : softmax warpgroup of query tile 1
+//   warp  8    : TMA producer (Q once, then K_j / V_j through a 3-stage ring each)
+//   warp  9    : TMEM allocator + MMA issuer (single elected thread)
+//
+// Per KV block j (64 keys) and tile t:     S_t = Q_t K_jᵀ   (UMMA 128x64x16, K-major A and B from smem, D in TMEM)
+//                                          softmax WG t: TMEM → regs, online softmax in log2 domain, P_t(bf16) → swizzled smem
+//                                          O_t += P_t V_j   (UMMA 128xDx16, B = V tile MN-major straight from the [kv, d] layout)
+// The issue order  PV(t,j) ; QK(t,j+1) ; commit(s_full[t])  makes "S(t,j+1) ready" imply "PV(t,j) complete", so the
+// softmax warpgroup may overwrite P_t and rescale O_t in TMEM without any further barrier.  O is rescaled lazily: only
+// when the running max grows by more than 2^8 (the stale reference max is used otherwise; exact after the final 1/l).
+//
+// Layouts: q [sq, b, hq, d], k/v [sk, b, hk, d] with arbitrary (16-byte aligned) s/b/h strides and contiguous d — the k/v
+// views produced by splitting a fused QKV projection are consumed in place.  out [sq, b, hq, d] contiguous,
+// lse [b, hq, sq] fp32 (natural log).  Causal masking is bottom-right aligned (kv ≤ q + sk − sq).
+// Replaces: TE DotProductAttention / cuDNN fused attention and the unfused baddbmm+softmax+bmm path (X6).
+#include "gemm_sm100_device.cuh"
+
+namespace mb200 {
+using namespace ptx;
+
+constexpr int FA_BM = 128;       // query rows per tile
+constexpr int FA_BN = 64;        // keys per block
+constexpr int FA_STAGES = 3;     // K and V ring depth
+constexpr int FA_THREADS = 320;
+constexpr float FA_RESCALE_THRESHOLD = 8.0f;  // log2 units
+
+struct FaParams {
+  int sq, sk, b, hq, hk;
+  int causal;
+  float scale_log2;              // softmax_scale * log2(e)
+  long q_sb, q_sh, k_sb, k_sh, v_sb, v_sh;  // element strides of batch / head inside one sequence row
+  void* out;
+  long o_pitch;                  // elements between consecutive query rows of out
+  float* lse;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int D>
+__global__ void __launch_bounds__(FA_THREADS, 1)
+fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v, const FaParams p) {
+  constexpr int DCH = D / 64;                          // 64-column (128-byte) chunks of the head dim
+  constexpr int Q_CHUNK_BYTES = FA_BM * 128;           // [128 rows x 128 B]
+  constexpr int Q_TILE_BYTES = DCH * Q_CHUNK_BYTES;
+  constexpr int KV_CHUNK_BYTES = FA_BN * 128;          // [64 rows x 128 B]
+  constexpr int KV_STAGE_BYTES = DCH * KV_CHUNK_BYTES;
+  constexpr int P_TILE_BYTES = FA_BM * 128;            // [128 rows x 64 bf16]
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t S_COL = 0, O_COL = 128;           // S_t at t*64, O_t at 128 + t*D
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_q = smem;                                        // 2 tiles
+  uint8_t* smem_k = smem_q + 2 * Q_TILE_BYTES;                   // FA_STAGES
+  uint8_t* smem_v = smem_k + FA_STAGES * KV_STAGE_BYTES;         // FA_STAGES
+  uint8_t* smem_p = smem_v + FA_STAGES * KV_STAGE_BYTES;         // 2 tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + 2 * P_TILE_BYTES);
+  uint64_t* q_full = bars;                       // 1
+  uint64_t* k_full = bars + 1;                   // FA_STAGES
+  uint64_t* k_empty = k_full + FA_STAGES;
+  uint64_t* v_full = k_empty + FA_STAGES;
+  uint64_t* v_empty = v_full + FA_STAGES;
+  uint64_t* s_full = v_empty + FA_STAGES;        // 2
+  uint64_t* p_ready = s_full + 2;                // 2
+  uint64_t* o_done = p_ready + 2;                // 2
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = (int)gridDim.x - 1 - (int)blockIdx.x;   // heaviest (latest) causal tiles are scheduled first
+  const int h = blockIdx.y, bi = blockIdx.z;
+  const int hkv = h / (p.hq / p.hk);
+  const int q0 = qt * 2 * FA_BM;
+  const int off = p.sk - p.sq;                           // bottom-right causal alignment
+  const int nkv = (p.sk + FA_BN - 1) / FA_BN;
+  int n_t[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int first = q0 + t * FA_BM;
+    if (first >= p.sq) {
+      n_t[t] = 0;
+    } else if (p.causal) {
+      const int last = min(first + FA_BM - 1, p.sq - 1) + off;
+      n_t[t] = last < 0 ? 0 : min(nkv, last / FA_BN + 1);
+    } else {
+      n_t[t] = nkv;
+    }
+  }
+  const int n = max(n_t[0], n_t[1]);
+
+  if (warp == 8 && lane == 0) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_k);
+    prefetch_tmap(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < FA_STAGES; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_ready[t], FA_BM);
+      mbar_init(&o_done[t], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc<TMEM_COLS>(tmem_holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 8) {
+    // ================================= TMA producer =====================================================
+    if (lane == 0 && n > 0) {
+      const int qcol = (int)(bi * p.q_sb + h * p.q_sh);
+      const int kcol = (int)(bi * p.k_sb + hkv * p.k_sh);
+      const int vcol = (int)(bi * p.v_sb + hkv * p.v_sh);
+      mbar_expect_tx(q_full, 2 * Q_TILE_BYTES);
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) tma_load_2d(smem_q + t * Q_TILE_BYTES + c * Q_CHUNK_BYTES, &tmap_q, q_full, qcol + c * 64, q0 + t * FA_BM);
+      for (int j = 0; j < n; ++j) {
+        const int s = j % FA_STAGES;
+        const uint32_t ph = (uint32_t)(j / FA_STAGES) & 1u;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_expect_tx(&k_full[s], KV_STAGE_BYTES);
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) tma_load_2d(smem_k + s * KV_STAGE_BYTES + c * KV_CHUNK_BYTES, &tmap_k, &k_full[s], kcol + c * 64, j * FA_BN);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_expect_tx(&v_full[s], KV_STAGE_BYTES);
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) tma_load_2d(smem_v + s * KV_STAGE_BYTES + c * KV_CHUNK_BYTES, &tmap_v, &v_full[s], vcol + c * 64, j * FA_BN);
+      }
+    }
+  } else if (warp == 9) {
+    // ================================= MMA issuer ===============================================================
+    if (lane == 0 && n > 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(FA_BM, FA_BN, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(FA_BM, D, false, true);
+      auto issue_qk = [&](int t, int s) {
+        const uint32_t qa = smem_u32(smem_q + t * Q_TILE_BYTES), ka = smem_u32(smem_k + s * KV_STAGE_BYTES);
+#pragma unroll
+        for (int c = 0; c < DCH; ++c)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16(tmem_base + S_COL + t * FA_BN, make_smem_desc_sw128(qa + c * Q_CHUNK_BYTES + kk * 32, 16, 1024),
+                     make_smem_desc_sw128(ka + c * KV_CHUNK_BYTES + kk * 32, 16, 1024), idesc_qk, (c > 0 || kk > 0) ? 1u : 0u);
+      };
+      auto issue_pv = [&](int t, int s, bool acc) {
+        const uint32_t pa = smem_u32(smem_p + t * P_TILE_BYTES), va = smem_u32(smem_v + s * KV_STAGE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < FA_BN / 16; ++kk)
+          umma_f16(tmem_base + O_COL + t * D, make_smem_desc_sw128(pa + kk * 32, 16, 1024), make_smem_desc_sw128(va + kk * 2048, KV_CHUNK_BYTES, 1024), idesc_pv,
+                   (acc || kk > 0) ? 1u : 0u);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      for (int t = 0; t < 2; ++t)
+        if (n_t[t] > 0) {
+          issue_qk(t, 0);
+          umma_commit(&s_full[t]);
+        }
+      umma_commit(&k_empty[0]);
+      for (int j = 0; j < n; ++j) {
+        const int s = j % FA_STAGES, s1 = (j + 1) % FA_STAGES;
+        mbar_wait(&v_full[s], (uint32_t)(j / FA_STAGES) & 1u);
+        if (j + 1 < n) mbar_wait(&k_full[s1], (uint32_t)((j + 1) / FA_STAGES) & 1u);
+        for (int t = 0; t < 2; ++t) {
+          if (j >= n_t[t]) continue;
+          mbar_wait(&p_ready[t], (uint32_t)j & 1u);
+          tc_fence_after();
+          issue_pv(t, s, j > 0);
+          if (j + 1 < n_t[t]) {
+            issue_qk(t, s1);
+            umma_commit(&s_full[t]);
+          } else {
+            umma_commit(&o_done[t]);
+          }
+        }
+        umma_commit(&v_empty[s]);
+        if (j + 1 < n) umma_commit(&k_empty[s1]);
+      }
+    }
+  } else {
+    // ================================= softmax warpgroups ================================================================
+    const int t = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const int q_idx = q0 + t * FA_BM + row;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_base + S_COL + t * FA_BN;
+    const uint32_t o_addr = tmem_base + lane_base + O_COL + t * D;
+    uint8_t* p_row = smem_p + t * P_TILE_BYTES + row * 128;
+    const int sw = row & 7;
+    float m_ref = -INFINITY, l = 0.f;
+    const int nb = n_t[t];
+    for (int j = 0; j < nb; ++j) {
+      mbar_wait(&s_full[t], (uint32_t)j & 1u);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32b_x32(s_addr, r0);
+      tmem_ld_32x32b_x32(s_addr + 32, r1);
+      tmem_ld_wait();
+      const int kv0 = j * FA_BN;
+      const int limit = p.causal ? min(p.sk - 1, q_idx + off) : p.sk - 1;   // last visible key of this row
+      if (kv0 + FA_BN - 1 > limit) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (kv0 + c > limit) r0[c] = 0xff800000u;        // -inf
+          if (kv0 + 32 + c > limit) r1[c] = 0xff800000u;
+        }
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[c]), __uint_as_float(r1[c])));
+      const float mx_scaled = mx * p.scale_log2;
+      float alpha = 1.f;
+      if (mx_scaled > m_ref + FA_RESCALE_THRESHOLD) {
+        alpha = fast_exp2(m_ref - mx_scaled);               // 0 on the first block (m_ref = -inf)
+        m_ref = mx_scaled;
+        l *= alpha;
+      }
+      const bool rescale = __any_sync(0xffffffffu, alpha != 1.f) && j > 0;
+      // p = 2^(s*scale - m_ref); written as bf16 into the 128B-swizzled K-major tile the PV MMA reads as operand A
+      float sum = 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = u * 8 + e * 2;
+          const float a0 = __uint_as_float(c < 32 ? r0[c] : r1[c - 32]);
+          const float a1 = __uint_as_float(c + 1 < 32 ? r0[c + 1] : r1[c + 1 - 32]);
+          const float p0 = fast_exp2(fmaf(a0, p.scale_log2, -m_ref));
+          const float p1 = fast_exp2(fmaf(a1, p.scale_log2, -m_ref));
+          sum += p0 + p1;
+          __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+          pk[e] = *reinterpret_cast<uint32_t*>(&hb);
+        }
+        *reinterpret_cast<uint4*>(p_row + ((u ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      l += sum;
+      if (rescale) {
+        // PV(t, j-1) is complete (see header) → O_t is stable: scale this row's accumulator in place
+#pragma unroll 1
+        for (int ch = 0; ch < D / 32; ++ch) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(o_addr + ch * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+          tmem_st_32x32b_x32(o_addr + ch * 32, o);
+        }
+        tmem_st_wait();
+      }
+      fence_proxy_async();   // generic-proxy smem writes of P → visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(&p_ready[t]);
+    }
+    if (nb > 0) {
+      mbar_wait(&o_done[t], 0);
+      tc_fence_after();
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      const bool valid = q_idx < p.sq;
+      __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)q_idx * p.o_pitch + ((size_t)bi * p.hq + h) * D;
+#pragma unroll 1
+      for (int ch = 0; ch < D / 32; ++ch) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(o_addr + ch * 32, o);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint32_t v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(o[g * 16 + 2 * e]) * inv, __uint_as_float(o[g * 16 + 2 * e + 1]) * inv);
+              v[e] = *reinterpret_cast<uint32_t*>(&hb);
+            }
+            st_global_v8(orow + ch * 32 + g * 16, v);
+          }
+        }
+      }
+      if (valid && p.lse != nullptr) p.lse[((size_t)bi * p.hq + h) * p.sq + q_idx] = m_ref * 0.6931471805599453f + logf(l);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+template <int D>
+static int launch_fa_fwd(const void* q, const void* k, const void* v, FaParams p, long q_ss, long k_ss, long v_ss, cudaStream_t s) {
+  constexpr int SMEM_BYTES = 2 * (FA_BM * D * 2) + 2 * FA_STAGES * (FA_BN * D * 2) + 2 * (FA_BM * 128) + 1024 + 256;
+  CUtensorMap tq, tk, tv;
+  bool ok = make_tmap_bf16_strided(&tq, q, p.sq, q_ss, q_ss * 2, 64, FA_BM);
+  ok &= make_tmap_bf16_strided(&tk, k, p.sk, k_ss, k_ss * 2, 64, FA_BN);
+  ok &= make_tmap_bf16_strided(&tv, v, p.sk, v_ss, v_ss * 2, 64, FA_BN);
+  if (!ok) return -1;
+  auto kern = fa_fwd_kernel<D>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return -3;
+    configured = true;
+  }
+  dim3 grid((p.sq + 2 * FA_BM - 1) / (2 * FA_BM), p.hq, p.b);
+  kern<<<grid, FA_THREADS, SMEM_BYTES, s>>>(tq, tk, tv, p);
+  return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+}  // namespace mb200
+
+using namespace mb200;
+
+// Strides are in elements; *_ss = sequence stride (row pitch), *_sb = batch stride, *_sh = head stride; d is contiguous.
+extern "C" int mb200_flash_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int sq, int sk, int b, int hq, int hk, int d, long q_ss,
+                                    long q_sb, long q_sh, long k_ss, long k_sb, long k_sh, long v_ss, long v_sb, long v_sh, float scale, int causal,
+                                    cudaStream_t s) {
+  if ((d != 64 && d != 128) || hq % hk != 0) return -10;
+  if ((q_ss | q_sb | q_sh | k_ss | k_sb | k_sh | v_ss | v_sb | v_sh) % 8 != 0) return -11;   // 16-byte alignment for TMA
+  FaParams p;
+  p.sq = sq; p.sk = sk; p.b = b; p.hq = hq; p.hk = hk; p.causal = causal;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.q_sb = q_sb; p.q_sh = q_sh; p.k_sb = k_sb; p.k_sh = k_sh; p.v_sb = v_sb; p.v_sh = v_sh;
+  p.out = out; p.o_pitch = (long)b * hq * d; p.lse = lse;
+  return d == 128 ? launch_fa_fwd<128>(q, k, v, p, q_ss, k_ss, v_ss, s) : launch_fa_fwd<64>(q, k, v, p, q_ss, k_ss, v_ss, s);
+}

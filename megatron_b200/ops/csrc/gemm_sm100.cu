@@ -298,10 +298,15 @@ static EncodeTiledFn get_encode_fn() {
 
 // row-major bf16 matrix [rows, cols]; box = {box_cols (inner, <= 64), box_rows}; 128B swizzle
 bool make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows) {
+  return make_tmap_bf16_strided(out, ptr, rows, cols, cols * 2, box_cols, box_rows);
+}
+
+// same, with an explicit row pitch in bytes (multiple of 16): views into wider buffers (e.g. q/k/v slices of a fused QKV output)
+bool make_tmap_bf16_strided(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes, uint32_t box_cols, uint32_t box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return false;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
+  cuuint64_t strides[1] = {row_pitch_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

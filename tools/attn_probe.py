@@ -29,3 +29,11 @@ try:
     bench("flash_attn2", lambda: flash_attn_func(q.transpose(0,1), k.transpose(0,1), v.transpose(0,1), causal=True).transpose(0,1))
 except Exception as e:
     print("flash_attn import failed", e)
+
+# our tcgen05 forward (+ cuDNN backward on its out/LSE) vs the all-library path
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from megatron_b200 import ops
+for impl in ("native", "library"):
+    ops.set_attention_impl(impl)
+    bench(f"megatron_b200[{impl}]", lambda: ops.flash_attention(q, k, v, causal=True))
