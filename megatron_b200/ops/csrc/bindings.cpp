@@ -323,6 +323,58 @@ std::vector<Tensor> flash_attn_fwd(const Tensor& q, const Tensor& k, const Tenso
 }
 #endif
 
+// dst's storage becomes an alias of src's storage (reference N4 ``share_storage``, tensor_parallel/random.py:41-80): lets
+// CheckpointWithoutOutput hand a recomputed activation back to every tensor that still references the discarded one.
+void share_storage(Tensor dst, const Tensor& src) {
+  TORCH_CHECK(dst.nbytes() <= src.storage().nbytes(), "share_storage: source storage too small");
+  dst.set_(src.storage(), dst.storage_offset(), dst.sizes(), dst.strides());
+}
+
+#ifdef MB200_HAVE_RUNTIME_NATIVE
+// tasks: int64 [n, 3] rows of (src_ptr, dst_ptr, nbytes) on the host; copied to the device and executed by ONE kernel
+void batched_copy(const Tensor& tasks_cpu, int64_t nblocks) {
+  TORCH_CHECK(!tasks_cpu.is_cuda() && tasks_cpu.scalar_type() == at::kLong && tasks_cpu.dim() == 2 && tasks_cpu.size(1) == 3, "batched_copy: int64 [n, 3] CPU tensor");
+  const int n = (int)tasks_cpu.size(0);
+  if (n == 0) return;
+  auto t = tasks_cpu.contiguous();
+  const int64_t* a = t.data_ptr<int64_t>();
+  auto prefix = at::empty({n}, t.options());
+  int64_t* pf = prefix.data_ptr<int64_t>();
+  unsigned long long total = 0;
+  for (int i = 0; i < n; ++i) {
+    pf[i] = (int64_t)total;
+    total += ((unsigned long long)a[3 * i + 2] + 65535ull) / 65536ull;
+  }
+  auto dev = at::Device(at::kCUDA, c10::cuda::current_device());
+  auto td = t.to(dev, /*non_blocking=*/false);
+  auto pd = prefix.to(dev, false);
+  mb200_batched_copy(td.data_ptr(), pd.data_ptr(), n, total, (int)nblocks, cur_stream());
+  c10::cuda::CUDACachingAllocator::recordStream(td.storage().data_ptr(), c10::cuda::getCurrentCUDAStream());
+  c10::cuda::CUDACachingAllocator::recordStream(pd.storage().data_ptr(), c10::cuda::getCurrentCUDAStream());
+}
+#endif
+
+#ifdef MB200_HAVE_GROUPED_GEMM_SM100
+// mode 0: (x [T,K], w [E,N,K]) -> out [T,N];  mode 1: (gy [T,N], w [E,N,K]) -> out [T,K];  mode 2: (gy [T,N], x [T,K]) -> out = gw [E,N,K]
+void grouped_gemm_bf16(const Tensor& a, const Tensor& b, Tensor out, const Tensor& offsets_cpu, int64_t mode, bool accumulate) {
+  TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && a.is_contiguous() && b.is_contiguous() && out.is_contiguous(),
+              "grouped_gemm_bf16: contiguous bf16 CUDA operands");
+  TORCH_CHECK(!offsets_cpu.is_cuda() && offsets_cpu.scalar_type() == at::kInt, "grouped_gemm_bf16: offsets must be a CPU int32 tensor");
+  c10::cuda::CUDAGuard g(a.device());
+  const int E = (int)offsets_cpu.numel() - 1;
+  const Tensor& w = mode == 2 ? out : b;
+  TORCH_CHECK(w.dim() == 3 && w.size(0) == E, "grouped_gemm_bf16: weight-shaped operand must be [E, N, K]");
+  const int dim_n = (int)w.size(1), dim_k = (int)w.size(2);
+  const int c_dtype = out.scalar_type() == at::kFloat ? 0 : 1;
+  TORCH_CHECK(mode == 2 || c_dtype == 1, "grouped_gemm_bf16: activations are bf16");
+  auto maps = at::empty({(int64_t)(2 * E * 128 + 64)}, a.options().dtype(at::kByte));
+  void* md = reinterpret_cast<void*>(((uintptr_t)maps.data_ptr() + 63) & ~(uintptr_t)63);
+  const int rc = mb200_grouped_gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), offsets_cpu.data_ptr<int>(), E, dim_n, dim_k, (int)mode, accumulate ? 1 : 0, c_dtype,
+                                         md, cur_stream());
+  TORCH_CHECK(rc == 0, "grouped_gemm_bf16 failed with code ", rc);
+}
+#endif
+
 // Attention backward through the cuDNN library (consumes OUR forward's out + log-sum-exp); [s, b, h, d] tensors in and out.
 std::vector<Tensor> attn_bwd_cudnn(const Tensor& go, const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& o, const Tensor& lse, bool causal, double scale) {
   c10::cuda::CUDAGuard g(q.device());
@@ -380,6 +432,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("nvl_allreduce", &nvl_allreduce);
 #endif
   m.def("attn_bwd_cudnn", &attn_bwd_cudnn);
+  m.def("share_storage", &share_storage);
+#ifdef MB200_HAVE_GROUPED_GEMM_SM100
+  m.def("grouped_gemm_bf16", &grouped_gemm_bf16);
+#endif
+#ifdef MB200_HAVE_RUNTIME_NATIVE
+  m.def("batched_copy", &batched_copy);
+#endif
 #ifdef MB200_HAVE_FLASH_ATTN_SM100
   m.def("flash_attn_fwd", &flash_attn_fwd);
 #endif

@@ -74,6 +74,33 @@ __device__ __forceinline__ uint4 mm_ld_reduce_bf16x8(const void* mc) {
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
+// NVLink round trips are microseconds: keep U independent 16-byte transfers in flight per thread (Little's law), i.e. issue all
+// loads of a batch before the first dependent store.  n = number of 16-byte vectors, tid/nthr = this thread's slot in the comm grid.
+template <int U>
+__device__ __forceinline__ void push_multicast(uint4* __restrict__ mc_dst, const uint4* __restrict__ src, size_t n, size_t tid, size_t nthr) {
+  size_t i = tid;
+  for (; i + (size_t)(U - 1) * nthr < n; i += (size_t)U * nthr) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = __ldg(src + i + (size_t)u * nthr);
+#pragma unroll
+    for (int u = 0; u < U; ++u) mm_st_v4(mc_dst + i + (size_t)u * nthr, v[u]);
+  }
+  for (; i < n; i += nthr) mm_st_v4(mc_dst + i, __ldg(src + i));
+}
+template <int U>
+__device__ __forceinline__ void pull_reduce_multicast(uint4* __restrict__ out, const uint4* __restrict__ mc_src, size_t n, size_t tid, size_t nthr) {
+  size_t i = tid;
+  for (; i + (size_t)(U - 1) * nthr < n; i += (size_t)U * nthr) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = mm_ld_reduce_bf16x8(mc_src + i + (size_t)u * nthr);
+#pragma unroll
+    for (int u = 0; u < U; ++u) out[i + (size_t)u * nthr] = v[u];
+  }
+  for (; i < n; i += nthr) out[i] = mm_ld_reduce_bf16x8(mc_src + i);
+}
+
 // position in the tile walk → M pair-tile index
 __device__ __forceinline__ int walk_to_mblk(const FusedParams& p, int pos) {
   const int C = p.chunks_per_rank, W = p.world;
@@ -119,7 +146,7 @@ fused_tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const size_t dst_off = ((size_t)p.rank * C + c) * chunk_vec;
         if (p.ag_dst_mc != nullptr) {
           uint4* dst = reinterpret_cast<uint4*>(p.ag_dst_mc) + dst_off;
-          for (size_t i = (size_t)cta * blockDim.x + threadIdx.x; i < chunk_vec; i += (size_t)nctas * blockDim.x) mm_st_v4(dst + i, src[i]);
+          push_multicast<8>(dst, src, chunk_vec, (size_t)cta * blockDim.x + threadIdx.x, (size_t)nctas * blockDim.x);
         } else {
           for (size_t i = (size_t)cta * blockDim.x + threadIdx.x; i < chunk_vec; i += (size_t)nctas * blockDim.x) {
             const uint4 v = src[i];
@@ -149,7 +176,7 @@ fused_tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const size_t dst_off = (size_t)p.rank * p.xag_vec;
         if (p.xag_dst_mc != nullptr) {
           uint4* dst = reinterpret_cast<uint4*>(p.xag_dst_mc) + dst_off;
-          for (size_t i = (size_t)cta * blockDim.x + threadIdx.x; i < p.xag_vec; i += (size_t)nctas * blockDim.x) mm_st_v4(dst + i, src[i]);
+          push_multicast<8>(dst, src, p.xag_vec, (size_t)cta * blockDim.x + threadIdx.x, (size_t)nctas * blockDim.x);
         } else {
           for (size_t i = (size_t)cta * blockDim.x + threadIdx.x; i < p.xag_vec; i += (size_t)nctas * blockDim.x) {
             const uint4 v = src[i];
@@ -181,10 +208,11 @@ fused_tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         __syncthreads();
         const size_t src_off = ((size_t)p.rank * C + c) * chunk_vec;
         uint4* out = reinterpret_cast<uint4*>(p.rs_out) + (size_t)c * chunk_vec;
-        for (size_t i = (size_t)cta * blockDim.x + threadIdx.x; i < chunk_vec; i += (size_t)nctas * blockDim.x) {
-          if (p.rs_src_mc != nullptr) {
-            out[i] = mm_ld_reduce_bf16x8(reinterpret_cast<const uint4*>(p.rs_src_mc) + src_off + i);
-          } else {
+        if (p.rs_src_mc != nullptr) {
+          pull_reduce_multicast<16>(out, reinterpret_cast<const uint4*>(p.rs_src_mc) + src_off, chunk_vec, (size_t)cta * blockDim.x + threadIdx.x,
+                                    (size_t)nctas * blockDim.x);
+        } else {
+          for (size_t i = (size_t)cta * blockDim.x + threadIdx.x; i < chunk_vec; i += (size_t)nctas * blockDim.x) {
             float acc[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc[k] = 0.f;

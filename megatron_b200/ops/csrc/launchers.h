@@ -40,5 +40,8 @@ int mb200_fused_tp_gemm(int mode, const void* A, const void* B, void* C, int M, 
                         int comm_clusters, cudaStream_t s);
 int mb200_flash_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int sq, int sk, int b, int hq, int hk, int d, long q_ss, long q_sb,
                          long q_sh, long k_ss, long k_sb, long k_sh, long v_ss, long v_sb, long v_sh, float scale, int causal, cudaStream_t s);
+void mb200_batched_copy(const void* tasks_dev, const void* chunk_prefix_dev, int ntasks, unsigned long long total_chunks, int nblocks, cudaStream_t s);
+int mb200_grouped_gemm_bf16(const void* a, const void* b, void* c, const int* offsets, int E, int dim_n, int dim_k, int mode, int accumulate, int c_dtype,
+                            void* maps_dev, cudaStream_t s);
 int mb200_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int layout, int accumulate, int c_dtype, cudaStream_t s);
 }

@@ -101,7 +101,16 @@ __global__ void __launch_bounds__(512) allgather_kernel(Peers pr, void* mc_base,
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   if (mc_base != nullptr) {
     uint4* mc = reinterpret_cast<uint4*>(mc_base) + off16;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += stride) multimem_st_v4(mc + i, src[i]);
+    // 8 independent loads in flight per thread before the first (fire-and-forget) multicast store
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    for (; i + 7 * stride < n16; i += 8 * stride) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(src + i + u * stride);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) multimem_st_v4(mc + i + u * stride, v[u]);
+    }
+    for (; i < n16; i += stride) multimem_st_v4(mc + i, __ldg(src + i));
   } else {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += stride) {
       const uint4 v = src[i];
@@ -123,15 +132,28 @@ __global__ void __launch_bounds__(512) reducescatter_kernel(Peers pr, const void
   const size_t n16 = shard_elems / VN;
   const size_t off16 = src_off_bytes / 16 + (size_t)rank * n16;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += stride) {
-    float acc[VN];
-    if (mc_base != nullptr) {
-      const uint4 v = sizeof(T) == 2 ? multimem_ld_reduce_bf16x8(reinterpret_cast<const uint4*>(mc_base) + off16 + i)
-                                     : multimem_ld_reduce_f32x4(reinterpret_cast<const uint4*>(mc_base) + off16 + i);
+  size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (mc_base != nullptr) {
+    // in-switch reduction: the round trip is several microseconds, so keep 8 ld_reduce per thread in flight
+    const uint4* mc = reinterpret_cast<const uint4*>(mc_base) + off16;
+    auto finish = [&](size_t i, const uint4& v) {
       const T* h = reinterpret_cast<const T*>(&v);
+      Vec<T> o;
 #pragma unroll
-      for (int k = 0; k < VN; ++k) acc[k] = to_f(h[k]);
-    } else {
+      for (int k = 0; k < VN; ++k) o.v[k] = from_f<T>(to_f(h[k]) * scale);
+      st16(out + i * VN, o);
+    };
+    for (; i0 + 7 * stride < n16; i0 += 8 * stride) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = sizeof(T) == 2 ? multimem_ld_reduce_bf16x8(mc + i0 + u * stride) : multimem_ld_reduce_f32x4(mc + i0 + u * stride);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) finish(i0 + u * stride, v[u]);
+    }
+    for (; i0 < n16; i0 += stride) finish(i0, sizeof(T) == 2 ? multimem_ld_reduce_bf16x8(mc + i0) : multimem_ld_reduce_f32x4(mc + i0));
+  } else {
+    for (size_t i = i0; i < n16; i += stride) {
+      float acc[VN];
 #pragma unroll
       for (int k = 0; k < VN; ++k) acc[k] = 0.f;
 #pragma unroll 1
@@ -141,11 +163,11 @@ __global__ void __launch_bounds__(512) reducescatter_kernel(Peers pr, const void
 #pragma unroll
         for (int k = 0; k < VN; ++k) acc[k] += to_f(h[k]);
       }
-    }
-    Vec<T> o;
+      Vec<T> o;
 #pragma unroll
-    for (int k = 0; k < VN; ++k) o.v[k] = from_f<T>(acc[k] * scale);
-    st16(out + i * VN, o);
+      for (int k = 0; k < VN; ++k) o.v[k] = from_f<T>(acc[k] * scale);
+      st16(out + i * VN, o);
+    }
   }
   trailing_barrier(pr, rank, world, epoch + 1, slot, ctrl, trailing != 0);
 }

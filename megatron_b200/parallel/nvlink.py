@@ -88,7 +88,9 @@ class NVLinkBackend:
         self.fused_flags = [p + _FUSED_FLAG_OFF for p in self.ptrs]
         self.fused_counters = torch.zeros(1024, dtype=torch.int32, device=self.device)
         self.fused_epoch = 0
-        self.fused_comm_clusters = int(os.environ.get("MEGATRON_B200_FUSED_COMM_CLUSTERS", "8"))
+        # CTA pairs reserved for communication inside a fused kernel (the rest of the 74 run the GEMM): pushes (AG) are
+        # fire-and-forget and need fewer; in-switch pull-reductions (RS) are round-trip bound and need more in flight
+        self.fused_comm_clusters = [int(os.environ.get("MEGATRON_B200_FUSED_COMM_CLUSTERS_AG", "6")), int(os.environ.get("MEGATRON_B200_FUSED_COMM_CLUSTERS_RS", "10"))]
         self.fused_calls = 0
         dist.barrier(group=group)
         self.barrier()
@@ -251,7 +253,7 @@ class NVLinkBackend:
             ag_src if ag_src is not None else empty, (mc + ag_off) if (mc and mode == 0) else 0, [p + ag_off for p in self.ptrs] if mode == 0 else [],
             (mc + rs_off) if (mc and mode == 1) else 0, [p + rs_off for p in self.ptrs] if mode == 1 else [], rs_out if rs_out is not None else empty,
             xag_src if xag_src is not None else empty, (mc + xag_off) if (mc and xag_src is not None) else 0,
-            [p + xag_off for p in self.ptrs] if xag_src is not None else [], self.fused_flags, self.fused_counters, self.fused_comm_clusters,
+            [p + xag_off for p in self.ptrs] if xag_src is not None else [], self.fused_flags, self.fused_counters, self.fused_comm_clusters[mode],
         )
         self.fused_calls += 1
         ops._count()

@@ -53,9 +53,14 @@ def main():
 
     results = {}
     refs = {}
-    modes = os.environ.get("MODES", "nccl,nvlink,fused").split(",")
+    modes = os.environ.get("MODES", "nccl,nvlink,fused:4:8,fused:8:12,fused:12:20").split(",")
     for mode in modes:
-        fused.set_mode(mode)
+        if mode.startswith("fused:"):  # fused:<AG comm clusters>:<RS comm clusters>
+            _, a, r = mode.split(":")
+            be.fused_comm_clusters = [int(a), int(r)]
+            fused.set_mode("fused")
+        else:
+            fused.set_mode(mode)
         for name, (kind, *args) in cases.items():
             outs = run(kind, args)
             outs = [o.float().clone() for o in outs]
