@@ -23,6 +23,8 @@ from .. import ops
 from ..core.utils import get_pg_rank, get_pg_size
 
 _MODE = os.environ.get("MEGATRON_B200_TP_COMM", "auto")  # auto | nccl | nvlink | fused
+# what "auto" means on this build: the fastest MEASURED mode on 2-8 B200s (profiles/r1_tp_comm.md)
+_AUTO_RESOLVES_TO = "nccl"
 
 
 def set_mode(mode: str) -> None:
@@ -32,12 +34,12 @@ def set_mode(mode: str) -> None:
 
 
 def get_mode() -> str:
-    return _MODE
+    return _AUTO_RESOLVES_TO if _MODE == "auto" else _MODE
 
 
 def _nvl(group, t):
     """NVLink backend (symmetric-heap collectives) or None."""
-    if not t.is_cuda or _MODE == "nccl":
+    if not t.is_cuda or get_mode() == "nccl":
         return None
     from . import collectives
 

@@ -55,3 +55,49 @@ def test_nccl_mem_shim_allocates_plain_memory_without_gpu():
     with nccl_allocator.nccl_mem(group=None) as mem:
         t = mem.alloc(16, torch.float32)
     assert t.shape == (16,) and float(t.abs().sum()) == 0.0
+
+
+def _serve(rank, world):
+    import asyncio
+    import json
+    import urllib.request
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.inference.engine import DynamicInferenceEngine
+    from megatron_b200.core.inference.sampling import SamplingParams
+    from megatron_b200.core.inference.text_generation import AsyncLLM, TextGenerationController, TextGenerationServer
+    from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
+    from megatron_b200.core.tokenizers.tokenizer import build_tokenizer
+    from megatron_b200.models.presets import build_gpt_model
+
+    ps.initialize_model_parallel(1, 1)
+    model_parallel_cuda_manual_seed(7)
+    model, _, p = build_gpt_model("tiny_llama", use_cpu_initialization=True)
+    model.eval()
+    tok = build_tokenizer("ByteLevel")
+    greedy = SamplingParams(temperature=0.0, num_tokens_to_generate=6)
+    ctl = TextGenerationController(DynamicInferenceEngine(model, vocab_size=256), tok)
+    direct = ctl.generate(["hello", "b200"], greedy)
+    srv = TextGenerationServer(ctl, port=0)
+    srv.start()
+    try:
+        req = urllib.request.Request(f"http://127.0.0.1:{srv.port}/api", data=json.dumps({"prompts": ["hello", "b200"], "tokens_to_generate": 6, "temperature": 0.0}).encode(), method="PUT")
+        out = json.loads(urllib.request.urlopen(req, timeout=60).read())
+        req = urllib.request.Request(f"http://127.0.0.1:{srv.port}/v1/completions", data=json.dumps({"prompt": "hello", "max_tokens": 6, "temperature": 0.0}).encode(), method="POST")
+        oai = json.loads(urllib.request.urlopen(req, timeout=60).read())
+    finally:
+        srv.stop()
+    assert out["segments"] == [d["tokens"] for d in direct] and len(out["segments"][0]) == 6
+    assert oai["choices"][0]["text"] == direct[0]["text"]
+
+    async def many():
+        llm = AsyncLLM(DynamicInferenceEngine(model, vocab_size=256), tok)
+        return await asyncio.gather(*[llm.generate_tokens(list(tok.tokenize(s)), greedy) for s in ("hello", "b200", "hello")])
+
+    reqs = asyncio.run(many())
+    assert reqs[0].generated_tokens == reqs[2].generated_tokens == direct[0]["tokens"] and reqs[1].generated_tokens == direct[1]["tokens"]
+    return True
+
+
+def test_text_generation_server_and_async_llm():
+    assert all(run_distributed(_serve, 1))
