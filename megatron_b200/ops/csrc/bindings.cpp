@@ -375,6 +375,23 @@ void grouped_gemm_bf16(const Tensor& a, const Tensor& b, Tensor out, const Tenso
 }
 #endif
 
+#ifdef MB200_HAVE_GEMM_FP8_SM100
+// a [M,K], b [N,K]: torch.float8_e4m3fn / float8_e5m2 -> bf16 [M,N] = alpha * a · bᵀ
+Tensor gemm_fp8_nt(const Tensor& a, const Tensor& b, double alpha, const c10::optional<Tensor>& alpha_dev) {
+  auto fmt = [](const Tensor& t) {
+    TORCH_CHECK(t.scalar_type() == at::kFloat8_e4m3fn || t.scalar_type() == at::kFloat8_e5m2, "gemm_fp8_nt: float8_e4m3fn / float8_e5m2 operands");
+    return t.scalar_type() == at::kFloat8_e4m3fn ? 0 : 1;
+  };
+  TORCH_CHECK(a.is_cuda() && a.dim() == 2 && b.dim() == 2 && a.is_contiguous() && b.is_contiguous() && a.size(1) == b.size(1), "gemm_fp8_nt: a [M,K], b [N,K] contiguous");
+  c10::cuda::CUDAGuard g(a.device());
+  auto c = at::empty({a.size(0), b.size(0)}, a.options().dtype(at::kBFloat16));
+  const int rc = mb200_gemm_fp8_nt(a.data_ptr(), b.data_ptr(), c.data_ptr(), (int)a.size(0), (int)b.size(0), (int)a.size(1), fmt(a), fmt(b), (float)alpha,
+                                   alpha_dev.has_value() ? alpha_dev->data_ptr<float>() : nullptr, cur_stream());
+  TORCH_CHECK(rc == 0, "gemm_fp8_nt failed with code ", rc);
+  return c;
+}
+#endif
+
 // Attention backward through the cuDNN library (consumes OUR forward's out + log-sum-exp); [s, b, h, d] tensors in and out.
 std::vector<Tensor> attn_bwd_cudnn(const Tensor& go, const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& o, const Tensor& lse, bool causal, double scale) {
   c10::cuda::CUDAGuard g(q.device());
@@ -433,6 +450,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 #endif
   m.def("attn_bwd_cudnn", &attn_bwd_cudnn);
   m.def("share_storage", &share_storage);
+#ifdef MB200_HAVE_GEMM_FP8_SM100
+  m.def("gemm_fp8_nt", &gemm_fp8_nt);
+#endif
 #ifdef MB200_HAVE_GROUPED_GEMM_SM100
   m.def("grouped_gemm_bf16", &grouped_gemm_bf16);
 #endif

@@ -314,6 +314,22 @@ bool make_tmap_bf16_strided(CUtensorMap* out, const void* ptr, uint64_t rows, ui
   return r == CUDA_SUCCESS;
 }
 
+}  // namespace mb200
+
+// one-byte elements (fp8): rows x cols bytes, box {128 bytes, box_rows}, 128B swizzle
+bool mb200_make_tmap_u8(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  mb200::EncodeTiledFn enc = mb200::get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols};
+  cuuint32_t box[2] = {128, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+namespace mb200 {
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

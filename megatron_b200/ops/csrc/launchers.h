@@ -43,5 +43,6 @@ int mb200_flash_attn_fwd(const void* q, const void* k, const void* v, void* out,
 void mb200_batched_copy(const void* tasks_dev, const void* chunk_prefix_dev, int ntasks, unsigned long long total_chunks, int nblocks, cudaStream_t s);
 int mb200_grouped_gemm_bf16(const void* a, const void* b, void* c, const int* offsets, int E, int dim_n, int dim_k, int mode, int accumulate, int c_dtype,
                             void* maps_dev, cudaStream_t s);
+int mb200_gemm_fp8_nt(const void* A, const void* B, void* C, int M, int N, int K, int a_fmt, int b_fmt, float alpha, const float* alpha_dev, cudaStream_t s);
 int mb200_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int layout, int accumulate, int c_dtype, cudaStream_t s);
 }

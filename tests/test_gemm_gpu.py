@@ -81,3 +81,22 @@ def test_autotuner_picks_a_candidate_and_is_correct():
     assert (ours - ref).abs().max() <= 2 * (lib - ref).abs().max() + 1e-3
     assert g.tuning_report(), "autotuner did not run"
     print(g.tuning_report()[-1])
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 512, 256), (1000, 768, 1024), (4096, 4096, 4096)])
+def test_fp8_gemm_matches_emulation(M, N, K):
+    """tcgen05 kind::f8f6f4 GEMM == the same FP8-quantised operands multiplied in fp32."""
+    from megatron_b200 import ops
+    from megatron_b200.core.fp8_utils import E4M3, E5M2, quantize
+
+    assert hasattr(ops.ext(), "gemm_fp8_nt"), "fp8 GEMM not built"
+    torch.manual_seed(0)
+    a = torch.randn(M, K, device="cuda")
+    b = torch.randn(N, K, device="cuda")
+    for da, db in ((E4M3, E4M3), (E5M2, E4M3)):
+        aq, ai = quantize(a, da)
+        bq, bi = quantize(b, db)
+        out = ops.ext().gemm_fp8_nt(aq, bq, 1.0, (ai * bi).float())
+        ref = (aq.float() @ bq.float().t()) * (ai * bi)
+        err = (out.float() - ref).abs().max().item() / ref.abs().max().item()
+        assert err < 1e-2, f"{da}x{db}: rel err {err}"
