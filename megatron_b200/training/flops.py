@@ -8,6 +8,9 @@ def num_floating_point_operations(*, num_layers, hidden_size, ffn_hidden_size, n
                                   seq_length, batch_size, swiglu=True, num_moe_experts=None, moe_router_topk=1, moe_layer_freq=1,
                                   moe_ffn_hidden_size=None, mtp_num_layers=0) -> float:
     s, B, h = seq_length, batch_size, hidden_size
+    ffn_hidden_size = ffn_hidden_size or 4 * hidden_size
+    kv_channels = kv_channels or hidden_size // num_attention_heads
+    num_query_groups = num_query_groups or num_attention_heads
     q_proj = kv_channels * num_attention_heads
     kv_proj = kv_channels * num_query_groups
     gate = 3 if swiglu else 2  # number of [h, ffn]-sized matrices in the FFN
