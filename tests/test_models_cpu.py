@@ -232,3 +232,38 @@ def _fsdp(rank, world):
 def test_fsdp_zero3_matches_full_batch_training():
     errs = run_distributed(_fsdp, 2)
     assert max(errs) < 1e-5
+
+
+def _export_distill_rl(rank, world):
+    _init()
+    from megatron_b200.core.export.hf_llama import hf_llama_to_megatron, megatron_to_hf_llama
+    from megatron_b200.models.presets import build_gpt_model
+    from megatron_b200.post_training.distillation import DistillationModel, vocab_parallel_kl
+    from megatron_b200.rl.grpo import group_advantages
+
+    model, cfg, p = build_gpt_model("tiny_llama", use_cpu_initialization=True)
+    sd = {k: v for k, v in model.state_dict().items() if isinstance(v, torch.Tensor) and "_extra_state" not in k}
+    hf = megatron_to_hf_llama(sd, cfg.num_attention_heads, cfg.num_query_groups, cfg.kv_channels)
+    assert hf["model.layers.0.self_attn.k_proj.weight"].shape == (cfg.num_query_groups * cfg.kv_channels, cfg.hidden_size)
+    back = hf_llama_to_megatron(hf, cfg.num_attention_heads, cfg.num_query_groups, cfg.kv_channels, tie_embeddings="output_layer.weight" not in sd)
+    for k, v in back.items():
+        assert torch.equal(v, sd[k]), k
+    # KD: zero when teacher == student, positive otherwise, gradients reach the student
+    a, b = torch.randn(2, 5, 16, requires_grad=True), torch.randn(2, 5, 16)
+    assert vocab_parallel_kl(a, a.detach()).abs().max().item() < 1e-6
+    kl = vocab_parallel_kl(a, b, temperature=2.0)
+    assert (kl > 0).all()
+    teacher, _, _ = build_gpt_model("tiny_llama", use_cpu_initialization=True)
+    dm = DistillationModel(model, teacher, alpha=0.5)
+    tok = torch.randint(0, 100, (2, 16))
+    pos = torch.arange(16)[None].expand(2, -1)
+    loss, stats = dm(tok, pos, None, tok)
+    loss.backward()
+    assert all(q.grad is None for q in teacher.parameters()) and any(q.grad is not None for q in model.parameters())
+    adv = group_advantages(torch.tensor([1.0, 0.0, 0.5, 0.5, 2.0, 2.0, 2.0, 2.0]), 4)
+    assert abs(adv[:4].mean().item()) < 1e-6 and adv[4:].abs().max().item() < 1e-3
+    return True
+
+
+def test_hf_export_roundtrip_distillation_and_grpo_advantages():
+    run_distributed(_export_distill_rl, 1)

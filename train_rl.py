@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""GRPO post-training of a GPT preset on a verifiable toy task (drop-in for the reference's ``train_rl.py`` entry point).
+
+    python train_rl.py --preset tiny_llama --iters 20 --group-size 8
+"""
+import argparse
+import copy
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--preset", default="tiny_llama")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--group-size", type=int, default=4)
+    ap.add_argument("--prompts-per-iter", type=int, default=4)
+    ap.add_argument("--lr", type=float, default=1e-3)
+    ap.add_argument("--vocab", type=int, default=64)
+    args = ap.parse_args()
+    import torch.distributed as dist
+
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29571")
+    if not dist.is_initialized():
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=0, world_size=1)
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
+    from megatron_b200.models.presets import build_gpt_model
+    from megatron_b200.rl.grpo import CountTokenEnv, GRPOConfig, GRPOTrainer
+
+    ps.initialize_model_parallel(1, 1)
+    model_parallel_cuda_manual_seed(1234)
+    model, _, p = build_gpt_model(args.preset, use_cpu_initialization=not torch.cuda.is_available())
+    ref, _, _ = build_gpt_model(args.preset, use_cpu_initialization=not torch.cuda.is_available())  # frozen reference policy
+    ref.load_state_dict(model.state_dict())
+    opt = torch.optim.AdamW(model.parameters(), lr=args.lr)
+    tr = GRPOTrainer(model, ref, opt, CountTokenEnv(args.vocab), GRPOConfig(group_size=args.group_size, max_new_tokens=8), vocab_size=args.vocab)
+    for it in range(args.iters):
+        s = tr.step(args.prompts_per_iter)
+        print(f"iter {it + 1:3d} | reward {float(s['reward']):.3f} | loss {float(s['loss']):+.4f} | kl {float(s['kl']):.5f}", flush=True)
+    return tr
+
+
+if __name__ == "__main__":
+    main()
