@@ -2,25 +2,25 @@
 record/replay of autograd nodes :786-945).
 
 B200-first rationale: a Llama-class layer launches ~40 kernels of 5-200 µs; at TP=8 the per-layer GPU time is
-< 1 ms and the Python/launch overhead becomes visible.  One graph per (layer, microbatch-shape) replays forward
+< 1 ms and the Python/launch overhead becomes visible.  One graph pair per (layer, input signature) replays forward
 and backward with two ``cudaGraphLaunch`` calls.
 
 Design (different from the reference's global record-then-capture pass):
 
-* ``CudaGraphManager`` is attached to a layer (``GraphableMegatronModule``).  The first ``warmup`` calls run eagerly
-  on a side stream (PyTorch's capture prerequisites), then forward and backward are captured as TWO graphs sharing
-  one private memory pool:   fwd graph: static inputs → static outputs;   bwd graph: static grad-outputs → static
-  grad-inputs + ``.grad`` / ``main_grad`` accumulation of the layer's parameters.
-* The graphs are wired into autograd through ``_GraphedLayerFn`` so the layer composes with eager neighbours,
-  pipeline schedules and activation recompute of *other* layers.
-* RNG: dropout inside a captured region uses PyTorch's graph-safe philox offsets; the tensor-parallel RNG tracker
-  states are registered with the graph (``register_generator_state``) when present.
+* ``CudaGraphManager`` is attached to a layer (``GraphableMegatronModule``).  The first ``warmup`` calls run eagerly,
+  then forward and backward are captured as TWO graphs sharing one private memory pool (``torch.cuda.make_graphed_callables``
+  does the capture: static input/output/grad buffers, warm-up on a side stream, autograd wiring); the manager adds what the
+  layer API needs around it — keyword tensor arguments, non-tensor outputs (``(hidden, None)``), one capture per input
+  signature (shape / dtype / requires_grad / training flag), and a permanent eager fallback.
+* The graphed callable is an autograd Function, so a graphed layer composes with eager neighbours, pipeline schedules
+  and activation recompute of *other* layers.
+* RNG: dropout inside a captured region uses PyTorch's graph-safe philox offsets.
 * On CPU (unit tests) and when capture fails (data-dependent control flow, e.g. MoE token drop), the manager
   permanently falls back to eager execution for that layer and records the reason in ``self.fallback_reason``.
 """
 from __future__ import annotations
 
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Any, Dict, List, Optional
 
 import torch
 
@@ -39,6 +39,7 @@ def is_graph_capturing() -> bool:
 
 
 def _flatten(out):
+    """→ (list of tensors, rebuild(list) -> original structure)."""
     if isinstance(out, torch.Tensor):
         return [out], lambda xs: xs[0]
     if isinstance(out, (tuple, list)):
@@ -55,53 +56,31 @@ def _flatten(out):
     raise TypeError(f"unsupported layer output type {type(out)}")
 
 
+class _Shim(torch.nn.Module):
+    """Positional-tensors-in / tensors-out view of a layer call, owning the layer's parameters (what the capture API expects)."""
+
+    def __init__(self, inner: torch.nn.Module, fn):
+        super().__init__()
+        self.inner = inner
+        self._fn = fn
+
+    def forward(self, *xs):
+        tensors, _ = _flatten(self._fn(*xs))
+        return tuple(tensors)
+
+
 class _Captured:
     """One (fwd graph, bwd graph) pair for a fixed input signature."""
 
-    def __init__(self, fn, params: List[torch.nn.Parameter], sample_args: Tuple[torch.Tensor, ...], pool):
-        self.params = [p for p in params if p.requires_grad]
-        self.static_in = [a.detach().clone().requires_grad_(a.requires_grad) for a in sample_args]
-        self.fwd_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.fwd_graph, pool=pool):
-            out = fn(*self.static_in)
-        self.static_out, self.rebuild = _flatten(out)
-        self.out_needs_grad = [o.requires_grad for o in self.static_out]
-        self.static_gout = [torch.zeros_like(o) if ng else None for o, ng in zip(self.static_out, self.out_needs_grad)]
-        self.grad_targets = [a for a in self.static_in if a.requires_grad] + self.params
-        self.bwd_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.bwd_graph, pool=pool):
-            grads = torch.autograd.grad(
-                [o for o, ng in zip(self.static_out, self.out_needs_grad) if ng],
-                self.grad_targets,
-                [g for g in self.static_gout if g is not None],
-                allow_unused=True,
-            )
-        self.static_gin = list(grads)
+    def __init__(self, module: torch.nn.Module, fn, sample_args):
+        with torch.no_grad():
+            _, self.rebuild = _flatten(fn(*sample_args))  # learn the output structure (which slots are tensors)
+        samples = tuple(a.detach().clone().requires_grad_(a.requires_grad) for a in sample_args)
+        self.graphed = torch.cuda.make_graphed_callables(_Shim(module, fn), samples, num_warmup_iters=3, pool=_shared_pool())
 
-
-class _GraphedLayerFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, cap: _Captured, n_in: int, *flat):
-        ins = flat[:n_in]
-        for s, a in zip(cap.static_in, ins):
-            if s.data_ptr() != a.data_ptr():
-                s.copy_(a)
-        cap.fwd_graph.replay()
-        ctx.cap = cap
-        return tuple(o.detach() for o in cap.static_out)
-
-    @staticmethod
-    def backward(ctx, *gouts):
-        cap = ctx.cap
-        for s, g in zip(cap.static_gout, gouts):
-            if s is not None and g is not None and s.data_ptr() != g.data_ptr():
-                s.copy_(g)
-        cap.bwd_graph.replay()
-        n_in_grad = sum(1 for a in cap.static_in if a.requires_grad)
-        gin_it = iter(cap.static_gin[:n_in_grad])
-        g_inputs = tuple((next(gin_it).detach() if a.requires_grad else None) for a in cap.static_in)
-        g_params = tuple(g.detach() if g is not None else None for g in cap.static_gin[n_in_grad:])
-        return (None, None) + g_inputs + g_params
+    def __call__(self, *flat_in):
+        outs = self.graphed(*flat_in)
+        return self.rebuild(list(outs) if isinstance(outs, (tuple, list)) else [outs])
 
 
 class CudaGraphManager:
@@ -117,7 +96,7 @@ class CudaGraphManager:
         self.share_pool = share_pool
 
     def should_graph(self, module, args, kwargs) -> bool:
-        """Graph only training/inference calls whose tensor arguments are all on the GPU and outside a capture."""
+        """Graph only calls whose tensor arguments are all on the GPU and that happen outside a capture."""
         if self.fallback_reason is not None or not torch.cuda.is_available() or is_graph_capturing():
             return False
         if kwargs.get("inference_context") is not None or kwargs.get("inference_params") is not None:
@@ -130,12 +109,7 @@ class CudaGraphManager:
 
     def __call__(self, module: torch.nn.Module, args: tuple, kwargs: dict):
         tensor_kw = {k: v for k, v in kwargs.items() if isinstance(v, torch.Tensor)}
-        if (
-            self.fallback_reason is not None
-            or not torch.cuda.is_available()
-            or not all(isinstance(a, torch.Tensor) and a.is_cuda for a in args)
-            or is_graph_capturing()
-        ):
+        if not self.should_graph(module, args, kwargs):
             return module._eager_forward(*args, **kwargs)
         self.calls += 1
         if self.calls <= self.warmup:
@@ -153,18 +127,13 @@ class CudaGraphManager:
 
             try:
                 torch.cuda.synchronize()
-                s = torch.cuda.Stream()
-                s.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(s):
-                    cap = _Captured(fn, list(module.parameters()), flat_in, _shared_pool() if self.share_pool else None)
-                torch.cuda.current_stream().wait_stream(s)
+                cap = _Captured(module, fn, flat_in)
             except Exception as e:  # capture is best-effort: keep training eagerly
                 self.fallback_reason = f"{type(e).__name__}: {e}"
                 torch.cuda.synchronize()
                 return module._eager_forward(*args, **kwargs)
             self.captured[sig] = cap
-        outs = _GraphedLayerFn.apply(cap, len(flat_in), *flat_in, *cap.params)
-        return cap.rebuild(list(outs))
+        return cap(*flat_in)
 
 
 class GraphableMixin:

@@ -392,6 +392,43 @@ Tensor gemm_fp8_nt(const Tensor& a, const Tensor& b, double alpha, const c10::op
 }
 #endif
 
+#ifdef MB200_HAVE_MOE_KERNELS
+// out[i] = scale[i] * in[src[i]]   (bf16 rows, hidden % 8 == 0)
+Tensor moe_gather_rows(const Tensor& in, const Tensor& src, const c10::optional<Tensor>& scale) {
+  TORCH_CHECK(in.is_cuda() && in.scalar_type() == at::kBFloat16 && in.dim() == 2 && in.is_contiguous() && in.size(1) % 8 == 0, "moe_gather_rows: contiguous bf16 [n, h], h % 8 == 0");
+  TORCH_CHECK(src.scalar_type() == at::kLong && src.is_contiguous(), "moe_gather_rows: int64 indices");
+  c10::cuda::CUDAGuard g(in.device());
+  auto out = at::empty({src.numel(), in.size(1)}, in.options());
+  mb200_moe_gather_rows(in.data_ptr(), out.data_ptr(), src.data_ptr<int64_t>(), scale.has_value() ? scale->data_ptr<float>() : nullptr, src.numel(), (int)in.size(1), cur_stream());
+  return out;
+}
+// out[t] = sum_k w[t,k] * in[pos[t,k]]   (pos < 0 skipped)
+Tensor moe_combine_rows(const Tensor& in, const Tensor& pos, const c10::optional<Tensor>& w) {
+  TORCH_CHECK(in.is_cuda() && in.scalar_type() == at::kBFloat16 && in.dim() == 2 && in.is_contiguous() && in.size(1) % 8 == 0, "moe_combine_rows: contiguous bf16 [n, h], h % 8 == 0");
+  TORCH_CHECK(pos.scalar_type() == at::kLong && pos.dim() == 2 && pos.is_contiguous(), "moe_combine_rows: int64 [T, k] positions");
+  c10::cuda::CUDAGuard g(in.device());
+  auto out = at::empty({pos.size(0), in.size(1)}, in.options());
+  mb200_moe_combine_rows(in.data_ptr(), out.data_ptr(), pos.data_ptr<int64_t>(), w.has_value() ? w->data_ptr<float>() : nullptr, pos.size(0), (int)pos.size(1), (int)in.size(1),
+                         cur_stream());
+  return out;
+}
+// logits fp32 [T, E] -> (probs [T,k] fp32, ids [T,k] int64, routing_map [T,E] bool, tokens_per_expert [E] int32)
+std::vector<Tensor> moe_topk_router(const Tensor& logits, const c10::optional<Tensor>& expert_bias, int64_t topk, int64_t score_fn, bool renormalize, double scaling) {
+  TORCH_CHECK(logits.is_cuda() && logits.scalar_type() == at::kFloat && logits.dim() == 2 && logits.is_contiguous(), "moe_topk_router: contiguous fp32 [T, E] logits");
+  c10::cuda::CUDAGuard g(logits.device());
+  const int T = (int)logits.size(0), E = (int)logits.size(1);
+  auto probs = at::empty({T, topk}, logits.options());
+  auto ids = at::empty({T, topk}, logits.options().dtype(at::kLong));
+  auto map = at::zeros({T, E}, logits.options().dtype(at::kBool));
+  auto tpe = at::zeros({E}, logits.options().dtype(at::kInt));
+  const int rc = mb200_moe_topk_router(logits.data_ptr<float>(), expert_bias.has_value() ? expert_bias->data_ptr<float>() : nullptr, T, E, (int)topk, (int)score_fn,
+                                       renormalize ? 1 : 0, (float)scaling, probs.data_ptr<float>(), ids.data_ptr<int64_t>(), reinterpret_cast<uint8_t*>(map.data_ptr()),
+                                       tpe.data_ptr<int>(), cur_stream());
+  TORCH_CHECK(rc == 0, "moe_topk_router failed with code ", rc);
+  return {probs, ids, map, tpe};
+}
+#endif
+
 // Attention backward through the cuDNN library (consumes OUR forward's out + log-sum-exp); [s, b, h, d] tensors in and out.
 std::vector<Tensor> attn_bwd_cudnn(const Tensor& go, const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& o, const Tensor& lse, bool causal, double scale) {
   c10::cuda::CUDAGuard g(q.device());
@@ -450,6 +487,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 #endif
   m.def("attn_bwd_cudnn", &attn_bwd_cudnn);
   m.def("share_storage", &share_storage);
+#ifdef MB200_HAVE_MOE_KERNELS
+  m.def("moe_gather_rows", &moe_gather_rows);
+  m.def("moe_combine_rows", &moe_combine_rows);
+  m.def("moe_topk_router", &moe_topk_router);
+#endif
 #ifdef MB200_HAVE_GEMM_FP8_SM100
   m.def("gemm_fp8_nt", &gemm_fp8_nt);
 #endif

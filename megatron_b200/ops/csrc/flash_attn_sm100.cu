@@ -44,6 +44,20 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// 2^x on the FMA/ALU pipes (degree-3 polynomial after magic-number range reduction; rel. error ~6e-4, below bf16 resolution of P).
+// The MUFU unit does 16 ex2/clk/SM while a 128x64 S tile needs 8192 of them — as long as the two MMAs of that tile.  Evaluating a
+// quarter of the exponentials here takes that work off the critical unit (same idea as FlashAttention-4's software exp2).
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -125.f);
+  const float r = x + 12582912.f;                 // 1.5 * 2^23: integer part of x lands in the low mantissa bits (round to nearest)
+  const float n = r - 12582912.f;
+  const float f = x - n;                          // [-0.5, 0.5]
+  float p = fmaf(f, 0.0555041f, 0.2402265f);
+  p = fmaf(p, f, 0.6931472f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+
 template <int D>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v, const FaParams p) {
@@ -221,9 +235,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           if (kv0 + 32 + c > limit) r1[c] = 0xff800000u;
         }
       }
-      float mx = -INFINITY;
+      // 8 independent max chains (a single 64-long dependent chain is ~300 cycles of pure latency per block)
+      float mxs[8];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[c]), __uint_as_float(r1[c])));
+      for (int c = 0; c < 8; ++c) mxs[c] = fmaxf(__uint_as_float(r0[c]), __uint_as_float(r1[c]));
+#pragma unroll
+      for (int c = 8; c < 32; ++c) mxs[c & 7] = fmaxf(mxs[c & 7], fmaxf(__uint_as_float(r0[c]), __uint_as_float(r1[c])));
+      const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])), fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
       const float mx_scaled = mx * p.scale_log2;
       float alpha = 1.f;
       if (mx_scaled > m_ref + FA_RESCALE_THRESHOLD) {
@@ -233,24 +251,27 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       }
       const bool rescale = __any_sync(0xffffffffu, alpha != 1.f) && j > 0;
       // p = 2^(s*scale - m_ref); written as bf16 into the 128B-swizzled K-major tile the PV MMA reads as operand A
-      float sum = 0.f;
+      float sums[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         uint32_t pk[4];
+        float su = 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int c = u * 8 + e * 2;
           const float a0 = __uint_as_float(c < 32 ? r0[c] : r1[c - 32]);
           const float a1 = __uint_as_float(c + 1 < 32 ? r0[c + 1] : r1[c + 1 - 32]);
-          const float p0 = fast_exp2(fmaf(a0, p.scale_log2, -m_ref));
-          const float p1 = fast_exp2(fmaf(a1, p.scale_log2, -m_ref));
-          sum += p0 + p1;
+          const float x0 = fmaf(a0, p.scale_log2, -m_ref), x1 = fmaf(a1, p.scale_log2, -m_ref);
+          const float p0 = fast_exp2(x0);
+          const float p1 = (e & 1) ? poly_exp2(x1) : fast_exp2(x1);   // every 4th exponential on the FMA pipe
+          su += p0 + p1;
           __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
           pk[e] = *reinterpret_cast<uint32_t*>(&hb);
         }
+        sums[u] = su;
         *reinterpret_cast<uint4*>(p_row + ((u ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
-      l += sum;
+      l += ((sums[0] + sums[1]) + (sums[2] + sums[3])) + ((sums[4] + sums[5]) + (sums[6] + sums[7]));
       if (rescale) {
         // PV(t, j-1) is complete (see header) → O_t is stable: scale this row's accumulator in place
 #pragma unroll 1

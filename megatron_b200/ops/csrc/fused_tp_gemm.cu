@@ -141,29 +141,34 @@ fused_tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       // ---- AG: push my shard chunk by chunk -------------------------------------------------------------
       const size_t row_bytes = (size_t)g.K * 2;
       const size_t chunk_vec = (size_t)CHUNK_ROWS * row_bytes / 16;
-      for (int c = 0; c < C; ++c) {
-        const uint4* src = reinterpret_cast<const uint4*>(p.ag_src) + (size_t)c * chunk_vec;
-        const size_t dst_off = ((size_t)p.rank * C + c) * chunk_vec;
+      // Work item = (chunk c, slice s): 8 rows of a 256-row chunk.  Every WARP walks its own items and fences its own stores, so
+      // the (multi-microsecond) system fences of different warps overlap with other warps' traffic; the warp that completes a
+      // chunk (32 slices) publishes the chunk flag on every rank.
+      constexpr int SLICES = 32;
+      const size_t slice_vec = chunk_vec / SLICES;
+      const int n_warps = nctas * (NUM_THREADS / 32), gwarp = cta * (NUM_THREADS / 32) + warp;
+      for (int item = gwarp; item < C * SLICES; item += n_warps) {
+        const int c = item / SLICES, sl = item % SLICES;
+        const size_t off = (size_t)c * chunk_vec + (size_t)sl * slice_vec;
+        const uint4* src = reinterpret_cast<const uint4*>(p.ag_src) + off;
+        const size_t dst_off = (size_t)p.rank * C * chunk_vec + off;
         if (p.ag_dst_mc != nullptr) {
-          uint4* dst = reinterpret_cast<uint4*>(p.ag_dst_mc) + dst_off;
-          push_multicast<8>(dst, src, chunk_vec, (size_t)cta * blockDim.x + threadIdx.x, (size_t)nctas * blockDim.x);
+          push_multicast<8>(reinterpret_cast<uint4*>(p.ag_dst_mc) + dst_off, src, slice_vec, (size_t)lane, 32);
         } else {
-          for (size_t i = (size_t)cta * blockDim.x + threadIdx.x; i < chunk_vec; i += (size_t)nctas * blockDim.x) {
+          for (size_t i = lane; i < slice_vec; i += 32) {
             const uint4 v = src[i];
             for (int d = 0; d < p.world; ++d) reinterpret_cast<uint4*>(p.ag_dst_peer[(p.rank + d) % p.world])[dst_off + i] = v;
           }
         }
         __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x < 32) {
-          uint32_t last = 0;
-          if (lane == 0) last = (atomicAdd(&p.counters[c], 1u) == (uint32_t)nctas - 1) ? 1u : 0u;
-          last = __shfl_sync(0xffffffffu, last, 0);
-          if (last) {
-            if (lane == 0) p.counters[c] = 0;
-            __threadfence_system();
-            if (lane < p.world) st_release_sys_u32(p.flags_peer[lane] + AG_OFF + p.rank * MAX_CHUNKS + c, p.epoch);
-          }
+        __syncwarp();
+        uint32_t last = 0;
+        if (lane == 0) last = (atomicAdd(&p.counters[c], 1u) == (uint32_t)SLICES - 1) ? 1u : 0u;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+          if (lane == 0) p.counters[c] = 0;
+          __threadfence();
+          if (lane < p.world) st_release_sys_u32(p.flags_peer[lane] + AG_OFF + p.rank * MAX_CHUNKS + c, p.epoch);
         }
       }
     } else {
@@ -171,27 +176,31 @@ fused_tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       const size_t row_vec = (size_t)g.N * 2 / 16;
       const size_t chunk_vec = (size_t)CHUNK_ROWS * row_vec;
       if (p.xag_vec != 0) {
-        // piggy-back all-gather while the first output chunks are still being computed
-        const uint4* src = reinterpret_cast<const uint4*>(p.xag_src);
-        const size_t dst_off = (size_t)p.rank * p.xag_vec;
-        if (p.xag_dst_mc != nullptr) {
-          uint4* dst = reinterpret_cast<uint4*>(p.xag_dst_mc) + dst_off;
-          push_multicast<8>(dst, src, p.xag_vec, (size_t)cta * blockDim.x + threadIdx.x, (size_t)nctas * blockDim.x);
-        } else {
-          for (size_t i = (size_t)cta * blockDim.x + threadIdx.x; i < p.xag_vec; i += (size_t)nctas * blockDim.x) {
-            const uint4 v = src[i];
-            for (int d = 0; d < p.world; ++d) reinterpret_cast<uint4*>(p.xag_dst_peer[(p.rank + d) % p.world])[dst_off + i] = v;
+        // piggy-back all-gather (the wgrad operand) while the first output chunks are still being computed; warp-granular items as in AG mode
+        constexpr size_t XSLICE = 4096;   // 64 KiB
+        const int n_items = (int)((p.xag_vec + XSLICE - 1) / XSLICE);
+        const int n_warps = nctas * (NUM_THREADS / 32), gwarp = cta * (NUM_THREADS / 32) + warp;
+        const uint4* src0 = reinterpret_cast<const uint4*>(p.xag_src);
+        const size_t base = (size_t)p.rank * p.xag_vec;
+        for (int item = gwarp; item < n_items; item += n_warps) {
+          const size_t off = (size_t)item * XSLICE;
+          const size_t n = min(XSLICE, p.xag_vec - off);
+          if (p.xag_dst_mc != nullptr) {
+            push_multicast<8>(reinterpret_cast<uint4*>(p.xag_dst_mc) + base + off, src0 + off, n, (size_t)lane, 32);
+          } else {
+            for (size_t i = lane; i < n; i += 32) {
+              const uint4 v = src0[off + i];
+              for (int d = 0; d < p.world; ++d) reinterpret_cast<uint4*>(p.xag_dst_peer[(p.rank + d) % p.world])[base + off + i] = v;
+            }
           }
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x < 32) {
+          __threadfence_system();
+          __syncwarp();
           uint32_t last = 0;
-          if (lane == 0) last = (atomicAdd(&p.counters[XAG_COUNTER], 1u) == (uint32_t)nctas - 1) ? 1u : 0u;
+          if (lane == 0) last = (atomicAdd(&p.counters[XAG_COUNTER], 1u) == (uint32_t)n_items - 1) ? 1u : 0u;
           last = __shfl_sync(0xffffffffu, last, 0);
           if (last) {
             if (lane == 0) p.counters[XAG_COUNTER] = 0;
-            __threadfence_system();
+            __threadfence();
             if (lane < p.world) st_release_sys_u32(p.flags_peer[lane] + XAG_OFF + p.rank, p.epoch);
           }
         }
@@ -351,7 +360,7 @@ fused_tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       if (p.mode == 1) {
         // publish: this warp's part of tile (m_blk, n_blk) is in Y.  The last of tiles_n * 16 warp-parts of the
         // 256-row block tells the owner rank that its chunk is complete on this rank.
-        __threadfence_system();
+        __threadfence();
         __syncwarp();
         if (lane == 0) {
           const uint32_t total = (uint32_t)tiles_n * 2u * EPI_WARPS;

@@ -44,5 +44,9 @@ void mb200_batched_copy(const void* tasks_dev, const void* chunk_prefix_dev, int
 int mb200_grouped_gemm_bf16(const void* a, const void* b, void* c, const int* offsets, int E, int dim_n, int dim_k, int mode, int accumulate, int c_dtype,
                             void* maps_dev, cudaStream_t s);
 int mb200_gemm_fp8_nt(const void* A, const void* B, void* C, int M, int N, int K, int a_fmt, int b_fmt, float alpha, const float* alpha_dev, cudaStream_t s);
+void mb200_moe_gather_rows(const void* in, void* out, const int64_t* src, const float* scale, int64_t n_out, int hidden, cudaStream_t s);
+void mb200_moe_combine_rows(const void* in, void* out, const int64_t* pos, const float* w, int64_t n_tokens, int topk, int hidden, cudaStream_t s);
+int mb200_moe_topk_router(const float* logits, const float* expert_bias, int T, int E, int topk, int score_fn, int renormalize, float scaling, float* probs, int64_t* ids,
+                          uint8_t* routing_map, int* tokens_per_expert, cudaStream_t s);
 int mb200_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int layout, int accumulate, int c_dtype, cudaStream_t s);
 }

@@ -18,6 +18,7 @@ def test_graphed_module_matches_eager():
         x = torch.randn(64, 256, device="cuda", requires_grad=True)
         xr = x.detach().clone().requires_grad_(True)
         y = net(x)
+        assert net.cudagraph_manager.fallback_reason is None, net.cudagraph_manager.fallback_reason
         yr = ref(xr)
         gy = torch.randn_like(yr)
         y.backward(gy)
