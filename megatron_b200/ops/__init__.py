@@ -464,3 +464,101 @@ def fused_adam(params32, grads, exp_avgs, exp_avg_sqs, lowp_params, *, lr, beta1
     gsv = float(grad_scale) if grad_scale is not None else 1.0
     for p, g, m, v, lp in zip(params32, grads, exp_avgs, exp_avg_sqs, lowp_params):
         ref.adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, adamw, gsv, lp)
+
+
+# =============================================================================
+# MoE: permutation / combination / routing (csrc/moe_kernels.cu)
+# =============================================================================
+
+
+def _moe_native(t: torch.Tensor) -> bool:
+    return _use_cuda(t) and hasattr(ext(), "moe_gather_rows") and t.dtype == torch.bfloat16 and t.dim() == 2 and t.shape[1] % 8 == 0
+
+
+class _GatherRowsFn(torch.autograd.Function):
+    """out[i] = scale[i] * x[idx[i]];  backward scatters (index_add) the rows back."""
+
+    @staticmethod
+    def forward(ctx, x, idx, scale):
+        ctx.save_for_backward(x, idx, scale if scale is not None else x.new_empty(0))
+        ctx.has_scale = scale is not None
+        _count()
+        return ext().moe_gather_rows(x.contiguous(), idx.contiguous(), scale.float().contiguous() if scale is not None else None)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, idx, scale = ctx.saved_tensors
+        g = g.contiguous()
+        gs = None
+        if ctx.has_scale:
+            gs = (g.float() * x.index_select(0, idx).float()).sum(-1).to(scale.dtype)
+            g = g * scale.unsqueeze(-1).to(g.dtype)
+        gx = torch.zeros_like(x).index_add_(0, idx, g)
+        return gx, None, gs
+
+
+class _CombineRowsFn(torch.autograd.Function):
+    """out[t] = Σ_k w[t,k] * x[pos[t,k]]  (pos < 0 skipped); deterministic fp32 accumulation, no atomics."""
+
+    @staticmethod
+    def forward(ctx, x, pos, w):
+        ctx.save_for_backward(x, pos, w if w is not None else x.new_empty(0))
+        ctx.has_w = w is not None
+        _count()
+        return ext().moe_combine_rows(x.contiguous(), pos.contiguous(), w.float().contiguous() if w is not None else None)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, pos, w = ctx.saved_tensors
+        g = g.contiguous()
+        T, K = pos.shape
+        valid = pos >= 0
+        rows = pos[valid]                                    # permuted rows that received a contribution
+        tok = torch.arange(T, device=pos.device).unsqueeze(1).expand(T, K)[valid]
+        gx = torch.zeros_like(x)
+        if ctx.has_w:
+            wv = w[valid].float()
+            gx[rows] = ext().moe_gather_rows(g, tok.contiguous(), wv.contiguous())
+            gw = torch.zeros_like(w, dtype=torch.float32)
+            gw[valid] = (x.index_select(0, rows).float() * g.index_select(0, tok).float()).sum(-1)
+            return gx, None, gw.to(w.dtype)
+        gx[rows] = ext().moe_gather_rows(g, tok.contiguous(), None)
+        return gx, None, None
+
+
+def moe_gather_rows(x: torch.Tensor, idx: torch.Tensor, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if _moe_native(x):
+        return _GatherRowsFn.apply(x, idx, scale)
+    out = x.index_select(0, idx)
+    return out * scale.unsqueeze(-1).to(out.dtype) if scale is not None else out
+
+
+def moe_combine_rows(x: torch.Tensor, pos: torch.Tensor, w: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [M, h] permuted rows; pos [T, k] int64 row of x feeding token t (or -1); w [T, k] weights."""
+    if _moe_native(x):
+        return _CombineRowsFn.apply(x, pos, w)
+    g = x.index_select(0, pos.clamp(min=0).reshape(-1)).view(*pos.shape, x.shape[1]).float()
+    m = (pos >= 0).unsqueeze(-1).float()
+    if w is not None:
+        m = m * w.unsqueeze(-1).float()
+    return (g * m).sum(1).to(x.dtype)
+
+
+def moe_topk_router(logits: torch.Tensor, topk: int, score_function: str = "softmax", pre_softmax: bool = False, expert_bias: Optional[torch.Tensor] = None,
+                    scaling_factor: Optional[float] = None):
+    """Selection part of the router in ONE kernel → (ids [T,k], routing_map [T,E] bool, tokens_per_expert [E] int32, probs [T,k] fp32).
+    The returned probs carry no autograd graph; callers that train the router re-derive them from the logits at ``ids``."""
+    fn = {"softmax": 0 if pre_softmax else 2, "sigmoid": 1}[score_function]
+    if _use_cuda(logits) and hasattr(ext(), "moe_topk_router") and logits.shape[1] <= 256 and topk <= 8:
+        _count()
+        probs, ids, rmap, tpe = ext().moe_topk_router(logits.detach().float().contiguous(), None if expert_bias is None else expert_bias.float().contiguous(), topk, fn,
+                                                      fn == 1, float(scaling_factor or 1.0))
+        return ids, rmap, tpe, probs
+    lf = logits.detach().float()
+    scores = torch.softmax(lf, -1) if fn == 0 else (torch.sigmoid(lf) if fn == 1 else lf)
+    key = scores + expert_bias.float() if expert_bias is not None else scores
+    ids = torch.topk(key, topk, dim=1).indices
+    vals = scores.gather(1, ids)
+    probs = torch.softmax(vals, -1) if fn == 2 else (vals / (vals.sum(-1, keepdim=True) + 1e-20) if (fn == 1 and topk > 1) else vals)
+    rmap = torch.zeros_like(lf, dtype=torch.bool).scatter(1, ids, True)
+    return ids, rmap, rmap.sum(0).int(), probs * float(scaling_factor or 1.0)
