@@ -258,7 +258,7 @@ class MoEFlexTokenDispatcher(MoEAlltoAllTokenDispatcher):
     def token_dispatch(self, tokens, probs):
         if self._fused is None:
             return super().token_dispatch(tokens, probs)
-        self._handle, out, out_probs, self.tokens_per_expert = self._fused.moe_dispatch(tokens, self.routing_map, probs, self.num_local_experts)
+        self._handle, out, out_probs, self.tokens_per_expert = self._fused.moe_dispatch(tokens, self.routing_map, probs, self.num_local_experts, topk=self.config.moe_router_topk)
         return out, out_probs
 
     def dispatch_postprocess(self, tokens, probs):

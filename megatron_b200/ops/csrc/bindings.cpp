@@ -412,6 +412,31 @@ Tensor moe_combine_rows(const Tensor& in, const Tensor& pos, const c10::optional
                          cur_stream());
   return out;
 }
+// rows of `in` (any dtype, row size multiple of 16 bytes) -> slot dst_slot[i] of peer dst_rank[i]'s buffer at byte offset dst_off
+void moe_push_rows(const Tensor& in, const Tensor& src_row, const Tensor& dst_rank, const Tensor& dst_slot, const std::vector<int64_t>& peer_ptrs, int64_t dst_off_bytes) {
+  TORCH_CHECK(in.is_cuda() && in.dim() == 2 && in.is_contiguous(), "moe_push_rows: contiguous 2-D CUDA tensor");
+  const int row_bytes = (int)(in.size(1) * in.element_size());
+  TORCH_CHECK(row_bytes % 16 == 0 && dst_off_bytes % 16 == 0, "moe_push_rows: 16-byte rows");
+  TORCH_CHECK(src_row.scalar_type() == at::kLong && dst_slot.scalar_type() == at::kLong && dst_rank.scalar_type() == at::kInt, "moe_push_rows: index dtypes");
+  c10::cuda::CUDAGuard g(in.device());
+  mb200_moe_push_rows(in.data_ptr(), src_row.data_ptr<int64_t>(), dst_rank.data_ptr<int>(), dst_slot.data_ptr<int64_t>(), peer_ptrs.data(), (int)peer_ptrs.size(),
+                      (size_t)dst_off_bytes, src_row.numel(), row_bytes, cur_stream());
+}
+// out[t] = sum_k w[t,k] * peer[rank[t,k]].buf[slot[t,k]] (bf16 rows, fp32 accumulate); raw=true: k = 1, bitwise copy of any dtype
+Tensor moe_pull_rows(const Tensor& rank, const Tensor& slot, const c10::optional<Tensor>& w, const std::vector<int64_t>& peer_ptrs, int64_t src_off_bytes, int64_t row_elems,
+                     at::ScalarType dtype, bool raw) {
+  TORCH_CHECK(rank.is_cuda() && rank.scalar_type() == at::kInt && slot.scalar_type() == at::kLong && rank.is_contiguous() && slot.is_contiguous(), "moe_pull_rows: index dtypes");
+  c10::cuda::CUDAGuard g(rank.device());
+  const int64_t n_out = slot.size(0);
+  const int topk = slot.dim() == 2 ? (int)slot.size(1) : 1;
+  auto out = at::empty({n_out, row_elems}, rank.options().dtype(dtype));
+  const int row_bytes = (int)(row_elems * out.element_size());
+  TORCH_CHECK(row_bytes % 16 == 0 && src_off_bytes % 16 == 0, "moe_pull_rows: 16-byte rows");
+  TORCH_CHECK(raw || dtype == at::kBFloat16, "moe_pull_rows: weighted combine needs bf16 rows");
+  mb200_moe_pull_rows(out.data_ptr(), rank.data_ptr<int>(), slot.data_ptr<int64_t>(), w.has_value() ? w->data_ptr<float>() : nullptr, peer_ptrs.data(), (int)peer_ptrs.size(),
+                      (size_t)src_off_bytes, n_out, topk, row_bytes, raw ? 1 : 0, cur_stream());
+  return out;
+}
 // logits fp32 [T, E] -> (probs [T,k] fp32, ids [T,k] int64, routing_map [T,E] bool, tokens_per_expert [E] int32)
 std::vector<Tensor> moe_topk_router(const Tensor& logits, const c10::optional<Tensor>& expert_bias, int64_t topk, int64_t score_fn, bool renormalize, double scaling) {
   TORCH_CHECK(logits.is_cuda() && logits.scalar_type() == at::kFloat && logits.dim() == 2 && logits.is_contiguous(), "moe_topk_router: contiguous fp32 [T, E] logits");
@@ -491,6 +516,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("moe_gather_rows", &moe_gather_rows);
   m.def("moe_combine_rows", &moe_combine_rows);
   m.def("moe_topk_router", &moe_topk_router);
+  m.def("moe_push_rows", &moe_push_rows);
+  m.def("moe_pull_rows", &moe_pull_rows);
 #endif
 #ifdef MB200_HAVE_GEMM_FP8_SM100
   m.def("gemm_fp8_nt", &gemm_fp8_nt);

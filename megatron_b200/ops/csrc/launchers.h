@@ -48,5 +48,9 @@ void mb200_moe_gather_rows(const void* in, void* out, const int64_t* src, const 
 void mb200_moe_combine_rows(const void* in, void* out, const int64_t* pos, const float* w, int64_t n_tokens, int topk, int hidden, cudaStream_t s);
 int mb200_moe_topk_router(const float* logits, const float* expert_bias, int T, int E, int topk, int score_fn, int renormalize, float scaling, float* probs, int64_t* ids,
                           uint8_t* routing_map, int* tokens_per_expert, cudaStream_t s);
+void mb200_moe_push_rows(const void* in, const int64_t* src_row, const int32_t* dst_rank, const int64_t* dst_slot, const int64_t* peer_ptrs, int world, size_t dst_off_bytes,
+                         int64_t n_pairs, int row_bytes, cudaStream_t s);
+void mb200_moe_pull_rows(void* out, const int32_t* rank, const int64_t* slot, const float* w, const int64_t* peer_ptrs, int world, size_t src_off_bytes, int64_t n_out,
+                         int topk, int row_bytes, int raw, cudaStream_t s);
 int mb200_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int layout, int accumulate, int c_dtype, cudaStream_t s);
 }

@@ -172,3 +172,76 @@ extern "C" int mb200_moe_topk_router(const float* logits, const float* expert_bi
                                                                                                     ids, routing_map, tokens_per_expert);
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
+
+// ---- expert-parallel dispatch / combine over NVLink peer memory -------------------------------------------------------------------
+// (replaces DeepEP / HybridEP / NCCL-EP + the permute kernels around them, SURVEY X16-X18: ONE kernel moves every token row
+//  straight into the slot of the destination rank's expert-grouped buffer, so the all-to-all and the permutation are the same pass)
+namespace mb200 {
+
+struct PeerPtrs {
+  void* p[8];
+};
+
+// push: row src_row[i] of `in` → peer dst_rank[i], row dst_slot[i] of its receive buffer (16-byte vectors, one CTA per pair)
+__global__ void __launch_bounds__(256) moe_push_rows_kernel(const uint4* __restrict__ in, const int64_t* __restrict__ src_row, const int32_t* __restrict__ dst_rank,
+                                                            const int64_t* __restrict__ dst_slot, PeerPtrs peers, size_t dst_off_vecs, int row_vecs) {
+  const int64_t i = blockIdx.x;
+  const uint4* ip = in + src_row[i] * row_vecs;
+  uint4* op = reinterpret_cast<uint4*>(peers.p[dst_rank[i]]) + dst_off_vecs + dst_slot[i] * row_vecs;
+  for (int v = threadIdx.x; v < row_vecs; v += blockDim.x) op[v] = __ldg(ip + v);
+}
+
+// pull: out[t] = Σ_k w[t,k] · peer[rank[t,k]].buf[slot[t,k]]   (slot < 0 skipped; fp32 accumulation; bf16 rows or raw 16-byte copy for k = 1)
+template <bool RAW>
+__global__ void __launch_bounds__(256) moe_pull_rows_kernel(uint4* __restrict__ out, const int32_t* __restrict__ rank, const int64_t* __restrict__ slot,
+                                                            const float* __restrict__ w, PeerPtrs peers, size_t src_off_vecs, int topk, int row_vecs) {
+  const int64_t t = blockIdx.x;
+  for (int v = threadIdx.x; v < row_vecs; v += blockDim.x) {
+    if (RAW) {
+      const int64_t s = slot[t];
+      out[t * row_vecs + v] = s < 0 ? make_uint4(0, 0, 0, 0) : reinterpret_cast<const uint4*>(peers.p[rank[t]])[src_off_vecs + s * row_vecs + v];
+      continue;
+    }
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int j = 0; j < topk; ++j) {
+      const int64_t s = slot[t * topk + j];
+      if (s < 0) continue;
+      const float wj = w != nullptr ? w[t * topk + j] : 1.f;
+      const uint4 x = reinterpret_cast<const uint4*>(peers.p[rank[t * topk + j]])[src_off_vecs + s * row_vecs + v];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&x);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(h[k]);
+        acc[2 * k] += wj * f.x;
+        acc[2 * k + 1] += wj * f.y;
+      }
+    }
+    uint4 o;
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) oh[k] = __floats2bfloat162_rn(acc[2 * k], acc[2 * k + 1]);
+    out[t * row_vecs + v] = o;
+  }
+}
+
+}  // namespace mb200
+
+extern "C" void mb200_moe_push_rows(const void* in, const int64_t* src_row, const int32_t* dst_rank, const int64_t* dst_slot, const int64_t* peer_ptrs, int world,
+                                    size_t dst_off_bytes, int64_t n_pairs, int row_bytes, cudaStream_t s) {
+  if (n_pairs == 0) return;
+  mb200::PeerPtrs pp;
+  for (int i = 0; i < 8; ++i) pp.p[i] = i < world ? reinterpret_cast<void*>(peer_ptrs[i]) : nullptr;
+  mb200::moe_push_rows_kernel<<<(unsigned)n_pairs, 256, 0, s>>>(reinterpret_cast<const uint4*>(in), src_row, dst_rank, dst_slot, pp, dst_off_bytes / 16, row_bytes / 16);
+}
+extern "C" void mb200_moe_pull_rows(void* out, const int32_t* rank, const int64_t* slot, const float* w, const int64_t* peer_ptrs, int world, size_t src_off_bytes,
+                                    int64_t n_out, int topk, int row_bytes, int raw, cudaStream_t s) {
+  if (n_out == 0) return;
+  mb200::PeerPtrs pp;
+  for (int i = 0; i < 8; ++i) pp.p[i] = i < world ? reinterpret_cast<void*>(peer_ptrs[i]) : nullptr;
+  if (raw)
+    mb200::moe_pull_rows_kernel<true><<<(unsigned)n_out, 256, 0, s>>>(reinterpret_cast<uint4*>(out), rank, slot, w, pp, src_off_bytes / 16, 1, row_bytes / 16);
+  else
+    mb200::moe_pull_rows_kernel<false><<<(unsigned)n_out, 256, 0, s>>>(reinterpret_cast<uint4*>(out), rank, slot, w, pp, src_off_bytes / 16, topk, row_bytes / 16);
+}

@@ -46,7 +46,10 @@ class _Handle:
             self.event = None
 
 
-class NVLinkBackend:
+from .nvlink_moe import NVLinkMoEMixin
+
+
+class NVLinkBackend(NVLinkMoEMixin):
     SLOT_MAIN, SLOT_SIDE, SLOT_DDP = 0, 1, 2
 
     def __init__(self, group, workspace_bytes: Optional[int] = None, heap_bytes: int = 0, use_multicast: Optional[bool] = None):
