@@ -205,37 +205,41 @@ fused_tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           }
         }
       }
-      for (int c = 0; c < C; ++c) {
-        if (threadIdx.x < 32) {
+      // Work item = (chunk c of MY shard, slice of 8 rows).  Warps walk their own items in chunk order: a warp waits only for the chunk
+      // its next slice belongs to, and ~200 warps keep ~1.5 MB of in-switch reductions in flight (the NVLink round trip is microseconds).
+      {
+        constexpr int SLICES = 32;
+        const size_t slice_vec = chunk_vec / SLICES;
+        const int n_warps = nctas * (NUM_THREADS / 32), gwarp = cta * (NUM_THREADS / 32) + warp;
+        for (int item = gwarp; item < C * SLICES; item += n_warps) {
+          const int c = item / SLICES, sl = item % SLICES;
           if (lane < p.world) {
             const uint32_t* f = p.flags_peer[p.rank] + RS_OFF + c * MAX_TP + lane;
             while ((int32_t)(ld_acquire_sys_u32(f) - p.epoch) < 0) {
             }
           }
           __syncwarp();
-        }
-        __syncthreads();
-        const size_t src_off = ((size_t)p.rank * C + c) * chunk_vec;
-        uint4* out = reinterpret_cast<uint4*>(p.rs_out) + (size_t)c * chunk_vec;
-        if (p.rs_src_mc != nullptr) {
-          pull_reduce_multicast<16>(out, reinterpret_cast<const uint4*>(p.rs_src_mc) + src_off, chunk_vec, (size_t)cta * blockDim.x + threadIdx.x,
-                                    (size_t)nctas * blockDim.x);
-        } else {
-          for (size_t i = (size_t)cta * blockDim.x + threadIdx.x; i < chunk_vec; i += (size_t)nctas * blockDim.x) {
-            float acc[8];
+          const size_t src_off = ((size_t)p.rank * C + c) * chunk_vec + (size_t)sl * slice_vec;
+          uint4* out = reinterpret_cast<uint4*>(p.rs_out) + (size_t)c * chunk_vec + (size_t)sl * slice_vec;
+          if (p.rs_src_mc != nullptr) {
+            pull_reduce_multicast<16>(out, reinterpret_cast<const uint4*>(p.rs_src_mc) + src_off, slice_vec, (size_t)lane, 32);
+          } else {
+            for (size_t i = lane; i < slice_vec; i += 32) {
+              float acc[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-            for (int d = 0; d < p.world; ++d) {
-              const uint4 v = reinterpret_cast<const uint4*>(p.rs_src_peer[(p.rank + d) % p.world])[src_off + i];
-              const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&v);
+              for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+              for (int d = 0; d < p.world; ++d) {
+                const uint4 v = reinterpret_cast<const uint4*>(p.rs_src_peer[(p.rank + d) % p.world])[src_off + i];
+                const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&v);
 #pragma unroll
-              for (int k = 0; k < 8; ++k) acc[k] += __bfloat162float(h[k]);
+                for (int k = 0; k < 8; ++k) acc[k] += __bfloat162float(h[k]);
+              }
+              uint4 o;
+              __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) ob[k] = __floats2bfloat162_rn(acc[2 * k], acc[2 * k + 1]);
+              out[i] = o;
             }
-            uint4 o;
-            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) ob[k] = __floats2bfloat162_rn(acc[2 * k], acc[2 * k + 1]);
-            out[i] = o;
           }
         }
       }
