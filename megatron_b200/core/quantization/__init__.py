@@ -1,0 +1,70 @@
+"""Per-layer quantisation recipes selected by glob patterns from a YAML file (reference ``core/quantization/`` 271 LoC).
+
+```yaml
+configs:
+  fp8_hybrid:  {recipe: tensorwise, fp8_format: hybrid}
+  bf16:        {recipe: none}
+matchers:
+  - {pattern: "decoder.layers.0.*", config: bf16}       # first layer stays bf16
+  - {pattern: "*.linear_fc1",       config: fp8_hybrid}
+  - {pattern: "*",                  config: bf16}
+```
+The first matching pattern wins.  ``RecipeConfig.match(module_path)`` returns the ``QuantizationConfig`` the layer builder passes to
+``core.fp8_utils.fp8_linear``."""
+from __future__ import annotations
+
+import fnmatch
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+
+@dataclass
+class QuantizationConfig:
+    name: str = "bf16"
+    recipe: str = "none"          # none | tensorwise | delayed
+    fp8_format: str = "hybrid"    # hybrid (e4m3 fwd / e5m2 grads) | e4m3
+    extra: Dict = field(default_factory=dict)
+
+    @property
+    def enabled(self) -> bool:
+        return self.recipe != "none"
+
+
+@dataclass
+class Matcher:
+    pattern: str
+    config: str
+
+
+class RecipeConfig:
+    def __init__(self, configs: Dict[str, QuantizationConfig], matchers: List[Matcher]):
+        self.configs, self.matchers = configs, matchers
+
+    @classmethod
+    def from_dict(cls, d: dict) -> "RecipeConfig":
+        cfgs = {}
+        for name, body in (d.get("configs") or {}).items():
+            body = dict(body or {})
+            cfgs[name] = QuantizationConfig(name=name, recipe=body.pop("recipe", "none"), fp8_format=body.pop("fp8_format", "hybrid"), extra=body)
+        ms = [Matcher(m["pattern"], m["config"]) for m in d.get("matchers") or []]
+        for m in ms:
+            if m.config not in cfgs:
+                raise KeyError(f"matcher '{m.pattern}' refers to unknown config '{m.config}'")
+        return cls(cfgs, ms)
+
+    @classmethod
+    def from_yaml_file(cls, path: str) -> "RecipeConfig":
+        import yaml
+
+        with open(path) as f:
+            return cls.from_dict(yaml.safe_load(f))
+
+    def match(self, module_path: str) -> Optional[QuantizationConfig]:
+        for m in self.matchers:
+            if fnmatch.fnmatchcase(module_path, m.pattern):
+                return self.configs[m.config]
+        return None
+
+
+def load_quantization_recipe(path: str) -> RecipeConfig:
+    return RecipeConfig.from_yaml_file(path)

@@ -293,6 +293,14 @@ def _cudnn_lse_ndim() -> int:
 _ATTN_IMPL = os.environ.get("MEGATRON_B200_ATTN", "auto")  # auto | native | library
 
 
+# what "auto" means on this build: the faster MEASURED forward at the Llama-3 8B shape (profiles/r1_attention.md)
+_ATTN_AUTO_RESOLVES_TO = "library"
+
+
+def _resolved_attn_impl() -> str:
+    return _ATTN_AUTO_RESOLVES_TO if _ATTN_IMPL == "auto" else _ATTN_IMPL
+
+
 def set_attention_impl(impl: str) -> None:
     global _ATTN_IMPL
     assert impl in ("auto", "native", "library")
@@ -300,7 +308,7 @@ def set_attention_impl(impl: str) -> None:
 
 
 def _native_attention_ok(q, k, v, causal, window) -> bool:
-    if _ATTN_IMPL == "library" or window is not None or not hasattr(ext(), "flash_attn_fwd"):
+    if _resolved_attn_impl() == "library" or window is not None or not hasattr(ext(), "flash_attn_fwd"):
         return False
     if q.dtype != torch.bfloat16 or q.shape[-1] not in (64, 128) or k.shape[-1] != q.shape[-1] or v.shape[-1] != q.shape[-1]:
         return False

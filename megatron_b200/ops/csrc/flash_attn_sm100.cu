@@ -9,9 +9,10 @@
 // Per KV block j (64 keys) and tile t:     S_t = Q_t K_jᵀ   (UMMA 128x64x16, K-major A and B from smem, D in TMEM)
 //                                          softmax WG t: TMEM → regs, online softmax in log2 domain, P_t(bf16) → swizzled smem
 //                                          O_t += P_t V_j   (UMMA 128xDx16, B = V tile MN-major straight from the [kv, d] layout)
-// The issue order  PV(t,j) ; QK(t,j+1) ; commit(s_full[t])  makes "S(t,j+1) ready" imply "PV(t,j) complete", so the
-// softmax warpgroup may overwrite P_t and rescale O_t in TMEM without any further barrier.  O is rescaled lazily: only
-// when the running max grows by more than 2^8 (the stale reference max is used otherwise; exact after the final 1/l).
+// S_t and P_t are double-buffered and the issuer runs one block ahead:  … PV(t,j) ; QK(t,j+2) ; commit(s_full[t][j%2]) …, so the
+// softmax of block j+1 never waits for a tensor-core round trip, and "S(t,j+2) ready" implies "PV(t,j) complete" (its P buffer may be
+// overwritten).  O is rescaled lazily — only when the running max grows by more than 2^8 (the stale reference max is used otherwise;
+// exact after the final 1/l) — and a rescale at block j first waits on pv_done[t] for PV(t,j-1), then happens before p_ready(j).
 //
 // Layouts: q [sq, b, hq, d], k/v [sk, b, hk, d] with arbitrary (16-byte aligned) s/b/h strides and contiguous d — the k/v
 // views produced by splitting a fused QKV projection are consumed in place.  out [sq, b, hq, d] contiguous,
@@ -68,24 +69,24 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   constexpr int KV_STAGE_BYTES = DCH * KV_CHUNK_BYTES;
   constexpr int P_TILE_BYTES = FA_BM * 128;            // [128 rows x 64 bf16]
   constexpr uint32_t TMEM_COLS = 512;
-  constexpr uint32_t S_COL = 0, O_COL = 128;           // S_t at t*64, O_t at 128 + t*D
+  constexpr uint32_t S_COL = 0, O_COL = 256;           // S[t][b] at (2t+b)*64, O_t at 256 + t*D
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;                                        // 2 tiles
   uint8_t* smem_k = smem_q + 2 * Q_TILE_BYTES;                   // FA_STAGES
   uint8_t* smem_v = smem_k + FA_STAGES * KV_STAGE_BYTES;         // FA_STAGES
-  uint8_t* smem_p = smem_v + FA_STAGES * KV_STAGE_BYTES;         // 2 tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + 2 * P_TILE_BYTES);
+  uint8_t* smem_p = smem_v + FA_STAGES * KV_STAGE_BYTES;         // 2 tiles x 2 buffers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + 4 * P_TILE_BYTES);
   uint64_t* q_full = bars;                       // 1
   uint64_t* k_full = bars + 1;                   // FA_STAGES
   uint64_t* k_empty = k_full + FA_STAGES;
   uint64_t* v_full = k_empty + FA_STAGES;
   uint64_t* v_empty = v_full + FA_STAGES;
-  uint64_t* s_full = v_empty + FA_STAGES;        // 2
-  uint64_t* p_ready = s_full + 2;                // 2
-  uint64_t* o_done = p_ready + 2;                // 2
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* s_full = v_empty + FA_STAGES;        // [tile][buffer] = 4
+  uint64_t* p_ready = s_full + 4;                // [tile][buffer] = 4
+  uint64_t* pv_done = p_ready + 4;               // [tile] = 2: one phase per PV(t, j)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = (int)gridDim.x - 1 - (int)blockIdx.x;   // heaviest (latest) causal tiles are scheduled first
@@ -120,11 +121,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
     }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1);
-      mbar_init(&p_ready[t], FA_BM);
-      mbar_init(&o_done[t], 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], FA_BM);
     }
+    mbar_init(&pv_done[0], 1);
+    mbar_init(&pv_done[1], 1);
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc<TMEM_COLS>(tmem_holder);
@@ -162,49 +164,51 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     if (lane == 0 && n > 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(FA_BM, FA_BN, false, false);
       constexpr uint32_t idesc_pv = make_idesc_bf16(FA_BM, D, false, true);
-      auto issue_qk = [&](int t, int s) {
+      auto issue_qk = [&](int t, int s, int buf) {
         const uint32_t qa = smem_u32(smem_q + t * Q_TILE_BYTES), ka = smem_u32(smem_k + s * KV_STAGE_BYTES);
 #pragma unroll
         for (int c = 0; c < DCH; ++c)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_f16(tmem_base + S_COL + t * FA_BN, make_smem_desc_sw128(qa + c * Q_CHUNK_BYTES + kk * 32, 16, 1024),
+            umma_f16(tmem_base + S_COL + (2 * t + buf) * FA_BN, make_smem_desc_sw128(qa + c * Q_CHUNK_BYTES + kk * 32, 16, 1024),
                      make_smem_desc_sw128(ka + c * KV_CHUNK_BYTES + kk * 32, 16, 1024), idesc_qk, (c > 0 || kk > 0) ? 1u : 0u);
       };
-      auto issue_pv = [&](int t, int s, bool acc) {
-        const uint32_t pa = smem_u32(smem_p + t * P_TILE_BYTES), va = smem_u32(smem_v + s * KV_STAGE_BYTES);
+      auto issue_pv = [&](int t, int s, int buf, bool acc) {
+        const uint32_t pa = smem_u32(smem_p + (2 * t + buf) * P_TILE_BYTES), va = smem_u32(smem_v + s * KV_STAGE_BYTES);
 #pragma unroll
         for (int kk = 0; kk < FA_BN / 16; ++kk)
           umma_f16(tmem_base + O_COL + t * D, make_smem_desc_sw128(pa + kk * 32, 16, 1024), make_smem_desc_sw128(va + kk * 2048, KV_CHUNK_BYTES, 1024), idesc_pv,
                    (acc || kk > 0) ? 1u : 0u);
       };
       mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      for (int t = 0; t < 2; ++t)
-        if (n_t[t] > 0) {
-          issue_qk(t, 0);
-          umma_commit(&s_full[t]);
-        }
-      umma_commit(&k_empty[0]);
+      // prologue: S(t,0) and S(t,1) are issued up front so the softmax warpgroups always have a block waiting
+      for (int j0 = 0; j0 < 2 && j0 < n; ++j0) {
+        mbar_wait(&k_full[j0], 0);
+        tc_fence_after();
+        for (int t = 0; t < 2; ++t)
+          if (j0 < n_t[t]) {
+            issue_qk(t, j0, j0);
+            umma_commit(&s_full[2 * t + j0]);
+          }
+        umma_commit(&k_empty[j0]);
+      }
       for (int j = 0; j < n; ++j) {
-        const int s = j % FA_STAGES, s1 = (j + 1) % FA_STAGES;
+        const int s = j % FA_STAGES, s2 = (j + 2) % FA_STAGES, buf = j & 1;
         mbar_wait(&v_full[s], (uint32_t)(j / FA_STAGES) & 1u);
-        if (j + 1 < n) mbar_wait(&k_full[s1], (uint32_t)((j + 1) / FA_STAGES) & 1u);
+        if (j + 2 < n) mbar_wait(&k_full[s2], (uint32_t)((j + 2) / FA_STAGES) & 1u);
         for (int t = 0; t < 2; ++t) {
           if (j >= n_t[t]) continue;
-          mbar_wait(&p_ready[t], (uint32_t)j & 1u);
+          mbar_wait(&p_ready[2 * t + buf], (uint32_t)(j >> 1) & 1u);
           tc_fence_after();
-          issue_pv(t, s, j > 0);
-          if (j + 1 < n_t[t]) {
-            issue_qk(t, s1);
-            umma_commit(&s_full[t]);
-          } else {
-            umma_commit(&o_done[t]);
+          issue_pv(t, s, buf, j > 0);
+          umma_commit(&pv_done[t]);
+          if (j + 2 < n_t[t]) {
+            issue_qk(t, s2, buf);              // S[t][buf] was drained before p_ready(t,j) was signalled
+            umma_commit(&s_full[2 * t + buf]);
           }
         }
         umma_commit(&v_empty[s]);
-        if (j + 1 < n) umma_commit(&k_empty[s1]);
+        if (j + 2 < n) umma_commit(&k_empty[s2]);
       }
     }
   } else {
@@ -213,14 +217,17 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     const int row = (warp & 3) * 32 + lane;
     const int q_idx = q0 + t * FA_BM + row;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t s_addr = tmem_base + lane_base + S_COL + t * FA_BN;
+    const uint32_t s_addr0 = tmem_base + lane_base + S_COL + 2 * t * FA_BN;
     const uint32_t o_addr = tmem_base + lane_base + O_COL + t * D;
-    uint8_t* p_row = smem_p + t * P_TILE_BYTES + row * 128;
+    uint8_t* p_row0 = smem_p + 2 * t * P_TILE_BYTES + row * 128;
     const int sw = row & 7;
     float m_ref = -INFINITY, l = 0.f;
     const int nb = n_t[t];
     for (int j = 0; j < nb; ++j) {
-      mbar_wait(&s_full[t], (uint32_t)j & 1u);
+      const int buf = j & 1;
+      const uint32_t s_addr = s_addr0 + buf * FA_BN;
+      uint8_t* p_row = p_row0 + buf * P_TILE_BYTES;
+      mbar_wait(&s_full[2 * t + buf], (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
       uint32_t r0[32], r1[32];
       tmem_ld_32x32b_x32(s_addr, r0);
@@ -272,8 +279,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         *reinterpret_cast<uint4*>(p_row + ((u ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       l += ((sums[0] + sums[1]) + (sums[2] + sums[3])) + ((sums[4] + sums[5]) + (sums[6] + sums[7]));
+      // Observe EVERY phase of pv_done in order (parity waits alias if a waiter lags two phases).  PV(t, j-1) was issued when this
+      // block's softmax started, so the wait is normally already satisfied here.
+      if (j > 0) mbar_wait(&pv_done[t], (uint32_t)(j - 1) & 1u);
       if (rescale) {
-        // PV(t, j-1) is complete (see header) → O_t is stable: scale this row's accumulator in place
+        // PV(t, j-1) is accumulated and PV(t, j) is not issued before p_ready(j): scale this row of O_t in place
+        tc_fence_after();
 #pragma unroll 1
         for (int ch = 0; ch < D / 32; ++ch) {
           uint32_t o[32];
@@ -287,10 +298,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       }
       fence_proxy_async();   // generic-proxy smem writes of P → visible to the tensor core (async proxy)
       tc_fence_before();
-      mbar_arrive(&p_ready[t]);
+      mbar_arrive(&p_ready[2 * t + buf]);
     }
     if (nb > 0) {
-      mbar_wait(&o_done[t], 0);
+      mbar_wait(&pv_done[t], (uint32_t)(nb - 1) & 1u);
       tc_fence_after();
       const float inv = l > 0.f ? 1.f / l : 0.f;
       const bool valid = q_idx < p.sq;
@@ -323,7 +334,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 
 template <int D>
 static int launch_fa_fwd(const void* q, const void* k, const void* v, FaParams p, long q_ss, long k_ss, long v_ss, cudaStream_t s) {
-  constexpr int SMEM_BYTES = 2 * (FA_BM * D * 2) + 2 * FA_STAGES * (FA_BN * D * 2) + 2 * (FA_BM * 128) + 1024 + 256;
+  constexpr int SMEM_BYTES = 2 * (FA_BM * D * 2) + 2 * FA_STAGES * (FA_BN * D * 2) + 4 * (FA_BM * 128) + 1024 + 256;
   CUtensorMap tq, tk, tv;
   bool ok = make_tmap_bf16_strided(&tq, q, p.sq, q_ss, q_ss * 2, 64, FA_BM);
   ok &= make_tmap_bf16_strided(&tk, k, p.sk, k_ss, k_ss * 2, 64, FA_BN);
