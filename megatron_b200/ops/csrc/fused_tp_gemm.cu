@@ -296,7 +296,9 @@ fused_tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m_blk = walk_to_mblk(p, tile / tiles_n), n_blk = tile % tiles_n;
+        int m_pos, n_blk;
+        tile_coords(tile, tiles_m, tiles_n, g.group_m, m_pos, n_blk);   // groups of walk positions sweep N together: weight tiles stay in L2
+        const int m_blk = walk_to_mblk(p, m_pos);
         if (p.mode == 0) {
           // wait until the 256-row chunk holding this tile's A rows has landed in the local gathered buffer
           const int r = m_blk / p.chunks_per_rank, c = m_blk % p.chunks_per_rank;
@@ -356,7 +358,9 @@ fused_tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m_blk = walk_to_mblk(p, tile / tiles_n), n_blk = tile % tiles_n;
+      int m_pos, n_blk;
+      tile_coords(tile, tiles_m, tiles_n, g.group_m, m_pos, n_blk);
+      const int m_blk = walk_to_mblk(p, m_pos);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       epilogue_tile<false>(Cptr, g, tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16), m_blk * PM + (int)cta_rank * BM + ew * 32 + lane, n_blk * BN, half * CH,
@@ -423,7 +427,8 @@ extern "C" int mb200_fused_tp_gemm(int mode, const void* A, const void* B, void*
   if (world > MAX_TP || M % (world * CHUNK_ROWS) != 0 || (M / world / CHUNK_ROWS) > MAX_CHUNKS) return -10;
   if (K % 8 != 0 || N % 8 != 0) return -11;
   FusedParams p;
-  p.g.M = M; p.g.N = N; p.g.K = K; p.g.ldc = N; p.g.accumulate = 0; p.g.group_m = 1;
+  p.g.M = M; p.g.N = N; p.g.K = K; p.g.ldc = N; p.g.accumulate = 0;
+  p.g.group_m = 8 < M / (2 * BM) ? 8 : (M / (2 * BM) > 0 ? M / (2 * BM) : 1);
   p.mode = mode; p.rank = rank; p.world = world; p.chunks_per_rank = M / world / CHUNK_ROWS; p.epoch = epoch; p.comm_clusters = 0;
   p.ag_src = ag_src; p.ag_dst_mc = reinterpret_cast<void*>(ag_dst_mc); p.rs_src_mc = reinterpret_cast<const void*>(rs_src_mc); p.rs_out = rs_out;
   p.xag_src = xag_src; p.xag_vec = xag_src ? (size_t)xag_bytes / 16 : 0; p.xag_dst_mc = reinterpret_cast<void*>(xag_dst_mc);

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 N=${NG:-8}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 600 $TR --master-port 29533 bench.py --gpus $N --steps 3 --warmup 3 --no-e2e --tp-comm nccl > gpurun_out/bench_n${N}_nccl.log 2>&1; echo "bench nccl rc=$?"; grep '^{' gpurun_out/bench_n${N}_nccl.log | cut -c1-900 || tail -25 gpurun_out/bench_n${N}_nccl.log
+timeout 600 $TR --master-port 29533 bench.py --gpus $N --steps 3 --warmup 3 --tp-comm nccl > gpurun_out/bench_n${N}_nccl.log 2>&1; echo "bench nccl rc=$?"; grep '^{' gpurun_out/bench_n${N}_nccl.log | cut -c1-900 || tail -25 gpurun_out/bench_n${N}_nccl.log
 MODES=${MODES:-nccl,fused:4:8,fused:8:12} ITERS=10 timeout 300 $TR --master-port 29511 tools/fused_tp_test.py > gpurun_out/fused_tp_test_n$N.log 2>&1; echo "fused test rc=$?"; grep -v "^\*\|OMP" gpurun_out/fused_tp_test_n$N.log | tail -60
 if [ "${FUSED:-1}" = "1" ]; then
   timeout 600 $TR --master-port 29534 bench.py --gpus $N --steps 3 --warmup 3 --no-e2e --tp-comm fused > gpurun_out/bench_n${N}_fused.log 2>&1; echo "bench fused rc=$?"; grep '^{' gpurun_out/bench_n${N}_fused.log | cut -c1-900 || tail -25 gpurun_out/bench_n${N}_fused.log
