@@ -89,7 +89,9 @@ class TrainEngine:
         ov.update(model_overrides or {})
         # NVLink (symmetric-memory) collectives for the TP group when on GPUs of one box
         if nvlink_collectives is None:
-            nvlink_collectives = self.device.type == "cuda" and tp > 1 and os.environ.get("MEGATRON_B200_TP_COMM", "auto") != "nccl"
+            from ..parallel import fused as _fused
+
+            nvlink_collectives = self.device.type == "cuda" and tp > 1 and _fused.get_mode() != "nccl"
         if nvlink_collectives:
             from ..parallel import collectives
 

@@ -1,0 +1,114 @@
+"""Small runtime components: PP layer layouts, quantisation recipes, FP8 emulation, masked datasets, fault injection, restart wrapper,
+hybrid layer allocation, MoE reference ops."""
+import pytest
+import torch
+
+
+def test_pipeline_layer_layout_parsing():
+    from megatron_b200.core.enums import LayerType
+    from megatron_b200.core.transformer.pipeline_parallel_layer_layout import PipelineParallelLayerLayout as L
+
+    lay = L.from_str("Et*3|(tt|)*2,m|L", 1)
+    assert [len(s) for s in lay.flat] == [4, 2, 2, 1, 1]
+    lay.validate_layer_layout(7, 1)
+    lay = L.from_str("Ett|tt|tt|ttL", 2)  # 4 stages over pp=2 → 2 virtual chunks each
+    assert lay.vpp == 2 and lay.get_layer_offset(vp_stage=1, pp_rank=1) == 6 and lay.get_num_layers_to_build(vp_stage=1, pp_rank=0) == 2
+    assert lay.get_layer_id_list(LayerType.decoder, 0, 1) == [2, 3]
+    with pytest.raises(ValueError):
+        L.from_str("Ex|L", 1)
+
+
+def test_quantization_recipe_first_match_wins():
+    from megatron_b200.core.quantization import RecipeConfig
+
+    r = RecipeConfig.from_dict({"configs": {"f8": {"recipe": "tensorwise", "fp8_format": "hybrid"}, "bf16": {"recipe": "none"}},
+                                "matchers": [{"pattern": "decoder.layers.0.*", "config": "bf16"}, {"pattern": "*.linear_fc1", "config": "f8"}]})
+    assert not r.match("decoder.layers.0.mlp.linear_fc1").enabled
+    assert r.match("decoder.layers.3.mlp.linear_fc1").enabled and r.match("embedding") is None
+    with pytest.raises(KeyError):
+        RecipeConfig.from_dict({"configs": {}, "matchers": [{"pattern": "*", "config": "nope"}]})
+
+
+def test_fp8_linear_emulation_forward_backward():
+    from megatron_b200.core.fp8_utils import E4M3, Fp8LinearState, fp8_linear, quantize
+
+    torch.manual_seed(0)
+    x = torch.randn(4, 16, 64, requires_grad=True)
+    w = (0.1 * torch.randn(32, 64)).requires_grad_(True)
+    y = fp8_linear(x, w)
+    y.sum().backward()
+    ref = x.detach() @ w.detach().t()
+    assert ((y.float() - ref).abs().max() / ref.abs().max()).item() < 0.08
+    gx_ref = torch.ones(4, 16, 32) @ w.detach()
+    assert ((x.grad - gx_ref).abs().max() / gx_ref.abs().max()).item() < 0.1 and w.grad.shape == w.shape
+    q, inv = quantize(torch.tensor([1.0, -448.0, 3.0]), E4M3)
+    assert torch.allclose(q.float() * inv, torch.tensor([1.0, -448.0, 3.0]), rtol=0.07)
+    st = Fp8LinearState(history_len=4)
+    for _ in range(3):
+        fp8_linear(x, w, recipe="delayed", metas=st.metas)
+    assert st.metas[0].amax_history.shape == (4,) and st.get_extra_state()[0]["scale"] is not None
+
+
+def test_masked_datasets_are_deterministic_and_well_formed():
+    from megatron_b200.core.datasets.masked_dataset import BERTMaskedDataset, MaskedDatasetConfig, T5MaskedDataset
+
+    c = MaskedDatasetConfig(sequence_length=64, vocab_size=1000, sequence_length_decoder=32)
+    b1, b2 = BERTMaskedDataset(c)[3], BERTMaskedDataset(c)[3]
+    assert all(torch.equal(b1[k], b2[k]) for k in b1)
+    assert b1["text"].shape == (64,) and 5 <= int(b1["loss_mask"].sum()) <= 12
+    sel = b1["loss_mask"].bool()
+    assert (b1["labels"][sel] != 0).all() and (b1["text"][0] == c.cls_id)
+    t = T5MaskedDataset(c)[5]
+    n_sent_enc = int((t["text_enc"] >= 1000 - c.num_sentinels).sum())
+    n_sent_dec = int((t["text_dec"] >= 1000 - c.num_sentinels).sum())
+    assert n_sent_enc == n_sent_dec >= 1 and t["text_dec"][0] == c.bos_id
+    assert int(t["loss_mask"].sum()) == int(t["dec_mask"].sum())
+
+
+def test_fault_injector_and_inprocess_restart():
+    from megatron_b200.core.fault_injector import Fault, FaultInjector, FaultInjectorConfig, InjectedFaultError
+    from megatron_b200.training.inprocess_restart import maybe_wrap_for_inprocess_restart
+
+    inj = FaultInjector(FaultInjectorConfig(fault_type=Fault.WORKLOAD_EXC, ranks=[0], at_iteration=2), rank=0, world_size=1)
+    inj.on_iteration(1)
+    with pytest.raises(InjectedFaultError):
+        inj.on_iteration(2)
+    inj.on_iteration(3)  # fires once
+    assert not FaultInjector(FaultInjectorConfig(ranks=[1]), rank=0, world_size=2).armed
+    calls = {"n": 0}
+
+    def flaky():
+        calls["n"] += 1
+        if calls["n"] < 3:
+            raise RuntimeError("transient")
+        return "done"
+
+    assert maybe_wrap_for_inprocess_restart(flaky, max_restarts=3)() == "done" and calls["n"] == 3
+    calls["n"] = 0
+    with pytest.raises(RuntimeError):
+        maybe_wrap_for_inprocess_restart(flaky, max_restarts=1)()
+
+
+def test_hybrid_layer_allocation():
+    from megatron_b200.core.ssm.mamba_hybrid_layer_allocation import allocate_layers
+
+    assert allocate_layers(4, override_pattern="M*M-") == ["M", "*", "M", "-"]
+    lay = allocate_layers(16, 0.25, 0.25)
+    assert lay.count("*") == 4 and lay.count("-") == 4 and lay.count("M") == 8
+    with pytest.raises(ValueError):
+        allocate_layers(3, override_pattern="MM")
+
+
+def test_moe_reference_ops_cpu():
+    from megatron_b200 import ops
+
+    torch.manual_seed(0)
+    x = torch.randn(6, 8)
+    out = ops.moe_gather_rows(x, torch.tensor([3, 1, 1, 5]), torch.tensor([1.0, 2.0, 3.0, 4.0]))
+    assert torch.allclose(out[2], 3.0 * x[1])
+    y = torch.randn(4, 8)
+    pos, w = torch.tensor([[0, 2], [1, -1], [3, 0]]), torch.rand(3, 2)
+    c = ops.moe_combine_rows(y, pos, w)
+    assert torch.allclose(c[1], w[1, 0] * y[1], atol=1e-6) and torch.allclose(c[0], w[0, 0] * y[0] + w[0, 1] * y[2], atol=1e-6)
+    ids, rmap, tpe, probs = ops.moe_topk_router(torch.randn(50, 8), 2, "softmax")
+    assert rmap.sum(1).eq(2).all() and int(tpe.sum()) == 100 and torch.allclose(probs.sum(1), torch.ones(50), atol=1e-5)
