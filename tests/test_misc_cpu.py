@@ -112,3 +112,20 @@ def test_moe_reference_ops_cpu():
     assert torch.allclose(c[1], w[1, 0] * y[1], atol=1e-6) and torch.allclose(c[0], w[0, 0] * y[0] + w[0, 1] * y[2], atol=1e-6)
     ids, rmap, tpe, probs = ops.moe_topk_router(torch.randn(50, 8), 2, "softmax")
     assert rmap.sum(1).eq(2).all() and int(tpe.sum()) == 100 and torch.allclose(probs.sum(1), torch.ones(50), atol=1e-5)
+
+
+def test_gated_delta_rule_chunked_matches_recurrence():
+    from megatron_b200.core.ssm.gated_delta_net import gated_delta_rule_chunked, gated_delta_rule_recurrent
+
+    torch.manual_seed(0)
+    b, l, h, dk, dv = 2, 50, 3, 8, 6
+    q = torch.nn.functional.normalize(torch.randn(b, l, h, dk), dim=-1)
+    k = torch.nn.functional.normalize(torch.randn(b, l, h, dk), dim=-1)
+    v, g, beta = torch.randn(b, l, h, dv), -torch.rand(b, l, h) * 0.3, torch.rand(b, l, h)
+    o1, s1 = gated_delta_rule_recurrent(q, k, v, g, beta)
+    o2, s2 = gated_delta_rule_chunked(q, k, v, g, beta, 16)
+    assert (o1 - o2).abs().max().item() < 1e-4 and (s1 - s2).abs().max().item() < 1e-4
+    # state carried across two calls == one long call
+    oa, sa = gated_delta_rule_chunked(q[:, :32], k[:, :32], v[:, :32], g[:, :32], beta[:, :32], 16)
+    ob, sb = gated_delta_rule_recurrent(q[:, 32:], k[:, 32:], v[:, 32:], g[:, 32:], beta[:, 32:], sa)
+    assert (torch.cat([oa, ob], 1) - o1).abs().max().item() < 1e-4
