@@ -23,8 +23,9 @@ from .. import ops
 from ..core.utils import get_pg_rank, get_pg_size
 
 _MODE = os.environ.get("MEGATRON_B200_TP_COMM", "auto")  # auto | nccl | nvlink | fused
-# what "auto" means on this build: the fastest MEASURED mode on 2-8 B200s (profiles/r1_tp_comm.md)
-_AUTO_RESOLVES_TO = "nccl"
+# what "auto" means on this build: the fastest MEASURED mode per TP size on B200 + NVSwitch (profiles/r1_tp_comm.md):
+# TP=8: fused 107.3k tok/s vs NCCL 82.5k (1.30x);  TP=2: communication is ~13 % of the step and the two are within noise -> NCCL.
+_AUTO_FUSED_MIN_TP = int(os.environ.get("MEGATRON_B200_FUSED_MIN_TP", "4"))
 
 
 def set_mode(mode: str) -> None:
@@ -33,13 +34,23 @@ def set_mode(mode: str) -> None:
     _MODE = mode
 
 
-def get_mode() -> str:
-    return _AUTO_RESOLVES_TO if _MODE == "auto" else _MODE
+def get_mode(group=None, world_size: Optional[int] = None) -> str:
+    """Resolved TP-communication mode for a group (or an explicit TP size)."""
+    if _MODE != "auto":
+        return _MODE
+    if world_size is None:
+        if group is not None:
+            world_size = get_pg_size(group)
+        else:
+            from ..core import parallel_state as ps
+
+            world_size = ps.get_tensor_model_parallel_world_size() if ps.model_parallel_is_initialized() else 1
+    return "fused" if world_size >= _AUTO_FUSED_MIN_TP else "nccl"
 
 
 def _nvl(group, t):
     """NVLink backend (symmetric-heap collectives) or None."""
-    if not t.is_cuda or get_mode() == "nccl":
+    if not t.is_cuda or get_mode(group) == "nccl":
         return None
     from . import collectives
 

@@ -241,7 +241,7 @@ class NVLinkBackend(NVLinkMoEMixin):
     def _fused_ok(self, M: int, N: int, K: int, *ts) -> bool:
         from . import fused
 
-        if fused.get_mode() not in ("fused", "auto") or not hasattr(ops.ext(), "fused_tp_gemm"):
+        if fused.get_mode(world_size=self.world) != "fused" or not hasattr(ops.ext(), "fused_tp_gemm"):
             return False
         if self.world > 8 or M % (self.world * 256) != 0 or M // self.world // 256 > 64 or K % 8 != 0 or N % 8 != 0:
             return False

@@ -91,7 +91,7 @@ class TrainEngine:
         if nvlink_collectives is None:
             from ..parallel import fused as _fused
 
-            nvlink_collectives = self.device.type == "cuda" and tp > 1 and _fused.get_mode() != "nccl"
+            nvlink_collectives = self.device.type == "cuda" and tp > 1 and _fused.get_mode(world_size=tp) != "nccl"
         if nvlink_collectives:
             from ..parallel import collectives
 
