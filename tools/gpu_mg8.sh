@@ -1,0 +1,13 @@
+#!/bin/bash
+# 2-GPU box: graph probe, N=2 bench fused vs nccl, N=1 bench with both attention implementations, step profile, attention probe
+mkdir -p gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
+timeout 900 python tools/graph_probe.py > gpurun_out/graph_probe2.log 2>&1; echo "graph probe rc=$?"; cut -c1-700 gpurun_out/graph_probe2.log
+for mode in fused nccl; do
+  timeout 600 $TR --master-port 29533 bench.py --gpus 2 --steps 3 --warmup 3 --no-e2e --tp-comm $mode > gpurun_out/bench_n2_${mode}_r2.log 2>&1; echo "bench n2 $mode rc=$?"; grep '^{' gpurun_out/bench_n2_${mode}_r2.log | cut -c1-420 || tail -20 gpurun_out/bench_n2_${mode}_r2.log
+done
+for impl in library native; do
+  MEGATRON_B200_ATTN=$impl timeout 900 python bench.py --gpus 1 --steps 3 --warmup 3 --no-e2e > gpurun_out/bench_n1_attn_$impl.log 2>&1; echo "bench n1 attn=$impl rc=$?"; grep '^{' gpurun_out/bench_n1_attn_$impl.log | cut -c1-420 || tail -20 gpurun_out/bench_n1_attn_$impl.log
+done
+timeout 600 python tools/step_profile.py --layers 4 > gpurun_out/step_profile_n1.log 2>&1; echo "step profile rc=$?"; tail -32 gpurun_out/step_profile_n1.log | cut -c1-170
+timeout 300 python tools/attn_probe.py 2>&1 | grep "megatron_b200\|sdpa-cudnn" > gpurun_out/attn_probe4.log; cat gpurun_out/attn_probe4.log
