@@ -12,7 +12,8 @@
 // S_t and P_t are double-buffered and the issuer runs one block ahead:  … PV(t,j) ; QK(t,j+2) ; commit(s_full[t][j%2]) …, so the
 // softmax of block j+1 never waits for a tensor-core round trip, and "S(t,j+2) ready" implies "PV(t,j) complete" (its P buffer may be
 // overwritten).  O is rescaled lazily — only when the running max grows by more than 2^8 (the stale reference max is used otherwise;
-// exact after the final 1/l) — and a rescale at block j first waits on pv_done[t] for PV(t,j-1), then happens before p_ready(j).
+// exact after the final 1/l) — and a rescale at block j first waits for PV(t,j-1) on one of FOUR rotating pv_done barriers (a parity wait is
+// only unambiguous within one phase of lag; with four barriers a rarely-taken wait can never alias), then happens before p_ready(j).
 //
 // Layouts: q [sq, b, hq, d], k/v [sk, b, hk, d] with arbitrary (16-byte aligned) s/b/h strides and contiguous d — the k/v
 // views produced by splitting a fused QKV projection are consumed in place.  out [sq, b, hq, d] contiguous,
@@ -85,8 +86,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   uint64_t* v_empty = v_full + FA_STAGES;
   uint64_t* s_full = v_empty + FA_STAGES;        // [tile][buffer] = 4
   uint64_t* p_ready = s_full + 4;                // [tile][buffer] = 4
-  uint64_t* pv_done = p_ready + 4;               // [tile] = 2: one phase per PV(t, j)
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* pv_done = p_ready + 4;               // [tile][j % 4] = 8: PV(t, j) commits to barrier j % 4 (phase j / 4)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_done + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = (int)gridDim.x - 1 - (int)blockIdx.x;   // heaviest (latest) causal tiles are scheduled first
@@ -125,8 +126,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       mbar_init(&s_full[i], 1);
       mbar_init(&p_ready[i], FA_BM);
     }
-    mbar_init(&pv_done[0], 1);
-    mbar_init(&pv_done[1], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&pv_done[i], 1);
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc<TMEM_COLS>(tmem_holder);
@@ -201,7 +201,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           mbar_wait(&p_ready[2 * t + buf], (uint32_t)(j >> 1) & 1u);
           tc_fence_after();
           issue_pv(t, s, buf, j > 0);
-          umma_commit(&pv_done[t]);
+          umma_commit(&pv_done[4 * t + (j & 3)]);
           if (j + 2 < n_t[t]) {
             issue_qk(t, s2, buf);              // S[t][buf] was drained before p_ready(t,j) was signalled
             umma_commit(&s_full[2 * t + buf]);
@@ -279,11 +279,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         *reinterpret_cast<uint4*>(p_row + ((u ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       l += ((sums[0] + sums[1]) + (sums[2] + sums[3])) + ((sums[4] + sums[5]) + (sums[6] + sums[7]));
-      // Observe EVERY phase of pv_done in order (parity waits alias if a waiter lags two phases).  PV(t, j-1) was issued when this
-      // block's softmax started, so the wait is normally already satisfied here.
-      if (j > 0) mbar_wait(&pv_done[t], (uint32_t)(j - 1) & 1u);
       if (rescale) {
-        // PV(t, j-1) is accumulated and PV(t, j) is not issued before p_ready(j): scale this row of O_t in place
+        // rare path: wait until PV(t, j-1) is accumulated (PV(t, j) is not issued before p_ready(j)), then scale this row of O_t in place
+        mbar_wait(&pv_done[4 * t + ((j - 1) & 3)], (uint32_t)((j - 1) >> 2) & 1u);
         tc_fence_after();
 #pragma unroll 1
         for (int ch = 0; ch < D / 32; ++ch) {
@@ -301,7 +299,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       mbar_arrive(&p_ready[2 * t + buf]);
     }
     if (nb > 0) {
-      mbar_wait(&pv_done[t], (uint32_t)(nb - 1) & 1u);
+      mbar_wait(&pv_done[4 * t + ((nb - 1) & 3)], (uint32_t)((nb - 1) >> 2) & 1u);
       tc_fence_after();
       const float inv = l > 0.f ? 1.f / l : 0.f;
       const bool valid = q_idx < p.sq;
