@@ -11,3 +11,4 @@ for impl in library native; do
 done
 timeout 600 python tools/step_profile.py --layers 4 > gpurun_out/step_profile_n1.log 2>&1; echo "step profile rc=$?"; tail -32 gpurun_out/step_profile_n1.log | cut -c1-170
 timeout 300 python tools/attn_probe.py 2>&1 | grep "megatron_b200\|sdpa-cudnn" > gpurun_out/attn_probe4.log; cat gpurun_out/attn_probe4.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'norm_fwd_kernel|norm_bwd_kernel|swiglu_fwd|swiglu_bwd|rope_kernel|ce_stats|ce_bwd|adam_kernel|l2norm_kernel' --launch-skip 10 --launch-count 11 -f -o gpurun_out/prof_memops python tools/ops_once.py > gpurun_out/ncu_memops.log 2>&1; echo "ncu memops rc=$?"; tail -2 gpurun_out/ncu_memops.log
