@@ -94,8 +94,15 @@ class TrainEngine:
             nvlink_collectives = self.device.type == "cuda" and tp > 1 and _fused.get_mode(world_size=tp) != "nccl"
         if nvlink_collectives:
             from ..parallel import collectives
+            from ..parallel import fused as _fused
 
-            collectives.enable_for_group(ps.get_tensor_model_parallel_group())
+            try:
+                collectives.enable_for_group(ps.get_tensor_model_parallel_group())
+            except Exception as e:  # no symmetric memory / NVLS on this box: keep training over NCCL (all ranks fail alike)
+                import warnings
+
+                warnings.warn(f"NVLink symmetric-memory runtime unavailable ({type(e).__name__}: {e}); TP collectives fall back to NCCL")
+                _fused.set_mode("nccl")
 
         vp = virtual_pipeline_model_parallel_size
         self.model_chunks = []
