@@ -168,6 +168,14 @@ def run_b200(args):
         e2e = {"value": tokens_per_step * args.steps / (e_wall / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": host.numel() * host.element_size(),
                "d2h_bytes_per_step": 4, "timing": "host wall clock incl. H2D inputs from pinned memory and D2H loss read, max over ranks"}
     peak = torch.cuda.max_memory_allocated() / 2**30
+    from megatron_b200.ops import gemm as _gemm
+    from megatron_b200.parallel import fused as _fusedmod
+
+    _tp_mode = _fusedmod.get_mode(world_size=world) if world > 1 else "n/a"
+    _gemm_wins = {}
+    for _key, _winner, _times in _gemm.tuning_report():
+        _gemm_wins[str(_winner).split(":")[0]] = _gemm_wins.get(str(_winner).split(":")[0], 0) + 1
+    _attn_impl = ops._resolved_attn_impl() if hasattr(ops, "_resolved_attn_impl") else "library"
     if rank == 0:
         flops = eng.flops_per_step * args.steps / (ms / 1e3)
         mp = {}
@@ -186,7 +194,8 @@ def run_b200(args):
                        "micro_batch": args.micro_batch, "seq_len": eng.seq_length, "parallelism": f"tp{world}" + ("+sp" if world > 1 else ""),
                        "l2_policy": "inputs larger than L2 (16 GB of bf16 weights + activations stream through the 126 MB L2 every step)",
                        "main_grads": "bf16", "optimizer": "fused AdamW, fp32 master+moments", "recompute": recompute or "none",
-                       "tp_comm": os.environ.get("MEGATRON_B200_TP_COMM", "auto"), "gemm": os.environ.get("MEGATRON_B200_GEMM", "auto")},
+                       "tp_comm": os.environ.get("MEGATRON_B200_TP_COMM", "auto"), "tp_comm_resolved": _tp_mode, "gemm": os.environ.get("MEGATRON_B200_GEMM", "auto"),
+                       "plain_gemm_shapes_tuned": _gemm_wins, "attention": _attn_impl},
         }
         print(json.dumps(out), flush=True)
     if world > 1:
