@@ -19,6 +19,9 @@ PRESETS: Dict[str, dict] = {
                          num_moe_experts=8, moe_router_topk=2),
     "gpt2_small": dict(num_layers=12, hidden_size=768, ffn_hidden_size=3072, num_attention_heads=12, num_query_groups=12, kv_channels=64,
                        vocab_size=50304, seq_length=1024, normalization="LayerNorm", swiglu=False, rotary_base=None, untie=False, bias=True),
+    "tiny_mixtral": dict(num_layers=2, hidden_size=256, ffn_hidden_size=512, num_attention_heads=4, num_query_groups=2, kv_channels=64,
+                         vocab_size=1024, seq_length=256, normalization="RMSNorm", swiglu=True, rotary_base=10000, untie=True, bias=False,
+                         num_moe_experts=4, moe_router_topk=2),
     "tiny_llama": dict(num_layers=2, hidden_size=256, ffn_hidden_size=512, num_attention_heads=4, num_query_groups=2, kv_channels=64,
                        vocab_size=1024, seq_length=256, normalization="RMSNorm", swiglu=True, rotary_base=10000, untie=True, bias=False),
 }

@@ -104,6 +104,12 @@ class TrainEngine:
                 warnings.warn(f"NVLink symmetric-memory runtime unavailable ({type(e).__name__}: {e}); TP collectives fall back to NCCL")
                 _fused.set_mode("nccl")
 
+        # expert-parallel NVLink dispatch/combine ("flex" dispatcher) needs a symmetric heap on the EP group
+        if self.device.type == "cuda" and expert_model_parallel_size > 1 and ov.get("moe_token_dispatcher_type") == "flex":
+            from ..parallel import collectives
+
+            collectives.enable_for_group(ps.get_expert_model_parallel_group())
+
         vp = virtual_pipeline_model_parallel_size
         self.model_chunks = []
         for v in range(vp or 1):
