@@ -129,3 +129,35 @@ def test_gated_delta_rule_chunked_matches_recurrence():
     oa, sa = gated_delta_rule_chunked(q[:, :32], k[:, :32], v[:, :32], g[:, :32], beta[:, :32], 16)
     ob, sb = gated_delta_rule_recurrent(q[:, 32:], k[:, 32:], v[:, 32:], g[:, 32:], beta[:, 32:], sa)
     assert (torch.cat([oa, ob], 1) - o1).abs().max().item() < 1e-4
+
+
+def _hetero(rank, world):
+    import json
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+    from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
+    from megatron_b200.core.transformer.heterogeneous import HeterogeneousTransformerConfig, get_gpt_heterogeneous_layer_spec
+    from megatron_b200.core.transformer.identity_op import IdentityOp
+
+    ps.initialize_model_parallel(1, 1)
+    model_parallel_cuda_manual_seed(1)
+    blocks = {"block_configs": [{"attention": {"n_heads_in_group": 2}, "ffn": {"ffn_mult": 2.0}},
+                                {"attention": {"no_op": True}, "ffn": {"ffn_hidden_size": 96}},
+                                {"attention": {"replace_with_linear": True}, "ffn": {"no_op": True}}]}
+    cfg = HeterogeneousTransformerConfig(num_layers=3, hidden_size=64, num_attention_heads=4, use_cpu_initialization=True, hidden_dropout=0.0, attention_dropout=0.0,
+                                         normalization="RMSNorm", add_bias_linear=False, heterogeneous_layers_config_encoded_json=json.dumps(blocks))
+    assert cfg.per_block_parameters[0].attention.num_query_groups == 2 and cfg.per_block_parameters[0].mlp.ffn_hidden_size == 256
+    m = GPTModel(cfg, get_gpt_heterogeneous_layer_spec(cfg), vocab_size=128, max_sequence_length=32, position_embedding_type="rope")
+    L = m.decoder.layers
+    assert isinstance(L[1].self_attention, IdentityOp) and isinstance(L[2].mlp, IdentityOp) and L[1].mlp.linear_fc2.weight.shape[1] == 96
+    tok = torch.randint(0, 128, (2, 16))
+    m(tok, torch.arange(16)[None].expand(2, -1), None, labels=tok).mean().backward()
+    assert all(p.grad is not None for p in m.parameters())
+    return True
+
+
+def test_heterogeneous_layer_specs():
+    from dist_utils import run_distributed
+
+    assert all(run_distributed(_hetero, 1))
