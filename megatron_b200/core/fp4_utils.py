@@ -1,0 +1,43 @@
+"""NVFP4 (E2M1 values, one E4M3 scale per 16-element block + one fp32 tensor scale) quantisation helpers (reference ``core/fp4_utils.py``).
+
+This round provides the numerics (quantise / dequantise, used for weight-only experiments and tests); the block-scaled tensor-core GEMM
+(``tcgen05.mma kind::mxf4nvf4`` with scale factors in TMEM) is not implemented yet — ``nvfp4_linear`` dequantises to bf16 and uses the
+bf16 tcgen05 GEMM."""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+
+_E2M1 = torch.tensor([0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0])
+BLOCK = 16
+
+
+def is_nvfp4tensor(t) -> bool:
+    return isinstance(t, tuple) and len(t) == 3 and getattr(t[0], "dtype", None) == torch.uint8
+
+
+def quantize_nvfp4(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """x [..., K] (K % 16 == 0) → (codes uint8 [..., K] sign<<3|index, block scales fp8-e4m3 [..., K/16], tensor scale fp32)."""
+    assert x.shape[-1] % BLOCK == 0
+    xf = x.float()
+    tscale = xf.abs().amax().clamp(min=1e-12) / (6.0 * 448.0)
+    xb = (xf / tscale).view(*x.shape[:-1], -1, BLOCK)
+    bscale = (xb.abs().amax(-1, keepdim=True) / 6.0).clamp(min=2.0**-9).to(torch.float8_e4m3fn)
+    y = xb / bscale.float()
+    grid = _E2M1.to(x.device)
+    idx = (y.abs().unsqueeze(-1) - grid).abs().argmin(-1)
+    codes = (idx | ((y < 0).to(torch.int64) << 3)).to(torch.uint8)
+    return codes.view(x.shape), bscale.squeeze(-1), tscale
+
+
+def dequantize_nvfp4(codes: torch.Tensor, bscale: torch.Tensor, tscale: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+    grid = _E2M1.to(codes.device)
+    mag = grid[(codes & 7).long()]
+    val = torch.where((codes & 8) > 0, -mag, mag).view(*codes.shape[:-1], -1, BLOCK)
+    return (val * bscale.float().unsqueeze(-1) * tscale).view(codes.shape).to(dtype)
+
+
+def nvfp4_linear(x: torch.Tensor, qweight) -> torch.Tensor:
+    """``x @ Wᵀ`` with a weight stored as NVFP4."""
+    return torch.nn.functional.linear(x, dequantize_nvfp4(*qweight, dtype=x.dtype))

@@ -14,6 +14,12 @@ import torch
 from . import reference as ref
 
 _BACKEND = os.environ.get("MEGATRON_B200_GEMM", "auto")
+
+
+def set_mode(mode: str) -> None:
+    """Switch the plain-GEMM provider at run time (``auto`` | ``tcgen05[:variant]`` | ``cublas``); used by the batch-invariant mode."""
+    global _BACKEND
+    _BACKEND = mode
 _CHOICE: Dict[Tuple, Tuple[str, int]] = {}
 _TUNE_LOG = []
 VARIANTS = {1: "1cta-128x256", 2: "1cta-128x128", 3: "2cta-256x256", 4: "2cta-256x128"}
