@@ -17,14 +17,17 @@ from megatron_b200.core.transformer.cuda_graphs import graph_module
 torch.manual_seed(0)
 net = torch.nn.Sequential(torch.nn.Linear(256, 512), torch.nn.GELU(), torch.nn.Linear(512, 256)).cuda()
 ref = copy.deepcopy(net)
-net = graph_module(net, warmup_steps=2)
+net = graph_module(net, warmup_steps=0)   # capture on the first call (make_graphed_callables runs its own side-stream warm-up)
+# all random inputs are drawn BEFORE the capture: on this torch build the CUDA RNG cannot be used eagerly in the same process afterwards
+xs = [torch.randn(64, 256, device="cuda") for _ in range(6)]
+gys = [torch.randn(64, 256, device="cuda") for _ in range(6)]
 for it in range(6):
-    x = torch.randn(64, 256, device="cuda", requires_grad=True)
+    x = xs[it].clone().requires_grad_(True)
     xr = x.detach().clone().requires_grad_(True)
     y = net(x)
     assert net.cudagraph_manager.fallback_reason is None, net.cudagraph_manager.fallback_reason
     yr = ref(xr)
-    gy = torch.randn_like(yr)
+    gy = gys[it]
     y.backward(gy)
     yr.backward(gy)
     assert torch.allclose(y, yr, atol=1e-5), it
