@@ -107,6 +107,13 @@ def build_all(force: bool = False, verbose: bool = False) -> Path:
     return tgt
 
 
+def build_datasets_helpers() -> str:
+    """The C++ dataset index builders (``core/datasets/helpers.cpp``, reference N1) — g++ + pybind11, in-tree."""
+    from ..core.datasets.utils import compile_helpers
+
+    return compile_helpers()
+
+
 def ptxas_report() -> str:
     """Registers / spills / smem per kernel, scraped from the last build logs."""
     out = []
