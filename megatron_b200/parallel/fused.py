@@ -24,8 +24,8 @@ from ..core.utils import get_pg_rank, get_pg_size
 
 _MODE = os.environ.get("MEGATRON_B200_TP_COMM", "auto")  # auto | nccl | nvlink | fused
 # what "auto" means on this build: the fastest MEASURED mode per TP size on B200 + NVSwitch (profiles/r1_tp_comm.md):
-# TP=8: fused 107.3k tok/s vs NCCL 82.5k (1.30x);  TP=2: communication is ~13 % of the step and the two are within noise -> NCCL.
-_AUTO_FUSED_MIN_TP = int(os.environ.get("MEGATRON_B200_FUSED_MIN_TP", "4"))
+# fused vs NCCL tokens/s on Llama-3 8B:  TP=8 107.3k vs 82.5k (1.30x);  TP=4 65.3k vs 59.4k (1.10x);  TP=2 36.5k vs 35.2k (1.03x).
+_AUTO_FUSED_MIN_TP = int(os.environ.get("MEGATRON_B200_FUSED_MIN_TP", "2"))
 
 
 def set_mode(mode: str) -> None:

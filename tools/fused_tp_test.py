@@ -13,6 +13,9 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+_LOCAL = [False]
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
@@ -42,7 +45,26 @@ def main():
         "row_bwd_proj": ("row_bwd", rnd(S // world, 1, H), rnd(S, 1, H // world), rnd(H, H // world, scale=0.02)),
     }
 
+    def run_local(kind, args):
+        """The GEMMs of the pair op alone on full-size local operands (no communication): the compute floor."""
+        if kind == "ag_gemm":
+            return (ops.gemm_nt(local_full[id(args[0])], args[1]),)
+        if kind == "gemm_rs":
+            return (ops.gemm_nt(args[0], args[1]),)
+        if kind == "col_bwd":   # dgrad + wgrad
+            return ops.gemm_nn(args[0], args[2]), ops.gemm_tn(args[0].reshape(-1, args[0].shape[-1]), local_full[id(args[1])].reshape(-1, args[1].shape[-1]), out_dtype=args[2].dtype)
+        full_gy = local_full[id(args[0])]
+        return ops.gemm_nn(full_gy, args[2]), ops.gemm_tn(full_gy.reshape(-1, full_gy.shape[-1]), args[1].reshape(-1, args[1].shape[-1]), out_dtype=args[2].dtype)
+
+    local_full = {}
+    for name, (kind, *args) in cases.items():
+        for t in args:
+            if t.dim() == 3 and t.shape[0] == S // world:
+                local_full[id(t)] = t.repeat(world, 1, 1)
+
     def run(kind, args):
+        if _LOCAL[0]:
+            return run_local(kind, args)
         if kind == "ag_gemm":
             return (fused.all_gather_gemm(args[0], args[1], g),)
         if kind == "gemm_rs":
@@ -51,11 +73,15 @@ def main():
             return fused.sp_linear_backward(args[0], args[1], args[2], g, True, False)
         return fused.row_linear_backward_sp(args[0], args[1], args[2], g, True, False)
 
+    _LOCAL[0] = False
     results = {}
     refs = {}
     modes = os.environ.get("MODES", "nccl,nvlink,fused:4:8,fused:8:12,fused:12:20").split(",")
     for mode in modes:
-        if mode.startswith("fused:"):  # fused:<AG comm clusters>:<RS comm clusters>
+        _LOCAL[0] = mode == "local"      # "local" = GEMMs only, no communication (compute floor; outputs are not compared)
+        if mode == "local":
+            fused.set_mode("nccl")
+        elif mode.startswith("fused:"):  # fused:<AG comm clusters>:<RS comm clusters>
             _, a, r = mode.split(":")
             be.fused_comm_clusters = [int(a), int(r)]
             fused.set_mode("fused")
@@ -67,7 +93,7 @@ def main():
             torch.cuda.synchronize()
             if mode == modes[0]:
                 refs[name] = outs
-            else:
+            elif mode != "local":
                 for i, (o, r) in enumerate(zip(outs, refs[name])):
                     err = (o - r).abs().max().item()
                     tol = 0.02 * r.abs().max().item() + 1e-2
@@ -89,8 +115,14 @@ def main():
             results.setdefault(name, {})[mode] = round(t.item() * 1e3, 1)
         if rank == 0:
             print(f"mode {mode} done (fused kernel launches so far: {be.fused_calls})", flush=True)
-    # plain local GEMM time for reference (no communication): the lower bound of each pair op
     fused.set_mode("nccl")
+    if rank == 0 and "local" in modes:
+        # exposed (non-overlapped) communication per op = time(mode) - time(GEMMs alone); per step = sum over the 8 pair ops x layers x micro-batches
+        layers, mb = 32, 4
+        for m in modes:
+            if m != "local":
+                per_layer = sum(max(0.0, results[n][m] - results[n]["local"]) for n in results)
+                print(f"exposed communication [{m}]: {per_layer:.0f} us/layer/micro-batch -> {per_layer * layers * mb / 1e3:.1f} ms/step (32 layers x 4 micro-batches)", flush=True)
     if rank == 0:
         print(json.dumps({"world": world, "seq": S, "unit": "us", "multicast": bool(be.mc), "results": results}, indent=1), flush=True)
     dist.barrier()
