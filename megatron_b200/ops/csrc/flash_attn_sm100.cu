@@ -4,7 +4,8 @@
 //   warps 0-3  : softmax warpgroup of query tile 0 (thread = one query row = one TMEM lane)
 //   warps 4-7  : softmax warpgroup of query tile 1
 //   warp  8    : TMA producer (Q once, then K_j / V_j through a 3-stage ring each)
-//   warp  9    : TMEM allocator + MMA issuer (single elected thread)
+//   warps 9,10 : MMA issuers, one elected thread per query tile (independent issue streams: no head-of-line blocking between
+//                the two tiles' P-ready hand-offs); warp 9 also owns the TMEM allocation
 //
 // Per KV block j (64 keys) and tile t:     S_t = Q_t K_jᵀ   (UMMA 128x64x16, K-major A and B from smem, D in TMEM)
 //                                          softmax WG t: TMEM → regs, online softmax in log2 domain, P_t(bf16) → swizzled smem
@@ -27,7 +28,7 @@ using namespace ptx;
 constexpr int FA_BM = 128;       // query rows per tile
 constexpr int FA_BN = 64;        // keys per block
 constexpr int FA_STAGES = 3;     // K and V ring depth
-constexpr int FA_THREADS = 320;
+constexpr int FA_THREADS = 352;   // 8 softmax warps + TMA producer + one MMA-issuing warp per query tile
 constexpr float FA_RESCALE_THRESHOLD = 8.0f;  // log2 units
 
 struct FaParams {
@@ -118,9 +119,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     mbar_init(q_full, 1);
     for (int i = 0; i < FA_STAGES; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], 2);   // one arrival per tile's issuer
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], 2);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
@@ -159,7 +160,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         for (int c = 0; c < DCH; ++c) tma_load_2d(smem_v + s * KV_STAGE_BYTES + c * KV_CHUNK_BYTES, &tmap_v, &v_full[s], vcol + c * 64, j * FA_BN);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 9 || warp == 10) {
     // ================================= MMA issuer ===============================================================
     if (lane == 0 && n > 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(FA_BM, FA_BN, false, false);
@@ -180,35 +181,43 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           umma_f16(tmem_base + O_COL + t * D, make_smem_desc_sw128(pa + kk * 32, 16, 1024), make_smem_desc_sw128(va + kk * 2048, KV_CHUNK_BYTES, 1024), idesc_pv,
                    (acc || kk > 0) ? 1u : 0u);
       };
+      const int t = warp - 9;
+      const int nt = n_t[t];
       mbar_wait(q_full, 0);
-      // prologue: S(t,0) and S(t,1) are issued up front so the softmax warpgroups always have a block waiting
+      // prologue: S(t,0) and S(t,1) are issued up front so the softmax warpgroup always has a block waiting
       for (int j0 = 0; j0 < 2 && j0 < n; ++j0) {
         mbar_wait(&k_full[j0], 0);
         tc_fence_after();
-        for (int t = 0; t < 2; ++t)
-          if (j0 < n_t[t]) {
-            issue_qk(t, j0, j0);
-            umma_commit(&s_full[2 * t + j0]);
-          }
-        umma_commit(&k_empty[j0]);
+        if (j0 < nt) {
+          issue_qk(t, j0, j0);
+          umma_commit(&s_full[2 * t + j0]);
+          umma_commit(&k_empty[j0]);
+        } else {
+          mbar_arrive(&k_empty[j0]);           // block not needed by this tile (causal): release our share of the stage
+        }
       }
       for (int j = 0; j < n; ++j) {
         const int s = j % FA_STAGES, s2 = (j + 2) % FA_STAGES, buf = j & 1;
         mbar_wait(&v_full[s], (uint32_t)(j / FA_STAGES) & 1u);
         if (j + 2 < n) mbar_wait(&k_full[s2], (uint32_t)((j + 2) / FA_STAGES) & 1u);
-        for (int t = 0; t < 2; ++t) {
-          if (j >= n_t[t]) continue;
+        if (j < nt) {
           mbar_wait(&p_ready[2 * t + buf], (uint32_t)(j >> 1) & 1u);
           tc_fence_after();
           issue_pv(t, s, buf, j > 0);
           umma_commit(&pv_done[4 * t + (j & 3)]);
-          if (j + 2 < n_t[t]) {
+          umma_commit(&v_empty[s]);
+        } else {
+          mbar_arrive(&v_empty[s]);
+        }
+        if (j + 2 < n) {
+          if (j + 2 < nt) {
             issue_qk(t, s2, buf);              // S[t][buf] was drained before p_ready(t,j) was signalled
             umma_commit(&s_full[2 * t + buf]);
+            umma_commit(&k_empty[s2]);
+          } else {
+            mbar_arrive(&k_empty[s2]);
           }
         }
-        umma_commit(&v_empty[s]);
-        if (j + 2 < n) umma_commit(&k_empty[s2]);
       }
     }
   } else {
