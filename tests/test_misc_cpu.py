@@ -161,3 +161,17 @@ def test_heterogeneous_layer_specs():
     from dist_utils import run_distributed
 
     assert all(run_distributed(_hetero, 1))
+
+
+def test_tp_comm_mode_resolution(monkeypatch):
+    from megatron_b200.parallel import fused
+
+    monkeypatch.setattr(fused, "_MODE", "auto")
+    monkeypatch.setattr(fused, "_AUTO_FUSED_MIN_TP", 2)
+    assert fused.get_mode(world_size=1) == "nccl" and fused.get_mode(world_size=2) == "fused" and fused.get_mode(world_size=8) == "fused"
+    monkeypatch.setattr(fused, "_AUTO_FUSED_MIN_TP", 4)
+    assert fused.get_mode(world_size=2) == "nccl"
+    monkeypatch.setattr(fused, "_MODE", "nvlink")
+    assert fused.get_mode(world_size=1) == "nvlink"
+    # CPU tensors never take the NVLink path, whatever the mode
+    assert fused._nvl(None, torch.zeros(1)) is None
