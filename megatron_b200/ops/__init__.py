@@ -263,7 +263,7 @@ class _FlashAttnFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, k, v, causal, scale):
-        o, lse = ext().flash_attn_fwd(q, k, v, causal, scale)
+        o, lse = ext().flash_attn_fwd(q, k, v, causal, scale, _FA_VARIANT)
         _count()
         ctx.save_for_backward(q, k, v, o, lse)
         ctx.causal, ctx.scale = causal, scale
@@ -291,6 +291,7 @@ def _cudnn_lse_ndim() -> int:
 
 
 _ATTN_IMPL = os.environ.get("MEGATRON_B200_ATTN", "auto")  # auto | native | library
+_FA_VARIANT = int(os.environ.get("MEGATRON_B200_FA_VARIANT", "0"))  # 0: P through shared memory, 1: P kept in tensor memory (TS MMA)
 
 
 # what "auto" means on this build: the faster MEASURED forward at the Llama-3 8B shape (profiles/r1_attention.md)

@@ -306,7 +306,7 @@ void nvl_allreduce(const std::vector<int64_t>& ptrs, const std::vector<int64_t>&
 
 #ifdef MB200_HAVE_FLASH_ATTN_SM100
 // q [sq, b, hq, d], k/v [sk, b, hk, d] (any s/b/h strides, d contiguous) -> (out [sq, b, hq, d], lse [b, hq, sq] fp32)
-std::vector<Tensor> flash_attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, bool causal, double scale) {
+std::vector<Tensor> flash_attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, bool causal, double scale, int64_t variant) {
   TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kBFloat16 && k.scalar_type() == at::kBFloat16 && v.scalar_type() == at::kBFloat16, "flash_attn_fwd: bf16 CUDA tensors");
   TORCH_CHECK(q.dim() == 4 && k.dim() == 4 && v.dim() == 4 && q.stride(3) == 1 && k.stride(3) == 1 && v.stride(3) == 1, "flash_attn_fwd: [s, b, h, d] with contiguous d");
   TORCH_CHECK(((uintptr_t)q.data_ptr() | (uintptr_t)k.data_ptr() | (uintptr_t)v.data_ptr()) % 16 == 0, "flash_attn_fwd: 16-byte aligned tensors");
@@ -317,7 +317,7 @@ std::vector<Tensor> flash_attn_fwd(const Tensor& q, const Tensor& k, const Tenso
   auto lse = at::empty({b, hq, sq}, q.options().dtype(at::kFloat));
   const int rc = mb200_flash_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), sq, sk, b, hq, hk, d, q.stride(0), q.stride(1),
                                       q.stride(2), k.stride(0), k.stride(1), k.stride(2), v.stride(0), v.stride(1), v.stride(2), (float)scale, causal ? 1 : 0,
-                                      cur_stream());
+                                      (int)variant, cur_stream());
   TORCH_CHECK(rc == 0, "flash_attn_fwd failed with code ", rc);
   return {out, lse};
 }
@@ -529,7 +529,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("batched_copy", &batched_copy);
 #endif
 #ifdef MB200_HAVE_FLASH_ATTN_SM100
-  m.def("flash_attn_fwd", &flash_attn_fwd);
+  m.def("flash_attn_fwd", &flash_attn_fwd, pybind11::arg("q"), pybind11::arg("k"), pybind11::arg("v"), pybind11::arg("causal"), pybind11::arg("scale"),
+        pybind11::arg("variant") = 0);
 #endif
 #ifdef MB200_HAVE_FUSED_TP_GEMM
   m.def("fused_tp_gemm", &fused_tp_gemm);

@@ -61,7 +61,9 @@ __device__ __forceinline__ float poly_exp2(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
 }
 
-template <int D>
+// P_TMEM: the bf16 probability tile is written back over the first 32 columns of its S buffer with tcgen05.st and the PV MMA reads operand A from
+// tensor memory (no shared-memory round trip, no proxy fence, half the smem operand traffic of PV); otherwise P goes through a swizzled smem tile.
+template <int D, bool P_TMEM>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v, const FaParams p) {
   constexpr int DCH = D / 64;                          // 64-column (128-byte) chunks of the head dim
@@ -177,9 +179,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       auto issue_pv = [&](int t, int s, int buf, bool acc) {
         const uint32_t pa = smem_u32(smem_p + (2 * t + buf) * P_TILE_BYTES), va = smem_u32(smem_v + s * KV_STAGE_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < FA_BN / 16; ++kk)
-          umma_f16(tmem_base + O_COL + t * D, make_smem_desc_sw128(pa + kk * 32, 16, 1024), make_smem_desc_sw128(va + kk * 2048, KV_CHUNK_BYTES, 1024), idesc_pv,
-                   (acc || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < FA_BN / 16; ++kk) {
+          if (P_TMEM)
+            umma_f16_ts(tmem_base + O_COL + t * D, tmem_base + S_COL + (2 * t + buf) * FA_BN + kk * 8, make_smem_desc_sw128(va + kk * 2048, KV_CHUNK_BYTES, 1024), idesc_pv,
+                        (acc || kk > 0) ? 1u : 0u);
+          else
+            umma_f16(tmem_base + O_COL + t * D, make_smem_desc_sw128(pa + kk * 32, 16, 1024), make_smem_desc_sw128(va + kk * 2048, KV_CHUNK_BYTES, 1024), idesc_pv,
+                     (acc || kk > 0) ? 1u : 0u);
+        }
       };
       const int t = warp - 9;
       const int nt = n_t[t];
@@ -268,6 +275,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       const bool rescale = __any_sync(0xffffffffu, alpha != 1.f) && j > 0;
       // p = 2^(s*scale - m_ref); written as bf16 into the 128B-swizzled K-major tile the PV MMA reads as operand A
       float sums[8];
+      uint32_t pw[32];   // the row's 64 probabilities as packed bf16 pairs (P_TMEM path)
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         uint32_t pk[4];
@@ -285,7 +293,16 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           pk[e] = *reinterpret_cast<uint32_t*>(&hb);
         }
         sums[u] = su;
-        *reinterpret_cast<uint4*>(p_row + ((u ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (P_TMEM) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) pw[u * 4 + e] = pk[e];
+        } else {
+          *reinterpret_cast<uint4*>(p_row + ((u ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      if (P_TMEM) {
+        tmem_st_32x32b_x32(s_addr, pw);   // P(j) overwrites columns 0..31 of S[t][buf]; this thread has already read its whole S row
+        tmem_st_wait();
       }
       l += ((sums[0] + sums[1]) + (sums[2] + sums[3])) + ((sums[4] + sums[5]) + (sums[6] + sums[7]));
       if (rescale) {
@@ -303,7 +320,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
         tmem_st_wait();
       }
-      fence_proxy_async();   // generic-proxy smem writes of P → visible to the tensor core (async proxy)
+      if (!P_TMEM) fence_proxy_async();   // generic-proxy smem writes of P → visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(&p_ready[2 * t + buf]);
     }
@@ -339,7 +356,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   if (warp == 9) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-template <int D>
+template <int D, bool P_TMEM>
 static int launch_fa_fwd(const void* q, const void* k, const void* v, FaParams p, long q_ss, long k_ss, long v_ss, cudaStream_t s) {
   constexpr int SMEM_BYTES = 2 * (FA_BM * D * 2) + 2 * FA_STAGES * (FA_BN * D * 2) + 4 * (FA_BM * 128) + 1024 + 256;
   CUtensorMap tq, tk, tv;
@@ -347,7 +364,7 @@ static int launch_fa_fwd(const void* q, const void* k, const void* v, FaParams p
   ok &= make_tmap_bf16_strided(&tk, k, p.sk, k_ss, k_ss * 2, 64, FA_BN);
   ok &= make_tmap_bf16_strided(&tv, v, p.sk, v_ss, v_ss * 2, 64, FA_BN);
   if (!ok) return -1;
-  auto kern = fa_fwd_kernel<D>;
+  auto kern = fa_fwd_kernel<D, P_TMEM>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return -3;
@@ -365,7 +382,7 @@ using namespace mb200;
 // Strides are in elements; *_ss = sequence stride (row pitch), *_sb = batch stride, *_sh = head stride; d is contiguous.
 extern "C" int mb200_flash_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int sq, int sk, int b, int hq, int hk, int d, long q_ss,
                                     long q_sb, long q_sh, long k_ss, long k_sb, long k_sh, long v_ss, long v_sb, long v_sh, float scale, int causal,
-                                    cudaStream_t s) {
+                                    int variant, cudaStream_t s) {
   if ((d != 64 && d != 128) || hq % hk != 0) return -10;
   if ((q_ss | q_sb | q_sh | k_ss | k_sb | k_sh | v_ss | v_sb | v_sh) % 8 != 0) return -11;   // 16-byte alignment for TMA
   FaParams p;
@@ -373,5 +390,6 @@ extern "C" int mb200_flash_attn_fwd(const void* q, const void* k, const void* v,
   p.scale_log2 = scale * 1.4426950408889634f;
   p.q_sb = q_sb; p.q_sh = q_sh; p.k_sb = k_sb; p.k_sh = k_sh; p.v_sb = v_sb; p.v_sh = v_sh;
   p.out = out; p.o_pitch = (long)b * hq * d; p.lse = lse;
-  return d == 128 ? launch_fa_fwd<128>(q, k, v, p, q_ss, k_ss, v_ss, s) : launch_fa_fwd<64>(q, k, v, p, q_ss, k_ss, v_ss, s);
+  if (variant == 1) return d == 128 ? launch_fa_fwd<128, true>(q, k, v, p, q_ss, k_ss, v_ss, s) : launch_fa_fwd<64, true>(q, k, v, p, q_ss, k_ss, v_ss, s);
+  return d == 128 ? launch_fa_fwd<128, false>(q, k, v, p, q_ss, k_ss, v_ss, s) : launch_fa_fwd<64, false>(q, k, v, p, q_ss, k_ss, v_ss, s);
 }

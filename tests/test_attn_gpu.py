@@ -34,7 +34,8 @@ def _ref(q, k, v, causal, scale):
         (2048, 2048, 1, 8, 2, 128, True),
     ],
 )
-def test_flash_fwd_matches_reference(sq, sk, b, hq, hk, d, causal):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_flash_fwd_matches_reference(sq, sk, b, hq, hk, d, causal, variant):
     from megatron_b200 import ops
 
     torch.manual_seed(0)
@@ -42,7 +43,7 @@ def test_flash_fwd_matches_reference(sq, sk, b, hq, hk, d, causal):
     k = torch.randn(sk, b, hk, d, device="cuda").bfloat16()
     v = torch.randn(sk, b, hk, d, device="cuda").bfloat16()
     scale = 1.0 / math.sqrt(d)
-    o, lse = ops.ext().flash_attn_fwd(q, k, v, causal, scale)
+    o, lse = ops.ext().flash_attn_fwd(q, k, v, causal, scale, variant)   # 0: P via smem, 1: P kept in TMEM (TS MMA)
     ro, rlse = _ref(q, k, v, causal, scale)
     assert torch.isfinite(o.float()).all()
     err = (o.float() - ro).abs().max().item()

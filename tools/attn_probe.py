@@ -34,6 +34,7 @@ except Exception as e:
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from megatron_b200 import ops
-for impl in ("native", "library"):
+for impl, variant in (("native", 0), ("native", 1), ("library", 0)):
     ops.set_attention_impl(impl)
-    bench(f"megatron_b200[{impl}]", lambda: ops.flash_attention(q, k, v, causal=True))
+    ops._FA_VARIANT = variant
+    bench(f"megatron_b200[{impl}{'' if impl == 'library' else ',P in TMEM' if variant else ',P via smem'}]", lambda: ops.flash_attention(q, k, v, causal=True))
