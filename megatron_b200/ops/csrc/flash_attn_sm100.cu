@@ -30,6 +30,9 @@ constexpr int FA_BN = 64;        // keys per block
 constexpr int FA_STAGES = 3;     // K and V ring depth
 constexpr int FA_THREADS = 352;   // 8 softmax warps + TMA producer + one MMA-issuing warp per query tile
 constexpr float FA_RESCALE_THRESHOLD = 8.0f;  // log2 units
+// ncu (profiles/r1_flash_attn_ncu.md): with one issuer per tile the softmax warps are ISSUE-bound (50 % issue slots, MUFU only 34 % busy), so the
+// 8-instruction software exp2 costs more than the MUFU slot it saves; kept for the regime where MUFU saturates (e.g. smaller head dims).
+constexpr bool FA_POLY_EXP2 = false;
 
 struct FaParams {
   int sq, sk, b, hq, hk;
@@ -287,7 +290,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           const float a1 = __uint_as_float(c + 1 < 32 ? r0[c + 1] : r1[c + 1 - 32]);
           const float x0 = fmaf(a0, p.scale_log2, -m_ref), x1 = fmaf(a1, p.scale_log2, -m_ref);
           const float p0 = fast_exp2(x0);
-          const float p1 = (e & 1) ? poly_exp2(x1) : fast_exp2(x1);   // every 4th exponential on the FMA pipe
+          const float p1 = (FA_POLY_EXP2 && (e & 1)) ? poly_exp2(x1) : fast_exp2(x1);   // optionally every 4th exponential on the FMA pipe
           su += p0 + p1;
           __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
           pk[e] = *reinterpret_cast<uint32_t*>(&hb);
