@@ -44,6 +44,11 @@ struct FaParams {
   float* lse;
 };
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -261,13 +266,17 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           if (kv0 + 32 + c > limit) r1[c] = 0xff800000u;
         }
       }
-      // 8 independent max chains (a single 64-long dependent chain is ~300 cycles of pure latency per block)
+      // row max with 3-input FMNMX3 (sm_100) in 8 independent chains: 32 instructions for 64 scores, no long dependent chain
       float mxs[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) mxs[c] = fmaxf(__uint_as_float(r0[c]), __uint_as_float(r1[c]));
+      for (int c = 0; c < 8; ++c) mxs[c] = fmax3(__uint_as_float(r0[c]), __uint_as_float(r1[c]), __uint_as_float(r0[c + 8]));
 #pragma unroll
-      for (int c = 8; c < 32; ++c) mxs[c & 7] = fmaxf(mxs[c & 7], fmaxf(__uint_as_float(r0[c]), __uint_as_float(r1[c])));
-      const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])), fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+      for (int c = 0; c < 8; ++c) mxs[c] = fmax3(mxs[c], __uint_as_float(r1[c + 8]), __uint_as_float(r0[c + 16]));
+#pragma unroll
+      for (int c = 0; c < 8; ++c) mxs[c] = fmax3(mxs[c], __uint_as_float(r1[c + 16]), __uint_as_float(r0[c + 24]));
+#pragma unroll
+      for (int c = 0; c < 8; ++c) mxs[c] = fmaxf(mxs[c], __uint_as_float(r1[c + 24]));
+      const float mx = fmaxf(fmax3(mxs[0], mxs[1], mxs[2]), fmaxf(fmax3(mxs[3], mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
       const float mx_scaled = mx * p.scale_log2;
       float alpha = 1.f;
       if (mx_scaled > m_ref + FA_RESCALE_THRESHOLD) {
