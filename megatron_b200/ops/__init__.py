@@ -291,7 +291,7 @@ def _cudnn_lse_ndim() -> int:
 
 
 _ATTN_IMPL = os.environ.get("MEGATRON_B200_ATTN", "auto")  # auto | native | library
-_FA_VARIANT = int(os.environ.get("MEGATRON_B200_FA_VARIANT", "0"))  # 0: P through shared memory, 1: P kept in tensor memory (TS MMA)
+_FA_VARIANT = int(os.environ.get("MEGATRON_B200_FA_VARIANT", "1"))  # 1 (default, measured 836 vs 786 TF): P kept in tensor memory (TS MMA); 0: P through shared memory
 
 
 # what "auto" means on this build: the faster MEASURED forward at the Llama-3 8B shape (profiles/r1_attention.md)
