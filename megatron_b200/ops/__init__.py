@@ -313,7 +313,7 @@ def _native_attention_ok(q, k, v, causal, window) -> bool:
         return False
     if q.dtype != torch.bfloat16 or q.shape[-1] not in (64, 128) or k.shape[-1] != q.shape[-1] or v.shape[-1] != q.shape[-1]:
         return False
-    if causal and k.shape[0] < q.shape[0]:
+    if (causal and k.shape[0] < q.shape[0]) or q.shape[0] < 128:   # decode-sized queries stay on the library path (untested regime for the 2x128-row tiling)
         return False
     strides_ok = all(t.stride(-1) == 1 and all(s % 8 == 0 for s in t.stride()[:-1]) and t.data_ptr() % 16 == 0 for t in (q, k, v))
     return strides_ok
