@@ -1,0 +1,318 @@
+// Flash attention backward for sm_100a (tcgen05 / TMEM / TMA): one CTA owns a 128-key block of one KV head and walks the query blocks
+// (64 queries) of every query head in its GQA group; dK and dV accumulate in tensor memory for the whole walk, dQ partials are added to
+// an fp32 buffer with coalesced red.global.add.
+//
+// Everything is computed in the TRANSPOSED orientation so that the key index is the MMA "M" (= TMEM lane) dimension:
+//   Sᵀ  = K_j Q_iᵀ            UMMA 128x64x16, A = K_j (K-major smem), B = Q_i (K-major smem)            → TMEM [kv, q]
+//   dPᵀ = V_j dO_iᵀ           same with V_j, dO_i                                                        → TMEM [kv, q]
+//   Pᵀ  = exp2(Sᵀ·c − lse_q)  ;  dSᵀ = Pᵀ ∘ (dPᵀ − D_q) · scale     (thread = one key row, 64 columns)   → bf16 over the same TMEM columns
+//   dV += Pᵀ dO_i             UMMA 128x128x16, A = Pᵀ FROM TMEM, B = dO_i (MN-major view of the same smem tile)
+//   dK += dSᵀ Q_i             UMMA 128x128x16, A = dSᵀ FROM TMEM, B = Q_i (MN-major view)
+//   dQᵀ = K_jᵀ dSᵀ            UMMA 128x64x16,  A = K_j (MN-major view), B = dSᵀ (bf16 copy in swizzled smem) → TMEM [d, q] → red.add to dQ
+// Warps 0-3: compute (thread = TMEM lane), warp 4: TMA producer, warp 5: MMA issuer + TMEM allocator.  This first version runs the MMA
+// and compute phases of a step back to back (no ping-pong yet); it is selectable with MEGATRON_B200_ATTN_BWD=native and validated against
+// fp32 autograd, the default backward stays the cuDNN library kernel until this one is pipelined.
+#include "gemm_sm100_device.cuh"
+
+namespace mb200 {
+using namespace ptx;
+
+constexpr int FB_KV = 128;      // keys per CTA
+constexpr int FB_Q = 64;        // queries per step
+constexpr int FB_THREADS = 192;
+constexpr int FB_D = 128;       // head dim (this version)
+
+struct FaBwdParams {
+  int sq, sk, b, hq, hk;
+  int causal;
+  float scale, scale_log2;
+  long q_sb, q_sh, k_sb, k_sh, v_sb, v_sh, do_sb, do_sh;   // element strides of batch / head inside one sequence row
+  const float* lse;      // [b, hq, sq] natural log
+  const float* delta;    // [b, hq, sq]  rowsum(dO ∘ O)
+  float* dq_acc;         // [sq, b, hq, d] fp32, zero-initialised
+  void* dk;              // [sk, b, hk, d] bf16
+  void* dv;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__global__ void __launch_bounds__(FB_THREADS, 1)
+fa_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+              const __grid_constant__ CUtensorMap tmap_do, const FaBwdParams p) {
+  constexpr int D = FB_D;
+  constexpr int KV_CHUNK = FB_KV * 128;            // [128 rows x 128 B]
+  constexpr int KV_BYTES = 2 * KV_CHUNK;           // K_j or V_j: 32 KiB
+  constexpr int Q_CHUNK = FB_Q * 128;              // [64 rows x 128 B]
+  constexpr int Q_BYTES = 2 * Q_CHUNK;             // Q_i or dO_i: 16 KiB
+  constexpr int DS_BYTES = FB_KV * 128;            // dSᵀ bf16 [128 kv x 64 q]: 16 KiB
+  constexpr int STAGES = 2;
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t DK_COL = 0, DV_COL = 128, ST_COL = 256, DPT_COL = 320, DQT_COL = 384;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_k = smem;
+  uint8_t* smem_v = smem_k + KV_BYTES;
+  uint8_t* smem_q = smem_v + KV_BYTES;                       // STAGES x Q_BYTES
+  uint8_t* smem_do = smem_q + STAGES * Q_BYTES;              // STAGES x Q_BYTES
+  uint8_t* smem_ds = smem_do + STAGES * Q_BYTES;             // DS_BYTES
+  float* smem_vec = reinterpret_cast<float*>(smem_ds + DS_BYTES);   // lse2[64] | delta[64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_vec + 2 * FB_Q);
+  uint64_t* kv_full = bars;              // 1
+  uint64_t* q_full = bars + 1;           // STAGES
+  uint64_t* q_empty = q_full + STAGES;   // STAGES
+  uint64_t* s_ready = q_empty + STAGES;  // 1
+  uint64_t* p_ready = s_ready + 1;       // 1 (128 arrivals)
+  uint64_t* dq_ready = p_ready + 1;      // 1
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(dq_ready + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jb = blockIdx.x, hkv = blockIdx.y, bi = blockIdx.z;
+  const int k0 = jb * FB_KV;
+  const int group = p.hq / p.hk;
+  const int off = p.sk - p.sq;
+  const int nq = (p.sq + FB_Q - 1) / FB_Q;
+  int i0 = 0;
+  if (p.causal) {
+    const int first_q = k0 - off;          // first query that can see key k0
+    i0 = first_q <= 0 ? 0 : first_q / FB_Q;
+  }
+  const int steps_per_head = nq > i0 ? nq - i0 : 0;
+  const int total_steps = steps_per_head * group;
+
+  if (warp == 4 && lane == 0) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_k);
+    prefetch_tmap(&tmap_v);
+    prefetch_tmap(&tmap_do);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+    }
+    mbar_init(s_ready, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(dq_ready, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc<TMEM_COLS>(tmem_holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 4) {
+    // ============================== TMA producer ==========================================================================
+    if (lane == 0 && total_steps > 0) {
+      const int kcol = (int)(bi * p.k_sb + hkv * p.k_sh), vcol = (int)(bi * p.v_sb + hkv * p.v_sh);
+      mbar_expect_tx(kv_full, 2 * KV_BYTES);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tma_load_2d(smem_k + c * KV_CHUNK, &tmap_k, kv_full, kcol + c * 64, k0);
+        tma_load_2d(smem_v + c * KV_CHUNK, &tmap_v, kv_full, vcol + c * 64, k0);
+      }
+      for (int st = 0; st < total_steps; ++st) {
+        const int h = hkv * group + st / steps_per_head, i = i0 + st % steps_per_head;
+        const int s = st % STAGES;
+        mbar_wait(&q_empty[s], ((uint32_t)(st / STAGES) & 1u) ^ 1u);
+        mbar_expect_tx(&q_full[s], 2 * Q_BYTES);
+        const int qcol = (int)(bi * p.q_sb + h * p.q_sh), docol = (int)(bi * p.do_sb + h * p.do_sh);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tma_load_2d(smem_q + s * Q_BYTES + c * Q_CHUNK, &tmap_q, &q_full[s], qcol + c * 64, i * FB_Q);
+          tma_load_2d(smem_do + s * Q_BYTES + c * Q_CHUNK, &tmap_do, &q_full[s], docol + c * 64, i * FB_Q);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ============================== MMA issuer ================================================================================
+    if (lane == 0 && total_steps > 0) {
+      constexpr uint32_t idesc_st = make_idesc_bf16(FB_KV, FB_Q, false, false);   // Sᵀ, dPᵀ : K-major A and B
+      constexpr uint32_t idesc_dkv = make_idesc_bf16(FB_KV, D, false, true);      // dV, dK : A from TMEM, B MN-major
+      constexpr uint32_t idesc_dqt = make_idesc_bf16(D, FB_Q, true, true);        // dQᵀ : A = K_jᵀ (MN-major), B = dSᵀ (MN-major)
+      const uint32_t ka = smem_u32(smem_k), va = smem_u32(smem_v), dsa = smem_u32(smem_ds);
+      mbar_wait(kv_full, 0);
+      for (int st = 0; st < total_steps; ++st) {
+        const int s = st % STAGES;
+        const uint32_t qa = smem_u32(smem_q + s * Q_BYTES), doa = smem_u32(smem_do + s * Q_BYTES);
+        mbar_wait(&q_full[s], (uint32_t)(st / STAGES) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t acc = (c > 0 || kk > 0) ? 1u : 0u;
+            umma_f16(tmem_base + ST_COL, make_smem_desc_sw128(ka + c * KV_CHUNK + kk * 32, 16, 1024), make_smem_desc_sw128(qa + c * Q_CHUNK + kk * 32, 16, 1024), idesc_st, acc);
+            umma_f16(tmem_base + DPT_COL, make_smem_desc_sw128(va + c * KV_CHUNK + kk * 32, 16, 1024), make_smem_desc_sw128(doa + c * Q_CHUNK + kk * 32, 16, 1024), idesc_st, acc);
+          }
+        umma_commit(s_ready);
+        mbar_wait(p_ready, (uint32_t)st & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < FB_Q / 16; ++kk) {
+          const uint32_t acc = (st > 0 || kk > 0) ? 1u : 0u;
+          // B = dO_i / Q_i read as [K = q rows, N = d]: MN-major, two 64-column chunks Q_CHUNK apart
+          umma_f16_ts(tmem_base + DV_COL, tmem_base + ST_COL + kk * 8, make_smem_desc_sw128(doa + kk * 2048, Q_CHUNK, 1024), idesc_dkv, acc);
+          umma_f16_ts(tmem_base + DK_COL, tmem_base + DPT_COL + kk * 8, make_smem_desc_sw128(qa + kk * 2048, Q_CHUNK, 1024), idesc_dkv, acc);
+        }
+#pragma unroll
+        for (int kk = 0; kk < FB_KV / 16; ++kk)
+          umma_f16(tmem_base + DQT_COL, make_smem_desc_sw128(ka + kk * 2048, KV_CHUNK, 1024), make_smem_desc_sw128(dsa + kk * 2048, DS_BYTES, 1024), idesc_dqt, kk > 0 ? 1u : 0u);
+        umma_commit(dq_ready);
+        umma_commit(&q_empty[s]);
+      }
+    }
+  } else {
+    // ============================== compute warps: thread = key row (Sᵀ / dPᵀ) and = head-dim row (dQᵀ) ==================================
+    const int row = warp * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int kv_idx = k0 + row;
+    uint8_t* ds_row = smem_ds + row * 128;
+    const int sw = row & 7;
+    for (int st = 0; st < total_steps; ++st) {
+      const int h = hkv * group + st / steps_per_head, i = i0 + st % steps_per_head;
+      const int q0 = i * FB_Q;
+      // per-query vectors of this step: lse (log2 domain) and delta
+      if (row < FB_Q) {
+        const int q = q0 + row;
+        smem_vec[row] = q < p.sq ? p.lse[((size_t)bi * p.hq + h) * p.sq + q] * 1.4426950408889634f : 0.f;
+      } else {
+        const int q = q0 + row - FB_Q;
+        smem_vec[row] = q < p.sq ? p.delta[((size_t)bi * p.hq + h) * p.sq + q] : 0.f;
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(s_ready, (uint32_t)st & 1u);
+      tc_fence_after();
+      uint32_t pw[32], dw[32];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t sv[32], dpv[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_base + ST_COL + half * 32, sv);
+        tmem_ld_32x32b_x32(tmem_base + lane_base + DPT_COL + half * 32, dpv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float pr[2], ds[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int qc = half * 32 + c + e, q = q0 + qc;
+            const bool ok = kv_idx < p.sk && q < p.sq && (!p.causal || kv_idx <= q + off);
+            const float pv = ok ? ex2(fmaf(__uint_as_float(sv[c + e]), p.scale_log2, -smem_vec[qc])) : 0.f;
+            pr[e] = pv;
+            ds[e] = pv * (__uint_as_float(dpv[c + e]) - smem_vec[FB_Q + qc]) * p.scale;
+          }
+          __nv_bfloat162 pb = __floats2bfloat162_rn(pr[0], pr[1]), db = __floats2bfloat162_rn(ds[0], ds[1]);
+          pw[half * 16 + c / 2] = *reinterpret_cast<uint32_t*>(&pb);
+          dw[half * 16 + c / 2] = *reinterpret_cast<uint32_t*>(&db);
+        }
+      }
+      // Pᵀ and dSᵀ (bf16 pairs) back over the first 32 columns of Sᵀ / dPᵀ; dSᵀ also into the swizzled smem tile read as operand B of dQᵀ
+      tmem_st_32x32b_x32(tmem_base + lane_base + ST_COL, pw);
+      tmem_st_32x32b_x32(tmem_base + lane_base + DPT_COL, dw);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) *reinterpret_cast<uint4*>(ds_row + ((u ^ sw) << 4)) = make_uint4(dw[u * 4], dw[u * 4 + 1], dw[u * 4 + 2], dw[u * 4 + 3]);
+      tmem_st_wait();
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+      // dQᵀ [d = row, 64 queries] → fp32 accumulation buffer (lanes = consecutive d: every red is a coalesced 128-byte segment)
+      mbar_wait(dq_ready, (uint32_t)st & 1u);
+      tc_fence_after();
+      float* dq_base = p.dq_acc + ((size_t)bi * p.hq + h) * D + row;
+      const size_t q_pitch = (size_t)p.b * p.hq * D;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t dq[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_base + DQT_COL + half * 32, dq);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int q = q0 + half * 32 + c;
+          if (q < p.sq) atomicAdd(dq_base + (size_t)q * q_pitch, __uint_as_float(dq[c]));
+        }
+      }
+      tc_fence_before();
+      named_bar_sync(1, 128);   // smem_vec and the dQᵀ columns are reused by the next step
+    }
+    // ---- epilogue: dK, dV [kv = row, d] → bf16 ------------------------------------------------------------------------------------
+    if (total_steps > 0) {
+      // the last dq_ready wait above also covers the final dV / dK accumulation (same commit)
+      tc_fence_after();
+      const bool valid = kv_idx < p.sk;
+      __nv_bfloat16* dk_row = reinterpret_cast<__nv_bfloat16*>(p.dk) + ((size_t)kv_idx * p.b * p.hk + (size_t)bi * p.hk + hkv) * D;
+      __nv_bfloat16* dv_row = reinterpret_cast<__nv_bfloat16*>(p.dv) + ((size_t)kv_idx * p.b * p.hk + (size_t)bi * p.hk + hkv) * D;
+#pragma unroll 1
+      for (int which = 0; which < 2; ++which) {
+#pragma unroll 1
+        for (int ch = 0; ch < D / 32; ++ch) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_base + (which ? DV_COL : DK_COL) + ch * 32, o);
+          tmem_ld_wait();
+          if (valid) {
+            __nv_bfloat16* dst = (which ? dv_row : dk_row) + ch * 32;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              uint32_t v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(o[g * 16 + 2 * e]), __uint_as_float(o[g * 16 + 2 * e + 1]));
+                v[e] = *reinterpret_cast<uint32_t*>(&hb);
+              }
+              st_global_v8(dst + g * 16, v);
+            }
+          }
+        }
+      }
+    } else if (kv_idx < p.sk) {
+      // no query sees this key block (cannot happen with sk >= sq causal, kept for safety): gradients are zero
+      uint4 z = make_uint4(0, 0, 0, 0);
+      __nv_bfloat16* dk_row = reinterpret_cast<__nv_bfloat16*>(p.dk) + ((size_t)kv_idx * p.b * p.hk + (size_t)bi * p.hk + hkv) * D;
+      __nv_bfloat16* dv_row = reinterpret_cast<__nv_bfloat16*>(p.dv) + ((size_t)kv_idx * p.b * p.hk + (size_t)bi * p.hk + hkv) * D;
+      for (int c = 0; c < D / 8; ++c) {
+        reinterpret_cast<uint4*>(dk_row)[c] = z;
+        reinterpret_cast<uint4*>(dv_row)[c] = z;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+}  // namespace mb200
+
+using namespace mb200;
+
+// q, do: [sq, b, hq, 128]; k, v: [sk, b, hk, 128] (element strides given, d contiguous); lse, delta: [b, hq, sq] fp32;
+// dq_acc: [sq, b, hq, 128] fp32 zero-initialised; dk, dv: [sk, b, hk, 128] bf16 contiguous.
+extern "C" int mb200_flash_attn_bwd(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta, float* dq_acc, void* dk,
+                                    void* dv, int sq, int sk, int b, int hq, int hk, int d, long q_ss, long q_sb, long q_sh, long k_ss, long k_sb, long k_sh,
+                                    long v_ss, long v_sb, long v_sh, long do_ss, long do_sb, long do_sh, float scale, int causal, cudaStream_t s) {
+  if (d != FB_D || hq % hk != 0) return -10;
+  if ((q_ss | q_sb | q_sh | k_ss | k_sb | k_sh | v_ss | v_sb | v_sh | do_ss | do_sb | do_sh) % 8 != 0) return -11;
+  constexpr int SMEM_BYTES = 2 * (2 * FB_KV * 128) + 2 * 2 * (2 * FB_Q * 128) + FB_KV * 128 + 2 * FB_Q * 4 + 1024 + 256;
+  CUtensorMap tq, tk, tv, tdo;
+  bool ok = make_tmap_bf16_strided(&tq, q, sq, q_ss, q_ss * 2, 64, FB_Q);
+  ok &= make_tmap_bf16_strided(&tk, k, sk, k_ss, k_ss * 2, 64, FB_KV);
+  ok &= make_tmap_bf16_strided(&tv, v, sk, v_ss, v_ss * 2, 64, FB_KV);
+  ok &= make_tmap_bf16_strided(&tdo, dout, sq, do_ss, do_ss * 2, 64, FB_Q);
+  if (!ok) return -1;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(fa_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return -3;
+    configured = true;
+  }
+  FaBwdParams p;
+  p.sq = sq; p.sk = sk; p.b = b; p.hq = hq; p.hk = hk; p.causal = causal;
+  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  p.q_sb = q_sb; p.q_sh = q_sh; p.k_sb = k_sb; p.k_sh = k_sh; p.v_sb = v_sb; p.v_sh = v_sh; p.do_sb = do_sb; p.do_sh = do_sh;
+  p.lse = lse; p.delta = delta; p.dq_acc = dq_acc; p.dk = dk; p.dv = dv;
+  dim3 grid((sk + FB_KV - 1) / FB_KV, hk, b);
+  fa_bwd_kernel<<<grid, FB_THREADS, SMEM_BYTES, s>>>(tq, tk, tv, tdo, p);
+  return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}

@@ -38,3 +38,8 @@ for impl, variant in (("native", 0), ("native", 1), ("library", 0)):
     ops.set_attention_impl(impl)
     ops._FA_VARIANT = variant
     bench(f"megatron_b200[{impl}{'' if impl == 'library' else ',P in TMEM' if variant else ',P via smem'}]", lambda: ops.flash_attention(q, k, v, causal=True))
+
+# our tcgen05 backward (first version) next to the cuDNN backward
+ops.set_attention_impl("native"); ops._FA_VARIANT = 1; ops._ATTN_BWD_IMPL = "native"
+bench("megatron_b200[native fwd + native bwd]", lambda: ops.flash_attention(q, k, v, causal=True))
+ops._ATTN_BWD_IMPL = "library"
