@@ -175,7 +175,7 @@ def run_b200(args):
     _gemm_wins = {}
     for _key, _winner, _times in _gemm.tuning_report():
         _gemm_wins[str(_winner).split(":")[0]] = _gemm_wins.get(str(_winner).split(":")[0], 0) + 1
-    _attn_impl = ops._resolved_attn_impl() if hasattr(ops, "_resolved_attn_impl") else "library"
+    _attn_impl = ops.attention_impl_for(eng.seq_length, args.micro_batch, 32 // world) if hasattr(ops, "attention_impl_for") else "library"
     if rank == 0:
         flops = eng.flops_per_step * args.steps / (ms / 1e3)
         mp = {}

@@ -303,11 +303,21 @@ _FA_VARIANT = int(os.environ.get("MEGATRON_B200_FA_VARIANT", "1"))  # 1 (default
 
 
 # what "auto" means on this build: the faster MEASURED forward at the Llama-3 8B shape (profiles/r1_attention.md)
-_ATTN_AUTO_RESOLVES_TO = "library"
+_ATTN_AUTO_RESOLVES_TO = "native"   # forward 943 TF (0.75x cuDNN) costs ~1 % of the step; backward is cuDNN on our (out, LSE) unless MEGATRON_B200_ATTN_BWD=native
 
 
 def _resolved_attn_impl() -> str:
     return _ATTN_AUTO_RESOLVES_TO if _ATTN_IMPL == "auto" else _ATTN_IMPL
+
+
+def attention_impl_for(sq: int, b: int, hq_local: int) -> str:
+    """What ``flash_attention`` will run for a bf16 [sq, b, hq_local, 128] causal problem on this build (for logs / bench reports)."""
+    impl = _resolved_attn_impl()
+    if impl == "native" and _ATTN_IMPL == "auto" and ((sq + 255) // 256) * hq_local * b < 2 * 148:
+        impl = "library"
+    if impl == "native":
+        return "tcgen05 forward (ours, P in TMEM)" + (" + tcgen05 backward (ours)" if _ATTN_BWD_IMPL == "native" else " + cuDNN backward on our (out, LSE)")
+    return "cuDNN SDPA (library) forward + backward"
 
 
 def set_attention_impl(impl: str) -> None:
@@ -319,6 +329,12 @@ def set_attention_impl(impl: str) -> None:
 def _native_attention_ok(q, k, v, causal, window) -> bool:
     if _resolved_attn_impl() == "library" or window is not None or not hasattr(ext(), "flash_attn_fwd"):
         return False
+    if _ATTN_IMPL == "auto":
+        # one CTA per (256 query rows, head): with fewer than two waves on 148 SMs the causal load imbalance is exposed
+        # (TP=8 leaves 4 heads x 32 tiles = 128 CTAs, bounded by the heaviest tile) — the library kernel handles that regime better
+        n_ctas = ((q.shape[0] + 255) // 256) * q.shape[2] * q.shape[1]
+        if n_ctas < 2 * 148:
+            return False
     if q.dtype != torch.bfloat16 or q.shape[-1] not in (64, 128) or k.shape[-1] != q.shape[-1] or v.shape[-1] != q.shape[-1]:
         return False
     if (causal and k.shape[0] < q.shape[0]) or q.shape[0] < 128:   # decode-sized queries stay on the library path (untested regime for the 2x128-row tiling)
