@@ -9,7 +9,7 @@
 //   dV += Pᵀ dO_i             UMMA 128x128x16, A = Pᵀ FROM TMEM, B = dO_i (MN-major view of the same smem tile)
 //   dK += dSᵀ Q_i             UMMA 128x128x16, A = dSᵀ FROM TMEM, B = Q_i (MN-major view)
 //   dQᵀ = K_jᵀ dSᵀ            UMMA 128x64x16,  A = K_j (MN-major view), B = dSᵀ (bf16 copy in swizzled smem) → TMEM [d, q] → red.add to dQ
-// Warps 0-3: compute (thread = TMEM lane), warp 4: TMA producer, warp 5: MMA issuer + TMEM allocator.  This first version runs the MMA
+// Warps 0-7: compute (thread = TMEM lane x column half), warp 8: TMA producer, warp 9: MMA issuer + TMEM allocator.  This first version runs the MMA
 // and compute phases of a step back to back (no ping-pong yet); it is selectable with MEGATRON_B200_ATTN_BWD=native and validated against
 // fp32 autograd, the default backward stays the cuDNN library kernel until this one is pipelined.
 #include "gemm_sm100_device.cuh"
@@ -19,7 +19,7 @@ using namespace ptx;
 
 constexpr int FB_KV = 128;      // keys per CTA
 constexpr int FB_Q = 64;        // queries per step
-constexpr int FB_THREADS = 192;
+constexpr int FB_THREADS = 320;   // 8 compute warps (two per TMEM lane quarter: each takes 32 of the 64 query columns) + producer + issuer
 constexpr int FB_D = 128;       // head dim (this version)
 
 struct FaBwdParams {
@@ -85,7 +85,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   const int steps_per_head = nq > i0 ? nq - i0 : 0;
   const int total_steps = steps_per_head * group;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     prefetch_tmap(&tmap_q);
     prefetch_tmap(&tmap_k);
     prefetch_tmap(&tmap_v);
@@ -96,17 +96,17 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       mbar_init(&q_empty[i], 1);
     }
     mbar_init(s_ready, 1);
-    mbar_init(p_ready, 128);
+    mbar_init(p_ready, 256);
     mbar_init(dq_ready, 1);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc<TMEM_COLS>(tmem_holder);
+  if (warp == 9) tmem_alloc<TMEM_COLS>(tmem_holder);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ============================== TMA producer ==========================================================================
     if (lane == 0 && total_steps > 0) {
       const int kcol = (int)(bi * p.k_sb + hkv * p.k_sh), vcol = (int)(bi * p.v_sb + hkv * p.v_sh);
@@ -129,7 +129,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ============================== MMA issuer ================================================================================
     if (lane == 0 && total_steps > 0) {
       constexpr uint32_t idesc_st = make_idesc_bf16(FB_KV, FB_Q, false, false);   // Sᵀ, dPᵀ : K-major A and B
@@ -169,32 +169,35 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     }
   } else {
     // ============================== compute warps: thread = key row (Sᵀ / dPᵀ) and = head-dim row (dQᵀ) ==================================
-    const int row = warp * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int half = warp >> 2;                          // which 32 of the 64 query columns this warp handles
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int kv_idx = k0 + row;
     uint8_t* ds_row = smem_ds + row * 128;
     const int sw = row & 7;
+    const int tid = threadIdx.x;                         // 0..255 among the compute warps
     for (int st = 0; st < total_steps; ++st) {
       const int h = hkv * group + st / steps_per_head, i = i0 + st % steps_per_head;
       const int q0 = i * FB_Q;
       // per-query vectors of this step: lse (log2 domain) and delta
-      if (row < FB_Q) {
-        const int q = q0 + row;
-        smem_vec[row] = q < p.sq ? p.lse[((size_t)bi * p.hq + h) * p.sq + q] * 1.4426950408889634f : 0.f;
-      } else {
-        const int q = q0 + row - FB_Q;
-        smem_vec[row] = q < p.sq ? p.delta[((size_t)bi * p.hq + h) * p.sq + q] : 0.f;
+      if (tid < FB_Q) {
+        const int q = q0 + tid;
+        smem_vec[tid] = q < p.sq ? p.lse[((size_t)bi * p.hq + h) * p.sq + q] * 1.4426950408889634f : 0.f;
+      } else if (tid < 2 * FB_Q) {
+        const int q = q0 + tid - FB_Q;
+        smem_vec[tid] = q < p.sq ? p.delta[((size_t)bi * p.hq + h) * p.sq + q] : 0.f;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       mbar_wait(s_ready, (uint32_t)st & 1u);
       tc_fence_after();
-      uint32_t pw[32], dw[32];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      uint32_t pw[16], dw[16];
+      {
         uint32_t sv[32], dpv[32];
         tmem_ld_32x32b_x32(tmem_base + lane_base + ST_COL + half * 32, sv);
         tmem_ld_32x32b_x32(tmem_base + lane_base + DPT_COL + half * 32, dpv);
         tmem_ld_wait();
+        // every thread of the pair (warp w, w+4) must have read its half of the row before either overwrites the first 32 columns
+        named_bar_sync(2, 256);
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
           float pr[2], ds[2];
@@ -207,26 +210,25 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             ds[e] = pv * (__uint_as_float(dpv[c + e]) - smem_vec[FB_Q + qc]) * p.scale;
           }
           __nv_bfloat162 pb = __floats2bfloat162_rn(pr[0], pr[1]), db = __floats2bfloat162_rn(ds[0], ds[1]);
-          pw[half * 16 + c / 2] = *reinterpret_cast<uint32_t*>(&pb);
-          dw[half * 16 + c / 2] = *reinterpret_cast<uint32_t*>(&db);
+          pw[c / 2] = *reinterpret_cast<uint32_t*>(&pb);
+          dw[c / 2] = *reinterpret_cast<uint32_t*>(&db);
         }
       }
-      // Pᵀ and dSᵀ (bf16 pairs) back over the first 32 columns of Sᵀ / dPᵀ; dSᵀ also into the swizzled smem tile read as operand B of dQᵀ
-      tmem_st_32x32b_x32(tmem_base + lane_base + ST_COL, pw);
-      tmem_st_32x32b_x32(tmem_base + lane_base + DPT_COL, dw);
+      // Pᵀ and dSᵀ (bf16 pairs) back over the first 32 columns of Sᵀ / dPᵀ (this warp: 16 of them); dSᵀ also into the swizzled smem tile (operand B of dQᵀ)
+      tmem_st_32x32b_x16(tmem_base + lane_base + ST_COL + half * 16, pw);
+      tmem_st_32x32b_x16(tmem_base + lane_base + DPT_COL + half * 16, dw);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) *reinterpret_cast<uint4*>(ds_row + ((u ^ sw) << 4)) = make_uint4(dw[u * 4], dw[u * 4 + 1], dw[u * 4 + 2], dw[u * 4 + 3]);
+      for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(ds_row + (((half * 4 + u) ^ sw) << 4)) = make_uint4(dw[u * 4], dw[u * 4 + 1], dw[u * 4 + 2], dw[u * 4 + 3]);
       tmem_st_wait();
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(p_ready);
-      // dQᵀ [d = row, 64 queries] → fp32 accumulation buffer (lanes = consecutive d: every red is a coalesced 128-byte segment)
+      // dQᵀ [d = row, this warp's 32 queries] → fp32 accumulation buffer (lanes = consecutive d: every red is a coalesced 128-byte segment)
       mbar_wait(dq_ready, (uint32_t)st & 1u);
       tc_fence_after();
       float* dq_base = p.dq_acc + ((size_t)bi * p.hq + h) * D + row;
       const size_t q_pitch = (size_t)p.b * p.hq * D;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      {
         uint32_t dq[32];
         tmem_ld_32x32b_x32(tmem_base + lane_base + DQT_COL + half * 32, dq);
         tmem_ld_wait();
@@ -237,7 +239,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
       }
       tc_fence_before();
-      named_bar_sync(1, 128);   // smem_vec and the dQᵀ columns are reused by the next step
+      named_bar_sync(1, 256);   // smem_vec and the dQᵀ columns are reused by the next step
     }
     // ---- epilogue: dK, dV [kv = row, d] → bf16 ------------------------------------------------------------------------------------
     if (total_steps > 0) {
@@ -249,7 +251,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 #pragma unroll 1
       for (int which = 0; which < 2; ++which) {
 #pragma unroll 1
-        for (int ch = 0; ch < D / 32; ++ch) {
+        for (int ch = half * (D / 64); ch < (half + 1) * (D / 64); ++ch) {
           uint32_t o[32];
           tmem_ld_32x32b_x32(tmem_base + lane_base + (which ? DV_COL : DK_COL) + ch * 32, o);
           tmem_ld_wait();
@@ -273,7 +275,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       uint4 z = make_uint4(0, 0, 0, 0);
       __nv_bfloat16* dk_row = reinterpret_cast<__nv_bfloat16*>(p.dk) + ((size_t)kv_idx * p.b * p.hk + (size_t)bi * p.hk + hkv) * D;
       __nv_bfloat16* dv_row = reinterpret_cast<__nv_bfloat16*>(p.dv) + ((size_t)kv_idx * p.b * p.hk + (size_t)bi * p.hk + hkv) * D;
-      for (int c = 0; c < D / 8; ++c) {
+      for (int c = half * (D / 16); c < (half + 1) * (D / 16); ++c) {
         reinterpret_cast<uint4*>(dk_row)[c] = z;
         reinterpret_cast<uint4*>(dv_row)[c] = z;
       }
@@ -281,7 +283,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == 9) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 }  // namespace mb200
