@@ -83,10 +83,17 @@ def initialize_megatron(argv=None, extra_args_provider=None, args_defaults: Opti
         from ..parallel import fused
 
         fused.set_mode(args.tp_comm)
-    if torch.cuda.is_available() and args.tensor_model_parallel_size > 1 and args.tp_comm != "nccl" and dist.get_backend() == "nccl":
-        from ..parallel import collectives
+    if torch.cuda.is_available() and args.tensor_model_parallel_size > 1 and dist.get_backend() == "nccl":
+        from ..parallel import collectives, fused
 
-        collectives.enable_for_group(ps.get_tensor_model_parallel_group())
+        if fused.get_mode(world_size=args.tensor_model_parallel_size) != "nccl":
+            try:
+                collectives.enable_for_group(ps.get_tensor_model_parallel_group())
+            except Exception as e:  # no symmetric memory on this box: NCCL + GEMM path
+                print_rank_0(f"WARNING: NVLink symmetric-memory runtime unavailable ({type(e).__name__}: {e}); TP collectives use NCCL")
+                fused.set_mode("nccl")
+        if args.expert_model_parallel_size > 1 and getattr(args, "moe_token_dispatcher_type", None) == "flex":
+            collectives.enable_for_group(ps.get_expert_model_parallel_group())
     return args
 
 
