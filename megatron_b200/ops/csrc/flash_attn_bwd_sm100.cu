@@ -39,6 +39,11 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __global__ void __launch_bounds__(FB_THREADS, 1)
@@ -198,20 +203,33 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         tmem_ld_wait();
         // every thread of the pair (warp w, w+4) must have read its half of the row before either overwrites the first 32 columns
         named_bar_sync(2, 256);
+        // ncu (first version): 56 issued instructions per score element, most of them integer — per-element mask predicates, generic-address
+        // loads of the lse/delta vectors and 64-bit address arithmetic for the reductions.  Interior blocks (no key/query padding, fully below
+        // the causal diagonal) take a predicate-free path; the vectors come in with ld.shared.v4.
+        const bool interior = (k0 + FB_KV <= p.sk) && (q0 + FB_Q <= p.sq) && (!p.causal || (k0 + FB_KV - 1 <= q0 + off));
+        const uint32_t vec_addr = smem_u32(smem_vec) + half * 32 * 4;
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float pr[2], ds[2];
+        for (int c4 = 0; c4 < 32; c4 += 4) {
+          const float4 l4 = lds_f4(vec_addr + c4 * 4), d4 = lds_f4(vec_addr + FB_Q * 4 + c4 * 4);
+          const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+          float pr[4], ds[4];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int qc = half * 32 + c + e, q = q0 + qc;
-            const bool ok = kv_idx < p.sk && q < p.sq && (!p.causal || kv_idx <= q + off);
-            const float pv = ok ? ex2(fmaf(__uint_as_float(sv[c + e]), p.scale_log2, -smem_vec[qc])) : 0.f;
+          for (int e = 0; e < 4; ++e) {
+            float pv = ex2(fmaf(__uint_as_float(sv[c4 + e]), p.scale_log2, -lv[e]));
+            if (!interior) {
+              const int q = q0 + half * 32 + c4 + e;
+              const bool ok = kv_idx < p.sk && q < p.sq && (!p.causal || kv_idx <= q + off);
+              pv = ok ? pv : 0.f;
+            }
             pr[e] = pv;
-            ds[e] = pv * (__uint_as_float(dpv[c + e]) - smem_vec[FB_Q + qc]) * p.scale;
+            ds[e] = pv * (__uint_as_float(dpv[c4 + e]) - dl[e]) * p.scale;
           }
-          __nv_bfloat162 pb = __floats2bfloat162_rn(pr[0], pr[1]), db = __floats2bfloat162_rn(ds[0], ds[1]);
-          pw[c / 2] = *reinterpret_cast<uint32_t*>(&pb);
-          dw[c / 2] = *reinterpret_cast<uint32_t*>(&db);
+          __nv_bfloat162 pb0 = __floats2bfloat162_rn(pr[0], pr[1]), pb1 = __floats2bfloat162_rn(pr[2], pr[3]);
+          __nv_bfloat162 db0 = __floats2bfloat162_rn(ds[0], ds[1]), db1 = __floats2bfloat162_rn(ds[2], ds[3]);
+          pw[c4 / 2] = *reinterpret_cast<uint32_t*>(&pb0);
+          pw[c4 / 2 + 1] = *reinterpret_cast<uint32_t*>(&pb1);
+          dw[c4 / 2] = *reinterpret_cast<uint32_t*>(&db0);
+          dw[c4 / 2 + 1] = *reinterpret_cast<uint32_t*>(&db1);
         }
       }
       // Pᵀ and dSᵀ (bf16 pairs) back over the first 32 columns of Sᵀ / dPᵀ (this warp: 16 of them); dSᵀ also into the swizzled smem tile (operand B of dQᵀ)
@@ -226,16 +244,25 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       // dQᵀ [d = row, this warp's 32 queries] → fp32 accumulation buffer (lanes = consecutive d: every red is a coalesced 128-byte segment)
       mbar_wait(dq_ready, (uint32_t)st & 1u);
       tc_fence_after();
-      float* dq_base = p.dq_acc + ((size_t)bi * p.hq + h) * D + row;
       const size_t q_pitch = (size_t)p.b * p.hq * D;
+      float* dq_ptr = p.dq_acc + (size_t)(q0 + half * 32) * q_pitch + ((size_t)bi * p.hq + h) * D + row;
+      const int q_left = p.sq - (q0 + half * 32);          // rows of this half that exist
       {
         uint32_t dq[32];
         tmem_ld_32x32b_x32(tmem_base + lane_base + DQT_COL + half * 32, dq);
         tmem_ld_wait();
+        if (q_left >= 32) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int q = q0 + half * 32 + c;
-          if (q < p.sq) atomicAdd(dq_base + (size_t)q * q_pitch, __uint_as_float(dq[c]));
+          for (int c = 0; c < 32; ++c) {
+            atomicAdd(dq_ptr, __uint_as_float(dq[c]));
+            dq_ptr += q_pitch;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            if (c < q_left) atomicAdd(dq_ptr, __uint_as_float(dq[c]));
+            dq_ptr += q_pitch;
+          }
         }
       }
       tc_fence_before();
