@@ -9,9 +9,11 @@
 //   dV += Pᵀ dO_i             UMMA 128x128x16, A = Pᵀ FROM TMEM, B = dO_i (MN-major view of the same smem tile)
 //   dK += dSᵀ Q_i             UMMA 128x128x16, A = dSᵀ FROM TMEM, B = Q_i (MN-major view)
 //   dQᵀ = K_jᵀ dSᵀ            UMMA 128x64x16,  A = K_j (MN-major view), B = dSᵀ (bf16 copy in swizzled smem) → TMEM [d, q] → red.add to dQ
-// Warps 0-7: compute (thread = TMEM lane x column half), warp 8: TMA producer, warp 9: MMA issuer + TMEM allocator.  This first version runs the MMA
-// and compute phases of a step back to back (no ping-pong yet); it is selectable with MEGATRON_B200_ATTN_BWD=native and validated against
-// fp32 autograd, the default backward stays the cuDNN library kernel until this one is pipelined.
+// Warps 0-7: compute (thread = TMEM lane x column half), warp 8: TMA producer, warp 9: MMA issuer + TMEM allocator.
+// Pipelining: dQᵀ of step s is written over the (already consumed) Sᵀ/Pᵀ columns of that step's score buffer, which frees enough tensor memory to
+// DOUBLE-BUFFER the score buffers (dK 128 + dV 128 + 2 x (Sᵀ 64 + dPᵀ 64) = 512 columns).  The issuer runs one step ahead with the two score MMAs,
+// the compute warps pull dQᵀ(s-1) into registers first (releasing its buffer), do the softmax/dS math of step s, and only then issue the
+// red.adds of step s-1 — so tensor work, math and reductions of neighbouring steps overlap.  Selectable with MEGATRON_B200_ATTN_BWD=native.
 #include "gemm_sm100_device.cuh"
 
 namespace mb200 {
@@ -57,7 +59,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   constexpr int DS_BYTES = FB_KV * 128;            // dSᵀ bf16 [128 kv x 64 q]: 16 KiB
   constexpr int STAGES = 2;
   constexpr uint32_t TMEM_COLS = 512;
-  constexpr uint32_t DK_COL = 0, DV_COL = 128, ST_COL = 256, DPT_COL = 320, DQT_COL = 384;
+  constexpr uint32_t DK_COL = 0, DV_COL = 128, BUF_COL = 256, BUF_STRIDE = 128, DPT_OFF = 64;   // score buffer b: Sᵀ at BUF_COL + 128 b, dPᵀ 64 columns further
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -66,15 +68,16 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   uint8_t* smem_q = smem_v + KV_BYTES;                       // STAGES x Q_BYTES
   uint8_t* smem_do = smem_q + STAGES * Q_BYTES;              // STAGES x Q_BYTES
   uint8_t* smem_ds = smem_do + STAGES * Q_BYTES;             // DS_BYTES
-  float* smem_vec = reinterpret_cast<float*>(smem_ds + DS_BYTES);   // lse2[64] | delta[64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_vec + 2 * FB_Q);
+  float* smem_vec = reinterpret_cast<float*>(smem_ds + DS_BYTES);   // 2 x (lse2[64] | delta[64]), by step parity
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_vec + 4 * FB_Q);
   uint64_t* kv_full = bars;              // 1
   uint64_t* q_full = bars + 1;           // STAGES
   uint64_t* q_empty = q_full + STAGES;   // STAGES
-  uint64_t* s_ready = q_empty + STAGES;  // 1
-  uint64_t* p_ready = s_ready + 1;       // 1 (128 arrivals)
-  uint64_t* dq_ready = p_ready + 1;      // 1
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(dq_ready + 1);
+  uint64_t* s_ready = q_empty + STAGES;  // [2] per score buffer
+  uint64_t* p_ready = s_ready + 2;       // 1 (256 arrivals, one phase per step)
+  uint64_t* dq_ready = p_ready + 1;      // [2]
+  uint64_t* dq_taken = dq_ready + 2;     // [2] (256 arrivals): dQᵀ has been pulled into registers, the buffer may be refilled
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(dq_taken + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jb = blockIdx.x, hkv = blockIdx.y, bi = blockIdx.z;
@@ -100,9 +103,12 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
     }
-    mbar_init(s_ready, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_ready[i], 1);
+      mbar_init(&dq_ready[i], 1);
+      mbar_init(&dq_taken[i], 256);
+    }
     mbar_init(p_ready, 256);
-    mbar_init(dq_ready, 1);
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc<TMEM_COLS>(tmem_holder);
@@ -141,10 +147,10 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       constexpr uint32_t idesc_dkv = make_idesc_bf16(FB_KV, D, false, true);      // dV, dK : A from TMEM, B MN-major
       constexpr uint32_t idesc_dqt = make_idesc_bf16(D, FB_Q, true, true);        // dQᵀ : A = K_jᵀ (MN-major), B = dSᵀ (MN-major)
       const uint32_t ka = smem_u32(smem_k), va = smem_u32(smem_v), dsa = smem_u32(smem_ds);
-      mbar_wait(kv_full, 0);
-      for (int st = 0; st < total_steps; ++st) {
+      auto issue_scores = [&](int st) {       // Sᵀ and dPᵀ of step st into score buffer st & 1
         const int s = st % STAGES;
         const uint32_t qa = smem_u32(smem_q + s * Q_BYTES), doa = smem_u32(smem_do + s * Q_BYTES);
+        const uint32_t st_col = tmem_base + BUF_COL + (st & 1) * BUF_STRIDE;
         mbar_wait(&q_full[s], (uint32_t)(st / STAGES) & 1u);
         tc_fence_after();
 #pragma unroll
@@ -152,23 +158,36 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint32_t acc = (c > 0 || kk > 0) ? 1u : 0u;
-            umma_f16(tmem_base + ST_COL, make_smem_desc_sw128(ka + c * KV_CHUNK + kk * 32, 16, 1024), make_smem_desc_sw128(qa + c * Q_CHUNK + kk * 32, 16, 1024), idesc_st, acc);
-            umma_f16(tmem_base + DPT_COL, make_smem_desc_sw128(va + c * KV_CHUNK + kk * 32, 16, 1024), make_smem_desc_sw128(doa + c * Q_CHUNK + kk * 32, 16, 1024), idesc_st, acc);
+            umma_f16(st_col, make_smem_desc_sw128(ka + c * KV_CHUNK + kk * 32, 16, 1024), make_smem_desc_sw128(qa + c * Q_CHUNK + kk * 32, 16, 1024), idesc_st, acc);
+            umma_f16(st_col + DPT_OFF, make_smem_desc_sw128(va + c * KV_CHUNK + kk * 32, 16, 1024), make_smem_desc_sw128(doa + c * Q_CHUNK + kk * 32, 16, 1024), idesc_st, acc);
           }
-        umma_commit(s_ready);
+        umma_commit(&s_ready[st & 1]);
+      };
+      mbar_wait(kv_full, 0);
+      issue_scores(0);
+      for (int st = 0; st < total_steps; ++st) {
+        const int s = st % STAGES, bsel = st & 1;
+        const uint32_t qa = smem_u32(smem_q + s * Q_BYTES), doa = smem_u32(smem_do + s * Q_BYTES);
+        const uint32_t st_col = tmem_base + BUF_COL + bsel * BUF_STRIDE;
+        if (st + 1 < total_steps) {
+          // one step ahead: the other score buffer is free once dQᵀ(st-1) has been pulled out of it
+          if (st >= 1) mbar_wait(&dq_taken[(st + 1) & 1], (uint32_t)((st - 1) >> 1) & 1u);
+          issue_scores(st + 1);
+        }
         mbar_wait(p_ready, (uint32_t)st & 1u);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < FB_Q / 16; ++kk) {
           const uint32_t acc = (st > 0 || kk > 0) ? 1u : 0u;
           // B = dO_i / Q_i read as [K = q rows, N = d]: MN-major, two 64-column chunks Q_CHUNK apart
-          umma_f16_ts(tmem_base + DV_COL, tmem_base + ST_COL + kk * 8, make_smem_desc_sw128(doa + kk * 2048, Q_CHUNK, 1024), idesc_dkv, acc);
-          umma_f16_ts(tmem_base + DK_COL, tmem_base + DPT_COL + kk * 8, make_smem_desc_sw128(qa + kk * 2048, Q_CHUNK, 1024), idesc_dkv, acc);
+          umma_f16_ts(tmem_base + DV_COL, st_col + kk * 8, make_smem_desc_sw128(doa + kk * 2048, Q_CHUNK, 1024), idesc_dkv, acc);
+          umma_f16_ts(tmem_base + DK_COL, st_col + DPT_OFF + kk * 8, make_smem_desc_sw128(qa + kk * 2048, Q_CHUNK, 1024), idesc_dkv, acc);
         }
+        // dQᵀ over the Sᵀ/Pᵀ columns of this buffer (the tensor pipe is in order: dV above has consumed Pᵀ)
 #pragma unroll
         for (int kk = 0; kk < FB_KV / 16; ++kk)
-          umma_f16(tmem_base + DQT_COL, make_smem_desc_sw128(ka + kk * 2048, KV_CHUNK, 1024), make_smem_desc_sw128(dsa + kk * 2048, DS_BYTES, 1024), idesc_dqt, kk > 0 ? 1u : 0u);
-        umma_commit(dq_ready);
+          umma_f16(st_col, make_smem_desc_sw128(ka + kk * 2048, KV_CHUNK, 1024), make_smem_desc_sw128(dsa + kk * 2048, DS_BYTES, 1024), idesc_dqt, kk > 0 ? 1u : 0u);
+        umma_commit(&dq_ready[bsel]);
         umma_commit(&q_empty[s]);
       }
     }
@@ -181,33 +200,63 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     uint8_t* ds_row = smem_ds + row * 128;
     const int sw = row & 7;
     const int tid = threadIdx.x;                         // 0..255 among the compute warps
+    const size_t q_pitch = (size_t)p.b * p.hq * D;
+    uint32_t dq[32];                 // dQᵀ of the previous step, held in registers across this step's math
+    float* dq_ptr = nullptr;
+    int q_left = 0;
+    auto pull_dq = [&](int sp) {     // step sp is complete on the tensor core: move this warp's 32 dQᵀ columns to registers, free the buffer
+      const int hp = hkv * group + sp / steps_per_head, qp = (i0 + sp % steps_per_head) * FB_Q + half * 32;
+      mbar_wait(&dq_ready[sp & 1], (uint32_t)(sp >> 1) & 1u);
+      tc_fence_after();
+      tmem_ld_32x32b_x32(tmem_base + lane_base + BUF_COL + (sp & 1) * BUF_STRIDE + half * 32, dq);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&dq_taken[sp & 1]);
+      dq_ptr = p.dq_acc + (size_t)qp * q_pitch + ((size_t)bi * p.hq + hp) * D + row;
+      q_left = p.sq - qp;
+    };
+    auto push_dq = [&]() {           // lanes = consecutive d: every red is a coalesced 128-byte segment
+      if (q_left >= 32) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          atomicAdd(dq_ptr, __uint_as_float(dq[c]));
+          dq_ptr += q_pitch;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (c < q_left) atomicAdd(dq_ptr, __uint_as_float(dq[c]));
+          dq_ptr += q_pitch;
+        }
+      }
+    };
     for (int st = 0; st < total_steps; ++st) {
       const int h = hkv * group + st / steps_per_head, i = i0 + st % steps_per_head;
       const int q0 = i * FB_Q;
+      const uint32_t st_addr = tmem_base + lane_base + BUF_COL + (st & 1) * BUF_STRIDE;
+      float* vec = smem_vec + (st & 1) * 2 * FB_Q;
+      if (st > 0) pull_dq(st - 1);
       // per-query vectors of this step: lse (log2 domain) and delta
       if (tid < FB_Q) {
         const int q = q0 + tid;
-        smem_vec[tid] = q < p.sq ? p.lse[((size_t)bi * p.hq + h) * p.sq + q] * 1.4426950408889634f : 0.f;
+        vec[tid] = q < p.sq ? p.lse[((size_t)bi * p.hq + h) * p.sq + q] * 1.4426950408889634f : 0.f;
       } else if (tid < 2 * FB_Q) {
         const int q = q0 + tid - FB_Q;
-        smem_vec[tid] = q < p.sq ? p.delta[((size_t)bi * p.hq + h) * p.sq + q] : 0.f;
+        vec[tid] = q < p.sq ? p.delta[((size_t)bi * p.hq + h) * p.sq + q] : 0.f;
       }
       named_bar_sync(1, 256);
-      mbar_wait(s_ready, (uint32_t)st & 1u);
+      mbar_wait(&s_ready[st & 1], (uint32_t)(st >> 1) & 1u);
       tc_fence_after();
       uint32_t pw[16], dw[16];
       {
         uint32_t sv[32], dpv[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_base + ST_COL + half * 32, sv);
-        tmem_ld_32x32b_x32(tmem_base + lane_base + DPT_COL + half * 32, dpv);
+        tmem_ld_32x32b_x32(st_addr + half * 32, sv);
+        tmem_ld_32x32b_x32(st_addr + DPT_OFF + half * 32, dpv);
         tmem_ld_wait();
         // every thread of the pair (warp w, w+4) must have read its half of the row before either overwrites the first 32 columns
         named_bar_sync(2, 256);
-        // ncu (first version): 56 issued instructions per score element, most of them integer — per-element mask predicates, generic-address
-        // loads of the lse/delta vectors and 64-bit address arithmetic for the reductions.  Interior blocks (no key/query padding, fully below
-        // the causal diagonal) take a predicate-free path; the vectors come in with ld.shared.v4.
         const bool interior = (k0 + FB_KV <= p.sk) && (q0 + FB_Q <= p.sq) && (!p.causal || (k0 + FB_KV - 1 <= q0 + off));
-        const uint32_t vec_addr = smem_u32(smem_vec) + half * 32 * 4;
+        const uint32_t vec_addr = smem_u32(vec) + half * 32 * 4;
 #pragma unroll
         for (int c4 = 0; c4 < 32; c4 += 4) {
           const float4 l4 = lds_f4(vec_addr + c4 * 4), d4 = lds_f4(vec_addr + FB_Q * 4 + c4 * 4);
@@ -233,44 +282,22 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
       }
       // Pᵀ and dSᵀ (bf16 pairs) back over the first 32 columns of Sᵀ / dPᵀ (this warp: 16 of them); dSᵀ also into the swizzled smem tile (operand B of dQᵀ)
-      tmem_st_32x32b_x16(tmem_base + lane_base + ST_COL + half * 16, pw);
-      tmem_st_32x32b_x16(tmem_base + lane_base + DPT_COL + half * 16, dw);
+      tmem_st_32x32b_x16(st_addr + half * 16, pw);
+      tmem_st_32x32b_x16(st_addr + DPT_OFF + half * 16, dw);
 #pragma unroll
       for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(ds_row + (((half * 4 + u) ^ sw) << 4)) = make_uint4(dw[u * 4], dw[u * 4 + 1], dw[u * 4 + 2], dw[u * 4 + 3]);
       tmem_st_wait();
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(p_ready);
-      // dQᵀ [d = row, this warp's 32 queries] → fp32 accumulation buffer (lanes = consecutive d: every red is a coalesced 128-byte segment)
-      mbar_wait(dq_ready, (uint32_t)st & 1u);
-      tc_fence_after();
-      const size_t q_pitch = (size_t)p.b * p.hq * D;
-      float* dq_ptr = p.dq_acc + (size_t)(q0 + half * 32) * q_pitch + ((size_t)bi * p.hq + h) * D + row;
-      const int q_left = p.sq - (q0 + half * 32);          // rows of this half that exist
-      {
-        uint32_t dq[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_base + DQT_COL + half * 32, dq);
-        tmem_ld_wait();
-        if (q_left >= 32) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            atomicAdd(dq_ptr, __uint_as_float(dq[c]));
-            dq_ptr += q_pitch;
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            if (c < q_left) atomicAdd(dq_ptr, __uint_as_float(dq[c]));
-            dq_ptr += q_pitch;
-          }
-        }
-      }
-      tc_fence_before();
-      named_bar_sync(1, 256);   // smem_vec and the dQᵀ columns are reused by the next step
+      if (st > 0) push_dq();          // reductions of step st-1 run while the tensor core works on step st
+    }
+    if (total_steps > 0) {
+      pull_dq(total_steps - 1);       // also covers the last dV / dK accumulation (same commit)
+      push_dq();
     }
     // ---- epilogue: dK, dV [kv = row, d] → bf16 ------------------------------------------------------------------------------------
     if (total_steps > 0) {
-      // the last dq_ready wait above also covers the final dV / dK accumulation (same commit)
       tc_fence_after();
       const bool valid = kv_idx < p.sk;
       __nv_bfloat16* dk_row = reinterpret_cast<__nv_bfloat16*>(p.dk) + ((size_t)kv_idx * p.b * p.hk + (size_t)bi * p.hk + hkv) * D;
@@ -324,7 +351,7 @@ extern "C" int mb200_flash_attn_bwd(const void* q, const void* k, const void* v,
                                     long v_ss, long v_sb, long v_sh, long do_ss, long do_sb, long do_sh, float scale, int causal, cudaStream_t s) {
   if (d != FB_D || hq % hk != 0) return -10;
   if ((q_ss | q_sb | q_sh | k_ss | k_sb | k_sh | v_ss | v_sb | v_sh | do_ss | do_sb | do_sh) % 8 != 0) return -11;
-  constexpr int SMEM_BYTES = 2 * (2 * FB_KV * 128) + 2 * 2 * (2 * FB_Q * 128) + FB_KV * 128 + 2 * FB_Q * 4 + 1024 + 256;
+  constexpr int SMEM_BYTES = 2 * (2 * FB_KV * 128) + 2 * 2 * (2 * FB_Q * 128) + FB_KV * 128 + 4 * FB_Q * 4 + 1024 + 256;
   CUtensorMap tq, tk, tv, tdo;
   bool ok = make_tmap_bf16_strided(&tq, q, sq, q_ss, q_ss * 2, 64, FB_Q);
   ok &= make_tmap_bf16_strided(&tk, k, sk, k_ss, k_ss * 2, 64, FB_KV);
