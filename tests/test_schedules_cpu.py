@@ -1,0 +1,170 @@
+"""Fine-grained schedule plans, forward/backward-overlapped 1F1B, hybrid-CP balancing, activation offload, bridge communicator."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dist_utils import run_distributed
+
+SEQ, VOCAB = 32, 128
+
+
+def _cfg(**kw):
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    base = dict(num_layers=3, hidden_size=64, num_attention_heads=4, num_query_groups=2, ffn_hidden_size=128, use_cpu_initialization=True,
+                normalization="RMSNorm", gated_linear_unit=True, activation_func=F.silu, add_bias_linear=False, hidden_dropout=0.0, attention_dropout=0.0)
+    base.update(kw)
+    return TransformerConfig(**base)
+
+
+def _model(cfg):
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_decoder_block_spec, get_gpt_layer_local_spec
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+
+    spec = get_gpt_decoder_block_spec(cfg) if cfg.num_moe_experts else get_gpt_layer_local_spec(normalization="RMSNorm")
+    return GPTModel(cfg, spec, vocab_size=VOCAB, max_sequence_length=SEQ, position_embedding_type="rope", share_embeddings_and_output_weights=False)
+
+
+def _batches(n, b=2, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    pos = torch.arange(SEQ)[None].expand(b, -1)
+    return [dict(tokens=torch.randint(0, VOCAB, (b, SEQ), generator=g), labels=torch.randint(0, VOCAB, (b, SEQ), generator=g), position_ids=pos)
+            for _ in range(n)]
+
+
+def _combined_worker(rank, world, moe):
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.pipeline_parallel.combined_1f1b import combined_1f1b_schedule_for_no_pipelining
+
+    ps.initialize_model_parallel()
+    kw = dict(num_moe_experts=4, moe_router_topk=2, moe_token_dispatcher_type="alltoall", moe_grouped_gemm=False, moe_aux_loss_coeff=0.0,
+              moe_shared_expert_intermediate_size=64) if moe else {}
+    torch.manual_seed(5)
+    m = _model(_cfg(**kw))
+    n_mb = 3
+    ref_losses = []
+    for b in _batches(n_mb):
+        l = m(b["tokens"], b["position_ids"], None, labels=b["labels"]).float().mean()
+        (l / n_mb).backward()
+        ref_losses.append(l.item())
+    ref = {n: p.grad.clone() for n, p in m.named_parameters()}
+    m.zero_grad(set_to_none=True)
+    losses = combined_1f1b_schedule_for_no_pipelining(data_iterator=iter(_batches(n_mb)), model=m, num_microbatches=n_mb)
+    assert [round(x.item(), 4) for x in losses] == [round(x, 4) for x in ref_losses], (losses, ref_losses)
+    for n, p in m.named_parameters():
+        assert p.grad is not None, n
+        assert torch.allclose(p.grad, ref[n], atol=1e-6, rtol=1e-4), n
+    ev = combined_1f1b_schedule_for_no_pipelining(data_iterator=iter(_batches(2)), model=m, num_microbatches=2, forward_only=True)
+    assert abs(ev[0].item() - ref_losses[0]) < 1e-4
+    return True
+
+
+@pytest.mark.parametrize("moe", [False, True])
+def test_combined_1f1b_matches_plain(moe):
+    assert run_distributed(_combined_worker, 1, moe) == [True]
+
+
+def test_schedule_node_detaches_and_returns_input_grads():
+    from megatron_b200.core.pipeline_parallel.utils import NoopScheduleNode, ScheduleNode
+
+    w = torch.randn(4, 4, requires_grad=True)
+    a = ScheduleNode(lambda x: (x @ w, x.sum(-1)), name="a")
+    b = ScheduleNode(lambda y, s: (y * 2).sum() + s.sum(), name="b")
+    x = torch.randn(3, 4, requires_grad=True)
+    out = b.forward(NoopScheduleNode().forward(a.forward(x)))
+    assert out.grad_fn is not None and a.outputs[0].grad_fn is not None
+    g = b.backward(torch.ones(()))
+    gx = a.backward(g)
+    ref = torch.autograd.grad(((x @ w) * 2).sum() + x.sum(), [x, w])
+    assert torch.allclose(gx, ref[0]) and torch.allclose(w.grad, ref[1])
+    assert a.inputs is None and b.outputs is None  # released
+
+
+def test_balanced_cp_scheduler_balances_and_covers():
+    from megatron_b200.core.pipeline_parallel.hybrid_cp_schedule import BalancedCPScheduler
+
+    sch = BalancedCPScheduler(max_seq_len_per_rank=1024, total_gpus=8)
+    assert sch.gpus_needed(1000) == 1 and sch.gpus_needed(1025) == 2 and sch.gpus_needed(5000) == 8
+    g = torch.Generator().manual_seed(0)
+    lens = [int(x) for x in torch.randint(64, 8192, (40,), generator=g)]
+    groups = sch.get_groups_and_subsamples(list(enumerate(lens)))
+    seen = []
+    for grp in groups:
+        assert len(grp.per_gpu) == 8
+        for sid, (start, size) in grp.placement.items():
+            assert size >= sch.gpus_needed(lens[sid]) and size & (size - 1) == 0 and start % size == 0  # aligned power-of-two CP blocks
+            for r in range(start, start + size):
+                assert sid in grp.per_gpu[r]
+            seen.append(sid)
+        for r in range(8):  # memory bound: tokens resident on a GPU never exceed the per-rank budget
+            assert sum(lens[s] / grp.placement[s][1] for s in grp.per_gpu[r]) <= 1024 + 1e-6
+    assert sorted(seen) == list(range(40))
+    # a lone medium sample is widened over the idle GPUs instead of leaving them dark
+    (only,) = sch.get_groups_and_subsamples([(0, 2048)])
+    assert only.placement[0] == (0, 8)
+    # short samples (cp = 1): groups are balanced around the largest piece
+    lens2 = [int(x) for x in torch.randint(100, 500, (64,), generator=g)]
+    sch2 = BalancedCPScheduler(max_seq_len_per_rank=2048, total_gpus=8)
+    first = sch2.get_groups_and_subsamples(list(enumerate(lens2)))[0]
+    loads = [sum(sch2.workload(lens2[s], 1) for s in first.per_gpu[r]) for r in range(8)]
+    assert min(loads) > 0 and max(loads) <= 1.5 * (sum(loads) / 8)
+
+
+def test_fine_grained_activation_offload_roundtrip():
+    from megatron_b200.core.pipeline_parallel.fine_grained_activation_offload import FineGrainedActivationOffloadingInterface as Off
+
+    torch.manual_seed(0)
+    lin1, lin2 = torch.nn.Linear(16, 64), torch.nn.Linear(64, 16)
+    x = torch.randn(8, 16, requires_grad=True)
+
+    def run(offload):
+        for p in list(lin1.parameters()) + list(lin2.parameters()):
+            p.grad = None
+        x.grad = None
+        mgr = Off(min_offload_numel=1) if offload else None
+        h = x
+        for i in range(3):
+            if offload:
+                with mgr.group(f"mlp{i}"):
+                    h = lin2(F.gelu(lin1(h)))
+                h = mgr.commit(h, f"mlp{i}")
+            else:
+                h = lin2(F.gelu(lin1(h)))
+        h.sum().backward()
+        return x.grad.clone(), lin1.weight.grad.clone(), mgr
+
+    g0, w0, _ = run(False)
+    g1, w1, mgr = run(True)
+    assert torch.allclose(g0, g1) and torch.allclose(w0, w1)
+    st = mgr.stats()
+    assert st["groups"] == 3 and st["tensors_offloaded"] >= 3 and st["bytes_offloaded"] > 0 and st["live"] == 0
+
+
+def _bridge_worker(rank, world):
+    import torch.distributed as dist
+
+    from megatron_b200.core.hyper_comm_grid import HyperCommGrid
+    from megatron_b200.core.pipeline_parallel.bridge_communicator import BridgeCommunicator
+
+    # encoder on ranks 0-1 (tp 1, dp 2), decoder on rank 2 (tp 1, dp 1): fan-in of the batch dimension
+    src = HyperCommGrid([1, 2], ["tp", "dp"], rank_offset=0)
+    dst = HyperCommGrid([1, 1], ["tp", "dp"], rank_offset=2)
+    bridge = BridgeCommunicator(src, dst, dim_mapping={"s": 0, "b": 1, "h": 2})
+    out = None
+    if bridge.is_src:
+        act = torch.full((4, 2, 8), float(rank + 1), requires_grad=True)
+        bridge.send_forward(act * 1.0)
+        g = bridge.recv_backward((4, 2, 8), torch.float32)
+        out = g.clone()
+    if bridge.is_dst:
+        got = bridge.recv_forward((4, 4, 8), torch.float32)
+        assert got.shape == (4, 4, 8) and torch.all(got[:, :2] == 1.0) and torch.all(got[:, 2:] == 2.0)
+        bridge.send_backward(torch.cat([torch.full((4, 2, 8), 10.0), torch.full((4, 2, 8), 20.0)], 1))
+        out = got.detach().clone()
+    dist.barrier()
+    return out
+
+
+def test_bridge_communicator_fan_in():
+    res = run_distributed(_bridge_worker, 3)
+    assert torch.all(res[0] == 10.0) and torch.all(res[1] == 20.0) and res[2].shape == (4, 4, 8)
