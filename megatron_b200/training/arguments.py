@@ -179,6 +179,21 @@ def build_parser() -> argparse.ArgumentParser:
     g.add_argument("--timing-log-option", default="minmax", choices=["max", "minmax", "all"])
     g.add_argument("--tensorboard-dir", default=None)
     g.add_argument("--wandb-project", default=None)
+    g.add_argument("--wandb-exp-name", default=None)
+    g.add_argument("--wandb-save-dir", default=None)
+    g.add_argument("--tensorboard-queue-size", type=int, default=1000)
+    g.add_argument("--enable-one-logger", action="store_true")
+    g.add_argument("--enable-ft-package", action="store_true", help="section-timeout hang detection (training/ft_integration.py)")
+    g.add_argument("--ft-timeout-step", type=float, default=None)
+    g.add_argument("--ft-timeout-setup", type=float, default=None)
+    g.add_argument("--ft-timeout-checkpointing", type=float, default=None)
+    g.add_argument("--simulated-fault", default=None, help="kind:delay_s[:rank], kind in {rank_killed, rank_hung}")
+    g.add_argument("--log-activations-interval", type=int, default=0)
+    g.add_argument("--log-dgrad-interval", type=int, default=0)
+    g.add_argument("--log-wgrad-interval", type=int, default=0)
+    g.add_argument("--activation-log-dir", default=None)
+    g.add_argument("--exit-signal-handler", action="store_true")
+    g.add_argument("--log-params-norm", action="store_true")
     g.add_argument("--log-straggler", action="store_true")
     g.add_argument("--eval-iters", type=int, default=0)
     g.add_argument("--eval-interval", type=int, default=1000)

@@ -76,6 +76,21 @@ def initialize_megatron(argv=None, extra_args_provider=None, args_defaults: Opti
         )
     model_parallel_cuda_manual_seed(args.seed)
     _GLOBALS["timers"] = Timers(args.timing_log_level, args.timing_log_option)
+    from . import global_vars
+
+    args.world_size = dist.get_world_size()
+    global_vars.set_global_variables(args)
+    _GLOBALS["tensorboard"], _GLOBALS["wandb"], _GLOBALS["one_logger"] = (global_vars.get_tensorboard_writer(), global_vars.get_wandb_writer(),
+                                                                          global_vars.get_one_logger())
+    if args.deterministic_mode:
+        from .determinism import enable_deterministic_mode
+
+        enable_deterministic_mode(strict=False)
+    if getattr(args, "enable_ft_package", False):
+        from . import ft_integration
+
+        ft_integration.setup(args, dist.get_rank())
+        ft_integration.maybe_setup_simulated_fault(args, dist.get_rank(), dist.get_world_size())
     initialize_rerun_state_machine(mode=args.rerun_mode, error_injection_rate=args.error_injection_rate)
     destroy_num_microbatches_calculator()
     init_num_microbatches_calculator(dist.get_rank(), args.rampup_batch_size, args.global_batch_size, args.micro_batch_size, args.data_parallel_size)
@@ -224,8 +239,10 @@ def training_log(loss_dict, total_loss_dict, learning_rate, iteration, loss_scal
     s = f" iteration {iteration:8d}/{args.train_iters:8d} | consumed samples: {args.consumed_train_samples:12d} |"
     s += f" elapsed time per iteration (ms): {elapsed_per_iter * 1000.0:.1f} | throughput per GPU (TFLOP/s/GPU): {tput:.1f} | tokens/s: {tok_s:.0f} |"
     s += f" learning rate: {learning_rate:.6E} | global batch size: {get_current_global_batch_size():5d} |"
+    logged = {}
     for k in list(total_loss_dict):
-        s += f" {k}: {total_loss_dict[k] / args.log_interval:.6E} |"
+        logged[k] = total_loss_dict[k] / args.log_interval
+        s += f" {k}: {logged[k]:.6E} |"
         total_loss_dict[k] = 0.0
     s += f" loss scale: {float(loss_scale):.1f} |"
     if grad_norm is not None:
@@ -233,10 +250,18 @@ def training_log(loss_dict, total_loss_dict, learning_rate, iteration, loss_scal
     if torch.cuda.is_available():
         s += f" mem-max-allocated-GiB: {torch.cuda.max_memory_allocated() / 2**30:.2f} |"
     print_rank_last(s)
-    tb = _GLOBALS.get("tensorboard")
-    if tb is not None:
-        tb.add_scalar("iteration-time", elapsed_per_iter, iteration)
-        tb.add_scalar("throughput", tput, iteration)
+    for w in (_GLOBALS.get("tensorboard"), _GLOBALS.get("wandb")):
+        if w is None:
+            continue
+        scal = {"iteration-time": elapsed_per_iter, "throughput": tput, "tokens-per-sec": tok_s, "learning-rate": learning_rate, "loss-scale": float(loss_scale),
+                "batch-size": get_current_global_batch_size(), **{k: float(v) for k, v in logged.items()}}
+        if grad_norm is not None:
+            scal["grad-norm"] = float(grad_norm)
+        if hasattr(w, "add_scalar"):
+            for k, v in scal.items():
+                w.add_scalar(k, v, iteration)
+        else:
+            w.log(scal, step=iteration)
     get_timers().log(normalizer=args.log_interval)
 
 
@@ -285,9 +310,27 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
     if args.manual_gc:
         gc.disable()
         gc.collect()
+    from . import ft_integration
+
+    one_logger = _GLOBALS.get("one_logger")
+    if one_logger is not None:
+        one_logger.on_train_start(iteration, args.consumed_train_samples, args.train_iters * args.global_batch_size, args.seq_length, args.train_iters, args.save,
+                                  args.async_save, True, args.num_floating_point_operations_so_far)
+    stat_loggers = []
+    if args.log_activations_interval or args.log_dgrad_interval or args.log_wgrad_interval:
+        from .activation_logging import ActivationLogger, DgradLogger, WgradLogger
+
+        out_dir = args.activation_log_dir or os.path.join(args.save or ".", "activation_logs")
+        rk = dist.get_rank() if dist.is_initialized() else 0
+        stat_loggers = [cls(model, out_dir, iv, rank=rk) for cls, iv in ((ActivationLogger, args.log_activations_interval), (DgradLogger, args.log_dgrad_interval),
+                                                                       (WgradLogger, args.log_wgrad_interval)) if iv]
     t_start = time.time()
     t_log = time.time()
     while iteration < args.train_iters:
+        ft_integration.on_training_step_start()
+        t_iter = time.time()
+        for sl in stat_loggers:
+            sl.begin_iteration(iteration + 1)
         if args.profile and iteration == args.profile_step_start and torch.cuda.is_available():
             torch.cuda.cudart().cudaProfilerStart()
         update_num_microbatches(args.consumed_train_samples, consistency_check=True)
@@ -299,6 +342,13 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
         if should_exit:
             sys.exit(exit_code)
         iteration += 1
+        ft_integration.on_training_step_end()
+        for sl in stat_loggers:
+            if hasattr(sl, "collect") and sl.handles:
+                sl.collect()
+            sl.end_iteration()
+        if one_logger is not None:
+            one_logger.track_iteration(time.time() - t_iter, get_current_global_batch_size(), args.seq_length, flops_per_iter)
         args.consumed_train_samples += get_current_global_batch_size()
         args.num_floating_point_operations_so_far += flops_per_iter
         if iteration % args.log_interval == 0:
@@ -338,6 +388,11 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
             print_rank_0(f"exiting program at iteration {iteration}")
             break
     checkpointing.maybe_finalize_async_save(blocking=True)
+    if one_logger is not None:
+        one_logger.on_train_end()
+    for w in (_GLOBALS.get("tensorboard"), _GLOBALS.get("wandb")):
+        if w is not None and hasattr(w, "flush"):
+            w.flush()
     args.iteration = iteration
     return iteration
 

@@ -1,0 +1,248 @@
+"""Training-program support: masks, writers, one-logger, signal handler, fault-tolerance monitor, activation logging, determinism, SFT / FIM data."""
+import json
+import os
+import signal
+import time
+
+import numpy as np
+import torch
+
+
+def test_ltor_masks_reset_positions_and_attention():
+    from megatron_b200.training.utils import get_ltor_masks_and_position_ids
+
+    eod = 9
+    data = torch.tensor([[1, 2, eod, 3, 4, 5, eod, 6], [1, 2, 3, 4, 5, 6, 7, 8]])
+    att, loss, pos = get_ltor_masks_and_position_ids(data, eod, reset_position_ids=True, reset_attention_mask=True, eod_mask_loss=True)
+    assert pos[0].tolist() == [0, 1, 2, 0, 1, 2, 3, 0] and pos[1].tolist() == list(range(8))
+    assert loss[0].tolist() == [1, 1, 0, 1, 1, 1, 0, 1]
+    # brute force: token i may attend token j iff j <= i and same document
+    doc = [0, 0, 0, 1, 1, 1, 1, 2]
+    for i in range(8):
+        for j in range(8):
+            assert bool(att[0, 0, i, j]) == (not (j <= i and doc[i] == doc[j]))
+    assert torch.equal(att[1, 0], torch.ones(8, 8, dtype=torch.bool).triu(1))
+    att2, _, pos2 = get_ltor_masks_and_position_ids(data, eod)
+    assert att2.shape == (1, 1, 8, 8) and pos2[0].tolist() == list(range(8))
+
+
+def test_scalar_writer_one_logger_and_wandb_hooks(tmp_path):
+    from types import SimpleNamespace
+
+    from megatron_b200.training import global_vars as gv
+    from megatron_b200.training import wandb_utils
+
+    args = SimpleNamespace(tensorboard_dir=str(tmp_path / "tb"), wandb_project="p", wandb_save_dir=str(tmp_path / "wb"), save=str(tmp_path), enable_one_logger=True,
+                           timing_log_level=0, timing_log_option="minmax", world_size=1)
+    os.environ["WANDB_MODE"] = "offline"
+    gv.set_global_variables(args)
+    try:
+        tb = gv.get_tensorboard_writer()
+        tb.add_scalar("lm loss", 2.5, 10)
+        tb.flush()
+        ol = gv.get_one_logger()
+        ol.on_train_start(0, 0, 100, 8, 10, str(tmp_path), False, True, 0.0)
+        ol.track_iteration(0.5, 4, 8, 1e12)
+        ol.track_iteration(1.5, 4, 8, 1e12)
+        ol.on_save_checkpoint_start(False)
+        ol.on_save_checkpoint_end(2, False)
+        ol.on_train_end()
+        assert ol.store_get("train_iterations_time_msecs_avg") == 1000.0 and ol.store_get("train_samples_end") == 8
+        assert ol.store_get("last_successful_save_checkpoint_iteration") == 2
+        recs = [json.loads(l) for l in open(ol.path)]
+        assert any("app_train_loop_finish_time" in r for r in recs)
+        w = gv.get_wandb_writer()
+        if not hasattr(w, "Artifact"):       # offline JSON sink
+            ck = tmp_path / "iter_0000002"
+            ck.mkdir()
+            tracker = tmp_path / "latest_checkpointed_iteration.txt"
+            tracker.write_text("2")
+            wandb_utils.on_save_checkpoint_success(str(ck), str(tracker), str(tmp_path), 2)
+            wandb_utils.on_load_checkpoint_success(str(ck), str(tmp_path))
+            assert [r for r in w.read() if r["tag"].startswith("checkpoint/")]
+    finally:
+        gv.unset_global_variables()
+
+
+def test_distributed_signal_handler_single_process():
+    from megatron_b200.training.dist_signal_handler import DistributedSignalHandler
+
+    prev = signal.getsignal(signal.SIGUSR1)
+    with DistributedSignalHandler(signal.SIGUSR1) as h:
+        assert h.signals_received() == [False]
+        os.kill(os.getpid(), signal.SIGUSR1)
+        time.sleep(0.05)
+        assert h.any_received()
+    assert signal.getsignal(signal.SIGUSR1) == prev
+
+
+def test_fault_tolerance_monitor_learns_timeouts_and_detects_hang(tmp_path):
+    from megatron_b200.training.ft_integration import FaultToleranceMonitor
+
+    mon = FaultToleranceMonitor(rank=0, save_dir=str(tmp_path), timeouts={"step": 0.3}, min_samples=3, poll_interval=0.05, abort=False, safety_factor=4.0).start()
+    for _ in range(3):
+        mon.start_section("step")
+        time.sleep(0.02)
+        mon.end_section("step")
+    assert mon.expired is None
+    t = mon.calc_timeouts()
+    assert 1.0 <= t["step"] < 2.0 and json.load(open(tmp_path / "ft_state.json"))["timeouts"]["step"] == t["step"]
+    mon.timeouts["step"] = 0.2
+    mon.start_section("step")
+    time.sleep(0.6)                      # never ends: the watchdog must fire
+    assert mon.expired is not None and mon.expired["section"] == "step"
+    assert json.load(open(tmp_path / "hang_rank0.json"))["section"] == "step"
+    mon.shutdown()
+    # a restarted monitor starts from the learned values
+    assert FaultToleranceMonitor(save_dir=str(tmp_path)).timeouts["step"] == t["step"]
+
+
+def test_activation_and_dgrad_logging(tmp_path):
+    from megatron_b200.training.activation_logging import ActivationLogger, DgradLogger, WgradLogger
+
+    class Blk(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.self_attention = torch.nn.Linear(8, 8)
+            self.mlp = torch.nn.Linear(8, 8)
+
+        def forward(self, x):
+            return self.mlp(torch.relu(self.self_attention(x)))
+
+    m = torch.nn.Sequential(Blk(), Blk())
+    act, dg, wg = (cls(m, str(tmp_path), interval=2, pattern=r".*(self_attention|mlp)$") for cls in (ActivationLogger, DgradLogger, WgradLogger))
+    for it in (1, 2):
+        armed = [l.begin_iteration(it) for l in (act, dg, wg)]
+        assert armed == [it == 2] * 3
+        x = torch.randn(4, 8, requires_grad=True)
+        m(x).sum().backward()
+        wg.collect() if armed[0] else None
+        paths = [l.end_iteration() for l in (act, dg, wg)]
+        assert all((p is not None) == (it == 2) for p in paths)
+    a = json.load(open(paths[0]))
+    d = json.load(open(paths[1]))
+    w = json.load(open(paths[2]))
+    assert set(a) == {"chunk0.0.self_attention", "chunk0.0.mlp", "chunk0.1.self_attention", "chunk0.1.mlp"} and set(d) == set(a)
+    assert a["chunk0.1.mlp"]["shape"] == [4, 8] and abs(d["chunk0.1.mlp"]["norm"] - (32 ** 0.5)) < 1e-5 and "chunk0.0.mlp.weight" in w
+    assert not act.handles and len(m[0].mlp._forward_hooks) == 0
+
+
+def test_determinism_digest_and_check():
+    from megatron_b200.training.determinism import check_determinism, model_digest, tensor_digest
+
+    torch.manual_seed(0)
+    a = torch.randn(16)
+    assert tensor_digest([a]) == tensor_digest([a.clone()]) != tensor_digest([a + 1e-7])
+    lin = torch.nn.Linear(4, 4)
+    d0 = model_digest(lin)
+    with torch.no_grad():
+        lin.weight[0, 0] += 1e-6
+    assert model_digest(lin) != d0
+
+    def run():
+        torch.manual_seed(3)
+        return [torch.randn(8) @ torch.randn(8, 8)]
+
+    assert len(set(check_determinism(run, 3))) == 1
+    import pytest
+
+    with pytest.raises(RuntimeError):
+        check_determinism(lambda: [torch.randn(4)], 2)
+
+
+class _Tok:
+    """Whitespace tokenizer with a growing vocabulary."""
+
+    def __init__(self):
+        self.v = {}
+
+    def tokenize(self, s):
+        return [self.v.setdefault(w, len(self.v) + 10) for w in s.replace("\n", " \n ").split(" ") if w]
+
+
+def test_sft_dataset_masks_and_packing():
+    from megatron_b200.training.datasets import SFTDataset, SFTDatasetConfig, pack_conversations
+
+    assert pack_conversations([5, 3, 3, 2, 6], 8) == [[4, 3], [0, 1], [2]]
+    tok = _Tok()
+    convs = [[{"role": "user", "content": "hi there"}, {"role": "assistant", "content": "hello you"}],
+             [{"role": "system", "content": "be brief"}, {"role": "user", "content": "q"}, {"role": "assistant", "content": "a"}]]
+    ds = SFTDataset(convs, tok, SFTDatasetConfig(sequence_length=40, pad_token_id=0, pack=True))
+    assert len(ds) == 1
+    it = ds[0]
+    assert it["tokens"].shape == (40,) and it["cu_seqlens"][0] == 0 and it["cu_seqlens"][-1] == 40
+    n_docs = 2
+    bounds = it["cu_seqlens"][: n_docs + 1].tolist()
+    inv = {v: k for k, v in tok.v.items()}
+    trained = [inv[int(t)] for t, m in zip(it["labels"], it["loss_mask"]) if m > 0]
+    assert sorted(trained) == sorted(["hello", "you<|end|>", "\n", "a<|end|>", "\n"])     # assistant bodies (+ end-of-turn), nothing else
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        assert it["position_ids"][lo:hi].tolist() == list(range(hi - lo))
+        assert torch.equal(it["tokens"][lo + 1 : hi], it["labels"][lo : hi - 1].where(it["loss_mask"][lo : hi - 1] > 0, it["tokens"][lo + 1 : hi]))
+    assert (it["labels"][it["loss_mask"] == 0] == -100).all()
+
+
+def test_fim_transform_preserves_tokens_and_length():
+    from megatron_b200.training.datasets import FIMConfig, GPTFIMDataset, apply_fim
+
+    cfg = FIMConfig(fim_rate=1.0, fim_spm_rate=0.0, prefix_id=100, middle_id=101, suffix_id=102, pad_id=103, eod_id=104)
+    doc = np.arange(10, 30)
+    toks = np.concatenate([doc, [104], np.arange(40, 52)])
+    out = apply_fim(toks, np.random.RandomState(0), cfg)
+    assert len(out) == len(toks) and out[20] == 104
+    first = out[:20]
+    assert first[0] == 100 and 101 in first and 102 in first
+    # PSM: prefix + middle + (suffix without its last three tokens) reassemble the document
+    i_s, i_m = int(np.where(first == 102)[0][0]), int(np.where(first == 101)[0][0])
+    p, s, m = first[1:i_s], first[i_s + 1 : i_m], first[i_m + 1 :]
+    assert np.array_equal(np.concatenate([p, m, s]), doc[:17])
+    spm = apply_fim(doc, np.random.RandomState(1), FIMConfig(fim_rate=1.0, fim_spm_rate=1.0, prefix_id=100, middle_id=101, suffix_id=102, eod_id=104))
+    assert spm[0] == 100 and spm[1] == 102
+    assert np.array_equal(apply_fim(doc, np.random.RandomState(0), FIMConfig(fim_rate=0.0, eod_id=104)), doc)
+
+    class Base(torch.utils.data.Dataset):
+        def __len__(self):
+            return 4
+
+        def __getitem__(self, i):
+            t = torch.arange(10, 31) + i
+            return {"tokens": t[:-1], "labels": t[1:], "loss_mask": torch.ones(20)}
+
+    ds = GPTFIMDataset(Base(), cfg, seed=7)
+    a, b = ds[2], ds[2]
+    assert torch.equal(a["tokens"], b["tokens"]) and a["tokens"].shape == (20,) and torch.equal(a["tokens"][1:], a["labels"][:-1])
+
+
+def _run_pretrain(tmp_path, extra, iters):
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "pretrain_gpt.py"), "--num-layers", "2", "--hidden-size", "64", "--num-attention-heads", "4", "--ffn-hidden-size", "128",
+           "--seq-length", "32", "--max-position-embeddings", "32", "--micro-batch-size", "2", "--global-batch-size", "4", "--train-iters", str(iters), "--lr", "1e-3",
+           "--mock-data", "--tokenizer-type", "NullTokenizer", "--vocab-size", "127", "--log-interval", "2", "--distributed-backend", "gloo", "--swiglu",
+           "--normalization", "RMSNorm", "--disable-bias-linear", "--position-embedding-type", "rope", "--untie-embeddings-and-output-weights",
+           "--save", str(tmp_path / "ckpt"), "--load", str(tmp_path / "ckpt"), "--save-interval", "4", "--eval-iters", "0", "--lr-decay-iters", "100"] + extra
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29631", RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", CUDA_VISIBLE_DEVICES="", WANDB_MODE="offline")
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return r.stdout
+
+
+def test_pretrain_cli_writers_ft_activation_logs_and_resume(tmp_path):
+    out = _run_pretrain(tmp_path, ["--tensorboard-dir", str(tmp_path / "tb"), "--enable-one-logger", "--enable-ft-package", "--log-activations-interval", "2",
+                                   "--log-wgrad-interval", "4", "--activation-log-dir", str(tmp_path / "act"), "--exit-interval", "4"], iters=6)
+    assert "iteration        4/" in out and "lm loss" in out and "iteration        6/" not in out
+    tb_dir = tmp_path / "tb"
+    assert tb_dir.exists() and any(tb_dir.iterdir())
+    if (tb_dir / "scalars.jsonl").exists():
+        tags = {json.loads(l)["tag"] for l in open(tb_dir / "scalars.jsonl")}
+        assert {"lm loss", "iteration-time", "learning-rate"} <= tags
+    acts = sorted(os.listdir(tmp_path / "act"))
+    assert [a for a in acts if a.startswith("activation_iter0000002")] and [a for a in acts if a.startswith("wgrad_iter0000004")]
+    assert json.load(open(tmp_path / "ckpt" / "ft_state.json"))["timeouts"]["checkpointing"] >= 1.0 if (tmp_path / "ckpt" / "ft_state.json").exists() else True
+    recs = [json.loads(l) for l in open(tmp_path / "ckpt" / "one_logger.jsonl")]
+    assert any(r.get("tracked_train_iterations") == 4 for r in recs)
+    # resume: picks up at iteration 4 and continues to 6
+    out2 = _run_pretrain(tmp_path, [], iters=6)
+    assert "iteration        6/" in out2 and "iteration        2/" not in out2
