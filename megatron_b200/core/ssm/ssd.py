@@ -55,11 +55,17 @@ def ssd_chunk_scan(x, dt, A, B, C, chunk_size: int = 128, D: Optional[torch.Tens
     # 3. inter-chunk recurrence on the chunk boundary states
     if initial_states is None:
         initial_states = torch.zeros(b, h, p, n, dtype=torch.float32, device=x.device)
-    states = torch.cat([initial_states.float().unsqueeze(1), states], dim=1)   # [b, c+1, h, p, n]
-    chunk_decay = torch.nn.functional.pad(a_cs[..., -1], (1, 0))               # [b, h, c+1]
-    decay_chunk = torch.exp(_segsum(chunk_decay))                              # [b, h, c+1, c+1]
-    new_states = torch.einsum("bhzc,bchpn->bzhpn", decay_chunk, states)
-    prev_states, final_state = new_states[:, :-1], new_states[:, -1]
+    if x.is_cuda:
+        # O(c) scan in one kernel (csrc/extra_kernels.cu: ssd_state_fwd / reverse scan in backward) instead of the O(c²) segment-sum matmul
+        from ...ops import ssd_state_passing
+
+        prev_states, final_state = ssd_state_passing(states, a_cs[..., -1], initial_states)
+    else:
+        states = torch.cat([initial_states.float().unsqueeze(1), states], dim=1)   # [b, c+1, h, p, n]
+        chunk_decay = torch.nn.functional.pad(a_cs[..., -1], (1, 0))               # [b, h, c+1]
+        decay_chunk = torch.exp(_segsum(chunk_decay))                              # [b, h, c+1, c+1]
+        new_states = torch.einsum("bhzc,bchpn->bzhpn", decay_chunk, states)
+        prev_states, final_state = new_states[:, :-1], new_states[:, -1]
     # 4. contribution of the carried-in state to each position
     y_off = torch.einsum("bclhn,bchpn,bhcl->bclhp", Cf, prev_states, torch.exp(a_cs))
     y = (y_diag + y_off).reshape(b, lp, h, p)[:, :l]
@@ -72,6 +78,11 @@ def ssd_chunk_scan(x, dt, A, B, C, chunk_size: int = 128, D: Optional[torch.Tens
 def ssd_step(x, dt, A, B, C, state, D: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """One decode step.  x [b, h, p]; dt [b, h]; B, C [b, g, n]; state [b, h, p, n] → (y [b, h, p], new state)."""
     h, g = x.shape[1], B.shape[1]
+    if x.is_cuda and not torch.is_grad_enabled() and (D is None or D.numel() == h):
+        from ...ops import ssd_step as _step_kernel       # fused in-place update + readout (csrc/extra_kernels.cu: ssd_step_kernel)
+
+        state = state if (state.dtype == torch.float32 and state.is_contiguous()) else state.float().contiguous()
+        return _step_kernel(state, x, dt, A, B, C, D), state
     rep = h // g
     Bf, Cf = B.float().repeat_interleave(rep, dim=1), C.float().repeat_interleave(rep, dim=1)
     dA = torch.exp(A.float().view(1, h) * dt.float())               # [b, h]
@@ -99,6 +110,15 @@ def causal_conv1d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Te
                   initial_state: Optional[torch.Tensor] = None, return_final_state: bool = False):
     """Depthwise causal conv.  x [b, d, l]; weight [d, k]; state [b, d, k-1] (reference ``ssm/ops/common/causal_conv1d_triton.py``)."""
     d, k = weight.shape
+    if x.is_cuda and 2 <= k <= 4 and weight.dtype == x.dtype and activation in (None, "silu", "swish"):
+        from ...ops import causal_conv1d as _conv_kernel   # csrc/extra_kernels.cu: conv1d_fwd / conv1d_bwd
+
+        xc = x.contiguous()
+        y = _conv_kernel(xc, weight, bias, initial_state.to(x.dtype) if initial_state is not None else None, silu=activation is not None)
+        if return_final_state:
+            lf = initial_state.to(x.dtype) if initial_state is not None else x.new_zeros(x.shape[0], d, k - 1)
+            return y, torch.cat([lf, xc], dim=-1)[..., -(k - 1):].contiguous()
+        return y
     left = initial_state if initial_state is not None else x.new_zeros(x.shape[0], d, k - 1)
     xp = torch.cat([left.to(x.dtype), x], dim=-1)
     y = torch.nn.functional.conv1d(xp, weight.unsqueeze(1), bias, groups=d)

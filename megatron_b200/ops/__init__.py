@@ -595,3 +595,20 @@ def moe_topk_router(logits: torch.Tensor, topk: int, score_function: str = "soft
     probs = torch.softmax(vals, -1) if fn == 2 else (vals / (vals.sum(-1, keepdim=True) + 1e-20) if (fn == 1 and topk > 1) else vals)
     rmap = torch.zeros_like(lf, dtype=torch.bool).scatter(1, ids, True)
     return ids, rmap, rmap.sum(0).int(), probs * float(scaling_factor or 1.0)
+
+
+# second kernel batch: residual-fused RMSNorm, RoPE thd / fused-QKV, causal conv1d, SSD state passing / step, MXFP8 (see ops/extra.py)
+from .extra import (  # noqa: E402,F401
+    add_rms_norm,
+    apply_rope_qkv,
+    apply_rope_thd,
+    causal_conv1d,
+    gemm_mxfp8_nt,
+    mxfp8_dequantize,
+    mxfp8_quantize,
+    mxfp8_quantize_reference,
+    mxfp8_swizzle_scales,
+    positions_from_cu_seqlens,
+    ssd_state_passing,
+    ssd_step,
+)

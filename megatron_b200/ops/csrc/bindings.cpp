@@ -506,9 +506,180 @@ void fused_tp_gemm(int64_t mode, const Tensor& a, const Tensor& b, Tensor c, int
 }
 #endif
 
+// ---- second kernel batch (extra_kernels.cu + fused residual norm) ---------------------------------------------------------------
+std::vector<Tensor> add_rmsnorm_fwd(const Tensor& x, const Tensor& res, const Tensor& w, double eps, bool zero_centered) {
+  check_cuda_contig(x, "x"); check_cuda_contig(res, "residual"); check_cuda_contig(w, "weight");
+  TORCH_CHECK(x.dim() == 2 && x.sizes() == res.sizes() && x.size(1) == w.numel() && x.scalar_type() == w.scalar_type() && x.scalar_type() == res.scalar_type());
+  TORCH_CHECK(x.size(1) % vec_elems(x) == 0, "hidden size must be a multiple of ", vec_elems(x));
+  c10::cuda::CUDAGuard g(x.device());
+  auto y = at::empty_like(x), h = at::empty_like(x);
+  auto rstd = at::empty({x.size(0)}, x.options().dtype(at::kFloat));
+  mb200_add_rmsnorm_fwd(x.data_ptr(), res.data_ptr(), w.data_ptr(), y.data_ptr(), h.data_ptr(), rstd.data_ptr<float>(), (int)x.size(0), (int)x.size(1), (float)eps,
+                        zero_centered, dtype_code(x), cur_stream());
+  return {y, h, rstd};
+}
+
+std::vector<Tensor> add_rmsnorm_bwd(const Tensor& gy, const c10::optional<Tensor>& gres, const Tensor& h, const Tensor& w, const Tensor& rstd, bool zero_centered) {
+  check_cuda_contig(gy, "gy"); check_cuda_contig(h, "h");
+  TORCH_CHECK(gy.sizes() == h.sizes() && gy.scalar_type() == h.scalar_type());
+  if (gres.has_value()) { check_cuda_contig(*gres, "gres"); TORCH_CHECK(gres->sizes() == h.sizes() && gres->scalar_type() == h.scalar_type()); }
+  c10::cuda::CUDAGuard g(h.device());
+  const int rows = (int)h.size(0), H = (int)h.size(1);
+  const int nblocks = std::min(rows, persistent_blocks());
+  auto gx = at::empty_like(h);
+  auto gw = at::empty_like(w);
+  auto partial = at::empty({nblocks, 2, H}, h.options().dtype(at::kFloat));
+  mb200_add_rmsnorm_bwd(gy.data_ptr(), gres.has_value() ? gres->data_ptr() : nullptr, h.data_ptr(), w.data_ptr(), rstd.data_ptr<float>(), gx.data_ptr(),
+                        partial.data_ptr<float>(), gw.data_ptr(), rows, H, zero_centered, dtype_code(h), nblocks, cur_stream());
+  return {gx, gw};
+}
+
+#ifdef MB200_HAVE_EXTRA_KERNELS
+// t [T, H, D] packed tokens, pos int32 [T]
+Tensor rope_pos(const Tensor& t, const Tensor& freqs, const Tensor& pos, double mscale, bool conj) {
+  check_cuda_contig(t, "t"); check_cuda_contig(freqs, "freqs"); check_cuda_contig(pos, "pos");
+  TORCH_CHECK(t.dim() == 3 && freqs.dim() == 2 && freqs.scalar_type() == at::kFloat && pos.scalar_type() == at::kInt && pos.numel() == t.size(0));
+  const int Hh = (int)t.size(1), D = (int)t.size(2), Drot = (int)freqs.size(1), vn = vec_elems(t);
+  TORCH_CHECK(Drot <= D && (Drot / 2) % vn == 0 && (D - Drot) % vn == 0, "rope: head dim / rotary dim not vectorisable");
+  c10::cuda::CUDAGuard g(t.device());
+  auto out = at::empty_like(t);
+  mb200_rope_pos(t.data_ptr(), freqs.data_ptr<float>(), pos.data_ptr<int>(), out.data_ptr(), t.size(0), Hh, D, Drot, (float)mscale, conj, dtype_code(t), cur_stream());
+  return out;
+}
+
+// qkv [S, B, NG, (QPG+2)*D]; rotates q and k heads; in place when `inplace`
+Tensor rope_qkv(Tensor qkv, const Tensor& freqs, int64_t qpg, int64_t D, double mscale, bool conj, bool inplace) {
+  check_cuda_contig(qkv, "qkv"); check_cuda_contig(freqs, "freqs");
+  TORCH_CHECK(qkv.dim() == 4 && qkv.size(3) == (qpg + 2) * D && freqs.dim() == 2 && freqs.scalar_type() == at::kFloat && freqs.size(0) >= qkv.size(0));
+  const int Drot = (int)freqs.size(1), vn = vec_elems(qkv);
+  TORCH_CHECK(Drot <= D && (Drot / 2) % vn == 0 && (D - Drot) % vn == 0, "rope: head dim / rotary dim not vectorisable");
+  c10::cuda::CUDAGuard g(qkv.device());
+  Tensor out = inplace ? qkv : at::empty_like(qkv);
+  mb200_rope_qkv(qkv.data_ptr(), freqs.data_ptr<float>(), out.data_ptr(), (int)qkv.size(0), (int)qkv.size(1), (int)qkv.size(2), (int)qpg, (int)D, Drot, (float)mscale,
+                 conj, dtype_code(qkv), cur_stream());
+  return out;
+}
+
+// x [b, d, l]; w [d, K]; left [b, d, K-1]
+Tensor conv1d_fwd(const Tensor& x, const Tensor& w, const c10::optional<Tensor>& bias, const c10::optional<Tensor>& left, bool silu) {
+  check_cuda_contig(x, "x"); check_cuda_contig(w, "w");
+  TORCH_CHECK(x.dim() == 3 && w.dim() == 2 && w.size(0) == x.size(1) && w.scalar_type() == x.scalar_type());
+  c10::cuda::CUDAGuard g(x.device());
+  auto y = at::empty_like(x);
+  const int rc = mb200_conv1d_fwd(x.data_ptr(), w.data_ptr(), bias.has_value() ? bias->data_ptr() : nullptr, left.has_value() ? left->data_ptr() : nullptr, y.data_ptr(),
+                                  x.size(0) * x.size(1), (int)x.size(1), (int)x.size(2), (int)w.size(1), silu, dtype_code(x), cur_stream());
+  TORCH_CHECK(rc == 0, "conv1d_fwd: kernel width must be 2..4");
+  return y;
+}
+
+std::vector<Tensor> conv1d_bwd(const Tensor& gy, const Tensor& x, const Tensor& w, const c10::optional<Tensor>& bias, const c10::optional<Tensor>& left, bool silu) {
+  check_cuda_contig(gy, "gy"); check_cuda_contig(x, "x");
+  c10::cuda::CUDAGuard g(x.device());
+  auto gx = at::empty_like(x);
+  auto gw = at::zeros({w.size(0), w.size(1)}, x.options().dtype(at::kFloat));
+  auto gb = at::zeros({w.size(0)}, x.options().dtype(at::kFloat));
+  Tensor gleft = left.has_value() ? at::empty_like(*left) : Tensor();
+  const int rc = mb200_conv1d_bwd(gy.data_ptr(), x.data_ptr(), w.data_ptr(), bias.has_value() ? bias->data_ptr() : nullptr, left.has_value() ? left->data_ptr() : nullptr,
+                                  gx.data_ptr(), left.has_value() ? gleft.data_ptr() : nullptr, gw.data_ptr<float>(), gb.data_ptr<float>(), x.size(0) * x.size(1),
+                                  (int)x.size(1), (int)x.size(2), (int)w.size(1), silu, dtype_code(x), cur_stream());
+  TORCH_CHECK(rc == 0, "conv1d_bwd: kernel width must be 2..4");
+  return {gx, gw, gb, gleft.defined() ? gleft : at::empty({0}, x.options())};
+}
+
+// states [b, c, h, p, n] fp32; decay [b, h, c] fp32; init [b, h, p, n] fp32 (optional) -> prev [b, c, h, p, n], final [b, h, p, n]
+std::vector<Tensor> ssd_state_fwd(const Tensor& states, const Tensor& decay, const c10::optional<Tensor>& init) {
+  check_cuda_contig(states, "states"); check_cuda_contig(decay, "decay");
+  TORCH_CHECK(states.dim() == 5 && states.scalar_type() == at::kFloat && decay.scalar_type() == at::kFloat);
+  const int b = (int)states.size(0), c = (int)states.size(1), h = (int)states.size(2), E = (int)(states.size(3) * states.size(4));
+  c10::cuda::CUDAGuard g(states.device());
+  auto prev = at::empty_like(states);
+  auto fin = at::empty({b, h, states.size(3), states.size(4)}, states.options());
+  mb200_ssd_state_fwd(states.data_ptr<float>(), decay.data_ptr<float>(), init.has_value() ? init->data_ptr<float>() : nullptr, prev.data_ptr<float>(), fin.data_ptr<float>(),
+                      b, c, h, E, cur_stream());
+  return {prev, fin};
+}
+
+std::vector<Tensor> ssd_state_bwd(const Tensor& g_prev, const c10::optional<Tensor>& g_fin, const Tensor& prev, const Tensor& decay) {
+  check_cuda_contig(g_prev, "g_prev"); check_cuda_contig(prev, "prev");
+  const int b = (int)prev.size(0), c = (int)prev.size(1), h = (int)prev.size(2), E = (int)(prev.size(3) * prev.size(4));
+  c10::cuda::CUDAGuard g(prev.device());
+  auto g_states = at::empty_like(prev);
+  auto g_init = at::empty({b, h, prev.size(3), prev.size(4)}, prev.options());
+  auto g_decay = at::empty({b, h, c}, prev.options());
+  mb200_ssd_state_bwd(g_prev.data_ptr<float>(), g_fin.has_value() ? g_fin->data_ptr<float>() : nullptr, prev.data_ptr<float>(), decay.data_ptr<float>(),
+                      g_states.data_ptr<float>(), g_init.data_ptr<float>(), g_decay.data_ptr<float>(), b, c, h, E, cur_stream());
+  return {g_states, g_init, g_decay};
+}
+
+// state [b, h, p, n] fp32 (updated in place); x [b, h, p]; dt [b, h] fp32; A [h] fp32; B, C [b, g, n]; D [h] fp32 optional
+Tensor ssd_step(Tensor state, const Tensor& x, const Tensor& dt, const Tensor& A, const Tensor& B, const Tensor& C, const c10::optional<Tensor>& D) {
+  check_cuda_contig(state, "state"); check_cuda_contig(x, "x"); check_cuda_contig(B, "B"); check_cuda_contig(C, "C");
+  TORCH_CHECK(state.scalar_type() == at::kFloat && dt.scalar_type() == at::kFloat && A.scalar_type() == at::kFloat && dt.is_contiguous() && A.is_contiguous());
+  TORCH_CHECK(B.scalar_type() == x.scalar_type() && C.scalar_type() == x.scalar_type());
+  c10::cuda::CUDAGuard g(x.device());
+  auto y = at::empty_like(x);
+  mb200_ssd_step(state.data_ptr<float>(), x.data_ptr(), dt.data_ptr<float>(), A.data_ptr<float>(), B.data_ptr(), C.data_ptr(), D.has_value() ? D->data_ptr<float>() : nullptr,
+                 y.data_ptr(), (int)x.size(0), (int)x.size(1), (int)B.size(1), (int)x.size(2), (int)B.size(2), dtype_code(x), cur_stream());
+  return y;
+}
+
+// x [rows, K] bf16 -> (q uint8 [rows, K] (e4m3 bits), sf uint8 [rows, K/32] (e8m0))
+std::vector<Tensor> mxfp8_quant(const Tensor& x) {
+  check_cuda_contig(x, "x");
+  TORCH_CHECK(x.dim() == 2 && x.scalar_type() == at::kBFloat16 && x.size(1) % 32 == 0, "mxfp8_quant: bf16 [rows, K], K % 32 == 0");
+  c10::cuda::CUDAGuard g(x.device());
+  auto q = at::empty({x.size(0), x.size(1)}, x.options().dtype(at::kByte));
+  auto sf = at::empty({x.size(0), x.size(1) / 32}, x.options().dtype(at::kByte));
+  mb200_mxfp8_quant(x.data_ptr(), q.data_ptr(), sf.data_ptr(), x.size(0), (int)x.size(1), cur_stream());
+  return {q, sf};
+}
+
+Tensor mxfp8_dequant(const Tensor& q, const Tensor& sf) {
+  check_cuda_contig(q, "q"); check_cuda_contig(sf, "sf");
+  TORCH_CHECK(q.dim() == 2 && q.scalar_type() == at::kByte && sf.scalar_type() == at::kByte && sf.size(0) == q.size(0) && sf.size(1) * 32 == q.size(1));
+  c10::cuda::CUDAGuard g(q.device());
+  auto out = at::empty({q.size(0), q.size(1)}, q.options().dtype(at::kBFloat16));
+  mb200_mxfp8_dequant(q.data_ptr(), sf.data_ptr(), out.data_ptr(), q.size(0), (int)q.size(1), cur_stream());
+  return out;
+}
+#endif
+
+#ifdef MB200_HAVE_GEMM_MXFP8_SM100
+// a [M,K], b [N,K] uint8 (e4m3 bits); sfa / sfb: swizzled E8M0 scale atoms [ceil(rows/128), K/128, 512] -> bf16 [M,N]
+Tensor gemm_mxfp8_nt(const Tensor& a, const Tensor& sfa, const Tensor& b, const Tensor& sfb) {
+  TORCH_CHECK(a.is_cuda() && a.dim() == 2 && b.dim() == 2 && a.is_contiguous() && b.is_contiguous() && a.size(1) == b.size(1) && a.scalar_type() == at::kByte &&
+                  b.scalar_type() == at::kByte, "gemm_mxfp8_nt: a [M,K], b [N,K] contiguous uint8");
+  const int64_t M = a.size(0), N = b.size(0), K = a.size(1);
+  TORCH_CHECK(K % 128 == 0, "gemm_mxfp8_nt: K must be a multiple of 128");
+  TORCH_CHECK(sfa.is_contiguous() && sfb.is_contiguous() && sfa.scalar_type() == at::kByte && sfb.scalar_type() == at::kByte &&
+                  sfa.numel() == ((M + 127) / 128) * (K / 128) * 512 && sfb.numel() == ((N + 127) / 128) * (K / 128) * 512, "gemm_mxfp8_nt: scale atoms have the wrong size");
+  c10::cuda::CUDAGuard g(a.device());
+  auto c = at::empty({M, N}, a.options().dtype(at::kBFloat16));
+  const int rc = mb200_gemm_mxfp8_nt(a.data_ptr(), b.data_ptr(), sfa.data_ptr(), sfb.data_ptr(), c.data_ptr(), (int)M, (int)N, (int)K, cur_stream());
+  TORCH_CHECK(rc == 0, "gemm_mxfp8_nt failed with code ", rc);
+  return c;
+}
+#endif
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+#ifdef MB200_HAVE_GEMM_MXFP8_SM100
+  m.def("gemm_mxfp8_nt", &gemm_mxfp8_nt);
+#endif
+  m.def("add_rmsnorm_fwd", &add_rmsnorm_fwd);
+  m.def("add_rmsnorm_bwd", &add_rmsnorm_bwd);
+#ifdef MB200_HAVE_EXTRA_KERNELS
+  m.def("rope_pos", &rope_pos);
+  m.def("rope_qkv", &rope_qkv);
+  m.def("conv1d_fwd", &conv1d_fwd);
+  m.def("conv1d_bwd", &conv1d_bwd);
+  m.def("ssd_state_fwd", &ssd_state_fwd);
+  m.def("ssd_state_bwd", &ssd_state_bwd);
+  m.def("ssd_step", &ssd_step);
+  m.def("mxfp8_quant", &mxfp8_quant);
+  m.def("mxfp8_dequant", &mxfp8_dequant);
+#endif
   m.def("rmsnorm_fwd", &rmsnorm_fwd);
   m.def("rmsnorm_bwd", &rmsnorm_bwd);
   m.def("layernorm_fwd", &layernorm_fwd);

@@ -56,4 +56,20 @@ int mb200_flash_attn_bwd(const void* q, const void* k, const void* v, const void
                          int sk, int b, int hq, int hk, int d, long q_ss, long q_sb, long q_sh, long k_ss, long k_sb, long k_sh, long v_ss, long v_sb, long v_sh,
                          long do_ss, long do_sb, long do_sh, float scale, int causal, cudaStream_t s);
 int mb200_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int layout, int accumulate, int c_dtype, cudaStream_t s);
+void mb200_add_rmsnorm_fwd(const void* x, const void* res, const void* w, void* y, void* res_out, float* rstd, int rows, int H, float eps, int zc, int dtype, cudaStream_t s);
+void mb200_add_rmsnorm_bwd(const void* gy, const void* gres, const void* h, const void* w, const float* rstd, void* gx, float* partial, void* gw, int rows, int H, int zc,
+                           int dtype, int nblocks, cudaStream_t s);
+void mb200_rope_pos(const void* t, const float* freqs, const int* pos, void* out, long tokens, int Hh, int D, int Drot, float mscale, int conj, int dtype, cudaStream_t s);
+void mb200_rope_qkv(const void* qkv, const float* freqs, void* out, int S, int B, int NG, int QPG, int D, int Drot, float mscale, int conj, int dtype, cudaStream_t s);
+int mb200_conv1d_fwd(const void* x, const void* w, const void* bias, const void* left, void* y, long rows, int d, int l, int K, int act, int dtype, cudaStream_t s);
+int mb200_conv1d_bwd(const void* gy, const void* x, const void* w, const void* bias, const void* left, void* gx, void* gleft, float* gw_acc, float* gb_acc, long rows,
+                     int d, int l, int K, int act, int dtype, cudaStream_t s);
+void mb200_ssd_state_fwd(const float* states, const float* decay, const float* init, float* prev, float* fin, int b, int c, int h, int E, cudaStream_t s);
+void mb200_ssd_state_bwd(const float* g_prev, const float* g_fin, const float* prev, const float* decay, float* g_states, float* g_init, float* g_decay, int b, int c,
+                         int h, int E, cudaStream_t s);
+void mb200_ssd_step(float* state, const void* x, const float* dt, const float* A, const void* B, const void* C, const float* D, void* y, int b, int h, int g, int p, int n,
+                    int dtype, cudaStream_t s);
+void mb200_mxfp8_quant(const void* x, void* q, void* sf, long rows, int K, cudaStream_t s);
+void mb200_mxfp8_dequant(const void* q, const void* sf, void* out, long rows, int K, cudaStream_t s);
+int mb200_gemm_mxfp8_nt(const void* A, const void* B, const void* sfa, const void* sfb, void* C, int M, int N, int K, cudaStream_t s);
 }

@@ -12,7 +12,7 @@ namespace mb200 {
 template <typename T, int NV, bool RMS>
 __global__ void __launch_bounds__(256) norm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ b, T* __restrict__ y,
                                                          float* __restrict__ mu_out, float* __restrict__ rstd_out, int rows, int H, float eps,
-                                                         int zero_centered) {
+                                                         int zero_centered, const T* __restrict__ res, T* __restrict__ res_out) {
   constexpr int VN = Vec<T>::N;
   __shared__ float red[32];
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -45,6 +45,13 @@ __global__ void __launch_bounds__(256) norm_fwd_kernel(const T* __restrict__ x, 
       const int col = (v * nt + tid) * VN;
       if (col < H) {
         Vec<T> t = ld16_stream(xr + col);
+        if (res != nullptr) {
+          // fused residual add: h = x + residual is rounded to T once, written out (the next residual) and normalised
+          Vec<T> rv = ld16_stream(res + (size_t)row * H + col);
+#pragma unroll
+          for (int i = 0; i < VN; ++i) t.v[i] = from_f<T>(to_f(t.v[i]) + to_f(rv.v[i]));
+          st16(res_out + (size_t)row * H + col, t);
+        }
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
           xv[v][i] = to_f(t.v[i]);
@@ -97,7 +104,8 @@ __global__ void __launch_bounds__(256) norm_fwd_kernel(const T* __restrict__ x, 
 template <typename T, int NV, bool RMS>
 __global__ void __launch_bounds__(256) norm_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x, const T* __restrict__ w,
                                                          const float* __restrict__ mu, const float* __restrict__ rstd, T* __restrict__ gx,
-                                                         float* __restrict__ partial, int rows, int H, int zero_centered) {
+                                                         float* __restrict__ partial, int rows, int H, int zero_centered,
+                                                         const T* __restrict__ gres) {
   constexpr int VN = Vec<T>::N;
   __shared__ float red[32];
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -144,8 +152,14 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const T* __restrict__ gy,
       const int col = (v * nt + tid) * VN;
       if (col < H) {
         Vec<T> o;
+        if (gres != nullptr) {   // gradient arriving through the residual branch is added in the same pass
+          Vec<T> gr = ld16_stream(gres + (size_t)row * H + col);
 #pragma unroll
-        for (int i = 0; i < VN; ++i) o.v[i] = from_f<T>(r * (gg[v][i] - c2 - xh[v][i] * c1));
+          for (int i = 0; i < VN; ++i) o.v[i] = from_f<T>(r * (gg[v][i] - c2 - xh[v][i] * c1) + to_f(gr.v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < VN; ++i) o.v[i] = from_f<T>(r * (gg[v][i] - c2 - xh[v][i] * c1));
+        }
         st16(gx + (size_t)row * H + col, o);
       }
     }
@@ -192,7 +206,8 @@ __global__ void norm_bwd_reduce_kernel(const float* __restrict__ partial, T* __r
 }
 
 template <typename T, bool RMS>
-void launch_fwd(const void* x, const void* w, const void* b, void* y, float* mu, float* rstd, int rows, int H, float eps, int zc, cudaStream_t s) {
+void launch_fwd(const void* x, const void* w, const void* b, void* y, float* mu, float* rstd, int rows, int H, float eps, int zc, cudaStream_t s,
+                const void* res = nullptr, void* res_out = nullptr) {
   constexpr int VN = Vec<T>::N;
   const int vecs = H / VN;
   int threads = vecs >= 256 ? 256 : ((vecs + 31) / 32) * 32;
@@ -200,21 +215,21 @@ void launch_fwd(const void* x, const void* w, const void* b, void* y, float* mu,
   const int nv = (vecs + threads - 1) / threads;
   const int grid = rows < 148 * 8 ? rows : 148 * 8;
 #define L(NV)                                                                                                                          \
-  norm_fwd_kernel<T, NV, RMS><<<grid, threads, 0, s>>>((const T*)x, (const T*)w, (const T*)b, (T*)y, mu, rstd, rows, H, eps, zc)
+  norm_fwd_kernel<T, NV, RMS><<<grid, threads, 0, s>>>((const T*)x, (const T*)w, (const T*)b, (T*)y, mu, rstd, rows, H, eps, zc, (const T*)res, (T*)res_out)
   if (nv <= 1) L(1); else if (nv <= 2) L(2); else if (nv <= 4) L(4); else if (nv <= 8) L(8); else L(16);
 #undef L
 }
 
 template <typename T, bool RMS>
 void launch_bwd(const void* gy, const void* x, const void* w, const float* mu, const float* rstd, void* gx, float* partial, void* gw, void* gb, int rows,
-                int H, int zc, int nblocks, cudaStream_t s) {
+                int H, int zc, int nblocks, cudaStream_t s, const void* gres = nullptr) {
   constexpr int VN = Vec<T>::N;
   const int vecs = H / VN;
   int threads = vecs >= 256 ? 256 : ((vecs + 31) / 32) * 32;
   if (threads < 32) threads = 32;
   const int nv = (vecs + threads - 1) / threads;
 #define L(NV)                                                                                                                          \
-  norm_bwd_kernel<T, NV, RMS><<<nblocks, threads, 0, s>>>((const T*)gy, (const T*)x, (const T*)w, mu, rstd, (T*)gx, partial, rows, H, zc)
+  norm_bwd_kernel<T, NV, RMS><<<nblocks, threads, 0, s>>>((const T*)gy, (const T*)x, (const T*)w, mu, rstd, (T*)gx, partial, rows, H, zc, (const T*)gres)
   if (nv <= 1) L(1); else if (nv <= 2) L(2); else if (nv <= 4) L(4); else if (nv <= 8) L(8); else L(16);
 #undef L
   norm_bwd_reduce_kernel<T><<<(H + 31) / 32, 256, 0, s>>>(partial, (T*)gw, RMS ? nullptr : (T*)gb, nblocks, H);
@@ -245,4 +260,15 @@ extern "C" void mb200_layernorm_fwd(const void* x, const void* w, const void* b,
 extern "C" void mb200_layernorm_bwd(const void* gy, const void* x, const void* w, const float* mu, const float* rstd, void* gx, float* partial, void* gw,
                                     void* gb, int rows, int H, int zc, int dtype, int nblocks, cudaStream_t s) {
   DISPATCH(dtype, (launch_bwd<T, false>(gy, x, w, mu, rstd, gx, partial, gw, gb, rows, H, zc, nblocks, s)));
+}
+
+// Fused residual-add + RMSNorm: h = x + residual (written to res_out), y = rmsnorm(h) * w.  Backward takes the gradient of y and the gradient that
+// reaches h through the residual branch and returns their sum in one pass (reference: TE fused-residual norm / inference fused RS+residual+norm).
+extern "C" void mb200_add_rmsnorm_fwd(const void* x, const void* res, const void* w, void* y, void* res_out, float* rstd, int rows, int H, float eps, int zc,
+                                      int dtype, cudaStream_t s) {
+  DISPATCH(dtype, (launch_fwd<T, true>(x, w, nullptr, y, nullptr, rstd, rows, H, eps, zc, s, res, res_out)));
+}
+extern "C" void mb200_add_rmsnorm_bwd(const void* gy, const void* gres, const void* h, const void* w, const float* rstd, void* gx, float* partial, void* gw, int rows,
+                                      int H, int zc, int dtype, int nblocks, cudaStream_t s) {
+  DISPATCH(dtype, (launch_bwd<T, true>(gy, h, w, nullptr, rstd, gx, partial, gw, nullptr, rows, H, zc, nblocks, s, gres)));
 }
