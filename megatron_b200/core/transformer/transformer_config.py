@@ -184,6 +184,7 @@ class TransformerConfig(ModelParallelConfig):
     use_mamba_mem_eff_path: bool = True
     mlp_chunks_for_prefill: int = 1
     mlp_chunks_for_training: int = 1
+    fused_residual_rmsnorm: bool = False  # attention residual add + pre-MLP RMSNorm in one kernel (ops.add_rms_norm); needs no dropout / bias
     heterogeneous_block_specs: bool = False
     hetereogenous_dist_checkpoint: bool = False
     transformer_impl: str = "b200"

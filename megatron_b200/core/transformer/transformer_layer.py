@@ -129,6 +129,13 @@ class TransformerLayer(GraphableMegatronModule, BaseTransformerLayer):
             return out if residual is None else out
         return fn((out, bias), residual, self.hidden_dropout)
 
+    def _can_fuse_residual_norm(self, attn_out) -> bool:
+        from .torch_norm import FusedNorm
+
+        n = self.pre_mlp_layernorm
+        return (self.config.fused_residual_rmsnorm and isinstance(n, FusedNorm) and n.normalization == "RMSNorm" and attn_out[1] is None
+                and (self.hidden_dropout == 0.0 or not self.training) and not self.recompute_pre_mlp_layernorm and isinstance(self.cross_attention, IdentityOp))
+
     def _norm_maybe_recompute(self, norm, x, flag):
         if flag and self.training:
             from ..tensor_parallel.random import CheckpointWithoutOutput
@@ -157,7 +164,14 @@ class TransformerLayer(GraphableMegatronModule, BaseTransformerLayer):
         )
         if ck is not None:
             ck.discard_output_and_register_recompute(attn_out[0])
-        hidden_states = self.self_attn_bda(self.training, self.config.bias_dropout_fusion)(attn_out, residual, self.hidden_dropout)
+        if self._can_fuse_residual_norm(attn_out):
+            # h = residual + attn_out and pre_mlp_layernorm(h) in ONE pass; _forward_mlp picks the normed tensor up instead of re-reading h
+            from ... import ops
+
+            n = self.pre_mlp_layernorm
+            self._prenormed, hidden_states = ops.add_rms_norm(attn_out[0], residual, n.weight, n.eps, n.zero_centered_gamma)
+        else:
+            hidden_states = self.self_attn_bda(self.training, self.config.bias_dropout_fusion)(attn_out, residual, self.hidden_dropout)
         if not isinstance(self.cross_attention, IdentityOp):
             residual = hidden_states
             normed = self.pre_cross_attn_layernorm(hidden_states)
@@ -171,7 +185,11 @@ class TransformerLayer(GraphableMegatronModule, BaseTransformerLayer):
     def _forward_mlp(self, hidden_states):
         nvtx_range_push("mlp")
         residual = hidden_states
-        normed, ck = self._norm_maybe_recompute(self.pre_mlp_layernorm, hidden_states, self.recompute_pre_mlp_layernorm)
+        pre = getattr(self, "_prenormed", None)
+        if pre is not None:
+            normed, ck, self._prenormed = pre, None, None
+        else:
+            normed, ck = self._norm_maybe_recompute(self.pre_mlp_layernorm, hidden_states, self.recompute_pre_mlp_layernorm)
         if self.recompute_mlp and self.training:
             from ..tensor_parallel.random import checkpoint
 

@@ -135,7 +135,57 @@ class RingAttention(torch.nn.Module):
             return self._all_gather(q, k, v, causal, scale)
         if self.kind in ("a2a",):
             return self._ulysses(q, k, v, causal, scale)
+        if self.kind in ("a2a+p2p",):
+            return self._hierarchical(q, k, v, causal, scale)
         return self._ring(q, k, v, causal, scale)
+
+    # ---- hierarchical: all-to-all over heads inside the inner group, ring over the outer group --------------------
+    def _hierarchical(self, q, k, v, causal, scale):
+        """``cp = a · p`` with ``hierarchical_context_parallel_sizes = [a, p]`` (reference ``cp_comm_type="a2a+p2p"``): the ``a`` ranks of an inner
+        group (one NVLink island) trade sequence for heads (Ulysses), so each holds ``h/a`` heads of the ``2a`` zig-zag chunks of its island; the
+        key/value blocks then travel around the ring of ``p`` islands.  Only ``p - 1`` ring steps with ``1/a`` of the heads each, instead of ``cp - 1``."""
+        groups = ps.get_hierarchical_context_parallel_groups()
+        g_in, g_out = groups[0], groups[1]
+        a, p_sz = dist.get_world_size(g_in), dist.get_world_size(g_out)
+        r_out = dist.get_rank(g_out)
+        s, b, h, d = q.shape
+        assert h % a == 0 and k.shape[2] % a == 0, "a2a+p2p needs query and key/value heads divisible by the inner context-parallel size"
+        c = s // 2
+
+        def seq_to_head(t):
+            hh = t.shape[2]
+            x = t.view(s, b, a, hh // a, t.shape[3]).permute(2, 0, 1, 3, 4).contiguous().view(a * s, b, hh // a, t.shape[3])
+            return _AllToAll.apply(g_in, x, None, None)          # blocks ordered by source inner rank, each [2c, ...] = (low chunk, high chunk)
+
+        def offsets(outer):                                     # global token offsets of the 2a chunks held by island ``outer`` (inner rank fastest)
+            offs = []
+            for i in range(a):
+                r = outer * a + i
+                offs += [r * c, (2 * self.cp - 1 - r) * c]
+            return offs
+
+        qf, kf, vf = seq_to_head(q), seq_to_head(k), seq_to_head(v)
+        dk = kf.shape[-1]
+        cur = torch.cat([kf, vf], dim=-1)
+        q_offs = offsets(r_out)
+        outs = [[] for _ in range(2 * a)]
+        lses = [[] for _ in range(2 * a)]
+        for step in range(p_sz):
+            src = (r_out - step) % p_sz
+            nxt = _RingShift.apply(cur, g_out, False) if step < p_sz - 1 else None
+            kk, vv = cur[..., :dk], cur[..., dk:]
+            k_offs = offsets(src)
+            for qi, qoff in enumerate(q_offs):
+                qc = qf[qi * c : (qi + 1) * c]
+                for ki, koff in enumerate(k_offs):
+                    if causal and koff > qoff + c - 1:
+                        continue
+                    o, l = attention_with_lse(qc, kk[ki * c : (ki + 1) * c], vv[ki * c : (ki + 1) * c], scale, causal, q_offset=qoff, k_offset=koff)
+                    outs[qi].append(o), lses[qi].append(l)
+            cur = nxt
+        merged = torch.cat([merge_partials(outs[i], lses[i]) for i in range(2 * a)], dim=0).to(q.dtype)     # [a * s, b, h/a, dv]
+        y = _AllToAll.apply(g_in, merged.contiguous(), None, None)
+        return y.view(a, s, b, h // a, y.shape[-1]).permute(1, 2, 0, 3, 4).reshape(s, b, h, y.shape[-1])
 
     # ---- all-gather KV ------------------------------------------------------------------------------------
     def _all_gather(self, q, k, v, causal, scale):

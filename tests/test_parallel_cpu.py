@@ -303,7 +303,7 @@ def _cp_worker(rank, world, kind, state):
     from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
     from megatron_b200.core.utils import get_batch_on_this_cp_rank
 
-    ps.initialize_model_parallel(context_parallel_size=world)
+    ps.initialize_model_parallel(context_parallel_size=world, hierarchical_context_parallel_sizes=[2, world // 2] if kind == "a2a+p2p" else None)
     model_parallel_cuda_manual_seed(1)
     cfg = _cfg(num_layers=2, context_parallel_size=world, cp_comm_type=kind)
     m = _model(cfg)
@@ -319,9 +319,9 @@ def _cp_worker(rank, world, kind, state):
     return float(loss_sum), {n: p.grad.clone() for n, p in m.named_parameters()}
 
 
-@pytest.mark.parametrize("kind", ["all_gather", "p2p", "a2a"])
+@pytest.mark.parametrize("kind", ["all_gather", "p2p", "a2a", "a2a+p2p"])
 def test_context_parallel_matches_single_process(kind):
-    world = 2
+    world = 4 if kind == "a2a+p2p" else 2
     torch.manual_seed(33)
     ref = _model(_cfg(num_layers=2))
     state = {n: p.detach().clone() for n, p in ref.named_parameters()}

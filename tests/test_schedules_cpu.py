@@ -168,3 +168,25 @@ def _bridge_worker(rank, world):
 def test_bridge_communicator_fan_in():
     res = run_distributed(_bridge_worker, 3)
     assert torch.all(res[0] == 10.0) and torch.all(res[1] == 20.0) and res[2].shape == (4, 4, 8)
+
+
+def _fused_norm_worker(rank, world):
+    from megatron_b200.core import parallel_state as ps
+
+    ps.initialize_model_parallel()
+    outs = []
+    for fused in (False, True):
+        torch.manual_seed(5)
+        m = _model(_cfg(fused_residual_rmsnorm=fused))
+        b = _batches(1)[0]
+        l = m(b["tokens"], b["position_ids"], None, labels=b["labels"]).float().mean()
+        l.backward()
+        outs.append((l.item(), {n: p.grad.clone() for n, p in m.named_parameters()}))
+    assert abs(outs[0][0] - outs[1][0]) < 1e-6
+    for n, g in outs[0][1].items():
+        assert torch.allclose(g, outs[1][1][n], atol=1e-6, rtol=1e-4), n
+    return True
+
+
+def test_fused_residual_rmsnorm_layer_path_matches_unfused():
+    assert run_distributed(_fused_norm_worker, 1) == [True]
