@@ -91,8 +91,48 @@ class _Fp8LinearFn(torch.autograd.Function):
         return gx, gw, None, None
 
 
+def _pad_rows(t: torch.Tensor, mult: int) -> torch.Tensor:
+    r = (-t.shape[0]) % mult
+    return t if r == 0 else torch.cat([t, t.new_zeros(r, t.shape[1])], dim=0)
+
+
+def _mx_gemm_nt(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """bf16 [M, N] = a [M, K] · b [N, K]ᵀ with both operands quantised to MXFP8 along K (1x32 blocks, E8M0 scales applied inside the tensor core)."""
+    from .. import ops
+
+    K = a.shape[1]
+    if K % 128:                      # zero padding along K leaves the product unchanged
+        pad = (-K) % 128
+        a, b = torch.nn.functional.pad(a, (0, pad)), torch.nn.functional.pad(b, (0, pad))
+    aq, asf = ops.mxfp8_quantize(a.to(torch.bfloat16))
+    bq, bsf = ops.mxfp8_quantize(b.to(torch.bfloat16))
+    return ops.gemm_mxfp8_nt(aq, asf, bq, bsf)
+
+
+class _Mxfp8LinearFn(torch.autograd.Function):
+    """MXFP8 recipe (reference ``fp8_recipe="mxfp8"``): every GEMM operand is quantised along ITS reduction dimension, so the backward GEMMs
+    re-quantise transposed copies (row-wise for fprop, column-wise for dgrad / wgrad) — the data flow of TE's MXFP8 tensors with both usages."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x2 = x.reshape(-1, x.shape[-1])
+        ctx.save_for_backward(x2, w)
+        ctx.x_shape = x.shape
+        return _mx_gemm_nt(x2, w).to(x.dtype).view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, w = ctx.saved_tensors
+        g2 = gy.reshape(-1, gy.shape[-1])
+        gx = _mx_gemm_nt(g2, w.t().contiguous()).to(x2.dtype).view(ctx.x_shape)          # [M, N] · [K, N]ᵀ, reduction over N
+        gw = _mx_gemm_nt(g2.t().contiguous(), x2.t().contiguous()).to(w.dtype)           # [N, M] · [K, M]ᵀ, reduction over M
+        return gx, gw
+
+
 def fp8_linear(x: torch.Tensor, w: torch.Tensor, recipe: str = "tensorwise", fp8_format: str = "hybrid", metas=None) -> torch.Tensor:
-    """``x [..., K] @ w [N, K]ᵀ`` with FP8 operands for all three GEMMs of the layer."""
+    """``x [..., K] @ w [N, K]ᵀ`` with FP8 operands for all three GEMMs of the layer.  ``recipe``: ``tensorwise`` | ``delayed`` | ``mxfp8``."""
+    if recipe == "mxfp8":
+        return _Mxfp8LinearFn.apply(x, w)
     grad_dtype = E5M2 if fp8_format == "hybrid" else E4M3
     if recipe == "delayed" and metas is None:
         raise ValueError("delayed scaling needs (input, weight, grad) Fp8Meta objects")

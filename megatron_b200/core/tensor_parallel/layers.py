@@ -259,6 +259,19 @@ def linear_with_frozen_weight(input, weight, bias, gradient_accumulation_fusion,
     return _FrozenLinearFn.apply(input, weight, bias, allreduce_dgrad, tp_group)
 
 
+def _fp8_active(config) -> bool:
+    if not getattr(config, "fp8", None):
+        return False
+    from ..fp8_utils import fp8_enabled
+
+    return fp8_enabled()
+
+
+def _fp8_recipe(config) -> str:
+    r = getattr(config, "fp8_recipe", None) or "tensorwise"
+    return {"delayed": "tensorwise", "blockwise": "mxfp8"}.get(r, r)      # delayed scaling needs per-layer meta objects: falls back to current scaling here
+
+
 class ColumnParallelLinear(torch.nn.Module):
     """Y = X Aᵀ with A sharded along its output dimension."""
 
@@ -345,6 +358,18 @@ class ColumnParallelLinear(torch.nn.Module):
             x = copy_to_tensor_model_parallel_region(input_, group=self.tp_group)
         if self.config.defer_embedding_wgrad_compute and self.embedding_activation_buffer is not None:
             self.embedding_activation_buffer.append(x)
+        if _fp8_active(self.config) and not self.explicit_expert_comm:
+            # FP8 / MXFP8 recipe: collectives through the autograd mappings, the three GEMMs of the layer through core.fp8_utils.fp8_linear
+            from ..fp8_utils import fp8_linear
+
+            xg = gather_from_sequence_parallel_region(x, tensor_parallel_output_grad=True, group=self.tp_group) if self.sequence_parallel else (
+                copy_to_tensor_model_parallel_region(x, group=self.tp_group) if self.allreduce_dgrad else x)
+            out_parallel = fp8_linear(xg, weight, recipe=_fp8_recipe(self.config), fp8_format=self.config.fp8)
+            if bias is not None:
+                out_parallel = out_parallel + bias
+            gather = self.gather_output if runtime_gather_output is None else runtime_gather_output
+            out = gather_from_tensor_model_parallel_region(out_parallel, group=self.tp_group) if gather else out_parallel
+            return out, (self.bias if self.skip_bias_add else None)
         fn = linear_with_grad_accumulation_and_async_allreduce if weight.requires_grad else linear_with_frozen_weight
         out_parallel = fn(
             input=x, weight=weight, bias=bias,
@@ -468,7 +493,13 @@ class RowParallelLinear(torch.nn.Module):
 
     def forward(self, input_):
         x = input_ if self.input_is_parallel else scatter_to_tensor_model_parallel_region(input_, group=self.tp_group)
-        if self.explicit_expert_comm:
+        if _fp8_active(self.config) and not self.explicit_expert_comm and self.weight.requires_grad:
+            from ..fp8_utils import fp8_linear
+
+            out = fp8_linear(x, self.weight, recipe=_fp8_recipe(self.config), fp8_format=self.config.fp8)
+            if get_pg_size(self.tp_group) > 1:
+                out = (reduce_scatter_to_sequence_parallel_region if self.sequence_parallel else reduce_from_tensor_model_parallel_region)(out, group=self.tp_group)
+        elif self.explicit_expert_comm:
             from ...parallel import fused
 
             out = _RowLinearFn.apply(x, self.weight, False, None, self.gradient_accumulation_fusion)

@@ -140,12 +140,16 @@ class TransformerBlock(GraphableMegatronModule):
             if self.config.recompute_granularity == "full" and self.training:
                 hidden_states = self._checkpointed_forward(hidden_states, attention_mask, context, context_mask, rotary_pos_emb, attention_bias, packed_seq_params)
             else:
+                from ..fp8_utils import get_fp8_context
+
                 for layer in self.layers:
-                    hidden_states, context = layer(
-                        hidden_states, attention_mask=attention_mask, context=context, context_mask=context_mask,
-                        rotary_pos_emb=rotary_pos_emb, attention_bias=attention_bias, inference_context=inference_context,
-                        packed_seq_params=packed_seq_params,
-                    )
+                    # per-layer FP8 scope: the linear layers inside consult fp8_enabled() (first / last layers may stay bf16)
+                    with get_fp8_context(self.config, layer.layer_number - 1):
+                        hidden_states, context = layer(
+                            hidden_states, attention_mask=attention_mask, context=context, context_mask=context_mask,
+                            rotary_pos_emb=rotary_pos_emb, attention_bias=attention_bias, inference_context=inference_context,
+                            packed_seq_params=packed_seq_params,
+                        )
         if self.final_layernorm is not None:
             hidden_states = self.final_layernorm(hidden_states)
             hidden_states = make_viewless_tensor(hidden_states, requires_grad=True, keep_graph=True)

@@ -46,7 +46,8 @@ def test_rope_thd_and_fused_qkv(dtype, tol):
     torch.manual_seed(1)
     cu = torch.tensor([0, 100, 613, 1024], device="cuda", dtype=torch.int32)
     t = torch.randn(1024, 8, 128, device="cuda", dtype=dtype, requires_grad=True)
-    freqs = torch.randn(1024, 128, device="cuda")
+    f = torch.randn(1024, 64, device="cuda")
+    freqs = torch.cat([f, f], dim=-1)          # Megatron convention: both rotary halves share the angle table
     out = ops.apply_rope_thd(t, cu, freqs)
     g = torch.randn_like(out)
     out.backward(g)
@@ -59,7 +60,8 @@ def test_rope_thd_and_fused_qkv(dtype, tol):
     # fused QKV: 4 groups x (2 q + k + v), partial rotary (64 of 128)
     s, b, ng, qpg, d = 257, 2, 4, 2, 128
     qkv = torch.randn(s, b, ng, (qpg + 2) * d, device="cuda", dtype=dtype, requires_grad=True)
-    fr = torch.randn(s, 64, device="cuda")
+    f = torch.randn(s, 32, device="cuda")
+    fr = torch.cat([f, f], dim=-1)
     o = ops.apply_rope_qkv(qkv, fr, qpg, d)
     go = torch.randn_like(o)
     o.backward(go)

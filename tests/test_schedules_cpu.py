@@ -190,3 +190,31 @@ def _fused_norm_worker(rank, world):
 
 def test_fused_residual_rmsnorm_layer_path_matches_unfused():
     assert run_distributed(_fused_norm_worker, 1) == [True]
+
+
+def _fp8_worker(rank, world, recipe):
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=world)
+    model_parallel_cuda_manual_seed(1)
+    losses = []
+    for fp8 in (None, "hybrid"):
+        torch.manual_seed(5)
+        kw = dict(fp8=fp8, fp8_recipe=recipe, first_last_layers_bf16=True, num_layers_at_start_in_bf16=1, num_layers_at_end_in_bf16=0) if fp8 else {}
+        m = _model(_cfg(hidden_size=128, ffn_hidden_size=256, tensor_model_parallel_size=world, sequence_parallel=world > 1, **kw))
+        b = _batches(1)[0]
+        l = m(b["tokens"], b["position_ids"], None, labels=b["labels"]).float().mean()
+        l.backward()
+        gn = torch.sqrt(sum(p.grad.float().pow(2).sum() for p in m.parameters() if p.grad is not None))
+        assert all(p.grad is not None for p in m.parameters())
+        losses.append((l.item(), gn.item()))
+    (l0, g0), (l1, g1) = losses
+    assert abs(l0 - l1) / l0 < 0.02 and abs(g0 - g1) / g0 < 0.15, losses        # quantised GEMMs perturb, they do not break, the step
+    assert l0 != l1                                                              # ... and they really ran
+    return True
+
+
+@pytest.mark.parametrize("recipe,world", [("tensorwise", 1), ("mxfp8", 1), ("mxfp8", 2)])
+def test_fp8_recipes_wired_into_tp_linears(recipe, world):
+    assert run_distributed(_fp8_worker, world, recipe) == [True] * world
