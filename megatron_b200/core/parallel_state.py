@@ -194,8 +194,8 @@ def initialize_model_parallel(
     assert not _INITIALIZED, "model parallel groups are already initialised"
     if use_sharp or sharp_enabled_group:
         warnings.warn("SHARP is an InfiniBand feature; ignored on a single NVSwitch box")
-    if gtp_remat_size != 1 or expert_gtp_remat_size != 1:
-        raise NotImplementedError("generalised TP weight rematerialisation is not implemented yet")
+    if expert_gtp_remat_size != 1:
+        raise NotImplementedError("expert-side GTP weight rematerialisation is not implemented (dense GTP is: gtp_remat_size)")
 
     world = local_world_size or dist.get_world_size()
     rank = dist.get_rank()
@@ -272,6 +272,20 @@ def initialize_model_parallel(
     register("intra_dp_cp", intra, gloo=True)
     if n_inst > 1:
         register("inter_dist_opt", inter)
+
+    # generalised TP weight rematerialisation: R adjacent ranks of every data-parallel group share one copy of each GTP weight (sharded along out-features);
+    # the ranks holding the SAME shard form the orthogonal group over which that shard's gradient is data-parallel-reduced
+    if gtp_remat_size > 1:
+        assert (dp * cp) % gtp_remat_size == 0, f"gtp_remat_size ({gtp_remat_size}) must divide dp*cp ({dp * cp})"
+        remat, ortho = [], []
+        for lst in dense.get_ranks("dp-cp"):
+            for i in range(0, len(lst), gtp_remat_size):
+                remat.append(lst[i : i + gtp_remat_size])
+            for j in range(gtp_remat_size):
+                ortho.append(lst[j::gtp_remat_size])
+        register("gtp_remat", remat)
+        register("dp_no_gtp", ortho)
+    _TOPOLOGY["gtp"] = gtp_remat_size
 
     # hierarchical context parallel (a2a inside NVLink island, ring across)
     del _HIERARCHICAL_CP_GROUPS[:]
@@ -478,6 +492,25 @@ def get_intra_distributed_optimizer_instance_group():
 
 def get_inter_distributed_optimizer_instance_group():
     return get_group("inter_dist_opt", check_initialized=False)
+
+
+def get_gtp_weight_remat_group(check_initialized: bool = True):
+    """Ranks that jointly hold one copy of every GTP-sharded weight (``None`` when ``gtp_remat_size == 1``)."""
+    return get_group("gtp_remat", check_initialized=False)
+
+
+def get_gtp_weight_remat_world_size() -> int:
+    return _ws("gtp_remat") if "gtp_remat" in _GROUPS else 1
+
+
+def get_gtp_weight_remat_rank() -> int:
+    return _rk("gtp_remat") if "gtp_remat" in _GROUPS else 0
+
+
+def get_data_parallel_group_without_gtp(check_initialized: bool = True):
+    """Data-parallel replicas of ONE GTP shard (the full dp-cp group when GTP is off)."""
+    g = get_group("dp_no_gtp", check_initialized=False)
+    return g if g is not None else get_data_parallel_group(with_context_parallel=True)
 
 
 def get_hierarchical_context_parallel_groups(check_initialized: bool = True):

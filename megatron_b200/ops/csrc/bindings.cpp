@@ -646,7 +646,7 @@ Tensor mxfp8_dequant(const Tensor& q, const Tensor& sf) {
 
 #ifdef MB200_HAVE_GEMM_MXFP8_SM100
 // a [M,K], b [N,K] uint8 (e4m3 bits); sfa / sfb: swizzled E8M0 scale atoms [ceil(rows/128), K/128, 512] -> bf16 [M,N]
-Tensor gemm_mxfp8_nt(const Tensor& a, const Tensor& sfa, const Tensor& b, const Tensor& sfb) {
+Tensor gemm_mxfp8_nt(const Tensor& a, const Tensor& sfa, const Tensor& b, const Tensor& sfb, int64_t tile) {
   TORCH_CHECK(a.is_cuda() && a.dim() == 2 && b.dim() == 2 && a.is_contiguous() && b.is_contiguous() && a.size(1) == b.size(1) && a.scalar_type() == at::kByte &&
                   b.scalar_type() == at::kByte, "gemm_mxfp8_nt: a [M,K], b [N,K] contiguous uint8");
   const int64_t M = a.size(0), N = b.size(0), K = a.size(1);
@@ -655,7 +655,7 @@ Tensor gemm_mxfp8_nt(const Tensor& a, const Tensor& sfa, const Tensor& b, const 
                   sfa.numel() == ((M + 127) / 128) * (K / 128) * 512 && sfb.numel() == ((N + 127) / 128) * (K / 128) * 512, "gemm_mxfp8_nt: scale atoms have the wrong size");
   c10::cuda::CUDAGuard g(a.device());
   auto c = at::empty({M, N}, a.options().dtype(at::kBFloat16));
-  const int rc = mb200_gemm_mxfp8_nt(a.data_ptr(), b.data_ptr(), sfa.data_ptr(), sfb.data_ptr(), c.data_ptr(), (int)M, (int)N, (int)K, cur_stream());
+  const int rc = mb200_gemm_mxfp8_nt(a.data_ptr(), b.data_ptr(), sfa.data_ptr(), sfb.data_ptr(), c.data_ptr(), (int)M, (int)N, (int)K, (int)tile, cur_stream());
   TORCH_CHECK(rc == 0, "gemm_mxfp8_nt failed with code ", rc);
   return c;
 }
@@ -665,7 +665,7 @@ Tensor gemm_mxfp8_nt(const Tensor& a, const Tensor& sfa, const Tensor& b, const 
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 #ifdef MB200_HAVE_GEMM_MXFP8_SM100
-  m.def("gemm_mxfp8_nt", &gemm_mxfp8_nt);
+  m.def("gemm_mxfp8_nt", &gemm_mxfp8_nt, pybind11::arg("a"), pybind11::arg("sfa"), pybind11::arg("b"), pybind11::arg("sfb"), pybind11::arg("tile") = 0);
 #endif
   m.def("add_rmsnorm_fwd", &add_rmsnorm_fwd);
   m.def("add_rmsnorm_bwd", &add_rmsnorm_bwd);

@@ -9,14 +9,15 @@
 // lane quarters): TMEM column c of lane l then holds the four k-scales of row (l % 32) + 32 c, and the MMA of k-step k selects byte k through the
 // a_sf_id / b_sf_id fields of the instruction descriptor.  tcgen05.cp and tcgen05.mma execute in issue order, so one SF buffer in TMEM suffices.
 //
-// Pipeline: same persistent producer / issuer / 8-warp epilogue structure as gemm_fp8_sm100.cu, 128 x 128 tiles (two accumulators of 128 columns + 8 SF columns).
+// Pipeline: same persistent producer / issuer / 8-warp epilogue structure as gemm_fp8_sm100.cu.  Two tile shapes: 128 x 256 with ONE accumulator (256 + 12 of the 512
+// TMEM columns; the epilogue is not overlapped, but operand traffic per flop is 2/3 of the small tile's — measured 1.66 PF at 128 x 128 was L2-bound) and 128 x 128 with
+// two accumulators for narrow N.
 #include "gemm_sm100_device.cuh"
 
 namespace mb200 {
 using namespace ptx;
 
 constexpr int MX_BK = 128;          // K elements (bytes) per block = four scale groups
-constexpr int MX_BN = 128;
 constexpr int MX_SF_BYTES = 512;    // one scale atom: 128 rows x 4 k-groups
 
 // cute::UMMA::InstrDescriptorBlockScaled: a/b format E4M3 (0), K-major, scale format E8M0 (bit 23), no c_format field (fp32 accumulate implied)
@@ -48,18 +49,22 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 
 struct MxParams {
   GemmParams g;
-  const uint8_t* sfa;   // [tiles_m][k_blocks][512]
-  const uint8_t* sfb;   // [tiles_n][k_blocks][512]
+  const uint8_t* sfa;   // [ceil(M/128)][k_blocks][512]
+  const uint8_t* sfb;   // [ceil(N/128)][k_blocks][512]
+  int n_atoms;          // ceil(N/128)
 };
 
+template <int BN, int ACC_BUFS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, __nv_bfloat16* __restrict__ C, const MxParams p) {
-  constexpr int BN = MX_BN;
+  constexpr int NB_ATOMS = BN / 128;                  // scale atoms of the B tile
+  constexpr int SF_STAGE = (1 + NB_ATOMS) * MX_SF_BYTES;
   constexpr int A_BYTES = BM * MX_BK, B_BYTES = BN * MX_BK;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES + 2 * MX_SF_BYTES;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES + SF_STAGE;
   constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
-  constexpr uint32_t TMEM_COLS = 512;                 // 2 x 128 accumulator columns + 4 + 4 scale columns, rounded up to a power of two
-  constexpr uint32_t SFA_COL = 2 * BN, SFB_COL = 2 * BN + 4;
+  constexpr uint32_t TMEM_COLS = 512;                 // accumulators + 4 (SFA) + 4 per 128 B rows (SFB), rounded up to a power of two
+  constexpr uint32_t SFA_COL = ACC_BUFS * BN, SFB_COL = ACC_BUFS * BN + 4;
+  static_assert(ACC_BUFS * BN + 4 + 4 * NB_ATOMS <= 512, "tensor memory budget");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -86,7 +91,7 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ACC_BUFS; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], EPI_WARPS);
     }
@@ -110,8 +115,14 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           tma_load_2d(smem_a + stage * A_BYTES, &tmap_a, &full_bar[stage], kb * MX_BK, m_blk * BM);
           tma_load_2d(smem_b + stage * B_BYTES, &tmap_b, &full_bar[stage], kb * MX_BK, n_blk * BN);
-          bulk_load_1d(smem_sf + stage * 2 * MX_SF_BYTES, p.sfa + ((size_t)m_blk * k_blocks + kb) * MX_SF_BYTES, MX_SF_BYTES, &full_bar[stage]);
-          bulk_load_1d(smem_sf + stage * 2 * MX_SF_BYTES + MX_SF_BYTES, p.sfb + ((size_t)n_blk * k_blocks + kb) * MX_SF_BYTES, MX_SF_BYTES, &full_bar[stage]);
+          bulk_load_1d(smem_sf + stage * SF_STAGE, p.sfa + ((size_t)m_blk * k_blocks + kb) * MX_SF_BYTES, MX_SF_BYTES, &full_bar[stage]);
+#pragma unroll
+          for (int a = 0; a < NB_ATOMS; ++a) {
+            // rows beyond N have no atom: clamp to the last one (their products land in columns that are never stored)
+            int nb = n_blk * NB_ATOMS + a;
+            nb = nb < p.n_atoms ? nb : p.n_atoms - 1;
+            bulk_load_1d(smem_sf + stage * SF_STAGE + (1 + a) * MX_SF_BYTES, p.sfb + ((size_t)nb * k_blocks + kb) * MX_SF_BYTES, MX_SF_BYTES, &full_bar[stage]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -128,9 +139,10 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + stage * A_BYTES), b_addr = smem_u32(smem_b + stage * B_BYTES);
-          const uint32_t sf_addr = smem_u32(smem_sf + stage * 2 * MX_SF_BYTES);
+          const uint32_t sf_addr = smem_u32(smem_sf + stage * SF_STAGE);
           utccp_32x128b_warpx4(tmem_base + SFA_COL, make_smem_desc_sf(sf_addr));
-          utccp_32x128b_warpx4(tmem_base + SFB_COL, make_smem_desc_sf(sf_addr + MX_SF_BYTES));
+#pragma unroll
+          for (int a = 0; a < NB_ATOMS; ++a) utccp_32x128b_warpx4(tmem_base + SFB_COL + 4 * a, make_smem_desc_sf(sf_addr + (1 + a) * MX_SF_BYTES));
 #pragma unroll
           for (int k = 0; k < MX_BK / 32; ++k)
             umma_mxf8(d_tmem, make_smem_desc_sw128(a_addr + k * 32, 16, 1024), make_smem_desc_sw128(b_addr + k * 32, 16, 1024), make_idesc_mxf8(BM, BN, k, k),
@@ -139,7 +151,7 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -182,7 +194,7 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           for (int j = 0; j < 32 && col0 + j < g.N; ++j) crow[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
         }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
     }
   }
   tc_fence_before();
@@ -196,15 +208,14 @@ using namespace mb200;
 
 bool mb200_make_tmap_u8(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
 
-// A [M,K], B [N,K] e4m3 bytes; sfa / sfb: swizzled scale atoms [ceil(rows/128)][K/128][512]; C [M,N] bf16.  K % 128 == 0.
-extern "C" int mb200_gemm_mxfp8_nt(const void* A, const void* B, const void* sfa, const void* sfb, void* C, int M, int N, int K, cudaStream_t s) {
-  if (K % MX_BK != 0 || N % 8 != 0) return -11;
-  constexpr int STAGE_BYTES = BM * MX_BK + MX_BN * MX_BK + 2 * MX_SF_BYTES;
+template <int BN, int ACC_BUFS>
+static int launch_mx(const void* A, const void* B, const void* sfa, const void* sfb, void* C, int M, int N, int K, cudaStream_t s) {
+  constexpr int STAGE_BYTES = BM * MX_BK + BN * MX_BK + (1 + BN / 128) * MX_SF_BYTES;
   constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
   constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
   CUtensorMap ta, tb;
-  if (!mb200_make_tmap_u8(&ta, A, M, K, BM) || !mb200_make_tmap_u8(&tb, B, N, K, MX_BN)) return -1;
-  auto kern = gemm_mxfp8_kernel;
+  if (!mb200_make_tmap_u8(&ta, A, M, K, BM) || !mb200_make_tmap_u8(&tb, B, N, K, BN)) return -1;
+  auto kern = gemm_mxfp8_kernel<BN, ACC_BUFS>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return -3;
@@ -214,8 +225,18 @@ extern "C" int mb200_gemm_mxfp8_nt(const void* A, const void* B, const void* sfa
   p.g.M = M; p.g.N = N; p.g.K = K; p.g.ldc = N; p.g.accumulate = 0; p.g.group_m = 8;
   p.sfa = reinterpret_cast<const uint8_t*>(sfa);
   p.sfb = reinterpret_cast<const uint8_t*>(sfb);
-  const int tiles = ((M + BM - 1) / BM) * ((N + MX_BN - 1) / MX_BN);
+  p.n_atoms = (N + 127) / 128;
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, reinterpret_cast<__nv_bfloat16*>(C), p);
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+// A [M,K], B [N,K] e4m3 bytes; sfa / sfb: swizzled scale atoms [ceil(rows/128)][K/128][512]; C [M,N] bf16.  K % 128 == 0.
+// tile: 0 = auto (128 x 256 when N > 128), 128 or 256 forces the tile width.
+extern "C" int mb200_gemm_mxfp8_nt(const void* A, const void* B, const void* sfa, const void* sfb, void* C, int M, int N, int K, int tile, cudaStream_t s) {
+  if (K % MX_BK != 0 || N % 8 != 0) return -11;
+  if (tile == 0) tile = N > 128 ? 256 : 128;
+  if (tile == 256) return launch_mx<256, 1>(A, B, sfa, sfb, C, M, N, K, s);
+  return launch_mx<128, 2>(A, B, sfa, sfb, C, M, N, K, s);
 }

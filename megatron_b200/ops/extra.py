@@ -252,11 +252,11 @@ def mxfp8_swizzle_scales(sf: torch.Tensor) -> torch.Tensor:
     return sf.view(R, 4, 32, kb // 4, 4).permute(0, 3, 2, 1, 4).contiguous().view(R, kb // 4, 512)
 
 
-def gemm_mxfp8_nt(a_q: torch.Tensor, a_sf: torch.Tensor, b_q: torch.Tensor, b_sf: torch.Tensor) -> torch.Tensor:
+def gemm_mxfp8_nt(a_q: torch.Tensor, a_sf: torch.Tensor, b_q: torch.Tensor, b_sf: torch.Tensor, tile: int = 0) -> torch.Tensor:
     """``C[M,N] (bf16) = dequant(A) · dequant(B)ᵀ`` with MXFP8 operands (payload uint8 ``[rows, K]`` + E8M0 scales ``[rows, K/32]``): block-scaled
     ``tcgen05.mma kind::mxf8f6f4`` on CUDA, dequantise-then-matmul reference elsewhere."""
     if _use_cuda(a_q):
-        out = ext().gemm_mxfp8_nt(a_q.contiguous(), mxfp8_swizzle_scales(a_sf), b_q.contiguous(), mxfp8_swizzle_scales(b_sf))
+        out = ext().gemm_mxfp8_nt(a_q.contiguous(), mxfp8_swizzle_scales(a_sf), b_q.contiguous(), mxfp8_swizzle_scales(b_sf), tile)
         _count()
         return out
     return (mxfp8_dequantize(a_q, a_sf).float() @ mxfp8_dequantize(b_q, b_sf).float().t()).to(torch.bfloat16)

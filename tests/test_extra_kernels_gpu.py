@@ -165,8 +165,9 @@ def test_mxfp8_quantize_matches_reference_and_bounds_error():
     assert torch.all(d[3, :64] == 0)
 
 
+@pytest.mark.parametrize("tile", [128, 256])
 @pytest.mark.parametrize("M,N,K", [(256, 256, 512), (300, 392, 1024), (1024, 4096, 4096)])
-def test_mxfp8_block_scaled_gemm(M, N, K):
+def test_mxfp8_block_scaled_gemm(M, N, K, tile):
     from megatron_b200 import ops
 
     torch.manual_seed(5)
@@ -176,7 +177,7 @@ def test_mxfp8_block_scaled_gemm(M, N, K):
     aq, asf = ops.mxfp8_quantize(a)
     bq, bsf = ops.mxfp8_quantize(b)
     n0 = ops.launch_count()
-    c = ops.gemm_mxfp8_nt(aq, asf, bq, bsf)
+    c = ops.gemm_mxfp8_nt(aq, asf, bq, bsf, tile=tile)
     assert ops.launch_count() == n0 + 1 and c.shape == (M, N) and c.dtype == torch.bfloat16
     ref = ops.mxfp8_dequantize(aq, asf).float() @ ops.mxfp8_dequantize(bq, bsf).float().t()
     _close(c, ref, 1e-2)

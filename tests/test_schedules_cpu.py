@@ -218,3 +218,55 @@ def _fp8_worker(rank, world, recipe):
 @pytest.mark.parametrize("recipe,world", [("tensorwise", 1), ("mxfp8", 1), ("mxfp8", 2)])
 def test_fp8_recipes_wired_into_tp_linears(recipe, world):
     assert run_distributed(_fp8_worker, world, recipe) == [True] * world
+
+
+def _gtp_worker(rank, world):
+    import torch.distributed as dist
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.distributed import DistributedDataParallel, DistributedDataParallelConfig
+    from megatron_b200.core.tensor_parallel.gtp_api import apply_gtp, gather_gtp_state_dict
+
+    ps.initialize_model_parallel(gtp_remat_size=2)
+    assert ps.get_gtp_weight_remat_world_size() == 2 and dist.get_world_size(ps.get_data_parallel_group_without_gtp()) == world // 2
+    batches = _batches(world, seed=11)
+
+    def run(gtp):
+        torch.manual_seed(5)
+        m = _model(_cfg())
+        ref_state = {n: p.detach().clone() for n, p in m.named_parameters()}
+        pre = apply_gtp(m, min_numel=1, prefetch=True) if gtp else None
+        ddp = DistributedDataParallel(m.config, DistributedDataParallelConfig(overlap_grad_reduce=False, use_distributed_optimizer=False), m)
+        b = batches[rank]
+        for _ in range(2):      # two micro-batches: outstanding records and prefetch chains are reused
+            l = ddp(b["tokens"], b["position_ids"], None, labels=b["labels"]).float().mean()
+            l.backward()
+        ddp.finish_grad_sync()
+        return m, pre, l.item(), ref_state
+
+    m0, _, l0, _ = run(False)
+    m1, pre, l1, ref_state = run(True)
+    assert abs(l0 - l1) < 1e-6
+    assert pre.stats["prefetch_hits"] > 0 and pre.stats["regathers"] > 0 and pre.stats["regather_prefetch_hits"] > 0, pre.stats
+    g0 = {n: p.main_grad.clone() for n, p in m0.named_parameters()}
+    r = ps.get_gtp_weight_remat_rank()
+    n_sharded = 0
+    for n, p in m1.named_parameters():
+        if n.endswith("weight_shard"):
+            full = g0[n.replace("weight_shard", "weight")]
+            k = full.shape[0] // 2
+            assert torch.allclose(p.main_grad, full[r * k : (r + 1) * k], atol=1e-6, rtol=1e-4), n
+            n_sharded += 1
+        else:
+            assert torch.allclose(p.main_grad, g0[n], atol=1e-6, rtol=1e-4), n
+    assert n_sharded >= 4 * 3           # qkv, proj, fc1, fc2 in each of the three layers
+    # no full weight survives a step: every gathered copy was released or consumed
+    assert all(not mod._gtp_outstanding for mod in pre.modules)
+    full_sd = gather_gtp_state_dict(m1)
+    for k, v in full_sd.items():
+        assert torch.equal(v, ref_state[k]), k
+    return True
+
+
+def test_gtp_weight_rematerialisation_matches_plain_ddp():
+    assert run_distributed(_gtp_worker, 4) == [True] * 4

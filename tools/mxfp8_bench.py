@@ -29,13 +29,14 @@ def main():
         q = [(ops.mxfp8_quantize(a), ops.mxfp8_quantize(b)) for a, b in zip(A, B)]
         sw = [((aq, ops.mxfp8_swizzle_scales(asf)), (bq, ops.mxfp8_swizzle_scales(bsf))) for (aq, asf), (bq, bsf) in q]
         ext = ops.ext()
-        t_mx = bench(lambda i: ext.gemm_mxfp8_nt(sw[i % nbuf][0][0], sw[i % nbuf][0][1], sw[i % nbuf][1][0], sw[i % nbuf][1][1]))
+        t_mx = bench(lambda i: ext.gemm_mxfp8_nt(sw[i % nbuf][0][0], sw[i % nbuf][0][1], sw[i % nbuf][1][0], sw[i % nbuf][1][1], 256))
+        t_mx128 = bench(lambda i: ext.gemm_mxfp8_nt(sw[i % nbuf][0][0], sw[i % nbuf][0][1], sw[i % nbuf][1][0], sw[i % nbuf][1][1], 128))
         f8 = [(a.to(torch.float8_e4m3fn), b.to(torch.float8_e4m3fn)) for a, b in zip(A, B)]
         t_f8 = bench(lambda i: ext.gemm_fp8_nt(f8[i % nbuf][0], f8[i % nbuf][1], 1.0, None))
         t_bf = bench(lambda i: ops.gemm_nt(A[i % nbuf], B[i % nbuf]))
         t_q = bench(lambda i: ops.mxfp8_quantize(A[i % nbuf]))
         fl = 2.0 * M * N * K
-        print(f"M{M} N{N} K{K}: mxfp8 {t_mx:.3f} ms ({fl / t_mx / 1e9:.0f} TF) | fp8 per-tensor {t_f8:.3f} ms ({fl / t_f8 / 1e9:.0f} TF) | bf16 {t_bf:.3f} ms ({fl / t_bf / 1e9:.0f} TF)"
+        print(f"M{M} N{N} K{K}: mxfp8[128x256] {t_mx:.3f} ms ({fl / t_mx / 1e9:.0f} TF) | mxfp8[128x128] {t_mx128:.3f} ms ({fl / t_mx128 / 1e9:.0f} TF) | fp8 per-tensor {t_f8:.3f} ms ({fl / t_f8 / 1e9:.0f} TF) | bf16 {t_bf:.3f} ms ({fl / t_bf / 1e9:.0f} TF)"
               f" | quantise A {t_q * 1e3:.0f} us ({(M * K * 3 + M * K / 32) / t_q / 1e9:.2f} TB/s)", flush=True)
 
 
