@@ -1,0 +1,123 @@
+"""Absorbed MLA (latent-space attention) and DeepSeek sparse attention."""
+import torch
+
+from dist_utils import run_distributed
+
+_KW = dict(use_cpu_initialization=True, hidden_dropout=0.0, attention_dropout=0.0)
+
+
+def _mla_cfg(**kw):
+    from megatron_b200.core.transformer.transformer_config import MLATransformerConfig
+
+    base = dict(num_layers=2, hidden_size=64, num_attention_heads=4, q_lora_rank=16, kv_lora_rank=24, qk_head_dim=16, qk_pos_emb_head_dim=8, v_head_dim=16,
+                ffn_hidden_size=128, gated_linear_unit=True, activation_func=torch.nn.functional.silu, add_bias_linear=False, rotary_scaling_factor=4.0,
+                original_max_position_embeddings=16, mscale_all_dim=1.0, qk_layernorm=True, **_KW)
+    base.update(kw)
+    return MLATransformerConfig(**base)
+
+
+def _absorbed(rank, world):
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.inference_params import InferenceParams
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+    from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
+    from megatron_b200.core.transformer.experimental_attention_variant import AbsorbedMLASelfAttention
+
+    ps.initialize_model_parallel()
+    model_parallel_cuda_manual_seed(1)
+    cfg = _mla_cfg()
+    spec = get_gpt_layer_local_spec(multi_latent_attention=True, qk_layernorm=True, normalization="RMSNorm")
+    torch.manual_seed(3)
+    ref = GPTModel(cfg, spec, vocab_size=128, max_sequence_length=64, position_embedding_type="none")
+    spec2 = get_gpt_layer_local_spec(multi_latent_attention=True, qk_layernorm=True, normalization="RMSNorm")
+    spec2.submodules.self_attention.module = AbsorbedMLASelfAttention
+    m = GPTModel(cfg, spec2, vocab_size=128, max_sequence_length=64, position_embedding_type="none")
+    m.load_state_dict(ref.state_dict())                       # same parameters, same checkpoints
+    assert isinstance(m.decoder.layers[0].self_attention, AbsorbedMLASelfAttention)
+    tok = torch.randint(0, 128, (2, 32))
+    pos = torch.arange(32)[None].expand(2, -1)
+    l0 = ref(tok, pos, None, labels=tok).mean()
+    l1 = m(tok, pos, None, labels=tok).mean()
+    assert abs(l0.item() - l1.item()) < 1e-5
+    l0.backward(), l1.backward()
+    for (n, p), (_, q) in zip(ref.named_parameters(), m.named_parameters()):
+        assert torch.allclose(p.grad, q.grad, atol=2e-5, rtol=1e-3), n
+    # decode on the latent cache: 32 = kv_lora_rank + rope dims per token and layer
+    m.eval()
+    with torch.no_grad():
+        full = m(tok, pos, None)
+        ip = InferenceParams(2, 64)
+        outs = [m(tok[:, :20], pos[:, :20], None, inference_context=ip)]
+        ip.sequence_len_offset = 20
+        for t in range(20, 32):
+            outs.append(m(tok[:, t : t + 1], pos[:, t : t + 1], None, inference_context=ip))
+            ip.sequence_len_offset += 1
+        assert (torch.cat(outs, 1) - full).abs().max().item() < 1e-4
+        assert ip.key_value_memory_dict[1].shape[-1] == 24 + 8
+    return True
+
+
+def test_absorbed_mla_matches_mla_and_decodes_on_latents():
+    assert run_distributed(_absorbed, 1) == [True]
+
+
+def test_dsa_helpers_topk_sparse_attention_and_loss():
+    from megatron_b200.core.transformer.experimental_attention_variant import dsa
+
+    # layer schedule: offset 2, every 3rd layer computes
+    comp = [dsa.source_dsa_compute_layer(l, 2, 3) for l in range(1, 10)]
+    assert comp == [1, 2, 3, 3, 3, 6, 6, 6, 9] and not dsa.is_dsa_skip_topk_layer(6, 2, 3) and dsa.is_dsa_skip_topk_layer(7, 2, 3)
+    x = torch.randn(5, 3, 16)
+    assert torch.allclose(dsa.rotate_activation(dsa.rotate_activation(x)), x, atol=1e-5)          # normalised Hadamard is an involution
+    torch.manual_seed(0)
+    sq, b, h, d, n, c, r = 12, 2, 3, 8, 4, 10, 6
+    q, w, k = torch.randn(sq, b, h, d), torch.rand(sq, b, h), torch.randn(sq, b, d)
+    sc = dsa.compute_index_scores(q, w, k)
+    ref = torch.stack([torch.stack([sum(w[t, bb, hh] * torch.relu(q[t, bb, hh] @ k[:, bb].T) for hh in range(h)) for t in range(sq)]) for bb in range(b)])
+    assert torch.allclose(sc, ref, atol=1e-5)
+    idx, valid = dsa.topk_causal_indices(sc, 4)
+    for bb in range(b):
+        for t in range(sq):
+            sel = idx[bb, t][valid[bb, t]].tolist()
+            assert all(s <= t for s in sel) and len(sel) == min(4, t + 1)
+            assert torch.allclose(sc[bb, t, sel].sort().values, torch.topk(sc[bb, t, : t + 1], len(sel)).values.sort().values)     # ties (relu zeros) may pick either key
+    # with k >= sequence length the sparse attention equals dense causal attention
+    q_abs, kv = torch.randn(sq, b, n, c), torch.randn(sq, b, c)
+    idx_all, valid_all = dsa.topk_causal_indices(sc, sq)
+    out = dsa.sparse_attention_topk(q_abs, kv, idx_all, valid_all, 0.3, r)
+    att = torch.einsum("sbnc,tbc->bnst", q_abs, kv) * 0.3
+    att = att.masked_fill(torch.ones(sq, sq, dtype=torch.bool).triu(1)[None, None], float("-inf")).softmax(-1)
+    dense = torch.einsum("bnst,tbr->sbnr", att, kv[..., :r])
+    assert torch.allclose(out, dense, atol=1e-5)
+    # the KL loss is zero when the index scores reproduce log of the (head-summed) attention distribution, positive otherwise
+    tgt = att.sum(1)
+    tgt = tgt / tgt.sum(-1, keepdim=True)
+    perfect = torch.log(tgt.clamp(min=1e-30))
+    assert dsa.compute_dsa_indexer_loss(perfect, q_abs, kv, 0.3, 1.0).item() < 1e-5
+    assert dsa.compute_dsa_indexer_loss(sc, q_abs, kv, 0.3, 1.0).item() > 1e-3
+    assert dsa.compute_dsa_indexer_loss(sc, q_abs, kv, 0.3, 1.0, idx, valid).item() >= 0
+
+
+def test_dsattention_trains_indexer_only_through_kl():
+    from types import SimpleNamespace
+
+    from megatron_b200.core.transformer.experimental_attention_variant import DSAttention
+
+    torch.manual_seed(1)
+    cfg = SimpleNamespace(hidden_size=32, use_cpu_initialization=True, params_dtype=torch.float32, layernorm_epsilon=1e-5, init_method=lambda w: torch.nn.init.normal_(w, std=0.1),
+                          dsa_indexer_n_heads=2, dsa_indexer_head_dim=8, dsa_indexer_topk=4, dsa_indexer_loss_coeff=0.5, dsa_topk_freq=2, dsa_skip_topk_offset=0)
+    a1 = DSAttention(cfg, layer_number=1, softmax_scale=0.25)
+    a2 = DSAttention(cfg, layer_number=2, softmax_scale=0.25)
+    assert a1.indexer is not None and a2.indexer is None
+    hs = torch.randn(10, 2, 32, requires_grad=True)
+    q_abs = torch.randn(10, 2, 3, 12, requires_grad=True)
+    kv = torch.randn(10, 2, 12, requires_grad=True)
+    a1.train()
+    out = a1(q_abs, kv, hs, v_width=8)
+    assert out.shape == (10, 2, 3, 8)
+    out2 = a2(q_abs, kv, hs, v_width=8, shared_indices=a1.last_indices)
+    (out.sum() + out2.sum()).backward()
+    assert all(p.grad is not None and p.grad.abs().sum() > 0 for p in a1.indexer.parameters())      # reached through the KL auto-scaler
+    assert hs.grad is None or hs.grad.abs().sum() == 0                                               # the index branch is detached from the trunk
+    assert q_abs.grad.abs().sum() > 0 and kv.grad.abs().sum() > 0
