@@ -121,3 +121,79 @@ def test_dsattention_trains_indexer_only_through_kl():
     assert all(p.grad is not None and p.grad.abs().sum() > 0 for p in a1.indexer.parameters())      # reached through the KL auto-scaler
     assert hs.grad is None or hs.grad.abs().sum() == 0                                               # the index branch is detached from the trunk
     assert q_abs.grad.abs().sum() > 0 and kv.grad.abs().sum() > 0
+
+
+def _spec(rank, world):
+    import torch.nn.functional as F
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.inference.data_parallel_coordinator import DataParallelInferenceCoordinator
+    from megatron_b200.core.inference.engine import DynamicInferenceEngine, StaticInferenceEngine
+    from megatron_b200.core.inference.sampling import SamplingParams
+    from megatron_b200.core.inference.speculative import SpeculativeDecoder, verify_draft_tokens
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    ps.initialize_model_parallel()
+
+    def build(seed, layers):
+        torch.manual_seed(seed)
+        cfg = TransformerConfig(num_layers=layers, hidden_size=64, num_attention_heads=4, ffn_hidden_size=128, gated_linear_unit=True, activation_func=F.silu,
+                                add_bias_linear=False, normalization="RMSNorm", **_KW)
+        return GPTModel(cfg, get_gpt_layer_local_spec(normalization="RMSNorm"), vocab_size=96, max_sequence_length=128, position_embedding_type="rope")
+
+    target, draft = build(1, 2), build(2, 1)
+    prompt = [5, 17, 3, 42, 8]
+    greedy = StaticInferenceEngine(target, max_sequence_length=128).generate([prompt], SamplingParams(temperature=0.0, num_tokens_to_generate=24))[0]
+    # a different (bad) draft: few acceptances, identical output
+    sd = SpeculativeDecoder(target, draft, num_speculative_tokens=3, max_sequence_length=128)
+    assert sd.generate(prompt, SamplingParams(temperature=0.0, num_tokens_to_generate=24)) == greedy
+    assert sd.stats.proposed > 0 and sd.stats.accepted <= sd.stats.proposed
+    # the target as its own draft: everything is accepted, k + 1 tokens per target forward
+    sd2 = SpeculativeDecoder(target, target, num_speculative_tokens=3, max_sequence_length=128)
+    assert sd2.generate(prompt, SamplingParams(temperature=0.0, num_tokens_to_generate=24)) == greedy
+    assert sd2.stats.acceptance_rate == 1.0 and sd2.stats.tokens_per_target_forward > 2.5
+    # rejection rule is distribution preserving: empirical next-token distribution ≈ target distribution
+    g = torch.Generator().manual_seed(0)
+    pt = torch.tensor([[0.1, 0.6, 0.3], [0.3, 0.3, 0.4]])
+    pdr = torch.tensor([[0.5, 0.25, 0.25]])
+    counts = torch.zeros(3)
+    for _ in range(4000):
+        d = torch.multinomial(pdr[0], 1, generator=g)
+        n, nxt = verify_draft_tokens(d, pdr, pt, g)
+        counts[int(d) if n == 1 else nxt] += 1
+    assert (counts / 4000 - pt[0]).abs().max() < 0.03
+    # DP coordinator: least-loaded routing over two continuous-batching engines, results identical to a single engine
+    e = [DynamicInferenceEngine(target, num_blocks=64, block_size=8, max_running=4, vocab_size=96) for _ in range(2)]
+    coord = DataParallelInferenceCoordinator(e)
+    prompts = [[5, 17, 3], [9, 9, 1, 4, 7, 7], [2], [30, 31, 32, 33]]
+    sp = SamplingParams(temperature=0.0, num_tokens_to_generate=6)
+    gids = [coord.add_request(p, sp) for p in prompts]
+    assert sorted(coord.placement.values()) == [0, 0, 1, 1]
+    res = coord.run_until_done()
+    ref = StaticInferenceEngine(target, max_sequence_length=128)
+    for gid, p in zip(gids, prompts):
+        assert res[gid].generated_tokens == ref.generate([p], sp)[0]
+    assert all(r.outstanding_tokens == 0 for r in coord.replicas)
+    coord.pause(0)
+    assert coord.placement[coord.add_request([1, 2], sp)] == 1
+    return True
+
+
+def test_speculative_decoding_and_dp_coordinator():
+    assert run_distributed(_spec, 1) == [True]
+
+
+def test_symmetric_memory_manager_fallback():
+    from megatron_b200.core.inference.symmetric_memory import SymmetricMemoryManager
+
+    m = SymmetricMemoryManager(max_bytes=1 << 12)
+    a = m.get_buffer("ar", (4, 8), torch.float32, device="cpu")
+    assert m.get_buffer("ar", (4, 8), torch.float32) is a and not a.is_symmetric
+    a.tensor.fill_(2.0)
+    assert a.all_reduce_().sum() == 64.0
+    import pytest
+
+    with pytest.raises(MemoryError):
+        m.get_buffer("big", (1 << 12,), torch.float32, device="cpu")
