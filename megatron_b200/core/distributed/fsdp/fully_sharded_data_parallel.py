@@ -92,11 +92,22 @@ class _Unit:
 
 class FullyShardedDataParallel(torch.nn.Module):
     def __init__(self, config, ddp_config, module: torch.nn.Module, fsdp_unit_modules: Optional[Sequence[type]] = None, group=None,
-                 disable_bucketing: bool = False, **_):
+                 disable_bucketing: bool = False, data_parallel_sharding_strategy: Optional[str] = None, outer_dp_group=None, prefetch: bool = True, **_):
+        """``data_parallel_sharding_strategy`` (reference ``--data-parallel-sharding-strategy``): ``optim_grads_params`` = ZeRO-3 (parameters released
+        outside their unit's compute), ``optim_grads`` = ZeRO-2 and ``optim`` = ZeRO-1 (parameters stay resident, only the all-gather after the
+        optimizer step remains; gradients still land reduce-scattered on the shard, which is what the sharded optimizer consumes).
+        ``outer_dp_group`` enables HSDP: shard inside ``group`` (one NVLink island), replicate across ``outer_dp_group`` — shard gradients are
+        all-reduced over the outer group once per step."""
         super().__init__()
         self.config, self.ddp_config, self.module = config, ddp_config, module
         self.group = group if group is not None else ps.get_data_parallel_group(with_context_parallel=True)
         self.world = dist.get_world_size(self.group)
+        self.strategy = data_parallel_sharding_strategy or getattr(ddp_config, "data_parallel_sharding_strategy", None) or "optim_grads_params"
+        assert self.strategy in ("optim", "optim_grads", "optim_grads_params", "no_shard"), self.strategy
+        self.release_params = self.strategy == "optim_grads_params"
+        self.outer_group = outer_dp_group
+        self.outer_world = dist.get_world_size(outer_dp_group) if outer_dp_group is not None else 1
+        self.prefetch = prefetch and self.release_params
         if fsdp_unit_modules is None:
             from ...transformer.transformer_layer import TransformerLayer
 
@@ -124,23 +135,33 @@ class FullyShardedDataParallel(torch.nn.Module):
                 self.units.append(u)
                 self._unit_of_module.setdefault(sub, u)
                 self._hook_unit(sub, u, is_root=name == "<root>")
-        self._scale = 1.0 / self.world if getattr(ddp_config, "average_in_collective", False) or True else 1.0
+        self._scale = 1.0 / (self.world * self.outer_world)
         self._sync = True
-        for u in self.units:
-            if u.name.startswith("<root>"):
-                continue
-            u.release()
+        self._layer_units = [u for u in self.units if not getattr(u, "is_root", False)]
+        for i, u in enumerate(self._layer_units):
+            u.index = i
+        if self.release_params:
+            for u in self._layer_units:
+                u.release()
 
     # ---- hooks ----------------------------------------------------------------------------------------------------
     def _hook_unit(self, sub: torch.nn.Module, u: _Unit, is_root: bool):
+        def neighbour(step):
+            i = getattr(u, "index", None)
+            if i is None or not self.prefetch:
+                return None
+            j = i + step
+            return self._layer_units[j] if 0 <= j < len(self._layer_units) else None
+
         def pre_fwd(mod, args):
             u.gather()
             u.wait()
+            nxt = neighbour(+1)
+            if nxt is not None:
+                nxt.gather(async_op=True)      # overlaps with this unit's compute
 
         def post_fwd(mod, args, out):
-            if not is_root and not torch.is_grad_enabled():
-                u.release()
-            elif not is_root:
+            if not is_root and self.release_params:
                 u.release()
             return out
 
@@ -148,6 +169,9 @@ class FullyShardedDataParallel(torch.nn.Module):
             u.gather()
             u.wait()
             u.pending = sum(1 for p in u.params if p.requires_grad)
+            prv = neighbour(-1)
+            if prv is not None:
+                prv.gather(async_op=True)
 
         sub.register_forward_pre_hook(pre_fwd)
         if not is_root:
@@ -158,7 +182,8 @@ class FullyShardedDataParallel(torch.nn.Module):
             u.pending -= 1
             if u.pending == 0 and not is_root:
                 u.reduce_scatter_grads(self._scale)
-                u.release()
+                if self.release_params:
+                    u.release()
 
         for p in u.params:
             p.register_post_accumulate_grad_hook(on_grad)
@@ -178,6 +203,8 @@ class FullyShardedDataParallel(torch.nn.Module):
         for u in self.units:
             if getattr(u, "is_root", False):
                 u.reduce_scatter_grads(self._scale)
+            if self.outer_group is not None and self.outer_world > 1:
+                dist.all_reduce(u.main_grad_shard, group=self.outer_group)     # HSDP: replicas of this shard live on the other islands
             u.master.grad = u.main_grad_shard
 
     start_grad_sync = finish_grad_sync
@@ -211,7 +238,7 @@ class FullyShardedDataParallel(torch.nn.Module):
             u.wait()
         sd = {k: v.detach().clone() for k, v in self.module.state_dict().items()}
         for u in self.units:
-            if not getattr(u, "is_root", False):
+            if not getattr(u, "is_root", False) and self.release_params:
                 u.release()
         return sd
 

@@ -270,3 +270,63 @@ def _gtp_worker(rank, world):
 
 def test_gtp_weight_rematerialisation_matches_plain_ddp():
     assert run_distributed(_gtp_worker, 4) == [True] * 4
+
+
+class _Blk(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a, self.b = torch.nn.Linear(16, 32), torch.nn.Linear(32, 16)
+
+    def forward(self, x):
+        return x + self.b(torch.tanh(self.a(x)))
+
+
+class _Net(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.inp, self.blocks, self.out = torch.nn.Linear(8, 16), torch.nn.ModuleList([_Blk() for _ in range(3)]), torch.nn.Linear(16, 4)
+
+    def forward(self, x):
+        x = self.inp(x)
+        for b in self.blocks:
+            x = b(x)
+        return self.out(x)
+
+
+def _fsdp_variants(rank, world, strategy, hsdp):
+    import torch.distributed as dist
+
+    from megatron_b200.core.distributed.fsdp import FullyShardedDataParallel
+
+    inner = outer = None
+    if hsdp:      # islands {0,1} {2,3}; replicas of a shard: {0,2} {1,3}
+        groups_in = [dist.new_group([0, 1]), dist.new_group([2, 3])]
+        groups_out = [dist.new_group([0, 2]), dist.new_group([1, 3])]
+        inner, outer = groups_in[rank // 2], groups_out[rank % 2]
+    torch.manual_seed(0)
+    ref, net = _Net(), _Net()
+    net.load_state_dict(ref.state_dict())
+    f = FullyShardedDataParallel(None, None, net, fsdp_unit_modules=(_Blk,), group=inner if hsdp else dist.group.WORLD, outer_dp_group=outer,
+                                 data_parallel_sharding_strategy=strategy)
+    opt, ropt = torch.optim.SGD(f.optimizer_parameters(), lr=0.1), torch.optim.SGD(ref.parameters(), lr=0.1)
+    for step in range(3):
+        torch.manual_seed(100 + step)
+        X, Y = torch.randn(world * 2, 8), torch.randn(world * 2, 4)
+        ropt.zero_grad()
+        ((ref(X) - Y) ** 2).mean().backward()
+        ropt.step()
+        f.zero_grad_buffer()
+        lo = rank * 2
+        ((f(X[lo : lo + 2]) - Y[lo : lo + 2]) ** 2).mean().backward()
+        f.finish_grad_sync()
+        opt.step()
+        f.post_optimizer_step()
+    resident = sum(u.resident for u in f.units)
+    assert resident == (1 if strategy == "optim_grads_params" else len(f.units)), (strategy, resident)
+    sd = f.gather_full_state_dict()
+    return max((sd[k] - v).abs().max().item() for k, v in ref.state_dict().items())
+
+
+@pytest.mark.parametrize("strategy,hsdp,world", [("optim_grads", False, 2), ("optim", False, 2), ("optim_grads_params", True, 4)])
+def test_fsdp_zero2_and_hsdp_match_full_batch_training(strategy, hsdp, world):
+    assert max(run_distributed(_fsdp_variants, world, strategy, hsdp)) < 1e-5
