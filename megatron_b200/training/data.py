@@ -76,8 +76,12 @@ def build_pretraining_data_loader(dataset, consumed_samples: int, args, dataload
         sampler = MegatronPretrainingRandomSampler(dataset, len(dataset), consumed_samples, args.micro_batch_size, dp_rank, dp_size, seed=args.seed)
     else:
         sampler = MegatronPretrainingSampler(len(dataset), consumed_samples, args.micro_batch_size, dp_rank, dp_size)
+    # a private generator: creating the iterator draws the worker base seed, which must not advance the global torch RNG — otherwise a resumed run
+    # (RNG restored from the checkpoint, then the loader rebuilt) diverges from the uninterrupted one at the first dropout
+    gen = torch.Generator()
+    gen.manual_seed(int(getattr(args, "seed", 1234)) + 7919 * dp_rank + consumed_samples)
     return torch.utils.data.DataLoader(dataset, batch_sampler=sampler, num_workers=getattr(args, "num_workers", 0), pin_memory=torch.cuda.is_available(),
-                                       persistent_workers=getattr(args, "num_workers", 0) > 0)
+                                       persistent_workers=getattr(args, "num_workers", 0) > 0, generator=gen)
 
 
 def get_batch_on_this_tp_rank(data_iterator, keys=("tokens", "labels", "loss_mask", "position_ids"), device=None):

@@ -1,0 +1,101 @@
+"""Inference TP layers, RADIO tower, Hugging Face wrappers, dataset merge tool."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import torch
+
+from dist_utils import run_distributed
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _inference_layers(rank, world):
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.tensor_parallel.inference_layers import InferenceColumnParallelLinear, InferenceRowParallelLinear, convert_to_inference_layers
+    from megatron_b200.core.tensor_parallel.layers import ColumnParallelLinear, RowParallelLinear
+    from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
+    from megatron_b200.core.transformer.torch_norm import FusedNorm
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=world)
+    model_parallel_cuda_manual_seed(1)
+    cfg = TransformerConfig(num_layers=1, hidden_size=32, num_attention_heads=4, use_cpu_initialization=True, tensor_model_parallel_size=world, sequence_parallel=True,
+                            normalization="RMSNorm", add_bias_linear=False)
+    torch.manual_seed(3)
+    col = ColumnParallelLinear(32, 64, config=cfg, init_method=cfg.init_method, bias=False, gather_output=False)
+    row = RowParallelLinear(64, 32, config=cfg, init_method=cfg.init_method, bias=False, input_is_parallel=True, skip_bias_add=True)
+    norm = FusedNorm(cfg, 32, eps=1e-5)
+    with torch.no_grad():
+        norm.weight.uniform_(0.5, 1.5)
+    torch.manual_seed(10 + rank)
+    x_shard, res_shard = torch.randn(8 // world, 2, 32), torch.randn(8 // world, 2, 32)
+    # training layers (autograd mappings) as the oracle
+    h, _ = col(x_shard)
+    y, _ = row(torch.tanh(h))
+    new_res = res_shard + y
+    normed = norm(new_res)
+    full = torch.cat([torch.empty_like(normed) for _ in range(world)])
+    torch.distributed.all_gather_into_tensor(full, normed.detach().contiguous(), group=ps.get_tensor_model_parallel_group())
+    mod = torch.nn.ModuleList([col, row])
+    convert_to_inference_layers(mod)
+    assert isinstance(col, InferenceColumnParallelLinear) and isinstance(row, InferenceRowParallelLinear)
+    h2, _ = col(x_shard)
+    normed2, res2 = row(torch.tanh(h2), residual=res_shard, norm=norm)
+    assert not h2.requires_grad and torch.allclose(h2, h.detach(), atol=1e-6)
+    assert torch.allclose(res2, new_res.detach(), atol=1e-5) and torch.allclose(normed2, full, atol=1e-5) and normed2.shape == (8, 2, 32)
+    out_plain, _ = row(torch.tanh(h2))
+    assert torch.allclose(out_plain, y.detach(), atol=1e-5)
+    return True
+
+
+def test_inference_tp_layers_match_training_layers():
+    assert run_distributed(_inference_layers, 2) == [True, True]
+
+
+def _towers(rank, world):
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.models.huggingface import build_hf_model
+    from megatron_b200.core.models.vision.radio import RADIOViTModel
+    from megatron_b200.core.models.vision.vit_layer_specs import get_vit_layer_with_local_spec
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    ps.initialize_model_parallel()
+    cfg = TransformerConfig(num_layers=1, hidden_size=32, num_attention_heads=4, use_cpu_initialization=True, hidden_dropout=0.0, attention_dropout=0.0)
+    m = RADIOViTModel(cfg, get_vit_layer_with_local_spec(), patch_dim=4, img_h=16, img_w=16, max_img_h=32, max_img_w=32, class_token_len=2, num_registers=3)
+    out = m(torch.randn(2, 3, 16, 16))
+    assert out.shape == (2, 2 + 16, 32)
+    out2 = m(torch.randn(1, 3, 32, 24))                  # another resolution through the interpolated position table
+    assert out2.shape == (1, 2 + 8 * 6, 32)
+    out.sum().backward()
+    assert m.position_embeddings.grad is not None and m.embedder.weight.grad is not None
+    import transformers
+
+    hf_cfg = transformers.BertConfig(hidden_size=32, num_hidden_layers=1, num_attention_heads=2, intermediate_size=64, vocab_size=50, max_position_embeddings=16)
+    w = build_hf_model(cfg, hf_config=hf_cfg, model_cls="BertModel")
+    hs = w(input_ids=torch.randint(0, 50, (2, 8)))
+    assert hs.shape == (2, 8, 32) and all(hasattr(p, "sequence_parallel") for p in w.parameters())
+    return True
+
+
+def test_radio_tower_and_hf_wrapper():
+    assert run_distributed(_towers, 1) == [True]
+
+
+def test_merge_datasets_tool(tmp_path):
+    from megatron_b200.core.datasets.indexed_dataset import IndexedDataset, IndexedDatasetBuilder, get_bin_path, get_idx_path
+
+    docs = {"a": [[1, 2, 3], [4, 5]], "b": [[6], [7, 8, 9, 10]]}
+    for name, dd in docs.items():
+        b = IndexedDatasetBuilder(get_bin_path(str(tmp_path / name)), dtype=np.int32)
+        for d in dd:
+            b.add_document(torch.tensor(d, dtype=torch.int32), [len(d)])
+        b.finalize(get_idx_path(str(tmp_path / name)))
+    out = tmp_path / "out"
+    out.mkdir()
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "merge_datasets.py"), "--input", str(tmp_path), "--output-prefix", str(out / "merged")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ds = IndexedDataset(str(out / "merged"))
+    assert [ds[i].tolist() for i in range(len(ds))] == docs["a"] + docs["b"]
