@@ -86,6 +86,8 @@ class TrainEngine:
         )
         if seq_length is not None:
             ov["seq_length"] = seq_length
+        if os.environ.get("MEGATRON_B200_FUSED_RESIDUAL_NORM") is not None:
+            ov["fused_residual_rmsnorm"] = os.environ["MEGATRON_B200_FUSED_RESIDUAL_NORM"] == "1"
         ov.update(model_overrides or {})
         # NVLink (symmetric-memory) collectives for the TP group when on GPUs of one box
         if nvlink_collectives is None:
