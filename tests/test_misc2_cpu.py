@@ -99,3 +99,44 @@ def test_merge_datasets_tool(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     ds = IndexedDataset(str(out / "merged"))
     assert [ds[i].tolist() for i in range(len(ds))] == docs["a"] + docs["b"]
+
+
+def _retro(rank, world):
+    import torch.nn.functional as F
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatron_b200.core.models.retro import RetroConfig, RetroModel
+    from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
+
+    ps.initialize_model_parallel()
+    model_parallel_cuda_manual_seed(1)
+    cfg = RetroConfig(num_layers=3, hidden_size=32, num_attention_heads=4, ffn_hidden_size=64, use_cpu_initialization=True, hidden_dropout=0.0, attention_dropout=0.0,
+                      retro_chunk_length=4, retro_num_neighbors=2, retro_retrieved_length=6, retro_encoder_num_layers=1, retro_decoder_cross_attention_layers=[2, 3],
+                      retro_encoder_hidden_dropout=0.0, retro_encoder_attention_dropout=0.0)
+    torch.manual_seed(2)
+    m = RetroModel(cfg, get_gpt_layer_local_spec(), vocab_size=64, max_sequence_length=32, position_embedding_type="learned_absolute")
+    b, n, l = 2, 16, 4
+    ids = torch.randint(0, 64, (b, n))
+    pos = torch.arange(n)[None].expand(b, -1)
+    ctx = torch.randint(0, 64, (b, l, 2, 6))
+    loss = m(ids, pos, None, context_input_ids=ctx, labels=ids).float().mean()
+    loss.backward()
+    missing = [n_ for n_, p in m.named_parameters() if p.grad is None]
+    assert not missing, missing
+    # autoregressive retrieval: the neighbours of chunk u are first visible to the LAST token of chunk u (position u·m + m - 1)
+    m.eval()
+    with torch.no_grad():
+        base = m(ids, pos, None, context_input_ids=ctx)
+        ctx2 = ctx.clone()
+        ctx2[:, 2] = torch.randint(0, 64, (b, 2, 6))            # change the neighbours of chunk 2 (tokens 8..11)
+        alt = m(ids, pos, None, context_input_ids=ctx2)
+        first_visible = 2 * 4 + 3
+        assert torch.allclose(base[:, :first_visible], alt[:, :first_visible], atol=1e-6)
+        assert (base[:, first_visible:] - alt[:, first_visible:]).abs().max() > 1e-5
+        assert not torch.allclose(m(ids, pos, None), base)      # retrieval changes the prediction at all
+    return True
+
+
+def test_retro_chunked_cross_attention_is_causal_in_the_neighbours():
+    assert run_distributed(_retro, 1) == [True]
