@@ -604,10 +604,12 @@ from .extra import (  # noqa: E402,F401
     apply_rope_thd,
     causal_conv1d,
     gemm_mxfp8_nt,
+    gemm_nvfp4_nt,
     mxfp8_dequantize,
     mxfp8_quantize,
     mxfp8_quantize_reference,
     mxfp8_swizzle_scales,
+    nvfp4_pack,
     positions_from_cu_seqlens,
     ssd_state_passing,
     ssd_step,

@@ -661,9 +661,30 @@ Tensor gemm_mxfp8_nt(const Tensor& a, const Tensor& sfa, const Tensor& b, const 
 }
 #endif
 
+#ifdef MB200_HAVE_GEMM_NVFP4_SM100
+// a [M,K/2], b [N,K/2] uint8 (two e2m1 codes per byte); sfa / sfb: swizzled UE4M3 scale atoms [ceil(rows/128), K/64, 512]; alpha_dev: product of the tensor scales
+Tensor gemm_nvfp4_nt(const Tensor& a, const Tensor& sfa, const Tensor& b, const Tensor& sfb, double alpha, const c10::optional<Tensor>& alpha_dev) {
+  TORCH_CHECK(a.is_cuda() && a.dim() == 2 && b.dim() == 2 && a.is_contiguous() && b.is_contiguous() && a.size(1) == b.size(1) && a.scalar_type() == at::kByte &&
+                  b.scalar_type() == at::kByte, "gemm_nvfp4_nt: a [M,K/2], b [N,K/2] contiguous uint8");
+  const int64_t M = a.size(0), N = b.size(0), K = a.size(1) * 2;
+  TORCH_CHECK(K % 256 == 0, "gemm_nvfp4_nt: K must be a multiple of 256");
+  TORCH_CHECK(sfa.is_contiguous() && sfb.is_contiguous() && sfa.scalar_type() == at::kByte && sfb.scalar_type() == at::kByte &&
+                  sfa.numel() == ((M + 127) / 128) * (K / 64) * 512 && sfb.numel() == ((N + 127) / 128) * (K / 64) * 512, "gemm_nvfp4_nt: scale atoms have the wrong size");
+  c10::cuda::CUDAGuard g(a.device());
+  auto c = at::empty({M, N}, a.options().dtype(at::kBFloat16));
+  const int rc = mb200_gemm_nvfp4_nt(a.data_ptr(), b.data_ptr(), sfa.data_ptr(), sfb.data_ptr(), c.data_ptr(), (int)M, (int)N, (int)K, (float)alpha,
+                                     alpha_dev.has_value() ? alpha_dev->data_ptr<float>() : nullptr, cur_stream());
+  TORCH_CHECK(rc == 0, "gemm_nvfp4_nt failed with code ", rc);
+  return c;
+}
+#endif
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+#ifdef MB200_HAVE_GEMM_NVFP4_SM100
+  m.def("gemm_nvfp4_nt", &gemm_nvfp4_nt);
+#endif
 #ifdef MB200_HAVE_GEMM_MXFP8_SM100
   m.def("gemm_mxfp8_nt", &gemm_mxfp8_nt, pybind11::arg("a"), pybind11::arg("sfa"), pybind11::arg("b"), pybind11::arg("sfb"), pybind11::arg("tile") = 0);
 #endif

@@ -260,3 +260,23 @@ def gemm_mxfp8_nt(a_q: torch.Tensor, a_sf: torch.Tensor, b_q: torch.Tensor, b_sf
         _count()
         return out
     return (mxfp8_dequantize(a_q, a_sf).float() @ mxfp8_dequantize(b_q, b_sf).float().t()).to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------------ NVFP4
+def nvfp4_pack(codes: torch.Tensor) -> torch.Tensor:
+    """One E2M1 code per byte ``[rows, K]`` → two per byte ``[rows, K/2]`` (element 2i in the low nibble)."""
+    return (codes[:, 0::2] | (codes[:, 1::2] << 4)).contiguous()
+
+
+def gemm_nvfp4_nt(a_codes: torch.Tensor, a_bscale: torch.Tensor, a_tscale, b_codes: torch.Tensor, b_bscale: torch.Tensor, b_tscale) -> torch.Tensor:
+    """``C[M,N] (bf16) = dequant(A) · dequant(B)ᵀ`` for NVFP4 operands as produced by ``core.fp4_utils.quantize_nvfp4`` (codes uint8 ``[rows, K]``, block scales
+    ``float8_e4m3fn [rows, K/16]``, fp32 tensor scale): block-scaled ``tcgen05.mma kind::mxf4nvf4`` on CUDA (K % 256 == 0), dequantise-then-matmul elsewhere."""
+    if _use_cuda(a_codes) and a_codes.shape[1] % 256 == 0 and hasattr(ext(), "gemm_nvfp4_nt"):
+        alpha = (torch.as_tensor(a_tscale, device=a_codes.device).float() * torch.as_tensor(b_tscale, device=a_codes.device).float()).reshape(1)
+        out = ext().gemm_nvfp4_nt(nvfp4_pack(a_codes), mxfp8_swizzle_scales(a_bscale.view(torch.uint8)), nvfp4_pack(b_codes),
+                                  mxfp8_swizzle_scales(b_bscale.view(torch.uint8)), 1.0, alpha)
+        _count()
+        return out
+    from ..core.fp4_utils import dequantize_nvfp4
+
+    return (dequantize_nvfp4(a_codes, a_bscale, a_tscale, torch.float32) @ dequantize_nvfp4(b_codes, b_bscale, b_tscale, torch.float32).t()).to(torch.bfloat16)

@@ -184,3 +184,21 @@ def test_mxfp8_block_scaled_gemm(M, N, K, tile):
     # and the quantised product tracks the bf16 product to fp8 accuracy
     full = a.float() @ b.float().t()
     assert ((c.float() - full).norm() / full.norm()).item() < 0.06
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 512), (300, 392, 1024), (1024, 2048, 4096)])
+def test_nvfp4_block_scaled_gemm(M, N, K):
+    from megatron_b200 import ops
+    from megatron_b200.core.fp4_utils import dequantize_nvfp4, quantize_nvfp4
+
+    torch.manual_seed(6)
+    a = torch.randn(M, K, device="cuda") * torch.exp2(torch.randint(-3, 4, (M, K // 16), device="cuda").float()).repeat_interleave(16, dim=1)
+    b = torch.randn(N, K, device="cuda") * torch.exp2(torch.randint(-3, 4, (N, K // 16), device="cuda").float()).repeat_interleave(16, dim=1)
+    qa, qb = quantize_nvfp4(a), quantize_nvfp4(b)
+    n0 = ops.launch_count()
+    c = ops.gemm_nvfp4_nt(*qa, *qb)
+    assert ops.launch_count() == n0 + 1 and c.shape == (M, N) and c.dtype == torch.bfloat16
+    ref = dequantize_nvfp4(*qa, torch.float32) @ dequantize_nvfp4(*qb, torch.float32).t()
+    _close(c, ref, 1e-2)
+    full = a @ b.t()
+    assert ((c.float() - full).norm() / full.norm()).item() < 0.2            # 4-bit payload: ~10 % relative error per operand
