@@ -17,7 +17,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 REPO = os.path.dirname(os.path.abspath(__file__))

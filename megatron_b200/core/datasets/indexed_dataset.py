@@ -10,7 +10,7 @@ from __future__ import annotations
 import os
 import struct
 from enum import Enum
-from typing import List, Optional, Tuple, Type, Union
+from typing import List, Optional, Union
 
 import numpy
 import torch

@@ -9,7 +9,7 @@ Deterministic per index (``numpy`` RNG seeded by ``seed + idx``) so resuming by 
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, Optional
+from typing import Dict
 
 import numpy as np
 import torch

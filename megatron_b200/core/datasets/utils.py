@@ -4,7 +4,6 @@ from __future__ import annotations
 import logging
 import os
 import subprocess
-import sys
 import sysconfig
 from enum import Enum
 from typing import List, Optional, Tuple

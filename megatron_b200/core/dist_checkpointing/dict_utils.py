@@ -1,7 +1,7 @@
 """Nested dict/list helpers (reference ``dist_checkpointing/dict_utils.py``)."""
 from __future__ import annotations
 
-from typing import Any, Callable, Iterable, Tuple, Union
+from typing import Callable, Iterable, Tuple
 
 import torch
 

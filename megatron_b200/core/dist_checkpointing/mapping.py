@@ -12,7 +12,6 @@ from dataclasses import dataclass, field, replace
 from itertools import chain
 from typing import Any, Callable, Dict, Optional, Tuple, Union
 
-import numpy as np
 import torch
 
 ReplicaId = Union[int, Tuple[int, ...]]

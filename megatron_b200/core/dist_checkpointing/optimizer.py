@@ -3,7 +3,7 @@
 from __future__ import annotations
 
 from dataclasses import replace
-from typing import Dict, Iterable, List, Union
+from typing import Dict, Iterable, Union
 
 import torch
 

@@ -2,14 +2,12 @@
 from __future__ import annotations
 
 import logging
-import os
 from pathlib import Path
-from typing import Any, Callable, Dict, Optional, Set, Tuple, Union
+from typing import Callable, Optional, Union
 
 import torch
 import torch.distributed as dist
 
-from . import core as _core
 from .core import CheckpointingConfig, CheckpointingException, maybe_load_config, save_config
 from .dict_utils import dict_list_map_inplace, extract_matching_values, merge, nested_values
 from .mapping import (

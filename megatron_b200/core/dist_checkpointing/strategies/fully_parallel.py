@@ -8,13 +8,12 @@ least-loaded holder; the chosen holder's replica id is rewritten to 0, everyone 
 from __future__ import annotations
 
 from collections import defaultdict
-from typing import Dict, List, Tuple
+from typing import Dict
 
-import torch
 import torch.distributed as dist
 
 from ..dict_utils import nested_values
-from ..mapping import ShardedStateDict, ShardedTensor, is_main_replica
+from ..mapping import ShardedStateDict, ShardedTensor
 
 
 def _shard_id(st: ShardedTensor):

@@ -9,16 +9,13 @@ from the ``(global_shape, global_offset, local_shape)`` triplet of each mcore Sh
 from __future__ import annotations
 
 import io
-import os
-import pickle
-from collections import defaultdict
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Any, Dict, List, Tuple
 
 import torch
 import torch.distributed as dist
 from torch.distributed.checkpoint import FileSystemReader, FileSystemWriter
 from torch.distributed.checkpoint.default_planner import DefaultLoadPlanner, DefaultSavePlanner
-from torch.distributed.checkpoint.metadata import BytesStorageMetadata, ChunkStorageMetadata, Metadata, MetadataIndex, TensorProperties, TensorStorageMetadata
+from torch.distributed.checkpoint.metadata import ChunkStorageMetadata, Metadata, MetadataIndex, TensorProperties, TensorStorageMetadata
 from torch.distributed.checkpoint.planner import LoadPlan, ReadItem, SavePlan, TensorWriteData, WriteItem, WriteItemType
 from torch.distributed.checkpoint.planner_helpers import create_read_items_for_chunk_list
 from torch.distributed.checkpoint.state_dict_loader import load as dcp_load

@@ -1,7 +1,7 @@
 """Key/prefix manipulation over sharded state dicts (reference ``dist_checkpointing/utils.py``)."""
 from __future__ import annotations
 
-from typing import Dict, Iterable, Tuple
+from typing import Dict, Tuple
 
 from .dict_utils import dict_list_map_inplace, extract_matching_values
 from .mapping import LocalNonpersistentObject, ShardedBase, ShardedObject, ShardedStateDict, ShardedTensor, ShardedTensorFactory, StateDict

@@ -3,10 +3,9 @@ from __future__ import annotations
 
 from collections import defaultdict
 from enum import Enum
-from typing import Dict, List, Optional, Set, Tuple
+from typing import Set
 
 import numpy as np
-import torch
 import torch.distributed as dist
 
 from .core import CheckpointingException

@@ -4,14 +4,14 @@ from __future__ import annotations
 
 import logging
 from contextlib import contextmanager
-from typing import Dict, List, Optional
+from typing import Dict, List
 
 import torch
 import torch.distributed as dist
 
 from .. import parallel_state as ps
 from ..transformer.transformer_config import TransformerConfig
-from ..utils import get_pg_size, log_single_rank
+from ..utils import get_pg_size
 from .data_parallel_base import _BaseDataParallel
 from .distributed_data_parallel_config import DistributedDataParallelConfig
 from .param_and_grad_buffer import _ParamAndGradBuffer, partition_buckets

@@ -9,7 +9,7 @@
 """
 from __future__ import annotations
 
-from typing import List, Optional, Union
+from typing import List, Optional
 
 import torch
 import torch.distributed as dist

@@ -18,7 +18,7 @@ layer's compute on a side stream.
 from __future__ import annotations
 
 from contextlib import contextmanager
-from typing import Dict, Iterable, List, Optional, Sequence
+from typing import Dict, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist

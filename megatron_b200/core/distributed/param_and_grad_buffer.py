@@ -16,7 +16,6 @@ Design differences:
 from __future__ import annotations
 
 import math
-from contextlib import nullcontext
 from enum import Enum
 from typing import Dict, List, Optional, Tuple
 

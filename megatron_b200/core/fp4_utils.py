@@ -1,8 +1,8 @@
 """NVFP4 (E2M1 values, one E4M3 scale per 16-element block + one fp32 tensor scale) quantisation helpers (reference ``core/fp4_utils.py``).
 
-This round provides the numerics (quantise / dequantise, used for weight-only experiments and tests); the block-scaled tensor-core GEMM
-(``tcgen05.mma kind::mxf4nvf4`` with scale factors in TMEM) is not implemented yet — ``nvfp4_linear`` dequantises to bf16 and uses the
-bf16 tcgen05 GEMM."""
+``quantize_nvfp4`` / ``dequantize_nvfp4`` define the numerics; ``nvfp4_linear`` runs W4A4 on the block-scaled tensor-core GEMM
+(``ops.gemm_nvfp4_nt`` → ``csrc/gemm_nvfp4_sm100.cu``: ``tcgen05.mma kind::mxf4nvf4.block_scale.block16``, scale factors in TMEM) when the shapes allow
+(CUDA, K % 256 == 0) with the activation quantised on the fly, or weight-only (dequantise + bf16 GEMM) otherwise."""
 from __future__ import annotations
 
 from typing import Tuple
@@ -38,6 +38,13 @@ def dequantize_nvfp4(codes: torch.Tensor, bscale: torch.Tensor, tscale: torch.Te
     return (val * bscale.float().unsqueeze(-1) * tscale).view(codes.shape).to(dtype)
 
 
-def nvfp4_linear(x: torch.Tensor, qweight) -> torch.Tensor:
-    """``x @ Wᵀ`` with a weight stored as NVFP4."""
+def nvfp4_linear(x: torch.Tensor, qweight, quantize_activation: bool = True) -> torch.Tensor:
+    """``x @ Wᵀ`` with a weight stored as NVFP4 ``(codes, block scales, tensor scale)``.  ``quantize_activation`` → W4A4 on the fp4 tensor cores."""
+    K = x.shape[-1]
+    if quantize_activation and x.is_cuda and K % 256 == 0:
+        from .. import ops
+
+        x2 = x.reshape(-1, K)
+        out = ops.gemm_nvfp4_nt(*quantize_nvfp4(x2), *qweight)
+        return out.to(x.dtype).view(*x.shape[:-1], out.shape[-1])
     return torch.nn.functional.linear(x, dequantize_nvfp4(*qweight, dtype=x.dtype))

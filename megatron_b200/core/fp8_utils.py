@@ -14,7 +14,7 @@ emulated FP8 (cast → fp32 matmul) so numerics tests run on CPU.
 from __future__ import annotations
 
 from contextlib import contextmanager, nullcontext
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Optional, Tuple
 
 import torch

@@ -14,7 +14,7 @@ The draft can be any callable with the model interface: a smaller model, or the 
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Callable, List, Optional
+from typing import List, Optional
 
 import torch
 

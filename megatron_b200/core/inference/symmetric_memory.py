@@ -5,7 +5,7 @@ The manager hands out named, shape-keyed tensors carved from the NVLink backend'
 mapping, NVLS multicast alias) and falls back to ordinary device tensors + NCCL when symmetric memory is unavailable (CPU tests, no NVSwitch)."""
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+from typing import Dict, Tuple
 
 import torch
 import torch.distributed as dist

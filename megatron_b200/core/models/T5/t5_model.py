@@ -13,7 +13,6 @@ from torch import Tensor
 from ... import tensor_parallel
 from ...enums import ModelType
 from ...transformer.module import MegatronModule
-from ...transformer.spec_utils import ModuleSpec
 from ...transformer.transformer_block import TransformerBlock
 from ...transformer.transformer_config import TransformerConfig
 from ..common.embeddings.language_model_embedding import LanguageModelEmbedding

@@ -10,7 +10,7 @@ from typing import Optional, Tuple
 
 from ..tensor_parallel.layers import ColumnParallelLinear, RowParallelLinear
 from ..transformer.dot_product_attention import DotProductAttention
-from ..transformer.torch_norm import FusedNorm, L2Norm
+from ..transformer.torch_norm import FusedNorm
 
 
 class BackendSpecProvider:

@@ -2,7 +2,6 @@
 (reference ``models/common/embeddings/language_model_embedding.py``)."""
 from __future__ import annotations
 
-from typing import Optional
 
 import torch
 

@@ -5,7 +5,7 @@ import math
 
 import torch
 
-from .rotary_pos_embedding import RotaryEmbedding, get_pos_emb_on_this_cp_rank
+from .rotary_pos_embedding import RotaryEmbedding
 
 
 def _find_correction_dim(num_rot, dim, base, max_pos):

@@ -1,7 +1,7 @@
 """Layer specs for GPT-family models (reference ``models/gpt/gpt_layer_specs.py:351-799``)."""
 from __future__ import annotations
 
-from typing import Optional, Union
+from typing import Optional
 
 from ...transformer.attention import SelfAttention, SelfAttentionSubmodules
 from ...transformer.enums import AttnMaskType

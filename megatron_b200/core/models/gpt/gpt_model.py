@@ -7,10 +7,8 @@ from __future__ import annotations
 
 from typing import Dict, Literal, Optional
 
-import torch
 from torch import Tensor
 
-from ... import parallel_state as ps
 from ... import tensor_parallel
 from ...dist_checkpointing.mapping import ShardedStateDict
 from ...enums import ModelType

@@ -4,7 +4,6 @@ from ...ssm.mamba_layer import MambaLayer, MambaLayerSubmodules
 from ...ssm.mamba_mixer import MambaMixer, MambaMixerSubmodules
 from ...transformer.attention import SelfAttention, SelfAttentionSubmodules
 from ...transformer.enums import AttnMaskType
-from ...transformer.identity_op import IdentityOp
 from ...transformer.mlp import MLP, MLPSubmodules
 from ...transformer.spec_utils import ModuleSpec
 from ...transformer.transformer_layer import TransformerLayer, TransformerLayerSubmodules, get_bias_dropout_add

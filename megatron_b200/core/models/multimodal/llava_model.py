@@ -4,7 +4,7 @@ images → CLIPViTModel → MultimodalProjector → spliced into the text embedd
 GPTModel.  Labels / loss mask are expanded consistently (image positions are never predicted)."""
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import Optional
 
 import torch
 

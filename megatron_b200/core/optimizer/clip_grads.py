@@ -6,7 +6,7 @@ over the gradients.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Union
+from typing import List, Union
 
 import torch
 import torch.distributed as dist

@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 
 from .. import parallel_state as ps
-from ..dist_checkpointing.mapping import ShardedObject, ShardedTensor
+from ..dist_checkpointing.mapping import ShardedTensor
 from ..utils import get_pg_rank, get_pg_size
 from .grad_scaler import MegatronGradScaler
 from .optimizer import MixedPrecisionOptimizer, Slot

@@ -15,9 +15,8 @@ norm, clip (scale pass), Adam, copy-to-model as separate passes.
 """
 from __future__ import annotations
 
-import math
 from abc import ABC, abstractmethod
-from typing import Callable, Dict, List, Optional, Tuple
+from typing import Callable, Dict, List, Optional
 
 import torch
 import torch.distributed as dist
@@ -27,7 +26,7 @@ from .. import parallel_state as ps
 from ..tensor_parallel import param_is_not_tensor_parallel_duplicate
 from ..transformer.module import param_is_not_shared
 from ..utils import get_pg_size
-from .clip_grads import clip_coefficient, count_zeros_fp32, get_grad_norm_fp32
+from .clip_grads import clip_coefficient, get_grad_norm_fp32
 from .grad_scaler import MegatronGradScaler
 from .optimizer_config import OptimizerConfig
 

@@ -12,7 +12,6 @@ that list.
 """
 from __future__ import annotations
 
-import os
 import warnings
 from datetime import timedelta
 from typing import Callable, Dict, List, Optional, Sequence

@@ -9,14 +9,12 @@ that is unit-tested on CPU without any process group.
 from __future__ import annotations
 
 import contextlib
-from functools import partial
-from typing import Callable, Iterator, List, Optional, Tuple, Union
+from typing import Iterator, List, Optional, Tuple, Union
 
 import torch
 from torch.autograd.variable import Variable
 
 from .. import parallel_state as ps
-from ..enums import ModelType
 from ..utils import get_attr_wrapped_model, get_model_config, get_model_type, get_pg_size
 from .p2p_communication import P2PCommunicator
 

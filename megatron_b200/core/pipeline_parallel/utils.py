@@ -12,8 +12,8 @@ On CPU (tests) streams are ``None`` and every node runs inline; the numerics are
 from __future__ import annotations
 
 from abc import ABC, abstractmethod
-from contextlib import contextmanager, nullcontext
-from typing import Callable, List, Optional, Sequence
+from contextlib import contextmanager
+from typing import Callable, List, Optional
 
 import torch
 import torch.distributed as dist

@@ -11,7 +11,7 @@ token-by-token definition (decode path and test oracle)."""
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Optional, Tuple, Union
+from typing import Optional, Union
 
 import torch
 import torch.nn.functional as F

@@ -13,7 +13,7 @@ from typing import Optional, Union
 
 import torch
 
-from ..utils import divide, get_pg_rank, get_pg_size, get_tensor_model_parallel_group_if_none
+from ..utils import divide, get_pg_size, get_tensor_model_parallel_group_if_none
 from ..transformer.module import MegatronModule
 from ..transformer.spec_utils import ModuleSpec, build_module
 from ..transformer.transformer_config import TransformerConfig

@@ -6,7 +6,6 @@ logit]) instead of the reference's three, and an in-place backward.
 """
 from __future__ import annotations
 
-import torch
 
 from ... import ops
 from ..utils import get_pg_rank, get_pg_size, get_tensor_model_parallel_group_if_none

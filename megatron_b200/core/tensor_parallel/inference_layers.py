@@ -10,12 +10,12 @@ On CUDA with the NVLink backend the reduce-scatter / all-gather are the multimem
 (≈ 10 µs per collective), so everything stays on one stream and is CUDA-graph capturable (no host syncs, static shapes)."""
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 import torch.distributed as dist
 
-from ..utils import get_pg_rank, get_pg_size
+from ..utils import get_pg_size
 from .layers import ColumnParallelLinear, RowParallelLinear
 
 

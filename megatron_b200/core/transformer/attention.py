@@ -7,13 +7,13 @@ Data flow per TP rank:  x[s/tp,b,h] --AG+GEMM--> qkv[s,b,(g·(q_per_g+2))·d]
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Optional, Tuple, Union
+from typing import Optional, Union
 
 import torch
 
 from ... import ops
 from ..enums import AttnMaskType
-from ..utils import divide, get_pg_rank, get_pg_size, get_tensor_model_parallel_group_if_none
+from ..utils import divide, get_pg_size, get_tensor_model_parallel_group_if_none
 from .module import MegatronModule
 from .spec_utils import ModuleSpec, build_module
 from .transformer_config import TransformerConfig

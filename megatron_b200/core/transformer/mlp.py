@@ -13,7 +13,7 @@ import torch.nn.functional as F
 
 from ... import ops
 from ..dist_checkpointing.mapping import ReplicaId, ShardedStateDict, ShardedTensor, ShardedTensorFactory
-from ..utils import get_pg_rank, get_pg_size, get_tensor_model_parallel_group_if_none
+from ..utils import get_tensor_model_parallel_group_if_none
 from .module import MegatronModule
 from .spec_utils import ModuleSpec, build_module
 from .transformer_config import TransformerConfig

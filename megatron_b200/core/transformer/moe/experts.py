@@ -15,7 +15,7 @@ import torch.nn.functional as F
 from .... import ops
 from ... import parallel_state as ps
 from ...dist_checkpointing.mapping import ShardedTensor
-from ...tensor_parallel.layers import _init_sharded_weight, set_tensor_model_parallel_attributes
+from ...tensor_parallel.layers import set_tensor_model_parallel_attributes
 from ...tensor_parallel.random import get_cuda_rng_tracker, get_expert_parallel_rng_tracker_name
 from ...utils import divide, get_pg_rank, get_pg_size
 from ..mlp import MLP, MLPSubmodules

@@ -4,7 +4,7 @@ top-k routing :766-1017, losses, ``MoEAuxLossAutoScaler``)."""
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Tuple, Union
+from typing import List, Optional
 
 import torch
 import torch.distributed as dist

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 
 from ... import parallel_state as ps
-from ...tensor_parallel.mappings import gather_from_sequence_parallel_region, reduce_from_tensor_model_parallel_region
+from ...tensor_parallel.mappings import reduce_from_tensor_model_parallel_region
 from ...utils import get_pg_size
 from ..module import MegatronModule
 from ..transformer_config import TransformerConfig

@@ -13,7 +13,7 @@ combine_preprocess → token_combine → combine_postprocess``.
 from __future__ import annotations
 
 from abc import ABC, abstractmethod
-from typing import List, Optional, Tuple
+from typing import List
 
 import torch
 import torch.distributed as dist

@@ -8,7 +8,7 @@ from __future__ import annotations
 import importlib
 import types
 from dataclasses import dataclass, field
-from typing import Any, Dict, Optional, Tuple, Union
+from typing import Any, Tuple, Union
 
 
 @dataclass

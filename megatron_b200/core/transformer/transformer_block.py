@@ -12,7 +12,7 @@ from .. import parallel_state as ps
 from ..dist_checkpointing.mapping import ShardedStateDict
 from ..tensor_parallel.random import checkpoint, get_cuda_rng_tracker
 from ..utils import make_viewless_tensor
-from .module import GraphableMegatronModule, MegatronModule
+from .module import GraphableMegatronModule
 from .spec_utils import ModuleSpec, build_module
 from .torch_norm import FusedNorm
 from .transformer_config import TransformerConfig

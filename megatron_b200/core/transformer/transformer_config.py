@@ -7,7 +7,6 @@ New B200-specific knobs are grouped at the end (``b200_*``).
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass, field
 from typing import Callable, List, Optional, Tuple, Union
 

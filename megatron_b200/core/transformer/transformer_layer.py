@@ -15,7 +15,7 @@ from ... import ops
 from .. import parallel_state as ps
 from ..utils import make_viewless_tensor, nvtx_range_pop, nvtx_range_push
 from .identity_op import IdentityFuncOp, IdentityOp
-from .module import GraphableMegatronModule, MegatronModule
+from .module import GraphableMegatronModule
 from .spec_utils import ModuleSpec, build_module
 from .transformer_config import TransformerConfig
 from .utils import sharded_state_dict_default

@@ -2,13 +2,13 @@
 (reference ``transformer/utils.py:96,252``)."""
 from __future__ import annotations
 
-from typing import Dict, Iterable, Optional, Tuple, Union
+from typing import Dict, Iterable, Optional, Tuple
 
 import torch
 
 from .. import parallel_state as ps
 from ..dist_checkpointing.mapping import ShardedObject, ShardedStateDict, StateDict
-from ..utils import get_pg_rank, make_sharded_tensor_for_checkpoint, make_tp_sharded_tensor_for_checkpoint
+from ..utils import make_sharded_tensor_for_checkpoint, make_tp_sharded_tensor_for_checkpoint
 
 
 def get_linear_layer(rows, columns, init_method, perform_initialization=True):

@@ -5,12 +5,11 @@ import functools
 import logging
 import math
 import operator
-import os
 import time
 import warnings
-from contextlib import contextmanager, nullcontext
+from contextlib import nullcontext
 from functools import reduce
-from typing import Any, Callable, Dict, List, Optional, Tuple, Union
+from typing import Any, Callable, Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist

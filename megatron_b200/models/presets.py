@@ -3,7 +3,6 @@ from __future__ import annotations
 
 from typing import Dict
 
-import torch
 import torch.nn.functional as F
 
 PRESETS: Dict[str, dict] = {

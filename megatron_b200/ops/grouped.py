@@ -11,7 +11,7 @@ from typing import List, Sequence
 
 import torch
 
-from . import _use_cuda, ext, gemm_nn, gemm_nt, gemm_tn, has_ext, _count
+from . import _use_cuda, ext, gemm_nn, gemm_nt, gemm_tn, _count
 
 
 def _offsets(tpe: Sequence[int]) -> List[int]:

@@ -7,7 +7,7 @@ the exact math of each fused kernel.
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Tuple
+from typing import List
 
 import torch
 import torch.nn.functional as F

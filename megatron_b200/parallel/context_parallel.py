@@ -13,8 +13,7 @@ causal work is balanced.  Two communication types:
 """
 from __future__ import annotations
 
-import math
-from typing import List, Optional, Tuple
+from typing import List, Tuple
 
 import torch
 import torch.distributed as dist

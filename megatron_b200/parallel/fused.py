@@ -20,7 +20,7 @@ import torch
 import torch.distributed as dist
 
 from .. import ops
-from ..core.utils import get_pg_rank, get_pg_size
+from ..core.utils import get_pg_size
 
 _MODE = os.environ.get("MEGATRON_B200_TP_COMM", "auto")  # auto | nccl | nvlink | fused
 # what "auto" means on this build: the fastest MEASURED mode per TP size on B200 + NVSwitch (profiles/r1_tp_comm.md):

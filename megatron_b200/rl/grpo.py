@@ -7,7 +7,7 @@ rollout engine share weights in place (no refit/reshard step is needed on a sing
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Callable, List, Optional, Sequence
+from typing import List, Optional, Sequence
 
 import torch
 

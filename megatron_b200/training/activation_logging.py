@@ -7,7 +7,7 @@ from __future__ import annotations
 import json
 import os
 import re
-from typing import Callable, Dict, List, Optional
+from typing import Dict, List, Optional
 
 import torch
 

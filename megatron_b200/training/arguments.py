@@ -7,7 +7,6 @@ TransformerEngine/Apex code paths are accepted and ignored (there is one native 
 from __future__ import annotations
 
 import argparse
-import dataclasses
 import os
 from typing import Optional
 

@@ -1,7 +1,7 @@
 """Resumable data samplers and loaders (reference ``megatron/training/datasets/data_samplers.py:19,121``)."""
 from __future__ import annotations
 
-from typing import Iterator, List, Optional
+from typing import Iterator, List
 
 import torch
 import torch.distributed as dist

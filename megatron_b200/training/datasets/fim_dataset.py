@@ -4,7 +4,7 @@ document is cut into (prefix, middle, suffix) at two random points and re-ordere
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Optional
+from typing import List
 
 import numpy as np
 import torch

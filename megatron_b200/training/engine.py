@@ -11,7 +11,6 @@ It wires together what the reference's ``megatron/training/training.py`` does in
 from __future__ import annotations
 
 import os
-from functools import partial
 from typing import Dict, Iterator, List, Optional
 
 import torch
@@ -19,7 +18,6 @@ import torch.distributed as dist
 
 from ..core import parallel_state as ps
 from ..core.distributed import DistributedDataParallel, DistributedDataParallelConfig, finalize_model_grads
-from ..core.num_microbatches_calculator import get_num_microbatches, init_num_microbatches_calculator, destroy_num_microbatches_calculator
 from ..core.optimizer import OptimizerConfig, get_megatron_optimizer
 from ..core.optimizer_param_scheduler import OptimizerParamScheduler
 from ..core.pipeline_parallel.schedules import get_forward_backward_func

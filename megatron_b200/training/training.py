@@ -6,12 +6,11 @@ LR scheduler → (load checkpoint) → data iterators → ``train()``: step / lo
 from __future__ import annotations
 
 import gc
-import math
 import os
 import signal
 import sys
 import time
-from typing import Callable, Dict, Iterator, List, Optional
+from typing import Callable, Dict, List, Optional
 
 import torch
 import torch.distributed as dist
@@ -34,7 +33,7 @@ from ..core.tensor_parallel.random import model_parallel_cuda_manual_seed
 from ..core.timers import Timers
 from ..core.utils import StragglerDetector
 from . import checkpointing
-from .arguments import core_transformer_config_from_args, parse_and_validate_args
+from .arguments import parse_and_validate_args
 from .engine import initialize_distributed
 from .flops import num_floating_point_operations
 

@@ -7,7 +7,6 @@
 import os
 import sys
 from dataclasses import replace
-from functools import partial
 
 import torch
 

@@ -1,5 +1,5 @@
 """Which library attention backends work for the Llama-3 shape on this box (time + peak memory)."""
-import time, torch, math
+import time, torch
 s,b,hq,hk,d = 8192,1,32,8,128
 q = torch.randn(s,b,hq,d, device="cuda", dtype=torch.bfloat16, requires_grad=True)
 k = torch.randn(s,b,hk,d, device="cuda", dtype=torch.bfloat16, requires_grad=True)

@@ -4,7 +4,6 @@
     python train_rl.py --preset tiny_llama --iters 20 --group-size 8
 """
 import argparse
-import copy
 import os
 import sys
 
