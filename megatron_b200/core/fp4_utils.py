@@ -45,6 +45,6 @@ def nvfp4_linear(x: torch.Tensor, qweight, quantize_activation: bool = True) -> 
         from .. import ops
 
         x2 = x.reshape(-1, K)
-        out = ops.gemm_nvfp4_nt(*quantize_nvfp4(x2), *qweight)
+        out = ops.gemm_nvfp4_nt(*ops.nvfp4_quantize(x2), *qweight)
         return out.to(x.dtype).view(*x.shape[:-1], out.shape[-1])
     return torch.nn.functional.linear(x, dequantize_nvfp4(*qweight, dtype=x.dtype))

@@ -610,6 +610,8 @@ from .extra import (  # noqa: E402,F401
     mxfp8_quantize_reference,
     mxfp8_swizzle_scales,
     nvfp4_pack,
+    nvfp4_quantize,
+    nvfp4_unpack,
     positions_from_cu_seqlens,
     ssd_state_passing,
     ssd_step,

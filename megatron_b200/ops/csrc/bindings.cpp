@@ -634,6 +634,18 @@ std::vector<Tensor> mxfp8_quant(const Tensor& x) {
   return {q, sf};
 }
 
+// x [rows, K] bf16, tscale fp32 device scalar -> (packed e2m1 uint8 [rows, K/2], ue4m3 block scales uint8 [rows, K/16])
+std::vector<Tensor> nvfp4_quant(const Tensor& x, const Tensor& tscale) {
+  check_cuda_contig(x, "x");
+  TORCH_CHECK(x.dim() == 2 && x.scalar_type() == at::kBFloat16 && x.size(1) % 16 == 0, "nvfp4_quant: bf16 [rows, K], K % 16 == 0");
+  TORCH_CHECK(tscale.is_cuda() && tscale.scalar_type() == at::kFloat && tscale.numel() == 1, "nvfp4_quant: tscale must be a 1-element fp32 CUDA tensor");
+  c10::cuda::CUDAGuard g(x.device());
+  auto q = at::empty({x.size(0), x.size(1) / 2}, x.options().dtype(at::kByte));
+  auto sf = at::empty({x.size(0), x.size(1) / 16}, x.options().dtype(at::kByte));
+  mb200_nvfp4_quant(x.data_ptr(), tscale.data_ptr<float>(), q.data_ptr(), sf.data_ptr(), x.size(0), (int)x.size(1), cur_stream());
+  return {q, sf};
+}
+
 Tensor mxfp8_dequant(const Tensor& q, const Tensor& sf) {
   check_cuda_contig(q, "q"); check_cuda_contig(sf, "sf");
   TORCH_CHECK(q.dim() == 2 && q.scalar_type() == at::kByte && sf.scalar_type() == at::kByte && sf.size(0) == q.size(0) && sf.size(1) * 32 == q.size(1));
@@ -700,6 +712,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ssd_step", &ssd_step);
   m.def("mxfp8_quant", &mxfp8_quant);
   m.def("mxfp8_dequant", &mxfp8_dequant);
+  m.def("nvfp4_quant", &nvfp4_quant);
 #endif
   m.def("rmsnorm_fwd", &rmsnorm_fwd);
   m.def("rmsnorm_bwd", &rmsnorm_bwd);

@@ -5,6 +5,7 @@
 //     selective_state_update.py) — the GEMM-shaped intra-chunk work stays on the tensor cores through batched GEMMs
 //   * MXFP8 (OCP microscaling: 32-element blocks, E8M0 shared exponent, E4M3 payload) quantise / dequantise (reference quantization/mxfp8_quantize.py)
 // All of them are bandwidth-bound: 16-byte accesses, one pass over the data, fp32 math in registers.
+#include <cuda_fp4.h>
 #include <cuda_fp8.h>
 
 #include "common.cuh"
@@ -340,6 +341,38 @@ __global__ void __launch_bounds__(256) mxfp8_dequant_kernel(const uint8_t* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------ NVFP4
+// x: [rows, K] bf16 (K % 16 == 0) → q: [rows, K/2] two E2M1 codes per byte (even k in the low nibble), sf: [rows, K/16] UE4M3 block scales.
+// tscale (device scalar) = amax(x) / (6 * 448) is the tensor-level scale; block scale = amax_block / (6 * tscale) rounded to E4M3 (≥ 2^-9);
+// payload = x / (block scale * tscale) rounded to nearest-even E2M1.  One thread per 16-element block.
+__global__ void __launch_bounds__(256) nvfp4_quant_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ tscale, uint8_t* __restrict__ q,
+                                                            uint8_t* __restrict__ sf, long nblocks) {
+  const float inv_t = 1.f / __ldg(tscale);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nblocks; i += (long)gridDim.x * blockDim.x) {
+    Vec<__nv_bfloat16> v0 = ld16_stream(x + i * 16), v1 = ld16_stream(x + i * 16 + 8);
+    float f[16], amax = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      f[k] = __bfloat162float(v0.v[k]) * inv_t;
+      f[8 + k] = __bfloat162float(v1.v[k]) * inv_t;
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) amax = fmaxf(amax, fabsf(f[k]));
+    const float want = fmaxf(amax * (1.f / 6.f), 0.001953125f);                       // 2^-9: smallest scale the reference allows
+    const uint8_t sb = (uint8_t)__nv_cvt_float_to_fp8(want, __NV_SATFINITE, __NV_E4M3);
+    const float sc = __half2float(__half(__nv_cvt_fp8_to_halfraw(sb, __NV_E4M3)));
+    const float inv = 1.f / sc;
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      lo |= (uint32_t)(__nv_cvt_float2_to_fp4x2(make_float2(f[2 * k] * inv, f[2 * k + 1] * inv), __NV_E2M1, cudaRoundNearest) & 0xff) << (8 * k);
+      hi |= (uint32_t)(__nv_cvt_float2_to_fp4x2(make_float2(f[8 + 2 * k] * inv, f[8 + 2 * k + 1] * inv), __NV_E2M1, cudaRoundNearest) & 0xff) << (8 * k);
+    }
+    *reinterpret_cast<uint2*>(q + i * 8) = make_uint2(lo, hi);
+    sf[i] = sb;
+  }
+}
+
 }  // namespace mb200
 
 using namespace mb200;
@@ -411,4 +444,9 @@ extern "C" void mb200_mxfp8_quant(const void* x, void* q, void* sf, long rows, i
 extern "C" void mb200_mxfp8_dequant(const void* q, const void* sf, void* out, long rows, int K, cudaStream_t s) {
   const long nvec = rows * K / 8;
   mxfp8_dequant_kernel<<<grid_cap(nvec, 256), 256, 0, s>>>((const uint8_t*)q, (const uint8_t*)sf, (__nv_bfloat16*)out, nvec);
+}
+
+extern "C" void mb200_nvfp4_quant(const void* x, const float* tscale, void* q, void* sf, long rows, int K, cudaStream_t s) {
+  const long nblocks = rows * K / 16;
+  nvfp4_quant_kernel<<<grid_cap(nblocks, 256), 256, 0, s>>>((const __nv_bfloat16*)x, tscale, (uint8_t*)q, (uint8_t*)sf, nblocks);
 }

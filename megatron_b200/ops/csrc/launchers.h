@@ -71,6 +71,7 @@ void mb200_ssd_step(float* state, const void* x, const float* dt, const float* A
                     int dtype, cudaStream_t s);
 void mb200_mxfp8_quant(const void* x, void* q, void* sf, long rows, int K, cudaStream_t s);
 void mb200_mxfp8_dequant(const void* q, const void* sf, void* out, long rows, int K, cudaStream_t s);
+void mb200_nvfp4_quant(const void* x, const float* tscale, void* q, void* sf, long rows, int K, cudaStream_t s);
 int mb200_gemm_mxfp8_nt(const void* A, const void* B, const void* sfa, const void* sfb, void* C, int M, int N, int K, int tile, cudaStream_t s);
 int mb200_gemm_nvfp4_nt(const void* A, const void* B, const void* sfa, const void* sfb, void* C, int M, int N, int K, float alpha, const float* alpha_dev, cudaStream_t s);
 }

@@ -268,15 +268,40 @@ def nvfp4_pack(codes: torch.Tensor) -> torch.Tensor:
     return (codes[:, 0::2] | (codes[:, 1::2] << 4)).contiguous()
 
 
+def nvfp4_unpack(packed: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(packed.shape[0], packed.shape[1] * 2, dtype=torch.uint8, device=packed.device)
+    out[:, 0::2], out[:, 1::2] = packed & 0xF, packed >> 4
+    return out
+
+
+def nvfp4_quantize(x: torch.Tensor):
+    """``x [rows, K]`` → ``(packed codes uint8 [rows, K/2], block scales float8_e4m3fn [rows, K/16], tensor scale fp32 [1])``: the CUDA quantiser
+    (one pass, no host sync: the tensor amax stays on the device) — same numerics as ``core.fp4_utils.quantize_nvfp4`` up to tie rounding."""
+    tscale = (x.detach().abs().amax().float().clamp(min=1e-12) / (6.0 * 448.0)).reshape(1)
+    if _use_cuda(x):
+        q, sf = ext().nvfp4_quant(x.to(torch.bfloat16).contiguous(), tscale)
+        _count()
+        return q, sf.view(torch.float8_e4m3fn), tscale
+    from ..core.fp4_utils import quantize_nvfp4
+
+    codes, bscale, t = quantize_nvfp4(x)
+    return nvfp4_pack(codes), bscale, t.reshape(1)
+
+
 def gemm_nvfp4_nt(a_codes: torch.Tensor, a_bscale: torch.Tensor, a_tscale, b_codes: torch.Tensor, b_bscale: torch.Tensor, b_tscale) -> torch.Tensor:
-    """``C[M,N] (bf16) = dequant(A) · dequant(B)ᵀ`` for NVFP4 operands as produced by ``core.fp4_utils.quantize_nvfp4`` (codes uint8 ``[rows, K]``, block scales
-    ``float8_e4m3fn [rows, K/16]``, fp32 tensor scale): block-scaled ``tcgen05.mma kind::mxf4nvf4`` on CUDA (K % 256 == 0), dequantise-then-matmul elsewhere."""
-    if _use_cuda(a_codes) and a_codes.shape[1] % 256 == 0 and hasattr(ext(), "gemm_nvfp4_nt"):
+    """``C[M,N] (bf16) = dequant(A) · dequant(B)ᵀ`` for NVFP4 operands (codes uint8 — one per byte ``[rows, K]`` as produced by ``core.fp4_utils.quantize_nvfp4`` or
+    packed ``[rows, K/2]`` as produced by ``nvfp4_quantize`` — block scales ``float8_e4m3fn [rows, K/16]``, fp32 tensor scale): block-scaled
+    ``tcgen05.mma kind::mxf4nvf4`` on CUDA (K % 256 == 0), dequantise-then-matmul elsewhere."""
+    K = a_bscale.shape[1] * 16
+    a_packed, b_packed = a_codes.shape[1] * 2 == K, b_codes.shape[1] * 2 == K
+    if _use_cuda(a_codes) and K % 256 == 0 and hasattr(ext(), "gemm_nvfp4_nt"):
         alpha = (torch.as_tensor(a_tscale, device=a_codes.device).float() * torch.as_tensor(b_tscale, device=a_codes.device).float()).reshape(1)
-        out = ext().gemm_nvfp4_nt(nvfp4_pack(a_codes), mxfp8_swizzle_scales(a_bscale.view(torch.uint8)), nvfp4_pack(b_codes),
-                                  mxfp8_swizzle_scales(b_bscale.view(torch.uint8)), 1.0, alpha)
+        out = ext().gemm_nvfp4_nt(a_codes.contiguous() if a_packed else nvfp4_pack(a_codes), mxfp8_swizzle_scales(a_bscale.view(torch.uint8)),
+                                  b_codes.contiguous() if b_packed else nvfp4_pack(b_codes), mxfp8_swizzle_scales(b_bscale.view(torch.uint8)), 1.0, alpha)
         _count()
         return out
     from ..core.fp4_utils import dequantize_nvfp4
 
-    return (dequantize_nvfp4(a_codes, a_bscale, a_tscale, torch.float32) @ dequantize_nvfp4(b_codes, b_bscale, b_tscale, torch.float32).t()).to(torch.bfloat16)
+    ac = nvfp4_unpack(a_codes) if a_packed else a_codes
+    bc = nvfp4_unpack(b_codes) if b_packed else b_codes
+    return (dequantize_nvfp4(ac, a_bscale, a_tscale, torch.float32) @ dequantize_nvfp4(bc, b_bscale, b_tscale, torch.float32).t()).to(torch.bfloat16)

@@ -202,3 +202,27 @@ def test_nvfp4_block_scaled_gemm(M, N, K):
     _close(c, ref, 1e-2)
     full = a @ b.t()
     assert ((c.float() - full).norm() / full.norm()).item() < 0.2            # 4-bit payload: ~10 % relative error per operand
+
+
+def test_nvfp4_quantise_kernel_and_w4a4_linear():
+    from megatron_b200 import ops
+    from megatron_b200.core.fp4_utils import dequantize_nvfp4, nvfp4_linear, quantize_nvfp4
+
+    torch.manual_seed(7)
+    x = (torch.randn(300, 1024, device="cuda") * torch.exp2(torch.randint(-4, 5, (300, 64), device="cuda").float()).repeat_interleave(16, dim=1)).to(torch.bfloat16)
+    x[5, :32] = 0
+    q, sf, t = ops.nvfp4_quantize(x)
+    codes_ref, sf_ref, t_ref = quantize_nvfp4(x)
+    assert torch.allclose(t, t_ref.reshape(1)) and q.shape == (300, 512)
+    assert (sf.view(torch.uint8) != sf_ref.view(torch.uint8)).float().mean().item() < 2e-3            # e4m3 rounding of the block scale
+    codes = ops.nvfp4_unpack(q)
+    same_scale = (sf.view(torch.uint8) == sf_ref.view(torch.uint8)).repeat_interleave(16, dim=1)
+    assert ((codes != codes_ref) & same_scale).float().mean().item() < 0.02                           # ties round to even on the hardware, to the lower code in the reference
+    d = dequantize_nvfp4(codes, sf, t, torch.float32)
+    d_ref = dequantize_nvfp4(codes_ref, sf_ref, t_ref, torch.float32)
+    xf = x.float()
+    assert (d - xf).norm() <= 1.02 * (d_ref - xf).norm() and torch.all(d[5, :32] == 0)
+    w = torch.randn(512, 1024, device="cuda") * 0.05
+    y = nvfp4_linear(x.view(3, 100, 1024), quantize_nvfp4(w))
+    ref = xf @ w.t()
+    assert y.shape == (3, 100, 512) and ((y.float().view(300, 512) - ref).norm() / ref.norm()).item() < 0.2
