@@ -129,10 +129,43 @@ class _Mxfp8LinearFn(torch.autograd.Function):
         return gx, gw
 
 
+def _nvf4_gemm_nt(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """bf16 [M, N] = a [M, K] · b [N, K]ᵀ with both operands quantised to NVFP4 along K (16-element blocks, UE4M3 block scales, fp32 tensor scale)."""
+    from .. import ops
+
+    K = a.shape[1]
+    if K % 256:
+        pad = (-K) % 256
+        a, b = torch.nn.functional.pad(a, (0, pad)), torch.nn.functional.pad(b, (0, pad))
+    return ops.gemm_nvfp4_nt(*ops.nvfp4_quantize(a), *ops.nvfp4_quantize(b))
+
+
+class _Nvfp4LinearFn(torch.autograd.Function):
+    """NVFP4 recipe (reference ``fp4_recipe="nvfp4"``): forward GEMM in 4-bit; the gradient GEMMs stay in MXFP8 — 4-bit gradients need stochastic rounding and
+    random Hadamard rotations to train stably, which this round does not implement, so the backward takes the next-cheapest exact-enough format."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x2 = x.reshape(-1, x.shape[-1])
+        ctx.save_for_backward(x2, w)
+        ctx.x_shape = x.shape
+        return _nvf4_gemm_nt(x2, w).to(x.dtype).view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, w = ctx.saved_tensors
+        g2 = gy.reshape(-1, gy.shape[-1])
+        gx = _mx_gemm_nt(g2, w.t().contiguous()).to(x2.dtype).view(ctx.x_shape)
+        gw = _mx_gemm_nt(g2.t().contiguous(), x2.t().contiguous()).to(w.dtype)
+        return gx, gw
+
+
 def fp8_linear(x: torch.Tensor, w: torch.Tensor, recipe: str = "tensorwise", fp8_format: str = "hybrid", metas=None) -> torch.Tensor:
-    """``x [..., K] @ w [N, K]ᵀ`` with FP8 operands for all three GEMMs of the layer.  ``recipe``: ``tensorwise`` | ``delayed`` | ``mxfp8``."""
+    """``x [..., K] @ w [N, K]ᵀ`` with FP8 operands for all three GEMMs of the layer.  ``recipe``: ``tensorwise`` | ``delayed`` | ``mxfp8`` | ``nvfp4`` (4-bit forward, MXFP8 backward)."""
     if recipe == "mxfp8":
         return _Mxfp8LinearFn.apply(x, w)
+    if recipe == "nvfp4":
+        return _Nvfp4LinearFn.apply(x, w)
     grad_dtype = E5M2 if fp8_format == "hybrid" else E4M3
     if recipe == "delayed" and metas is None:
         raise ValueError("delayed scaling needs (input, weight, grad) Fp8Meta objects")
