@@ -21,4 +21,6 @@ class FusedScaleMaskSoftmax(torch.nn.Module):
             sink = softmax_offset.reshape(1, -1, 1, 1).float().expand(x.shape[0], -1, x.shape[2], 1)
             p = torch.softmax(torch.cat([x, sink], dim=-1), dim=-1)[..., :-1]
             return p.to(input.dtype)
-        return ref.scaled_masked_softmax(input, None if mask is None else mask.bool(), self.scale or 1.0, causal=causal)
+        from ... import ops
+
+        return ops.scaled_masked_softmax(input, None if mask is None else mask.bool(), self.scale or 1.0, causal=causal)

@@ -613,6 +613,9 @@ from .extra import (  # noqa: E402,F401
     nvfp4_quantize,
     nvfp4_unpack,
     positions_from_cu_seqlens,
+    quick_geglu,
+    scaled_masked_softmax,
+    squared_relu,
     ssd_state_passing,
     ssd_step,
 )

@@ -646,6 +646,44 @@ std::vector<Tensor> nvfp4_quant(const Tensor& x, const Tensor& tscale) {
   return {q, sf};
 }
 
+// x [b, h, sq, sk]; mask uint8 [b, 1, sq, sk] (optional)
+Tensor softmax_fwd(const Tensor& x, const c10::optional<Tensor>& mask, double scale, bool causal) {
+  check_cuda_contig(x, "x");
+  TORCH_CHECK(x.dim() == 4, "softmax_fwd: [b, h, sq, sk]");
+  if (mask.has_value()) { check_cuda_contig(*mask, "mask"); TORCH_CHECK(mask->scalar_type() == at::kByte && mask->numel() == x.size(0) * x.size(2) * x.size(3), "softmax_fwd: mask must be uint8 [b, 1, sq, sk]"); }
+  c10::cuda::CUDAGuard g(x.device());
+  auto y = at::empty_like(x);
+  mb200_softmax_fwd(x.data_ptr(), mask.has_value() ? mask->data_ptr() : nullptr, y.data_ptr(), x.size(0) * x.size(1) * x.size(2), (int)x.size(1), (int)x.size(2), (int)x.size(3),
+                    (float)scale, causal, dtype_code(x), cur_stream());
+  return y;
+}
+Tensor softmax_bwd(const Tensor& gy, const Tensor& y, double scale) {
+  check_cuda_contig(gy, "gy"); check_cuda_contig(y, "y");
+  c10::cuda::CUDAGuard g(y.device());
+  auto gx = at::empty_like(y);
+  mb200_softmax_bwd(gy.data_ptr(), y.data_ptr(), gx.data_ptr(), y.numel() / y.size(-1), (int)y.size(-1), (float)scale, dtype_code(y), cur_stream());
+  return gx;
+}
+// mode 0: squared ReLU on [rows, F]; mode 1: quick-GeGLU, x [rows, 2F] -> [rows, F]
+Tensor act_fwd(const Tensor& x, int64_t mode) {
+  check_cuda_contig(x, "x");
+  TORCH_CHECK(x.dim() == 2, "act_fwd: 2-D input");
+  const int64_t F = mode == 0 ? x.size(1) : x.size(1) / 2;
+  TORCH_CHECK(F % vec_elems(x) == 0, "act_fwd: width must be a multiple of ", vec_elems(x));
+  c10::cuda::CUDAGuard g(x.device());
+  auto y = at::empty({x.size(0), F}, x.options());
+  mb200_act_fwd(x.data_ptr(), y.data_ptr(), x.size(0), (int)F, (int)mode, dtype_code(x), cur_stream());
+  return y;
+}
+Tensor act_bwd(const Tensor& g_, const Tensor& x, int64_t mode) {
+  check_cuda_contig(g_, "g"); check_cuda_contig(x, "x");
+  const int64_t F = mode == 0 ? x.size(1) : x.size(1) / 2;
+  c10::cuda::CUDAGuard g(x.device());
+  auto gx = at::empty_like(x);
+  mb200_act_bwd(g_.data_ptr(), x.data_ptr(), gx.data_ptr(), x.size(0), (int)F, (int)mode, dtype_code(x), cur_stream());
+  return gx;
+}
+
 Tensor mxfp8_dequant(const Tensor& q, const Tensor& sf) {
   check_cuda_contig(q, "q"); check_cuda_contig(sf, "sf");
   TORCH_CHECK(q.dim() == 2 && q.scalar_type() == at::kByte && sf.scalar_type() == at::kByte && sf.size(0) == q.size(0) && sf.size(1) * 32 == q.size(1));
@@ -713,6 +751,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("mxfp8_quant", &mxfp8_quant);
   m.def("mxfp8_dequant", &mxfp8_dequant);
   m.def("nvfp4_quant", &nvfp4_quant);
+  m.def("softmax_fwd", &softmax_fwd);
+  m.def("softmax_bwd", &softmax_bwd);
+  m.def("act_fwd", &act_fwd);
+  m.def("act_bwd", &act_bwd);
 #endif
   m.def("rmsnorm_fwd", &rmsnorm_fwd);
   m.def("rmsnorm_bwd", &rmsnorm_bwd);

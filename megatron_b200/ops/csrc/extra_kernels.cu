@@ -373,6 +373,105 @@ __global__ void __launch_bounds__(256) nvfp4_quant_kernel(const __nv_bfloat16* _
   }
 }
 
+// ------------------------------------------------------------------------------------------------ scale + mask + softmax (unfused attention path)
+// x, y: [rows, sk] with rows = b * h * sq; mask: uint8 [b, 1, sq, sk] (non-zero = masked with -10000 like the reference) or null; causal aligns the diagonal to the
+// bottom-right (sk >= sq).  One CTA per row, three passes over a row that is L1/L2 resident (this is the arbitrary-mask fallback, not the flash path).
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const T* __restrict__ x, const uint8_t* __restrict__ mask, T* __restrict__ y, int h, int sq, int sk, float scale,
+                                                            int causal) {
+  __shared__ float red[32];
+  const long row = blockIdx.x;
+  const int qi = (int)(row % sq);
+  const long bi = row / ((long)h * sq);
+  const T* xr = x + row * sk;
+  const uint8_t* mr = mask != nullptr ? mask + (bi * sq + qi) * (long)sk : nullptr;
+  const int limit = causal ? qi + (sk - sq) : sk - 1;        // last visible key
+  auto val = [&](int j) -> float {
+    if (j > limit) return -INFINITY;
+    float v = to_f(xr[j]) * scale;
+    return (mr != nullptr && mr[j]) ? -10000.f : v;
+  };
+  float m = -INFINITY;
+  for (int j = threadIdx.x; j < sk; j += blockDim.x) m = fmaxf(m, val(j));
+  m = block_max(m, red);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < sk; j += blockDim.x) sum += __expf(val(j) - m);
+  sum = block_sum(sum, red);
+  const float inv = 1.f / sum;
+  T* yr = y + row * sk;
+  for (int j = threadIdx.x; j < sk; j += blockDim.x) yr[j] = from_f<T>(__expf(val(j) - m) * inv);
+}
+
+// gx = scale * y * (gy - Σ gy·y)
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ y, T* __restrict__ gx, int sk, float scale) {
+  __shared__ float red[32];
+  const long row = blockIdx.x;
+  const T* gr = gy + row * sk;
+  const T* yr = y + row * sk;
+  float dot = 0.f;
+  for (int j = threadIdx.x; j < sk; j += blockDim.x) dot += to_f(gr[j]) * to_f(yr[j]);
+  dot = block_sum(dot, red);
+  for (int j = threadIdx.x; j < sk; j += blockDim.x) gx[row * sk + j] = from_f<T>(scale * to_f(yr[j]) * (to_f(gr[j]) - dot));
+}
+
+// ------------------------------------------------------------------------------------------------ squared ReLU and quick-GeGLU (vectorised elementwise)
+// mode 0: y = relu(x)^2 over n elements.   mode 1: x = [a | b] halves of width F per row, y = a·σ(1.702 a) · b
+template <typename T>
+__global__ void __launch_bounds__(256) act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long rows, int F, int mode) {
+  constexpr int VN = Vec<T>::N;
+  const long nvec = rows * F / VN;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
+    const long r = (i * VN) / F;
+    const int c = (int)((i * VN) % F);
+    Vec<T> o;
+    if (mode == 0) {
+      Vec<T> a = ld16_stream(x + i * VN);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) {
+        const float v = fmaxf(to_f(a.v[k]), 0.f);
+        o.v[k] = from_f<T>(v * v);
+      }
+    } else {
+      Vec<T> a = ld16_stream(x + r * 2 * F + c), b = ld16_stream(x + r * 2 * F + F + c);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) {
+        const float av = to_f(a.v[k]);
+        o.v[k] = from_f<T>(av / (1.f + __expf(-1.702f * av)) * to_f(b.v[k]));
+      }
+    }
+    st16(y + i * VN, o);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ g, const T* __restrict__ x, T* __restrict__ gx, long rows, int F, int mode) {
+  constexpr int VN = Vec<T>::N;
+  const long nvec = rows * F / VN;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
+    const long r = (i * VN) / F;
+    const int c = (int)((i * VN) % F);
+    Vec<T> gv = ld16_stream(g + i * VN);
+    if (mode == 0) {
+      Vec<T> a = ld16_stream(x + i * VN), o;
+#pragma unroll
+      for (int k = 0; k < VN; ++k) o.v[k] = from_f<T>(2.f * fmaxf(to_f(a.v[k]), 0.f) * to_f(gv.v[k]));
+      st16(gx + i * VN, o);
+    } else {
+      Vec<T> a = ld16_stream(x + r * 2 * F + c), b = ld16_stream(x + r * 2 * F + F + c), oa, ob;
+#pragma unroll
+      for (int k = 0; k < VN; ++k) {
+        const float av = to_f(a.v[k]), bv = to_f(b.v[k]), gg = to_f(gv.v[k]);
+        const float sg = 1.f / (1.f + __expf(-1.702f * av));
+        oa.v[k] = from_f<T>(gg * bv * sg * (1.f + 1.702f * av * (1.f - sg)));
+        ob.v[k] = from_f<T>(gg * av * sg);
+      }
+      st16(gx + r * 2 * F + c, oa);
+      st16(gx + r * 2 * F + F + c, ob);
+    }
+  }
+}
+
 }  // namespace mb200
 
 using namespace mb200;
@@ -449,4 +548,17 @@ extern "C" void mb200_mxfp8_dequant(const void* q, const void* sf, void* out, lo
 extern "C" void mb200_nvfp4_quant(const void* x, const float* tscale, void* q, void* sf, long rows, int K, cudaStream_t s) {
   const long nblocks = rows * K / 16;
   nvfp4_quant_kernel<<<grid_cap(nblocks, 256), 256, 0, s>>>((const __nv_bfloat16*)x, tscale, (uint8_t*)q, (uint8_t*)sf, nblocks);
+}
+
+extern "C" void mb200_softmax_fwd(const void* x, const void* mask, void* y, long rows, int h, int sq, int sk, float scale, int causal, int dtype, cudaStream_t s) {
+  DISPATCH_T(dtype, (softmax_fwd_kernel<T><<<(unsigned)rows, 256, 0, s>>>((const T*)x, (const uint8_t*)mask, (T*)y, h, sq, sk, scale, causal)));
+}
+extern "C" void mb200_softmax_bwd(const void* gy, const void* y, void* gx, long rows, int sk, float scale, int dtype, cudaStream_t s) {
+  DISPATCH_T(dtype, (softmax_bwd_kernel<T><<<(unsigned)rows, 256, 0, s>>>((const T*)gy, (const T*)y, (T*)gx, sk, scale)));
+}
+extern "C" void mb200_act_fwd(const void* x, void* y, long rows, int F, int mode, int dtype, cudaStream_t s) {
+  DISPATCH_T(dtype, (act_fwd_kernel<T><<<grid_cap(rows * F / Vec<T>::N, 256), 256, 0, s>>>((const T*)x, (T*)y, rows, F, mode)));
+}
+extern "C" void mb200_act_bwd(const void* g, const void* x, void* gx, long rows, int F, int mode, int dtype, cudaStream_t s) {
+  DISPATCH_T(dtype, (act_bwd_kernel<T><<<grid_cap(rows * F / Vec<T>::N, 256), 256, 0, s>>>((const T*)g, (const T*)x, (T*)gx, rows, F, mode)));
 }

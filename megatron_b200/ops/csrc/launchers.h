@@ -71,6 +71,10 @@ void mb200_ssd_step(float* state, const void* x, const float* dt, const float* A
                     int dtype, cudaStream_t s);
 void mb200_mxfp8_quant(const void* x, void* q, void* sf, long rows, int K, cudaStream_t s);
 void mb200_mxfp8_dequant(const void* q, const void* sf, void* out, long rows, int K, cudaStream_t s);
+void mb200_softmax_fwd(const void* x, const void* mask, void* y, long rows, int h, int sq, int sk, float scale, int causal, int dtype, cudaStream_t s);
+void mb200_softmax_bwd(const void* gy, const void* y, void* gx, long rows, int sk, float scale, int dtype, cudaStream_t s);
+void mb200_act_fwd(const void* x, void* y, long rows, int F, int mode, int dtype, cudaStream_t s);
+void mb200_act_bwd(const void* g, const void* x, void* gx, long rows, int F, int mode, int dtype, cudaStream_t s);
 void mb200_nvfp4_quant(const void* x, const float* tscale, void* q, void* sf, long rows, int K, cudaStream_t s);
 int mb200_gemm_mxfp8_nt(const void* A, const void* B, const void* sfa, const void* sfb, void* C, int M, int N, int K, int tile, cudaStream_t s);
 int mb200_gemm_nvfp4_nt(const void* A, const void* B, const void* sfa, const void* sfb, void* C, int M, int N, int K, float alpha, const float* alpha_dev, cudaStream_t s);

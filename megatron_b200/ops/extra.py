@@ -305,3 +305,62 @@ def gemm_nvfp4_nt(a_codes: torch.Tensor, a_bscale: torch.Tensor, a_tscale, b_cod
     ac = nvfp4_unpack(a_codes) if a_packed else a_codes
     bc = nvfp4_unpack(b_codes) if b_packed else b_codes
     return (dequantize_nvfp4(ac, a_bscale, a_tscale, torch.float32) @ dequantize_nvfp4(bc, b_bscale, b_tscale, torch.float32).t()).to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------------ scale-mask-softmax, squared ReLU, quick-GeGLU
+class _ScaledMaskedSoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mask, scale, causal):
+        y = ext().softmax_fwd(x.contiguous(), mask, float(scale), causal)
+        _count()
+        ctx.save_for_backward(y)
+        ctx.scale = float(scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        gx = ext().softmax_bwd(gy.contiguous(), y, ctx.scale)
+        _count()
+        return gx, None, None, None
+
+
+def scaled_masked_softmax(x: torch.Tensor, mask: Optional[torch.Tensor], scale: float = 1.0, causal: bool = False) -> torch.Tensor:
+    """``softmax(scale · x + mask)`` over the last dim of ``[b, h, sq, sk]`` (``mask`` bool ``[b, 1, sq, sk]``, True = masked; ``causal`` = bottom-right aligned
+    triangle) — the unfused attention path's kernel (reference ``fused_softmax.py`` / the ``scaled_*_softmax_cuda`` extensions)."""
+    if _use_cuda(x) and x.dim() == 4 and (mask is None or (mask.dim() == 4 and mask.shape[1] == 1 and mask.shape[0] == x.shape[0])):
+        m8 = None if mask is None else mask.to(torch.uint8).expand(x.shape[0], 1, x.shape[2], x.shape[3]).contiguous()
+        return _ScaledMaskedSoftmaxFn.apply(x, m8, scale, causal)
+    return ref.scaled_masked_softmax(x, mask, scale, causal=causal)
+
+
+class _ActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2, mode):
+        ctx.save_for_backward(x2)
+        ctx.mode = mode
+        y = ext().act_fwd(x2, mode)
+        _count()
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (x2,) = ctx.saved_tensors
+        gx = ext().act_bwd(g.contiguous(), x2, ctx.mode)
+        _count()
+        return gx, None
+
+
+def squared_relu(x: torch.Tensor) -> torch.Tensor:
+    if _use_cuda(x) and x.shape[-1] % 8 == 0:
+        return _ActFn.apply(x.reshape(-1, x.shape[-1]).contiguous(), 0).view(x.shape)
+    return torch.pow(torch.relu(x), 2)
+
+
+def quick_geglu(y: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``[..., 2F] → [..., F]``: ``a · σ(1.702 a) · b`` with ``(a, b) = chunk(y + bias)``."""
+    yb = y if bias is None else y + bias
+    if _use_cuda(yb) and (yb.shape[-1] // 2) % 8 == 0:
+        return _ActFn.apply(yb.reshape(-1, yb.shape[-1]).contiguous(), 1).view(*yb.shape[:-1], yb.shape[-1] // 2)
+    a, b = yb.chunk(2, dim=-1)
+    return a * torch.sigmoid(1.702 * a) * b

@@ -226,3 +226,34 @@ def test_nvfp4_quantise_kernel_and_w4a4_linear():
     y = nvfp4_linear(x.view(3, 100, 1024), quantize_nvfp4(w))
     ref = xf @ w.t()
     assert y.shape == (3, 100, 512) and ((y.float().view(300, 512) - ref).norm() / ref.norm()).item() < 0.2
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+def test_scaled_masked_softmax_and_activations(dtype, tol):
+    from megatron_b200 import ops
+    from megatron_b200.ops import reference as ref
+
+    torch.manual_seed(8)
+    b, h, sq, sk = 2, 3, 70, 133
+    x = torch.randn(b, h, sq, sk, device="cuda", dtype=dtype, requires_grad=True)
+    mask = torch.rand(b, 1, sq, sk, device="cuda") > 0.8
+    for m, causal in ((mask, False), (None, True), (None, False)):
+        y = ops.scaled_masked_softmax(x, m, 0.37, causal=causal)
+        g = torch.randn_like(y)
+        (gx,) = torch.autograd.grad(y, x, g)
+        xf = x.detach().float().requires_grad_()
+        yf = ref.scaled_masked_softmax(xf, m, 0.37, causal=causal)
+        (gxf,) = torch.autograd.grad(yf, xf, g.float())
+        _close(y, yf, tol)
+        _close(gx, gxf, tol)
+        assert torch.allclose(y.float().sum(-1), torch.ones(b, h, sq, device="cuda"), atol=2e-2 if dtype == torch.bfloat16 else 1e-5)
+    z = torch.randn(37, 4, 256, device="cuda", dtype=dtype, requires_grad=True)
+    for fn, rf in ((ops.squared_relu, lambda t: torch.relu(t) ** 2), (ops.quick_geglu, lambda t: (lambda a, bb: a * torch.sigmoid(1.702 * a) * bb)(*t.chunk(2, -1)))):
+        out = fn(z)
+        g = torch.randn_like(out)
+        (gz,) = torch.autograd.grad(out, z, g)
+        zf = z.detach().float().requires_grad_()
+        of = rf(zf)
+        (gzf,) = torch.autograd.grad(of, zf, g.float())
+        _close(out, of, tol)
+        _close(gz, gzf, tol)
