@@ -1,4 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:"gemm_(mxfp8|nvfp4)_kernel" --launch-skip 4 --launch-count 2 -f -o gpurun_out/prof_lowp_gemm python tools/lowp_gemm_once.py > gpurun_out/ncu_lowp.log 2>&1; echo "ncu rc=$?"; tail -3 gpurun_out/ncu_lowp.log
-ls -la gpurun_out/prof_lowp_gemm.ncu-rep
+timeout 900 python -m pytest tests -q -m gpu --ignore=tests/test_nvlink_gpu.py --ignore=tests/test_nvlink_moe_gpu.py --ignore=tests/test_moe_e2e_gpu.py > gpurun_out/final_gpu_suite2.log 2>&1; echo "gpu suite rc=$?"; grep -E "passed|failed|FAILED|Error" gpurun_out/final_gpu_suite2.log | tail -12 | cut -c1-300
