@@ -35,10 +35,10 @@ def _jsonable(o: Any, depth: int = 0):
         return {str(k): _jsonable(v, depth + 1) for k, v in o.items()}
     if isinstance(o, (list, tuple, set)):
         return [_jsonable(v, depth + 1) for v in o]
+    if isinstance(o, torch.nn.Module):       # before the callable test: modules are callable
+        return {"module": type(o).__qualname__, "children": {n: type(c).__qualname__ for n, c in o.named_children()}}
     if isinstance(o, type) or callable(o):
         return f"{getattr(o, '__module__', '')}.{getattr(o, '__qualname__', repr(o))}"
-    if isinstance(o, torch.nn.Module):
-        return {"module": type(o).__qualname__, "children": {n: type(c).__qualname__ for n, c in o.named_children()}}
     return repr(o)
 
 

@@ -246,3 +246,56 @@ def test_pretrain_cli_writers_ft_activation_logs_and_resume(tmp_path):
     # resume: picks up at iteration 4 and continues to 6
     out2 = _run_pretrain(tmp_path, [], iters=6)
     assert "iteration        6/" in out2 and "iteration        2/" not in out2
+
+
+def test_config_logger_initialize_helpers_and_param_norm(tmp_path):
+    from types import SimpleNamespace
+
+    from megatron_b200.core.config_logger import has_config_logger_enabled, log_config_to_disk
+    from megatron_b200.training import async_utils
+    from megatron_b200.training.initialize import init_autoresume, set_random_seed
+    from megatron_b200.training.utils import calc_params_l2_norm, report_memory
+
+    cfg = SimpleNamespace(config_logger_dir=str(tmp_path / "cfg"))
+    assert has_config_logger_enabled(cfg) and not has_config_logger_enabled(SimpleNamespace())
+    lin = torch.nn.Linear(4, 4)
+    f0 = log_config_to_disk(cfg, {"self": lin, "config": cfg, "dtype": torch.bfloat16, "fn": torch.relu, "module": lin, "shape": (2, 3)}, prefix="Linear", rank_str="0")
+    f1 = log_config_to_disk(cfg, {"x": torch.zeros(2, 2)}, prefix="Linear", rank_str="0")
+    d0, d1 = json.load(open(f0)), json.load(open(f1))
+    assert f0.endswith("Linear.rank_0.iter0.json") and f1.endswith("iter1.json") and "self" not in d0
+    assert d0["dtype"] == "torch.bfloat16" and d0["module"]["module"] == "Linear" and d1["x"] == {"tensor": [2, 2], "dtype": "torch.float32"}
+    s = set_random_seed(77)
+    a = torch.rand(3)
+    set_random_seed(77)
+    assert s == 77 and torch.equal(a, torch.rand(3))
+    import pytest
+
+    with pytest.raises(ValueError):
+        set_random_seed(0)
+    lin = torch.nn.Linear(3, 2, bias=False)
+    with torch.no_grad():
+        lin.weight.fill_(2.0)
+    for p in lin.parameters():
+        p.tensor_model_parallel = True
+    assert abs(calc_params_l2_norm(lin) - (6 * 4.0) ** 0.5) < 1e-6
+    assert "no CUDA device" in report_memory("x") or "allocated" in report_memory("x")
+    sentinel = tmp_path / "resume_now"
+    os.environ["MEGATRON_B200_AUTORESUME_FILE"] = str(sentinel)
+    try:
+        ar = init_autoresume()
+        assert not ar.termination_requested()
+        sentinel.write_text("1")
+        assert ar.termination_requested()
+        ar.request_resume()
+        assert not sentinel.exists()
+    finally:
+        del os.environ["MEGATRON_B200_AUTORESUME_FILE"]
+    # async queue wrapper: schedule a request, finalise it, queue is empty again
+    from megatron_b200.core.dist_checkpointing.strategies.async_utils import AsyncRequest
+
+    done = []
+    async_utils.schedule_async_save(AsyncRequest(lambda p: open(p, "w").write("x"), (str(tmp_path / "blob"),), [lambda: done.append(1)]))
+    assert not async_utils.is_empty_async_queue()
+    async_utils.maybe_finalize_async_save(blocking=True)
+    assert async_utils.is_empty_async_queue() and done == [1] and (tmp_path / "blob").read_text() == "x"
+    async_utils.reset_persistent_async_worker()
