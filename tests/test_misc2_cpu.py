@@ -140,3 +140,49 @@ def _retro(rank, world):
 
 def test_retro_chunked_cross_attention_is_causal_in_the_neighbours():
     assert run_distributed(_retro, 1) == [True]
+
+
+def _mixtral_export(rank, world):
+    import torch.nn.functional as F
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.export.hf_mixtral import hf_mixtral_to_megatron, hub_to_fused_experts_layout, megatron_to_hf_mixtral
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_decoder_block_spec
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    ps.initialize_model_parallel()
+    out = []
+    for grouped in (True, False):
+        cfg = TransformerConfig(num_layers=2, hidden_size=32, num_attention_heads=4, num_query_groups=2, ffn_hidden_size=48, use_cpu_initialization=True, normalization="RMSNorm",
+                                gated_linear_unit=True, activation_func=F.silu, add_bias_linear=False, hidden_dropout=0.0, attention_dropout=0.0, num_moe_experts=4,
+                                moe_router_topk=2, moe_grouped_gemm=grouped, moe_token_dispatcher_type="alltoall", moe_aux_loss_coeff=0.0)
+        torch.manual_seed(4)
+        m = GPTModel(cfg, get_gpt_decoder_block_spec(cfg), vocab_size=64, max_sequence_length=16, position_embedding_type="rope", share_embeddings_and_output_weights=False)
+        sd = {k: v for k, v in m.state_dict().items() if isinstance(v, torch.Tensor) and "_extra_state" not in k}
+        hf = megatron_to_hf_mixtral(sd, 4, 2, 8)
+        assert hf["model.layers.1.block_sparse_moe.experts.3.w2.weight"].shape == (32, 48) and hf["model.layers.0.block_sparse_moe.gate.weight"].shape == (4, 32)
+        back = hf_mixtral_to_megatron(hf, 4, 2, 8, grouped=grouped)
+        assert set(back) == set(sd), (set(back) ^ set(sd))
+        assert all(torch.equal(back[k], sd[k]) for k in sd)
+        # the HF-layout weights really are a Mixtral: load them into transformers' implementation and compare logits
+        import transformers
+
+        hc = transformers.MixtralConfig(vocab_size=64, hidden_size=32, intermediate_size=48, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                                        num_local_experts=4, num_experts_per_tok=2, max_position_embeddings=16, rms_norm_eps=cfg.layernorm_epsilon, rope_theta=10000.0,
+                                        tie_word_embeddings=False, attention_dropout=0.0, router_jitter_noise=0.0)
+        hm = transformers.MixtralForCausalLM(hc).eval()
+        sd_hf = hub_to_fused_experts_layout(hf) if any(k.endswith("experts.gate_up_proj") for k in hm.state_dict()) else hf
+        missing, unexpected = hm.load_state_dict(sd_hf, strict=False)
+        assert not unexpected and all("rotary" in k or "inv_freq" in k for k in missing), (missing, unexpected)
+        tok = torch.randint(0, 64, (2, 16))
+        with torch.no_grad():
+            ours = m.eval()(tok, torch.arange(16)[None].expand(2, -1), None)
+            theirs = hm(tok).logits
+        out.append((ours - theirs).abs().max().item())
+    return out
+
+
+def test_hf_mixtral_roundtrip_and_logits_match_transformers():
+    (errs,) = run_distributed(_mixtral_export, 1)
+    assert max(errs) < 2e-4, errs
