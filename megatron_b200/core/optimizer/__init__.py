@@ -61,7 +61,15 @@ def _get_megatron_optimizer_based_on_param_groups(config: OptimizerConfig, model
         g.setdefault("eps", config.adam_eps)
     lowp = config.fp16 or config.bf16
     scaler = _make_scaler(config)
-    if config.use_distributed_optimizer:
+    from .emerging_optimizers import needs_whole_matrices
+
+    dp_ws = torch.distributed.get_world_size(data_parallel_group) if (data_parallel_group is not None and torch.distributed.is_initialized()) else 1
+    if needs_whole_matrices(config.optimizer) and (config.use_distributed_optimizer or getattr(config, "use_layer_wise_distributed_optimizer", False)) and dp_ws > 1:
+        # Muon-class rules cannot run on ZeRO-1 flat ranges: distribute by parameter ownership instead
+        from .layer_wise_optimizer import LayerWiseDistributedOptimizer
+
+        return LayerWiseDistributedOptimizer(config, model_chunks, param_groups, data_parallel_group, scaler, model_parallel_group)
+    if config.use_distributed_optimizer and not needs_whole_matrices(config.optimizer):
         opt = DistributedOptimizer(param_groups, config, scaler, None, model_chunks, per_model_buffers or {}, data_parallel_group,
                                    data_parallel_group_gloo, data_parallel_group_idx, distributed_optimizer_instance_id)
     elif lowp:

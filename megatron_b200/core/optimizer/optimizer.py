@@ -151,6 +151,15 @@ class MegatronOptimizer(ABC):
         elif self.config.optimizer in ("sgd", "lion"):
             if s.momentum is None:
                 s.momentum = torch.zeros_like(s.master)
+        elif self.config.optimizer == "muon":
+            from .muon import is_muon_param
+
+            if is_muon_param(s.param, s.master):
+                if s.momentum is None:
+                    s.momentum = torch.zeros_like(s.master)
+            elif s.exp_avg is None:        # embeddings, norms, biases, heads: AdamW
+                s.exp_avg = torch.zeros_like(s.master, dtype=self.config.exp_avg_dtype)
+                s.exp_avg_sq = torch.zeros_like(s.master, dtype=self.config.exp_avg_sq_dtype)
 
     def _apply_update(self, grad_scale: Optional[torch.Tensor]):
         cfg = self.config
@@ -191,6 +200,21 @@ class MegatronOptimizer(ABC):
                     s.momentum.mul_(b2).add_(g, alpha=1 - b2)
                     if s.lowp is not None:
                         s.lowp.copy_(s.master)
+            elif cfg.optimizer == "muon":
+                from .muon import is_muon_param, muon_step
+
+                gs = float(grad_scale) if grad_scale is not None else 1.0
+                mu = [s for s in slots if is_muon_param(s.param, s.master)]
+                rest = [s for s in slots if not is_muon_param(s.param, s.master)]
+                for s in mu:
+                    muon_step(s.master, s.grad.float() * gs, s.momentum, lr=lr, weight_decay=wd, config=cfg, param=s.param)
+                    if s.lowp is not None:
+                        s.lowp.copy_(s.master)
+                if rest:
+                    b1, b2 = group.get("betas", (cfg.adam_beta1, cfg.adam_beta2))
+                    ops.fused_adam([s.master for s in rest], [s.grad for s in rest], [s.exp_avg for s in rest], [s.exp_avg_sq for s in rest], [s.lowp for s in rest],
+                                   lr=lr, beta1=b1, beta2=b2, eps=group.get("eps", cfg.adam_eps), weight_decay=wd, step=self.step_count[gi], adamw=True,
+                                   grad_scale=grad_scale)
             else:
                 raise NotImplementedError(cfg.optimizer)
 

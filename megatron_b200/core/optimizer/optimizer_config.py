@@ -31,6 +31,18 @@ class OptimizerConfig:
     adam_eps: float = 1e-08
     decoupled_weight_decay: bool = True
     sgd_momentum: float = 0.9
+    # Muon (emerging optimizers): orthogonalised momentum for 2-D weights, AdamW for everything else
+    muon_momentum: float = 0.95
+    muon_nesterov: bool = True
+    muon_ns_steps: int = 5
+    muon_scale_mode: str = "spectral"        # spectral: sqrt(max(1, out/in)) | shape: 0.2 * sqrt(max(out, in)) (match-AdamW-RMS) | none
+    muon_tp_mode: str = "blockwise"          # blockwise: orthogonalise each TP shard | duplicated: gather the full matrix over TP first
+    muon_extra_scale: float = 1.0
+    qk_clip_threshold: Optional[float] = None  # MuonClip: cap on the max attention logit (None = off)
+    qk_clip_alpha: float = 0.5
+    optimizer_cpu_offload: bool = False
+    optimizer_offload_fraction: float = 1.0
+    overlap_cpu_optimizer_d2h_h2d: bool = False
     use_distributed_optimizer: bool = False
     overlap_param_gather: bool = False
     overlap_param_gather_with_optimizer_step: bool = False

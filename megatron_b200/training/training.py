@@ -178,6 +178,7 @@ def setup_model_and_optimizer(model_provider_func: Callable):
         clip_grad=args.clip_grad, use_distributed_optimizer=args.use_distributed_optimizer, adam_beta1=args.adam_beta1, adam_beta2=args.adam_beta2,
         adam_eps=args.adam_eps, loss_scale=args.loss_scale, initial_loss_scale=args.initial_loss_scale, min_loss_scale=args.min_loss_scale,
         loss_scale_window=args.loss_scale_window, hysteresis=args.hysteresis, overlap_param_gather=args.overlap_param_gather, timers=get_timers(),
+        muon_momentum=getattr(args, "muon_momentum", 0.95), muon_ns_steps=getattr(args, "muon_ns_steps", 5), muon_tp_mode=getattr(args, "muon_tp_mode", "blockwise"),
     )
     optimizer = get_megatron_optimizer(opt_cfg, model)
     scheduler = get_optimizer_param_scheduler(optimizer)
