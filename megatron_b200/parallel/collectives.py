@@ -24,7 +24,9 @@ def enable_for_group(group, **kwargs):
 
     be = _BACKENDS.get(id(group))
     if be is None:
-        be = NVLinkBackend(group, **kwargs)
+        from .nvlink_debug import maybe_wrap
+
+        be = maybe_wrap(NVLinkBackend(group, **kwargs), group)      # MEGATRON_B200_NVL_DEBUG=1: every collective is cross-checked against NCCL
         _BACKENDS[id(group)] = be
     return be
 

@@ -201,3 +201,71 @@ def test_torch_fsdp2_adapter_matches_full_batch_training():
 
         pytest.skip(f"torch FSDP2 not usable on CPU here: {str(e)[-200:]}")
     assert max(errs) < 1e-5
+
+
+class _GlooBackend:
+    """Stand-in with the NVLinkBackend surface, implemented over gloo, with a switchable fault."""
+
+    def __init__(self, group, corrupt=None, skip_on_rank=None):
+        import torch.distributed as dist
+
+        self.group, self.corrupt, self.skip_on_rank, self.rank = group, corrupt, skip_on_rank, dist.get_rank()
+
+    def all_gather(self, x):
+        import torch.distributed as dist
+
+        out = x.new_empty((x.shape[0] * dist.get_world_size(self.group),) + tuple(x.shape[1:]))
+        dist.all_gather_into_tensor(out, x.contiguous(), group=self.group)
+        if self.corrupt == "all_gather" and self.rank == 1:
+            out.view(-1)[3] += 1e-3          # a single torn element
+        return out
+
+    def reduce_scatter(self, x, scale=1.0):
+        import torch.distributed as dist
+
+        out = x.new_empty((x.shape[0] // dist.get_world_size(self.group),) + tuple(x.shape[1:]))
+        dist.reduce_scatter_tensor(out, x.contiguous(), group=self.group)
+        if self.corrupt == "reduce_scatter":
+            out = out * 1.5
+        return out * scale
+
+    def gemm_reduce_scatter(self, x, w):
+        return self.reduce_scatter(torch.matmul(x, w.t()))
+
+    def all_gather_gemm(self, x, w):
+        return torch.matmul(self.all_gather(x), w.t())
+
+
+def _nvl_debug(rank, world):
+    import pytest
+    import torch.distributed as dist
+
+    from megatron_b200.parallel.nvlink_debug import CheckedNVLinkBackend, NVLinkProtocolError
+
+    g = dist.group.WORLD
+    torch.manual_seed(rank)
+    x, w = torch.randn(4, 8), torch.randn(6, 8)
+    ok = CheckedNVLinkBackend(_GlooBackend(g), g, sync_every=2)
+    assert ok.all_gather(x).shape == (8, 8) and ok.reduce_scatter(torch.randn(4, 8)).shape == (2, 8)
+    assert ok.all_gather_gemm(x, w).shape == (8, 6) and ok.gemm_reduce_scatter(torch.randn(4, 8), w).shape == (2, 6)
+    assert ok.checked == 4 and ok.seq == 4
+    bad = CheckedNVLinkBackend(_GlooBackend(g, corrupt="all_gather"), g)
+    if rank == 1:
+        with pytest.raises(NVLinkProtocolError, match="bitwise"):
+            bad.all_gather(x)
+    else:
+        bad.all_gather(x)
+    bad2 = CheckedNVLinkBackend(_GlooBackend(g, corrupt="reduce_scatter"), g)
+    with pytest.raises(NVLinkProtocolError, match="max error"):
+        bad2.reduce_scatter(torch.randn(4, 8) + 3)
+    # diverging operation sequences are reported instead of dead-locking in the flag protocol
+    div = CheckedNVLinkBackend(_GlooBackend(g), g, sync_every=1)
+    div._hash.update(b"rank-specific" if rank == 0 else b"other")
+    with pytest.raises(NVLinkProtocolError, match="sequence diverged"):
+        div.all_gather(x)
+    dist.barrier()
+    return True
+
+
+def test_nvlink_debug_checker_detects_corruption_and_divergence():
+    assert run_distributed(_nvl_debug, 2) == [True, True]
