@@ -196,13 +196,19 @@ def build_parser() -> argparse.ArgumentParser:
     g.add_argument("--activation-log-dir", default=None)
     g.add_argument("--exit-signal-handler", action="store_true")
     g.add_argument("--log-params-norm", action="store_true")
+    g.add_argument("--use-pytorch-profiler", action="store_true", help="torch.profiler chrome trace for iterations [--profile-step-start, --profile-step-end)")
+    g.add_argument("--pytorch-profiler-collect-shapes", action="store_true")
+    g.add_argument("--pytorch-profiler-collect-callstack", action="store_true")
+    g.add_argument("--record-memory-history", action="store_true", help="torch.cuda.memory._record_memory_history + snapshot dump at exit")
+    g.add_argument("--memory-snapshot-path", default="snapshot.pickle")
+    g.add_argument("--trace-spans", default=None, help="JSON-lines file for job/startup/train spans (core/telemetry)")
+    g.add_argument("--prometheus-port", type=int, default=None)
     g.add_argument("--log-straggler", action="store_true")
     g.add_argument("--eval-iters", type=int, default=0)
     g.add_argument("--eval-interval", type=int, default=1000)
     g.add_argument("--profile", action="store_true")
     g.add_argument("--profile-step-start", type=int, default=10)
     g.add_argument("--profile-step-end", type=int, default=12)
-    g.add_argument("--use-pytorch-profiler", action="store_true")
     g.add_argument("--error-injection-rate", type=int, default=0)
     g.add_argument("--rerun-mode", default="disabled", choices=["disabled", "validate_results", "report_stats"])
     return p

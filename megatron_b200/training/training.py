@@ -324,9 +324,21 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
         rk = dist.get_rank() if dist.is_initialized() else 0
         stat_loggers = [cls(model, out_dir, iv, rank=rk) for cls, iv in ((ActivationLogger, args.log_activations_interval), (DgradLogger, args.log_dgrad_interval),
                                                                        (WgradLogger, args.log_wgrad_interval)) if iv]
+    from ..core import telemetry
+
+    if getattr(args, "trace_spans", None):
+        telemetry.set_recorder(telemetry.SpanRecorder(path=args.trace_spans))
+    metrics = telemetry.TrainingMetrics(prometheus_port=getattr(args, "prometheus_port", None)) if getattr(args, "prometheus_port", None) else None
+    torch_prof = None
+    if getattr(args, "record_memory_history", False) and torch.cuda.is_available():
+        torch.cuda.memory._record_memory_history(max_entries=100000)
     t_start = time.time()
     t_log = time.time()
     while iteration < args.train_iters:
+        if getattr(args, "use_pytorch_profiler", False) and iteration == args.profile_step_start and torch_prof is None:
+            acts = [torch.profiler.ProfilerActivity.CPU] + ([torch.profiler.ProfilerActivity.CUDA] if torch.cuda.is_available() else [])
+            torch_prof = torch.profiler.profile(activities=acts, record_shapes=args.pytorch_profiler_collect_shapes, with_stack=args.pytorch_profiler_collect_callstack)
+            torch_prof.__enter__()
         ft_integration.on_training_step_start()
         t_iter = time.time()
         for sl in stat_loggers:
@@ -334,7 +346,7 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
         if args.profile and iteration == args.profile_step_start and torch.cuda.is_available():
             torch.cuda.cudart().cudaProfilerStart()
         update_num_microbatches(args.consumed_train_samples, consistency_check=True)
-        with straggler():
+        with straggler(), telemetry.span("train.iteration", iteration=iteration + 1):
             loss_dict, skipped, should_ckpt, should_exit, exit_code, grad_norm, _ = train_step(forward_step_func, train_data_iterator, model, optimizer, opt_param_scheduler, config)
         if should_ckpt and args.save:
             checkpointing.save_checkpoint(iteration, model, optimizer, opt_param_scheduler, args.save, vars_for_ckpt(args), args.num_floating_point_operations_so_far,
@@ -349,6 +361,15 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
             sl.end_iteration()
         if one_logger is not None:
             one_logger.track_iteration(time.time() - t_iter, get_current_global_batch_size(), args.seq_length, flops_per_iter)
+        if metrics is not None:
+            metrics.record_iteration(iteration_time_s=time.time() - t_iter, tokens=get_current_global_batch_size() * args.seq_length, flops=flops_per_iter,
+                                     world=dist.get_world_size() if dist.is_initialized() else 1, grad_norm=float(grad_norm) if grad_norm is not None else None)
+        if torch_prof is not None and iteration == args.profile_step_end:
+            torch_prof.__exit__(None, None, None)
+            out_dir = os.path.join(os.path.dirname(os.path.abspath(args.tensorboard_dir)) if args.tensorboard_dir else (args.save or "."), "torch_profile")
+            os.makedirs(out_dir, exist_ok=True)
+            torch_prof.export_chrome_trace(os.path.join(out_dir, f"rank-{dist.get_rank() if dist.is_initialized() else 0}.json.gz"))
+            torch_prof = None
         args.consumed_train_samples += get_current_global_batch_size()
         args.num_floating_point_operations_so_far += flops_per_iter
         if iteration % args.log_interval == 0:
@@ -388,6 +409,9 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
             print_rank_0(f"exiting program at iteration {iteration}")
             break
     checkpointing.maybe_finalize_async_save(blocking=True)
+    if getattr(args, "record_memory_history", False) and torch.cuda.is_available():
+        torch.cuda.memory._dump_snapshot(args.memory_snapshot_path)
+        torch.cuda.memory._record_memory_history(enabled=None)
     if one_logger is not None:
         one_logger.on_train_end()
     for w in (_GLOBALS.get("tensorboard"), _GLOBALS.get("wandb")):

@@ -299,3 +299,32 @@ def test_config_logger_initialize_helpers_and_param_norm(tmp_path):
     async_utils.maybe_finalize_async_save(blocking=True)
     assert async_utils.is_empty_async_queue() and done == [1] and (tmp_path / "blob").read_text() == "x"
     async_utils.reset_persistent_async_worker()
+
+
+def test_telemetry_spans_and_metrics(tmp_path):
+    from megatron_b200.core import telemetry
+
+    assert telemetry.span("train.iteration").__enter__() is None          # disabled: shared no-op
+    rec = telemetry.SpanRecorder(path=str(tmp_path / "spans.jsonl"), enabled_groups=["train"])
+    telemetry.set_recorder(rec)
+    try:
+        with telemetry.span("train.loop"):
+            for i in range(3):
+                with telemetry.span("train.iteration", iteration=i):
+                    with telemetry.span("layer.attention"):        # group not enabled: skipped
+                        time.sleep(0.001)
+        try:
+            with telemetry.span("train.optimizer_step"):
+                raise ValueError
+        except ValueError:
+            pass
+    finally:
+        telemetry.set_recorder(None)
+    s = rec.summary()
+    assert s["train.iteration"]["count"] == 3 and s["train.loop"]["count"] == 1 and "layer.attention" not in s
+    rows = [json.loads(l) for l in open(tmp_path / "spans.jsonl")]
+    assert [r["parent"] for r in rows if r["name"] == "train.iteration"] == ["train.loop"] * 3
+    assert [r for r in rows if r["name"] == "train.optimizer_step"][0]["error"] == "ValueError"
+    m = telemetry.TrainingMetrics()
+    m.record_iteration(iteration_time_s=0.5, tokens=1000, flops=2e12, world=2, loss=3.0, lr=1e-4)
+    assert m.values["train.tokens_per_second"] == 2000 and m.values["train.tflops_per_gpu"] == 2.0 and m.values["train.lm_loss"] == 3.0
