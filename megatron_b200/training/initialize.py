@@ -84,3 +84,35 @@ def init_autoresume(args=None) -> Optional[object]:
                 pass
 
     return _AutoResume()
+
+
+def setup_nccl_flight_recorder(dump_dir: Optional[str] = None, buffer_size: int = 2000, dump_on_timeout: bool = True) -> dict:
+    """Wire PyTorch's NCCL flight recorder for hang / desync post-mortems (reference ``initialize.py:291-333``): a ring of the last ``buffer_size`` collectives per
+    rank, dumped to ``<dump_dir>/nccl_trace_rank_<r>`` when the watchdog fires.  Must run BEFORE ``init_process_group``."""
+    env = {"TORCH_NCCL_TRACE_BUFFER_SIZE": str(buffer_size), "TORCH_NCCL_DUMP_ON_TIMEOUT": "1" if dump_on_timeout else "0", "TORCH_NCCL_ASYNC_ERROR_HANDLING": "1"}
+    if dump_dir:
+        os.makedirs(dump_dir, exist_ok=True)
+        env["TORCH_NCCL_DEBUG_INFO_TEMP_FILE"] = os.path.join(dump_dir, "nccl_trace_rank_")
+    for k, v in env.items():
+        os.environ.setdefault(k, v)
+    return env
+
+
+def update_pg_timeout(timeout_minutes: float, groups=None) -> int:
+    """Shorten / lengthen the collective timeout of live process groups (reference ``parallel_state.update_pg_timeout``): long during start-up and
+    checkpoint loading, short in steady state so a dead rank is noticed quickly.  Returns how many groups were updated."""
+    from datetime import timedelta
+
+    if not dist.is_initialized():
+        return 0
+    setter = getattr(dist.distributed_c10d, "_set_pg_timeout", None)
+    if setter is None:
+        return 0
+    n = 0
+    for g in (groups if groups is not None else [dist.group.WORLD]):
+        try:
+            setter(timedelta(minutes=timeout_minutes), g)
+            n += 1
+        except Exception:       # gloo groups have no adjustable watchdog
+            pass
+    return n

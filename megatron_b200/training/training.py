@@ -65,6 +65,10 @@ def initialize_megatron(argv=None, extra_args_provider=None, args_defaults: Opti
         if getattr(args, k, None) is None:
             setattr(args, k, v)
     _GLOBALS["args"] = args
+    if getattr(args, "nccl_flight_recorder_dir", None):
+        from .initialize import setup_nccl_flight_recorder
+
+        setup_nccl_flight_recorder(args.nccl_flight_recorder_dir)
     initialize_distributed("gloo" if (args.distributed_backend == "gloo" or not torch.cuda.is_available()) else "nccl")
     if not ps.is_initialized():
         ps.initialize_model_parallel(
@@ -389,6 +393,11 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
         if args.eval_interval and args.eval_iters and iteration % args.eval_interval == 0 and valid_data_iterator is not None:
             res = evaluate(forward_step_func, valid_data_iterator, model, args.eval_iters)
             print_rank_last(f" validation loss at iteration {iteration} | " + " | ".join(f"{k}: {v:.6E}" for k, v in res.items()))
+        iv = getattr(args, "check_weight_hash_across_dp_replicas_interval", None)
+        if iv and iteration % iv == 0:
+            from ..core.utils import check_param_hashes_across_dp_replicas
+
+            assert check_param_hashes_across_dp_replicas(model, cross_check=True), f"parameter hashes differ across data-parallel replicas at iteration {iteration}"
         if args.manual_gc and args.manual_gc_interval and iteration % args.manual_gc_interval == 0:
             gc.collect()
         checkpointing.maybe_finalize_async_save(blocking=False)
