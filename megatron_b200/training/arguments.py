@@ -203,6 +203,9 @@ def build_parser() -> argparse.ArgumentParser:
     g.add_argument("--memory-snapshot-path", default="snapshot.pickle")
     g.add_argument("--trace-spans", default=None, help="JSON-lines file for job/startup/train spans (core/telemetry)")
     g.add_argument("--prometheus-port", type=int, default=None)
+    g.add_argument("--use-checkpoint-args", action="store_true", help="take the model architecture arguments from the checkpoint in --load")
+    g.add_argument("--non-persistent-save-interval", type=int, default=None, help="local (node-storage) recovery checkpoint every N iterations")
+    g.add_argument("--non-persistent-local-ckpt-dir", default=None)
     g.add_argument("--nccl-flight-recorder-dir", default=None, help="dump the last collectives of every rank here when the NCCL watchdog fires")
     g.add_argument("--check-weight-hash-across-dp-replicas-interval", type=int, default=None)
     g.add_argument("--log-straggler", action="store_true")

@@ -182,3 +182,116 @@ def common_rng_shape_changed(ckpt: str, sd) -> bool:
     if want is None:
         return False
     return want.unique_key not in md.state_dict_metadata
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------------
+# checkpoint args → current args   (reference ``load_args_from_checkpoint`` :2199, ``check_checkpoint_args`` :176)
+# ---------------------------------------------------------------------------------------------------------------------------------------------
+_ARCH_ARGS = ("num_layers", "hidden_size", "ffn_hidden_size", "num_attention_heads", "num_query_groups", "kv_channels", "seq_length", "max_position_embeddings",
+              "position_embedding_type", "normalization", "swiglu", "untie_embeddings_and_output_weights", "add_bias_linear", "disable_bias_linear", "vocab_size",
+              "padded_vocab_size", "make_vocab_size_divisible_by", "num_experts", "moe_router_topk", "moe_ffn_hidden_size", "multi_latent_attention", "qk_layernorm",
+              "rotary_base", "rotary_percent", "tokenizer_type", "group_query_attention")
+
+
+def load_args_from_checkpoint(args, load_dir: Optional[str] = None, iteration: Optional[int] = None, force: bool = True):
+    """``--use-checkpoint-args``: take the model-architecture arguments from the checkpoint so a run (or an inference server) only needs ``--load``.
+    Returns ``(args, checkpoint_args_dict)``; parallelism, batch sizes and paths are never overwritten."""
+    load_dir = load_dir or getattr(args, "load", None)
+    if not load_dir:
+        return args, None
+    tracker = get_checkpoint_tracker_filename(load_dir)
+    if iteration is None:
+        if not os.path.isfile(tracker):
+            return args, None
+        iteration, _ = read_metadata(tracker)
+    saved = dist_checkpointing.load_common_state_dict(get_checkpoint_name(load_dir, iteration)).get("args") or {}
+    for k in _ARCH_ARGS:
+        if k in saved and saved[k] is not None and (force or getattr(args, k, None) is None):
+            setattr(args, k, saved[k])
+    return args, saved
+
+
+def check_checkpoint_args(args, saved: Dict[str, Any], keys=("num_layers", "hidden_size", "num_attention_heads", "num_query_groups", "ffn_hidden_size", "padded_vocab_size",
+                                                             "position_embedding_type", "normalization")) -> None:
+    """The architecture of a resumed run must match what was saved (parallel sizes may differ: the checkpoint is resharded on load)."""
+    bad = {k: (saved[k], getattr(args, k, None)) for k in keys if k in saved and saved[k] is not None and getattr(args, k, None) is not None and saved[k] != getattr(args, k)}
+    if bad:
+        raise ValueError("checkpoint / command-line architecture mismatch: " + ", ".join(f"{k}: checkpoint {a} vs argument {b}" for k, (a, b) in bad.items()))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------------
+# local (non-persistent) checkpoints   (reference ``CheckpointType.LOCAL`` :513, ``checkpointing.py:1834-1905``)
+# ---------------------------------------------------------------------------------------------------------------------------------------------
+def _local_name(local_dir: str, iteration: int, rank: int) -> str:
+    return os.path.join(local_dir, f"iter_{iteration:07d}", f"rank_{rank:05d}.pt")
+
+
+def save_local_checkpoint(iteration: int, model: List, optimizer, opt_param_scheduler, local_dir: str, keep_last: int = 1, replicate_to_buddy: bool = False) -> str:
+    """Fast recovery point on NODE-LOCAL storage: every rank dumps its own shards (model, optimizer, scheduler, RNG) with one ``torch.save`` — no global metadata, no
+    resharding, so it is as fast as the local disk / ramdisk and only reusable with the same parallel layout.  ``replicate_to_buddy`` also stores the blob of the
+    next rank (ring) so a replaced node can be refilled from its neighbour.  A cluster-wide MIN over the newest complete iteration decides what is loadable."""
+    rank = _rank()
+    state = {"iteration": iteration, "model": [m.state_dict() for m in model], "rng": get_rng_state().data[0] if hasattr(get_rng_state(), "data") else None,
+             "optimizer": optimizer.state_dict() if optimizer is not None and hasattr(optimizer, "state_dict") else None,
+             "opt_param_scheduler": opt_param_scheduler.state_dict() if opt_param_scheduler is not None else None,
+             "world": dist.get_world_size() if dist.is_initialized() else 1}
+    path = _local_name(local_dir, iteration, rank)
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    tmp = path + ".tmp"
+    torch.save(state, tmp)
+    os.replace(tmp, path)           # atomic: a crash mid-write never leaves a half file under the final name
+    if replicate_to_buddy and dist.is_initialized() and dist.get_world_size() > 1:
+        world = dist.get_world_size()
+        blob = [None] * world
+        dist.all_gather_object(blob, (rank, open(path, "rb").read() if os.path.getsize(path) < (1 << 30) else None))
+        src_rank, data = blob[(rank + 1) % world]
+        if data is not None:
+            with open(_local_name(local_dir, iteration, src_rank) + ".buddy", "wb") as f:
+                f.write(data)
+    with open(os.path.join(local_dir, f"latest_local_rank_{rank:05d}.txt"), "w") as f:
+        f.write(str(iteration))
+    its = sorted(int(d.split("_")[1]) for d in os.listdir(local_dir) if d.startswith("iter_"))
+    for old in its[:-keep_last] if keep_last else []:
+        shutil.rmtree(os.path.join(local_dir, f"iter_{old:07d}"), ignore_errors=True)
+    return path
+
+
+def find_latest_local_checkpoint(local_dir: str) -> int:
+    """Newest iteration that EVERY rank can load (−1 when there is none)."""
+    rank = _rank()
+    mine = -1
+    p = os.path.join(local_dir, f"latest_local_rank_{rank:05d}.txt")
+    if os.path.isfile(p):
+        it = int(open(p).read().strip())
+        if os.path.isfile(_local_name(local_dir, it, rank)) or os.path.isfile(_local_name(local_dir, it, rank) + ".buddy"):
+            mine = it
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor([mine], device="cuda" if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        mine = int(t.item())
+    return mine
+
+
+def load_local_checkpoint(model: List, optimizer, opt_param_scheduler, local_dir: str, iteration: Optional[int] = None) -> int:
+    it = find_latest_local_checkpoint(local_dir) if iteration is None else iteration
+    if it < 0:
+        return -1
+    path = _local_name(local_dir, it, _rank())
+    if not os.path.isfile(path):
+        path += ".buddy"
+    state = torch.load(path, map_location="cpu", weights_only=False)
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if state.get("world", world) != world:
+        raise RuntimeError(f"local checkpoint was written with world size {state['world']}, now {world}: use the global (resharding) checkpoint")
+    for m, sd in zip(model, state["model"]):
+        m.load_state_dict(sd)
+    if optimizer is not None and state.get("optimizer") is not None:
+        optimizer.load_state_dict(state["optimizer"])
+    if opt_param_scheduler is not None and state.get("opt_param_scheduler") is not None:
+        opt_param_scheduler.load_state_dict(state["opt_param_scheduler"])
+    if state.get("rng") is not None:
+        try:
+            set_rng_state(state["rng"])
+        except Exception:
+            pass
+    return it

@@ -401,6 +401,8 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
         if args.manual_gc and args.manual_gc_interval and iteration % args.manual_gc_interval == 0:
             gc.collect()
         checkpointing.maybe_finalize_async_save(blocking=False)
+        if getattr(args, "non_persistent_save_interval", None) and getattr(args, "non_persistent_local_ckpt_dir", None) and iteration % args.non_persistent_save_interval == 0:
+            checkpointing.save_local_checkpoint(iteration, model, optimizer, opt_param_scheduler, args.non_persistent_local_ckpt_dir, replicate_to_buddy=True)
         saved = False
         if args.save and args.save_interval and iteration % args.save_interval == 0:
             checkpointing.save_checkpoint(iteration, model, optimizer if not args.no_save_optim else None, opt_param_scheduler, args.save, vars_for_ckpt(args),

@@ -269,3 +269,63 @@ def _nvl_debug(rank, world):
 
 def test_nvlink_debug_checker_detects_corruption_and_divergence():
     assert run_distributed(_nvl_debug, 2) == [True, True]
+
+
+def _local_ckpt(rank, world, tmp):
+    import os
+
+    import torch.distributed as dist
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.training import checkpointing as ck
+
+    ps.initialize_model_parallel()
+    torch.manual_seed(rank)                      # every rank holds DIFFERENT state (as TP / PP shards would)
+    net = _Net()
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-2)
+    for _ in range(2):
+        opt.zero_grad()
+        (net(torch.randn(4, 8)) ** 2).mean().backward()
+        opt.step()
+    assert ck.find_latest_local_checkpoint(tmp) == -1
+    ck.save_local_checkpoint(5, [net], opt, None, tmp, keep_last=1, replicate_to_buddy=True)
+    ck.save_local_checkpoint(9, [net], opt, None, tmp, keep_last=1, replicate_to_buddy=True)
+    assert not os.path.exists(os.path.join(tmp, "iter_0000005")) and ck.find_latest_local_checkpoint(tmp) == 9
+    want = {k: v.clone() for k, v in net.state_dict().items()}
+    step_before = opt.state_dict()["state"][0]["step"].clone()
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(1.0)
+    dist.barrier()
+    if rank == 0:                                # this node lost its disk: refill from the copy its ring neighbour keeps
+        os.remove(os.path.join(tmp, "iter_0000009", "rank_00000.pt"))
+    dist.barrier()
+    assert ck.load_local_checkpoint([net], opt, None, tmp) == 9
+    assert all(torch.equal(v, net.state_dict()[k]) for k, v in want.items())
+    assert torch.equal(opt.state_dict()["state"][0]["step"], step_before)
+    return True
+
+
+def test_local_checkpoint_roundtrip_with_buddy_replica(tmp_path):
+    assert run_distributed(_local_ckpt, 2, str(tmp_path)) == [True, True]
+
+
+def test_load_args_from_checkpoint_and_arch_check(tmp_path):
+    from types import SimpleNamespace
+
+    import pytest
+
+    from megatron_b200.training import checkpointing as ck
+
+    d = tmp_path / "iter_0000003"
+    d.mkdir()
+    torch.save({"args": {"num_layers": 4, "hidden_size": 64, "num_attention_heads": 4, "swiglu": True, "tensor_model_parallel_size": 8, "lr": 1.0}}, d / "common.pt")
+    (tmp_path / "latest_checkpointed_iteration.txt").write_text("3")
+    args = SimpleNamespace(load=str(tmp_path), num_layers=None, hidden_size=32, tensor_model_parallel_size=2, lr=0.1, swiglu=False)
+    args, saved = ck.load_args_from_checkpoint(args)
+    assert args.num_layers == 4 and args.hidden_size == 64 and args.swiglu is True
+    assert args.tensor_model_parallel_size == 2 and args.lr == 0.1          # layout / optimisation arguments are never taken from the checkpoint
+    ck.check_checkpoint_args(args, saved)
+    args.hidden_size = 128
+    with pytest.raises(ValueError, match="hidden_size"):
+        ck.check_checkpoint_args(args, saved)
