@@ -197,3 +197,57 @@ def test_symmetric_memory_manager_fallback():
 
     with pytest.raises(MemoryError):
         m.get_buffer("big", (1 << 12,), torch.float32, device="cpu")
+
+
+def _disagg(rank, world):
+    import torch.distributed as dist
+    import torch.nn.functional as F
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.inference.disaggregation import DecodeWorker, InProcessTransport, PrefillWorker, TorchDistTransport
+    from megatron_b200.core.inference.engine import DynamicInferenceEngine, StaticInferenceEngine
+    from megatron_b200.core.inference.sampling import SamplingParams
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    ps.initialize_model_parallel()            # tp = 1: every rank holds a full replica; rank 0 = prefill pool, rank 1 = decode pool
+    torch.manual_seed(1)
+    cfg = TransformerConfig(num_layers=2, hidden_size=64, num_attention_heads=4, num_query_groups=2, ffn_hidden_size=128, gated_linear_unit=True, activation_func=F.silu,
+                            add_bias_linear=False, normalization="RMSNorm", **_KW)
+    model = GPTModel(cfg, get_gpt_layer_local_spec(normalization="RMSNorm"), vocab_size=96, max_sequence_length=128, position_embedding_type="rope")
+    prompts = [[5, 17, 3, 42, 8, 1, 2], [9, 9], [30, 31, 32, 33, 34]]
+    sp = SamplingParams(temperature=0.0, num_tokens_to_generate=8, stop_token_ids=(95,))
+    ref = StaticInferenceEngine(model, max_sequence_length=128)
+    expected = [ref.generate([p], sp)[0] for p in prompts]
+    mk = lambda: DynamicInferenceEngine(model, num_blocks=64, block_size=4, max_running=4, vocab_size=96)  # noqa: E731
+    # same process
+    pre, dec, tr = PrefillWorker(mk()), DecodeWorker(mk()), InProcessTransport()
+    for i, p in enumerate(prompts):
+        tr.send(pre.prefill(i, p, sp))
+    assert pre.engine.cache.allocator.num_free == 64           # prefill pages are handed over, not kept
+    while (pl := tr.recv()) is not None:
+        assert dec.admit(pl)
+    out = dec.run_until_done()
+    assert [out[i].generated_tokens for i in range(3)] == expected and tr.bytes_moved > 0
+    # across ranks over torch.distributed
+    t = TorchDistTransport()
+    if rank == 0:
+        w = PrefillWorker(mk())
+        for i, p in enumerate(prompts):
+            t.send(w.prefill(i, p, sp), dst=1)
+        res = None
+    else:
+        w = DecodeWorker(mk())
+        for _ in prompts:
+            assert w.admit(t.recv(src=0))
+        fin = w.run_until_done()
+        res = [fin[i].generated_tokens for i in range(3)]
+        assert res == expected
+    dist.barrier()
+    return res
+
+
+def test_prefill_decode_disaggregation_matches_single_engine():
+    res = run_distributed(_disagg, 2)
+    assert res[0] is None and res[1] is not None
