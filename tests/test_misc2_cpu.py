@@ -215,3 +215,55 @@ def test_simple_mcore_train_loop_example_tp2():
                         os.path.join(ROOT, "examples", "run_simple_mcore_train_loop.py"), "--tp", "2", "--iters", "3"], capture_output=True, text=True, timeout=600,
                        env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
     assert r.returncode == 0 and "checkpoint round trip ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def _rl_infra(rank, world):
+    import torch.nn.functional as F
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.inference.sampling import SamplingParams
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+    from megatron_b200.rl.agent import RewardOnlyAgent, Rollout, RolloutBank, WeightedMultiAgent
+    from megatron_b200.rl.inference_interface import LocalEngineInference, WeightRefitter
+
+    ps.initialize_model_parallel()
+
+    def build(seed):
+        torch.manual_seed(seed)
+        cfg = TransformerConfig(num_layers=1, hidden_size=32, num_attention_heads=2, ffn_hidden_size=64, gated_linear_unit=True, activation_func=F.silu, add_bias_linear=False,
+                                normalization="RMSNorm", use_cpu_initialization=True, hidden_dropout=0.0, attention_dropout=0.0)
+        return GPTModel(cfg, get_gpt_layer_local_spec(normalization="RMSNorm"), vocab_size=32, max_sequence_length=64, position_embedding_type="rope")
+
+    policy, gen_model = build(1), build(2)
+    even = RewardOnlyAgent(lambda n: [[1, 2, 3]] * n, lambda p, c: float(sum(t % 2 == 0 for t in c)))
+    odd = RewardOnlyAgent(lambda n: [[4, 5]] * n, lambda p, c: float(sum(t % 2 == 1 for t in c)))
+    agent = WeightedMultiAgent([even, odd], [0.5, 0.5], seed=3)
+    sp = SamplingParams(temperature=1.0, num_tokens_to_generate=5, seed=0)
+    for dynamic in (False, True):
+        inf = LocalEngineInference(gen_model, vocab_size=32, dynamic=dynamic, num_blocks=64, block_size=4) if dynamic else LocalEngineInference(gen_model, vocab_size=32)
+        inf.set_policy_version(7)
+        groups = agent.rollout_groups(inf, n_prompts=3, group_size=4, sampling=sp)
+        assert len(groups) == 3 and all(len(g) == 4 for g in groups)
+        for g in groups:
+            for r in g:
+                assert len(r.completion) == 5 and r.policy_version == 7
+                want = sum(t % 2 == (0 if r.prompt == [1, 2, 3] else 1) for t in r.completion)
+                assert r.reward == float(want)
+        assert gen_model.training       # generation restores the mode
+    # refit: generation model takes the policy's weights
+    rf = WeightRefitter(policy, gen_model)
+    assert rf.refit() == 1 and all(torch.equal(a, b) for a, b in zip(policy.parameters(), gen_model.parameters()))
+    # bank: staleness and uninformative groups
+    bank = RolloutBank(max_staleness=1)
+    mk = lambda v, rewards: [Rollout([1], [2], r, v) for r in rewards]  # noqa: E731
+    bank.add([mk(3, [0, 1]), mk(5, [1, 1]), mk(5, [0, 2]), mk(6, [3, 1]), mk(6, [0, 1])])
+    got = bank.sample(2, current_version=6)
+    assert [min(r.policy_version for r in g) for g in got] == [5, 6] and bank.dropped_stale == 1           # version 3 is too old
+    assert len(bank) == 2                                                                                  # the all-equal group and the unused fresh one stay
+    return True
+
+
+def test_rl_agents_inference_interface_refit_and_rollout_bank():
+    assert run_distributed(_rl_infra, 1) == [True]
