@@ -267,3 +267,66 @@ def _rl_infra(rank, world):
 
 def test_rl_agents_inference_interface_refit_and_rollout_bank():
     assert run_distributed(_rl_infra, 1) == [True]
+
+
+def _elastic(rank, world):
+    import torch.nn.functional as F
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+    from megatron_b200.elastification import BudgetSampler, ElasticBudget, ElasticController, distillation_step, extract_mlp_subnetwork
+
+    ps.initialize_model_parallel()
+    torch.manual_seed(2)
+    cfg = TransformerConfig(num_layers=3, hidden_size=32, num_attention_heads=4, ffn_hidden_size=64, gated_linear_unit=True, activation_func=F.silu, add_bias_linear=False,
+                            normalization="RMSNorm", use_cpu_initialization=True, hidden_dropout=0.0, attention_dropout=0.0)
+    m = GPTModel(cfg, get_gpt_layer_local_spec(normalization="RMSNorm"), vocab_size=48, max_sequence_length=16, position_embedding_type="rope")
+    tok = torch.randint(0, 48, (2, 16))
+    pos = torch.arange(16)[None].expand(2, -1)
+    fwd = lambda mod, b: mod(b, pos, None)  # noqa: E731
+    base = fwd(m, tok).detach()
+    ctl = ElasticController(m)
+    assert torch.equal(fwd(m, tok), base)                                   # full budget = the original model, bit for bit
+    ctl.calibrate([tok, torch.randint(0, 48, (2, 16))], fwd)
+    assert sorted(m.decoder.layers[0].elastic_ffn_rank.tolist()) == list(range(64)) and sorted(ctl.layer_rank.tolist()) == [0, 1, 2]
+    assert torch.equal(fwd(m, tok), base)                                   # ranking alone changes nothing
+    # nestedness: the half-width network's active units are a subset of the three-quarter one's
+    r = m.decoder.layers[1].elastic_ffn_rank
+    assert set(torch.nonzero(r < 32).flatten().tolist()) <= set(torch.nonzero(r < 48).flatten().tolist())
+    ctl.set_budget(ElasticBudget(ffn_fraction=0.5, head_fraction=0.5))
+    half = fwd(m, tok).detach()
+    assert not torch.allclose(half, base) and 0.45 < ctl.active_parameter_fraction() < 0.55
+    # the masked MLP equals a physically sliced one
+    L = m.decoder.layers[0]
+    sub = extract_mlp_subnetwork(L, 0.5)
+    assert sub["linear_fc1.weight"].shape == (64, 32) and sub["linear_fc2.weight"].shape == (32, 32)
+    x = torch.randn(5, 2, 32)
+    masked, _ = L.mlp(x)
+    g, u = (x @ sub["linear_fc1.weight"].t()).chunk(2, -1)
+    assert torch.allclose(masked, (F.silu(g) * u) @ sub["linear_fc2.weight"].t(), atol=1e-5)
+    # importance ordering is useful: keeping the top half hurts less than keeping the bottom half
+    err_top = (half - base).pow(2).mean()
+    for Lx in m.decoder.layers:
+        Lx.elastic_ffn_rank.copy_(63 - Lx.elastic_ffn_rank)
+        Lx.elastic_head_rank.copy_(3 - Lx.elastic_head_rank)
+    err_bottom = (fwd(m, tok).detach() - base).pow(2).mean()
+    for Lx in m.decoder.layers:
+        Lx.elastic_ffn_rank.copy_(63 - Lx.elastic_ffn_rank)
+        Lx.elastic_head_rank.copy_(3 - Lx.elastic_head_rank)
+    assert err_top < err_bottom
+    # layer dropping and one sandwich-rule distillation step
+    ctl.set_budget(ElasticBudget(layer_fraction=2 / 3))
+    assert not torch.allclose(fwd(m, tok), base)
+    loss = distillation_step(ctl, BudgetSampler(ffn=(0.5, 1.0), heads=(0.5, 1.0), n_random=1), tok, fwd,
+                             lambda lg, b: F.cross_entropy(lg.reshape(-1, lg.shape[-1]).float(), b.reshape(-1)))
+    loss.backward()
+    assert all(p.grad is not None for p in m.parameters())
+    ctl.remove()
+    assert torch.equal(fwd(m, tok), base)
+    return True
+
+
+def test_elastic_nested_subnetworks():
+    assert run_distributed(_elastic, 1) == [True]
