@@ -17,8 +17,10 @@ def is_nvfp4tensor(t) -> bool:
     return isinstance(t, tuple) and len(t) == 3 and getattr(t[0], "dtype", None) == torch.uint8
 
 
-def quantize_nvfp4(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """x [..., K] (K % 16 == 0) → (codes uint8 [..., K] sign<<3|index, block scales fp8-e4m3 [..., K/16], tensor scale fp32)."""
+def quantize_nvfp4(x: torch.Tensor, stochastic: bool = False, generator=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """x [..., K] (K % 16 == 0) → (codes uint8 [..., K] sign<<3|index, block scales fp8-e4m3 [..., K/16], tensor scale fp32).
+    ``stochastic``: round each magnitude up or down to the neighbouring grid points with probability proportional to proximity — unbiased
+    (E[q] = x), which is what gradients need at 4 bits (nearest rounding systematically loses the small components)."""
     assert x.shape[-1] % BLOCK == 0
     xf = x.float()
     tscale = xf.abs().amax().clamp(min=1e-12) / (6.0 * 448.0)
@@ -26,7 +28,16 @@ def quantize_nvfp4(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.T
     bscale = (xb.abs().amax(-1, keepdim=True) / 6.0).clamp(min=2.0**-9).to(torch.float8_e4m3fn)
     y = xb / bscale.float()
     grid = _E2M1.to(x.device)
-    idx = (y.abs().unsqueeze(-1) - grid).abs().argmin(-1)
+    if stochastic:
+        a = y.abs().clamp(max=6.0)
+        hi = torch.searchsorted(grid, a.contiguous(), right=False).clamp(1, 7)         # first grid point >= a
+        lo = hi - 1
+        g_lo, g_hi = grid[lo], grid[hi]
+        p_hi = ((a - g_lo) / (g_hi - g_lo)).clamp(0, 1)
+        u = torch.rand(a.shape, device=a.device, generator=generator)
+        idx = torch.where(u < p_hi, hi, lo)
+    else:
+        idx = (y.abs().unsqueeze(-1) - grid).abs().argmin(-1)
     codes = (idx | ((y < 0).to(torch.int64) << 3)).to(torch.uint8)
     return codes.view(x.shape), bscale.squeeze(-1), tscale
 
@@ -48,3 +59,16 @@ def nvfp4_linear(x: torch.Tensor, qweight, quantize_activation: bool = True) -> 
         out = ops.gemm_nvfp4_nt(*ops.nvfp4_quantize(x2), *qweight)
         return out.to(x.dtype).view(*x.shape[:-1], out.shape[-1])
     return torch.nn.functional.linear(x, dequantize_nvfp4(*qweight, dtype=x.dtype))
+
+
+def hadamard16(x: torch.Tensor) -> torch.Tensor:
+    """Orthonormal 16-point Walsh-Hadamard transform on consecutive groups of 16 along the last dim (its own inverse).  Applied to BOTH operands of a
+    GEMM along the reduction dimension it leaves the product unchanged (Hᵀ H = I) while spreading outliers over the 16-element scaling block."""
+    shp = x.shape
+    y = x.float().reshape(-1, 16)
+    h = 1
+    while h < 16:
+        y = y.view(-1, 16 // (2 * h), 2, h)
+        y = torch.stack([y[:, :, 0] + y[:, :, 1], y[:, :, 0] - y[:, :, 1]], dim=2).reshape(-1, 16)
+        h *= 2
+    return (y * 0.25).view(shp).to(x.dtype)

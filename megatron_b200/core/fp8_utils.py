@@ -140,32 +140,55 @@ def _nvf4_gemm_nt(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return ops.gemm_nvfp4_nt(*ops.nvfp4_quantize(a), *ops.nvfp4_quantize(b))
 
 
+def _nvf4_gemm_nt_sr(a: torch.Tensor, b: torch.Tensor, a_stochastic: bool, rht: bool) -> torch.Tensor:
+    """NVFP4 GEMM for the backward pass: optional random-Hadamard-free deterministic 16-point Hadamard on the reduction dim of both operands (``rht``) and
+    stochastic rounding of the gradient operand ``a``."""
+    from .. import ops
+    from .fp4_utils import hadamard16, quantize_nvfp4
+
+    K = a.shape[1]
+    pad = (-K) % 256
+    if pad:
+        a, b = torch.nn.functional.pad(a, (0, pad)), torch.nn.functional.pad(b, (0, pad))
+    if rht:
+        a, b = hadamard16(a), hadamard16(b)
+    qa = quantize_nvfp4(a, stochastic=True) if a_stochastic else ops.nvfp4_quantize(a)
+    if a_stochastic:
+        qa = (ops.nvfp4_pack(qa[0]), qa[1], qa[2].reshape(1))
+    return ops.gemm_nvfp4_nt(*qa, *ops.nvfp4_quantize(b))
+
+
 class _Nvfp4LinearFn(torch.autograd.Function):
-    """NVFP4 recipe (reference ``fp4_recipe="nvfp4"``): forward GEMM in 4-bit; the gradient GEMMs stay in MXFP8 — 4-bit gradients need stochastic rounding and
-    random Hadamard rotations to train stably, which this round does not implement, so the backward takes the next-cheapest exact-enough format."""
+    """NVFP4 recipe (reference ``fp4_recipe="nvfp4"``).  Forward GEMM in 4 bits (nearest rounding).  ``full_fp4`` runs dgrad and wgrad in 4 bits as well, with
+    the two ingredients that make 4-bit gradients trainable: stochastic rounding of the gradient operand (unbiased) and a 16-point Hadamard rotation along
+    the reduction dimension of the wgrad GEMM (outlier spreading; cancels in the product).  Without ``full_fp4`` the backward GEMMs use MXFP8."""
 
     @staticmethod
-    def forward(ctx, x, w):
+    def forward(ctx, x, w, full_fp4):
         x2 = x.reshape(-1, x.shape[-1])
         ctx.save_for_backward(x2, w)
-        ctx.x_shape = x.shape
+        ctx.x_shape, ctx.full_fp4 = x.shape, full_fp4
         return _nvf4_gemm_nt(x2, w).to(x.dtype).view(*x.shape[:-1], w.shape[0])
 
     @staticmethod
     def backward(ctx, gy):
         x2, w = ctx.saved_tensors
         g2 = gy.reshape(-1, gy.shape[-1])
-        gx = _mx_gemm_nt(g2, w.t().contiguous()).to(x2.dtype).view(ctx.x_shape)
-        gw = _mx_gemm_nt(g2.t().contiguous(), x2.t().contiguous()).to(w.dtype)
-        return gx, gw
+        if ctx.full_fp4:
+            gx = _nvf4_gemm_nt_sr(g2, w.t().contiguous(), a_stochastic=True, rht=False).to(x2.dtype).view(ctx.x_shape)
+            gw = _nvf4_gemm_nt_sr(g2.t().contiguous(), x2.t().contiguous(), a_stochastic=True, rht=True).to(w.dtype)
+        else:
+            gx = _mx_gemm_nt(g2, w.t().contiguous()).to(x2.dtype).view(ctx.x_shape)
+            gw = _mx_gemm_nt(g2.t().contiguous(), x2.t().contiguous()).to(w.dtype)
+        return gx, gw, None
 
 
 def fp8_linear(x: torch.Tensor, w: torch.Tensor, recipe: str = "tensorwise", fp8_format: str = "hybrid", metas=None) -> torch.Tensor:
     """``x [..., K] @ w [N, K]ᵀ`` with FP8 operands for all three GEMMs of the layer.  ``recipe``: ``tensorwise`` | ``delayed`` | ``mxfp8`` | ``nvfp4`` (4-bit forward, MXFP8 backward)."""
     if recipe == "mxfp8":
         return _Mxfp8LinearFn.apply(x, w)
-    if recipe == "nvfp4":
-        return _Nvfp4LinearFn.apply(x, w)
+    if recipe in ("nvfp4", "nvfp4_full"):
+        return _Nvfp4LinearFn.apply(x, w, recipe == "nvfp4_full")
     grad_dtype = E5M2 if fp8_format == "hybrid" else E4M3
     if recipe == "delayed" and metas is None:
         raise ValueError("delayed scaling needs (input, weight, grad) Fp8Meta objects")

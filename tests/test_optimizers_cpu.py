@@ -329,3 +329,19 @@ def test_load_args_from_checkpoint_and_arch_check(tmp_path):
     args.hidden_size = 128
     with pytest.raises(ValueError, match="hidden_size"):
         ck.check_checkpoint_args(args, saved)
+
+
+def test_nvfp4_stochastic_rounding_is_unbiased_and_hadamard_cancels():
+    from megatron_b200.core.fp4_utils import dequantize_nvfp4, hadamard16, quantize_nvfp4
+
+    torch.manual_seed(0)
+    x = torch.randn(64, 256)
+    assert torch.allclose(hadamard16(hadamard16(x)), x, atol=1e-5)
+    a, b = torch.randn(8, 64), torch.randn(5, 64)
+    assert torch.allclose(hadamard16(a) @ hadamard16(b).t(), a @ b.t(), atol=1e-4)
+    g = torch.Generator().manual_seed(1)
+    avg = sum(dequantize_nvfp4(*quantize_nvfp4(x, stochastic=True, generator=g), torch.float32) for _ in range(100)) / 100
+    nearest = dequantize_nvfp4(*quantize_nvfp4(x), torch.float32)
+    assert (avg - x).abs().mean() < 0.25 * (nearest - x).abs().mean()          # the stochastic estimate converges to x, nearest rounding does not
+    codes, _, _ = quantize_nvfp4(x, stochastic=True, generator=g)
+    assert codes.max() <= 15 and set((codes & 7).unique().tolist()) <= set(range(8))

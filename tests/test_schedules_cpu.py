@@ -210,12 +210,12 @@ def _fp8_worker(rank, world, recipe):
         assert all(p.grad is not None for p in m.parameters())
         losses.append((l.item(), gn.item()))
     (l0, g0), (l1, g1) = losses
-    assert abs(l0 - l1) / l0 < (0.05 if recipe == "nvfp4" else 0.02) and abs(g0 - g1) / g0 < (0.3 if recipe == "nvfp4" else 0.15), losses        # quantised GEMMs perturb, they do not break, the step
+    assert abs(l0 - l1) / l0 < (0.05 if recipe.startswith("nvfp4") else 0.02) and abs(g0 - g1) / g0 < (0.5 if recipe == "nvfp4_full" else 0.3 if recipe == "nvfp4" else 0.15), losses        # quantised GEMMs perturb, they do not break, the step
     assert l0 != l1                                                              # ... and they really ran
     return True
 
 
-@pytest.mark.parametrize("recipe,world", [("tensorwise", 1), ("mxfp8", 1), ("mxfp8", 2), ("nvfp4", 1)])
+@pytest.mark.parametrize("recipe,world", [("tensorwise", 1), ("mxfp8", 1), ("mxfp8", 2), ("nvfp4", 1), ("nvfp4_full", 1)])
 def test_fp8_recipes_wired_into_tp_linears(recipe, world):
     assert run_distributed(_fp8_worker, world, recipe) == [True] * world
 
