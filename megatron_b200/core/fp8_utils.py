@@ -109,6 +109,48 @@ def _mx_gemm_nt(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return ops.gemm_mxfp8_nt(aq, asf, bq, bsf)
 
 
+class _Mxfp8SPColumnFn(torch.autograd.Function):
+    """Sequence-parallel column linear with the MXFP8 recipe and a QUANTISED all-gather: the activation shard is quantised row-wise before it goes on the
+    wire (1.03 bytes/element instead of 2) and the gathered payload feeds the block-scaled GEMM as is.  Backward re-gathers in bf16 (the wgrad GEMM
+    reduces over tokens and needs column-wise blocks) and reduce-scatters dgrad, like the bf16 path."""
+
+    @staticmethod
+    def forward(ctx, x, w, group):
+        from .. import ops
+        from ..parallel.quantized_collectives import all_gather_mxfp8
+
+        s_local = x.shape[0]
+        x2 = x.reshape(-1, x.shape[-1])                               # [s/tp · b, K] — rows of one rank are contiguous in the gathered [s · b, K]
+        K = x2.shape[1]
+        assert K % 128 == 0, "quantised all-gather needs hidden % 128 == 0"
+        xq, xsf = all_gather_mxfp8(x2, group)
+        wq, wsf = ops.mxfp8_quantize(w.to(torch.bfloat16))
+        y = ops.gemm_mxfp8_nt(xq, xsf, wq, wsf)
+        ctx.save_for_backward(x, w)
+        ctx.group = group
+        ws = xq.shape[0] // x2.shape[0]
+        return y.to(x.dtype).view(s_local * ws, *x.shape[1:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        import torch.distributed as dist
+
+        x, w = ctx.saved_tensors
+        ws = dist.get_world_size(ctx.group)
+        full = x.new_empty((x.shape[0] * ws,) + tuple(x.shape[1:]))
+        dist.all_gather_into_tensor(full, x.contiguous(), group=ctx.group)
+        g2 = gy.reshape(-1, gy.shape[-1])
+        gx_full = _mx_gemm_nt(g2, w.t().contiguous()).to(x.dtype).view(full.shape)
+        gx = x.new_empty(x.shape)
+        dist.reduce_scatter_tensor(gx, gx_full.contiguous(), group=ctx.group)
+        gw = _mx_gemm_nt(g2.t().contiguous(), full.reshape(-1, full.shape[-1]).t().contiguous()).to(w.dtype)
+        return gx, gw, None
+
+
+def mxfp8_sp_column_linear(x: torch.Tensor, w: torch.Tensor, group) -> torch.Tensor:
+    return _Mxfp8SPColumnFn.apply(x, w, group)
+
+
 class _Mxfp8LinearFn(torch.autograd.Function):
     """MXFP8 recipe (reference ``fp8_recipe="mxfp8"``): every GEMM operand is quantised along ITS reduction dimension, so the backward GEMMs
     re-quantise transposed copies (row-wise for fprop, column-wise for dgrad / wgrad) — the data flow of TE's MXFP8 tensors with both usages."""

@@ -362,9 +362,15 @@ class ColumnParallelLinear(torch.nn.Module):
             # FP8 / MXFP8 recipe: collectives through the autograd mappings, the three GEMMs of the layer through core.fp8_utils.fp8_linear
             from ..fp8_utils import fp8_linear
 
-            xg = gather_from_sequence_parallel_region(x, tensor_parallel_output_grad=True, group=self.tp_group) if self.sequence_parallel else (
-                copy_to_tensor_model_parallel_region(x, group=self.tp_group) if self.allreduce_dgrad else x)
-            out_parallel = fp8_linear(xg, weight, recipe=_fp8_recipe(self.config), fp8_format=self.config.fp8)
+            if self.sequence_parallel and _fp8_recipe(self.config) == "mxfp8" and getattr(self.config, "fp8_quantized_all_gather", True) and x.shape[-1] % 128 == 0 \
+                    and get_pg_size(self.tp_group) > 1:
+                from ..fp8_utils import mxfp8_sp_column_linear
+
+                out_parallel = mxfp8_sp_column_linear(x, weight, self.tp_group)        # activation shard goes on the wire as MXFP8 (half the bytes)
+            else:
+                xg = gather_from_sequence_parallel_region(x, tensor_parallel_output_grad=True, group=self.tp_group) if self.sequence_parallel else (
+                    copy_to_tensor_model_parallel_region(x, group=self.tp_group) if self.allreduce_dgrad else x)
+                out_parallel = fp8_linear(xg, weight, recipe=_fp8_recipe(self.config), fp8_format=self.config.fp8)
             if bias is not None:
                 out_parallel = out_parallel + bias
             gather = self.gather_output if runtime_gather_output is None else runtime_gather_output

@@ -345,3 +345,45 @@ def test_nvfp4_stochastic_rounding_is_unbiased_and_hadamard_cancels():
     assert (avg - x).abs().mean() < 0.25 * (nearest - x).abs().mean()          # the stochastic estimate converges to x, nearest rounding does not
     codes, _, _ = quantize_nvfp4(x, stochastic=True, generator=g)
     assert codes.max() <= 15 and set((codes & 7).unique().tolist()) <= set(range(8))
+
+
+def _qag(rank, world):
+    import torch.distributed as dist
+
+    from megatron_b200 import ops
+    from megatron_b200.core.fp8_utils import fp8_linear, mxfp8_sp_column_linear
+    from megatron_b200.parallel.quantized_collectives import all_gather_dequantized, all_gather_mxfp8, wire_bytes
+
+    g = dist.group.WORLD
+    torch.manual_seed(rank)
+    x = torch.randn(6, 128) * (rank + 1)
+    q, sf = all_gather_mxfp8(x, g)
+    full = torch.empty(6 * world, 128)
+    dist.all_gather_into_tensor(full, x)
+    q_ref, sf_ref = ops.mxfp8_quantize(full.bfloat16())
+    assert torch.equal(q, q_ref) and torch.equal(sf, sf_ref)                 # quantise-then-gather == gather-then-quantise, bit for bit
+    d = all_gather_dequantized(x.view(3, 2, 128), g)
+    assert d.shape == (3 * world, 2, 128) and ((d.reshape(-1, 128).float() - full).norm() / full.norm()) < 0.05
+    assert wire_bytes(1 << 20, True) / wire_bytes(1 << 20, False) < 0.52
+    # sequence-parallel column linear on the quantised gather == MXFP8 linear on the bf16-gathered input
+    torch.manual_seed(7)
+    w = (torch.randn(40, 128) * 0.1).requires_grad_()
+    xs = torch.randn(4, 2, 128, requires_grad=True)                          # [s/tp, b, h]
+    y = mxfp8_sp_column_linear(xs, w, g)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xs2, w2 = xs.detach().clone().requires_grad_(), w.detach().clone().requires_grad_()
+    fullx = torch.empty(4 * world, 2, 128)
+    dist.all_gather_into_tensor(fullx, xs2.detach())
+    fullx.requires_grad_()
+    y2 = fp8_linear(fullx, w2, recipe="mxfp8")
+    y2.backward(gy)
+    assert torch.allclose(y, y2, atol=1e-6)
+    gx_ref = torch.empty_like(xs)
+    dist.reduce_scatter_tensor(gx_ref, fullx.grad.contiguous())
+    assert torch.allclose(xs.grad, gx_ref, atol=1e-5) and torch.allclose(w.grad, w2.grad, atol=1e-5)
+    return True
+
+
+def test_quantised_all_gather_commutes_and_feeds_the_block_scaled_gemm():
+    assert run_distributed(_qag, 2) == [True, True]
