@@ -330,3 +330,45 @@ def _elastic(rank, world):
 
 def test_elastic_nested_subnetworks():
     assert run_distributed(_elastic, 1) == [True]
+
+
+def _ptq(rank, world):
+    import torch.nn.functional as F
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+    from megatron_b200.post_training.quantize import PTQConfig, calibrate, export_quantized_state_dict, quantize_model
+
+    ps.initialize_model_parallel()
+    tok = torch.randint(0, 64, (2, 16))
+    pos = torch.arange(16)[None].expand(2, -1)
+    fwd = lambda m, b: m(b, pos, None)  # noqa: E731
+    errs = {}
+    for fmt in ("fp8", "mxfp8", "nvfp4", "w4a16"):
+        torch.manual_seed(3)
+        cfg = TransformerConfig(num_layers=2, hidden_size=256, num_attention_heads=4, ffn_hidden_size=512, gated_linear_unit=True, activation_func=F.silu, add_bias_linear=False,
+                                normalization="RMSNorm", use_cpu_initialization=True, hidden_dropout=0.0, attention_dropout=0.0)
+        m = GPTModel(cfg, get_gpt_layer_local_spec(normalization="RMSNorm"), vocab_size=64, max_sequence_length=16, position_embedding_type="rope").eval()
+        with torch.no_grad():
+            base = fwd(m, tok)
+        pcfg = PTQConfig(default=fmt, matchers=[("*output_layer*", "none"), ("decoder.layers.0.self_attention.linear_qkv", "none")])
+        amax = calibrate(m, [tok], fwd, pcfg)
+        assert "decoder.layers.1.mlp.linear_fc1" in amax and "output_layer" not in amax
+        before = sum(p.numel() * p.element_size() for p in m.parameters())
+        states = quantize_model(m, pcfg, amax)
+        assert len(states) == 7 and "decoder.layers.0.self_attention.linear_qkv" not in states            # 2 x (qkv, proj, fc1, fc2) minus the excluded qkv
+        after = sum(p.numel() * p.element_size() for p in m.parameters()) + sum(s.nbytes() for s in states.values())
+        assert after < before * (0.62 if fmt in ("fp8", "mxfp8") else 0.5)
+        with torch.no_grad():
+            q = fwd(m, tok)
+        errs[fmt] = ((q - base).norm() / base.norm()).item()
+        sd = export_quantized_state_dict(m, states)
+        assert "decoder.layers.1.mlp.linear_fc2.weight_q" in sd and "decoder.layers.1.mlp.linear_fc2.weight" not in sd and "output_layer.weight" in sd
+    assert errs["fp8"] < 0.08 and errs["mxfp8"] < 0.08 and errs["w4a16"] < 0.25 and errs["nvfp4"] < 0.35 and errs["w4a16"] <= errs["nvfp4"] + 1e-6, errs
+    return True
+
+
+def test_post_training_quantisation_formats():
+    assert run_distributed(_ptq, 1) == [True]
