@@ -16,10 +16,33 @@ from .optimizer_config import OptimizerConfig
 logger = logging.getLogger(__name__)
 
 
+def _match_override(name: str, p, overrides):
+    """``overrides``: ``{pattern | callable(name, param) | ParamKey-like with .name / .attr: {"lr_mult"|"max_lr"|"min_lr"|"wd_mult"|"weight_decay"|...: value}}`` — first match wins
+    (reference ``get_megatron_optimizer(config_overrides=...)``: per-parameter optimizer settings keyed by name globs / attributes)."""
+    import fnmatch
+
+    for key, ov in (overrides or {}).items():
+        if callable(key):
+            hit = key(name, p)
+        elif isinstance(key, str):
+            hit = fnmatch.fnmatch(name, key)
+        else:
+            names = getattr(key, "name", None) or ()
+            attrs = getattr(key, "attr", None) or ()
+            names = (names,) if isinstance(names, str) else names
+            attrs = (attrs,) if isinstance(attrs, str) else attrs
+            hit = any(fnmatch.fnmatch(name, n) for n in names) or any(getattr(p, a, False) for a in attrs)
+        if hit:
+            return tuple(sorted(ov.items()))
+    return ()
+
+
 def _get_param_groups(model_chunks: List, no_weight_decay_cond: Optional[Callable], scale_lr_cond: Optional[Callable], lr_mult: float,
-                      lr: float, min_lr: float, decoupled_lr: Optional[float], decoupled_min_lr: Optional[float], default_wd: float = 0.01) -> List[Dict]:
-    """Bucket params by (wd_mult, lr_mult, is_expert_parallel, is_decoupled_lr).
-    Default rule: biases and 1-D tensors (norm gains) get no weight decay."""
+                      lr: float, min_lr: float, decoupled_lr: Optional[float], decoupled_min_lr: Optional[float], default_wd: float = 0.01,
+                      config_overrides=None, mup_width_mult: Optional[float] = None) -> List[Dict]:
+    """Bucket params by (wd_mult, lr_mult, is_expert_parallel, is_decoupled_lr, overrides).
+    Default rule: biases and 1-D tensors (norm gains) get no weight decay.  ``mup_width_mult`` (= hidden / base hidden) applies the µP Adam rule: matrix-like
+    hidden weights train with ``lr / width_mult``, vector-like parameters (embeddings, norms, biases) keep the base learning rate."""
     use_decoupled = decoupled_lr is not None
     buckets: Dict[Tuple, List] = {}
     for chunk in model_chunks:
@@ -35,12 +58,19 @@ def _get_param_groups(model_chunks: List, no_weight_decay_cond: Optional[Callabl
             wd_mult = 0.0 if no_wd else 1.0
             lm = lr_mult if scale_lr else 1.0
             dec = use_decoupled and getattr(p, "is_embedding_or_output_parameter", False)
-            buckets.setdefault((wd_mult, lm, is_expert, dec), []).append(p)
+            if mup_width_mult and mup_width_mult != 1.0 and p.dim() >= 2 and not getattr(p, "is_embedding_or_output_parameter", False) and "embedding" not in name:
+                lm = lm / mup_width_mult
+            ov = _match_override(name, p, config_overrides)
+            buckets.setdefault((wd_mult, lm, is_expert, dec, ov), []).append(p)
     groups = []
-    for (wd_mult, lm, is_expert, dec), params in buckets.items():
+    for (wd_mult, lm, is_expert, dec, ov), params in buckets.items():
+        ovd = dict(ov)
+        wd_mult, lm = ovd.pop("wd_mult", wd_mult), ovd.pop("lr_mult", lm)
+        max_lr = ovd.pop("max_lr", decoupled_lr if dec else lr)
         g = dict(params=params, wd_mult=wd_mult, lr_mult=lm, is_expert_parallel=is_expert, is_decoupled_lr=dec,
-                 max_lr=(decoupled_lr if dec else lr), min_lr=(decoupled_min_lr if dec and decoupled_min_lr is not None else min_lr),
-                 lr=(decoupled_lr if dec else lr) * lm if lr is not None else None, weight_decay=default_wd * wd_mult)
+                 max_lr=max_lr, min_lr=ovd.pop("min_lr", decoupled_min_lr if dec and decoupled_min_lr is not None else min_lr),
+                 lr=max_lr * lm if max_lr is not None else None, weight_decay=ovd.pop("weight_decay", default_wd * wd_mult))
+        g.update(ovd)            # anything else (betas, eps, ...) goes straight into the group
         groups.append(g)
     return groups
 
@@ -88,8 +118,12 @@ def get_megatron_optimizer(config: OptimizerConfig, model_chunks: List, no_weigh
                            use_gloo_process_groups: bool = True, pg_collection=None, dump_param_to_param_group_map=None) -> MegatronOptimizer:
     """Dense and expert-parallel parameters get separate optimizers (their data-parallel
     groups differ) chained into one."""
+    mup = None
+    if getattr(config, "use_mup", False) and getattr(config, "mup_base_hidden_size", None):
+        mc = get_model_config(model_chunks[0])
+        mup = mc.hidden_size / config.mup_base_hidden_size
     groups = _get_param_groups(model_chunks, no_weight_decay_cond, scale_lr_cond, lr_mult, config.lr, config.min_lr,
-                               config.decoupled_lr, config.decoupled_min_lr, config.weight_decay)
+                               config.decoupled_lr, config.decoupled_min_lr, config.weight_decay, config_overrides=config_overrides, mup_width_mult=mup)
     dense = [g for g in groups if not g["is_expert_parallel"]]
     expert = [g for g in groups if g["is_expert_parallel"]]
     init = ps.is_initialized()

@@ -40,6 +40,8 @@ class OptimizerConfig:
     muon_extra_scale: float = 1.0
     qk_clip_threshold: Optional[float] = None  # MuonClip: cap on the max attention logit (None = off)
     qk_clip_alpha: float = 0.5
+    use_mup: bool = False                      # maximal-update parametrisation: hidden-matrix lr scaled by base_hidden / hidden
+    mup_base_hidden_size: Optional[int] = None
     optimizer_cpu_offload: bool = False
     optimizer_offload_fraction: float = 1.0
     overlap_cpu_optimizer_d2h_h2d: bool = False

@@ -387,3 +387,27 @@ def _qag(rank, world):
 
 def test_quantised_all_gather_commutes_and_feeds_the_block_scaled_gemm():
     assert run_distributed(_qag, 2) == [True, True]
+
+
+def test_param_group_overrides_and_mup_scaling():
+    from dataclasses import dataclass
+
+    from megatron_b200.core.optimizer import _get_param_groups
+
+    @dataclass(frozen=True)
+    class ParamKey:
+        name: tuple = ()
+        attr: tuple = ()
+
+    net = _Net()
+    net.a.weight.is_embedding_or_output_parameter = True
+    key = ParamKey(name=("c.*",))
+    groups = _get_param_groups([net], None, None, 1.0, 1e-3, 1e-5, None, None, 0.1,
+                               config_overrides={"b.weight": {"lr_mult": 0.5, "weight_decay": 0.0}, key: {"max_lr": 5e-4, "betas": (0.8, 0.9)}}, mup_width_mult=4.0)
+    by_param = {id(p): g for g in groups for p in g["params"]}
+    gb, gc, ga, gn = by_param[id(net.b.weight)], by_param[id(net.c.weight)], by_param[id(net.a.weight)], by_param[id(net.norm.weight)]
+    assert gb["lr"] == 1e-3 * 0.5 and gb["weight_decay"] == 0.0                       # explicit override wins over the µP multiplier
+    assert gc["max_lr"] == 5e-4 and gc["betas"] == (0.8, 0.9) and abs(gc["lr"] - 5e-4 / 4.0) < 1e-12 and by_param[id(net.c.bias)]["max_lr"] == 5e-4
+    assert ga["lr"] == 1e-3 and gn["lr"] == 1e-3 and gn["weight_decay"] == 0.0          # embedding-like and vector parameters keep the base lr under µP
+    plain = _get_param_groups([net], None, None, 1.0, 1e-3, 1e-5, None, None, 0.1)
+    assert all(g["lr"] == 1e-3 for g in plain) and len(plain) == 2
