@@ -411,3 +411,29 @@ def test_param_group_overrides_and_mup_scaling():
     assert ga["lr"] == 1e-3 and gn["lr"] == 1e-3 and gn["weight_decay"] == 0.0          # embedding-like and vector parameters keep the base lr under µP
     plain = _get_param_groups([net], None, None, 1.0, 1e-3, 1e-5, None, None, 0.1)
     assert all(g["lr"] == 1e-3 for g in plain) and len(plain) == 2
+
+
+def _varcoll(rank, world):
+    import torch.distributed as dist
+
+    from megatron_b200.parallel.collectives import all_gather_v, reduce_scatter_v
+
+    sizes = [3, 0, 5][:world]
+    torch.manual_seed(rank)
+    x = torch.randn(sizes[rank], 4)
+    full = all_gather_v(x, sizes, dist.group.WORLD)
+    assert full.shape == (sum(sizes), 4)
+    off = sum(sizes[:rank])
+    assert torch.equal(full[off : off + sizes[rank]], x)
+    objs = [None] * world
+    dist.all_gather_object(objs, x)
+    assert torch.equal(full, torch.cat(objs))
+    y = torch.arange(sum(sizes) * 2, dtype=torch.float32).view(-1, 2) * (rank + 1)
+    out = reduce_scatter_v(y, sizes, dist.group.WORLD)
+    want = torch.arange(sum(sizes) * 2, dtype=torch.float32).view(-1, 2)[off : off + sizes[rank]] * sum(range(1, world + 1))
+    assert torch.equal(out, want)
+    return True
+
+
+def test_variable_count_all_gather_and_reduce_scatter():
+    assert run_distributed(_varcoll, 3) == [True] * 3
