@@ -112,6 +112,9 @@ class MambaMixer(MegatronModule):
                                     C.view(b, self.ngroups_local, self.d_state), ssm_state, D)
             ssm_state.copy_(new_state)
             y = y.reshape(1, b, di)
+        elif self._cp_size() > 1:
+            y = self._forward_context_parallel(z, xBC, dt, A, D)
+            z = None
         else:
             xc = xBC.permute(1, 2, 0)                                # [b, conv_dim, l]
             want_state = inference_context is not None
@@ -127,8 +130,54 @@ class MambaMixer(MegatronModule):
                 res, ssm_state = res
                 inference_context.key_value_memory_dict[("mamba", self.layer_number)] = (conv_state.clone(), ssm_state.clone())
             y = res.reshape(b, l, di).permute(1, 0, 2)               # [l, b, d_inner_local]
-        y = self._gated_norm(y, z)
+        if z is not None:
+            y = self._gated_norm(y, z)
         return self.out_proj(y)
+
+    # ---- context parallel ---------------------------------------------------------------------------------------------
+    def _cp_size(self) -> int:
+        from .. import parallel_state as ps
+
+        return ps.get_context_parallel_world_size() if ps.is_initialized() else 1
+
+    def _forward_context_parallel(self, z, xBC, dt, A, D):
+        """Sequence-sharded activations are re-sharded to head blocks (one all-to-all per tensor), the conv + scan run over the FULL sequence for ``1/cp`` of the
+        heads / groups with the matching parameter slices, and the result goes back to the sequence sharding.  Parameters stay replicated over CP; every
+        rank only produces gradients for its slice and the DP×CP gradient reduction adds them up."""
+        from .. import parallel_state as ps
+        from ...parallel.context_parallel import channel_to_seq, seq_to_channel
+
+        group, cp, r = ps.get_context_parallel_group(), ps.get_context_parallel_world_size(), ps.get_context_parallel_rank()
+        di, ng, nh, ds, hd = self.d_inner_local, self.ngroups_local, self.nheads_local, self.d_state, self.headdim
+        assert nh % cp == 0 and ng % cp == 0, "Mamba context parallelism needs heads and groups divisible by the CP size"
+        x, B, C = torch.split(xBC, [di, ng * ds, ng * ds], dim=-1)
+        zc, xc, Bc, Cc, dtc = (seq_to_channel(t.contiguous(), group, cp) for t in (z, x, B, C, dt))
+        dil, ngl, nhl = di // cp, ng // cp, nh // cp
+        xs, bs_, cs_ = slice(r * dil, (r + 1) * dil), slice(di + r * ngl * ds, di + (r + 1) * ngl * ds), slice(di + ng * ds + r * ngl * ds, di + ng * ds + (r + 1) * ngl * ds)
+        w = torch.cat([self.conv1d_weight[xs], self.conv1d_weight[bs_], self.conv1d_weight[cs_]], dim=0)
+        bias = None if self.conv1d_bias is None else torch.cat([self.conv1d_bias[xs], self.conv1d_bias[bs_], self.conv1d_bias[cs_]], dim=0)
+        l, b = xc.shape[:2]
+        conv_in = torch.cat([xc, Bc, Cc], dim=-1).permute(1, 2, 0)                        # [b, conv_dim/cp, l]
+        conv_out = causal_conv1d(conv_in, w, bias, "silu").permute(0, 2, 1)              # [b, l, conv_dim/cp]
+        xl, Bl, Cl = torch.split(conv_out, [dil, ngl * ds, ngl * ds], dim=-1)
+        hs = slice(r * nhl, (r + 1) * nhl)
+        dtp = torch.nn.functional.softplus(dtc.float().permute(1, 0, 2) + self.dt_bias[hs])
+        Dl = (D.view(nh, -1)[hs] if self.D_has_hdim else D[hs])
+        y = ssd_chunk_scan(xl.reshape(b, l, nhl, hd), dtp, A[hs], Bl.reshape(b, l, ngl, ds), Cl.reshape(b, l, ngl, ds), self.chunk_size, Dl)
+        y = y.reshape(b, l, dil).permute(1, 0, 2)                                        # [l, b, d_inner/cp]
+        # gated norm on the local group block
+        if not self.rmsnorm:
+            y = y * torch.nn.functional.silu(zc)
+        else:
+            gs = di // ng
+            if not self.norm_before_gate:
+                y = y * torch.nn.functional.silu(zc)
+            yf = y.float().view(l, b, ngl, gs)
+            yf = yf * torch.rsqrt(yf.pow(2).mean(-1, keepdim=True) + self.config.layernorm_epsilon)
+            y = (yf.view(l, b, dil) * self.norm_weight[xs].float()).to(y.dtype)
+            if self.norm_before_gate:
+                y = y * torch.nn.functional.silu(zc)
+        return channel_to_seq(y.contiguous(), group, cp)
 
     def sharded_state_dict(self, prefix="", sharded_offsets=(), metadata=None):
         from ..transformer.utils import make_sharded_tensors_for_checkpoint, sharded_state_dict_default

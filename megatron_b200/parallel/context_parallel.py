@@ -251,3 +251,25 @@ class RingAttention(torch.nn.Module):
         qf, kf, vf = seq_to_head(q), seq_to_head(k), seq_to_head(v)
         o = ops.flash_attention(qf, kf, vf, causal=causal, scale=scale)
         return head_to_seq(o, q.shape[0])
+
+
+# ---- sequence ⇄ channel re-sharding for recurrent layers (Mamba context parallel; reference ``ssm/mamba_context_parallel.py``) -----------------------------------
+def seq_to_channel(t: torch.Tensor, group, cp: int) -> torch.Tensor:
+    """``[l/cp (zig-zag shard), b, C]`` → ``[l (natural order), b, C/cp]``: this rank ends up with the WHOLE sequence for its block of channels, which is
+    what a causal conv / selective scan needs (they are sequential along l but independent across channels)."""
+    l, b, C = t.shape
+    assert C % cp == 0
+    x = t.view(l, b, cp, C // cp).permute(2, 0, 1, 3).contiguous().view(cp * l, b, C // cp)
+    return _zigzag_to_natural(_AllToAll.apply(group, x, None, None), cp)
+
+
+def channel_to_seq(t: torch.Tensor, group, cp: int) -> torch.Tensor:
+    """Inverse of ``seq_to_channel``: ``[l, b, C/cp]`` → ``[l/cp (zig-zag shard), b, C]``."""
+    L, b, Cc = t.shape
+    c = L // (2 * cp)
+    chunks = t.view(2 * cp, c, b, Cc)
+    order = []
+    for r in range(cp):
+        order += [chunks[r], chunks[2 * cp - 1 - r]]
+    y = _AllToAll.apply(group, torch.cat(order, dim=0).contiguous(), None, None)          # [cp (source = channel block), l/cp, b, C/cp]
+    return y.view(cp, 2 * c, b, Cc).permute(1, 2, 0, 3).reshape(2 * c, b, cp * Cc)

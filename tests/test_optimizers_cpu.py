@@ -437,3 +437,38 @@ def _varcoll(rank, world):
 
 def test_variable_count_all_gather_and_reduce_scatter():
     assert run_distributed(_varcoll, 3) == [True] * 3
+
+
+def _mamba_cp(rank, world, state):
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.models.mamba.mamba_layer_specs import mamba_stack_spec
+    from megatron_b200.core.models.mamba.mamba_model import MambaModel
+    from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+    from megatron_b200.core.utils import get_batch_on_this_cp_rank
+
+    ps.initialize_model_parallel(context_parallel_size=world)
+    model_parallel_cuda_manual_seed(1)
+    cfg = TransformerConfig(num_layers=2, hidden_size=64, num_attention_heads=4, normalization="RMSNorm", add_bias_linear=False, use_cpu_initialization=True,
+                            hidden_dropout=0.0, attention_dropout=0.0, context_parallel_size=world)
+    cfg.mamba_state_dim, cfg.mamba_head_dim, cfg.mamba_num_groups = 16, 16, 2
+    m = MambaModel(cfg, mamba_stack_spec, 128, 64, hybrid_override_pattern="MM", position_embedding_type="none")
+    if state is not None:
+        m.load_state_dict(state)
+    torch.manual_seed(9)
+    tok = torch.randint(0, 128, (2, 32))
+    pos = torch.arange(32)[None].expand(2, -1)
+    local = get_batch_on_this_cp_rank({"tokens": tok, "labels": tok, "position_ids": pos}) if world > 1 else {"tokens": tok, "labels": tok, "position_ids": pos}
+    out = m(local["tokens"], local["position_ids"], None, labels=local["labels"])
+    loss_sum = out.float().sum()
+    (loss_sum / (2 * 32)).backward()
+    return float(loss_sum), {n: p.grad.clone() for n, p in m.named_parameters()}, ({k: v.clone() for k, v in m.state_dict().items() if isinstance(v, torch.Tensor)} if state is None else None)
+
+
+def test_mamba_context_parallel_matches_single_rank():
+    (l1, g1, state), = run_distributed(_mamba_cp, 1, None)
+    res = run_distributed(_mamba_cp, 2, state)
+    assert abs(sum(r[0] for r in res) - l1) / abs(l1) < 1e-5
+    for n, g in g1.items():
+        got = sum(r[1][n] for r in res)
+        assert torch.allclose(got, g, atol=3e-5, rtol=1e-3), (n, (got - g).abs().max())
