@@ -104,6 +104,29 @@ def run_resume(case_dir: str, cfg: dict) -> None:
             raise AssertionError(f"resume mismatch at iteration {step}: {tail[step]} vs uninterrupted {full[step]}")
 
 
+def run_reshard(case_dir: str, cfg: dict, rtol: float = 2e-3) -> None:
+    """Reference ``*_reshard_*`` cases: save under layout A, resume under layout B — the loss curve must continue as if nothing happened (to fp tolerance: the
+    reduction orders of the two layouts differ)."""
+    import copy
+
+    n = int(cfg["TRAIN_ITERS"])
+    half = n // 2
+    a, b = copy.deepcopy(cfg), copy.deepcopy(cfg)
+    a["MODEL_ARGS"].update(cfg.get("LAYOUT_A") or {})
+    b["MODEL_ARGS"].update(cfg.get("LAYOUT_B") or {})
+    with tempfile.TemporaryDirectory() as tmp:
+        launch(a, ["--train-iters", str(n)], os.path.join(tmp, "tb_full"))
+        ck = os.path.join(tmp, "ckpt")
+        common = ["--train-iters", str(n), "--save", ck, "--load", ck, "--save-interval", str(half)]
+        launch(a, common + ["--exit-interval", str(half)], os.path.join(tmp, "tb_a"))
+        launch(b, common, os.path.join(tmp, "tb_b"))
+        full, tail = read_scalars(os.path.join(tmp, "tb_full"))["lm loss"], read_scalars(os.path.join(tmp, "tb_b"))["lm loss"]
+    assert min(tail) == half + 1, f"resumed run did not start at iteration {half + 1}: {sorted(tail)}"
+    for step in range(half + 1, n + 1):
+        if abs(full[step] - tail[step]) > rtol * abs(full[step]):
+            raise AssertionError(f"reshard-resume mismatch at iteration {step}: {tail[step]} vs {full[step]}")
+
+
 def run_case(case_dir: str, update_golden: bool = False, platform: str = "cpu") -> None:
     cfg = yaml.safe_load(open(os.path.join(case_dir, "model_config.yaml")))
     types = cfg.get("TEST_TYPE", ["regular"])
@@ -111,6 +134,8 @@ def run_case(case_dir: str, update_golden: bool = False, platform: str = "cpu") 
         run_regular(case_dir, cfg, update_golden, platform)
     if "ckpt-resume" in types and not update_golden:
         run_resume(case_dir, cfg)
+    if "ckpt-reshard" in types and not update_golden:
+        run_reshard(case_dir, cfg)
 
 
 if __name__ == "__main__":
