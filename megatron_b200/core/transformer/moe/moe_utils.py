@@ -82,15 +82,21 @@ def group_limited_topk(scores: torch.Tensor, topk: int, num_tokens: int, num_exp
 
 def topk_routing_with_score_function(logits: torch.Tensor, topk: int, use_pre_softmax: bool = False, num_groups: Optional[int] = None,
                                      group_topk: Optional[int] = None, scaling_factor: Optional[float] = None, score_function: str = "softmax",
-                                     expert_bias: Optional[torch.Tensor] = None, fused: bool = False):
-    """→ (routing_probs [T, E] dense with zeros off the top-k, routing_map [T, E] bool)."""
+                                     expert_bias: Optional[torch.Tensor] = None, fused: bool = False, router_replay=None):
+    """→ (routing_probs [T, E] dense with zeros off the top-k, routing_map [T, E] bool).
+    ``router_replay`` (``RouterReplay``) may record or override the selected indices."""
     assert logits.dim() == 2, f"expected 2D logits [num_tokens, num_experts], got {logits.dim()}"
     T, E = logits.shape
 
-    def pick(scores, k):
+    def _pick(scores, k):
         if num_groups:
             return group_limited_topk(scores, k, T, E, num_groups, group_topk)
         return torch.topk(scores, k=k, dim=1)
+
+    def pick(scores, k):
+        if router_replay is not None:
+            return router_replay.get_replay_topk(scores, k, _pick)
+        return _pick(scores, k)
 
     if score_function == "softmax":
         if use_pre_softmax:

@@ -66,6 +66,11 @@ class TopKRouter(Router):
         self.routing_type = config.moe_router_load_balancing_type
         self.score_function = config.moe_router_score_function
         self.input_jitter = None
+        self.router_replay = None
+        if getattr(config, "moe_enable_routing_replay", False):
+            from .router_replay import RouterReplay
+
+            self.router_replay = RouterReplay()
         self.enable_expert_bias = config.moe_router_enable_expert_bias
         if self.enable_expert_bias:
             dev = self.weight.device
@@ -135,6 +140,7 @@ class TopKRouter(Router):
         probs, routing_map = topk_routing_with_score_function(
             logits, self.topk, use_pre_softmax=cfg.moe_router_pre_softmax, num_groups=cfg.moe_router_num_groups, group_topk=cfg.moe_router_group_topk,
             scaling_factor=cfg.moe_router_topk_scaling_factor, score_function=self.score_function, expert_bias=self.expert_bias,
+            router_replay=self.router_replay,
         )
         if cfg.moe_expert_capacity_factor is not None:
             probs, routing_map = apply_router_token_dropping(probs, routing_map, self.topk, cfg.moe_expert_capacity_factor,
