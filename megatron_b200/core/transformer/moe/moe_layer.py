@@ -68,9 +68,22 @@ class MoELayer(BaseMoELayer):
             self.shared_experts = build_module(submodules.shared_experts, config=config, pg_collection=pg_collection)
         if layer_number is not None:
             self.router.set_layer_number(layer_number)
+        self._training_dispatcher = self.token_dispatcher
+        if config.inference_moe_token_dispatcher_type is not None:
+            self.set_inference_dispatcher(config.inference_moe_token_dispatcher_type)
 
     def route(self, hidden_states):
         return self.router(hidden_states)
+
+    def set_inference_dispatcher(self, kind: Optional[str]):
+        """Swap in a static-shape serving dispatcher (``nccl`` | ``nvls``); ``None`` restores the training one."""
+        if kind is None:
+            self.token_dispatcher = self._training_dispatcher
+            return
+        from .token_dispatcher_inference import get_inference_token_dispatcher
+
+        self.token_dispatcher = get_inference_token_dispatcher(kind)(self.num_local_experts, self.local_expert_indices, config=self.config,
+                                                                     pg_collection=self.pg_collection)
 
     def _forward_impl(self, hidden_states):
         if self.training and self.config.tensor_model_parallel_size > 1 and not self.config.sequence_parallel:
@@ -82,7 +95,13 @@ class MoELayer(BaseMoELayer):
         x, p = d.dispatch_preprocess(hidden_states, routing_map, probs)
         x, p = d.token_dispatch(x, p)
         x, tokens_per_expert, p = d.dispatch_postprocess(x, p)
-        out, mlp_bias = self.experts(x, tokens_per_expert, p)
+        if self.config.moe_paged_stash and self.training:
+            from .paged_stash import get_paged_stash_context
+
+            with get_paged_stash_context(True, getattr(d, "num_valid_tokens", None)):
+                out, mlp_bias = self.experts(x, tokens_per_expert, p)
+        else:
+            out, mlp_bias = self.experts(x, tokens_per_expert, p)
         out = d.combine_preprocess(out)
         out = d.token_combine(out)
         out = d.combine_postprocess(out)

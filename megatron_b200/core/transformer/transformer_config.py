@@ -145,6 +145,10 @@ class TransformerConfig(ModelParallelConfig):
     moe_enable_deepep: bool = False
     moe_flex_dispatcher_backend: str = "b200"
     moe_per_layer_logging: bool = False
+    moe_enable_routing_replay: bool = False
+    moe_paged_stash: bool = False
+    moe_paged_stash_page_size: int = 64
+    inference_moe_token_dispatcher_type: Optional[str] = None   # None | nccl | nvls (static-shape serving dispatchers)
     moe_expert_capacity_factor: Optional[float] = None
     moe_pad_expert_input_to_capacity: bool = False
     moe_token_drop_policy: str = "probs"
