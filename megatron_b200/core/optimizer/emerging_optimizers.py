@@ -7,6 +7,8 @@ from typing import Dict
 EMERGING_OPTIMIZERS: Dict[str, dict] = {
     "muon": {"module": "megatron_b200.core.optimizer.muon", "needs_whole_matrices": True,
              "doc": "orthogonalised momentum (Newton-Schulz) for 2-D hidden weights, AdamW for the rest; pair with LayerWiseDistributedOptimizer under DP"},
+    "soap": {"module": "megatron_b200.core.optimizer.soap", "needs_whole_matrices": True,
+             "doc": "AdamW in the eigenbasis of Shampoo's Kronecker factors (one-sided above soap_max_precond_dim); AdamW for 1-D / embedding parameters"},
     "lion": {"module": "megatron_b200.core.optimizer.optimizer", "needs_whole_matrices": False, "doc": "sign of interpolated momentum, one state per parameter"},
 }
 

@@ -34,11 +34,12 @@ from .optimizer_config import OptimizerConfig
 class Slot:
     """A contiguous run of elements updated together."""
 
-    __slots__ = ("param", "grad_fn", "master", "lowp", "exp_avg", "exp_avg_sq", "momentum", "group", "name")
+    __slots__ = ("param", "grad_fn", "master", "lowp", "exp_avg", "exp_avg_sq", "momentum", "group", "name", "extra")
 
     def __init__(self, param, grad_fn, master, lowp, group, name=None):
         self.param, self.grad_fn, self.master, self.lowp, self.group, self.name = param, grad_fn, master, lowp, group, name
         self.exp_avg = self.exp_avg_sq = self.momentum = None
+        self.extra = None        # rule-specific matrices (SOAP: Kronecker statistics and their eigenbases)
 
     @property
     def grad(self):
@@ -160,6 +161,14 @@ class MegatronOptimizer(ABC):
             elif s.exp_avg is None:        # embeddings, norms, biases, heads: AdamW
                 s.exp_avg = torch.zeros_like(s.master, dtype=self.config.exp_avg_dtype)
                 s.exp_avg_sq = torch.zeros_like(s.master, dtype=self.config.exp_avg_sq_dtype)
+        elif self.config.optimizer == "soap":
+            from .soap import init_soap_state, is_soap_param
+
+            if s.exp_avg is None:
+                s.exp_avg = torch.zeros_like(s.master, dtype=torch.float32)
+                s.exp_avg_sq = torch.zeros_like(s.master, dtype=torch.float32)
+            if s.extra is None and is_soap_param(s.param, s.master):
+                s.extra = init_soap_state(s.master, self.config.soap_max_precond_dim)
 
     def _apply_update(self, grad_scale: Optional[torch.Tensor]):
         cfg = self.config
@@ -215,6 +224,23 @@ class MegatronOptimizer(ABC):
                     ops.fused_adam([s.master for s in rest], [s.grad for s in rest], [s.exp_avg for s in rest], [s.exp_avg_sq for s in rest], [s.lowp for s in rest],
                                    lr=lr, beta1=b1, beta2=b2, eps=group.get("eps", cfg.adam_eps), weight_decay=wd, step=self.step_count[gi], adamw=True,
                                    grad_scale=grad_scale)
+            elif cfg.optimizer == "soap":
+                from .soap import soap_step
+
+                gs = float(grad_scale) if grad_scale is not None else 1.0
+                b1, b2 = group.get("betas", (cfg.adam_beta1, cfg.adam_beta2))
+                so = [s for s in slots if s.extra is not None]
+                rest = [s for s in slots if s.extra is None]
+                for s in so:
+                    soap_step(s.master, s.grad.float() * gs, s.exp_avg, s.exp_avg_sq, s.extra, lr=lr, beta1=b1, beta2=b2, eps=group.get("eps", cfg.adam_eps),
+                              weight_decay=wd, step=self.step_count[gi], shampoo_beta=cfg.soap_shampoo_beta,
+                              precondition_frequency=cfg.soap_precondition_frequency, precondition_warmup=cfg.soap_precondition_warmup)
+                    if s.lowp is not None:
+                        s.lowp.copy_(s.master)
+                if rest:
+                    ops.fused_adam([s.master for s in rest], [s.grad for s in rest], [s.exp_avg for s in rest], [s.exp_avg_sq for s in rest], [s.lowp for s in rest],
+                                   lr=lr, beta1=b1, beta2=b2, eps=group.get("eps", cfg.adam_eps), weight_decay=wd, step=self.step_count[gi], adamw=True,
+                                   grad_scale=grad_scale)
             else:
                 raise NotImplementedError(cfg.optimizer)
 
@@ -225,6 +251,9 @@ class MegatronOptimizer(ABC):
             v = getattr(s, k)
             if v is not None:
                 d[k] = v
+        if s.extra:
+            for k, v in s.extra.items():
+                d[f"extra.{k}"] = v if torch.is_tensor(v) else torch.tensor(v)
         return d
 
     def _groups_meta(self):
@@ -357,7 +386,13 @@ class Float16OptimizerWithFloat16Params(MixedPrecisionOptimizer):
             if st:
                 self._init_slot_state(s)
                 for k, v in st.items():
-                    getattr(s, k).copy_(v)
+                    if k.startswith("extra."):
+                        name = k[len("extra."):]
+                        if s.extra is None:
+                            s.extra = {}
+                        s.extra[name] = (v.clone() if v.dim() else (bool(v) if v.dtype == torch.bool else int(v))) if torch.is_tensor(v) else v
+                    else:
+                        getattr(s, k).copy_(v)
         if self.grad_scaler and state_dict.get("grad_scaler"):
             self.grad_scaler.load_state_dict(state_dict["grad_scaler"])
         masters = state_dict.get("fp32_from_fp16_params")

@@ -38,6 +38,10 @@ class OptimizerConfig:
     muon_scale_mode: str = "spectral"        # spectral: sqrt(max(1, out/in)) | shape: 0.2 * sqrt(max(out, in)) (match-AdamW-RMS) | none
     muon_tp_mode: str = "blockwise"          # blockwise: orthogonalise each TP shard | duplicated: gather the full matrix over TP first
     muon_extra_scale: float = 1.0
+    soap_shampoo_beta: float = 0.95          # EMA of the Kronecker statistics G Gᵀ / Gᵀ G
+    soap_precondition_frequency: int = 10    # steps between eigenbasis refreshes
+    soap_max_precond_dim: int = 8192         # a side larger than this keeps the identity basis (one-sided SOAP)
+    soap_precondition_warmup: bool = True    # the first step only seeds the statistics
     qk_clip_threshold: Optional[float] = None  # MuonClip: cap on the max attention logit (None = off)
     qk_clip_alpha: float = 0.5
     use_mup: bool = False                      # maximal-update parametrisation: hidden-matrix lr scaled by base_hidden / hidden
@@ -59,5 +63,5 @@ class OptimizerConfig:
     def __post_init__(self):
         if self.fp16 and self.bf16:
             raise ValueError("fp16 and bf16 are mutually exclusive")
-        if self.optimizer not in ("adam", "sgd", "lion", "muon"):
+        if self.optimizer not in ("adam", "sgd", "lion", "muon", "soap"):
             raise ValueError(f"unknown optimizer {self.optimizer}")

@@ -63,7 +63,10 @@ def build_parser() -> argparse.ArgumentParser:
     g.add_argument("--train-samples", type=int, default=None)
     g.add_argument("--exit-interval", type=int, default=None)
     g.add_argument("--exit-duration-in-mins", type=int, default=None)
-    g.add_argument("--optimizer", default="adam", choices=["adam", "sgd", "lion", "muon"])
+    g.add_argument("--optimizer", default="adam", choices=["adam", "sgd", "lion", "muon", "soap"])
+    g.add_argument("--soap-shampoo-beta", type=float, default=0.95)
+    g.add_argument("--soap-precondition-frequency", type=int, default=10)
+    g.add_argument("--soap-max-precond-dim", type=int, default=8192)
     g.add_argument("--muon-momentum", type=float, default=0.95)
     g.add_argument("--muon-ns-steps", type=int, default=5)
     g.add_argument("--muon-tp-mode", default="blockwise", choices=["blockwise", "duplicated"])
