@@ -147,6 +147,44 @@ def _new_group(ranks, backend=None, timeout=None, desc=None, pg_options=None):
         return dist.new_group(ranks, **kwargs)
 
 
+_NCCL_OPTION_FIELDS = ("cga_cluster_size", "max_ctas", "min_ctas", "net_name")
+
+
+def load_nccl_communicator_config(path: Optional[str]) -> dict:
+    """YAML ``{group name: {cga_cluster_size, max_ctas, min_ctas, net_name, is_high_priority_stream}}`` (reference :168-200, :713-722).
+    On an NVSwitch box the useful knobs are ``max_ctas`` (how many SMs a collective may take away from overlapped GEMMs) and the
+    stream priority; unknown group names or fields are rejected so a typo does not silently tune nothing."""
+    if not path:
+        return {}
+    import yaml
+
+    with open(path) as f:
+        cfg = yaml.safe_load(f) or {}
+    known = set(_GROUP_TABLE) | {"embd", "pos_embd", "intra_dp_cp", "inter_dist_opt", "intra_dist_opt", "hcp", "default"}
+    for name, fields in cfg.items():
+        if name not in known:
+            raise ValueError(f"{path}: unknown process group '{name}' (known: {sorted(known)})")
+        bad = set(fields) - set(_NCCL_OPTION_FIELDS) - {"is_high_priority_stream"}
+        if bad:
+            raise ValueError(f"{path}: unknown NCCL option(s) {sorted(bad)} for group '{name}'")
+        if str(fields.get("net_name", "ib")).lower() not in ("ib", "socket"):
+            raise RuntimeError(f"net_name ({fields['net_name']}) is not supported; accepted values: 'IB' or 'socket'")
+    return cfg
+
+
+def get_nccl_options(pg_name: str, nccl_comm_cfgs: dict, high_priority: bool = False):
+    """``ProcessGroupNCCL.Options`` for one group, or ``None`` to take NCCL's defaults."""
+    fields = dict(nccl_comm_cfgs.get("default", {}))
+    fields.update(nccl_comm_cfgs.get(pg_name, {}))
+    if not fields and not high_priority:
+        return None
+    opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=bool(fields.get("is_high_priority_stream", high_priority)))
+    for k in _NCCL_OPTION_FIELDS:
+        if k in fields:
+            setattr(opts.config, k, fields[k])
+    return opts
+
+
 def create_group(ranks=None, timeout=None, backend=None, pg_options=None, use_local_synchronization=False, group_desc=None):
     """Thin wrapper kept for API parity (reference ``parallel_state.py:232``)."""
     return _new_group(ranks, backend=backend, timeout=timeout, desc=group_desc, pg_options=pg_options)
@@ -229,10 +267,16 @@ def initialize_model_parallel(
 
     _TOPOLOGY.update(dict(tp=tp, pp=pp, cp=cp, ep=ep, dp=dp, etp=etp, edp=edp, world=world))
 
+    nccl_cfgs = load_nccl_communicator_config(nccl_communicator_config_path)
+    hp_groups = set(high_priority_stream_groups or [])
+
     def register(name, rank_lists, gloo=False, backend=None):
         mine = None
+        opts = None
+        if not backend_is_cpu and (backend in (None, "nccl")):
+            opts = get_nccl_options(name, nccl_cfgs, high_priority=name in hp_groups)
         for ranks in rank_lists:
-            pg = _new_group(ranks, backend=backend, timeout=timeout, desc=name.upper())
+            pg = _new_group(ranks, backend=backend, timeout=timeout, desc=name.upper(), pg_options=opts)
             gpg = None
             if gloo and create_gloo_process_groups:
                 gpg = pg if backend_is_cpu else _new_group(ranks, backend="gloo", timeout=timeout, desc=name.upper() + "_GLOO")

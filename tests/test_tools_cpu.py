@@ -1,0 +1,117 @@
+"""Command-line tools: parallel preprocessing, checkpoint inspector, routing analysis, per-dataset sequence counts, NCCL group options."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tools", "checkpoint"))
+sys.path.insert(0, os.path.join(ROOT, "tools", "moe_routing"))
+
+
+def _corpus(path, n=200):
+    rng = np.random.default_rng(0)
+    docs = []
+    with open(path, "w") as f:
+        for i in range(n):
+            ids = rng.integers(1, 90, size=int(rng.integers(1, 40))).tolist()
+            docs.append(ids)
+            f.write(json.dumps({"text": " ".join(map(str, ids)), "meta": i}) + "\n")
+            if i % 17 == 0:
+                f.write("\n")                                     # blank lines are skipped
+    return docs
+
+
+def test_preprocess_data_fast_keeps_order_and_matches_serial(tmp_path):
+    import preprocess_data_fast as fast
+
+    from megatron_b200.core.datasets.indexed_dataset import IndexedDataset
+
+    src = tmp_path / "c.jsonl"
+    docs = _corpus(src)
+    ranges = fast.line_aligned_ranges(str(src), 7)
+    assert ranges[0][0] == 0 and ranges[-1][1] == os.path.getsize(src) and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    with open(src, "rb") as f:
+        for s, _ in ranges[1:]:
+            f.seek(s - 1)
+            assert f.read(1) == b"\n"                              # every range starts at a line start
+    common = ["--input", str(src), "--tokenizer-type", "NullTokenizer", "--vocab-size", "100", "--append-eod"]
+    n1 = fast.main(common + ["--output-prefix", str(tmp_path / "serial"), "--workers", "1", "--chunks-per-worker", "1"])
+    n2 = fast.main(common + ["--output-prefix", str(tmp_path / "par"), "--workers", "3", "--chunks-per-worker", "2"])
+    assert n1 == n2 == len(docs)
+    a, b = IndexedDataset(str(tmp_path / "serial_text_document")), IndexedDataset(str(tmp_path / "par_text_document"))
+    assert len(a) == len(b) == len(docs)
+    for i in (0, 1, 57, 199):
+        assert np.array_equal(a[i], b[i]) and a[i][:-1].tolist() == docs[i]
+    assert np.array_equal(a.index.document_indices, b.index.document_indices)
+    assert not [f for f in os.listdir(tmp_path) if ".part" in f]     # partial files are cleaned up
+
+    import build_sequences_per_dataset as bs
+
+    out = bs.main(["--data-path", "0.5", str(tmp_path / "serial_text_document"), "0.5", str(tmp_path / "par_text_document"),
+                   "--per-dataset-sequences-path", str(tmp_path / "seq.json")])
+    assert list(out.values()) == [(200, 200), (200, 200)]
+
+
+def test_checkpoint_inspector_inspect_diff_rename(tmp_path, capsys):
+    import checkpoint_inspector as ci
+    import torch.distributed.checkpoint as dcp
+    from torch.distributed.checkpoint import FileSystemWriter
+
+    a = {"decoder.layers.0.w": torch.arange(12.0).view(3, 4), "decoder.final.b": torch.ones(4, dtype=torch.bfloat16)}
+    b = {"decoder.layers.0.w": a["decoder.layers.0.w"] + 0.5, "extra": torch.zeros(2)}
+    dcp.save(a, storage_writer=FileSystemWriter(str(tmp_path / "a")), no_dist=True)
+    dcp.save(b, storage_writer=FileSystemWriter(str(tmp_path / "b")), no_dist=True)
+    meta = ci.main(["inspect", str(tmp_path / "a")])
+    assert meta["decoder.layers.0.w"] == ((3, 4), torch.float32) and meta["decoder.final.b"][1] == torch.bfloat16
+    assert "2 entries" in capsys.readouterr().out
+    only_a, only_b, changed, worst = ci.main(["diff", str(tmp_path / "a"), str(tmp_path / "b"), "--values"])
+    assert only_a == ["decoder.final.b"] and only_b == ["extra"] and not changed and abs(worst["decoder.layers.0.w"] - 0.5) < 1e-6
+    ci.main(["rename", str(tmp_path / "a"), str(tmp_path / "c"), "--sub", r"^decoder\.", "encoder."])
+    got = ci.load_full(str(tmp_path / "c"))
+    assert set(got) == {"encoder.layers.0.w", "encoder.final.b"} and torch.equal(got["encoder.layers.0.w"], a["decoder.layers.0.w"])
+
+
+def test_routing_analysis_from_tracer_records(tmp_path):
+    import analyze_routing as ar
+
+    from megatron_b200.core.transformer.moe.router_trace import RouterTracer
+
+    tr = RouterTracer(str(tmp_path), flush_every=100)
+    same = torch.tensor([[0, 1], [0, 1], [2, 3], [0, 1]])
+    for step in range(3):
+        tr.record_indices(same, module_name="decoder.layers.0.mlp.router")                     # skewed, perfectly repeatable
+        tr.record_indices(torch.tensor([[step % 4, (step + 1) % 4]] * 4), module_name="decoder.layers.1.mlp.router")
+        tr.advance_step()
+    tr.flush()
+    rep = ar.main([tr.trace_dir, "--num-experts", "4", "--json", str(tmp_path / "r.json")])
+    l0, l1 = rep["decoder/0"], rep["decoder/1"]
+    assert l0["repeat_fraction"] == 1.0 and l0["slots"] == 24 and abs(l0["load"][0] - 3 / 8) < 1e-6 and abs(l0["imbalance_max_over_mean"] - 1.5) < 1e-6
+    assert l1["repeat_fraction"] == 0.0 and l0["entropy"] < 1.0 and l0["dead_experts"] == 0
+    assert json.load(open(tmp_path / "r.json"))["decoder/1"]["records"] == 3
+
+
+def test_nccl_communicator_config_parsing(tmp_path):
+    from megatron_b200.core import parallel_state as ps
+
+    p = tmp_path / "nccl.yaml"
+    p.write_text("tp:\n  max_ctas: 8\n  cga_cluster_size: 2\n  is_high_priority_stream: true\ndp:\n  min_ctas: 2\ndefault:\n  max_ctas: 24\n")
+    cfg = ps.load_nccl_communicator_config(str(p))
+    tp = ps.get_nccl_options("tp", cfg)
+    assert tp.is_high_priority_stream and tp.config.max_ctas == 8 and tp.config.cga_cluster_size == 2
+    dp = ps.get_nccl_options("dp", cfg)
+    assert dp.config.min_ctas == 2 and dp.config.max_ctas == 24 and not dp.is_high_priority_stream      # group fields over the defaults
+    assert ps.get_nccl_options("pp", {}) is None and ps.get_nccl_options("pp", {}, high_priority=True).is_high_priority_stream
+    p.write_text("tpp:\n  max_ctas: 8\n")
+    with pytest.raises(ValueError):
+        ps.load_nccl_communicator_config(str(p))
+    p.write_text("tp:\n  max_cta: 8\n")
+    with pytest.raises(ValueError):
+        ps.load_nccl_communicator_config(str(p))
+    p.write_text("tp:\n  net_name: tcp\n")
+    with pytest.raises(RuntimeError):
+        ps.load_nccl_communicator_config(str(p))
