@@ -115,3 +115,76 @@ def test_nccl_communicator_config_parsing(tmp_path):
     p.write_text("tp:\n  net_name: tcp\n")
     with pytest.raises(RuntimeError):
         ps.load_nccl_communicator_config(str(p))
+
+
+def test_trtllm_export_layout_split_and_distributed_variant(tmp_path):
+    from megatron_b200.core.export.trtllm import (DistributedTRTLLMWeightsConverter, ExportConfig, TRTLLMLayers, TRTLLMWeightsConverter, pad_vocab_size,
+                                                   save_trtllm_checkpoint, trtllm_model_config)
+    from megatron_b200.core.export.hf_llama import megatron_to_hf_llama
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    torch.manual_seed(0)
+    cfg = TransformerConfig(num_layers=2, hidden_size=32, num_attention_heads=8, num_query_groups=2, ffn_hidden_size=48, gated_linear_unit=True,
+                            activation_func=torch.nn.functional.silu, add_bias_linear=False, use_cpu_initialization=True)
+    h, d, g, r = 32, cfg.kv_channels, 2, 4
+    sd = {"embedding.word_embeddings.weight": torch.randn(100, h), "output_layer.weight": torch.randn(100, h), "decoder.final_layernorm.weight": torch.randn(h)}
+    for i in range(2):
+        p = f"decoder.layers.{i}."
+        sd.update({p + "self_attention.linear_qkv.weight": torch.randn(g * (r + 2) * d, h), p + "self_attention.linear_proj.weight": torch.randn(h, r * g * d),
+                   p + "mlp.linear_fc1.weight": torch.randn(96, h), p + "mlp.linear_fc2.weight": torch.randn(h, 48), p + "input_layernorm.weight": torch.randn(h),
+                   p + "pre_mlp_layernorm.weight": torch.randn(h), p + "self_attention.linear_qkv._extra_state": None})
+    hf = megatron_to_hf_llama(sd, 8, 2, d)
+    assert TRTLLMLayers.return_layer_name_and_number("decoder.layers.12.mlp.linear_fc1.weight") == ("decoder.layers.mlp.linear_fc1.weight", 12)
+    for tp in (1, 2, 4):                                             # tp 4 > 2 KV groups → K/V heads replicated
+        ex = ExportConfig(inference_tp_size=tp, dtype=torch.float32)
+        ranks = TRTLLMWeightsConverter(ex, cfg).convert(sd, vocab_size=100)
+        assert len(ranks) == tp
+        qn, kn = 8 * d // tp, max(2 // tp, 1) * d
+        qkv = [w["transformer.layers.1.attention.qkv.weight"] for w in ranks]
+        assert all(t.shape == (qn + 2 * kn, h) for t in qkv)
+        assert torch.equal(torch.cat([t[:qn] for t in qkv]), hf["model.layers.1.self_attn.q_proj.weight"])
+        k_all = torch.cat([t[qn : qn + kn] for t in qkv])
+        want_k = hf["model.layers.1.self_attn.k_proj.weight"].view(2, d, h).repeat_interleave(max(tp // 2, 1), 0).reshape(-1, h)
+        assert torch.equal(k_all, want_k)
+        assert torch.equal(torch.cat([w["transformer.layers.0.mlp.fc.weight"] for w in ranks]), hf["model.layers.0.mlp.gate_proj.weight"])
+        assert torch.equal(torch.cat([w["transformer.layers.0.mlp.gate.weight"] for w in ranks]), hf["model.layers.0.mlp.up_proj.weight"])
+        assert torch.equal(torch.cat([w["transformer.layers.0.mlp.proj.weight"] for w in ranks], 1), sd["decoder.layers.0.mlp.linear_fc2.weight"])
+        assert torch.equal(torch.cat([w["transformer.layers.0.attention.dense.weight"] for w in ranks], 1), sd["decoder.layers.0.self_attention.linear_proj.weight"])
+        emb = torch.cat([w["transformer.vocab_embedding.weight"] for w in ranks])
+        assert emb.shape[0] == pad_vocab_size(100, tp) and torch.equal(emb[:100], sd["embedding.word_embeddings.weight"]) and float(emb[100:].abs().sum()) == 0
+        assert all(torch.equal(w["transformer.ln_f.weight"], sd["decoder.final_layernorm.weight"]) for w in ranks)
+    # distributed variant: rank r converts its own training shard and lands on the same tensors
+    tp = 2
+    ranks = TRTLLMWeightsConverter(ExportConfig(tp, dtype=torch.float32), cfg).convert(sd, vocab_size=128)
+    for rk in range(tp):
+        shard = {}
+        for k, v in sd.items():
+            if v is None:
+                continue
+            if "linear_qkv" in k or "word_embeddings" in k or "output_layer" in k:
+                vv = torch.cat([v, v.new_zeros(128 - v.shape[0], h)]) if v.shape[0] == 100 else v
+                shard[k] = vv.chunk(tp, 0)[rk]
+            elif "linear_fc1" in k:
+                shard[k] = torch.cat([v.chunk(2, 0)[0].chunk(tp, 0)[rk], v.chunk(2, 0)[1].chunk(tp, 0)[rk]])
+            elif "linear_fc2" in k or "linear_proj" in k:
+                shard[k] = v.chunk(tp, 1)[rk]
+            else:
+                shard[k] = v
+        got = DistributedTRTLLMWeightsConverter(ExportConfig(tp, dtype=torch.float32), cfg, rk, tp).convert(shard, vocab_size=128)
+        assert got.keys() == ranks[rk].keys()
+        for k in got:
+            assert torch.equal(got[k], ranks[rk][k]), k
+    # MoE experts (grouped layout) are stacked per layer with [up ; gate] halves
+    mcfg = TransformerConfig(num_layers=1, hidden_size=32, num_attention_heads=8, num_query_groups=2, ffn_hidden_size=48, num_moe_experts=4, moe_ffn_hidden_size=16,
+                             gated_linear_unit=True, activation_func=torch.nn.functional.silu, add_bias_linear=False, use_cpu_initialization=True)
+    msd = {"decoder.layers.0.mlp.experts.weight1": torch.randn(4, 32, h), "decoder.layers.0.mlp.experts.weight2": torch.randn(4, h, 16),
+           "decoder.layers.0.mlp.router.weight": torch.randn(4, h), "embedding.word_embeddings.weight": torch.randn(64, h)}
+    mr = TRTLLMWeightsConverter(ExportConfig(2, dtype=torch.float32), mcfg).convert(msd)
+    fc = torch.cat([w["transformer.layers.0.mlp.fc.weight"] for w in mr], 1)          # [E, 2 * (2 * 8), h] rank-major halves
+    assert fc.shape == (4, 32, h) and torch.equal(mr[0]["transformer.layers.0.mlp.fc.weight"][:, :8], msd["decoder.layers.0.mlp.experts.weight1"][:, 16:24])
+    assert torch.equal(torch.cat([w["transformer.layers.0.mlp.proj.weight"] for w in mr], 2), msd["decoder.layers.0.mlp.experts.weight2"])
+    assert torch.equal(mr[1]["lm_head.weight"], mr[1]["transformer.vocab_embedding.weight"])          # tied when no output layer
+    conf = trtllm_model_config(cfg, 100, 4096, ExportConfig(2))
+    assert conf["vocab_size"] == 128 and conf["mapping"]["tp_size"] == 2 and conf["num_key_value_heads"] == 2 and conf["hidden_act"] == "swiglu"
+    save_trtllm_checkpoint(str(tmp_path / "trt"), ranks, conf)
+    assert os.path.exists(tmp_path / "trt" / "config.json") and len([f for f in os.listdir(tmp_path / "trt") if f.startswith("rank")]) == 2
