@@ -89,8 +89,17 @@ class DynamicInferenceEngine:
     attention layers' ``paged`` hook (``set_paged_context``), which keeps this engine independent of the
     attention kernel: prefill = full causal attention on the prompt, decode = 1 query against the gathered cache."""
 
-    def __init__(self, model, num_blocks: int = 256, block_size: int = 16, max_running: int = 16, vocab_size: Optional[int] = None):
+    def __init__(self, model, num_blocks: int = 256, block_size: int = 16, max_running: int = 16, vocab_size: Optional[int] = None,
+                 batched_decode: Optional[bool] = None):
         self.model = model
+        # one forward for ALL running requests' next token (block-table attention); models whose attention is not the standard
+        # ``Attention`` (MLA latent cache, Mamba state) keep the per-request path
+        if batched_decode is None:
+            from ..transformer.attention import SelfAttention
+
+            batched_decode = all(isinstance(getattr(l, "self_attention", None), SelfAttention) for l in model.decoder.layers)
+        self.batched_decode = batched_decode
+        self.decode_forwards = 0
         cfg = model.config
         dev = next(model.parameters()).device
         dt = next(model.parameters()).dtype
@@ -148,10 +157,25 @@ class DynamicInferenceEngine:
         return logits[0, -1]
 
     @torch.no_grad()
+    def _forward_decode_batch(self, reqs: List[InferenceRequest]) -> torch.Tensor:
+        """→ next-token logits ``[B, vocab]`` for ``reqs`` from a single forward."""
+        from .kv_cache import BatchedDecodeContext
+
+        rids = [r.request_id for r in reqs]
+        ctx = BatchedDecodeContext(self.cache, rids, [l.self_attention.layer_number for l in self.model.decoder.layers])
+        toks = torch.tensor([[r.generated_tokens[-1]] for r in reqs], device=self.device)
+        logits = self.model(toks, ctx.lengths[:, None], None, inference_context=ctx)          # [B, 1, vocab]
+        for r in rids:
+            self.cache.lengths[r] += 1
+        self.decode_forwards += 1
+        return logits[:, -1]
+
+    @torch.no_grad()
     def step(self) -> List[InferenceRequest]:
         """Admit what fits, run one token for every running request, retire the finished ones."""
         self.model.eval()
         newly_finished: List[InferenceRequest] = []
+        admitted: List[InferenceRequest] = []
         while self.waiting and len(self.running) < self.max_running:
             req = self.waiting[0]
             need = len(req.prompt_tokens) + req.sampling_params.num_tokens_to_generate
@@ -162,16 +186,24 @@ class DynamicInferenceEngine:
             logits = self._forward_request(req, req.prompt_tokens, 0)  # prefill
             self._emit(req, logits)
             self.running.append(req)
+            admitted.append(req)
+        ready = []
         for req in list(self.running):
-            if req.status == "finished":
+            if req.status == "finished" or req in admitted:
                 continue
             if len(req.generated_tokens) >= req.sampling_params.num_tokens_to_generate:
                 continue
             cur = self.cache.lengths[req.request_id]
             if not self.cache.ensure_capacity(req.request_id, cur + 1):
                 continue  # out of blocks this step; try again after others finish
-            logits = self._forward_request(req, [req.generated_tokens[-1]], cur)
-            self._emit(req, logits)
+            ready.append(req)
+        if ready and self.batched_decode:
+            for req, logits in zip(ready, self._forward_decode_batch(ready)):
+                self._emit(req, logits)
+        else:
+            for req in ready:
+                logits = self._forward_request(req, [req.generated_tokens[-1]], self.cache.lengths[req.request_id])
+                self._emit(req, logits)
         for req in list(self.running):
             sp = req.sampling_params
             if len(req.generated_tokens) >= sp.num_tokens_to_generate or (req.generated_tokens and req.generated_tokens[-1] in sp.stop_token_ids):

@@ -75,3 +75,48 @@ class PagedKVCache:
         k = self.k[layer, table[:nblk]].reshape(-1, *self.k.shape[3:])[:length]
         v = self.v[layer, table[:nblk]].reshape(-1, *self.v.shape[3:])[:length]
         return k, v
+
+
+    # ---- batched decode: every running request advances by one token in ONE forward --------------------------------
+    def batch_tables(self, rids: List[int]) -> Tuple[torch.Tensor, torch.Tensor]:
+        """→ (block table ``[B, max_blocks]`` padded with block 0, current lengths ``[B]``) on the cache's device."""
+        dev = self.k.device
+        width = max(len(self.block_tables[r]) for r in rids)
+        table = torch.zeros(len(rids), width, dtype=torch.long)
+        for i, r in enumerate(rids):
+            t = self.block_tables[r]
+            table[i, : len(t)] = torch.tensor(t)
+        return table.to(dev), torch.tensor([self.lengths[r] for r in rids], dtype=torch.long, device=dev)
+
+    def append_batch(self, layer: int, table: torch.Tensor, positions: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> None:
+        """``k, v [B, kv_heads, head_dim]``: request ``i``'s new entry goes to its position ``positions[i]``."""
+        blk = table.gather(1, (positions // self.block_size).unsqueeze(1)).squeeze(1)
+        off = positions % self.block_size
+        self.k[layer, blk, off] = k
+        self.v[layer, blk, off] = v
+
+    def gather_batch(self, layer: int, table: torch.Tensor, max_len: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """→ ``K, V [B, L, kv_heads, head_dim]`` with ``L = ceil(max_len / block) · block``; rows past a request's length are whatever the
+        padded blocks hold — the caller masks them."""
+        nblk = (max_len + self.block_size - 1) // self.block_size
+        t = table[:, :nblk]
+        B = t.shape[0]
+        return self.k[layer][t].reshape(B, nblk * self.block_size, *self.k.shape[3:]), self.v[layer][t].reshape(B, nblk * self.block_size, *self.v.shape[3:])
+
+
+class BatchedDecodeContext:
+    """Inference context of one batched decode step (understood by ``Attention.forward``): request ``i`` of the batch sits at
+    position ``lengths[i]``, its K/V history lives in the paged cache behind row ``i`` of ``block_table``."""
+
+    is_batched_decode = True
+
+    def __init__(self, cache: PagedKVCache, rids: List[int], layer_numbers: List[int]):
+        self.cache, self.rids = cache, rids
+        self.block_table, self.lengths = cache.batch_tables(rids)
+        self.max_len = int(max(cache.lengths[r] for r in rids)) + 1
+        self.max_sequence_length = self.max_len                      # rotary table length
+        self.max_batch_size = len(rids)
+        self.sequence_len_offset = 0
+        self.batch_size_offset = 0
+        self.key_value_memory_dict: Dict = {}
+        self.layer_index = {n: i for i, n in enumerate(layer_numbers)}

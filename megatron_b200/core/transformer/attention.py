@@ -101,6 +101,29 @@ class Attention(MegatronModule):
             mask_type = AttnMaskType.no_mask
         return query, key, value, rotary_pos_emb, mask_type
 
+    def _batched_paged_decode(self, ctx, query, key, value, rotary_pos_emb):
+        """One new token for each of B requests with DIFFERENT histories (continuous batching): ``query/key/value [1, B, heads, d]``.
+        Every request is rotated at its own position, its K/V entry is written to its page, and it attends to its own prefix —
+        one masked attention over the block-table gather instead of B separate forwards (the GEMMs around it see B rows)."""
+        assert query.size(0) == 1, "batched decode advances every request by exactly one token"
+        pos = ctx.lengths
+        if rotary_pos_emb is not None:
+            q_pos, k_pos = rotary_pos_emb
+            # requests along the "sequence" axis so each row gets its own angle
+            query = ops.apply_rope(query.transpose(0, 1).contiguous(), q_pos[pos], self.config.rotary_interleaved).transpose(0, 1)
+            key = ops.apply_rope(key.transpose(0, 1).contiguous(), k_pos[pos], self.config.rotary_interleaved).transpose(0, 1)
+        li = ctx.layer_index[self.layer_number]
+        ctx.cache.append_batch(li, ctx.block_table, pos, key[0], value[0])
+        K, V = ctx.cache.gather_batch(li, ctx.block_table, ctx.max_len)            # [B, L, hk, d]
+        B, L, hk, d = K.shape
+        h = query.size(2)
+        q = query[0].view(B, hk, h // hk, 1, d)                                     # query heads grouped under their KV head
+        K, V = K.permute(0, 2, 1, 3).unsqueeze(2), V.permute(0, 2, 1, 3).unsqueeze(2)   # [B, hk, 1, L, d]
+        mask = (torch.arange(L, device=pos.device)[None, :] <= pos[:, None]).view(B, 1, 1, 1, L)
+        scale = getattr(self.core_attention, "softmax_scale", None) or d ** -0.5
+        out = torch.nn.functional.scaled_dot_product_attention(q, K.expand(B, hk, h // hk, L, d), V.expand(B, hk, h // hk, L, d), attn_mask=mask, scale=scale)
+        return out.reshape(B, h * d).unsqueeze(0)
+
     def get_query_key_value_tensors(self, hidden_states, key_value_states=None):
         raise NotImplementedError
 
@@ -111,6 +134,9 @@ class Attention(MegatronModule):
         query, key, value = self.get_query_key_value_tensors(hidden_states, key_value_states)
         if rotary_pos_emb is not None and not isinstance(rotary_pos_emb, tuple):
             rotary_pos_emb = (rotary_pos_emb, rotary_pos_emb)
+        if inference_context is not None and getattr(inference_context, "is_batched_decode", False):
+            core_out = self._batched_paged_decode(inference_context, query, key, value, rotary_pos_emb)
+            return self.linear_proj(core_out)
         n_new = key.size(0)
         query, key_c, value_c, rotary_pos_emb, mask_type = self._adjust_key_value_for_inference(inference_context, query, key, value, rotary_pos_emb)
         if rotary_pos_emb is not None:

@@ -251,3 +251,42 @@ def _disagg(rank, world):
 def test_prefill_decode_disaggregation_matches_single_engine():
     res = run_distributed(_disagg, 2)
     assert res[0] is None and res[1] is not None
+
+
+def _batched_decode(rank, world):
+    import torch.nn.functional as F
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.inference.engine import DynamicInferenceEngine, StaticInferenceEngine
+    from megatron_b200.core.inference.sampling import SamplingParams
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    ps.initialize_model_parallel()
+    torch.manual_seed(3)
+    cfg = TransformerConfig(num_layers=2, hidden_size=64, num_attention_heads=8, num_query_groups=2, ffn_hidden_size=128, gated_linear_unit=True, activation_func=F.silu,
+                            add_bias_linear=False, normalization="RMSNorm", **_KW)
+    model = GPTModel(cfg, get_gpt_layer_local_spec(normalization="RMSNorm"), vocab_size=96, max_sequence_length=128, position_embedding_type="rope")
+    prompts = [[5, 17, 3, 42, 8, 1, 2, 7, 7, 7, 11], [9, 9], [30, 31, 32, 33, 34], [1], [2, 3, 4, 5, 6, 7, 8, 9, 10]]
+    gens = [6, 11, 3, 9, 7]                                     # requests leave at different steps; the 5th is admitted late (max_running 4)
+    ref = StaticInferenceEngine(model, max_sequence_length=128)
+    want = [ref.generate([p], SamplingParams(temperature=0.0, num_tokens_to_generate=n))[0] for p, n in zip(prompts, gens)]
+    out = {}
+    for batched in (True, False):
+        e = DynamicInferenceEngine(model, num_blocks=64, block_size=4, max_running=4, vocab_size=96, batched_decode=batched)
+        ids = [e.add_request(p, SamplingParams(temperature=0.0, num_tokens_to_generate=n, return_log_probs=True)) for p, n in zip(prompts, gens)]
+        fin = e.run_until_done()
+        out[batched] = ([fin[i].generated_tokens for i in ids], [fin[i].log_probs for i in ids], e.decode_forwards, e.steps)
+        assert e.cache.allocator.num_free == 64
+    assert out[True][0] == out[False][0] == want
+    for a, b in zip(out[True][1], out[False][1]):
+        assert torch.allclose(torch.tensor(a), torch.tensor(b), atol=1e-4)
+    assert e.batched_decode is False and DynamicInferenceEngine(model, num_blocks=8, block_size=4).batched_decode is True       # auto-detected for standard attention
+    # one forward per step instead of one per running request
+    assert 0 < out[True][2] <= out[True][3] and out[False][2] == 0
+    return True
+
+
+def test_batched_paged_decode_matches_per_request_decode():
+    run_distributed(_batched_decode, 1)
