@@ -96,6 +96,52 @@ def _serve(rank, world):
 
     reqs = asyncio.run(many())
     assert reqs[0].generated_tokens == reqs[2].generated_tokens == direct[0]["tokens"] and reqs[1].generated_tokens == direct[1]["tokens"]
+
+    # streaming: token-list items per engine step, text deltas that concatenate to the blocking result, two streams interleaved
+    async def streams():
+        llm = AsyncLLM(DynamicInferenceEngine(model, vocab_size=256), tok)
+
+        async def collect(s):
+            return [d async for d in llm.generate_stream(s, greedy)]
+
+        async def ids(s):
+            return [i async for i in llm.stream_tokens(list(tok.tokenize(s)), greedy)]
+
+        return await asyncio.gather(collect("hello"), collect("b200"), ids("hello"))
+
+    a, b, c = asyncio.run(streams())
+    assert "".join(a) == direct[0]["text"] and "".join(b) == direct[1]["text"]
+    assert [t for item in c for t in item] == direct[0]["tokens"] and len(c) == 6               # one token per step
+
+    # incremental detokenizer holds back an incomplete UTF-8 sequence
+    from megatron_b200.core.inference.text_generation import IncrementalDetokenizer
+
+    det = IncrementalDetokenizer(tok)
+    euro = list("€".encode())                                                                   # 3 bytes
+    assert det.add(list(b"a") + euro[:1]) == "a" and det.add(euro[1:2]) == "" and det.add(euro[2:]) == "€" and det.add(list(b"!"), final=True) == "!"
+
+    # OpenAI chat + SSE streaming + health through the client
+    from megatron_b200.core.inference.inference_client import InferenceClient
+
+    srv = TextGenerationServer(TextGenerationController(DynamicInferenceEngine(model, vocab_size=256), tok), port=0)
+    srv.start()
+    try:
+        cl = InferenceClient(port=srv.port)
+        assert cl.health()["status"] == "ok"
+        msgs = [{"role": "user", "content": "hi"}]
+        chat = cl.chat(msgs, max_tokens=6, temperature=0.0)
+        want = ctl.generate(["user: hi\nassistant: "], greedy)[0]
+        assert chat["choices"][0]["message"]["content"] == want["text"] and chat["usage"]["completion_tokens"] == 6
+        assert "".join(cl.stream(msgs, max_tokens=6, temperature=0.0)) == want["text"]
+        assert "".join(cl.stream("hello", max_tokens=6, temperature=0.0)) == direct[0]["text"]
+        assert cl.generate(["hello"], 6, temperature=0.0)[0] == "hello" + direct[0]["text"]
+        try:
+            cl.chat([{"role": "user"}])
+            raise AssertionError("malformed message accepted")
+        except urllib.error.HTTPError as e:
+            assert e.code == 400
+    finally:
+        srv.stop()
     return True
 
 
