@@ -90,7 +90,7 @@ class DynamicInferenceEngine:
     attention kernel: prefill = full causal attention on the prompt, decode = 1 query against the gathered cache."""
 
     def __init__(self, model, num_blocks: int = 256, block_size: int = 16, max_running: int = 16, vocab_size: Optional[int] = None,
-                 batched_decode: Optional[bool] = None):
+                 batched_decode: Optional[bool] = None, enable_prefix_caching: bool = False):
         self.model = model
         # one forward for ALL running requests' next token (block-table attention); models whose attention is not the standard
         # ``Attention`` (MLA latent cache, Mamba state) keep the per-request path
@@ -100,11 +100,12 @@ class DynamicInferenceEngine:
             batched_decode = all(isinstance(getattr(l, "self_attention", None), SelfAttention) for l in model.decoder.layers)
         self.batched_decode = batched_decode
         self.decode_forwards = 0
+        self.prefill_tokens = 0
         cfg = model.config
         dev = next(model.parameters()).device
         dt = next(model.parameters()).dtype
         tp = cfg.tensor_model_parallel_size
-        self.cache = PagedKVCache(cfg.num_layers, num_blocks, block_size, max(cfg.num_query_groups // tp, 1), cfg.kv_channels, dt, dev)
+        self.cache = PagedKVCache(cfg.num_layers, num_blocks, block_size, max(cfg.num_query_groups // tp, 1), cfg.kv_channels, dt, dev, enable_prefix_caching)
         self.waiting: Deque[InferenceRequest] = deque()
         self.running: List[InferenceRequest] = []
         self.finished: Dict[int, InferenceRequest] = {}
@@ -179,11 +180,14 @@ class DynamicInferenceEngine:
         while self.waiting and len(self.running) < self.max_running:
             req = self.waiting[0]
             need = len(req.prompt_tokens) + req.sampling_params.num_tokens_to_generate
-            if not self.cache.can_admit(need) or not self.cache.add_request(req.request_id, len(req.prompt_tokens)):
+            if not self.cache.can_admit(need) or not self.cache.add_request(req.request_id, len(req.prompt_tokens), req.prompt_tokens):
                 break
             self.waiting.popleft()
             req.status = "running"
-            logits = self._forward_request(req, req.prompt_tokens, 0)  # prefill
+            hit = self.cache.prefix_hit_tokens.get(req.request_id, 0)       # leading tokens whose K/V are already cached
+            self.prefill_tokens += len(req.prompt_tokens) - hit
+            logits = self._forward_request(req, req.prompt_tokens[hit:], hit)  # prefill (of the uncached tail)
+            self.cache.register_prefix(req.request_id, req.prompt_tokens)
             self._emit(req, logits)
             self.running.append(req)
             admitted.append(req)

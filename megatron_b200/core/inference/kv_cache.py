@@ -9,43 +9,128 @@ import torch
 
 
 class KVBlockAllocator:
-    def __init__(self, num_blocks: int):
+    """Free list + (optional) prefix cache (reference ``contexts/kv_block_allocator.py``: ``enable_prefix_caching``, LRU / ref-zero eviction).
+
+    With prefix caching a FULL block whose content is determined by the token prefix that produced it is registered under the chained
+    hash of that prefix.  Blocks are reference counted; when the last request using a registered block leaves, the block is not freed
+    but parked in an LRU of evictable blocks, so a later request with the same prefix (system prompt, few-shot header, chat history)
+    re-pins it instead of recomputing the prefill.  Allocation takes free blocks first and evicts least-recently-used parked ones
+    only when it must."""
+
+    def __init__(self, num_blocks: int, enable_prefix_caching: bool = False):
+        from collections import OrderedDict
+
         self.num_blocks = num_blocks
+        self.enable_prefix_caching = enable_prefix_caching
         self.free: List[int] = list(range(num_blocks - 1, -1, -1))
+        self.ref = [0] * num_blocks
+        self.hash_of: Dict[int, int] = {}            # block -> prefix hash
+        self.block_of: Dict[int, int] = {}           # prefix hash -> block
+        self.parked = OrderedDict()                  # ref-zero registered blocks, oldest first
+        self.hits = self.evictions = 0
 
     def allocate(self, n: int) -> Optional[List[int]]:
-        if n > len(self.free):
+        if n > self.num_free:
             return None
-        return [self.free.pop() for _ in range(n)]
+        out = []
+        for _ in range(n):
+            if self.free:
+                b = self.free.pop()
+            else:
+                b, _ = self.parked.popitem(last=False)
+                self.block_of.pop(self.hash_of.pop(b), None)
+                self.evictions += 1
+            self.ref[b] = 1
+            out.append(b)
+        return out
 
     def release(self, blocks: List[int]):
-        self.free.extend(reversed(blocks))
+        for b in reversed(blocks):
+            self.ref[b] -= 1
+            if self.ref[b] > 0:
+                continue
+            if b in self.hash_of:
+                self.parked[b] = None
+                self.parked.move_to_end(b)
+            else:
+                self.free.append(b)
 
     @property
     def num_free(self) -> int:
-        return len(self.free)
+        return len(self.free) + len(self.parked)
+
+    # ---- prefix cache ------------------------------------------------------------------------
+    @staticmethod
+    def chain_hashes(tokens: List[int], block_size: int) -> List[int]:
+        """Hash of every FULL block, each folded over the previous one so equal hashes mean equal prefixes."""
+        out, h = [], 0
+        for i in range(0, len(tokens) - len(tokens) % block_size, block_size):
+            h = hash((h, tuple(tokens[i : i + block_size])))
+            out.append(h)
+        return out
+
+    def lookup_and_pin(self, hashes: List[int]) -> List[int]:
+        """Longest run of leading hashes that are cached → their blocks, pinned for the caller."""
+        got = []
+        for h in hashes:
+            b = self.block_of.get(h)
+            if b is None:
+                break
+            if self.ref[b] == 0:
+                self.parked.pop(b, None)
+            self.ref[b] += 1
+            got.append(b)
+        self.hits += len(got)
+        return got
+
+    def register(self, block: int, h: int) -> None:
+        if h in self.block_of or block in self.hash_of:
+            return                                   # first writer wins; a concurrent duplicate stays private
+        self.hash_of[block], self.block_of[h] = h, block
 
 
 class PagedKVCache:
     """``k/v`` pools: [layers, num_blocks, block_size, kv_heads, head_dim]."""
 
-    def __init__(self, num_layers: int, num_blocks: int, block_size: int, kv_heads: int, head_dim: int, dtype, device):
+    def __init__(self, num_layers: int, num_blocks: int, block_size: int, kv_heads: int, head_dim: int, dtype, device, enable_prefix_caching: bool = False):
         self.block_size = block_size
+        self.enable_prefix_caching = enable_prefix_caching
+        self.prefix_hit_tokens: Dict[int, int] = {}
         self.k = torch.zeros(num_layers, num_blocks, block_size, kv_heads, head_dim, dtype=dtype, device=device)
         self.v = torch.zeros_like(self.k)
-        self.allocator = KVBlockAllocator(num_blocks)
+        self.allocator = KVBlockAllocator(num_blocks, enable_prefix_caching)
         self.block_tables: Dict[int, List[int]] = {}
         self.lengths: Dict[int, int] = {}
 
     def can_admit(self, num_tokens: int) -> bool:
         return self.allocator.num_free >= (num_tokens + self.block_size - 1) // self.block_size
 
-    def add_request(self, rid: int, num_tokens: int) -> bool:
-        blocks = self.allocator.allocate((num_tokens + self.block_size - 1) // self.block_size)
+    def add_request(self, rid: int, num_tokens: int, prompt_tokens: Optional[List[int]] = None) -> bool:
+        """Reserve blocks for ``num_tokens``.  With prefix caching and the prompt given, leading blocks already in the cache are reused:
+        ``prefix_hit_tokens[rid]`` says how many prompt tokens need no prefill (at least one token is always left to compute, because
+        the logits of the last prompt position are needed)."""
+        shared: List[int] = []
+        if self.enable_prefix_caching and prompt_tokens is not None:
+            hashes = self.allocator.chain_hashes(list(prompt_tokens), self.block_size)
+            if len(hashes) * self.block_size == len(prompt_tokens):
+                hashes = hashes[:-1]
+            shared = self.allocator.lookup_and_pin(hashes)
+        need = (num_tokens + self.block_size - 1) // self.block_size - len(shared)
+        blocks = self.allocator.allocate(max(need, 0))
         if blocks is None:
+            self.allocator.release(shared)
             return False
-        self.block_tables[rid], self.lengths[rid] = blocks, 0
+        self.block_tables[rid] = shared + blocks
+        self.lengths[rid] = len(shared) * self.block_size
+        self.prefix_hit_tokens[rid] = len(shared) * self.block_size
         return True
+
+    def register_prefix(self, rid: int, prompt_tokens: List[int]) -> None:
+        """After the prefill: publish this request's full prompt blocks for later requests."""
+        if not self.enable_prefix_caching:
+            return
+        for b, h in zip(self.block_tables[rid], self.allocator.chain_hashes(list(prompt_tokens), self.block_size)):
+            self.allocator.register(b, h)
 
     def ensure_capacity(self, rid: int, new_len: int) -> bool:
         need = (new_len + self.block_size - 1) // self.block_size - len(self.block_tables[rid])
@@ -59,6 +144,7 @@ class PagedKVCache:
     def release(self, rid: int):
         self.allocator.release(self.block_tables.pop(rid))
         self.lengths.pop(rid)
+        self.prefix_hit_tokens.pop(rid, None)
 
     def append(self, layer: int, rid: int, k: torch.Tensor, v: torch.Tensor, start: int):
         """k, v: [n, kv_heads, head_dim] for positions [start, start+n) of request ``rid``."""

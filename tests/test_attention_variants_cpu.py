@@ -290,3 +290,61 @@ def _batched_decode(rank, world):
 
 def test_batched_paged_decode_matches_per_request_decode():
     run_distributed(_batched_decode, 1)
+
+
+def _prefix_cache(rank, world):
+    import torch.nn.functional as F
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.inference.engine import DynamicInferenceEngine
+    from megatron_b200.core.inference.kv_cache import KVBlockAllocator
+    from megatron_b200.core.inference.sampling import SamplingParams
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    # allocator: pin / park / evict
+    al = KVBlockAllocator(4, enable_prefix_caching=True)
+    hs = al.chain_hashes(list(range(10)), 4)
+    assert len(hs) == 2 and hs != al.chain_hashes([9] + list(range(1, 10)), 4) and hs[0] == al.chain_hashes(list(range(4)) + [7, 7, 7, 7], 4)[0]
+    blocks = al.allocate(3)
+    al.register(blocks[0], hs[0]), al.register(blocks[1], hs[1])
+    al.release(blocks)
+    assert al.num_free == 4 and len(al.parked) == 2                     # registered blocks are parked, not freed
+    assert al.lookup_and_pin(hs) == blocks[:2] and al.num_free == 2
+    al.release(blocks[:2])
+    got = al.allocate(4)                                                # needs the parked ones → evicts them, oldest first
+    assert sorted(got) == [0, 1, 2, 3] and al.evictions == 2 and al.lookup_and_pin(hs) == []
+
+    ps.initialize_model_parallel()
+    torch.manual_seed(4)
+    cfg = TransformerConfig(num_layers=2, hidden_size=64, num_attention_heads=4, num_query_groups=2, ffn_hidden_size=128, gated_linear_unit=True, activation_func=F.silu,
+                            add_bias_linear=False, normalization="RMSNorm", **_KW)
+    model = GPTModel(cfg, get_gpt_layer_local_spec(normalization="RMSNorm"), vocab_size=96, max_sequence_length=128, position_embedding_type="rope")
+    system = [7, 3, 9, 1, 4, 4, 8, 2, 6, 6, 5, 1, 3]                     # 13 tokens = 3 full blocks of 4 + 1
+    prompts = [system + [20, 21], system + [30], system[:8] + [40, 41, 42], system]
+    sp = SamplingParams(temperature=0.0, num_tokens_to_generate=5)
+    plain = DynamicInferenceEngine(model, num_blocks=64, block_size=4, max_running=1, vocab_size=96)
+    ids = [plain.add_request(p, sp) for p in prompts]
+    want = [plain.run_until_done()[i].generated_tokens for i in ids]
+    eng = DynamicInferenceEngine(model, num_blocks=64, block_size=4, max_running=1, vocab_size=96, enable_prefix_caching=True)
+    ids = [eng.add_request(p, sp) for p in prompts]
+    fin = eng.run_until_done()
+    assert [fin[i].generated_tokens for i in ids] == want
+    # request 0 computes everything; 1 reuses 12 tokens, 2 reuses 8, 3 (identical to the system prompt, 13 tokens) reuses 12
+    assert plain.prefill_tokens == sum(map(len, prompts)) and eng.prefill_tokens == 15 + (14 - 12) + (11 - 8) + (13 - 12)
+    assert eng.cache.allocator.num_free == 64 and eng.cache.allocator.hits == 3 + 2 + 3
+    # concurrent sharing: both requests hold the same physical blocks while running
+    eng2 = DynamicInferenceEngine(model, num_blocks=64, block_size=4, max_running=4, vocab_size=96, enable_prefix_caching=True)
+    a = eng2.add_request(prompts[0], sp)
+    eng2.step()
+    b = eng2.add_request(prompts[1], sp)
+    eng2.step()
+    assert eng2.cache.block_tables[a][:3] == eng2.cache.block_tables[b][:3] and eng2.cache.allocator.ref[eng2.cache.block_tables[a][0]] == 2
+    fin2 = eng2.run_until_done()
+    assert [fin2[a].generated_tokens, fin2[b].generated_tokens] == want[:2]
+    return True
+
+
+def test_prefix_caching_reuses_blocks_and_matches_uncached_generation():
+    run_distributed(_prefix_cache, 1)
