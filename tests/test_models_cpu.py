@@ -267,3 +267,74 @@ def _export_distill_rl(rank, world):
 
 def test_hf_export_roundtrip_distillation_and_grpo_advantages():
     run_distributed(_export_distill_rl, 1)
+
+
+def _fsdp_ckpt_save(rank, world, path):
+    import torch.distributed as dist
+
+    from megatron_b200.core.dist_checkpointing import serialization
+    from megatron_b200.core.distributed.fsdp import FullyShardedDataParallel
+    from megatron_b200.core.transformer import fsdp_dtensor_checkpoint as fc
+
+    torch.manual_seed(0)
+    net = _Net()
+    f = FullyShardedDataParallel(None, None, net, fsdp_unit_modules=(_Blk,), group=dist.group.WORLD)
+    opt = torch.optim.Adam(f.optimizer_parameters(), lr=0.05)
+    for step in range(2):
+        torch.manual_seed(100 + step)
+        X, Y = torch.randn(world * 2, 8), torch.randn(world * 2, 4)
+        f.zero_grad_buffer()
+        ((f(X[rank * 2 : rank * 2 + 2]) - Y[rank * 2 : rank * 2 + 2]) ** 2).mean().backward()
+        f.finish_grad_sync()
+        opt.step()
+        f.post_optimizer_step()
+    moments = {"exp_avg": [opt.state[u.master]["exp_avg"] for u in f.units]}
+    sd = fc.fsdp_model_space_sharded_state_dict(f, extra_states=moments)
+    assert all(st.global_shape == (dict(net.named_parameters())[k.split(".exp_avg")[0]].numel(),) for k, st in sd.items())
+    serialization.save(sd, path)
+    full = f.gather_full_state_dict()
+    # same world, different content → load restores
+    with torch.no_grad():
+        for u in f.units:
+            u.master.data.add_(1.0)
+    fc.load_fsdp_model_space(f, path)
+    assert fc.validate_loaded_state_dict(f, full) == []
+    if rank == 0:
+        torch.save({k: v for k, v in full.items()}, path + "_full.pt")
+    return True
+
+
+def _fsdp_ckpt_load(rank, world, path, plain):
+    import torch.distributed as dist
+
+    full = torch.load(path + "_full.pt")
+
+    from megatron_b200.core.distributed.fsdp import FullyShardedDataParallel
+    from megatron_b200.core.transformer import fsdp_dtensor_checkpoint as fc
+
+    torch.manual_seed(9)                                         # different init: everything must come from the checkpoint
+    net = _Net()
+    if plain:
+        fc.load_plain_module_from_model_space(net, path)
+        got = net.state_dict()
+    else:
+        # different world size AND different unit boundaries (whole model as one unit) than at save time
+        f = FullyShardedDataParallel(None, None, net, fsdp_unit_modules=(), group=dist.group.WORLD)
+        extra = {"exp_avg": [torch.zeros_like(u.master.data) for u in f.units]}
+        fc.load_fsdp_model_space(f, path, extra_states=extra)
+        got = f.gather_full_state_dict()
+        assert float(sum(e.abs().sum() for e in extra["exp_avg"])) > 0
+    return max((got[k].float() - v.float()).abs().max().item() for k, v in full.items())
+
+
+def test_fsdp_model_space_checkpoint_reshards_across_world_sizes_and_into_plain_modules(tmp_path):
+    from megatron_b200.core.transformer import fsdp_dtensor_checkpoint as fc
+
+    assert all(run_distributed(_fsdp_ckpt_save, 2, str(tmp_path / "ck")))
+    assert max(run_distributed(_fsdp_ckpt_load, 3, str(tmp_path / "ck"), False)) == 0.0
+    assert max(run_distributed(_fsdp_ckpt_load, 1, str(tmp_path / "ck"), True)) == 0.0
+    assert fc.expert_param_global_key("d.mlp.experts.local_experts.1.linear_fc1.weight", 2, 4) == "d.mlp.experts.9.linear_fc1.weight"
+    assert fc.expert_param_local_key("d.mlp.experts.9.linear_fc1.weight", 2, 4) == "d.mlp.experts.local_experts.1.linear_fc1.weight"
+    assert fc.expert_param_local_key("d.mlp.experts.9.linear_fc1.weight", 0, 4) is None and fc.get_expert_index_from_key("a.experts.7.w") == 7
+    assert fc.flatten_state_dict({"a": {"b": [1, {"c": 2}]}}) == {"a.b.0": 1, "a.b.1.c": 2}
+    assert fc.print_diff_in_state_dicts(["a", "b"], ["b", "c"]) == (["c"], ["a"]) and fc._strip_wrapper_prefixes("module.module.x.module.y") == "x.y"
