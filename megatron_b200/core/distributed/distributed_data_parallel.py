@@ -49,13 +49,15 @@ class DistributedDataParallel(_BaseDataParallel):
             self.tp_group, self.pp_group, self.ep_group = pg_collection.tp, pg_collection.pp, getattr(pg_collection, "ep", None)
 
         self.param_to_name: Dict[torch.nn.Parameter, str] = {}
-        dense, expert, gtp = [], [], []
+        dense, expert, gtp, egtp = [], [], [], []
         for name, p in self.module.named_parameters():
             if not p.requires_grad:
                 continue
             p.grad_added_to_main_grad = False
             self.param_to_name[p] = name
-            if getattr(p, "gtp_sharded", False):
+            if getattr(p, "gtp_sharded", False) and getattr(p, "gtp_expert", False):
+                egtp.append(p)      # expert-side GTP shard: reduce over the expert replicas of this shard
+            elif getattr(p, "gtp_sharded", False):
                 gtp.append(p)       # shard of a GTP weight: its gradient is already summed over the remat group, reduce over the orthogonal replicas only
             else:
                 (dense if getattr(p, "allreduce", True) else expert).append(p)
@@ -77,6 +79,10 @@ class DistributedDataParallel(_BaseDataParallel):
             gtp_group = ps.get_data_parallel_group_without_gtp()
             gtp_scale = dense_scale if not ddp_config.average_in_collective else get_pg_size(gtp_group) / max(dp_ws, 1)
             self.expert_parallel_buffers += self._allocate(gtp, gtp_group, gtp_scale)
+        if egtp:
+            eg = ps.get_expert_data_parallel_group_without_gtp()
+            e_scale = expert_scale if not ddp_config.average_in_collective else get_pg_size(eg) / max(dp_ws, 1)
+            self.expert_parallel_buffers += self._allocate(egtp, eg, e_scale)
         single = self.bucket_size is None
         self.bucket_groups = partition_buckets(self.buffers, force_single_bucket_group=single)
         self.expert_parallel_bucket_groups = partition_buckets(self.expert_parallel_buffers, force_single_bucket_group=single)
@@ -203,7 +209,7 @@ class DistributedDataParallel(_BaseDataParallel):
         for p in self.module.parameters():
             group = self.expt_dp_group if not getattr(p, "allreduce", True) else self.dp_group
             if getattr(p, "gtp_sharded", False):
-                group = ps.get_data_parallel_group_without_gtp()
+                group = ps.get_expert_data_parallel_group_without_gtp() if getattr(p, "gtp_expert", False) else ps.get_data_parallel_group_without_gtp()
             if group is None or get_pg_size(group) == 1:
                 continue
             dist.broadcast(p.data, src=dist.get_process_group_ranks(group)[0], group=group)

@@ -231,8 +231,6 @@ def initialize_model_parallel(
     assert not _INITIALIZED, "model parallel groups are already initialised"
     if use_sharp or sharp_enabled_group:
         warnings.warn("SHARP is an InfiniBand feature; ignored on a single NVSwitch box")
-    if expert_gtp_remat_size != 1:
-        raise NotImplementedError("expert-side GTP weight rematerialisation is not implemented (dense GTP is: gtp_remat_size)")
 
     world = local_world_size or dist.get_world_size()
     rank = dist.get_rank()
@@ -329,6 +327,18 @@ def initialize_model_parallel(
         register("gtp_remat", remat)
         register("dp_no_gtp", ortho)
     _TOPOLOGY["gtp"] = gtp_remat_size
+    # expert-side GTP: the same construction over the EXPERT data-parallel groups (expert weights have their own dp axis under EP)
+    if expert_gtp_remat_size > 1:
+        assert edp % expert_gtp_remat_size == 0, f"expert_gtp_remat_size ({expert_gtp_remat_size}) must divide the expert data-parallel size ({edp})"
+        remat, ortho = [], []
+        for lst in expert.get_ranks("dp"):
+            for i in range(0, len(lst), expert_gtp_remat_size):
+                remat.append(lst[i : i + expert_gtp_remat_size])
+            for j in range(expert_gtp_remat_size):
+                ortho.append(lst[j::expert_gtp_remat_size])
+        register("egtp_remat", remat)
+        register("expt_dp_no_egtp", ortho)
+    _TOPOLOGY["egtp"] = expert_gtp_remat_size
 
     # hierarchical context parallel (a2a inside NVLink island, ring across)
     del _HIERARCHICAL_CP_GROUPS[:]
@@ -554,6 +564,20 @@ def get_data_parallel_group_without_gtp(check_initialized: bool = True):
     """Data-parallel replicas of ONE GTP shard (the full dp-cp group when GTP is off)."""
     g = get_group("dp_no_gtp", check_initialized=False)
     return g if g is not None else get_data_parallel_group(with_context_parallel=True)
+
+
+def get_expert_gtp_weight_remat_group(check_initialized: bool = True):
+    """Ranks that jointly hold one copy of every GTP-sharded EXPERT weight (``None`` when ``expert_gtp_remat_size == 1``)."""
+    return get_group("egtp_remat", check_initialized=False)
+
+
+def get_expert_gtp_weight_remat_world_size() -> int:
+    return _ws("egtp_remat") if "egtp_remat" in _GROUPS else 1
+
+
+def get_expert_data_parallel_group_without_gtp(check_initialized: bool = True):
+    g = get_group("expt_dp_no_egtp", check_initialized=False)
+    return g if g is not None else get_group("expt_dp", check_initialized=False)
 
 
 def get_hierarchical_context_parallel_groups(check_initialized: bool = True):

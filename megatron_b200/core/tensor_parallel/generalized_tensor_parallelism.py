@@ -131,45 +131,53 @@ class GTPPrefetcher:
         self._fwd.clear()
 
 
-def convert_linear_to_gtp(module: torch.nn.Module, prefetcher: Optional[GTPPrefetcher] = None, group=None) -> torch.nn.Module:
-    """Shard ``module.weight`` ([out, in], out % R == 0) over the remat group, in place.  Works for ``ColumnParallelLinear`` / ``RowParallelLinear`` /
-    ``torch.nn.Linear`` — anything that reads ``self.weight`` in ``forward``."""
+def convert_linear_to_gtp(module: torch.nn.Module, prefetcher: Optional[GTPPrefetcher] = None, group=None, attr: str = "weight", expert: bool = False) -> torch.nn.Module:
+    """Shard ``module.<attr>`` along dim 0 (``[out, in]`` with out % R == 0, or the expert axis of a grouped ``[L, …]`` weight) over the remat group,
+    in place.  Works for ``ColumnParallelLinear`` / ``RowParallelLinear`` / ``torch.nn.Linear`` / ``GroupedMLP`` — anything that reads
+    ``self.<attr>`` in ``forward``.  ``expert=True`` tags the shard so DDP reduces it over the expert replicas."""
     if prefetcher is None:
         prefetcher = GTPPrefetcher(group=group, prefetch=False)
     group = prefetcher.group
     r, rank = dist.get_world_size(group), dist.get_rank(group)
-    w = module.weight
+    w = getattr(module, attr)
     assert w.shape[0] % r == 0, f"out-features {w.shape[0]} not divisible by the GTP remat size {r}"
     n = w.shape[0] // r
     shard = torch.nn.Parameter(w.detach()[rank * n : (rank + 1) * n].clone(), requires_grad=w.requires_grad)
-    for attr in ("tensor_model_parallel", "partition_dim", "partition_stride", "sequence_parallel", "allreduce", "is_embedding_or_output_parameter"):
-        if hasattr(w, attr):
-            setattr(shard, attr, getattr(w, attr))
+    for tag in ("tensor_model_parallel", "partition_dim", "partition_stride", "sequence_parallel", "allreduce", "is_embedding_or_output_parameter"):
+        if hasattr(w, tag):
+            setattr(shard, tag, getattr(w, tag))
     shard.gtp_sharded = True
+    shard.gtp_expert = expert
     shard.gtp_full_shape = tuple(w.shape)
-    del module._parameters["weight"]
-    module.register_parameter("weight_shard", shard)
+    del module._parameters[attr]
+    shard_name = f"{attr}_shard"
+    module.register_parameter(shard_name, shard)
     module.gtp_group = group
     module.gtp_prefetcher = prefetcher
-    module.gtp_index = prefetcher.register(module)
+    # the prefetcher reads ``.weight_shard`` of whatever it registered: give every converted attribute its own handle
+    handle = module if attr == "weight" else _AttrHandle(module, shard_name)
+    index = prefetcher.register(handle)
+    if attr == "weight":
+        module.gtp_index = index
+    module.__dict__.setdefault("gtp_attrs", {})[attr] = index
 
     def pre_hook(mod, args):
-        buf = mod.gtp_prefetcher.forward_weight(mod.gtp_index)
-        object.__setattr__(mod, "weight", _GTPGather.apply(mod.weight_shard, mod.gtp_group, buf))
+        buf = mod.gtp_prefetcher.forward_weight(index)
+        object.__setattr__(mod, attr, _GTPGather.apply(getattr(mod, shard_name), mod.gtp_group, buf))
 
     def post_hook(mod, args, output):
-        full = mod.__dict__.pop("weight")
+        full = mod.__dict__.pop(attr)
         out = output[0] if isinstance(output, tuple) else output
         if not (torch.is_grad_enabled() and isinstance(out, torch.Tensor) and out.requires_grad):
             return
         rec = _Outstanding(full)
         rec.store.resize_(0)                 # the full weight is gone until this layer's backward needs it
-        mod._gtp_outstanding.append(rec)
+        handle._gtp_outstanding.append(rec)
 
         def regather(grad):                  # runs right before this layer's backward node
-            mod.gtp_prefetcher.backward_weight(mod.gtp_index, rec)
-            if rec in mod._gtp_outstanding:
-                mod._gtp_outstanding.remove(rec)
+            mod.gtp_prefetcher.backward_weight(index, rec)
+            if rec in handle._gtp_outstanding:
+                handle._gtp_outstanding.remove(rec)
             return grad
 
         out.register_hook(regather)
@@ -177,6 +185,42 @@ def convert_linear_to_gtp(module: torch.nn.Module, prefetcher: Optional[GTPPrefe
     module.register_forward_pre_hook(pre_hook)
     module.register_forward_hook(post_hook)
     return module
+
+
+class _AttrHandle:
+    """What the prefetcher needs from a registered weight (``weight_shard``, its own ``_gtp_outstanding`` list) for an attribute that is not called
+    ``weight`` — a module with two converted attributes (``GroupedMLP.weight1 / weight2``) gets two independent links in the chain."""
+
+    def __init__(self, module, shard_name):
+        self._m, self._n = module, shard_name
+        self._gtp_outstanding = []
+
+    @property
+    def weight_shard(self):
+        return getattr(self._m, self._n)
+
+
+def apply_expert_gtp(model: torch.nn.Module, prefetch: bool = True) -> "GTPPrefetcher":
+    """Expert-side GTP (reference EGTP groups, ``parallel_state`` ``expert_gtp_remat_size``): shard every expert weight over the expert remat group.
+    ``GroupedMLP`` shards its stacked ``weight1 / weight2`` along the local-expert axis (``L % R == 0``), ``SequentialMLP`` experts shard each linear's
+    out-features like the dense case."""
+    from ..transformer.moe.experts import GroupedMLP, SequentialMLP
+
+    group = ps.get_expert_gtp_weight_remat_group()
+    assert group is not None, "initialize_model_parallel(expert_gtp_remat_size=R) first"
+    pre = GTPPrefetcher(group=group, prefetch=prefetch)
+    r = dist.get_world_size(group)
+    for _, mod in list(model.named_modules()):
+        if isinstance(mod, GroupedMLP):
+            assert mod.weight1.shape[0] % r == 0, f"{mod.weight1.shape[0]} local experts cannot be sharded over an expert remat group of {r}"
+            convert_linear_to_gtp(mod, pre, attr="weight1", expert=True)
+            convert_linear_to_gtp(mod, pre, attr="weight2", expert=True)
+        elif isinstance(mod, SequentialMLP):
+            for e in mod.local_experts:
+                for lin in (e.linear_fc1, e.linear_fc2):
+                    if lin.weight.shape[0] % r == 0:
+                        convert_linear_to_gtp(lin, pre, expert=True)
+    return pre
 
 
 def apply_gtp(model: torch.nn.Module, min_numel: int = 1 << 20, prefetch: bool = True, predicate=None) -> GTPPrefetcher:

@@ -280,3 +280,53 @@ def _serving_dispatch(rank, world, kind, grouped):
 @pytest.mark.parametrize("kind,grouped", [("nccl", False), ("nvls", True)])
 def test_static_shape_serving_dispatchers_match_training_dispatcher(kind, grouped):
     run_distributed(_serving_dispatch, 2, kind, grouped)
+
+
+def _egtp(rank, world, grouped):
+    import torch.distributed as dist
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.distributed import DistributedDataParallel, DistributedDataParallelConfig
+    from megatron_b200.core.tensor_parallel.gtp_api import apply_expert_gtp
+    from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
+
+    ps.initialize_model_parallel(expert_gtp_remat_size=2)
+    model_parallel_cuda_manual_seed(1)
+    assert ps.get_expert_gtp_weight_remat_world_size() == 2 and dist.get_world_size(ps.get_expert_data_parallel_group_without_gtp()) == world // 2
+
+    def run(gtp):
+        torch.manual_seed(5)
+        model_parallel_cuda_manual_seed(1)                    # the expert-parallel RNG stream must restart too: both runs need the same weights
+        cfg, mlp = _moe_layer(grouped=grouped)
+        pre = apply_expert_gtp(mlp, prefetch=True) if gtp else None
+        ddp = DistributedDataParallel(cfg, DistributedDataParallelConfig(overlap_grad_reduce=False, use_distributed_optimizer=False), mlp)
+        x = torch.randn(6, 2, 32, generator=torch.Generator().manual_seed(50 + rank))
+        for _ in range(2):
+            y, _ = ddp(x)
+            y.float().square().mean().backward()
+        ddp.finish_grad_sync()
+        return mlp, pre, y
+
+    m0, _, y0 = run(False)
+    m1, pre, y1 = run(True)
+    assert torch.allclose(y0, y1, atol=1e-6)
+    assert pre.stats["gathers"] > 0 and pre.stats["regathers"] > 0 and all(not h._gtp_outstanding for h in pre.modules)
+    g0 = {n: p.main_grad.clone() for n, p in m0.named_parameters()}
+    r = dist.get_rank(ps.get_expert_gtp_weight_remat_group())
+    n_sharded = 0
+    for n, p in m1.named_parameters():
+        if n.endswith("_shard"):
+            full = g0[n[: -len("_shard")]]
+            k = full.shape[0] // 2
+            assert p.shape[0] == k and getattr(p, "gtp_expert", False)
+            assert torch.allclose(p.main_grad, full[r * k : (r + 1) * k], atol=1e-6, rtol=1e-4), n
+            n_sharded += 1
+        else:
+            assert torch.allclose(p.main_grad, g0[n], atol=1e-6, rtol=1e-4), n
+    assert n_sharded == (2 if grouped else 8)              # weight1/weight2 stacked, or fc1+fc2 of each of the 4 experts
+    return True
+
+
+@pytest.mark.parametrize("grouped", [True, False])
+def test_expert_side_gtp_matches_plain_ddp(grouped):
+    assert run_distributed(_egtp, 4, grouped) == [True] * 4
