@@ -90,7 +90,7 @@ class DynamicInferenceEngine:
     attention kernel: prefill = full causal attention on the prompt, decode = 1 query against the gathered cache."""
 
     def __init__(self, model, num_blocks: int = 256, block_size: int = 16, max_running: int = 16, vocab_size: Optional[int] = None,
-                 batched_decode: Optional[bool] = None, enable_prefix_caching: bool = False):
+                 batched_decode: Optional[bool] = None, enable_prefix_caching: bool = False, decode_batch_buckets: Optional[List[int]] = None):
         self.model = model
         # one forward for ALL running requests' next token (block-table attention); models whose attention is not the standard
         # ``Attention`` (MLA latent cache, Mamba state) keep the per-request path
@@ -100,6 +100,9 @@ class DynamicInferenceEngine:
             batched_decode = all(isinstance(getattr(l, "self_attention", None), SelfAttention) for l in model.decoder.layers)
         self.batched_decode = batched_decode
         self.decode_forwards = 0
+        # static decode shapes (CUDA-graph buckets): the batch is padded up to the next bucket, the attended length to a block multiple
+        self.decode_batch_buckets = sorted(decode_batch_buckets) if decode_batch_buckets else None
+        self.decode_shapes_seen = set()
         self.prefill_tokens = 0
         cfg = model.config
         dev = next(model.parameters()).device
@@ -163,9 +166,15 @@ class DynamicInferenceEngine:
         from .kv_cache import BatchedDecodeContext
 
         rids = [r.request_id for r in reqs]
-        ctx = BatchedDecodeContext(self.cache, rids, [l.self_attention.layer_number for l in self.model.decoder.layers])
-        toks = torch.tensor([[r.generated_tokens[-1]] for r in reqs], device=self.device)
-        logits = self.model(toks, ctx.lengths[:, None], None, inference_context=ctx)          # [B, 1, vocab]
+        pad_to = None
+        if self.decode_batch_buckets:
+            pad_to = next((b for b in self.decode_batch_buckets if b >= len(rids)), len(rids))
+        ctx = BatchedDecodeContext(self.cache, rids, [l.self_attention.layer_number for l in self.model.decoder.layers], pad_to,
+                                   self.cache.block_size * 4 if self.decode_batch_buckets else 1)
+        last = [[r.generated_tokens[-1]] for r in reqs] + [[0]] * (ctx.lengths.numel() - len(reqs))
+        toks = torch.tensor(last, device=self.device)
+        self.decode_shapes_seen.add((toks.shape[0], ctx.max_len))
+        logits = self.model(toks, ctx.lengths[:, None], None, inference_context=ctx)[: len(reqs)]   # [B, 1, vocab]
         for r in rids:
             self.cache.lengths[r] += 1
         self.decode_forwards += 1

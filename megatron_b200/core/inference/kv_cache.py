@@ -102,6 +102,15 @@ class PagedKVCache:
         self.block_tables: Dict[int, List[int]] = {}
         self.lengths: Dict[int, int] = {}
 
+    def scratch_block(self) -> int:
+        """A block that belongs to no request (allocated on first use, never released): padding rows of a bucketed batch write here."""
+        if getattr(self, "_scratch", None) is None:
+            got = self.allocator.allocate(1)
+            if got is None:
+                raise RuntimeError("no free KV block left for the padding scratch block")
+            self._scratch = got[0]
+        return self._scratch
+
     def can_admit(self, num_tokens: int) -> bool:
         return self.allocator.num_free >= (num_tokens + self.block_size - 1) // self.block_size
 
@@ -196,10 +205,24 @@ class BatchedDecodeContext:
 
     is_batched_decode = True
 
-    def __init__(self, cache: PagedKVCache, rids: List[int], layer_numbers: List[int]):
+    def __init__(self, cache: PagedKVCache, rids: List[int], layer_numbers: List[int], pad_to: Optional[int] = None, max_len_multiple: int = 1):
+        """``pad_to``: static batch size (a CUDA-graph bucket) — the extra rows are dummies at position 0 whose K/V land in the cache's scratch
+        block and whose logits are dropped.  ``max_len_multiple`` rounds the attended length up so the gather shape changes rarely."""
         self.cache, self.rids = cache, rids
         self.block_table, self.lengths = cache.batch_tables(rids)
+        self.num_real = len(rids)
+        if pad_to is not None and pad_to > len(rids):
+            extra = pad_to - len(rids)
+            scratch = cache.scratch_block()
+            self.block_table = torch.cat([self.block_table, torch.full((extra, self.block_table.shape[1]), scratch, dtype=torch.long, device=self.block_table.device)])
+            self.lengths = torch.cat([self.lengths, self.lengths.new_zeros(extra)])
         self.max_len = int(max(cache.lengths[r] for r in rids)) + 1
+        if max_len_multiple > 1:
+            self.max_len = -(-self.max_len // max_len_multiple) * max_len_multiple
+            need = -(-self.max_len // cache.block_size) - self.block_table.shape[1]
+            if need > 0:                                             # columns past a request's blocks are masked out: any valid block id will do
+                filler = torch.full((self.block_table.shape[0], need), cache.scratch_block(), dtype=torch.long, device=self.block_table.device)
+                self.block_table = torch.cat([self.block_table, filler], dim=1)
         self.max_sequence_length = self.max_len                      # rotary table length
         self.max_batch_size = len(rids)
         self.sequence_len_offset = 0

@@ -285,6 +285,13 @@ def _batched_decode(rank, world):
     assert e.batched_decode is False and DynamicInferenceEngine(model, num_blocks=8, block_size=4).batched_decode is True       # auto-detected for standard attention
     # one forward per step instead of one per running request
     assert 0 < out[True][2] <= out[True][3] and out[False][2] == 0
+    # bucketed (static-shape) decode: batch padded to {2, 4}, attended length to multiples of 16 → same tokens, few distinct shapes
+    e = DynamicInferenceEngine(model, num_blocks=64, block_size=4, max_running=4, vocab_size=96, decode_batch_buckets=[2, 4])
+    ids = [e.add_request(p, SamplingParams(temperature=0.0, num_tokens_to_generate=n)) for p, n in zip(prompts, gens)]
+    fin = e.run_until_done()
+    assert [fin[i].generated_tokens for i in ids] == want
+    assert {b for b, _ in e.decode_shapes_seen} <= {2, 4} and all(L % 16 == 0 for _, L in e.decode_shapes_seen) and len(e.decode_shapes_seen) <= 4
+    assert e.cache.allocator.num_free == 63                      # everything released except the scratch block
     return True
 
 
