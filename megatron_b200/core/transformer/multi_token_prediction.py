@@ -170,11 +170,56 @@ def get_mtp_layer_spec(transformer_layer_spec: ModuleSpec, use_transformer_engin
     )
 
 
-def get_mtp_num_layers_to_build(config: TransformerConfig, vp_stage=None) -> int:
-    from .. import parallel_state as ps
+def _layout_of(config):
+    lay = getattr(config, "pipeline_model_parallel_layout", None)
+    if isinstance(lay, str):
+        from .pipeline_parallel_layer_layout import PipelineParallelLayerLayout
 
+        lay = PipelineParallelLayerLayout.from_str(lay, config.pipeline_model_parallel_size)
+    return lay
+
+
+def mtp_on_this_rank(config: TransformerConfig, ignore_virtual: bool = True, vp_stage=None, pp_rank=None) -> bool:
+    """Reference ``multi_token_prediction.py:788``: with an explicit pipeline layout the ``m`` symbols say where the MTP layers live (any stage
+    from the one holding the last decoder layer onwards); without one they sit on the last stage."""
+    from .. import parallel_state as ps
+    from ..enums import LayerType
+
+    if not config.mtp_num_layers:
+        return False
+    lay = _layout_of(config)
+    if lay is None:
+        return ps.is_pipeline_last_stage(ignore_virtual=ignore_virtual, vp_stage=vp_stage) if ps.model_parallel_is_initialized() else True
+    r = pp_rank if pp_rank is not None else (ps.get_pipeline_model_parallel_rank() if ps.model_parallel_is_initialized() else 0)
+    stages = lay.layout[r]
+    if not ignore_virtual and len(stages) > 1:
+        assert vp_stage is not None, "vp_stage must be passed when virtual pipeline parallelism is on"
+        return stages[vp_stage].count(LayerType.mtp) > 0
+    return any(st.count(LayerType.mtp) > 0 for st in stages)
+
+
+def get_mtp_num_layers_to_build(config: TransformerConfig, vp_stage=None, pp_rank=None) -> int:
+    from .. import parallel_state as ps
+    from ..enums import LayerType
+
+    lay = _layout_of(config)
+    if lay is not None and config.mtp_num_layers:
+        r = pp_rank if pp_rank is not None else (ps.get_pipeline_model_parallel_rank() if ps.model_parallel_is_initialized() else 0)
+        return lay.get_num_layers_to_build(LayerType.mtp, vp_stage, r)
     last = ps.is_pipeline_last_stage(ignore_virtual=False, vp_stage=vp_stage) if ps.model_parallel_is_initialized() else True
     return (config.mtp_num_layers or 0) if last else 0
+
+
+def get_mtp_layer_offset(config: TransformerConfig, vp_stage=None, pp_rank=None) -> int:
+    """Depth index of the first MTP layer built on this (pp rank, vp stage) — MTP layers may be spread over several stages."""
+    from .. import parallel_state as ps
+    from ..enums import LayerType
+
+    lay = _layout_of(config)
+    if lay is None:
+        return 0
+    r = pp_rank if pp_rank is not None else (ps.get_pipeline_model_parallel_rank() if ps.model_parallel_is_initialized() else 0)
+    return lay.get_layer_offset(LayerType.mtp, vp_stage, r)
 
 
 def get_mtp_block_spec(config: TransformerConfig, transformer_layer_spec: ModuleSpec, use_transformer_engine: bool = False, vp_stage=None):

@@ -61,6 +61,16 @@ class PipelineParallelLayerLayout:
         assert flat.count(LayerType.loss) == 1 and LayerType.loss in self.flat[-1], "the loss must be on the last stage"
         assert flat.count(LayerType.decoder) == num_layers, f"layout has {flat.count(LayerType.decoder)} decoder layers, config has {num_layers}"
         assert flat.count(LayerType.mtp) == (mtp_num_layers or 0), "MTP layer count mismatch"
+        # MTP layers consume the final hidden state: none may precede the last decoder layer, and (standalone placement) a stage made only of
+        # ``m`` symbols is legal as long as it sits between the last decoder layer and the loss
+        order = [x for x in flat if x in (LayerType.decoder, LayerType.mtp)]
+        if LayerType.mtp in order:
+            first_m = order.index(LayerType.mtp)
+            assert LayerType.decoder not in order[first_m:], "MTP layers must come after every decoder layer"
+
+    def mtp_standalone_stages(self) -> List[int]:
+        """Flat stage indices that hold MTP layers and nothing else (reference ``mtp_standalone``)."""
+        return [i for i, st in enumerate(self.flat) if st and all(x == LayerType.mtp for x in st)]
 
     def get_num_layers_to_build(self, layer_type: LayerType = LayerType.decoder, vp_stage: Optional[int] = None, pp_rank: int = 0) -> int:
         return self.layout[pp_rank][vp_stage or 0].count(layer_type)

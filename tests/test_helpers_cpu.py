@@ -181,3 +181,35 @@ def test_msc_shim_typed_helpers_and_rank_probes(tmp_path, monkeypatch):
     _rank_utils.log_single_rank(lg, logging.INFO, "y", rank=0)
     _rank_utils.log_single_rank(lg, logging.INFO, "z", rank=-3)
     assert [a[1] for a in seen] == ["x", "z"]
+
+
+def test_mtp_placement_follows_the_pipeline_layout():
+    from megatron_b200.core.enums import LayerType
+    from megatron_b200.core.transformer.multi_token_prediction import get_mtp_layer_offset, get_mtp_num_layers_to_build, mtp_on_this_rank
+    from megatron_b200.core.transformer.pipeline_parallel_layer_layout import PipelineParallelLayerLayout
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    lay = PipelineParallelLayerLayout.from_str("Et*2|t*2|m|mL", 4)             # MTP depth 0 on a stage of its own, depth 1 with the loss
+    lay.validate_layer_layout(num_layers=4, mtp_num_layers=2)
+    assert lay.mtp_standalone_stages() == [2]
+    cfg = TransformerConfig(num_layers=4, hidden_size=16, num_attention_heads=2, mtp_num_layers=2, pipeline_model_parallel_size=4, pipeline_dtype=torch.float32, use_cpu_initialization=True)
+    cfg.pipeline_model_parallel_layout = lay
+    assert [mtp_on_this_rank(cfg, pp_rank=r) for r in range(4)] == [False, False, True, True]
+    assert [get_mtp_num_layers_to_build(cfg, pp_rank=r) for r in range(4)] == [0, 0, 1, 1] and [get_mtp_layer_offset(cfg, pp_rank=r) for r in (2, 3)] == [0, 1]
+    cfg.pipeline_model_parallel_layout = "Et*2|t*2|m|mL"                       # the string form is parsed on demand
+    assert mtp_on_this_rank(cfg, pp_rank=2) and not mtp_on_this_rank(cfg, pp_rank=1)
+    cfg.pipeline_model_parallel_layout = None
+    assert mtp_on_this_rank(cfg) and get_mtp_num_layers_to_build(cfg) == 2     # no layout, no process groups: single stage holds them
+    cfg.mtp_num_layers = None
+    assert not mtp_on_this_rank(cfg)
+    bad = PipelineParallelLayerLayout.from_str("Etm|ttL", 2)
+    try:
+        bad.validate_layer_layout(num_layers=3, mtp_num_layers=1)
+        raise SystemExit("an MTP layer in front of decoder layers was accepted")
+    except AssertionError:
+        pass
+    vpp = PipelineParallelLayerLayout.from_str("Et|t|t|t|m|L", 2)              # 2 ranks x 3 virtual chunks; MTP on rank 0's third chunk
+    cfg2 = TransformerConfig(num_layers=4, hidden_size=16, num_attention_heads=2, mtp_num_layers=1, pipeline_model_parallel_size=2, pipeline_dtype=torch.float32, use_cpu_initialization=True)
+    cfg2.pipeline_model_parallel_layout = vpp
+    assert vpp.layout[0][2] == [LayerType.mtp] and mtp_on_this_rank(cfg2, pp_rank=0) and not mtp_on_this_rank(cfg2, pp_rank=1)
+    assert mtp_on_this_rank(cfg2, ignore_virtual=False, vp_stage=2, pp_rank=0) and not mtp_on_this_rank(cfg2, ignore_virtual=False, vp_stage=0, pp_rank=0)
