@@ -117,11 +117,13 @@ class Attention(MegatronModule):
         K, V = ctx.cache.gather_batch(li, ctx.block_table, ctx.max_len)            # [B, L, hk, d]
         B, L, hk, d = K.shape
         h = query.size(2)
-        q = query[0].view(B, hk, h // hk, 1, d)                                     # query heads grouped under their KV head
-        K, V = K.permute(0, 2, 1, 3).unsqueeze(2), V.permute(0, 2, 1, 3).unsqueeze(2)   # [B, hk, 1, L, d]
-        mask = (torch.arange(L, device=pos.device)[None, :] <= pos[:, None]).view(B, 1, 1, 1, L)
+        rep = h // hk
+        q = query[0].reshape(B * hk, rep, 1, d)                                     # 4-D: (request x KV head) batch, the group's query heads as "heads"
+        K = K.permute(0, 2, 1, 3).reshape(B * hk, 1, L, d).expand(B * hk, rep, L, d)
+        V = V.permute(0, 2, 1, 3).reshape(B * hk, 1, L, d).expand(B * hk, rep, L, d)
+        mask = (torch.arange(L, device=pos.device)[None, :] <= pos[:, None]).repeat_interleave(hk, 0).view(B * hk, 1, 1, L)
         scale = getattr(self.core_attention, "softmax_scale", None) or d ** -0.5
-        out = torch.nn.functional.scaled_dot_product_attention(q, K.expand(B, hk, h // hk, L, d), V.expand(B, hk, h // hk, L, d), attn_mask=mask, scale=scale)
+        out = torch.nn.functional.scaled_dot_product_attention(q, K, V, attn_mask=mask, scale=scale)
         return out.reshape(B, h * d).unsqueeze(0)
 
     def get_query_key_value_tensors(self, hidden_states, key_value_states=None):
