@@ -1,26 +1,46 @@
 #!/usr/bin/env python
-"""Headline benchmark: Llama-3-8B training throughput, TP=N (+sequence parallel), bf16.
+"""Headline benchmark: Llama-3-8B training throughput at TP=N, bf16 compute, fp32 main grads.
 
     python bench.py --gpus 1 --steps 5 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus 8 --steps 5 --warmup 3
     python bench.py --impl reference ...      # unmodified NVIDIA/Megatron-LM from baseline/_ref
 
-Prints ONE JSON line on rank 0 (contract in the task statement).  `value` = whole-job tokens/s,
-device-timed with CUDA events around exactly K optimizer steps, max over ranks.
+Both arms print ONE JSON line on rank 0 with the IDENTICAL ``metric`` string and the same workload:
+
+  * the same Llama-3-8B architecture, TP=N **without** sequence parallelism (the stock reference's local norm
+    asserts ``not sequence_parallel``), ``selective(core_attn)`` activation recompute, fp32 main-grad accumulation
+    (reference default with ``--bf16``: ``megatron/training/arguments.py:1204-1217``), AdamW(lr 3e-4, wd 0.1,
+    betas 0.9/0.95, clip 1.0), global batch 4 x seq 8192, micro-batch 1;
+  * the same initial weights (every parameter generated from a name-seeded generator as the FULL tensor and
+    sliced to this TP rank's shard) and the same synthetic tokens, so ``loss_by_step`` of the two arms is
+    comparable step by step (tolerance: bf16 noise);
+  * ``value`` = whole-job tokens/s, device-timed with CUDA events around exactly K optimizer steps, max over ranks.
+
+The repo arm additionally reports the configuration it is designed for (TP=N + sequence parallel through the fused
+AG->GEMM / GEMM->RS kernels, no recompute) under ``config.sp_variant`` — NOT comparable with the reference arm
+(which cannot run SP), reported for the scaling picture only.
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
+import math
 import os
 import subprocess
 import sys
 import tempfile
 import time
+import zlib
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+
+METRIC = "tokens/sec (whole job, device-timed, max over ranks), Llama-3-8B TP=N, bf16 compute, fp32 main grads, no sequence parallel, selective(core_attn) recompute"
+LLAMA3_8B = dict(num_layers=32, hidden=4096, ffn=14336, heads=32, groups=8, kv=128, vocab=128256, seq=8192)
+LR, MIN_LR, WD, CLIP, BETA1, BETA2 = 3e-4, 3e-5, 0.1, 1.0, 0.9, 0.95
+DATA_SEED = 17
 
 
 def parse():
@@ -36,7 +56,9 @@ def parse():
     ap.add_argument("--layers", type=int, default=None, help="DEV ONLY: fewer layers (result is flagged invalid)")
     ap.add_argument("--tp-comm", default=None, choices=[None, "nccl", "nvlink", "fused"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sp-variant", action="store_true", help="skip the second (TP=N + sequence parallel) measurement of the repo arm")
     ap.add_argument("--recompute", default="auto")
+    ap.add_argument("--main-grads", default="fp32", choices=["fp32", "bf16"])
     return ap.parse_args()
 
 
@@ -94,7 +116,7 @@ def env_rank():
 
 
 def timed_loop(torch, dist, step_fn, steps, world):
-    """barrier + sync, K steps between CUDA events, sync + barrier; returns max-over-ranks ms."""
+    """barrier + sync, K steps between CUDA events, sync + barrier; returns max-over-ranks (device ms, wall ms)."""
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -114,7 +136,101 @@ def timed_loop(torch, dist, step_fn, steps, world):
     return float(ms[0]), float(ms[1])
 
 
+def synthetic_tokens(torch, n_seq, seq, vocab):
+    """The benchmark's data: uniform random token ids [n_seq, seq+1] (inputs = [:, :-1], labels = [:, 1:])."""
+    g = torch.Generator().manual_seed(DATA_SEED)
+    return torch.randint(0, vocab, (n_seq, seq + 1), generator=g, dtype=torch.int64)
+
+
+def deterministic_init(torch, named_params, tp_rank, tp_world, num_layers):
+    """Identical initial weights for both arms and every TP size: each parameter is generated as the FULL
+    (unsharded) fp32 tensor on the device from a generator seeded by crc32(name), then this rank's slice along
+    ``partition_dim`` is copied into the local shard.  Matrices ~ N(0, 0.02) (output projections scaled by
+    1/sqrt(2L) like Megatron's ``scaled_init_method_normal``), norm weights = 1, biases = 0."""
+    gen = torch.Generator(device="cuda")
+    n = 0
+    with torch.no_grad():
+        for name, p in named_params:
+            name = name.replace("module.", "")
+            if p.dim() == 1:
+                p.fill_(1.0 if "norm" in name and name.endswith("weight") else 0.0)
+                continue
+            sharded = bool(getattr(p, "tensor_model_parallel", False)) and tp_world > 1
+            dim = int(getattr(p, "partition_dim", -1))
+            full_shape = list(p.shape)
+            if sharded:
+                full_shape[dim] *= tp_world
+            gen.manual_seed(zlib.crc32(name.encode()))
+            std = 0.02 / math.sqrt(2.0 * num_layers) if (".linear_proj." in name or ".linear_fc2." in name) else 0.02
+            full = torch.empty(full_shape, dtype=torch.float32, device="cuda").normal_(0.0, std, generator=gen)
+            shard = full.chunk(tp_world, dim=dim)[tp_rank] if sharded else full
+            p.copy_(shard.to(p.dtype))
+            del full
+            n += 1
+    return n
+
+
+def losses_to_dict(torch, loss_tensors):
+    vals = torch.stack([l.detach().float().reshape(()) for l in loss_tensors]).cpu().tolist() if loss_tensors else []
+    return {str(i + 1): round(float(v), 5) for i, v in enumerate(vals)}
+
+
 # ------------------------------------------------------------------------------------------------
+def _b200_variant(args, torch, dist, rank, world, local, *, sequence_parallel, recompute, main_grads_fp32, want_e2e, sample_clocks):
+    """Build a TrainEngine, run W warm-up + K timed steps (+ the e2e loop).  Returns a dict of plain floats."""
+    from megatron_b200 import ops
+    from megatron_b200.training.engine import TrainEngine
+
+    overrides = {}
+    if args.layers:
+        overrides["num_layers"] = args.layers
+    eng = TrainEngine(args.model, tensor_model_parallel_size=world, sequence_parallel=sequence_parallel, micro_batch_size=args.micro_batch,
+                      global_batch_size=args.global_batch, seq_length=args.seq, bf16=True, model_overrides=overrides, lr=LR, min_lr=MIN_LR,
+                      weight_decay=WD, clip_grad=CLIP, grad_reduce_in_fp32=main_grads_fp32, **recompute)
+    from megatron_b200.core import parallel_state as ps
+
+    n_init = 0
+    for chunk in eng.model_chunks:
+        n_init += deterministic_init(torch, chunk.named_parameters(), ps.get_tensor_model_parallel_rank(), world, eng.preset["num_layers"])
+    eng.optimizer.reload_model_params()
+    host = synthetic_tokens(torch, eng.num_microbatches * args.micro_batch, eng.seq_length, eng.preset["vocab_size"]).pin_memory()
+    dev_tokens = host.to("cuda")
+    losses = []
+
+    def step_dev():
+        losses.append(eng.train_step(dev_tokens))
+
+    def step_e2e():
+        losses.append(eng.train_step(host))
+        return float(losses[-1])                  # D2H read of the step's loss every step
+
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local)
+    if rank == 0 and sample_clocks:
+        sampler.start()
+    ops.reset_launch_count()
+    ms, _wall = timed_loop(torch, dist, step_dev, args.steps, world)
+    launches = ops.launch_count()
+    clocks = sampler.stop() if (rank == 0 and sample_clocks) else {}
+    tokens_per_step = args.global_batch * eng.seq_length
+    res = {"value": tokens_per_step * args.steps / (ms / 1e3), "ms_per_step": ms / args.steps, "gpu_launches": launches, "clocks": clocks,
+           "tflops_per_gpu": eng.flops_per_step * args.steps / (ms / 1e3) / world / 1e12, "seq_length": eng.seq_length, "params_initialised": n_init}
+    if want_e2e:
+        step_e2e()
+        _, e_wall = timed_loop(torch, dist, step_e2e, args.steps, world)
+        res["e2e"] = {"value": tokens_per_step * args.steps / (e_wall / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": host.numel() * host.element_size(),
+                      "d2h_bytes_per_step": 4, "timing": "host wall clock incl. H2D of the step's tokens from pinned memory and D2H loss read, max over ranks"}
+    res["loss_by_step"] = losses_to_dict(torch, losses)
+    res["peak_mem_gib"] = torch.cuda.max_memory_allocated() / 2**30
+    # drop every reference to the engine so a second variant fits
+    del eng, dev_tokens, losses, step_dev, step_e2e
+    gc.collect()
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
+    return res
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -125,58 +241,53 @@ def run_b200(args):
     if args.tp_comm:
         os.environ["MEGATRON_B200_TP_COMM"] = args.tp_comm
     from megatron_b200 import ops
-    from megatron_b200.training.engine import TrainEngine
+    from megatron_b200.training import engine as _engine
 
     torch.cuda.set_device(local)
-    overrides = {}
-    if args.layers:
-        overrides["num_layers"] = args.layers
-    recompute = {}
+    _engine.initialize_distributed()
+    fp32_grads = args.main_grads == "fp32"
     if args.recompute == "auto":
-        # 1 GPU holds all 8B parameters + optimizer state: recompute the cheap ops' outputs
-        recompute = dict(recompute_granularity="selective", recompute_modules=["layernorm", "mlp_act"]) if world == 1 else {}
+        # one GPU holds all 8B parameters + fp32 grads + optimizer state (135 GiB): also recompute the cheap ops' outputs
+        mods = ["core_attn", "layernorm", "mlp_act"] if world == 1 else ["core_attn"]
+        recompute = dict(recompute_granularity="selective", recompute_modules=mods)
     elif args.recompute == "full":
         recompute = dict(recompute_granularity="full", recompute_method="uniform", recompute_num_layers=1)
-    eng = TrainEngine(args.model, tensor_model_parallel_size=world, sequence_parallel=world > 1, micro_batch_size=args.micro_batch,
-                      global_batch_size=args.global_batch, seq_length=args.seq, bf16=True, model_overrides=overrides, **recompute)
-    host = eng.synthetic_batch(pinned=True, seed=rank * 0 + 17)
-    dev_tokens = host.to("cuda")
-    last = {}
+    elif args.recompute == "none":
+        recompute = {}
+    else:
+        recompute = dict(recompute_granularity="selective", recompute_modules=args.recompute.split(","))
 
-    def step_dev():
-        last["loss"] = eng.train_step(dev_tokens)
+    main = _b200_variant(args, torch, dist, rank, world, local, sequence_parallel=False, recompute=recompute, main_grads_fp32=fp32_grads,
+                         want_e2e=not args.no_e2e, sample_clocks=True)
+    # fused-vs-NCCL self check of every GEMM<->collective pair op on this model's shapes (N >= 2)
+    pair_err = None
+    if world > 1:
+        try:
+            from megatron_b200.parallel.selfcheck import pair_op_self_check
 
-    def step_e2e():
-        last["loss_host"] = float(eng.train_step(host))  # H2D of inputs + D2H of the loss every step
-
-    for _ in range(args.warmup):
-        step_dev()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ops.reset_launch_count()
-    ms, wall_ms = timed_loop(torch, dist, step_dev, args.steps, world)
-    launches = ops.launch_count()
-    clocks = sampler.stop() if rank == 0 else {}
-    tokens_per_step = args.global_batch * eng.seq_length
-    value = tokens_per_step * args.steps / (ms / 1e3)
-    e2e = None
-    if not args.no_e2e:
-        step_e2e()
-        _, e_wall = timed_loop(torch, dist, step_e2e, args.steps, world)
-        e2e = {"value": tokens_per_step * args.steps / (e_wall / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": host.numel() * host.element_size(),
-               "d2h_bytes_per_step": 4, "timing": "host wall clock incl. H2D inputs from pinned memory and D2H loss read, max over ranks"}
-    peak = torch.cuda.max_memory_allocated() / 2**30
+            pair_err = pair_op_self_check(dist.group.WORLD, seq=main["seq_length"], quick=True)
+        except Exception as e:  # never lose the headline over the self check
+            pair_err = {"error": f"{type(e).__name__}: {e}"[:200]}
     from megatron_b200.ops import gemm as _gemm
     from megatron_b200.parallel import fused as _fusedmod
 
-    _tp_mode = _fusedmod.get_mode(world_size=world) if world > 1 else "n/a"
-    _gemm_wins = {}
+    tp_mode = _fusedmod.get_mode(world_size=world) if world > 1 else "n/a"
+    gemm_wins = {}
     for _key, _winner, _times in _gemm.tuning_report():
-        _gemm_wins[str(_winner).split(":")[0]] = _gemm_wins.get(str(_winner).split(":")[0], 0) + 1
-    _attn_impl = ops.attention_impl_for(eng.seq_length, args.micro_batch, 32 // world) if hasattr(ops, "attention_impl_for") else "library"
+        gemm_wins[str(_winner).split(":")[0]] = gemm_wins.get(str(_winner).split(":")[0], 0) + 1
+    attn_impl = ops.attention_impl_for(main["seq_length"], args.micro_batch, 32 // world) if hasattr(ops, "attention_impl_for") else "library"
+
+    sp = None
+    if world > 1 and not args.no_sp_variant:
+        try:
+            v = _b200_variant(args, torch, dist, rank, world, local, sequence_parallel=True, recompute={}, main_grads_fp32=fp32_grads,
+                              want_e2e=False, sample_clocks=False)
+            sp = {"parallelism": f"tp{world}+sp", "recompute": "none", "value": v["value"], "unit": "tokens/s", "ms_per_step": v["ms_per_step"],
+                  "tflops_per_gpu": v["tflops_per_gpu"], "gpu_launches": v["gpu_launches"], "peak_mem_gib": v["peak_mem_gib"],
+                  "loss_by_step": v["loss_by_step"], "note": "the design point of this repo (fused AG->GEMM / GEMM->RS kernels); the stock reference cannot run it"}
+        except BaseException as e:  # noqa: BLE001 — the headline above must still be printed
+            sp = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0:
-        flops = eng.flops_per_step * args.steps / (ms / 1e3)
         mp = {}
         try:
             mp = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
@@ -184,32 +295,37 @@ def run_b200(args):
             pass
         peak_tf = mp.get("bf16_tflops_sustained", 1400.0)
         out = {
-            "metric": "tokens/sec (whole job, device-timed, max over ranks), Llama-3-8B TP=N + sequence parallel", "value": value, "unit": "tokens/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random token ids of the named shape; random-init weights)",
-            "impl": "b200", "tflops_per_gpu": flops / world / 1e12, "mfu_of_measured_sustained_cublas": flops / world / 1e12 / peak_tf,
-            "loss": float(last["loss"]), "peak_mem_gib": peak, "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
+            "metric": METRIC, "value": main["value"], "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic (uniform random token ids of the named shape, seed 17; name-seeded random-init weights identical in both arms)",
+            "impl": "b200", "tflops_per_gpu": main["tflops_per_gpu"], "mfu_of_measured_sustained_cublas": main["tflops_per_gpu"] / peak_tf,
+            "loss_by_step": main["loss_by_step"], "peak_mem_gib": main["peak_mem_gib"], "gpu_launches": main["gpu_launches"], "clocks": main["clocks"],
+            "e2e": main.get("e2e"), "pair_op_max_rel_err": pair_err,
             "config": {"model": args.model + (f"[layers={args.layers} DEV-INVALID]" if args.layers else ""), "global_batch": args.global_batch,
-                       "micro_batch": args.micro_batch, "seq_len": eng.seq_length, "parallelism": f"tp{world}" + ("+sp" if world > 1 else ""),
+                       "micro_batch": args.micro_batch, "seq_len": main["seq_length"], "parallelism": f"tp{world}", "sequence_parallel": False,
                        "l2_policy": "inputs larger than L2 (16 GB of bf16 weights + activations stream through the 126 MB L2 every step)",
-                       "main_grads": "bf16", "optimizer": "fused AdamW, fp32 master+moments", "recompute": recompute or "none",
-                       "tp_comm": os.environ.get("MEGATRON_B200_TP_COMM", "auto"), "tp_comm_resolved": _tp_mode, "gemm": os.environ.get("MEGATRON_B200_GEMM", "auto"),
-                       "plain_gemm_shapes_tuned": _gemm_wins, "attention": _attn_impl},
+                       "main_grads": args.main_grads, "optimizer": f"AdamW lr={LR} wd={WD} betas=({BETA1},{BETA2}) clip={CLIP}; fused multi-tensor kernel, fp32 master+moments",
+                       "recompute": recompute or "none", "tp_comm": os.environ.get("MEGATRON_B200_TP_COMM", "auto"), "tp_comm_resolved": tp_mode,
+                       "gemm": os.environ.get("MEGATRON_B200_GEMM", "auto"), "plain_gemm_shapes_tuned": gemm_wins, "attention": attn_impl,
+                       "sp_variant": sp},
         }
         print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    try:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
     """The UNMODIFIED reference (baseline/_ref, megatron-core 0.20.0) through its public API:
-    parallel_state → GPTModel(local spec) → DistributedDataParallel → get_megatron_optimizer →
-    get_forward_backward_func → finalize_model_grads.  TransformerEngine/Apex are not installed, so
+    parallel_state -> GPTModel(local spec) -> DistributedDataParallel -> get_megatron_optimizer ->
+    get_forward_backward_func -> finalize_model_grads.  TransformerEngine/Apex are not installed, so
     this is the reference's stock "local" path (cuBLAS + NCCL, unfused attention, torch AdamW).
-    The local backend asserts `not sequence_parallel` for its norm layers, so TP=N runs WITHOUT
-    sequence parallelism (all-reduce TP) — the closest configuration the stock code supports."""
+    Same workload as the repo arm (see the module docstring): TP=N without sequence parallelism,
+    selective(core_attn) recompute, fp32 main grads, identical initial weights and tokens."""
     ref = os.path.join(REPO, "baseline", "_ref")
     if not os.path.isdir(os.path.join(ref, "megatron", "core")):
         print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref is not installed (pip install --no-deps --target baseline/_ref /root/reference)"}))
@@ -229,8 +345,6 @@ def run_reference(args):
     os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "1")
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     try:
-        from functools import partial
-
         import torch.nn.functional as F
         from megatron.core import parallel_state
         from megatron.core.distributed import DistributedDataParallel, DistributedDataParallelConfig
@@ -246,10 +360,13 @@ def run_reference(args):
             print(json.dumps({"impl": "reference", "unavailable": f"import failed: {type(e).__name__}: {e}"[:300]}))
         return
 
-    P = dict(num_layers=args.layers or 32, hidden=4096, ffn=14336, heads=32, groups=8, kv=128, vocab=128256, seq=args.seq or 8192)
+    P = dict(LLAMA3_8B)
+    P["num_layers"] = args.layers or P["num_layers"]
+    P["seq"] = args.seq or P["seq"]
     assert args.model == "llama3_8b", "reference arm implements the headline config only"
     parallel_state.initialize_model_parallel(tensor_model_parallel_size=world)
     model_parallel_cuda_manual_seed(1234)
+    fp32_grads = args.main_grads == "fp32"
 
     def build(recompute):
         cfg = TransformerConfig(
@@ -260,16 +377,16 @@ def run_reference(args):
         )
         m = GPTModel(cfg, get_gpt_layer_local_spec(normalization="RMSNorm"), vocab_size=P["vocab"], max_sequence_length=P["seq"], parallel_output=True,
                      share_embeddings_and_output_weights=False, position_embedding_type="rope", rotary_base=500000).cuda()
-        ddp = DistributedDataParallel(cfg, DistributedDataParallelConfig(grad_reduce_in_fp32=False, overlap_grad_reduce=False, use_distributed_optimizer=True), m)
-        opt = get_megatron_optimizer(OptimizerConfig(optimizer="adam", lr=3e-4, min_lr=3e-5, weight_decay=0.1, bf16=True, params_dtype=torch.bfloat16,
-                                                     clip_grad=1.0, use_distributed_optimizer=True, adam_beta1=0.9, adam_beta2=0.95), [ddp])
+        n_init = deterministic_init(torch, m.named_parameters(), parallel_state.get_tensor_model_parallel_rank(), world, P["num_layers"])
+        ddp = DistributedDataParallel(cfg, DistributedDataParallelConfig(grad_reduce_in_fp32=fp32_grads, overlap_grad_reduce=False, use_distributed_optimizer=True), m)
+        opt = get_megatron_optimizer(OptimizerConfig(optimizer="adam", lr=LR, min_lr=MIN_LR, weight_decay=WD, bf16=True, params_dtype=torch.bfloat16,
+                                                     clip_grad=CLIP, use_distributed_optimizer=True, adam_beta1=BETA1, adam_beta2=BETA2), [ddp])
         cfg.finalize_model_grads_func = finalize_model_grads
         cfg.no_sync_func = ddp.no_sync
-        return cfg, ddp, opt
+        return cfg, ddp, opt, n_init
 
     nmb = args.global_batch // args.micro_batch
-    g = torch.Generator().manual_seed(17)
-    host = torch.randint(0, P["vocab"], (nmb * args.micro_batch, P["seq"] + 1), generator=g, dtype=torch.int64).pin_memory()
+    host = synthetic_tokens(torch, nmb * args.micro_batch, P["seq"], P["vocab"]).pin_memory()
     dev_tokens = host.cuda()
     pos = torch.arange(P["seq"], device="cuda").unsqueeze(0).expand(args.micro_batch, -1).contiguous()
     fwd_bwd = get_forward_backward_func()
@@ -283,6 +400,7 @@ def run_reference(args):
         return model(b[:, :-1].contiguous(), pos, None, labels=b[:, 1:].contiguous()), loss_func
 
     state = {}
+    losses = []
 
     def make_step(tokens_fn, sync_loss):
         def step():
@@ -290,11 +408,13 @@ def run_reference(args):
             state["ddp"].zero_grad_buffer()
             state["opt"].zero_grad()
             it = iter(t[i * args.micro_batch : (i + 1) * args.micro_batch] for i in range(nmb))
-            losses = fwd_bwd(forward_step_func=fstep, data_iterator=it, model=state["ddp"], num_microbatches=nmb, seq_length=P["seq"],
-                             micro_batch_size=args.micro_batch, forward_only=False)
+            out = fwd_bwd(forward_step_func=fstep, data_iterator=it, model=state["ddp"], num_microbatches=nmb, seq_length=P["seq"],
+                          micro_batch_size=args.micro_batch, forward_only=False)
             state["opt"].step()
-            l = torch.stack([d["lm loss"] for d in losses]).mean()
-            state["loss"] = float(l) if sync_loss else l
+            l = torch.stack([d["lm loss"] for d in out]).mean()
+            losses.append(l)
+            if sync_loss:
+                return float(l)
         return step
 
     full = dict(recompute_granularity="full", recompute_method="uniform", recompute_num_layers=1)
@@ -303,16 +423,18 @@ def run_reference(args):
                 ("full(uniform,1)+bf16-softmax", dict(full, attention_softmax_in_fp32=False))]
     if world == 1:
         # measured on the 180 GB part: selective recompute OOMs at TP=1 (fp32 [32,8192,8192] scores on top of
-        # 120 GiB of parameter/optimizer state) and a failed attempt fragments the heap — start from full recompute
+        # >= 120 GiB of parameter/optimizer state) and a failed attempt fragments the heap — start from full recompute
         attempts = attempts[1:]
     if os.environ.get("REF_RECOMPUTE"):
         attempts = [a for a in attempts if a[0].startswith(os.environ["REF_RECOMPUTE"])] or attempts
     used = None
+    n_init = 0
     for name, rc in attempts:
         try:
             state.clear()
+            losses.clear()
             torch.cuda.empty_cache()
-            state["cfg"], state["ddp"], state["opt"] = build(rc)
+            state["cfg"], state["ddp"], state["opt"], n_init = build(rc)
             step_dev = make_step(lambda: dev_tokens, False)
             for _ in range(args.warmup):
                 step_dev()
@@ -323,8 +445,6 @@ def run_reference(args):
             if rank == 0:
                 print(f"[reference] OOM with recompute={name}: {str(e)[:300]}", file=sys.stderr, flush=True)
             state.clear()
-            import gc
-
             gc.collect()
             torch.cuda.empty_cache()
             continue
@@ -333,7 +453,8 @@ def run_reference(args):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if not int(ok):
         if rank == 0:
-            print(json.dumps({"impl": "reference", "unavailable": "reference local path runs out of memory on this config even with full activation recompute"}))
+            print(json.dumps({"impl": "reference", "metric": METRIC, "n_gpus": world,
+                              "unavailable": "reference local path runs out of memory on this config even with full activation recompute (unfused fp32 [32,8192,8192] attention scores + torch AdamW temporaries on top of the parameter/optimizer state)"}))
         return
     sampler = ClockSampler(local)
     if rank == 0:
@@ -347,17 +468,21 @@ def run_reference(args):
         step_e2e = make_step(lambda: host.cuda(non_blocking=True), True)
         step_e2e()
         _, e_wall = timed_loop(torch, dist, step_e2e, args.steps, world)
-        e2e = {"value": tokens_per_step * args.steps / (e_wall / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": host.numel() * 8, "d2h_bytes_per_step": 4}
+        e2e = {"value": tokens_per_step * args.steps / (e_wall / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": host.numel() * 8, "d2h_bytes_per_step": 4,
+               "timing": "host wall clock incl. H2D of the step's tokens from pinned memory and D2H loss read, max over ranks"}
+    loss_by_step = losses_to_dict(torch, losses)
     if rank == 0:
-        loss = state.get("loss")
         print(json.dumps({
-            "impl": "reference", "metric": "tokens/sec (whole job, device-timed, max over ranks), Llama-3-8B TP=N", "value": value, "unit": "tokens/s",
+            "impl": "reference", "metric": METRIC, "value": value, "unit": "tokens/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "loss": float(loss) if loss is not None else None, "clocks": clocks, "e2e": e2e,
-            "peak_mem_gib": torch.cuda.max_memory_allocated() / 2**30,
+            "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic (uniform random token ids of the named shape, seed 17; name-seeded random-init weights identical in both arms)",
+            "loss_by_step": loss_by_step, "clocks": clocks, "e2e": e2e, "peak_mem_gib": torch.cuda.max_memory_allocated() / 2**30,
             "config": {"model": args.model + (f"[layers={args.layers} DEV-INVALID]" if args.layers else ""), "global_batch": args.global_batch,
-                       "micro_batch": args.micro_batch, "seq_len": P["seq"], "parallelism": f"tp{world} (no SP: local backend asserts not sequence_parallel)",
-                       "recompute": used, "backend": "megatron-core 0.20.0 local spec (TE/Apex absent): cuBLAS + NCCL + torch AdamW, unfused attention"},
+                       "micro_batch": args.micro_batch, "seq_len": P["seq"], "parallelism": f"tp{world}", "sequence_parallel": False,
+                       "main_grads": args.main_grads, "optimizer": f"AdamW lr={LR} wd={WD} betas=({BETA1},{BETA2}) clip={CLIP}; torch.optim.AdamW behind megatron DistributedOptimizer",
+                       "recompute": used, "params_initialised": n_init,
+                       "backend": "megatron-core 0.20.0 local spec (TE/Apex absent): cuBLAS + NCCL + torch AdamW, unfused attention"},
         }), flush=True)
     if world > 1:
         dist.barrier()

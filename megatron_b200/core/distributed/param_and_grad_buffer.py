@@ -95,15 +95,22 @@ class _ParamAndGradBucketGroup:
             from ...parallel import collectives
 
             nvl = collectives.backend_for(self.group)
+        # Reference semantics (param_and_grad_buffer.py:600-700): always pre-multiply by gradient_scaling_factor (expert /
+        # GTP factors survive average_in_collective); averaging adds a further 1/group_size, fused into the kernel or ReduceOp.AVG.
         scale = b.gradient_scaling_factor
+        avg = bool(cfg.average_in_collective)
         if nvl is not None:
+            eff = scale / self.group_size if avg else scale
             if cfg.use_distributed_optimizer:
-                return nvl.reduce_scatter_scaled_(b.grad_data, scale, async_op=async_op)
-            return nvl.all_reduce_scaled_(b.grad_data, scale, async_op=async_op)
+                return nvl.reduce_scatter_scaled_(b.grad_data, eff, async_op=async_op)
+            return nvl.all_reduce_scaled_(b.grad_data, eff, async_op=async_op)
         op = dist.ReduceOp.SUM
-        if cfg.average_in_collective and b.grad_data.is_cuda:
-            op = dist.ReduceOp.AVG
-        elif scale != 1.0:
+        if avg:
+            if b.grad_data.is_cuda and dist.get_backend(self.group) == "nccl":
+                op = dist.ReduceOp.AVG
+            else:
+                scale = scale / self.group_size          # gloo has no AVG: SUM x 1/group_size
+        if scale != 1.0:
             b.grad_data.mul_(scale)
         if cfg.use_distributed_optimizer:
             local = shard_buffer(b.grad_data, self.group_size)[self.rank]

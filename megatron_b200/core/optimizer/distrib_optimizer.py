@@ -196,20 +196,46 @@ class DistributedOptimizer(MixedPrecisionOptimizer):
         self._dp_reshardable_layout = by_bucket
         return out
 
-    def _gather_full(self, src_of_slot) -> Dict[torch.nn.Parameter, torch.Tensor]:
-        """All-gather per-param pieces over the DP group into model-shaped fp32 tensors."""
+    def _gather_full(self, src_of_slot, templates_only: bool = False) -> Dict[torch.nn.Parameter, torch.Tensor]:
+        """Model-shaped fp32 tensors of one optimizer state, staged on the HOST.
+
+        One all-gather per bucket (its dp shards are contiguous slices of the bucket), never a full-model buffer: the
+        device high-water mark is one bucket, and nothing stays resident after the checkpoint call (the reference gathers
+        per bucket to dp rank 0 as well, ``distrib_optimizer.py:1300-1420``).  ``templates_only`` (loading): no
+        communication, just empty destinations."""
         full: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        pin = torch.cuda.is_available()
+        if templates_only:
+            for buf in self.buffers:
+                for p in buf.param_index_map:
+                    full[p] = torch.empty(p.shape, dtype=torch.float32)
+            return full
+        pieces: Dict[Tuple[int, int], List[Tuple[Slot, Range]]] = {}
+        for bi, bid, si, rng in self.slot_meta:
+            pieces.setdefault((bi, bid), []).append((self.slots[si], rng))
         for bi, buf in enumerate(self.buffers):
-            flat = torch.zeros(buf.numel, dtype=torch.float32, device=buf.grad_data.device)
-            for (b2, bid, si, rng) in self.slot_meta:
-                if b2 == bi:
-                    src = src_of_slot(self.slots[si])
+            params_of_bucket: Dict[int, list] = {}
+            for p, (s, e, bid) in buf.param_index_map.items():
+                params_of_bucket.setdefault(bid, []).append((p, s, e))
+            for bid, bucket in enumerate(buf.buckets):
+                n = bucket.grad_data.numel()
+                shard = n // self.dp_size
+                w0 = bucket.offset + self.dp_rank * shard
+                mine = torch.zeros(shard, dtype=torch.float32, device=bucket.grad_data.device)
+                for slot, rng in pieces.get((bi, bid), []):
+                    src = src_of_slot(slot)
                     if src is not None:
-                        flat[rng.start : rng.end] = src
-            if self.dp_size > 1:
-                dist.all_reduce(flat, group=self.data_parallel_group)  # disjoint ranges ⇒ sum = gather
-            for p, (s, e, _) in buf.param_index_map.items():
-                full[p] = flat[s:e].view(p.shape)
+                        mine[rng.start - w0 : rng.end - w0] = src
+                if self.dp_size > 1:
+                    flat = torch.empty(n, dtype=torch.float32, device=mine.device)
+                    dist.all_gather_into_tensor(flat, mine, group=self.data_parallel_group)
+                else:
+                    flat = mine
+                for p, s, e in params_of_bucket.get(bid, []):
+                    host = torch.empty(p.shape, dtype=torch.float32, pin_memory=pin)
+                    host.copy_(flat[s - bucket.offset : e - bucket.offset].view(p.shape))
+                    full[p] = host
+                del flat, mine
         return full
 
     def _sharded_fully_reshardable(self, model_sharded_state_dict, is_loading: bool):
@@ -222,10 +248,8 @@ class DistributedOptimizer(MixedPrecisionOptimizer):
         id_map = get_param_id_to_sharded_param_map(model_sharded_state_dict, params)
         out = self._common()
         st = {}
-        self._full_tensors = {}
         for nm in names:
-            full = self._gather_full(lambda s, _nm=nm: s.master if _nm == "param" else getattr(s, _nm))
-            self._full_tensors[nm] = full
+            full = self._gather_full(lambda s, _nm=nm: s.master if _nm == "param" else getattr(s, _nm), templates_only=is_loading)
             for i, p in enumerate(params):
                 key_nm = "fp32_param" if nm == "param" else nm
                 st.setdefault(i, {})[key_nm] = make_sharded_optimizer_tensor(id_map[i], full[p], prefix=f"optimizer.state.{key_nm}")

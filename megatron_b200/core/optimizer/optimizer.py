@@ -174,10 +174,11 @@ class MegatronOptimizer(ABC):
         cfg = self.config
         for gi, group in enumerate(self.param_groups):
             slots = [s for s in self.slots if s.group == gi and s.grad is not None and s.master.numel() > 0]
-            if not slots:
-                continue
+            # every rank counts every group's step (a dp rank may hold no slot of a group; the saved common "step" must agree)
             self.step_count[gi] += 1
             group["step"] = self.step_count[gi]
+            if not slots:
+                continue
             lr, wd = group["lr"], group.get("weight_decay", 0.0)
             for s in slots:
                 self._init_slot_state(s)

@@ -70,7 +70,9 @@ def set_current_microbatch(model, microbatch_id):
 def forward_step_calc_loss(model, output_tensor, loss_func, config, vp_stage, collect_non_loss_data, num_microbatches, forward_data_store,
                            cp_group_size=None, is_last_stage=None):
     """Run the user loss on the last stage; returns ``(output_tensor, num_tokens)``."""
-    num_tokens = torch.tensor(0, dtype=torch.int)
+    # on the accelerator (reference: device="cuda") so the pp broadcast / dp x cp all-reduce in finalize_model_grads work over NCCL
+    _dev = output_tensor.device if isinstance(output_tensor, torch.Tensor) else (output_tensor[0].device if output_tensor else torch.device("cpu"))
+    num_tokens = torch.tensor(0, dtype=torch.int, device=_dev)
     if is_last_stage is None:
         is_last_stage = ps.is_pipeline_last_stage(ignore_virtual=False, vp_stage=vp_stage)
     if cp_group_size is None:
@@ -92,12 +94,36 @@ def forward_step_calc_loss(model, output_tensor, loss_func, config, vp_stage, co
             forward_data_store.append(loss_func(output_tensor, non_loss_data=True))
     if config.timers is not None:
         pass
-    # MoE auxiliary losses are scaled by the same factor as the main loss
-    if getattr(config, "num_moe_experts", None) is not None:
-        from ..transformer.moe.moe_utils import MoEAuxLossAutoScaler
+    # Auxiliary losses injected through autograd "scaler" functions must see the same factor as the main loss
+    # (reference schedules.py:355-397): loss_scale * cp / num_microbatches, or the bare loss scale with per-token loss.
+    per_token = config.calculate_per_token_loss
+    has_moe = getattr(config, "num_moe_experts", None) is not None
+    has_mtp = getattr(config, "mtp_num_layers", None) is not None
+    has_dsa = getattr(config, "experimental_attention_variant", None) == "dsa" or float(getattr(config, "dsa_indexer_loss_coeff", 0.0) or 0.0) > 0
+    if has_moe or has_mtp or has_dsa:
+        dev = output_tensor.device if isinstance(output_tensor, torch.Tensor) else (
+            torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() and not config.use_cpu_initialization else torch.device("cpu"))
 
-        loss_scale = config.grad_scale_func(torch.ones(1, device=output_tensor.device)) if config.grad_scale_func is not None else torch.ones(1, device=output_tensor.device)
-        MoEAuxLossAutoScaler.set_loss_scale(loss_scale if config.calculate_per_token_loss else loss_scale / num_microbatches)
+        def _scale(func):
+            one = torch.ones(1, device=dev)
+            return func(one) if func is not None else one
+
+        cp_scale = cp_group_size if cp_group_size is not None else 1
+        if has_moe:
+            from ..transformer.moe.moe_utils import MoEAuxLossAutoScaler
+
+            ls = _scale(config.grad_scale_func)
+            MoEAuxLossAutoScaler.set_loss_scale(ls if per_token else ls * cp_scale / num_microbatches)
+        if has_mtp:
+            from ..transformer.multi_token_prediction import MTPLossAutoScaler
+
+            ls = _scale(getattr(config, "mtp_grad_scale_func", None) or config.grad_scale_func)
+            MTPLossAutoScaler.set_loss_scale(ls if per_token else ls / num_microbatches)
+        if has_dsa:
+            from ..transformer.experimental_attention_variant.dsa import DSAIndexerLossAutoScaler
+
+            ls = _scale(config.grad_scale_func)
+            DSAIndexerLossAutoScaler.set_loss_scale(ls if per_token else ls * cp_scale / num_microbatches)
     return output_tensor, num_tokens
 
 

@@ -209,10 +209,11 @@ class _TPLinearFn(torch.autograd.Function):
             # module overlaps the two pairs on separate streams / in-kernel.
             gx, gw = fused.sp_linear_backward(gy, x, weight, ctx.tp_group, wgrad_needed, ctx.grad_accum_fusion)
         else:
-            gx = fused.gemm_nn(gy, weight)
             handle = None
             if ctx.allreduce_dgrad and get_pg_size(ctx.tp_group) > 1:
-                handle = fused.all_reduce_async(gx, ctx.tp_group)
+                gx, handle = fused.dgrad_all_reduce(gy, weight, ctx.tp_group)      # fused GEMM->AR kernel, or GEMM + async collective
+            else:
+                gx = fused.gemm_nn(gy, weight)
             if wgrad_needed:
                 gw = fused.wgrad(gy, x, weight, ctx.grad_accum_fusion)
             if handle is not None:

@@ -138,7 +138,11 @@ class MoEAlltoAllTokenDispatcher(MoETokenDispatcher):
         L, E = self.num_local_experts, self.num_experts
         local_counts = routing_map.sum(dim=0).long()  # [E]
         if self.drop_and_pad:
-            cap = routing_map.shape[0] * self.config.moe_router_topk // E
+            # the SAME capacity the router's token dropping encoded in routing_map (reference token_dispatcher.py: get_capacity with the factor)
+            from .moe_utils import get_capacity
+
+            assert self.config.moe_expert_capacity_factor is not None, "moe_pad_expert_input_to_capacity requires moe_expert_capacity_factor"
+            cap = get_capacity(routing_map.shape[0] * self.config.moe_router_topk, E, self.config.moe_expert_capacity_factor)
             self.capacity = cap
             self.num_out_tokens = cap * E
             self.input_splits = self.output_splits = None

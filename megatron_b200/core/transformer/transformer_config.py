@@ -24,6 +24,11 @@ class TransformerConfig(ModelParallelConfig):
     num_layers: int = 0
     mtp_num_layers: Optional[int] = None
     mtp_loss_scaling_factor: Optional[float] = 0.1
+    mtp_grad_scale_func: Optional[Callable] = None
+    # experimental attention variants (reference transformer_config.py:301-311): 'dsa' | 'gdn' | 'gated_delta_net'
+    experimental_attention_variant: Optional[str] = None
+    experimental_attention_variant_loss_scale_func: Optional[Callable] = None
+    dsa_indexer_loss_coeff: float = 0.0
     num_layers_in_first_pipeline_stage: Optional[int] = None
     num_layers_in_last_pipeline_stage: Optional[int] = None
     pipeline_model_parallel_layout: Optional[Union[str, list]] = None

@@ -19,6 +19,7 @@
 // Buffer reuse needs no extra barrier: buffers are double-buffered by the host and every op needs data from
 // every peer, so a rank can only be two ops ahead of a peer that has finished reading the buffer being reused.
 // Replaces TE userbuffers `ub_overlap_ag/rs` and the NCCL calls in tensor_parallel/layers.py.
+#include <cstdio>
 #include <mutex>
 
 #include "gemm_sm100_device.cuh"
@@ -31,10 +32,11 @@ constexpr int CHUNK_ROWS = 256;   // = pair-tile rows
 constexpr int MAX_CHUNKS = 64;    // chunks per rank shard
 constexpr int AG_OFF = 0, RS_OFF = MAX_TP * MAX_CHUNKS, XAG_OFF = 2 * MAX_TP * MAX_CHUNKS;
 constexpr int XAG_COUNTER = MAX_TP * MAX_CHUNKS;  // index into the local counters array
+constexpr int AR_COUNTER = XAG_COUNTER + 8;        // + chunk: comm-warp counters of an all-reduce launch (counters array holds 1024 uint32)
 
 struct FusedParams {
   GemmParams g;
-  int mode;                 // 0 = AG, 1 = RS
+  int mode;                 // 0 = AG, 1 = RS, 2 = AR (GEMM -> all-reduce, result in place in the symmetric Y on every rank)
   int rank, world;
   int chunks_per_rank;      // rows_per_rank / 256
   int comm_clusters;        // clusters [0, comm_clusters) run the collective (scheduled first), the rest run the GEMM
@@ -63,6 +65,25 @@ __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Spin until *f has reached `epoch` (wrap-safe signed compare).  A peer that died or a protocol bug must not hang the box: after
+// SPIN_TIMEOUT_NS the kernel reports which flag it was waiting for and traps (the host sees a launch failure, not a deadlock).
+constexpr uint64_t SPIN_TIMEOUT_NS = 20ull * 1000000000ull;
+__device__ __forceinline__ void spin_until(const uint32_t* f, uint32_t epoch, int what) {
+  if ((int32_t)(ld_acquire_sys_u32(f) - epoch) >= 0) return;
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t it = 0;
+  while ((int32_t)(ld_acquire_sys_u32(f) - epoch) < 0) {
+    if ((++it & 0x3FFu) == 0 && globaltimer_ns() - t0 > SPIN_TIMEOUT_NS) {
+      printf("[mb200 fused_tp_gemm] flag wait timed out: kind=%d flag=%p have=%u want=%u block=%d\n", what, (const void*)f, ld_acquire_sys_u32(f), epoch, (int)blockIdx.x);
+      __trap();
+    }
+  }
 }
 __device__ __forceinline__ void mm_st_v4(void* mc, uint4 v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -99,6 +120,19 @@ __device__ __forceinline__ void pull_reduce_multicast(uint4* __restrict__ out, c
     for (int u = 0; u < U; ++u) out[i + (size_t)u * nthr] = v[u];
   }
   for (; i < n; i += nthr) out[i] = mm_ld_reduce_bf16x8(mc_src + i);
+}
+
+template <int U>
+__device__ __forceinline__ void reduce_broadcast_multicast(uint4* __restrict__ mc, size_t n, size_t tid, size_t nthr) {
+  size_t i = tid;
+  for (; i + (size_t)(U - 1) * nthr < n; i += (size_t)U * nthr) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = mm_ld_reduce_bf16x8(mc + i + (size_t)u * nthr);
+#pragma unroll
+    for (int u = 0; u < U; ++u) mm_st_v4(mc + i + (size_t)u * nthr, v[u]);
+  }
+  for (; i < n; i += nthr) mm_st_v4(mc + i, mm_ld_reduce_bf16x8(mc + i));
 }
 
 // position in the tile walk → M pair-tile index
@@ -214,13 +248,46 @@ fused_tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         for (int item = gwarp; item < C * SLICES; item += n_warps) {
           const int c = item / SLICES, sl = item % SLICES;
           if (lane < p.world) {
-            const uint32_t* f = p.flags_peer[p.rank] + RS_OFF + c * MAX_TP + lane;
-            while ((int32_t)(ld_acquire_sys_u32(f) - p.epoch) < 0) {
-            }
+            spin_until(p.flags_peer[p.rank] + RS_OFF + c * MAX_TP + lane, p.epoch, 1);
           }
           __syncwarp();
           const size_t src_off = ((size_t)p.rank * C + c) * chunk_vec + (size_t)sl * slice_vec;
           uint4* out = reinterpret_cast<uint4*>(p.rs_out) + (size_t)c * chunk_vec + (size_t)sl * slice_vec;
+          if (p.mode == 2) {
+            // all-reduce: the reduced rows go straight back into EVERY rank's Y (in place: only this warp reads these elements, and each
+            // element's broadcast store depends on its own reduction load), then the chunk is announced like an all-gather chunk
+            if (p.rs_src_mc != nullptr) {
+              reduce_broadcast_multicast<16>(reinterpret_cast<uint4*>(const_cast<void*>(p.rs_src_mc)) + src_off, slice_vec, (size_t)lane, 32);
+            } else {
+              for (size_t i = lane; i < slice_vec; i += 32) {
+                float acc[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+                for (int d = 0; d < p.world; ++d) {
+                  const uint4 v = reinterpret_cast<const uint4*>(p.rs_src_peer[(p.rank + d) % p.world])[src_off + i];
+                  const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) acc[k] += __bfloat162float(h[k]);
+                }
+                uint4 o;
+                __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ob[k] = __floats2bfloat162_rn(acc[2 * k], acc[2 * k + 1]);
+                for (int d = 0; d < p.world; ++d) reinterpret_cast<uint4*>(const_cast<void*>(p.rs_src_peer[(p.rank + d) % p.world]))[src_off + i] = o;
+              }
+            }
+            __threadfence_system();
+            __syncwarp();
+            uint32_t last = 0;
+            if (lane == 0) last = (atomicAdd(&p.counters[AR_COUNTER + c], 1u) == (uint32_t)SLICES - 1) ? 1u : 0u;
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+              if (lane == 0) p.counters[AR_COUNTER + c] = 0;
+              __threadfence();
+              if (lane < p.world) st_release_sys_u32(p.flags_peer[lane] + AG_OFF + p.rank * MAX_CHUNKS + c, p.epoch);
+            }
+            continue;
+          }
           if (p.rs_src_mc != nullptr) {
             pull_reduce_multicast<16>(out, reinterpret_cast<const uint4*>(p.rs_src_mc) + src_off, slice_vec, (size_t)lane, 32);
           } else {
@@ -243,12 +310,18 @@ fused_tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           }
         }
       }
+      if (p.mode == 2) {
+        // the kernel may not complete before every owner has written its reduced chunks into my Y: comm warps share the (rank, chunk) flags
+        const int n_warps = nctas * (NUM_THREADS / 32), gwarp = cta * (NUM_THREADS / 32) + warp;
+        for (int item = gwarp * 32 + lane; item < p.world * C; item += n_warps * 32) {
+          const int r = item / C, c = item % C;
+          spin_until(p.flags_peer[p.rank] + AG_OFF + r * MAX_CHUNKS + c, p.epoch, 3);
+        }
+      }
       if (p.xag_vec != 0 && cta == 0 && threadIdx.x < 32) {
         // the kernel may not complete before every peer's piggy-back shard has landed here
         if (lane < p.world) {
-          const uint32_t* f = p.flags_peer[p.rank] + XAG_OFF + lane;
-          while ((int32_t)(ld_acquire_sys_u32(f) - p.epoch) < 0) {
-          }
+          spin_until(p.flags_peer[p.rank] + XAG_OFF + lane, p.epoch, 2);
         }
       }
     }
@@ -302,9 +375,7 @@ fused_tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         if (p.mode == 0) {
           // wait until the 256-row chunk holding this tile's A rows has landed in the local gathered buffer
           const int r = m_blk / p.chunks_per_rank, c = m_blk % p.chunks_per_rank;
-          const uint32_t* f = p.flags_peer[p.rank] + AG_OFF + r * MAX_CHUNKS + c;
-          while ((int32_t)(ld_acquire_sys_u32(f) - p.epoch) < 0) {
-          }
+          spin_until(p.flags_peer[p.rank] + AG_OFF + r * MAX_CHUNKS + c, p.epoch, 0);
           fence_proxy_async_global();  // peer (generic-proxy) writes → our TMA (async-proxy) reads
         }
         const int m0 = m_blk * PM + (int)cta_rank * BM;
@@ -365,7 +436,7 @@ fused_tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       tc_fence_after();
       epilogue_tile<false>(Cptr, g, tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16), m_blk * PM + (int)cta_rank * BM + ew * 32 + lane, n_blk * BN, half * CH,
                            (half + 1) * CH, lane, &tmem_empty[acc], !leader);
-      if (p.mode == 1) {
+      if (p.mode >= 1) {
         // publish: this warp's part of tile (m_blk, n_blk) is in Y.  The last of tiles_n * 16 warp-parts of the
         // 256-row block tells the owner rank that its chunk is complete on this rank.
         __threadfence();

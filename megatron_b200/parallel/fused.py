@@ -146,12 +146,23 @@ def gemm_reduce_scatter(x: torch.Tensor, w: torch.Tensor, group) -> torch.Tensor
 
 
 def gemm_all_reduce(x: torch.Tensor, w: torch.Tensor, group) -> torch.Tensor:
+    """Row linear forward without SP: ``X Wᵀ`` then all-reduce (one fused kernel on the NVLink backend)."""
     be = _nvl(group, x)
-    y = gemm_nt(x, w)
     if be is not None:
-        return be.all_reduce(y)
+        return be.gemm_all_reduce(x, w, 0)
+    y = gemm_nt(x, w)
     dist.all_reduce(y, group=group)
     return y
+
+
+def dgrad_all_reduce(gy: torch.Tensor, w: torch.Tensor, group):
+    """Column linear dgrad without SP: ``dY W`` then all-reduce.  Returns ``(gx, handle)``: the fused kernel has already
+    reduced when it returns (handle None); the NCCL path returns the async handle so the wgrad GEMM overlaps the collective."""
+    be = _nvl(group, gy)
+    if be is not None:
+        return be.gemm_all_reduce(gy, w, 1), None
+    gx = gemm_nn(gy, w)
+    return gx, dist.all_reduce(gx, group=group, async_op=True)
 
 
 def sp_linear_backward(gy, x, weight, group, wgrad_needed: bool, accumulate: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:

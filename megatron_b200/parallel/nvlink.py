@@ -52,10 +52,16 @@ from .nvlink_moe import NVLinkMoEMixin
 class NVLinkBackend(NVLinkMoEMixin):
     SLOT_MAIN, SLOT_SIDE, SLOT_DDP = 0, 1, 2
 
-    def __init__(self, group, workspace_bytes: Optional[int] = None, heap_bytes: int = 0, use_multicast: Optional[bool] = None):
+    def __init__(self, group, workspace_bytes: Optional[int] = None, heap_bytes: int = 0, use_multicast: Optional[bool] = None, peer_heaps=None):
+        """``peer_heaps``: optional list of ``world`` uint8 CUDA tensors (this rank's own allocation at index ``rank``, the others mapped through
+        CUDA IPC) to use as the symmetric heap instead of ``torch.distributed._symmetric_memory`` — the P2P (no multicast) protocol then also runs
+        between processes that share ONE GPU, which is how the single-GPU CI box exercises the flag protocols (``tests/test_nvlink_ipc_gpu.py``)."""
+        assert ops.has_ext() and hasattr(ops.ext(), "nvl_allgather"), "native NVLink kernels are not built"
+        if peer_heaps is not None:
+            self._init_from_peer_heaps(group, peer_heaps)
+            return
         import torch.distributed._symmetric_memory as symm_mem
 
-        assert ops.has_ext() and hasattr(ops.ext(), "nvl_allgather"), "native NVLink kernels are not built"
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -93,6 +99,37 @@ class NVLinkBackend(NVLinkMoEMixin):
         self.fused_epoch = 0
         # CTA pairs reserved for communication inside a fused kernel (the rest of the 74 run the GEMM): pushes (AG) are
         # fire-and-forget and need fewer; in-switch pull-reductions (RS) are round-trip bound and need more in flight
+        self.fused_comm_clusters = [int(os.environ.get("MEGATRON_B200_FUSED_COMM_CLUSTERS_AG", "6")), int(os.environ.get("MEGATRON_B200_FUSED_COMM_CLUSTERS_RS", "10"))]
+        self.fused_calls = 0
+        dist.barrier(group=group)
+        self.barrier()
+
+    def _init_from_peer_heaps(self, group, peer_heaps):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        assert len(peer_heaps) == self.world and self.world <= MAX_RANKS
+        self.device = peer_heaps[self.rank].device
+        self._peer_heaps = list(peer_heaps)          # keep the IPC mappings alive
+        self.buf = peer_heaps[self.rank]
+        self.heap_bytes = self.buf.numel()
+        flag_bytes = _align(_FLAG_BYTES, 1 << 16)
+        self.ws_bytes = ((self.heap_bytes - flag_bytes) // 2) & ~((1 << 16) - 1)
+        self._symm = None
+        self.ptrs = [int(t.data_ptr()) for t in peer_heaps]
+        self.mc = 0
+        self.flags = list(self.ptrs)
+        self.ws_off = [flag_bytes, flag_bytes + self.ws_bytes]
+        self.user_off = self.ws_off[1] + self.ws_bytes
+        self._user_cursor = self.user_off
+        self.ctrl = torch.zeros(NUM_SLOTS * 4, dtype=torch.int32, device=self.device)
+        self.epoch = [0] * NUM_SLOTS
+        self._ws_turn = [0] * NUM_SLOTS
+        self.side_stream = torch.cuda.Stream()
+        self.nblocks = int(os.environ.get("MEGATRON_B200_NVL_BLOCKS", "32"))
+        self.fused_flags = [p + _FUSED_FLAG_OFF for p in self.ptrs]
+        self.fused_counters = torch.zeros(1024, dtype=torch.int32, device=self.device)
+        self.fused_epoch = 0
         self.fused_comm_clusters = [int(os.environ.get("MEGATRON_B200_FUSED_COMM_CLUSTERS_AG", "6")), int(os.environ.get("MEGATRON_B200_FUSED_COMM_CLUSTERS_RS", "10"))]
         self.fused_calls = 0
         dist.barrier(group=group)
@@ -254,9 +291,9 @@ class NVLinkBackend(NVLinkMoEMixin):
         ops.ext().fused_tp_gemm(
             mode, a, b, c, b_layout, self.rank, self.fused_epoch,
             ag_src if ag_src is not None else empty, (mc + ag_off) if (mc and mode == 0) else 0, [p + ag_off for p in self.ptrs] if mode == 0 else [],
-            (mc + rs_off) if (mc and mode == 1) else 0, [p + rs_off for p in self.ptrs] if mode == 1 else [], rs_out if rs_out is not None else empty,
+            (mc + rs_off) if (mc and mode >= 1) else 0, [p + rs_off for p in self.ptrs] if mode >= 1 else [], rs_out if rs_out is not None else empty,
             xag_src if xag_src is not None else empty, (mc + xag_off) if (mc and xag_src is not None) else 0,
-            [p + xag_off for p in self.ptrs] if xag_src is not None else [], self.fused_flags, self.fused_counters, self.fused_comm_clusters[mode],
+            [p + xag_off for p in self.ptrs] if xag_src is not None else [], self.fused_flags, self.fused_counters, self.fused_comm_clusters[min(mode, 1)],
         )
         self.fused_calls += 1
         ops._count()
@@ -295,6 +332,29 @@ class NVLinkBackend(NVLinkMoEMixin):
             full = self._view(off + ybytes, xag.numel() * self.world, xag.dtype).view(xag.shape[0] * self.world, xag.shape[1])
         self._fused_launch(1, x2, w, y, b_layout, rs_off=off, rs_out=out, xag_src=xag, xag_off=off + ybytes)
         return out, full
+
+    def _fused_gemm_ar(self, x: torch.Tensor, w: torch.Tensor, b_layout: int) -> torch.Tensor:
+        """One kernel: tcgen05 CTAs write partial tiles to symmetric memory; the owner of each 256-row block reduces it in the
+        switch (``multimem.ld_reduce``) and broadcasts the sum back into EVERY rank's buffer (``multimem.st``), in place.
+        Returns a VIEW of the symmetric workspace [M, N] (valid until two collectives later: consume or copy at once)."""
+        x2 = x.reshape(-1, x.shape[-1])
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        M, K = x2.shape
+        N = w.shape[0] if b_layout == 0 else w.shape[1]
+        off = self._workspace(self.SLOT_MAIN, _align(M * N * 2, 1 << 12))
+        y = self._view(off, M * N, x.dtype).view(M, N)
+        self._fused_launch(2, x2, w, y, b_layout, rs_off=off)
+        return y
+
+    def gemm_all_reduce(self, x: torch.Tensor, w: torch.Tensor, b_layout: int = 0) -> torch.Tensor:
+        """``X op(W)`` summed over the group (non-SP row-parallel forward: b_layout 0 = W[N,K]; column-parallel dgrad: 1 = W[K,N])."""
+        rows = x.numel() // x.shape[-1]
+        N = w.shape[0] if b_layout == 0 else w.shape[1]
+        if self._fused_ok(rows, N, x.shape[-1], x, w):
+            return self._fused_gemm_ar(x, w, b_layout).view(*x.shape[:-1], N).clone()
+        y = self.symmetric_like((*x.shape[:-1], N), x.dtype)
+        (ops.gemm_nt if b_layout == 0 else ops.gemm_nn)(x, w, out=y)
+        return self.all_reduce(y).clone()
 
     def all_gather_gemm(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
         rows = x.numel() // x.shape[-1]

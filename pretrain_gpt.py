@@ -59,12 +59,15 @@ def loss_func(loss_mask: torch.Tensor, output_tensor: torch.Tensor):
     rsm = get_rerun_state_machine()
     if args.check_for_nan_in_loss_and_grad or args.rerun_mode != "disabled":
         rsm.validate_result(total, rejection_func=lambda x: not bool(torch.isfinite(torch.as_tensor(x)).all()), message="found NaN/Inf in local forward loss", fatal=True)
+    local_total, local_ntok = total, ntok
     if args.context_parallel_size > 1:
         t = torch.stack([total, ntok])
         torch.distributed.all_reduce(t, group=ps.get_context_parallel_group())
         total, ntok = t[0], t[1]
     if args.calculate_per_token_loss:
-        return total, ntok.int(), {"lm loss": (total / ntok.clamp(min=1)).detach()}
+        # the schedule / finalize_model_grads sum num_tokens over dp x cp themselves: hand back the LOCAL sum and count
+        # (reference pretrain_gpt.py loss_func); the CP-reduced mean is for logging only
+        return local_total, local_ntok.detach().to(torch.int), {"lm loss": (total / ntok.clamp(min=1)).detach()}
     loss = total / ntok.clamp(min=1)
     return loss, {"lm loss": loss.detach()}
 

@@ -1,0 +1,89 @@
+"""Run the UNMODIFIED reference GPTModel (baseline/_ref) on CPU/gloo and dump loss + grads (test helper, run as a script).
+
+The reference assumes CUDA in three places that do not touch the math (device of the RoPE table, the default causal mask, the
+CUDA RNG tracker around dropout with p=0).  This harness patches those call sites from the outside; no reference file is edited.
+
+    torchrun/spawn env: RANK WORLD_SIZE MASTER_ADDR MASTER_PORT;  argv: out_prefix tp
+"""
+import contextlib
+import os
+import sys
+import zlib
+
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(REPO, "baseline", "_ref"))
+sys.path = [p for p in sys.path if os.path.abspath(p or ".") != REPO]
+torch.cuda.current_device = lambda: torch.device("cpu")
+import torch.distributed as dist  # noqa: E402
+
+
+def seeded_full(name, shape, std=0.05):
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()))
+    return torch.empty(shape).normal_(0, std, generator=g)
+
+
+def init_params(named_params, tp_rank, tp_world):
+    """Same rule as bench.py::deterministic_init: FULL tensor from a name-seeded generator, then this rank's slice."""
+    with torch.no_grad():
+        for n, p in named_params:
+            if p.dim() == 1:
+                p.fill_(1.0)
+                continue
+            sharded = bool(getattr(p, "tensor_model_parallel", False)) and tp_world > 1
+            dim = int(getattr(p, "partition_dim", -1))
+            shape = list(p.shape)
+            if sharded:
+                shape[dim] *= tp_world
+            full = seeded_full(n, shape)
+            p.copy_(full.chunk(tp_world, dim=dim)[tp_rank] if sharded else full)
+
+
+CFG = dict(num_layers=2, hidden_size=64, ffn_hidden_size=128, num_attention_heads=4, num_query_groups=2, kv_channels=16, vocab=128, seq=32, batch=2)
+
+
+def tokens():
+    return torch.randint(0, CFG["vocab"], (CFG["batch"], CFG["seq"] + 1), generator=torch.Generator().manual_seed(1))
+
+
+def main():
+    out_prefix, tp = sys.argv[1], int(sys.argv[2])
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import torch.nn.functional as F
+    import megatron.core.tensor_parallel as _tp
+    import megatron.core.tensor_parallel.random as _tpr
+    from megatron.core import parallel_state
+    from megatron.core.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatron.core.models.gpt.gpt_model import GPTModel
+    from megatron.core.transformer.transformer_config import TransformerConfig
+
+    class _NoRng:
+        def fork(self, *a, **k):
+            return contextlib.nullcontext()
+
+    _tp.get_cuda_rng_tracker = _tpr.get_cuda_rng_tracker = lambda *a, **k: _NoRng()
+    parallel_state.initialize_model_parallel(tensor_model_parallel_size=tp)
+    cfg = TransformerConfig(
+        num_layers=CFG["num_layers"], hidden_size=CFG["hidden_size"], ffn_hidden_size=CFG["ffn_hidden_size"], num_attention_heads=CFG["num_attention_heads"],
+        num_query_groups=CFG["num_query_groups"], kv_channels=CFG["kv_channels"], normalization="RMSNorm", gated_linear_unit=True, activation_func=F.silu,
+        add_bias_linear=False, hidden_dropout=0.0, attention_dropout=0.0, use_cpu_initialization=True, bias_activation_fusion=False, bias_dropout_fusion=False,
+        masked_softmax_fusion=False, gradient_accumulation_fusion=False, perform_initialization=False, tensor_model_parallel_size=tp,
+    )
+    m = GPTModel(cfg, get_gpt_layer_local_spec(normalization="RMSNorm"), vocab_size=CFG["vocab"], max_sequence_length=CFG["seq"], parallel_output=True,
+                 share_embeddings_and_output_weights=False, position_embedding_type="rope", rotary_base=10000)
+    init_params(m.named_parameters(), parallel_state.get_tensor_model_parallel_rank(), tp)
+    tok = tokens()
+    s = CFG["seq"]
+    pos = torch.arange(s).unsqueeze(0).expand(CFG["batch"], -1).contiguous()
+    mask = torch.triu(torch.ones(s, s), diagonal=1).bool()[None, None]
+    loss = m(tok[:, :-1].contiguous(), pos, mask, labels=tok[:, 1:].contiguous()).float().mean()
+    loss.backward()
+    torch.save({"loss": float(loss), "grads": {n: p.grad.clone() for n, p in m.named_parameters()}}, f"{out_prefix}.rank{rank}.pt")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,16 @@ def _worker(rank, world, port, q):
         dist.reduce_scatter_tensor(ref, part.contiguous())
         got = fused.gemm_reduce_scatter(xs, w2, g)
         assert torch.allclose(got.float(), ref, atol=0.08, rtol=0.05), f"gemm_reduce_scatter mismatch {(got.float()-ref).abs().max()}"
+        # every pair op (SP AG->GEMM / GEMM->RS fwd+bwd, no-SP GEMM->AR fwd+bwd) in fused mode vs NCCL + fp32 matmul: Llama-3-8B shapes,
+        # back-to-back workspace/flag reuse (repeats) and one deliberately late rank (skew)
+        from megatron_b200.parallel.selfcheck import pair_op_self_check
+
+        fused.set_mode("fused")
+        res = pair_op_self_check(g, seq=8192, quick=False, repeats=2, skew_rank=world - 1)
+        assert res["max"] < 2.5e-2, res
+        out["pair_ops"] = res
+        out["fused_calls"] = be.fused_calls
+        assert be.fused_calls >= 20, "fused kernels did not run"
         torch.cuda.synchronize()
         dist.barrier()
         q.put((rank, "ok", out))

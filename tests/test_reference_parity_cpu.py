@@ -1,0 +1,89 @@
+"""Loss and gradient parity with the UNMODIFIED reference (``baseline/_ref``, megatron-core 0.20.0) on identical weights and tokens.
+
+The same name-seeded full-tensor initialisation that ``bench.py`` applies to both arms is applied to a tiny Llama-style GPT in both
+frameworks (TP=1 and TP=2 over gloo); forward loss and every parameter gradient must agree to fp32 round-off.  This is the contract
+behind ``bench.py``'s ``loss_by_step`` comparison: same parameter names, same shard layout (interleaved QKV groups, [gate; up] fc1
+halves), same math.  Skipped when the reference is not installed."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(REPO, "baseline", "_ref", "megatron", "core")
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="baseline/_ref (the reference install) is absent")
+
+
+def _run_reference(tmp_path, tp):
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    prefix = str(tmp_path / f"ref_tp{tp}")
+    procs = []
+    for r in range(tp):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(tp), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(REPO, "tests", "helpers", "ref_cpu_model.py"), prefix, str(tp)], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=600)
+        assert p.returncode == 0, out[-3000:]
+    return [torch.load(f"{prefix}.rank{r}.pt") for r in range(tp)]
+
+
+def _ours(rank, world, tp):
+    sys.path.insert(0, os.path.join(REPO, "tests", "helpers"))
+    import torch.nn.functional as F
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+    import zlib
+
+    CFG = dict(num_layers=2, hidden_size=64, ffn_hidden_size=128, num_attention_heads=4, num_query_groups=2, kv_channels=16, vocab=128, seq=32, batch=2)
+    ps.initialize_model_parallel(tensor_model_parallel_size=tp)
+    cfg = TransformerConfig(
+        num_layers=CFG["num_layers"], hidden_size=CFG["hidden_size"], ffn_hidden_size=CFG["ffn_hidden_size"], num_attention_heads=CFG["num_attention_heads"],
+        num_query_groups=CFG["num_query_groups"], kv_channels=CFG["kv_channels"], normalization="RMSNorm", gated_linear_unit=True, activation_func=F.silu,
+        add_bias_linear=False, hidden_dropout=0.0, attention_dropout=0.0, use_cpu_initialization=True, gradient_accumulation_fusion=False,
+        perform_initialization=False, tensor_model_parallel_size=tp,
+    )
+    m = GPTModel(cfg, get_gpt_layer_local_spec(normalization="RMSNorm"), vocab_size=CFG["vocab"], max_sequence_length=CFG["seq"], parallel_output=True,
+                 share_embeddings_and_output_weights=False, position_embedding_type="rope", rotary_base=10000)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.dim() == 1:
+                p.fill_(1.0)
+                continue
+            sharded = bool(getattr(p, "tensor_model_parallel", False)) and tp > 1
+            dim = int(getattr(p, "partition_dim", -1))
+            shape = list(p.shape)
+            if sharded:
+                shape[dim] *= tp
+            g = torch.Generator().manual_seed(zlib.crc32(n.encode()))
+            full = torch.empty(shape).normal_(0, 0.05, generator=g)
+            p.copy_(full.chunk(tp, dim=dim)[ps.get_tensor_model_parallel_rank()] if sharded else full)
+    tok = torch.randint(0, CFG["vocab"], (CFG["batch"], CFG["seq"] + 1), generator=torch.Generator().manual_seed(1))
+    pos = torch.arange(CFG["seq"]).unsqueeze(0).expand(CFG["batch"], -1).contiguous()
+    loss = m(tok[:, :-1].contiguous(), pos, None, labels=tok[:, 1:].contiguous()).float().mean()
+    loss.backward()
+    return {"loss": float(loss), "grads": {n: p.grad.clone() for n, p in m.named_parameters()}, "names": [n for n, _ in m.named_parameters()]}
+
+
+@pytest.mark.parametrize("tp", [1, 2])
+def test_loss_and_grad_parity_with_reference(tmp_path, tp):
+    from dist_utils import run_distributed
+
+    ref = _run_reference(tmp_path, tp)
+    ours = run_distributed(_ours, tp, tp)
+    for r in range(tp):
+        assert sorted(ours[r]["names"]) == sorted(ref[r]["grads"].keys()), "parameter names differ from the reference's"
+        assert abs(ours[r]["loss"] - ref[r]["loss"]) < 2e-5, (ours[r]["loss"], ref[r]["loss"])
+        for n, g in ref[r]["grads"].items():
+            go = ours[r]["grads"][n]
+            err = float((go - g).abs().max() / g.abs().max().clamp(min=1e-12))
+            assert err < 2e-4, f"rank {r} grad {n}: rel err {err}"

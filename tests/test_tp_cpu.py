@@ -102,3 +102,18 @@ def test_gpt_tp2_sequence_parallel_matches_single():
 
 def test_gpt2_style_tp2_sp_layernorm_gelu():
     _check(sp=True, swiglu=False, norm="LayerNorm")
+
+
+def _selfcheck_worker(rank, world):
+    from megatron_b200.parallel.selfcheck import pair_op_self_check
+    import torch.distributed as dist
+
+    return pair_op_self_check(dist.group.WORLD, seq=world * 64, hidden=64, ffn=128, qkv=96, quick=False, repeats=2)
+
+
+def test_pair_op_self_check_gloo():
+    """The bench's fused-vs-collective self check runs (trivially passes) on the gloo decomposition of the pair ops."""
+    from dist_utils import run_distributed
+
+    res = run_distributed(_selfcheck_worker, 2)
+    assert res[0]["max"] < 1e-4 and len(res[0]) >= 12, res[0]
