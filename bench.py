@@ -10,7 +10,7 @@ Both arms print ONE JSON line on rank 0 with the IDENTICAL ``metric`` string and
 
   * the same Llama-3-8B architecture, TP=N **without** sequence parallelism (the stock reference's local norm
     asserts ``not sequence_parallel``), ``selective(core_attn)`` activation recompute, fp32 main-grad accumulation
-    (reference default with ``--bf16``: ``megatron/training/arguments.py:1204-1217``), AdamW(lr 3e-4, wd 0.1,
+    (reference default with ``--bf16``: ``megatron/training/arguments.py:1204-1217``), AdamW(lr 1e-5, wd 0.1,
     betas 0.9/0.95, clip 1.0), global batch 4 x seq 8192, micro-batch 1;
   * the same initial weights (every parameter generated from a name-seeded generator as the FULL tensor and
     sliced to this TP rank's shard) and the same synthetic tokens, so ``loss_by_step`` of the two arms is
