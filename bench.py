@@ -138,10 +138,11 @@ def timed_loop(torch, dist, step_fn, steps, world):
     return float(ms[0]), float(ms[1])
 
 
-def synthetic_tokens(torch, n_seq, seq, vocab):
-    """The benchmark's data: uniform random token ids [n_seq, seq+1] (inputs = [:, :-1], labels = [:, 1:])."""
+def synthetic_tokens(torch, n_seq, seq, vocab, n_steps):
+    """The benchmark's data: a DIFFERENT batch of uniform random token ids for every optimizer step, [n_steps, n_seq, seq+1]
+    (inputs = [..., :-1], labels = [..., 1:]); the same stream in both arms (seeded CPU generator)."""
     g = torch.Generator().manual_seed(DATA_SEED)
-    return torch.randint(0, vocab, (n_seq, seq + 1), generator=g, dtype=torch.int64)
+    return torch.randint(0, vocab, (n_steps, n_seq, seq + 1), generator=g, dtype=torch.int64)
 
 
 def deterministic_init(torch, named_params, tp_rank, tp_world, num_layers):
@@ -195,16 +196,17 @@ def _b200_variant(args, torch, dist, rank, world, local, *, sequence_parallel, r
     for chunk in eng.model_chunks:
         n_init += deterministic_init(torch, chunk.named_parameters(), ps.get_tensor_model_parallel_rank(), world, eng.preset["num_layers"])
     eng.optimizer.reload_model_params()
-    host = synthetic_tokens(torch, eng.num_microbatches * args.micro_batch, eng.seq_length, eng.preset["vocab_size"]).pin_memory()
+    n_total = args.warmup + 2 * args.steps + 1
+    host = synthetic_tokens(torch, eng.num_microbatches * args.micro_batch, eng.seq_length, eng.preset["vocab_size"], n_total).pin_memory()
     dev_tokens = host.to("cuda")
     losses = []
 
     def step_dev():
-        losses.append(eng.train_step(dev_tokens))
+        losses.append(eng.train_step(dev_tokens[len(losses)]))
 
     def step_e2e():
-        losses.append(eng.train_step(host))
-        return float(losses[-1])                  # D2H read of the step's loss every step
+        losses.append(eng.train_step(host[len(losses)]))     # H2D copy of this step's tokens from pinned memory
+        return float(losses[-1])                             # D2H read of the step's loss every step
 
     for _ in range(args.warmup):
         step_dev()
@@ -221,7 +223,7 @@ def _b200_variant(args, torch, dist, rank, world, local, *, sequence_parallel, r
     if want_e2e:
         step_e2e()
         _, e_wall = timed_loop(torch, dist, step_e2e, args.steps, world)
-        res["e2e"] = {"value": tokens_per_step * args.steps / (e_wall / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": host.numel() * host.element_size(),
+        res["e2e"] = {"value": tokens_per_step * args.steps / (e_wall / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": host[0].numel() * host.element_size(),
                       "d2h_bytes_per_step": 4, "timing": "host wall clock incl. H2D of the step's tokens from pinned memory and D2H loss read, max over ranks"}
     res["loss_by_step"] = losses_to_dict(torch, losses)
     res["peak_mem_gib"] = torch.cuda.max_memory_allocated() / 2**30
@@ -299,7 +301,7 @@ def run_b200(args):
         out = {
             "metric": METRIC, "value": main["value"], "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic (uniform random token ids of the named shape, seed 17; name-seeded random-init weights identical in both arms)",
+            "data": "synthetic (a fresh batch of uniform random token ids of the named shape every step, seed 17; name-seeded random-init weights identical in both arms)",
             "impl": "b200", "tflops_per_gpu": main["tflops_per_gpu"], "mfu_of_measured_sustained_cublas": main["tflops_per_gpu"] / peak_tf,
             "loss_by_step": main["loss_by_step"], "peak_mem_gib": main["peak_mem_gib"], "gpu_launches": main["gpu_launches"], "clocks": main["clocks"],
             "e2e": main.get("e2e"), "pair_op_max_rel_err": pair_err,
@@ -388,14 +390,17 @@ def run_reference(args):
         return cfg, ddp, opt, n_init
 
     nmb = args.global_batch // args.micro_batch
-    host = synthetic_tokens(torch, nmb * args.micro_batch, P["seq"], P["vocab"]).pin_memory()
+    n_total = args.warmup + 2 * args.steps + 1
+    host = synthetic_tokens(torch, nmb * args.micro_batch, P["seq"], P["vocab"], n_total).pin_memory()
     dev_tokens = host.cuda()
     pos = torch.arange(P["seq"], device="cuda").unsqueeze(0).expand(args.micro_batch, -1).contiguous()
     fwd_bwd = get_forward_backward_func()
 
     def loss_func(out):
         loss = out.float().mean()
-        return loss, {"lm loss": loss.detach()}
+        # clone: the reference schedule scales the returned loss IN PLACE by 1/num_microbatches (schedules.py:343-346), which would
+        # also rescale a detached alias of it
+        return loss, {"lm loss": loss.detach().clone()}
 
     def fstep(it, model):
         b = next(it)
@@ -437,7 +442,7 @@ def run_reference(args):
             losses.clear()
             torch.cuda.empty_cache()
             state["cfg"], state["ddp"], state["opt"], n_init = build(rc)
-            step_dev = make_step(lambda: dev_tokens, False)
+            step_dev = make_step(lambda: dev_tokens[len(losses)], False)
             for _ in range(args.warmup):
                 step_dev()
             torch.cuda.synchronize()
@@ -467,10 +472,10 @@ def run_reference(args):
     value = tokens_per_step * args.steps / (ms / 1e3)
     e2e = None
     if not args.no_e2e:
-        step_e2e = make_step(lambda: host.cuda(non_blocking=True), True)
+        step_e2e = make_step(lambda: host[len(losses)].cuda(non_blocking=True), True)
         step_e2e()
         _, e_wall = timed_loop(torch, dist, step_e2e, args.steps, world)
-        e2e = {"value": tokens_per_step * args.steps / (e_wall / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": host.numel() * 8, "d2h_bytes_per_step": 4,
+        e2e = {"value": tokens_per_step * args.steps / (e_wall / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": host[0].numel() * 8, "d2h_bytes_per_step": 4,
                "timing": "host wall clock incl. H2D of the step's tokens from pinned memory and D2H loss read, max over ranks"}
     loss_by_step = losses_to_dict(torch, losses)
     if rank == 0:
@@ -478,7 +483,7 @@ def run_reference(args):
             "impl": "reference", "metric": METRIC, "value": value, "unit": "tokens/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic (uniform random token ids of the named shape, seed 17; name-seeded random-init weights identical in both arms)",
+            "data": "synthetic (a fresh batch of uniform random token ids of the named shape every step, seed 17; name-seeded random-init weights identical in both arms)",
             "loss_by_step": loss_by_step, "clocks": clocks, "e2e": e2e, "peak_mem_gib": torch.cuda.max_memory_allocated() / 2**30,
             "config": {"model": args.model + (f"[layers={args.layers} DEV-INVALID]" if args.layers else ""), "global_batch": args.global_batch,
                        "micro_batch": args.micro_batch, "seq_len": P["seq"], "parallelism": f"tp{world}", "sequence_parallel": False,

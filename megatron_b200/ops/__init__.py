@@ -275,11 +275,10 @@ class _FlashAttnFn(torch.autograd.Function):
         # backward = cuDNN library kernel fed with OUR forward's (out, log-sum-exp); a native tcgen05 backward is the next step
         go = go.contiguous()
         if _ATTN_BWD_IMPL == "native" and hasattr(ext(), "flash_attn_bwd") and q.shape[-1] == 128:
-            # our tcgen05 backward (csrc/flash_attn_bwd_sm100.cu): dK/dV accumulate in TMEM, dQ through an fp32 red.add buffer
-            delta = (go.float() * o.float()).sum(-1).permute(1, 2, 0).contiguous()      # [b, h, sq]
-            dq32, dk, dv = ext().flash_attn_bwd(go, q, k, v, lse, delta, ctx.causal, ctx.scale)
-            _count()
-            return dq32.to(q.dtype), dk, dv, None, None
+            # our tcgen05 backward (csrc/flash_attn_bwd_sm100.cu): dK/dV accumulate in TMEM while dS tiles stream to a bf16 scratch by TMA; dQ = dS K in a second tcgen05 kernel
+            dq, dk, dv = ext().flash_attn_bwd(go, q, k, v, o, lse, ctx.causal, ctx.scale, _ATTN_BWD_SPLIT_HEADS)
+            _count(4 if _ATTN_BWD_SPLIT_HEADS != 0 else 3)
+            return dq, dk, dv, None, None
         lse_lib = lse.unsqueeze(-1) if _cudnn_lse_ndim() == 4 else lse
         dq, dk, dv = ext().attn_bwd_cudnn(go, q, k, v, o, lse_lib, ctx.causal, ctx.scale)
         return dq, dk, dv, None, None
@@ -299,6 +298,7 @@ def _cudnn_lse_ndim() -> int:
 
 _ATTN_IMPL = os.environ.get("MEGATRON_B200_ATTN", "auto")  # auto | native | library
 _ATTN_BWD_IMPL = os.environ.get("MEGATRON_B200_ATTN_BWD", "library")  # library (cuDNN on our out/LSE) | native (tcgen05 backward, first version)
+_ATTN_BWD_SPLIT_HEADS = int(os.environ.get("MEGATRON_B200_ATTN_BWD_SPLIT_HEADS", "-1"))  # -1: split the GQA group over CTAs when the grid would leave SMs idle (few local heads)
 _FA_VARIANT = int(os.environ.get("MEGATRON_B200_FA_VARIANT", "1"))  # 1 (default, measured 836 vs 786 TF): P kept in tensor memory (TS MMA); 0: P through shared memory
 
 

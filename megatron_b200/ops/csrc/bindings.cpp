@@ -324,19 +324,26 @@ std::vector<Tensor> flash_attn_fwd(const Tensor& q, const Tensor& k, const Tenso
 #endif
 
 #ifdef MB200_HAVE_FLASH_ATTN_BWD_SM100
-// go, q [sq,b,hq,128]; k, v [sk,b,hk,128]; lse, delta [b,hq,sq] fp32 -> (dq fp32 [sq,b,hq,128], dk bf16, dv bf16)
-std::vector<Tensor> flash_attn_bwd(const Tensor& go, const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& lse, const Tensor& delta, bool causal, double scale) {
-  TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kBFloat16 && go.scalar_type() == at::kBFloat16, "flash_attn_bwd: bf16 CUDA tensors");
-  TORCH_CHECK(q.stride(3) == 1 && k.stride(3) == 1 && v.stride(3) == 1 && go.stride(3) == 1, "flash_attn_bwd: contiguous head dim");
-  TORCH_CHECK(lse.is_contiguous() && delta.is_contiguous() && lse.scalar_type() == at::kFloat && delta.scalar_type() == at::kFloat, "flash_attn_bwd: fp32 [b,h,s] stats");
+// go, q, o [sq,b,hq,128]; k, v [sk,b,hk,128]; lse [b,hq,sq] fp32 -> (dq, dk, dv) bf16.  split_heads: -1 = decide from the grid size.
+// Heads are processed in chunks so that the bf16 dS scratch ([heads, sk, sq]) stays under max_scratch_mb.
+std::vector<Tensor> flash_attn_bwd(const Tensor& go, const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& o, const Tensor& lse, bool causal, double scale,
+                                   int64_t split_heads, int64_t max_scratch_mb) {
+  TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kBFloat16 && go.scalar_type() == at::kBFloat16 && o.scalar_type() == at::kBFloat16, "flash_attn_bwd: bf16 CUDA tensors");
+  TORCH_CHECK(q.stride(3) == 1 && k.stride(3) == 1 && v.stride(3) == 1 && go.stride(3) == 1 && o.stride(3) == 1, "flash_attn_bwd: contiguous head dim");
+  TORCH_CHECK(lse.is_contiguous() && lse.scalar_type() == at::kFloat, "flash_attn_bwd: fp32 [b,h,s] log-sum-exp");
   c10::cuda::CUDAGuard g(q.device());
   const int sq = (int)q.size(0), b = (int)q.size(1), hq = (int)q.size(2), d = (int)q.size(3), sk = (int)k.size(0), hk = (int)k.size(2);
-  auto dq = at::zeros({sq, b, hq, d}, q.options().dtype(at::kFloat));
+  auto dq = at::empty({sq, b, hq, d}, q.options());
   auto dk = at::empty({sk, b, hk, d}, q.options());
   auto dv = at::empty({sk, b, hk, d}, q.options());
-  const int rc = mb200_flash_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), go.data_ptr(), lse.data_ptr<float>(), delta.data_ptr<float>(), dq.data_ptr<float>(),
-                                      dk.data_ptr(), dv.data_ptr(), sq, sk, b, hq, hk, d, q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
-                                      v.stride(0), v.stride(1), v.stride(2), go.stride(0), go.stride(1), go.stride(2), (float)scale, causal ? 1 : 0, cur_stream());
+  auto delta = at::empty({b, hq, sq}, q.options().dtype(at::kFloat));
+  const int sh = split_heads < 0 ? mb200_flash_attn_bwd_split_heads(sk, b, hq, hk) : (int)split_heads;
+  const size_t bytes = mb200_flash_attn_bwd_scratch_bytes(sq, sk, b, hq, hk, sh);
+  auto scratch = at::empty({(int64_t)bytes}, q.options().dtype(at::kByte));
+  const int rc = mb200_flash_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), go.data_ptr(), o.data_ptr(), lse.data_ptr<float>(), delta.data_ptr<float>(), dq.data_ptr(),
+                                      dk.data_ptr(), dv.data_ptr(), scratch.data_ptr(), sh, sq, sk, b, hq, hk, d, q.stride(0), q.stride(1), q.stride(2), k.stride(0),
+                                      k.stride(1), k.stride(2), v.stride(0), v.stride(1), v.stride(2), go.stride(0), go.stride(1), go.stride(2), o.stride(0), o.stride(1),
+                                      o.stride(2), (float)scale, causal ? 1 : 0, cur_stream());
   TORCH_CHECK(rc == 0, "flash_attn_bwd failed with code ", rc);
   return {dq, dk, dv};
 }
@@ -779,7 +786,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("attn_bwd_cudnn", &attn_bwd_cudnn);
   m.def("share_storage", &share_storage);
 #ifdef MB200_HAVE_FLASH_ATTN_BWD_SM100
-  m.def("flash_attn_bwd", &flash_attn_bwd);
+  m.def("flash_attn_bwd", &flash_attn_bwd, pybind11::arg("go"), pybind11::arg("q"), pybind11::arg("k"), pybind11::arg("v"), pybind11::arg("o"), pybind11::arg("lse"),
+        pybind11::arg("causal"), pybind11::arg("scale"), pybind11::arg("split_heads") = -1, pybind11::arg("max_scratch_mb") = 0);
 #endif
 #ifdef MB200_HAVE_MOE_KERNELS
   m.def("moe_gather_rows", &moe_gather_rows);

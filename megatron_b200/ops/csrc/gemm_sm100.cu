@@ -314,6 +314,20 @@ bool make_tmap_bf16_strided(CUtensorMap* out, const void* ptr, uint64_t rows, ui
   return r == CUDA_SUCCESS;
 }
 
+// bf16 [d2][d1][d0] with d0 contiguous; pitches in bytes (multiples of 16); box = {box0 (<= 64), box1, 1}; 128B swizzle.
+// Out-of-bounds parts of a box are clipped on stores and zero-filled on loads PER outer index (tiles never bleed into the next matrix).
+bool make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_bytes, uint64_t pitch2_bytes, uint32_t box0, uint32_t box1) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {pitch1_bytes, pitch2_bytes};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 }  // namespace mb200
 
 // one-byte elements (fp8): rows x cols bytes, box {128 bytes, box_rows}, 128B swizzle

@@ -182,6 +182,7 @@ __device__ __forceinline__ void epilogue_tile(void* __restrict__ Cptr, const Gem
 // row-major bf16 matrix [rows, cols]; box = {box_cols (inner, <= 64), box_rows}; 128B swizzle (defined in gemm_sm100.cu)
 bool make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows);
 bool make_tmap_bf16_strided(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes, uint32_t box_cols, uint32_t box_rows);
+bool make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_bytes, uint64_t pitch2_bytes, uint32_t box0, uint32_t box1);
 int num_sms();
 
 }  // namespace mb200

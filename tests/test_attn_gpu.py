@@ -93,9 +93,12 @@ def test_flash_attention_autograd_matches_reference():
         assert err < 3e-2, f"d{name} rel err {err}"
 
 
-@pytest.mark.parametrize("sq,sk,b,hq,hk,causal", [(512, 512, 1, 8, 2, True), (384, 384, 2, 4, 4, True), (256, 640, 1, 4, 2, False), (128, 640, 1, 4, 1, True), (1000, 1000, 1, 2, 1, True)])
-def test_flash_bwd_native_matches_reference(sq, sk, b, hq, hk, causal):
-    """tcgen05 backward (dK/dV in TMEM, dQ via fp32 red.add) vs fp32 autograd of the reference attention."""
+@pytest.mark.parametrize("split_heads", [0, 1])
+@pytest.mark.parametrize("sq,sk,b,hq,hk,causal", [(512, 512, 1, 8, 2, True), (384, 384, 2, 4, 4, True), (256, 640, 1, 4, 2, False), (128, 640, 1, 4, 1, True), (1000, 1000, 1, 2, 1, True),
+                                                  (1024, 1024, 1, 4, 1, True), (2048, 2048, 1, 8, 2, True), (330, 330, 1, 2, 2, False)])
+def test_flash_bwd_native_matches_reference(sq, sk, b, hq, hk, causal, split_heads):
+    """tcgen05 backward (delta kernel -> dK/dV in TMEM + dS spilled by TMA -> dQ = dS K GEMM kernel; fused-heads and split-heads grids)
+    vs fp32 autograd of the reference attention."""
     from megatron_b200 import ops
 
     assert hasattr(ops.ext(), "flash_attn_bwd"), "native attention backward not built"
@@ -110,10 +113,40 @@ def test_flash_bwd_native_matches_reference(sq, sk, b, hq, hk, causal):
     ro.backward(go.float())
     refs = [t.grad.float().clone() for t in (q, k, v)]
     o, lse = ops.ext().flash_attn_fwd(q.detach(), k.detach(), v.detach(), causal, scale, 1)
-    delta = (go.float() * o.float()).sum(-1).permute(1, 2, 0).contiguous()
-    dq, dk, dv = ops.ext().flash_attn_bwd(go, q.detach(), k.detach(), v.detach(), lse, delta, causal, scale)
+    # poison the allocator's free blocks so that a read of a never-written scratch tile shows up as NaN
+    junk = torch.full((64 << 20,), float("nan"), device="cuda")
+    del junk
+    dq, dk, dv = ops.ext().flash_attn_bwd(go, q.detach(), k.detach(), v.detach(), o, lse, causal, scale, split_heads)
     torch.cuda.synchronize()
     for name, a, r in zip("qkv", (dq, dk, dv), refs):
         assert torch.isfinite(a.float()).all(), f"d{name} has non-finite values"
         err = (a.float() - r).abs().max().item() / (r.abs().max().item() + 1e-6)
         assert err < 3e-2, f"d{name} rel err {err}"
+
+
+def test_flash_attention_autograd_native_backward():
+    """ops.flash_attention end to end with the native backward selected (the default of this build): strided q/k/v views of a fused QKV tensor."""
+    from megatron_b200 import ops
+
+    torch.manual_seed(5)
+    s, b, g, r, d = 1024, 1, 2, 4, 128
+    mixed = torch.randn(s, b, g, (r + 2) * d, device="cuda").bfloat16().requires_grad_(True)
+    q, k, v = torch.split(mixed, [r * d, d, d], dim=3)
+    q = q.reshape(s, b, g * r, d)
+    scale = 1.0 / math.sqrt(d)
+    old = ops._ATTN_BWD_IMPL
+    ops._ATTN_BWD_IMPL = "native"
+    try:
+        out = ops.flash_attention(q, k, v, causal=True, scale=scale)
+        go = torch.randn_like(out)
+        out.backward(go)
+    finally:
+        ops._ATTN_BWD_IMPL = old
+    got = mixed.grad.float().clone()
+    mixed.grad = None
+    q2, k2, v2 = torch.split(mixed, [r * d, d, d], dim=3)
+    ro, _ = _ref(q2.reshape(s, b, g * r, d), k2, v2, True, scale)
+    ro.backward(go.float())
+    ref = mixed.grad.float()
+    err = (got - ref).abs().max().item() / (ref.abs().max().item() + 1e-6)
+    assert err < 3e-2, err
