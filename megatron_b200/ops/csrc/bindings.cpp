@@ -336,7 +336,7 @@ std::vector<Tensor> flash_attn_bwd(const Tensor& go, const Tensor& q, const Tens
   auto dq = at::empty({sq, b, hq, d}, q.options());
   auto dk = at::empty({sk, b, hk, d}, q.options());
   auto dv = at::empty({sk, b, hk, d}, q.options());
-  auto delta = at::empty({b, hq, sq}, q.options().dtype(at::kFloat));
+  auto delta = at::empty({b, hq, (sq + 63) / 64, 128}, q.options().dtype(at::kFloat));   // per 64-query block: lse*log2e | rowsum(dO o O)*scale
   const int sh = split_heads < 0 ? mb200_flash_attn_bwd_split_heads(sk, b, hq, hk) : (int)split_heads;
   const size_t bytes = mb200_flash_attn_bwd_scratch_bytes(sq, sk, b, hq, hk, sh);
   auto scratch = at::empty({(int64_t)bytes}, q.options().dtype(at::kByte));

@@ -23,6 +23,9 @@
 // Split-heads mode (grid.y = query heads; fp32 dK/dV partials + fa_bwd_reduce_kernel) keeps all 148 SMs busy when a TP rank owns
 // only a few heads (TP=8: 4 query heads / 1 KV head -> 64 CTAs otherwise).
 // Warps 0-7: compute (thread = TMEM lane x column half), warp 8: TMA producer, warp 9: MMA issuer + TMEM allocator.
+#include <cstdlib>
+#include <type_traits>
+
 #include "gemm_sm100_device.cuh"
 
 namespace mb200 {
@@ -32,15 +35,16 @@ constexpr int FB_KV = 128;      // keys per CTA
 constexpr int FB_Q = 64;        // queries per step
 constexpr int FB_THREADS = 320;   // 8 compute warps (two per TMEM lane quarter: each takes 32 of the 64 query columns) + producer + issuer
 constexpr int FB_D = 128;       // head dim (this version)
+constexpr int FB_STAGES = 3;    // Q_i / dO_i ring: the load of step st+2 must be in flight while step st's dV/dK MMAs still hold their stage (2 stages put a TMA round trip on every step)
 
 struct FaBwdParams {
   int sq, sk, b, hq, hk;
   int causal;
   int split_heads;       // 1: blockIdx.y = query head, dK/dV leave as fp32 partials [b, hq, sk, d]
+  int dbg;               // bottleneck experiments (MB200_FA_BWD_DBG): 1 skip the score math, 2 skip the dS TMA store, 4 skip dV/dK MMAs, 8 skip score MMAs — results are WRONG
   float scale, scale_log2;
   long q_sb, q_sh, k_sb, k_sh, v_sb, v_sh, do_sb, do_sh;   // element strides of batch / head inside one sequence row
-  const float* lse;      // [b, hq, sq] natural log
-  const float* delta;    // [b, hq, sq]  rowsum(dO o O)
+  const float* vec;      // [b, hq, ceil(sq/64), 128]: per 64-query block lse*log2e | delta*scale (fa_delta_kernel)
   void* dk;              // [sk, b, hk, d] bf16
   void* dv;
   float* dk_part;        // split-heads: [b, hq, sk, d] fp32
@@ -70,29 +74,44 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 
-// ---- delta = rowsum(dO o O) ------------------------------------------------------------------------------------------------------
-// one warp per (q, b, h) row of 128 bf16: lane reads 8 bytes of each tensor
-__global__ void fa_delta_kernel(const __nv_bfloat16* __restrict__ go, const __nv_bfloat16* __restrict__ o, float* __restrict__ delta, int sq, int b, int hq, long go_ss,
-                                long go_sb, long go_sh, long o_ss, long o_sb, long o_sh) {
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- per-query vectors -------------------------------------------------------------------------------------------------------------
+// vec[((b*hq + h) * nq64 + i) * 128 + {0..63: lse * log2(e) | 64..127: rowsum(dO o O) * scale}] for the 64 queries of block i (zero beyond sq): the 512 bytes
+// a dK/dV step needs, contiguous, so that the TMA producer fetches them with ONE bulk copy next to Q_i / dO_i (no thread of the compute warps waits on a
+// global load).  One warp per (q, b, h) row of 128 bf16: lane reads 8 bytes of each tensor.
+__global__ void fa_delta_kernel(const __nv_bfloat16* __restrict__ go, const __nv_bfloat16* __restrict__ o, const float* __restrict__ lse, float* __restrict__ vec, int sq,
+                                int b, int hq, float scale, long go_ss, long go_sb, long go_sh, long o_ss, long o_sb, long o_sh) {
   const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  const long total = (long)sq * b * hq;
+  const int nq64 = (sq + FB_Q - 1) / FB_Q;
+  const long total = (long)nq64 * FB_Q * b * hq;
   if (row >= total) return;
   const int h = (int)(row % hq), bi = (int)((row / hq) % b), q = (int)(row / ((long)hq * b));
-  const uint2 a = *reinterpret_cast<const uint2*>(go + q * go_ss + bi * go_sb + h * go_sh + lane * 4);
-  const uint2 c = *reinterpret_cast<const uint2*>(o + q * o_ss + bi * o_sb + h * o_sh + lane * 4);
-  const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
-  const __nv_bfloat162* ch = reinterpret_cast<const __nv_bfloat162*>(&c);
-  float s = 0.f;
+  float s = 0.f, l = 0.f;
+  if (q < sq) {
+    const uint2 a = *reinterpret_cast<const uint2*>(go + q * go_ss + bi * go_sb + h * go_sh + lane * 4);
+    const uint2 c = *reinterpret_cast<const uint2*>(o + q * o_ss + bi * o_sb + h * o_sh + lane * 4);
+    const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* ch = reinterpret_cast<const __nv_bfloat162*>(&c);
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float2 x = __bfloat1622float2(ah[i]), y = __bfloat1622float2(ch[i]);
-    s = fmaf(x.x, y.x, s);
-    s = fmaf(x.y, y.y, s);
+    for (int i = 0; i < 2; ++i) {
+      const float2 x = __bfloat1622float2(ah[i]), y = __bfloat1622float2(ch[i]);
+      s = fmaf(x.x, y.x, s);
+      s = fmaf(x.y, y.y, s);
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+    if (lane == 0) l = lse[((long)bi * hq + h) * sq + q] * 1.4426950408889634f;
   }
-#pragma unroll
-  for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-  if (lane == 0) delta[((long)bi * hq + h) * sq + q] = s;
+  if (lane == 0) {
+    float* dst = vec + (((long)bi * hq + h) * nq64 + q / FB_Q) * (2 * FB_Q) + (q % FB_Q);
+    dst[0] = l;
+    dst[FB_Q] = s * scale;
+  }
 }
 
 // ---- dK / dV (+ dSt spill) ---------------------------------------------------------------------------------------------------------
@@ -105,7 +124,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   constexpr int Q_CHUNK = FB_Q * 128;              // [64 rows x 128 B]
   constexpr int Q_BYTES = 2 * Q_CHUNK;             // Q_i or dO_i: 16 KiB
   constexpr int DS_BYTES = FB_KV * 128;            // dST bf16 [128 kv x 64 q]: 16 KiB
-  constexpr int STAGES = 2;
+  constexpr int STAGES = FB_STAGES;
   constexpr uint32_t TMEM_COLS = 512;
   constexpr uint32_t DK_COL = 0, DV_COL = 128, BUF_COL = 256, BUF_STRIDE = 128, DPT_OFF = 64;   // score buffer b: ST at BUF_COL + 128 b, dPT 64 columns further
 
@@ -116,15 +135,16 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   uint8_t* smem_q = smem_v + KV_BYTES;                       // STAGES x Q_BYTES
   uint8_t* smem_do = smem_q + STAGES * Q_BYTES;              // STAGES x Q_BYTES
   uint8_t* smem_ds = smem_do + STAGES * Q_BYTES;             // 2 x DS_BYTES (a TMA store may still be reading the previous step's tile)
-  float* smem_vec = reinterpret_cast<float*>(smem_ds + 2 * DS_BYTES);   // 2 x (lse2[64] | delta[64]), by step parity
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_vec + 4 * FB_Q);
+  float* smem_vec = reinterpret_cast<float*>(smem_ds + 2 * DS_BYTES);   // STAGES x (lse2[64] | delta_s[64]): arrives with Q_i / dO_i on q_full
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_vec + STAGES * 2 * FB_Q);
   uint64_t* kv_full = bars;              // 1
   uint64_t* q_full = bars + 1;           // STAGES
   uint64_t* q_empty = q_full + STAGES;   // STAGES
   uint64_t* s_ready = q_empty + STAGES;  // [2] per score buffer
-  uint64_t* p_ready = s_ready + 2;       // 1 (256 arrivals, one phase per step)
+  uint64_t* p_ready = s_ready + 2;       // 1 (8 arrivals = compute warps, one phase per step)
   uint64_t* acc_done = p_ready + 1;      // 1: all dV / dK MMAs have completed
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_done + 1);
+  uint64_t* ds_free = acc_done + 1;      // [2]: the TMA store that was reading dS tile b has finished with it
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(ds_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jb = blockIdx.x, bi = blockIdx.z;
@@ -155,8 +175,10 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       mbar_init(&q_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) mbar_init(&s_ready[i], 1);
-    mbar_init(p_ready, 256);
+    mbar_init(p_ready, 8);      // ONE arrival per compute warp: 256 per-thread arrivals serialise on the smem atomic unit (measured: >1,000 cycles per step)
     mbar_init(acc_done, 1);
+    mbar_init(&ds_free[0], 1);
+    mbar_init(&ds_free[1], 1);
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc<TMEM_COLS>(tmem_holder);
@@ -179,7 +201,9 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const int h = h_first + st / steps_per_head, i = i0 + st % steps_per_head;
         const int s = st % STAGES;
         mbar_wait(&q_empty[s], ((uint32_t)(st / STAGES) & 1u) ^ 1u);
-        mbar_expect_tx(&q_full[s], 2 * Q_BYTES);
+        if (p.dbg & 16) { mbar_arrive(&q_full[s]); continue; }
+        mbar_expect_tx(&q_full[s], 2 * Q_BYTES + 2 * FB_Q * 4);
+        bulk_load(smem_vec + s * 2 * FB_Q, p.vec + (((size_t)bi * p.hq + h) * nq + i) * (2 * FB_Q), 2 * FB_Q * 4, &q_full[s]);
         const int qcol = (int)(bi * p.q_sb + h * p.q_sh), docol = (int)(bi * p.do_sb + h * p.do_sh);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -193,20 +217,25 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     if (lane == 0 && total_steps > 0) {
       constexpr uint32_t idesc_st = make_idesc_bf16(FB_KV, FB_Q, false, false);   // ST, dPT : K-major A and B
       constexpr uint32_t idesc_dkv = make_idesc_bf16(FB_KV, D, false, true);      // dV, dK : A from TMEM, B MN-major
-      const uint32_t ka = smem_u32(smem_k), va = smem_u32(smem_v);
+      // The issuing thread is on the critical path of every step (24 MMAs): descriptors are a precomputed low word + an immediate, never rebuilt.
+      constexpr uint32_t HI = smem_desc_hi_sw128(1024);
+      const uint32_t k_lo = smem_desc_lo(smem_u32(smem_k), 16), v_lo = smem_desc_lo(smem_u32(smem_v), 16);
+      const uint32_t q_lo0 = smem_desc_lo(smem_u32(smem_q), 16), do_lo0 = smem_desc_lo(smem_u32(smem_do), 16);                 // K-major views (B of ST / dPT)
+      const uint32_t qmn_lo0 = smem_desc_lo(smem_u32(smem_q), Q_CHUNK), domn_lo0 = smem_desc_lo(smem_u32(smem_do), Q_CHUNK);     // MN-major views (B of dK / dV)
       auto issue_scores = [&](int st) {       // ST and dPT of step st into score buffer st & 1
         const int s = st % STAGES;
-        const uint32_t qa = smem_u32(smem_q + s * Q_BYTES), doa = smem_u32(smem_do + s * Q_BYTES);
+        const uint32_t q_lo = q_lo0 + s * (Q_BYTES >> 4), do_lo = do_lo0 + s * (Q_BYTES >> 4);
         const uint32_t st_col = tmem_base + BUF_COL + (st & 1) * BUF_STRIDE;
         mbar_wait(&q_full[s], (uint32_t)(st / STAGES) & 1u);
         tc_fence_after();
+        if (!(p.dbg & 8))
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint32_t acc = (c > 0 || kk > 0) ? 1u : 0u;
-            umma_f16(st_col, make_smem_desc_sw128(ka + c * KV_CHUNK + kk * 32, 16, 1024), make_smem_desc_sw128(qa + c * Q_CHUNK + kk * 32, 16, 1024), idesc_st, acc);
-            umma_f16(st_col + DPT_OFF, make_smem_desc_sw128(va + c * KV_CHUNK + kk * 32, 16, 1024), make_smem_desc_sw128(doa + c * Q_CHUNK + kk * 32, 16, 1024), idesc_st, acc);
+            umma_f16(st_col, smem_desc_at(k_lo, HI, c * KV_CHUNK + kk * 32), smem_desc_at(q_lo, HI, c * Q_CHUNK + kk * 32), idesc_st, acc);
+            umma_f16(st_col + DPT_OFF, smem_desc_at(v_lo, HI, c * KV_CHUNK + kk * 32), smem_desc_at(do_lo, HI, c * Q_CHUNK + kk * 32), idesc_st, acc);
           }
         umma_commit(&s_ready[st & 1]);
       };
@@ -214,7 +243,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       issue_scores(0);
       for (int st = 0; st < total_steps; ++st) {
         const int s = st % STAGES, bsel = st & 1;
-        const uint32_t qa = smem_u32(smem_q + s * Q_BYTES), doa = smem_u32(smem_do + s * Q_BYTES);
+        const uint32_t qmn_lo = qmn_lo0 + s * (Q_BYTES >> 4), domn_lo = domn_lo0 + s * (Q_BYTES >> 4);
         const uint32_t st_col = tmem_base + BUF_COL + bsel * BUF_STRIDE;
         // One step ahead.  Score buffer (st+1)&1 was last used by step st-1: its ST/dPT were read by the compute warps before p_ready(st-1)
         // (waited on below in the previous iteration) and its PT/dST are operands of the dV/dK MMAs issued in that iteration — the tensor
@@ -222,12 +251,15 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         if (st + 1 < total_steps) issue_scores(st + 1);
         mbar_wait(p_ready, (uint32_t)st & 1u);
         tc_fence_after();
+        if (!(p.dbg & 4))
 #pragma unroll
         for (int kk = 0; kk < FB_Q / 16; ++kk) {
           const uint32_t acc = (st > 0 || kk > 0) ? 1u : 0u;
           // B = dO_i / Q_i read as [K = q rows, N = d]: MN-major, two 64-column chunks Q_CHUNK apart
-          umma_f16_ts(tmem_base + DV_COL, st_col + kk * 8, make_smem_desc_sw128(doa + kk * 2048, Q_CHUNK, 1024), idesc_dkv, acc);
-          umma_f16_ts(tmem_base + DK_COL, st_col + DPT_OFF + kk * 8, make_smem_desc_sw128(qa + kk * 2048, Q_CHUNK, 1024), idesc_dkv, acc);
+          // PT / dST (bf16 pairs) of query half hf live in columns [32 hf, 32 hf + 16) of the ST / dPT region: each compute warp overwrote only columns it had read itself
+          const uint32_t a_col = (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8);
+          umma_f16_ts(tmem_base + DV_COL, st_col + a_col, smem_desc_at(domn_lo, HI, kk * 2048), idesc_dkv, acc);
+          umma_f16_ts(tmem_base + DK_COL, st_col + DPT_OFF + a_col, smem_desc_at(qmn_lo, HI, kk * 2048), idesc_dkv, acc);
         }
         umma_commit(&q_empty[s]);
       }
@@ -241,74 +273,95 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const int kv_idx = k0 + row;
     const int sw = row & 7;
     const int tid = threadIdx.x;                         // 0..255 among the compute warps
-    for (int st = 0; st < total_steps; ++st) {
-      const int h = h_first + st / steps_per_head, i = i0 + st % steps_per_head;
-      const int q0 = i * FB_Q;
-      const uint32_t st_addr = tmem_base + lane_base + BUF_COL + (st & 1) * BUF_STRIDE;
-      float* vec = smem_vec + (st & 1) * 2 * FB_Q;
-      uint8_t* ds_row = smem_ds + (st & 1) * DS_BYTES + row * 128;
-      // the TMA store of step st-2 must have finished READING this step's dS tile before anybody overwrites it
-      if (tid == 0) tma_store_wait_read<1>();
-      // per-query vectors of this step: lse (log2 domain) and delta
-      if (tid < FB_Q) {
-        const int q = q0 + tid;
-        vec[tid] = q < p.sq ? p.lse[((size_t)bi * p.hq + h) * p.sq + q] * 1.4426950408889634f : 0.f;
-      } else if (tid < 2 * FB_Q) {
-        const int q = q0 + tid - FB_Q;
-        vec[tid] = q < p.sq ? p.delta[((size_t)bi * p.hq + h) * p.sq + q] : 0.f;
+    // 8 columns of a half row: PT = exp2(ST c - lse), dST = PT (dPT scale - delta scale); MASKED only on tiles that touch a boundary or the causal diagonal
+    auto score_math8 = [&](const uint32_t* sv, const uint32_t* dpv, uint32_t* pw, uint32_t* dw, uint32_t vec_addr, int qbase, auto masked) {
+      constexpr bool MASKED = decltype(masked)::value;
+#pragma unroll
+      for (int c4 = 0; c4 < 8; c4 += 4) {
+        const float4 l4 = lds_f4(vec_addr + c4 * 4), d4 = lds_f4(vec_addr + FB_Q * 4 + c4 * 4);
+        const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+        float pr[4], ds[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float pv = ex2(fmaf(__uint_as_float(sv[c4 + e]), p.scale_log2, -lv[e]));
+          if (MASKED) {
+            const int q = qbase + c4 + e;
+            const bool ok = kv_idx < p.sk && q < p.sq && (!p.causal || kv_idx <= q + off);
+            pv = ok ? pv : 0.f;
+          }
+          pr[e] = pv;
+          ds[e] = pv * fmaf(__uint_as_float(dpv[c4 + e]), p.scale, -dl[e]);
+        }
+        __nv_bfloat162 pb0 = __floats2bfloat162_rn(pr[0], pr[1]), pb1 = __floats2bfloat162_rn(pr[2], pr[3]);
+        __nv_bfloat162 db0 = __floats2bfloat162_rn(ds[0], ds[1]), db1 = __floats2bfloat162_rn(ds[2], ds[3]);
+        pw[c4 / 2] = *reinterpret_cast<uint32_t*>(&pb0);
+        pw[c4 / 2 + 1] = *reinterpret_cast<uint32_t*>(&pb1);
+        dw[c4 / 2] = *reinterpret_cast<uint32_t*>(&db0);
+        dw[c4 / 2 + 1] = *reinterpret_cast<uint32_t*>(&db1);
       }
-      named_bar_sync(1, 256);
+    };
+    // The 32 columns of this warp in FOUR chunks of 8, software-pipelined: the tensor-memory loads of chunk c+1 are in flight while chunk c is being computed
+    // (tcgen05.wait::ld covers every load issued so far, so each wait is placed after the NEXT chunk's loads have been issued).  Tensor-memory reads are the
+    // scarce resource of this kernel (64 KB of fp32 scores per step); a load-everything-then-compute order serialised them with the MUFU/FMA work.
+    auto score_pipeline = [&](uint32_t st_addr, uint32_t (&pw)[16], uint32_t (&dw)[16], uint32_t vec_addr, int q0, auto masked) {
+      uint32_t sv[2][8], dpv[2][8];
+      tmem_ld_32x32b_x8(st_addr + half * 32, sv[0]);
+      tmem_ld_32x32b_x8(st_addr + DPT_OFF + half * 32, dpv[0]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld_wait();
+        if (c < 3) {
+          tmem_ld_32x32b_x8(st_addr + half * 32 + (c + 1) * 8, sv[(c + 1) & 1]);
+          tmem_ld_32x32b_x8(st_addr + DPT_OFF + half * 32 + (c + 1) * 8, dpv[(c + 1) & 1]);
+        }
+        score_math8(sv[c & 1], dpv[c & 1], pw + c * 4, dw + c * 4, vec_addr + c * 32, q0 + half * 32 + c * 8, masked);
+      }
+    };
+    int h = h_first, i = i0;                             // (head, query block) of the current step, advanced incrementally
+    for (int st = 0; st < total_steps; ++st) {
+      const int q0 = i * FB_Q;
+      const int s = st % STAGES;
+      const uint32_t st_addr = tmem_base + lane_base + BUF_COL + (st & 1) * BUF_STRIDE;
+      uint8_t* ds_row = smem_ds + (st & 1) * DS_BYTES + row * 128;
+      mbar_wait(&q_full[s], (uint32_t)(st / STAGES) & 1u);       // acquire on the barrier the bulk copy of this step's vectors completed on (long since satisfied)
       mbar_wait(&s_ready[st & 1], (uint32_t)(st >> 1) & 1u);
       tc_fence_after();
       uint32_t pw[16], dw[16];
       {
-        uint32_t sv[32], dpv[32];
-        tmem_ld_32x32b_x32(st_addr + half * 32, sv);
-        tmem_ld_32x32b_x32(st_addr + DPT_OFF + half * 32, dpv);
-        tmem_ld_wait();
-        // every thread of the pair (warp w, w+4) must have read its half of the row before either overwrites the first 32 columns
-        named_bar_sync(2, 256);
         const bool interior = (k0 + FB_KV <= p.sk) && (q0 + FB_Q <= p.sq) && (!p.causal || (k0 + FB_KV - 1 <= q0 + off));
-        const uint32_t vec_addr = smem_u32(vec) + half * 32 * 4;
+        const uint32_t vec_addr = smem_u32(smem_vec + s * 2 * FB_Q) + half * 32 * 4;
+        if (p.dbg & 1) {
 #pragma unroll
-        for (int c4 = 0; c4 < 32; c4 += 4) {
-          const float4 l4 = lds_f4(vec_addr + c4 * 4), d4 = lds_f4(vec_addr + FB_Q * 4 + c4 * 4);
-          const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
-          float pr[4], ds[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float pv = ex2(fmaf(__uint_as_float(sv[c4 + e]), p.scale_log2, -lv[e]));
-            if (!interior) {
-              const int q = q0 + half * 32 + c4 + e;
-              const bool ok = kv_idx < p.sk && q < p.sq && (!p.causal || kv_idx <= q + off);
-              pv = ok ? pv : 0.f;
-            }
-            pr[e] = pv;
-            ds[e] = pv * (__uint_as_float(dpv[c4 + e]) - dl[e]) * p.scale;
-          }
-          __nv_bfloat162 pb0 = __floats2bfloat162_rn(pr[0], pr[1]), pb1 = __floats2bfloat162_rn(pr[2], pr[3]);
-          __nv_bfloat162 db0 = __floats2bfloat162_rn(ds[0], ds[1]), db1 = __floats2bfloat162_rn(ds[2], ds[3]);
-          pw[c4 / 2] = *reinterpret_cast<uint32_t*>(&pb0);
-          pw[c4 / 2 + 1] = *reinterpret_cast<uint32_t*>(&pb1);
-          dw[c4 / 2] = *reinterpret_cast<uint32_t*>(&db0);
-          dw[c4 / 2 + 1] = *reinterpret_cast<uint32_t*>(&db1);
-        }
+          for (int e = 0; e < 16; ++e) pw[e] = dw[e] = (uint32_t)(st + e);
+        } else if (interior) score_pipeline(st_addr, pw, dw, vec_addr, q0, std::false_type{});
+        else score_pipeline(st_addr, pw, dw, vec_addr, q0, std::true_type{});
       }
-      // PT and dST (bf16 pairs) back over the first 32 columns of ST / dPT (this warp: 16 of them); dST also into the swizzled smem tile that leaves by TMA
-      tmem_st_32x32b_x16(st_addr + half * 16, pw);
-      tmem_st_32x32b_x16(st_addr + DPT_OFF + half * 16, dw);
+      // PT and dST (bf16 pairs) back over the first 16 of the 32 columns this warp has just read (no other warp touches them); dST also into the swizzled smem
+      // tile that leaves by TMA
+      if (!(p.dbg & 64)) {
+        tmem_st_32x32b_x16(st_addr + half * 32, pw);
+        tmem_st_32x32b_x16(st_addr + DPT_OFF + half * 32, dw);
+      }
+      // the TMA store of step st-2 must have finished READING this dS tile before it is overwritten (flag set by thread 0 one step ago)
+      if (st >= 2) mbar_wait(&ds_free[st & 1], (uint32_t)((st >> 1) - 1) & 1u);
 #pragma unroll
       for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(ds_row + (((half * 4 + u) ^ sw) << 4)) = make_uint4(dw[u * 4], dw[u * 4 + 1], dw[u * 4 + 2], dw[u * 4 + 3]);
       tmem_st_wait();
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(p_ready);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
       if (tid == 0) {
         // all 256 writers have fenced and arrived: the tile is complete and visible to the async proxy
         mbar_wait(p_ready, (uint32_t)st & 1u);
-        tma_store_3d(&tmap_ds, smem_ds + (st & 1) * DS_BYTES, q0, k0, bi * p.hq + h);
+        if (!(p.dbg & 2)) tma_store_3d(&tmap_ds, smem_ds + (st & 1) * DS_BYTES, q0, k0, bi * p.hq + h);
         tma_store_commit();
+        if (st >= 1) {
+          tma_store_wait_read<1>();                    // store(st-1) has read its tile: release it for step st+1
+          mbar_arrive(&ds_free[(st + 1) & 1]);
+        }
       }
+      if (++i == nq) { i = i0; ++h; }
     }
     // ---- epilogue: dK, dV [kv = row, d] ------------------------------------------------------------------------------------------
     if (total_steps > 0) {
@@ -425,6 +478,7 @@ constexpr int DQ_BM = 128, DQ_BK = 128, DQ_STAGES = 3;
 constexpr int DQ_A_BYTES = DQ_BK * DQ_BM * 2;     // dSt tile: [128 keys][128 q] bf16 as two 64-q chunks of [128 rows x 128 B]
 constexpr int DQ_B_BYTES = DQ_BK * FB_D * 2;      // K tile:   [128 keys][128 d]
 constexpr int DQ_STAGE_BYTES = DQ_A_BYTES + DQ_B_BYTES;
+static_assert(DQ_A_BYTES == DQ_B_BYTES, "the dQ issuer derives the B descriptor from the A descriptor");
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_ds, const __grid_constant__ CUtensorMap tmap_k, const FaDqParams p) {
@@ -513,11 +567,10 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_ds, const __grid_const
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * DQ_STAGE_BYTES), b_addr = a_addr + DQ_A_BYTES;
+          const uint32_t a_lo = smem_desc_lo(smem_u32(smem + stage * DQ_STAGE_BYTES), DQ_A_BYTES / 2), b_lo = a_lo + (DQ_A_BYTES >> 4);   // same LBO for both (DQ_A_BYTES == DQ_B_BYTES)
 #pragma unroll
           for (int kk = 0; kk < DQ_BK / UMMA_K; ++kk)
-            umma_f16(d_tmem, make_smem_desc_sw128(a_addr + kk * 2048, DQ_A_BYTES / 2, 1024), make_smem_desc_sw128(b_addr + kk * 2048, DQ_B_BYTES / 2, 1024), idesc,
-                     (kb > 0 || kk > 0) ? 1u : 0u);
+            umma_f16(d_tmem, smem_desc_at(a_lo, smem_desc_hi_sw128(1024), kk * 2048), smem_desc_at(b_lo, smem_desc_hi_sw128(1024), kk * 2048), idesc, (kb > 0 || kk > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (++stage == DQ_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -589,14 +642,14 @@ extern "C" int mb200_flash_attn_bwd_split_heads(int sk, int b, int hq, int hk) {
 }
 
 // q, do, o: [sq, b, hq, 128]; k, v: [sk, b, hk, 128] (element strides given, d contiguous); lse: [b, hq, sq] fp32;
-// delta: [b, hq, sq] fp32 scratch (filled here); dq: [sq, b, hq, 128] bf16 contiguous; dk, dv: [sk, b, hk, 128] bf16 contiguous.
-extern "C" int mb200_flash_attn_bwd(const void* q, const void* k, const void* v, const void* dout, const void* out, const float* lse, float* delta, void* dq, void* dk,
+// vec: [b, hq, ceil(sq/64), 128] fp32 scratch (filled here); dq: [sq, b, hq, 128] bf16 contiguous; dk, dv: [sk, b, hk, 128] bf16 contiguous.
+extern "C" int mb200_flash_attn_bwd(const void* q, const void* k, const void* v, const void* dout, const void* out, const float* lse, float* vec, void* dq, void* dk,
                                     void* dv, void* scratch, int split_heads, int sq, int sk, int b, int hq, int hk, int d, long q_ss, long q_sb, long q_sh, long k_ss,
                                     long k_sb, long k_sh, long v_ss, long v_sb, long v_sh, long do_ss, long do_sb, long do_sh, long o_ss, long o_sb, long o_sh, float scale,
                                     int causal, cudaStream_t s) {
   if (d != FB_D || hq % hk != 0) return -10;
   if ((q_ss | q_sb | q_sh | k_ss | k_sb | k_sh | v_ss | v_sb | v_sh | do_ss | do_sb | do_sh | o_ss | o_sb | o_sh) % 8 != 0) return -11;
-  constexpr int SMEM_DKV = 2 * (2 * FB_KV * 128) + 2 * 2 * (2 * FB_Q * 128) + 2 * FB_KV * 128 + 4 * FB_Q * 4 + 1024 + 256;
+  constexpr int SMEM_DKV = 2 * (2 * FB_KV * 128) + FB_STAGES * 2 * (2 * FB_Q * 128) + 2 * FB_KV * 128 + FB_STAGES * 2 * FB_Q * 4 + 1024 + 256;
   constexpr int SMEM_DQ = DQ_STAGES * DQ_STAGE_BYTES + 1024 + 256;
   const size_t sq_al = ((size_t)sq + 7) / 8 * 8;
   CUtensorMap tq, tk, tv, tdo, tds, tk2;
@@ -614,16 +667,20 @@ extern "C" int mb200_flash_attn_bwd(const void* q, const void* k, const void* v,
     configured = true;
   }
   {
-    const long rows = (long)sq * b * hq;
+    const long rows = (long)((sq + FB_Q - 1) / FB_Q) * FB_Q * b * hq;
     const int wpb = 8;
-    fa_delta_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(out), delta,
-                                                                          sq, b, hq, do_ss, do_sb, do_sh, o_ss, o_sb, o_sh);
+    fa_delta_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(out), lse, vec,
+                                                                          sq, b, hq, scale, do_ss, do_sb, do_sh, o_ss, o_sb, o_sh);
   }
   FaBwdParams p;
   p.sq = sq; p.sk = sk; p.b = b; p.hq = hq; p.hk = hk; p.causal = causal; p.split_heads = split_heads;
+  {
+    static const int dbg = getenv("MB200_FA_BWD_DBG") ? atoi(getenv("MB200_FA_BWD_DBG")) : 0;
+    p.dbg = dbg;
+  }
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   p.q_sb = q_sb; p.q_sh = q_sh; p.k_sb = k_sb; p.k_sh = k_sh; p.v_sb = v_sb; p.v_sh = v_sh; p.do_sb = do_sb; p.do_sh = do_sh;
-  p.lse = lse; p.delta = delta; p.dk = dk; p.dv = dv;
+  p.vec = vec; p.dk = dk; p.dv = dv;
   size_t ds_bytes = (size_t)b * hq * sk * sq_al * 2;
   ds_bytes = (ds_bytes + 255) / 256 * 256;
   p.dk_part = split_heads ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + ds_bytes) : nullptr;

@@ -135,7 +135,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], FA_BM);
+      mbar_init(&p_ready[i], FA_BM / 32);
     }
     for (int i = 0; i < 8; ++i) mbar_init(&pv_done[i], 1);
     fence_mbar_init();
@@ -334,7 +334,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       }
       if (!P_TMEM) fence_proxy_async();   // generic-proxy smem writes of P → visible to the tensor core (async proxy)
       tc_fence_before();
-      mbar_arrive(&p_ready[2 * t + buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[2 * t + buf]);     // one arrival per warp (4 per tile): per-thread arrivals serialise on the smem atomic unit
     }
     if (nb > 0) {
       mbar_wait(&pv_done[4 * t + ((nb - 1) & 3)], (uint32_t)((nb - 1) >> 2) & 1u);

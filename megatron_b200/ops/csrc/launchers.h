@@ -52,7 +52,7 @@ void mb200_moe_push_rows(const void* in, const int64_t* src_row, const int32_t* 
                          int64_t n_pairs, int row_bytes, cudaStream_t s);
 void mb200_moe_pull_rows(void* out, const int32_t* rank, const int64_t* slot, const float* w, const int64_t* peer_ptrs, int world, size_t src_off_bytes, int64_t n_out,
                          int topk, int row_bytes, int raw, cudaStream_t s);
-int mb200_flash_attn_bwd(const void* q, const void* k, const void* v, const void* dout, const void* out, const float* lse, float* delta, void* dq, void* dk, void* dv,
+int mb200_flash_attn_bwd(const void* q, const void* k, const void* v, const void* dout, const void* out, const float* lse, float* vec, void* dq, void* dk, void* dv,
                          void* scratch, int split_heads, int sq, int sk, int b, int hq, int hk, int d, long q_ss, long q_sb, long q_sh, long k_ss, long k_sb, long k_sh,
                          long v_ss, long v_sb, long v_sh, long do_ss, long do_sb, long do_sh, long o_ss, long o_sb, long o_sh, float scale, int causal, cudaStream_t s);
 size_t mb200_flash_attn_bwd_scratch_bytes(int sq, int sk, int b, int hq, int hk, int split_heads);
