@@ -276,7 +276,10 @@ class _FlashAttnFn(torch.autograd.Function):
         go = go.contiguous()
         if _ATTN_BWD_IMPL == "native" and hasattr(ext(), "flash_attn_bwd") and q.shape[-1] == 128:
             # our tcgen05 backward (csrc/flash_attn_bwd_sm100.cu): dK/dV accumulate in TMEM while dS tiles stream to a bf16 scratch by TMA; dQ = dS K in a second tcgen05 kernel
-            dq, dk, dv = ext().flash_attn_bwd(go, q, k, v, o, lse, ctx.causal, ctx.scale, _ATTN_BWD_SPLIT_HEADS)
+            try:
+                dq, dk, dv = ext().flash_attn_bwd(go, q, k, v, o, lse, ctx.causal, ctx.scale, _ATTN_BWD_SPLIT_HEADS)
+            except RuntimeError as e:
+                raise RuntimeError(f"{e}; go {tuple(go.shape)} {go.stride()} q {q.stride()} k {k.stride()} v {v.stride()} o {o.stride()} ptrs {[t.data_ptr() % 16 for t in (go, q, k, v, o)]}") from e
             _count(4 if _ATTN_BWD_SPLIT_HEADS != 0 else 3)
             return dq, dk, dv, None, None
         lse_lib = lse.unsqueeze(-1) if _cudnn_lse_ndim() == 4 else lse
@@ -297,13 +300,13 @@ def _cudnn_lse_ndim() -> int:
 
 
 _ATTN_IMPL = os.environ.get("MEGATRON_B200_ATTN", "auto")  # auto | native | library
-_ATTN_BWD_IMPL = os.environ.get("MEGATRON_B200_ATTN_BWD", "library")  # library (cuDNN on our out/LSE) | native (tcgen05 backward, first version)
-_ATTN_BWD_SPLIT_HEADS = int(os.environ.get("MEGATRON_B200_ATTN_BWD_SPLIT_HEADS", "-1"))  # -1: split the GQA group over CTAs when the grid would leave SMs idle (few local heads)
+_ATTN_BWD_IMPL = os.environ.get("MEGATRON_B200_ATTN_BWD", "native")  # native: our two-kernel tcgen05 backward (csrc/flash_attn_bwd_sm100.cu) | library: cuDNN on our (out, LSE)
+_ATTN_BWD_SPLIT_HEADS = int(os.environ.get("MEGATRON_B200_ATTN_BWD_SPLIT_HEADS", "-1"))  # -1: one CTA per (key block, QUERY head) whenever the model has GQA (measured faster at every head count: 4x the CTAs, better tail balance); 0: one CTA per KV head
 _FA_VARIANT = int(os.environ.get("MEGATRON_B200_FA_VARIANT", "1"))  # 1 (default, measured 836 vs 786 TF): P kept in tensor memory (TS MMA); 0: P through shared memory
 
 
 # what "auto" means on this build: the faster MEASURED forward at the Llama-3 8B shape (profiles/r1_attention.md)
-_ATTN_AUTO_RESOLVES_TO = "native"   # forward 943 TF (0.75x cuDNN) costs ~1 % of the step; backward is cuDNN on our (out, LSE) unless MEGATRON_B200_ATTN_BWD=native
+_ATTN_AUTO_RESOLVES_TO = "native"   # our tcgen05 kernels at every TP size (few-head grids use mirrored tile pairing / split-heads); "library" = cuDNN, for comparisons
 
 
 def _resolved_attn_impl() -> str:
@@ -313,10 +316,10 @@ def _resolved_attn_impl() -> str:
 def attention_impl_for(sq: int, b: int, hq_local: int) -> str:
     """What ``flash_attention`` will run for a bf16 [sq, b, hq_local, 128] causal problem on this build (for logs / bench reports)."""
     impl = _resolved_attn_impl()
-    if impl == "native" and _ATTN_IMPL == "auto" and ((sq + 255) // 256) * hq_local * b < 2 * 148:
-        impl = "library"
     if impl == "native":
-        return "tcgen05 forward (ours, P in TMEM)" + (" + tcgen05 backward (ours)" if _ATTN_BWD_IMPL == "native" else " + cuDNN backward on our (out, LSE)")
+        grid = ((sq + 255) // 256) * hq_local * b
+        fwd = "tcgen05 forward (ours, P in TMEM" + (", mirrored tile pairing" if grid <= 148 * 3 // 2 else "") + ")"
+        return fwd + (" + tcgen05 backward (ours: dK/dV kernel + dQ=dS.K kernel)" if _ATTN_BWD_IMPL == "native" else " + cuDNN backward on our (out, LSE)")
     return "cuDNN SDPA (library) forward + backward"
 
 
@@ -329,12 +332,6 @@ def set_attention_impl(impl: str) -> None:
 def _native_attention_ok(q, k, v, causal, window) -> bool:
     if _resolved_attn_impl() == "library" or window is not None or not hasattr(ext(), "flash_attn_fwd"):
         return False
-    if _ATTN_IMPL == "auto":
-        # one CTA per (256 query rows, head): with fewer than two waves on 148 SMs the causal load imbalance is exposed
-        # (TP=8 leaves 4 heads x 32 tiles = 128 CTAs, bounded by the heaviest tile) — the library kernel handles that regime better
-        n_ctas = ((q.shape[0] + 255) // 256) * q.shape[2] * q.shape[1]
-        if n_ctas < 2 * 148:
-            return False
     if q.dtype != torch.bfloat16 or q.shape[-1] not in (64, 128) or k.shape[-1] != q.shape[-1] or v.shape[-1] != q.shape[-1]:
         return False
     if (causal and k.shape[0] < q.shape[0]) or q.shape[0] < 128:   # decode-sized queries stay on the library path (untested regime for the 2x128-row tiling)

@@ -20,6 +20,8 @@
 // views produced by splitting a fused QKV projection are consumed in place.  out [sq, b, hq, d] contiguous,
 // lse [b, hq, sq] fp32 (natural log).  Causal masking is bottom-right aligned (kv ≤ q + sk − sq).
 // Replaces: TE DotProductAttention / cuDNN fused attention and the unfused baddbmm+softmax+bmm path (X6).
+#include <cstdlib>
+
 #include "gemm_sm100_device.cuh"
 
 namespace mb200 {
@@ -37,6 +39,7 @@ constexpr bool FA_POLY_EXP2 = false;
 struct FaParams {
   int sq, sk, b, hq, hk;
   int causal;
+  int pair_mode;                 // 0: a CTA owns two neighbouring query tiles, 1: mirrored tiles (x, T-1-x) — see the kernel
   float scale_log2;              // softmax_scale * log2(e)
   long q_sb, q_sh, k_sb, k_sh, v_sb, v_sh;  // element strides of batch / head inside one sequence row
   void* out;
@@ -102,15 +105,27 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = (int)gridDim.x - 1 - (int)blockIdx.x;   // heaviest (latest) causal tiles are scheduled first
+  // Which two 128-row query tiles this CTA owns.  pair_mode 0: neighbours (2 qt, 2 qt + 1) — both tiles need (almost) the same K/V blocks, the ping-pong
+  // runs for the whole walk; with several waves of CTAs, heaviest first.  pair_mode 1 ("mirrored", for grids of at most ~one wave, e.g. 4 local heads
+  // under TP=8): tiles (x, T-1-x) — every CTA then owns T+1 causal blocks instead of 2..2T, so the single wave is balanced (the heavy tile finishes solo).
+  const int n_tiles = (p.sq + FA_BM - 1) / FA_BM;
+  int tile_row0[2];
+  if (p.pair_mode == 0) {
+    tile_row0[0] = qt * 2 * FA_BM;
+    tile_row0[1] = tile_row0[0] + FA_BM;
+  } else {
+    tile_row0[0] = (int)blockIdx.x * FA_BM;
+    tile_row0[1] = (n_tiles - 1 - (int)blockIdx.x) * FA_BM;
+    if (tile_row0[1] == tile_row0[0]) tile_row0[1] = p.sq;      // odd tile count: the middle CTA owns one tile
+  }
   const int h = blockIdx.y, bi = blockIdx.z;
   const int hkv = h / (p.hq / p.hk);
-  const int q0 = qt * 2 * FA_BM;
   const int off = p.sk - p.sq;                           // bottom-right causal alignment
   const int nkv = (p.sk + FA_BN - 1) / FA_BN;
   int n_t[2];
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
-    const int first = q0 + t * FA_BM;
+    const int first = tile_row0[t];
     if (first >= p.sq) {
       n_t[t] = 0;
     } else if (p.causal) {
@@ -156,7 +171,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 #pragma unroll
       for (int t = 0; t < 2; ++t)
 #pragma unroll
-        for (int c = 0; c < DCH; ++c) tma_load_2d(smem_q + t * Q_TILE_BYTES + c * Q_CHUNK_BYTES, &tmap_q, q_full, qcol + c * 64, q0 + t * FA_BM);
+        for (int c = 0; c < DCH; ++c) tma_load_2d(smem_q + t * Q_TILE_BYTES + c * Q_CHUNK_BYTES, &tmap_q, q_full, qcol + c * 64, min(tile_row0[t], p.sq - 1));
       for (int j = 0; j < n; ++j) {
         const int s = j % FA_STAGES;
         const uint32_t ph = (uint32_t)(j / FA_STAGES) & 1u;
@@ -175,25 +190,27 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     if (lane == 0 && n > 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(FA_BM, FA_BN, false, false);
       constexpr uint32_t idesc_pv = make_idesc_bf16(FA_BM, D, false, true);
+      // descriptors = a precomputed low word + an immediate (the issuing threads are on the critical path of every KV block)
+      constexpr uint32_t HI = smem_desc_hi_sw128(1024);
+      const uint32_t q_lo0 = smem_desc_lo(smem_u32(smem_q), 16), k_lo0 = smem_desc_lo(smem_u32(smem_k), 16), p_lo0 = smem_desc_lo(smem_u32(smem_p), 16);
+      const uint32_t v_lo0 = smem_desc_lo(smem_u32(smem_v), KV_CHUNK_BYTES);
       auto issue_qk = [&](int t, int s, int buf) {
-        const uint32_t qa = smem_u32(smem_q + t * Q_TILE_BYTES), ka = smem_u32(smem_k + s * KV_STAGE_BYTES);
+        const uint32_t q_lo = q_lo0 + t * (Q_TILE_BYTES >> 4), k_lo = k_lo0 + s * (KV_STAGE_BYTES >> 4);
 #pragma unroll
         for (int c = 0; c < DCH; ++c)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_f16(tmem_base + S_COL + (2 * t + buf) * FA_BN, make_smem_desc_sw128(qa + c * Q_CHUNK_BYTES + kk * 32, 16, 1024),
-                     make_smem_desc_sw128(ka + c * KV_CHUNK_BYTES + kk * 32, 16, 1024), idesc_qk, (c > 0 || kk > 0) ? 1u : 0u);
+            umma_f16(tmem_base + S_COL + (2 * t + buf) * FA_BN, smem_desc_at(q_lo, HI, c * Q_CHUNK_BYTES + kk * 32), smem_desc_at(k_lo, HI, c * KV_CHUNK_BYTES + kk * 32),
+                     idesc_qk, (c > 0 || kk > 0) ? 1u : 0u);
       };
       auto issue_pv = [&](int t, int s, int buf, bool acc) {
-        const uint32_t pa = smem_u32(smem_p + (2 * t + buf) * P_TILE_BYTES), va = smem_u32(smem_v + s * KV_STAGE_BYTES);
+        const uint32_t p_lo = p_lo0 + (2 * t + buf) * (P_TILE_BYTES >> 4), v_lo = v_lo0 + s * (KV_STAGE_BYTES >> 4);
 #pragma unroll
         for (int kk = 0; kk < FA_BN / 16; ++kk) {
           if (P_TMEM)
-            umma_f16_ts(tmem_base + O_COL + t * D, tmem_base + S_COL + (2 * t + buf) * FA_BN + kk * 8, make_smem_desc_sw128(va + kk * 2048, KV_CHUNK_BYTES, 1024), idesc_pv,
-                        (acc || kk > 0) ? 1u : 0u);
+            umma_f16_ts(tmem_base + O_COL + t * D, tmem_base + S_COL + (2 * t + buf) * FA_BN + kk * 8, smem_desc_at(v_lo, HI, kk * 2048), idesc_pv, (acc || kk > 0) ? 1u : 0u);
           else
-            umma_f16(tmem_base + O_COL + t * D, make_smem_desc_sw128(pa + kk * 32, 16, 1024), make_smem_desc_sw128(va + kk * 2048, KV_CHUNK_BYTES, 1024), idesc_pv,
-                     (acc || kk > 0) ? 1u : 0u);
+            umma_f16(tmem_base + O_COL + t * D, smem_desc_at(p_lo, HI, kk * 32), smem_desc_at(v_lo, HI, kk * 2048), idesc_pv, (acc || kk > 0) ? 1u : 0u);
         }
       };
       const int t = warp - 9;
@@ -239,7 +256,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     // ================================= softmax warpgroups ================================================================
     const int t = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
-    const int q_idx = q0 + t * FA_BM + row;
+    const int q_idx = tile_row0[t] + row;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t s_addr0 = tmem_base + lane_base + S_COL + 2 * t * FA_BN;
     const uint32_t o_addr = tmem_base + lane_base + O_COL + t * D;
@@ -384,6 +401,9 @@ static int launch_fa_fwd(const void* q, const void* k, const void* v, FaParams p
     configured = true;
   }
   dim3 grid((p.sq + 2 * FA_BM - 1) / (2 * FA_BM), p.hq, p.b);
+  // mirrored pairing when the whole grid is at most ~1.5 waves and the mask is causal (otherwise every tile costs the same)
+  p.pair_mode = (p.causal && p.sq == p.sk && (long)grid.x * grid.y * grid.z <= (long)num_sms() * 3 / 2 && grid.x > 1) ? 1 : 0;
+  if (const char* e = getenv("MB200_FA_PAIR_MODE")) p.pair_mode = atoi(e);
   kern<<<grid, FA_THREADS, SMEM_BYTES, s>>>(tq, tk, tv, p);
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }

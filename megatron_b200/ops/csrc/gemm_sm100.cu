@@ -18,6 +18,8 @@
 // Replaces cuBLAS-through-torch.matmul and Apex `wgrad_gemm_accum_fp32`.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <stdio.h>
 
@@ -284,7 +286,18 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// cuTensorMapEncodeTiled is a DRIVER call: it fails with CUDA_ERROR_INVALID_CONTEXT (201) on a thread that has not yet bound the primary context —
+// e.g. PyTorch's autograd thread when the caching allocator served every allocation from its cache and no runtime call has run there yet.
+static void ensure_context_on_this_thread() {
+  static thread_local bool ready = false;
+  if (!ready) {
+    cudaFree(nullptr);
+    ready = true;
+  }
+}
+
 static EncodeTiledFn get_encode_fn() {
+  ensure_context_on_this_thread();
   static EncodeTiledFn fn = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -311,6 +324,9 @@ bool make_tmap_bf16_strided(CUtensorMap* out, const void* ptr, uint64_t rows, ui
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS && getenv("MB200_DEBUG_TMAP"))
+    fprintf(stderr, "[mb200] cuTensorMapEncodeTiled failed (%d): ptr %p rows %llu cols %llu pitch %llu box %u x %u\n", (int)r, ptr, (unsigned long long)rows,
+            (unsigned long long)cols, (unsigned long long)row_pitch_bytes, box_cols, box_rows);
   return r == CUDA_SUCCESS;
 }
 

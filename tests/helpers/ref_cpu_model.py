@@ -3,7 +3,7 @@
 The reference assumes CUDA in three places that do not touch the math (device of the RoPE table, the default causal mask, the
 CUDA RNG tracker around dropout with p=0).  This harness patches those call sites from the outside; no reference file is edited.
 
-    torchrun/spawn env: RANK WORLD_SIZE MASTER_ADDR MASTER_PORT;  argv: out_prefix tp
+    torchrun/spawn env: RANK WORLD_SIZE MASTER_ADDR MASTER_PORT;  argv: out_prefix tp [grads | save <dir> | load <dir>]
 """
 import contextlib
 import os
@@ -16,6 +16,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, os.path.join(REPO, "baseline", "_ref"))
 sys.path = [p for p in sys.path if os.path.abspath(p or ".") != REPO]
 torch.cuda.current_device = lambda: torch.device("cpu")
+torch.cuda.synchronize = lambda *a, **k: None
 import torch.distributed as dist  # noqa: E402
 
 
@@ -73,6 +74,29 @@ def main():
     )
     m = GPTModel(cfg, get_gpt_layer_local_spec(normalization="RMSNorm"), vocab_size=CFG["vocab"], max_sequence_length=CFG["seq"], parallel_output=True,
                  share_embeddings_and_output_weights=False, position_embedding_type="rope", rotary_base=10000)
+    mode = sys.argv[3] if len(sys.argv) > 3 else "grads"
+    if mode in ("save", "load"):
+        # checkpoint interop: the reference writes (or reads back) a torch_dist distributed checkpoint of this model
+        from megatron.core import dist_checkpointing
+
+        ckpt_dir = sys.argv[4]
+        tp_rank = parallel_state.get_tensor_model_parallel_rank()
+        if mode == "save":
+            init_params(m.named_parameters(), tp_rank, tp)
+            dist_checkpointing.save(m.sharded_state_dict(), ckpt_dir)
+        else:
+            with torch.no_grad():
+                for _, p in m.named_parameters():
+                    p.zero_()
+            sd = dist_checkpointing.load(m.sharded_state_dict(), ckpt_dir)
+            m.load_state_dict(sd, strict=False)
+            got = {n: p.detach().clone() for n, p in m.named_parameters()}
+            init_params(m.named_parameters(), tp_rank, tp)       # what the writer initialised
+            worst = max(float((got[n] - p.detach()).abs().max()) for n, p in m.named_parameters())
+            torch.save({"max_abs_diff": worst, "n_params": len(got)}, f"{out_prefix}.rank{rank}.pt")
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     init_params(m.named_parameters(), parallel_state.get_tensor_model_parallel_rank(), tp)
     tok = tokens()
     s = CFG["seq"]

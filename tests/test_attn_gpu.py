@@ -37,6 +37,19 @@ def _ref(q, k, v, causal, scale):
 @pytest.mark.parametrize("variant", [0, 1])
 def test_flash_fwd_matches_reference(sq, sk, b, hq, hk, d, causal, variant):
     from megatron_b200 import ops
+    _fwd_case(ops, sq, sk, b, hq, hk, d, causal, variant)
+
+
+@pytest.mark.parametrize("sq,hq,hk", [(2048, 4, 1), (1024, 2, 2), (1152, 2, 1), (1000, 4, 2)])
+def test_flash_fwd_mirrored_pairing(sq, hq, hk, monkeypatch):
+    """Few-head grids (TP=8): a CTA owns query tiles (x, T-1-x); even / odd tile counts and a ragged last tile."""
+    from megatron_b200 import ops
+
+    monkeypatch.setenv("MB200_FA_PAIR_MODE", "1")
+    _fwd_case(ops, sq, sq, 1, hq, hk, 128, True, 1)
+
+
+def _fwd_case(ops, sq, sk, b, hq, hk, d, causal, variant):
 
     torch.manual_seed(0)
     q = torch.randn(sq, b, hq, d, device="cuda").bfloat16()

@@ -87,3 +87,108 @@ def test_loss_and_grad_parity_with_reference(tmp_path, tp):
             go = ours[r]["grads"][n]
             err = float((go - g).abs().max() / g.abs().max().clamp(min=1e-12))
             assert err < 2e-4, f"rank {r} grad {n}: rel err {err}"
+
+
+# ---- distributed-checkpoint interop ("cross-load a checkpoint with the reference") --------------------------------------
+
+
+def _spawn_reference(tmp_path, tp, *extra):
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    prefix = str(tmp_path / f"ref_{extra[0]}_tp{tp}")
+    procs = []
+    for r in range(tp):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(tp), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(REPO, "tests", "helpers", "ref_cpu_model.py"), prefix, str(tp), *extra], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=600)
+        assert p.returncode == 0, out[-3000:]
+    return prefix
+
+
+def _our_model(tp):
+    import torch.nn.functional as F
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=tp)
+    cfg = TransformerConfig(num_layers=2, hidden_size=64, ffn_hidden_size=128, num_attention_heads=4, num_query_groups=2, kv_channels=16, normalization="RMSNorm",
+                            gated_linear_unit=True, activation_func=F.silu, add_bias_linear=False, hidden_dropout=0.0, attention_dropout=0.0, use_cpu_initialization=True,
+                            gradient_accumulation_fusion=False, perform_initialization=False, tensor_model_parallel_size=tp)
+    m = GPTModel(cfg, get_gpt_layer_local_spec(normalization="RMSNorm"), vocab_size=128, max_sequence_length=32, parallel_output=True,
+                 share_embeddings_and_output_weights=False, position_embedding_type="rope", rotary_base=10000)
+    return m, ps.get_tensor_model_parallel_rank()
+
+
+def _seeded_init(m, tp_rank, tp):
+    import zlib
+
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.dim() == 1:
+                p.fill_(1.0)
+                continue
+            sharded = bool(getattr(p, "tensor_model_parallel", False)) and tp > 1
+            dim = int(getattr(p, "partition_dim", -1))
+            shape = list(p.shape)
+            if sharded:
+                shape[dim] *= tp
+            g = torch.Generator().manual_seed(zlib.crc32(n.encode()))
+            full = torch.empty(shape).normal_(0, 0.05, generator=g)
+            p.copy_(full.chunk(tp, dim=dim)[tp_rank] if sharded else full)
+
+
+def _ours_save(rank, world, tp, ckpt_dir):
+    from megatron_b200.core import dist_checkpointing
+
+    m, tp_rank = _our_model(tp)
+    _seeded_init(m, tp_rank, tp)
+    dist_checkpointing.save(m.sharded_state_dict(), ckpt_dir)
+    return True
+
+
+def _ours_load(rank, world, tp, ckpt_dir):
+    from megatron_b200.core import dist_checkpointing
+
+    m, tp_rank = _our_model(tp)
+    with torch.no_grad():
+        for _, p in m.named_parameters():
+            p.zero_()
+    sd = dist_checkpointing.load(m.sharded_state_dict(), ckpt_dir)
+    m.load_state_dict(sd, strict=False)
+    got = {n: p.detach().clone() for n, p in m.named_parameters()}
+    _seeded_init(m, tp_rank, tp)
+    return max(float((got[n] - p.detach()).abs().max()) for n, p in m.named_parameters())
+
+
+@pytest.mark.parametrize("tp_write,tp_read", [(2, 1), (1, 2)])
+def test_reference_loads_our_checkpoint(tmp_path, tp_write, tp_read):
+    """A torch_dist checkpoint written by this framework (TP=tp_write) is read by the UNMODIFIED reference at another TP size."""
+    from dist_utils import run_distributed
+
+    ckpt = tmp_path / "ckpt_ours"
+    ckpt.mkdir()
+    run_distributed(_ours_save, tp_write, tp_write, str(ckpt))
+    prefix = _spawn_reference(tmp_path, tp_read, "load", str(ckpt))
+    for r in range(tp_read):
+        res = torch.load(f"{prefix}.rank{r}.pt")
+        assert res["n_params"] == 15 and res["max_abs_diff"] == 0.0, res
+
+
+@pytest.mark.parametrize("tp_write,tp_read", [(2, 1), (1, 2)])
+def test_we_load_reference_checkpoint(tmp_path, tp_write, tp_read):
+    """...and a checkpoint written by the reference is read by this framework, resharded."""
+    from dist_utils import run_distributed
+
+    ckpt = tmp_path / "ckpt_ref"
+    ckpt.mkdir()
+    _spawn_reference(tmp_path, tp_write, "save", str(ckpt))
+    diffs = run_distributed(_ours_load, tp_read, tp_read, str(ckpt))
+    assert all(d == 0.0 for d in diffs), diffs
