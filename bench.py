@@ -166,7 +166,12 @@ def deterministic_init(torch, named_params, tp_rank, tp_world, num_layers):
             gen.manual_seed(zlib.crc32(name.encode()))
             std = 0.02 / math.sqrt(2.0 * num_layers) if (".linear_proj." in name or ".linear_fc2." in name) else 0.02
             full = torch.empty(full_shape, dtype=torch.float32, device="cuda").normal_(0.0, std, generator=gen)
-            shard = full.chunk(tp_world, dim=dim)[tp_rank] if sharded else full
+            if sharded and name.endswith("linear_fc1.weight"):
+                # SwiGLU: the logical matrix is [gate; up]; a TP rank holds [gate chunk r; up chunk r] — the model is then the SAME function at every TP size
+                ga, up = full.chunk(2, dim=0)
+                shard = torch.cat([ga.chunk(tp_world, dim=0)[tp_rank], up.chunk(tp_world, dim=0)[tp_rank]], dim=0)
+            else:
+                shard = full.chunk(tp_world, dim=dim)[tp_rank] if sharded else full
             p.copy_(shard.to(p.dtype))
             del full
             n += 1

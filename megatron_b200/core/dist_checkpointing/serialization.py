@@ -90,10 +90,21 @@ def save(sharded_state_dict: ShardedStateDict, checkpoint_dir: str, sharded_stra
 
 
 def load_common_state_dict(checkpoint_dir: str) -> StateDict:
+    """Non-sharded part of a checkpoint.  Two on-disk formats (reference serialization.py:198-229): the legacy ``common.pt`` (what this framework
+    writes; the reference still reads it) and the current one, a single ShardedObject ``common_state`` inside the torch_dist files."""
     p = Path(checkpoint_dir) / COMMON_STATE_FNAME
-    if not p.exists():
+    if p.exists():
+        return torch.load(p, map_location="cpu", weights_only=False)
+    try:
+        from .mapping import ShardedObject
+        from .strategies import torch_dist
+
+        so = ShardedObject("common_state", None, (1,), (0,))
+        loaded = torch_dist.load_sharded([], [so], str(checkpoint_dir), process_group=None, no_dist=True)
+        common = loaded.get(so.unique_key)
+        return common if isinstance(common, dict) else {}
+    except (KeyError, FileNotFoundError):
         return {}
-    return torch.load(p, map_location="cpu", weights_only=False)
 
 
 def load_content_metadata(checkpoint_dir: str) -> Optional[dict]:

@@ -66,8 +66,9 @@ class MCoreSavePlanner(DefaultSavePlanner):
     def resolve_data(self, write_item: WriteItem):
         obj = self._by_index[write_item.index]
         if isinstance(obj, ShardedObject):
+            # on-disk format of a ShardedObject (reference strategies/torch.py:317-322): a pickled LIST of the data of every local object with this key
             buf = io.BytesIO()
-            torch.save(obj.data, buf)
+            torch.save([obj.data], buf)
             buf.seek(0)
             return buf
         return _view(obj).contiguous()
@@ -116,7 +117,9 @@ class MCoreLoadPlanner(DefaultLoadPlanner):
         return new_plan
 
     def load_bytes(self, read_item: ReadItem, value: io.BytesIO) -> None:
-        self.loaded_objects[read_item.dest_index.fqn] = torch.load(value, weights_only=False)
+        payload = torch.load(value, weights_only=False)
+        # reference format: [data] (one entry per local object of that key)
+        self.loaded_objects[read_item.dest_index.fqn] = payload[0] if isinstance(payload, list) and len(payload) == 1 else payload
 
     def resolve_tensor(self, read_item: ReadItem) -> torch.Tensor:
         st = self._dst[(read_item.dest_index.fqn, tuple(read_item.dest_index.offset))]
@@ -144,13 +147,13 @@ def save_sharded(sharded_tensors: List[ShardedTensor], sharded_objects: List[Sha
     dcp_save({}, storage_writer=writer, planner=planner, process_group=process_group, no_dist=_no_dist(process_group))
 
 
-def load_sharded(sharded_tensors: List[ShardedTensor], sharded_objects: List[ShardedObject], checkpoint_dir: str, process_group=None) -> Dict[str, Any]:
+def load_sharded(sharded_tensors: List[ShardedTensor], sharded_objects: List[ShardedObject], checkpoint_dir: str, process_group=None, no_dist: bool = False) -> Dict[str, Any]:
     """Fills ``st.data`` of every requested ShardedTensor in place; returns {unique_key: object}."""
     for st in sharded_tensors:
         if st.data is None:
             st.init_data(device="cpu")
     planner = MCoreLoadPlanner(sharded_tensors, sharded_objects)
-    dcp_load({}, storage_reader=FileSystemReader(checkpoint_dir), planner=planner, process_group=process_group, no_dist=_no_dist(process_group))
+    dcp_load({}, storage_reader=FileSystemReader(checkpoint_dir), planner=planner, process_group=process_group, no_dist=no_dist or _no_dist(process_group))
     return planner.loaded_objects
 
 

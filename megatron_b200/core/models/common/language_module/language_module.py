@@ -68,7 +68,9 @@ class LanguageModule(MegatronModule):
             self._tie_in_sharded_state_dict(sd, out_w, first_key, metadata)
         elif self.post_process and out_w in sd:
             sd[out_w].allow_shape_mismatch = True
-        sd.pop(out_extra, None) if out_extra in sd and sd[out_extra] is None else None
+        # GPT checkpoints never store an extra state for the output layer (reference gpt_model.py sharded_state_dict pops it after checking it is empty)
+        extra = sd.pop(out_extra, None)
+        assert not (extra is not None and getattr(extra, "data", None)), f"expected the output layer extra state to be empty, got {extra}"
         return sd
 
     def _tie_in_sharded_state_dict(self, sd, output_layer_weight_key, first_stage_word_emb_key, metadata=None):

@@ -344,10 +344,11 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       }
       // the TMA store of step st-2 must have finished READING this dS tile before it is overwritten (flag set by thread 0 one step ago)
       if (st >= 2) mbar_wait(&ds_free[st & 1], (uint32_t)((st >> 1) - 1) & 1u);
+      if (!(p.dbg & 512))
 #pragma unroll
       for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(ds_row + (((half * 4 + u) ^ sw) << 4)) = make_uint4(dw[u * 4], dw[u * 4 + 1], dw[u * 4 + 2], dw[u * 4 + 3]);
-      tmem_st_wait();
-      fence_proxy_async();
+      if (!(p.dbg & 128)) tmem_st_wait();
+      if (!(p.dbg & 256)) fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);

@@ -38,7 +38,12 @@ def init_params(named_params, tp_rank, tp_world):
             if sharded:
                 shape[dim] *= tp_world
             full = seeded_full(n, shape)
-            p.copy_(full.chunk(tp_world, dim=dim)[tp_rank] if sharded else full)
+            if sharded and n.endswith("linear_fc1.weight"):
+                # SwiGLU: the logical matrix is [gate; up]; a TP rank holds [gate chunk r; up chunk r] (TP-size-invariant model)
+                g, u = full.chunk(2, dim=0)
+                p.copy_(torch.cat([g.chunk(tp_world, dim=0)[tp_rank], u.chunk(tp_world, dim=0)[tp_rank]], dim=0))
+            else:
+                p.copy_(full.chunk(tp_world, dim=dim)[tp_rank] if sharded else full)
 
 
 CFG = dict(num_layers=2, hidden_size=64, ffn_hidden_size=128, num_attention_heads=4, num_query_groups=2, kv_channels=16, vocab=128, seq=32, batch=2)

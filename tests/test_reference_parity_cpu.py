@@ -66,7 +66,12 @@ def _ours(rank, world, tp):
                 shape[dim] *= tp
             g = torch.Generator().manual_seed(zlib.crc32(n.encode()))
             full = torch.empty(shape).normal_(0, 0.05, generator=g)
-            p.copy_(full.chunk(tp, dim=dim)[ps.get_tensor_model_parallel_rank()] if sharded else full)
+            r = ps.get_tensor_model_parallel_rank()
+            if sharded and n.endswith("linear_fc1.weight"):
+                ga, up = full.chunk(2, dim=0)
+                p.copy_(torch.cat([ga.chunk(tp, dim=0)[r], up.chunk(tp, dim=0)[r]], dim=0))
+            else:
+                p.copy_(full.chunk(tp, dim=dim)[r] if sharded else full)
     tok = torch.randint(0, CFG["vocab"], (CFG["batch"], CFG["seq"] + 1), generator=torch.Generator().manual_seed(1))
     pos = torch.arange(CFG["seq"]).unsqueeze(0).expand(CFG["batch"], -1).contiguous()
     loss = m(tok[:, :-1].contiguous(), pos, None, labels=tok[:, 1:].contiguous()).float().mean()
@@ -142,7 +147,11 @@ def _seeded_init(m, tp_rank, tp):
                 shape[dim] *= tp
             g = torch.Generator().manual_seed(zlib.crc32(n.encode()))
             full = torch.empty(shape).normal_(0, 0.05, generator=g)
-            p.copy_(full.chunk(tp, dim=dim)[tp_rank] if sharded else full)
+            if sharded and n.endswith("linear_fc1.weight"):
+                ga, up = full.chunk(2, dim=0)
+                p.copy_(torch.cat([ga.chunk(tp, dim=0)[tp_rank], up.chunk(tp, dim=0)[tp_rank]], dim=0))
+            else:
+                p.copy_(full.chunk(tp, dim=dim)[tp_rank] if sharded else full)
 
 
 def _ours_save(rank, world, tp, ckpt_dir):
