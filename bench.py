@@ -61,7 +61,24 @@ def parse():
     ap.add_argument("--no-sp-variant", action="store_true", help="skip the second (TP=N + sequence parallel) measurement of the repo arm")
     ap.add_argument("--recompute", default="auto")
     ap.add_argument("--main-grads", default="fp32", choices=["fp32", "bf16"])
+    # the other BASELINE.json configurations (repo arm): --model gpt3_6.7b | mixtral_8x7b | llama3_70b with their parallel layout
+    ap.add_argument("--tp", type=int, default=None)
+    ap.add_argument("--pp", type=int, default=None)
+    ap.add_argument("--vp", type=int, default=None)
+    ap.add_argument("--ep", type=int, default=None)
+    ap.add_argument("--dispatcher", default=None, help="MoE token dispatcher: alltoall | allgather | flex (NVLink push/pull)")
     return ap.parse_args()
+
+
+# BASELINE.json configs 3-5: (tp, pp, vp, ep) for 8 GPUs, global batch, recompute, main-grad dtype, sequence parallel
+OTHER_CONFIGS = {
+    "gpt3_6.7b": dict(tp=4, pp=2, vp=2, ep=1, global_batch=8, recompute={}, main_grads="fp32", sp=True,
+                      metric="tokens/sec (whole job, device-timed, max over ranks), GPT-3 6.7B TP=4 x PP=2 interleaved 1F1B, bf16"),
+    "mixtral_8x7b": dict(tp=1, pp=1, vp=None, ep=8, global_batch=8, recompute=dict(recompute_granularity="selective", recompute_modules=["core_attn"]), main_grads="fp32", sp=False,
+                         metric="tokens/sec (whole job, device-timed, max over ranks), Mixtral 8x7B EP=8, bf16"),
+    "llama3_70b": dict(tp=8, pp=1, vp=None, ep=1, global_batch=4, recompute=dict(recompute_granularity="full", recompute_method="uniform", recompute_num_layers=1), main_grads="bf16", sp=True,
+                       metric="tokens/sec (whole job, device-timed, max over ranks), Llama-3 70B TP=8 + sequence parallel, distributed optimizer, bf16"),
+}
 
 
 class ClockSampler:
@@ -240,10 +257,100 @@ def _b200_variant(args, torch, dist, rank, world, local, *, sequence_parallel, r
     return res
 
 
+def run_b200_other(args):
+    """Repo arm for the other BASELINE.json configurations (PP / EP / 70B).  Same timing contract; synthetic data; the model's own random init."""
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, REPO)
+    rank, world, local = env_rank()
+    assert world == args.gpus, f"launched with WORLD_SIZE={world} but --gpus {args.gpus}"
+    from megatron_b200 import ops
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.training import engine as _engine
+
+    torch.cuda.set_device(local)
+    _engine.initialize_distributed()
+    c = dict(OTHER_CONFIGS.get(args.model, dict(tp=1, pp=1, vp=None, ep=1, global_batch=world, recompute={}, main_grads="fp32", sp=False, metric=f"tokens/sec, {args.model}")))
+    tp, pp, vp, ep = args.tp or c["tp"], args.pp or c["pp"], args.vp if args.vp is not None else c["vp"], args.ep or c["ep"]
+    if world < tp * pp:          # fewer GPUs than the named layout: shrink TP first (DEV runs)
+        tp = max(1, world // pp)
+    if pp == 1:
+        vp = None
+    dp = world // (tp * pp)
+    ep = min(ep, dp * tp) if ep > 1 else 1
+    gb = args.global_batch if args.global_batch != 4 or args.model not in OTHER_CONFIGS else c["global_batch"]
+    gb = max(gb, dp * args.micro_batch * (pp if pp > 1 else 1))
+    overrides = {}
+    if args.layers:
+        overrides["num_layers"] = args.layers
+    if args.dispatcher:
+        overrides["moe_token_dispatcher_type"] = args.dispatcher
+    fp32_grads = (args.main_grads if args.main_grads != "fp32" or args.model not in OTHER_CONFIGS else c["main_grads"]) == "fp32"
+    eng = _engine.TrainEngine(args.model, tensor_model_parallel_size=tp, pipeline_model_parallel_size=pp, virtual_pipeline_model_parallel_size=vp,
+                              expert_model_parallel_size=ep, sequence_parallel=c["sp"] and tp > 1, micro_batch_size=args.micro_batch, global_batch_size=gb,
+                              seq_length=args.seq, bf16=True, model_overrides=overrides, lr=LR, min_lr=MIN_LR, weight_decay=WD, clip_grad=CLIP,
+                              grad_reduce_in_fp32=fp32_grads, **c["recompute"])
+    n_total = args.warmup + 2 * args.steps + 1
+    per_rank = eng.num_microbatches * args.micro_batch
+    g = torch.Generator().manual_seed(DATA_SEED + ps.get_data_parallel_rank())
+    host = torch.randint(0, eng.preset["vocab_size"], (n_total, per_rank, eng.seq_length + 1), generator=g, dtype=torch.int64).pin_memory()
+    dev_tokens = host.to("cuda")
+    losses = []
+
+    def step_dev():
+        losses.append(eng.train_step(dev_tokens[len(losses)]))
+
+    def step_e2e():
+        losses.append(eng.train_step(host[len(losses)]))
+        return float(losses[-1])
+
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.reset_launch_count()
+    ms, _ = timed_loop(torch, dist, step_dev, args.steps, world)
+    launches = ops.launch_count()
+    clocks = sampler.stop() if rank == 0 else {}
+    tokens_per_step = gb * eng.seq_length
+    value = tokens_per_step * args.steps / (ms / 1e3)
+    e2e = None
+    if not args.no_e2e:
+        step_e2e()
+        _, e_wall = timed_loop(torch, dist, step_e2e, args.steps, world)
+        e2e = {"value": tokens_per_step * args.steps / (e_wall / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": host[0].numel() * 8, "d2h_bytes_per_step": 4}
+    # the loss lives on the last pipeline stage: take the max over ranks of the per-step values (other stages report 0)
+    lv = torch.stack([l.detach().float().reshape(()) for l in losses]).cuda()
+    dist.all_reduce(lv, op=dist.ReduceOp.MAX)
+    peak = torch.tensor([torch.cuda.max_memory_allocated() / 2**30], device="cuda")
+    dist.all_reduce(peak, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({
+            "metric": c["metric"], "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic (fresh random token batch per step; random-init weights)",
+            "impl": "b200", "tflops_per_gpu": eng.flops_per_step * args.steps / (ms / 1e3) / world / 1e12, "loss_by_step": {str(i + 1): round(float(v), 5) for i, v in enumerate(lv.tolist())},
+            "peak_mem_gib_max_over_ranks": float(peak), "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
+            "config": {"model": args.model + (f"[layers={args.layers} DEV-INVALID]" if args.layers else ""), "global_batch": gb, "micro_batch": args.micro_batch,
+                       "seq_len": eng.seq_length, "parallelism": f"tp{tp}" + ("+sp" if c["sp"] and tp > 1 else "") + f" pp{pp}" + (f" vp{vp}" if vp else "") + f" ep{ep} dp{dp}",
+                       "num_microbatches": eng.num_microbatches, "main_grads": "fp32" if fp32_grads else "bf16", "recompute": c["recompute"] or "none",
+                       "moe_dispatcher": getattr(eng.config, "moe_token_dispatcher_type", None) if eng.config.num_moe_experts else None,
+                       "l2_policy": "inputs larger than L2 (weights + activations stream through the 126 MB L2 every step)"},
+        }), flush=True)
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        pass
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
 
+    if args.model != "llama3_8b":
+        return run_b200_other(args)
     sys.path.insert(0, REPO)
     rank, world, local = env_rank()
     assert world == args.gpus, f"launched with WORLD_SIZE={world} but --gpus {args.gpus}"
@@ -372,7 +479,10 @@ def run_reference(args):
     P = dict(LLAMA3_8B)
     P["num_layers"] = args.layers or P["num_layers"]
     P["seq"] = args.seq or P["seq"]
-    assert args.model == "llama3_8b", "reference arm implements the headline config only"
+    if args.model != "llama3_8b":
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": f"the reference arm drives the headline config (llama3_8b, TP=N) only; --model {args.model} is a repo-arm measurement"}))
+        return
     parallel_state.initialize_model_parallel(tensor_model_parallel_size=world)
     model_parallel_cuda_manual_seed(1234)
     fp32_grads = args.main_grads == "fp32"
