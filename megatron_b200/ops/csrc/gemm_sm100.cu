@@ -153,17 +153,21 @@ gemm_1cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // =========================================================================================================
 // 2-CTA kernel: a CTA pair owns a 256 x BN tile; CTA r stages A rows [r*128, +128) and B rows [r*BN/2, +BN/2)
 // =========================================================================================================
-template <bool A_MN, bool B_MN, bool C_F32, int BN>
+template <bool A_MN, bool B_MN, bool C_F32, int BN, bool TMA_EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, void* __restrict__ Cptr, GemmParams p) {
+gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_c, void* __restrict__ Cptr,
+                 GemmParams p) {
   constexpr int BNH = BN / 2;                       // B rows staged by each CTA
   constexpr int B_STAGE_BYTES = BNH * BK * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // per CTA
-  constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
+  constexpr int EPI_BYTES = TMA_EPI ? EPI_SMEM_BYTES : 0;     // staging tiles of the TMA-store epilogue come out of the stage budget
+  constexpr int STAGES = (SMEM_BUDGET - EPI_BYTES) / STAGE_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;
   constexpr int PM = 2 * BM;                        // pair tile rows
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_epi = smem_base;
+  uint8_t* smem = smem_base + EPI_BYTES;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -266,16 +270,21 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int ew = (warp - 4) & 3, half = (warp - 4) >> 2;
     constexpr int CH = BN / 32 / 2;
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, epi_parity = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       int m_blk, n_blk;
       tile_coords(tile, tiles_m, tiles_n, p.group_m, m_blk, n_blk);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<C_F32>(Cptr, p, tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16), m_blk * PM + (int)cta_rank * BM + ew * 32 + lane, n_blk * BN, half * CH,
-                           (half + 1) * CH, lane, &tmem_empty[acc], !leader);
+      if (TMA_EPI)
+        epilogue_tile_tma<C_F32>(&tmap_c, smem_epi + (warp - 4) * EPI_BYTES_PER_WARP, epi_parity, p, tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16),
+                                 m_blk * PM + (int)cta_rank * BM + ew * 32, n_blk * BN, half * CH, (half + 1) * CH, lane, &tmem_empty[acc], !leader);
+      else
+        epilogue_tile<C_F32>(Cptr, p, tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16), m_blk * PM + (int)cta_rank * BM + ew * 32 + lane, n_blk * BN, half * CH,
+                             (half + 1) * CH, lane, &tmem_empty[acc], !leader);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (TMA_EPI && lane == 0) tma_store_wait_read<0>();   // the staging tiles must outlive the stores that read them
   }
   tc_fence_before();
   cluster_sync_all();
@@ -330,6 +339,18 @@ bool make_tmap_bf16_strided(CUtensorMap* out, const void* ptr, uint64_t rows, ui
   return r == CUDA_SUCCESS;
 }
 
+// row-major fp32 matrix [rows, cols]; box = {box_cols (inner, <= 32), box_rows}; 128B swizzle (TMA-store / reduce-add epilogue of fp32 outputs)
+bool make_tmap_f32_strided(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes, uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_pitch_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // bf16 [d2][d1][d0] with d0 contiguous; pitches in bytes (multiples of 16); box = {box0 (<= 64), box1, 1}; 128B swizzle.
 // Out-of-bounds parts of a box are clipped on stores and zero-filled on loads PER outer index (tiles never bleed into the next matrix).
 bool make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_bytes, uint64_t pitch2_bytes, uint32_t box0, uint32_t box1) {
@@ -370,27 +391,33 @@ int num_sms() {
   return n;
 }
 
-template <bool A_MN, bool B_MN, bool C_F32, int BN, bool TWO_CTA>
+template <bool A_MN, bool B_MN, bool C_F32, int BN, bool TWO_CTA, bool TMA_EPI>
 static int launch(const void* A, const void* B, void* C, GemmParams p, cudaStream_t s) {
+  static_assert(TWO_CTA || !TMA_EPI, "the TMA-store epilogue is implemented for the 2-CTA kernels");
   constexpr int BNH = TWO_CTA ? BN / 2 : BN;  // B rows per CTA
   constexpr int STAGE_BYTES = A_STAGE_BYTES + BNH * BK * 2;
-  constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
-  constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-  CUtensorMap ta, tb;
+  constexpr int EPI_BYTES = TMA_EPI ? EPI_SMEM_BYTES : 0;
+  constexpr int STAGES = (SMEM_BUDGET - EPI_BYTES) / STAGE_BYTES;
+  constexpr int SMEM_BYTES = EPI_BYTES + STAGES * STAGE_BYTES + 1024 + 256;
+  CUtensorMap ta, tb, tc;
   bool ok = true;
   ok &= A_MN ? make_tmap_bf16(&ta, A, p.K, p.M, 64, BK) : make_tmap_bf16(&ta, A, p.M, p.K, BK, BM);
   ok &= B_MN ? make_tmap_bf16(&tb, B, p.K, p.N, 64, BK) : make_tmap_bf16(&tb, B, p.N, p.K, BK, BNH);
+  if (TMA_EPI)
+    ok &= C_F32 ? make_tmap_f32_strided(&tc, C, p.M, p.N, (uint64_t)p.ldc * 4, 32, 32) : make_tmap_bf16_strided(&tc, C, p.M, p.N, (uint64_t)p.ldc * 2, 64, 32);
+  else
+    tc = ta;
   if (!ok) return -1;
   static bool configured = false;
   if (TWO_CTA) {
-    auto kern = gemm_2cta_kernel<A_MN, B_MN, C_F32, BN>;
+    auto kern = gemm_2cta_kernel<A_MN, B_MN, C_F32, BN, TMA_EPI>;
     if (!configured) {
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return -3;
       configured = true;
     }
     const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN);
     const int clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
-    kern<<<clusters * 2, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, C, p);
+    kern<<<clusters * 2, NUM_THREADS, SMEM_BYTES, s>>>(ta, tb, tc, C, p);
   } else {
     auto kern = gemm_1cta_kernel<A_MN, B_MN, C_F32, BN>;
     if (!configured) {
@@ -404,11 +431,11 @@ static int launch(const void* A, const void* B, void* C, GemmParams p, cudaStrea
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
-template <int BN, bool TWO_CTA>
+template <int BN, bool TWO_CTA, bool TMA_EPI = false>
 static int dispatch_layout(const void* A, const void* B, void* C, const GemmParams& p, int layout, bool f32, cudaStream_t s) {
-  if (layout == 0) return f32 ? launch<false, false, true, BN, TWO_CTA>(A, B, C, p, s) : launch<false, false, false, BN, TWO_CTA>(A, B, C, p, s);
-  if (layout == 1) return f32 ? launch<false, true, true, BN, TWO_CTA>(A, B, C, p, s) : launch<false, true, false, BN, TWO_CTA>(A, B, C, p, s);
-  if (layout == 2) return f32 ? launch<true, true, true, BN, TWO_CTA>(A, B, C, p, s) : launch<true, true, false, BN, TWO_CTA>(A, B, C, p, s);
+  if (layout == 0) return f32 ? launch<false, false, true, BN, TWO_CTA, TMA_EPI>(A, B, C, p, s) : launch<false, false, false, BN, TWO_CTA, TMA_EPI>(A, B, C, p, s);
+  if (layout == 1) return f32 ? launch<false, true, true, BN, TWO_CTA, TMA_EPI>(A, B, C, p, s) : launch<false, true, false, BN, TWO_CTA, TMA_EPI>(A, B, C, p, s);
+  if (layout == 2) return f32 ? launch<true, true, true, BN, TWO_CTA, TMA_EPI>(A, B, C, p, s) : launch<true, true, false, BN, TWO_CTA, TMA_EPI>(A, B, C, p, s);
   return -2;
 }
 
@@ -416,7 +443,7 @@ static int dispatch_layout(const void* A, const void* B, void* C, const GemmPara
 
 using namespace mb200;
 
-// variant: 0 = heuristic, 1 = 1cta/256, 2 = 1cta/128, 3 = 2cta/256, 4 = 2cta/128.  returns 0 on success.
+// variant: 0 = heuristic, 1 = 1cta/256, 2 = 1cta/128, 3 = 2cta/256, 4 = 2cta/128, 5 / 6 = 3 / 4 with the TMA-store epilogue.  returns 0 on success.
 extern "C" int mb200_gemm_bf16_v(const void* A, const void* B, void* C, int M, int N, int K, int layout, int accumulate, int c_dtype, int variant,
                                  cudaStream_t s) {
   GemmParams p;
@@ -434,6 +461,8 @@ extern "C" int mb200_gemm_bf16_v(const void* A, const void* B, void* C, int M, i
     case 2: return dispatch_layout<128, false>(A, B, C, p, layout, f32, s);
     case 3: return dispatch_layout<256, true>(A, B, C, p, layout, f32, s);
     case 4: return dispatch_layout<128, true>(A, B, C, p, layout, f32, s);
+    case 5: return dispatch_layout<256, true, true>(A, B, C, p, layout, f32, s);   // 2-CTA 256x256 + TMA-store / reduce-add epilogue
+    case 6: return dispatch_layout<128, true, true>(A, B, C, p, layout, f32, s);   // 2-CTA 256x128 + TMA-store / reduce-add epilogue
     default: return -5;
   }
 }

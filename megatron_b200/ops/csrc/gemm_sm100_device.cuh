@@ -179,6 +179,79 @@ __device__ __forceinline__ void epilogue_tile(void* __restrict__ Cptr, const Gem
 }
 
 
+// ---- TMA-store epilogue ------------------------------------------------------------------------------------------------------------
+// The direct epilogue above writes one 32-byte sector per thread and row (32 scattered sectors per warp instruction); on short-K problems
+// (TP=8 proj: K = 512) the tile's stores then cost as much as its MMAs.  Here a warp converts its 32 rows x 128 bytes (64 bf16 / 32 fp32 columns),
+// writes them into its own 128B-swizzled 4 KiB staging tile (conflict-free 16-byte st.shared), and ONE elected lane hands the tile to the TMA unit:
+// full 128-byte lines, asynchronous, clipped at the matrix edge by hardware.  `accumulate` (wgrad into fp32/bf16 main_grad) uses the TMA
+// reduce-add instead of a read-modify-write through registers.  Two staging tiles per warp alternate; `wait_group.read 1` keeps one store in flight.
+constexpr int EPI_TILE_BYTES = 32 * 128;
+constexpr int EPI_BYTES_PER_WARP = 2 * EPI_TILE_BYTES;
+constexpr int EPI_SMEM_BYTES = EPI_WARPS * EPI_BYTES_PER_WARP;   // 64 KiB
+
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tmap, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+// this warp's 32 TMEM lanes (rows row0 .. row0+31) x columns [c_begin*32, c_end*32) of the tile at column col_base.  `epi` = this warp's two staging tiles
+// (1024-byte aligned), `parity` alternates between them across calls.
+template <bool C_F32>
+__device__ __forceinline__ void epilogue_tile_tma(const CUtensorMap* tmap_c, uint8_t* epi, uint32_t& parity, const GemmParams& p, uint32_t t_base, int row0, int col_base,
+                                                  int c_begin, int c_end, int lane, uint64_t* done_bar, bool done_remote) {
+  constexpr int CPS = C_F32 ? 1 : 2;      // 32-column TMEM chunks per 128-byte store row
+  const int sw = lane & 7;
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; c += CPS) {
+    uint32_t r[CPS][32];
+#pragma unroll
+    for (int u = 0; u < CPS; ++u) tmem_ld_32x32b_x32(t_base + (c + u) * 32, r[u]);
+    tmem_ld_wait();
+    if (c + CPS >= c_end) {
+      // all of this warp's TMEM reads are done: hand the accumulator back before the stores
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (done_remote) mbar_arrive_remote(done_bar, 0); else mbar_arrive(done_bar);
+      }
+    }
+    const int col0 = col_base + c * 32;
+    if (row0 >= p.M || col0 >= p.N) continue;
+    uint8_t* tile = epi + (parity & 1u) * EPI_TILE_BYTES;
+    parity ^= 1u;
+    // the store that last used this staging tile (two stores ago) must have finished reading it
+    if (lane == 0) tma_store_wait_read<1>();
+    __syncwarp();
+    uint8_t* my_row = tile + lane * 128;
+    if (C_F32) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = make_uint4(r[0][4 * j], r[0][4 * j + 1], r[0][4 * j + 2], r[0][4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int e = 8 * j + 2 * q;         // column within the 64-column row
+          __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[e >> 5][e & 31]), __uint_as_float(r[(e + 1) >> 5][(e + 1) & 31]));
+          v[q] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = make_uint4(v[0], v[1], v[2], v[3]);
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      if (p.accumulate) tma_reduce_add_2d(tmap_c, tile, col0, row0); else tma_store_2d(tmap_c, tile, col0, row0);
+      tma_store_commit();
+    }
+  }
+}
+
+// row-major fp32 matrix [rows, cols]; box = {box_cols (<= 32), box_rows}; 128B swizzle (defined in gemm_sm100.cu)
+bool make_tmap_f32_strided(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes, uint32_t box_cols, uint32_t box_rows);
 // row-major bf16 matrix [rows, cols]; box = {box_cols (inner, <= 64), box_rows}; 128B swizzle (defined in gemm_sm100.cu)
 bool make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows);
 bool make_tmap_bf16_strided(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes, uint32_t box_cols, uint32_t box_rows);

@@ -22,7 +22,7 @@ def set_mode(mode: str) -> None:
     _BACKEND = mode
 _CHOICE: Dict[Tuple, Tuple[str, int]] = {}
 _TUNE_LOG = []
-VARIANTS = {1: "1cta-128x256", 2: "1cta-128x128", 3: "2cta-256x256", 4: "2cta-256x128"}
+VARIANTS = {1: "1cta-128x256", 2: "1cta-128x128", 3: "2cta-256x256", 4: "2cta-256x128", 5: "2cta-256x256-tma-epilogue", 6: "2cta-256x128-tma-epilogue"}
 
 
 def set_gemm_backend(name: str):

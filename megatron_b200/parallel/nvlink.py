@@ -245,22 +245,37 @@ class NVLinkBackend(NVLinkMoEMixin):
         return _Handle(ev)
 
     # ---- DDP / distributed-optimizer buffers (must be allocated with alloc_symmetric) --------------------
+    def _run_ddp(self, fn, async_op: bool, *keep):
+        """Run a DDP collective.  ``async_op``: on this backend's side stream, ordered after the work already queued on the caller's stream; returns a handle
+        whose ``wait()`` makes the caller's stream wait for it (reference semantics of ``async_op=True``: param_and_grad_buffer.py:600-785 — the bucket's
+        reduce-scatter overlaps the rest of the backward pass, the parameter all-gather overlaps the next forward).  Ops of one backend share the side
+        stream and the DDP flag slot, so they execute in issue order on every rank."""
+        if not async_op:
+            fn()
+            return None
+        cur = torch.cuda.current_stream()
+        s = self.side_stream
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):
+            fn()
+            ev = torch.cuda.Event()
+            ev.record(s)
+        for t in keep:
+            t.record_stream(s)
+        return _Handle(ev)
+
     def reduce_scatter_scaled_(self, grad_data: torch.Tensor, scale: float, async_op: bool = False):
-        """In place: my shard of ``grad_data`` ← scale * Σ_ranks shard (scale + reduce + cast fused)."""
+        """In place: my shard of ``grad_data`` <- scale * sum over ranks of that shard (scale + reduce + cast fused in one multimem kernel)."""
         n = grad_data.numel() // self.world
         mine = grad_data[self.rank * n : (self.rank + 1) * n]
         if self._region_of(grad_data) is None:
-            dist.reduce_scatter_tensor(mine, grad_data.mul_(scale), group=self.group)
-            return None
-        self.reduce_scatter(grad_data.view(self.world, n), slot=self.SLOT_DDP, scale=scale, out=mine.view(1, n), trailing=True)
-        return None
+            return dist.reduce_scatter_tensor(mine, grad_data.mul_(scale), group=self.group, async_op=async_op)
+        return self._run_ddp(lambda: self.reduce_scatter(grad_data.view(self.world, n), slot=self.SLOT_DDP, scale=scale, out=mine.view(1, n), trailing=True), async_op, grad_data)
 
     def all_reduce_scaled_(self, grad_data: torch.Tensor, scale: float, async_op: bool = False):
         if self._region_of(grad_data) is None:
-            dist.all_reduce(grad_data.mul_(scale), group=self.group)
-            return None
-        self.all_reduce(grad_data, slot=self.SLOT_DDP, scale=scale)
-        return None
+            return dist.all_reduce(grad_data.mul_(scale), group=self.group, async_op=async_op)
+        return self._run_ddp(lambda: self.all_reduce(grad_data, slot=self.SLOT_DDP, scale=scale), async_op, grad_data)
 
     def all_gather_inplace_(self, param_data: torch.Tensor, async_op: bool = False):
         """Publish my shard of ``param_data`` to the same offset on every rank (multicast store)."""
@@ -268,11 +283,9 @@ class NVLinkBackend(NVLinkMoEMixin):
         mine = param_data[self.rank * n : (self.rank + 1) * n]
         reg = self._region_of(param_data)
         if reg is None:
-            dist.all_gather_into_tensor(param_data, mine.clone(), group=self.group)
-            return None
+            return dist.all_gather_into_tensor(param_data, mine.clone(), group=self.group, async_op=async_op)
         ptrs, mc, off = reg
-        self._ag_into(mine, ptrs, mc, off, self.SLOT_DDP)
-        return None
+        return self._run_ddp(lambda: self._ag_into(mine, ptrs, mc, off, self.SLOT_DDP), async_op, param_data)
 
     # ---- pair ops used by the TP layers ---------------------------------------------------------------------
     def _fused_ok(self, M: int, N: int, K: int, *ts) -> bool:

@@ -97,13 +97,36 @@ class TrainEngine:
             from ..parallel import fused as _fused
 
             try:
-                collectives.enable_for_group(ps.get_tensor_model_parallel_group())
+                # workspace = two halves, each holding the largest fused pair-op footprint: a [seq*mbs, hidden] bf16 partial-sum / gathered buffer PLUS the
+                # piggy-backed all-gather of the wgrad operand of the same size (Llama-3 70B: 2 x 128 MiB per half)
+                from ..models.presets import PRESETS
+
+                pr = PRESETS.get(model, {})
+                rows = (seq_length or pr.get("seq_length", 0)) * micro_batch_size
+                hid = (model_overrides or {}).get("hidden_size", pr.get("hidden_size", 0))
+                need = 4 * rows * hid * 2 + (8 << 20)
+                env_mb = os.environ.get("MEGATRON_B200_NVL_WORKSPACE_MB")
+                ws_bytes = (int(env_mb) << 20) if env_mb else max(320 << 20, need)
+                collectives.enable_for_group(ps.get_tensor_model_parallel_group(), workspace_bytes=ws_bytes)
             except Exception as e:  # no symmetric memory / NVLS on this box: keep training over NCCL (all ranks fail alike)
                 import warnings
 
                 warnings.warn(f"NVLink symmetric-memory runtime unavailable ({type(e).__name__}: {e}); TP collectives fall back to NCCL")
                 _fused.set_mode("nccl")
 
+        # data-parallel gradient reduce-scatter / parameter all-gather over NVLink: the DDP buffers are then allocated from this group's symmetric heap
+        # (MEGATRON_B200_DP_COMM=nccl keeps torch.distributed)
+        if self.device.type == "cuda" and os.environ.get("MEGATRON_B200_DP_COMM", "nvlink") != "nccl":
+            dp_group = ps.get_data_parallel_group(with_context_parallel=True)
+            if dist.get_world_size(dp_group) > 1 and expert_model_parallel_size == 1:
+                from ..parallel import collectives
+
+                try:
+                    collectives.enable_for_group(dp_group, workspace_bytes=64 << 20)
+                except Exception as e:
+                    import warnings
+
+                    warnings.warn(f"NVLink symmetric-memory runtime unavailable for the DP group ({type(e).__name__}: {e}); gradients reduce over NCCL")
         # expert-parallel NVLink dispatch/combine ("flex" dispatcher) needs a symmetric heap on the EP group
         if self.device.type == "cuda" and expert_model_parallel_size > 1 and ov.get("moe_token_dispatcher_type") == "flex":
             from ..parallel import collectives

@@ -12,7 +12,7 @@ SHAPES = [
     (8192, 4096, 512),   # proj @ tp=8
     (384, 16032, 1024),  # LM-head shard, N not a multiple of 256
 ]
-VARIANTS = [1, 2, 3, 4]  # 1cta-128x256, 1cta-128x128, 2cta-256x256, 2cta-256x128
+VARIANTS = [1, 2, 3, 4, 5, 6]  # 1cta-128x256, 1cta-128x128, 2cta-256x256, 2cta-256x128, 5/6 = 3/4 with the TMA-store (reduce-add when accumulating) epilogue
 
 
 def _ops(variant):

@@ -26,7 +26,7 @@ for name in only:
     x = torch.randn(M, K, device="cuda").bfloat16(); w = torch.randn(N, K, device="cuda").bfloat16(); gy = torch.randn(M, N, device="cuda").bfloat16()
     fl = 2.0 * M * N * K
     res = {"shape": name, "MNK": [M, N, K]}
-    for be in ("tcgen05:1", "tcgen05:2", "tcgen05:3", "tcgen05:4", "cublas"):
+    for be in ("tcgen05:3", "tcgen05:4", "tcgen05:5", "tcgen05:6", "cublas"):
         ops.set_gemm_backend(be)
         res[f"fwd_{be}"] = fl / timeit(lambda: ops.gemm_nt(x, w)) / 1e9
         res[f"dgrad_{be}"] = fl / timeit(lambda: ops.gemm_nn(gy, w)) / 1e9
