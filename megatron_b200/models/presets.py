@@ -9,6 +9,8 @@ PRESETS: Dict[str, dict] = {
     # Llama-3 8B: examples/llama/train_llama3_8b_h100_fp8.sh MODEL_ARGS in the reference
     "llama3_8b": dict(num_layers=32, hidden_size=4096, ffn_hidden_size=14336, num_attention_heads=32, num_query_groups=8, kv_channels=128,
                       vocab_size=128256, seq_length=8192, normalization="RMSNorm", swiglu=True, rotary_base=500000, untie=True, bias=False),
+    "llama3_8b_dp": dict(num_layers=32, hidden_size=4096, ffn_hidden_size=14336, num_attention_heads=32, num_query_groups=8, kv_channels=128,
+                         vocab_size=128256, seq_length=8192, normalization="RMSNorm", swiglu=True, rotary_base=500000, untie=True, bias=False),   # same model; a second name so that bench.py routes it through the generic (DP / PP / EP) arm
     "llama3_70b": dict(num_layers=80, hidden_size=8192, ffn_hidden_size=28672, num_attention_heads=64, num_query_groups=8, kv_channels=128,
                        vocab_size=128256, seq_length=8192, normalization="RMSNorm", swiglu=True, rotary_base=500000, untie=True, bias=False),
     "gpt3_6.7b": dict(num_layers=32, hidden_size=4096, ffn_hidden_size=16384, num_attention_heads=32, num_query_groups=32, kv_channels=128,
