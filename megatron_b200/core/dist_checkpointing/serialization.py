@@ -47,7 +47,7 @@ def _split(sharded_state_dict):
 
 def save(sharded_state_dict: ShardedStateDict, checkpoint_dir: str, sharded_strategy=None, common_strategy=None, validate_access_integrity: bool = True,
          async_sharded_save: bool = False, preprocess_common_before_consistancy_check: Optional[Callable] = None, content_metadata: Optional[dict] = None,
-         async_strategy: str = "thread", verify_integrity: bool = False, process_group=None) -> Optional[AsyncRequest]:
+         async_strategy: str = "process", verify_integrity: bool = False, process_group=None) -> Optional[AsyncRequest]:
     """Write a sharded state dict.  ShardedTensors/Objects go to DCP ``.distcp`` files (each main
     replica writes its shard), everything else goes to ``common.pt`` (rank 0)."""
     checkpoint_dir = Path(checkpoint_dir)
@@ -79,7 +79,18 @@ def save(sharded_state_dict: ShardedStateDict, checkpoint_dir: str, sharded_stra
         write_common_and_config()
         _barrier(process_group)
         return None
-    # async: stage device tensors to host now, write in the background, finalize later
+    if async_strategy in ("process", "mcore", "nvrx"):
+        # collective planning + host staging now; file writing in the persistent worker process; metadata commit at finalize (collective)
+        from .strategies.async_utils import ProcessAsyncRequest
+
+        final_plan, payloads, metadata = torch_dist.plan_save(tensors, objects, str(checkpoint_dir), process_group)
+
+        def commit(results):
+            torch_dist.commit_save(results, metadata, str(checkpoint_dir), process_group)
+            write_common_and_config()
+
+        return ProcessAsyncRequest(torch_dist.write_planned, (final_plan, payloads, str(checkpoint_dir)), [commit])
+    # async on a thread: stage device tensors to host now, write in the background, finalize later
     for st in tensors:
         if st.data is not None and st.data.is_cuda:
             st.data = st.data.detach().to("cpu", non_blocking=True)

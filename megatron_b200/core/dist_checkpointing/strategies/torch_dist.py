@@ -166,3 +166,82 @@ def load_tensors_metadata(checkpoint_dir: str) -> Dict[str, ShardedTensor]:
             shape = tuple(v.size)
             out[k] = ShardedTensor(k, None, v.properties.dtype, shape, shape, (0,) * len(shape), (1,) * len(shape))
     return out
+
+# ---- save split into plan (collective, caller) / write (any process) / commit (collective, caller) -------------------------------------------------------
+# Reference: strategies/filesystem_async.py:114-440 + async_utils.py:237-349 — the planning and the metadata commit are collective and stay on the training
+# process; the file writing (the slow part) runs in a persistent worker PROCESS fed with host copies of the shards in shared memory.
+
+
+class _ResolvedPlanner(DefaultSavePlanner):
+    """Planner stand-in for the writer process: every write item's payload has been resolved (host tensors in shared memory / raw bytes) before the hand-off."""
+
+    def __init__(self, payloads: Dict[MetadataIndex, Any]):
+        super().__init__()
+        self._payloads = payloads
+
+    def resolve_data(self, write_item: WriteItem):
+        d = self._payloads[write_item.index]
+        return io.BytesIO(d) if isinstance(d, (bytes, bytearray)) else d
+
+
+def plan_save(sharded_tensors: List[ShardedTensor], sharded_objects: List[ShardedObject], checkpoint_dir: str, process_group=None):
+    """Collective planning.  Returns ``(final_plan, payloads, global_metadata_or_None)``; payload tensors are host copies (shared memory), detached from the
+    training state, so training may overwrite the originals as soon as this returns."""
+    no_dist = _no_dist(process_group)
+    planner = MCoreSavePlanner(sharded_tensors, sharded_objects)
+    writer = FileSystemWriter(checkpoint_dir, sync_files=False)
+    rank = 0 if no_dist else dist.get_rank(process_group)
+    world = 1 if no_dist else dist.get_world_size(process_group)
+    coordinator = rank == 0
+    planner.set_up_planner({}, None, coordinator)
+    writer.set_up_storage_writer(coordinator)
+    local_plan = writer.prepare_local_plan(planner.create_local_plan())
+    if no_dist:
+        plans = [local_plan]
+    else:
+        plans = [None] * world
+        dist.all_gather_object(plans, local_plan, group=process_group)
+    metadata = None
+    if coordinator:
+        plans, metadata = planner.create_global_plan(plans)
+        plans = writer.prepare_global_plan(plans)
+    if no_dist:
+        final_plan = plans[0]
+    else:
+        out = [None]
+        dist.scatter_object_list(out, plans if coordinator else None, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
+        final_plan = out[0]
+    final_plan = planner.finish_plan(final_plan)
+    payloads: Dict[MetadataIndex, Any] = {}
+    for item in final_plan.items:
+        data = planner.resolve_data(item)
+        if isinstance(data, io.BytesIO):
+            payloads[item.index] = data.getvalue()
+        else:
+            host = data.detach().to("cpu", copy=True).contiguous()
+            payloads[item.index] = host.share_memory_()
+    return final_plan, payloads, metadata
+
+
+def write_planned(final_plan, payloads, checkpoint_dir: str, thread_count: int = 2):
+    """The file writing of one rank; safe to run in another process (no process group, no CUDA).  Returns the WriteResults."""
+    writer = FileSystemWriter(checkpoint_dir, thread_count=thread_count, sync_files=False)
+    writer.set_up_storage_writer(False)
+    fut = writer.write_data(final_plan, _ResolvedPlanner(payloads))
+    fut.wait()
+    return fut.value()
+
+
+def commit_save(results, metadata, checkpoint_dir: str, process_group=None):
+    """Collective: gather every rank's WriteResults; the coordinator writes ``.metadata``."""
+    no_dist = _no_dist(process_group)
+    if no_dist:
+        all_results = [results]
+    else:
+        world = dist.get_world_size(process_group)
+        all_results = [None] * world
+        dist.all_gather_object(all_results, results, group=process_group)
+    if metadata is not None:
+        writer = FileSystemWriter(checkpoint_dir, sync_files=False)
+        writer.set_up_storage_writer(True)
+        writer.finish(metadata, all_results)

@@ -335,3 +335,51 @@ def test_context_parallel_matches_single_process(kind):
     for n, p in ref.named_parameters():
         got = sum(r[1][n] for r in res)
         assert torch.allclose(got, p.grad, atol=3e-5, rtol=1e-4), (n, (got - p.grad).abs().max())
+
+
+def _async_process_save_worker(rank, world, ckpt_dir):
+    """Async save through the persistent writer PROCESS: the model keeps training (weights are overwritten) while the files are written; the checkpoint
+    must hold the values at save time; loading it back at a different TP layout (world 2 -> plain tensors) must reproduce them."""
+    import torch
+
+    from megatron_b200.core import dist_checkpointing as dc
+    from megatron_b200.core.dist_checkpointing.mapping import ShardedObject, ShardedTensor
+    from megatron_b200.core.dist_checkpointing.strategies.async_utils import AsyncCallsQueue, ProcessAsyncRequest
+
+    torch.manual_seed(0)
+    full = torch.arange(64 * 8, dtype=torch.float32).reshape(64, 8)
+    mine = full.chunk(world, dim=0)[rank].clone()
+    repl = torch.full((5,), 3.0)
+    sd = {"w": ShardedTensor.from_rank_offsets("w", mine, (0, rank, world)), "r": ShardedTensor.from_rank_offsets("r", repl, replica_id=rank),
+          "obj": ShardedObject("obj", {"step": 7}, (1,), (0,), replica_id=rank), "iteration": 7}
+    req = dc.save(sd, ckpt_dir, async_sharded_save=True, async_strategy="process")
+    assert isinstance(req, ProcessAsyncRequest)
+    q = AsyncCallsQueue()
+    q.schedule_async_request(req)
+    mine.fill_(-1.0)          # training goes on: the staged copy must not alias the live tensor
+    repl.fill_(-1.0)
+    done = []
+    import time
+
+    t0 = time.time()
+    while not done and time.time() - t0 < 120:
+        done = q.maybe_finalize_async_calls(blocking=False)
+        time.sleep(0.05)
+    assert done == [1], "async save did not finalize"
+    out = {"w": ShardedTensor.from_rank_offsets("w", torch.zeros(64 // world, 8), (0, rank, world)), "r": ShardedTensor.from_rank_offsets("r", torch.zeros(5), replica_id=rank),
+           "obj": ShardedObject("obj", None, (1,), (0,), replica_id=rank)}
+    loaded = dc.load(out, ckpt_dir)
+    assert torch.equal(loaded["w"], full.chunk(world, dim=0)[rank]) and torch.equal(loaded["r"], torch.full((5,), 3.0))
+    assert loaded["obj"] == {"step": 7} and loaded["iteration"] == 7
+    from megatron_b200.core.dist_checkpointing.strategies.async_utils import PersistentWriterProcess
+
+    PersistentWriterProcess.get().close()
+    return True
+
+
+def test_async_save_in_worker_process(tmp_path):
+    from dist_utils import run_distributed
+
+    d = tmp_path / "ck"
+    d.mkdir()
+    assert all(run_distributed(_async_process_save_worker, 2, str(d)))
