@@ -147,7 +147,12 @@ def load(sharded_state_dict: ShardedStateDict, checkpoint_dir: str, sharded_stra
             tensors = [t for t in tensors if t.key not in missing]
             objects = [o for o in objects if o.unique_key not in missing]
             logger.warning("keys missing from the checkpoint are left untouched: %s", sorted(missing)[:20])
-    loaded_objs = torch_dist.load_sharded(tensors, objects, str(checkpoint_dir), process_group)
+    if sharded_strategy is not None and hasattr(sharded_strategy, "plan") and hasattr(sharded_strategy, "load"):
+        # fully-parallel load: each replicated shard is read by ONE rank of the strategy's group and exchanged (strategies/fully_parallel.py)
+        loaded_objs = sharded_strategy.load(tensors, objects, str(checkpoint_dir),
+                                            lambda ts, os_: torch_dist.load_sharded(ts, os_, str(checkpoint_dir), process_group, no_dist=True))
+    else:
+        loaded_objs = torch_dist.load_sharded(tensors, objects, str(checkpoint_dir), process_group)
 
     def unwrap(v):
         if isinstance(v, ShardedTensor):
@@ -189,4 +194,25 @@ def load_plain_tensors(checkpoint_dir: str) -> StateDict:
 
 
 def remove_sharded_tensors(checkpoint_dir: str, key_prefix: str):
-    raise NotImplementedError("in-place checkpoint surgery is not supported; rewrite the checkpoint instead")
+    """Drop every tensor / object whose key starts with ``key_prefix`` from a torch_dist checkpoint (reference ``strategies/torch.py:960-1010``): the entries
+    disappear from ``.metadata`` (state-dict metadata and storage index), so loads no longer see them; the bytes stay in the ``.distcp`` files until the
+    checkpoint is rewritten.  Rank 0 only; call it behind a barrier."""
+    import pickle
+
+    from torch.distributed.checkpoint import FileSystemReader
+
+    if _rank() != 0:
+        return
+    md = FileSystemReader(str(checkpoint_dir)).read_metadata()
+    drop = {k for k in md.state_dict_metadata if k.startswith(key_prefix)}
+    if not drop:
+        logger.warning("remove_sharded_tensors: no key starts with %r in %s", key_prefix, checkpoint_dir)
+        return
+    md.state_dict_metadata = {k: v for k, v in md.state_dict_metadata.items() if k not in drop}
+    if getattr(md, "storage_data", None):
+        md.storage_data = {idx: info for idx, info in md.storage_data.items() if idx.fqn not in drop}
+    path = Path(checkpoint_dir) / ".metadata"
+    tmp = path.with_suffix(".tmp")
+    with open(tmp, "wb") as f:
+        pickle.dump(md, f)
+    tmp.replace(path)

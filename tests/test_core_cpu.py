@@ -312,3 +312,21 @@ def test_inference_kv_cache_matches_full_forward():
             outs.append(o)
         inc = torch.cat(outs, dim=1)
     assert torch.allclose(full, inc, atol=1e-4), (full - inc).abs().max()
+
+
+def test_remove_sharded_tensors(tmp_path):
+    import torch
+
+    from megatron_b200.core import dist_checkpointing as dc
+    from megatron_b200.core.dist_checkpointing.mapping import ShardedTensor
+    from megatron_b200.core.dist_checkpointing.serialization import load_tensors_metadata, remove_sharded_tensors
+
+    d = tmp_path / "ck"
+    d.mkdir()
+    sd = {"a.w": ShardedTensor.from_rank_offsets("a.w", torch.ones(4, 4)), "opt.m": ShardedTensor.from_rank_offsets("opt.m", torch.zeros(4)), "opt.v": ShardedTensor.from_rank_offsets("opt.v", torch.zeros(4))}
+    dc.save(sd, str(d))
+    assert set(load_tensors_metadata(str(d))) == {"a.w", "opt.m", "opt.v"}
+    remove_sharded_tensors(str(d), "opt.")
+    assert set(load_tensors_metadata(str(d))) == {"a.w"}
+    out = dc.load({"a.w": ShardedTensor.from_rank_offsets("a.w", torch.zeros(4, 4))}, str(d))
+    assert torch.equal(out["a.w"], torch.ones(4, 4))

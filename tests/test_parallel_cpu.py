@@ -383,3 +383,41 @@ def test_async_save_in_worker_process(tmp_path):
     d = tmp_path / "ck"
     d.mkdir()
     assert all(run_distributed(_async_process_save_worker, 2, str(d)))
+
+
+def _fully_parallel_load_worker(rank, world, ckpt_dir):
+    """4 ranks = TP 2 x DP 2: every TP shard is requested by both DP replicas; with the fully-parallel load strategy each shard is read from storage by ONE
+    of them (about half the bytes per rank) and received from the peer otherwise; results equal a plain load."""
+    import torch
+    import torch.distributed as dist
+
+    from megatron_b200.core import dist_checkpointing as dc
+    from megatron_b200.core.dist_checkpointing.mapping import ShardedTensor
+    from megatron_b200.core.dist_checkpointing.strategies.fully_parallel import FullyParallelLoadStrategyWrapper
+
+    tp, dp = 2, world // 2
+    tp_rank, dp_rank = rank % tp, rank // tp
+    dp_groups = [dist.new_group([t + tp * d for d in range(dp)]) for t in range(tp)]
+    names = [f"layer{i}.w" for i in range(6)]
+    fulls = {n: torch.arange(32 * 16, dtype=torch.float32).reshape(32, 16) * (i + 1) for i, n in enumerate(names)}
+
+    def make(zero):
+        return {n: ShardedTensor.from_rank_offsets(n, (torch.zeros(16, 16) if zero else fulls[n].chunk(tp, 0)[tp_rank].clone()), (0, tp_rank, tp), replica_id=dp_rank) for n in names}
+
+    dc.save(make(False), ckpt_dir)
+    for algo in ("broadcast", "gather_object"):
+        strat = FullyParallelLoadStrategyWrapper(parallelization_group=dp_groups[tp_rank], exchange_algo=algo)
+        out = dc.load(make(True), ckpt_dir, sharded_strategy=strat)
+        for n in names:
+            assert torch.equal(out[n], fulls[n].chunk(tp, 0)[tp_rank]), (algo, n)
+        st = strat.last_stats
+        assert st["shards_read"] == 3 and st["shards_received"] == 3, (algo, st)      # 6 shards per rank, half read, half received
+    return True
+
+
+def test_fully_parallel_load_reads_each_shard_once(tmp_path):
+    from dist_utils import run_distributed
+
+    d = tmp_path / "ck"
+    d.mkdir()
+    assert all(run_distributed(_fully_parallel_load_worker, 4, str(d)))
