@@ -134,6 +134,15 @@ class DynamicInferenceEngine:
         cache, rid = self.cache, req.request_id
         toks = torch.tensor([tokens], device=self.device)
         pos = torch.arange(start, start + len(tokens), device=self.device)[None]
+        if start == 0 and self.batched_decode:
+            # prompt without a cached prefix: plain causal attention over the prompt (flash kernel); every layer appends its K/V to the request's pages itself
+            # — no per-layer contiguous K/V staging buffers, no gather of the (empty) history
+            from .kv_cache import PagedPrefillContext
+
+            ctx = PagedPrefillContext(cache, rid, len(tokens), [l.self_attention.layer_number for l in self.model.decoder.layers])
+            logits = self.model(toks, pos, None, inference_context=ctx)
+            cache.lengths[rid] = len(tokens)
+            return logits[0, -1]
 
         class _Ctx:  # duck-typed inference context understood by Attention._adjust_key_value_for_inference
             max_sequence_length = start + len(tokens)
@@ -211,8 +220,7 @@ class DynamicInferenceEngine:
                 continue  # out of blocks this step; try again after others finish
             ready.append(req)
         if ready and self.batched_decode:
-            for req, logits in zip(ready, self._forward_decode_batch(ready)):
-                self._emit(req, logits)
+            self._emit_batch(ready, self._forward_decode_batch(ready))
         else:
             for req in ready:
                 logits = self._forward_request(req, [req.generated_tokens[-1]], self.cache.lengths[req.request_id])
@@ -236,6 +244,27 @@ class DynamicInferenceEngine:
         if sp.return_log_probs:
             req.log_probs.append(float(torch.log_softmax(logits.float(), -1)[tok]))
         req.generated_tokens.append(tok)
+
+    def _emit_batch(self, reqs: List[InferenceRequest], logits: torch.Tensor):
+        """Sample the next token of every request of a decode step with ONE device→host transfer per group of equal sampling parameters (the per-request
+        ``int(...)`` of ``_emit`` costs a host sync per request and token)."""
+        groups: Dict[tuple, List[int]] = {}
+        for i, r in enumerate(reqs):
+            sp = r.sampling_params
+            groups.setdefault((sp.temperature, sp.top_k, sp.top_p, sp.return_log_probs), []).append(i)
+        now = None
+        for (temp, top_k, top_p, want_lp), idxs in groups.items():
+            lg = logits[idxs].float() if len(idxs) != len(reqs) else logits.float()
+            toks = sample(lg, temp, top_k, top_p, None, self.vocab_size)
+            lps = torch.log_softmax(lg, -1).gather(1, toks[:, None]).squeeze(1).tolist() if want_lp else None
+            for j, (i, t) in enumerate(zip(idxs, toks.tolist())):
+                r = reqs[i]
+                if r.first_token_time is None:
+                    now = now or time.time()
+                    r.first_token_time = now
+                if lps is not None:
+                    r.log_probs.append(lps[j])
+                r.generated_tokens.append(int(t))
 
     def run_until_done(self) -> Dict[int, InferenceRequest]:
         while self.has_unfinished():

@@ -223,9 +223,38 @@ class BatchedDecodeContext:
             if need > 0:                                             # columns past a request's blocks are masked out: any valid block id will do
                 filler = torch.full((self.block_table.shape[0], need), cache.scratch_block(), dtype=torch.long, device=self.block_table.device)
                 self.block_table = torch.cat([self.block_table, filler], dim=1)
+        # int32 copies for the paged-attention kernels (made once per step, not once per layer)
+        self.block_table_i32 = self.block_table.to(torch.int32).contiguous()
+        self.positions_i32 = self.lengths.to(torch.int32).contiguous()
+        self.lengths_incl_i32 = (self.lengths + 1).to(torch.int32).contiguous()
         self.max_sequence_length = self.max_len                      # rotary table length
         self.max_batch_size = len(rids)
         self.sequence_len_offset = 0
         self.batch_size_offset = 0
         self.key_value_memory_dict: Dict = {}
         self.layer_index = {n: i for i, n in enumerate(layer_numbers)}
+
+
+class PagedPrefillContext:
+    """Inference context of a prefill WITHOUT cached prefix (understood by ``Attention.forward``): causal attention over the prompt itself, and each
+    layer writes its rotated K / V for positions [0, n) straight into the request's pages."""
+
+    is_paged_prefill = True
+
+    def __init__(self, cache: PagedKVCache, rid: int, num_tokens: int, layer_numbers: List[int]):
+        self.cache, self.rid, self.num_tokens = cache, rid, num_tokens
+        self.layer_index = {n: i for i, n in enumerate(layer_numbers)}
+        pos = torch.arange(num_tokens, device=cache.k.device)
+        table = torch.tensor(cache.block_tables[rid], device=cache.k.device)
+        self.blk, self.off = table[pos // cache.block_size], pos % cache.block_size
+        self.max_sequence_length = num_tokens
+        self.max_batch_size = 1
+        self.sequence_len_offset = 0
+        self.batch_size_offset = 0
+        self.key_value_memory_dict: Dict = {}
+
+    def store(self, layer_number: int, key: torch.Tensor, value: torch.Tensor) -> None:
+        """``key, value [n, 1, kv_heads, d]`` (already rotated)."""
+        li = self.layer_index[layer_number]
+        self.cache.k[li, self.blk, self.off] = key[:, 0]
+        self.cache.v[li, self.blk, self.off] = value[:, 0]

@@ -113,18 +113,12 @@ class Attention(MegatronModule):
             query = ops.apply_rope(query.transpose(0, 1).contiguous(), q_pos[pos], self.config.rotary_interleaved).transpose(0, 1)
             key = ops.apply_rope(key.transpose(0, 1).contiguous(), k_pos[pos], self.config.rotary_interleaved).transpose(0, 1)
         li = ctx.layer_index[self.layer_number]
-        ctx.cache.append_batch(li, ctx.block_table, pos, key[0], value[0])
-        K, V = ctx.cache.gather_batch(li, ctx.block_table, ctx.max_len)            # [B, L, hk, d]
-        B, L, hk, d = K.shape
-        h = query.size(2)
-        rep = h // hk
-        q = query[0].reshape(B * hk, rep, 1, d)                                     # 4-D: (request x KV head) batch, the group's query heads as "heads"
-        K = K.permute(0, 2, 1, 3).reshape(B * hk, 1, L, d).expand(B * hk, rep, L, d)
-        V = V.permute(0, 2, 1, 3).reshape(B * hk, 1, L, d).expand(B * hk, rep, L, d)
-        mask = (torch.arange(L, device=pos.device)[None, :] <= pos[:, None]).repeat_interleave(hk, 0).view(B * hk, 1, 1, L)
-        scale = getattr(self.core_attention, "softmax_scale", None) or d ** -0.5
-        out = torch.nn.functional.scaled_dot_product_attention(q, K, V, attn_mask=mask, scale=scale)
-        return out.reshape(B, h * d).unsqueeze(0)
+        scale = getattr(self.core_attention, "softmax_scale", None) or query.size(3) ** -0.5
+        # fused KV append (one kernel for K and V through the block table) + flash-decoding over the pages: no gather of the history, no [B, L] mask
+        table = getattr(ctx, "block_table_i32", ctx.block_table)
+        ops.paged_kv_append(key[0], value[0], ctx.cache.k[li], ctx.cache.v[li], table, getattr(ctx, "positions_i32", pos))
+        out = ops.paged_attention_decode(query[0], ctx.cache.k[li], ctx.cache.v[li], table, getattr(ctx, "lengths_incl_i32", pos + 1), scale, ctx.max_len)
+        return out.reshape(out.shape[0], -1).unsqueeze(0)
 
     def get_query_key_value_tensors(self, hidden_states, key_value_states=None):
         raise NotImplementedError
@@ -138,6 +132,16 @@ class Attention(MegatronModule):
             rotary_pos_emb = (rotary_pos_emb, rotary_pos_emb)
         if inference_context is not None and getattr(inference_context, "is_batched_decode", False):
             core_out = self._batched_paged_decode(inference_context, query, key, value, rotary_pos_emb)
+            return self.linear_proj(core_out)
+        if inference_context is not None and getattr(inference_context, "is_paged_prefill", False):
+            # prompt with no cached prefix: ordinary causal attention; the rotated K / V go straight into the request's pages
+            if rotary_pos_emb is not None:
+                q_pos, k_pos = rotary_pos_emb
+                n = key.size(0)
+                query = ops.apply_rope(query, q_pos[:n], self.config.rotary_interleaved)
+                key = ops.apply_rope(key, k_pos[:n], self.config.rotary_interleaved)
+            inference_context.store(self.layer_number, key, value)
+            core_out = self.core_attention(query, key, value, attention_mask, attn_mask_type=self.attn_mask_type, attention_bias=attention_bias, packed_seq_params=packed_seq_params)
             return self.linear_proj(core_out)
         n_new = key.size(0)
         query, key_c, value_c, rotary_pos_emb, mask_type = self._adjust_key_value_for_inference(inference_context, query, key, value, rotary_pos_emb)

@@ -364,6 +364,49 @@ def flash_attention(q, k, v, causal: bool = True, scale: Optional[float] = None,
 
 
 # =============================================================================
+# Paged-KV decode (inference)
+# =============================================================================
+
+
+def paged_kv_append(k_new, v_new, k_pool, v_pool, block_table, positions) -> None:
+    """Write one new K/V entry per request into its page (``k_new/v_new [B, hk, d]``; pools ``[num_blocks, block_size, hk, d]`` of ONE layer;
+    ``block_table [B, W]`` / ``positions [B]``).  One CUDA kernel for K and V (``csrc/paged_attention.cu``); index ops on CPU."""
+    if _use_cuda(k_new) and hasattr(ext(), "paged_kv_append") and k_new.dtype == torch.bfloat16:
+        ext().paged_kv_append(k_new.contiguous(), v_new.contiguous(), k_pool, v_pool, block_table.to(torch.int32).contiguous(), positions.to(torch.int32).contiguous())
+        _count()
+        return
+    bs = k_pool.shape[1]
+    pos = positions.long()
+    blk = block_table.long().gather(1, (pos // bs).unsqueeze(1)).squeeze(1)
+    k_pool[blk, pos % bs] = k_new
+    v_pool[blk, pos % bs] = v_new
+
+
+def paged_attention_decode(q, k_pool, v_pool, block_table, lengths, scale: float, max_len: int):
+    """One new query token per request attends to its own paged history: ``q [B, hq, d]`` → ``[B, hq, d]``; ``lengths [B]`` counts the valid tokens INCLUDING
+    the one just appended.  CUDA: flash-decoding over the block table (split-KV, GQA heads share every K/V load), no gather; CPU: masked SDPA over a gather."""
+    B, hq, d = q.shape
+    hk = k_pool.shape[2]
+    if _use_cuda(q) and hasattr(ext(), "paged_decode") and q.dtype == torch.bfloat16 and d in (64, 128) and hq % hk == 0 and hq // hk in (1, 2, 4, 8):
+        out = ext().paged_decode(q.contiguous(), k_pool, v_pool, block_table.to(torch.int32).contiguous(), lengths.to(torch.int32).contiguous(), float(scale), int(max_len))
+        _count(2)
+        return out
+    bs = k_pool.shape[1]
+    nblk = (int(max_len) + bs - 1) // bs
+    t = block_table.long()[:, :nblk]
+    K = k_pool[t].reshape(B, nblk * bs, hk, d)
+    V = v_pool[t].reshape(B, nblk * bs, hk, d)
+    rep = hq // hk
+    L = nblk * bs
+    qf = q.reshape(B * hk, rep, 1, d)
+    Kf = K.permute(0, 2, 1, 3).reshape(B * hk, 1, L, d).expand(B * hk, rep, L, d)
+    Vf = V.permute(0, 2, 1, 3).reshape(B * hk, 1, L, d).expand(B * hk, rep, L, d)
+    mask = (torch.arange(L, device=q.device)[None, :] < lengths.long()[:, None]).repeat_interleave(hk, 0).view(B * hk, 1, 1, L)
+    out = torch.nn.functional.scaled_dot_product_attention(qf, Kf, Vf, attn_mask=mask, scale=scale)
+    return out.reshape(B, hq, d)
+
+
+# =============================================================================
 # Cross entropy (vocab-parallel, fused)
 # =============================================================================
 

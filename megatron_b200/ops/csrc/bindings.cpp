@@ -356,6 +356,42 @@ void share_storage(Tensor dst, const Tensor& src) {
   dst.set_(src.storage(), dst.storage_offset(), dst.sizes(), dst.strides());
 }
 
+#ifdef MB200_HAVE_PAGED_ATTENTION
+// k_new, v_new [B, hk, d] -> pools [num_blocks, block_size, hk, d] (one layer) at block_table[b, positions[b] / block_size], offset positions[b] % block_size
+void paged_kv_append(const Tensor& k_new, const Tensor& v_new, Tensor k_pool, Tensor v_pool, const Tensor& block_table, const Tensor& positions) {
+  TORCH_CHECK(k_new.is_cuda() && k_new.scalar_type() == at::kBFloat16 && k_pool.scalar_type() == at::kBFloat16 && k_new.is_contiguous() && v_new.is_contiguous(), "paged_kv_append: contiguous bf16 CUDA k/v");
+  TORCH_CHECK(k_pool.is_contiguous() && v_pool.is_contiguous() && k_pool.dim() == 4, "paged_kv_append: pools [num_blocks, block_size, hk, d] contiguous");
+  TORCH_CHECK(block_table.scalar_type() == at::kInt && positions.scalar_type() == at::kInt && block_table.is_contiguous() && positions.is_contiguous(), "paged_kv_append: int32 block table / positions");
+  c10::cuda::CUDAGuard g(k_new.device());
+  const int B = (int)k_new.size(0), hk = (int)k_new.size(1), d = (int)k_new.size(2);
+  TORCH_CHECK((hk * d) % 8 == 0 && k_pool.size(2) == hk && k_pool.size(3) == d);
+  mb200_paged_kv_append(k_new.data_ptr(), v_new.data_ptr(), k_pool.data_ptr(), v_pool.data_ptr(), block_table.data_ptr<int32_t>(), positions.data_ptr<int32_t>(), B,
+                        (int)block_table.size(1), (int)k_pool.size(1), hk, d, cur_stream());
+}
+
+// q [B, hq, d] -> out [B, hq, d]: attention of one new token per request over its pages (lengths include the new token)
+Tensor paged_decode(const Tensor& q, const Tensor& k_pool, const Tensor& v_pool, const Tensor& block_table, const Tensor& lengths, double scale, int64_t max_len) {
+  TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kBFloat16 && q.is_contiguous() && k_pool.is_contiguous() && v_pool.is_contiguous() && k_pool.scalar_type() == at::kBFloat16, "paged_decode: contiguous bf16 CUDA tensors");
+  TORCH_CHECK(block_table.scalar_type() == at::kInt && lengths.scalar_type() == at::kInt && block_table.is_contiguous() && lengths.is_contiguous(), "paged_decode: int32 block table / lengths");
+  c10::cuda::CUDAGuard g(q.device());
+  const int B = (int)q.size(0), hq = (int)q.size(1), d = (int)q.size(2), hk = (int)k_pool.size(2), bs = (int)k_pool.size(1);
+  // enough CTAs for two waves; a split is a whole number of 128-token steps (4 warps x 32 tokens)
+  int nsplit = (int)((2 * 148 + (int64_t)B * hk - 1) / ((int64_t)B * hk));
+  const int max_steps = (int)((max_len + 127) / 128);
+  nsplit = std::max(1, std::min(nsplit, max_steps));
+  const int tokens_per_split = ((max_steps + nsplit - 1) / nsplit) * 128;
+  nsplit = (int)((max_len + tokens_per_split - 1) / tokens_per_split);
+  nsplit = std::max(1, nsplit);
+  auto o_part = at::empty({(int64_t)B * hq * nsplit * d}, q.options().dtype(at::kFloat));
+  auto ml_part = at::empty({(int64_t)B * hq * nsplit * 2}, q.options().dtype(at::kFloat));
+  auto out = at::empty_like(q);
+  const int rc = mb200_paged_decode(q.data_ptr(), k_pool.data_ptr(), v_pool.data_ptr(), block_table.data_ptr<int32_t>(), lengths.data_ptr<int32_t>(), o_part.data_ptr<float>(),
+                                    ml_part.data_ptr<float>(), out.data_ptr(), B, hq, hk, d, (int)block_table.size(1), bs, (float)scale, nsplit, tokens_per_split, cur_stream());
+  TORCH_CHECK(rc == 0, "paged_decode: unsupported head dim / GQA ratio (d in {64,128}, hq/hk in {1,2,4,8}); code ", rc);
+  return out;
+}
+#endif
+
 #ifdef MB200_HAVE_RUNTIME_NATIVE
 // tasks: int64 [n, 3] rows of (src_ptr, dst_ptr, nbytes) on the host; copied to the device and executed by ONE kernel
 void batched_copy(const Tensor& tasks_cpu, int64_t nblocks) {
@@ -788,6 +824,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 #ifdef MB200_HAVE_FLASH_ATTN_BWD_SM100
   m.def("flash_attn_bwd", &flash_attn_bwd, pybind11::arg("go"), pybind11::arg("q"), pybind11::arg("k"), pybind11::arg("v"), pybind11::arg("o"), pybind11::arg("lse"),
         pybind11::arg("causal"), pybind11::arg("scale"), pybind11::arg("split_heads") = -1, pybind11::arg("max_scratch_mb") = 0);
+#endif
+#ifdef MB200_HAVE_PAGED_ATTENTION
+  m.def("paged_kv_append", &paged_kv_append);
+  m.def("paged_decode", &paged_decode);
 #endif
 #ifdef MB200_HAVE_MOE_KERNELS
   m.def("moe_gather_rows", &moe_gather_rows);

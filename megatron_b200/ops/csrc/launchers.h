@@ -57,6 +57,10 @@ int mb200_flash_attn_bwd(const void* q, const void* k, const void* v, const void
                          long v_ss, long v_sb, long v_sh, long do_ss, long do_sb, long do_sh, long o_ss, long o_sb, long o_sh, float scale, int causal, cudaStream_t s);
 size_t mb200_flash_attn_bwd_scratch_bytes(int sq, int sk, int b, int hq, int hk, int split_heads);
 int mb200_flash_attn_bwd_split_heads(int sk, int b, int hq, int hk);
+void mb200_paged_kv_append(const void* k_new, const void* v_new, void* k_pool, void* v_pool, const int32_t* block_table, const int32_t* positions, int B, int table_width,
+                           int block_size, int hk, int d, cudaStream_t s);
+int mb200_paged_decode(const void* q, const void* k_pool, const void* v_pool, const int32_t* block_table, const int32_t* lengths, float* o_part, float* ml_part, void* out,
+                       int B, int hq, int hk, int d, int table_width, int block_size, float scale, int nsplit, int tokens_per_split, cudaStream_t s);
 int mb200_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int layout, int accumulate, int c_dtype, cudaStream_t s);
 void mb200_add_rmsnorm_fwd(const void* x, const void* res, const void* w, void* y, void* res_out, float* rstd, int rows, int H, float eps, int zc, int dtype, cudaStream_t s);
 void mb200_add_rmsnorm_bwd(const void* gy, const void* gres, const void* h, const void* w, const float* rstd, void* gx, float* partial, void* gw, int rows, int H, int zc,
