@@ -90,8 +90,19 @@ class DynamicInferenceEngine:
     attention kernel: prefill = full causal attention on the prompt, decode = 1 query against the gathered cache."""
 
     def __init__(self, model, num_blocks: int = 256, block_size: int = 16, max_running: int = 16, vocab_size: Optional[int] = None,
-                 batched_decode: Optional[bool] = None, enable_prefix_caching: bool = False, decode_batch_buckets: Optional[List[int]] = None):
+                 batched_decode: Optional[bool] = None, enable_prefix_caching: bool = False, decode_batch_buckets: Optional[List[int]] = None,
+                 enable_cuda_graphs: bool = False):
         self.model = model
+        # CUDA-graphed decode (reference dynamic_engine.py: cuda-graph batch-size buckets): one captured graph per (batch bucket, attended-length bucket, table
+        # width); a step copies the block table / positions / last tokens into the graph's static tensors and replays it — the ~500 kernel launches of an
+        # eager decode step (16 ms of host time on an 8B model) collapse into one.  Needs static shapes, hence the buckets.
+        self.enable_cuda_graphs = enable_cuda_graphs
+        self._graphs: Dict[tuple, tuple] = {}
+        self.graph_replays = 0
+        if enable_cuda_graphs and not decode_batch_buckets:
+            decode_batch_buckets = [b for b in (1, 2, 4, 8, 16, 32, 64, 128, 256) if b <= max(1, max_running)] or [max_running]
+            if decode_batch_buckets[-1] < max_running:
+                decode_batch_buckets.append(max_running)
         # one forward for ALL running requests' next token (block-table attention); models whose attention is not the standard
         # ``Attention`` (MLA latent cache, Mamba state) keep the per-request path
         if batched_decode is None:
@@ -183,11 +194,41 @@ class DynamicInferenceEngine:
         last = [[r.generated_tokens[-1]] for r in reqs] + [[0]] * (ctx.lengths.numel() - len(reqs))
         toks = torch.tensor(last, device=self.device)
         self.decode_shapes_seen.add((toks.shape[0], ctx.max_len))
-        logits = self.model(toks, ctx.lengths[:, None], None, inference_context=ctx)[: len(reqs)]   # [B, 1, vocab]
+        if self.enable_cuda_graphs and toks.is_cuda:
+            logits = self._graphed_decode(toks, ctx)[: len(reqs)]
+        else:
+            logits = self.model(toks, ctx.lengths[:, None], None, inference_context=ctx)[: len(reqs)]   # [B, 1, vocab]
         for r in rids:
             self.cache.lengths[r] += 1
         self.decode_forwards += 1
         return logits[:, -1]
+
+    def _graphed_decode(self, toks: torch.Tensor, ctx) -> torch.Tensor:
+        key = (toks.shape[0], ctx.max_len, ctx.block_table.shape[1])
+        entry = self._graphs.get(key)
+        if entry is None:
+            s_toks, s_ctx = toks.clone(), ctx            # this step's context becomes the graph's static context
+            # eager warm-up on a side stream (autotuning, lazy initialisation) — also the correct result for this step
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.model(s_toks, s_ctx.lengths[:, None], None, inference_context=s_ctx)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.model(s_toks, s_ctx.lengths[:, None], None, inference_context=s_ctx)
+            self._graphs[key] = entry = (graph, s_toks, s_ctx, out)
+            # the warm-up and the capture both appended this step's K/V at the same slot (idempotent); replay once so `out` holds this step's logits
+            graph.replay()
+            self.graph_replays += 1
+            return out.clone()
+        graph, s_toks, s_ctx, out = entry
+        s_toks.copy_(toks)
+        s_ctx.copy_from(ctx)
+        graph.replay()
+        self.graph_replays += 1
+        return out.clone()
 
     @torch.no_grad()
     def step(self) -> List[InferenceRequest]:

@@ -235,6 +235,20 @@ class BatchedDecodeContext:
         self.layer_index = {n: i for i, n in enumerate(layer_numbers)}
 
 
+def _bdc_copy_from(self, other: "BatchedDecodeContext") -> None:
+    """Refresh a (CUDA-graph static) context in place with another step's tables and positions; shapes must match (same bucket)."""
+    assert self.block_table.shape == other.block_table.shape and self.lengths.shape == other.lengths.shape and self.max_len == other.max_len
+    self.block_table.copy_(other.block_table)
+    self.lengths.copy_(other.lengths)
+    self.block_table_i32.copy_(other.block_table_i32)
+    self.positions_i32.copy_(other.positions_i32)
+    self.lengths_incl_i32.copy_(other.lengths_incl_i32)
+    self.rids, self.num_real = other.rids, other.num_real
+
+
+BatchedDecodeContext.copy_from = _bdc_copy_from
+
+
 class PagedPrefillContext:
     """Inference context of a prefill WITHOUT cached prefix (understood by ``Attention.forward``): causal attention over the prompt itself, and each
     layer writes its rotated K / V for positions [0, n) straight into the request's pages."""

@@ -55,19 +55,20 @@ def engine_bench():
     m = m.cuda().eval()
     B, OUT, IN = int(os.environ.get("BATCH", "32")), int(os.environ.get("OUT", "256")), 60
     for batch in ([1, 8, B] if os.environ.get("SWEEP", "1") == "1" else [B]):
-        eng = DynamicInferenceEngine(m, num_blocks=batch * ((IN + OUT) // 16 + 2) + 8, block_size=16, max_running=batch, vocab_size=p["vocab_size"])
-        g = torch.Generator().manual_seed(0)
-        for _ in range(batch):
-            eng.add_request(torch.randint(0, p["vocab_size"], (IN,), generator=g).tolist(), SamplingParams(temperature=0.0, num_tokens_to_generate=OUT))
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        eng.step()                                    # admission + prefill of every request (+ first token)
-        torch.cuda.synchronize(); t1 = time.perf_counter()
-        done = eng.run_until_done()
-        torch.cuda.synchronize(); t2 = time.perf_counter()
-        gen = sum(len(r.generated_tokens) for r in done.values())
-        print(json.dumps({"bench": "dynamic_engine", "model": f"llama3_8b[{layers} layers]", "batch": batch, "prompt_tokens": IN, "output_tokens": OUT,
-                          "throughput_tok_per_sec": round(gen / (t2 - t0), 1), "tpot_ms_per_tok": round((t2 - t1) * 1e3 / (OUT - 1), 2), "prefill_ms": round((t1 - t0) * 1e3, 1),
-                          "decode_forwards": eng.decode_forwards, "reference_gpt16b_moe_H100": {"throughput": 324.8, "tpot_ms": 98.5, "batch": 32}}), flush=True)
+      for graphs in ([False, True] if os.environ.get("GRAPHS", "1") == "1" else [False]):
+          eng = DynamicInferenceEngine(m, num_blocks=batch * ((IN + OUT) // 16 + 8) + 16, block_size=16, max_running=batch, vocab_size=p["vocab_size"], enable_cuda_graphs=graphs)
+          g = torch.Generator().manual_seed(0)
+          for _ in range(batch):
+              eng.add_request(torch.randint(0, p["vocab_size"], (IN,), generator=g).tolist(), SamplingParams(temperature=0.0, num_tokens_to_generate=OUT))
+          torch.cuda.synchronize(); t0 = time.perf_counter()
+          eng.step()                                    # admission + prefill of every request (+ first token)
+          torch.cuda.synchronize(); t1 = time.perf_counter()
+          done = eng.run_until_done()
+          torch.cuda.synchronize(); t2 = time.perf_counter()
+          gen = sum(len(r.generated_tokens) for r in done.values())
+          print(json.dumps({"bench": "dynamic_engine", "model": f"llama3_8b[{layers} layers]", "batch": batch, "prompt_tokens": IN, "output_tokens": OUT,
+                            "throughput_tok_per_sec": round(gen / (t2 - t0), 1), "tpot_ms_per_tok": round((t2 - t1) * 1e3 / (OUT - 1), 2), "prefill_ms": round((t1 - t0) * 1e3, 1),
+                            "cuda_graphs": graphs, "graphs_captured": len(eng._graphs), "decode_forwards": eng.decode_forwards, "first_tokens": list(done.values())[0].generated_tokens[:6], "reference_gpt16b_moe_H100": {"throughput": 324.8, "tpot_ms": 98.5, "batch": 32}}), flush=True)
 
 if __name__ == "__main__":
     kernel_bench()
