@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--no-sp-variant", action="store_true", help="skip the second (TP=N + sequence parallel) measurement of the repo arm")
     ap.add_argument("--recompute", default="auto")
     ap.add_argument("--main-grads", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "mxfp8"], help="repo arm: mxfp8 = block-scaled E4M3 operands (tcgen05 kind::mxf8f6f4.block_scale) for every "
+                    "linear layer's fprop/dgrad/wgrad GEMM (reference: --fp8-format e4m3 --fp8-recipe mxfp8), bf16 activations, fp32 master weights")
     # the other BASELINE.json configurations (repo arm): --model gpt3_6.7b | mixtral_8x7b | llama3_70b with their parallel layout
     ap.add_argument("--tp", type=int, default=None)
     ap.add_argument("--pp", type=int, default=None)
@@ -209,6 +211,8 @@ def _b200_variant(args, torch, dist, rank, world, local, *, sequence_parallel, r
     overrides = {}
     if args.layers:
         overrides["num_layers"] = args.layers
+    if args.dtype == "mxfp8":
+        overrides.update(fp8="e4m3", fp8_recipe="mxfp8")
     eng = TrainEngine(args.model, tensor_model_parallel_size=world, sequence_parallel=sequence_parallel, micro_batch_size=args.micro_batch,
                       global_batch_size=args.global_batch, seq_length=args.seq, bf16=True, model_overrides=overrides, lr=LR, min_lr=MIN_LR,
                       weight_decay=WD, clip_grad=CLIP, grad_reduce_in_fp32=main_grads_fp32, **recompute)
@@ -411,8 +415,9 @@ def run_b200(args):
             pass
         peak_tf = mp.get("bf16_tflops_sustained", 1400.0)
         out = {
-            "metric": METRIC, "value": main["value"], "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "metric": METRIC + ("" if args.dtype == "bf16" else f" [{args.dtype} linear layers]"), "value": main["value"], "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic (a fresh batch of uniform random token ids of the named shape every step, seed 17; name-seeded random-init weights identical in both arms)",
             "impl": "b200", "tflops_per_gpu": main["tflops_per_gpu"], "mfu_of_measured_sustained_cublas": main["tflops_per_gpu"] / peak_tf,
             "loss_by_step": main["loss_by_step"], "peak_mem_gib": main["peak_mem_gib"], "gpu_launches": main["gpu_launches"], "clocks": main["clocks"],
