@@ -1,5 +1,7 @@
 from __future__ import annotations
 
+import json
+import os
 from abc import ABC, abstractmethod
 from typing import Any, Dict, List, Optional, Union
 
@@ -155,9 +157,40 @@ class MegatronTokenizer:
             return ByteLevelTokenizer()
         if lib == "sentencepiece":
             return SentencePieceTokenizer(tokenizer_path)
+        if isinstance(metadata_path, str) or (metadata_path is None and tokenizer_path and os.path.isdir(tokenizer_path) and os.path.exists(os.path.join(tokenizer_path, "tokenizer_metadata.json"))):
+            # reference layout: a ``tokenizer_metadata.json`` next to the tokenizer files names the library (``write_metadata``)
+            with open(metadata_path if isinstance(metadata_path, str) else os.path.join(tokenizer_path, "tokenizer_metadata.json")) as f:
+                meta = json.load(f)
+            return MegatronTokenizer.from_pretrained(tokenizer_path, {**meta, **({} if not isinstance(metadata_path, dict) else metadata_path)}, **{**meta.get("kwargs", {}), **kwargs})
+        if lib == "tiktoken":
+            from .text.tiktoken_tokenizer import TikTokenTokenizer
+
+            return TikTokenTokenizer(tokenizer_path, **{k: v for k, v in kwargs.items() if k in ("pattern", "vocab_size", "num_special_tokens", "special_tokens")})
+        if lib == "sft":
+            from .text.sft_tokenizer import SFTTokenizer
+
+            base = MegatronTokenizer.from_pretrained(tokenizer_path, {"library": kwargs.pop("base_library", "huggingface")}, **kwargs)
+            return SFTTokenizer(base, kwargs.get("prompt_format", "chatml"))
+        if lib in ("multimodal", "null-multimodal"):
+            from .vision.multimodal_tokenizer import MultimodalTokenizer
+
+            base = NullTokenizer(kwargs.get("vocab_size", 256)) if lib == "null-multimodal" else MegatronTokenizer.from_pretrained(
+                tokenizer_path, {"library": kwargs.pop("base_library", "huggingface")})
+            return MultimodalTokenizer(base, kwargs.get("num_image_tokens", 576), kwargs.get("image_token_id"))
         if lib in ("huggingface", None) and tokenizer_path:
             return HuggingFaceTokenizer(tokenizer_path, **{k: v for k, v in kwargs.items() if k != "vocab_size"})
         raise ValueError(f"cannot build a tokenizer from library={lib!r}, path={tokenizer_path!r}")
+
+    @staticmethod
+    def write_metadata(tokenizer_path: str, tokenizer_library: str, model_type: Optional[str] = None, chat_template: Optional[str] = None, overwrite: bool = False,
+                       metadata_path: Optional[str] = None, **kwargs) -> str:
+        """Describe a tokenizer directory / file so ``from_pretrained(path)`` can restore it without arguments (reference ``megatron_tokenizer.py:write_metadata``)."""
+        target = metadata_path or os.path.join(tokenizer_path if os.path.isdir(tokenizer_path) else os.path.dirname(tokenizer_path), "tokenizer_metadata.json")
+        if os.path.exists(target) and not overwrite:
+            raise FileExistsError(f"{target} exists (overwrite=False)")
+        with open(target, "w") as f:
+            json.dump({"library": tokenizer_library, "model_type": model_type, "chat_template": chat_template, "kwargs": kwargs}, f, indent=1)
+        return target
 
 
 def build_tokenizer(tokenizer_type: str, vocab_size: Optional[int] = None, tokenizer_model: Optional[str] = None, **kw):
@@ -170,4 +203,8 @@ def build_tokenizer(tokenizer_type: str, vocab_size: Optional[int] = None, token
         return SentencePieceTokenizer(tokenizer_model)
     if t in ("huggingfacetokenizer", "hf"):
         return HuggingFaceTokenizer(tokenizer_model, **kw)
+    if t in ("tiktokentokenizer", "tiktoken"):
+        from .text.tiktoken_tokenizer import TikTokenTokenizer
+
+        return TikTokenTokenizer(tokenizer_model, vocab_size=vocab_size, **kw)
     raise ValueError(f"unknown tokenizer type {tokenizer_type}")
