@@ -328,3 +328,61 @@ def test_telemetry_spans_and_metrics(tmp_path):
     m = telemetry.TrainingMetrics()
     m.record_iteration(iteration_time_s=0.5, tokens=1000, flops=2e12, world=2, loss=3.0, lr=1e-4)
     assert m.values["train.tokens_per_second"] == 2000 and m.values["train.tflops_per_gpu"] == 2.0 and m.values["train.lm_loss"] == 3.0
+
+
+def _reference_flops_fn():
+    """The reference's analytic model, extracted from its source (pure python) — None when /root/reference is not there."""
+    import ast
+    import os
+
+    path = "/root/reference/megatron/training/training.py"
+    if not os.path.exists(path):
+        return None
+    src = open(path).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "num_floating_point_operations"][0]
+    ns = {}
+    exec("def is_linear_attention_variant(v): return v in ('gdn', 'gdn2', 'gated_delta_net')\n"
+         "def is_gated_delta_net_variant(v): return v in ('gdn', 'gdn2', 'gated_delta_net')\n"
+         "def is_hybrid_model(args): return False\n" + ast.get_source_segment(src, fn), ns)
+    return ns["num_floating_point_operations"]
+
+
+def test_flops_model_matches_reference_accounting():
+    import argparse
+
+    import pytest
+
+    from megatron_b200.training.flops import causal_pairs, num_floating_point_operations as ours
+
+    ref = _reference_flops_fn()
+    if ref is None:
+        pytest.skip("reference sources not available")
+
+    def A(**k):
+        d = dict(seq_length=8192, hidden_size=4096, num_layers=32, ffn_hidden_size=14336, num_attention_heads=32, group_query_attention=True, num_query_groups=8, kv_channels=128,
+                 padded_vocab_size=128256, swiglu=True, num_experts=None, moe_layer_freq=1, moe_router_topk=1, moe_ffn_hidden_size=None, moe_latent_size=None,
+                 moe_shared_expert_intermediate_size=None, mtp_num_layers=None, multi_latent_attention=False, experimental_attention_variant=None, attention_output_gate=False,
+                 hybrid_layer_pattern=None)
+        d.update(k)
+        return argparse.Namespace(**d)
+
+    base = dict(num_layers=32, hidden_size=4096, ffn_hidden_size=14336, num_attention_heads=32, num_query_groups=8, kv_channels=128, vocab_size=128256, seq_length=8192)
+    close = lambda a, b: abs(a - b) <= 1e-9 * abs(b)
+    assert close(ours(**base, batch_size=4), ref(A(), 4))                                                                  # Llama-3 8B
+    assert close(ours(**{**base, "seq_length": 4096, "vocab_size": 32000}, batch_size=8, num_moe_experts=8, moe_router_topk=2, moe_shared_expert_intermediate_size=2048),
+                 ref(A(num_experts=8, moe_router_topk=2, seq_length=4096, padded_vocab_size=32000, moe_shared_expert_intermediate_size=2048), 8))   # MoE + shared expert
+    assert close(ours(**base, batch_size=2, num_moe_experts=16, moe_router_topk=4, moe_layer_freq=[0, 1] * 16, moe_ffn_hidden_size=2048, mtp_num_layers=1),
+                 ref(A(num_experts=16, moe_router_topk=4, moe_layer_freq=[0, 1] * 16, moe_ffn_hidden_size=2048, mtp_num_layers=1), 2))             # interleaved MoE + MTP
+    mla = dict(q_lora_rank=1536, kv_lora_rank=512, qk_head_dim=128, qk_pos_emb_head_dim=64, v_head_dim=128)
+    assert close(ours(**{**base, "num_query_groups": 32}, batch_size=2, multi_latent_attention=True, **mla),
+                 ref(A(multi_latent_attention=True, group_query_attention=False, num_query_groups=32, **mla), 2))                                  # MLA
+    # THD: real tokens and sum of squared sub-sequence lengths
+    lens = [1000, 3000, 4192] * 2
+    assert close(ours(**base, batch_size=2, seq_lens=lens), ref(A(), 2, seqlen_squared_sum_in_batch=sum(l * l for l in lens), total_real_tokens_in_batch=sum(lens)))
+    # gated-delta-net linear attention every layer but each 4th
+    lin = dict(linear_key_head_dim=128, linear_value_head_dim=128, linear_num_key_heads=16, linear_num_value_heads=32, linear_conv_kernel_dim=4)
+    assert close(ours(**base, batch_size=2, linear_attention_freq=4),
+                 ref(A(experimental_attention_variant="gated_delta_net", linear_attention_freq=4, **lin), 2))
+    # sliding window (ours only): never more than full causal attention, equal when the window covers the sequence
+    assert ours(**base, batch_size=1, window_size=(1024, 0)) < ours(**base, batch_size=1) == ours(**base, batch_size=1, window_size=(8192, 0))
+    assert causal_pairs(10, 4) == 4 * 10 - 8
