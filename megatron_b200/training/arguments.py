@@ -271,13 +271,41 @@ def validate_args(args, world_size: Optional[int] = None):
     return args
 
 
-def parse_args(argv=None, extra_args_provider=None, ignore_unknown_args: bool = False):
+def config_classes():
+    """The dataclasses whose fields become command-line options (after the hand-written, reference-named flags)."""
+    from ..core.distributed import DistributedDataParallelConfig
+    from ..core.optimizer import OptimizerConfig
+    from ..core.transformer.transformer_config import TransformerConfig
+
+    return (TransformerConfig, OptimizerConfig, DistributedDataParallelConfig)          # TransformerConfig includes ModelParallelConfig's fields
+
+
+def build_full_parser(extra_args_provider=None) -> argparse.ArgumentParser:
+    """Hand-written flags (reference names) + one generated flag for every remaining config-dataclass field + ``--yaml-cfg``."""
+    from .argument_utils import add_dataclass_arguments
+
     parser = build_parser()
+    if not any(a.dest == "yaml_cfg" for a in parser._actions):
+        parser.add_argument("--yaml-cfg", type=str, default=None, help="YAML file whose (optionally nested) keys are argument names; command-line flags win")
     if extra_args_provider is not None:
         parser = extra_args_provider(parser)
-    args, unknown = parser.parse_known_args(argv)
+    for cls in config_classes():
+        add_dataclass_arguments(parser, cls, title=f"{cls.__name__} (generated)")
+    return parser
+
+
+def parse_args(argv=None, extra_args_provider=None, ignore_unknown_args: bool = False):
+    import sys as _sys
+
+    parser = build_full_parser(extra_args_provider)
+    argv_list = list(_sys.argv[1:] if argv is None else argv)
+    args, unknown = parser.parse_known_args(argv_list)
     if unknown and not ignore_unknown_args:
         parser.error(f"unrecognized arguments: {' '.join(unknown)}")
+    if getattr(args, "yaml_cfg", None):
+        from .argument_utils import apply_yaml, explicit_dests, load_yaml_config
+
+        apply_yaml(args, load_yaml_config(args.yaml_cfg), parser, explicit_dests(parser, argv_list))
     if args.model is not None:
         from ..models.presets import PRESETS
 
@@ -333,4 +361,14 @@ def core_transformer_config_from_args(args):
                   moe_aux_loss_coeff=args.moe_aux_loss_coeff, moe_z_loss_coeff=args.moe_z_loss_coeff, moe_token_dispatcher_type=args.moe_token_dispatcher_type,
                   moe_grouped_gemm=args.moe_grouped_gemm, moe_ffn_hidden_size=args.moe_ffn_hidden_size, moe_layer_freq=args.moe_layer_freq,
                   moe_shared_expert_intermediate_size=args.moe_shared_expert_intermediate_size, moe_expert_capacity_factor=args.moe_expert_capacity_factor)
+    # every other TransformerConfig field that has a (generated) flag and was given a non-default value
+    import dataclasses as _dc
+
+    for f in _dc.fields(TransformerConfig):
+        if f.name in kw or not f.init or not hasattr(args, f.name):
+            continue
+        v = getattr(args, f.name)
+        default = f.default if f.default is not _dc.MISSING else (f.default_factory() if f.default_factory is not _dc.MISSING else None)
+        if v is not None and v != default:
+            kw[f.name] = v
     return TransformerConfig(**kw)

@@ -386,3 +386,37 @@ def test_flops_model_matches_reference_accounting():
     # sliding window (ours only): never more than full causal attention, equal when the window covers the sequence
     assert ours(**base, batch_size=1, window_size=(1024, 0)) < ours(**base, batch_size=1) == ours(**base, batch_size=1, window_size=(8192, 0))
     assert causal_pairs(10, 4) == 4 * 10 - 8
+
+
+def test_generated_flags_and_yaml_config(tmp_path):
+    """Every config-dataclass field is a flag; a YAML file sets the same things; the command line wins; typos are errors."""
+    import pytest
+
+    from megatron_b200.training.arguments import build_full_parser, core_transformer_config_from_args, parse_args
+    from megatron_b200.training.argument_utils import args_to_yaml, dataclass_from_args
+    from megatron_b200.core.optimizer import OptimizerConfig
+
+    parser = build_full_parser()
+    n_flags = sum(1 for a in parser._actions if a.option_strings)
+    assert n_flags > 350, n_flags                      # 184 hand-written + ~200 generated ones
+    base = ["--num-layers", "2", "--hidden-size", "64", "--num-attention-heads", "4", "--seq-length", "32", "--max-position-embeddings", "32", "--micro-batch-size", "1",
+            "--global-batch-size", "1", "--vocab-size", "128"]
+    # generated flags reach the config objects
+    from megatron_b200.training.arguments import validate_args
+
+    a = validate_args(parse_args(base + ["--moe-router-num-groups", "2", "--no-apply-rope-fusion", "--adam-beta2", "0.9", "--layernorm-zero-centered-gamma"]), world_size=1)
+    cfg = core_transformer_config_from_args(a)
+    assert cfg.layernorm_zero_centered_gamma is True and getattr(cfg, "moe_router_num_groups", None) == 2
+    assert dataclass_from_args(OptimizerConfig, a).adam_beta2 == 0.9
+    # YAML: nested sections, kebab or snake keys; explicit flags win; unknown keys raise
+    y = tmp_path / "run.yaml"
+    y.write_text("model:\n  num_layers: 4\n  hidden-size: 128\n  qk_layernorm: true\noptimizer:\n  lr: 0.001\n  adam_beta2: 0.8\n")
+    b = parse_args(base[2:] + ["--num-layers", "6", "--yaml-cfg", str(y)])
+    assert b.num_layers == 6 and b.hidden_size == 64 and b.qk_layernorm is True and b.lr == 0.001 and b.adam_beta2 == 0.8
+    c = parse_args(["--num-attention-heads", "4", "--seq-length", "32", "--max-position-embeddings", "32", "--micro-batch-size", "1", "--global-batch-size", "1",
+                    "--vocab-size", "128", "--yaml-cfg", str(y)])
+    assert c.num_layers == 4 and c.hidden_size == 128
+    (tmp_path / "bad.yaml").write_text("num_layerz: 3\n")
+    with pytest.raises(ValueError, match="num_layerz"):
+        parse_args(base + ["--yaml-cfg", str(tmp_path / "bad.yaml")])
+    assert "TransformerConfig" in args_to_yaml(b, (type(cfg),)) and "num_layers: 6" in args_to_yaml(b, (type(cfg),))
