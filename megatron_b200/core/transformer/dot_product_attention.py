@@ -66,10 +66,16 @@ class DotProductAttention(MegatronModule):
             (attention_mask is None or causal)
             and attention_bias is None
             and (self.dropout_p == 0.0 or not self.training)
-            and packed_seq_params is None
         )
+        cu = None
+        if packed_seq_params is not None:
+            # THD: the token dim holds several packed sequences ([t, 1, h, d]); attention must not cross their boundaries (reference: TE's thd kernels
+            # driven by cu_seqlens, extensions/transformer_engine.py:1460-1530).  Ours: a band mask inside the native kernels / a block-diagonal mask on CPU.
+            cu = packed_seq_params.cu_seqlens_q_padded if getattr(packed_seq_params, "cu_seqlens_q_padded", None) is not None else packed_seq_params.cu_seqlens_q
+            fusable = fusable and causal and b == 1 and key.shape[0] == sq
+            assert fusable, "packed sequences need causal self-attention without bias / dropout in THD layout [t, 1, h, d]"
         if fusable:
-            ctx = ops.flash_attention(query, key, value, causal=causal, scale=self.softmax_scale, window=self.config.window_size)
+            ctx = ops.flash_attention(query, key, value, causal=causal, scale=self.softmax_scale, window=self.config.window_size, cu_seqlens=cu)
             return ctx.reshape(sq, b, -1)
         return self._unfused(query, key, value, attention_mask, causal, attention_bias)
 

@@ -262,11 +262,11 @@ class _FlashAttnFn(torch.autograd.Function):
     """sm_100a flash attention (``csrc/flash_attn_sm100.cu``); q/k/v layout [s, b, h, d]."""
 
     @staticmethod
-    def forward(ctx, q, k, v, causal, scale):
-        o, lse = ext().flash_attn_fwd(q, k, v, causal, scale, _FA_VARIANT)
+    def forward(ctx, q, k, v, causal, scale, row_lo=None, col_hi=None):
+        o, lse = ext().flash_attn_fwd(q, k, v, causal, scale, _FA_VARIANT, row_lo)
         _count()
         ctx.save_for_backward(q, k, v, o, lse)
-        ctx.causal, ctx.scale = causal, scale
+        ctx.causal, ctx.scale, ctx.band = causal, scale, (row_lo, col_hi)
         return o
 
     @staticmethod
@@ -277,14 +277,15 @@ class _FlashAttnFn(torch.autograd.Function):
         if _ATTN_BWD_IMPL == "native" and hasattr(ext(), "flash_attn_bwd") and q.shape[-1] == 128:
             # our tcgen05 backward (csrc/flash_attn_bwd_sm100.cu): dK/dV accumulate in TMEM while dS tiles stream to a bf16 scratch by TMA; dQ = dS K in a second tcgen05 kernel
             try:
-                dq, dk, dv = ext().flash_attn_bwd(go, q, k, v, o, lse, ctx.causal, ctx.scale, _ATTN_BWD_SPLIT_HEADS)
+                dq, dk, dv = ext().flash_attn_bwd(go, q, k, v, o, lse, ctx.causal, ctx.scale, _ATTN_BWD_SPLIT_HEADS, 0, ctx.band[0], ctx.band[1])
             except RuntimeError as e:
                 raise RuntimeError(f"{e}; go {tuple(go.shape)} {go.stride()} q {q.stride()} k {k.stride()} v {v.stride()} o {o.stride()} ptrs {[t.data_ptr() % 16 for t in (go, q, k, v, o)]}") from e
             _count(4 if _ATTN_BWD_SPLIT_HEADS != 0 else 3)
-            return dq, dk, dv, None, None
+            return dq, dk, dv, None, None, None, None
+        assert ctx.band[0] is None, "band masks (sliding window / packed sequences) need the native backward (head dim 128)"
         lse_lib = lse.unsqueeze(-1) if _cudnn_lse_ndim() == 4 else lse
         dq, dk, dv = ext().attn_bwd_cudnn(go, q, k, v, o, lse_lib, ctx.causal, ctx.scale)
-        return dq, dk, dv, None, None
+        return dq, dk, dv, None, None, None, None
 
 
 _CUDNN_LSE_NDIM = None
@@ -329,9 +330,50 @@ def set_attention_impl(impl: str) -> None:
     _ATTN_IMPL = impl
 
 
-def _native_attention_ok(q, k, v, causal, window) -> bool:
-    if _resolved_attn_impl() == "library" or window is not None or not hasattr(ext(), "flash_attn_fwd"):
+_BAND_CACHE: dict = {}
+
+
+def attention_band(sq: int, sk: int, window=None, cu_seqlens=None, device="cpu"):
+    """The monotone band of a causal mask with a sliding window and / or packed sequences, as the two int32 arrays our kernels take:
+    ``row_lo[q]`` = first key query q sees, ``col_hi[k]`` = one past the last query that sees key k (the other edge of both is the causal diagonal
+    ``k <= q + sk - sq``).  ``window = (left, right)`` in the reference's convention (q sees keys ``>= q + off - left``; ``left < 0`` = unbounded);
+    ``cu_seqlens`` = cumulative lengths of sequences packed along the token dim (self-attention: the same boundaries for queries and keys).
+    Returns ``None`` when there is nothing to restrict."""
+    left = window[0] if window is not None and window[0] is not None and window[0] >= 0 else None
+    if left is None and cu_seqlens is None:
+        return None
+    key = (sq, sk, left, str(device), None if cu_seqlens is None else (cu_seqlens.data_ptr(), cu_seqlens._version, cu_seqlens.numel()))
+    hit = _BAND_CACHE.get(key)
+    if hit is not None:
+        return hit[0], hit[1]
+    off = sk - sq
+    qpos, kpos = torch.arange(sq, device=device), torch.arange(sk, device=device)
+    row_lo, col_hi = torch.zeros(sq, dtype=torch.long, device=device), torch.full((sk,), sq, dtype=torch.long, device=device)
+    if left is not None:
+        row_lo = torch.maximum(row_lo, qpos + off - left)
+        col_hi = torch.minimum(col_hi, kpos - off + left + 1)
+    if cu_seqlens is not None:
+        assert sq == sk, "packed sequences: self-attention only (same boundaries for queries and keys)"
+        cu = cu_seqlens.to(device=device, dtype=torch.long)
+        sid = torch.bucketize(qpos, cu[1:], right=True).clamp_(max=cu.numel() - 2)     # trailing pad tokens join the last sequence
+        row_lo = torch.maximum(row_lo, cu[sid])
+        col_hi = torch.minimum(col_hi, torch.where(sid == cu.numel() - 2, torch.full_like(sid, sq), cu[sid + 1]))
+    band = (row_lo.clamp_(min=0).to(torch.int32).contiguous(), col_hi.clamp_(min=0, max=sq).to(torch.int32).contiguous())
+    if len(_BAND_CACHE) > 64:
+        _BAND_CACHE.clear()
+    _BAND_CACHE[key] = band + (cu_seqlens,)          # keep the key tensor alive: its data_ptr is part of the key
+    return band
+
+
+def _native_attention_ok(q, k, v, causal, window, cu_seqlens=None) -> bool:
+    if _resolved_attn_impl() == "library" or not hasattr(ext(), "flash_attn_fwd"):
         return False
+    banded = cu_seqlens is not None or (window is not None and window[0] is not None and window[0] >= 0)
+    if banded:                                                  # band masks: causal only, native backward only (head dim 128), packed = one batch row
+        if not causal or q.shape[-1] != 128 or _ATTN_BWD_IMPL != "native" or not hasattr(ext(), "flash_attn_bwd"):
+            return False
+        if (window is not None and len(window) > 1 and window[1] not in (0, -1, None)) or (cu_seqlens is not None and (q.shape[1] != 1 or q.shape[0] != k.shape[0])):
+            return False
     if q.dtype != torch.bfloat16 or q.shape[-1] not in (64, 128) or k.shape[-1] != q.shape[-1] or v.shape[-1] != q.shape[-1]:
         return False
     if (causal and k.shape[0] < q.shape[0]) or q.shape[0] < 128:   # decode-sized queries stay on the library path (untested regime for the 2x128-row tiling)
@@ -340,13 +382,19 @@ def _native_attention_ok(q, k, v, causal, window) -> bool:
     return strides_ok
 
 
-def flash_attention(q, k, v, causal: bool = True, scale: Optional[float] = None, window=None):
-    """Fused attention; GQA when ``k.shape[2] < q.shape[2]``.  Returns ``[sq, b, hq, d]``."""
+def flash_attention(q, k, v, causal: bool = True, scale: Optional[float] = None, window=None, cu_seqlens=None):
+    """Fused attention; GQA when ``k.shape[2] < q.shape[2]``.  Returns ``[sq, b, hq, d]``.  ``window = (left, right)``: sliding window; ``cu_seqlens``: the
+    token dim holds several packed sequences (THD; ``b == 1``) that must not see each other.  Both run inside the native kernels as a band mask."""
     import math
 
     scale = scale if scale is not None else 1.0 / math.sqrt(q.shape[-1])
-    if _use_cuda(q) and _native_attention_ok(q, k, v, causal, window):
-        return _FlashAttnFn.apply(q, k, v, causal, scale)
+    if _use_cuda(q) and _native_attention_ok(q, k, v, causal, window, cu_seqlens):
+        band = attention_band(q.shape[0], k.shape[0], window, cu_seqlens, q.device)
+        if band is None:
+            return _FlashAttnFn.apply(q, k, v, causal, scale)
+        return _FlashAttnFn.apply(q, k, v, causal, scale, band[0], band[1])
+    if cu_seqlens is not None:
+        return ref.attention_fwd(q, k, v, causal, scale, window, cu_seqlens)
     if q.is_cuda:
         # library path (cuDNN/flash SDPA) for shapes the native kernel does not cover
         qb, kb, vb = (t.permute(1, 2, 0, 3) for t in (q, k, v))

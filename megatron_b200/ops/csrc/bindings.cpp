@@ -306,7 +306,8 @@ void nvl_allreduce(const std::vector<int64_t>& ptrs, const std::vector<int64_t>&
 
 #ifdef MB200_HAVE_FLASH_ATTN_SM100
 // q [sq, b, hq, d], k/v [sk, b, hk, d] (any s/b/h strides, d contiguous) -> (out [sq, b, hq, d], lse [b, hq, sq] fp32)
-std::vector<Tensor> flash_attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, bool causal, double scale, int64_t variant) {
+// row_lo (optional int32 [sq]): first visible key of every query, monotone non-decreasing — the band mask of sliding windows / packed sequences (with b == 1)
+std::vector<Tensor> flash_attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, bool causal, double scale, int64_t variant, const c10::optional<Tensor>& row_lo) {
   TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kBFloat16 && k.scalar_type() == at::kBFloat16 && v.scalar_type() == at::kBFloat16, "flash_attn_fwd: bf16 CUDA tensors");
   TORCH_CHECK(q.dim() == 4 && k.dim() == 4 && v.dim() == 4 && q.stride(3) == 1 && k.stride(3) == 1 && v.stride(3) == 1, "flash_attn_fwd: [s, b, h, d] with contiguous d");
   TORCH_CHECK(((uintptr_t)q.data_ptr() | (uintptr_t)k.data_ptr() | (uintptr_t)v.data_ptr()) % 16 == 0, "flash_attn_fwd: 16-byte aligned tensors");
@@ -315,9 +316,14 @@ std::vector<Tensor> flash_attn_fwd(const Tensor& q, const Tensor& k, const Tenso
   TORCH_CHECK(!causal || sk >= sq, "flash_attn_fwd: causal needs sk >= sq");
   auto out = at::empty({sq, b, hq, d}, q.options());
   auto lse = at::empty({b, hq, sq}, q.options().dtype(at::kFloat));
+  const int* lo = nullptr;
+  if (row_lo.has_value() && row_lo->defined()) {
+    TORCH_CHECK(causal && row_lo->is_cuda() && row_lo->scalar_type() == at::kInt && row_lo->is_contiguous() && row_lo->numel() == sq, "flash_attn_fwd: row_lo must be int32 [sq] on the GPU, with a causal mask");
+    lo = row_lo->data_ptr<int>();
+  }
   const int rc = mb200_flash_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), sq, sk, b, hq, hk, d, q.stride(0), q.stride(1),
                                       q.stride(2), k.stride(0), k.stride(1), k.stride(2), v.stride(0), v.stride(1), v.stride(2), (float)scale, causal ? 1 : 0,
-                                      (int)variant, cur_stream());
+                                      (int)variant, lo, cur_stream());
   TORCH_CHECK(rc == 0, "flash_attn_fwd failed with code ", rc);
   return {out, lse};
 }
@@ -327,7 +333,7 @@ std::vector<Tensor> flash_attn_fwd(const Tensor& q, const Tensor& k, const Tenso
 // go, q, o [sq,b,hq,128]; k, v [sk,b,hk,128]; lse [b,hq,sq] fp32 -> (dq, dk, dv) bf16.  split_heads: -1 = decide from the grid size.
 // Heads are processed in chunks so that the bf16 dS scratch ([heads, sk, sq]) stays under max_scratch_mb.
 std::vector<Tensor> flash_attn_bwd(const Tensor& go, const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& o, const Tensor& lse, bool causal, double scale,
-                                   int64_t split_heads, int64_t max_scratch_mb) {
+                                   int64_t split_heads, int64_t max_scratch_mb, const c10::optional<Tensor>& row_lo, const c10::optional<Tensor>& col_hi) {
   TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kBFloat16 && go.scalar_type() == at::kBFloat16 && o.scalar_type() == at::kBFloat16, "flash_attn_bwd: bf16 CUDA tensors");
   TORCH_CHECK(q.stride(3) == 1 && k.stride(3) == 1 && v.stride(3) == 1 && go.stride(3) == 1 && o.stride(3) == 1, "flash_attn_bwd: contiguous head dim");
   TORCH_CHECK(lse.is_contiguous() && lse.scalar_type() == at::kFloat, "flash_attn_bwd: fp32 [b,h,s] log-sum-exp");
@@ -337,13 +343,21 @@ std::vector<Tensor> flash_attn_bwd(const Tensor& go, const Tensor& q, const Tens
   auto dk = at::empty({sk, b, hk, d}, q.options());
   auto dv = at::empty({sk, b, hk, d}, q.options());
   auto delta = at::empty({b, hq, (sq + 63) / 64, 128}, q.options().dtype(at::kFloat));   // per 64-query block: lse*log2e | rowsum(dO o O)*scale
+  const int *lo = nullptr, *hi = nullptr;
+  if (row_lo.has_value() && row_lo->defined()) {
+    TORCH_CHECK(col_hi.has_value() && col_hi->defined(), "flash_attn_bwd: row_lo and col_hi come together");
+    TORCH_CHECK(causal && row_lo->scalar_type() == at::kInt && col_hi->scalar_type() == at::kInt && row_lo->is_contiguous() && col_hi->is_contiguous() && row_lo->numel() == sq && col_hi->numel() == sk,
+                "flash_attn_bwd: row_lo int32 [sq], col_hi int32 [sk], causal mask");
+    lo = row_lo->data_ptr<int>();
+    hi = col_hi->data_ptr<int>();
+  }
   const int sh = split_heads < 0 ? mb200_flash_attn_bwd_split_heads(sk, b, hq, hk) : (int)split_heads;
   const size_t bytes = mb200_flash_attn_bwd_scratch_bytes(sq, sk, b, hq, hk, sh);
   auto scratch = at::empty({(int64_t)bytes}, q.options().dtype(at::kByte));
   const int rc = mb200_flash_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), go.data_ptr(), o.data_ptr(), lse.data_ptr<float>(), delta.data_ptr<float>(), dq.data_ptr(),
                                       dk.data_ptr(), dv.data_ptr(), scratch.data_ptr(), sh, sq, sk, b, hq, hk, d, q.stride(0), q.stride(1), q.stride(2), k.stride(0),
                                       k.stride(1), k.stride(2), v.stride(0), v.stride(1), v.stride(2), go.stride(0), go.stride(1), go.stride(2), o.stride(0), o.stride(1),
-                                      o.stride(2), (float)scale, causal ? 1 : 0, cur_stream());
+                                      o.stride(2), (float)scale, causal ? 1 : 0, lo, hi, cur_stream());
   TORCH_CHECK(rc == 0, "flash_attn_bwd failed with code ", rc);
   return {dq, dk, dv};
 }
@@ -823,7 +837,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("share_storage", &share_storage);
 #ifdef MB200_HAVE_FLASH_ATTN_BWD_SM100
   m.def("flash_attn_bwd", &flash_attn_bwd, pybind11::arg("go"), pybind11::arg("q"), pybind11::arg("k"), pybind11::arg("v"), pybind11::arg("o"), pybind11::arg("lse"),
-        pybind11::arg("causal"), pybind11::arg("scale"), pybind11::arg("split_heads") = -1, pybind11::arg("max_scratch_mb") = 0);
+        pybind11::arg("causal"), pybind11::arg("scale"), pybind11::arg("split_heads") = -1, pybind11::arg("max_scratch_mb") = 0, pybind11::arg("row_lo") = pybind11::none(),
+        pybind11::arg("col_hi") = pybind11::none());
 #endif
 #ifdef MB200_HAVE_PAGED_ATTENTION
   m.def("paged_kv_append", &paged_kv_append);
@@ -847,7 +862,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 #endif
 #ifdef MB200_HAVE_FLASH_ATTN_SM100
   m.def("flash_attn_fwd", &flash_attn_fwd, pybind11::arg("q"), pybind11::arg("k"), pybind11::arg("v"), pybind11::arg("causal"), pybind11::arg("scale"),
-        pybind11::arg("variant") = 0);
+        pybind11::arg("variant") = 0, pybind11::arg("row_lo") = pybind11::none());
 #endif
 #ifdef MB200_HAVE_FUSED_TP_GEMM
   m.def("fused_tp_gemm", &fused_tp_gemm);

@@ -49,6 +49,8 @@ struct FaBwdParams {
   void* dv;
   float* dk_part;        // split-heads: [b, hq, sk, d] fp32
   float* dv_part;
+  const int* col_hi;     // optional [sk]: one past the LAST query that sees each key (monotone non-decreasing) — sliding windows / packed sequences; the lower
+                         // edge of a key's visibility is the causal diagonal
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -160,7 +162,14 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const int first_q = k0 - off;          // first query that can see key k0
     i0 = first_q <= 0 ? 0 : (first_q / FB_Q) & ~1;   // even: the dQ kernel reads 128-query tiles, both 64-query halves of a visited tile must be written
   }
-  const int steps_per_head = nq > i0 ? nq - i0 : 0;
+  int i_end = nq;
+  int hi_min = 0x7fffffff;
+  if (p.col_hi != nullptr) {
+    hi_min = p.col_hi[k0];
+    const int hi_max = p.col_hi[min(k0 + FB_KV - 1, p.sk - 1)];
+    i_end = min(nq, ((hi_max + FB_Q - 1) / FB_Q + 1) & ~1);          // even again: whole 128-query tiles of the dS scratch are written
+  }
+  const int steps_per_head = i_end > i0 ? i_end - i0 : 0;
   const int total_steps = steps_per_head * n_heads;
 
   if (warp == 8 && lane == 0) {
@@ -271,6 +280,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int kv_idx = k0 + row;
+    const int hi = p.col_hi != nullptr ? p.col_hi[min(kv_idx, p.sk - 1)] : 0x7fffffff;
     const int sw = row & 7;
     const int tid = threadIdx.x;                         // 0..255 among the compute warps
     // 8 columns of a half row: PT = exp2(ST c - lse), dST = PT (dPT scale - delta scale); MASKED only on tiles that touch a boundary or the causal diagonal
@@ -286,7 +296,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           float pv = ex2(fmaf(__uint_as_float(sv[c4 + e]), p.scale_log2, -lv[e]));
           if (MASKED) {
             const int q = qbase + c4 + e;
-            const bool ok = kv_idx < p.sk && q < p.sq && (!p.causal || kv_idx <= q + off);
+            const bool ok = kv_idx < p.sk && q < p.sq && q < hi && (!p.causal || kv_idx <= q + off);
             pv = ok ? pv : 0.f;
           }
           pr[e] = pv;
@@ -328,7 +338,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       tc_fence_after();
       uint32_t pw[16], dw[16];
       {
-        const bool interior = (k0 + FB_KV <= p.sk) && (q0 + FB_Q <= p.sq) && (!p.causal || (k0 + FB_KV - 1 <= q0 + off));
+        const bool interior = (k0 + FB_KV <= p.sk) && (q0 + FB_Q <= p.sq) && (q0 + FB_Q <= hi_min) && (!p.causal || (k0 + FB_KV - 1 <= q0 + off));
         const uint32_t vec_addr = smem_u32(smem_vec + s * 2 * FB_Q) + half * 32 * 4;
         if (p.dbg & 1) {
 #pragma unroll
@@ -362,7 +372,7 @@ fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           mbar_arrive(&ds_free[(st + 1) & 1]);
         }
       }
-      if (++i == nq) { i = i0; ++h; }
+      if (++i == i_end) { i = i0; ++h; }
     }
     // ---- epilogue: dK, dV [kv = row, d] ------------------------------------------------------------------------------------------
     if (total_steps > 0) {
@@ -474,6 +484,7 @@ struct FaDqParams {
   int sq, sk, b, hq, hk, causal;
   long k_sb, k_sh;
   void* dq;              // [sq, b, hq, d] bf16 contiguous
+  const int* row_lo;     // optional [sq]: first visible key of every query (band masks): key blocks before it were never written to the dS scratch
 };
 constexpr int DQ_BM = 128, DQ_BK = 128, DQ_STAGES = 3;
 constexpr int DQ_A_BYTES = DQ_BK * DQ_BM * 2;     // dSt tile: [128 keys][128 q] bf16 as two 64-q chunks of [128 rows x 128 B]
@@ -499,15 +510,17 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_ds, const __grid_const
   const int off = p.sk - p.sq;
   const int group = p.hq / p.hk;
   // tile index -> (query block, head): latest (= heaviest under a causal mask) query blocks first
-  auto tile_of = [&](int t, int& qb, int& bh, int& n_kb) {
+  auto tile_of = [&](int t, int& qb, int& bh, int& kb_lo, int& n_kb) {
     qb = nqb - 1 - t / heads;
     bh = t % heads;
+    kb_lo = p.row_lo != nullptr ? max(p.row_lo[qb * DQ_BM], 0) / DQ_BK : 0;
     if (p.causal) {
       const int last = min(qb * DQ_BM + DQ_BM - 1, p.sq - 1) + off;
       n_kb = last < 0 ? 0 : min(nkb, last / DQ_BK + 1);
     } else {
       n_kb = nkb;
     }
+    kb_lo = min(kb_lo, n_kb);
   };
 
   if (warp == 0 && lane == 0) {
@@ -536,11 +549,11 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_ds, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int qb, bh, n_kb;
-        tile_of(t, qb, bh, n_kb);
+        int qb, bh, kb_lo, n_kb;
+        tile_of(t, qb, bh, kb_lo, n_kb);
         const int bi = bh / p.hq, h = bh % p.hq;
         const int kcol = (int)(bi * p.k_sb + (h / group) * p.k_sh);
-        for (int kb = 0; kb < n_kb; ++kb) {
+        for (int kb = kb_lo; kb < n_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], DQ_STAGE_BYTES);
           uint8_t* sa = smem + stage * DQ_STAGE_BYTES;
@@ -560,22 +573,22 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_ds, const __grid_const
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int qb, bh, n_kb;
-        tile_of(t, qb, bh, n_kb);
+        int qb, bh, kb_lo, n_kb;
+        tile_of(t, qb, bh, kb_lo, n_kb);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * FB_D;
-        for (int kb = 0; kb < n_kb; ++kb) {
+        for (int kb = kb_lo; kb < n_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_lo = smem_desc_lo(smem_u32(smem + stage * DQ_STAGE_BYTES), DQ_A_BYTES / 2), b_lo = a_lo + (DQ_A_BYTES >> 4);   // same LBO for both (DQ_A_BYTES == DQ_B_BYTES)
 #pragma unroll
           for (int kk = 0; kk < DQ_BK / UMMA_K; ++kk)
-            umma_f16(d_tmem, smem_desc_at(a_lo, smem_desc_hi_sw128(1024), kk * 2048), smem_desc_at(b_lo, smem_desc_hi_sw128(1024), kk * 2048), idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+            umma_f16(d_tmem, smem_desc_at(a_lo, smem_desc_hi_sw128(1024), kk * 2048), smem_desc_at(b_lo, smem_desc_hi_sw128(1024), kk * 2048), idesc, (kb > kb_lo || kk > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (++stage == DQ_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);      // with n_kb == 0 this completes at once and the epilogue writes zeros
+        umma_commit(&tmem_full[acc]);      // with n_kb == kb_lo this completes at once and the epilogue writes zeros
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -584,8 +597,8 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_ds, const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      int qb, bh, n_kb;
-      tile_of(t, qb, bh, n_kb);
+      int qb, bh, kb_lo, n_kb;
+      tile_of(t, qb, bh, kb_lo, n_kb);
       const int bi = bh / p.hq, h = bh % p.hq;
       const int q = qb * DQ_BM + ew * 32 + lane;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -607,7 +620,7 @@ fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_ds, const __grid_const
             uint32_t v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const float x0 = n_kb > 0 ? __uint_as_float(r[g * 16 + 2 * e]) : 0.f, x1 = n_kb > 0 ? __uint_as_float(r[g * 16 + 2 * e + 1]) : 0.f;
+              const float x0 = n_kb > kb_lo ? __uint_as_float(r[g * 16 + 2 * e]) : 0.f, x1 = n_kb > kb_lo ? __uint_as_float(r[g * 16 + 2 * e + 1]) : 0.f;
               __nv_bfloat162 hb = __floats2bfloat162_rn(x0, x1);
               v[e] = *reinterpret_cast<uint32_t*>(&hb);
             }
@@ -648,7 +661,7 @@ extern "C" int mb200_flash_attn_bwd_split_heads(int sk, int b, int hq, int hk) {
 extern "C" int mb200_flash_attn_bwd(const void* q, const void* k, const void* v, const void* dout, const void* out, const float* lse, float* vec, void* dq, void* dk,
                                     void* dv, void* scratch, int split_heads, int sq, int sk, int b, int hq, int hk, int d, long q_ss, long q_sb, long q_sh, long k_ss,
                                     long k_sb, long k_sh, long v_ss, long v_sb, long v_sh, long do_ss, long do_sb, long do_sh, long o_ss, long o_sb, long o_sh, float scale,
-                                    int causal, cudaStream_t s) {
+                                    int causal, const int* row_lo, const int* col_hi, cudaStream_t s) {
   if (d != FB_D || hq % hk != 0) return -10;
   if ((q_ss | q_sb | q_sh | k_ss | k_sb | k_sh | v_ss | v_sb | v_sh | do_ss | do_sb | do_sh | o_ss | o_sb | o_sh) % 8 != 0) return -11;
   constexpr int SMEM_DKV = 2 * (2 * FB_KV * 128) + FB_STAGES * 2 * (2 * FB_Q * 128) + 2 * FB_KV * 128 + FB_STAGES * 2 * FB_Q * 4 + 1024 + 256;
@@ -681,7 +694,7 @@ extern "C" int mb200_flash_attn_bwd(const void* q, const void* k, const void* v,
   }
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   p.q_sb = q_sb; p.q_sh = q_sh; p.k_sb = k_sb; p.k_sh = k_sh; p.v_sb = v_sb; p.v_sh = v_sh; p.do_sb = do_sb; p.do_sh = do_sh;
-  p.vec = vec; p.dk = dk; p.dv = dv;
+  p.vec = vec; p.dk = dk; p.dv = dv; p.col_hi = col_hi;
   size_t ds_bytes = (size_t)b * hq * sk * sq_al * 2;
   ds_bytes = (ds_bytes + 255) / 256 * 256;
   p.dk_part = split_heads ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + ds_bytes) : nullptr;
@@ -690,7 +703,7 @@ extern "C" int mb200_flash_attn_bwd(const void* q, const void* k, const void* v,
   fa_bwd_dkv_kernel<<<grid, FB_THREADS, SMEM_DKV, s>>>(tq, tk, tv, tdo, tds, p);
   if (split_heads) fa_bwd_reduce_kernel<<<num_sms() * 4, 256, 0, s>>>(p.dk_part, p.dv_part, reinterpret_cast<__nv_bfloat16*>(dk), reinterpret_cast<__nv_bfloat16*>(dv), sk, b, hq, hk);
   FaDqParams dqp;
-  dqp.sq = sq; dqp.sk = sk; dqp.b = b; dqp.hq = hq; dqp.hk = hk; dqp.causal = causal; dqp.k_sb = k_sb; dqp.k_sh = k_sh; dqp.dq = dq;
+  dqp.sq = sq; dqp.sk = sk; dqp.b = b; dqp.hq = hq; dqp.hk = hk; dqp.causal = causal; dqp.k_sb = k_sb; dqp.k_sh = k_sh; dqp.dq = dq; dqp.row_lo = row_lo;
   const int tiles = ((sq + DQ_BM - 1) / DQ_BM) * b * hq;
   fa_bwd_dq_kernel<<<tiles < num_sms() ? tiles : num_sms(), NUM_THREADS, SMEM_DQ, s>>>(tds, tk2, dqp);
   return cudaGetLastError() == cudaSuccess ? 0 : -4;

@@ -45,6 +45,7 @@ struct FaParams {
   void* out;
   long o_pitch;                  // elements between consecutive query rows of out
   float* lse;
+  const int* row_lo;             // optional [sq]: first visible key of every query row (monotone non-decreasing) — sliding windows and packed sequences
 };
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
@@ -135,6 +136,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       n_t[t] = nkv;
     }
   }
+  // Band masks (sliding window / packed sequences): keys before row_lo[q] are hidden.  row_lo is monotone, so the CTA's walk starts at the block holding the
+  // first visible key of its first row; every index below is RELATIVE to that block (jlo) except the K/V coordinates and the mask.
+  int jlo = 0;
+  if (p.row_lo != nullptr && tile_row0[0] < p.sq) jlo = min(max(p.row_lo[tile_row0[0]], 0) / FA_BN, max(n_t[0] - 1, 0));   // tile 0 is the earlier one (pair_mode 0 with a band)
+  n_t[0] = max(n_t[0] - jlo, 0);
+  n_t[1] = max(n_t[1] - jlo, 0);
   const int n = max(n_t[0], n_t[1]);
 
   if (warp == 8 && lane == 0) {
@@ -178,11 +185,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         mbar_wait(&k_empty[s], ph ^ 1);
         mbar_expect_tx(&k_full[s], KV_STAGE_BYTES);
 #pragma unroll
-        for (int c = 0; c < DCH; ++c) tma_load_2d(smem_k + s * KV_STAGE_BYTES + c * KV_CHUNK_BYTES, &tmap_k, &k_full[s], kcol + c * 64, j * FA_BN);
+        for (int c = 0; c < DCH; ++c) tma_load_2d(smem_k + s * KV_STAGE_BYTES + c * KV_CHUNK_BYTES, &tmap_k, &k_full[s], kcol + c * 64, (j + jlo) * FA_BN);
         mbar_wait(&v_empty[s], ph ^ 1);
         mbar_expect_tx(&v_full[s], KV_STAGE_BYTES);
 #pragma unroll
-        for (int c = 0; c < DCH; ++c) tma_load_2d(smem_v + s * KV_STAGE_BYTES + c * KV_CHUNK_BYTES, &tmap_v, &v_full[s], vcol + c * 64, j * FA_BN);
+        for (int c = 0; c < DCH; ++c) tma_load_2d(smem_v + s * KV_STAGE_BYTES + c * KV_CHUNK_BYTES, &tmap_v, &v_full[s], vcol + c * 64, (j + jlo) * FA_BN);
       }
     }
   } else if (warp == 9 || warp == 10) {
@@ -264,6 +271,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     const int sw = row & 7;
     float m_ref = -INFINITY, l = 0.f;
     const int nb = n_t[t];
+    const int lo = (p.row_lo != nullptr && q_idx < p.sq) ? p.row_lo[q_idx] : 0;   // first visible key of this row
     for (int j = 0; j < nb; ++j) {
       const int buf = j & 1;
       const uint32_t s_addr = s_addr0 + buf * FA_BN;
@@ -274,13 +282,20 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       tmem_ld_32x32b_x32(s_addr, r0);
       tmem_ld_32x32b_x32(s_addr + 32, r1);
       tmem_ld_wait();
-      const int kv0 = j * FA_BN;
+      const int kv0 = (j + jlo) * FA_BN;
       const int limit = p.causal ? min(p.sk - 1, q_idx + off) : p.sk - 1;   // last visible key of this row
       if (kv0 + FA_BN - 1 > limit) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           if (kv0 + c > limit) r0[c] = 0xff800000u;        // -inf
           if (kv0 + 32 + c > limit) r1[c] = 0xff800000u;
+        }
+      }
+      if (kv0 < lo) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (kv0 + c < lo) r0[c] = 0xff800000u;
+          if (kv0 + 32 + c < lo) r1[c] = 0xff800000u;
         }
       }
       // row max with 3-input FMNMX3 (sm_100) in 8 independent chains: 32 instructions for 64 scores, no long dependent chain
@@ -302,6 +317,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         l *= alpha;
       }
       const bool rescale = __any_sync(0xffffffffu, alpha != 1.f) && j > 0;
+      // a row whose band starts in a later block has seen only -inf so far: exponentiate against 0 instead of -inf (−inf − (−inf) is NaN); every p is then 0
+      const float m_sub = (m_ref == -INFINITY) ? 0.f : m_ref;
       // p = 2^(s*scale - m_ref); written as bf16 into the 128B-swizzled K-major tile the PV MMA reads as operand A
       float sums[8];
       uint32_t pw[32];   // the row's 64 probabilities as packed bf16 pairs (P_TMEM path)
@@ -314,7 +331,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           const int c = u * 8 + e * 2;
           const float a0 = __uint_as_float(c < 32 ? r0[c] : r1[c - 32]);
           const float a1 = __uint_as_float(c + 1 < 32 ? r0[c + 1] : r1[c + 1 - 32]);
-          const float x0 = fmaf(a0, p.scale_log2, -m_ref), x1 = fmaf(a1, p.scale_log2, -m_ref);
+          const float x0 = fmaf(a0, p.scale_log2, -m_sub), x1 = fmaf(a1, p.scale_log2, -m_sub);
           const float p0 = fast_exp2(x0);
           const float p1 = (FA_POLY_EXP2 && (e & 1)) ? poly_exp2(x1) : fast_exp2(x1);   // optionally every 4th exponential on the FMA pipe
           su += p0 + p1;
@@ -402,8 +419,8 @@ static int launch_fa_fwd(const void* q, const void* k, const void* v, FaParams p
   }
   dim3 grid((p.sq + 2 * FA_BM - 1) / (2 * FA_BM), p.hq, p.b);
   // mirrored pairing when the whole grid is at most ~1.5 waves and the mask is causal (otherwise every tile costs the same)
-  p.pair_mode = (p.causal && p.sq == p.sk && (long)grid.x * grid.y * grid.z <= (long)num_sms() * 3 / 2 && grid.x > 1) ? 1 : 0;
-  if (const char* e = getenv("MB200_FA_PAIR_MODE")) p.pair_mode = atoi(e);
+  p.pair_mode = (p.causal && p.row_lo == nullptr && p.sq == p.sk && (long)grid.x * grid.y * grid.z <= (long)num_sms() * 3 / 2 && grid.x > 1) ? 1 : 0;
+  if (const char* e = getenv("MB200_FA_PAIR_MODE")) p.pair_mode = p.row_lo == nullptr ? atoi(e) : 0;
   kern<<<grid, FA_THREADS, SMEM_BYTES, s>>>(tq, tk, tv, p);
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
@@ -415,14 +432,14 @@ using namespace mb200;
 // Strides are in elements; *_ss = sequence stride (row pitch), *_sb = batch stride, *_sh = head stride; d is contiguous.
 extern "C" int mb200_flash_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int sq, int sk, int b, int hq, int hk, int d, long q_ss,
                                     long q_sb, long q_sh, long k_ss, long k_sb, long k_sh, long v_ss, long v_sb, long v_sh, float scale, int causal,
-                                    int variant, cudaStream_t s) {
+                                    int variant, const int* row_lo, cudaStream_t s) {
   if ((d != 64 && d != 128) || hq % hk != 0) return -10;
   if ((q_ss | q_sb | q_sh | k_ss | k_sb | k_sh | v_ss | v_sb | v_sh) % 8 != 0) return -11;   // 16-byte alignment for TMA
   FaParams p;
   p.sq = sq; p.sk = sk; p.b = b; p.hq = hq; p.hk = hk; p.causal = causal;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.q_sb = q_sb; p.q_sh = q_sh; p.k_sb = k_sb; p.k_sh = k_sh; p.v_sb = v_sb; p.v_sh = v_sh;
-  p.out = out; p.o_pitch = (long)b * hq * d; p.lse = lse;
+  p.out = out; p.o_pitch = (long)b * hq * d; p.lse = lse; p.row_lo = row_lo;
   if (variant == 1) return d == 128 ? launch_fa_fwd<128, true>(q, k, v, p, q_ss, k_ss, v_ss, s) : launch_fa_fwd<64, true>(q, k, v, p, q_ss, k_ss, v_ss, s);
   return d == 128 ? launch_fa_fwd<128, false>(q, k, v, p, q_ss, k_ss, v_ss, s) : launch_fa_fwd<64, false>(q, k, v, p, q_ss, k_ss, v_ss, s);
 }

@@ -39,7 +39,7 @@ int mb200_fused_tp_gemm(int mode, const void* A, const void* B, void* C, int M, 
                         const void* xag_src, int64_t xag_bytes, int64_t xag_dst_mc, const int64_t* xag_dst_peer, const int64_t* flags_peer, void* counters,
                         int comm_clusters, cudaStream_t s);
 int mb200_flash_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int sq, int sk, int b, int hq, int hk, int d, long q_ss, long q_sb,
-                         long q_sh, long k_ss, long k_sb, long k_sh, long v_ss, long v_sb, long v_sh, float scale, int causal, int variant, cudaStream_t s);
+                         long q_sh, long k_ss, long k_sb, long k_sh, long v_ss, long v_sb, long v_sh, float scale, int causal, int variant, const int* row_lo, cudaStream_t s);
 void mb200_batched_copy(const void* tasks_dev, const void* chunk_prefix_dev, int ntasks, unsigned long long total_chunks, int nblocks, cudaStream_t s);
 int mb200_grouped_gemm_bf16(const void* a, const void* b, void* c, const int* offsets, int E, int dim_n, int dim_k, int mode, int accumulate, int c_dtype,
                             void* maps_dev, cudaStream_t s);
@@ -54,7 +54,8 @@ void mb200_moe_pull_rows(void* out, const int32_t* rank, const int64_t* slot, co
                          int topk, int row_bytes, int raw, cudaStream_t s);
 int mb200_flash_attn_bwd(const void* q, const void* k, const void* v, const void* dout, const void* out, const float* lse, float* vec, void* dq, void* dk, void* dv,
                          void* scratch, int split_heads, int sq, int sk, int b, int hq, int hk, int d, long q_ss, long q_sb, long q_sh, long k_ss, long k_sb, long k_sh,
-                         long v_ss, long v_sb, long v_sh, long do_ss, long do_sb, long do_sh, long o_ss, long o_sb, long o_sh, float scale, int causal, cudaStream_t s);
+                         long v_ss, long v_sb, long v_sh, long do_ss, long do_sb, long do_sh, long o_ss, long o_sb, long o_sh, float scale, int causal, const int* row_lo,
+                         const int* col_hi, cudaStream_t s);
 size_t mb200_flash_attn_bwd_scratch_bytes(int sq, int sk, int b, int hq, int hk, int split_heads);
 int mb200_flash_attn_bwd_split_heads(int sk, int b, int hq, int hk);
 void mb200_paged_kv_append(const void* k_new, const void* v_new, void* k_pool, void* v_pool, const int32_t* block_table, const int32_t* positions, int B, int table_width,

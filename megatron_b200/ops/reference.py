@@ -169,7 +169,7 @@ def scaled_masked_softmax(x, mask, scale, causal=False):
     return torch.softmax(xf, dim=-1).to(x.dtype)
 
 
-def attention_fwd(q, k, v, causal=True, scale=None, window=None):
+def attention_fwd(q, k, v, causal=True, scale=None, window=None, cu_seqlens=None):
     """q: [sq, b, hq, d]; k, v: [sk, b, hk, d] (GQA when hk < hq).  Returns [sq, b, hq, dv]."""
     sq, b, hq, d = q.shape
     sk, _, hk, _ = k.shape
@@ -186,6 +186,11 @@ def attention_fwd(q, k, v, causal=True, scale=None, window=None):
         idx_q = torch.arange(sq, device=q.device)[:, None] + (sk - sq)
         idx_k = torch.arange(sk, device=q.device)[None, :]
         s = s.masked_fill(idx_k < idx_q - window[0], float("-inf"))
+    if cu_seqlens is not None:                            # packed sequences along the token dim: block-diagonal
+        cu = cu_seqlens.to(device=q.device, dtype=torch.long)
+        sid_q = torch.bucketize(torch.arange(sq, device=q.device), cu[1:], right=True).clamp_(max=cu.numel() - 2)
+        sid_k = torch.bucketize(torch.arange(sk, device=q.device), cu[1:], right=True).clamp_(max=cu.numel() - 2)
+        s = s.masked_fill(sid_q[:, None] != sid_k[None, :], float("-inf"))
     p = torch.softmax(s, dim=-1)
     o = torch.matmul(p, vf)
     return o.permute(2, 0, 1, 3).to(q.dtype).contiguous()

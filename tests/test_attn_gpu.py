@@ -163,3 +163,82 @@ def test_flash_attention_autograd_native_backward():
     ref = mixed.grad.float()
     err = (got - ref).abs().max().item() / (ref.abs().max().item() + 1e-6)
     assert err < 3e-2, err
+
+
+def _band_ref(q, k, v, scale, window, cu):
+    from megatron_b200.ops import reference as ref
+
+    return ref.attention_fwd(q.float(), k.float(), v.float(), True, scale, window, cu)
+
+
+@pytest.mark.parametrize("split_heads", [0, 1])
+@pytest.mark.parametrize(
+    "sq,sk,hq,hk,window,cu",
+    [
+        (1024, 1024, 4, 2, (200, 0), None),                  # sliding window narrower than a tile pair
+        (2048, 2048, 4, 1, (511, 0), None),
+        (1000, 1000, 2, 2, (64, 0), None),                   # ragged, window of one key block
+        (384, 640, 2, 1, (100, 0), None),                    # bottom-right aligned window
+        (1024, 1024, 4, 2, None, [0, 300, 301, 640, 1024]),  # packed sequences incl. a length-1 one and boundaries off the tile grid
+        (2048, 2048, 2, 1, None, [0, 128, 1024, 2000]),      # trailing pad tokens (cu[-1] < t)
+        (1536, 1536, 2, 2, (150, 0), [0, 700, 1536]),        # both
+    ],
+)
+def test_flash_band_masks_native_fwd_bwd(sq, sk, hq, hk, window, cu, split_heads):
+    """Sliding window / packed sequences run INSIDE the tcgen05 kernels as a monotone band (row_lo / col_hi): forward, dK/dV kernel and dQ kernel vs
+    fp32 autograd of the dense-masked reference."""
+    from megatron_b200 import ops
+
+    torch.manual_seed(11)
+    d = 128
+    q = torch.randn(sq, 1, hq, d, device="cuda").bfloat16().requires_grad_(True)
+    k = torch.randn(sk, 1, hk, d, device="cuda").bfloat16().requires_grad_(True)
+    v = torch.randn(sk, 1, hk, d, device="cuda").bfloat16().requires_grad_(True)
+    go = torch.randn(sq, 1, hq, d, device="cuda").bfloat16()
+    cu_t = torch.tensor(cu, device="cuda", dtype=torch.int32) if cu is not None else None
+    scale = 1.0 / math.sqrt(d)
+    ro = _band_ref(q, k, v, scale, window, cu_t)
+    ro.backward(go.float())
+    refs = [t.grad.float().clone() for t in (q, k, v)]
+    lo, hi = ops.attention_band(sq, sk, window, cu_t, q.device)
+    o, lse = ops.ext().flash_attn_fwd(q.detach(), k.detach(), v.detach(), True, scale, 1, lo)
+    err = (o.float() - ro.float()).abs().max().item()
+    assert torch.isfinite(o.float()).all() and err < 2e-2, f"forward abs err {err}"
+    junk = torch.full((64 << 20,), float("nan"), device="cuda")
+    del junk
+    dq, dk, dv = ops.ext().flash_attn_bwd(go, q.detach(), k.detach(), v.detach(), o, lse, True, scale, split_heads, 0, lo, hi)
+    torch.cuda.synchronize()
+    for name, a, r in zip("qkv", (dq, dk, dv), refs):
+        assert torch.isfinite(a.float()).all(), f"d{name} has non-finite values"
+        e = (a.float() - r).abs().max().item() / (r.abs().max().item() + 1e-6)
+        assert e < 3e-2, f"d{name} rel err {e}"
+
+
+def test_packed_sequences_through_dot_product_attention():
+    """ops.flash_attention(cu_seqlens=...) == running every packed sequence on its own (values and gradients), and the native path was taken."""
+    from megatron_b200 import ops
+
+    torch.manual_seed(2)
+    lens = [384, 129, 511]
+    t, hq, hk, d = sum(lens), 4, 2, 128
+    cu = torch.tensor([0, 384, 513, 1024], device="cuda", dtype=torch.int32)
+    q, k, v = (torch.randn(t, 1, h, d, device="cuda").bfloat16().requires_grad_(True) for h in (hq, hk, hk))
+    ops.reset_launch_count()
+    out = ops.flash_attention(q, k, v, causal=True, cu_seqlens=cu)
+    assert ops.launch_count() >= 1, "packed attention fell off the native kernels"
+    go = torch.randn_like(out)
+    out.backward(go)
+    got = [out.float()] + [x.grad.float().clone() for x in (q, k, v)]
+    for x in (q, k, v):
+        x.grad = None
+    outs, s0 = [], 0
+    for n in lens:
+        o = ops.flash_attention(q[s0:s0 + n], k[s0:s0 + n], v[s0:s0 + n], causal=True) if n >= 128 else _band_ref(q[s0:s0 + n], k[s0:s0 + n], v[s0:s0 + n], 1 / math.sqrt(d), None, None).bfloat16()
+        outs.append(o)
+        s0 += n
+    sep = torch.cat(outs, 0)
+    sep.backward(go)
+    want = [sep.float()] + [x.grad.float() for x in (q, k, v)]
+    for name, a, r in zip(["out", "dq", "dk", "dv"], got, want):
+        e = (a - r).abs().max().item() / (r.abs().max().item() + 1e-6)
+        assert e < 3e-2, f"{name} rel err {e}"
