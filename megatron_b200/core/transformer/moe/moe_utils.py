@@ -13,9 +13,37 @@ import torch.distributed as dist
 # ---- losses -----------------------------------------------------------------------------------
 def switch_load_balancing_loss_func(probs: torch.Tensor, tokens_per_expert: torch.Tensor, total_num_tokens: int, topk: int, num_experts: int,
                                     moe_aux_loss_coeff: float, fused: bool = False) -> torch.Tensor:
-    """Switch-Transformer aux loss: ``E * coeff / (T^2 * k) * sum_e (sum_t p_te) * count_e``."""
+    """Switch-Transformer aux loss: ``E * coeff / (T^2 * k) * sum_e (sum_t p_te) * count_e``.  ``fused`` (reference: TE ``fused_moe_aux_loss``): one
+    deterministic two-stage reduction kernel over the [T, E] probabilities and a broadcast backward (``ops/csrc/routing_kernels.cu``)."""
+    if fused and probs.dim() == 2 and probs.is_cuda and probs.dtype == torch.float32:
+        from .... import ops
+
+        if ops.has_ext() and hasattr(ops.ext(), "moe_aux_loss_fwd"):
+            return _FusedAuxLoss.apply(probs, tokens_per_expert, num_experts * moe_aux_loss_coeff / (topk * total_num_tokens * total_num_tokens))
     aggregated = probs.sum(dim=0) if probs.dim() == 2 else probs
     return torch.sum(aggregated * tokens_per_expert) * (num_experts * moe_aux_loss_coeff / (topk * total_num_tokens * total_num_tokens))
+
+
+class _FusedAuxLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, probs, tokens_per_expert, coeff):
+        from .... import ops
+
+        tpe = tokens_per_expert.float().contiguous()
+        loss = ops.ext().moe_aux_loss_fwd(probs.contiguous(), tpe, float(coeff))
+        ops._count(2)
+        ctx.save_for_backward(tpe)
+        ctx.coeff, ctx.T = float(coeff), probs.shape[0]
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        from .... import ops
+
+        (tpe,) = ctx.saved_tensors
+        gp = ops.ext().moe_aux_loss_bwd(tpe, g.float().contiguous(), ctx.coeff, ctx.T)
+        ops._count()
+        return gp, None, None
 
 
 def z_loss_func(logits: torch.Tensor, z_loss_coeff: float) -> torch.Tensor:

@@ -115,7 +115,11 @@ class TopKRouter(Router):
             tokens_per_expert = tokens_per_expert.clone()
             dist.all_reduce(tokens_per_expert, group=ps.get_data_parallel_group())
             total = total * ps.get_data_parallel_world_size()
-        loss = switch_load_balancing_loss_func(aggregated, tokens_per_expert, total, self.topk, self.num_experts, coeff)
+        if self.config.moe_router_fusion and total == T and probs_for_loss.dim() == 2:
+            # no cross-rank probability mass to add: the fused kernel reduces the [T, E] probabilities against the counts directly (no [E] intermediate)
+            loss = switch_load_balancing_loss_func(probs_for_loss.float(), tokens_per_expert, total, self.topk, self.num_experts, coeff, fused=True)
+        else:
+            loss = switch_load_balancing_loss_func(aggregated, tokens_per_expert, total, self.topk, self.num_experts, coeff)
         save_to_aux_losses_tracker("load_balancing_loss", loss / coeff, self.layer_number, self.config.num_layers)
         return MoEAuxLossAutoScaler.apply(activation, loss)
 

@@ -123,6 +123,7 @@ class MLASelfAttention(MegatronModule):
             bias=c.add_bias_linear, input_is_parallel=True, skip_bias_add=True, is_expert=False, tp_group=self.tp_group,
         )
         self.sequence_parallel = c.sequence_parallel and ws > 1
+        self.fused_rope = True   # CUDA: in-place rotary on q and the one-kernel kv split (fusions/fused_mla_yarn_rope_apply.py); off → split / rotate / cat in PyTorch
 
     # ---- projections ------------------------------------------------------------------------------------------
     def _expand_kv(self, kv_latent, k_pe):
@@ -131,6 +132,11 @@ class MLASelfAttention(MegatronModule):
         kv, _ = self.linear_kv_up_proj(kv_latent)
         s, b = kv.shape[:2]
         kv = kv.view(s, b, self.n_local, c.qk_head_dim + c.v_head_dim)
+        if kv.is_cuda and self.fused_rope:
+            # split + broadcast of the shared rotary key + concatenate in ONE kernel (k_pe is already rotated here); backward sums the rotary gradient over heads
+            from ..fusions.fused_mla_yarn_rope_apply import fused_apply_mla_rope_for_kv
+
+            return fused_apply_mla_rope_for_kv(kv, k_pe, None, c.qk_pos_emb_head_dim, c.qk_head_dim, c.v_head_dim)
         k_nope, v = torch.split(kv, [c.qk_head_dim, c.v_head_dim], dim=-1)
         k = torch.cat([k_nope, k_pe.expand(s, b, self.n_local, c.qk_pos_emb_head_dim)], dim=-1)
         return k, v
@@ -158,10 +164,16 @@ class MLASelfAttention(MegatronModule):
         if isinstance(emb, tuple):
             emb, mscale = emb
         ang = emb[off:total]
-        q_nope, q_pe = torch.split(q, [c.qk_head_dim, c.qk_pos_emb_head_dim], dim=-1)
-        q_pe = _apply_rope(q_pe, ang, mscale, c.rotary_interleaved)
         k_pe = _apply_rope(k_pe, ang, mscale, c.rotary_interleaved)
-        q = torch.cat([q_nope, q_pe], dim=-1)
+        if q.is_cuda and q.is_contiguous() and self.fused_rope and c.qk_pos_emb_head_dim <= 64:
+            # rotate the trailing rotary channels of every head in place: no split / rotate / concatenate round trip over q
+            from ..fusions.fused_mla_yarn_rope_apply import fused_apply_mla_rope_for_q
+
+            q = fused_apply_mla_rope_for_q(q, ang, c.qk_head_dim, c.qk_pos_emb_head_dim, mscale, c.rotary_interleaved)
+        else:
+            q_nope, q_pe = torch.split(q, [c.qk_head_dim, c.qk_pos_emb_head_dim], dim=-1)
+            q_pe = _apply_rope(q_pe, ang, mscale, c.rotary_interleaved)
+            q = torch.cat([q_nope, q_pe], dim=-1)
         return q, kv_latent, k_pe
 
     def forward(self, hidden_states, attention_mask, key_value_states=None, inference_context=None, rotary_pos_emb=None,
@@ -206,5 +218,10 @@ class MLASelfAttention(MegatronModule):
         kv = torch.nn.functional.linear(kv_latent, self.linear_kv_up_proj.weight)
         s, b = kv.shape[:2]
         kv = kv.view(s, b, self.n_local, c.qk_head_dim + c.v_head_dim)
+        if kv.is_cuda and self.fused_rope:
+            # split + broadcast of the shared rotary key + concatenate in ONE kernel (k_pe is already rotated here); backward sums the rotary gradient over heads
+            from ..fusions.fused_mla_yarn_rope_apply import fused_apply_mla_rope_for_kv
+
+            return fused_apply_mla_rope_for_kv(kv, k_pe, None, c.qk_pos_emb_head_dim, c.qk_head_dim, c.v_head_dim)
         k_nope, v = torch.split(kv, [c.qk_head_dim, c.v_head_dim], dim=-1)
         return torch.cat([k_nope, k_pe.expand(s, b, self.n_local, c.qk_pos_emb_head_dim)], dim=-1), v

@@ -370,6 +370,116 @@ void share_storage(Tensor dst, const Tensor& src) {
   dst.set_(src.storage(), dst.storage_offset(), dst.sizes(), dst.strides());
 }
 
+#ifdef MB200_HAVE_ROUTING_KERNELS
+// ---- router bookkeeping + MLA rotary (routing_kernels.cu) ---------------------------------------------------------------------------------------------
+std::vector<Tensor> indices_to_multihot(const Tensor& idx, const Tensor& probs, int64_t E) {
+  check_cuda_contig(idx, "indices"); check_cuda_contig(probs, "probs");
+  TORCH_CHECK(idx.dim() == 2 && idx.scalar_type() == at::kLong && probs.scalar_type() == at::kFloat && probs.sizes() == idx.sizes(), "indices_to_multihot: int64 [T, k] + fp32 [T, k]");
+  c10::cuda::CUDAGuard g(idx.device());
+  auto map = at::empty({idx.size(0), E}, idx.options().dtype(at::kBool));
+  auto out = at::empty({idx.size(0), E}, probs.options());
+  mb200_indices_to_multihot(idx.data_ptr<int64_t>(), probs.data_ptr<float>(), (uint8_t*)map.data_ptr(), out.data_ptr<float>(), idx.size(0), (int)idx.size(1), (int)E, cur_stream());
+  return {map, out};
+}
+// scatter = false: g [T, E] -> [T, k]; true: g [T, k] -> [T, E]
+Tensor multihot_probs_grad(const Tensor& idx, const Tensor& g, int64_t E, bool scatter) {
+  check_cuda_contig(idx, "indices"); check_cuda_contig(g, "grad");
+  TORCH_CHECK(idx.scalar_type() == at::kLong && g.scalar_type() == at::kFloat && g.size(0) == idx.size(0) && g.size(1) == (scatter ? idx.size(1) : E));
+  c10::cuda::CUDAGuard gd(idx.device());
+  auto out = at::empty({idx.size(0), scatter ? E : idx.size(1)}, g.options());
+  mb200_multihot_probs_grad(idx.data_ptr<int64_t>(), g.data_ptr<float>(), out.data_ptr<float>(), idx.size(0), (int)idx.size(1), (int)E, scatter ? 1 : 0, cur_stream());
+  return out;
+}
+std::vector<Tensor> multihot_to_indices(const Tensor& map, const Tensor& probs, int64_t k) {
+  check_cuda_contig(map, "map"); check_cuda_contig(probs, "probs");
+  TORCH_CHECK(map.dim() == 2 && map.scalar_type() == at::kBool && probs.scalar_type() == at::kFloat && probs.sizes() == map.sizes(), "multihot_to_indices: bool [T, E] + fp32 [T, E]");
+  c10::cuda::CUDAGuard g(map.device());
+  auto idx = at::empty({map.size(0), k}, map.options().dtype(at::kLong));
+  auto out = at::empty({map.size(0), k}, probs.options());
+  mb200_multihot_to_indices((const uint8_t*)map.data_ptr(), probs.data_ptr<float>(), idx.data_ptr<int64_t>(), out.data_ptr<float>(), map.size(0), (int)k, (int)map.size(1), cur_stream());
+  return {idx, out};
+}
+Tensor pad_routing_map(const Tensor& map, int64_t multiple) {
+  check_cuda_contig(map, "map");
+  TORCH_CHECK(map.dim() == 2 && map.scalar_type() == at::kBool && multiple > 0, "pad_routing_map: bool [T, E]");
+  c10::cuda::CUDAGuard g(map.device());
+  auto out = at::empty_like(map);
+  mb200_pad_routing_map((const uint8_t*)map.data_ptr(), (uint8_t*)out.data_ptr(), map.size(0), (int)map.size(1), (int)multiple, cur_stream());
+  return out;
+}
+Tensor moe_aux_loss_fwd(const Tensor& probs, const Tensor& tpe, double coeff) {
+  check_cuda_contig(probs, "probs"); check_cuda_contig(tpe, "tokens_per_expert");
+  TORCH_CHECK(probs.dim() == 2 && probs.scalar_type() == at::kFloat && tpe.scalar_type() == at::kFloat && tpe.numel() == probs.size(1), "moe_aux_loss: fp32 probs [T, E], fp32 tokens_per_expert [E]");
+  c10::cuda::CUDAGuard g(probs.device());
+  const int nblocks = (int)std::max<int64_t>(1, std::min<int64_t>(296, probs.size(0) / 8));
+  auto partial = at::empty({nblocks}, probs.options());
+  auto loss = at::empty({}, probs.options());
+  mb200_moe_aux_loss_fwd(probs.data_ptr<float>(), tpe.data_ptr<float>(), partial.data_ptr<float>(), nblocks, loss.data_ptr<float>(), probs.size(0), (int)probs.size(1), (float)coeff, cur_stream());
+  return loss;
+}
+Tensor moe_aux_loss_bwd(const Tensor& tpe, const Tensor& gloss, double coeff, int64_t T) {
+  check_cuda_contig(tpe, "tokens_per_expert");
+  TORCH_CHECK(tpe.scalar_type() == at::kFloat && gloss.scalar_type() == at::kFloat && gloss.numel() == 1 && gloss.is_cuda());
+  c10::cuda::CUDAGuard g(tpe.device());
+  auto gp = at::empty({T, tpe.numel()}, tpe.options());
+  mb200_moe_aux_loss_bwd(tpe.data_ptr<float>(), gloss.data_ptr<float>(), (float)coeff, gp.data_ptr<float>(), T, (int)tpe.numel(), cur_stream());
+  return gp;
+}
+// x [..., H, nope + emb] contiguous, rotated IN PLACE; ang fp32 [positions, emb]; pos (optional int64 [rows]) else position = row / batch
+// out-of-place (returns a new tensor: untouched channels copied in the same pass) unless `inplace`
+Tensor mla_rope_inplace(Tensor x, const Tensor& ang, const c10::optional<Tensor>& pos, int64_t nope, int64_t emb, int64_t batch, double mscale, bool interleaved, bool inverse,
+                        bool inplace) {
+  check_cuda_contig(x, "x"); check_cuda_contig(ang, "angles");
+  TORCH_CHECK(x.dim() >= 2 && x.size(-1) == nope + emb && ang.scalar_type() == at::kFloat && ang.size(-1) == emb, "mla_rope_inplace: x [..., H, nope + emb], angles fp32 [positions, emb]");
+  const int H = (int)x.size(-2);
+  const long rows = x.numel() / (H * (nope + emb));
+  const int64_t* pp = nullptr;
+  if (pos.has_value() && pos->defined()) {
+    TORCH_CHECK(pos->is_cuda() && pos->scalar_type() == at::kLong && pos->is_contiguous() && pos->numel() == rows, "mla_rope_inplace: int64 positions, one per row");
+    pp = pos->data_ptr<int64_t>();
+  } else {
+    TORCH_CHECK(ang.numel() / emb >= (rows + batch - 1) / batch, "mla_rope_inplace: not enough angle rows");
+  }
+  c10::cuda::CUDAGuard g(x.device());
+  Tensor out = inplace ? x : at::empty_like(x);
+  const int rc = mb200_mla_rope_inplace(x.data_ptr(), out.data_ptr(), ang.data_ptr<float>(), pp, rows, H, (int)nope, (int)emb, (int)batch, (float)mscale, interleaved, inverse,
+                                        dtype_code(x), cur_stream());
+  TORCH_CHECK(rc == 0, "mla_rope_inplace: rotary dim must be even and <= 64");
+  return out;
+}
+// forward: (kv [rows.., H, kd + vd], k_pe [rows.., emb]) -> (key [.., H, kd + emb], value [.., H, vd]); backward: (dkey, dvalue) -> (dkv, dk_pe)
+std::vector<Tensor> mla_kv_split(const Tensor& a, const Tensor& b, const c10::optional<Tensor>& ang, const c10::optional<Tensor>& pos, int64_t kd, int64_t vd, int64_t emb, int64_t batch,
+                                 double mscale, bool interleaved, bool backward) {
+  check_cuda_contig(a, "a"); check_cuda_contig(b, "b");
+  TORCH_CHECK(a.scalar_type() == b.scalar_type() && a.dim() >= 2);
+  const int H = (int)a.size(-2);
+  const long rows = a.numel() / (H * a.size(-1));
+  if (!backward) { TORCH_CHECK(a.size(-1) == kd + vd && b.numel() == rows * emb, "mla_kv_split: kv [.., H, kd + vd], k_pe [.., emb]"); }
+  else { TORCH_CHECK(a.size(-1) == kd + emb && b.size(-1) == vd && b.numel() == rows * H * vd, "mla_kv_split backward: dkey [.., H, kd + emb], dvalue [.., H, vd]"); }
+  const float* ap = nullptr;
+  const int64_t* pp = nullptr;
+  if (ang.has_value() && ang->defined()) {
+    TORCH_CHECK(ang->is_cuda() && ang->scalar_type() == at::kFloat && ang->is_contiguous() && ang->size(-1) == emb);
+    ap = ang->data_ptr<float>();
+  }
+  if (pos.has_value() && pos->defined()) {
+    TORCH_CHECK(pos->is_cuda() && pos->scalar_type() == at::kLong && pos->is_contiguous() && pos->numel() == rows);
+    pp = pos->data_ptr<int64_t>();
+  }
+  c10::cuda::CUDAGuard g(a.device());
+  auto lead = a.sizes().vec();
+  lead.pop_back();
+  auto s0 = lead, s1 = lead;
+  s0.push_back(backward ? kd + vd : kd + emb);
+  if (backward) { s1.pop_back(); s1.push_back(1); s1.push_back(emb); } else { s1.push_back(vd); }
+  auto o0 = at::empty(s0, a.options()), o1 = at::empty(s1, a.options());
+  const int rc = mb200_mla_kv_split(a.data_ptr(), b.data_ptr(), ap, pp, o0.data_ptr(), o1.data_ptr(), rows, H, (int)kd, (int)vd, (int)emb, (int)batch, (float)mscale, interleaved,
+                                    backward, dtype_code(a), cur_stream());
+  TORCH_CHECK(rc == 0, "mla_kv_split: rotary dim must be even and <= 256");
+  return {o0, o1};
+}
+#endif
+
 #ifdef MB200_HAVE_PAGED_ATTENTION
 // k_new, v_new [B, hk, d] -> pools [num_blocks, block_size, hk, d] (one layer) at block_table[b, positions[b] / block_size], offset positions[b] % block_size
 void paged_kv_append(const Tensor& k_new, const Tensor& v_new, Tensor k_pool, Tensor v_pool, const Tensor& block_table, const Tensor& positions) {
@@ -839,6 +949,16 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("flash_attn_bwd", &flash_attn_bwd, pybind11::arg("go"), pybind11::arg("q"), pybind11::arg("k"), pybind11::arg("v"), pybind11::arg("o"), pybind11::arg("lse"),
         pybind11::arg("causal"), pybind11::arg("scale"), pybind11::arg("split_heads") = -1, pybind11::arg("max_scratch_mb") = 0, pybind11::arg("row_lo") = pybind11::none(),
         pybind11::arg("col_hi") = pybind11::none());
+#endif
+#ifdef MB200_HAVE_ROUTING_KERNELS
+  m.def("indices_to_multihot", &indices_to_multihot);
+  m.def("multihot_probs_grad", &multihot_probs_grad);
+  m.def("multihot_to_indices", &multihot_to_indices);
+  m.def("pad_routing_map", &pad_routing_map);
+  m.def("moe_aux_loss_fwd", &moe_aux_loss_fwd);
+  m.def("moe_aux_loss_bwd", &moe_aux_loss_bwd);
+  m.def("mla_rope_inplace", &mla_rope_inplace);
+  m.def("mla_kv_split", &mla_kv_split);
 #endif
 #ifdef MB200_HAVE_PAGED_ATTENTION
   m.def("paged_kv_append", &paged_kv_append);

@@ -56,6 +56,16 @@ int mb200_flash_attn_bwd(const void* q, const void* k, const void* v, const void
                          void* scratch, int split_heads, int sq, int sk, int b, int hq, int hk, int d, long q_ss, long q_sb, long q_sh, long k_ss, long k_sb, long k_sh,
                          long v_ss, long v_sb, long v_sh, long do_ss, long do_sb, long do_sh, long o_ss, long o_sb, long o_sh, float scale, int causal, const int* row_lo,
                          const int* col_hi, cudaStream_t s);
+void mb200_indices_to_multihot(const int64_t* idx, const float* probs, uint8_t* map, float* probs_out, long T, int k, int E, cudaStream_t s);
+void mb200_multihot_probs_grad(const int64_t* idx, const float* g_in, float* g_out, long T, int k, int E, int scatter, cudaStream_t s);
+void mb200_multihot_to_indices(const uint8_t* map, const float* probs, int64_t* idx, float* probs_out, long T, int k, int E, cudaStream_t s);
+void mb200_pad_routing_map(const uint8_t* in, uint8_t* out, long T, int E, int multiple, cudaStream_t s);
+void mb200_moe_aux_loss_fwd(const float* probs, const float* tpe, float* partial, int nblocks, float* loss, long T, int E, float coeff, cudaStream_t s);
+void mb200_moe_aux_loss_bwd(const float* tpe, const float* gloss, float coeff, float* gprobs, long T, int E, cudaStream_t s);
+int mb200_mla_rope_inplace(const void* src, void* x, const float* ang, const int64_t* pos, long rows, int H, int nope, int emb, int batch, float mscale, int interleaved, int inverse, int dtype,
+                           cudaStream_t s);
+int mb200_mla_kv_split(const void* a, const void* b, const float* ang, const int64_t* pos, void* o0, void* o1, long rows, int H, int kd, int vd, int emb, int batch, float mscale,
+                       int interleaved, int backward, int dtype, cudaStream_t s);
 size_t mb200_flash_attn_bwd_scratch_bytes(int sq, int sk, int b, int hq, int hk, int split_heads);
 int mb200_flash_attn_bwd_split_heads(int sk, int b, int hq, int hk);
 void mb200_paged_kv_append(const void* k_new, const void* v_new, void* k_pool, void* v_pool, const int32_t* block_table, const int32_t* positions, int B, int table_width,

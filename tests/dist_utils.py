@@ -15,7 +15,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _entry(rank, world, port, fn, args, q):
+def _entry(rank, world, port, fn, args, q, done):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     torch.set_num_threads(1)
     try:
@@ -32,13 +32,17 @@ def _entry(rank, world, port, fn, args, q):
             dist.destroy_process_group()
         except Exception:
             pass
+        # tensors in the payload travel as file descriptors served by THIS process (torch.multiprocessing reductions): stay alive until the parent has
+        # rebuilt them, otherwise it sees FileNotFoundError on the resource-sharer socket (a race that showed up under load)
+        done.wait(120)
 
 
 def run_distributed(fn, world, *args, timeout=300):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
+    done = ctx.Event()
     port = _free_port()
-    procs = [ctx.Process(target=_entry, args=(r, world, port, fn, args, q)) for r in range(world)]
+    procs = [ctx.Process(target=_entry, args=(r, world, port, fn, args, q, done)) for r in range(world)]
     for p in procs:
         p.start()
     results = {}
@@ -49,6 +53,7 @@ def run_distributed(fn, world, *args, timeout=300):
                 raise RuntimeError(f"rank {rank} failed:\n{payload}")
             results[rank] = payload
     finally:
+        done.set()
         for p in procs:
             p.join(timeout=10)
             if p.is_alive():
