@@ -72,6 +72,50 @@ def verify_draft_tokens(draft_tokens: torch.Tensor, draft_probs: torch.Tensor, t
     return n, int(nxt)
 
 
+def verify_draft_tokens_batched(draft_tokens: torch.Tensor, draft_probs: Optional[torch.Tensor], target_probs: torch.Tensor, u_accept: Optional[torch.Tensor] = None,
+                                u_sample: Optional[torch.Tensor] = None, generator: Optional[torch.Generator] = None):
+    """A whole decode batch at once, no host sync (reference ``text_generation_controllers/mtp_utils_triton.py``: verify + rewind counts).
+
+    ``draft_tokens [B, k]``; ``draft_probs [B, k, V]`` or ``None`` (greedy / MTP drafts: one-hot on the draft token); ``target_probs [B, k + 1, V]``;
+    ``u_accept [B, k]`` / ``u_sample [B]`` uniforms (drawn here when omitted).  → ``(n_accepted [B], next_token [B])`` int64 on the device; the caller rewinds
+    each KV cache to ``len + n_accepted``.  Acceptance: ``u < min(1, p_t / p_d)``; the follow-up token is drawn from ``normalise(max(p_t - p_d, 0))`` (or the
+    bonus row) by an inverse-CDF walk in vocabulary order, so CPU and GPU agree given the same uniforms.  CUDA: one block per sequence (``csrc/misc_kernels.cu``)."""
+    B, k = draft_tokens.shape
+    dev = draft_tokens.device
+    if u_accept is None:
+        u_accept = torch.rand(B, k, device=dev, generator=generator)
+    if u_sample is None:
+        u_sample = torch.rand(B, device=dev, generator=generator)
+    from ... import ops
+
+    if draft_tokens.is_cuda and ops.has_ext() and hasattr(ops.ext(), "spec_verify"):
+        n, nxt = ops.ext().spec_verify(draft_tokens.long().contiguous(), None if draft_probs is None else draft_probs.float().contiguous(), target_probs.float().contiguous(),
+                                       u_accept.float().contiguous(), u_sample.float().contiguous())
+        ops._count()
+        return n, nxt
+    tp = target_probs.float()
+    V = tp.shape[-1]
+    dp = draft_probs.float() if draft_probs is not None else torch.nn.functional.one_hot(draft_tokens.long(), V).float()
+    idx = draft_tokens.long().unsqueeze(-1)
+    pt = tp[:, :k].gather(-1, idx).squeeze(-1)
+    pd = dp.gather(-1, idx).squeeze(-1).clamp(min=1e-20) if draft_probs is not None else torch.ones_like(pt)
+    accept = u_accept < (pt / pd).clamp(max=1.0)
+    n = torch.cumprod(accept.to(torch.int64), dim=1).sum(1)                                   # length of the accepted prefix
+    rows = torch.arange(B, device=dev)
+    trow = tp[rows, n]
+    drow = torch.where((n < k).unsqueeze(-1), dp[rows, n.clamp(max=k - 1)] if k > 0 else torch.zeros_like(trow), torch.zeros_like(trow))
+    resid = (trow - drow).clamp(min=0)
+    dead = resid.sum(-1, keepdim=True) <= 0
+    dist = torch.where(dead, trow, resid)
+    cdf = dist.cumsum(-1)
+    thr = (u_sample.float() * cdf[:, -1]).unsqueeze(-1)
+    hit = (cdf > thr) & (dist > 0)
+    any_hit = hit.any(-1)
+    first = hit.float().argmax(-1)
+    last_nz = (V - 1) - (dist > 0).flip(-1).float().argmax(-1)
+    return n, torch.where(any_hit, first, last_nz)
+
+
 class SpeculativeDecoder:
     def __init__(self, target, draft, num_speculative_tokens: int = 4, max_sequence_length: int = 2048, vocab_size: Optional[int] = None):
         self.target, self.draft, self.k = target, draft, num_speculative_tokens

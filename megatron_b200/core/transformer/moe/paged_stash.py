@@ -25,6 +25,13 @@ from typing import Any, Dict, Optional, Tuple
 
 import torch
 
+from .... import ops
+
+
+def _stash_kernel_ok(t: torch.Tensor, buf) -> bool:
+    return (t.is_cuda and ops.has_ext() and hasattr(ops.ext(), "paged_stash") and t.dtype == buf.dtype and (buf.hidden_size * t.element_size()) % 16 == 0
+            and t.shape[-1] == buf.hidden_size)
+
 
 class PagedStashBuffer:
     """``pages [P + 1, page_size, H]`` (the last page is scratch) with a device-resident free ring."""
@@ -118,7 +125,12 @@ class PagedTensor:
         max_pages = -(-self.shape[0] // buf.page_size)
         need = (self.num_tokens.to(torch.int64) + buf.page_size - 1) // buf.page_size
         ids, ok = buf._alloc(need, max_pages, 0)
-        buf.pages.view(-1, buf.hidden_size).index_copy_(0, self._row_index(buf, ids, buf.num_pages), t)
+        if _stash_kernel_ok(t, buf):
+            # one kernel: rows below the device-resident token count go to their page, nothing else is touched (reference paged_stash_copy_kernel)
+            ops.ext().paged_stash(t.contiguous(), buf.pages, ids, self.num_tokens.to(torch.int64).reshape(1), buf.page_size, False)
+            ops._count()
+        else:
+            buf.pages.view(-1, buf.hidden_size).index_copy_(0, self._row_index(buf, ids, buf.num_pages), t)
         self.where = torch.where(ok, 0, 2)
         self.page_ids = ids
         if buf.host_pages is not None:
@@ -134,6 +146,14 @@ class PagedTensor:
         self._tensor = None              # the worst-case buffer can be reused now
 
     def reload_from_stash(self, buf: PagedStashBuffer) -> torch.Tensor:
+        if buf.host_pages is None and buf.pages.is_cuda and _stash_kernel_ok(buf.pages.view(-1, buf.hidden_size), buf):
+            # gather + zero-fill of the rows beyond the valid count in one kernel (reference paged_stash_pop_kernel)
+            out = torch.empty(self.shape[0], buf.hidden_size, device=self.device, dtype=buf.dtype)
+            ops.ext().paged_stash(out, buf.pages, self.page_ids, self.num_tokens.to(torch.int64).reshape(1), buf.page_size, True)
+            ops._count()
+            buf._release(self.page_ids, 0)
+            self.page_ids = None
+            return out.view(self.shape)
         out = buf.pages.view(-1, buf.hidden_size).index_select(0, self._row_index(buf, self.page_ids, buf.num_pages))
         if buf.host_pages is not None:
             idx_h = self._row_index(buf, self.host_ids, buf.num_host_pages)

@@ -245,7 +245,35 @@ def apply_rope(t, freqs, interleaved: bool = False, mscale: float = 1.0):
 # =============================================================================
 
 
+class _BiasDropoutAddFn(torch.autograd.Function):
+    """``residual + dropout(x + bias)`` in one pass (``csrc/misc_kernels.cu``); the keep mask is a function of the generator's (seed, offset) at call time and is
+    regenerated in the backward — nothing but two integers is saved."""
+
+    @staticmethod
+    def forward(ctx, x, bias, residual, prob):
+        y, seed, offset = ext().bias_dropout_add_fwd(x, bias, residual, prob)
+        _count()
+        ctx.prob, ctx.seed, ctx.offset, ctx.has_bias = prob, seed, offset, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        gx = ext().bias_dropout_add_bwd(g, ctx.prob, ctx.seed, ctx.offset) if ctx.prob > 0 else g
+        if ctx.prob > 0:
+            _count()
+        gb = gx.reshape(-1, gx.shape[-1]).sum(0) if ctx.has_bias and ctx.needs_input_grad[1] else None
+        return gx, gb, g, None
+
+
 def bias_dropout_add(x, bias, residual, prob: float, training: bool):
+    p = float(prob) if training else 0.0
+    if (_use_cuda(x) and (p > 0.0 or bias is not None) and hasattr(ext(), "bias_dropout_add_fwd") and x.dtype in (torch.bfloat16, torch.float16, torch.float32)
+            and x.dtype == residual.dtype and x.shape == residual.shape and x.is_contiguous() and residual.is_contiguous() and x.shape[-1] % 8 == 0
+            and (bias is None or (bias.dtype == x.dtype and bias.numel() == x.shape[-1] and bias.is_contiguous()))
+            and x.data_ptr() % 16 == 0 and residual.data_ptr() % 16 == 0 and (bias is None or bias.data_ptr() % 16 == 0)
+            and not (p > 0.0 and torch.cuda.is_current_stream_capturing())):
+        return _BiasDropoutAddFn.apply(x, bias, residual, p)
     if bias is not None:
         x = x + bias
     if prob > 0.0 and training:

@@ -24,7 +24,7 @@ ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 KERNEL_SOURCES = ["norm.cu", "elementwise.cu", "cross_entropy.cu", "multi_tensor.cu", "gemm_sm100.cu"]
-OPTIONAL_SOURCES = ["flash_attn_sm100.cu", "nvlink_collectives.cu", "fused_tp_gemm.cu", "grouped_gemm_sm100.cu", "moe_kernels.cu", "runtime_native.cu", "gemm_fp8_sm100.cu", "flash_attn_bwd_sm100.cu", "extra_kernels.cu", "gemm_mxfp8_sm100.cu", "gemm_nvfp4_sm100.cu", "paged_attention.cu", "routing_kernels.cu"]
+OPTIONAL_SOURCES = ["flash_attn_sm100.cu", "nvlink_collectives.cu", "fused_tp_gemm.cu", "grouped_gemm_sm100.cu", "moe_kernels.cu", "runtime_native.cu", "gemm_fp8_sm100.cu", "flash_attn_bwd_sm100.cu", "extra_kernels.cu", "gemm_mxfp8_sm100.cu", "gemm_nvfp4_sm100.cu", "paged_attention.cu", "routing_kernels.cu", "misc_kernels.cu"]
 
 
 def _nvcc() -> str:

@@ -8,6 +8,9 @@
 #include <unordered_map>
 #include <vector>
 
+#include <ATen/cuda/CUDAGeneratorImpl.h>
+#include <ATen/cuda/CUDAGraphsUtils.cuh>
+
 #include "launchers.h"
 
 namespace {
@@ -477,6 +480,79 @@ std::vector<Tensor> mla_kv_split(const Tensor& a, const Tensor& b, const c10::op
                                     backward, dtype_code(a), cur_stream());
   TORCH_CHECK(rc == 0, "mla_kv_split: rotary dim must be even and <= 256");
   return {o0, o1};
+}
+#endif
+
+#ifdef MB200_HAVE_MISC_KERNELS
+// ---- paged stash / speculative verify / bias-dropout-add (misc_kernels.cu) ------------------------------------------------------------------------------
+// flat [T_max, H] <-> pages [(P + 1) * page_size, H]; page_ids int64 [ceil(T_max / page_size)] (scratch id in unused slots); num_tokens int64 device scalar
+void paged_stash(Tensor flat, Tensor pages, const Tensor& page_ids, const Tensor& num_tokens, int64_t page_size, bool pop) {
+  check_cuda_contig(flat, "flat"); check_cuda_contig(pages, "pages"); check_cuda_contig(page_ids, "page_ids");
+  TORCH_CHECK(flat.dim() == 2 && flat.scalar_type() == pages.scalar_type() && page_ids.scalar_type() == at::kLong && num_tokens.is_cuda() && num_tokens.scalar_type() == at::kLong &&
+              num_tokens.numel() == 1, "paged_stash: flat [T, H], int64 page ids, int64 device token count");
+  TORCH_CHECK(page_ids.numel() * page_size >= flat.size(0), "paged_stash: page table too short");
+  check_aligned16(flat, "flat"); check_aligned16(pages, "pages");
+  c10::cuda::CUDAGuard g(flat.device());
+  const int rc = mb200_paged_stash(flat.data_ptr(), pages.data_ptr(), page_ids.data_ptr<int64_t>(), num_tokens.data_ptr<int64_t>(), flat.size(0), flat.size(1) * flat.element_size(),
+                                   (int)page_size, pop ? 1 : 0, cur_stream());
+  TORCH_CHECK(rc == 0, "paged_stash: row size must be a multiple of 16 bytes");
+}
+// -> (n_accepted int64 [B], next_token int64 [B])
+std::vector<Tensor> spec_verify(const Tensor& draft_tokens, const c10::optional<Tensor>& draft_probs, const Tensor& target_probs, const Tensor& u_accept, const Tensor& u_sample) {
+  check_cuda_contig(draft_tokens, "draft_tokens"); check_cuda_contig(target_probs, "target_probs"); check_cuda_contig(u_accept, "u_accept"); check_cuda_contig(u_sample, "u_sample");
+  const int B = (int)draft_tokens.size(0), k = (int)draft_tokens.size(1), V = (int)target_probs.size(2);
+  TORCH_CHECK(draft_tokens.scalar_type() == at::kLong && target_probs.scalar_type() == at::kFloat && target_probs.size(0) == B && target_probs.size(1) == k + 1 &&
+              u_accept.scalar_type() == at::kFloat && u_accept.numel() == (int64_t)B * k && u_sample.scalar_type() == at::kFloat && u_sample.numel() == B, "spec_verify: shapes");
+  const float* dp = nullptr;
+  if (draft_probs.has_value() && draft_probs->defined()) {
+    check_cuda_contig(*draft_probs, "draft_probs");
+    TORCH_CHECK(draft_probs->scalar_type() == at::kFloat && draft_probs->numel() == (int64_t)B * k * V);
+    dp = draft_probs->data_ptr<float>();
+  }
+  c10::cuda::CUDAGuard g(draft_tokens.device());
+  auto n = at::empty({B}, draft_tokens.options()), nxt = at::empty({B}, draft_tokens.options());
+  mb200_spec_verify(draft_tokens.data_ptr<int64_t>(), dp, target_probs.data_ptr<float>(), u_accept.data_ptr<float>(), u_sample.data_ptr<float>(), n.data_ptr<int64_t>(),
+                    nxt.data_ptr<int64_t>(), B, k, V, cur_stream());
+  return {n, nxt};
+}
+// y = residual + dropout(x + bias, p); the mask is regenerated in the backward from (seed, offset) taken from the current CUDA generator here
+std::tuple<Tensor, int64_t, int64_t> bias_dropout_add_fwd(const Tensor& x, const c10::optional<Tensor>& bias, const Tensor& residual, double p) {
+  check_cuda_contig(x, "x"); check_cuda_contig(residual, "residual");
+  TORCH_CHECK(x.sizes() == residual.sizes() && x.scalar_type() == residual.scalar_type(), "bias_dropout_add: x and residual must match");
+  check_aligned16(x, "x"); check_aligned16(residual, "residual");
+  const int H = (int)x.size(-1);
+  const void* bp = nullptr;
+  if (bias.has_value() && bias->defined()) {
+    check_cuda_contig(*bias, "bias");
+    TORCH_CHECK(bias->numel() == H && bias->scalar_type() == x.scalar_type(), "bias_dropout_add: bias [H] in x's dtype");
+    check_aligned16(*bias, "bias");
+    bp = bias->data_ptr();
+  }
+  c10::cuda::CUDAGuard g(x.device());
+  uint64_t seed = 0, offset = 0;
+  if (p > 0.0) {
+    int grid;
+    const long draws = mb200_bias_dropout_add_draws(x.numel(), dtype_code(x), &grid);
+    auto gen = at::get_generator_or_default<at::CUDAGeneratorImpl>(c10::nullopt, at::cuda::detail::getDefaultCUDAGenerator());
+    std::lock_guard<std::mutex> lock(gen->mutex_);
+    at::PhiloxCudaState st = gen->philox_cuda_state((uint64_t)draws);
+    TORCH_CHECK(!st.captured_, "bias_dropout_add: not capturable (the Python wrapper uses the eager path under CUDA-graph capture)");
+    seed = st.seed_.val;
+    offset = st.offset_.val;
+  }
+  auto y = at::empty_like(x);
+  const int rc = mb200_bias_dropout_add(x.data_ptr(), bp, residual.data_ptr(), y.data_ptr(), x.numel(), H, (float)p, seed, offset, 0, dtype_code(x), cur_stream());
+  TORCH_CHECK(rc == 0, "bias_dropout_add: sizes must be multiples of the 16-byte vector");
+  return {y, (int64_t)seed, (int64_t)offset};
+}
+Tensor bias_dropout_add_bwd(const Tensor& gy, double p, int64_t seed, int64_t offset) {
+  check_cuda_contig(gy, "gy");
+  c10::cuda::CUDAGuard g(gy.device());
+  auto gx = at::empty_like(gy);
+  const int rc = mb200_bias_dropout_add(gy.data_ptr(), nullptr, nullptr, gx.data_ptr(), gy.numel(), (int)gy.size(-1), (float)p, (uint64_t)seed, (uint64_t)offset, 1, dtype_code(gy),
+                                        cur_stream());
+  TORCH_CHECK(rc == 0, "bias_dropout_add_bwd: sizes must be multiples of the 16-byte vector");
+  return gx;
 }
 #endif
 
@@ -959,6 +1035,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("moe_aux_loss_bwd", &moe_aux_loss_bwd);
   m.def("mla_rope_inplace", &mla_rope_inplace);
   m.def("mla_kv_split", &mla_kv_split);
+#endif
+#ifdef MB200_HAVE_MISC_KERNELS
+  m.def("paged_stash", &paged_stash);
+  m.def("spec_verify", &spec_verify);
+  m.def("bias_dropout_add_fwd", &bias_dropout_add_fwd);
+  m.def("bias_dropout_add_bwd", &bias_dropout_add_bwd);
 #endif
 #ifdef MB200_HAVE_PAGED_ATTENTION
   m.def("paged_kv_append", &paged_kv_append);

@@ -66,6 +66,12 @@ int mb200_mla_rope_inplace(const void* src, void* x, const float* ang, const int
                            cudaStream_t s);
 int mb200_mla_kv_split(const void* a, const void* b, const float* ang, const int64_t* pos, void* o0, void* o1, long rows, int H, int kd, int vd, int emb, int batch, float mscale,
                        int interleaved, int backward, int dtype, cudaStream_t s);
+int mb200_paged_stash(void* flat, void* pages, const int64_t* page_ids, const int64_t* num_tokens, long t_max, long row_bytes, int page_size, int pop, cudaStream_t s);
+void mb200_spec_verify(const int64_t* draft_tokens, const float* draft_probs, const float* target_probs, const float* u_accept, const float* u_sample, int64_t* n_accepted,
+                       int64_t* next_token, int B, int k, int V, cudaStream_t s);
+long mb200_bias_dropout_add_draws(long numel, int dtype, int* grid_out);
+int mb200_bias_dropout_add(const void* x, const void* bias, const void* residual, void* y, long numel, int H, float p, unsigned long long seed, unsigned long long offset,
+                           int backward, int dtype, cudaStream_t s);
 size_t mb200_flash_attn_bwd_scratch_bytes(int sq, int sk, int b, int hq, int hk, int split_heads);
 int mb200_flash_attn_bwd_split_heads(int sk, int b, int hq, int hk);
 void mb200_paged_kv_append(const void* k_new, const void* v_new, void* k_pool, void* v_pool, const int32_t* block_table, const int32_t* positions, int B, int table_width,
