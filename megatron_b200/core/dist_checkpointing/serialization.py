@@ -47,9 +47,12 @@ def _split(sharded_state_dict):
 
 def save(sharded_state_dict: ShardedStateDict, checkpoint_dir: str, sharded_strategy=None, common_strategy=None, validate_access_integrity: bool = True,
          async_sharded_save: bool = False, preprocess_common_before_consistancy_check: Optional[Callable] = None, content_metadata: Optional[dict] = None,
-         async_strategy: str = "process", verify_integrity: bool = False, process_group=None) -> Optional[AsyncRequest]:
+         async_strategy: str = "process", verify_integrity: bool = False, process_group=None, cached_structure: bool = False) -> Optional[AsyncRequest]:
     """Write a sharded state dict.  ShardedTensors/Objects go to DCP ``.distcp`` files (each main
-    replica writes its shard), everything else goes to ``common.pt`` (rank 0)."""
+    replica writes its shard), everything else goes to ``common.pt`` (rank 0).  ``cached_structure`` (the reference's
+    ``ckpt_assume_constant_structure``): reuse the previous save's plan and global metadata when no rank's structure changed — one integer
+    all-reduce instead of the plan gather / merge / scatter (``strategies/torch_dist.SavePlanCache``); access-integrity validation (another
+    all-gather of every shard's metadata) is then also done only on a cache miss."""
     checkpoint_dir = Path(checkpoint_dir)
     if _rank() == 0:
         checkpoint_dir.mkdir(parents=True, exist_ok=True)
@@ -62,7 +65,8 @@ def save(sharded_state_dict: ShardedStateDict, checkpoint_dir: str, sharded_stra
     apply_factories(sharded)
     if sharded_strategy is not None and hasattr(sharded_strategy, "apply_saving_parallelization"):
         sharded_strategy.apply_saving_parallelization(sharded)
-    if validate_access_integrity:
+    plan_cache = torch_dist.get_plan_cache(process_group) if cached_structure else None
+    if validate_access_integrity and (plan_cache is None or plan_cache.fingerprint is None):
         validate_sharding_integrity(sharded, process_group)
     tensors = [s for s in nested_values(sharded) if isinstance(s, ShardedTensor)]
     objects = [s for s in nested_values(sharded) if isinstance(s, ShardedObject)]
@@ -75,7 +79,11 @@ def save(sharded_state_dict: ShardedStateDict, checkpoint_dir: str, sharded_stra
             save_config(CheckpointingConfig("torch_dist", 1), str(checkpoint_dir))
 
     if not async_sharded_save:
-        torch_dist.save_sharded(tensors, objects, str(checkpoint_dir), process_group)
+        if plan_cache is not None:
+            final_plan, payloads, metadata = torch_dist.plan_save(tensors, objects, str(checkpoint_dir), process_group, cache=plan_cache)
+            torch_dist.commit_save(torch_dist.write_planned(final_plan, payloads, str(checkpoint_dir)), metadata, str(checkpoint_dir), process_group)
+        else:
+            torch_dist.save_sharded(tensors, objects, str(checkpoint_dir), process_group)
         write_common_and_config()
         _barrier(process_group)
         return None
@@ -83,7 +91,7 @@ def save(sharded_state_dict: ShardedStateDict, checkpoint_dir: str, sharded_stra
         # collective planning + host staging now; file writing in the persistent worker process; metadata commit at finalize (collective)
         from .strategies.async_utils import ProcessAsyncRequest
 
-        final_plan, payloads, metadata = torch_dist.plan_save(tensors, objects, str(checkpoint_dir), process_group)
+        final_plan, payloads, metadata = torch_dist.plan_save(tensors, objects, str(checkpoint_dir), process_group, cache=plan_cache)
 
         def commit(results):
             torch_dist.commit_save(results, metadata, str(checkpoint_dir), process_group)

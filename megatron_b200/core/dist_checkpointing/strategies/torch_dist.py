@@ -9,7 +9,7 @@ from the ``(global_shape, global_offset, local_shape)`` triplet of each mcore Sh
 from __future__ import annotations
 
 import io
-from typing import Any, Dict, List, Tuple
+from typing import Optional, Any, Dict, List, Tuple
 
 import torch
 import torch.distributed as dist
@@ -184,9 +184,66 @@ class _ResolvedPlanner(DefaultSavePlanner):
         return io.BytesIO(d) if isinstance(d, (bytes, bytearray)) else d
 
 
-def plan_save(sharded_tensors: List[ShardedTensor], sharded_objects: List[ShardedObject], checkpoint_dir: str, process_group=None):
+class SavePlanCache:
+    """Save plans survive from one checkpoint to the next (reference ``strategies/torch.py:700-790``: cached central plan / local plan / global metadata).
+
+    The expensive part of planning is collective: every rank's local plan is pickled to the coordinator, merged, de-duplicated and scattered back.  A training
+    run saves the SAME structure every time, so each rank fingerprints its local plan (keys, offsets, shapes, dtypes, object keys); if every rank's fingerprint
+    matches its cached one — agreed with ONE integer all-reduce — the cached final plan and (on the coordinator) the cached global metadata are reused."""
+
+    def __init__(self):
+        self.fingerprint = None
+        self.final_plan = None
+        self.metadata = None
+        self.hits = 0
+        self.misses = 0
+
+    @staticmethod
+    def fingerprint_of(local_plan) -> int:
+        import hashlib
+
+        h = hashlib.sha1()
+        for it in local_plan.items:
+            idx = it.index
+            h.update(repr((idx.fqn, tuple(idx.offset) if idx.offset is not None else None, int(it.type.value) if hasattr(it.type, "value") else str(it.type))).encode())
+            td = getattr(it, "tensor_data", None)
+            if td is not None:
+                h.update(repr((tuple(td.size), str(td.properties.dtype), tuple(td.chunk.offsets), tuple(td.chunk.sizes))).encode())
+        return int.from_bytes(h.digest()[:7], "little")
+
+    def lookup(self, fp: int, process_group, no_dist: bool) -> bool:
+        mine = self.fingerprint is not None and self.fingerprint == fp
+        if no_dist:
+            ok = mine
+        else:
+            dev = "cuda" if dist.get_backend(process_group) == "nccl" else "cpu"
+            t = torch.tensor([1 if mine else 0], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=process_group)
+            ok = bool(t.item())
+        if ok:
+            self.hits += 1
+        else:
+            self.misses += 1
+        return ok
+
+    def store(self, fp: int, final_plan, metadata) -> None:
+        self.fingerprint, self.final_plan, self.metadata = fp, final_plan, metadata
+
+
+_PLAN_CACHES: Dict[Any, SavePlanCache] = {}
+
+
+def get_plan_cache(process_group=None) -> SavePlanCache:
+    """One cache per process group (``None`` = the world)."""
+    return _PLAN_CACHES.setdefault(id(process_group) if process_group is not None else None, SavePlanCache())
+
+
+def plan_save(sharded_tensors: List[ShardedTensor], sharded_objects: List[ShardedObject], checkpoint_dir: str, process_group=None, cache: Optional[SavePlanCache] = None):
     """Collective planning.  Returns ``(final_plan, payloads, global_metadata_or_None)``; payload tensors are host copies (shared memory), detached from the
-    training state, so training may overwrite the originals as soon as this returns."""
+    training state, so training may overwrite the originals as soon as this returns.  With ``cache`` an unchanged structure skips the plan gather / merge /
+    scatter (see ``SavePlanCache``)."""
+    import copy
+
     no_dist = _no_dist(process_group)
     planner = MCoreSavePlanner(sharded_tensors, sharded_objects)
     writer = FileSystemWriter(checkpoint_dir, sync_files=False)
@@ -196,22 +253,28 @@ def plan_save(sharded_tensors: List[ShardedTensor], sharded_objects: List[Sharde
     planner.set_up_planner({}, None, coordinator)
     writer.set_up_storage_writer(coordinator)
     local_plan = writer.prepare_local_plan(planner.create_local_plan())
-    if no_dist:
-        plans = [local_plan]
+    fp = SavePlanCache.fingerprint_of(local_plan) if cache is not None else None
+    if cache is not None and cache.lookup(fp, process_group, no_dist):
+        final_plan, metadata = cache.final_plan, (copy.deepcopy(cache.metadata) if cache.metadata is not None else None)
     else:
-        plans = [None] * world
-        dist.all_gather_object(plans, local_plan, group=process_group)
-    metadata = None
-    if coordinator:
-        plans, metadata = planner.create_global_plan(plans)
-        plans = writer.prepare_global_plan(plans)
-    if no_dist:
-        final_plan = plans[0]
-    else:
-        out = [None]
-        dist.scatter_object_list(out, plans if coordinator else None, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
-        final_plan = out[0]
-    final_plan = planner.finish_plan(final_plan)
+        if no_dist:
+            plans = [local_plan]
+        else:
+            plans = [None] * world
+            dist.all_gather_object(plans, local_plan, group=process_group)
+        metadata = None
+        if coordinator:
+            plans, metadata = planner.create_global_plan(plans)
+            plans = writer.prepare_global_plan(plans)
+        if no_dist:
+            final_plan = plans[0]
+        else:
+            out = [None]
+            dist.scatter_object_list(out, plans if coordinator else None, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
+            final_plan = out[0]
+        final_plan = planner.finish_plan(final_plan)
+        if cache is not None:
+            cache.store(fp, final_plan, copy.deepcopy(metadata) if metadata is not None else None)
     payloads: Dict[MetadataIndex, Any] = {}
     for item in final_plan.items:
         data = planner.resolve_data(item)

@@ -115,6 +115,18 @@ def build_parser() -> argparse.ArgumentParser:
     g.add_argument("--ckpt-fully-parallel-save", action="store_true", default=True)
     g.add_argument("--dist-ckpt-optim-fully-reshardable", action="store_true", default=True)
     g.add_argument("--keep-last-checkpoints", type=int, default=None)
+    g.add_argument("--ckpt-assume-constant-structure", action="store_true", help="reuse the previous save's plan and metadata when the checkpoint structure did not change")
+    g.add_argument("--ckpt-fully-parallel-load", action="store_true", help="each DP-replicated shard is read from storage once per dp-cp group and exchanged")
+    g.add_argument("--dist-ckpt-strictness", default="assume_ok_unexpected",
+                   choices=["assume_ok_unexpected", "log_unexpected", "log_all", "raise_unexpected", "raise_all", "return_unexpected", "return_all", "ignore_all"])
+    g.add_argument("--ckpt-step", type=int, default=None, help="load this iteration instead of the newest one")
+    g.add_argument("--exit-on-missing-checkpoint", action="store_true", help="with --load set and nothing to load: exit instead of training from scratch")
+    g.add_argument("--pretrained-checkpoint", default=None, help="weights to start from when --load holds no checkpoint (finetuning)")
+    g.add_argument("--no-save-rng", action="store_true")
+    g.add_argument("--non-persistent-ckpt-type", default=None, choices=["global", "local", "in_memory"], help="kind of the frequent recovery checkpoint")
+    g.add_argument("--non-persistent-global-ckpt-dir", default=None)
+    g.add_argument("--non-persistent-local-ckpt-algo", default="fully_parallel", choices=["fully_parallel", "atomic"])
+    g.add_argument("--use-persistent-ckpt-worker", action="store_true", default=True, help="async saves write from one long-lived worker process (default)")
 
     g = p.add_argument_group("mixed precision")
     g.add_argument("--fp16", action="store_true")

@@ -93,9 +93,11 @@ def generate_state_dict(args: Dict[str, Any], model: List, optimizer, opt_param_
 
 def save_checkpoint(iteration: int, model: List, optimizer, opt_param_scheduler, save_dir: str, args: Optional[Dict[str, Any]] = None,
                     num_floating_point_operations_so_far: float = 0.0, async_save: bool = False, fully_parallel_save: bool = True,
-                    keep_last: Optional[int] = None, rerun_state=None, optim_sharding_type: str = "fully_reshardable"):
+                    keep_last: Optional[int] = None, rerun_state=None, optim_sharding_type: str = "fully_reshardable",
+                    assume_constant_structure: bool = False):
     """Collective over all ranks.  Returns after the checkpoint is durable (or, with ``async_save``,
-    after staging; call ``maybe_finalize_async_save`` from the training loop)."""
+    after staging; call ``maybe_finalize_async_save`` from the training loop).  ``assume_constant_structure`` (``--ckpt-assume-constant-structure``): reuse the
+    previous save's plan / metadata when nothing changed structurally (dist_checkpointing SavePlanCache)."""
     ckpt = get_checkpoint_name(save_dir, iteration)
     if _rank() == 0:
         os.makedirs(save_dir, exist_ok=True)
@@ -116,7 +118,7 @@ def save_checkpoint(iteration: int, model: List, optimizer, opt_param_scheduler,
             if keep_last:
                 _cleanup_old(save_dir, keep_last)
 
-    req = dist_checkpointing.save(sd, ckpt, sharded_strategy=strategy, async_sharded_save=async_save)
+    req = dist_checkpointing.save(sd, ckpt, sharded_strategy=strategy, async_sharded_save=async_save, cached_structure=assume_constant_structure)
     if req is not None:
         req.add_finalize_fn(write_tracker)
         _ASYNC_QUEUE.schedule_async_request(req)
@@ -138,9 +140,12 @@ def _cleanup_old(save_dir: str, keep_last: int):
 
 
 def load_checkpoint(model: List, optimizer, opt_param_scheduler, load_dir: str, iteration: Optional[int] = None, load_optim: bool = True,
-                    load_rng: bool = True, strict: bool = True, optim_sharding_type: Optional[str] = None) -> Tuple[int, float]:
+                    load_rng: bool = True, strict: bool = True, optim_sharding_type: Optional[str] = None, fully_parallel_load: bool = False,
+                    dist_ckpt_strictness: Optional[str] = None) -> Tuple[int, float]:
     """Returns ``(iteration, num_floating_point_operations_so_far)``; (0, 0) when nothing to load.
-    TP/PP/DP may differ from the run that saved (resharding happens in ``dist_checkpointing.load``)."""
+    TP/PP/DP may differ from the run that saved (resharding happens in ``dist_checkpointing.load``).  ``fully_parallel_load`` (``--ckpt-fully-parallel-load``):
+    every DP-replicated shard is read from storage by ONE rank of the dp-cp group and exchanged; ``dist_ckpt_strictness``: how key mismatches between the
+    checkpoint and the model are treated (``--dist-ckpt-strictness``, the StrictHandling values)."""
     tracker = get_checkpoint_tracker_filename(load_dir)
     if iteration is None:
         if not os.path.isfile(tracker):
@@ -157,7 +162,18 @@ def load_checkpoint(model: List, optimizer, opt_param_scheduler, load_dir: str, 
         sd.pop("rng_state", None)
     elif common_rng_shape_changed(ckpt, sd):
         sd.pop("rng_state", None)  # parallel layout changed: RNG streams cannot be mapped
-    loaded = dist_checkpointing.load(sd, ckpt)
+    kw = {}
+    if fully_parallel_load and ps.is_initialized() and ps.get_data_parallel_world_size(with_context_parallel=True) > 1:
+        from ..core.dist_checkpointing.strategies.fully_parallel import FullyParallelLoadStrategyWrapper
+
+        kw["sharded_strategy"] = FullyParallelLoadStrategyWrapper(None, ps.get_data_parallel_group(with_context_parallel=True))
+    if dist_ckpt_strictness is not None:
+        kw["strict"] = dist_ckpt_strictness
+    loaded = dist_checkpointing.load(sd, ckpt, **kw)
+    if isinstance(loaded, tuple):            # strictness modes that return the mismatching keys
+        loaded, missing, unexpected = loaded
+        if _rank() == 0 and (missing or unexpected):
+            print(f" > checkpoint key mismatch: {len(missing)} missing, {len(unexpected)} unexpected", flush=True)
     for i, m in enumerate(model):
         key = "model" if len(model) == 1 else f"model{i}"
         m.load_state_dict(loaded[key], strict=strict)
@@ -295,3 +311,118 @@ def load_local_checkpoint(model: List, optimizer, opt_param_scheduler, local_dir
         except Exception:
             pass
     return it
+
+
+# ---- non-persistent checkpoints (reference checkpointing.py:513, 1834-1905: CheckpointType.GLOBAL / LOCAL, ``--non-persistent-ckpt-type``) ------------------------
+_IN_MEMORY: Dict[str, Any] = {}
+
+
+def _host_copy(obj):
+    if isinstance(obj, torch.Tensor):
+        return obj.detach().to("cpu", copy=True)
+    if isinstance(obj, dict):
+        return {k: _host_copy(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_host_copy(v) for v in obj)
+    return obj
+
+
+def save_non_persistent_checkpoint(iteration: int, model: List, optimizer, opt_param_scheduler, kind: str, save_dir: Optional[str] = None, global_dir: Optional[str] = None,
+                                   local_dir: Optional[str] = None, args: Optional[Dict[str, Any]] = None, num_floating_point_operations_so_far: float = 0.0,
+                                   async_save: bool = False, local_algo: str = "fully_parallel") -> Optional[str]:
+    """A frequent recovery point that is NOT part of the persistent series: only the newest one is kept.
+
+    * ``global``: a regular (resharding-capable) distributed checkpoint under ``global_dir`` (default ``<save>/non_persistent``) with its own tracker file;
+    * ``local``: every rank dumps its own shards to node-local storage (``save_local_checkpoint``; ``local_algo='fully_parallel'`` additionally replicates each
+      blob to the next rank so that a replaced node can be refilled, ``'atomic'`` does not);
+    * ``in_memory``: a host copy kept in this process (survives an in-process restart, see ``inprocess_restart.py``)."""
+    if kind == "global":
+        d = global_dir or os.path.join(save_dir, "non_persistent")
+        return save_checkpoint(iteration, model, optimizer, opt_param_scheduler, d, args, num_floating_point_operations_so_far, async_save=async_save, keep_last=1,
+                               assume_constant_structure=True)
+    if kind == "local":
+        assert local_dir, "--non-persistent-local-ckpt-dir is required for local non-persistent checkpoints"
+        return save_local_checkpoint(iteration, model, optimizer, opt_param_scheduler, local_dir, replicate_to_buddy=local_algo == "fully_parallel")
+    if kind == "in_memory":
+        _IN_MEMORY.clear()
+        _IN_MEMORY.update(iteration=iteration, model=[_host_copy(m.state_dict()) for m in model],
+                          optimizer=_host_copy(optimizer.state_dict()) if optimizer is not None and hasattr(optimizer, "state_dict") else None,
+                          opt_param_scheduler=opt_param_scheduler.state_dict() if opt_param_scheduler is not None else None,
+                          flops=num_floating_point_operations_so_far, rng=get_rng_state().data[0] if hasattr(get_rng_state(), "data") else None)
+        return "in_memory"
+    raise ValueError(f"unknown non-persistent checkpoint type {kind!r} (global | local | in_memory)")
+
+
+def load_in_memory_checkpoint(model: List, optimizer, opt_param_scheduler) -> Tuple[int, float]:
+    if not _IN_MEMORY:
+        return -1, 0.0
+    for m, sd in zip(model, _IN_MEMORY["model"]):
+        m.load_state_dict(sd)
+    if optimizer is not None and _IN_MEMORY.get("optimizer") is not None:
+        optimizer.load_state_dict(_IN_MEMORY["optimizer"])
+    if opt_param_scheduler is not None and _IN_MEMORY.get("opt_param_scheduler") is not None:
+        opt_param_scheduler.load_state_dict(_IN_MEMORY["opt_param_scheduler"])
+    if _IN_MEMORY.get("rng") is not None:
+        try:
+            set_rng_state(_IN_MEMORY["rng"])
+        except Exception:
+            pass
+    return int(_IN_MEMORY["iteration"]), float(_IN_MEMORY["flops"])
+
+
+def _latest_iteration(ckpt_root: Optional[str]) -> int:
+    if not ckpt_root:
+        return -1
+    t = get_checkpoint_tracker_filename(ckpt_root)
+    if not os.path.isfile(t):
+        return -1
+    it, release = read_metadata(t)
+    return -1 if release else it
+
+
+def load_latest_checkpoint(model: List, optimizer, opt_param_scheduler, load_dir: Optional[str], non_persistent_global_dir: Optional[str] = None,
+                           non_persistent_local_dir: Optional[str] = None, pretrained_checkpoint: Optional[str] = None, ckpt_step: Optional[int] = None,
+                           exit_on_missing_checkpoint: bool = False, **load_kw) -> Tuple[int, float, str]:
+    """The reference's start-up policy (``_load_base_checkpoint``, checkpointing.py:1230-1330): among the persistent series in ``load_dir``, the non-persistent
+    global checkpoint and the node-local one, resume from the NEWEST iteration (all ranks agree on it); with nothing to resume from, fall back to
+    ``pretrained_checkpoint`` (weights only, iteration 0).  → ``(iteration, flops, source)`` with source in persistent | non_persistent_global | local |
+    in_memory | pretrained | none."""
+    cands = []
+    if ckpt_step is not None:
+        cands.append((ckpt_step, "persistent"))
+    else:
+        cands.append((_latest_iteration(load_dir), "persistent"))
+        ng = non_persistent_global_dir or (os.path.join(load_dir, "non_persistent") if load_dir else None)
+        cands.append((_latest_iteration(ng), "non_persistent_global"))
+        if non_persistent_local_dir:
+            cands.append((find_latest_local_checkpoint(non_persistent_local_dir), "local"))
+        if _IN_MEMORY:
+            cands.append((int(_IN_MEMORY["iteration"]), "in_memory"))
+    it, src = max(cands, key=lambda c: c[0])
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        # filesystem views can differ between nodes: agree on rank 0's choice
+        box = [(it, src)]
+        dist.broadcast_object_list(box, src=0)
+        it, src = box[0]
+    if it < 0:
+        if pretrained_checkpoint:
+            kw = dict(load_kw)
+            kw.update(load_optim=False, load_rng=False)
+            _, fl = load_checkpoint(model, None, None, pretrained_checkpoint, **kw)
+            return 0, 0.0, "pretrained"
+        if exit_on_missing_checkpoint:
+            if _rank() == 0:
+                print(">> '--exit-on-missing-checkpoint' set, and no checkpoint found: exiting", flush=True)
+            if dist.is_initialized():
+                dist.barrier()
+            raise SystemExit(0)
+        return 0, 0.0, "none"
+    if src == "persistent":
+        i, fl = load_checkpoint(model, optimizer, opt_param_scheduler, load_dir, iteration=it if ckpt_step is not None else None, **load_kw)
+    elif src == "non_persistent_global":
+        i, fl = load_checkpoint(model, optimizer, opt_param_scheduler, non_persistent_global_dir or os.path.join(load_dir, "non_persistent"), **load_kw)
+    elif src == "local":
+        i, fl = load_local_checkpoint(model, optimizer, opt_param_scheduler, non_persistent_local_dir, iteration=it), 0.0
+    else:
+        i, fl = load_in_memory_checkpoint(model, optimizer, opt_param_scheduler)
+    return i, fl, src

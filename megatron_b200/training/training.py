@@ -187,12 +187,15 @@ def setup_model_and_optimizer(model_provider_func: Callable):
     optimizer = get_megatron_optimizer(opt_cfg, model)
     scheduler = get_optimizer_param_scheduler(optimizer)
     args.iteration, args.num_floating_point_operations_so_far = 0, 0.0
-    if args.load:
-        it, fl = checkpointing.load_checkpoint(model, optimizer, scheduler, args.load, load_optim=not (args.no_load_optim or args.finetune),
-                                               load_rng=not (args.no_load_rng or args.finetune))
+    if args.load or getattr(args, "pretrained_checkpoint", None):
+        it, fl, src = checkpointing.load_latest_checkpoint(
+            model, optimizer, scheduler, args.load, getattr(args, "non_persistent_global_ckpt_dir", None), getattr(args, "non_persistent_local_ckpt_dir", None),
+            getattr(args, "pretrained_checkpoint", None), getattr(args, "ckpt_step", None), getattr(args, "exit_on_missing_checkpoint", False),
+            load_optim=not (args.no_load_optim or args.finetune), load_rng=not (args.no_load_rng or args.finetune),
+            fully_parallel_load=getattr(args, "ckpt_fully_parallel_load", False), dist_ckpt_strictness=getattr(args, "dist_ckpt_strictness", None))
         args.iteration = 0 if args.finetune else it
         args.num_floating_point_operations_so_far = fl
-        print_rank_0(f" > loaded checkpoint from {args.load} at iteration {it}")
+        print_rank_0(f" > loaded {src} checkpoint (from {args.load}) at iteration {it}")
     return model, optimizer, scheduler
 
 
@@ -401,12 +404,17 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
         if args.manual_gc and args.manual_gc_interval and iteration % args.manual_gc_interval == 0:
             gc.collect()
         checkpointing.maybe_finalize_async_save(blocking=False)
-        if getattr(args, "non_persistent_save_interval", None) and getattr(args, "non_persistent_local_ckpt_dir", None) and iteration % args.non_persistent_save_interval == 0:
-            checkpointing.save_local_checkpoint(iteration, model, optimizer, opt_param_scheduler, args.non_persistent_local_ckpt_dir, replicate_to_buddy=True)
+        if getattr(args, "non_persistent_save_interval", None) and iteration % args.non_persistent_save_interval == 0:
+            kind = getattr(args, "non_persistent_ckpt_type", None) or ("local" if getattr(args, "non_persistent_local_ckpt_dir", None) else None)
+            if kind is not None:
+                checkpointing.save_non_persistent_checkpoint(iteration, model, optimizer, opt_param_scheduler, kind, args.save, getattr(args, "non_persistent_global_ckpt_dir", None),
+                                                             getattr(args, "non_persistent_local_ckpt_dir", None), vars_for_ckpt(args), args.num_floating_point_operations_so_far,
+                                                             async_save=args.async_save, local_algo=getattr(args, "non_persistent_local_ckpt_algo", "fully_parallel"))
         saved = False
         if args.save and args.save_interval and iteration % args.save_interval == 0:
             checkpointing.save_checkpoint(iteration, model, optimizer if not args.no_save_optim else None, opt_param_scheduler, args.save, vars_for_ckpt(args),
-                                          args.num_floating_point_operations_so_far, async_save=args.async_save, keep_last=args.keep_last_checkpoints)
+                                          args.num_floating_point_operations_so_far, async_save=args.async_save, keep_last=args.keep_last_checkpoints,
+                                          assume_constant_structure=getattr(args, 'ckpt_assume_constant_structure', False))
             saved = True
         stop = exit_flag["sig"] or (args.exit_interval and iteration % args.exit_interval == 0) or \
             (args.exit_duration_in_mins and (time.time() - t_start) / 60.0 > args.exit_duration_in_mins)

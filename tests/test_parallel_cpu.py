@@ -421,3 +421,97 @@ def test_fully_parallel_load_reads_each_shard_once(tmp_path):
     d = tmp_path / "ck"
     d.mkdir()
     assert all(run_distributed(_fully_parallel_load_worker, 4, str(d)))
+
+
+def _cached_plan_worker(rank, world, base):
+    """Three saves with `cached_structure`: the first plans collectively (miss), the second reuses the plan (hit) and still writes the NEW values, a save with a
+    changed structure on one rank falls back to full planning on every rank (miss) — and each checkpoint loads back correctly (sync and async-process paths)."""
+    import os
+
+    import torch
+
+    from megatron_b200.core import dist_checkpointing as dc
+    from megatron_b200.core.dist_checkpointing.mapping import ShardedObject, ShardedTensor
+    from megatron_b200.core.dist_checkpointing.strategies import torch_dist
+    from megatron_b200.core.dist_checkpointing.strategies.async_utils import AsyncCallsQueue, PersistentWriterProcess
+
+    def sd(step, extra=False):
+        w = torch.full((4, 6), float(step * 10 + rank))
+        out = {"w": ShardedTensor.from_rank_offsets("w", w, (0, rank, world)), "r": ShardedTensor.from_rank_offsets("r", torch.full((3,), float(step)), replica_id=rank),
+               "obj": ShardedObject("obj", {"step": step}, (1,), (0,), replica_id=rank), "iteration": step}
+        if extra:
+            out["new"] = ShardedTensor.from_rank_offsets("new", torch.full((2,), float(rank)), (0, rank, world))
+        return out
+
+    cache = torch_dist.get_plan_cache(None)
+    dirs = []
+    for step, extra, use_async in [(1, False, False), (2, False, False), (3, False, True), (4, True, False)]:
+        d = os.path.join(base, f"s{step}")
+        if rank == 0:
+            os.makedirs(d)
+        torch.distributed.barrier()
+        req = dc.save(sd(step, extra), d, cached_structure=True, async_sharded_save=use_async)
+        if use_async:
+            q = AsyncCallsQueue()
+            q.schedule_async_request(req)
+            q.maybe_finalize_async_calls(blocking=True)
+        dirs.append((step, extra, d))
+    assert (cache.misses, cache.hits) == (2, 2), (cache.misses, cache.hits)
+    for step, extra, d in dirs:
+        tmpl = {"w": ShardedTensor.from_rank_offsets("w", torch.zeros(4, 6), (0, rank, world)), "r": ShardedTensor.from_rank_offsets("r", torch.zeros(3), replica_id=rank),
+                "obj": ShardedObject("obj", None, (1,), (0,), replica_id=rank)}
+        if extra:
+            tmpl["new"] = ShardedTensor.from_rank_offsets("new", torch.zeros(2), (0, rank, world))
+        got = dc.load(tmpl, d)
+        assert torch.equal(got["w"], torch.full((4, 6), float(step * 10 + rank))) and torch.equal(got["r"], torch.full((3,), float(step))) and got["obj"] == {"step": step}
+        assert got["iteration"] == step and (not extra or torch.equal(got["new"], torch.full((2,), float(rank))))
+    PersistentWriterProcess.get().close()
+    return True
+
+
+def test_cached_save_plans(tmp_path):
+    from dist_utils import run_distributed
+
+    assert all(run_distributed(_cached_plan_worker, 2, str(tmp_path)))
+
+
+def _tensor_aware_worker(rank, world):
+    """Local-checkpoint container: pop → (pickle the hollow skeleton, ship the tensors) → refill → state dict; `fully_parallel` keeps DP-replicated tensors on
+    the first rank of the group only and re-broadcasts them, rank-private shards stay where they are."""
+    import pickle
+
+    import torch
+
+    from megatron_b200.core.dist_checkpointing.mapping import ShardedObject, ShardedTensor
+    from megatron_b200.core.dist_checkpointing.tensor_aware_state_dict import MCoreTensorAwareStateDict as TASD
+
+    def gen(fill):
+        return {"model": {"repl": ShardedTensor.from_rank_offsets("repl", torch.full((4, 3), fill), replica_id=(0, 0, rank)),
+                          "mine": ShardedTensor.from_rank_offsets("mine", torch.full((2,), fill + rank), (0, rank, world), replica_id=(0, 0, 0))},
+                "obj": ShardedObject("o", {"k": fill}, (1,), (0,), replica_id=rank), "iteration": 7}
+
+    for algo in ("atomic", "fully_parallel"):
+        t = TASD.from_state_dict(gen(5.0), algo=algo, parallelization_group=None)
+        n_stored = len(list(t.tensors))
+        assert n_stored == (2 if algo == "atomic" or rank == 0 else 1), (algo, rank, n_stored)
+        tensors = t.pop_tensors()
+        assert t.is_hollow
+        t2 = pickle.loads(pickle.dumps(t))
+        t2.init_tensors()
+        t2.insert_tensors([x.clone() for x in tensors])
+        t2.copy_tensors_to_cpu()
+        t2.restore_tensor_device()
+        sd = t2.to_state_dict(gen(0.0))
+        assert torch.equal(sd["model"]["repl"], torch.full((4, 3), 5.0)) and torch.equal(sd["model"]["mine"], torch.full((2,), 5.0 + rank))
+        assert sd["obj"] == {"k": 5.0} and sd["iteration"] == 7
+    try:
+        TASD.from_state_dict(gen(1.0), algo="two_stage")
+    except NotImplementedError:
+        return True
+    return False
+
+
+def test_tensor_aware_state_dict_local_checkpoint_container():
+    from dist_utils import run_distributed
+
+    assert all(run_distributed(_tensor_aware_worker, 2))

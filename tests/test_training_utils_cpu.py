@@ -248,6 +248,32 @@ def test_pretrain_cli_writers_ft_activation_logs_and_resume(tmp_path):
     assert "iteration        6/" in out2 and "iteration        2/" not in out2
 
 
+def test_pretrain_cli_non_persistent_checkpoints_and_load_policy(tmp_path):
+    """--non-persistent-ckpt-type global: a recovery checkpoint every 2 iterations beside the persistent series (every 4, cached save plans); the restart resumes
+    from the NEWEST of the two (iteration 6, non-persistent), then a fresh run elsewhere starts from it as --pretrained-checkpoint weights at iteration 0."""
+    common = ["--non-persistent-save-interval", "2", "--non-persistent-ckpt-type", "global", "--ckpt-assume-constant-structure", "--ckpt-fully-parallel-load",
+              "--dist-ckpt-strictness", "log_all"]
+    out = _run_pretrain(tmp_path, common + ["--exit-interval", "6"], iters=8)
+    assert "iteration        6/" in out and "iteration        8/" not in out
+    np_dir = tmp_path / "ckpt" / "non_persistent"
+    assert (np_dir / "latest_checkpointed_iteration.txt").read_text().strip() == "6"
+    assert sorted(d for d in os.listdir(np_dir) if d.startswith("iter_")) == ["iter_0000006"]                   # only the newest is kept
+    # exit at 6 also wrote the persistent series' iteration 6; remove it so that the non-persistent one is strictly newer
+    import shutil
+
+    shutil.rmtree(tmp_path / "ckpt" / "iter_0000006")
+    (tmp_path / "ckpt" / "latest_checkpointed_iteration.txt").write_text("4")
+    out2 = _run_pretrain(tmp_path, common, iters=8)
+    assert "loaded non_persistent_global checkpoint" in out2 and "at iteration 6" in out2 and "iteration        8/" in out2 and "iteration        6/" not in out2
+    # finetune-style start from pretrained weights: nothing in --load, iteration restarts at 0
+    ft = tmp_path / "ft"
+    out3 = _run_pretrain(ft, ["--pretrained-checkpoint", str(tmp_path / "ckpt"), "--exit-interval", "2"], iters=4)
+    assert "loaded pretrained checkpoint" in out3 and "iteration        2/" in out3
+    # --exit-on-missing-checkpoint
+    out4 = _run_pretrain(tmp_path / "none", ["--exit-on-missing-checkpoint"], iters=2)
+    assert "no checkpoint found" in out4 and "iteration        2/" not in out4
+
+
 def test_config_logger_initialize_helpers_and_param_norm(tmp_path):
     from types import SimpleNamespace
 
