@@ -28,7 +28,8 @@ class InferenceRequest:
     sampling_params: SamplingParams = field(default_factory=SamplingParams)
     generated_tokens: List[int] = field(default_factory=list)
     log_probs: List[float] = field(default_factory=list)
-    status: str = "waiting"  # waiting | running | finished
+    status: str = "waiting"  # waiting | prefilling (chunked prefill under way) | running | finished
+    prefill_pos: int = 0     # prompt tokens whose K/V are in the cache
     arrival_time: float = field(default_factory=time.time)
     first_token_time: Optional[float] = None
     finish_time: Optional[float] = None
@@ -91,8 +92,13 @@ class DynamicInferenceEngine:
 
     def __init__(self, model, num_blocks: int = 256, block_size: int = 16, max_running: int = 16, vocab_size: Optional[int] = None,
                  batched_decode: Optional[bool] = None, enable_prefix_caching: bool = False, decode_batch_buckets: Optional[List[int]] = None,
-                 enable_cuda_graphs: bool = False):
+                 enable_cuda_graphs: bool = False, max_prefill_tokens_per_step: Optional[int] = None):
         self.model = model
+        # Chunked prefill (reference dynamic_context.py / dynamic_engine.py: ``max_tokens`` per step + chunked-prefill requests): a step spends at most this many
+        # prompt tokens on prefill, so a long prompt is spread over several steps while the running requests keep producing one token per step (bounded
+        # inter-token latency).  A partially prefilled request holds its pages, sits in ``running`` with status "prefilling" and emits nothing yet.
+        self.max_prefill_tokens_per_step = max_prefill_tokens_per_step
+        self.prefill_chunks = 0
         # CUDA-graphed decode (reference dynamic_engine.py: cuda-graph batch-size buckets): one captured graph per (batch bucket, attended-length bucket, table
         # width); a step copies the block table / positions / last tokens into the graph's static tensors and replays it — the ~500 kernel launches of an
         # eager decode step (16 ms of host time on an 8B model) collapse into one.  Needs static shapes, hence the buckets.
@@ -236,23 +242,43 @@ class DynamicInferenceEngine:
         self.model.eval()
         newly_finished: List[InferenceRequest] = []
         admitted: List[InferenceRequest] = []
-        while self.waiting and len(self.running) < self.max_running:
+        budget = self.max_prefill_tokens_per_step if self.max_prefill_tokens_per_step else float("inf")
+
+        def prefill_some(req: InferenceRequest) -> None:
+            """Run the next chunk of ``req``'s prompt (all of it when the budget allows); the first token is emitted with the last chunk."""
+            nonlocal budget
+            n_prompt = len(req.prompt_tokens)
+            take = int(min(n_prompt - req.prefill_pos, budget))
+            if take <= 0:
+                return
+            start = req.prefill_pos
+            logits = self._forward_request(req, req.prompt_tokens[start:start + take], start)
+            req.prefill_pos += take
+            budget -= take
+            self.prefill_tokens += take
+            self.prefill_chunks += 1
+            if req.prefill_pos >= n_prompt:
+                req.status = "running"
+                self.cache.register_prefix(req.request_id, req.prompt_tokens)
+                self._emit(req, logits)
+            admitted.append(req)                                       # no decode for it in this step
+
+        for req in self.running:                                       # 1. chunked prefills under way, oldest first
+            if req.status == "prefilling" and budget > 0:
+                prefill_some(req)
+        while self.waiting and len(self.running) < self.max_running and budget > 0:      # 2. admissions
             req = self.waiting[0]
             need = len(req.prompt_tokens) + req.sampling_params.num_tokens_to_generate
             if not self.cache.can_admit(need) or not self.cache.add_request(req.request_id, len(req.prompt_tokens), req.prompt_tokens):
                 break
             self.waiting.popleft()
-            req.status = "running"
-            hit = self.cache.prefix_hit_tokens.get(req.request_id, 0)       # leading tokens whose K/V are already cached
-            self.prefill_tokens += len(req.prompt_tokens) - hit
-            logits = self._forward_request(req, req.prompt_tokens[hit:], hit)  # prefill (of the uncached tail)
-            self.cache.register_prefix(req.request_id, req.prompt_tokens)
-            self._emit(req, logits)
+            req.status = "prefilling"
+            req.prefill_pos = self.cache.prefix_hit_tokens.get(req.request_id, 0)       # leading tokens whose K/V are already cached
             self.running.append(req)
-            admitted.append(req)
+            prefill_some(req)
         ready = []
         for req in list(self.running):
-            if req.status == "finished" or req in admitted:
+            if req.status in ("finished", "prefilling") or req in admitted:
                 continue
             if len(req.generated_tokens) >= req.sampling_params.num_tokens_to_generate:
                 continue
@@ -268,6 +294,8 @@ class DynamicInferenceEngine:
                 self._emit(req, logits)
         for req in list(self.running):
             sp = req.sampling_params
+            if req.status == "prefilling":
+                continue
             if len(req.generated_tokens) >= sp.num_tokens_to_generate or (req.generated_tokens and req.generated_tokens[-1] in sp.stop_token_ids):
                 req.status, req.finish_time = "finished", time.time()
                 self.cache.release(req.request_id)

@@ -292,6 +292,21 @@ def _batched_decode(rank, world):
     assert [fin[i].generated_tokens for i in ids] == want
     assert {b for b, _ in e.decode_shapes_seen} <= {2, 4} and all(L % 16 == 0 for _, L in e.decode_shapes_seen) and len(e.decode_shapes_seen) <= 4
     assert e.cache.allocator.num_free == 63                      # everything released except the scratch block
+    # chunked prefill: at most 4 prompt tokens per step — the 11-token prompt takes 3 steps, during which the already running requests keep decoding;
+    # tokens are identical, and the first token of the long prompt comes out only with its last chunk
+    e = DynamicInferenceEngine(model, num_blocks=64, block_size=4, max_running=4, vocab_size=96, max_prefill_tokens_per_step=4)
+    order = [1, 3, 0, 2, 4]                                       # short prompts first so that decodes are running while the long one prefills
+    ids = {i: e.add_request(prompts[i], SamplingParams(temperature=0.0, num_tokens_to_generate=gens[i])) for i in order}
+    seen_prefilling_while_decoding = False
+    while e.has_unfinished():
+        e.step()
+        pre = [r for r in e.running if r.status == "prefilling"]
+        if pre and e.decode_forwards > 0:
+            seen_prefilling_while_decoding = True
+            assert all(not r.generated_tokens and 0 < r.prefill_pos < len(r.prompt_tokens) for r in pre)
+    assert [e.finished[ids[i]].generated_tokens for i in range(5)] == want
+    assert seen_prefilling_while_decoding and e.prefill_chunks >= 3 + 1 + 2 + 1 + 3 - 2 and e.prefill_tokens == sum(len(p) for p in prompts)
+    assert e.cache.allocator.num_free == 64
     return True
 
 
@@ -355,3 +370,63 @@ def _prefix_cache(rank, world):
 
 def test_prefix_caching_reuses_blocks_and_matches_uncached_generation():
     run_distributed(_prefix_cache, 1)
+
+
+def _zmq_serving(rank, world):
+    import socket
+    import time
+
+    import torch.nn.functional as F
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.inference.engine import DynamicInferenceEngine, StaticInferenceEngine
+    from megatron_b200.core.inference.sampling import SamplingParams
+    from megatron_b200.core.inference.zmq_coordinator import ZMQInferenceClient, start_in_threads
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    ps.initialize_model_parallel()
+
+    def build():
+        torch.manual_seed(3)
+        cfg = TransformerConfig(num_layers=2, hidden_size=64, num_attention_heads=8, num_query_groups=2, ffn_hidden_size=128, gated_linear_unit=True, activation_func=F.silu,
+                                add_bias_linear=False, normalization="RMSNorm", **_KW)
+        return GPTModel(cfg, get_gpt_layer_local_spec(normalization="RMSNorm"), vocab_size=96, max_sequence_length=128, position_embedding_type="rope").eval()
+
+    models = [build(), build()]                                   # two data-parallel replicas (same weights), one engine + one worker thread each
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    engines = [DynamicInferenceEngine(m, num_blocks=64, block_size=4, max_running=4, vocab_size=96) for m in models]
+    coord_thread, workers = start_in_threads(engines, port)
+    client = ZMQInferenceClient(port)
+    prompts = [[5, 17, 3, 42, 8, 1, 2, 7], [9, 9], [30, 31, 32, 33, 34], [1], [2, 3, 4, 5, 6, 7, 8, 9, 10], [4, 4, 4]]
+    sp = SamplingParams(temperature=0.0, num_tokens_to_generate=6, return_log_probs=True)
+    ref = StaticInferenceEngine(build(), max_sequence_length=128)
+    want = [ref.generate([p], SamplingParams(temperature=0.0, num_tokens_to_generate=6))[0] for p in prompts]
+    got = client.generate(prompts, sp)
+    assert got == want
+    st = client.stats()
+    assert sum(st["served"]) == 6 and min(st["served"]) >= 1 and st["outstanding_tokens"] == [0, 0]      # both replicas took work, nothing left outstanding
+    assert all(len(client.results[i]["log_probs"]) == 6 and client.results[i]["ttft"] is not None for i in range(6))
+    # pause: engines acknowledge and stop stepping; submitted work waits until unpause
+    client.pause_engines()
+    t0 = time.time()
+    while client.stats()["paused_acks"] < 2 and time.time() - t0 < 10:
+        time.sleep(0.02)
+    rid = client.submit([7, 8, 9], sp)
+    time.sleep(0.3)
+    assert rid not in client.results and not client.sock.poll(0)
+    client.unpause_engines()
+    assert client.collect([rid])[rid]["generated_tokens"] == ref.generate([[7, 8, 9]], SamplingParams(temperature=0.0, num_tokens_to_generate=6))[0]
+    client.stop()
+    coord_thread.join(10)
+    for w in workers:
+        w.join(10)
+    assert not coord_thread.is_alive() and not any(w.is_alive() for w in workers)
+    return True
+
+
+def test_zmq_coordinator_routes_between_data_parallel_engines():
+    run_distributed(_zmq_serving, 1)
