@@ -84,6 +84,131 @@ def merge_partials(outs: List[torch.Tensor], lses: List[torch.Tensor]) -> torch.
     return acc
 
 
+# ---- ring attention on block kernels --------------------------------------------------------------------------------------------------------------------
+# The ring is written against two block primitives so that the SAME schedule runs on the tcgen05 kernels (CUDA, bf16, head dim 128) and on a PyTorch
+# formulation (CPU tests, other shapes):
+#   block_fwd(q, k, v)                       -> (out, lse)          one (query chunk, key chunk) pair; chunks are aligned, so a pair is either fully visible
+#   block_bwd(go, q, k, v, out_final, lse_final) -> (dq, dk, dv)    (non-causal), the diagonal (causal, sq == sk) or invisible (skipped)
+# The backward of a pair uses the FINAL (merged) output and log-sum-exp of the query rows: P = exp(S - lse_final), dS = P o (dP - rowsum(dO o O_final)) — exactly
+# what our native backward kernels take as inputs, so no partial results are kept from the forward.
+
+
+def _native_block_ok(q, k) -> bool:
+    from .. import ops
+
+    return (q.is_cuda and ops.has_ext() and hasattr(ops.ext(), "flash_attn_bwd") and q.dtype == torch.bfloat16 and q.shape[-1] == 128 and k.shape[-1] == 128
+            and q.shape[0] >= 128 and k.shape[0] >= 128 and q.shape[2] % k.shape[2] == 0)
+
+
+def block_fwd(q, k, v, scale: float, causal: bool):
+    """→ (out [sq, b, h, d] in q's dtype, lse [b, h, sq] fp32)."""
+    if _native_block_ok(q, k):
+        from .. import ops
+
+        o, lse = ops.ext().flash_attn_fwd(q, k, v, causal, scale, 1)
+        ops._count()
+        return o, lse
+    with torch.no_grad():
+        o, lse = attention_with_lse(q, k, v, scale, causal)
+    return o.to(q.dtype), lse
+
+
+def block_bwd(go, q, k, v, out_final, lse_final, scale: float, causal: bool):
+    """→ (dq, dk, dv) of one pair given the merged output / log-sum-exp of its query rows."""
+    if _native_block_ok(q, k):
+        from .. import ops
+
+        dq, dk, dv = ops.ext().flash_attn_bwd(go.contiguous(), q, k, v, out_final.contiguous(), lse_final.contiguous(), causal, scale, -1)
+        ops._count(3)
+        return dq, dk, dv
+    sq, b, hq, d = q.shape
+    sk, hk = k.shape[0], k.shape[2]
+    rep = hq // hk
+    qf, gof, of = (t.permute(1, 2, 0, 3).float() for t in (q, go, out_final))
+    kf, vf = k.permute(1, 2, 0, 3).float(), v.permute(1, 2, 0, 3).float()
+    if rep > 1:
+        kf, vf = kf.repeat_interleave(rep, dim=1), vf.repeat_interleave(rep, dim=1)
+    sc = torch.matmul(qf, kf.transpose(-1, -2)) * scale
+    if causal:
+        sc = sc.masked_fill(torch.ones(sq, sk, dtype=torch.bool, device=q.device).triu(1), float("-inf"))
+    pr = torch.exp(sc - lse_final.unsqueeze(-1))
+    dv = torch.matmul(pr.transpose(-1, -2), gof)
+    ds = pr * (torch.matmul(gof, vf.transpose(-1, -2)) - (gof * of).sum(-1, keepdim=True)) * scale
+    dq = torch.matmul(ds, kf)
+    dk = torch.matmul(ds.transpose(-1, -2), qf)
+    if rep > 1:
+        dk, dv = dk.view(b, hk, rep, sk, d).sum(2), dv.view(b, hk, rep, sk, v.shape[-1]).sum(2)
+    return dq.permute(2, 0, 1, 3).to(q.dtype), dk.permute(2, 0, 1, 3).to(k.dtype), dv.permute(2, 0, 1, 3).to(v.dtype)
+
+
+def _merge_into(acc_o, acc_l, o, l):
+    """Online-softmax merge of one more partial (o in any dtype, accumulators fp32)."""
+    if acc_o is None:
+        return o.float(), l.clone()
+    new_l = torch.logaddexp(acc_l, l)
+    wa, wb = torch.exp(acc_l - new_l).permute(2, 0, 1).unsqueeze(-1), torch.exp(l - new_l).permute(2, 0, 1).unsqueeze(-1)
+    return acc_o * wa + o.float() * wb, new_l
+
+
+class _RingAttnFn(torch.autograd.Function):
+    """Zig-zag ring attention: K/V blocks circulate (next hop in flight while the current block is used); in the backward dK/dV travel WITH their block and arrive
+    home after a full turn.  ``shift(x, reverse)`` moves a tensor one hop; ``rank`` / ``cp`` place the chunks."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, scale, causal, rank, cp, shift):
+        c = q.shape[0] // 2
+        my_offs = [rank * c, (2 * cp - 1 - rank) * c]
+        acc = [[None, None], [None, None]]
+        cur = torch.cat([k, v], dim=-1)
+        dk_ = k.shape[-1]
+        for step in range(cp):
+            src = (rank - step) % cp
+            nxt = shift(cur, False) if step < cp - 1 else None
+            src_offs = [src * c, (2 * cp - 1 - src) * c]
+            for qi, qoff in enumerate(my_offs):
+                for ki, koff in enumerate(src_offs):
+                    if causal and koff > qoff:
+                        continue
+                    o, l = block_fwd(q[qi * c:(qi + 1) * c], cur[ki * c:(ki + 1) * c, ..., :dk_], cur[ki * c:(ki + 1) * c, ..., dk_:], scale, causal and koff == qoff)
+                    acc[qi] = list(_merge_into(acc[qi][0], acc[qi][1], o, l))
+            cur = nxt
+        out = torch.cat([acc[0][0], acc[1][0]], dim=0).to(q.dtype)
+        lse = torch.cat([acc[0][1], acc[1][1]], dim=-1)                       # [b, h, 2c]
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.args = (scale, causal, rank, cp, shift)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        q, k, v, out, lse = ctx.saved_tensors
+        scale, causal, rank, cp, shift = ctx.args
+        c = q.shape[0] // 2
+        my_offs = [rank * c, (2 * cp - 1 - rank) * c]
+        go = go.contiguous()
+        dq = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
+        dk_ = k.shape[-1]
+        cur = torch.cat([k, v], dim=-1)
+        dcur = torch.zeros(cur.shape, dtype=torch.float32, device=q.device)     # gradient of the block currently held; travels with it
+        for step in range(cp):
+            src = (rank - step) % cp
+            nxt = shift(cur, False) if step < cp - 1 else None
+            src_offs = [src * c, (2 * cp - 1 - src) * c]
+            for qi, qoff in enumerate(my_offs):
+                qs = slice(qi * c, (qi + 1) * c)
+                for ki, koff in enumerate(src_offs):
+                    if causal and koff > qoff:
+                        continue
+                    ks = slice(ki * c, (ki + 1) * c)
+                    g_q, g_k, g_v = block_bwd(go[qs], q[qs], cur[ks][..., :dk_], cur[ks][..., dk_:], out[qs], lse[..., qs].contiguous(), scale, causal and koff == qoff)
+                    dq[qs] += g_q.float()
+                    dcur[ks, ..., :dk_] += g_k.float()
+                    dcur[ks, ..., dk_:] += g_v.float()
+            # the gradient follows its block: one hop per step, and a last hop after the final step brings it back to the block's owner
+            dcur = shift(dcur, False)
+            cur = nxt
+        return dq.to(q.dtype), dcur[..., :dk_].to(k.dtype), dcur[..., dk_:].to(v.dtype), None, None, None, None, None
+
+
 class _RingShift(torch.autograd.Function):
     """Send a tensor to the next CP rank and receive from the previous one (backward: the reverse)."""
 
@@ -201,26 +326,8 @@ class RingAttention(torch.nn.Module):
 
     # ---- ring (p2p) -------------------------------------------------------------------------------------------
     def _ring(self, q, k, v, causal, scale):
-        c, my_offs = self._chunk_offsets(q.shape[0])
-        kv = torch.cat([k, v], dim=-1)
-        outs = [[], []]
-        lses = [[], []]
-        cur = kv
-        for step in range(self.cp):
-            src_rank = (self.rank - step) % self.cp
-            nxt = _RingShift.apply(cur, self.group, False) if step < self.cp - 1 else None
-            kk, vv = cur[..., : k.shape[-1]], cur[..., k.shape[-1] :]
-            src_offs = [src_rank * c, (2 * self.cp - 1 - src_rank) * c]
-            for qi, qoff in enumerate(my_offs):
-                qc = q[qi * c : (qi + 1) * c]
-                for ki, koff in enumerate(src_offs):
-                    if causal and koff > qoff + c - 1:
-                        continue  # block entirely in the future
-                    o, l = attention_with_lse(qc, kk[ki * c : (ki + 1) * c], vv[ki * c : (ki + 1) * c], scale, causal, q_offset=qoff, k_offset=koff)
-                    outs[qi].append(o), lses[qi].append(l)
-            cur = nxt
-        merged = [merge_partials(outs[i], lses[i]) for i in range(2)]
-        return torch.cat(merged, dim=0).to(q.dtype)
+        group = self.group
+        return _RingAttnFn.apply(q, k.contiguous(), v.contiguous(), scale, causal, self.rank, self.cp, lambda x, reverse: _RingShift._shift(x, group, reverse))
 
     # ---- Ulysses (a2a) --------------------------------------------------------------------------------------------
     def _ulysses(self, q, k, v, causal, scale):

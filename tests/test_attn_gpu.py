@@ -242,3 +242,33 @@ def test_packed_sequences_through_dot_product_attention():
     for name, a, r in zip(["out", "dq", "dk", "dv"], got, want):
         e = (a - r).abs().max().item() / (r.abs().max().item() + 1e-6)
         assert e < 3e-2, f"{name} rel err {e}"
+
+
+@pytest.mark.parametrize("hq,hk", [(4, 1), (2, 2)])
+def test_ring_attention_blocks_on_native_kernels(hq, hk):
+    """The context-parallel ring's block primitives on the tcgen05 kernels (one rank = two zig-zag chunks: a full pair, two diagonal pairs, merge by
+    log-sum-exp; backward of every pair from the MERGED output / lse) == plain causal attention over the whole local sequence."""
+    from megatron_b200 import ops
+    from megatron_b200.parallel.context_parallel import _RingAttnFn, _native_block_ok
+
+    torch.manual_seed(8)
+    s, d = 1024, 128
+    q = torch.randn(s, 1, hq, d, device="cuda").bfloat16().requires_grad_(True)
+    k = torch.randn(s, 1, hk, d, device="cuda").bfloat16().requires_grad_(True)
+    v = torch.randn(s, 1, hk, d, device="cuda").bfloat16().requires_grad_(True)
+    go = torch.randn(s, 1, hq, d, device="cuda").bfloat16()
+    assert _native_block_ok(q[:512], k[:512])
+    scale = 1.0 / math.sqrt(d)
+    ops.reset_launch_count()
+    out = _RingAttnFn.apply(q, k, v, scale, True, 0, 1, lambda x, reverse: x)
+    out.backward(go)
+    assert ops.launch_count() >= 3 + 9                       # 3 forward pairs + 3 backward pairs (3 kernels each)
+    got = [out.float()] + [t.grad.float().clone() for t in (q, k, v)]
+    for t in (q, k, v):
+        t.grad = None
+    ro, _ = _ref(q, k, v, True, scale)
+    ro.backward(go.float())
+    want = [ro.float()] + [t.grad.float() for t in (q, k, v)]
+    for name, a, r in zip(["out", "dq", "dk", "dv"], got, want):
+        e = (a - r).abs().max().item() / (r.abs().max().item() + 1e-6)
+        assert e < 3e-2, f"{name} rel err {e}"

@@ -515,3 +515,38 @@ def test_tensor_aware_state_dict_local_checkpoint_container():
     from dist_utils import run_distributed
 
     assert all(run_distributed(_tensor_aware_worker, 2))
+
+
+def _ring_fn_worker(rank, world):
+    """_RingAttnFn over 4 ranks (zig-zag chunks, GQA, manual ring backward with travelling dK/dV) vs plain attention on the gathered sequence."""
+    import torch.distributed as dist
+
+    from megatron_b200.ops import reference as ref
+    from megatron_b200.parallel.context_parallel import _RingAttnFn, _RingShift
+
+    torch.manual_seed(5)
+    cp, c, b, hq, hk, d = world, 6, 2, 4, 2, 8
+    s = 2 * cp * c
+    full = [torch.randn(s, b, h, d) for h in (hq, hk, hk)]
+    go_full = torch.randn(s, b, hq, d)
+    idx = torch.cat([torch.arange(rank * c, (rank + 1) * c), torch.arange((2 * cp - 1 - rank) * c, (2 * cp - rank) * c)])
+    q, k, v = (t[idx].clone().requires_grad_(True) for t in full)
+    group = dist.group.WORLD
+    for causal in (True, False):
+        for t in (q, k, v):
+            t.grad = None
+        out = _RingAttnFn.apply(q, k, v, 0.3, causal, rank, cp, lambda x, reverse: _RingShift._shift(x, group, reverse))
+        out.backward(go_full[idx])
+        fq, fk, fv = (t.clone().requires_grad_(True) for t in full)
+        want = ref.attention_fwd(fq, fk, fv, causal, 0.3)
+        want.backward(go_full)
+        assert torch.allclose(out, want[idx], atol=1e-5), (causal, (out - want[idx]).abs().max())
+        for got, w in ((q.grad, fq.grad), (k.grad, fk.grad), (v.grad, fv.grad)):
+            assert torch.allclose(got, w[idx], atol=1e-5), (causal, (got - w[idx]).abs().max())
+    return True
+
+
+def test_ring_attention_function_four_ranks():
+    from dist_utils import run_distributed
+
+    assert all(run_distributed(_ring_fn_worker, 4))
