@@ -22,7 +22,9 @@ class GRPOConfig:
     temperature: float = 1.0
     clip_eps: float = 0.2
     kl_beta: float = 0.01
-    entropy_coef: float = 0.0
+    entropy_coef: float = 0.0                      # weight of the (sampled-token) entropy bonus (reference --grpo-entropy-term-weight)
+    clip_eps_upper: Optional[float] = None         # asymmetric clipping (reference --grpo-clamp-eps-upper); None = clip_eps
+    filter_groups_with_same_reward: bool = False   # groups whose rollouts all scored the same carry no signal: drop them from the loss
 
 
 class Environment:
@@ -69,11 +71,14 @@ def grpo_loss(logp, old_logp, ref_logp, advantages, mask, cfg: GRPOConfig):
     """All [b, s-1]; ``mask`` selects completion tokens.  Returns (loss, stats)."""
     ratio = torch.exp(logp - old_logp)
     adv = advantages.unsqueeze(-1)
-    pg = -torch.min(ratio * adv, torch.clamp(ratio, 1 - cfg.clip_eps, 1 + cfg.clip_eps) * adv)
+    hi = cfg.clip_eps if cfg.clip_eps_upper is None else cfg.clip_eps_upper
+    pg = -torch.min(ratio * adv, torch.clamp(ratio, 1 - cfg.clip_eps, 1 + hi) * adv)
     # unbiased low-variance KL estimator k3 = exp(ref - logp) - (ref - logp) - 1
     d = ref_logp - logp
     kl = torch.exp(d) - d - 1.0
     per_tok = pg + cfg.kl_beta * kl
+    if cfg.entropy_coef:
+        per_tok = per_tok + cfg.entropy_coef * logp          # minimising E[log p] of the sampled tokens = maximising the policy's entropy estimate
     denom = mask.sum().clamp(min=1)
     loss = (per_tok * mask).sum() / denom
     return loss, {"pg": ((pg * mask).sum() / denom).detach(), "kl": ((kl * mask).sum() / denom).detach(), "ratio_max": (ratio * mask).max().detach()}
@@ -107,6 +112,10 @@ class GRPOTrainer:
     def step(self, n_prompts: int = 4, inner_epochs: int = 1):
         tokens, mask, rewards = self.rollout(n_prompts)
         adv = group_advantages(rewards, self.cfg.group_size)
+        if self.cfg.filter_groups_with_same_reward:
+            r = rewards.view(-1, self.cfg.group_size)
+            informative = (r.max(dim=1).values > r.min(dim=1).values).repeat_interleave(self.cfg.group_size)
+            mask = mask * informative.unsqueeze(-1).to(mask.dtype)
         with torch.no_grad():
             old = sequence_logprobs(self.model, tokens, self.vocab)
             ref = sequence_logprobs(self.ref, tokens, self.vocab)

@@ -303,6 +303,10 @@ def build_full_parser(extra_args_provider=None) -> argparse.ArgumentParser:
         parser = extra_args_provider(parser)
     for cls in config_classes():
         add_dataclass_arguments(parser, cls, title=f"{cls.__name__} (generated)")
+    if not os.environ.get("MB200_NO_REFERENCE_FLAGS"):
+        from .reference_flags import add_reference_compat_flags
+
+        add_reference_compat_flags(parser)             # the reference's remaining flag names (accepted; wired / native / inert: see reference_flags.py)
     return parser
 
 
@@ -318,6 +322,17 @@ def parse_args(argv=None, extra_args_provider=None, ignore_unknown_args: bool = 
         from .argument_utils import apply_yaml, explicit_dests, load_yaml_config
 
         apply_yaml(args, load_yaml_config(args.yaml_cfg), parser, explicit_dests(parser, argv_list))
+    if not os.environ.get("MB200_NO_REFERENCE_FLAGS"):
+        from .reference_flags import apply_reference_compat, inert_flags_in_use
+
+        apply_reference_compat(args)
+        inert = inert_flags_in_use(args, parser)
+        if inert:
+            msg = f"reference flags accepted but without effect in this build: {' '.join(inert)}"
+            if getattr(args, "strict_reference_flags", False):
+                parser.error(msg)
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(f"WARNING: {msg}", flush=True)
     if args.model is not None:
         from ..models.presets import PRESETS
 
@@ -350,6 +365,10 @@ def core_transformer_config_from_args(args):
     act = F.silu if args.swiglu else F.gelu
     if args.squared_relu:
         from ..ops.reference import squared_relu as act  # noqa: F811
+    if getattr(args, "openai_gelu", False):                      # tanh-approximated GeLU
+        act = lambda x: F.gelu(x, approximate="tanh")            # noqa: E731
+    if getattr(args, "quick_geglu", False):                      # x * sigmoid(1.702 x), gated
+        act = lambda x: x * torch.sigmoid(1.702 * x)             # noqa: E731
     kw = dict(
         num_layers=args.num_layers, hidden_size=args.hidden_size, ffn_hidden_size=args.ffn_hidden_size, num_attention_heads=args.num_attention_heads,
         num_query_groups=args.num_query_groups, kv_channels=args.kv_channels, hidden_dropout=args.hidden_dropout, attention_dropout=args.attention_dropout,
@@ -365,7 +384,8 @@ def core_transformer_config_from_args(args):
         recompute_method=args.recompute_method, recompute_num_layers=args.recompute_num_layers, recompute_modules=args.recompute_modules,
         deterministic_mode=args.deterministic_mode, overlap_p2p_comm=args.overlap_p2p_comm, batch_p2p_comm=not args.overlap_p2p_comm,
         calculate_per_token_loss=args.calculate_per_token_loss, tp_comm_overlap=args.tp_comm_overlap, cp_comm_type=args.cp_comm_type,
-        bias_activation_fusion=True, bias_dropout_fusion=True, apply_rope_fusion=True, masked_softmax_fusion=True,
+        bias_activation_fusion=getattr(args, "bias_swiglu_fusion", True) if args.swiglu else getattr(args, "bias_gelu_fusion", True), bias_dropout_fusion=True,
+        apply_rope_fusion=getattr(args, "apply_rope_fusion", True), masked_softmax_fusion=True,
         fp8=args.fp8_format, fp8_recipe=args.fp8_recipe if args.fp8_format else "delayed",
     )
     if args.num_experts:
@@ -383,4 +403,43 @@ def core_transformer_config_from_args(args):
         default = f.default if f.default is not _dc.MISSING else (f.default_factory() if f.default_factory is not _dc.MISSING else None)
         if v is not None and v != default:
             kw[f.name] = v
+    if getattr(args, "quick_geglu", False):
+        kw["gated_linear_unit"] = True
+    if getattr(args, "openai_gelu", False) or getattr(args, "quick_geglu", False):
+        kw["bias_activation_fusion"] = False                      # the fused bias+activation kernels cover gelu / silu / quick_gelu / squared_relu only
+    if getattr(args, "init_method_xavier_uniform", False):
+        kw["init_method"] = torch.nn.init.xavier_uniform_
+        kw["output_layer_init_method"] = torch.nn.init.xavier_uniform_
+    if getattr(args, "multi_latent_attention", False):
+        # DeepSeek-style attention: its dimensions / YaRN parameters come from the reference-named flags (--q-lora-rank, --kv-lora-rank, --qk-head-dim,
+        # --qk-pos-emb-head-dim, --v-head-dim, --rope-type, --rotary-scaling-factor, --mscale, --mscale-all-dim, --yarn-*) when given
+        from ..core.transformer.transformer_config import MLATransformerConfig
+
+        for f in _dc.fields(MLATransformerConfig):
+            if f.name in kw or not f.init:
+                continue
+            v = getattr(args, f.name, None)
+            if v is not None and f.name not in {ff.name for ff in _dc.fields(TransformerConfig)}:
+                kw[f.name] = v
+        if kw.get("rope_type", "yarn") != "yarn":
+            kw["apply_rope_fusion"] = False
+        return MLATransformerConfig(**kw)
     return TransformerConfig(**kw)
+
+
+def ddp_config_from_args(args):
+    """``DistributedDataParallelConfig`` from the hand-written flags plus every same-named (generated or reference-compatible) option."""
+    import dataclasses as _dc
+
+    from ..core.distributed import DistributedDataParallelConfig
+
+    kw = dict(grad_reduce_in_fp32=args.accumulate_allreduce_grads_in_fp32, overlap_grad_reduce=args.overlap_grad_reduce, overlap_param_gather=args.overlap_param_gather,
+              use_distributed_optimizer=args.use_distributed_optimizer, check_for_nan_in_grad=args.check_for_nan_in_loss_and_grad, bucket_size=args.ddp_bucket_size)
+    for f in _dc.fields(DistributedDataParallelConfig):
+        if f.name in kw or not hasattr(args, f.name):
+            continue
+        v = getattr(args, f.name)
+        default = f.default if f.default is not _dc.MISSING else None
+        if v is not None and v != default:
+            kw[f.name] = v
+    return DistributedDataParallelConfig(**kw)

@@ -126,7 +126,10 @@ _MON: Optional[FaultToleranceMonitor] = None
 
 def setup(args, rank: int = 0) -> FaultToleranceMonitor:
     global _MON
-    _MON = FaultToleranceMonitor(rank=rank, save_dir=getattr(args, "save", None),
+    extra = {}
+    if getattr(args, "ft_num_warmup_iters", None):          # reference --ft-num-warmup-iters: step samples needed before the learned step timeout replaces the configured one
+        extra["min_samples"] = int(args.ft_num_warmup_iters)
+    _MON = FaultToleranceMonitor(rank=rank, save_dir=getattr(args, "save", None), **extra,
                                  timeouts={k: v for k, v in dict(setup=getattr(args, "ft_timeout_setup", None), step=getattr(args, "ft_timeout_step", None),
                                                                  checkpointing=getattr(args, "ft_timeout_checkpointing", None)).items() if v}).start()
     _MON.start_section("setup")

@@ -139,11 +139,12 @@ def get_model(model_provider_func: Callable, wrap_with_ddp: bool = True) -> List
     if not wrap_with_ddp:
         return chunks
     config = chunks[0].config
-    ddp_config = DistributedDataParallelConfig(
-        grad_reduce_in_fp32=args.accumulate_allreduce_grads_in_fp32, overlap_grad_reduce=args.overlap_grad_reduce,
-        overlap_param_gather=args.overlap_param_gather, use_distributed_optimizer=args.use_distributed_optimizer,
-        check_for_nan_in_grad=args.check_for_nan_in_loss_and_grad, bucket_size=args.ddp_bucket_size,
-    )
+    from .arguments import ddp_config_from_args
+
+    ddp_config = ddp_config_from_args(args)
+    if getattr(args, "ddp_num_buckets", None):
+        n_params = sum(p.numel() for c in chunks for p in c.parameters())
+        ddp_config.bucket_size = max(1, -(-n_params // args.ddp_num_buckets))
     model = [DistributedDataParallel(config, ddp_config, c, disable_bucketing=(i > 0)) for i, c in enumerate(chunks)]
     for c in chunks:
         c.config = config

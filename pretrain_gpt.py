@@ -30,7 +30,14 @@ from megatron_b200.training.training import get_args, pretrain, print_rank_0  # 
 def model_provider(pre_process=True, post_process=True, vp_stage=None) -> GPTModel:
     args = get_args()
     config = core_transformer_config_from_args(args)
-    if args.num_experts:
+    if getattr(args, "spec", None):
+        # --spec module function: a user-supplied layer spec (reference pretrain_gpt.py model_provider: import_module(args.spec))
+        import importlib
+
+        mod, fn = args.spec[:2] if isinstance(args.spec, (list, tuple)) else str(args.spec).rsplit(".", 1)
+        spec = getattr(importlib.import_module(mod), fn)
+        spec = spec(config) if callable(spec) and not hasattr(spec, "submodules") else spec
+    elif args.num_experts:
         spec = get_gpt_decoder_block_spec(config, vp_stage=vp_stage)
     else:
         spec = get_gpt_layer_local_spec(normalization=args.normalization, qk_layernorm=args.qk_layernorm, multi_latent_attention=args.multi_latent_attention)
@@ -81,16 +88,50 @@ def forward_step(data_iterator, model: GPTModel):
 def train_valid_test_datasets_provider(train_val_test_num_samples):
     args = get_args()
     tokenizer = build_tokenizer(args.tokenizer_type, vocab_size=args.vocab_size, tokenizer_model=args.tokenizer_model)
+    per_split = [getattr(args, k, None) for k in ("train_data_path", "valid_data_path", "test_data_path")]
+    use_per_split = not args.mock_data and any(per_split)            # --train-data-path / --valid-data-path / --test-data-path instead of --data-path + --split
     cfg = GPTDatasetConfig(
-        random_seed=args.seed, sequence_length=args.seq_length, blend=None if args.mock_data else get_blend_from_list(args.data_path), split=args.split,
+        random_seed=args.seed, sequence_length=args.seq_length,
+        blend=None if (args.mock_data or use_per_split) else get_blend_from_list(args.data_path), split=None if use_per_split else args.split,
+        blend_per_split=[get_blend_from_list(p) if p else None for p in per_split] if use_per_split else None,
         path_to_cache=args.data_cache_path, tokenizer=tokenizer, reset_position_ids=args.reset_position_ids, reset_attention_mask=args.reset_attention_mask,
-        eod_mask_loss=args.eod_mask_loss, create_attention_mask=False,
+        eod_mask_loss=args.eod_mask_loss, create_attention_mask=False, mmap_bin_files=getattr(args, "mmap_bin_files", True),
+        num_dataset_builder_threads=getattr(args, "num_dataset_builder_threads", 1) or 1,
     )
     cls = MockGPTDataset if args.mock_data else GPTDataset
     print_rank_0("> building train, validation, and test datasets for GPT ...")
     is_built = lambda: ps.get_tensor_model_parallel_rank() == 0 and (ps.is_pipeline_first_stage(ignore_virtual=True) or ps.is_pipeline_last_stage(ignore_virtual=True))  # noqa: E731
-    return BlendedMegatronDatasetBuilder(cls, train_val_test_num_samples, lambda: True, cfg).build()
+    out = BlendedMegatronDatasetBuilder(cls, train_val_test_num_samples, lambda: True, cfg).build()
+    if getattr(args, "fim_data", False):
+        # fill-in-the-middle: documents are re-ordered (prefix / suffix / middle) with sentinel tokens (reference pretrain_gpt.py --fim-data, GPTFIMDataset)
+        from megatron_b200.training.datasets.fim_dataset import FIMConfig, GPTFIMDataset
+
+        def tok_id(flag, default):
+            v = getattr(args, flag, None)
+            if v is None:
+                return default
+            if isinstance(v, int) or str(v).lstrip("-").isdigit():
+                return int(v)
+            try:
+                ids = tokenizer.tokenize(v) if hasattr(tokenizer, "tokenize") else []
+            except (ValueError, KeyError):                      # the tokenizer has no such special token (e.g. NullTokenizer): reserve ids at the top of the vocabulary
+                ids = []
+            return int(ids[0]) if len(ids) == 1 else default
+
+        v = args.padded_vocab_size if getattr(args, "padded_vocab_size", None) else args.vocab_size
+        fim = FIMConfig(fim_rate=getattr(args, "fim_rate", 0.5), fim_spm_rate=getattr(args, "fim_spm_rate", 0.5), prefix_id=tok_id("fim_prefix_token", v - 5),
+                        middle_id=tok_id("fim_middle_token", v - 4), suffix_id=tok_id("fim_suffix_token", v - 3), pad_id=tok_id("fim_pad_token", v - 2),
+                        eod_id=tok_id("fim_eod_token", getattr(tokenizer, "eod", v - 1)))
+        out = tuple(GPTFIMDataset(d, fim, seed=args.seed) if i == 0 and d is not None else d for i, d in enumerate(out))
+    return out
 
 
 if __name__ == "__main__":
-    pretrain(train_valid_test_datasets_provider, model_provider, forward_step, args_defaults={"tokenizer_type": "NullTokenizer"})
+    run = pretrain
+    if "--inprocess-restart" in sys.argv:
+        # recoverable failures restart the training function inside this process (reference pretrain_gpt.py: inprocess_restart.maybe_wrap_for_inprocess_restart)
+        from megatron_b200.training.inprocess_restart import maybe_wrap_for_inprocess_restart
+
+        budget = int(sys.argv[sys.argv.index("--inprocess-max-iterations") + 1]) if "--inprocess-max-iterations" in sys.argv else 5
+        run = maybe_wrap_for_inprocess_restart(pretrain, max_restarts=budget)
+    run(train_valid_test_datasets_provider, model_provider, forward_step, args_defaults={"tokenizer_type": "NullTokenizer"})

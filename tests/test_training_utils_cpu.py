@@ -446,3 +446,52 @@ def test_generated_flags_and_yaml_config(tmp_path):
     with pytest.raises(ValueError, match="num_layerz"):
         parse_args(base + ["--yaml-cfg", str(tmp_path / "bad.yaml")])
     assert "TransformerConfig" in args_to_yaml(b, (type(cfg),)) and "num_layers: 6" in args_to_yaml(b, (type(cfg),))
+
+
+def test_reference_flag_table(monkeypatch):
+    import pytest
+
+    """Every flag of the reference's training parsers parses here; WIRED names are really consumed somewhere; inert ones are reported (and fatal under --strict)."""
+    import glob
+    import re
+
+    from megatron_b200.training import reference_flags as rf
+    from megatron_b200.training.arguments import build_full_parser, core_transformer_config_from_args, ddp_config_from_args, parse_args, validate_args
+    from megatron_b200.training.reference_flags_table import REFERENCE_FLAG_TABLE
+
+    parser = build_full_parser()
+    known = {s for a in parser._actions for s in a.option_strings}
+    assert len(REFERENCE_FLAG_TABLE) > 300 and all(f in known for row in REFERENCE_FLAG_TABLE for f in row[0])
+    assert len(known) > 800
+    # WIRED / ALWAYS_ON are honest: each dest is read by name outside the table module itself, or translated in reference_flags.py
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = ""
+    for f in glob.glob(os.path.join(root, "megatron_b200/**/*.py"), recursive=True) + glob.glob(os.path.join(root, "*.py")) + glob.glob(os.path.join(root, "tools/*.py")):
+        if not f.endswith("reference_flags_table.py"):
+            text = open(f).read()
+            if f.endswith("reference_flags.py"):
+                text = text[text.index("def apply_reference_compat"):]          # the dictionaries themselves do not count as a use
+            src += text
+    read = set(re.findall(r"args\.([a-z_0-9]+)", src)) | set(re.findall(r"""["']([a-z_0-9]+)["']""", src))      # attribute reads and names passed to getattr / loops
+    missing = sorted(d for d in rf.WIRED if d not in read)
+    assert not missing, f"listed as wired but never read: {missing}"
+    base = ["--num-layers", "2", "--hidden-size", "64", "--num-attention-heads", "4", "--micro-batch-size", "1", "--seq-length", "32", "--vocab-size", "128"]
+    args = parse_args(base + ["--tp-size", "2", "--no-rope-fusion", "--multi-latent-attention", "--q-lora-rank", "32", "--kv-lora-rank", "16", "--qk-head-dim", "16",
+                              "--qk-pos-emb-head-dim", "8", "--v-head-dim", "16", "--yarn-beta-fast", "16", "--ddp-average-in-collective", "--ddp-pad-buckets-for-high-nccl-busbw",
+                              "--checkpoint-activations", "--grad-reduce-in-bf16", "--openai-gelu", "--bf16"])
+    assert args.tensor_model_parallel_size == 2 and args.recompute_granularity == "full" and args.accumulate_allreduce_grads_in_fp32 is False
+    validate_args(args, world_size=2)
+    cfg = core_transformer_config_from_args(args)
+    assert type(cfg).__name__ == "MLATransformerConfig" and (cfg.q_lora_rank, cfg.kv_lora_rank, cfg.qk_head_dim, cfg.qk_pos_emb_head_dim, cfg.v_head_dim, cfg.beta_fast) == (32, 16, 16, 8, 16, 16)
+    assert cfg.apply_rope_fusion is False and abs(float(cfg.activation_func(torch.tensor(1.0))) - float(torch.nn.functional.gelu(torch.tensor(1.0), approximate="tanh"))) < 1e-7
+    ddp = ddp_config_from_args(args)
+    assert ddp.average_in_collective and ddp.pad_buckets_for_high_nccl_busbw and ddp.grad_reduce_in_fp32 is False
+    assert parse_args(base).apply_rope_fusion is True                                              # the reference's command-line default
+    # inert flags: reported, fatal when strict
+    args = parse_args(base + ["--dino-head-hidden-size", "99"])
+    assert rf.inert_flags_in_use(args, build_full_parser()) == ["--dino-head-hidden-size"]
+    with pytest.raises(SystemExit):
+        parse_args(base + ["--dino-head-hidden-size", "99", "--strict-reference-flags"])
+    kw = rf.engine_kwargs_from_args(parse_args(base + ["--inference-dynamic-batching-block-size", "32", "--inference-max-requests", "8", "--enable-chunked-prefill",
+                                                       "--inference-dynamic-batching-num-cuda-graphs", "4", "--inference-dynamic-batching-prefix-caching"]))
+    assert kw == {"block_size": 32, "max_running": 8, "max_prefill_tokens_per_step": 2048, "enable_prefix_caching": True, "enable_cuda_graphs": True, "decode_batch_buckets": [2, 4, 6, 8]}

@@ -20,7 +20,25 @@ def main():
     ap.add_argument("--engine", choices=["static", "dynamic"], default="dynamic")
     ap.add_argument("--load", default=None)
     ap.add_argument("--tokenizer", default="byte")
+    # the reference's engine flags (megatron/training/arguments.py _add_inference_args)
+    ap.add_argument("--inference-dynamic-batching", action="store_true")
+    ap.add_argument("--use-legacy-static-engine", action="store_true")
+    ap.add_argument("--inference-dynamic-batching-block-size", type=int, default=None)
+    ap.add_argument("--inference-dynamic-batching-max-requests", type=int, default=None)
+    ap.add_argument("--inference-max-requests", type=int, default=None)
+    ap.add_argument("--inference-dynamic-batching-max-tokens", type=int, default=None)
+    ap.add_argument("--enable-chunked-prefill", action="store_true")
+    ap.add_argument("--inference-dynamic-batching-prefix-caching", dest="inference_dynamic_batching_enable_prefix_caching", action="store_true")
+    ap.add_argument("--inference-dynamic-batching-num-cuda-graphs", type=int, default=None)
+    ap.add_argument("--decode-only-cuda-graphs", action="store_true")
     args = ap.parse_args()
+    if args.use_legacy_static_engine:
+        args.engine = "static"
+    elif args.inference_dynamic_batching:
+        args.engine = "dynamic"
+    from megatron_b200.training.reference_flags import apply_reference_compat, engine_kwargs_from_args
+
+    apply_reference_compat(args)
     import torch.distributed as dist
 
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -45,7 +63,7 @@ def main():
     from megatron_b200.core.tokenizers.tokenizer import build_tokenizer
 
     tok = build_tokenizer("ByteLevel") if args.tokenizer == "byte" else MegatronTokenizer.from_pretrained(args.tokenizer)
-    eng = DynamicInferenceEngine(model) if args.engine == "dynamic" else StaticInferenceEngine(model, tok)
+    eng = DynamicInferenceEngine(model, **engine_kwargs_from_args(args)) if args.engine == "dynamic" else StaticInferenceEngine(model, tok)
     srv = TextGenerationServer(TextGenerationController(eng, tok), args.host, args.port)
     print(f"serving {args.preset} on http://{args.host}:{args.port}/api", flush=True)
     srv.start(background=False)
