@@ -90,6 +90,9 @@ class GRPOTrainer:
         for p in self.ref.parameters():
             p.requires_grad = False
         self.engine = StaticInferenceEngine(model, max_batch_size=256, max_sequence_length=512, vocab_size=vocab_size)
+        from .rl_profiling import RLProfiler
+
+        self.profiler = RLProfiler(enabled=False)
 
     @torch.no_grad()
     def rollout(self, n_prompts: int):
@@ -110,21 +113,26 @@ class GRPOTrainer:
         return tokens, mask, rewards.to(dev)
 
     def step(self, n_prompts: int = 4, inner_epochs: int = 1):
-        tokens, mask, rewards = self.rollout(n_prompts)
+        prof = self.profiler
+        with prof.phase("rollout"):
+            tokens, mask, rewards = self.rollout(n_prompts)
+        prof.count("rollout", tokens=int(mask.sum()), sequences=tokens.shape[0])
         adv = group_advantages(rewards, self.cfg.group_size)
         if self.cfg.filter_groups_with_same_reward:
             r = rewards.view(-1, self.cfg.group_size)
             informative = (r.max(dim=1).values > r.min(dim=1).values).repeat_interleave(self.cfg.group_size)
             mask = mask * informative.unsqueeze(-1).to(mask.dtype)
-        with torch.no_grad():
+        with torch.no_grad(), prof.phase("logprobs", tokens=2 * tokens.numel()):
             old = sequence_logprobs(self.model, tokens, self.vocab)
             ref = sequence_logprobs(self.ref, tokens, self.vocab)
         stats = {}
-        for _ in range(inner_epochs):
-            logp = sequence_logprobs(self.model, tokens, self.vocab)
-            loss, stats = grpo_loss(logp, old, ref, adv, mask, self.cfg)
-            self.opt.zero_grad()
-            loss.backward()
-            self.opt.step()
+        with prof.phase("train", tokens=inner_epochs * tokens.numel()):
+            for _ in range(inner_epochs):
+                logp = sequence_logprobs(self.model, tokens, self.vocab)
+                loss, stats = grpo_loss(logp, old, ref, adv, mask, self.cfg)
+                self.opt.zero_grad()
+                loss.backward()
+                self.opt.step()
         stats.update(loss=loss.detach(), reward=rewards.mean())
+        prof.end_iteration(reward=float(rewards.mean()))
         return stats

@@ -64,12 +64,17 @@ def shutdown():
 
 
 def _teardown():
-    from ..core import parallel_state as ps
-
     try:
-        ps.destroy_model_parallel()
+        from .training import destroy_global_state
+
+        destroy_global_state()          # args / timers / writers, micro-batch calculator, rerun state machine, model-parallel groups, async-save queue
     except Exception:
-        pass
+        from ..core import parallel_state as ps
+
+        try:
+            ps.destroy_model_parallel()
+        except Exception:
+            pass
     if torch.cuda.is_available():
         torch.cuda.empty_cache()
 

@@ -200,6 +200,44 @@ def setup_model_and_optimizer(model_provider_func: Callable):
     return model, optimizer, scheduler
 
 
+def append_to_progress_log(string: str, barrier: bool = True) -> None:
+    """``--log-progress``: one line per job start / checkpoint / exit in ``<save>/progress.txt`` with the job id, world size and cumulative FLOPs — enough to
+    reconstruct a run's throughput history across restarts (reference ``training.py:3722-3745``)."""
+    args = get_args()
+    if not getattr(args, "log_progress", False) or not args.save:
+        return
+    if barrier and dist.is_initialized():
+        dist.barrier()
+    if not dist.is_initialized() or dist.get_rank() == 0:
+        os.makedirs(args.save, exist_ok=True)
+        job = os.environ.get("SLURM_JOB_ID", os.environ.get("TORCHELASTIC_RUN_ID", "-"))
+        with open(os.path.join(args.save, "progress.txt"), "a") as f:
+            f.write(f"{time.strftime('%Y-%m-%d %H:%M:%S')}\tJob ID: {job}\t# GPUs: {dist.get_world_size() if dist.is_initialized() else 1}\t{string}\n")
+
+
+def destroy_global_state() -> None:
+    """Everything a re-entry of ``pretrain`` in the same process must not inherit (reference ``training.py:694-720``, used by the in-process restart): global
+    args / timers / writers, the micro-batch calculator, the rerun state machine, model-parallel groups and the async-checkpoint queue."""
+    from ..core import parallel_state as ps
+    from ..core.rerun_state_machine import destroy_rerun_state_machine
+    from . import checkpointing
+    from .global_vars import destroy_global_vars
+
+    try:
+        checkpointing.maybe_finalize_async_save(blocking=True)
+    except Exception:
+        pass
+    destroy_global_vars()
+    try:
+        from ..core.num_microbatches_calculator import destroy_num_microbatches_calculator
+
+        destroy_num_microbatches_calculator()
+    except ImportError:
+        pass
+    destroy_rerun_state_machine()
+    ps.destroy_model_parallel()
+
+
 # ---------------------------------------------------------------------------------------------------------
 def train_step(forward_step_func, data_iterator, model, optimizer, opt_param_scheduler, config):
     """One optimizer step, wrapped by the rerun state machine (fault attribution, reference :3010-3260)."""
@@ -313,6 +351,7 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
         vocab_size=getattr(args, "padded_vocab_size", args.vocab_size), seq_length=args.seq_length, batch_size=args.global_batch_size, swiglu=args.swiglu,
         num_moe_experts=args.num_experts, moe_router_topk=args.moe_router_topk,
     )
+    append_to_progress_log(f"Starting job\titeration: {iteration}\tFLOPs so far: {args.num_floating_point_operations_so_far:.4e}")
     straggler = StragglerDetector()
     straggler.configure(dist.get_world_size() if dist.is_initialized() else 1, dist.get_rank() if dist.is_initialized() else 0, enabled=args.log_straggler)
     if args.manual_gc:
@@ -417,6 +456,8 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
                                           args.num_floating_point_operations_so_far, async_save=args.async_save, keep_last=args.keep_last_checkpoints,
                                           assume_constant_structure=getattr(args, 'ckpt_assume_constant_structure', False))
             saved = True
+            append_to_progress_log(f"Saved checkpoint\titeration: {iteration}\tFLOPs so far: {args.num_floating_point_operations_so_far:.4e}\ttokens so far: {args.consumed_train_samples * args.seq_length:.4e}",
+                                   barrier=False)
         stop = exit_flag["sig"] or (args.exit_interval and iteration % args.exit_interval == 0) or \
             (args.exit_duration_in_mins and (time.time() - t_start) / 60.0 > args.exit_duration_in_mins)
         if dist.is_initialized() and (exit_flag["sig"] or args.exit_duration_in_mins):

@@ -252,8 +252,10 @@ def test_pretrain_cli_non_persistent_checkpoints_and_load_policy(tmp_path):
     """--non-persistent-ckpt-type global: a recovery checkpoint every 2 iterations beside the persistent series (every 4, cached save plans); the restart resumes
     from the NEWEST of the two (iteration 6, non-persistent), then a fresh run elsewhere starts from it as --pretrained-checkpoint weights at iteration 0."""
     common = ["--non-persistent-save-interval", "2", "--non-persistent-ckpt-type", "global", "--ckpt-assume-constant-structure", "--ckpt-fully-parallel-load",
-              "--dist-ckpt-strictness", "log_all"]
+              "--dist-ckpt-strictness", "log_all", "--log-progress"]
     out = _run_pretrain(tmp_path, common + ["--exit-interval", "6"], iters=8)
+    prog = (tmp_path / "ckpt" / "progress.txt").read_text().splitlines()
+    assert prog[0].split("\t")[3] == "Starting job" and any("Saved checkpoint\titeration: 4" in l for l in prog) and "FLOPs so far" in prog[-1]
     assert "iteration        6/" in out and "iteration        8/" not in out
     np_dir = tmp_path / "ckpt" / "non_persistent"
     assert (np_dir / "latest_checkpointed_iteration.txt").read_text().strip() == "6"

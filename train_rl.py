@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--rl-default-temperature", type=float, default=None)
     ap.add_argument("--perform-rl-step", action="store_true", help="accepted: this entry point always performs RL steps")
     ap.add_argument("--train-iters", type=int, default=None)
+    ap.add_argument("--rl-profile", action="store_true", help="time the rollout / log-prob / train phases of every iteration")
+    ap.add_argument("--rl-profile-dir", default=None)
     args = ap.parse_args()
     if args.grpo_group_size:
         args.group_size = args.grpo_group_size
@@ -69,9 +71,16 @@ def main():
         cfg.temperature = args.rl_default_temperature
     cfg.filter_groups_with_same_reward = args.grpo_filter_groups_with_same_reward
     tr = GRPOTrainer(model, ref, opt, CountTokenEnv(args.vocab), cfg, vocab_size=args.vocab)
+    if args.rl_profile:
+        from megatron_b200.rl.rl_profiling import RLProfiler
+
+        tr.profiler = RLProfiler(enabled=True, out_dir=args.rl_profile_dir or ".")
     for it in range(args.iters):
         s = tr.step(args.prompts_per_iter, inner_epochs=args.grpo_iterations)
         print(f"iter {it + 1:3d} | reward {float(s['reward']):.3f} | loss {float(s['loss']):+.4f} | kl {float(s['kl']):.5f}", flush=True)
+    if args.rl_profile:
+        path = tr.profiler.dump()
+        print(f"rl profile: {path}  summary: {tr.profiler.summary()}", flush=True)
     return tr
 
 
