@@ -198,7 +198,7 @@ class FullyShardedDataParallel(torch.nn.Module):
                 u.pending = len(u.params)
         return self.module(*args, **kwargs)
 
-    def finish_grad_sync(self):
+    def finish_grad_sync(self, force_all_reduce: bool = False):
         """Root-unit gradients (embedding, final norm, head) are reduced here; layer units were reduced in backward."""
         for u in self.units:
             if getattr(u, "is_root", False):
@@ -244,6 +244,49 @@ class FullyShardedDataParallel(torch.nn.Module):
 
     def state_dict(self, *a, **k):
         return self.module.state_dict(*a, **k)
+
+    def scale_gradients(self, factor: float) -> None:
+        """Per-token loss normalisation (``finalize_model_grads`` divides by the global token count)."""
+        for u in self.units:
+            u.main_grad_shard.mul_(factor)
+
+    def broadcast_params(self) -> None:
+        """Make every data-parallel rank start from rank 0's parameters: each unit's shard is a slice of the SAME flat vector only if the ranks initialised
+        identically — here rank 0's full flat buffer is broadcast and re-sliced."""
+        for u in self.units:
+            was = u.resident
+            u.gather()
+            u.wait()
+            dist.broadcast(u.flat, src=dist.get_global_rank(self.group, 0), group=self.group)
+            lo = u.rank * u.shard_size
+            u.shard.copy_(u.flat[lo:lo + u.shard_size])
+            u.master.data.copy_(u.shard)
+            if not was and self.release_params and not getattr(u, "is_root", False):
+                u.release()
+
+    def load_state_dict(self, sd, strict: bool = True):
+        """Accepts either this wrapper's sharded form (``fsdp.unit{i}.master`` → master shards) or a full module state dict."""
+        if any(k.startswith("fsdp.unit") or ".fsdp.unit" in k for k in sd):
+            for i, u in enumerate(self.units):
+                key = next((k for k in sd if k.endswith(f"fsdp.unit{i}.master")), None)
+                if key is None:
+                    if strict:
+                        raise KeyError(f"fsdp.unit{i}.master missing from the checkpoint")
+                    continue
+                u.master.data.copy_(sd[key])
+            self.post_optimizer_step()
+            return
+        for u in self.units:
+            u.gather()
+            u.wait()
+        out = self.module.load_state_dict(sd, strict=strict)
+        for u in self.units:
+            lo = u.rank * u.shard_size
+            u.shard.copy_(u.flat[lo:lo + u.shard_size])
+            u.master.data.copy_(u.shard)
+            if self.release_params and not getattr(u, "is_root", False):
+                u.release()
+        return out
 
     def sharded_state_dict(self, prefix: str = "", *a, **k):
         from ...dist_checkpointing.mapping import ShardedTensor

@@ -214,6 +214,7 @@ def build_parser() -> argparse.ArgumentParser:
     g.add_argument("--use-pytorch-profiler", action="store_true", help="torch.profiler chrome trace for iterations [--profile-step-start, --profile-step-end)")
     g.add_argument("--pytorch-profiler-collect-shapes", action="store_true")
     g.add_argument("--pytorch-profiler-collect-callstack", action="store_true")
+    g.add_argument("--use-torch-fsdp2", action="store_true", help="shard with torch.distributed.fsdp.fully_shard instead of the in-house FSDP units")
     g.add_argument("--log-progress", action="store_true", help="append job start / checkpoint lines with cumulative FLOPs to <save>/progress.txt")
     g.add_argument("--record-memory-history", action="store_true", help="torch.cuda.memory._record_memory_history + snapshot dump at exit")
     g.add_argument("--memory-snapshot-path", default="snapshot.pickle")

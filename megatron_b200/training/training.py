@@ -141,6 +141,26 @@ def get_model(model_provider_func: Callable, wrap_with_ddp: bool = True) -> List
     config = chunks[0].config
     from .arguments import ddp_config_from_args
 
+    if getattr(args, "use_megatron_fsdp", False) or getattr(args, "use_torch_fsdp2", False):
+        # parameters / gradients / optimizer state sharded over the data-parallel group (reference --use-megatron-fsdp + --data-parallel-sharding-strategy,
+        # --use-torch-fsdp2); this build supports it for TP = PP = 1
+        assert args.tensor_model_parallel_size == 1 and args.pipeline_model_parallel_size == 1, "FSDP in the training loop needs TP = PP = 1 in this build"
+        ddp_config = ddp_config_from_args(args)
+        if getattr(args, "use_torch_fsdp2", False):
+            from ..core.distributed.torch_fully_sharded_data_parallel import TorchFullyShardedDataParallel
+
+            model = [TorchFullyShardedDataParallel(config, ddp_config, c, reshard_after_forward=getattr(args, "torch_fsdp2_reshard_after_forward", True)) for c in chunks]
+        else:
+            from ..core.distributed.fsdp.mcore_fsdp_adapter import wrap_model_with_fsdp
+
+            model = wrap_model_with_fsdp(chunks, config, ddp_config, strategy=getattr(args, "data_parallel_sharding_strategy", None) or "optim_grads_params")
+            if ps.get_data_parallel_world_size() > 1:
+                for m in model:
+                    m.broadcast_params()
+        for c in chunks:
+            c.config = config
+        return model
+
     ddp_config = ddp_config_from_args(args)
     if getattr(args, "ddp_num_buckets", None):
         n_params = sum(p.numel() for c in chunks for p in c.parameters())
@@ -185,7 +205,12 @@ def setup_model_and_optimizer(model_provider_func: Callable):
         loss_scale_window=args.loss_scale_window, hysteresis=args.hysteresis, overlap_param_gather=args.overlap_param_gather, timers=get_timers(),
         muon_momentum=getattr(args, "muon_momentum", 0.95), muon_ns_steps=getattr(args, "muon_ns_steps", 5), muon_tp_mode=getattr(args, "muon_tp_mode", "blockwise"),
     )
-    optimizer = get_megatron_optimizer(opt_cfg, model)
+    if getattr(args, "use_megatron_fsdp", False):
+        from ..core.distributed.fsdp.mcore_fsdp_adapter import FSDPOptimizer
+
+        optimizer = FSDPOptimizer(model, opt_cfg, ps.get_model_parallel_group())
+    else:
+        optimizer = get_megatron_optimizer(opt_cfg, model)
     scheduler = get_optimizer_param_scheduler(optimizer)
     args.iteration, args.num_floating_point_operations_so_far = 0, 0.0
     if args.load or getattr(args, "pretrained_checkpoint", None):

@@ -276,6 +276,42 @@ def test_pretrain_cli_non_persistent_checkpoints_and_load_policy(tmp_path):
     assert "no checkpoint found" in out4 and "iteration        2/" not in out4
 
 
+def _run_pretrain_world(tmp_path, extra, iters, world, port):
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(root, "pretrain_gpt.py"), "--num-layers", "2", "--hidden-size", "64", "--num-attention-heads", "4", "--ffn-hidden-size", "128",
+           "--seq-length", "32", "--max-position-embeddings", "32", "--micro-batch-size", "2", "--global-batch-size", "8", "--train-iters", str(iters), "--lr", "1e-3",
+           "--mock-data", "--tokenizer-type", "NullTokenizer", "--vocab-size", "127", "--log-interval", "1", "--distributed-backend", "gloo", "--swiglu",
+           "--normalization", "RMSNorm", "--disable-bias-linear", "--position-embedding-type", "rope", "--untie-embeddings-and-output-weights", "--seed", "11",
+           "--save", str(tmp_path / "ckpt"), "--load", str(tmp_path / "ckpt"), "--save-interval", "100", "--eval-iters", "0", "--lr-decay-iters", "100"] + extra
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", WANDB_MODE="offline")
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return r.stdout
+
+
+def _losses(out):
+    import re
+
+    return [float(x) for x in re.findall(r"lm loss: ([0-9.E+-]+)", out)]
+
+
+def test_pretrain_cli_megatron_fsdp_matches_ddp(tmp_path):
+    """--use-megatron-fsdp (ZeRO-3 units + FSDPOptimizer on the master shards) on 2 gloo ranks follows the same loss curve as plain DDP + Adam, saves, and resumes."""
+    ddp = _losses(_run_pretrain_world(tmp_path / "ddp", ["--exit-interval", "4"], 4, 2, 29641))
+    fs_out = _run_pretrain_world(tmp_path / "fsdp", ["--use-megatron-fsdp", "--data-parallel-sharding-strategy", "optim_grads_params", "--exit-interval", "4"], 6, 2, 29642)
+    fs = _losses(fs_out)
+    assert len(ddp) == 4 and len(fs) == 4
+    assert all(abs(a - b) < 2e-3 * abs(a) for a, b in zip(ddp, fs)), (ddp, fs)
+    assert fs[-1] < fs[0]
+    out2 = _run_pretrain_world(tmp_path / "fsdp", ["--use-megatron-fsdp", "--data-parallel-sharding-strategy", "optim_grads_params"], 6, 2, 29643)
+    assert "at iteration 4" in out2 and "iteration        6/" in out2 and "iteration        3/" not in out2
+    assert _losses(out2)[0] < fs[0]                               # continues from the trained state, not from scratch
+
+
 def test_config_logger_initialize_helpers_and_param_norm(tmp_path):
     from types import SimpleNamespace
 
