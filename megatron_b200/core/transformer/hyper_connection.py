@@ -77,3 +77,117 @@ class HyperConnection(MegatronModule):
     def forward(self, h: torch.Tensor, layer_fn):
         x, saved = self.width_connection(h)
         return self.depth_connection(h, layer_fn(x), saved)
+
+
+# ---- manifold-constrained hyper-connections (mHC) -----------------------------------------------------------------------------------------
+# reference ``transformer/hyper_connection.py:54-712`` (DeepSeek's mHC): the residual stream is n-wide, ``x_{l+1} = H_res x_l + H_postᵀ F(H_pre x_l)``, and the
+# stream-mixing matrix H_res is constrained to the Birkhoff polytope (doubly stochastic: it mixes but never amplifies), obtained from unconstrained logits by
+# Sinkhorn–Knopp iterations.  All three mappings are input-dependent: one projection of the RMS-scaled n·C-wide state gives n + n + n² numbers per token.
+
+
+def sinkhorn_normalize(m: torch.Tensor, iterations: int, eps: float = 1e-6) -> torch.Tensor:
+    """Alternate row / column normalisation of a positive matrix [..., n, n]."""
+    for _ in range(iterations):
+        m = m / m.sum(dim=-1, keepdim=True).clamp(min=eps)
+        m = m / m.sum(dim=-2, keepdim=True).clamp(min=eps)
+    return m
+
+
+class SinkhornKnopp(torch.autograd.Function):
+    """logits [..., n, n] → doubly stochastic matrix.  Only ``exp(logits − rowmax)`` is kept for the backward, which re-runs the iterations under autograd
+    (n is 2–8: the iterations are cheap, the activations of 20 iterations per token per layer are not).  The row-max shift does not change the result: the
+    first row normalisation cancels any per-row factor."""
+
+    @staticmethod
+    def forward(ctx, logits, iterations: int):
+        m0 = torch.exp(logits - logits.max(dim=-1, keepdim=True).values)
+        ctx.save_for_backward(m0)
+        ctx.iterations = iterations
+        return sinkhorn_normalize(m0, iterations)
+
+    @staticmethod
+    def backward(ctx, g):
+        (m0,) = ctx.saved_tensors
+        with torch.enable_grad():
+            leaf = m0.detach().requires_grad_(True)
+            out = sinkhorn_normalize(leaf, ctx.iterations)
+            (gm0,) = torch.autograd.grad(out, leaf, g)
+        return gm0 * m0, None            # d exp(x) / dx = exp(x)
+
+
+class HyperConnectionModule(MegatronModule):
+    """One mHC site (there are two per transformer layer: around attention and around the MLP)."""
+
+    def __init__(self, config, layer_number: int):
+        super().__init__(config)
+        self.layer_number = layer_number
+        self.n = n = config.mhc_num_residual_streams
+        self.hidden_size = c = config.hidden_size
+        self.sinkhorn_iterations = config.mhc_sinkhorn_iterations
+        dev = "cpu" if (config.use_cpu_initialization or not torch.cuda.is_available()) else torch.cuda.current_device()
+        self.mapping_proj = torch.nn.Linear(n * c, n * n + 2 * n, bias=False, device=dev, dtype=config.params_dtype)
+        a = config.mhc_init_gating_factor
+        self.alpha_pre = torch.nn.Parameter(torch.full((1,), a, device=dev))
+        self.alpha_post = torch.nn.Parameter(torch.full((1,), a, device=dev))
+        self.alpha_res = torch.nn.Parameter(torch.full((1,), a, device=dev))
+        self.bias = torch.nn.Parameter(torch.zeros(n * n + 2 * n, device=dev))
+        self.norm_eps = 1e-6
+        if getattr(config, "perform_initialization", True):
+            torch.nn.init.xavier_uniform_(self.mapping_proj.weight)
+        for p in self.parameters():
+            setattr(p, "sequence_parallel", bool(config.sequence_parallel))     # replicated over TP, fed by sequence-sharded activations
+
+    # ---- mappings ----------------------------------------------------------------------------------------------------------------------
+    def compute_mappings(self, x: torch.Tensor):
+        """x [s, b, n·C] → h_pre [s, b, n] ∈ (0, 1), h_post [s, b, n] ∈ (0, 2), h_res [s, b, n, n] doubly stochastic."""
+        n = self.n
+        s, b, nc = x.shape
+        r = 1.0 / (x.float().norm(dim=-1, keepdim=True) / (nc ** 0.5) + self.norm_eps)
+        proj = self.mapping_proj(x).float()
+        alpha = torch.cat([self.alpha_pre.expand(n), self.alpha_post.expand(n), self.alpha_res.expand(n * n)]).float()
+        h = r * proj * alpha + self.bias.float()
+        h_pre = torch.sigmoid(h[..., :n])
+        h_post = 2.0 * torch.sigmoid(h[..., n:2 * n])
+        h_res = SinkhornKnopp.apply(h[..., 2 * n:].reshape(s, b, n, n), self.sinkhorn_iterations)
+        return h_pre, h_post, h_res
+
+    def aggregate(self, x: torch.Tensor, h_pre: torch.Tensor) -> torch.Tensor:
+        """n streams → the layer input: Σ_i h_pre_i · x_i."""
+        s, b, nc = x.shape
+        return torch.einsum("sbn,sbnc->sbc", h_pre.to(x.dtype), x.view(s, b, self.n, nc // self.n))
+
+    def apply_h_post(self, y: torch.Tensor, h_post: torch.Tensor) -> torch.Tensor:
+        """layer output [s, b, C] → n streams [s, b, n·C]: stream i receives h_post_i · y."""
+        s, b, c = y.shape
+        return (h_post.to(y.dtype).unsqueeze(-1) * y.unsqueeze(2)).reshape(s, b, self.n * c)
+
+    def apply_h_res(self, h_res: torch.Tensor, residual: torch.Tensor) -> torch.Tensor:
+        """stream mixing: out_i = Σ_j H_res[i, j] · x_j."""
+        s, b, nc = residual.shape
+        return torch.einsum("sbij,sbjc->sbic", h_res.to(residual.dtype), residual.view(s, b, self.n, nc // self.n)).reshape(s, b, nc)
+
+    def forward(self, hidden_states: torch.Tensor):
+        """→ (layer input [s, b, C], h_res, h_post)."""
+        h_pre, h_post, h_res = self.compute_mappings(hidden_states)
+        return self.aggregate(hidden_states, h_pre), h_res, h_post
+
+    def fused_h_res_h_post_bda(self, h_res, residual, h_post, x_with_bias, dropout_prob: float, training: bool) -> torch.Tensor:
+        """``H_res · residual + H_postᵀ · dropout(x + bias)`` — the bias-dropout-add of an mHC layer."""
+        x, bias = x_with_bias
+        if bias is not None:
+            x = x + bias
+        if dropout_prob > 0.0 and training:
+            x = torch.nn.functional.dropout(x, p=dropout_prob, training=True)
+        return self.apply_h_res(h_res, residual) + self.apply_h_post(x, h_post)
+
+    @staticmethod
+    def input_expand(x: torch.Tensor, n: int) -> torch.Tensor:
+        """[s, b, C] → [s, b, n·C]: every stream starts as a copy of the embedding."""
+        s, b, c = x.shape
+        return x.unsqueeze(2).expand(s, b, n, c).reshape(s, b, n * c)
+
+    @staticmethod
+    def output_contract(x: torch.Tensor, n: int) -> torch.Tensor:
+        """[s, b, n·C] → [s, b, C]: mean over the streams (so that contract(expand(x)) == x)."""
+        s, b, nc = x.shape
+        return x.view(s, b, n, nc // n).mean(dim=2)

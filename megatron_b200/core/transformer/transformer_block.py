@@ -136,6 +136,11 @@ class TransformerBlock(GraphableMegatronModule):
             hidden_states = self.input_tensor
         hidden_states = make_viewless_tensor(hidden_states, requires_grad=True, keep_graph=True)
         rng_ctx = get_cuda_rng_tracker().fork() if (self.config.sequence_parallel and get_cuda_rng_tracker().is_initialized()) else nullcontext()
+        mhc = getattr(self.config, "enable_mhc_connections", False)
+        if mhc:
+            from .hyper_connection import HyperConnectionModule
+
+            hidden_states = HyperConnectionModule.input_expand(hidden_states, self.config.mhc_num_residual_streams)      # [s, b, C] → n streams
         with rng_ctx:
             if self.config.recompute_granularity == "full" and self.training:
                 hidden_states = self._checkpointed_forward(hidden_states, attention_mask, context, context_mask, rotary_pos_emb, attention_bias, packed_seq_params)
@@ -150,6 +155,8 @@ class TransformerBlock(GraphableMegatronModule):
                             rotary_pos_emb=rotary_pos_emb, attention_bias=attention_bias, inference_context=inference_context,
                             packed_seq_params=packed_seq_params,
                         )
+        if mhc:
+            hidden_states = HyperConnectionModule.output_contract(hidden_states, self.config.mhc_num_residual_streams)   # mean of the streams
         if self.final_layernorm is not None:
             hidden_states = self.final_layernorm(hidden_states)
             hidden_states = make_viewless_tensor(hidden_states, requires_grad=True, keep_graph=True)

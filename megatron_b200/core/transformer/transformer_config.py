@@ -91,6 +91,11 @@ class TransformerConfig(ModelParallelConfig):
     memory_efficient_layer_norm: bool = False
     bias_dropout_fusion: bool = False
     apply_rope_fusion: bool = False
+    enable_mhc_connections: bool = False          # manifold-constrained hyper-connections: n-wide residual stream (transformer/hyper_connection.py)
+    mhc_num_residual_streams: int = 4
+    mhc_sinkhorn_iterations: int = 20
+    mhc_init_gating_factor: float = 0.01
+    mhc_recompute_layer_num: Optional[int] = None
     fused_single_qkv_rope: bool = False
     fused_residual_rmsnorm: bool = False
     use_fused_weighted_squared_relu: bool = False
@@ -253,6 +258,15 @@ class TransformerConfig(ModelParallelConfig):
                     raise ValueError("num_moe_experts must be divisible by moe_router_num_groups")
                 if self.moe_router_group_topk is None:
                     raise ValueError("group-limited routing needs moe_router_group_topk")
+        if self.enable_mhc_connections:
+            if self.mtp_num_layers:
+                raise ValueError("enable_mhc_connections is not compatible with multi-token prediction")
+            if self.recompute_granularity == "full":
+                raise ValueError("enable_mhc_connections supports selective recompute only")
+            if self.pipeline_model_parallel_size > 1:
+                raise ValueError("enable_mhc_connections needs pipeline_model_parallel_size == 1 in this build (the n-wide stream does not cross stages yet)")
+            if self.mhc_num_residual_streams < 1 or self.mhc_sinkhorn_iterations < 1:
+                raise ValueError("mhc_num_residual_streams and mhc_sinkhorn_iterations must be positive")
         if self.recompute_granularity is not None:
             if self.recompute_granularity not in ("full", "selective"):
                 raise ValueError("recompute_granularity must be 'full' or 'selective'")

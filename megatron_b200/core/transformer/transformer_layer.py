@@ -116,6 +116,12 @@ class TransformerLayer(GraphableMegatronModule, BaseTransformerLayer):
         if hasattr(self.mlp, "set_layer_number"):
             self.mlp.set_layer_number(self.layer_number)
         self.mlp_bda = build_module(submodules.mlp_bda)
+        self.mhc = bool(getattr(config, "enable_mhc_connections", False))
+        if self.mhc:
+            from .hyper_connection import HyperConnectionModule
+
+            self.self_attention_hyper_connection = HyperConnectionModule(config, self.layer_number)
+            self.mlp_hyper_connection = HyperConnectionModule(config, self.layer_number)
         rm = set(config.recompute_modules or []) if config.recompute_granularity == "selective" else set()
         self.recompute_input_layernorm = "layernorm" in rm and not isinstance(self.input_layernorm, IdentityOp)
         self.recompute_pre_mlp_layernorm = "layernorm" in rm and not isinstance(self.pre_mlp_layernorm, IdentityOp)
@@ -156,6 +162,16 @@ class TransformerLayer(GraphableMegatronModule, BaseTransformerLayer):
 
     def _forward_attention(self, hidden_states, attention_mask, context, context_mask, rotary_pos_emb, attention_bias, inference_context, packed_seq_params):
         nvtx_range_push("attn")
+        if self.mhc:
+            # n-wide residual stream: the layer reads Σ h_pre_i x_i and writes H_res x + H_postᵀ F(·) (hyper_connection.HyperConnectionModule)
+            hc = self.self_attention_hyper_connection
+            residual = hidden_states
+            x, h_res, h_post = hc(hidden_states)
+            attn_out = self.self_attention(self.input_layernorm(x), attention_mask=attention_mask, inference_context=inference_context, rotary_pos_emb=rotary_pos_emb,
+                                           attention_bias=attention_bias, packed_seq_params=packed_seq_params)
+            hidden_states = hc.fused_h_res_h_post_bda(h_res, residual, h_post, attn_out, self.hidden_dropout, self.training)
+            nvtx_range_pop("attn")
+            return hidden_states, context
         residual = hidden_states
         normed, ck = self._norm_maybe_recompute(self.input_layernorm, hidden_states, self.recompute_input_layernorm)
         attn_out = self.self_attention(
@@ -184,6 +200,14 @@ class TransformerLayer(GraphableMegatronModule, BaseTransformerLayer):
 
     def _forward_mlp(self, hidden_states):
         nvtx_range_push("mlp")
+        if self.mhc:
+            hc = self.mlp_hyper_connection
+            residual = hidden_states
+            x, h_res, h_post = hc(hidden_states)
+            mlp_out = self.mlp(self.pre_mlp_layernorm(x))
+            hidden_states = hc.fused_h_res_h_post_bda(h_res, residual, h_post, mlp_out, self.hidden_dropout, self.training)
+            nvtx_range_pop("mlp")
+            return make_viewless_tensor(hidden_states, requires_grad=hidden_states.requires_grad, keep_graph=True)
         residual = hidden_states
         pre = getattr(self, "_prenormed", None)
         if pre is not None:
