@@ -102,6 +102,11 @@ class GPTModel(LanguageModule):
             )
         if self.pre_process or self.post_process:
             self.setup_embeddings_and_output_layer()
+        if getattr(config, "quant_recipe", None) is not None:
+            # per-layer precision from module-path globs (core/quantization): which projections run FP8 / MXFP8 / NVFP4, which stay bf16
+            from ...quantization import apply_quantization_recipe
+
+            self.quantized_layers = apply_quantization_recipe(self, config.quant_recipe)
 
     def set_input_tensor(self, input_tensor: Tensor) -> None:
         if not isinstance(input_tensor, list):

@@ -9,8 +9,10 @@ matchers:
   - {pattern: "*.linear_fc1",       config: fp8_hybrid}
   - {pattern: "*",                  config: bf16}
 ```
-The first matching pattern wins.  ``RecipeConfig.match(module_path)`` returns the ``QuantizationConfig`` the layer builder passes to
-``core.fp8_utils.fp8_linear``."""
+The first matching pattern wins.  ``apply_quantization_recipe(model, recipe)`` attaches the matching ``QuantizationConfig`` to every tensor-parallel linear
+layer (``module.quant_config``); the layers consult it before the model-wide ``config.fp8`` / autocast state (``tensor_parallel/layers.py::_fp8_choice``), so a
+recipe can quantise single projections, keep the first / last layers or the output head in bf16, or mix MXFP8 and NVFP4.  ``TransformerConfig.quant_recipe``
+(a ``RecipeConfig`` or a YAML path; reference ``--te-precision-config-file`` / ``--kitchen-config-file``) is applied by ``GPTModel`` at construction."""
 from __future__ import annotations
 
 import fnmatch
@@ -21,7 +23,7 @@ from typing import Dict, List, Optional
 @dataclass
 class QuantizationConfig:
     name: str = "bf16"
-    recipe: str = "none"          # none | tensorwise | delayed
+    recipe: str = "none"          # none | tensorwise | delayed | mxfp8 (blockwise) | nvfp4
     fp8_format: str = "hybrid"    # hybrid (e4m3 fwd / e5m2 grads) | e4m3
     extra: Dict = field(default_factory=dict)
 
@@ -68,3 +70,23 @@ class RecipeConfig:
 
 def load_quantization_recipe(path: str) -> RecipeConfig:
     return RecipeConfig.from_yaml_file(path)
+
+
+def get_quant_config_or_none(module_path: str, recipe: Optional[RecipeConfig]) -> Optional[QuantizationConfig]:
+    return recipe.match(module_path) if recipe is not None else None
+
+
+def apply_quantization_recipe(model, recipe) -> Dict[str, str]:
+    """Attach per-layer configs; returns {module path: config name} for the layers that matched (handy for logging what runs in which precision)."""
+    from ..tensor_parallel.layers import ColumnParallelLinear, RowParallelLinear
+
+    if isinstance(recipe, str):
+        recipe = load_quantization_recipe(recipe)
+    chosen: Dict[str, str] = {}
+    for name, mod in model.named_modules():
+        if isinstance(mod, (ColumnParallelLinear, RowParallelLinear)):
+            qc = recipe.match(name)
+            if qc is not None:
+                mod.quant_config = qc
+                chosen[name] = qc.name
+    return chosen

@@ -273,6 +273,18 @@ def _fp8_recipe(config) -> str:
     return {"delayed": "tensorwise", "blockwise": "mxfp8"}.get(r, r)      # delayed scaling needs per-layer meta objects: falls back to current scaling here
 
 
+def _fp8_choice(module):
+    """→ ``(recipe, fp8_format)`` for THIS layer or ``None`` (bf16).  A per-layer ``quant_config`` (attached by ``core.quantization.apply_quantization_recipe``
+    from glob matchers over module paths) wins over the model-wide ``config.fp8`` / autocast state."""
+    qc = getattr(module, "quant_config", None)
+    if qc is not None:
+        if not qc.enabled:
+            return None
+        return {"delayed": "tensorwise", "blockwise": "mxfp8"}.get(qc.recipe, qc.recipe), qc.fp8_format
+    cfg = module.config
+    return (_fp8_recipe(cfg), cfg.fp8) if _fp8_active(cfg) else None
+
+
 class ColumnParallelLinear(torch.nn.Module):
     """Y = X Aᵀ with A sharded along its output dimension."""
 
@@ -359,11 +371,12 @@ class ColumnParallelLinear(torch.nn.Module):
             x = copy_to_tensor_model_parallel_region(input_, group=self.tp_group)
         if self.config.defer_embedding_wgrad_compute and self.embedding_activation_buffer is not None:
             self.embedding_activation_buffer.append(x)
-        if _fp8_active(self.config) and not self.explicit_expert_comm:
+        fp8 = _fp8_choice(self)
+        if fp8 is not None and not self.explicit_expert_comm:
             # FP8 / MXFP8 recipe: collectives through the autograd mappings, the three GEMMs of the layer through core.fp8_utils.fp8_linear
             from ..fp8_utils import fp8_linear
 
-            if self.sequence_parallel and _fp8_recipe(self.config) == "mxfp8" and getattr(self.config, "fp8_quantized_all_gather", True) and x.shape[-1] % 128 == 0 \
+            if self.sequence_parallel and fp8[0] == "mxfp8" and getattr(self.config, "fp8_quantized_all_gather", True) and x.shape[-1] % 128 == 0 \
                     and get_pg_size(self.tp_group) > 1:
                 from ..fp8_utils import mxfp8_sp_column_linear
 
@@ -371,7 +384,7 @@ class ColumnParallelLinear(torch.nn.Module):
             else:
                 xg = gather_from_sequence_parallel_region(x, tensor_parallel_output_grad=True, group=self.tp_group) if self.sequence_parallel else (
                     copy_to_tensor_model_parallel_region(x, group=self.tp_group) if self.allreduce_dgrad else x)
-                out_parallel = fp8_linear(xg, weight, recipe=_fp8_recipe(self.config), fp8_format=self.config.fp8)
+                out_parallel = fp8_linear(xg, weight, recipe=fp8[0], fp8_format=fp8[1])
             if bias is not None:
                 out_parallel = out_parallel + bias
             gather = self.gather_output if runtime_gather_output is None else runtime_gather_output
@@ -500,10 +513,11 @@ class RowParallelLinear(torch.nn.Module):
 
     def forward(self, input_):
         x = input_ if self.input_is_parallel else scatter_to_tensor_model_parallel_region(input_, group=self.tp_group)
-        if _fp8_active(self.config) and not self.explicit_expert_comm and self.weight.requires_grad:
+        fp8 = _fp8_choice(self)
+        if fp8 is not None and not self.explicit_expert_comm and self.weight.requires_grad:
             from ..fp8_utils import fp8_linear
 
-            out = fp8_linear(x, self.weight, recipe=_fp8_recipe(self.config), fp8_format=self.config.fp8)
+            out = fp8_linear(x, self.weight, recipe=fp8[0], fp8_format=fp8[1])
             if get_pg_size(self.tp_group) > 1:
                 out = (reduce_scatter_to_sequence_parallel_region if self.sequence_parallel else reduce_from_tensor_model_parallel_region)(out, group=self.tp_group)
         elif self.explicit_expert_comm:

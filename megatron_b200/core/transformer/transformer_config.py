@@ -91,6 +91,7 @@ class TransformerConfig(ModelParallelConfig):
     memory_efficient_layer_norm: bool = False
     bias_dropout_fusion: bool = False
     apply_rope_fusion: bool = False
+    quant_recipe: Optional[object] = None          # core.quantization.RecipeConfig or a YAML path: per-layer FP8 / MXFP8 / NVFP4 / bf16 by module-path globs
     enable_mhc_connections: bool = False          # manifold-constrained hyper-connections: n-wide residual stream (transformer/hyper_connection.py)
     mhc_num_residual_streams: int = 4
     mhc_sinkhorn_iterations: int = 20

@@ -412,6 +412,9 @@ def core_transformer_config_from_args(args):
     if getattr(args, "init_method_xavier_uniform", False):
         kw["init_method"] = torch.nn.init.xavier_uniform_
         kw["output_layer_init_method"] = torch.nn.init.xavier_uniform_
+    recipe_file = getattr(args, "te_precision_config_file", None) or getattr(args, "kitchen_config_file", None)
+    if recipe_file:
+        kw["quant_recipe"] = recipe_file                        # YAML of per-layer precision matchers (core/quantization)
     if getattr(args, "multi_latent_attention", False):
         # DeepSeek-style attention: its dimensions / YaRN parameters come from the reference-named flags (--q-lora-rank, --kv-lora-rank, --qk-head-dim,
         # --qk-pos-emb-head-dim, --v-head-dim, --rope-type, --rotary-scaling-factor, --mscale, --mscale-all-dim, --yarn-*) when given

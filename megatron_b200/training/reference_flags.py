@@ -77,7 +77,8 @@ WIRED: Dict[str, str] = {
     "init_method_xavier_uniform": "xavier-uniform init", "spec": "user layer spec (module, function) in pretrain_gpt.py", "mmap_bin_files": "GPTDatasetConfig.mmap_bin_files (--no-mmap-bin-files)",
     "num_dataset_builder_threads": "GPTDatasetConfig.num_dataset_builder_threads", "fim_data": "GPTFIMDataset around the train split", "fim_rate": "FIMConfig.fim_rate", "fim_spm_rate": "FIMConfig.fim_spm_rate",
     "fim_prefix_token": "FIMConfig.prefix_id", "fim_middle_token": "FIMConfig.middle_id", "fim_suffix_token": "FIMConfig.suffix_id", "fim_pad_token": "FIMConfig.pad_id", "fim_eod_token": "FIMConfig.eod_id",
-    "ft_num_warmup_iters": "FaultToleranceMonitor.min_samples",
+    "ft_num_warmup_iters": "FaultToleranceMonitor.min_samples", "te_precision_config_file": "TransformerConfig.quant_recipe (per-layer precision YAML)",
+    "kitchen_config_file": "TransformerConfig.quant_recipe (per-layer precision YAML)",
     # serving (tools/run_text_generation_server.py through engine_kwargs_from_args)
     "inference_dynamic_batching_block_size": "engine block_size", "inference_dynamic_batching_max_requests": "engine max_running", "inference_max_requests": "engine max_running",
     "inference_dynamic_batching_max_tokens": "engine max_prefill_tokens_per_step", "enable_chunked_prefill": "engine max_prefill_tokens_per_step (2048 when no budget is given)",

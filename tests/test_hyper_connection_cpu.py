@@ -80,3 +80,46 @@ def _mhc_worker(rank, world):
 
 def test_mhc_module_layer_formula_and_gpt_training():
     assert run_distributed(_mhc_worker, 1) == [True]
+
+
+def _quant_recipe_worker(rank, world, path):
+    """A per-layer precision recipe: fc1 of every layer in FP8 (tensorwise), layer 0 and everything else bf16 — the chosen layers really take the FP8 path
+    (their output differs from bf16 by quantisation noise, the others are bit-identical) and the model still trains."""
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+    from megatron_b200.core.quantization import RecipeConfig, load_quantization_recipe
+    from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    ps.initialize_model_parallel()
+    recipe = load_quantization_recipe(path)
+    assert isinstance(recipe, RecipeConfig) and recipe.match("decoder.layers.0.mlp.linear_fc1").name == "bf16" and recipe.match("decoder.layers.1.mlp.linear_fc1").name == "fp8"
+    kw = dict(num_layers=2, hidden_size=64, num_attention_heads=4, ffn_hidden_size=128, add_bias_linear=False, normalization="RMSNorm", use_cpu_initialization=True,
+              hidden_dropout=0.0, attention_dropout=0.0, bias_dropout_fusion=False)
+    outs = {}
+    for name, qr in (("plain", None), ("recipe", path)):
+        model_parallel_cuda_manual_seed(5)
+        torch.manual_seed(5)
+        m = GPTModel(TransformerConfig(quant_recipe=qr, **kw), get_gpt_layer_local_spec(normalization="RMSNorm"), vocab_size=64, max_sequence_length=16, position_embedding_type="rope")
+        if qr:
+            assert m.quantized_layers["decoder.layers.1.mlp.linear_fc1"] == "fp8" and m.quantized_layers["decoder.layers.0.mlp.linear_fc1"] == "bf16"
+            assert m.quantized_layers["output_layer"] == "bf16" and m.decoder.layers[1].mlp.linear_fc1.quant_config.enabled
+        tokens = torch.randint(0, 64, (2, 16), generator=torch.Generator().manual_seed(1))
+        pos = torch.arange(16)[None].expand(2, -1)
+        x = torch.randn(16, 2, 64, generator=torch.Generator().manual_seed(2))
+        outs[name] = (m.decoder.layers[0].mlp.linear_fc1(x)[0].detach(), m.decoder.layers[1].mlp.linear_fc1(x)[0].detach())
+        loss = m(tokens, pos, None, labels=tokens.roll(-1, 1)).mean()
+        loss.backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    assert torch.equal(outs["plain"][0], outs["recipe"][0])                                    # layer 0 stays bf16 / fp32: identical
+    d = (outs["plain"][1] - outs["recipe"][1]).abs().max().item()
+    assert 0 < d < 0.1 * outs["plain"][1].abs().max().item()                                  # layer 1 fc1 went through the FP8 GEMM
+    return True
+
+
+def test_per_layer_quantization_recipe(tmp_path):
+    p = tmp_path / "recipe.yaml"
+    p.write_text("configs:\n  fp8: {recipe: tensorwise, fp8_format: hybrid}\n  bf16: {recipe: none}\nmatchers:\n  - {pattern: 'decoder.layers.0.*', config: bf16}\n"
+                 "  - {pattern: '*.linear_fc1', config: fp8}\n  - {pattern: '*', config: bf16}\n")
+    assert run_distributed(_quant_recipe_worker, 1, str(p)) == [True]
