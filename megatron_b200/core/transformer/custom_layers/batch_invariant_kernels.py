@@ -6,7 +6,10 @@ Sources of batch-size dependence and how this framework removes them when the mo
   variant (1-CTA 128×256) instead of the per-shape autotuner choice, so every output element is always reduced in the same k-block order.
 * log-softmax / mean / norms: reductions run per row with a fixed tree, independent of the number of rows — already invariant.
 * attention: the KV block size (64) and the in-order accumulation over KV blocks do not depend on the batch — invariant; the mode forces
-  the native kernel (library kernels may pick split-KV heuristics by batch size)."""
+  the native kernel (library kernels may pick split-KV heuristics by batch size).
+* paged decode: the flash-decoding kernel normally sizes its KV splits from (batch, longest request) to fill the GPU; the mode pins the split length to 512
+  tokens, so split boundaries sit at fixed absolute positions and the partials of a request are combined in the same order whatever it is batched with
+  (``tests/test_paged_attention_gpu.py::test_paged_decode_is_batch_invariant_in_the_mode``)."""
 from __future__ import annotations
 
 import contextlib

@@ -464,7 +464,11 @@ def paged_attention_decode(q, k_pool, v_pool, block_table, lengths, scale: float
     B, hq, d = q.shape
     hk = k_pool.shape[2]
     if _use_cuda(q) and hasattr(ext(), "paged_decode") and q.dtype == torch.bfloat16 and d in (64, 128) and hq % hk == 0 and hq // hk in (1, 2, 4, 8):
-        out = ext().paged_decode(q.contiguous(), k_pool, v_pool, block_table.to(torch.int32).contiguous(), lengths.to(torch.int32).contiguous(), float(scale), int(max_len))
+        from ..core.transformer.custom_layers.batch_invariant_kernels import is_batch_invariant_mode_enabled
+
+        # batch-invariant mode: split boundaries at fixed positions (512 tokens) so that a request's reduction order does not depend on its batch
+        out = ext().paged_decode(q.contiguous(), k_pool, v_pool, block_table.to(torch.int32).contiguous(), lengths.to(torch.int32).contiguous(), float(scale), int(max_len),
+                                 512 if is_batch_invariant_mode_enabled() else 0)
         _count(2)
         return out
     bs = k_pool.shape[1]

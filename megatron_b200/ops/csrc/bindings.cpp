@@ -570,7 +570,10 @@ void paged_kv_append(const Tensor& k_new, const Tensor& v_new, Tensor k_pool, Te
 }
 
 // q [B, hq, d] -> out [B, hq, d]: attention of one new token per request over its pages (lengths include the new token)
-Tensor paged_decode(const Tensor& q, const Tensor& k_pool, const Tensor& v_pool, const Tensor& block_table, const Tensor& lengths, double scale, int64_t max_len) {
+// fixed_tokens_per_split > 0: split boundaries at fixed absolute positions irrespective of the batch (batch-invariant mode: a request's result is then
+// bitwise independent of what it is co-scheduled with); 0: size the splits for two waves of CTAs
+Tensor paged_decode(const Tensor& q, const Tensor& k_pool, const Tensor& v_pool, const Tensor& block_table, const Tensor& lengths, double scale, int64_t max_len,
+                    int64_t fixed_tokens_per_split) {
   TORCH_CHECK(q.is_cuda() && q.scalar_type() == at::kBFloat16 && q.is_contiguous() && k_pool.is_contiguous() && v_pool.is_contiguous() && k_pool.scalar_type() == at::kBFloat16, "paged_decode: contiguous bf16 CUDA tensors");
   TORCH_CHECK(block_table.scalar_type() == at::kInt && lengths.scalar_type() == at::kInt && block_table.is_contiguous() && lengths.is_contiguous(), "paged_decode: int32 block table / lengths");
   c10::cuda::CUDAGuard g(q.device());
@@ -579,7 +582,8 @@ Tensor paged_decode(const Tensor& q, const Tensor& k_pool, const Tensor& v_pool,
   int nsplit = (int)((2 * 148 + (int64_t)B * hk - 1) / ((int64_t)B * hk));
   const int max_steps = (int)((max_len + 127) / 128);
   nsplit = std::max(1, std::min(nsplit, max_steps));
-  const int tokens_per_split = ((max_steps + nsplit - 1) / nsplit) * 128;
+  int tokens_per_split = ((max_steps + nsplit - 1) / nsplit) * 128;
+  if (fixed_tokens_per_split > 0) tokens_per_split = (int)((fixed_tokens_per_split + 127) / 128 * 128);
   nsplit = (int)((max_len + tokens_per_split - 1) / tokens_per_split);
   nsplit = std::max(1, nsplit);
   auto o_part = at::empty({(int64_t)B * hq * nsplit * d}, q.options().dtype(at::kFloat));
@@ -1044,7 +1048,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 #endif
 #ifdef MB200_HAVE_PAGED_ATTENTION
   m.def("paged_kv_append", &paged_kv_append);
-  m.def("paged_decode", &paged_decode);
+  m.def("paged_decode", &paged_decode, pybind11::arg("q"), pybind11::arg("k_pool"), pybind11::arg("v_pool"), pybind11::arg("block_table"), pybind11::arg("lengths"),
+        pybind11::arg("scale"), pybind11::arg("max_len"), pybind11::arg("fixed_tokens_per_split") = 0);
 #endif
 #ifdef MB200_HAVE_MOE_KERNELS
   m.def("moe_gather_rows", &moe_gather_rows);

@@ -103,3 +103,41 @@ def test_dynamic_engine_cuda_graph_decode_matches_eager():
         if graphs:
             assert eng.graph_replays > 0 and len(eng._graphs) >= 1
     assert outs[0] == outs[1]
+
+
+def test_paged_decode_is_batch_invariant_in_the_mode():
+    """Batch-invariant mode: a request's decode attention is bitwise the same alone, in a batch of 8, and next to a much longer request (which changes the
+    default split sizing); without the mode the bits may differ (they do for this shape) while values agree to rounding."""
+    import math
+
+    from megatron_b200 import ops
+    from megatron_b200.core.transformer.custom_layers.batch_invariant_kernels import set_batch_invariant_mode
+
+    torch.manual_seed(0)
+    hq, hk, d, bs = 32, 8, 128, 16
+    lens = [700, 1500, 333, 4096, 64, 2049, 900, 17]
+    width = (max(lens) + bs - 1) // bs
+    nb = sum((l + bs - 1) // bs for l in lens) + 1
+    kp = torch.randn(nb, bs, hk, d, device="cuda").bfloat16()
+    vp = torch.randn_like(kp)
+    table = torch.zeros(len(lens), width, dtype=torch.int32, device="cuda")
+    nxt = 1
+    for i, l in enumerate(lens):
+        n = (l + bs - 1) // bs
+        table[i, :n] = torch.arange(nxt, nxt + n, dtype=torch.int32, device="cuda")
+        nxt += n
+    q = torch.randn(len(lens), hq, d, device="cuda").bfloat16()
+    L = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    scale = 1 / math.sqrt(d)
+
+    def run(idx):
+        sel = torch.tensor(idx, device="cuda")
+        return ops.paged_attention_decode(q[sel], kp, vp, table[sel], L[sel], scale, max(lens[i] for i in idx))
+
+    with set_batch_invariant_mode(True):
+        full = run(list(range(8)))
+        for i in (0, 2, 3, 7):
+            assert torch.equal(run([i])[0], full[i]), f"request {i} alone differs from the batch of 8"
+        assert torch.equal(run([2, 3])[0], full[2]) and torch.equal(run([7, 0, 5])[1], full[0])
+    loose = run(list(range(8)))
+    assert (loose.float() - full.float()).abs().max().item() < 2e-2
