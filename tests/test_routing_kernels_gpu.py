@@ -134,7 +134,9 @@ def test_mla_attention_uses_the_fused_rope_kernels():
     if not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29733")
         dist.init_process_group("nccl", rank=0, world_size=1)
-    ps.initialize_model_parallel()
+    mine = not ps.model_parallel_is_initialized()             # another test of this process may have left the groups up
+    if mine:
+        ps.initialize_model_parallel()
     try:
         model_parallel_cuda_manual_seed(7)
         cfg = MLATransformerConfig(num_layers=1, hidden_size=512, num_attention_heads=8, q_lora_rank=128, kv_lora_rank=128, qk_head_dim=64, qk_pos_emb_head_dim=32,
@@ -153,4 +155,5 @@ def test_mla_attention_uses_the_fused_rope_kernels():
         assert (outs[0][0] - outs[1][0]).abs().max().item() < 2e-2 * outs[1][0].abs().max().item()
         assert (outs[0][1] - outs[1][1]).abs().max().item() < 3e-2 * outs[1][1].abs().max().item()
     finally:
-        ps.destroy_model_parallel()
+        if mine:
+            ps.destroy_model_parallel()
