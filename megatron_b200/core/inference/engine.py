@@ -125,6 +125,11 @@ class DynamicInferenceEngine:
         dev = next(model.parameters()).device
         dt = next(model.parameters()).dtype
         tp = cfg.tensor_model_parallel_size
+        ol = getattr(model, "output_layer", None)
+        if tp > 1 and ol is not None and getattr(ol, "gather_output", True) is False:
+            # a training-style model returns vocabulary-PARALLEL logits: every TP rank would sample from its own shard.  Serving needs the gathered distribution.
+            ol.gather_output = True
+            model.parallel_output = False
         self.cache = PagedKVCache(cfg.num_layers, num_blocks, block_size, max(cfg.num_query_groups // tp, 1), cfg.kv_channels, dt, dev, enable_prefix_caching)
         self.waiting: Deque[InferenceRequest] = deque()
         self.running: List[InferenceRequest] = []

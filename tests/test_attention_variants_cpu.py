@@ -430,3 +430,64 @@ def _zmq_serving(rank, world):
 
 def test_zmq_coordinator_routes_between_data_parallel_engines():
     run_distributed(_zmq_serving, 1)
+
+
+def _tp2_serving(rank, world):
+    """The dynamic engine on a TP=2 model (2 gloo ranks, each with its half of the KV heads in its own paged cache): every rank runs the same schedule and
+    emits the same tokens as the TP=1 static engine — incl. chunked prefill and bucketed decode."""
+    import torch.nn.functional as F
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.inference.engine import DynamicInferenceEngine, StaticInferenceEngine
+    from megatron_b200.core.inference.sampling import SamplingParams
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+    from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    def build(tp):
+        cfg = TransformerConfig(num_layers=2, hidden_size=64, num_attention_heads=8, num_query_groups=4, ffn_hidden_size=128, gated_linear_unit=True, activation_func=F.silu,
+                                add_bias_linear=False, normalization="RMSNorm", tensor_model_parallel_size=tp, **_KW)
+        # serving models gather the vocabulary-parallel logits (parallel_output=False): every TP rank samples from the full distribution
+        return GPTModel(cfg, get_gpt_layer_local_spec(normalization="RMSNorm"), vocab_size=96, max_sequence_length=128, position_embedding_type="rope", parallel_output=False).eval()
+
+    # TP=1 reference weights, built identically on every rank, then sharded by hand into the TP=2 model
+    ps.initialize_model_parallel(tensor_model_parallel_size=1)
+    model_parallel_cuda_manual_seed(3)
+    torch.manual_seed(3)
+    full = build(1)
+    prompts = [[5, 17, 3, 42, 8, 1, 2, 7, 7, 7, 11], [9, 9], [30, 31, 32, 33, 34], [1]]
+    gens = [6, 9, 3, 7]
+    ref = StaticInferenceEngine(full, max_sequence_length=128)
+    want = [ref.generate([p], SamplingParams(temperature=0.0, num_tokens_to_generate=n))[0] for p, n in zip(prompts, gens)]
+    sd = {k: v.clone() for k, v in full.state_dict().items() if isinstance(v, torch.Tensor)}
+    ps.destroy_model_parallel()
+    ps.initialize_model_parallel(tensor_model_parallel_size=2)
+    model_parallel_cuda_manual_seed(3)
+    tp_model = build(2)
+    with torch.no_grad():
+        for name, p in tp_model.named_parameters():
+            w = sd[name]
+            if p.shape == w.shape:
+                p.copy_(w)
+            elif name.endswith("linear_qkv.weight"):                    # [groups x (q per group + k + v) x d, h]: split by query group
+                p.copy_(w.view(4, -1, w.shape[-1]).chunk(2, 0)[rank].reshape(p.shape))
+            elif name.endswith("linear_fc1.weight"):                    # [gate; up] each split over TP
+                g, u = w.chunk(2, 0)
+                p.copy_(torch.cat([g.chunk(2, 0)[rank], u.chunk(2, 0)[rank]], 0))
+            else:
+                dim = 0 if p.shape[0] != w.shape[0] else 1
+                p.copy_(w.chunk(2, dim)[rank])
+    tp_model.output_layer.gather_output, tp_model.parallel_output = False, True      # a training-style model: the engine switches it to gathered logits itself
+    for kw in (dict(), dict(max_prefill_tokens_per_step=4), dict(decode_batch_buckets=[2, 4])):
+        e = DynamicInferenceEngine(tp_model, num_blocks=64, block_size=4, max_running=4, vocab_size=96, **kw)
+        assert tp_model.output_layer.gather_output is True
+        assert e.cache.k.shape[3] == 2                                  # this rank's half of the 4 KV heads
+        ids = [e.add_request(p, SamplingParams(temperature=0.0, num_tokens_to_generate=n)) for p, n in zip(prompts, gens)]
+        fin = e.run_until_done()
+        assert [fin[i].generated_tokens for i in ids] == want, (rank, kw)
+    return True
+
+
+def test_dynamic_engine_on_tensor_parallel_model():
+    assert all(run_distributed(_tp2_serving, 2))
