@@ -100,3 +100,23 @@ def test_fp8_gemm_matches_emulation(M, N, K):
         ref = (aq.float() @ bq.float().t()) * (ai * bi)
         err = (out.float() - ref).abs().max().item() / ref.abs().max().item()
         assert err < 1e-2, f"{da}x{db}: rel err {err}"
+
+
+def test_gemm_is_batch_invariant_in_the_mode():
+    """Batch-invariant mode pins ONE tcgen05 variant (no autotuner, no library, no split-K): a row's result does not depend on how many other rows are in the
+    batch — bitwise — for the forward (NT) and the dgrad (NN) GEMMs of a linear layer."""
+    from megatron_b200 import ops
+    from megatron_b200.core.transformer.custom_layers.batch_invariant_kernels import set_batch_invariant_mode
+
+    torch.manual_seed(0)
+    K, N = 4096, 1536
+    x = torch.randn(4096, K, device="cuda").bfloat16()
+    w = torch.randn(N, K, device="cuda").bfloat16()
+    gy = torch.randn(4096, N, device="cuda").bfloat16()
+    with set_batch_invariant_mode(True):
+        full_f, full_b = ops.gemm_nt(x, w), ops.gemm_nn(gy, w)
+        for m in (1, 8, 129, 1000, 2048):
+            assert torch.equal(ops.gemm_nt(x[:m].contiguous(), w), full_f[:m]), f"forward rows differ at batch {m}"
+            assert torch.equal(ops.gemm_nn(gy[:m].contiguous(), w), full_b[:m]), f"dgrad rows differ at batch {m}"
+        assert torch.equal(ops.gemm_nt(x[1000:1016].contiguous(), w), full_f[1000:1016])      # and not on where in the batch the row sits
+    _check(full_f, x.float() @ w.float().t(), K)
