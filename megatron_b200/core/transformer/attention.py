@@ -36,6 +36,28 @@ class CrossAttentionSubmodules:
     linear_proj: Union[ModuleSpec, type] = None
 
 
+def packed_positions(cu_seqlens: torch.Tensor, total: int) -> torch.Tensor:
+    """Position of every token inside its own sequence, for a pack described by cumulative lengths (tokens after the last boundary continue the last sequence)."""
+    cu = cu_seqlens.to(dtype=torch.long)
+    idx = torch.arange(total, device=cu.device)
+    sid = torch.bucketize(idx, cu[1:], right=True).clamp_(max=cu.numel() - 2)
+    return idx - cu[sid]
+
+
+def _packed_angles(angles: torch.Tensor, psp, total: int, which: str) -> torch.Tensor:
+    cu = getattr(psp, f"cu_seqlens_{which}_padded", None)
+    if cu is None:
+        cu = getattr(psp, f"cu_seqlens_{which}")
+    cache = psp.__dict__.setdefault("_angle_rows", {})
+    key = (which, total, angles.data_ptr())
+    if key not in cache:
+        pos = packed_positions(cu.to(angles.device), total)
+        assert int(pos.max()) < angles.shape[0], f"rotary table has {angles.shape[0]} rows, the longest packed sequence needs {int(pos.max()) + 1}"
+        cache.clear()
+        cache[key] = angles[pos]
+    return cache[key]
+
+
 class Attention(MegatronModule):
     """Shared machinery: KV cache for inference, RoPE, core attention, output projection."""
 
@@ -147,7 +169,13 @@ class Attention(MegatronModule):
         query, key_c, value_c, rotary_pos_emb, mask_type = self._adjust_key_value_for_inference(inference_context, query, key, value, rotary_pos_emb)
         if rotary_pos_emb is not None:
             q_pos, k_pos = rotary_pos_emb
-            if inference_context is None:
+            if inference_context is None and packed_seq_params is not None and getattr(packed_seq_params, "qkv_format", "thd") == "thd":
+                # packed (THD) batch: positions restart at every sequence boundary — gather the angle rows by per-token position, ONE rope call per tensor
+                # (reference: TE's thd rope kernels driven by cu_seqlens, rope_utils.py:180-260)
+                q_pos, k_pos = _packed_angles(q_pos, packed_seq_params, query.size(0), "q"), _packed_angles(k_pos, packed_seq_params, key_c.size(0), "kv")
+                query = ops.apply_rope(query, q_pos, self.config.rotary_interleaved)
+                key_c = ops.apply_rope(key_c, k_pos, self.config.rotary_interleaved)
+            elif inference_context is None:
                 query = ops.apply_rope(query, q_pos, self.config.rotary_interleaved)
                 key_c = ops.apply_rope(key_c, k_pos, self.config.rotary_interleaved)
             else:

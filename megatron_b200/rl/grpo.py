@@ -25,6 +25,8 @@ class GRPOConfig:
     entropy_coef: float = 0.0                      # weight of the (sampled-token) entropy bonus (reference --grpo-entropy-term-weight)
     clip_eps_upper: Optional[float] = None         # asymmetric clipping (reference --grpo-clamp-eps-upper); None = clip_eps
     filter_groups_with_same_reward: bool = False   # groups whose rollouts all scored the same carry no signal: drop them from the loss
+    use_sequence_packing: bool = False             # log-probs / training on packed (THD) rows instead of padded ones (rl/sequence_packing_utils.py)
+    packing_bin_size: int = 512
 
 
 class Environment:
@@ -112,6 +114,19 @@ class GRPOTrainer:
             mask[i, len(p) - 1 : len(o) - 1] = 1.0   # positions whose TARGET is a completion token
         return tokens, mask, rewards.to(dev)
 
+    def _packed_logprobs(self, model, tokens: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+        """Same ``[b, s - 1]`` result as ``sequence_logprobs`` but computed on packed rows: padding never enters the model."""
+        from .sequence_packing_utils import build_packed_batch, pack_sequences, packed_sequence_logprobs, unpack
+
+        lens = [int(mask[i].nonzero().max()) + 2 if mask[i].any() else 1 for i in range(tokens.shape[0])]       # real length = last completion target + 1
+        seqs = [tokens[i, :n].tolist() for i, n in enumerate(lens)]
+        out = torch.zeros(tokens.shape[0], tokens.shape[1] - 1, device=tokens.device)
+        for idx in pack_sequences(lens, self.cfg.packing_bin_size):
+            pb = build_packed_batch(seqs, [1] * len(seqs), idx, device=tokens.device)
+            for i, lp in zip(pb.seq_index, unpack(packed_sequence_logprobs(model, pb, self.vocab), pb)):
+                out[i, : lp.numel()] = lp
+        return out
+
     def step(self, n_prompts: int = 4, inner_epochs: int = 1):
         prof = self.profiler
         with prof.phase("rollout"):
@@ -122,13 +137,14 @@ class GRPOTrainer:
             r = rewards.view(-1, self.cfg.group_size)
             informative = (r.max(dim=1).values > r.min(dim=1).values).repeat_interleave(self.cfg.group_size)
             mask = mask * informative.unsqueeze(-1).to(mask.dtype)
+        lp_fn = (lambda m: self._packed_logprobs(m, tokens, mask)) if self.cfg.use_sequence_packing else (lambda m: sequence_logprobs(m, tokens, self.vocab))
         with torch.no_grad(), prof.phase("logprobs", tokens=2 * tokens.numel()):
-            old = sequence_logprobs(self.model, tokens, self.vocab)
-            ref = sequence_logprobs(self.ref, tokens, self.vocab)
+            old = lp_fn(self.model)
+            ref = lp_fn(self.ref)
         stats = {}
         with prof.phase("train", tokens=inner_epochs * tokens.numel()):
             for _ in range(inner_epochs):
-                logp = sequence_logprobs(self.model, tokens, self.vocab)
+                logp = lp_fn(self.model)
                 loss, stats = grpo_loss(logp, old, ref, adv, mask, self.cfg)
                 self.opt.zero_grad()
                 loss.backward()

@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--rl-default-temperature", type=float, default=None)
     ap.add_argument("--perform-rl-step", action="store_true", help="accepted: this entry point always performs RL steps")
     ap.add_argument("--train-iters", type=int, default=None)
+    ap.add_argument("--rl-use-sequence-packing", action="store_true", help="log-probs / training on packed (THD) rows: no padding enters the model")
+    ap.add_argument("--rl-sequence-packing-bin-size", type=int, default=512)
     ap.add_argument("--rl-profile", action="store_true", help="time the rollout / log-prob / train phases of every iteration")
     ap.add_argument("--rl-profile-dir", default=None)
     args = ap.parse_args()
@@ -70,6 +72,7 @@ def main():
     if args.rl_default_temperature is not None:
         cfg.temperature = args.rl_default_temperature
     cfg.filter_groups_with_same_reward = args.grpo_filter_groups_with_same_reward
+    cfg.use_sequence_packing, cfg.packing_bin_size = args.rl_use_sequence_packing, args.rl_sequence_packing_bin_size
     tr = GRPOTrainer(model, ref, opt, CountTokenEnv(args.vocab), cfg, vocab_size=args.vocab)
     if args.rl_profile:
         from megatron_b200.rl.rl_profiling import RLProfiler
