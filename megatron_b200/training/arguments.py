@@ -131,6 +131,7 @@ def build_parser() -> argparse.ArgumentParser:
     g = p.add_argument_group("mixed precision")
     g.add_argument("--fp16", action="store_true")
     g.add_argument("--bf16", action="store_true")
+    g.add_argument("--no-bf16-tiny", dest="bf16", action="store_false", help="examples' TINY (CPU smoke) mode: undo an earlier --bf16")
     g.add_argument("--loss-scale", type=float, default=None)
     g.add_argument("--initial-loss-scale", type=float, default=2**32)
     g.add_argument("--min-loss-scale", type=float, default=1.0)
