@@ -53,7 +53,8 @@ def _packed_angles(angles: torch.Tensor, psp, total: int, which: str) -> torch.T
     if key not in cache:
         pos = packed_positions(cu.to(angles.device), total)
         assert int(pos.max()) < angles.shape[0], f"rotary table has {angles.shape[0]} rows, the longest packed sequence needs {int(pos.max()) + 1}"
-        cache.clear()
+        if len(cache) >= 4:                         # q and kv entries of the current rotary table; anything older belongs to a previous table
+            cache.clear()
         cache[key] = angles[pos]
     return cache[key]
 
