@@ -161,9 +161,10 @@ class _RingAttnFn(torch.autograd.Function):
         acc = [[None, None], [None, None]]
         cur = torch.cat([k, v], dim=-1)
         dk_ = k.shape[-1]
+        overlap = hasattr(shift, "start")
         for step in range(cp):
             src = (rank - step) % cp
-            nxt = shift(cur, False) if step < cp - 1 else None
+            nxt = (shift.start(cur, False) if overlap else shift(cur, False)) if step < cp - 1 else None      # next block in flight while this one is used
             src_offs = [src * c, (2 * cp - 1 - src) * c]
             for qi, qoff in enumerate(my_offs):
                 for ki, koff in enumerate(src_offs):
@@ -171,7 +172,7 @@ class _RingAttnFn(torch.autograd.Function):
                         continue
                     o, l = block_fwd(q[qi * c:(qi + 1) * c], cur[ki * c:(ki + 1) * c, ..., :dk_], cur[ki * c:(ki + 1) * c, ..., dk_:], scale, causal and koff == qoff)
                     acc[qi] = list(_merge_into(acc[qi][0], acc[qi][1], o, l))
-            cur = nxt
+            cur = shift.finish(nxt) if (overlap and nxt is not None) else nxt
         out = torch.cat([acc[0][0], acc[1][0]], dim=0).to(q.dtype)
         lse = torch.cat([acc[0][1], acc[1][1]], dim=-1)                       # [b, h, 2c]
         ctx.save_for_backward(q, k, v, out, lse)
@@ -189,10 +190,13 @@ class _RingAttnFn(torch.autograd.Function):
         dk_ = k.shape[-1]
         cur = torch.cat([k, v], dim=-1)
         dcur = torch.zeros(cur.shape, dtype=torch.float32, device=q.device)     # gradient of the block currently held; travels with it
+        overlap = hasattr(shift, "start")
+        pending_d = None                                                        # the gradient hop of the previous step, still in flight
         for step in range(cp):
             src = (rank - step) % cp
-            nxt = shift(cur, False) if step < cp - 1 else None
+            nxt = (shift.start(cur, False) if overlap else shift(cur, False)) if step < cp - 1 else None
             src_offs = [src * c, (2 * cp - 1 - src) * c]
+            contrib = []
             for qi, qoff in enumerate(my_offs):
                 qs = slice(qi * c, (qi + 1) * c)
                 for ki, koff in enumerate(src_offs):
@@ -201,11 +205,21 @@ class _RingAttnFn(torch.autograd.Function):
                     ks = slice(ki * c, (ki + 1) * c)
                     g_q, g_k, g_v = block_bwd(go[qs], q[qs], cur[ks][..., :dk_], cur[ks][..., dk_:], out[qs], lse[..., qs].contiguous(), scale, causal and koff == qoff)
                     dq[qs] += g_q.float()
-                    dcur[ks, ..., :dk_] += g_k.float()
-                    dcur[ks, ..., dk_:] += g_v.float()
+                    contrib.append((ks, g_k, g_v))
+            if pending_d is not None:
+                dcur = shift.finish(pending_d)                                  # arrives while this step's pairs were being computed
+            for ks, g_k, g_v in contrib:
+                dcur[ks, ..., :dk_] += g_k.float()
+                dcur[ks, ..., dk_:] += g_v.float()
             # the gradient follows its block: one hop per step, and a last hop after the final step brings it back to the block's owner
-            dcur = shift(dcur, False)
-            cur = nxt
+            if overlap:
+                pending_d = shift.start(dcur, False)
+                cur = shift.finish(nxt) if nxt is not None else None
+            else:
+                dcur = shift(dcur, False)
+                cur = nxt
+        if pending_d is not None:
+            dcur = shift.finish(pending_d)
         return dq.to(q.dtype), dcur[..., :dk_].to(k.dtype), dcur[..., dk_:].to(v.dtype), None, None, None, None, None
 
 
@@ -237,6 +251,42 @@ class _RingShift(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         return _RingShift._shift(g, ctx.group, not ctx.reverse), None, None
+
+    @staticmethod
+    def start(x, group, reverse=False):
+        """Post the send / receive of one hop and return ``(receive buffer, requests)`` without waiting: the transfer runs on the communicator's stream while the
+        caller computes on the block it already holds."""
+        ranks = dist.get_process_group_ranks(group)
+        me = dist.get_rank(group)
+        n = len(ranks)
+        dst = ranks[(me - 1) % n] if reverse else ranks[(me + 1) % n]
+        src = ranks[(me + 1) % n] if reverse else ranks[(me - 1) % n]
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        ops_ = [dist.P2POp(dist.isend, x, dst, group), dist.P2POp(dist.irecv, out, src, group)]
+        return out, dist.batch_isend_irecv(ops_), x          # x is kept alive until the send has completed
+
+    @staticmethod
+    def finish(handle):
+        out, reqs, _keep = handle
+        for r in reqs:
+            r.wait()
+        return out
+
+
+class _AsyncRing:
+    """``shift`` object for ``_RingAttnFn``: ``start`` / ``finish`` overlap each hop with the block computation; calling it does a blocking hop."""
+
+    def __init__(self, group):
+        self.group = group
+
+    def __call__(self, x, reverse=False):
+        return _RingShift.finish(_RingShift.start(x, self.group, reverse))
+
+    def start(self, x, reverse=False):
+        return _RingShift.start(x, self.group, reverse)
+
+    finish = staticmethod(_RingShift.finish)
 
 
 class RingAttention(torch.nn.Module):
@@ -326,8 +376,7 @@ class RingAttention(torch.nn.Module):
 
     # ---- ring (p2p) -------------------------------------------------------------------------------------------
     def _ring(self, q, k, v, causal, scale):
-        group = self.group
-        return _RingAttnFn.apply(q, k.contiguous(), v.contiguous(), scale, causal, self.rank, self.cp, lambda x, reverse: _RingShift._shift(x, group, reverse))
+        return _RingAttnFn.apply(q, k.contiguous(), v.contiguous(), scale, causal, self.rank, self.cp, _AsyncRing(self.group))
 
     # ---- Ulysses (a2a) --------------------------------------------------------------------------------------------
     def _ulysses(self, q, k, v, causal, scale):

@@ -535,7 +535,9 @@ def _ring_fn_worker(rank, world):
     for causal in (True, False):
         for t in (q, k, v):
             t.grad = None
-        out = _RingAttnFn.apply(q, k, v, 0.3, causal, rank, cp, lambda x, reverse: _RingShift._shift(x, group, reverse))
+        from megatron_b200.parallel.context_parallel import _AsyncRing
+
+        out = _RingAttnFn.apply(q, k, v, 0.3, causal, rank, cp, _AsyncRing(group) if causal else (lambda x, reverse: _RingShift._shift(x, group, reverse)))
         out.backward(go_full[idx])
         fq, fk, fv = (t.clone().requires_grad_(True) for t in full)
         want = ref.attention_fwd(fq, fk, fv, causal, 0.3)
