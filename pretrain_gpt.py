@@ -80,7 +80,19 @@ def loss_func(loss_mask: torch.Tensor, output_tensor: torch.Tensor):
 
 
 def forward_step(data_iterator, model: GPTModel):
+    args = get_args()
     tokens, labels, loss_mask, position_ids = get_batch(data_iterator)
+    if getattr(args, "reset_attention_mask", False) and getattr(args, "reset_position_ids", False) and tokens is not None \
+            and args.pipeline_model_parallel_size == 1 and args.context_parallel_size == 1:
+        # documents must not attend to each other: flatten the micro-batch into ONE packed row and hand the boundaries to the attention kernels as cu_seqlens
+        # (band mask inside the tcgen05 kernels, RoPE restarting per document) instead of materialising a dense [b, 1, s, s] mask
+        from megatron_b200.core.packed_seq_params import packed_seq_params_from_documents
+        from megatron_b200.training.global_vars import get_tokenizer
+
+        b, s = tokens.shape
+        psp = packed_seq_params_from_documents(tokens, get_tokenizer().eod)
+        out = model(tokens.reshape(1, b * s), position_ids.reshape(1, b * s), None, labels=labels.reshape(1, b * s), packed_seq_params=psp)
+        return out.reshape(b, s), partial(loss_func, loss_mask)
     out = model(tokens, position_ids, None, labels=labels)
     return out, partial(loss_func, loss_mask)
 

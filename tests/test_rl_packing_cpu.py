@@ -74,3 +74,46 @@ def _packing_worker(rank, world):
 
 def test_packed_logprobs_and_grpo_step_match_padded():
     assert run_distributed(_packing_worker, 1) == [True]
+
+
+def _doc_mask_worker(rank, world):
+    """--reset-attention-mask --reset-position-ids through the packed path == every document run on its own (per-token losses and gradients)."""
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.datasets.gpt_dataset import _get_ltor_masks_and_position_ids
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+    from megatron_b200.core.packed_seq_params import packed_seq_params_from_documents
+    from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    ps.initialize_model_parallel()
+    model_parallel_cuda_manual_seed(4)
+    torch.manual_seed(4)
+    cfg = TransformerConfig(num_layers=2, hidden_size=32, num_attention_heads=4, ffn_hidden_size=64, gated_linear_unit=True, activation_func=F.silu, add_bias_linear=False,
+                            normalization="RMSNorm", use_cpu_initialization=True, hidden_dropout=0.0, attention_dropout=0.0, bias_dropout_fusion=False)
+    model = GPTModel(cfg, get_gpt_layer_local_spec(normalization="RMSNorm"), vocab_size=64, max_sequence_length=32, position_embedding_type="rope")
+    eod, b, s = 63, 2, 32
+    tokens = torch.randint(0, 62, (b, s), generator=torch.Generator().manual_seed(0))
+    tokens[0, 9] = tokens[0, 20] = tokens[1, 4] = tokens[1, 31] = eod            # 3 + 2 documents; one eod exactly at the end of a row
+    labels = tokens.roll(-1, 1)
+    pid = torch.stack([_get_ltor_masks_and_position_ids(tokens[i], eod, True, True, False, False)[2] for i in range(b)])
+    # reference: every document alone through the model (a causal model with a dense mask would need the unfused path; per-document runs are unambiguous)
+    bounds = [(0, 0, 10), (0, 10, 21), (0, 21, 32), (1, 0, 5), (1, 5, 32)]
+    dense = torch.zeros(b, s)
+    for r, lo, hi in bounds:
+        t = tokens[r:r + 1, lo:hi]
+        dense[r, lo:hi] = model(t, torch.arange(hi - lo)[None], None, labels=labels[r:r + 1, lo:hi])[0]
+    dense.sum().backward()
+    g_dense = [p.grad.clone() for p in model.parameters()]
+    model.zero_grad()
+    psp = packed_seq_params_from_documents(tokens, eod)
+    assert psp.cu_seqlens_q.tolist() == [0, 10, 21, 32, 37, 64] and psp.max_seqlen_q == 27
+    packed = model(tokens.reshape(1, b * s), pid.reshape(1, b * s), None, labels=labels.reshape(1, b * s), packed_seq_params=psp).reshape(b, s)
+    packed.sum().backward()
+    assert torch.allclose(packed, dense, atol=1e-5), (packed - dense).abs().max()
+    assert all(torch.allclose(p.grad, g, atol=1e-5) for p, g in zip(model.parameters(), g_dense))
+    return True
+
+
+def test_document_masking_through_packed_attention_matches_per_document_runs():
+    assert run_distributed(_doc_mask_worker, 1) == [True]
