@@ -72,8 +72,14 @@ class DotProductAttention(MegatronModule):
             # THD: the token dim holds several packed sequences ([t, 1, h, d]); attention must not cross their boundaries (reference: TE's thd kernels
             # driven by cu_seqlens, extensions/transformer_engine.py:1460-1530).  Ours: a band mask inside the native kernels / a block-diagonal mask on CPU.
             cu = packed_seq_params.cu_seqlens_q_padded if getattr(packed_seq_params, "cu_seqlens_q_padded", None) is not None else packed_seq_params.cu_seqlens_q
-            fusable = fusable and causal and b == 1 and key.shape[0] == sq
-            assert fusable, "packed sequences need causal self-attention without bias / dropout in THD layout [t, 1, h, d]"
+            assert causal and b == 1 and key.shape[0] == sq, "packed sequences need causal self-attention in THD layout [t, 1, h, d]"
+            if not fusable:
+                # attention dropout / bias: the unfused path with the block-diagonal causal mask spelled out (O(t²) memory — the kernels cover the dropout-free case)
+                pos = torch.arange(sq, device=query.device)
+                cul = cu.to(device=query.device, dtype=torch.long)
+                sid = torch.bucketize(pos, cul[1:], right=True).clamp_(max=cul.numel() - 2)
+                blocked = (sid[:, None] != sid[None, :]) | (pos[None, :] > pos[:, None])
+                return self._unfused(query, key, value, blocked.view(1, 1, sq, sq), False, attention_bias)
         if fusable:
             ctx = ops.flash_attention(query, key, value, causal=causal, scale=self.softmax_scale, window=self.config.window_size, cu_seqlens=cu)
             return ctx.reshape(sq, b, -1)

@@ -79,6 +79,16 @@ def loss_func(loss_mask: torch.Tensor, output_tensor: torch.Tensor):
     return loss, {"lm loss": loss.detach()}
 
 
+_EOD = {}
+
+
+def _eod_token(args) -> int:
+    """End-of-document id of the run's tokenizer (built once; the dataset provider builds its own instance on the data ranks only)."""
+    if "id" not in _EOD:
+        _EOD["id"] = build_tokenizer(args.tokenizer_type, vocab_size=args.vocab_size, tokenizer_model=args.tokenizer_model).eod
+    return _EOD["id"]
+
+
 def forward_step(data_iterator, model: GPTModel):
     args = get_args()
     tokens, labels, loss_mask, position_ids = get_batch(data_iterator)
@@ -87,10 +97,9 @@ def forward_step(data_iterator, model: GPTModel):
         # documents must not attend to each other: flatten the micro-batch into ONE packed row and hand the boundaries to the attention kernels as cu_seqlens
         # (band mask inside the tcgen05 kernels, RoPE restarting per document) instead of materialising a dense [b, 1, s, s] mask
         from megatron_b200.core.packed_seq_params import packed_seq_params_from_documents
-        from megatron_b200.training.global_vars import get_tokenizer
 
         b, s = tokens.shape
-        psp = packed_seq_params_from_documents(tokens, get_tokenizer().eod)
+        psp = packed_seq_params_from_documents(tokens, _eod_token(args))
         out = model(tokens.reshape(1, b * s), position_ids.reshape(1, b * s), None, labels=labels.reshape(1, b * s), packed_seq_params=psp)
         return out.reshape(b, s), partial(loss_func, loss_mask)
     out = model(tokens, position_ids, None, labels=labels)
