@@ -511,6 +511,14 @@ def vars_for_ckpt(args) -> dict:
     return {k: v for k, v in vars(args).items() if isinstance(v, (int, float, str, bool, type(None), list, tuple))}
 
 
+def get_train_valid_test_num_samples(args) -> List[int]:
+    """How many samples each split must be able to serve for this run (reference ``training.get_train_valid_test_num_samples``): the dataset builders size
+    their shuffled index caches from these numbers, which is why ``tools/prepare_cache.py`` must compute them exactly like the training job."""
+    n_train = args.train_iters * args.global_batch_size
+    n_eval = (args.train_iters // max(args.eval_interval, 1) + 1) * args.eval_iters * args.global_batch_size
+    return [n_train, n_eval, args.eval_iters * args.global_batch_size]
+
+
 def pretrain(train_valid_test_dataset_provider: Callable, model_provider: Callable, forward_step_func: Callable, argv=None,
              extra_args_provider=None, args_defaults: Optional[dict] = None):
     """Main entry (reference ``pretrain`` :1500).  ``dataset_provider(num_samples[3]) -> (train, valid, test)``
@@ -519,9 +527,7 @@ def pretrain(train_valid_test_dataset_provider: Callable, model_provider: Callab
     args = initialize_megatron(argv, extra_args_provider, args_defaults)
     model, optimizer, scheduler = setup_model_and_optimizer(model_provider)
     config = model[0].module.config if hasattr(model[0], "module") else model[0].config
-    n_train = args.train_iters * args.global_batch_size
-    n_eval = (args.train_iters // max(args.eval_interval, 1) + 1) * args.eval_iters * args.global_batch_size
-    train_ds, valid_ds, test_ds = train_valid_test_dataset_provider([n_train, n_eval, args.eval_iters * args.global_batch_size])
+    train_ds, valid_ds, test_ds = train_valid_test_dataset_provider(get_train_valid_test_num_samples(args))
     from .data import build_pretraining_data_loader
 
     consumed = args.iteration * args.global_batch_size

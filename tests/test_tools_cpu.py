@@ -188,3 +188,38 @@ def test_trtllm_export_layout_split_and_distributed_variant(tmp_path):
     assert conf["vocab_size"] == 128 and conf["mapping"]["tp_size"] == 2 and conf["num_key_value_heads"] == 2 and conf["hidden_act"] == "swiglu"
     save_trtllm_checkpoint(str(tmp_path / "trt"), ranks, conf)
     assert os.path.exists(tmp_path / "trt" / "config.json") and len([f for f in os.listdir(tmp_path / "trt") if f.startswith("rank")]) == 2
+
+
+def test_prepare_cache_then_pretrain_reuses_it(tmp_path):
+    """tools/prepare_cache.py builds the dataset index caches with the training job's own arguments; the training run then finds every index in the cache
+    (no new files) and trains on the real data."""
+    import subprocess
+
+    import prepare_cache
+    import preprocess_data_fast as fast
+
+    src = tmp_path / "c.jsonl"
+    _corpus(src, n=400)
+    fast.main(["--input", str(src), "--tokenizer-type", "NullTokenizer", "--vocab-size", "100", "--append-eod", "--output-prefix", str(tmp_path / "corp"), "--workers", "1"])
+    cache = tmp_path / "cache"
+    common = ["--num-layers", "2", "--hidden-size", "32", "--num-attention-heads", "4", "--seq-length", "32", "--max-position-embeddings", "32", "--micro-batch-size", "2",
+              "--global-batch-size", "4", "--train-iters", "3", "--lr", "1e-3", "--tokenizer-type", "NullTokenizer", "--vocab-size", "100", "--data-path",
+              str(tmp_path / "corp_text_document"), "--split", "90,5,5", "--data-cache-path", str(cache), "--eval-iters", "1", "--eval-interval", "100", "--seed", "7"]
+    rep = prepare_cache.main(common)
+    assert rep["requested_samples"] == {"train": 12, "valid": 4, "test": 4} and rep["built"]["train"] >= 12 and rep["cache_files"] >= 6
+    before = sorted(os.listdir(cache))
+    with pytest.raises(SystemExit):
+        prepare_cache.main(common + ["--mock-data"])
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29661", RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "pretrain_gpt.py")] + common + ["--log-interval", "1", "--distributed-backend", "gloo", "--lr-decay-iters", "10"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "iteration        3/       3" in r.stdout
+    assert sorted(os.listdir(cache)) == before                      # the job found everything it needed
+
+
+def test_run_inference_performance_test_cpu():
+    import run_inference_performance_test as perf
+
+    out = perf.main(["--num-requests", "3", "--prompt-length", "12", "--num-tokens-to-generate", "4", "--inference-dynamic-batching-max-tokens", "8"])
+    assert out["requests"] == 3 and out["throughput_tok_per_sec"] > 0 and out["prefill_chunks"] >= 3 * 2 - 1 and out["decode_forwards"] >= 3
