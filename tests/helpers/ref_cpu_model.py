@@ -49,6 +49,11 @@ def init_params(named_params, tp_rank, tp_world):
 CFG = dict(num_layers=2, hidden_size=64, ffn_hidden_size=128, num_attention_heads=4, num_query_groups=2, kv_channels=16, vocab=128, seq=32, batch=2)
 
 
+# REF_VARIANT=moe: 4 experts, top-2, softmax-then-top-k router with the switch aux loss, all-gather dispatcher, one expert MLP per expert (no grouped GEMM)
+MOE_KW = dict(num_moe_experts=4, moe_router_topk=2, moe_token_dispatcher_type="allgather", moe_router_load_balancing_type="aux_loss", moe_aux_loss_coeff=0.02,
+              moe_grouped_gemm=False, moe_ffn_hidden_size=96) if os.environ.get("REF_VARIANT") == "moe" else {}
+
+
 def tokens():
     return torch.randint(0, CFG["vocab"], (CFG["batch"], CFG["seq"] + 1), generator=torch.Generator().manual_seed(1))
 
@@ -76,8 +81,10 @@ def main():
         num_query_groups=CFG["num_query_groups"], kv_channels=CFG["kv_channels"], normalization="RMSNorm", gated_linear_unit=True, activation_func=F.silu,
         add_bias_linear=False, hidden_dropout=0.0, attention_dropout=0.0, use_cpu_initialization=True, bias_activation_fusion=False, bias_dropout_fusion=False,
         masked_softmax_fusion=False, gradient_accumulation_fusion=False, perform_initialization=False, tensor_model_parallel_size=tp,
+        **MOE_KW,
     )
-    m = GPTModel(cfg, get_gpt_layer_local_spec(normalization="RMSNorm"), vocab_size=CFG["vocab"], max_sequence_length=CFG["seq"], parallel_output=True,
+    spec = get_gpt_layer_local_spec(num_experts=MOE_KW.get("num_moe_experts"), moe_grouped_gemm=False, normalization="RMSNorm") if MOE_KW else get_gpt_layer_local_spec(normalization="RMSNorm")
+    m = GPTModel(cfg, spec, vocab_size=CFG["vocab"], max_sequence_length=CFG["seq"], parallel_output=True,
                  share_embeddings_and_output_weights=False, position_embedding_type="rope", rotary_base=10000)
     mode = sys.argv[3] if len(sys.argv) > 3 else "grads"
     if mode in ("save", "load"):

@@ -16,7 +16,7 @@ REF = os.path.join(REPO, "baseline", "_ref", "megatron", "core")
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="baseline/_ref (the reference install) is absent")
 
 
-def _run_reference(tmp_path, tp):
+def _run_reference(tmp_path, tp, variant=""):
     import socket
 
     with socket.socket() as s:
@@ -25,7 +25,7 @@ def _run_reference(tmp_path, tp):
     prefix = str(tmp_path / f"ref_tp{tp}")
     procs = []
     for r in range(tp):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(tp), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(tp), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1", REF_VARIANT=variant)
         procs.append(subprocess.Popen([sys.executable, os.path.join(REPO, "tests", "helpers", "ref_cpu_model.py"), prefix, str(tp)], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     for p in procs:
@@ -34,7 +34,7 @@ def _run_reference(tmp_path, tp):
     return [torch.load(f"{prefix}.rank{r}.pt") for r in range(tp)]
 
 
-def _ours(rank, world, tp):
+def _ours(rank, world, tp, variant=""):
     sys.path.insert(0, os.path.join(REPO, "tests", "helpers"))
     import torch.nn.functional as F
 
@@ -51,8 +51,11 @@ def _ours(rank, world, tp):
         num_query_groups=CFG["num_query_groups"], kv_channels=CFG["kv_channels"], normalization="RMSNorm", gated_linear_unit=True, activation_func=F.silu,
         add_bias_linear=False, hidden_dropout=0.0, attention_dropout=0.0, use_cpu_initialization=True, gradient_accumulation_fusion=False,
         perform_initialization=False, tensor_model_parallel_size=tp,
+        **(dict(num_moe_experts=4, moe_router_topk=2, moe_token_dispatcher_type="allgather", moe_router_load_balancing_type="aux_loss", moe_aux_loss_coeff=0.02,
+                moe_grouped_gemm=False, moe_ffn_hidden_size=96) if variant == "moe" else {}),
     )
-    m = GPTModel(cfg, get_gpt_layer_local_spec(normalization="RMSNorm"), vocab_size=CFG["vocab"], max_sequence_length=CFG["seq"], parallel_output=True,
+    spec = get_gpt_layer_local_spec(num_experts=4, moe_grouped_gemm=False, normalization="RMSNorm") if variant == "moe" else get_gpt_layer_local_spec(normalization="RMSNorm")
+    m = GPTModel(cfg, spec, vocab_size=CFG["vocab"], max_sequence_length=CFG["seq"], parallel_output=True,
                  share_embeddings_and_output_weights=False, position_embedding_type="rope", rotary_base=10000)
     with torch.no_grad():
         for n, p in m.named_parameters():
@@ -92,6 +95,20 @@ def test_loss_and_grad_parity_with_reference(tmp_path, tp):
             go = ours[r]["grads"][n]
             err = float((go - g).abs().max() / g.abs().max().clamp(min=1e-12))
             assert err < 2e-4, f"rank {r} grad {n}: rel err {err}"
+
+
+def test_moe_loss_and_grad_parity_with_reference(tmp_path):
+    """A 4-expert top-2 MoE GPT (router + aux loss, all-gather dispatcher, per-expert MLPs): same parameter names, loss and gradients as the unmodified reference."""
+    from dist_utils import run_distributed
+
+    ref = _run_reference(tmp_path, 1, "moe")[0]
+    ours = run_distributed(_ours, 1, 1, "moe")[0]
+    assert sorted(ours["names"]) == sorted(ref["grads"].keys()), (sorted(set(ours["names"]) ^ set(ref["grads"].keys())))
+    assert any("router" in n for n in ours["names"]) and any("local_experts" in n for n in ours["names"])
+    assert abs(ours["loss"] - ref["loss"]) < 2e-5, (ours["loss"], ref["loss"])
+    for n, g in ref["grads"].items():
+        err = float((ours["grads"][n] - g).abs().max() / g.abs().max().clamp(min=1e-12))
+        assert err < 5e-4, f"grad {n}: rel err {err}"
 
 
 # ---- distributed-checkpoint interop (SURVEY 7.4-6: "cross-load a checkpoint with the reference") --------------------------------------
