@@ -17,6 +17,33 @@ sys.path.insert(0, os.path.join(REPO, "baseline", "_ref"))
 sys.path = [p for p in sys.path if os.path.abspath(p or ".") != REPO]
 torch.cuda.current_device = lambda: torch.device("cpu")
 torch.cuda.synchronize = lambda *a, **k: None
+
+
+class _HostStream:
+    """Stand-in for the side streams the reference creates for device-to-host copies (MoE all-to-all dispatcher): on CPU everything is synchronous."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def wait_stream(self, *a, **k):
+        pass
+
+    def synchronize(self):
+        pass
+
+    def record_event(self, *a, **k):
+        return self
+
+    def wait_event(self, *a, **k):
+        pass
+
+    wait = query = lambda self, *a, **k: True
+
+
+torch.cuda.Stream = _HostStream
+torch.cuda.Event = _HostStream
+torch.cuda.current_stream = lambda *a, **k: _HostStream()
+torch.cuda.stream = lambda *a, **k: contextlib.nullcontext()
 import torch.distributed as dist  # noqa: E402
 
 
@@ -50,8 +77,9 @@ CFG = dict(num_layers=2, hidden_size=64, ffn_hidden_size=128, num_attention_head
 
 
 # REF_VARIANT=moe: 4 experts, top-2, softmax-then-top-k router with the switch aux loss, all-gather dispatcher, one expert MLP per expert (no grouped GEMM)
-MOE_KW = dict(num_moe_experts=4, moe_router_topk=2, moe_token_dispatcher_type="allgather", moe_router_load_balancing_type="aux_loss", moe_aux_loss_coeff=0.02,
-              moe_grouped_gemm=False, moe_ffn_hidden_size=96) if os.environ.get("REF_VARIANT") == "moe" else {}
+_V = os.environ.get("REF_VARIANT", "")
+MOE_KW = dict(num_moe_experts=4, moe_router_topk=2, moe_token_dispatcher_type="allgather", moe_router_load_balancing_type="aux_loss",
+              moe_aux_loss_coeff=0.02, moe_grouped_gemm=False, moe_ffn_hidden_size=96, **({"expert_model_parallel_size": 2} if _V == "moe_ep2" else {})) if _V.startswith("moe") else {}
 
 
 def tokens():
@@ -75,7 +103,7 @@ def main():
             return contextlib.nullcontext()
 
     _tp.get_cuda_rng_tracker = _tpr.get_cuda_rng_tracker = lambda *a, **k: _NoRng()
-    parallel_state.initialize_model_parallel(tensor_model_parallel_size=tp)
+    parallel_state.initialize_model_parallel(tensor_model_parallel_size=tp, **({"expert_model_parallel_size": 2} if _V == "moe_ep2" else {}))
     cfg = TransformerConfig(
         num_layers=CFG["num_layers"], hidden_size=CFG["hidden_size"], ffn_hidden_size=CFG["ffn_hidden_size"], num_attention_heads=CFG["num_attention_heads"],
         num_query_groups=CFG["num_query_groups"], kv_channels=CFG["kv_channels"], normalization="RMSNorm", gated_linear_unit=True, activation_func=F.silu,
@@ -111,8 +139,10 @@ def main():
         return
     init_params(m.named_parameters(), parallel_state.get_tensor_model_parallel_rank(), tp)
     tok = tokens()
+    if _V == "moe_ep2":                      # EP ranks are data-parallel ranks for the dense part: each sees its own half of the batch
+        tok = tok[rank:rank + 1]
     s = CFG["seq"]
-    pos = torch.arange(s).unsqueeze(0).expand(CFG["batch"], -1).contiguous()
+    pos = torch.arange(s).unsqueeze(0).expand(tok.shape[0], -1).contiguous()
     mask = torch.triu(torch.ones(s, s), diagonal=1).bool()[None, None]
     loss = m(tok[:, :-1].contiguous(), pos, mask, labels=tok[:, 1:].contiguous()).float().mean()
     loss.backward()

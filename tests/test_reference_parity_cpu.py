@@ -16,22 +16,24 @@ REF = os.path.join(REPO, "baseline", "_ref", "megatron", "core")
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="baseline/_ref (the reference install) is absent")
 
 
-def _run_reference(tmp_path, tp, variant=""):
+def _run_reference(tmp_path, tp, variant="", world=None):
     import socket
+
+    world = world or tp
 
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     prefix = str(tmp_path / f"ref_tp{tp}")
     procs = []
-    for r in range(tp):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(tp), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1", REF_VARIANT=variant)
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1", REF_VARIANT=variant)
         procs.append(subprocess.Popen([sys.executable, os.path.join(REPO, "tests", "helpers", "ref_cpu_model.py"), prefix, str(tp)], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     for p in procs:
         out, _ = p.communicate(timeout=600)
         assert p.returncode == 0, out[-3000:]
-    return [torch.load(f"{prefix}.rank{r}.pt") for r in range(tp)]
+    return [torch.load(f"{prefix}.rank{r}.pt") for r in range(world)]
 
 
 def _ours(rank, world, tp, variant=""):
@@ -45,16 +47,17 @@ def _ours(rank, world, tp, variant=""):
     import zlib
 
     CFG = dict(num_layers=2, hidden_size=64, ffn_hidden_size=128, num_attention_heads=4, num_query_groups=2, kv_channels=16, vocab=128, seq=32, batch=2)
-    ps.initialize_model_parallel(tensor_model_parallel_size=tp)
+    ep2 = variant == "moe_ep2"
+    ps.initialize_model_parallel(tensor_model_parallel_size=tp, **({"expert_model_parallel_size": 2} if ep2 else {}))
     cfg = TransformerConfig(
         num_layers=CFG["num_layers"], hidden_size=CFG["hidden_size"], ffn_hidden_size=CFG["ffn_hidden_size"], num_attention_heads=CFG["num_attention_heads"],
         num_query_groups=CFG["num_query_groups"], kv_channels=CFG["kv_channels"], normalization="RMSNorm", gated_linear_unit=True, activation_func=F.silu,
         add_bias_linear=False, hidden_dropout=0.0, attention_dropout=0.0, use_cpu_initialization=True, gradient_accumulation_fusion=False,
         perform_initialization=False, tensor_model_parallel_size=tp,
-        **(dict(num_moe_experts=4, moe_router_topk=2, moe_token_dispatcher_type="allgather", moe_router_load_balancing_type="aux_loss", moe_aux_loss_coeff=0.02,
-                moe_grouped_gemm=False, moe_ffn_hidden_size=96) if variant == "moe" else {}),
+        **(dict(num_moe_experts=4, moe_router_topk=2, moe_token_dispatcher_type="allgather", moe_router_load_balancing_type="aux_loss",
+                moe_aux_loss_coeff=0.02, moe_grouped_gemm=False, moe_ffn_hidden_size=96, **({"expert_model_parallel_size": 2} if ep2 else {})) if variant.startswith("moe") else {}),
     )
-    spec = get_gpt_layer_local_spec(num_experts=4, moe_grouped_gemm=False, normalization="RMSNorm") if variant == "moe" else get_gpt_layer_local_spec(normalization="RMSNorm")
+    spec = get_gpt_layer_local_spec(num_experts=4, moe_grouped_gemm=False, normalization="RMSNorm") if variant.startswith("moe") else get_gpt_layer_local_spec(normalization="RMSNorm")
     m = GPTModel(cfg, spec, vocab_size=CFG["vocab"], max_sequence_length=CFG["seq"], parallel_output=True,
                  share_embeddings_and_output_weights=False, position_embedding_type="rope", rotary_base=10000)
     with torch.no_grad():
@@ -76,7 +79,9 @@ def _ours(rank, world, tp, variant=""):
             else:
                 p.copy_(full.chunk(tp, dim=dim)[r] if sharded else full)
     tok = torch.randint(0, CFG["vocab"], (CFG["batch"], CFG["seq"] + 1), generator=torch.Generator().manual_seed(1))
-    pos = torch.arange(CFG["seq"]).unsqueeze(0).expand(CFG["batch"], -1).contiguous()
+    if ep2:
+        tok = tok[rank:rank + 1]
+    pos = torch.arange(CFG["seq"]).unsqueeze(0).expand(tok.shape[0], -1).contiguous()
     loss = m(tok[:, :-1].contiguous(), pos, None, labels=tok[:, 1:].contiguous()).float().mean()
     loss.backward()
     return {"loss": float(loss), "grads": {n: p.grad.clone() for n, p in m.named_parameters()}, "names": [n for n, _ in m.named_parameters()]}
@@ -111,6 +116,22 @@ def test_moe_loss_and_grad_parity_with_reference(tmp_path):
         assert err < 5e-4, f"grad {n}: rel err {err}"
 
 
+def test_moe_expert_parallel_parity_with_reference(tmp_path):
+    """Expert parallel 2 over gloo (2 of the 4 experts per rank, each rank feeds its own half of the batch; the all-gather dispatcher — the reference's all-to-all
+    dispatcher passes tensor split sizes that gloo rejects): per-rank loss and gradients, incl. the expert weights that received tokens from the OTHER rank,
+    equal the unmodified reference's."""
+    from dist_utils import run_distributed
+
+    ref = _run_reference(tmp_path, 1, "moe_ep2", world=2)
+    ours = run_distributed(_ours, 2, 1, "moe_ep2")
+    for r in range(2):
+        assert sorted(ours[r]["names"]) == sorted(ref[r]["grads"].keys())
+        assert abs(ours[r]["loss"] - ref[r]["loss"]) < 2e-5, (r, ours[r]["loss"], ref[r]["loss"])
+        for n, g in ref[r]["grads"].items():
+            err = float((ours[r]["grads"][n] - g).abs().max() / g.abs().max().clamp(min=1e-12))
+            assert err < 5e-4, f"rank {r} grad {n}: rel err {err}"
+
+
 # ---- distributed-checkpoint interop (SURVEY 7.4-6: "cross-load a checkpoint with the reference") --------------------------------------
 
 
@@ -122,8 +143,8 @@ def _spawn_reference(tmp_path, tp, *extra):
         port = s.getsockname()[1]
     prefix = str(tmp_path / f"ref_{extra[0]}_tp{tp}")
     procs = []
-    for r in range(tp):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(tp), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
         procs.append(subprocess.Popen([sys.executable, os.path.join(REPO, "tests", "helpers", "ref_cpu_model.py"), prefix, str(tp), *extra], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     for p in procs:
@@ -140,7 +161,8 @@ def _our_model(tp):
     from megatron_b200.core.models.gpt.gpt_model import GPTModel
     from megatron_b200.core.transformer.transformer_config import TransformerConfig
 
-    ps.initialize_model_parallel(tensor_model_parallel_size=tp)
+    ep2 = variant == "moe_ep2"
+    ps.initialize_model_parallel(tensor_model_parallel_size=tp, **({"expert_model_parallel_size": 2} if ep2 else {}))
     cfg = TransformerConfig(num_layers=2, hidden_size=64, ffn_hidden_size=128, num_attention_heads=4, num_query_groups=2, kv_channels=16, normalization="RMSNorm",
                             gated_linear_unit=True, activation_func=F.silu, add_bias_linear=False, hidden_dropout=0.0, attention_dropout=0.0, use_cpu_initialization=True,
                             gradient_accumulation_fusion=False, perform_initialization=False, tensor_model_parallel_size=tp)
