@@ -143,8 +143,8 @@ def _spawn_reference(tmp_path, tp, *extra):
         port = s.getsockname()[1]
     prefix = str(tmp_path / f"ref_{extra[0]}_tp{tp}")
     procs = []
-    for r in range(world):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+    for r in range(tp):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(tp), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
         procs.append(subprocess.Popen([sys.executable, os.path.join(REPO, "tests", "helpers", "ref_cpu_model.py"), prefix, str(tp), *extra], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     for p in procs:
@@ -161,8 +161,7 @@ def _our_model(tp):
     from megatron_b200.core.models.gpt.gpt_model import GPTModel
     from megatron_b200.core.transformer.transformer_config import TransformerConfig
 
-    ep2 = variant == "moe_ep2"
-    ps.initialize_model_parallel(tensor_model_parallel_size=tp, **({"expert_model_parallel_size": 2} if ep2 else {}))
+    ps.initialize_model_parallel(tensor_model_parallel_size=tp)
     cfg = TransformerConfig(num_layers=2, hidden_size=64, ffn_hidden_size=128, num_attention_heads=4, num_query_groups=2, kv_channels=16, normalization="RMSNorm",
                             gated_linear_unit=True, activation_func=F.silu, add_bias_linear=False, hidden_dropout=0.0, attention_dropout=0.0, use_cpu_initialization=True,
                             gradient_accumulation_fusion=False, perform_initialization=False, tensor_model_parallel_size=tp)
