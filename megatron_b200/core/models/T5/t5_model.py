@@ -36,8 +36,17 @@ class T5LMHead(MegatronModule):
 
 
 def t5_extended_attention_mask(masks):
-    """[b, sq, sk] keep-masks (1 = attend) → [b, 1, sq, sk] bool with True = masked."""
-    return [None if m is None else (m.unsqueeze(1) < 0.5) for m in masks]
+    """→ [b, 1, sq, sk] bool with True = masked.  Accepts the reference's calling convention (already-extended boolean masks ``[b, 1, sq, sk]``, True = masked:
+    what ``pretrain_t5.py`` builds) and this framework's ``[b, sq, sk]`` keep-masks (1 = attend)."""
+    out = []
+    for m in masks:
+        if m is None:
+            out.append(None)
+        elif m.dim() == 4:
+            out.append(m if m.dtype == torch.bool else m > 0.5)
+        else:
+            out.append(m.unsqueeze(1) < 0.5)
+    return out
 
 
 def t5_position_ids(token_ids: Tensor) -> Tensor:

@@ -104,6 +104,10 @@ def main():
 
     _tp.get_cuda_rng_tracker = _tpr.get_cuda_rng_tracker = lambda *a, **k: _NoRng()
     parallel_state.initialize_model_parallel(tensor_model_parallel_size=tp, **({"expert_model_parallel_size": 2} if _V == "moe_ep2" else {}))
+    if _V == "bert":
+        return bert_main(out_prefix, rank, F, TransformerConfig)
+    if _V == "t5":
+        return t5_main(out_prefix, rank, TransformerConfig)
     cfg = TransformerConfig(
         num_layers=CFG["num_layers"], hidden_size=CFG["hidden_size"], ffn_hidden_size=CFG["ffn_hidden_size"], num_attention_heads=CFG["num_attention_heads"],
         num_query_groups=CFG["num_query_groups"], kv_channels=CFG["kv_channels"], normalization="RMSNorm", gated_linear_unit=True, activation_func=F.silu,
@@ -147,6 +151,71 @@ def main():
     loss = m(tok[:, :-1].contiguous(), pos, mask, labels=tok[:, 1:].contiguous()).float().mean()
     loss.backward()
     torch.save({"loss": float(loss), "grads": {n: p.grad.clone() for n, p in m.named_parameters()}}, f"{out_prefix}.rank{rank}.pt")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def bert_main(out_prefix, rank, F, TransformerConfig):
+    """BERT (learned positions, token types, LM head + binary head, padding mask) from the reference's local spec."""
+    from megatron.core.models.bert.bert_layer_specs import bert_layer_local_spec
+    from megatron.core.models.bert.bert_model import BertModel
+
+    cfg = TransformerConfig(num_layers=2, hidden_size=64, ffn_hidden_size=128, num_attention_heads=4, hidden_dropout=0.0, attention_dropout=0.0, use_cpu_initialization=True,
+                            bias_activation_fusion=False, bias_dropout_fusion=False, masked_softmax_fusion=False, gradient_accumulation_fusion=False, perform_initialization=False,
+                            layernorm_epsilon=1e-5)
+    m = BertModel(cfg, num_tokentypes=2, transformer_layer_spec=bert_layer_local_spec, vocab_size=128, max_sequence_length=32, parallel_output=True, add_binary_head=True)
+    init_params(m.named_parameters(), 0, 1)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.dim() == 1 and ("bias" in n):
+                p.copy_(seeded_full(n, list(p.shape), 0.02))
+    g = torch.Generator().manual_seed(3)
+    tok = torch.randint(0, 128, (2, 32), generator=g)
+    types = torch.randint(0, 2, (2, 32), generator=g)
+    pad = torch.ones(2, 32, dtype=torch.long)
+    pad[1, 25:] = 0
+    labels = torch.randint(0, 128, (2, 32), generator=g)
+    lm_loss, binary = m(tok, pad, tokentype_ids=types, lm_labels=labels)
+    loss = (lm_loss.float() * pad).sum() / pad.sum() + binary.float().logsumexp(-1).mean()
+    loss.backward()
+    torch.save({"loss": float(loss), "grads": {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}}, f"{out_prefix}.rank{rank}.pt")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def t5_inputs():
+    g = torch.Generator().manual_seed(5)
+    b, se, sd = 2, 24, 12
+    enc = torch.randint(0, 128, (b, se), generator=g)
+    dec = torch.randint(0, 128, (b, sd), generator=g)
+    labels = torch.randint(0, 128, (b, sd), generator=g)
+    enc_keep = torch.ones(b, se)
+    enc_keep[1, 20:] = 0
+    enc_mask = enc_keep[:, :, None] * enc_keep[:, None, :]                                  # [b, se, se] 1 = attend
+    dec_mask = torch.tril(torch.ones(sd, sd))[None].expand(b, -1, -1).contiguous()
+    x_mask = torch.ones(b, sd, 1) * enc_keep[:, None, :]
+    return enc, dec, enc_mask, dec_mask, x_mask, labels
+
+
+def t5_main(out_prefix, rank, TransformerConfig):
+    """T5 encoder-decoder (learned positions, cross attention, shared embeddings + LM head bias) from the reference's local block specs."""
+    from megatron.core.models.T5.t5_model import T5Model
+    from megatron.core.models.T5.t5_spec import get_t5_decoder_with_local_block_spec, get_t5_encoder_with_local_block_spec
+
+    kw = dict(hidden_size=64, ffn_hidden_size=128, num_attention_heads=4, kv_channels=16, hidden_dropout=0.0, attention_dropout=0.0, use_cpu_initialization=True,
+              bias_activation_fusion=False, bias_dropout_fusion=False, masked_softmax_fusion=False, gradient_accumulation_fusion=False, perform_initialization=False)
+    cfg, enc_cfg = TransformerConfig(num_layers=2, **kw), TransformerConfig(num_layers=2, **kw)
+    m = T5Model(cfg, enc_cfg, get_t5_encoder_with_local_block_spec(2), get_t5_decoder_with_local_block_spec(2), vocab_size=128, max_sequence_length=32, parallel_output=True,
+                share_embeddings_and_output_weights=True)
+    init_params(m.named_parameters(), 0, 1)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.dim() == 1 and "bias" in n:
+                p.copy_(seeded_full(n, list(p.shape), 0.02))
+    enc, dec, enc_mask, dec_mask, x_mask, labels = t5_inputs()
+    loss = m(enc, dec, (enc_mask < 0.5).unsqueeze(1), (dec_mask < 0.5).unsqueeze(1), (x_mask < 0.5).unsqueeze(1), lm_labels=labels).float().mean()
+    loss.backward()
+    torch.save({"loss": float(loss), "grads": {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}}, f"{out_prefix}.rank{rank}.pt")
     dist.barrier()
     dist.destroy_process_group()
 

@@ -132,6 +132,111 @@ def test_moe_expert_parallel_parity_with_reference(tmp_path):
             assert err < 5e-4, f"rank {r} grad {n}: rel err {err}"
 
 
+def _ours_bert(rank, world):
+    import zlib
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.models.bert.bert_layer_specs import bert_layer_local_spec
+    from megatron_b200.core.models.bert.bert_model import BertModel
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    ps.initialize_model_parallel()
+    cfg = TransformerConfig(num_layers=2, hidden_size=64, ffn_hidden_size=128, num_attention_heads=4, hidden_dropout=0.0, attention_dropout=0.0, use_cpu_initialization=True,
+                            gradient_accumulation_fusion=False, perform_initialization=False, layernorm_epsilon=1e-5, bias_dropout_fusion=False)
+    m = BertModel(cfg, num_tokentypes=2, transformer_layer_spec=bert_layer_local_spec, vocab_size=128, max_sequence_length=32, parallel_output=True, add_binary_head=True)
+
+    def seeded(n, shape, std):
+        return torch.empty(shape).normal_(0, std, generator=torch.Generator().manual_seed(zlib.crc32(n.encode())))
+
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.dim() == 1:
+                p.copy_(seeded(n, list(p.shape), 0.02)) if "bias" in n else p.fill_(1.0)
+            else:
+                p.copy_(seeded(n, list(p.shape), 0.05))
+    g = torch.Generator().manual_seed(3)
+    tok = torch.randint(0, 128, (2, 32), generator=g)
+    types = torch.randint(0, 2, (2, 32), generator=g)
+    pad = torch.ones(2, 32, dtype=torch.long)
+    pad[1, 25:] = 0
+    labels = torch.randint(0, 128, (2, 32), generator=g)
+    lm_loss, binary = m(tok, pad, tokentype_ids=types, lm_labels=labels)
+    loss = (lm_loss.float() * pad).sum() / pad.sum() + binary.float().logsumexp(-1).mean()
+    loss.backward()
+    return {"loss": float(loss), "grads": {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}, "names": [n for n, p in m.named_parameters() if p.grad is not None]}
+
+
+def test_bert_parity_with_reference(tmp_path):
+    """BERT (token types, learned positions, padding mask, LM head, pooler + binary head): parameter names, loss and gradients equal the unmodified reference's."""
+    from dist_utils import run_distributed
+
+    ref = _run_reference(tmp_path, 1, "bert")[0]
+    ours = run_distributed(_ours_bert, 1)[0]
+    assert sorted(ours["names"]) == sorted(ref["grads"].keys()), sorted(set(ours["names"]) ^ set(ref["grads"].keys()))
+    assert abs(ours["loss"] - ref["loss"]) < 2e-5, (ours["loss"], ref["loss"])
+    for n, g in ref["grads"].items():
+        err = float((ours["grads"][n] - g).abs().max() / g.abs().max().clamp(min=1e-12))
+        assert err < 5e-4, f"grad {n}: rel err {err}"
+
+
+def _ours_t5(rank, world):
+    import zlib
+
+    sys.path.insert(0, os.path.join(REPO, "tests", "helpers"))
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.models.T5.t5_model import T5Model
+    from megatron_b200.core.models.T5.t5_spec import get_t5_decoder_with_local_block_spec, get_t5_encoder_with_local_block_spec
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    ps.initialize_model_parallel()
+    kw = dict(hidden_size=64, ffn_hidden_size=128, num_attention_heads=4, kv_channels=16, hidden_dropout=0.0, attention_dropout=0.0, use_cpu_initialization=True,
+              gradient_accumulation_fusion=False, perform_initialization=False, bias_dropout_fusion=False)
+    cfg, enc_cfg = TransformerConfig(num_layers=2, **kw), TransformerConfig(num_layers=2, **kw)
+    # the TE-less reference resolves the block's ``layer_norm=TENorm`` to nothing (no final layer norms); build the same structure here
+    enc_spec, dec_spec = get_t5_encoder_with_local_block_spec(2), get_t5_decoder_with_local_block_spec(2)
+    enc_spec.layer_norm = dec_spec.layer_norm = None
+    m = T5Model(cfg, enc_cfg, enc_spec, dec_spec, vocab_size=128, max_sequence_length=32, parallel_output=True, share_embeddings_and_output_weights=True)
+
+    def seeded(n, shape, std):
+        return torch.empty(shape).normal_(0, std, generator=torch.Generator().manual_seed(zlib.crc32(n.encode())))
+
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.dim() == 1:
+                p.copy_(seeded(n, list(p.shape), 0.02)) if "bias" in n else p.fill_(1.0)
+            else:
+                p.copy_(seeded(n, list(p.shape), 0.05))
+    g = torch.Generator().manual_seed(5)
+    b, se, sd = 2, 24, 12
+    enc = torch.randint(0, 128, (b, se), generator=g)
+    dec = torch.randint(0, 128, (b, sd), generator=g)
+    labels = torch.randint(0, 128, (b, sd), generator=g)
+    enc_keep = torch.ones(b, se)
+    enc_keep[1, 20:] = 0
+    enc_mask = enc_keep[:, :, None] * enc_keep[:, None, :]
+    dec_mask = torch.tril(torch.ones(sd, sd))[None].expand(b, -1, -1).contiguous()
+    x_mask = torch.ones(b, sd, 1) * enc_keep[:, None, :]
+    # the reference's calling convention: already-extended boolean masks, True = masked
+    loss = m(enc, dec, (enc_mask < 0.5).unsqueeze(1), (dec_mask < 0.5).unsqueeze(1), (x_mask < 0.5).unsqueeze(1), lm_labels=labels).float().mean()
+    loss.backward()
+    loss2 = m(enc, dec, enc_mask, dec_mask, x_mask, lm_labels=labels).float().mean()             # this framework's keep-mask convention gives the same result
+    assert abs(float(loss2) - float(loss)) < 1e-6
+    return {"loss": float(loss), "grads": {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}, "names": [n for n, p in m.named_parameters() if p.grad is not None]}
+
+
+def test_t5_parity_with_reference(tmp_path):
+    """T5 encoder-decoder (cross attention, padding / causal / cross masks, shared embeddings + LM-head bias): names, loss and gradients equal the reference's."""
+    from dist_utils import run_distributed
+
+    ref = _run_reference(tmp_path, 1, "t5")[0]
+    ours = run_distributed(_ours_t5, 1)[0]
+    assert sorted(ours["names"]) == sorted(ref["grads"].keys()), sorted(set(ours["names"]) ^ set(ref["grads"].keys()))
+    assert abs(ours["loss"] - ref["loss"]) < 2e-5, (ours["loss"], ref["loss"])
+    for n, g in ref["grads"].items():
+        err = float((ours["grads"][n] - g).abs().max() / g.abs().max().clamp(min=1e-12))
+        assert err < 5e-4, f"grad {n}: rel err {err}"
+
+
 # ---- distributed-checkpoint interop (SURVEY 7.4-6: "cross-load a checkpoint with the reference") --------------------------------------
 
 
