@@ -44,7 +44,8 @@ class CLIPViTModel(MegatronModule):
             self.class_token = torch.nn.Parameter(torch.randn(1, class_token_len, c.hidden_size, device=dev, dtype=c.params_dtype))
         self.ln_pre = ln_pre_impl(c, c.hidden_size, eps=c.layernorm_epsilon) if (ln_pre_impl is not None and model_subtype == "clip") else None
         self.decoder = TransformerBlock(config=c, spec=transformer_layer_spec, pre_process=True, post_process=False, pg_collection=pg_collection)
-        self.ln_post = ln_post_impl(c, c.hidden_size, eps=c.layernorm_epsilon) if ln_post_impl is not None else None
+        # which norms exist follows the model family, as in the reference (clip_vit_model.py:87-113): CLIP normalises BEFORE the blocks, SigLIP after, InternViT neither
+        self.ln_post = ln_post_impl(c, c.hidden_size, eps=c.layernorm_epsilon) if (ln_post_impl is not None and model_subtype == "siglip") else None
         self.model_type = None
 
     def set_input_tensor(self, input_tensor):

@@ -40,6 +40,7 @@ class _HostStream:
     wait = query = lambda self, *a, **k: True
 
 
+torch.Tensor.cuda = lambda self, *a, **k: self          # the reference's vision tower moves its position ids with .cuda()
 torch.cuda.Stream = _HostStream
 torch.cuda.Event = _HostStream
 torch.cuda.current_stream = lambda *a, **k: _HostStream()
@@ -108,6 +109,8 @@ def main():
         return bert_main(out_prefix, rank, F, TransformerConfig)
     if _V == "t5":
         return t5_main(out_prefix, rank, TransformerConfig)
+    if _V == "vit":
+        return vit_main(out_prefix, rank, TransformerConfig)
     cfg = TransformerConfig(
         num_layers=CFG["num_layers"], hidden_size=CFG["hidden_size"], ffn_hidden_size=CFG["ffn_hidden_size"], num_attention_heads=CFG["num_attention_heads"],
         num_query_groups=CFG["num_query_groups"], kv_channels=CFG["kv_channels"], normalization="RMSNorm", gated_linear_unit=True, activation_func=F.silu,
@@ -216,6 +219,32 @@ def t5_main(out_prefix, rank, TransformerConfig):
     loss = m(enc, dec, (enc_mask < 0.5).unsqueeze(1), (dec_mask < 0.5).unsqueeze(1), (x_mask < 0.5).unsqueeze(1), lm_labels=labels).float().mean()
     loss.backward()
     torch.save({"loss": float(loss), "grads": {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}}, f"{out_prefix}.rank{rank}.pt")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def vit_main(out_prefix, rank, TransformerConfig):
+    """CLIP ViT tower (conv patch embedding, class token, learned positions, pre-norm, bidirectional attention) from the reference's local layer spec."""
+    from megatron.core.models.vision.clip_vit_model import CLIPViTModel
+    from megatron.core.models.vision.vit_layer_specs import get_vit_layer_with_local_spec
+    from megatron.core.transformer.torch_norm import WrappedTorchNorm
+
+    cfg = TransformerConfig(num_layers=2, hidden_size=64, ffn_hidden_size=128, num_attention_heads=4, hidden_dropout=0.0, attention_dropout=0.0, use_cpu_initialization=True,
+                            bias_activation_fusion=False, bias_dropout_fusion=False, masked_softmax_fusion=False, gradient_accumulation_fusion=False, perform_initialization=False)
+    m = CLIPViTModel(cfg, get_vit_layer_with_local_spec(), ln_pre_impl=WrappedTorchNorm, ln_post_impl=WrappedTorchNorm, patch_dim=14, img_h=28, img_w=28)
+    init_params(m.named_parameters(), 0, 1)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.dim() == 1 and "bias" in n:
+                p.copy_(seeded_full(n, list(p.shape), 0.02))
+            if p.dim() > 2:
+                p.copy_(seeded_full(n, list(p.shape), 0.05))
+    x = torch.randn(2, 3, 28, 28, generator=torch.Generator().manual_seed(7))
+    out = m(x)
+    w = torch.randn(out.shape, generator=torch.Generator().manual_seed(8))
+    loss = (out.float() * w).mean()
+    loss.backward()
+    torch.save({"loss": float(loss), "shape": tuple(out.shape), "grads": {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}}, f"{out_prefix}.rank{rank}.pt")
     dist.barrier()
     dist.destroy_process_group()
 

@@ -237,6 +237,52 @@ def test_t5_parity_with_reference(tmp_path):
         assert err < 5e-4, f"grad {n}: rel err {err}"
 
 
+def _ours_vit(rank, world):
+    import zlib
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.models.vision.clip_vit_model import CLIPViTModel
+    from megatron_b200.core.models.vision.vit_layer_specs import get_vit_layer_with_local_spec
+    from megatron_b200.core.transformer.torch_norm import FusedNorm
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    ps.initialize_model_parallel()
+    cfg = TransformerConfig(num_layers=2, hidden_size=64, ffn_hidden_size=128, num_attention_heads=4, hidden_dropout=0.0, attention_dropout=0.0, use_cpu_initialization=True,
+                            gradient_accumulation_fusion=False, perform_initialization=False, bias_dropout_fusion=False)
+    m = CLIPViTModel(cfg, get_vit_layer_with_local_spec(), ln_pre_impl=FusedNorm, ln_post_impl=FusedNorm, patch_dim=14, img_h=28, img_w=28)
+
+    def seeded(n, shape, std):
+        return torch.empty(shape).normal_(0, std, generator=torch.Generator().manual_seed(zlib.crc32(n.encode())))
+
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.dim() == 1:
+                p.copy_(seeded(n, list(p.shape), 0.02)) if "bias" in n else p.fill_(1.0)
+            else:
+                p.copy_(seeded(n, list(p.shape), 0.05))
+    x = torch.randn(2, 3, 28, 28, generator=torch.Generator().manual_seed(7))
+    out = m(x)
+    w = torch.randn(out.shape, generator=torch.Generator().manual_seed(8))
+    loss = (out.float() * w).mean()
+    loss.backward()
+    return {"loss": float(loss), "shape": tuple(out.shape), "grads": {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None},
+            "names": [n for n, p in m.named_parameters() if p.grad is not None]}
+
+
+def test_clip_vit_parity_with_reference(tmp_path):
+    """CLIP ViT tower (conv patch embedding, class token, learned positions, pre-norm): output shape, parameter names, loss and gradients equal the reference's."""
+    from dist_utils import run_distributed
+
+    ref = _run_reference(tmp_path, 1, "vit")[0]
+    ours = run_distributed(_ours_vit, 1)[0]
+    assert ours["shape"] == ref["shape"]
+    assert sorted(ours["names"]) == sorted(ref["grads"].keys()), sorted(set(ours["names"]) ^ set(ref["grads"].keys()))
+    assert abs(ours["loss"] - ref["loss"]) < 1e-6, (ours["loss"], ref["loss"])
+    for n, g in ref["grads"].items():
+        err = float((ours["grads"][n] - g).abs().max() / g.abs().max().clamp(min=1e-12))
+        assert err < 5e-4, f"grad {n}: rel err {err}"
+
+
 # ---- distributed-checkpoint interop (SURVEY 7.4-6: "cross-load a checkpoint with the reference") --------------------------------------
 
 
