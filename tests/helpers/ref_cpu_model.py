@@ -40,6 +40,34 @@ class _HostStream:
     wait = query = lambda self, *a, **k: True
 
 
+
+
+def _cpu_device_factories():
+    """The reference spells ``device='cuda'`` literally in a few factory calls (optimizer scale tensors, found-inf flags): send those to the CPU."""
+    def wrap(fn):
+        def inner(*a, **k):
+            d = k.get("device")
+            if d is not None and "cuda" in str(d):
+                k["device"] = "cpu"
+            return fn(*a, **k)
+        return inner
+    for name in ("tensor", "zeros", "ones", "empty", "full", "zeros_like", "ones_like", "empty_like", "arange", "randn", "rand"):
+        setattr(torch, name, wrap(getattr(torch, name)))
+
+
+_cpu_device_factories()
+_orig_type = torch.Tensor.type
+
+
+def _type(self, *a, **k):
+    """``tensor.type()`` is compared against 'torch.cuda.FloatTensor' in the reference's gradient clipping: report CPU tensors under the CUDA name."""
+    if not a and not k:
+        r = _orig_type(self)
+        return r if r.startswith("torch.cuda") else r.replace("torch.", "torch.cuda.", 1)
+    return _orig_type(self, *a, **k)
+
+
+torch.Tensor.type = _type
 torch.Tensor.cuda = lambda self, *a, **k: self          # the reference's vision tower moves its position ids with .cuda()
 torch.cuda.Stream = _HostStream
 torch.cuda.Event = _HostStream
@@ -151,6 +179,35 @@ def main():
     s = CFG["seq"]
     pos = torch.arange(s).unsqueeze(0).expand(tok.shape[0], -1).contiguous()
     mask = torch.triu(torch.ones(s, s), diagonal=1).bool()[None, None]
+    if _V == "optim":
+        # three optimizer steps through the reference's optimizer stack (param groups with / without weight decay, global-norm clipping, the LR scheduler)
+        from megatron.core.optimizer import OptimizerConfig, get_megatron_optimizer
+        from megatron.core.optimizer_param_scheduler import OptimizerParamScheduler
+
+        ocfg = OptimizerConfig(optimizer="adam", lr=1e-2, min_lr=1e-3, weight_decay=0.1, adam_beta1=0.9, adam_beta2=0.95, adam_eps=1e-8, clip_grad=0.5, bf16=False, fp16=False,
+                               use_distributed_optimizer=False)
+        from megatron.core.distributed import DistributedDataParallel, DistributedDataParallelConfig
+
+        m = DistributedDataParallel(cfg, DistributedDataParallelConfig(grad_reduce_in_fp32=True, overlap_grad_reduce=False, use_distributed_optimizer=False), m)
+        opt = get_megatron_optimizer(ocfg, [m])
+        sched = OptimizerParamScheduler(opt, init_lr=0.0, max_lr=1e-2, min_lr=1e-3, lr_warmup_steps=2, lr_decay_steps=10, lr_decay_style="cosine", start_wd=0.1, end_wd=0.1,
+                                        wd_incr_steps=10, wd_incr_style="constant")
+        losses, norms = [], []
+        for it in range(3):
+            m.zero_grad_buffer()
+            opt.zero_grad()
+            loss = m(tok[:, :-1].contiguous(), pos, mask, labels=tok[:, 1:].contiguous()).float().mean()
+            loss.backward()
+            m.finish_grad_sync()
+            ok, gn, _ = opt.step()
+            sched.step(increment=1)
+            losses.append(float(loss))
+            norms.append(float(gn))
+        torch.save({"losses": losses, "grad_norms": norms, "lr": [g["lr"] for g in opt.param_groups], "params": {n: p.detach().clone() for n, p in m.module.named_parameters()}},
+                   f"{out_prefix}.rank{rank}.pt")
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     loss = m(tok[:, :-1].contiguous(), pos, mask, labels=tok[:, 1:].contiguous()).float().mean()
     loss.backward()
     torch.save({"loss": float(loss), "grads": {n: p.grad.clone() for n, p in m.named_parameters()}}, f"{out_prefix}.rank{rank}.pt")
