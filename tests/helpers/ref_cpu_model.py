@@ -179,16 +179,20 @@ def main():
     s = CFG["seq"]
     pos = torch.arange(s).unsqueeze(0).expand(tok.shape[0], -1).contiguous()
     mask = torch.triu(torch.ones(s, s), diagonal=1).bool()[None, None]
-    if _V == "optim":
+    if _V in ("optim", "distopt"):
+        dist_opt = _V == "distopt"
+        if dist_opt:                       # DP = 2: every rank trains on its own sample
+            tok = tok[rank:rank + 1]
+            pos = pos[:1]
         # three optimizer steps through the reference's optimizer stack (param groups with / without weight decay, global-norm clipping, the LR scheduler)
         from megatron.core.optimizer import OptimizerConfig, get_megatron_optimizer
         from megatron.core.optimizer_param_scheduler import OptimizerParamScheduler
 
         ocfg = OptimizerConfig(optimizer="adam", lr=1e-2, min_lr=1e-3, weight_decay=0.1, adam_beta1=0.9, adam_beta2=0.95, adam_eps=1e-8, clip_grad=0.5, bf16=False, fp16=False,
-                               use_distributed_optimizer=False)
+                               use_distributed_optimizer=dist_opt)
         from megatron.core.distributed import DistributedDataParallel, DistributedDataParallelConfig
 
-        m = DistributedDataParallel(cfg, DistributedDataParallelConfig(grad_reduce_in_fp32=True, overlap_grad_reduce=False, use_distributed_optimizer=False), m)
+        m = DistributedDataParallel(cfg, DistributedDataParallelConfig(grad_reduce_in_fp32=True, overlap_grad_reduce=False, use_distributed_optimizer=dist_opt), m)
         opt = get_megatron_optimizer(ocfg, [m])
         sched = OptimizerParamScheduler(opt, init_lr=0.0, max_lr=1e-2, min_lr=1e-3, lr_warmup_steps=2, lr_decay_steps=10, lr_decay_style="cosine", start_wd=0.1, end_wd=0.1,
                                         wd_incr_steps=10, wd_incr_style="constant")
