@@ -18,3 +18,4 @@ def __getattr__(name):
 
         return importlib.import_module(".dist_checkpointing", __name__)
     raise AttributeError(name)
+from .safe_globals import register_safe_globals, safe_load_from_bytes  # noqa: E402,F401

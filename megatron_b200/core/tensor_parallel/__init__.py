@@ -35,4 +35,6 @@ from .random import (
 )
 from .utils import gather_split_1d_tensor, split_tensor_along_last_dim, split_tensor_into_1d_equal_chunks
 
+from .inference_layers import InferenceColumnParallelLinear, InferenceRowParallelLinear, convert_to_inference_layers  # noqa: E402
+
 __all__ = [n for n in dir() if not n.startswith("_")]

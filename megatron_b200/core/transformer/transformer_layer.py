@@ -258,3 +258,13 @@ def get_bias_dropout_add(training: bool, fused: bool):
         return ops.bias_dropout_add(x, bias, residual, prob, training)
 
     return f
+
+
+class HyperConnectionTransformerLayer(TransformerLayer):
+    """``TransformerLayer`` with the n-wide mHC residual stream (reference ``transformer_layer.py`` keeps this as a subclass; here the base class already switches
+    on ``config.enable_mhc_connections`` — the subclass only insists that the switch is on, so specs written for the reference resolve to the same behaviour)."""
+
+    def __init__(self, config, *args, **kwargs):
+        if not getattr(config, "enable_mhc_connections", False):
+            raise ValueError("HyperConnectionTransformerLayer requires config.enable_mhc_connections=True")
+        super().__init__(config, *args, **kwargs)

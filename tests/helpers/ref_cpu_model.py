@@ -132,6 +132,8 @@ def main():
             return contextlib.nullcontext()
 
     _tp.get_cuda_rng_tracker = _tpr.get_cuda_rng_tracker = lambda *a, **k: _NoRng()
+    if _V == "pp2":
+        return pp_main(out_prefix, rank, F, TransformerConfig, GPTModel, get_gpt_layer_local_spec, parallel_state)
     parallel_state.initialize_model_parallel(tensor_model_parallel_size=tp, **({"expert_model_parallel_size": 2} if _V == "moe_ep2" else {}))
     if _V == "bert":
         return bert_main(out_prefix, rank, F, TransformerConfig)
@@ -280,6 +282,50 @@ def t5_main(out_prefix, rank, TransformerConfig):
     loss = m(enc, dec, (enc_mask < 0.5).unsqueeze(1), (dec_mask < 0.5).unsqueeze(1), (x_mask < 0.5).unsqueeze(1), lm_labels=labels).float().mean()
     loss.backward()
     torch.save({"loss": float(loss), "grads": {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}}, f"{out_prefix}.rank{rank}.pt")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def pp_main(out_prefix, rank, F, TransformerConfig, GPTModel, get_gpt_layer_local_spec, parallel_state):
+    """Pipeline parallel 2 (1F1B, 4 micro-batches) through the reference's schedule: 4 layers, 2 per stage, untied embeddings."""
+    from functools import partial
+
+    from megatron.core.pipeline_parallel import get_forward_backward_func
+
+    parallel_state.initialize_model_parallel(pipeline_model_parallel_size=2)
+    pre, post = parallel_state.is_pipeline_first_stage(), parallel_state.is_pipeline_last_stage()
+    cfg = TransformerConfig(num_layers=4, hidden_size=64, ffn_hidden_size=128, num_attention_heads=4, num_query_groups=2, kv_channels=16, normalization="RMSNorm",
+                            gated_linear_unit=True, activation_func=F.silu, add_bias_linear=False, hidden_dropout=0.0, attention_dropout=0.0, use_cpu_initialization=True,
+                            bias_activation_fusion=False, bias_dropout_fusion=False, masked_softmax_fusion=False, gradient_accumulation_fusion=False, perform_initialization=False,
+                            pipeline_model_parallel_size=2, pipeline_dtype=torch.float32)
+    m = GPTModel(cfg, get_gpt_layer_local_spec(normalization="RMSNorm"), vocab_size=128, max_sequence_length=32, pre_process=pre, post_process=post, parallel_output=True,
+                 share_embeddings_and_output_weights=False, position_embedding_type="rope", rotary_base=10000)
+    # layer names are LOCAL (layers.0 / layers.1 on both stages): seed by the GLOBAL name so that stage 1 holds layers 2 and 3 of the same 4-layer model
+    off = 0 if pre else 2
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            gname = n
+            if ".layers." in n:
+                head, rest = n.split(".layers.")
+                i, tail = rest.split(".", 1)
+                gname = f"{head}.layers.{int(i) + off}.{tail}"
+            p.fill_(1.0) if p.dim() == 1 else p.copy_(seeded_full(gname, list(p.shape)))
+    toks = torch.randint(0, 128, (4, 2, 33), generator=torch.Generator().manual_seed(2))            # 4 micro-batches of 2 sequences
+    mask = torch.triu(torch.ones(32, 32), diagonal=1).bool()[None, None]
+    pos = torch.arange(32).unsqueeze(0).expand(2, -1).contiguous()
+
+    def loss_func(output):
+        loss = output.float().mean()
+        return loss, {"lm loss": loss.detach().clone()}
+
+    def forward_step(data_iterator, model):
+        t = next(data_iterator)
+        return model(t[:, :-1].contiguous(), pos, mask, labels=t[:, 1:].contiguous()), loss_func
+
+    fb = get_forward_backward_func()
+    out = fb(forward_step_func=forward_step, data_iterator=iter(toks), model=[m], num_microbatches=4, seq_length=32, micro_batch_size=2, forward_only=False)
+    losses = [float(d["lm loss"]) for d in out] if post else []
+    torch.save({"losses": losses, "grads": {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}}, f"{out_prefix}.rank{rank}.pt")
     dist.barrier()
     dist.destroy_process_group()
 
