@@ -292,6 +292,8 @@ def pp_main(out_prefix, rank, F, TransformerConfig, GPTModel, get_gpt_layer_loca
 
     from megatron.core.pipeline_parallel import get_forward_backward_func
 
+    # (the interleaved schedule of the reference does not produce self-consistent losses over gloo — its batched p2p exchanges same-shaped tensors in both
+    # directions without tags — so only the non-interleaved schedule is compared; our interleaved schedule is checked against the single-process model elsewhere)
     parallel_state.initialize_model_parallel(pipeline_model_parallel_size=2)
     pre, post = parallel_state.is_pipeline_first_stage(), parallel_state.is_pipeline_last_stage()
     cfg = TransformerConfig(num_layers=4, hidden_size=64, ffn_hidden_size=128, num_attention_heads=4, num_query_groups=2, kv_channels=16, normalization="RMSNorm",
