@@ -54,9 +54,16 @@ class BlendedMegatronDatasetBuilder:
                 out.append(None)
                 continue
             if weights is None:
-                out.append(self._guard(BlendedDataset, parts, [len(p) for p in parts], None, self.config))
+                # blend by the components' own sizes; a requested size caps it (reference blended_megatron_dataset_builder.py:205-216)
+                lens = [len(p) for p in parts]
+                size_i = min(sizes[i], sum(lens)) if sizes[i] is not None else None
+                out.append(self._guard(BlendedDataset, parts, lens, size_i, self.config))
             else:
-                out.append(self._guard(BlendedDataset, parts, normalize(weights), sizes[i], self.config))
+                # the blend serves Σ_d ceil(target · w_d) samples — the per-dataset targets are rounded UP one by one, so the blend can be a few samples longer
+                # than the request (reference :196-200); matching it keeps the blending indices (and therefore the data order) identical
+                w = normalize(weights)
+                size_i = None if sizes[i] is None else sum(int(math.ceil(sizes[i] * wi)) for wi in w)
+                out.append(self._guard(BlendedDataset, parts, w, size_i, self.config))
         return out
 
     def _build_splits(self, dataset_path: Optional[str], sizes: List[Optional[int]], force_full=None):

@@ -517,3 +517,56 @@ def test_we_load_reference_checkpoint(tmp_path, tp_write, tp_read):
     _spawn_reference(tmp_path, tp_write, "save", str(ckpt))
     diffs = run_distributed(_ours_load, tp_read, tp_read, str(ckpt))
     assert all(d == 0.0 for d in diffs), diffs
+
+
+# ---- data pipeline -----------------------------------------------------------------------------------------------------------------------------
+
+
+def _write_corpus(prefix, n_docs, seed):
+    import numpy as np
+
+    from megatron_b200.core.datasets.indexed_dataset import IndexedDatasetBuilder
+
+    rng = np.random.default_rng(seed)
+    b = IndexedDatasetBuilder(prefix + ".bin", dtype=np.int32)
+    for _ in range(n_docs):
+        doc = rng.integers(1, 99, size=int(rng.integers(3, 60))).tolist() + [99]
+        b.add_document(np.asarray(doc, dtype=np.int32), [len(doc)])
+    b.finalize(prefix + ".idx")
+
+
+@pytest.mark.parametrize("blend", [False, True])
+def test_gpt_dataset_samples_match_reference(tmp_path, blend):
+    """The reference reads the .bin/.idx files THIS framework writes, and both build the same train / valid / test samples from them (document shuffle, sample
+    index, blending of two corpora, loss masks, reset position ids) for the same seed — a run switched over sees the same data order."""
+    from megatron_b200.core.datasets import BlendedMegatronDatasetBuilder, GPTDatasetConfig
+    from megatron_b200.core.datasets.gpt_dataset import GPTDataset
+    from megatron_b200.core.datasets.utils import get_blend_from_list
+
+    _write_corpus(str(tmp_path / "a"), 300, 1)
+    _write_corpus(str(tmp_path / "b"), 200, 2)
+    blend_args = ["0.7", str(tmp_path / "a"), "0.3", str(tmp_path / "b")] if blend else ["1.0", str(tmp_path / "a")]
+    counts = [64, 12, 8]
+    out = tmp_path / "ref.pt"
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(REPO, "tests", "helpers", "ref_data.py"), str(out), str(tmp_path / "ref_cache"), "32", "1234", "80,15,5", *map(str, counts), *blend_args],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    ref = torch.load(out)
+
+    class Tok:
+        eod = 99
+        unique_identifiers = {"class": "TestTokenizer", "eod": 99}
+
+    cfg = GPTDatasetConfig(random_seed=1234, sequence_length=32, blend=get_blend_from_list(blend_args), split="80,15,5", path_to_cache=str(tmp_path / "our_cache"), tokenizer=Tok(),
+                           reset_position_ids=True, reset_attention_mask=False, eod_mask_loss=True, create_attention_mask=False, mmap_bin_files=False)
+    ours = BlendedMegatronDatasetBuilder(GPTDataset, counts, lambda: True, cfg).build()
+    for name, ds in zip(("train", "valid", "test"), ours):
+        assert (ds is None) == (ref[name] is None)
+        if ds is None:
+            continue
+        assert len(ds) == ref[name]["len"], (name, len(ds), ref[name]["len"])
+        for i, want in ref[name]["samples"].items():
+            got = ds[i]
+            for k, v in want.items():
+                assert torch.equal(torch.as_tensor(got[k]).to(v.dtype), v), (name, i, k)
