@@ -123,7 +123,29 @@ class TopKRouter(Router):
         save_to_aux_losses_tracker("load_balancing_loss", loss / coeff, self.layer_number, self.config.num_layers)
         return MoEAuxLossAutoScaler.apply(activation, loss)
 
+    def _seq_aux_loss(self, scores, routing_map, activation, seq_length: int, bsz: int):
+        """Per-SEQUENCE load balancing (DeepSeek-V3; reference ``router.py:450-500``): the batch dimension is folded into the expert dimension
+        (``[s·b, E] → [s, b·E]``), so the switch loss sums one term per sequence; divided by the batch size it is their mean."""
+        coeff = self.config.moe_aux_loss_coeff
+        coeff = coeff if not isinstance(coeff, (list, tuple)) else coeff[0]
+        if not coeff or not self.training or not torch.is_grad_enabled():
+            return activation
+        sc = scores.reshape(seq_length, -1)
+        rm = routing_map.reshape(seq_length, -1)
+        tokens_per_expert = rm.sum(dim=0).float()
+        total = seq_length
+        aggregated = sc.sum(dim=0)
+        if self.tp_cp_group is not None and get_pg_size(self.tp_cp_group) > 1:          # the sequence is split over tp x cp under SP / CP
+            tokens_per_expert = tokens_per_expert.clone()
+            dist.all_reduce(tokens_per_expert, group=self.tp_cp_group)
+            aggregated = reduce_from_tensor_model_parallel_region(aggregated, group=self.tp_cp_group)
+            total = seq_length * get_pg_size(self.tp_cp_group)
+        loss = switch_load_balancing_loss_func(aggregated, tokens_per_expert, total, self.topk, self.num_experts, coeff) / bsz
+        save_to_aux_losses_tracker("seq_load_balancing_loss", loss / coeff, self.layer_number, self.config.num_layers)
+        return MoEAuxLossAutoScaler.apply(activation, loss)
+
     def routing(self, logits: torch.Tensor):
+        seq_length, bsz = (logits.shape[0], logits.shape[1]) if logits.dim() == 3 else (logits.shape[0], 1)
         logits = logits.view(-1, self.num_experts)
         logits = self.apply_z_loss(logits)
         cfg = self.config
@@ -155,7 +177,14 @@ class TopKRouter(Router):
             else:
                 s = torch.sigmoid(logits.float())
                 scores = s / (s.sum(-1, keepdim=True) + 1e-20)
-            probs = self._aux_loss(scores, routing_map, probs)
+            # the balancing losses look at the PLAIN top-k of the normalised scores, not at the map actually routed with (group limits, expert bias, capacity
+            # drops must not leak into the balancing signal) — reference moe_utils.compute_routing_scores_for_aux_loss
+            _, top_idx = torch.topk(scores, k=self.topk, dim=1)
+            map_for_loss = torch.zeros_like(logits).int().scatter(1, top_idx, 1).bool()
+            if self.routing_type == "seq_aux_loss":
+                probs = self._seq_aux_loss(scores, map_for_loss, probs, seq_length, bsz)
+            else:
+                probs = self._aux_loss(scores, map_for_loss, probs)
         if self.enable_expert_bias and torch.is_grad_enabled():
             with torch.no_grad():
                 self.local_tokens_per_expert += routing_map.sum(dim=0)

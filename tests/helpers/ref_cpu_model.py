@@ -109,6 +109,13 @@ CFG = dict(num_layers=2, hidden_size=64, ffn_hidden_size=128, num_attention_head
 _V = os.environ.get("REF_VARIANT", "")
 MOE_KW = dict(num_moe_experts=4, moe_router_topk=2, moe_token_dispatcher_type="allgather", moe_router_load_balancing_type="aux_loss",
               moe_aux_loss_coeff=0.02, moe_grouped_gemm=False, moe_ffn_hidden_size=96, **({"expert_model_parallel_size": 2} if _V == "moe_ep2" else {})) if _V.startswith("moe") else {}
+if _V == "moe_dsv3":        # DeepSeek-V3 style router: sigmoid scores, group-limited top-k, scaling factor, per-sequence aux loss, z-loss, one shared expert
+    MOE_KW.update(num_moe_experts=8, moe_router_topk=4, moe_router_score_function="sigmoid", moe_router_num_groups=2, moe_router_group_topk=1, moe_router_topk_scaling_factor=2.5,
+                  moe_router_load_balancing_type="seq_aux_loss", moe_aux_loss_coeff=0.01, moe_z_loss_coeff=1e-3, moe_shared_expert_intermediate_size=64, moe_ffn_hidden_size=48,
+                  moe_router_pre_softmax=False)
+    import json as _json
+
+    MOE_KW.update(_json.loads(os.environ.get("REF_MOE_OVERRIDE", "{}")))
 
 
 def tokens():

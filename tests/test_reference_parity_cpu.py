@@ -57,7 +57,12 @@ def _ours(rank, world, tp, variant=""):
         **(dict(num_moe_experts=4, moe_router_topk=2, moe_token_dispatcher_type="allgather", moe_router_load_balancing_type="aux_loss",
                 moe_aux_loss_coeff=0.02, moe_grouped_gemm=False, moe_ffn_hidden_size=96, **({"expert_model_parallel_size": 2} if ep2 else {})) if variant.startswith("moe") else {}),
     )
-    spec = get_gpt_layer_local_spec(num_experts=4, moe_grouped_gemm=False, normalization="RMSNorm") if variant.startswith("moe") else get_gpt_layer_local_spec(normalization="RMSNorm")
+    if variant == "moe_dsv3":
+        cfg = TransformerConfig(**{**{f.name: getattr(cfg, f.name) for f in __import__("dataclasses").fields(cfg) if f.init}, **dict(
+            num_moe_experts=8, moe_router_topk=4, moe_router_score_function="sigmoid", moe_router_num_groups=2, moe_router_group_topk=1, moe_router_topk_scaling_factor=2.5,
+            moe_router_load_balancing_type="seq_aux_loss", moe_aux_loss_coeff=0.01, moe_z_loss_coeff=1e-3, moe_shared_expert_intermediate_size=64, moe_ffn_hidden_size=48,
+            moe_router_pre_softmax=False), **__import__("json").loads(os.environ.get("REF_MOE_OVERRIDE", "{}"))})
+    spec = get_gpt_layer_local_spec(num_experts=cfg.num_moe_experts, moe_grouped_gemm=False, normalization="RMSNorm") if variant.startswith("moe") else get_gpt_layer_local_spec(normalization="RMSNorm")
     m = GPTModel(cfg, spec, vocab_size=CFG["vocab"], max_sequence_length=CFG["seq"], parallel_output=True,
                  share_embeddings_and_output_weights=False, position_embedding_type="rope", rotary_base=10000)
     with torch.no_grad():
@@ -114,6 +119,21 @@ def test_moe_loss_and_grad_parity_with_reference(tmp_path):
     for n, g in ref["grads"].items():
         err = float((ours["grads"][n] - g).abs().max() / g.abs().max().clamp(min=1e-12))
         assert err < 5e-4, f"grad {n}: rel err {err}"
+
+
+def test_moe_deepseek_style_router_parity_with_reference(tmp_path):
+    """8 experts, top-4 from 1 of 2 groups, sigmoid scores with a scaling factor, per-sequence aux loss, z-loss, a shared expert: names, loss and gradients equal the
+    unmodified reference's."""
+    from dist_utils import run_distributed
+
+    ref = _run_reference(tmp_path, 1, "moe_dsv3")[0]
+    ours = run_distributed(_ours, 1, 1, "moe_dsv3")[0]
+    assert sorted(ours["names"]) == sorted(ref["grads"].keys()), sorted(set(ours["names"]) ^ set(ref["grads"].keys()))
+    assert any("shared_experts" in n for n in ours["names"])
+    assert abs(ours["loss"] - ref["loss"]) < 2e-5, (ours["loss"], ref["loss"])
+    for n, g in ref["grads"].items():
+        err = float((ours["grads"][n] - g).abs().max() / g.abs().max().clamp(min=1e-12))
+        assert err < 1e-3, f"grad {n}: rel err {err}"
 
 
 def test_moe_expert_parallel_parity_with_reference(tmp_path):
