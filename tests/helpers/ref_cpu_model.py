@@ -113,6 +113,10 @@ if _V == "moe_dsv3":        # DeepSeek-V3 style router: sigmoid scores, group-li
     MOE_KW.update(num_moe_experts=8, moe_router_topk=4, moe_router_score_function="sigmoid", moe_router_num_groups=2, moe_router_group_topk=1, moe_router_topk_scaling_factor=2.5,
                   moe_router_load_balancing_type="seq_aux_loss", moe_aux_loss_coeff=0.01, moe_z_loss_coeff=1e-3, moe_shared_expert_intermediate_size=64, moe_ffn_hidden_size=48,
                   moe_router_pre_softmax=False)
+if _V == "moe_drop":        # capacity-limited routing: drop by probability, pad every expert's input to the capacity; the all-to-all dispatcher (EP = 1: no communication)
+    MOE_KW.update(moe_token_dispatcher_type="alltoall", moe_expert_capacity_factor=1.0, moe_token_drop_policy="probs", moe_pad_expert_input_to_capacity=True,
+                  moe_router_pre_softmax=True)
+if _V.startswith("moe"):
     import json as _json
 
     MOE_KW.update(_json.loads(os.environ.get("REF_MOE_OVERRIDE", "{}")))

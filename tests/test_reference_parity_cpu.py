@@ -62,6 +62,9 @@ def _ours(rank, world, tp, variant=""):
             num_moe_experts=8, moe_router_topk=4, moe_router_score_function="sigmoid", moe_router_num_groups=2, moe_router_group_topk=1, moe_router_topk_scaling_factor=2.5,
             moe_router_load_balancing_type="seq_aux_loss", moe_aux_loss_coeff=0.01, moe_z_loss_coeff=1e-3, moe_shared_expert_intermediate_size=64, moe_ffn_hidden_size=48,
             moe_router_pre_softmax=False), **__import__("json").loads(os.environ.get("REF_MOE_OVERRIDE", "{}"))})
+    if variant == "moe_drop":
+        cfg = TransformerConfig(**{**{f.name: getattr(cfg, f.name) for f in __import__("dataclasses").fields(cfg) if f.init}, **dict(
+            moe_token_dispatcher_type="alltoall", moe_expert_capacity_factor=1.0, moe_token_drop_policy="probs", moe_pad_expert_input_to_capacity=True, moe_router_pre_softmax=True)})
     spec = get_gpt_layer_local_spec(num_experts=cfg.num_moe_experts, moe_grouped_gemm=False, normalization="RMSNorm") if variant.startswith("moe") else get_gpt_layer_local_spec(normalization="RMSNorm")
     m = GPTModel(cfg, spec, vocab_size=CFG["vocab"], max_sequence_length=CFG["seq"], parallel_output=True,
                  share_embeddings_and_output_weights=False, position_embedding_type="rope", rotary_base=10000)
@@ -130,6 +133,20 @@ def test_moe_deepseek_style_router_parity_with_reference(tmp_path):
     ours = run_distributed(_ours, 1, 1, "moe_dsv3")[0]
     assert sorted(ours["names"]) == sorted(ref["grads"].keys()), sorted(set(ours["names"]) ^ set(ref["grads"].keys()))
     assert any("shared_experts" in n for n in ours["names"])
+    assert abs(ours["loss"] - ref["loss"]) < 2e-5, (ours["loss"], ref["loss"])
+    for n, g in ref["grads"].items():
+        err = float((ours["grads"][n] - g).abs().max() / g.abs().max().clamp(min=1e-12))
+        assert err < 1e-3, f"grad {n}: rel err {err}"
+
+
+def test_moe_capacity_drop_and_pad_parity_with_reference(tmp_path):
+    """Capacity factor 1.0 with probability-based token dropping and padding to capacity (all-to-all dispatcher): the same tokens are dropped, the loss and every
+    gradient equal the unmodified reference's."""
+    from dist_utils import run_distributed
+
+    ref = _run_reference(tmp_path, 1, "moe_drop")[0]
+    ours = run_distributed(_ours, 1, 1, "moe_drop")[0]
+    assert sorted(ours["names"]) == sorted(ref["grads"].keys())
     assert abs(ours["loss"] - ref["loss"]) < 2e-5, (ours["loss"], ref["loss"])
     for n, g in ref["grads"].items():
         err = float((ours["grads"][n] - g).abs().max() / g.abs().max().clamp(min=1e-12))
