@@ -40,6 +40,30 @@ class FaultInjectorConfig:
     at_iteration: Optional[int] = None        # … or when the training loop reports this iteration
     gpu_sleep_s: float = 30.0
     seed: int = 1234
+    start_iteration: Optional[int] = None     # with ``delay_s``: the countdown starts when the training loop reports this iteration, not at construction
+
+    @classmethod
+    def from_args(cls, args, world_size: int) -> Optional["FaultInjectorConfig"]:
+        """The reference command line (``--fault-injector-*``, ``training/config/resilience_config.py:FaultInjectorConfig``): explicit ``ranks`` or
+        ``num_ranks`` seeded picks; one fault kind drawn from ``fault_types`` by ``fault_probabilities``; a fixed ``fault_delay`` or an exponential draw with
+        mean ``mtti_seconds`` (plus ``offset_seconds``), counted from ``delay_start_iteration`` when given.  ``None`` when no fault is configured."""
+        names = ("fault_injector_ranks", "fault_injector_num_ranks", "fault_injector_fault_types", "fault_injector_fault_probabilities", "fault_injector_fault_delay",
+                 "fault_injector_delay_start_iteration", "fault_injector_mtti_seconds", "fault_injector_offset_seconds", "fault_injector_seed")
+        vals = {n[len("fault_injector_"):]: getattr(args, n, None) for n in names}
+        g = vals.get
+        kinds = [k.strip().lower() for k in (g("fault_types") or "").split(",") if k.strip()]
+        if not kinds:
+            return None
+        rng = random.Random(g("seed") if g("seed") is not None else 1234)
+        ranks = [int(r) for r in str(g("ranks")).split(",")] if g("ranks") else sorted(rng.sample(range(world_size), min(g("num_ranks") or 1, world_size)))
+        probs = [float(x) for x in (g("fault_probabilities") or "").split(",") if x.strip()] or [1.0] * len(kinds)
+        assert len(probs) == len(kinds), "--fault-injector-fault-probabilities needs one entry per fault type"
+        kind = rng.choices(kinds, weights=probs)[0]
+        delay = g("fault_delay")
+        if delay is None and g("mtti_seconds"):
+            delay = rng.expovariate(1.0 / g("mtti_seconds"))
+        delay = (delay or 0.0) + (g("offset_seconds") or 0.0)
+        return cls(fault_type=Fault(kind), ranks=ranks, delay_s=delay, seed=g("seed") if g("seed") is not None else 1234, start_iteration=g("delay_start_iteration"))
 
 
 class FaultInjector:
@@ -54,7 +78,11 @@ class FaultInjector:
         self.fired = False
         self._pending_exc = False
         self._thread: Optional[threading.Thread] = None
-        if self.armed and cfg.delay_s is not None:
+        if self.armed and cfg.delay_s is not None and cfg.start_iteration is None:
+            self._start_timer()
+
+    def _start_timer(self):
+        if self._thread is None:
             self._thread = threading.Thread(target=self._timer, daemon=True)
             self._thread.start()
 
@@ -66,6 +94,8 @@ class FaultInjector:
         """Call once per training iteration (``training.train`` does when ``--inject-fault`` is set)."""
         if self.armed and not self.fired and self.cfg.at_iteration is not None and iteration >= self.cfg.at_iteration:
             self.fire()
+        if self.armed and not self.fired and self.cfg.delay_s is not None and self.cfg.start_iteration is not None and iteration >= self.cfg.start_iteration:
+            self._start_timer()
         self.maybe_raise()
 
     def maybe_raise(self):

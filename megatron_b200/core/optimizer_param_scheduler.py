@@ -31,12 +31,15 @@ class OptimizerParamScheduler:
         self.num_steps = 0
         self.step(0)
 
-    def get_wd(self) -> float:
+    def get_wd(self, param_group: Optional[dict] = None) -> float:
+        """``param_group`` may carry its own ``start_wd`` / ``end_wd`` (reference ``ParamGroupOverride``)."""
+        start_wd = self.start_wd if param_group is None else param_group.get("start_wd", self.start_wd)
+        end_wd = self.end_wd if param_group is None else param_group.get("end_wd", self.end_wd)
         if self.num_steps > self.wd_incr_steps:
-            return self.end_wd
+            return end_wd
         if self.wd_incr_style == "constant":
-            assert self.start_wd == self.end_wd
-            return self.end_wd
+            assert start_wd == end_wd
+            return end_wd
         r = float(self.num_steps) / float(self.wd_incr_steps)
         if self.wd_incr_style == "linear":
             c = r
@@ -44,7 +47,7 @@ class OptimizerParamScheduler:
             c = 0.5 * (math.cos(math.pi * (1 - r)) + 1.0)
         else:
             raise Exception(f"{self.wd_incr_style} weight decay increment style is not supported")
-        return self.start_wd + c * (self.end_wd - self.start_wd)
+        return start_wd + c * (end_wd - start_wd)
 
     def get_lr(self, param_group: dict) -> float:
         max_lr = param_group.get("max_lr", self.max_lr)
@@ -79,10 +82,13 @@ class OptimizerParamScheduler:
 
     def step(self, increment: int) -> None:
         self.num_steps += increment
-        wd = self.get_wd()
         for g in self.optimizer.param_groups:
-            g["lr"] = self.get_lr(g) * g.get("lr_mult", 1.0)
-            g["weight_decay"] = wd * g.get("wd_mult", 1.0)
+            lr = self.get_lr(g) * g.get("lr_mult", 1.0)      # lr_mult: this framework's multiplier; the reference folds it into per-group max_lr / min_lr
+            if hasattr(g.get("lr"), "fill_"):
+                g["lr"].fill_(lr)                              # tensor lr (captured optimizers): update in place
+            else:
+                g["lr"] = lr
+            g["weight_decay"] = self.get_wd(g) * g.get("wd_mult", 1.0)
 
     def state_dict(self) -> dict:
         return {k: getattr(self, k) for k in ("max_lr", "lr_warmup_steps", "num_steps", "lr_decay_style", "lr_decay_steps", "min_lr", "start_wd", "end_wd", "wd_incr_style", "wd_incr_steps")}

@@ -17,6 +17,27 @@ from ..tokenizer import MegatronTokenizerBase
 # tiktoken's cl100k-style splitter without the unicode-property classes `re` lacks: contractions, letters, digit runs (<= 3), punctuation, whitespace
 DEFAULT_PATTERN = r"""'(?i:[sdmt]|ll|ve|re)|[^\r\n\w]?[^\W\d_]+|\d{1,3}| ?[^\s\w]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+"""
 DEFAULT_SPECIAL = ["<unk>", "<s>", "</s>"]
+# the two named splitters of the reference command line (``--tiktoken-pattern v1|v2``): the public cl100k-style pattern and the case-aware one used by
+# tekken-style vocabularies.  Both need unicode property classes, i.e. the ``regex`` package; without it the ``re`` approximation above is used.
+NAMED_PATTERNS = {
+    "v1": r"""(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+""",
+    "v2": r"""[^\r\n\p{L}\p{N}]?[\p{Lu}\p{Lt}\p{Lm}\p{Lo}\p{M}]*[\p{Ll}\p{Lm}\p{Lo}\p{M}]+|[^\r\n\p{L}\p{N}]?[\p{Lu}\p{Lt}\p{Lm}\p{Lo}\p{M}]+[\p{Ll}\p{Lm}\p{Lo}\p{M}]*|\p{N}| ?[^\s\p{L}\p{N}]+[\r\n/]*|\s*[\r\n]+|\s+(?!\S)|\s+""",
+}
+
+
+def compile_pattern(pattern: Optional[str]):
+    """``None`` → the built-in ``re`` splitter; ``"v1"`` / ``"v2"`` → the reference's named patterns; anything else is a regular expression (compiled with
+    ``regex`` when it uses ``\\p{..}`` classes)."""
+    if pattern is None:
+        return re.compile(DEFAULT_PATTERN)
+    text = NAMED_PATTERNS.get(pattern, pattern)
+    if "\\p{" in text:
+        try:
+            import regex
+        except ImportError:
+            return re.compile(DEFAULT_PATTERN)
+        return regex.compile(text)
+    return re.compile(text)
 
 
 def load_tiktoken_ranks(path: str, vocab_size: Optional[int] = None) -> Dict[bytes, int]:
@@ -64,7 +85,7 @@ class TikTokenTokenizer(MegatronTokenizerBase):
         self.num_special_tokens = num_special_tokens
         self.ranks = load_tiktoken_ranks(path, None if vocab_size is None else vocab_size - num_special_tokens)
         self.decoder = {v: k for k, v in self.ranks.items()}
-        self.pattern = re.compile(pattern or DEFAULT_PATTERN)
+        self.pattern = compile_pattern(pattern)
         self._special_ids = {t: i for i, t in enumerate(special)}
         self._special_re = re.compile("|".join(re.escape(t) for t in sorted(special, key=len, reverse=True)))
         self._vocab_size = num_special_tokens + len(self.ranks)

@@ -46,9 +46,10 @@ class MegatronTokenizerBase(ABC):
 class NullTokenizer(MegatronTokenizerBase):
     """Whitespace-separated integers; the last id is EOD (``--tokenizer-type NullTokenizer``)."""
 
-    def __init__(self, vocab_size: int):
+    def __init__(self, vocab_size: int, eod_id: Optional[int] = None, pad_id: Optional[int] = None):
         self._vocab_size_without_eod = int(vocab_size)
-        self._eod_id = self._vocab_size_without_eod
+        self._eod_id = self._vocab_size_without_eod if eod_id is None else int(eod_id)      # --null-tokenizer-eod-id
+        self._pad_id = -1 if pad_id is None else int(pad_id)                                  # --null-tokenizer-pad-id (-1: no pad token)
 
     def tokenize(self, text: str) -> List[int]:
         return [int(x) for x in text.split()]
@@ -63,6 +64,10 @@ class NullTokenizer(MegatronTokenizerBase):
     @property
     def eod(self) -> int:
         return self._eod_id
+
+    @property
+    def pad(self) -> int:
+        return self._pad_id
 
     @property
     def unique_identifiers(self):
@@ -86,10 +91,11 @@ class ByteLevelTokenizer(MegatronTokenizerBase):
 
 
 class SentencePieceTokenizer(MegatronTokenizerBase):
-    def __init__(self, model_file: str):
+    def __init__(self, model_file: str, chat_template: Optional[str] = None, **_ignored):
         import sentencepiece
 
         self.sp = sentencepiece.SentencePieceProcessor(model_file=model_file)
+        self.chat_template = chat_template
 
     def tokenize(self, text: str) -> List[int]:
         return self.sp.encode(text)
@@ -115,13 +121,16 @@ class SentencePieceTokenizer(MegatronTokenizerBase):
 
 
 class HuggingFaceTokenizer(MegatronTokenizerBase):
-    def __init__(self, path: str, **kw):
+    def __init__(self, path: str, include_special_tokens: bool = False, chat_template: Optional[str] = None, **kw):
         import transformers
 
         self.tk = transformers.AutoTokenizer.from_pretrained(path, **kw)
+        self.include_special_tokens = include_special_tokens       # reference ``--tokenizer-hf-no-include-special-tokens`` turns this off
+        if chat_template is not None:
+            self.tk.chat_template = chat_template
 
     def tokenize(self, text: str) -> List[int]:
-        return self.tk.encode(text, add_special_tokens=False)
+        return self.tk.encode(text, add_special_tokens=self.include_special_tokens)
 
     def detokenize(self, ids: List[int]) -> str:
         return self.tk.decode(list(map(int, ids)))
@@ -193,17 +202,41 @@ class MegatronTokenizer:
         return target
 
 
+def build_tokenizer_from_args(args):
+    """The tokenizer a training / serving command line describes (reference ``tokenizers/utils/build_tokenizer.py:build_tokenizer``): tokenizer type and model
+    plus the per-library switches (``--null-tokenizer-eod-id``, ``--tiktoken-pattern``, ``--tokenizer-hf-no-use-fast``, ``--trust-remote-code``,
+    ``--chat-template``, ``--tokenizer-special-tokens``, ``--tokenizer-metadata``)."""
+    g = lambda n, d=None: getattr(args, n, d)  # noqa: E731
+    if g("tokenizer_metadata"):
+        return MegatronTokenizer.from_pretrained(g("tokenizer_model"), g("tokenizer_metadata"))
+    t = (g("tokenizer_type") or "NullTokenizer").lower()
+    special = g("tokenizer_special_tokens") or g("special_tokens")
+    kw = {}
+    if t == "nulltokenizer":
+        kw = {"eod_id": g("null_tokenizer_eod_id"), "pad_id": g("null_tokenizer_pad_id")}
+    elif t in ("tiktokentokenizer", "tiktoken", "tiktokenizer"):
+        kw = {"pattern": g("tiktoken_pattern"), "num_special_tokens": g("tiktoken_num_special_tokens", 1000) or 1000, "special_tokens": special}
+    elif t in ("huggingfacetokenizer", "hf"):
+        kw = {"use_fast": not g("tokenizer_hf_no_use_fast", False), "trust_remote_code": bool(g("trust_remote_code", False)),
+              "include_special_tokens": not g("tokenizer_hf_no_include_special_tokens", False), "chat_template": g("chat_template")}
+        if special:
+            kw["additional_special_tokens"] = list(special)
+    elif t in ("sentencepiecetokenizer", "llama2tokenizer", "gptsentencepiecetokenizer"):
+        kw = {"chat_template": g("chat_template"), "legacy": g("tokenizer_sentencepiece_legacy", False)}
+    return build_tokenizer(g("tokenizer_type") or "NullTokenizer", vocab_size=g("vocab_size"), tokenizer_model=g("tokenizer_model"), **kw)
+
+
 def build_tokenizer(tokenizer_type: str, vocab_size: Optional[int] = None, tokenizer_model: Optional[str] = None, **kw):
     t = tokenizer_type.lower()
     if t == "nulltokenizer":
-        return NullTokenizer(vocab_size)
+        return NullTokenizer(vocab_size, **{k: v for k, v in kw.items() if k in ("eod_id", "pad_id")})
     if t in ("bytelevel", "byteleveltokenizer"):
         return ByteLevelTokenizer()
     if t in ("sentencepiecetokenizer", "llama2tokenizer", "gptsentencepiecetokenizer"):
-        return SentencePieceTokenizer(tokenizer_model)
+        return SentencePieceTokenizer(tokenizer_model, **kw)
     if t in ("huggingfacetokenizer", "hf"):
         return HuggingFaceTokenizer(tokenizer_model, **kw)
-    if t in ("tiktokentokenizer", "tiktoken"):
+    if t in ("tiktokentokenizer", "tiktoken", "tiktokenizer"):
         from .text.tiktoken_tokenizer import TikTokenTokenizer
 
         return TikTokenTokenizer(tokenizer_model, vocab_size=vocab_size, **kw)

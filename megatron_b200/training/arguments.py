@@ -244,6 +244,13 @@ def validate_args(args, world_size: Optional[int] = None):
         raise ValueError(f"world size {world_size} is not divisible by tp*pp*cp = {mp}")
     args.world_size = world_size
     args.data_parallel_size = world_size // mp
+    args._global_batch_size_given = args.global_batch_size is not None
+    if getattr(args, "step_batch_size_schedule", None) is not None:
+        from ..core.num_microbatches_calculator import StepBatchsizeNumMicroBatchesCalculator as _Step
+
+        if args._global_batch_size_given:
+            raise ValueError("Cannot specify both --step-batch-size-schedule and --global-batch-size")
+        args.global_batch_size = _Step._parse_schedule(args.step_batch_size_schedule, args.seq_length)[-1][1]   # the final (steady-state) batch size
     if args.global_batch_size is None:
         args.global_batch_size = args.micro_batch_size * args.data_parallel_size
     if args.global_batch_size % (args.micro_batch_size * args.data_parallel_size) != 0:
@@ -274,11 +281,15 @@ def validate_args(args, world_size: Optional[int] = None):
         args.train_iters = 0
     if args.train_iters is None:
         args.train_iters = args.train_samples // args.global_batch_size
+        args._train_iters_from_samples = True              # recomputed against the batch-size schedule once the calculator exists (update_train_iters)
     if args.lr_warmup_fraction is not None and (args.lr_warmup_iters or args.lr_warmup_samples):
         raise ValueError("--lr-warmup-fraction is exclusive with --lr-warmup-iters/--lr-warmup-samples")
-    if args.vocab_size is not None:
-        m = args.make_vocab_size_divisible_by * args.tensor_model_parallel_size
-        args.padded_vocab_size = (args.vocab_size + m - 1) // m * m
+    if args.vocab_size is not None and getattr(args, "padded_vocab_size", None) is None:      # --padded-vocab-size pins it (e.g. to match a checkpoint)
+        if getattr(args, "pad_vocab_size", True):
+            m = args.make_vocab_size_divisible_by * args.tensor_model_parallel_size
+            args.padded_vocab_size = (args.vocab_size + (getattr(args, "vocab_extra_ids", 0) or 0) + m - 1) // m * m
+        else:
+            args.padded_vocab_size = args.vocab_size + (getattr(args, "vocab_extra_ids", 0) or 0)      # --no-pad-vocab-size
     if args.num_query_groups is None:
         args.num_query_groups = args.num_attention_heads
     if args.expert_model_parallel_size > 1 and args.num_experts is None:

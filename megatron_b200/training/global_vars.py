@@ -120,7 +120,7 @@ def _build_wandb(args):
     try:
         import wandb
 
-        wandb.init(dir=save_dir, name=getattr(args, "wandb_exp_name", None), project=project, config=vars(args), mode=os.environ.get("WANDB_MODE", "offline"))
+        wandb.init(dir=save_dir, name=getattr(args, "wandb_exp_name", None), project=project, entity=getattr(args, "wandb_entity", None), config=vars(args), mode=os.environ.get("WANDB_MODE", "offline"))
         return wandb
     except Exception:
         return ScalarFileWriter(save_dir, filename="wandb_offline.jsonl")

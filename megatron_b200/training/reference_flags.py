@@ -79,6 +79,30 @@ WIRED: Dict[str, str] = {
     "fim_prefix_token": "FIMConfig.prefix_id", "fim_middle_token": "FIMConfig.middle_id", "fim_suffix_token": "FIMConfig.suffix_id", "fim_pad_token": "FIMConfig.pad_id", "fim_eod_token": "FIMConfig.eod_id",
     "ft_num_warmup_iters": "FaultToleranceMonitor.min_samples", "te_precision_config_file": "TransformerConfig.quant_recipe (per-layer precision YAML)",
     "kitchen_config_file": "TransformerConfig.quant_recipe (per-layer precision YAML)",
+    # training loop (training/training.py)
+    "step_batch_size_schedule": "StepBatchsizeNumMicroBatchesCalculator (thresholds in tokens)", "decrease_batch_size_if_needed": "micro-batch calculator rounds the batch down",
+    "iterations_to_skip": "train loop fast-forwards the data iterator", "train_sync_interval": "device synchronize every N iterations", "skip_train": "pretrain() goes straight to evaluation",
+    "start_eval_at_iter": "first in-training evaluation", "manual_gc_eval": "gc.collect around evaluation (--no-manual-gc-eval)", "empty_unused_memory_level": "empty_cache after fwd/bwd (1) and after the optimizer (2)",
+    "exit_signal": "signal that requests checkpoint-and-exit", "lr_wsd_decay_samples": "OptimizerParamScheduler.wsd_decay_steps (sample-based runs)",
+    "override_opt_param_scheduler": "OptimizerParamScheduler.override_opt_param_scheduler", "use_checkpoint_opt_param_scheduler": "OptimizerParamScheduler.use_checkpoint_opt_param_scheduler",
+    "error_injection_type": "RerunErrorInjector kind", "check_for_spiky_loss": "loss_func spike validation through the rerun state machine (pretrain_gpt.py)",
+    "use_tp_pp_dp_mapping": "initialize_model_parallel(order='tp-cp-ep-pp-dp')", "nccl_communicator_config_path": "initialize_model_parallel(nccl_communicator_config_path=)",
+    "high_priority_stream_groups": "initialize_model_parallel(high_priority_stream_groups=)",
+    "data_parallel_random_init": "seed + 10 * dp_rank, parameters broadcast from the first replica", "batch_invariant_mode": "enable_batch_invariant_mode()", "logging_level": "root logger level",
+    "profile_ranks": "ranks that start the profiler", "record_shapes": "torch profiler record_shapes",
+    "tensorboard_log_interval": "writer cadence", "log_timers_to_tensorboard": "Timers.write", "log_loss_scale_to_tensorboard": "loss-scale scalar (--no-log-loss-scale-to-tensorboard)",
+    "log_validation_ppl_to_tensorboard": "validation ppl scalars", "log_memory_to_tensorboard": "allocator scalars", "log_memory_interval": "allocator scalar cadence",
+    "log_world_size_to_tensorboard": "world-size scalar", "wandb_entity": "wandb.init(entity=)",
+    "fault_injector_ranks": "FaultInjectorConfig.from_args", "fault_injector_num_ranks": "FaultInjectorConfig.from_args", "fault_injector_fault_types": "FaultInjectorConfig.from_args",
+    "fault_injector_fault_probabilities": "FaultInjectorConfig.from_args", "fault_injector_fault_delay": "FaultInjectorConfig.from_args",
+    "fault_injector_delay_start_iteration": "FaultInjectorConfig.from_args", "fault_injector_mtti_seconds": "FaultInjectorConfig.from_args",
+    "fault_injector_offset_seconds": "FaultInjectorConfig.from_args", "fault_injector_seed": "FaultInjectorConfig.from_args",
+    # tokenizer / vocabulary
+    "padded_vocab_size": "pins the padded vocabulary", "pad_vocab_size": "--no-pad-vocab-size: no rounding", "vocab_extra_ids": "added before padding",
+    "null_tokenizer_eod_id": "NullTokenizer eod", "null_tokenizer_pad_id": "NullTokenizer pad", "tiktoken_pattern": "TikTokenTokenizer splitter (v1 / v2 / regex)",
+    "tiktoken_num_special_tokens": "TikTokenTokenizer special slots", "tokenizer_special_tokens": "tokenizer special tokens", "tokenizer_hf_no_use_fast": "AutoTokenizer use_fast=False",
+    "tokenizer_hf_no_include_special_tokens": "HF encode without special tokens", "trust_remote_code": "AutoTokenizer trust_remote_code", "chat_template": "tokenizer chat template",
+    "tokenizer_metadata": "MegatronTokenizer.from_pretrained(metadata)", "tokenizer_sentencepiece_legacy": "accepted by the SentencePiece wrapper",
     # serving (tools/run_text_generation_server.py through engine_kwargs_from_args)
     "inference_dynamic_batching_block_size": "engine block_size", "inference_dynamic_batching_max_requests": "engine max_running", "inference_max_requests": "engine max_running",
     "inference_dynamic_batching_max_tokens": "engine max_prefill_tokens_per_step", "enable_chunked_prefill": "engine max_prefill_tokens_per_step (2048 when no budget is given)",
@@ -92,6 +116,10 @@ ALWAYS_ON: Dict[str, str] = {
     "use_mcore_models": "there is no legacy model path", "inference_dynamic_batching": "the dynamic engine is the default engine", "perform_rl_step": "train_rl.py always performs RL steps",
     "inprocess_restart": "handled by pretrain_gpt.py before argument parsing (sys.argv)", "inprocess_max_iterations": "handled by pretrain_gpt.py before argument parsing (sys.argv)",
     "ckpt_fully_parallel_save": "fully-parallel save is the default; --no-ckpt-fully-parallel-save is read by name",
+    "auto_detect_ckpt_format": "the loader always detects the format from the checkpoint metadata", "use_dist_ckpt_deprecated": "checkpoints are always distributed",
+    "dist_ckpt_format_deprecated": "torch_dist is the only format", "deprecated_use_mcore_models": "there is no legacy model path", "local_rank": "LOCAL_RANK comes from the launcher environment",
+    "lazy_mpu_init": "model-parallel state is always initialised by initialize_megatron", "disable_jit_fuser": "there is no JIT fuser: fusions are CUDA kernels",
+"ckpt_load_validate_sharding_integrity": "sharding integrity is always validated on load",
 }
 
 

@@ -6,6 +6,7 @@ LR scheduler → (load checkpoint) → data iterators → ``train()``: step / lo
 from __future__ import annotations
 
 import gc
+import math
 import os
 import signal
 import sys
@@ -76,8 +77,19 @@ def initialize_megatron(argv=None, extra_args_provider=None, args_defaults: Opti
             virtual_pipeline_model_parallel_size=args.virtual_pipeline_model_parallel_size, context_parallel_size=args.context_parallel_size,
             expert_model_parallel_size=args.expert_model_parallel_size, expert_tensor_parallel_size=args.expert_tensor_parallel_size,
             distributed_timeout_minutes=args.distributed_timeout_minutes, create_gloo_process_groups=False,
+            order="tp-cp-ep-pp-dp" if getattr(args, "use_tp_pp_dp_mapping", False) else "tp-cp-ep-dp-pp",
+            nccl_communicator_config_path=getattr(args, "nccl_communicator_config_path", None), high_priority_stream_groups=getattr(args, "high_priority_stream_groups", None) or None,
         )
-    model_parallel_cuda_manual_seed(args.seed)
+    # --data-parallel-random-init: every data-parallel replica draws from its own stream (parameters are broadcast from the first replica after wrapping)
+    model_parallel_cuda_manual_seed(args.seed + (10 * ps.get_data_parallel_rank() if getattr(args, "data_parallel_random_init", False) else 0))
+    if getattr(args, "batch_invariant_mode", False):
+        from ..core.transformer.custom_layers.batch_invariant_kernels import enable_batch_invariant_mode
+
+        enable_batch_invariant_mode()
+    if getattr(args, "logging_level", None) is not None:
+        import logging
+
+        logging.getLogger().setLevel(args.logging_level)
     _GLOBALS["timers"] = Timers(args.timing_log_level, args.timing_log_option)
     from . import global_vars
 
@@ -94,9 +106,17 @@ def initialize_megatron(argv=None, extra_args_provider=None, args_defaults: Opti
 
         ft_integration.setup(args, dist.get_rank())
         ft_integration.maybe_setup_simulated_fault(args, dist.get_rank(), dist.get_world_size())
-    initialize_rerun_state_machine(mode=args.rerun_mode, error_injection_rate=args.error_injection_rate)
+    initialize_rerun_state_machine(mode=args.rerun_mode, error_injection_rate=args.error_injection_rate, error_injection_type=getattr(args, "error_injection_type", "transient_error"))
     destroy_num_microbatches_calculator()
-    init_num_microbatches_calculator(dist.get_rank(), args.rampup_batch_size, args.global_batch_size, args.micro_batch_size, args.data_parallel_size)
+    schedule = getattr(args, "step_batch_size_schedule", None)
+    init_num_microbatches_calculator(dist.get_rank(), args.rampup_batch_size, args.global_batch_size, args.micro_batch_size, args.data_parallel_size,
+                                     decrease_batch_size_if_needed=bool(getattr(args, "decrease_batch_size_if_needed", False)), step_batch_size_schedule=schedule,
+                                     seq_length=args.seq_length if schedule else None)
+    update_train_iters(args)
+    from ..core.fault_injector import FaultInjector, FaultInjectorConfig
+
+    fi_cfg = FaultInjectorConfig.from_args(args, dist.get_world_size())
+    _GLOBALS["fault_injector"] = FaultInjector(fi_cfg) if fi_cfg is not None else None
     if args.tp_comm != "auto":
         from ..parallel import fused
 
@@ -174,10 +194,37 @@ def get_model(model_provider_func: Callable, wrap_with_ddp: bool = True) -> List
     return model
 
 
+def update_train_iters(args) -> None:
+    """Sample-based runs (``--train-samples``): the iteration count follows the batch-size schedule (reference ``training.update_train_iters`` :2155)."""
+    if not getattr(args, "train_samples", None) or (args.train_iters and not getattr(args, "_train_iters_from_samples", False)):
+        return
+    if getattr(args, "step_batch_size_schedule", None) is not None or args.rampup_batch_size:
+        iters, consumed = 0, 0
+        while consumed < args.train_samples:
+            update_num_microbatches(consumed, consistency_check=False)
+            consumed += get_current_global_batch_size()
+            iters += 1
+        update_num_microbatches(0, consistency_check=False)
+        args.train_iters = iters
+    else:
+        args.train_iters = args.train_samples // args.global_batch_size
+    print_rank_0(f"setting training iterations to {args.train_iters}")
+
+
+def consumed_samples_at(iteration: int) -> int:
+    """Samples consumed after ``iteration`` steps under the active batch-size schedule (constant: ``iteration * global_batch_size``)."""
+    consumed = 0
+    for _ in range(iteration):
+        update_num_microbatches(consumed, consistency_check=False)
+        consumed += get_current_global_batch_size()
+    update_num_microbatches(consumed, consistency_check=False)
+    return consumed
+
+
 def get_optimizer_param_scheduler(optimizer):
     args = get_args()
     gbs = args.global_batch_size
-    if args.train_iters:
+    if args.train_iters and not getattr(args, "train_samples", None):
         decay = (args.lr_decay_iters or args.train_iters) * gbs
         wd_steps = args.train_iters * gbs
         warm = args.lr_warmup_fraction * decay if args.lr_warmup_fraction is not None else args.lr_warmup_iters * gbs
@@ -186,12 +233,13 @@ def get_optimizer_param_scheduler(optimizer):
         decay = args.lr_decay_samples or args.train_samples
         wd_steps = args.train_samples
         warm = args.lr_warmup_fraction * decay if args.lr_warmup_fraction is not None else args.lr_warmup_samples
-        wsd = None
+        wsd = getattr(args, "lr_wsd_decay_samples", None)
     return OptimizerParamScheduler(
         optimizer, init_lr=args.lr_warmup_init, max_lr=args.lr, min_lr=args.min_lr, lr_warmup_steps=int(warm), lr_decay_steps=max(int(decay), int(warm) + 1),
         lr_decay_style=args.lr_decay_style, start_wd=args.start_weight_decay if args.start_weight_decay is not None else args.weight_decay,
         end_wd=args.end_weight_decay if args.end_weight_decay is not None else args.weight_decay, wd_incr_steps=max(int(wd_steps), 1),
-        wd_incr_style=args.weight_decay_incr_style, use_checkpoint_opt_param_scheduler=False, wsd_decay_steps=wsd, lr_wsd_decay_style=args.lr_wsd_decay_style,
+        wd_incr_style=args.weight_decay_incr_style, use_checkpoint_opt_param_scheduler=bool(getattr(args, "use_checkpoint_opt_param_scheduler", False)),
+        override_opt_param_scheduler=bool(getattr(args, "override_opt_param_scheduler", False)), wsd_decay_steps=wsd, lr_wsd_decay_style=args.lr_wsd_decay_style,
     )
 
 
@@ -221,6 +269,7 @@ def setup_model_and_optimizer(model_provider_func: Callable):
             fully_parallel_load=getattr(args, "ckpt_fully_parallel_load", False), dist_ckpt_strictness=getattr(args, "dist_ckpt_strictness", None))
         args.iteration = 0 if args.finetune else it
         args.num_floating_point_operations_so_far = fl
+        args.consumed_train_samples = consumed_samples_at(args.iteration)
         print_rank_0(f" > loaded {src} checkpoint (from {args.load}) at iteration {it}")
     return model, optimizer, scheduler
 
@@ -278,9 +327,14 @@ def train_step(forward_step_func, data_iterator, model, optimizer, opt_param_sch
     should_checkpoint, should_exit, exit_code = rerun.should_checkpoint_and_exit()
     if should_exit:
         return {}, True, should_checkpoint, should_exit, exit_code, None, None
+    empty_level = getattr(args, "empty_unused_memory_level", 0) or 0
+    if empty_level >= 1 and torch.cuda.is_available():
+        torch.cuda.empty_cache()                       # after forward / backward (reference :3149)
     timers("optimizer", log_level=1).start(barrier=args.timing_log_level > 1)
     update_successful, grad_norm, num_zeros = optimizer.step()
     timers("optimizer").stop()
+    if empty_level >= 2 and torch.cuda.is_available():
+        torch.cuda.empty_cache()                       # after the optimizer step too (reference :3229)
     if update_successful:
         opt_param_scheduler.step(increment=get_num_microbatches() * args.micro_batch_size * args.data_parallel_size)
         skipped = 0
@@ -321,11 +375,23 @@ def training_log(loss_dict, total_loss_dict, learning_rate, iteration, loss_scal
     if torch.cuda.is_available():
         s += f" mem-max-allocated-GiB: {torch.cuda.max_memory_allocated() / 2**30:.2f} |"
     print_rank_last(s)
+    g = lambda n, d=None: getattr(args, n, d)  # noqa: E731
+    tb_every = g("tensorboard_log_interval", 1) or 1
     for w in (_GLOBALS.get("tensorboard"), _GLOBALS.get("wandb")):
-        if w is None:
+        if w is None or iteration % tb_every != 0:
             continue
-        scal = {"iteration-time": elapsed_per_iter, "throughput": tput, "tokens-per-sec": tok_s, "learning-rate": learning_rate, "loss-scale": float(loss_scale),
+        scal = {"iteration-time": elapsed_per_iter, "throughput": tput, "tokens-per-sec": tok_s, "learning-rate": learning_rate,
                 "batch-size": get_current_global_batch_size(), **{k: float(v) for k, v in logged.items()}}
+        if g("log_loss_scale_to_tensorboard", True):
+            scal["loss-scale"] = float(loss_scale)
+        if g("log_world_size_to_tensorboard", False):
+            scal["world-size"] = world
+        if g("log_memory_to_tensorboard", False) and torch.cuda.is_available() and iteration % (g("log_memory_interval") or 1) == 0:
+            st = torch.cuda.memory_stats()
+            scal.update({"mem-reserved-bytes": st["reserved_bytes.all.current"], "mem-allocated-bytes": st["allocated_bytes.all.current"],
+                         "mem-max-allocated-bytes": st["allocated_bytes.all.peak"], "mem-allocated-count": st["allocation.all.current"]})
+        if g("log_timers_to_tensorboard", False) and hasattr(w, "add_scalar") and get_timers()._timers:
+            get_timers().write(list(get_timers()._timers), w, iteration, normalizer=args.log_interval, reset=False)
         if grad_norm is not None:
             scal["grad-norm"] = float(grad_norm)
         if hasattr(w, "add_scalar"):
@@ -369,7 +435,11 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
         config.grad_sync_func = model[0].start_grad_sync if len(model) == 1 else [m.start_grad_sync for m in model]
     total_loss_dict: Dict[str, float] = {}
     exit_flag = {"sig": False}
-    signal.signal(signal.SIGTERM, lambda *_: exit_flag.__setitem__("sig", True))
+    exit_sig = getattr(args, "exit_signal", None) or "SIGTERM"                 # --exit-signal NAME (reference TrainingConfig.exit_signal), SIGTERM by default
+    exit_sig = getattr(signal, exit_sig if str(exit_sig).startswith("SIG") else f"SIG{exit_sig}") if isinstance(exit_sig, str) else exit_sig
+    signal.signal(exit_sig, lambda *_: exit_flag.__setitem__("sig", True))
+    skip_iters = set(getattr(args, "iterations_to_skip", None) or [])
+    args.skipped_train_samples = getattr(args, "skipped_train_samples", 0)
     flops_per_iter = num_floating_point_operations(
         num_layers=args.num_layers, hidden_size=args.hidden_size, ffn_hidden_size=args.ffn_hidden_size, num_attention_heads=args.num_attention_heads,
         num_query_groups=args.num_query_groups, kv_channels=args.kv_channels or args.hidden_size // args.num_attention_heads,
@@ -406,18 +476,33 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
         torch.cuda.memory._record_memory_history(max_entries=100000)
     t_start = time.time()
     t_log = time.time()
+    prof_ranks = getattr(args, "profile_ranks", None) or []
+    profile_here = not prof_ranks or (dist.get_rank() if dist.is_initialized() else 0) in prof_ranks       # --profile-ranks: empty = every rank
     while iteration < args.train_iters:
-        if getattr(args, "use_pytorch_profiler", False) and iteration == args.profile_step_start and torch_prof is None:
+        if getattr(args, "use_pytorch_profiler", False) and profile_here and iteration == args.profile_step_start and torch_prof is None:
             acts = [torch.profiler.ProfilerActivity.CPU] + ([torch.profiler.ProfilerActivity.CUDA] if torch.cuda.is_available() else [])
-            torch_prof = torch.profiler.profile(activities=acts, record_shapes=args.pytorch_profiler_collect_shapes, with_stack=args.pytorch_profiler_collect_callstack)
+            torch_prof = torch.profiler.profile(activities=acts, record_shapes=args.pytorch_profiler_collect_shapes or getattr(args, "record_shapes", False),
+                                                with_stack=args.pytorch_profiler_collect_callstack)
             torch_prof.__enter__()
         ft_integration.on_training_step_start()
+        if _GLOBALS.get("fault_injector") is not None:
+            _GLOBALS["fault_injector"].on_iteration(iteration + 1)
         t_iter = time.time()
         for sl in stat_loggers:
             sl.begin_iteration(iteration + 1)
-        if args.profile and iteration == args.profile_step_start and torch.cuda.is_available():
+        if args.profile and profile_here and iteration == args.profile_step_start and torch.cuda.is_available():
             torch.cuda.cudart().cudaProfilerStart()
         update_num_microbatches(args.consumed_train_samples, consistency_check=True)
+        if (iteration + 1) in skip_iters:
+            # fast-forward the data iterator by one global batch and move on: no forward, no update (reference ``--iterations-to-skip`` :4648)
+            for _ in range(get_num_microbatches()):
+                if train_data_iterator is not None:
+                    next(train_data_iterator)
+            iteration += 1
+            args.consumed_train_samples += get_current_global_batch_size()
+            args.skipped_train_samples += get_current_global_batch_size()
+            ft_integration.on_training_step_end()
+            continue
         with straggler(), telemetry.span("train.iteration", iteration=iteration + 1):
             loss_dict, skipped, should_ckpt, should_exit, exit_code, grad_norm, _ = train_step(forward_step_func, train_data_iterator, model, optimizer, opt_param_scheduler, config)
         if should_ckpt and args.save:
@@ -426,6 +511,8 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
         if should_exit:
             sys.exit(exit_code)
         iteration += 1
+        if getattr(args, "train_sync_interval", None) and iteration % args.train_sync_interval == 0 and torch.cuda.is_available():
+            torch.cuda.synchronize()                     # keep the host from running ahead of the device (reference :3972)
         ft_integration.on_training_step_end()
         for sl in stat_loggers:
             if hasattr(sl, "collect") and sl.handles:
@@ -456,10 +543,27 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
         else:
             for k, v in loss_dict.items():
                 total_loss_dict[k] = total_loss_dict.get(k, 0.0) + float(v)
-        if args.profile and iteration == args.profile_step_end and torch.cuda.is_available():
+        if args.profile and profile_here and iteration == args.profile_step_end and torch.cuda.is_available():
             torch.cuda.cudart().cudaProfilerStop()
-        if args.eval_interval and args.eval_iters and iteration % args.eval_interval == 0 and valid_data_iterator is not None:
+        if args.eval_interval and args.eval_iters and iteration % args.eval_interval == 0 and valid_data_iterator is not None and \
+                (getattr(args, "start_eval_at_iter", None) is None or iteration >= args.start_eval_at_iter):
+            gc_eval = args.manual_gc and getattr(args, "manual_gc_eval", True)
+            if gc_eval:
+                gc.collect()                            # collect before / after evaluation so its garbage does not land inside a training step
             res = evaluate(forward_step_func, valid_data_iterator, model, args.eval_iters)
+            if gc_eval:
+                gc.collect(generation=0)
+            for w in (_GLOBALS.get("tensorboard"), _GLOBALS.get("wandb")):
+                if w is None:
+                    continue
+                vals = {f"{k} validation": v for k, v in res.items()}
+                if getattr(args, "log_validation_ppl_to_tensorboard", False):
+                    vals.update({f"{k} validation ppl": math.exp(min(20.0, v)) for k, v in res.items()})
+                if hasattr(w, "add_scalar"):
+                    for k, v in vals.items():
+                        w.add_scalar(k, v, iteration)
+                else:
+                    w.log(vals, step=iteration)
             print_rank_last(f" validation loss at iteration {iteration} | " + " | ".join(f"{k}: {v:.6E}" for k, v in res.items()))
         iv = getattr(args, "check_weight_hash_across_dp_replicas_interval", None)
         if iv and iteration % iv == 0:
@@ -530,11 +634,13 @@ def pretrain(train_valid_test_dataset_provider: Callable, model_provider: Callab
     train_ds, valid_ds, test_ds = train_valid_test_dataset_provider(get_train_valid_test_num_samples(args))
     from .data import build_pretraining_data_loader
 
-    consumed = args.iteration * args.global_batch_size
+    consumed = getattr(args, "consumed_train_samples", None)
+    if consumed is None:
+        consumed = args.iteration * args.global_batch_size
     train_it = RerunDataIterator(iter(build_pretraining_data_loader(train_ds, consumed, args))) if train_ds is not None else None
     valid_it = iter(build_pretraining_data_loader(valid_ds, 0, args)) if valid_ds is not None else None
     print_rank_0("training ...")
-    if args.train_iters > 0:
+    if args.train_iters > 0 and not getattr(args, "skip_train", False):
         train(forward_step_func, model, optimizer, scheduler, train_it, valid_it, config)
     if args.eval_iters and valid_it is not None:
         res = evaluate(forward_step_func, valid_it, model, args.eval_iters)

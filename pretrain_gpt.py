@@ -20,7 +20,7 @@ from megatron_b200.core.datasets.utils import get_blend_from_list  # noqa: E402
 from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_decoder_block_spec, get_gpt_layer_local_spec  # noqa: E402
 from megatron_b200.core.models.gpt.gpt_model import GPTModel  # noqa: E402
 from megatron_b200.core.rerun_state_machine import get_rerun_state_machine  # noqa: E402
-from megatron_b200.core.tokenizers import build_tokenizer  # noqa: E402
+from megatron_b200.core.tokenizers import build_tokenizer, build_tokenizer_from_args  # noqa: E402,F401
 from megatron_b200.core.utils import get_batch_on_this_cp_rank  # noqa: E402
 from megatron_b200.training.arguments import core_transformer_config_from_args  # noqa: E402
 from megatron_b200.training.data import get_batch_on_this_tp_rank  # noqa: E402
@@ -66,6 +66,10 @@ def loss_func(loss_mask: torch.Tensor, output_tensor: torch.Tensor):
     rsm = get_rerun_state_machine()
     if args.check_for_nan_in_loss_and_grad or args.rerun_mode != "disabled":
         rsm.validate_result(total, rejection_func=lambda x: not bool(torch.isfinite(torch.as_tensor(x)).all()), message="found NaN/Inf in local forward loss", fatal=True)
+    if getattr(args, "check_for_spiky_loss", False):
+        # a loss far above anything seen in the first 100 observations: not fatal, but it goes through the rerun protocol (transient vs persistent fault)
+        rsm.validate_result((total / ntok.clamp(min=1)).detach(), rejection_func=lambda x: rsm.is_unexpectedly_large(float(x), threshold=10.0, context="loss"),
+                            message="Spiky loss", tolerance=0.0, fatal=False)
     local_total, local_ntok = total, ntok
     if args.context_parallel_size > 1:
         t = torch.stack([total, ntok])
@@ -85,7 +89,7 @@ _EOD = {}
 def _eod_token(args) -> int:
     """End-of-document id of the run's tokenizer (built once; the dataset provider builds its own instance on the data ranks only)."""
     if "id" not in _EOD:
-        _EOD["id"] = build_tokenizer(args.tokenizer_type, vocab_size=args.vocab_size, tokenizer_model=args.tokenizer_model).eod
+        _EOD["id"] = build_tokenizer_from_args(args).eod
     return _EOD["id"]
 
 
@@ -108,7 +112,7 @@ def forward_step(data_iterator, model: GPTModel):
 
 def train_valid_test_datasets_provider(train_val_test_num_samples):
     args = get_args()
-    tokenizer = build_tokenizer(args.tokenizer_type, vocab_size=args.vocab_size, tokenizer_model=args.tokenizer_model)
+    tokenizer = build_tokenizer_from_args(args)
     per_split = [getattr(args, k, None) for k in ("train_data_path", "valid_data_path", "test_data_path")]
     use_per_split = not args.mock_data and any(per_split)            # --train-data-path / --valid-data-path / --test-data-path instead of --data-path + --split
     cfg = GPTDatasetConfig(

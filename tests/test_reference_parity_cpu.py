@@ -607,3 +607,73 @@ def test_gpt_dataset_samples_match_reference(tmp_path, blend):
             got = ds[i]
             for k, v in want.items():
                 assert torch.equal(torch.as_tensor(got[k]).to(v.dtype), v), (name, i, k)
+
+
+# ---- pure-Python subsystems: schedules, micro-batch ramp-up, rank enumeration ------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ref_pure():
+    r = subprocess.run([sys.executable, os.path.join(REPO, "tests", "helpers", "ref_pure.py")], cwd="/tmp", capture_output=True, text=True, timeout=600)
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("JSON:")]
+    assert line, r.stdout[-2000:] + r.stderr[-2000:]
+    import json
+
+    return json.loads(line[0][5:])
+
+
+def _pure_cfg():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_ref_pure_cfg", os.path.join(REPO, "tests", "helpers", "ref_pure.py"))
+    src = open(spec.origin).read().split("class _Opt")[0].split("SCHEDULES = ")[1]
+    ns = {}
+    exec("SCHEDULES = " + src, ns)
+    return ns
+
+
+def test_lr_wd_schedules_match_reference(ref_pure):
+    from megatron_b200.core.optimizer_param_scheduler import OptimizerParamScheduler
+
+    cfg = _pure_cfg()
+
+    class Opt:
+        def __init__(self):
+            self.param_groups = [{"lr": 0.0, "weight_decay": 0.0, "lr_mult": 1.0, "wd_mult": 1.0},
+                                 {"lr": 0.0, "weight_decay": 0.0, "wd_mult": 0.5, "max_lr": 5e-4, "min_lr": 5e-5, "start_wd": 0.2, "end_wd": 0.2}]
+
+    for kw, want in zip(cfg["SCHEDULES"], ref_pure["sched"]):
+        opt = Opt()
+        s = OptimizerParamScheduler(opt, **kw)
+        for step, row in enumerate(want):
+            s.step(increment=1)
+            got = [[g["lr"], g["weight_decay"]] for g in opt.param_groups]
+            for (glr, gwd), (rlr, rwd) in zip(got, row):
+                assert glr == pytest.approx(rlr, rel=1e-12, abs=1e-18), (kw["lr_decay_style"], step)
+                assert gwd == pytest.approx(rwd, rel=1e-12, abs=1e-18), (kw["wd_incr_style"], step)
+
+
+def test_microbatch_schedules_match_reference(ref_pure):
+    from megatron_b200.core.num_microbatches_calculator import (destroy_num_microbatches_calculator, get_current_global_batch_size, get_num_microbatches,
+                                                                 init_num_microbatches_calculator, update_num_microbatches)
+
+    cfg = _pure_cfg()
+    for kw, want in zip(cfg["RAMPS"], ref_pure["ramp"]):
+        destroy_num_microbatches_calculator()
+        init_num_microbatches_calculator(rank=0, **kw)
+        got = []
+        for consumed in range(0, 320, 8):
+            update_num_microbatches(consumed, consistency_check=False)
+            got.append([get_num_microbatches(), get_current_global_batch_size()])
+        destroy_num_microbatches_calculator()
+        assert got == want, kw
+
+
+def test_rank_generator_matches_reference(ref_pure):
+    from megatron_b200.core.parallel_state import RankGenerator
+
+    cfg = _pure_cfg()
+    for kw, want in zip(cfg["GRIDS"], ref_pure["ranks"]):
+        g = RankGenerator(**kw)
+        for tok in cfg["TOKENS"]:
+            if isinstance(want[tok], str):
+                continue
+            assert g.get_ranks(tok) == want[tok], (kw, tok)

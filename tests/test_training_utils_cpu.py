@@ -5,6 +5,7 @@ import signal
 import time
 
 import numpy as np
+import pytest
 import torch
 
 
@@ -533,3 +534,92 @@ def test_reference_flag_table(monkeypatch):
     kw = rf.engine_kwargs_from_args(parse_args(base + ["--inference-dynamic-batching-block-size", "32", "--inference-max-requests", "8", "--enable-chunked-prefill",
                                                        "--inference-dynamic-batching-num-cuda-graphs", "4", "--inference-dynamic-batching-prefix-caching"]))
     assert kw == {"block_size": 32, "max_running": 8, "max_prefill_tokens_per_step": 2048, "enable_prefix_caching": True, "enable_cuda_graphs": True, "decode_batch_buckets": [2, 4, 6, 8]}
+
+
+def test_step_batch_size_schedule_and_skipped_iterations_through_pretrain(tmp_path):
+    """``--step-batch-size-schedule`` (token thresholds) drives the global batch size, ``--train-samples`` is converted to iterations against it and
+    ``--iterations-to-skip`` consumes the data of an iteration without training on it (reference ``training.py:2155`` / ``:4648``)."""
+    import re
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "pretrain_gpt.py"), "--num-layers", "1", "--hidden-size", "32", "--num-attention-heads", "2", "--ffn-hidden-size", "64", "--seq-length", "32",
+           "--max-position-embeddings", "32", "--micro-batch-size", "2", "--lr", "1e-3", "--lr-decay-samples", "100", "--lr-warmup-samples", "4", "--mock-data", "--tokenizer-type",
+           "NullTokenizer", "--vocab-size", "127", "--log-interval", "1", "--distributed-backend", "gloo", "--eval-iters", "0", "--seed", "1234", "--step-batch-size-schedule", "0:2 256:4",
+           "--train-samples", "24", "--iterations-to-skip", "3", "--train-sync-interval", "2", "--empty-unused-memory-level", "2", "--strict-reference-flags"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "CUDA_VISIBLE_DEVICES": "", "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": "29741"}, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    rows = re.findall(r"iteration\s+(\d+)/\s+(\d+) \| consumed samples:\s+(\d+).*?global batch size:\s+(\d+)", r.stdout)
+    assert [(int(i), int(c), int(b)) for i, _, c, b in rows] == [(1, 2, 2), (2, 4, 2), (4, 8, 2), (5, 12, 4), (6, 16, 4), (7, 20, 4), (8, 24, 4)]
+    assert all(int(n) == 8 for _, n, _, _ in rows)
+
+
+def test_fault_injector_from_reference_flags():
+    import argparse
+
+    from megatron_b200.core.fault_injector import Fault, FaultInjector, FaultInjectorConfig, InjectedFaultError
+
+    assert FaultInjectorConfig.from_args(argparse.Namespace(), 4) is None
+    ns = argparse.Namespace(fault_injector_fault_types="workload_exc,sigterm", fault_injector_fault_probabilities="1.0,0.0", fault_injector_ranks="0,2", fault_injector_fault_delay=0.05,
+                            fault_injector_delay_start_iteration=3, fault_injector_seed=7)
+    cfg = FaultInjectorConfig.from_args(ns, 4)
+    assert cfg.fault_type == Fault.WORKLOAD_EXC and list(cfg.ranks) == [0, 2] and cfg.start_iteration == 3 and cfg.delay_s == pytest.approx(0.05)
+    inj = FaultInjector(cfg, rank=2, world_size=4)
+    inj.on_iteration(1)
+    time.sleep(0.15)
+    inj.on_iteration(2)                                   # the countdown has not started yet
+    inj.on_iteration(3)
+    time.sleep(0.3)
+    with pytest.raises(InjectedFaultError):
+        inj.on_iteration(4)
+    assert not FaultInjector(cfg, rank=1, world_size=4).armed
+    picks = FaultInjectorConfig.from_args(argparse.Namespace(fault_injector_fault_types="gpu_sleep", fault_injector_num_ranks=2, fault_injector_mtti_seconds=100.0, fault_injector_offset_seconds=5.0), 8)
+    assert len(picks.ranks) == 2 and picks.delay_s > 5.0 and picks == FaultInjectorConfig.from_args(
+        argparse.Namespace(fault_injector_fault_types="gpu_sleep", fault_injector_num_ranks=2, fault_injector_mtti_seconds=100.0, fault_injector_offset_seconds=5.0), 8)
+
+
+def test_tokenizer_flags_and_vocab_padding():
+    import argparse
+
+    from megatron_b200.core.tokenizers import build_tokenizer_from_args
+    from megatron_b200.core.tokenizers.text.tiktoken_tokenizer import compile_pattern
+    from megatron_b200.training.arguments import parse_args, validate_args
+
+    tok = build_tokenizer_from_args(argparse.Namespace(tokenizer_type="NullTokenizer", vocab_size=100, null_tokenizer_eod_id=7, null_tokenizer_pad_id=3))
+    assert tok.eod == 7 and tok.pad == 3 and tok.vocab_size == 101
+    assert build_tokenizer_from_args(argparse.Namespace(tokenizer_type="NullTokenizer", vocab_size=100)).eod == 100
+    # the named splitters keep case runs / digits apart the way the reference patterns do
+    assert compile_pattern("v1").findall("Hello world's 123") == ["Hello", " world", "'s", " ", "1", "2", "3"]
+    assert compile_pattern("v2").findall("helloWorld HTTPServer") == ["hello", "World", " HTTPServer"]
+    base = ["--num-layers", "1", "--hidden-size", "32", "--num-attention-heads", "2", "--seq-length", "16", "--max-position-embeddings", "16", "--micro-batch-size", "1", "--vocab-size", "1000"]
+    a = validate_args(parse_args(base + ["--vocab-extra-ids", "5", "--make-vocab-size-divisible-by", "128"]), world_size=1)
+    assert a.padded_vocab_size == 1024
+    assert validate_args(parse_args(base + ["--no-pad-vocab-size"]), world_size=1).padded_vocab_size == 1000
+    assert validate_args(parse_args(base + ["--padded-vocab-size", "2048"]), world_size=1).padded_vocab_size == 2048
+    with pytest.raises(ValueError):
+        validate_args(parse_args(base + ["--step-batch-size-schedule", "0:8", "--global-batch-size", "8"]), world_size=1)
+    assert validate_args(parse_args(base + ["--step-batch-size-schedule", "0:8 1K:16"]), world_size=1).global_batch_size == 16
+
+
+def test_every_flag_of_the_reference_runtime_parser_is_accepted():
+    """Build the reference's REAL parser (dataclass-generated groups included) in a subprocess and check each option string parses here with the same arity."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir(os.path.join(root, "baseline", "_ref", "megatron")) or not os.path.isdir("/root/reference/megatron/training"):
+        pytest.skip("reference not installed")
+    sys.path.insert(0, os.path.join(root, "tools"))
+    from gen_reference_flag_table import _introspect
+
+    ref = _introspect("/root/reference")
+    assert len(ref) > 700
+    from megatron_b200.training.arguments import build_full_parser
+
+    ours = {f: a for a in build_full_parser()._actions for f in a.option_strings}
+    missing = [f for r in ref for f in r["flags"] if f not in ours]
+    assert not missing, missing
+    arity = [(r["flags"][0], r["nargs"], ours[r["flags"][0]].nargs) for r in ref if (r["nargs"] == 0) != (ours[r["flags"][0]].nargs == 0)]
+    assert not arity, arity

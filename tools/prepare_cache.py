@@ -19,7 +19,7 @@ def main(argv=None):
     from megatron_b200.core.datasets import BlendedMegatronDatasetBuilder, GPTDatasetConfig
     from megatron_b200.core.datasets.gpt_dataset import GPTDataset
     from megatron_b200.core.datasets.utils import get_blend_from_list
-    from megatron_b200.core.tokenizers import build_tokenizer
+    from megatron_b200.core.tokenizers import build_tokenizer_from_args
     from megatron_b200.training.arguments import parse_args, validate_args
     from megatron_b200.training.training import get_train_valid_test_num_samples
 
@@ -32,7 +32,7 @@ def main(argv=None):
             raise SystemExit(f"prepare_cache: --{bad.replace('_', '-')} has nothing to cache")
     if not args.data_cache_path:
         raise SystemExit("prepare_cache: --data-cache-path is required (that is where the indices go)")
-    tokenizer = build_tokenizer(args.tokenizer_type, vocab_size=args.vocab_size, tokenizer_model=args.tokenizer_model)
+    tokenizer = build_tokenizer_from_args(args)
     per_split = [getattr(args, k, None) for k in ("train_data_path", "valid_data_path", "test_data_path")]
     use_per_split = any(per_split)
     cfg = GPTDatasetConfig(
