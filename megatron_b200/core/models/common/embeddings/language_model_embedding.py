@@ -57,6 +57,8 @@ class LanguageModelEmbedding(MegatronModule):
         if tokentype_ids is not None:
             assert self.tokentype_embeddings is not None
             emb = emb + self.tokentype_embeddings(tokentype_ids).permute(1, 0, 2)
+        if getattr(self.config, "use_mup", False) and self.config.mup_embedding_mult != 1.0:
+            emb = emb * self.config.mup_embedding_mult
         if self.config.fp32_residual_connection:
             emb = emb.float()
         if self.config.sequence_parallel:

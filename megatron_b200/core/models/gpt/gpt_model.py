@@ -95,7 +95,8 @@ class GPTModel(LanguageModule):
             else:
                 self.embedding_activation_buffer = self.grad_output_buffer = None
             self.output_layer = tensor_parallel.ColumnParallelLinear(
-                config.hidden_size, vocab_size, config=config, init_method=config.init_method, bias=False, skip_bias_add=False,
+                config.hidden_size, vocab_size, config=config, bias=False, skip_bias_add=False,
+                init_method=config.embedding_init_method if getattr(config, "use_mup", False) and not share_embeddings_and_output_weights else config.init_method,
                 gather_output=not parallel_output,
                 skip_weight_param_allocation=pre_process and share_embeddings_and_output_weights,
                 embedding_activation_buffer=self.embedding_activation_buffer, grad_output_buffer=self.grad_output_buffer,
@@ -170,6 +171,8 @@ class GPTModel(LanguageModule):
         if inference_context is not None and getattr(inference_context, "materialize_only_last_token_logits", False):
             hidden_states = hidden_states[-1:, :, :]
         logits, _ = self.output_layer(hidden_states, weight=output_weight, runtime_gather_output=runtime_gather_output)
+        if getattr(self.config, "use_mup", False) and self.config.mup_output_mult != 1.0:
+            logits = logits * self.config.mup_output_mult            # muP: logits stay O(1) as the width grows
         if labels is None:
             return logits.transpose(0, 1).contiguous()  # [b, s, v/tp]
         return self.compute_language_model_loss(labels, logits)

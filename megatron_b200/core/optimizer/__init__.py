@@ -58,12 +58,13 @@ def _get_param_groups(model_chunks: List, no_weight_decay_cond: Optional[Callabl
             wd_mult = 0.0 if no_wd else 1.0
             lm = lr_mult if scale_lr else 1.0
             dec = use_decoupled and getattr(p, "is_embedding_or_output_parameter", False)
-            if mup_width_mult and mup_width_mult != 1.0 and p.dim() >= 2 and not getattr(p, "is_embedding_or_output_parameter", False) and "embedding" not in name:
+            mup_hidden = bool(mup_width_mult and mup_width_mult != 1.0 and p.dim() >= 2 and not getattr(p, "is_embedding_or_output_parameter", False) and "embedding" not in name)
+            if mup_hidden:
                 lm = lm / mup_width_mult
             ov = _match_override(name, p, config_overrides)
-            buckets.setdefault((wd_mult, lm, is_expert, dec, ov), []).append(p)
+            buckets.setdefault((wd_mult, lm, is_expert, dec, ov, mup_hidden), []).append(p)
     groups = []
-    for (wd_mult, lm, is_expert, dec, ov), params in buckets.items():
+    for (wd_mult, lm, is_expert, dec, ov, mup_hidden), params in buckets.items():
         ovd = dict(ov)
         wd_mult, lm = ovd.pop("wd_mult", wd_mult), ovd.pop("lr_mult", lm)
         max_lr = ovd.pop("max_lr", decoupled_lr if dec else lr)
@@ -71,6 +72,8 @@ def _get_param_groups(model_chunks: List, no_weight_decay_cond: Optional[Callabl
                  max_lr=max_lr, min_lr=ovd.pop("min_lr", decoupled_min_lr if dec and decoupled_min_lr is not None else min_lr),
                  lr=max_lr * lm if max_lr is not None else None, weight_decay=ovd.pop("weight_decay", default_wd * wd_mult))
         g.update(ovd)            # anything else (betas, eps, ...) goes straight into the group
+        if mup_hidden:
+            g["mup_hidden"] = True
         groups.append(g)
     return groups
 
@@ -119,11 +122,16 @@ def get_megatron_optimizer(config: OptimizerConfig, model_chunks: List, no_weigh
     """Dense and expert-parallel parameters get separate optimizers (their data-parallel
     groups differ) chained into one."""
     mup = None
+    mc = get_model_config(model_chunks[0])
     if getattr(config, "use_mup", False) and getattr(config, "mup_base_hidden_size", None):
-        mc = get_model_config(model_chunks[0])
         mup = mc.hidden_size / config.mup_base_hidden_size
+    elif getattr(mc, "use_mup", False):
+        mup = mc.mup_width_mult                                        # the model config carries the width multiplier (--use-mup)
     groups = _get_param_groups(model_chunks, no_weight_decay_cond, scale_lr_cond, lr_mult, config.lr, config.min_lr,
                                config.decoupled_lr, config.decoupled_min_lr, config.weight_decay, config_overrides=config_overrides, mup_width_mult=mup)
+    for g in groups:
+        if g.pop("mup_hidden", False) and config.optimizer == "adam" and "eps" not in g:
+            g["eps"] = config.adam_eps / mup           # µP Adam: the epsilon of width-scaled matrices shrinks with their gradients (reference get_mup_config_overrides)
     dense = [g for g in groups if not g["is_expert_parallel"]]
     expert = [g for g in groups if g["is_expert_parallel"]]
     init = ps.is_initialized()

@@ -7,6 +7,8 @@ New B200-specific knobs are grouped at the end (``b200_*``).
 """
 from __future__ import annotations
 
+import math
+
 from dataclasses import dataclass, field
 from typing import Callable, List, Optional, Tuple, Union
 
@@ -38,6 +40,16 @@ class TransformerConfig(ModelParallelConfig):
     num_attention_heads: int = 0
     attention_backend: AttnBackend = AttnBackend.auto
     softmax_scale: Optional[float] = None
+    # maximal-update parametrisation (reference ``transformer_config.py:428-475``): widths change, hyper-parameters transfer.  With ``use_mup`` the hidden
+    # init std shrinks by 1/sqrt(m), the output-projection init by another depth factor, attention scores are scaled by 1/d_head (``mup_attn_scale_power`` 1.0)
+    # instead of 1/sqrt(d_head), embeddings are multiplied by ``mup_embedding_mult`` and logits by ``mup_output_mult`` (auto 1/m), m = hidden / base hidden.
+    use_mup: bool = False
+    mup_width_mult: float = 1.0
+    mup_base_hidden_size: Optional[int] = None
+    mup_embedding_mult: float = 1.0
+    mup_output_mult: float = 1.0
+    mup_base_head_dim: Optional[float] = None
+    mup_attn_scale_power: float = 1.0
     softmax_type: str = "vanilla"
     num_query_groups: Optional[int] = None
     ffn_hidden_size: Optional[int] = None
@@ -305,13 +317,31 @@ class TransformerConfig(ModelParallelConfig):
             self.activation_func, "__name__", ""
         ) not in ("quick_gelu", "squared_relu"):
             raise ValueError("bias_activation_fusion supports gelu / silu (SwiGLU) / quick_gelu")
-        if self.init_method is None:
-            self.init_method = init_method_normal(self.init_method_std)
-        if self.output_layer_init_method is None:
-            self.output_layer_init_method = scaled_init_method_normal(self.init_method_std, max(self.num_layers, 1))
+        if self.use_mup:
+            if self.mup_base_hidden_size is None:
+                self.mup_base_hidden_size = self.hidden_size
+            if self.mup_base_hidden_size <= 0:
+                raise ValueError("mup_base_hidden_size must be positive")
+            self.mup_width_mult = self.hidden_size / self.mup_base_hidden_size
+            if self.softmax_scale is None:
+                kv = self.kv_channels or self.hidden_size // self.num_attention_heads
+                self.softmax_scale = (1.0 if self.mup_base_head_dim is None else self.mup_base_head_dim**0.5) / (kv**self.mup_attn_scale_power)
+            if self.mup_output_mult == 1.0 and self.mup_width_mult != 1.0:
+                self.mup_output_mult = 1.0 / self.mup_width_mult
+            if self.init_method is not None or self.output_layer_init_method is not None:
+                import warnings
+
+                warnings.warn("use_mup is enabled but a custom init_method / output_layer_init_method is set: the muP initialisation assumptions may not hold", UserWarning)
+        # the embedding init is fixed BEFORE the hidden init picks up the muP width factor: embeddings keep the base std
         if self.embedding_init_method is None:
             std = self.embedding_init_method_std or self.init_method_std
-            self.embedding_init_method = init_method_normal(std)
+            self.embedding_init_method = init_method_normal(std) if (self.init_method is None or std != self.init_method_std) else self.init_method
+        depth_mult = 2.0 if not self.is_hybrid_model else 1.0
+        width = self.mup_width_mult if self.use_mup else 1.0
+        if self.init_method is None:
+            self.init_method = init_method_normal(self.init_method_std / math.sqrt(width))
+        if self.output_layer_init_method is None:
+            self.output_layer_init_method = scaled_init_method_normal(self.init_method_std / math.sqrt(width), max(self.num_layers, 1), multiplier=depth_mult)
         if self.cp_comm_type is not None and isinstance(self.cp_comm_type, list):
             if len(self.cp_comm_type) != self.num_layers:
                 raise ValueError("cp_comm_type list length must equal num_layers")

@@ -94,10 +94,11 @@ def generate_state_dict(args: Dict[str, Any], model: List, optimizer, opt_param_
 def save_checkpoint(iteration: int, model: List, optimizer, opt_param_scheduler, save_dir: str, args: Optional[Dict[str, Any]] = None,
                     num_floating_point_operations_so_far: float = 0.0, async_save: bool = False, fully_parallel_save: bool = True,
                     keep_last: Optional[int] = None, rerun_state=None, optim_sharding_type: str = "fully_reshardable",
-                    assume_constant_structure: bool = False):
+                    assume_constant_structure: bool = False, retain_interval: Optional[int] = None):
     """Collective over all ranks.  Returns after the checkpoint is durable (or, with ``async_save``,
     after staging; call ``maybe_finalize_async_save`` from the training loop).  ``assume_constant_structure`` (``--ckpt-assume-constant-structure``): reuse the
-    previous save's plan / metadata when nothing changed structurally (dist_checkpointing SavePlanCache)."""
+    previous save's plan / metadata when nothing changed structurally (dist_checkpointing SavePlanCache).  ``retain_interval`` (``--save-retain-interval``): once
+    the new checkpoint is durable, the PREVIOUS one is deleted unless its iteration is a multiple of the interval (or it is a symbolic link)."""
     ckpt = get_checkpoint_name(save_dir, iteration)
     if _rank() == 0:
         os.makedirs(save_dir, exist_ok=True)
@@ -113,10 +114,18 @@ def save_checkpoint(iteration: int, model: List, optimizer, opt_param_scheduler,
 
     def write_tracker():
         if _rank() == 0:
-            with open(get_checkpoint_tracker_filename(save_dir), "w") as f:
+            tracker, prev = get_checkpoint_tracker_filename(save_dir), 0
+            if retain_interval and os.path.isfile(tracker):
+                text = open(tracker).read().strip()
+                prev = int(text) if text.isdigit() else 0
+            with open(tracker, "w") as f:
                 f.write(str(iteration))
             if keep_last:
                 _cleanup_old(save_dir, keep_last)
+            if retain_interval and prev > 0 and prev != iteration and prev % retain_interval != 0:
+                old = get_checkpoint_name(save_dir, prev)
+                if not os.path.islink(old):
+                    shutil.rmtree(old, ignore_errors=True)
 
     req = dist_checkpointing.save(sd, ckpt, sharded_strategy=strategy, async_sharded_save=async_save, cached_structure=assume_constant_structure)
     if req is not None:

@@ -583,7 +583,7 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
         if args.save and args.save_interval and iteration % args.save_interval == 0:
             checkpointing.save_checkpoint(iteration, model, optimizer if not args.no_save_optim else None, opt_param_scheduler, args.save, vars_for_ckpt(args),
                                           args.num_floating_point_operations_so_far, async_save=args.async_save, keep_last=args.keep_last_checkpoints,
-                                          assume_constant_structure=getattr(args, 'ckpt_assume_constant_structure', False))
+                                          assume_constant_structure=getattr(args, 'ckpt_assume_constant_structure', False), retain_interval=getattr(args, "save_retain_interval", None))
             saved = True
             append_to_progress_log(f"Saved checkpoint\titeration: {iteration}\tFLOPs so far: {args.num_floating_point_operations_so_far:.4e}\ttokens so far: {args.consumed_train_samples * args.seq_length:.4e}",
                                    barrier=False)

@@ -6,6 +6,7 @@ CUDA RNG tracker around dropout with p=0).  This harness patches those call site
     torchrun/spawn env: RANK WORLD_SIZE MASTER_ADDR MASTER_PORT;  argv: out_prefix tp [grads | save <dir> | load <dir>]
 """
 import contextlib
+import json
 import os
 import sys
 import zlib
@@ -157,7 +158,7 @@ def main():
         num_query_groups=CFG["num_query_groups"], kv_channels=CFG["kv_channels"], normalization="RMSNorm", gated_linear_unit=True, activation_func=F.silu,
         add_bias_linear=False, hidden_dropout=0.0, attention_dropout=0.0, use_cpu_initialization=True, bias_activation_fusion=False, bias_dropout_fusion=False,
         masked_softmax_fusion=False, gradient_accumulation_fusion=False, perform_initialization=False, tensor_model_parallel_size=tp,
-        **MOE_KW,
+        **MOE_KW, **json.loads(os.environ.get("REF_CFG_OVERRIDE", "{}")),
     )
     spec = get_gpt_layer_local_spec(num_experts=MOE_KW.get("num_moe_experts"), moe_grouped_gemm=False, normalization="RMSNorm") if MOE_KW else get_gpt_layer_local_spec(normalization="RMSNorm")
     m = GPTModel(cfg, spec, vocab_size=CFG["vocab"], max_sequence_length=CFG["seq"], parallel_output=True,

@@ -123,3 +123,49 @@ def test_per_layer_quantization_recipe(tmp_path):
     p.write_text("configs:\n  fp8: {recipe: tensorwise, fp8_format: hybrid}\n  bf16: {recipe: none}\nmatchers:\n  - {pattern: 'decoder.layers.0.*', config: bf16}\n"
                  "  - {pattern: '*.linear_fc1', config: fp8}\n  - {pattern: '*', config: bf16}\n")
     assert run_distributed(_quant_recipe_worker, 1, str(p)) == [True]
+
+
+def test_mup_config_init_and_optimizer_groups():
+    """µP: hidden init std shrinks by 1/sqrt(m), embeddings keep the base std, softmax scale is 1/d_head, logits are multiplied by 1/m, and the optimizer trains
+    hidden matrices with lr / m and eps / m while vector-like and embedding parameters keep the base values (reference ``transformer_config.py:2530-2605``,
+    ``optimizer/__init__.py:get_mup_config_overrides``)."""
+    import os
+
+    import torch
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+    from megatron_b200.core.optimizer import OptimizerConfig, get_megatron_optimizer
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    cfg = TransformerConfig(num_layers=2, hidden_size=256, num_attention_heads=4, use_mup=True, mup_base_hidden_size=64, init_method_std=0.02, use_cpu_initialization=True)
+    assert cfg.mup_width_mult == 4.0 and cfg.mup_output_mult == 0.25 and cfg.softmax_scale == 1.0 / 64
+    t = torch.empty(512, 512)
+    assert abs(float(cfg.init_method(t).std()) - 0.01) < 1e-3 and abs(float(cfg.embedding_init_method(t).std()) - 0.02) < 2e-3
+    assert abs(float(cfg.output_layer_init_method(t).std()) - 0.02 / (2.0 * 2.0)) < 1e-3
+    base = TransformerConfig(num_layers=2, hidden_size=256, num_attention_heads=4, use_mup=True, use_cpu_initialization=True)
+    assert base.mup_width_mult == 1.0 and base.mup_output_mult == 1.0
+    own = not torch.distributed.is_initialized()
+    if own:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29762")
+        torch.distributed.init_process_group("gloo", rank=0, world_size=1)
+    if not ps.is_initialized():
+        ps.initialize_model_parallel()
+    try:
+        m = GPTModel(cfg, get_gpt_layer_local_spec(), vocab_size=64, max_sequence_length=16, share_embeddings_and_output_weights=False)
+        opt = get_megatron_optimizer(OptimizerConfig(optimizer="adam", lr=1e-2, min_lr=0.0, adam_eps=1e-8, weight_decay=0.0), [m])
+        by_param = {id(p): g for g in opt.param_groups for p in g["params"]} if hasattr(opt, "param_groups") else {}
+        named = dict(m.named_parameters())
+        hidden = by_param[id(named["decoder.layers.0.mlp.linear_fc1.weight"])]
+        emb = by_param[id(named["embedding.word_embeddings.weight"])]
+        out = by_param[id(named["output_layer.weight"])]
+        norm = by_param[id(named["decoder.final_layernorm.weight"])]
+        assert hidden["lr_mult"] == 0.25 and abs(hidden["eps"] - 2.5e-9) < 1e-15
+        for g in (emb, out, norm):
+            assert g["lr_mult"] == 1.0 and g["eps"] == 1e-8
+    finally:
+        ps.destroy_model_parallel()
+        if own:
+            torch.distributed.destroy_process_group()

@@ -53,7 +53,7 @@ def _ours(rank, world, tp, variant=""):
         num_layers=CFG["num_layers"], hidden_size=CFG["hidden_size"], ffn_hidden_size=CFG["ffn_hidden_size"], num_attention_heads=CFG["num_attention_heads"],
         num_query_groups=CFG["num_query_groups"], kv_channels=CFG["kv_channels"], normalization="RMSNorm", gated_linear_unit=True, activation_func=F.silu,
         add_bias_linear=False, hidden_dropout=0.0, attention_dropout=0.0, use_cpu_initialization=True, gradient_accumulation_fusion=False,
-        perform_initialization=False, tensor_model_parallel_size=tp,
+        perform_initialization=False, tensor_model_parallel_size=tp, **__import__("json").loads(os.environ.get("REF_CFG_OVERRIDE", "{}")),
         **(dict(num_moe_experts=4, moe_router_topk=2, moe_token_dispatcher_type="allgather", moe_router_load_balancing_type="aux_loss",
                 moe_aux_loss_coeff=0.02, moe_grouped_gemm=False, moe_ffn_hidden_size=96, **({"expert_model_parallel_size": 2} if ep2 else {})) if variant.startswith("moe") else {}),
     )
@@ -147,6 +147,22 @@ def test_moe_capacity_drop_and_pad_parity_with_reference(tmp_path):
     ref = _run_reference(tmp_path, 1, "moe_drop")[0]
     ours = run_distributed(_ours, 1, 1, "moe_drop")[0]
     assert sorted(ours["names"]) == sorted(ref["grads"].keys())
+    assert abs(ours["loss"] - ref["loss"]) < 2e-5, (ours["loss"], ref["loss"])
+    for n, g in ref["grads"].items():
+        err = float((ours["grads"][n] - g).abs().max() / g.abs().max().clamp(min=1e-12))
+        assert err < 1e-3, f"grad {n}: rel err {err}"
+
+
+def test_mup_parity_with_reference(tmp_path, monkeypatch):
+    """Maximal-update parametrisation on (width multiplier 2, embedding multiplier 2): attention scaled by 1/d_head, embeddings and logits multiplied — the
+    loss and every gradient equal the unmodified reference's; and the run differs from the plain one (the switch is not a no-op)."""
+    from dist_utils import run_distributed
+
+    plain = run_distributed(_ours, 1, 1, "")[0]
+    monkeypatch.setenv("REF_CFG_OVERRIDE", '{"use_mup": true, "mup_base_hidden_size": 32, "mup_embedding_mult": 2.0}')
+    ref = _run_reference(tmp_path, 1, "")[0]
+    ours = run_distributed(_ours, 1, 1, "")[0]
+    assert abs(ours["loss"] - plain["loss"]) > 1e-3
     assert abs(ours["loss"] - ref["loss"]) < 2e-5, (ours["loss"], ref["loss"])
     for n, g in ref["grads"].items():
         err = float((ours["grads"][n] - g).abs().max() / g.abs().max().clamp(min=1e-12))
