@@ -1,4 +1,5 @@
 """Specs for the hybrid Mamba stack (reference ``models/mamba/mamba_layer_specs.py``)."""
+from ...ssm.gated_delta_net import GatedDeltaNet, GatedDeltaNetSubmodules
 from ...ssm.mamba_block import MambaStack, MambaStackSubmodules
 from ...ssm.mamba_layer import MambaLayer, MambaLayerSubmodules
 from ...ssm.mamba_mixer import MambaMixer, MambaMixerSubmodules
@@ -19,6 +20,14 @@ mamba_stack_spec = ModuleSpec(
             submodules=MambaLayerSubmodules(
                 norm=_b.layer_norm(),
                 mixer=ModuleSpec(module=MambaMixer, submodules=MambaMixerSubmodules(in_proj=_b.column_parallel_linear(), out_proj=_b.row_parallel_linear())),
+                mamba_bda=get_bias_dropout_add,
+            ),
+        ),
+        gdn_layer=ModuleSpec(                   # ``G`` in the hybrid pattern: the same pre-norm residual wrapper around a gated-delta-net mixer
+            module=MambaLayer,
+            submodules=MambaLayerSubmodules(
+                norm=_b.layer_norm(),
+                mixer=ModuleSpec(module=GatedDeltaNet, submodules=GatedDeltaNetSubmodules(in_proj=_b.column_parallel_linear(), out_proj=_b.row_parallel_linear())),
                 mamba_bda=get_bias_dropout_add,
             ),
         ),

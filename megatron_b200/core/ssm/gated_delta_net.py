@@ -53,9 +53,11 @@ def gated_delta_rule_chunked(q, k, v, g, beta, chunk_size: int = 64, initial_sta
     gf = g.float().view(b, n, C, h).permute(0, 3, 1, 2)                  # [b, h, n, C]
     bf = beta.float().view(b, n, C, h).permute(0, 3, 1, 2)
     gc = gf.cumsum(-1)                                                    # in-chunk cumulative log-decay
-    decay = torch.exp(gc.unsqueeze(-1) - gc.unsqueeze(-2))               # [.., i, j] = exp(gc_i − gc_j)
     strict = torch.tril(torch.ones(C, C, dtype=torch.bool, device=q.device), -1)
     incl = torch.tril(torch.ones(C, C, dtype=torch.bool, device=q.device), 0)
+    # [.., i, j] = exp(gc_i − gc_j) for j <= i.  The upper triangle is masked BEFORE the exponential: there the exponent is positive and overflows for
+    # strong decays, and an inf that is only zeroed afterwards turns into NaN in the backward (inf * 0)
+    decay = torch.exp((gc.unsqueeze(-1) - gc.unsqueeze(-2)).masked_fill(~incl, float("-inf")))
     kb = kf * bf.unsqueeze(-1)
     # (I + A) u = β v  and  (I + A) w = β k·exp(gc), with A_ij = β_i (k_i·k_j) exp(gc_i − gc_j) for j < i   (WY representation)
     A = (torch.einsum("bhnid,bhnjd->bhnij", kb, kf) * decay).masked_fill(~strict, 0.0)
@@ -86,38 +88,43 @@ class GatedDeltaNet(MegatronModule):
     """Mixer: in_proj → [q | k | v | z | β | g] ; short causal conv on q,k,v ; l2norm(q,k) ; gated delta rule ; RMSNorm(o)·silu(z) ; out_proj."""
 
     def __init__(self, config, submodules: GatedDeltaNetSubmodules, d_model: Optional[int] = None, layer_number: Optional[int] = None, num_heads: Optional[int] = None,
-                 head_k_dim: int = 128, head_v_dim: int = 128, conv_kernel: int = 4, chunk_size: int = 64, pg_collection=None, **_):
+                 head_k_dim: int = 128, head_v_dim: int = 128, conv_kernel: int = 4, chunk_size: int = 64, pg_collection=None, num_value_heads: Optional[int] = None, **_):
         super().__init__(config)
         d_model = d_model or config.hidden_size
+        # the reference's ``--linear-*`` options (``transformer_config.linear_*``) win over the constructor defaults when the config carries them
+        g = lambda n: getattr(config, n, None)  # noqa: E731
+        head_k_dim, head_v_dim, conv_kernel = g("linear_key_head_dim") or head_k_dim, g("linear_value_head_dim") or head_v_dim, g("linear_conv_kernel_dim") or conv_kernel
+        num_heads, num_value_heads = g("linear_num_key_heads") or num_heads, g("linear_num_value_heads") or num_value_heads
         self.layer_number, self.chunk_size, self.conv_kernel = layer_number, chunk_size, conv_kernel
         self.tp_group = pg_collection.tp if pg_collection is not None and getattr(pg_collection, "tp", None) is not None else get_tensor_model_parallel_group_if_none(None)
         ws = get_pg_size(self.tp_group)
-        self.h = num_heads or config.num_attention_heads
+        self.h = num_heads or config.num_attention_heads                     # key heads; TP shards them, each carries ``r`` value heads
+        self.r = divide(num_value_heads, self.h) if num_value_heads else 1
         self.h_local = divide(self.h, ws)
         self.dk, self.dv = head_k_dim, head_v_dim
-        proj = self.h * (2 * self.dk + 2 * self.dv + 2)
+        proj = self.h * (2 * self.dk + self.r * (2 * self.dv + 2))
         self.in_proj = build_module(submodules.in_proj, d_model, proj, config=config, init_method=config.init_method, gather_output=False, bias=False,
                                     skip_bias_add=False, is_expert=False, tp_group=self.tp_group)
         dev = self.in_proj.weight.device
-        conv_dim = self.h_local * (2 * self.dk + self.dv)
+        conv_dim = self.h_local * (2 * self.dk + self.r * self.dv)
         self.conv_weight = torch.nn.Parameter(torch.empty(conv_dim, conv_kernel, device=dev, dtype=config.params_dtype).uniform_(-0.5, 0.5))
-        self.A_log = torch.nn.Parameter(torch.log(torch.empty(self.h_local, device=dev).uniform_(1, 16)).float())
-        self.dt_bias = torch.nn.Parameter(torch.zeros(self.h_local, device=dev, dtype=torch.float32))
+        self.A_log = torch.nn.Parameter(torch.log(torch.empty(self.h_local * self.r, device=dev).uniform_(1, 16)).float())
+        self.dt_bias = torch.nn.Parameter(torch.zeros(self.h_local * self.r, device=dev, dtype=torch.float32))
         self.norm_weight = torch.nn.Parameter(torch.ones(self.dv, device=dev, dtype=config.params_dtype))
         for p in (self.conv_weight, self.A_log, self.dt_bias):
             setattr(p, "tensor_model_parallel", True)
             setattr(p, "partition_dim", 0)
-        self.out_proj = build_module(submodules.out_proj, self.h * self.dv, d_model, config=config, init_method=config.output_layer_init_method, bias=False,
+        self.out_proj = build_module(submodules.out_proj, self.h * self.r * self.dv, d_model, config=config, init_method=config.output_layer_init_method, bias=False,
                                      input_is_parallel=True, skip_bias_add=True, is_expert=False, tp_group=self.tp_group)
 
     def forward(self, hidden_states, inference_context=None, *, inference_params=None, **_):
         inference_context = inference_context or inference_params
         x, _ = self.in_proj(hidden_states)                              # [l, b, h_local*(2dk+2dv+2)]
         l, b = x.shape[:2]
-        hl, dk, dv = self.h_local, self.dk, self.dv
-        x = x.view(l, b, hl, 2 * dk + 2 * dv + 2)
-        qkv, z, beta_raw, g_raw = torch.split(x, [2 * dk + dv, dv, 1, 1], dim=-1)
-        qkv = qkv.permute(1, 2, 3, 0).reshape(b, hl * (2 * dk + dv), l)   # [b, conv_dim, l]
+        hl, dk, dv, r = self.h_local, self.dk, self.dv, self.r
+        x = x.view(l, b, hl, 2 * dk + r * (2 * dv + 2))
+        qkv, z, beta_raw, g_raw = torch.split(x, [2 * dk + r * dv, r * dv, r, r], dim=-1)
+        qkv = qkv.permute(1, 2, 3, 0).reshape(b, hl * (2 * dk + r * dv), l)   # [b, conv_dim, l]
         decode = inference_context is not None and inference_context.sequence_len_offset > 0 and l == 1
         key = ("gdn", self.layer_number)
         if decode:
@@ -127,12 +134,15 @@ class GatedDeltaNet(MegatronModule):
             qkv = causal_conv1d(qkv, self.conv_weight, None, "silu", return_final_state=inference_context is not None)
             if inference_context is not None:
                 qkv, conv_state = qkv
-        qkv = qkv.view(b, hl, 2 * dk + dv, l).permute(0, 3, 1, 2)         # [b, l, h, ·]
-        q, k, v = torch.split(qkv, [dk, dk, dv], dim=-1)
+        qkv = qkv.view(b, hl, 2 * dk + r * dv, l).permute(0, 3, 1, 2)     # [b, l, h, ·]
+        q, k, v = torch.split(qkv, [dk, dk, r * dv], dim=-1)
         q = F.normalize(q.float(), dim=-1).to(v.dtype) * (dk ** -0.5)
         k = F.normalize(k.float(), dim=-1).to(v.dtype)
-        beta = torch.sigmoid(beta_raw.squeeze(-1).float()).permute(1, 0, 2)                                   # [b, l, h]
-        g = (-torch.exp(self.A_log) * F.softplus(g_raw.squeeze(-1).float() + self.dt_bias)).permute(1, 0, 2)  # log-decay ≤ 0
+        if r > 1:                                                          # each key head serves r value heads
+            q, k = q.repeat_interleave(r, dim=2), k.repeat_interleave(r, dim=2)
+            v, z = v.reshape(b, l, hl * r, dv), z.reshape(l, b, hl * r, dv)
+        beta = torch.sigmoid(beta_raw.reshape(l, b, hl * r).float()).permute(1, 0, 2)                                   # [b, l, h_v]
+        g = (-torch.exp(self.A_log) * F.softplus(g_raw.reshape(l, b, hl * r).float() + self.dt_bias)).permute(1, 0, 2)  # log-decay ≤ 0
         if decode:
             o, S_new = gated_delta_rule_recurrent(q, k, v, g, beta, S)
             S.copy_(S_new)
@@ -143,5 +153,5 @@ class GatedDeltaNet(MegatronModule):
         of = o.float()
         of = of * torch.rsqrt(of.pow(2).mean(-1, keepdim=True) + self.config.layernorm_epsilon) * self.norm_weight.float()
         of = of * F.silu(z.permute(1, 0, 2, 3).float())
-        y = of.to(hidden_states.dtype).permute(1, 0, 2, 3).reshape(l, b, hl * dv)
+        y = of.to(hidden_states.dtype).permute(1, 0, 2, 3).reshape(l, b, hl * r * dv)
         return self.out_proj(y)

@@ -21,6 +21,7 @@ class MambaStackSubmodules:
     attention_layer: Union[ModuleSpec, type] = IdentityOp
     mlp_layer: Union[ModuleSpec, type] = IdentityOp
     moe_layer: Union[ModuleSpec, type] = IdentityOp
+    gdn_layer: Union[ModuleSpec, type] = IdentityOp
 
 
 class MambaStack(MegatronModule):
@@ -41,6 +42,8 @@ class MambaStack(MegatronModule):
             n = off + i + 1
             if sym == Symbols.MAMBA:
                 layer = build_module(submodules.mamba_layer, config=config, residual_in_fp32=residual_in_fp32, layer_number=n, **kw)
+            elif sym == Symbols.GDN:
+                layer = build_module(submodules.gdn_layer, config=config, residual_in_fp32=residual_in_fp32, layer_number=n, **kw)
             elif sym == Symbols.ATTENTION:
                 layer = build_module(submodules.attention_layer, config=config, layer_number=n, **kw)
             elif sym == Symbols.MLP:

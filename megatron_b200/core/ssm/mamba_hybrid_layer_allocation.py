@@ -1,12 +1,13 @@
-"""Hybrid layer pattern: ``M`` = Mamba, ``*`` = attention, ``-`` = MLP, ``E`` = MoE (reference ``ssm/mamba_hybrid_layer_allocation.py``)."""
+"""Hybrid layer pattern: ``M`` = Mamba, ``G`` = gated delta net, ``*`` = attention, ``-`` = MLP, ``E`` = MoE (reference ``models/hybrid/hybrid_layer_allocation.py``
+``Symbols``)."""
 from __future__ import annotations
 
 from typing import List, Optional
 
 
 class Symbols:
-    MAMBA, ATTENTION, MLP, MOE = "M", "*", "-", "E"
-    VALID = {MAMBA, ATTENTION, MLP, MOE}
+    MAMBA, ATTENTION, MLP, MOE, GDN = "M", "*", "-", "E", "G"
+    VALID = {MAMBA, ATTENTION, MLP, MOE, GDN}
 
 
 def _allocate_auto(total: int, attn_ratio: float, mlp_ratio: float) -> List[str]:

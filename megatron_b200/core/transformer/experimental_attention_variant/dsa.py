@@ -145,36 +145,42 @@ class DSAIndexer(MegatronModule):
     def __init__(self, config, submodules: Optional[DSAIndexerSubmodules] = None, q_in_features: Optional[int] = None, rope_dim: int = 0):
         super().__init__(config)
         c = config
-        self.n_heads = getattr(c, "dsa_indexer_n_heads", 4)
-        self.head_dim = getattr(c, "dsa_indexer_head_dim", 32)
-        self.topk = getattr(c, "dsa_indexer_topk", 64)
-        self.use_relu = getattr(c, "dsa_indexer_use_relu", True)
+        self.n_heads = getattr(c, "dsa_indexer_n_heads", None) or 4
+        self.head_dim = getattr(c, "dsa_indexer_head_dim", None) or 32
+        self.topk = getattr(c, "dsa_indexer_topk", None) or 64
+        self.use_relu = getattr(c, "dsa_indexer_use_relu", True) and getattr(c, "dsa_indexer_scoring_relu", True)
+        self.rotate = getattr(c, "dsa_indexer_rotate_activation", True)
+        self.rope_interleaved = getattr(c, "dsa_indexer_rope_interleaved", False)
+        self.k_norm_fp32 = getattr(c, "dsa_indexer_k_norm_fp32", False)
         self.rope_dim = rope_dim
         q_in = q_in_features or c.hidden_size
         dev = "cpu" if (c.use_cpu_initialization or not torch.cuda.is_available()) else torch.cuda.current_device()
         lin = lambda i, o: torch.nn.Linear(i, o, bias=False, device=dev, dtype=c.params_dtype)  # noqa: E731  (replicated: the index branch is tiny)
         self.linear_wq_b = lin(q_in, self.n_heads * self.head_dim)
         self.linear_wk = lin(c.hidden_size, self.head_dim)
-        self.k_norm = torch.nn.LayerNorm(self.head_dim, eps=c.layernorm_epsilon, device=dev, dtype=c.params_dtype)
+        self.k_norm = torch.nn.LayerNorm(self.head_dim, eps=getattr(c, "dsa_indexer_k_norm_epsilon", None) or c.layernorm_epsilon, device=dev, dtype=c.params_dtype)
         self.linear_weights_proj = lin(c.hidden_size, self.n_heads)
         for m in (self.linear_wq_b, self.linear_wk, self.linear_weights_proj):
             c.init_method(m.weight)
         self.softmax_scale = self.head_dim ** -0.5
 
     def _rope(self, t, angles):
+        had = rotate_activation if self.rotate else (lambda x: x)
         if self.rope_dim == 0 or angles is None:
-            return rotate_activation(t)
+            return had(t)
         from .... import ops
 
         rot, rest = t[..., : self.rope_dim], t[..., self.rope_dim :]
-        rot = ops.apply_rope(rot.contiguous(), angles, False, 1.0)
-        return rotate_activation(torch.cat([rot, rest], dim=-1))
+        rot = ops.apply_rope(rot.contiguous(), angles, self.rope_interleaved, 1.0)
+        return had(torch.cat([rot, rest], dim=-1))
 
     def forward(self, hidden_states, q_source=None, angles=None, q_offset: int = 0, k_cache: Optional[torch.Tensor] = None):
         """hidden_states [s, b, h]; q_source defaults to the hidden state.  → (index_scores [b, sq, sk], topk idx, valid, k_idx)."""
         s, b = hidden_states.shape[:2]
         q = self.linear_wq_b(hidden_states if q_source is None else q_source).view(s, b, self.n_heads, self.head_dim)
-        k = self.k_norm(self.linear_wk(hidden_states)).unsqueeze(2)
+        k = self.linear_wk(hidden_states)
+        k = (torch.nn.functional.layer_norm(k.float(), (self.head_dim,), self.k_norm.weight.float(), self.k_norm.bias.float(), self.k_norm.eps).to(k.dtype)
+             if self.k_norm_fp32 else self.k_norm(k)).unsqueeze(2)
         q, k = self._rope(q, angles), self._rope(k, angles).squeeze(2)
         if k_cache is not None:
             k = torch.cat([k_cache, k], dim=0)

@@ -31,6 +31,22 @@ class TransformerConfig(ModelParallelConfig):
     experimental_attention_variant: Optional[str] = None
     experimental_attention_variant_loss_scale_func: Optional[Callable] = None
     dsa_indexer_loss_coeff: float = 0.0
+    # gated delta net mixer geometry (reference ``--linear-*``); None = the mixer's constructor arguments
+    linear_conv_kernel_dim: Optional[int] = None
+    linear_key_head_dim: Optional[int] = None
+    linear_value_head_dim: Optional[int] = None
+    linear_num_key_heads: Optional[int] = None
+    linear_num_value_heads: Optional[int] = None
+    # DeepSeek sparse attention index branch (reference ``transformer_config.py:315-357``); None = the module defaults (4 heads x 32, top-64)
+    dsa_indexer_n_heads: Optional[int] = None
+    dsa_indexer_head_dim: Optional[int] = None
+    dsa_indexer_topk: Optional[int] = None
+    dsa_indexer_use_sparse_loss: bool = False
+    dsa_indexer_rope_interleaved: bool = False         # MLA-style interleaved rotation of the rope slice
+    dsa_indexer_rotate_activation: bool = True         # Hadamard rotation of q / k before scoring
+    dsa_indexer_scoring_relu: bool = True              # ReLU on q.k before the head weighting
+    dsa_indexer_k_norm_epsilon: Optional[float] = None
+    dsa_indexer_k_norm_fp32: bool = False
     num_layers_in_first_pipeline_stage: Optional[int] = None
     num_layers_in_last_pipeline_stage: Optional[int] = None
     pipeline_model_parallel_layout: Optional[Union[str, list]] = None

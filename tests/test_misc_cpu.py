@@ -175,3 +175,53 @@ def test_tp_comm_mode_resolution(monkeypatch):
     assert fused.get_mode(world_size=1) == "nvlink"
     # CPU tensors never take the NVLink path, whatever the mode
     assert fused._nvl(None, torch.zeros(1)) is None
+
+
+def _gdn_hybrid(rank, world):
+    import types
+
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.models.mamba.mamba_layer_specs import mamba_stack_spec
+    from megatron_b200.core.models.mamba.mamba_model import MambaModel
+    from megatron_b200.core.ssm.gated_delta_net import GatedDeltaNet, gated_delta_rule_chunked
+    from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
+    from megatron_b200.core.transformer.transformer_config import TransformerConfig
+
+    ps.initialize_model_parallel(1, 1)
+    model_parallel_cuda_manual_seed(1)
+    # the reference's --linear-* geometry: 2 key heads x 16, 4 value heads x 16 (two value heads share a key head), conv kernel 4
+    cfg = TransformerConfig(num_layers=4, hidden_size=64, num_attention_heads=4, use_cpu_initialization=True, hidden_dropout=0.0, attention_dropout=0.0, is_hybrid_model=True,
+                            linear_key_head_dim=16, linear_value_head_dim=16, linear_num_key_heads=2, linear_num_value_heads=4, linear_conv_kernel_dim=4)
+    m = MambaModel(cfg, mamba_stack_spec, vocab_size=64, max_sequence_length=32, hybrid_override_pattern="G*G-")
+    mixers = [l.mixer for l in m.decoder.layers if hasattr(l, "mixer")]
+    assert [type(x) for x in mixers] == [GatedDeltaNet, GatedDeltaNet] and mixers[0].r == 2 and mixers[0].A_log.shape == (4,)
+    assert mixers[0].in_proj.weight.shape == (2 * (2 * 16 + 2 * (2 * 16 + 2)), 64) and mixers[0].out_proj.weight.shape == (64, 64)
+    tok = torch.randint(0, 64, (2, 32), generator=torch.Generator().manual_seed(0))
+    pos = torch.arange(32).unsqueeze(0).expand(2, -1)
+    loss = m(tok, pos, None, labels=tok).mean()
+    loss.backward()
+    # strong decays (A up to 16) used to overflow exp() above the diagonal of the in-chunk decay matrix: finite forward, NaN backward
+    bad = [n for n, p in m.named_parameters() if p.grad is None or not torch.isfinite(p.grad).all()]
+    assert not bad and float(mixers[0].in_proj.weight.grad.abs().sum()) > 0, bad
+    q, k, v = torch.randn(1, 64, 2, 8), torch.randn(1, 64, 2, 8), torch.randn(1, 64, 2, 8, requires_grad=True)
+    g = torch.full((1, 64, 2), -12.0, requires_grad=True)
+    o, _ = gated_delta_rule_chunked(q, k, v, g, torch.rand(1, 64, 2), 64)
+    o.sum().backward()
+    assert torch.isfinite(g.grad).all() and torch.isfinite(v.grad).all()
+    # prefill + one decode step equals the full forward (conv state and delta-rule state are carried in the inference context)
+    mixer = mixers[0].eval()
+    x = torch.randn(9, 2, 64)
+    with torch.no_grad():
+        full = mixer(x)[0]
+        ctx = types.SimpleNamespace(sequence_len_offset=0, key_value_memory_dict={})
+        head = mixer(x[:8], inference_context=ctx)[0]
+        ctx.sequence_len_offset = 8
+        last = mixer(x[8:], inference_context=ctx)[0]
+    assert (torch.cat([head, last]) - full).abs().max().item() < 1e-4
+    return True
+
+
+def test_gated_delta_net_layers_in_the_hybrid_stack():
+    from dist_utils import run_distributed
+
+    assert run_distributed(_gdn_hybrid, 1) == [True]
