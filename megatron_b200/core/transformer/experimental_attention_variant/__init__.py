@@ -1,4 +1,4 @@
-from .absorbed_mla import AbsorbedMLASelfAttention  # noqa: F401
+from .absorbed_mla import AbsorbedMLASelfAttention, DSAMLASelfAttention  # noqa: F401
 from .dsa import (  # noqa: F401
     DSAIndexer,
     DSAIndexerLossAutoScaler,

@@ -58,18 +58,57 @@ class AbsorbedMLASelfAttention(MLASelfAttention):
         inference_context = inference_context or inference_params
         c = self.config
         q_abs, kv, w_uv = self.absorbed_qkv(hidden_states, inference_context)
-        q_off = 0
-        if inference_context is not None:          # latent cache: exactly the [kv_latent | k_pe] rows, nothing is ever expanded per head
-            kvd = inference_context.key_value_memory_dict
-            if self.layer_number not in kvd:
-                kvd[self.layer_number] = torch.empty(inference_context.max_sequence_length, inference_context.max_batch_size, kv.shape[-1], dtype=kv.dtype, device=kv.device)
-            cache = kvd[self.layer_number]
-            s0, b0 = inference_context.sequence_len_offset, inference_context.batch_size_offset
-            s1, b1 = s0 + kv.shape[0], b0 + kv.shape[1]
-            cache[s0:s1, b0:b1] = kv
-            kv, q_off = cache[:s1, b0:b1], s0
+        kv, q_off = self._latent_cache(kv, inference_context)
         causal = self.attn_mask_type == AttnMaskType.causal
-        out_lat = self.latent_attention(q_abs, kv, causal, q_off)
+        out_lat = self.core_latent_attention(q_abs, kv, causal, q_off, hidden_states)
         out = torch.einsum("sbnr,ndr->sbnd", out_lat, w_uv.to(out_lat.dtype))
         s, b = out.shape[:2]
         return self.linear_proj(out.reshape(s, b, self.n_local * c.v_head_dim))
+
+    def _latent_cache(self, kv, inference_context):
+        """Latent KV cache: exactly the [kv_latent | k_pe] rows, nothing is ever expanded per head.  → (all keys so far, offset of the new queries)."""
+        if inference_context is None:
+            return kv, 0
+        kvd = inference_context.key_value_memory_dict
+        if self.layer_number not in kvd:
+            kvd[self.layer_number] = torch.empty(inference_context.max_sequence_length, inference_context.max_batch_size, kv.shape[-1], dtype=kv.dtype, device=kv.device)
+        cache = kvd[self.layer_number]
+        s0, b0 = inference_context.sequence_len_offset, inference_context.batch_size_offset
+        s1, b1 = s0 + kv.shape[0], b0 + kv.shape[1]
+        cache[s0:s1, b0:b1] = kv
+        return cache[:s1, b0:b1], s0
+
+    def core_latent_attention(self, q_abs, kv, causal, q_off, hidden_states):
+        """Dense latent attention; sparse variants (``DSAMLASelfAttention``) override this."""
+        return self.latent_attention(q_abs, kv, causal, q_off)
+
+
+class DSAMLASelfAttention(AbsorbedMLASelfAttention):
+    """Absorbed MLA whose core is DeepSeek sparse attention: an index branch scores every causal key per query, the top-k survive, and the latent attention runs
+    on those rows only (reference ``experimental_attention_variant/dsa.py`` ``DSAttention`` inside the MLA layer built by
+    ``experimental_attention_variant_module_specs.get_dsa_module_spec_for_backend``).  With ``dsa_indexer_topk_freq > 1`` only every n-th layer owns an indexer;
+    the layers in between reuse its indices (handed over through ``config``-scoped storage, the layers of one model run in order)."""
+
+    def __init__(self, config, submodules, layer_number: int = 1, **kw):
+        super().__init__(config, submodules, layer_number=layer_number, **kw)
+        from .dsa import DSAttention
+
+        self.dsa = DSAttention(config, layer_number=self.layer_number, softmax_scale=self.softmax_scale)
+
+    def core_latent_attention(self, q_abs, kv, causal, q_off, hidden_states):
+        from .dsa import source_dsa_compute_layer
+
+        if self.sequence_parallel:
+            from ...tensor_parallel.mappings import gather_from_sequence_parallel_region
+
+            hidden_states = gather_from_sequence_parallel_region(hidden_states, group=self.tp_group)
+        if kv.shape[0] != hidden_states.shape[0]:
+            raise NotImplementedError("DSA with a KV cache needs the index keys cached as well: use the dense absorbed MLA for incremental decoding")
+        store = self.config.__dict__.setdefault("_dsa_shared_indices", {})
+        shared = None
+        if self.dsa.indexer is None:
+            shared = store[source_dsa_compute_layer(self.layer_number, self.dsa.skip_offset, self.dsa.topk_freq)]
+        out = self.dsa(q_abs, kv, hidden_states, v_width=self.config.kv_lora_rank, q_offset=q_off, shared_indices=shared)
+        if self.dsa.indexer is not None:
+            store[self.layer_number] = self.dsa.last_indices
+        return out

@@ -200,8 +200,9 @@ class DSAttention(MegatronModule):
         self.softmax_scale = softmax_scale
         self.loss_coeff = getattr(config, "dsa_indexer_loss_coeff", 0.0)
         self.sparse_loss = getattr(config, "dsa_indexer_use_sparse_loss", False)
-        self.skip_offset = getattr(config, "dsa_skip_topk_offset", 0)
-        self.topk_freq = getattr(config, "dsa_topk_freq", 1)
+        # reference names first (``dsa_indexer_skip_topk_offset`` / ``dsa_indexer_topk_freq``), this framework's earlier short names as a fallback
+        self.skip_offset = getattr(config, "dsa_indexer_skip_topk_offset", None) or getattr(config, "dsa_skip_topk_offset", 0) or 0
+        self.topk_freq = getattr(config, "dsa_indexer_topk_freq", None) or getattr(config, "dsa_topk_freq", 1) or 1
         self.computes_topk = not is_dsa_skip_topk_layer(layer_number, self.skip_offset, self.topk_freq)
         ind = submodules.indexer if submodules is not None and submodules.indexer is not None else DSAIndexer
         self.indexer = build_module(ind, config, q_in_features=q_in_features) if self.computes_topk else None

@@ -55,6 +55,8 @@ class _GroupedLinearFn(torch.autograd.Function):
 class GroupedMLP(MegatronModule):
     def __init__(self, num_local_experts: int, config: TransformerConfig, submodules: Optional[MLPSubmodules] = None, pg_collection=None):
         super().__init__(config)
+        if config.add_bias_linear:
+            raise ValueError("the grouped-GEMM experts have no bias terms: use add_bias_linear=False (--disable-bias-linear) or moe_grouped_gemm=False")
         self.num_local_experts = num_local_experts
         self.ep_group, self.tp_group, self.expt_dp_group = _expert_groups(pg_collection)
         tp = get_pg_size(self.tp_group)
@@ -152,14 +154,15 @@ class SequentialMLP(MegatronModule):
             probs = None
         chunks = torch.split(permuted_tokens, tpe)
         pchunks = torch.split(probs, tpe) if probs is not None else [None] * len(tpe)
-        outs, biases = [], []
+        outs = []
         for expert, x, p in zip(self.local_experts, chunks, pchunks):
             o, b = expert(x, per_token_scale=p.unsqueeze(-1) if p is not None else None)
-            outs.append(o)
             if self.add_bias and b is not None:
-                biases.append(b.expand_as(o))
-        out = torch.cat(outs, dim=0)
-        return out, (torch.cat(biases, dim=0) if biases else None)
+                # the output bias of an expert belongs to the tokens routed to it, weighted like the rest of its output: fold it in here — the
+                # combine step only knows about one tensor (the reference asserts ``mlp_bias is None`` after the experts, moe_layer.py:568)
+                o = o + (b * p.unsqueeze(-1).to(b.dtype) if p is not None else b)
+            outs.append(o)
+        return torch.cat(outs, dim=0), None
 
     def sharded_state_dict(self, prefix: str = "", sharded_offsets: tuple = (), metadata: Optional[dict] = None):
         ep, epr = get_pg_size(self.ep_group), get_pg_rank(self.ep_group)

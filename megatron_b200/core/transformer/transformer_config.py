@@ -31,6 +31,7 @@ class TransformerConfig(ModelParallelConfig):
     experimental_attention_variant: Optional[str] = None
     experimental_attention_variant_loss_scale_func: Optional[Callable] = None
     dsa_indexer_loss_coeff: float = 0.0
+    linear_attention_freq: Optional[Union[int, List[int]]] = None      # gdn variant: int N = one softmax layer after every N-1 linear ones, or a 0/1 list
     # gated delta net mixer geometry (reference ``--linear-*``); None = the mixer's constructor arguments
     linear_conv_kernel_dim: Optional[int] = None
     linear_key_head_dim: Optional[int] = None
@@ -42,6 +43,8 @@ class TransformerConfig(ModelParallelConfig):
     dsa_indexer_head_dim: Optional[int] = None
     dsa_indexer_topk: Optional[int] = None
     dsa_indexer_use_sparse_loss: bool = False
+    dsa_indexer_topk_freq: int = 1                     # > 1: only every n-th layer owns an indexer, the layers in between reuse its top-k
+    dsa_indexer_skip_topk_offset: int = 0
     dsa_indexer_rope_interleaved: bool = False         # MLA-style interleaved rotation of the rope slice
     dsa_indexer_rotate_activation: bool = True         # Hadamard rotation of q / k before scoring
     dsa_indexer_scoring_relu: bool = True              # ReLU on q.k before the head weighting

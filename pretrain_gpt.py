@@ -37,6 +37,11 @@ def model_provider(pre_process=True, post_process=True, vp_stage=None) -> GPTMod
         mod, fn = args.spec[:2] if isinstance(args.spec, (list, tuple)) else str(args.spec).rsplit(".", 1)
         spec = getattr(importlib.import_module(mod), fn)
         spec = spec(config) if callable(spec) and not hasattr(spec, "submodules") else spec
+    elif getattr(config, "experimental_attention_variant", None):
+        # --experimental-attention-variant gdn|dsa: linear-attention / sparse-attention layers following --linear-attention-freq and the MoE pattern
+        from megatron_b200.core.models.gpt.experimental_attention_variant_module_specs import get_transformer_block_with_experimental_attention_variant_spec
+
+        spec = get_transformer_block_with_experimental_attention_variant_spec(config, vp_stage=vp_stage)
     elif args.num_experts:
         spec = get_gpt_decoder_block_spec(config, vp_stage=vp_stage)
     else:

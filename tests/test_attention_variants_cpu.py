@@ -1,4 +1,5 @@
 """Absorbed MLA (latent-space attention) and DeepSeek sparse attention."""
+import pytest
 import torch
 
 from dist_utils import run_distributed
@@ -491,3 +492,59 @@ def _tp2_serving(rank, world):
 
 def test_dynamic_engine_on_tensor_parallel_model():
     assert all(run_distributed(_tp2_serving, 2))
+
+
+def _variant_specs(rank, world):
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.models.gpt.experimental_attention_variant_module_specs import (get_linear_attention_pattern, get_moe_layer_pattern,
+                                                                                          get_transformer_block_with_experimental_attention_variant_spec,
+                                                                                          normalize_experimental_attention_variant)
+    from megatron_b200.core.models.gpt.gpt_model import GPTModel
+    from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
+    from megatron_b200.core.transformer.transformer_config import MLATransformerConfig, TransformerConfig
+
+    ps.initialize_model_parallel(1, 1)
+    model_parallel_cuda_manual_seed(1)
+    tok = torch.randint(0, 64, (2, 32), generator=torch.Generator().manual_seed(0))
+    pos = torch.arange(32).unsqueeze(0).expand(2, -1)
+    # linear attention: gated-delta-net mixers in the attention slot of 3 layers out of 4 (freq 4), softmax attention in the fourth; MoE in every other layer
+    cfg = TransformerConfig(num_layers=4, hidden_size=64, num_attention_heads=4, use_cpu_initialization=True, hidden_dropout=0.0, attention_dropout=0.0,
+                            experimental_attention_variant="gdn", linear_attention_freq=4, linear_key_head_dim=16, linear_value_head_dim=16, linear_num_key_heads=2,
+                            linear_num_value_heads=4, num_moe_experts=4, moe_router_topk=2, moe_layer_freq=2, moe_ffn_hidden_size=32)
+    assert get_linear_attention_pattern(cfg) == [1, 1, 1, 0] and get_moe_layer_pattern(cfg) == [1, 0, 1, 0]
+    with pytest.warns(DeprecationWarning):
+        assert normalize_experimental_attention_variant("gated_delta_net") == "gdn"
+    m = GPTModel(cfg, get_transformer_block_with_experimental_attention_variant_spec(cfg), vocab_size=64, max_sequence_length=32, position_embedding_type="rope")
+    assert [type(l.self_attention).__name__ for l in m.decoder.layers] == ["GatedDeltaNetAttention"] * 3 + ["SelfAttention"]
+    assert [type(l.mlp).__name__ for l in m.decoder.layers] == ["MoELayer", "MLP", "MoELayer", "MLP"]
+    m(tok, pos, None, labels=tok).mean().backward()            # MoE experts with bias terms: the expert output bias is folded into the expert output
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    # sparse attention: every layer is absorbed MLA with the DSA core; indexers in layers 1 and 3, layers 2 and 4 reuse their top-k
+    mc = MLATransformerConfig(num_layers=4, hidden_size=64, num_attention_heads=4, use_cpu_initialization=True, hidden_dropout=0.0, attention_dropout=0.0, q_lora_rank=32,
+                              kv_lora_rank=32, qk_head_dim=16, qk_pos_emb_head_dim=8, v_head_dim=16, rope_type="rope", experimental_attention_variant="dsa",
+                              dsa_indexer_n_heads=2, dsa_indexer_head_dim=16, dsa_indexer_topk=8, dsa_indexer_loss_coeff=0.1, dsa_indexer_topk_freq=2, add_bias_linear=False)
+    m2 = GPTModel(mc, get_transformer_block_with_experimental_attention_variant_spec(mc), vocab_size=64, max_sequence_length=32, position_embedding_type="rope")
+    assert [l.self_attention.dsa.indexer is not None for l in m2.decoder.layers] == [True, False, True, False]
+    loss = m2(tok, pos, None, labels=tok).mean()
+    loss.backward()
+    assert all(float(p.grad.abs().sum()) > 0 for p in m2.decoder.layers[0].self_attention.dsa.parameters())      # trained through the KL term only
+    # with top-k >= sequence length the sparse core sees every causal key: same loss as the dense absorbed-MLA model with the same weights
+    from megatron_b200.core.models.gpt.gpt_layer_specs import get_gpt_layer_local_spec
+    from megatron_b200.core.transformer.experimental_attention_variant import AbsorbedMLASelfAttention
+
+    full = MLATransformerConfig(**{**{f.name: getattr(mc, f.name) for f in __import__("dataclasses").fields(mc) if f.init}, "dsa_indexer_topk": 64, "dsa_indexer_loss_coeff": 0.0})
+    m3 = GPTModel(full, get_transformer_block_with_experimental_attention_variant_spec(full), vocab_size=64, max_sequence_length=32, position_embedding_type="rope")
+    dense_spec = get_gpt_layer_local_spec(multi_latent_attention=True)
+    dense_spec.submodules.self_attention.module = AbsorbedMLASelfAttention
+    m4 = GPTModel(full, dense_spec, vocab_size=64, max_sequence_length=32, position_embedding_type="rope")
+    missing = m4.load_state_dict({k: v for k, v in m3.state_dict().items() if ".dsa." not in k}, strict=False)
+    assert not missing.missing_keys
+    with torch.no_grad():
+        assert abs(float(m3(tok, pos, None, labels=tok).mean()) - float(m4(tok, pos, None, labels=tok).mean())) < 1e-4
+    return True
+
+
+def test_experimental_attention_variant_block_specs():
+    from dist_utils import run_distributed
+
+    assert run_distributed(_variant_specs, 1) == [True]
