@@ -12,7 +12,7 @@ from ..transformer.module import MegatronModule
 from ..transformer.spec_utils import ModuleSpec, build_module
 from ..transformer.transformer_config import TransformerConfig
 from ..utils import make_viewless_tensor
-from .mamba_hybrid_layer_allocation import Symbols, allocate_layers
+from .mamba_hybrid_layer_allocation import Symbols, allocate_layers, parse_hybrid_pattern
 
 
 @dataclass
@@ -22,6 +22,8 @@ class MambaStackSubmodules:
     mlp_layer: Union[ModuleSpec, type] = IdentityOp
     moe_layer: Union[ModuleSpec, type] = IdentityOp
     gdn_layer: Union[ModuleSpec, type] = IdentityOp
+    mla_layer: Union[ModuleSpec, type] = IdentityOp
+    dsa_layer: Union[ModuleSpec, type] = IdentityOp
 
 
 class MambaStack(MegatronModule):
@@ -33,8 +35,18 @@ class MambaStack(MegatronModule):
         self.input_tensor = None
         layout = allocate_layers(config.num_layers, hybrid_attention_ratio, hybrid_mlp_ratio, hybrid_override_pattern)
         pp = ps.get_pipeline_model_parallel_world_size() if ps.model_parallel_is_initialized() else 1
-        per = config.num_layers // pp
-        off = (ps.get_pipeline_model_parallel_rank() if pp > 1 else 0) * per
+        segments = parse_hybrid_pattern(hybrid_override_pattern)[1] if hybrid_override_pattern else None
+        if segments is not None and pp > 1:
+            # "|" in the pattern: explicit (possibly uneven) pipeline split
+            if len(segments) != pp:
+                raise ValueError(f"the hybrid pattern has {len(segments)} pipeline segments, the job has {pp} pipeline stages")
+            r = ps.get_pipeline_model_parallel_rank()
+            off, per = sum(segments[:r]), segments[r]
+        else:
+            if config.num_layers % pp != 0:
+                raise ValueError(f"{config.num_layers} layers cannot be split evenly over {pp} pipeline stages: mark the stage boundaries with '|' in the hybrid pattern")
+            per = config.num_layers // pp
+            off = (ps.get_pipeline_model_parallel_rank() if pp > 1 else 0) * per
         self.layer_type_list = layout[off : off + per]
         self.layers = torch.nn.ModuleList()
         kw = {"pg_collection": pg_collection} if pg_collection is not None else {}
@@ -46,6 +58,10 @@ class MambaStack(MegatronModule):
                 layer = build_module(submodules.gdn_layer, config=config, residual_in_fp32=residual_in_fp32, layer_number=n, **kw)
             elif sym == Symbols.ATTENTION:
                 layer = build_module(submodules.attention_layer, config=config, layer_number=n, **kw)
+            elif sym == Symbols.MLA:
+                layer = build_module(submodules.mla_layer, config=config, layer_number=n, **kw)
+            elif sym == Symbols.DS_ATTENTION:
+                layer = build_module(submodules.dsa_layer, config=config, layer_number=n, **kw)
             elif sym == Symbols.MLP:
                 layer = build_module(submodules.mlp_layer, config=config, layer_number=n, **kw)
             else:

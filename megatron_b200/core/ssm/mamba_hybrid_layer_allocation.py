@@ -1,13 +1,22 @@
 """Hybrid layer pattern: ``M`` = Mamba, ``G`` = gated delta net, ``*`` = attention, ``-`` = MLP, ``E`` = MoE (reference ``models/hybrid/hybrid_layer_allocation.py``
-``Symbols``)."""
+``Symbols``); ``+`` = multi-latent attention, ``D`` = DeepSeek sparse attention; ``|`` marks pipeline-stage boundaries (``"M*M*|M*M-"``: the first four
+layers on stage 0, the rest on stage 1 — uneven splits allowed) and everything after ``/`` describes multi-token-prediction layers."""
 from __future__ import annotations
 
 from typing import List, Optional
 
 
 class Symbols:
-    MAMBA, ATTENTION, MLP, MOE, GDN = "M", "*", "-", "E", "G"
-    VALID = {MAMBA, ATTENTION, MLP, MOE, GDN}
+    MAMBA, ATTENTION, MLP, MOE, GDN, MLA, DS_ATTENTION = "M", "*", "-", "E", "G", "+", "D"
+    PIPE, MTP_SEPARATOR = "|", "/"
+    VALID = {MAMBA, ATTENTION, MLP, MOE, GDN, MLA, DS_ATTENTION}
+
+
+def parse_hybrid_pattern(pattern: str):
+    """``"M*|M-/MM"`` → (flat main layout ``['M','*','M','-']``, layers per pipeline segment ``[2, 2]`` or None when there is no ``|``, MTP patterns ``['MM']``)."""
+    main, *mtp = pattern.split(Symbols.MTP_SEPARATOR)
+    segments = main.split(Symbols.PIPE)
+    return list(main.replace(Symbols.PIPE, "")), ([len(s) for s in segments] if len(segments) > 1 else None), mtp
 
 
 def _allocate_auto(total: int, attn_ratio: float, mlp_ratio: float) -> List[str]:
@@ -30,7 +39,7 @@ def _allocate_auto(total: int, attn_ratio: float, mlp_ratio: float) -> List[str]
 
 def allocate_layers(total_layers: int, target_attention_ratio: float = 0.0, target_mlp_ratio: float = 0.0, override_pattern: Optional[str] = None) -> List[str]:
     if override_pattern:
-        layout = list(override_pattern)
+        layout = parse_hybrid_pattern(override_pattern)[0]
         bad = set(layout) - Symbols.VALID
         if bad:
             raise ValueError(f"invalid symbols {bad} in hybrid pattern; valid: {sorted(Symbols.VALID)}")

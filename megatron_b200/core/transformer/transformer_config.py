@@ -319,7 +319,8 @@ class TransformerConfig(ModelParallelConfig):
         if self.distribute_saved_activations and self.sequence_parallel:
             raise ValueError("distribute_saved_activations is incompatible with sequence_parallel")
         vp = self.virtual_pipeline_model_parallel_size
-        if self.pipeline_model_parallel_size > 1 and self.pipeline_model_parallel_layout is None:
+        if self.pipeline_model_parallel_size > 1 and self.pipeline_model_parallel_layout is None and not self.is_hybrid_model:
+            # (hybrid stacks split by their layer pattern: "|" separators allow uneven stages, and the stack validates the split itself)
             n = self.num_layers
             first, last = self.num_layers_in_first_pipeline_stage, self.num_layers_in_last_pipeline_stage
             mid_stages = self.pipeline_model_parallel_size - (first is not None) - (last is not None)

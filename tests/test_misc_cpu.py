@@ -225,3 +225,44 @@ def test_gated_delta_net_layers_in_the_hybrid_stack():
     from dist_utils import run_distributed
 
     assert run_distributed(_gdn_hybrid, 1) == [True]
+
+
+def _hybrid_symbols(rank, world):
+    from megatron_b200.core import parallel_state as ps
+    from megatron_b200.core.models.mamba.mamba_layer_specs import mamba_stack_spec
+    from megatron_b200.core.models.mamba.mamba_model import MambaModel
+    from megatron_b200.core.ssm.mamba_hybrid_layer_allocation import parse_hybrid_pattern
+    from megatron_b200.core.tensor_parallel.random import model_parallel_cuda_manual_seed
+    from megatron_b200.core.transformer.transformer_config import MLATransformerConfig
+
+    assert parse_hybrid_pattern("M*M*|M-G+D/MM/MM") == (list("M*M*M-G+D"), [4, 5], ["MM", "MM"])
+    assert parse_hybrid_pattern("M*-") == (list("M*-"), None, [])
+    ps.initialize_model_parallel(1, world)                       # pipeline parallel over the ranks
+    model_parallel_cuda_manual_seed(1)
+    cfg = MLATransformerConfig(num_layers=5, hidden_size=64, num_attention_heads=4, use_cpu_initialization=True, hidden_dropout=0.0, attention_dropout=0.0, is_hybrid_model=True,
+                               q_lora_rank=32, kv_lora_rank=32, qk_head_dim=16, qk_pos_emb_head_dim=8, v_head_dim=16, rope_type="rope", add_bias_linear=False,
+                               dsa_indexer_n_heads=2, dsa_indexer_head_dim=16, dsa_indexer_topk=8, pipeline_model_parallel_size=world, pipeline_dtype=torch.float32,
+                               linear_key_head_dim=16, linear_value_head_dim=16, linear_num_key_heads=2, mamba_head_dim=16, mamba_num_groups=2, mamba_state_dim=16)
+    # "|": stage 0 takes three layers, stage 1 two — an uneven split that num_layers // pp could not express
+    m = MambaModel(cfg, mamba_stack_spec, vocab_size=64, max_sequence_length=32, hybrid_override_pattern="G+D|-M" if world == 2 else "G+D-M",
+                   pre_process=ps.is_pipeline_first_stage(), post_process=ps.is_pipeline_last_stage(), position_embedding_type="rope")
+    def kind(layer):
+        for name in ("mixer", "self_attention", "mlp"):
+            mod = getattr(layer, name, None)
+            if mod is not None and type(mod).__name__ != "IdentityOp":
+                return type(mod).__name__
+
+    kinds = [kind(l) for l in m.decoder.layers]
+    if world == 1:
+        tok = torch.randint(0, 64, (2, 32), generator=torch.Generator().manual_seed(0))
+        loss = m(tok, torch.arange(32).unsqueeze(0).expand(2, -1), None, labels=tok).mean()
+        loss.backward()
+        assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+    return kinds
+
+
+def test_hybrid_pattern_latent_attention_symbols_and_pipeline_separators():
+    from dist_utils import run_distributed
+
+    assert run_distributed(_hybrid_symbols, 1) == [["GatedDeltaNet", "MLASelfAttention", "DSAMLASelfAttention", "MLP", "MambaMixer"]]
+    assert run_distributed(_hybrid_symbols, 2) == [["GatedDeltaNet", "MLASelfAttention", "DSAMLASelfAttention"], ["MLP", "MambaMixer"]]
