@@ -251,10 +251,12 @@ def _local_name(local_dir: str, iteration: int, rank: int) -> str:
     return os.path.join(local_dir, f"iter_{iteration:07d}", f"rank_{rank:05d}.pt")
 
 
-def save_local_checkpoint(iteration: int, model: List, optimizer, opt_param_scheduler, local_dir: str, keep_last: int = 1, replicate_to_buddy: bool = False) -> str:
+def save_local_checkpoint(iteration: int, model: List, optimizer, opt_param_scheduler, local_dir: str, keep_last: int = 1, replicate_to_buddy: bool = False,
+                          replication_jump: Optional[int] = None, replication_factor: int = 2) -> str:
     """Fast recovery point on NODE-LOCAL storage: every rank dumps its own shards (model, optimizer, scheduler, RNG) with one ``torch.save`` — no global metadata, no
     resharding, so it is as fast as the local disk / ramdisk and only reusable with the same parallel layout.  ``replicate_to_buddy`` also stores the blob of the
-    next rank (ring) so a replaced node can be refilled from its neighbour.  A cluster-wide MIN over the newest complete iteration decides what is loadable."""
+    next rank (ring) so a replaced node can be refilled from its neighbour; ``replication_jump`` J / ``replication_factor`` F (``--replication-jump`` /
+    ``--replication-factor``): rank n also keeps the blobs of ranks n+J, n+2J, … (F - 1 of them; J = ranks per node puts the replicas on other nodes).  A cluster-wide MIN over the newest complete iteration decides what is loadable."""
     rank = _rank()
     state = {"iteration": iteration, "model": [m.state_dict() for m in model], "rng": get_rng_state().data[0] if hasattr(get_rng_state(), "data") else None,
              "optimizer": optimizer.state_dict() if optimizer is not None and hasattr(optimizer, "state_dict") else None,
@@ -269,10 +271,12 @@ def save_local_checkpoint(iteration: int, model: List, optimizer, opt_param_sche
         world = dist.get_world_size()
         blob = [None] * world
         dist.all_gather_object(blob, (rank, open(path, "rb").read() if os.path.getsize(path) < (1 << 30) else None))
-        src_rank, data = blob[(rank + 1) % world]
-        if data is not None:
-            with open(_local_name(local_dir, iteration, src_rank) + ".buddy", "wb") as f:
-                f.write(data)
+        jump = replication_jump or 1
+        for k in range(1, max(replication_factor, 2)):
+            src_rank, data = blob[(rank + k * jump) % world]
+            if data is not None and src_rank != rank:
+                with open(_local_name(local_dir, iteration, src_rank) + ".buddy", "wb") as f:
+                    f.write(data)
     with open(os.path.join(local_dir, f"latest_local_rank_{rank:05d}.txt"), "w") as f:
         f.write(str(iteration))
     its = sorted(int(d.split("_")[1]) for d in os.listdir(local_dir) if d.startswith("iter_"))
@@ -338,7 +342,8 @@ def _host_copy(obj):
 
 def save_non_persistent_checkpoint(iteration: int, model: List, optimizer, opt_param_scheduler, kind: str, save_dir: Optional[str] = None, global_dir: Optional[str] = None,
                                    local_dir: Optional[str] = None, args: Optional[Dict[str, Any]] = None, num_floating_point_operations_so_far: float = 0.0,
-                                   async_save: bool = False, local_algo: str = "fully_parallel") -> Optional[str]:
+                                   async_save: bool = False, local_algo: str = "fully_parallel", replication: Optional[bool] = None, replication_jump: Optional[int] = None,
+                                   replication_factor: int = 2) -> Optional[str]:
     """A frequent recovery point that is NOT part of the persistent series: only the newest one is kept.
 
     * ``global``: a regular (resharding-capable) distributed checkpoint under ``global_dir`` (default ``<save>/non_persistent``) with its own tracker file;
@@ -351,7 +356,8 @@ def save_non_persistent_checkpoint(iteration: int, model: List, optimizer, opt_p
                                assume_constant_structure=True)
     if kind == "local":
         assert local_dir, "--non-persistent-local-ckpt-dir is required for local non-persistent checkpoints"
-        return save_local_checkpoint(iteration, model, optimizer, opt_param_scheduler, local_dir, replicate_to_buddy=local_algo == "fully_parallel")
+        return save_local_checkpoint(iteration, model, optimizer, opt_param_scheduler, local_dir, replicate_to_buddy=(local_algo == "fully_parallel") if replication is None else replication,
+                                     replication_jump=replication_jump, replication_factor=replication_factor)
     if kind == "in_memory":
         _IN_MEMORY.clear()
         _IN_MEMORY.update(iteration=iteration, model=[_host_copy(m.state_dict()) for m in model],

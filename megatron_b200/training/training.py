@@ -578,7 +578,9 @@ def train(forward_step_func, model, optimizer, opt_param_scheduler, train_data_i
             if kind is not None:
                 checkpointing.save_non_persistent_checkpoint(iteration, model, optimizer, opt_param_scheduler, kind, args.save, getattr(args, "non_persistent_global_ckpt_dir", None),
                                                              getattr(args, "non_persistent_local_ckpt_dir", None), vars_for_ckpt(args), args.num_floating_point_operations_so_far,
-                                                             async_save=args.async_save, local_algo=getattr(args, "non_persistent_local_ckpt_algo", "fully_parallel"))
+                                                             async_save=args.async_save, local_algo=getattr(args, "non_persistent_local_ckpt_algo", "fully_parallel"),
+                                                             replication=True if getattr(args, "replication", False) else None, replication_jump=getattr(args, "replication_jump", None),
+                                                             replication_factor=getattr(args, "replication_factor", 2) or 2)
         saved = False
         if args.save and args.save_interval and iteration % args.save_interval == 0:
             checkpointing.save_checkpoint(iteration, model, optimizer if not args.no_save_optim else None, opt_param_scheduler, args.save, vars_for_ckpt(args),
