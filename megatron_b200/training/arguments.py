@@ -370,7 +370,14 @@ def parse_args(argv=None, extra_args_provider=None, ignore_unknown_args: bool = 
 
 
 def parse_and_validate_args(argv=None, **kw):
-    return validate_args(parse_args(argv, **kw))
+    args = parse_args(argv, **kw)
+    if getattr(args, "use_checkpoint_args", False) or getattr(args, "use_mp_args_from_checkpoint_args", False):
+        # --use-checkpoint-args: the checkpoint describes the architecture; --use-mp-args-from-checkpoint-args: and the model-parallel layout it was saved with
+        from .checkpointing import load_args_from_checkpoint
+
+        load_args_from_checkpoint(args, architecture=bool(getattr(args, "use_checkpoint_args", False)),
+                                  model_parallel=bool(getattr(args, "use_mp_args_from_checkpoint_args", False)))
+    return validate_args(args)
 
 
 def core_transformer_config_from_args(args):

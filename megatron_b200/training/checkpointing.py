@@ -218,9 +218,15 @@ _ARCH_ARGS = ("num_layers", "hidden_size", "ffn_hidden_size", "num_attention_hea
               "rotary_base", "rotary_percent", "tokenizer_type", "group_query_attention")
 
 
-def load_args_from_checkpoint(args, load_dir: Optional[str] = None, iteration: Optional[int] = None, force: bool = True):
-    """``--use-checkpoint-args``: take the model-architecture arguments from the checkpoint so a run (or an inference server) only needs ``--load``.
-    Returns ``(args, checkpoint_args_dict)``; parallelism, batch sizes and paths are never overwritten."""
+_MP_ARGS = ("tensor_model_parallel_size", "pipeline_model_parallel_size", "virtual_pipeline_model_parallel_size", "num_layers_per_virtual_pipeline_stage",
+            "expert_model_parallel_size", "expert_tensor_parallel_size", "context_parallel_size", "sequence_parallel")
+
+
+def load_args_from_checkpoint(args, load_dir: Optional[str] = None, iteration: Optional[int] = None, force: bool = True, architecture: bool = True,
+                              model_parallel: bool = False):
+    """``--use-checkpoint-args``: take the model-architecture arguments from the checkpoint so a run (or an inference server) only needs ``--load``;
+    ``--use-mp-args-from-checkpoint-args`` (``model_parallel``): also the model-parallel sizes it was saved with (reference ``checkpointing.py:2355``).
+    Returns ``(args, checkpoint_args_dict)``; batch sizes and paths are never overwritten."""
     load_dir = load_dir or getattr(args, "load", None)
     if not load_dir:
         return args, None
@@ -230,7 +236,7 @@ def load_args_from_checkpoint(args, load_dir: Optional[str] = None, iteration: O
             return args, None
         iteration, _ = read_metadata(tracker)
     saved = dist_checkpointing.load_common_state_dict(get_checkpoint_name(load_dir, iteration)).get("args") or {}
-    for k in _ARCH_ARGS:
+    for k in (_ARCH_ARGS if architecture else ()) + (_MP_ARGS if model_parallel else ()):
         if k in saved and saved[k] is not None and (force or getattr(args, k, None) is None):
             setattr(args, k, saved[k])
     return args, saved

@@ -325,6 +325,9 @@ def test_load_args_from_checkpoint_and_arch_check(tmp_path):
     args, saved = ck.load_args_from_checkpoint(args)
     assert args.num_layers == 4 and args.hidden_size == 64 and args.swiglu is True
     assert args.tensor_model_parallel_size == 2 and args.lr == 0.1          # layout / optimisation arguments are never taken from the checkpoint
+    mp = SimpleNamespace(load=str(tmp_path), num_layers=2, hidden_size=32, tensor_model_parallel_size=2, lr=0.1)
+    ck.load_args_from_checkpoint(mp, architecture=False, model_parallel=True)          # --use-mp-args-from-checkpoint-args alone: layout yes, architecture no
+    assert mp.tensor_model_parallel_size == 8 and mp.num_layers == 2 and mp.lr == 0.1
     ck.check_checkpoint_args(args, saved)
     args.hidden_size = 128
     with pytest.raises(ValueError, match="hidden_size"):
