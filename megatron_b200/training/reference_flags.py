@@ -100,6 +100,7 @@ WIRED: Dict[str, str] = {
     "replication": "local checkpoints keep copies of other ranks' blobs", "replication_jump": "spacing between a rank and the ranks holding its replicas",
     "replication_factor": "number of holders of each blob",
     "use_mp_args_from_checkpoint_args": "load_args_from_checkpoint(model_parallel=True)",
+    "enable_experimental": "core.config.set_experimental_flag(True)",
     "save_retain_interval": "save_checkpoint(retain_interval=): the previous checkpoint is deleted unless its iteration is a multiple",
     # tokenizer / vocabulary
     "padded_vocab_size": "pins the padded vocabulary", "pad_vocab_size": "--no-pad-vocab-size: no rounding", "vocab_extra_ids": "added before padding",

@@ -86,6 +86,10 @@ def initialize_megatron(argv=None, extra_args_provider=None, args_defaults: Opti
         from ..core.transformer.custom_layers.batch_invariant_kernels import enable_batch_invariant_mode
 
         enable_batch_invariant_mode()
+    if getattr(args, "enable_experimental", False):
+        from ..core import config as _core_config
+
+        _core_config.set_experimental_flag(True)
     if getattr(args, "logging_level", None) is not None:
         import logging
 
