@@ -89,21 +89,32 @@ class RemoteHTTPInference(InferenceInterface):
 
 
 class WeightRefitter:
-    """Push the trainer's weights into a generation model that does not share storage with it (reference: refit through ``core/resharding``).  ``mode='copy'`` is
-    the same-layout fast path (parameter-wise copy, one fused kernel per dtype on GPU); other layouts go through ``resharding.plan`` / ``execute``."""
+    """Push the trainer's weights into a generation model that does not share storage with it (reference: ``resharding/refit.py::swap_model_weights``).
+    Same layout and one process: parameter-wise copy.  Different layouts, or a distributed job: the refit planner + a copy service
+    (``method`` = ``--refit-method``: ``nccl`` | ``gloo`` | ``nvlink``; the reference's ``nvshmem`` resolves to ``nvlink``)."""
 
-    def __init__(self, src_model, dst_model):
+    def __init__(self, src_model, dst_model, method: str = "nccl", group=None, src_rank_offset: int = 0, dst_rank_offset: int = 0):
         self.src, self.dst = src_model, dst_model
+        self.method, self.group, self.offsets = method, group, (src_rank_offset, dst_rank_offset)
         self.version = 0
+
+    def _same_layout(self) -> bool:
+        if self.src is None or self.dst is None:
+            return False
+        src = dict(self.src.named_parameters())
+        dst = dict(self.dst.named_parameters())
+        return src.keys() == dst.keys() and all(src[n].shape == dst[n].shape for n in src)
 
     @torch.no_grad()
     def refit(self) -> int:
-        src = dict(self.src.named_parameters())
-        n = 0
-        for name, p in self.dst.named_parameters():
-            if name in src and src[name].shape == p.shape:
+        import torch.distributed as dist
+        if self._same_layout() and not (dist.is_initialized() and dist.get_world_size(self.group) > 1 and any(self.offsets)):
+            src = dict(self.src.named_parameters())
+            for name, p in self.dst.named_parameters():
                 p.copy_(src[name])
-                n += 1
-        assert n == len(src), f"refit covered {n} of {len(src)} parameters: layouts differ, use core.resharding"
+        else:
+            from ..core.resharding import swap_model_weights
+            method = self.method if (dist.is_initialized() and dist.get_backend(self.group) != "gloo") else "gloo"
+            swap_model_weights(self.src, self.dst, method, group=self.group, src_rank_offset=self.offsets[0], dst_rank_offset=self.offsets[1])
         self.version += 1
         return self.version
