@@ -3,6 +3,13 @@ import os
 import subprocess
 import sys
 
+
+def _free_port():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
 import numpy as np
 import torch
 
@@ -211,7 +218,7 @@ def test_every_module_imports_and_entry_scripts_compile():
 
 
 def test_simple_mcore_train_loop_example_tp2():
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29587",
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
                         os.path.join(ROOT, "examples", "run_simple_mcore_train_loop.py"), "--tp", "2", "--iters", "3"], capture_output=True, text=True, timeout=600,
                        env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
     assert r.returncode == 0 and "checkpoint round trip ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
