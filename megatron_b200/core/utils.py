@@ -487,3 +487,385 @@ class StragglerDetector:
         self._ev.clear(), self._cpu.clear(), self._bdata.clear()
         self.last_report = rec
         return True
+
+
+# =====================================================================================================================
+# Round-2 additions: small public helpers of the reference's ``core/utils.py`` that user code imports by name
+# =====================================================================================================================
+import asyncio as _asyncio
+import functools as _functools
+import inspect as _inspect
+import warnings as _warnings
+
+
+def null_decorator(*args, **kwargs):
+    """Stand-in for an optional decorator (``@jit_fuser``-style): usable bare or with arguments (reference ``utils.py:90``)."""
+    if len(args) == 1 and not kwargs and callable(args[0]):
+        return args[0]
+    return lambda fn: fn
+
+
+class ExperimentalNotEnabledError(Exception):
+    """An experimental API was used without ``config.set_experimental_flag(True)`` / ``--enable-experimental``."""
+
+
+def _experimental_enabled() -> bool:
+    try:
+        from . import config as _cfg
+        return bool(_cfg.is_experimental_enabled())
+    except Exception:
+        return False
+
+
+def experimental_api(fn):
+    """Calls raise ``ExperimentalNotEnabledError`` unless experimental features are switched on."""
+    @_functools.wraps(fn)
+    def wrapped(*a, **k):
+        if not _experimental_enabled():
+            raise ExperimentalNotEnabledError(f"{fn.__qualname__} is experimental: enable it with --enable-experimental")
+        return fn(*a, **k)
+    wrapped._experimental = True
+    return wrapped
+
+
+def experimental_cls(introduced_with_version: str):
+    """Class decorator: instantiation requires the experimental switch; the version is recorded for the deprecation policy."""
+    def deco(cls):
+        init = cls.__init__
+
+        @_functools.wraps(init)
+        def guarded(self, *a, **k):
+            if not _experimental_enabled():
+                raise ExperimentalNotEnabledError(f"{cls.__qualname__} (since {introduced_with_version}) is experimental: enable it with --enable-experimental")
+            init(self, *a, **k)
+        cls.__init__ = guarded
+        cls._experimental_since = introduced_with_version
+        return cls
+    return deco
+
+
+def _pkg_version(name: str):
+    from importlib.metadata import PackageNotFoundError, version
+    from packaging.version import Version
+    try:
+        return Version(version(name))
+    except PackageNotFoundError:
+        return None
+
+
+def _min_version(have, want: str, check_equality: bool) -> bool:
+    from packaging.version import Version
+    if have is None:
+        return False
+    return have >= Version(want) if check_equality else have > Version(want)
+
+
+def get_torch_version():
+    from packaging.version import Version
+    return Version(torch.__version__.split("+")[0])
+
+
+def get_fa_version():
+    return _pkg_version("flash-attn")
+
+
+def is_fa_min_version(version, check_equality=True):
+    return _min_version(get_fa_version(), version, check_equality)
+
+
+def get_mamba_version():
+    return _pkg_version("mamba-ssm")
+
+
+def is_mamba_min_version(version, check_equality=True):
+    return _min_version(get_mamba_version(), version, check_equality)
+
+
+def get_causal_conv1d_version():
+    return _pkg_version("causal-conv1d")
+
+
+def is_causal_conv1d_min_version(version, check_equality=True):
+    return _min_version(get_causal_conv1d_version(), version, check_equality)
+
+
+def get_flashinfer_version():
+    return _pkg_version("flashinfer-python") or _pkg_version("flashinfer")
+
+
+def is_flashinfer_min_version(version, check_equality=True):
+    return _min_version(get_flashinfer_version(), version, check_equality)
+
+
+def get_emerging_optimizers_version():
+    return _pkg_version("emerging-optimizers")
+
+
+def is_emerging_optimizers_min_version(version, check_equality=True):
+    return _min_version(get_emerging_optimizers_version(), version, check_equality)
+
+
+def accepts_parameter(fn, name: str) -> bool:
+    """Does ``fn`` take a parameter called ``name`` (or ``**kwargs``)?  Used to pass newer arguments to older callbacks."""
+    try:
+        params = _inspect.signature(fn).parameters
+    except (TypeError, ValueError):
+        return False
+    return name in params or any(p.kind is _inspect.Parameter.VAR_KEYWORD for p in params.values())
+
+
+def round_up_to_nearest_multiple(value: int, multiple: int) -> int:
+    return value if multiple <= 0 else -(-value // multiple) * multiple
+
+
+class WrappedTensor:
+    """A one-slot box: the callee ``unwrap()``s the tensor, after which the box no longer keeps it alive — lets a function
+    free its INPUT as soon as it has consumed it although the caller's frame still holds the box (reference ``utils.py:1003``)."""
+
+    def __init__(self, tensor: torch.Tensor):
+        self._t = [tensor]
+
+    def unwrap(self) -> torch.Tensor:
+        if not self._t:
+            raise RuntimeError("WrappedTensor was already unwrapped")
+        return self._t.pop()
+
+
+def mup_scaled_init_method_normal(sigma: float, num_layers: int, width_mult: float, multiplier: float = 2.0):
+    """muP output-projection init: the depth-scaled std, divided by sqrt(width multiplier)."""
+    std = sigma / math.sqrt(multiplier * num_layers) / math.sqrt(max(width_mult, 1e-12))
+
+    def init_(t):
+        return torch.nn.init.normal_(t, mean=0.0, std=std)
+    return init_
+
+
+def to_local_if_dtensor(t):
+    return t.to_local() if hasattr(t, "to_local") and type(t).__name__ == "DTensor" else t
+
+
+def get_full_tensor_if_necessary(t):
+    return t.full_tensor() if hasattr(t, "full_tensor") and type(t).__name__ == "DTensor" else t
+
+
+def get_data_parallel_group_if_dtensor(t, data_parallel_group=None):
+    """The group a DTensor parameter is sharded over (FSDP2), else the given / global data-parallel group."""
+    if type(t).__name__ == "DTensor":
+        mesh = t.device_mesh
+        return mesh.get_group(0) if mesh.ndim >= 1 else data_parallel_group
+    return data_parallel_group
+
+
+def local_multi_tensor_applier(op, noop_flag_buffer, tensor_lists, *args):
+    """Apex ``multi_tensor_applier`` calling convention on top of the local ops (reference ``utils.py:1311``)."""
+    return op(2048 * 32, noop_flag_buffer, tensor_lists, *args)
+
+
+def is_submodule(module: torch.nn.Module, parent_module: torch.nn.Module, strict: bool = True) -> bool:
+    if strict and module is parent_module:
+        return False
+    return any(m is module for m in parent_module.modules())
+
+
+def is_using_quantization_scales(config) -> bool:
+    """Do the parameters carry scaling factors that a checkpoint / refit has to move too (fp8 / fp4 recipes)?"""
+    return bool(getattr(config, "fp8", None) or getattr(config, "fp4", None))
+
+
+def drain_embedding_wgrad_compute(config, embedding_activation_buffer, grad_output_buffer, weight, tp_group=None):
+    """Deferred weight-gradient GEMMs of the output layer (``--defer-embedding-wgrad-compute``): for every stashed
+    (activation, grad-output) pair accumulate ``dW += gyᵀ · x`` into ``weight.main_grad`` (fp32 ``beta = 1`` epilogue of the
+    tcgen05 GEMM on CUDA).  With sequence parallelism the stashed activation is the local shard and is all-gathered first."""
+    from .. import ops as _ops
+    tp = get_pg_size(tp_group) if tp_group is not None else 1
+    while embedding_activation_buffer:
+        x, gy = embedding_activation_buffer.pop(0), grad_output_buffer.pop(0)
+        if getattr(config, "sequence_parallel", False) and tp > 1:
+            full = torch.empty((x.shape[0] * tp,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+            torch.distributed.all_gather_into_tensor(full, x.contiguous(), group=tp_group)
+            x = full
+        x2, g2 = x.reshape(-1, x.shape[-1]), gy.reshape(-1, gy.shape[-1])
+        if hasattr(weight, "main_grad") and weight.main_grad is not None:
+            if x2.is_cuda and hasattr(_ops, "wgrad_accumulate"):
+                _ops.wgrad_accumulate(g2, x2, weight.main_grad)
+            else:
+                weight.main_grad.add_((g2.float().t() @ x2.float()).to(weight.main_grad.dtype))
+        else:
+            gw = g2.t().to(x2.dtype) @ x2
+            weight.grad = gw if weight.grad is None else weight.grad + gw
+
+
+def ensure_params_ready(module: torch.nn.Module) -> None:
+    """Block until asynchronous parameter all-gathers (distributed optimizer overlap, FSDP prefetch) that target ``module``'s
+    parameters have completed — call before reading weights outside the normal forward (evaluation hooks, export, refit)."""
+    seen = set()
+    for m in module.modules():
+        for attr in ("finish_param_sync", "wait_for_param_gather"):
+            fn = getattr(m, attr, None)
+            if callable(fn) and id(fn) not in seen:
+                seen.add(id(fn))
+                fn()
+    if torch.cuda.is_available():
+        torch.cuda.current_stream().synchronize()
+
+
+_BATCH_KEYS = ("tokens", "labels", "loss_mask", "attention_mask", "position_ids", "cu_seqlens", "cu_seqlens_padded", "max_seqlen", "local_cp_size")
+_DTYPES = (torch.int64, torch.int32, torch.float32, torch.bfloat16, torch.float16, torch.bool, torch.uint8)
+
+
+def get_batch_on_this_tp_rank(batch, has_cu_seqlens: bool = False, is_hybrid_cp: bool = False, create_attention_mask_in_dataloader: bool = False,
+                              broadcast_src_rank: Optional[int] = None, broadcast_group=None, cp_size: int = 1, tp_rank: Optional[int] = None, micro_batch_size: int = 0,
+                              seq_length: int = 0, mtp_on_this_rank: bool = False, pipeline_model_parallel_size: int = 1, is_pipeline_first_stage: bool = True,
+                              is_pipeline_last_stage: bool = True):
+    """TP rank 0 read the micro-batch; give it to the other TP ranks (reference ``utils.py:2167``).
+
+    The reference issues one broadcast per tensor (up to nine, plus length prefixes for the variable-size ``cu_seqlens``).
+    Here it is TWO: a fixed 128-word int64 header (which keys, dtypes, shapes) and one byte payload with every tensor packed
+    back to back — on NVLink the cost of a micro-batch broadcast is launch latency, not bytes.  Which tensors a pipeline stage
+    needs follows the reference: tokens / position ids on the first stage, labels / loss mask on the last, both where MTP lives;
+    the attention mask only when the data loader builds it."""
+    group = broadcast_group if broadcast_group is not None else get_tensor_model_parallel_group_if_none(None)
+    if get_pg_size(group) == 1:
+        return batch
+    rank = tp_rank if tp_rank is not None else get_pg_rank(group)
+    src = broadcast_src_rank if broadcast_src_rank is not None else get_pg_src_rank(group)
+    want = set()
+    if pipeline_model_parallel_size == 1 or mtp_on_this_rank or is_pipeline_first_stage:
+        want |= {"tokens", "position_ids"}
+    if pipeline_model_parallel_size == 1 or mtp_on_this_rank or is_pipeline_last_stage:
+        want |= {"labels", "loss_mask"}
+    if create_attention_mask_in_dataloader:
+        want.add("attention_mask")
+    if has_cu_seqlens or is_hybrid_cp:
+        want |= {"cu_seqlens", "cu_seqlens_padded", "max_seqlen"}
+    if is_hybrid_cp:
+        want.add("local_cp_size")
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.distributed.get_backend(group) == "nccl" else torch.device("cpu")
+    header = torch.zeros(128, dtype=torch.int64, device=dev)
+    tensors = []
+    if rank == 0:
+        ents = []
+        for ki, k in enumerate(_BATCH_KEYS):
+            v = batch.get(k) if batch is not None else None
+            if k not in want or v is None:
+                continue
+            v = v if torch.is_tensor(v) else torch.as_tensor(v)
+            assert v.dim() <= 4, f"{k}: at most 4 dimensions"
+            ents.append([ki, _DTYPES.index(v.dtype), v.dim()] + list(v.shape) + [0] * (4 - v.dim()))
+            tensors.append(v.to(dev).contiguous())
+        header[0] = len(ents)
+        if ents:
+            header[1:1 + 7 * len(ents)] = torch.tensor(ents, dtype=torch.int64).reshape(-1)
+    torch.distributed.broadcast(header, src, group=group)
+    h = header.tolist()
+    metas = [(_BATCH_KEYS[h[1 + 7 * i]], _DTYPES[h[2 + 7 * i]], tuple(h[4 + 7 * i: 4 + 7 * i + h[3 + 7 * i]])) for i in range(h[0])]
+    sizes = [-(-(math.prod(s) if s else 1) * torch.empty((), dtype=dt).element_size() // 16) * 16 for _, dt, s in metas]
+    payload = torch.empty(sum(sizes), dtype=torch.uint8, device=dev)
+    if rank == 0:
+        off = 0
+        for t, n in zip(tensors, sizes):
+            nb = t.numel() * t.element_size()
+            payload[off:off + nb].copy_(t.reshape(-1).view(torch.uint8))
+            off += n
+    if payload.numel():
+        torch.distributed.broadcast(payload, src, group=group)
+    out = {k: None for k in _BATCH_KEYS}
+    off = 0
+    for (k, dt, shape), n in zip(metas, sizes):
+        nb = (math.prod(shape) if shape else 1) * torch.empty((), dtype=dt).element_size()
+        out[k] = payload[off:off + nb].view(dt).view(shape).clone() if rank != 0 else batch[k]
+        off += n
+    return out
+
+
+def _merge_cu_seqlens(cu: torch.Tensor, seq_length: int) -> torch.Tensor:
+    """[mbs, n] per-sample cumulative lengths (padded by repeating the last value) -> one 1-D cumulative vector over the
+    flattened ``mbs * seq_length`` token stream."""
+    parts = [cu.new_zeros(1)]
+    for i in range(cu.shape[0]):
+        row = torch.unique_consecutive(cu[i])
+        row = row[row > 0] if row.numel() and row[0] == 0 else row
+        parts.append(row + i * seq_length)
+    return torch.cat(parts)
+
+
+def flatten_batch_for_packed_sequences(batch):
+    """``micro_batch_size > 1`` with packed sequences: THD attention wants ONE token stream and one 1-D ``cu_seqlens``
+    (reference ``utils.py:2613``).  Sequence tensors go from [mbs, s] to [1, mbs*s]."""
+    cu = batch.get("cu_seqlens")
+    if cu is None:
+        return batch
+    if cu.dim() == 1:
+        cu = cu.unsqueeze(0)
+    seq_length = next((batch[k].shape[1] for k in ("tokens", "labels", "loss_mask", "position_ids") if batch.get(k) is not None), int(cu[0, -1]))
+    batch["cu_seqlens"] = _merge_cu_seqlens(cu, seq_length).unsqueeze(0)
+    if batch.get("cu_seqlens_padded") is not None:
+        p = batch["cu_seqlens_padded"]
+        batch["cu_seqlens_padded"] = _merge_cu_seqlens(p if p.dim() == 2 else p.unsqueeze(0), seq_length).unsqueeze(0)
+    if batch.get("max_seqlen") is not None:
+        batch["max_seqlen"] = torch.as_tensor(batch["max_seqlen"]).max().reshape(1)
+    for k in ("tokens", "labels", "loss_mask", "position_ids"):
+        if batch.get(k) is not None:
+            batch[k] = batch[k].reshape(1, -1)
+    return batch
+
+
+def get_asyncio_loop(loop=None):
+    """The running loop, else the thread's current loop, else a fresh one installed as current (servers call this from threads)."""
+    if loop is not None:
+        return loop
+    try:
+        return _asyncio.get_running_loop()
+    except RuntimeError:
+        pass
+    try:
+        lp = _asyncio.get_event_loop_policy().get_event_loop()
+        if not lp.is_closed():
+            return lp
+    except RuntimeError:
+        pass
+    lp = _asyncio.new_event_loop()
+    _asyncio.set_event_loop(lp)
+    return lp
+
+
+def trace_async_exceptions(fn=None, *, verbose: bool = False):
+    """Decorator for coroutines run as fire-and-forget tasks: an exception is logged with its traceback at the point it
+    happens (an un-awaited task would swallow it until garbage collection), then re-raised."""
+    def deco(f):
+        if not _asyncio.iscoroutinefunction(f):
+            raise TypeError("trace_async_exceptions decorates coroutine functions")
+
+        @_functools.wraps(f)
+        async def wrapped(*a, **k):
+            try:
+                return await f(*a, **k)
+            except _asyncio.CancelledError:
+                raise
+            except Exception:
+                logger.exception("exception in async task %s", f.__qualname__)
+                raise
+        return wrapped
+    return deco(fn) if fn is not None else deco
+
+
+def deprecate_args(*deprecated_names, message: str = ""):
+    """Warn when a caller still passes one of ``deprecated_names`` as a keyword; the argument is dropped."""
+    def deco(fn):
+        @_functools.wraps(fn)
+        def wrapped(*a, **k):
+            for n in deprecated_names:
+                if n in k:
+                    _warnings.warn(f"{fn.__qualname__}: argument '{n}' is deprecated and ignored. {message}".strip(), DeprecationWarning, stacklevel=2)
+                    k.pop(n)
+            return fn(*a, **k)
+        return wrapped
+    return deco
+
+
+def deprecate_inference_params(inference_context, inference_params):
+    """``inference_params=`` was renamed ``inference_context=``: accept the old keyword with a warning."""
+    if inference_context is None and inference_params is not None:
+        _warnings.warn("`inference_params` is deprecated, pass `inference_context`", DeprecationWarning, stacklevel=3)
+        return inference_params
+    return inference_context

@@ -1,0 +1,125 @@
+"""Round-2 helpers in core/utils.py and core/transformer/utils.py."""
+import asyncio
+import warnings
+
+import pytest
+import torch
+
+from dist_utils import run_distributed
+
+
+def test_small_helpers():
+    from megatron_b200.core import config as mcfg, utils as U
+
+    assert U.null_decorator(len) is len and U.null_decorator(nopython=True)(len) is len
+    assert U.round_up_to_nearest_multiple(13, 8) == 16 and U.round_up_to_nearest_multiple(16, 8) == 16
+    assert U.accepts_parameter(lambda a, b=1: 0, "b") and not U.accepts_parameter(lambda a: 0, "b") and U.accepts_parameter(lambda **k: 0, "zz")
+    box = U.WrappedTensor(torch.ones(2))
+    assert box.unwrap().sum() == 2
+    with pytest.raises(RuntimeError):
+        box.unwrap()
+    assert U.get_torch_version().major >= 2 and not U.is_mamba_min_version("0.0.1")
+    lin = torch.nn.Linear(2, 2)
+    seq = torch.nn.Sequential(lin)
+    assert U.is_submodule(lin, seq) and not U.is_submodule(seq, seq) and U.is_submodule(seq, seq, strict=False)
+
+    @U.experimental_api
+    def f():
+        return 1
+
+    @U.experimental_cls("0.20")
+    class C:
+        def __init__(self):
+            self.x = 1
+    mcfg.set_experimental_flag(False)
+    with pytest.raises(U.ExperimentalNotEnabledError):
+        f()
+    with pytest.raises(U.ExperimentalNotEnabledError):
+        C()
+    mcfg.set_experimental_flag(True)
+    assert f() == 1 and C().x == 1
+    mcfg.set_experimental_flag(False)
+
+    @U.deprecate_args("old")
+    def g(a, new=0):
+        return a + new
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert g(1, old=5, new=2) == 3 and any("old" in str(x.message) for x in w)
+    assert U.deprecate_inference_params("ctx", "params") == "ctx"
+
+    @U.trace_async_exceptions
+    async def boom():
+        raise ValueError("x")
+    with pytest.raises(ValueError):
+        U.get_asyncio_loop().run_until_complete(boom())
+    std = torch.stack([U.mup_scaled_init_method_normal(0.02, 4, 4.0)(torch.empty(4096)).std() for _ in range(4)]).mean()
+    assert abs(float(std) - 0.02 / (8 ** 0.5) / 2) < 2e-4
+
+
+def test_flatten_batch_for_packed_sequences():
+    from megatron_b200.core.utils import flatten_batch_for_packed_sequences
+
+    batch = {"tokens": torch.arange(16).view(2, 8), "labels": torch.arange(16).view(2, 8), "loss_mask": torch.ones(2, 8), "position_ids": torch.arange(8).repeat(2, 1),
+             "cu_seqlens": torch.tensor([[0, 3, 8, 8], [0, 5, 6, 8]]), "max_seqlen": torch.tensor([5, 5])}
+    out = flatten_batch_for_packed_sequences(batch)
+    assert out["tokens"].shape == (1, 16) and out["cu_seqlens"].tolist() == [[0, 3, 8, 13, 14, 16]] and out["max_seqlen"].tolist() == [5]
+
+
+def _tp_batch_worker(rank, world):
+    import torch.distributed as dist
+
+    from megatron_b200.core.utils import get_batch_on_this_tp_rank
+
+    full = {"tokens": torch.arange(12).view(2, 6), "labels": torch.arange(12).view(2, 6) + 1, "loss_mask": torch.rand(2, 6), "position_ids": torch.arange(6).repeat(2, 1),
+            "attention_mask": None, "cu_seqlens": torch.tensor([[0, 2, 6]], dtype=torch.int32), "max_seqlen": torch.tensor([4], dtype=torch.int32)}
+    torch.manual_seed(0)
+    full["loss_mask"] = torch.rand(2, 6)
+    mine = full if rank == 0 else None
+    out = get_batch_on_this_tp_rank(mine, has_cu_seqlens=True, broadcast_src_rank=0, broadcast_group=dist.group.WORLD, tp_rank=rank)
+    for k in ("tokens", "labels", "loss_mask", "position_ids", "cu_seqlens", "max_seqlen"):
+        assert torch.equal(out[k], full[k]) and out[k].dtype == full[k].dtype, k
+    assert out["attention_mask"] is None
+    # last pipeline stage without MTP: no tokens travel
+    out = get_batch_on_this_tp_rank(mine, broadcast_src_rank=0, broadcast_group=dist.group.WORLD, tp_rank=rank, pipeline_model_parallel_size=2,
+                                    is_pipeline_first_stage=False, is_pipeline_last_stage=True)
+    if rank != 0:
+        assert out["tokens"] is None and torch.equal(out["labels"], full["labels"])
+    return True
+
+
+def test_get_batch_on_this_tp_rank_two_broadcasts():
+    assert all(run_distributed(_tp_batch_worker, 2))
+
+
+def test_transformer_utils_additions():
+    from megatron_b200.core.transformer import utils as TU
+
+    m = TU.get_sliding_window_causal_mask(4, 6, (2, 0))
+    # query 0 sits at key position 2: sees keys 0..2
+    assert m[0].tolist() == [False, False, False, True, True, True] and m[3].tolist() == [True, True, True, False, False, False]
+    assert TU.is_layer_window_attention((128, 0), 4, 3) and not TU.is_layer_window_attention((128, 0), 4, 4) and not TU.is_layer_window_attention(None, None, 1)
+    assert TU.is_layer_window_attention((128, 0), [1, 0, 1], 3) and not TU.is_layer_window_attention((128, 0), [1, 0, 1], 2)
+    x = torch.randn(64)
+    assert torch.allclose(TU.openai_gelu(x), torch.nn.functional.gelu(x, approximate="tanh"), atol=1e-6)
+    assert torch.allclose(TU.erf_gelu(x), torch.nn.functional.gelu(x), atol=1e-6)
+    assert torch.equal(TU.cat_with_oom_fallback([torch.ones(2), torch.zeros(1)]), torch.tensor([1.0, 1.0, 0.0]))
+
+    class Cfg:
+        sequence_parallel = True
+        cuda_graph_impl = "local"
+
+    class Layer(torch.nn.Module):
+        def __init__(self, cfg):
+            super().__init__()
+            self.config, self.sequence_parallel = cfg, True
+            self.w = torch.nn.Parameter(torch.zeros(1))
+            self.w.sequence_parallel = True
+
+    cfg = Cfg()
+    net = torch.nn.Sequential(Layer(cfg), Layer(cfg))
+    TU.set_model_to_sequence_parallel(net, False, exclude_modules=["1"])
+    assert net[0].sequence_parallel is False and net[0].w.sequence_parallel is False and net[1].sequence_parallel is True and cfg.sequence_parallel is False
+    assert TU.set_model_config_attribute(net, "cuda_graph_impl", "none") == 1 and cfg.cuda_graph_impl == "none"
+    TU.toggle_cuda_graphs(net, "full")
+    assert cfg.cuda_graph_impl == "full"
