@@ -108,3 +108,120 @@ def validate_integrity_and_strict_load(sharded_state_dict, strict: StrictHandlin
     if strict in (StrictHandling.RAISE_UNEXPECTED, StrictHandling.RAISE_ALL) and (missing or (strict == StrictHandling.RAISE_ALL and unexpected)):
         raise CheckpointingException(f"missing keys in checkpoint: {sorted(missing)[:10]}…; unexpected: {sorted(unexpected)[:10]}…")
     return missing, unexpected
+
+
+# ---- round-2 additions: strict-flag parsing, non-strict load adjustment, mismatch reports, file integrity manifest -------
+import hashlib as _hashlib
+import json as _json
+import logging as _logging
+import os as _os
+from concurrent.futures import ThreadPoolExecutor as _Pool
+
+_log = _logging.getLogger(__name__)
+INTEGRITY_FNAME = "integrity.json"          # same file name and schema as the reference, so either side can verify the other's
+_HASH_ALGORITHM = "sha256"
+
+
+def parse_strict_flag(strict) -> StrictHandling:
+    """``'log_all'`` / ``StrictHandling.LOG_ALL`` -> the enum (reference ``validation.py:107``)."""
+    if isinstance(strict, StrictHandling):
+        return strict
+    try:
+        return StrictHandling(strict)
+    except ValueError as e:
+        raise ValueError(f"invalid strict flag '{strict}': one of {[s.value for s in StrictHandling]}") from e
+
+
+def verify_checkpoint(checkpoint_dir: str) -> None:
+    from .core import check_is_distributed_checkpoint
+    if not _os.path.isdir(str(checkpoint_dir)):
+        raise CheckpointingException(f"Checkpoint directory {checkpoint_dir} does not exist")
+    if not check_is_distributed_checkpoint(checkpoint_dir):
+        raise CheckpointingException(f"{checkpoint_dir} is not a distributed checkpoint")
+
+
+def adjust_non_strict_load(sharded_state_dict: ShardedStateDict, sharded_keys_to_remove: Set[str]) -> ShardedStateDict:
+    """Drop the requested entries the checkpoint does not have, so that a non-strict load leaves those tensors untouched."""
+    def keep(x):
+        if isinstance(x, ShardedTensor):
+            return x.key not in sharded_keys_to_remove
+        if isinstance(x, ShardedObject):
+            return x.unique_key not in sharded_keys_to_remove and x.key not in sharded_keys_to_remove
+        return True
+
+    def walk(d):
+        if isinstance(d, dict):
+            return {k: walk(v) for k, v in d.items() if keep(v)}
+        if isinstance(d, list):
+            return [walk(v) for v in d if keep(v)]
+        return d
+    return walk(sharded_state_dict)
+
+
+def maybe_report_missing_and_unexpected_keys(strict: StrictHandling, missing_keys: Set[str], unexpected_keys: Set[str], raise_error: bool = True) -> None:
+    """Log or raise according to the strictness (reference ``validation.py:285``).  "missing" = requested but not in the
+    checkpoint is reported under the *unexpected* policies (the application expected them), as in the reference."""
+    if not missing_keys and not unexpected_keys:
+        return
+    parts = []
+    if missing_keys:
+        parts.append(f"Missing keys (in the checkpoint, not requested): {sorted(missing_keys)[:20]}{' …' if len(missing_keys) > 20 else ''}")
+    if unexpected_keys:
+        parts.append(f"Unexpected keys (requested, not in the checkpoint): {sorted(unexpected_keys)[:20]}{' …' if len(unexpected_keys) > 20 else ''}")
+    msg = "Some keys found in the checkpoint are missing in the provided sharded state dict or vice versa. " + " ".join(parts)
+    raise_all = strict == StrictHandling.RAISE_ALL and (missing_keys or unexpected_keys)
+    raise_unexp = strict == StrictHandling.RAISE_UNEXPECTED and unexpected_keys
+    if raise_error and (raise_all or raise_unexp):
+        raise CheckpointingException(msg)
+    if strict in (StrictHandling.LOG_ALL, StrictHandling.LOG_UNEXPECTED, StrictHandling.RAISE_ALL, StrictHandling.RAISE_UNEXPECTED):
+        _log.warning(msg)
+
+
+def _compute_file_hash(path: str, chunk: int = 8 << 20) -> str:
+    h = _hashlib.sha256()
+    with open(path, "rb") as f:
+        while True:
+            b = f.read(chunk)
+            if not b:
+                break
+            h.update(b)
+    return h.hexdigest()
+
+
+def _manifest_files(checkpoint_dir: str):
+    return sorted(e for e in _os.listdir(checkpoint_dir) if e != INTEGRITY_FNAME and _os.path.isfile(_os.path.join(checkpoint_dir, e)))
+
+
+def save_integrity_manifest(checkpoint_dir: str, workers: int = 8) -> None:
+    """SHA-256 of every file of the checkpoint -> ``integrity.json`` (call on ONE rank after the save has been finalized).
+    Hashing releases the GIL, so a small thread pool reads the shard files concurrently (NVMe / parallel FS bound)."""
+    names = _manifest_files(checkpoint_dir)
+    with _Pool(max(1, min(workers, len(names) or 1))) as pool:
+        digests = list(pool.map(lambda n: _compute_file_hash(_os.path.join(checkpoint_dir, n)), names))
+    tmp = _os.path.join(checkpoint_dir, INTEGRITY_FNAME + ".tmp")
+    with open(tmp, "w") as f:
+        _json.dump({"algorithm": _HASH_ALGORITHM, "files": dict(zip(names, digests))}, f, indent=2)
+    _os.replace(tmp, _os.path.join(checkpoint_dir, INTEGRITY_FNAME))
+
+
+def verify_integrity_manifest(checkpoint_dir: str, workers: int = 8) -> None:
+    """Raise ``CheckpointingException`` listing every missing, extra or corrupted file.  A checkpoint without a manifest
+    passes with a warning (older checkpoints)."""
+    path = _os.path.join(checkpoint_dir, INTEGRITY_FNAME)
+    if not _os.path.isfile(path):
+        _log.warning("no %s in %s: integrity not verified", INTEGRITY_FNAME, checkpoint_dir)
+        return
+    with open(path) as f:
+        payload = _json.load(f)
+    if payload.get("algorithm") != _HASH_ALGORITHM:
+        raise CheckpointingException(f"integrity manifest uses unsupported algorithm {payload.get('algorithm')!r}")
+    want = payload.get("files", {})
+    have = set(_manifest_files(checkpoint_dir))
+    problems = [f"missing file: {n}" for n in sorted(set(want) - have)] + [f"file not in manifest: {n}" for n in sorted(have - set(want))]
+    names = sorted(set(want) & have)
+    with _Pool(max(1, min(workers, len(names) or 1))) as pool:
+        for n, d in zip(names, pool.map(lambda n: _compute_file_hash(_os.path.join(checkpoint_dir, n)), names)):
+            if d != want[n]:
+                problems.append(f"hash mismatch: {n}")
+    if problems:
+        raise CheckpointingException(f"checkpoint {checkpoint_dir} failed the integrity check: " + "; ".join(problems))

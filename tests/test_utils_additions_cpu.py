@@ -123,3 +123,46 @@ def test_transformer_utils_additions():
     assert TU.set_model_config_attribute(net, "cuda_graph_impl", "none") == 1 and cfg.cuda_graph_impl == "none"
     TU.toggle_cuda_graphs(net, "full")
     assert cfg.cuda_graph_impl == "full"
+
+
+def test_checkpoint_integrity_manifest_and_strict_helpers(tmp_path):
+    import os
+    import sys
+
+    from megatron_b200.core import dist_checkpointing as dc
+    from megatron_b200.core.dist_checkpointing import validation as V
+    from megatron_b200.core.dist_checkpointing.core import CheckpointingException
+    from megatron_b200.core.dist_checkpointing.mapping import ShardedTensor
+
+    ck = str(tmp_path / "ck")
+    os.makedirs(ck)
+    sd = {"a": ShardedTensor.from_rank_offsets("a", torch.arange(6.0)), "b": ShardedTensor.from_rank_offsets("b", torch.ones(3))}
+    dc.save(sd, ck)
+    V.verify_checkpoint(ck)
+    with pytest.raises(CheckpointingException):
+        V.verify_checkpoint(str(tmp_path / "nope"))
+    V.save_integrity_manifest(ck)
+    V.verify_integrity_manifest(ck)
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    if os.path.isdir(ref):                                   # the unmodified reference accepts our manifest
+        sys.path.insert(0, ref)
+        try:
+            from megatron.core.dist_checkpointing.validation import verify_integrity_manifest as ref_verify
+            ref_verify(ck)
+        finally:
+            sys.path.remove(ref)
+    victim = next(n for n in sorted(os.listdir(ck)) if n.endswith(".distcp"))
+    with open(os.path.join(ck, victim), "r+b") as f:
+        f.seek(10)
+        f.write(b"\xff\xfe")
+    with pytest.raises(CheckpointingException, match="hash mismatch"):
+        V.verify_integrity_manifest(ck)
+    assert V.parse_strict_flag("log_all") is V.StrictHandling.LOG_ALL and V.parse_strict_flag(V.StrictHandling.RAISE_ALL) is V.StrictHandling.RAISE_ALL
+    with pytest.raises(ValueError):
+        V.parse_strict_flag("bogus")
+    pruned = V.adjust_non_strict_load({"m": dict(sd), "l": [sd["a"]]}, {"a"})
+    assert list(pruned["m"]) == ["b"] and pruned["l"] == []
+    with pytest.raises(CheckpointingException):
+        V.maybe_report_missing_and_unexpected_keys(V.StrictHandling.RAISE_ALL, {"x"}, set())
+    V.maybe_report_missing_and_unexpected_keys(V.StrictHandling.LOG_ALL, {"x"}, {"y"})
+    V.maybe_report_missing_and_unexpected_keys(V.StrictHandling.RAISE_UNEXPECTED, {"x"}, set())     # only "unexpected" raises here
