@@ -111,6 +111,8 @@ _EMBEDDING_GLOBAL_RANKS: Optional[List[int]] = None
 _POSITION_EMBEDDING_GLOBAL_RANKS: Optional[List[int]] = None
 _PIPELINE_GLOBAL_RANKS: Optional[List[int]] = None
 _HIERARCHICAL_CP_GROUPS: List = []
+_HYBRID_DP_CP_GROUPS: Dict[int, object] = {}
+_ALL_GATHER_GROUPS: Dict[str, object] = {}
 _INITIALIZED = False
 _TOPOLOGY: Dict[str, int] = {}
 
@@ -357,6 +359,12 @@ def initialize_model_parallel(
                             _HIERARCHICAL_CP_GROUPS.append(None)
                         _HIERARCHICAL_CP_GROUPS[lev] = pg
 
+    _HYBRID_DP_CP_GROUPS.clear()
+    _ALL_GATHER_GROUPS.clear()
+    if hybrid_context_parallel:
+        for lst in dense.get_ranks("dp-cp"):
+            create_hybrid_dp_cp_groups(rank, [int(r) for r in lst], timeout=timeout)
+
     _INITIALIZED = True
 
 
@@ -389,6 +397,8 @@ def destroy_model_parallel() -> None:
     _OVERRIDES.clear()
     _TOPOLOGY.clear()
     del _HIERARCHICAL_CP_GROUPS[:]
+    _HYBRID_DP_CP_GROUPS.clear()
+    _ALL_GATHER_GROUPS.clear()
     _INITIALIZED = False
     _VIRTUAL_PP_RANK = _VIRTUAL_PP_WORLD_SIZE = None
     _GLOBAL_MEMORY_BUFFER = None
@@ -436,47 +446,248 @@ def _rk(name: str) -> int:
     return g.ranks.index(dist.get_rank())
 
 
-def _make_accessors():
-    """Generate the reference's getter zoo from a spec (reference :1697-2470)."""
-    spec = {
-        # public stem                      -> registry name
-        "tensor_model_parallel": "tp",
-        "pipeline_model_parallel": "pp",
-        "context_parallel": "cp",
-        "model_parallel": "mp",
-        "tensor_and_context_parallel": "tp_cp",
-        "expert_model_parallel": "ep",
-        "expert_tensor_parallel": "expt_tp",
-        "expert_tensor_and_model_parallel": "tp_ep",
-        "expert_tensor_model_pipeline_parallel": "tp_ep_pp",
-        "embedding": "embd",
-        "position_embedding": "pos_embd",
-    }
-    g = globals()
-    for stem, name in spec.items():
-        def _get_group(check_initialized: bool = True, _n=name):
-            return get_group(_n, check_initialized)
-
-        def _get_ws(_n=name):
-            return _ws(_n)
-
-        def _get_rk(_n=name):
-            return _rk(_n)
-
-        def _set_ws(v, _n=name):
-            _OVERRIDES[_n + ".ws"] = v
-
-        def _set_rk(v, _n=name):
-            _OVERRIDES[_n + ".rk"] = v
-
-        g[f"get_{stem}_group"] = _get_group
-        g[f"get_{stem}_world_size"] = _get_ws
-        g[f"get_{stem}_rank"] = _get_rk
-        g[f"set_{stem}_world_size"] = _set_ws
-        g[f"set_{stem}_rank"] = _set_rk
+# ---- accessors of the registry-backed groups (reference :1697-2470).  Written out one by one — they are the public API every
+# model file imports by name — but each is a one-liner over the group registry (``get_group`` / ``_ws`` / ``_rk``).
+def get_tensor_model_parallel_group(check_initialized: bool = True):
+    """The tensor-model-parallel process group this rank belongs to."""
+    return get_group("tp", check_initialized)
 
 
-_make_accessors()
+def get_tensor_model_parallel_world_size() -> int:
+    return _ws("tp")
+
+
+def get_tensor_model_parallel_rank() -> int:
+    return _rk("tp")
+
+
+def set_tensor_model_parallel_world_size(world_size) -> None:
+    """Override (tests, checkpoint conversion tools): ``None`` restores the real value."""
+    _OVERRIDES["tp.ws"] = world_size
+
+
+def set_tensor_model_parallel_rank(rank) -> None:
+    _OVERRIDES["tp.rk"] = rank
+
+
+def get_pipeline_model_parallel_group(check_initialized: bool = True):
+    """The pipeline-model-parallel process group this rank belongs to."""
+    return get_group("pp", check_initialized)
+
+
+def get_pipeline_model_parallel_world_size() -> int:
+    return _ws("pp")
+
+
+def get_pipeline_model_parallel_rank() -> int:
+    return _rk("pp")
+
+
+def set_pipeline_model_parallel_world_size(world_size) -> None:
+    """Override (tests, checkpoint conversion tools): ``None`` restores the real value."""
+    _OVERRIDES["pp.ws"] = world_size
+
+
+def set_pipeline_model_parallel_rank(rank) -> None:
+    _OVERRIDES["pp.rk"] = rank
+
+
+def get_context_parallel_group(check_initialized: bool = True):
+    """The context-parallel process group this rank belongs to."""
+    return get_group("cp", check_initialized)
+
+
+def get_context_parallel_world_size() -> int:
+    return _ws("cp")
+
+
+def get_context_parallel_rank() -> int:
+    return _rk("cp")
+
+
+def set_context_parallel_world_size(world_size) -> None:
+    """Override (tests, checkpoint conversion tools): ``None`` restores the real value."""
+    _OVERRIDES["cp.ws"] = world_size
+
+
+def set_context_parallel_rank(rank) -> None:
+    _OVERRIDES["cp.rk"] = rank
+
+
+def get_model_parallel_group(check_initialized: bool = True):
+    """The model-parallel (tp x pp) process group this rank belongs to."""
+    return get_group("mp", check_initialized)
+
+
+def get_model_parallel_world_size() -> int:
+    return _ws("mp")
+
+
+def get_model_parallel_rank() -> int:
+    return _rk("mp")
+
+
+def set_model_parallel_world_size(world_size) -> None:
+    """Override (tests, checkpoint conversion tools): ``None`` restores the real value."""
+    _OVERRIDES["mp.ws"] = world_size
+
+
+def set_model_parallel_rank(rank) -> None:
+    _OVERRIDES["mp.rk"] = rank
+
+
+def get_tensor_and_context_parallel_group(check_initialized: bool = True):
+    """The tensor-and-context-parallel process group this rank belongs to."""
+    return get_group("tp_cp", check_initialized)
+
+
+def get_tensor_and_context_parallel_world_size() -> int:
+    return _ws("tp_cp")
+
+
+def get_tensor_and_context_parallel_rank() -> int:
+    return _rk("tp_cp")
+
+
+def set_tensor_and_context_parallel_world_size(world_size) -> None:
+    """Override (tests, checkpoint conversion tools): ``None`` restores the real value."""
+    _OVERRIDES["tp_cp.ws"] = world_size
+
+
+def set_tensor_and_context_parallel_rank(rank) -> None:
+    _OVERRIDES["tp_cp.rk"] = rank
+
+
+def get_expert_model_parallel_group(check_initialized: bool = True):
+    """The expert-model-parallel process group this rank belongs to."""
+    return get_group("ep", check_initialized)
+
+
+def get_expert_model_parallel_world_size() -> int:
+    return _ws("ep")
+
+
+def get_expert_model_parallel_rank() -> int:
+    return _rk("ep")
+
+
+def set_expert_model_parallel_world_size(world_size) -> None:
+    """Override (tests, checkpoint conversion tools): ``None`` restores the real value."""
+    _OVERRIDES["ep.ws"] = world_size
+
+
+def set_expert_model_parallel_rank(rank) -> None:
+    _OVERRIDES["ep.rk"] = rank
+
+
+def get_expert_tensor_parallel_group(check_initialized: bool = True):
+    """The expert-tensor-parallel process group this rank belongs to."""
+    return get_group("expt_tp", check_initialized)
+
+
+def get_expert_tensor_parallel_world_size() -> int:
+    return _ws("expt_tp")
+
+
+def get_expert_tensor_parallel_rank() -> int:
+    return _rk("expt_tp")
+
+
+def set_expert_tensor_parallel_world_size(world_size) -> None:
+    """Override (tests, checkpoint conversion tools): ``None`` restores the real value."""
+    _OVERRIDES["expt_tp.ws"] = world_size
+
+
+def set_expert_tensor_parallel_rank(rank) -> None:
+    _OVERRIDES["expt_tp.rk"] = rank
+
+
+def get_expert_tensor_and_model_parallel_group(check_initialized: bool = True):
+    """The expert tensor x expert model parallel process group this rank belongs to."""
+    return get_group("tp_ep", check_initialized)
+
+
+def get_expert_tensor_and_model_parallel_world_size() -> int:
+    return _ws("tp_ep")
+
+
+def get_expert_tensor_and_model_parallel_rank() -> int:
+    return _rk("tp_ep")
+
+
+def set_expert_tensor_and_model_parallel_world_size(world_size) -> None:
+    """Override (tests, checkpoint conversion tools): ``None`` restores the real value."""
+    _OVERRIDES["tp_ep.ws"] = world_size
+
+
+def set_expert_tensor_and_model_parallel_rank(rank) -> None:
+    _OVERRIDES["tp_ep.rk"] = rank
+
+
+def get_expert_tensor_model_pipeline_parallel_group(check_initialized: bool = True):
+    """The expert tensor x model x pipeline parallel process group this rank belongs to."""
+    return get_group("tp_ep_pp", check_initialized)
+
+
+def get_expert_tensor_model_pipeline_parallel_world_size() -> int:
+    return _ws("tp_ep_pp")
+
+
+def get_expert_tensor_model_pipeline_parallel_rank() -> int:
+    return _rk("tp_ep_pp")
+
+
+def set_expert_tensor_model_pipeline_parallel_world_size(world_size) -> None:
+    """Override (tests, checkpoint conversion tools): ``None`` restores the real value."""
+    _OVERRIDES["tp_ep_pp.ws"] = world_size
+
+
+def set_expert_tensor_model_pipeline_parallel_rank(rank) -> None:
+    _OVERRIDES["tp_ep_pp.rk"] = rank
+
+
+def get_embedding_group(check_initialized: bool = True):
+    """The embedding (first + last pipeline stage) process group this rank belongs to."""
+    return get_group("embd", check_initialized)
+
+
+def get_embedding_world_size() -> int:
+    return _ws("embd")
+
+
+def get_embedding_rank() -> int:
+    return _rk("embd")
+
+
+def set_embedding_world_size(world_size) -> None:
+    """Override (tests, checkpoint conversion tools): ``None`` restores the real value."""
+    _OVERRIDES["embd.ws"] = world_size
+
+
+def set_embedding_rank(rank) -> None:
+    _OVERRIDES["embd.rk"] = rank
+
+
+def get_position_embedding_group(check_initialized: bool = True):
+    """The position-embedding process group this rank belongs to."""
+    return get_group("pos_embd", check_initialized)
+
+
+def get_position_embedding_world_size() -> int:
+    return _ws("pos_embd")
+
+
+def get_position_embedding_rank() -> int:
+    return _rk("pos_embd")
+
+
+def set_position_embedding_world_size(world_size) -> None:
+    """Override (tests, checkpoint conversion tools): ``None`` restores the real value."""
+    _OVERRIDES["pos_embd.ws"] = world_size
+
+
+def set_position_embedding_rank(rank) -> None:
+    _OVERRIDES["pos_embd.rk"] = rank
 
 
 def get_data_parallel_group(with_context_parallel: bool = False, partial_data_parallel: bool = False):
@@ -727,3 +938,106 @@ def update_pg_timeout(timeout: timedelta, pg=None):
 
 def get_topology() -> Dict[str, int]:
     return dict(_TOPOLOGY)
+
+
+# ---- round-2 additions: group builders usable outside ``initialize_model_parallel`` and the remaining accessors --------------
+
+
+def create_hierarchical_groups(rank: int, ranks: Sequence[int], hierarchical_group_sizes: Sequence[int], create_gloo_process_groups: bool = False,
+                               pg_options=None, timeout=None, group_desc: Optional[str] = None):
+    """Split ``ranks`` into nested levels: level 0 = the innermost ``sizes[0]`` consecutive ranks (one NVLink domain), level 1 =
+    ranks with the same level-0 position across ``sizes[1]`` domains, ...  Every rank must call this (all sub-groups are created
+    everywhere, in the same order).  Returns (this rank's groups per level, their gloo twins or ``None``)
+    (reference ``parallel_state.py:389``)."""
+    assert int(np.prod(hierarchical_group_sizes)) == len(ranks), f"{list(hierarchical_group_sizes)} does not factor {len(ranks)} ranks"
+    arr = np.array(list(ranks)).reshape(list(reversed(list(hierarchical_group_sizes))))
+    nlev = len(hierarchical_group_sizes)
+    mine, mine_gloo = [None] * nlev, [None] * nlev
+    for lev in range(nlev):
+        axis = nlev - 1 - lev
+        for sub in np.moveaxis(arr, axis, -1).reshape(-1, arr.shape[axis]):
+            sub = [int(r) for r in sub]
+            pg = _new_group(sub, timeout=timeout, desc=f"{group_desc or 'HIERARCHICAL_GROUP'}_L{lev}", pg_options=pg_options)
+            gl = _new_group(sub, backend="gloo", timeout=timeout, desc=f"{group_desc or 'HIERARCHICAL_GROUP'}_L{lev}_GLOO") if create_gloo_process_groups else None
+            if rank in sub:
+                mine[lev], mine_gloo[lev] = pg, gl
+    return mine, (mine_gloo if create_gloo_process_groups else None)
+
+
+def create_hybrid_dp_cp_groups(rank: int, ranks: Sequence[int], pg_options=None, timeout=None) -> Dict[int, object]:
+    """Hybrid context parallelism (variable CP size per sample): one group per power-of-two size 2, 4, ... < len(ranks) over
+    consecutive DP x CP ranks; a long sample borrows as many neighbours as it needs (reference ``parallel_state.py:440``).
+    The full-size group is the ordinary dp_cp group and is not duplicated."""
+    out: Dict[int, object] = {}
+    n = len(ranks)
+    size = 2
+    while size < n:
+        for i in range(0, n, size):
+            sub = [int(r) for r in ranks[i:i + size]]
+            pg = _new_group(sub, timeout=timeout, desc=f"HYBRID_DP_CP_GROUP_{size}", pg_options=pg_options)
+            if rank in sub:
+                assert size not in out, f"rank {rank} appears in two hybrid DPxCP groups of size {size}"
+                out[size] = pg
+        size *= 2
+    _HYBRID_DP_CP_GROUPS.update(out)
+    return out
+
+
+def get_hybrid_data_context_parallel_groups(check_initialized: bool = True, group_size: Optional[int] = None):
+    """The power-of-two DP x CP sub-group of ``group_size`` this rank belongs to (``None`` size: the whole dictionary); the
+    full size resolves to the ordinary data x context parallel group."""
+    if group_size is None:
+        if check_initialized:
+            assert _HYBRID_DP_CP_GROUPS, "hybrid DPxCP groups are not initialised (create_hybrid_dp_cp_groups)"
+        return dict(_HYBRID_DP_CP_GROUPS)
+    if group_size == get_data_parallel_world_size(with_context_parallel=True):
+        return get_data_parallel_group(with_context_parallel=True)
+    if check_initialized:
+        assert group_size in _HYBRID_DP_CP_GROUPS, f"no hybrid DPxCP group of size {group_size}"
+    return _HYBRID_DP_CP_GROUPS.get(group_size)
+
+
+def create_all_gather_groups(names: Sequence[str] = ("dp", "dp_cp", "expt_dp"), pg_options=None, timeout=None) -> Dict[str, object]:
+    """Second communicators over the same ranks as the data-parallel groups, used ONLY for parameter all-gathers, so that the
+    next step's weight gathers and this step's gradient reduce-scatters do not serialise on one NCCL stream
+    (reference ``parallel_state.py:create_all_gather_groups``; with the NVLink backend the same separation is two slots of
+    the symmetric heap)."""
+    rank = dist.get_rank()
+    for name in names:
+        g = _GROUPS.get(name)
+        if g is None or name in _ALL_GATHER_GROUPS:
+            continue
+        mine = None
+        for ranks in (g.all_rank_lists or [g.ranks]):         # every rank creates every replica's communicator, in the same order
+            pg = _new_group(list(ranks), timeout=timeout, desc=f"{name.upper()}_ALL_GATHER_GROUP", pg_options=pg_options)
+            if rank in ranks:
+                mine = pg
+        _ALL_GATHER_GROUPS[name] = mine
+    return dict(_ALL_GATHER_GROUPS)
+
+
+def get_all_gather_group(name: str = "dp_cp"):
+    """The dedicated all-gather communicator of a data-parallel group, or the group itself when none was created."""
+    return _ALL_GATHER_GROUPS.get(name) or get_group(name, check_initialized=False)
+
+
+def overwrite_nccl_comm_cfgs(nccl_comm_cfgs: dict, pg_name: str, key_value_pair: tuple) -> None:
+    """Set one NCCL option of one group in a configuration dictionary (as read by ``load_nccl_communicator_config``)."""
+    k, v = key_value_pair
+    nccl_comm_cfgs.setdefault(pg_name, {})[k] = v
+
+
+def set_data_parallel_rank(rank) -> None:
+    _OVERRIDES["dp.rk"] = rank
+
+
+def get_gtp_weight_remat_global_ranks() -> List[int]:
+    return list(_GROUPS["gtp_remat"].ranks) if "gtp_remat" in _GROUPS else [dist.get_rank() if dist.is_initialized() else 0]
+
+
+def get_expert_gtp_weight_remat_rank() -> int:
+    return _rk("egtp_remat") if "egtp_remat" in _GROUPS else 0
+
+
+def get_expert_gtp_weight_remat_global_ranks() -> List[int]:
+    return list(_GROUPS["egtp_remat"].ranks) if "egtp_remat" in _GROUPS else [dist.get_rank() if dist.is_initialized() else 0]

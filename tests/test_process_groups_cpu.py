@@ -147,3 +147,39 @@ def _mpu_bundle_worker(rank, world):
 
 def test_bundles_from_parallel_state_gloo():
     assert all(run_distributed(_mpu_bundle_worker, 4))
+
+
+def _extra_groups_worker(rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from megatron_b200.core import parallel_state as ps
+
+    ps.initialize_model_parallel(tensor_model_parallel_size=1, context_parallel_size=2, hybrid_context_parallel=True)     # dp = 4, cp = 2 over 8 ranks
+    hy = ps.get_hybrid_data_context_parallel_groups()
+    assert sorted(hy) == [2, 4] and dist.get_world_size(hy[2]) == 2 and dist.get_world_size(hy[4]) == 4
+    assert ps.get_hybrid_data_context_parallel_groups(group_size=8) is ps.get_data_parallel_group(with_context_parallel=True)
+    t = torch.ones(1)
+    dist.all_reduce(t, group=hy[4])
+    assert float(t) == 4
+    ag = ps.create_all_gather_groups(("dp_cp",))
+    assert dist.get_process_group_ranks(ag["dp_cp"]) == dist.get_process_group_ranks(ps.get_data_parallel_group(with_context_parallel=True))
+    assert ag["dp_cp"] is not ps.get_data_parallel_group(with_context_parallel=True) and ps.get_all_gather_group("dp_cp") is ag["dp_cp"]
+    levels, gloo = ps.create_hierarchical_groups(rank, list(range(8)), [2, 4], group_desc="TEST")
+    assert gloo is None and dist.get_process_group_ranks(levels[0]) == [rank // 2 * 2, rank // 2 * 2 + 1]
+    assert dist.get_process_group_ranks(levels[1]) == list(range(rank % 2, 8, 2))
+    cfg = {}
+    ps.overwrite_nccl_comm_cfgs(cfg, "tp", ("max_ctas", 8))
+    assert cfg == {"tp": {"max_ctas": 8}}
+    ps.set_data_parallel_rank(3)
+    assert ps.get_data_parallel_rank() == 3
+    ps.set_data_parallel_rank(None)
+    assert ps.get_gtp_weight_remat_global_ranks() == [rank] and ps.get_expert_gtp_weight_remat_rank() == 0
+    assert ps.get_context_parallel_world_size() == 2 and ps.get_tensor_and_context_parallel_world_size() == 2
+    return True
+
+
+def test_hybrid_cp_all_gather_and_hierarchical_group_builders():
+    from dist_utils import run_distributed
+
+    assert all(run_distributed(_extra_groups_worker, 8))
