@@ -86,23 +86,31 @@ def sparse_attention_topk(q_abs: torch.Tensor, kv: torch.Tensor, idx: torch.Tens
 
 
 def compute_dsa_indexer_loss(index_scores: torch.Tensor, q_abs: torch.Tensor, kv: torch.Tensor, scale: float, loss_coeff: float,
-                             idx: Optional[torch.Tensor] = None, valid: Optional[torch.Tensor] = None, q_offset: int = 0) -> torch.Tensor:
+                             idx: Optional[torch.Tensor] = None, valid: Optional[torch.Tensor] = None, q_offset: int = 0,
+                             cu_seqlens: Optional[torch.Tensor] = None, query_valid_rows: Optional[torch.Tensor] = None,
+                             calculate_per_token_loss: bool = False) -> torch.Tensor:
     """KL( p_attn ‖ softmax(I) ), where p_attn is the main branch's attention distribution summed over heads and renormalised (detached).
-    With ``idx`` (sparse variant) both distributions are restricted to the selected keys; otherwise they cover all causal keys."""
+    With ``idx`` (sparse variant) both distributions are restricted to the selected keys; otherwise they cover all causal keys.
+    ``cu_seqlens`` (packed batch, b = 1): visibility is additionally confined to the query's own sequence; ``query_valid_rows``
+    [b, sq] removes padding rows from the average; ``calculate_per_token_loss`` returns the sum (the trainer normalises)."""
+    from .dsa_indexer_loss import indexer_loss_from_target, normalize_indexer_target
+    from .dsa_masking import build_valid_mask_from_starts_ends, generate_varlen_mask_params_for_positions
     b, sq, sk = index_scores.shape
     with torch.no_grad():
         att = torch.einsum("sbnc,tbc->bnst", q_abs.float(), kv.float()) * scale
         qpos = torch.arange(sq, device=att.device)[:, None] + q_offset
         future = torch.arange(sk, device=att.device)[None, :] > qpos
+        if cu_seqlens is not None:
+            st, en = generate_varlen_mask_params_for_positions(cu_seqlens, qpos.view(-1))
+            future = ~build_valid_mask_from_starts_ends(st, en, torch.arange(sk, device=att.device))
         att = torch.softmax(att.masked_fill(future[None, None], float("-inf")), dim=-1).sum(dim=1)          # [b, sq, sk]
     logits = index_scores.masked_fill(future[None], float("-inf"))
     if idx is not None:
         att = torch.gather(att, 2, idx) * valid
         logits = torch.gather(logits, 2, idx).masked_fill(~valid, float("-inf"))
-    target = att / att.sum(dim=-1, keepdim=True).clamp(min=1e-20)
+    visible = torch.isfinite(logits)
     logp = torch.log_softmax(logits, dim=-1)
-    kl = torch.where(target > 0, target * (torch.log(target.clamp(min=1e-20)) - logp), torch.zeros_like(target)).sum(dim=-1)
-    return loss_coeff * kl.mean()
+    return indexer_loss_from_target(normalize_indexer_target(att), logp, loss_coeff, query_valid_rows, calculate_per_token_loss, visible)
 
 
 class DSAIndexerLossAutoScaler(torch.autograd.Function):
