@@ -301,3 +301,112 @@ def track_moe_metrics(loss_scale, iteration, writer=None, wandb_writer=None, tot
                     writer.add_scalar(f"moe/{name}_layer_{i}", lv, iteration)
     clear_aux_losses_tracker()
     return out
+
+
+# ---- round-2 additions: helpers the router / dispatchers expose by name (reference ``moe_utils.py``) ---------------------
+RandomSTE = _RandomSTE
+
+
+def get_tokens_per_expert_and_token_count(routing_map: torch.Tensor, reduce_group=None, topk: Optional[int] = None, with_padding_mask: bool = False):
+    """(global tokens per expert, local token count, global token count).  With a padding mask the routing map has all-zero rows
+    for padding tokens, so the counts come from the map itself (``sum / topk``) instead of its height."""
+    local = routing_map.sum(dim=0)
+    world = torch.distributed.get_world_size(reduce_group) if (reduce_group is not None and torch.distributed.is_initialized()) else 1
+    glob = local.clone()
+    if world > 1:
+        torch.distributed.all_reduce(glob, group=reduce_group)
+    if with_padding_mask:
+        assert topk, "topk is needed to count tokens under a padding mask"
+        return glob, local.sum() / topk, glob.sum() / topk
+    return glob, routing_map.shape[0], routing_map.shape[0] * world
+
+
+def compute_routing_scores_for_aux_loss(logits: torch.Tensor, topk: int, score_function: str, fused: bool = False, padding_mask: Optional[torch.Tensor] = None):
+    """Scores used by the balancing losses: NORMALISED over all experts (softmax, or sigmoid / sqrt-softplus divided by their
+    row sum) with the plain top-k map of those scores — independent of the bias / group limits the real routing applies.
+    ``padding_mask``: True = padding token (contributes nothing).  ``fused`` selects the CUDA top-k kernel on GPU."""
+    x = logits.float()
+    if score_function == "softmax":
+        scores = torch.softmax(x, dim=-1)
+    elif score_function in ("sigmoid", "sqrtsoftplus"):
+        scores = torch.sigmoid(x) if score_function == "sigmoid" else torch.nn.functional.softplus(x).sqrt()
+        scores = scores / (scores.sum(dim=-1, keepdim=True) + 1e-20)
+    else:
+        raise ValueError(f"Invalid score_function: {score_function}")
+    top = torch.topk(scores, k=topk, dim=1).indices
+    routing_map = torch.zeros_like(logits, dtype=torch.bool).scatter_(1, top, True)
+    if padding_mask is not None:
+        keep = (~padding_mask).unsqueeze(-1)
+        routing_map, scores = routing_map & keep, scores * keep
+    return routing_map, scores
+
+
+def get_updated_expert_bias(tokens_per_expert: torch.Tensor, expert_bias: torch.Tensor, expert_bias_update_rate: float, tp_dp_cp_group=None) -> torch.Tensor:
+    """Aux-loss-free balancing (arXiv 2408.15664): experts that received fewer tokens than the average get their routing bias
+    raised by ``rate``, the others lowered.  Counts are summed over every rank that sees different tokens of the step.
+    Accepts stacked [num_layers, num_experts] inputs so that ONE all-reduce serves all layers."""
+    with torch.no_grad():
+        if tp_dp_cp_group is None and torch.distributed.is_initialized():
+            from ... import parallel_state as ps
+            tp_dp_cp_group = ps.get_tensor_and_data_parallel_group(with_context_parallel=True) if ps.model_parallel_is_initialized() else None
+        if tp_dp_cp_group is not None and torch.distributed.get_world_size(tp_dp_cp_group) > 1:
+            torch.distributed.all_reduce(tokens_per_expert, group=tp_dp_cp_group)
+        mean = tokens_per_expert.sum(dim=-1, keepdim=True) / tokens_per_expert.shape[-1]
+        return expert_bias + torch.sign(mean - tokens_per_expert) * expert_bias_update_rate
+
+
+def maybe_move_tensor_to_cpu(tensor, as_numpy: bool = False, record_stream: bool = False):
+    """Non-blocking device->pinned-host copy of small routing statistics (tokens per expert); ``record_stream`` keeps the
+    source alive until the copy has run when the caller drops it immediately."""
+    if torch.is_tensor(tensor) and tensor.is_cuda:
+        host = torch.empty(tensor.shape, dtype=tensor.dtype, device="cpu", pin_memory=True)
+        host.copy_(tensor, non_blocking=True)
+        if record_stream:
+            tensor.record_stream(torch.cuda.current_stream())
+        tensor = host
+    return tensor.numpy() if (as_numpy and torch.is_tensor(tensor)) else tensor
+
+
+class RouterGatingLinearFunction(torch.autograd.Function):
+    """Gating GEMM in ``router_dtype`` (fp32 / fp64) without keeping up-cast copies of the activations: inputs are saved in
+    their own dtype and re-cast in backward; gradients come back in the inputs' dtypes."""
+
+    @staticmethod
+    def forward(ctx, inp, weight, bias, router_dtype):
+        ctx.save_for_backward(inp, weight, bias)
+        ctx.router_dtype = router_dtype
+        x = inp.reshape(-1, inp.shape[-1]).to(router_dtype)
+        out = x @ weight.to(router_dtype).t()
+        if bias is not None:
+            out = out + bias.to(router_dtype)
+        return out.view(*inp.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, g):
+        inp, weight, bias = ctx.saved_tensors
+        dt = ctx.router_dtype
+        g2 = g.reshape(-1, g.shape[-1]).to(dt)
+        gi = (g2 @ weight.to(dt)).to(inp.dtype).view(inp.shape) if ctx.needs_input_grad[0] else None
+        gw = (g2.t() @ inp.reshape(-1, inp.shape[-1]).to(dt)).to(weight.dtype) if ctx.needs_input_grad[1] else None
+        gb = g2.sum(0).to(bias.dtype) if (bias is not None and ctx.needs_input_grad[2]) else None
+        return gi, gw, gb, None
+
+
+def router_gating_linear(inp: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], router_dtype: torch.dtype):
+    return RouterGatingLinearFunction.apply(inp, weight, bias, router_dtype)
+
+
+def get_align_size_for_quantization(config) -> int:
+    """Multiple every expert's token count is padded to so that the block-scaled grouped GEMM sees whole scale blocks:
+    128 rows (one scale atom of the tcgen05 block-scaled MMA) for MXFP8 / NVFP4, 16 for per-tensor FP8, none for bf16."""
+    if getattr(config, "fp4", None):
+        return 128
+    if getattr(config, "fp8", None):
+        return 128 if getattr(config, "fp8_recipe", None) in ("mxfp8", "blockwise") else 16
+    return 0
+
+
+def get_default_pg_collection():
+    """The process groups MoE layers use when none are passed: read from the global parallel state."""
+    from ...process_groups_config import ProcessGroupCollection
+    return ProcessGroupCollection.use_mpu_process_groups()

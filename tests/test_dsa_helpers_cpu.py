@@ -88,3 +88,42 @@ def test_valid_rows_from_padded_packing():
     v = extract_query_valid_rows_from_packed_seq_params(p, 8, "cpu")
     assert v.tolist() == [True, True, True, False, True, True, False, False]
     assert normalize_query_valid_rows(v, b=2, sq=8, device="cpu").shape == (2, 8)
+
+
+def test_moe_utils_additions_match_reference():
+    from megatron_b200.core.transformer.moe import moe_utils as M
+
+    if not os.path.isdir(REF):
+        pytest.skip("baseline/_ref is not installed")
+    sys.path.insert(0, REF)
+    try:
+        from megatron.core.transformer.moe import moe_utils as R
+    finally:
+        sys.path.remove(REF)
+    torch.manual_seed(0)
+    logits = torch.randn(10, 8)
+    pad = torch.rand(10) > 0.7
+    for fn in ("softmax", "sigmoid", "sqrtsoftplus"):
+        for pm in (None, pad):
+            m1, s1 = M.compute_routing_scores_for_aux_loss(logits, 2, fn, padding_mask=pm)
+            m2, s2 = R.compute_routing_scores_for_aux_loss(logits, 2, fn, padding_mask=pm)
+            assert torch.equal(m1.bool(), m2.bool()) and torch.allclose(s1, s2, atol=1e-7), fn
+    cnt = torch.tensor([[5.0, 1.0, 3.0, 3.0], [2.0, 2.0, 2.0, 2.0]])
+    new = M.get_updated_expert_bias(cnt.clone(), torch.zeros(2, 4), 0.01)
+    assert torch.allclose(new, torch.tensor([[-0.01, 0.01, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0]]))
+    rm = torch.tensor([[1, 1, 0], [0, 0, 0], [1, 0, 1]], dtype=torch.bool)
+    g, loc, tot = M.get_tokens_per_expert_and_token_count(rm, None, topk=2, with_padding_mask=True)
+    assert g.tolist() == [2, 1, 1] and float(loc) == 2.0 and float(tot) == 2.0
+    # fp32 gating of bf16 activations: gradients return in bf16 and match autograd of the plain formula
+    x = torch.randn(6, 16, dtype=torch.bfloat16, requires_grad=True)
+    w = torch.randn(4, 16, dtype=torch.bfloat16, requires_grad=True)
+    out = M.router_gating_linear(x, w, None, torch.float32)
+    assert out.dtype == torch.float32
+    gout = torch.randn_like(out)
+    gx, gw = torch.autograd.grad(out, (x, w), gout)
+    rx, rw = torch.autograd.grad(x.float() @ w.float().t(), (x, w), gout)
+    assert gx.dtype == torch.bfloat16 and torch.allclose(gx.float(), rx.float(), atol=2e-2, rtol=2e-2) and torch.allclose(gw.float(), rw.float(), atol=5e-2, rtol=2e-2)
+
+    class C:
+        fp8, fp4, fp8_recipe = "e4m3", None, "mxfp8"
+    assert M.get_align_size_for_quantization(C) == 128
