@@ -169,56 +169,9 @@ def graph_module(module: torch.nn.Module, warmup_steps: int = 3) -> torch.nn.Mod
     return module
 
 
-class FullCudaGraphWrapper:
-    """Capture a WHOLE forward-backward step in one graph (reference ``core/full_cuda_graph.py:138-267``).
-
-    ``wrapped(*, data_iterator, ...)`` copies the next batch into static buffers, replays the graph and returns
-    the static loss tensors.  The wrapped function must be capture-safe (static shapes, no host sync)."""
-
-    def __init__(self, forward_backward_func, cuda_graph_warmup_steps: int = 1):
-        self.fn = forward_backward_func
-        self.warmup = cuda_graph_warmup_steps
-        self.calls = {"train": 0, "eval": 0}
-        self.graph: Dict[str, torch.cuda.CUDAGraph] = {}
-        self.static_batches: Dict[str, List[dict]] = {}
-        self.result: Dict[str, Any] = {}
-
-    class _StaticIter:
-        def __init__(self, batches):
-            self.batches, self.i = batches, 0
-
-        def __iter__(self):
-            return self
-
-        def __next__(self):
-            b = self.batches[self.i % len(self.batches)]
-            self.i += 1
-            return b
-
-    def _read(self, data_iterator, n: int, mode: str):
-        new = [next(data_iterator) for _ in range(n)]
-        if mode not in self.static_batches:
-            self.static_batches[mode] = [{k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in b.items()} for b in new]
-        else:
-            for s, b in zip(self.static_batches[mode], new):
-                for k, v in b.items():
-                    if isinstance(v, torch.Tensor):
-                        s[k].copy_(v, non_blocking=True)
-        return self._StaticIter(self.static_batches[mode])
-
-    def __call__(self, *, data_iterator, num_microbatches: int, forward_only: bool = False, **kwargs):
-        mode = "eval" if forward_only else "train"
-        if not torch.cuda.is_available():
-            return self.fn(data_iterator=data_iterator, num_microbatches=num_microbatches, forward_only=forward_only, **kwargs)
-        it = self._read(data_iterator, num_microbatches, mode)
-        self.calls[mode] += 1
-        if self.calls[mode] <= self.warmup:
-            return self.fn(data_iterator=it, num_microbatches=num_microbatches, forward_only=forward_only, **kwargs)
-        if mode not in self.graph:
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=_shared_pool()):
-                self.result[mode] = self.fn(data_iterator=it, num_microbatches=num_microbatches, forward_only=forward_only, **kwargs)
-            self.graph[mode] = g
-        self.graph[mode].replay()
-        return self.result[mode]
+def __getattr__(name):
+    # the whole-step graph lives in ``core/full_cuda_graph.py``; kept importable from here (lazy: that module imports this one)
+    if name == "FullCudaGraphWrapper":
+        from ..full_cuda_graph import FullCudaGraphWrapper
+        return FullCudaGraphWrapper
+    raise AttributeError(name)

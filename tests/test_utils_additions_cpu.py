@@ -166,3 +166,34 @@ def test_checkpoint_integrity_manifest_and_strict_helpers(tmp_path):
         V.maybe_report_missing_and_unexpected_keys(V.StrictHandling.RAISE_ALL, {"x"}, set())
     V.maybe_report_missing_and_unexpected_keys(V.StrictHandling.LOG_ALL, {"x"}, {"y"})
     V.maybe_report_missing_and_unexpected_keys(V.StrictHandling.RAISE_UNEXPECTED, {"x"}, set())     # only "unexpected" raises here
+
+
+def test_full_iteration_graph_static_buffers_on_cpu():
+    from megatron_b200.core.full_cuda_graph import FullCudaGraphWrapper, StaticBufferLoader, clone_tensors_in_struct, copy_tensors_in_struct
+
+    a = {"tokens": torch.arange(6).view(2, 3), "meta": ("x", [torch.ones(2)])}
+    s = clone_tensors_in_struct(a, "cpu")
+    ptr = s["tokens"].data_ptr()
+    b = {"tokens": torch.arange(6).view(2, 3) + 10, "meta": ("y", [torch.zeros(2)])}
+    s = copy_tensors_in_struct(s, b)
+    assert s["tokens"].data_ptr() == ptr and s["tokens"][0, 0] == 10 and s["meta"][0] == "y" and s["meta"][1][0].sum() == 0
+    with pytest.raises(ValueError):
+        copy_tensors_in_struct(s, {"tokens": torch.zeros(2, 4), "meta": b["meta"]})
+    seen = []
+
+    def fwd_bwd(*, data_iterator, num_microbatches, forward_only=False):
+        out = [next(data_iterator) for _ in range(num_microbatches)]
+        seen.append([(o["x"].data_ptr(), int(o["x"].sum())) for o in out])
+        return [o["x"].sum() for o in out]
+
+    w = FullCudaGraphWrapper(fwd_bwd, cuda_graph_warmup_steps=1, device="cpu")
+    data = iter([{"x": torch.full((2,), float(i))} for i in range(8)])
+    w(data_iterator=data, num_microbatches=2)
+    w(data_iterator=data, num_microbatches=2)
+    w(data_iterator=data, num_microbatches=2, forward_only=True)
+    assert [p for p, _ in seen[0]] == [p for p, _ in seen[1]], "the same static buffers are read every step"
+    assert [v for _, v in seen[0]] == [0, 2] and [v for _, v in seen[1]] == [4, 6] and [v for _, v in seen[2]] == [8, 10]
+    assert {p for p, _ in seen[2]}.isdisjoint({p for p, _ in seen[0]}), "validation has its own buffers"
+    ld = StaticBufferLoader("cpu")
+    with pytest.raises(IndexError):
+        ld.load("training", 1, {"x": torch.zeros(1)})
