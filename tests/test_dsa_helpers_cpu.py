@@ -127,3 +127,36 @@ def test_moe_utils_additions_match_reference():
     class C:
         fp8, fp4, fp8_recipe = "e4m3", None, "mxfp8"
     assert M.get_align_size_for_quantization(C) == 128
+
+
+def test_hybrid_pattern_helpers_match_reference():
+    from megatron_b200.core.models.hybrid import hybrid_layer_allocation as M
+
+    if not os.path.isdir(REF):
+        pytest.skip("baseline/_ref is not installed")
+    sys.path.insert(0, REF)
+    try:
+        from megatron.core.models.hybrid import hybrid_layer_allocation as R
+    finally:
+        sys.path.remove(REF)
+    for n in (1, 7, 24, 52, 56):
+        for ar, mr in ((0.0, 0.0), (0.1, 0.0), (0.08, 0.5), (0.25, 0.25), (0.5, 0.5), (1.0, 0.0)):
+            assert M.pattern_from_ratios(n, ar, mr) == R.pattern_from_ratios(n, ar, mr), (n, ar, mr)
+    pat = "M-M-|M-M*-/MM/MM"
+    p, r = M.parse_hybrid_pattern(pat), R.parse_hybrid_pattern(pat)
+    assert (p.main_pattern, p.mtp_pattern, p.mtp_num_depths) == (r.main_pattern, r.mtp_pattern, r.mtp_num_depths)
+    assert M.get_hybrid_total_layer_count(pat) == R.get_hybrid_total_layer_count(pat) == 9
+    assert M.get_hybrid_total_pipeline_segment_count(pat) == R.get_hybrid_total_pipeline_segment_count(pat) == 2
+    mine, ref = M.get_hybrid_layer_counts(pat), R.get_hybrid_layer_counts(pat)
+    assert all(mine[k] == v for k, v in ref.items())
+    assert M.select_pipeline_segment("M-M-|M-M*-", pp_rank=1, pp_size=2) == (list("M-M*-"), 4)
+    assert M.select_pipeline_segment("MM|**|--|EE", pp_rank=1, pp_size=2, vp_stage=1) == (list("EE"), 6)
+    assert M.select_pipeline_segment("MMMMMMMM", pp_rank=2, pp_size=4) == (list("MM"), 4)
+    assert M.select_pipeline_segment("M" * 10, pp_rank=3, pp_size=4, first_stage_layers=1, last_stage_layers=3) == (list("MMM"), 7)
+    with pytest.raises(ValueError):
+        M.select_pipeline_segment("MMM", pp_rank=0, pp_size=2)
+    with pytest.raises(ValueError):
+        M.parse_hybrid_pattern("MM/M*/MM")
+    lt = list("M*M-*")
+    got, want = M.get_layer_maps_from_layer_type_list(lt), R.get_layer_maps_from_layer_type_list(lt)
+    assert all(got[k] == v for k, v in want.items())
