@@ -131,3 +131,99 @@ class FaultInjector:
             os.kill(os.getpid(), signal.SIGSTOP)
         elif k == Fault.OS_ABORT:
             os.abort()
+
+
+# ---- function-style API over the reference's flat ``fault_injector_*`` configuration (reference ``fault_injector.py:104-233``) ----
+# ``config`` is any object with the ``fault_injector_*`` attributes (the parsed command line, or ``training.config`` objects).
+_RNG: Optional[random.Random] = None
+_ACTIVE: Optional[FaultInjector] = None
+
+
+def _rng(config) -> random.Random:
+    global _RNG
+    if _RNG is None:
+        seed = getattr(config, "fault_injector_seed", None)
+        _RNG = random.Random(seed if seed is not None else 1234)
+    return _RNG
+
+
+def _csv(v):
+    return [x.strip() for x in str(v).split(",") if x.strip()]
+
+
+def get_fault_ranks(config, world_size: Optional[int] = None):
+    """Explicit ``fault_injector_ranks`` ("3" / "1,5") or ``fault_injector_num_ranks`` random ranks — never rank 0, which keeps
+    the logs and the rendezvous store alive."""
+    import torch.distributed as dist
+    world = world_size if world_size is not None else dist.get_world_size()
+    forced, n = getattr(config, "fault_injector_ranks", None), getattr(config, "fault_injector_num_ranks", None)
+    if forced is not None:
+        assert n is None, "give either fault_injector_ranks or fault_injector_num_ranks"
+        ranks = [int(r) for r in _csv(forced)]
+        assert ranks and all(0 <= r < world for r in ranks), f"fault ranks must lie in [0, {world - 1}]"
+        return ranks
+    assert n is not None, "give either fault_injector_ranks or fault_injector_num_ranks"
+    return _rng(config).sample(range(1, world), k=n)
+
+
+def get_fault(config) -> Fault:
+    kinds = [Fault(k.lower()) if k.lower() in Fault._value2member_map_ else Fault[k.upper()] for k in _csv(getattr(config, "fault_injector_fault_types", None) or "")]
+    assert kinds, "fault_injector_fault_types must name at least one fault"
+    p = getattr(config, "fault_injector_fault_probabilities", None)
+    probs = [float(x) for x in _csv(p)] if p is not None else [1.0] * len(kinds)
+    assert len(probs) == len(kinds), "one probability per fault type"
+    return _rng(config).choices(kinds, weights=probs, k=1)[0]
+
+
+def should_setup_fault_injection_at_start(config) -> bool:
+    return getattr(config, "fault_injector_delay_start_iteration", None) is None
+
+
+def should_setup_fault_injection_at_iteration(config, iteration: int) -> bool:
+    it = getattr(config, "fault_injector_delay_start_iteration", None)
+    return it is not None and it == iteration
+
+
+def get_fault_delay(config) -> float:
+    """Fixed delay, or an exponential inter-arrival draw with mean ``fault_injector_mtti_seconds`` (+ offset): a fleet with a
+    given mean time to interrupt."""
+    d = getattr(config, "fault_injector_fault_delay", None)
+    if d is not None:
+        return float(d)
+    mtti = getattr(config, "fault_injector_mtti_seconds", None)
+    assert mtti is not None, "fault_injector_fault_delay or fault_injector_mtti_seconds must be given"
+    import math
+    return float(getattr(config, "fault_injector_offset_seconds", None) or 0.0) - math.log(1.0 - _rng(config).random()) * mtti
+
+
+def setup_fault_injection(config) -> Optional[FaultInjector]:
+    """Rank 0 draws the plan (which ranks, which fault, when) and broadcasts it — one tensor: slot r = fault id or NaN, last
+    slot = delay — so that the ranks agree even when their RNG streams do not.  Target ranks arm a ``FaultInjector`` (timer
+    thread); the training loop polls it (``maybe_raise``) for the exception-type faults."""
+    global _ACTIVE
+    import math
+
+    import torch.distributed as dist
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+    order = list(Fault)
+    dev = torch.device("cuda", torch.cuda.current_device()) if (dist.is_initialized() and dist.get_backend() == "nccl") else torch.device("cpu")
+    plan = torch.full((world + 1,), float("nan"), dtype=torch.float64, device=dev)
+    if rank == 0:
+        fault = get_fault(config)
+        for r in get_fault_ranks(config, world):
+            plan[r] = float(order.index(fault))
+        plan[world] = get_fault_delay(config)
+    if world > 1:
+        dist.broadcast(plan, src=0)
+    mine = float(plan[rank])
+    if math.isnan(mine):
+        return None
+    fault, delay = order[int(mine)], float(plan[world])
+    import logging
+    logging.getLogger(__name__).warning("FAULT INJECTION: rank %d will inject %s in %.1f s", rank, fault.name, delay)
+    _ACTIVE = FaultInjector(FaultInjectorConfig(fault_type=fault, ranks=[rank], delay_s=delay), rank=rank, world_size=world)
+    return _ACTIVE
+
+
+def get_active_fault_injector() -> Optional[FaultInjector]:
+    return _ACTIVE

@@ -197,3 +197,38 @@ def test_full_iteration_graph_static_buffers_on_cpu():
     ld = StaticBufferLoader("cpu")
     with pytest.raises(IndexError):
         ld.load("training", 1, {"x": torch.zeros(1)})
+
+
+def _fault_plan_worker(rank, world):
+    import time
+    from types import SimpleNamespace
+
+    from megatron_b200.core import fault_injector as F
+
+    cfg = SimpleNamespace(fault_injector_ranks=None, fault_injector_num_ranks=1, fault_injector_fault_types="workload_exc", fault_injector_fault_probabilities=None,
+                          fault_injector_fault_delay=0.05, fault_injector_delay_start_iteration=None, fault_injector_mtti_seconds=None,
+                          fault_injector_offset_seconds=None, fault_injector_seed=7 + rank)          # different seeds: only rank 0's draw counts
+    assert F.should_setup_fault_injection_at_start(cfg) and not F.should_setup_fault_injection_at_iteration(cfg, 3)
+    inj = F.setup_fault_injection(cfg)
+    time.sleep(0.3)
+    hit = False
+    if inj is not None:
+        try:
+            inj.maybe_raise()
+        except F.InjectedFaultError:
+            hit = True
+    return (inj is not None, hit)
+
+
+def test_fault_plan_is_drawn_on_rank0_and_broadcast():
+    from types import SimpleNamespace
+
+    from megatron_b200.core import fault_injector as F
+
+    out = run_distributed(_fault_plan_worker, 3)
+    armed = [o[0] for o in out]
+    assert armed[0] is False and sum(armed) == 1, "one random rank, never rank 0"
+    assert all(hit == a for a, hit in out)
+    cfg = SimpleNamespace(fault_injector_ranks="1,2", fault_injector_num_ranks=None, fault_injector_fault_delay=None, fault_injector_mtti_seconds=100.0,
+                          fault_injector_offset_seconds=5.0, fault_injector_seed=1, fault_injector_fault_types="sigkill,gpu_sleep", fault_injector_fault_probabilities="0,1")
+    assert F.get_fault_ranks(cfg, 4) == [1, 2] and F.get_fault(cfg) is F.Fault.GPU_SLEEP and F.get_fault_delay(cfg) > 5.0
