@@ -77,6 +77,10 @@ def save(sharded_state_dict: ShardedStateDict, checkpoint_dir: str, sharded_stra
             if content_metadata is not None:
                 torch.save(content_metadata, checkpoint_dir / "content_metadata.pt")
             save_config(CheckpointingConfig("torch_dist", 1), str(checkpoint_dir))
+            if verify_integrity:
+                # every shard file is on disk by now (sync: after the collective write; async: inside the finalize step)
+                from .validation import save_integrity_manifest
+                save_integrity_manifest(str(checkpoint_dir))
 
     if not async_sharded_save:
         if plan_cache is not None:
@@ -138,6 +142,19 @@ def load(sharded_state_dict: ShardedStateDict, checkpoint_dir: str, sharded_stra
     cfg = maybe_load_config(str(checkpoint_dir))
     if cfg is None:
         raise CheckpointingException(f"{checkpoint_dir} is not a distributed checkpoint")
+    if verify_integrity:
+        # one rank re-hashes the files (reading a checkpoint world-size times would be the dominant cost); everybody learns the verdict
+        from .validation import verify_integrity_manifest
+        verdict = [None]
+        if _rank() == 0:
+            try:
+                verify_integrity_manifest(str(checkpoint_dir))
+            except CheckpointingException as e:
+                verdict = [str(e)]
+        if torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            torch.distributed.broadcast_object_list(verdict, src=0)
+        if verdict[0] is not None:
+            raise CheckpointingException(verdict[0])
     if cfg.sharded_backend not in ("torch_dist",):
         raise CheckpointingException(f"unsupported sharded backend {cfg.sharded_backend}")
     strict = StrictHandling(strict) if not isinstance(strict, StrictHandling) else strict

@@ -91,6 +91,15 @@ def generate_state_dict(args: Dict[str, Any], model: List, optimizer, opt_param_
     return sd
 
 
+_VERIFY_INTEGRITY = False
+
+
+def configure(verify_integrity: bool = False) -> None:
+    """``--verify-integrity``: write a SHA-256 manifest (``integrity.json``) with every checkpoint and check it before loading one."""
+    global _VERIFY_INTEGRITY
+    _VERIFY_INTEGRITY = bool(verify_integrity)
+
+
 def save_checkpoint(iteration: int, model: List, optimizer, opt_param_scheduler, save_dir: str, args: Optional[Dict[str, Any]] = None,
                     num_floating_point_operations_so_far: float = 0.0, async_save: bool = False, fully_parallel_save: bool = True,
                     keep_last: Optional[int] = None, rerun_state=None, optim_sharding_type: str = "fully_reshardable",
@@ -127,7 +136,8 @@ def save_checkpoint(iteration: int, model: List, optimizer, opt_param_scheduler,
                 if not os.path.islink(old):
                     shutil.rmtree(old, ignore_errors=True)
 
-    req = dist_checkpointing.save(sd, ckpt, sharded_strategy=strategy, async_sharded_save=async_save, cached_structure=assume_constant_structure)
+    req = dist_checkpointing.save(sd, ckpt, sharded_strategy=strategy, async_sharded_save=async_save, cached_structure=assume_constant_structure,
+                                   verify_integrity=_VERIFY_INTEGRITY)
     if req is not None:
         req.add_finalize_fn(write_tracker)
         _ASYNC_QUEUE.schedule_async_request(req)
@@ -178,7 +188,7 @@ def load_checkpoint(model: List, optimizer, opt_param_scheduler, load_dir: str, 
         kw["sharded_strategy"] = FullyParallelLoadStrategyWrapper(None, ps.get_data_parallel_group(with_context_parallel=True))
     if dist_ckpt_strictness is not None:
         kw["strict"] = dist_ckpt_strictness
-    loaded = dist_checkpointing.load(sd, ckpt, **kw)
+    loaded = dist_checkpointing.load(sd, ckpt, verify_integrity=_VERIFY_INTEGRITY, **kw)
     if isinstance(loaded, tuple):            # strictness modes that return the mismatching keys
         loaded, missing, unexpected = loaded
         if _rank() == 0 and (missing or unexpected):

@@ -60,6 +60,7 @@ def add_reference_compat_flags(parser: argparse.ArgumentParser) -> List[str]:
 # dest of a table flag -> what consumes it here.  ``tests/test_training_utils_cpu.py::test_reference_flag_table`` checks that every name listed is really read
 # (by ``apply_reference_compat`` / ``engine_kwargs_from_args`` below or somewhere else in the tree), so this list cannot drift into wishful thinking.
 WIRED: Dict[str, str] = {
+    "verify_integrity": "SHA-256 checkpoint manifest written on save / checked on load (training.checkpointing.configure)",
     # spellings of options that exist under another name
     "tp_size": "tensor_model_parallel_size", "model_parallel_size": "tensor_model_parallel_size (legacy)", "ep_size": "expert_model_parallel_size", "batch_size": "micro_batch_size (legacy)",
     "warmup": "lr_warmup_fraction (legacy)", "checkpoint_activations": "recompute_granularity = full (deprecated spelling)", "grad_reduce_in_bf16": "accumulate_allreduce_grads_in_fp32 = False",

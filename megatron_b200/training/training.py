@@ -635,6 +635,7 @@ def pretrain(train_valid_test_dataset_provider: Callable, model_provider: Callab
     datasets; ``model_provider(pre_process, post_process, vp_stage) -> module``;
     ``forward_step_func(data_iterator, model) -> (output, loss_func)``."""
     args = initialize_megatron(argv, extra_args_provider, args_defaults)
+    checkpointing.configure(verify_integrity=getattr(args, "verify_integrity", False))
     model, optimizer, scheduler = setup_model_and_optimizer(model_provider)
     config = model[0].module.config if hasattr(model[0], "module") else model[0].config
     train_ds, valid_ds, test_ds = train_valid_test_dataset_provider(get_train_valid_test_num_samples(args))

@@ -232,3 +232,22 @@ def test_fault_plan_is_drawn_on_rank0_and_broadcast():
     cfg = SimpleNamespace(fault_injector_ranks="1,2", fault_injector_num_ranks=None, fault_injector_fault_delay=None, fault_injector_mtti_seconds=100.0,
                           fault_injector_offset_seconds=5.0, fault_injector_seed=1, fault_injector_fault_types="sigkill,gpu_sleep", fault_injector_fault_probabilities="0,1")
     assert F.get_fault_ranks(cfg, 4) == [1, 2] and F.get_fault(cfg) is F.Fault.GPU_SLEEP and F.get_fault_delay(cfg) > 5.0
+
+
+def test_verify_integrity_through_save_and_load(tmp_path):
+    import os
+
+    from megatron_b200.core import dist_checkpointing as dc
+    from megatron_b200.core.dist_checkpointing.core import CheckpointingException
+    from megatron_b200.core.dist_checkpointing.mapping import ShardedTensor
+
+    ck = str(tmp_path / "ck")
+    os.makedirs(ck)
+    dc.save({"a": ShardedTensor.from_rank_offsets("a", torch.arange(4.0))}, ck, verify_integrity=True)
+    assert os.path.isfile(os.path.join(ck, "integrity.json"))
+    out = dc.load({"a": ShardedTensor.from_rank_offsets("a", torch.zeros(4))}, ck, verify_integrity=True)
+    assert torch.equal(out["a"], torch.arange(4.0))
+    with open(os.path.join(ck, "common.pt"), "ab") as f:
+        f.write(b"x")
+    with pytest.raises(CheckpointingException, match="hash mismatch"):
+        dc.load({"a": ShardedTensor.from_rank_offsets("a", torch.zeros(4))}, ck, verify_integrity=True)
