@@ -52,7 +52,8 @@ class SafeUnpickler(pickle.Unpickler):
     _SAFE_MODULE_ATTR_PREFIXES = (("torch", ("float", "bfloat", "int", "uint", "bool", "complex", "half", "double", "long", "short")),)
 
     def find_class(self, module: str, name: str):
-        if (module, name) == ("torch.storage", "_load_from_bytes"):
+        # (the reference package, when imported in the same process, re-points torch's tensor pickling at ITS reader: same meaning)
+        if (module, name) in (("torch.storage", "_load_from_bytes"), ("megatron.core.safe_globals", "safe_load_from_bytes")):
             return safe_load_from_bytes                                  # the weights_only reader instead of a nested full unpickle
         if (module, name) in self._SAFE_CLASSES:
             return super().find_class(module, name)
